@@ -1,0 +1,213 @@
+"""ctypes loader for the two CPU checkers declared in oracle/oracle_api.h.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py. The product package
+(my_lidar_graph_slam_v2_b200) never imports this module.
+
+  load("reference") -> oracle/_ref/libcsm_ref.so  (unmodified reference TUs)
+  load("port")      -> oracle/libcsm_port.so      (oracle/port.cpp restatement)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class OrcResult(C.Structure):
+    _fields_ = [
+        ("found", C.c_int32), ("best_x", C.c_int32), ("best_y", C.c_int32),
+        ("best_t", C.c_int32), ("win_x", C.c_int32), ("win_y", C.c_int32),
+        ("win_t", C.c_int32), ("n_known", C.c_int32),
+        ("sum_value", C.c_int64),
+        ("step_x", C.c_double), ("step_y", C.c_double), ("step_t", C.c_double),
+        ("score", C.c_double), ("known_rate", C.c_double),
+        ("n_processed", C.c_int32), ("n_ignored", C.c_int32),
+        ("best_sensor_pose", C.c_double * 3), ("est_pose", C.c_double * 3),
+        ("norm_cost", C.c_double), ("cov", C.c_double * 9),
+    ]
+
+    def asdict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+def build(kind=None):
+    """Build the checkers with oracle/Makefile (ref only if /root/reference exists)."""
+    targets = ["port", "ref"] if kind is None else [{"reference": "ref"}.get(kind, kind)]
+    subprocess.run(["make", "-s", "-C", HERE, "-j8"] + targets, check=True)
+
+
+_PATHS = {
+    "reference": os.path.join(HERE, "_ref", "libcsm_ref.so"),
+    "port": os.path.join(HERE, "libcsm_port.so"),
+}
+
+
+def available(kind):
+    return os.path.exists(_PATHS[kind])
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Oracle:
+    def __init__(self, kind):
+        path = _PATHS[kind]
+        if not os.path.exists(path):
+            build(kind)
+        self.kind = kind
+        lib = C.CDLL(path)
+        self.lib = lib
+        dp = C.POINTER(C.c_double)
+        u16p = C.POINTER(C.c_uint16)
+        i32p = C.POINTER(C.c_int32)
+        rp = C.POINTER(OrcResult)
+        lib.orc_kind.restype = C.c_char_p
+        lib.orc_grid_create.restype = C.c_void_p
+        lib.orc_grid_create.argtypes = [u16p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        lib.orc_grid_destroy.argtypes = [C.c_void_p]
+        lib.orc_precompute.argtypes = [C.c_void_p, C.c_int, u16p]
+        lib.orc_precompute_pyramid.argtypes = [C.c_void_p, C.c_int, u16p]
+        common = [C.c_void_p, dp, dp, C.c_int, dp, dp]
+        lib.orc_match_rt.argtypes = common + [C.c_int] + [C.c_double] * 5 + [rp]
+        lib.orc_match_bb.argtypes = common + [C.c_int] + [C.c_double] * 5 + [rp]
+        lib.orc_match_grid.argtypes = common + [C.c_double] * 8 + [rp]
+        lib.orc_loopdet_create.restype = C.c_void_p
+        lib.orc_loopdet_create.argtypes = [C.c_int] + [C.c_double] * 5 + [C.c_int]
+        lib.orc_loopdet_destroy.argtypes = [C.c_void_p]
+        lib.orc_loopdet_clear_cache.argtypes = [C.c_void_p]
+        lib.orc_loopdet_detect.argtypes = [
+            C.c_void_p, C.c_int, C.POINTER(C.c_void_p), i32p, dp, i32p, dp,
+            C.c_int, C.c_int, dp, dp, rp, dp]
+        assert lib.orc_kind().decode() == kind
+
+    # -- grids ------------------------------------------------------------
+    def grid(self, dense, res, off_x, off_y):
+        dense = np.ascontiguousarray(dense, dtype=np.uint16)
+        h = self.lib.orc_grid_create(
+            dense.ctypes.data_as(C.POINTER(C.c_uint16)), dense.shape[0],
+            dense.shape[1], res, off_x, off_y)
+        if not h:
+            raise ValueError("orc_grid_create failed (rows/cols must be multiples of 16)")
+        return OracleGrid(self, h, dense.shape)
+
+    # -- matchers ---------------------------------------------------------
+    @staticmethod
+    def _scan(angles, ranges, init_pose, rel_pose):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        p = np.ascontiguousarray(init_pose, dtype=np.float64)
+        q = np.ascontiguousarray(rel_pose if rel_pose is not None else (0.0, 0.0, 0.0),
+                                 dtype=np.float64)
+        return a, r, p, q
+
+    def match_rt(self, grid, angles, ranges, init_pose, low_res, rng, thr=(0.0, 0.0), rel_pose=None):
+        a, r, p, q = self._scan(angles, ranges, init_pose, rel_pose)
+        out = OrcResult()
+        rc = self.lib.orc_match_rt(grid.h, _dptr(a), _dptr(r), len(a), _dptr(p), _dptr(q),
+                                   low_res, rng[0], rng[1], rng[2], thr[0], thr[1], C.byref(out))
+        assert rc == 0
+        return out
+
+    def match_bb(self, grid, angles, ranges, init_pose, hmax, rng, thr=(0.0, 0.0), rel_pose=None):
+        a, r, p, q = self._scan(angles, ranges, init_pose, rel_pose)
+        out = OrcResult()
+        rc = self.lib.orc_match_bb(grid.h, _dptr(a), _dptr(r), len(a), _dptr(p), _dptr(q),
+                                   hmax, rng[0], rng[1], rng[2], thr[0], thr[1], C.byref(out))
+        assert rc == 0
+        return out
+
+    def match_grid(self, grid, angles, ranges, init_pose, rng, step, thr=(0.0, 0.0), rel_pose=None):
+        a, r, p, q = self._scan(angles, ranges, init_pose, rel_pose)
+        out = OrcResult()
+        rc = self.lib.orc_match_grid(grid.h, _dptr(a), _dptr(r), len(a), _dptr(p), _dptr(q),
+                                     rng[0], rng[1], rng[2], step[0], step[1], step[2],
+                                     thr[0], thr[1], C.byref(out))
+        assert rc == 0
+        return out
+
+    def loop_detector(self, hmax, rng, thr, n_threads=1):
+        return OracleLoopDetector(self, hmax, rng, thr, n_threads)
+
+
+class OracleGrid:
+    def __init__(self, oracle, h, shape):
+        self.oracle, self.h, self.shape = oracle, h, shape
+
+    def precompute(self, win):
+        out = np.empty(self.shape, dtype=np.uint16)
+        self.oracle.lib.orc_precompute(self.h, win, out.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return out
+
+    def pyramid(self, hmax):
+        out = np.empty((hmax + 1,) + tuple(self.shape), dtype=np.uint16)
+        self.oracle.lib.orc_precompute_pyramid(self.h, hmax, out.ctypes.data_as(C.POINTER(C.c_uint16)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.oracle.lib.orc_grid_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OracleLoopDetector:
+    def __init__(self, oracle, hmax, rng, thr, n_threads):
+        self.oracle = oracle
+        self.n_threads = n_threads
+        self.h = oracle.lib.orc_loopdet_create(hmax, rng[0], rng[1], rng[2], thr[0], thr[1], n_threads)
+
+    def clear_cache(self):
+        self.oracle.lib.orc_loopdet_clear_cache(self.h)
+
+    def detect(self, grids, map_ids, map_poses, scan_idx, scan_poses, angles, ranges):
+        """grids: list[OracleGrid] per query; angles/ranges: (n_scans, n_beams)."""
+        nq = len(grids)
+        gh = (C.c_void_p * nq)(*[g.h for g in grids])
+        mid = np.ascontiguousarray(map_ids, dtype=np.int32)
+        sid = np.ascontiguousarray(scan_idx, dtype=np.int32)
+        mp = np.ascontiguousarray(map_poses, dtype=np.float64).reshape(nq, 3)
+        sp = np.ascontiguousarray(scan_poses, dtype=np.float64).reshape(nq, 3)
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        assert a.ndim == 2 and a.shape == r.shape
+        out = (OrcResult * nq)()
+        el = C.c_double(0.0)
+        i32p = C.POINTER(C.c_int32)
+        rc = self.oracle.lib.orc_loopdet_detect(
+            self.h, nq, gh, mid.ctypes.data_as(i32p), _dptr(mp), sid.ctypes.data_as(i32p),
+            _dptr(sp), a.shape[0], a.shape[1], _dptr(a), _dptr(r), out, C.byref(el))
+        assert rc == 0
+        return list(out), el.value
+
+    def close(self):
+        if self.h:
+            self.oracle.lib.orc_loopdet_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_CACHE = {}
+
+
+def load(kind="reference"):
+    if kind not in _CACHE:
+        _CACHE[kind] = Oracle(kind)
+    return _CACHE[kind]

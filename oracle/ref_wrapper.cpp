@@ -1,0 +1,585 @@
+/* ref_wrapper.cpp -- drives the UNMODIFIED reference implementation through
+ * the C interface of oracle_api.h.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle_api.h). This file is compiled together
+ * with the reference translation units where they lie under /root/reference
+ * (recipe: oracle/Makefile, output: oracle/_ref/libcsm_ref.so). All matching
+ * decisions are taken by the reference classes
+ *   ScanMatcherCorrelative  (scan_matcher_correlative.cpp:92-244),
+ *   ScanMatcherBranchBound  (scan_matcher_branch_bound.cpp:87-278),
+ *   ScanMatcherGridSearch   (scan_matcher_grid_search.cpp:69-178),
+ *   LoopDetectorBranchBound (loop_detector_branch_bound.cpp:59-156),
+ *   PrecomputeGridMap(s)    (grid_map_builder.cpp:987-1065);
+ * this wrapper only builds their inputs from plain arrays and decodes the
+ * window indices / integer score at the pose the reference returned.
+ */
+
+#include "oracle_api.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "my_lidar_graph_slam/pose.hpp"
+#include "my_lidar_graph_slam/point.hpp"
+#include "my_lidar_graph_slam/metric/metric.hpp"
+#include "my_lidar_graph_slam/sensor/sensor_data.hpp"
+#include "my_lidar_graph_slam/mapping/grid_map_types.hpp"
+#include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
+#include "my_lidar_graph_slam/mapping/cost_function_square_error.hpp"
+#include "my_lidar_graph_slam/mapping/score_function_pixel_accurate.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_correlative.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_grid_search.hpp"
+#include "my_lidar_graph_slam/mapping/loop_detector.hpp"
+#include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/pose_graph.hpp"
+
+using namespace MyLidarGraphSlam;
+using namespace MyLidarGraphSlam::Mapping;
+
+namespace {
+
+constexpr int kBlockSize = 16;
+constexpr double kCovarianceScale = 1e4;
+
+struct RefGrid
+{
+    GridMap mMap;
+    explicit RefGrid(GridMap&& map) : mMap(std::move(map)) { }
+};
+
+std::atomic<int> gNameCounter { 0 };
+
+std::string UniqueName(const char* prefix)
+{
+    return std::string(prefix) + "#" + std::to_string(gNameCounter++);
+}
+
+Sensor::ScanDataPtr<double> MakeScan(const double* angles,
+                                     const double* ranges, const int n,
+                                     const double relPose[3])
+{
+    std::vector<double> a(angles, angles + n);
+    std::vector<double> r(ranges, ranges + n);
+    const double rmin = *std::min_element(r.begin(), r.end());
+    const double rmax = *std::max_element(r.begin(), r.end());
+    const double amin = *std::min_element(a.begin(), a.end());
+    const double amax = *std::max_element(a.begin(), a.end());
+    const RobotPose2D<double> zero { 0.0, 0.0, 0.0 };
+    const RobotPose2D<double> rel { relPose[0], relPose[1], relPose[2] };
+    return std::make_shared<Sensor::ScanData<double>>(
+        "oracle", 0.0, zero, zero, rel, rmin, rmax, amin, amax,
+        std::move(a), std::move(r));
+}
+
+int LastInt(const std::string& id)
+{
+    auto* seq = Metric::MetricManager::Instance()->ValueSequenceMetric<int>(id);
+    const std::size_t n = seq->NumOfValues();
+    const int v = (n > 0) ? seq->ValueAt(n - 1) : 0;
+    seq->Reset();
+    return v;
+}
+
+float LastFloat(const std::string& id)
+{
+    auto* seq =
+        Metric::MetricManager::Instance()->ValueSequenceMetric<float>(id);
+    const std::size_t n = seq->NumOfValues();
+    const float v = (n > 0) ? seq->ValueAt(n - 1) : 0.0f;
+    seq->Reset();
+    return v;
+}
+
+void ResetMatcherMetrics(const std::string& name, bool gridSearch)
+{
+    auto* mgr = Metric::MetricManager::Instance();
+    static const char* ints[] = { ".InputSetupTime", ".OptimizationTime",
+        ".WinSizeX", ".WinSizeY", ".WinSizeTheta", ".NumOfIgnoredNodes",
+        ".NumOfProcessedNodes", ".NumOfScans", ".NumOfScoreEvaluations",
+        ".NumOfScoreUpdates" };
+    static const char* floats[] = { ".DiffTranslation", ".DiffRotation",
+        ".StepSizeX", ".StepSizeY", ".StepSizeTheta", ".ScoreValue",
+        ".CostValue" };
+    (void)gridSearch;
+    for (const char* s : ints)
+        mgr->ValueSequenceMetric<int>(name + s)->Reset();
+    for (const char* s : floats)
+        mgr->ValueSequenceMetric<float>(name + s)->Reset();
+}
+
+void FillSummary(const ScanMatchingSummary& summary, orc_result* out)
+{
+    out->found = summary.mPoseFound ? 1 : 0;
+    out->est_pose[0] = summary.mEstimatedPose.mX;
+    out->est_pose[1] = summary.mEstimatedPose.mY;
+    out->est_pose[2] = summary.mEstimatedPose.mTheta;
+    out->norm_cost = summary.mNormalizedCost;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            out->cov[r * 3 + c] = summary.mEstimatedCovariance(r, c);
+}
+
+/* Diagnostics at the returned pose: the per-node score of
+ * score_function_pixel_accurate.cpp:16-58 (re-projection per pose) */
+void DiagnosePixelAccurate(const GridMap& map,
+                           const Sensor::ScanDataPtr<double>& scan,
+                           const RobotPose2D<double>& pose, orc_result* out)
+{
+    ScorePixelAccurate scoreFunc;
+    const auto summary = scoreFunc.Score(map, scan, pose);
+    out->score = summary.mNormalizedScore;
+    out->known_rate = summary.mKnownRate;
+    std::int64_t sum = 0;
+    int known = 0;
+    for (std::size_t i = 0; i < scan->NumOfScans(); ++i) {
+        const Point2D<double> hit = scan->HitPoint(pose, i);
+        const Point2D<int> idx = map.PositionToIndex(hit.mX, hit.mY);
+        const std::uint16_t v = map.ValueOr(idx.mY, idx.mX, 0);
+        if (v != 0) { sum += v; ++known; }
+    }
+    out->sum_value = sum;
+    out->n_known = known;
+}
+
+/* Diagnostics for the real-time correlative matcher: indices are computed
+ * once per angle and shifted by integers (scan_matcher_correlative.cpp:161-168,
+ * 301-336) */
+void DiagnoseShifted(const GridMap& map,
+                     const Sensor::ScanDataPtr<double>& scan,
+                     const RobotPose2D<double>& anglePose,
+                     const int offX, const int offY, orc_result* out)
+{
+    double sumScore = 0.0;
+    std::int64_t sum = 0;
+    int known = 0;
+    const std::size_t n = scan->NumOfScans();
+    for (std::size_t i = 0; i < n; ++i) {
+        const Point2D<double> hit = scan->HitPoint(anglePose, i);
+        const Point2D<int> idx = map.PositionToIndex(hit.mX, hit.mY);
+        const double prob = map.ProbabilityOr(idx.mY + offY, idx.mX + offX, 0.0);
+        if (prob == 0.0)
+            continue;
+        sumScore += prob;
+        sum += map.ValueOr(idx.mY + offY, idx.mX + offX, 0);
+        ++known;
+    }
+    out->score = sumScore / static_cast<double>(n);
+    out->known_rate = static_cast<double>(known) / static_cast<double>(n);
+    out->sum_value = sum;
+    out->n_known = known;
+}
+
+void SearchStep(const GridMap& map, const Sensor::ScanDataPtr<double>& scan,
+                double& stepX, double& stepY, double& stepT)
+{
+    /* scan_matcher_correlative.cpp:255-274 (private there) */
+    const double res = map.Resolution();
+    const double maxRange = *std::max_element(
+        scan->Ranges().cbegin(), scan->Ranges().cend());
+    const double theta = res / maxRange;
+    stepX = res;
+    stepY = res;
+    stepT = std::acos(1.0 - 0.5 * theta * theta);
+}
+
+void DecodeWindow(const GridMap& map, const Sensor::ScanDataPtr<double>& scan,
+                  const RobotPose2D<double>& initPose,
+                  const ScanMatchingSummary& summary,
+                  const double rangeX, const double rangeY, const double rangeT,
+                  orc_result* out, RobotPose2D<double>& sensorPose,
+                  RobotPose2D<double>& bestPose)
+{
+    sensorPose = Compound(initPose, scan->RelativeSensorPose());
+    SearchStep(map, scan, out->step_x, out->step_y, out->step_t);
+    out->win_x = static_cast<int>(std::ceil(0.5 * rangeX / out->step_x));
+    out->win_y = static_cast<int>(std::ceil(0.5 * rangeY / out->step_y));
+    out->win_t = static_cast<int>(std::ceil(0.5 * rangeT / out->step_t));
+    const RobotPose2D<double> best =
+        Compound(summary.mEstimatedPose, scan->RelativeSensorPose());
+    out->best_x = static_cast<int>(std::lround(
+        (best.mX - sensorPose.mX) / out->step_x));
+    out->best_y = static_cast<int>(std::lround(
+        (best.mY - sensorPose.mY) / out->step_y));
+    out->best_t = static_cast<int>(std::lround(
+        (best.mTheta - sensorPose.mTheta) / out->step_t));
+    /* Rebuild the pose exactly like the matchers do */
+    bestPose = RobotPose2D<double> {
+        sensorPose.mX + out->best_x * out->step_x,
+        sensorPose.mY + out->best_y * out->step_y,
+        sensorPose.mTheta + out->best_t * out->step_t };
+    out->best_sensor_pose[0] = bestPose.mX;
+    out->best_sensor_pose[1] = bestPose.mY;
+    out->best_sensor_pose[2] = bestPose.mTheta;
+}
+
+/* Dense row-major copy, one ValueOr per cell. GridMap::CopyValues is not used:
+ * for 16-bit buffers CopyValuesInternal advances the destination by
+ * count / sizeof(U) elements (grid_map.cpp:343,349), i.e. by half a row */
+template <typename MapType>
+void Flatten(const MapType& map, uint16_t* out)
+{
+    const int rows = map.Rows();
+    const int cols = map.Cols();
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c)
+            out[static_cast<std::size_t>(r) * cols + c] = map.ValueOr(r, c, 0);
+}
+
+/* Final matcher that hands the coarse estimate through unchanged: the
+ * sub-pixel refiners (scan_matcher_hill_climbing / linear_solver) are
+ * outside the hot path */
+class PassThroughMatcher final : public ScanMatcher
+{
+public:
+    PassThroughMatcher() : ScanMatcher("PassThrough") { }
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override
+    {
+        return ScanMatchingSummary { true, 0.0, query.mMapLocalInitialPose,
+                                     query.mMapLocalInitialPose,
+                                     Eigen::Matrix3d::Zero() };
+    }
+};
+
+struct RefLoopDetector
+{
+    int    mHeightMax;
+    double mRangeX, mRangeY, mRangeT, mScoreThr, mKnownThr;
+    int    mNumThreads;
+    std::vector<std::shared_ptr<ScanMatcherBranchBound>> mMatchers;
+    std::vector<std::unique_ptr<LoopDetectorBranchBound>> mDetectors;
+
+    void Build()
+    {
+        this->mMatchers.clear();
+        this->mDetectors.clear();
+        for (int i = 0; i < this->mNumThreads; ++i) {
+            auto scoreFunc = std::make_shared<ScorePixelAccurate>();
+            auto costFunc = std::make_shared<CostSquareError>(kCovarianceScale);
+            auto matcher = std::make_shared<ScanMatcherBranchBound>(
+                UniqueName("LoopBB"), scoreFunc, costFunc, this->mHeightMax,
+                this->mRangeX, this->mRangeY, this->mRangeT);
+            auto finalMatcher = std::make_shared<PassThroughMatcher>();
+            this->mMatchers.push_back(matcher);
+            this->mDetectors.push_back(
+                std::make_unique<LoopDetectorBranchBound>(
+                    UniqueName("LoopDet"), matcher, finalMatcher,
+                    this->mScoreThr, this->mKnownThr));
+        }
+    }
+};
+
+} /* namespace */
+
+extern "C" {
+
+const char* orc_kind(void) { return "reference"; }
+
+void* orc_grid_create(const uint16_t* dense, int rows, int cols,
+                      double resolution, double offset_x, double offset_y)
+{
+    if (rows <= 0 || cols <= 0 || rows % kBlockSize || cols % kBlockSize)
+        return nullptr;
+    GridMap map { resolution, kBlockSize, rows / kBlockSize, cols / kBlockSize,
+                  Point2D<double> { offset_x, offset_y } };
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const std::uint16_t v = dense[static_cast<std::size_t>(r) * cols + c];
+            if (v != 0)
+                map.SetValue(r, c, v);
+        }
+    return new RefGrid(std::move(map));
+}
+
+void orc_grid_destroy(void* grid)
+{
+    delete static_cast<RefGrid*>(grid);
+}
+
+int orc_precompute(void* grid, int win, uint16_t* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    const ConstMap precomp = PrecomputeGridMap(map, win);
+    Flatten(precomp, out);
+    return 0;
+}
+
+int orc_precompute_pyramid(void* grid, int hmax, uint16_t* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    std::vector<ConstMap> maps;
+    PrecomputeGridMaps(map, maps, hmax);
+    const std::size_t cells =
+        static_cast<std::size_t>(map.Rows()) * map.Cols();
+    for (std::size_t h = 0; h < maps.size(); ++h)
+        Flatten(maps[h], out + h * cells);
+    return 0;
+}
+
+int orc_match_rt(void* grid, const double* angles, const double* ranges, int n,
+                 const double init_pose[3], const double rel_sensor_pose[3],
+                 int low_res, double range_x, double range_y, double range_t,
+                 double score_thr, double known_thr, orc_result* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    const auto scan = MakeScan(angles, ranges, n, rel_sensor_pose);
+    const RobotPose2D<double> initPose {
+        init_pose[0], init_pose[1], init_pose[2] };
+    const std::string name = UniqueName("RT");
+    ScanMatcherCorrelative matcher {
+        name, std::make_shared<CostSquareError>(kCovarianceScale),
+        low_res, range_x, range_y, range_t };
+    const ConstMap precomp = matcher.ComputeCoarserMap(map);
+    const ScanMatchingSummary summary = matcher.OptimizePose(
+        map, precomp, scan, initPose, score_thr, known_thr);
+
+    *out = orc_result { };
+    FillSummary(summary, out);
+    RobotPose2D<double> sensorPose, bestPose;
+    DecodeWindow(map, scan, initPose, summary, range_x, range_y, range_t,
+                 out, sensorPose, bestPose);
+    const RobotPose2D<double> anglePose {
+        sensorPose.mX, sensorPose.mY,
+        sensorPose.mTheta + out->step_t * out->best_t };
+    DiagnoseShifted(map, scan, anglePose, out->best_x, out->best_y, out);
+    out->n_processed = LastInt(name + ".NumOfProcessedNodes");
+    out->n_ignored = LastInt(name + ".NumOfIgnoredNodes");
+    ResetMatcherMetrics(name, false);
+    return 0;
+}
+
+int orc_match_bb(void* grid, const double* angles, const double* ranges, int n,
+                 const double init_pose[3], const double rel_sensor_pose[3],
+                 int hmax, double range_x, double range_y, double range_t,
+                 double score_thr, double known_thr, orc_result* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    const auto scan = MakeScan(angles, ranges, n, rel_sensor_pose);
+    const RobotPose2D<double> initPose {
+        init_pose[0], init_pose[1], init_pose[2] };
+    const std::string name = UniqueName("BB");
+    ScanMatcherBranchBound matcher {
+        name, std::make_shared<ScorePixelAccurate>(),
+        std::make_shared<CostSquareError>(kCovarianceScale),
+        hmax, range_x, range_y, range_t };
+    const std::vector<ConstMap> pyramid = matcher.ComputeCoarserMaps(map);
+    const ScanMatchingSummary summary = matcher.OptimizePose(
+        map, pyramid, scan, initPose, score_thr, known_thr);
+
+    *out = orc_result { };
+    FillSummary(summary, out);
+    RobotPose2D<double> sensorPose, bestPose;
+    DecodeWindow(map, scan, initPose, summary, range_x, range_y, range_t,
+                 out, sensorPose, bestPose);
+    DiagnosePixelAccurate(map, scan, bestPose, out);
+    out->n_processed = LastInt(name + ".NumOfProcessedNodes");
+    out->n_ignored = LastInt(name + ".NumOfIgnoredNodes");
+    ResetMatcherMetrics(name, false);
+    return 0;
+}
+
+int orc_match_grid(void* grid, const double* angles, const double* ranges, int n,
+                   const double init_pose[3], const double rel_sensor_pose[3],
+                   double range_x, double range_y, double range_t,
+                   double step_x, double step_y, double step_t,
+                   double score_thr, double known_thr, orc_result* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    const auto scan = MakeScan(angles, ranges, n, rel_sensor_pose);
+    const RobotPose2D<double> initPose {
+        init_pose[0], init_pose[1], init_pose[2] };
+    const std::string name = UniqueName("GS");
+    ScanMatcherGridSearch matcher {
+        name, std::make_shared<ScorePixelAccurate>(),
+        std::make_shared<CostSquareError>(kCovarianceScale),
+        range_x, range_y, range_t, step_x, step_y, step_t };
+    const ScanMatchingSummary summary = matcher.OptimizePose(
+        map, scan, initPose, score_thr, known_thr);
+
+    *out = orc_result { };
+    FillSummary(summary, out);
+    out->step_x = step_x;
+    out->step_y = step_y;
+    out->step_t = step_t;
+    const RobotPose2D<double> sensorPose =
+        Compound(initPose, scan->RelativeSensorPose());
+    const RobotPose2D<double> best =
+        Compound(summary.mEstimatedPose, scan->RelativeSensorPose());
+    /* Decode the loop indices with the same accumulating loops as
+     * scan_matcher_grid_search.cpp:118-120 */
+    auto decode = [](const double radius, const double step,
+                     const double base, const double value, double& outPose) {
+        int bestIdx = 0;
+        double bestErr = 1e300;
+        int idx = 0;
+        for (double d = -radius; d <= radius; d += step, ++idx) {
+            const double err = std::fabs((base + d) - value);
+            if (err < bestErr) { bestErr = err; bestIdx = idx; outPose = base + d; }
+        }
+        return bestIdx;
+    };
+    RobotPose2D<double> bestPose = sensorPose;
+    if (summary.mPoseFound) {
+        out->best_x = decode(range_x / 2.0, step_x, sensorPose.mX, best.mX,
+                             bestPose.mX);
+        out->best_y = decode(range_y / 2.0, step_y, sensorPose.mY, best.mY,
+                             bestPose.mY);
+        out->best_t = decode(range_t / 2.0, step_t, sensorPose.mTheta,
+                             best.mTheta, bestPose.mTheta);
+    } else {
+        out->best_x = out->best_y = out->best_t = -1;
+    }
+    out->best_sensor_pose[0] = bestPose.mX;
+    out->best_sensor_pose[1] = bestPose.mY;
+    out->best_sensor_pose[2] = bestPose.mTheta;
+    DiagnosePixelAccurate(map, scan, bestPose, out);
+    out->n_processed = LastInt(name + ".NumOfScoreEvaluations");
+    out->n_ignored = LastInt(name + ".NumOfScoreUpdates");
+    ResetMatcherMetrics(name, true);
+    return 0;
+}
+
+void* orc_loopdet_create(int hmax, double range_x, double range_y, double range_t,
+                         double score_thr, double known_thr, int n_threads)
+{
+    auto* det = new RefLoopDetector;
+    det->mHeightMax = hmax;
+    det->mRangeX = range_x;
+    det->mRangeY = range_y;
+    det->mRangeT = range_t;
+    det->mScoreThr = score_thr;
+    det->mKnownThr = known_thr;
+    det->mNumThreads = std::max(1, n_threads);
+    det->Build();
+    return det;
+}
+
+void orc_loopdet_destroy(void* det)
+{
+    delete static_cast<RefLoopDetector*>(det);
+}
+
+void orc_loopdet_clear_cache(void* det)
+{
+    /* The reference never evicts its pyramid cache
+     * (loop_detector_branch_bound.cpp:83-89): rebuild the detectors */
+    static_cast<RefLoopDetector*>(det)->Build();
+}
+
+int orc_loopdet_detect(void* detPtr, int n_queries,
+                       void* const* grids, const int32_t* map_ids,
+                       const double* map_global_poses,
+                       const int32_t* scan_idx, const double* scan_global_poses,
+                       int n_scans, int n_beams,
+                       const double* angles, const double* ranges,
+                       orc_result* out, double* elapsed_s)
+{
+    auto* det = static_cast<RefLoopDetector*>(detPtr);
+    const double rel[3] = { 0.0, 0.0, 0.0 };
+
+    /* Build the pose-graph objects the queries refer to */
+    std::vector<Sensor::ScanDataPtr<double>> scans;
+    for (int s = 0; s < n_scans; ++s)
+        scans.push_back(MakeScan(angles + static_cast<std::size_t>(s) * n_beams,
+                                 ranges + static_cast<std::size_t>(s) * n_beams,
+                                 n_beams, rel));
+
+    std::vector<std::unique_ptr<LocalMap>> localMaps;
+    std::vector<std::unique_ptr<LocalMapNode>> localMapNodes;
+    std::vector<std::unique_ptr<ScanNode>> scanNodes;
+    std::vector<std::unique_ptr<ScanNode>> refScanNodes;
+    localMaps.reserve(n_queries);
+    for (int q = 0; q < n_queries; ++q) {
+        const LocalMapId mapId { map_ids[q] };
+        GridMap copy = static_cast<RefGrid*>(grids[q])->mMap;
+        auto localMap = std::make_unique<LocalMap>(
+            mapId, std::move(copy), NodeId { 0 });
+        localMap->mFinished = true;
+        localMaps.push_back(std::move(localMap));
+        const RobotPose2D<double> mapPose { map_global_poses[3 * q],
+            map_global_poses[3 * q + 1], map_global_poses[3 * q + 2] };
+        localMapNodes.push_back(std::make_unique<LocalMapNode>(mapId, mapPose));
+        const RobotPose2D<double> scanPose { scan_global_poses[3 * q],
+            scan_global_poses[3 * q + 1], scan_global_poses[3 * q + 2] };
+        const RobotPose2D<double> zero { 0.0, 0.0, 0.0 };
+        /* Query scan node: Id = query index so results can be mapped back */
+        scanNodes.push_back(std::make_unique<ScanNode>(
+            NodeId { q }, LocalMapId { -1 }, zero, scans[scan_idx[q]], scanPose));
+        /* Reference scan node inside the local map (only its local pose and
+         * map Id are read, loop_detector_branch_bound.cpp:110-118) */
+        refScanNodes.push_back(std::make_unique<ScanNode>(
+            NodeId { n_queries + q }, mapId, zero, scans[scan_idx[q]], mapPose));
+    }
+
+    const int nThreads = det->mNumThreads;
+    std::vector<LoopDetectionResultVector> results(nThreads);
+    std::vector<double> times(nThreads, 0.0);
+
+    auto worker = [&](const int t) {
+        const int begin = static_cast<int>(
+            static_cast<long long>(n_queries) * t / nThreads);
+        const int end = static_cast<int>(
+            static_cast<long long>(n_queries) * (t + 1) / nThreads);
+        LoopDetectionQueryVector queries;
+        queries.reserve(end - begin);
+        for (int q = begin; q < end; ++q)
+            queries.emplace_back(*scanNodes[q], *refScanNodes[q],
+                                 *localMaps[q], *localMapNodes[q]);
+        const auto t0 = std::chrono::steady_clock::now();
+        results[t] = det->mDetectors[t]->Detect(queries);
+        const auto t1 = std::chrono::steady_clock::now();
+        times[t] = std::chrono::duration<double>(t1 - t0).count();
+    };
+
+    if (nThreads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int t = 0; t < nThreads; ++t)
+            threads.emplace_back(worker, t);
+        for (auto& th : threads)
+            th.join();
+    }
+
+    if (elapsed_s != nullptr)
+        *elapsed_s = *std::max_element(times.begin(), times.end());
+
+    for (int q = 0; q < n_queries; ++q) {
+        out[q] = orc_result { };
+        out[q].best_x = out[q].best_y = out[q].best_t = 0;
+    }
+
+    for (int t = 0; t < nThreads; ++t) {
+        for (const auto& result : results[t]) {
+            const int q = result.mScanNodeId.mId;
+            orc_result* o = &out[q];
+            const GridMap& map = localMaps[q]->mMap;
+            const auto& scan = scans[scan_idx[q]];
+            const RobotPose2D<double> initPose = InverseCompound(
+                localMapNodes[q]->mGlobalPose, scanNodes[q]->mGlobalPose);
+            const ScanMatchingSummary summary {
+                true, 0.0, initPose, result.mRelativePose,
+                result.mEstimatedCovMat };
+            FillSummary(summary, o);
+            RobotPose2D<double> sensorPose, bestPose;
+            DecodeWindow(map, scan, initPose, summary, det->mRangeX,
+                         det->mRangeY, det->mRangeT, o, sensorPose, bestPose);
+            DiagnosePixelAccurate(map, scan, bestPose, o);
+        }
+    }
+
+    /* Keep the metric registry from growing without bound */
+    for (int t = 0; t < nThreads; ++t)
+        ResetMatcherMetrics(det->mMatchers[t]->Name(), false);
+
+    return 0;
+}
+
+} /* extern "C" */
