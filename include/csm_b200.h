@@ -1,0 +1,216 @@
+/* csm_b200.h -- C ABI of the B200-native correlative scan matching /
+ * loop-detection hot path (libcsm_b200.so).
+ *
+ * This is the drop-in boundary: plain C types, no exceptions, no torch types.
+ * It is what a host-side adapter class deriving from the reference's
+ * ScanMatcher / LoopDetector plugin interfaces binds to (see INTEGRATION.md and
+ * my_lidar_graph_slam_v2_b200/host/). The boundary sits where the reference's
+ * own accelerator offload puts it: the register/DMA calls of
+ * scan_matcher_correlative_fpga.cpp:277-311 (SetParameterRegisters /
+ * SendScanData / SendGridMap / ReceiveResult), with a device-side map cache
+ * keyed by LocalMapId like scan_matcher_correlative_fpga.cpp:261-270,301-304.
+ *
+ * Citations are paths relative to the reference repository root.
+ *
+ * Conventions
+ *  - Every function returns CSM_OK (0) or a negative CSM_E_* status;
+ *    csm_last_error(h) gives a message. "No pose found" is a normal result
+ *    (csm_result.found == 0), not an error (scan_matcher_correlative.cpp:201).
+ *  - One handle per matcher / detector instance. A handle owns one CUDA
+ *    stream and all its device buffers; the library has no process-global
+ *    mutable state, so the front-end matcher and the back-end loop detector
+ *    (two threads, lidar_graph_slam.cpp:777-779) use separate handles
+ *    concurrently. A single handle must not be used from two threads at once.
+ *  - All host pointers are borrowed for the duration of the call only.
+ *  - There is no CPU fallback: every entry point fails with CSM_E_CUDA when
+ *    no CUDA device is usable.
+ */
+#ifndef CSM_B200_H
+#define CSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSM_OK              0
+#define CSM_E_INVALID      -1   /* bad argument */
+#define CSM_E_CUDA         -2   /* CUDA runtime error (see csm_last_error) */
+#define CSM_E_NOT_FOUND    -3   /* unknown map / scan id */
+#define CSM_E_CAPACITY     -4   /* a device-side queue overflowed */
+#define CSM_E_UNSUPPORTED  -5   /* parameter outside the supported range */
+
+/* csm_result.flags */
+#define CSM_FLAG_FP_MARGIN   1  /* a projected hit point lies within the FP
+                                 * guard band of a cell boundary (DESIGN.md
+                                 * "FP index parity"); result computed with
+                                 * device trigonometry may differ from glibc */
+#define CSM_FLAG_KEY_TIE     2  /* the winning integer key is shared by
+                                 * another candidate; first in reference
+                                 * iteration order was taken */
+#define CSM_FLAG_EDGE        4  /* B&B: a hit index minus the window is
+                                 * negative (bound not admissible at the
+                                 * low-index edge) */
+
+typedef struct csm_context* csm_handle;
+
+/* Result of one match. Mirrors what the reference matchers decide before the
+ * CPU epilogue (Cost / ComputeCovariance / MoveBackward,
+ * scan_matcher_correlative.cpp:199-219). */
+typedef struct csm_result
+{
+    int32_t found;            /* poseFound: best score > score threshold */
+    int32_t best_x;           /* RT / B&B: window index in cells (bestWinX, Node::mX);
+                                 grid search: index into dx[] (-1 if not found) */
+    int32_t best_y;
+    int32_t best_t;
+    int64_t sum_value;        /* sum of u16 cell values over known cells at the best pose */
+    int32_t n_known;          /* number of known (non-zero) cells at the best pose */
+    int32_t flags;            /* CSM_FLAG_* */
+    double  normalized_score; /* sum of probabilities / N, accumulated in scan
+                                 order in double like score_function_pixel_accurate.cpp:21-57 */
+    int32_t n_processed;      /* nodes expanded / coarse cells refined on the device */
+    int32_t n_ignored;        /* nodes pruned / coarse cells skipped on the device */
+} csm_result;
+
+/* One loop-detection query (loop_detector.hpp:27-55 after the adapter has
+ * resolved references to ids and computed the map-local sensor pose with
+ * InverseCompound + Compound, loop_detector_branch_bound.cpp:97-98,
+ * scan_matcher_branch_bound.cpp:124-125). */
+typedef struct csm_loop_query
+{
+    int64_t map_id;           /* LocalMapId::mId of the reference local map (uploaded, pyramid built) */
+    int64_t scan_id;          /* id of a scan uploaded with csm_upload_scan */
+    double  sensor_pose[3];   /* map-local sensor pose (x, y, theta) */
+    int32_t win_x;            /* half windows: ceil(0.5 * range / step), :141-146 */
+    int32_t win_y;
+    int32_t win_t;
+    int32_t reserved;
+    double  step_x;           /* search steps, scan_matcher_branch_bound.cpp:293-312 */
+    double  step_y;
+    double  step_t;
+    double  score_thr;        /* normalized score threshold */
+    double  known_thr;        /* known-rate threshold */
+} csm_loop_query;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int  csm_version(void);
+int  csm_device_count(void);
+/* device: CUDA ordinal. flags: reserved, pass 0. */
+int  csm_create(int device, unsigned flags, csm_handle* out);
+int  csm_destroy(csm_handle h);
+const char* csm_last_error(csm_handle h);
+/* The handle's CUDA stream (cudaStream_t) for event timing by the caller */
+void* csm_stream(csm_handle h);
+/* Block until everything enqueued on the handle's stream has finished */
+int  csm_synchronize(csm_handle h);
+/* Number of kernels this handle has launched so far */
+int64_t csm_launch_count(csm_handle h);
+/* Page-locked host memory for the caller's upload buffers (fast H2D) */
+void* csm_alloc_pinned(size_t bytes);
+void  csm_free_pinned(void* p);
+
+/* ---- grid maps ---------------------------------------------------------
+ * Replaces GridMap storage lookups (grid_map.cpp:385-397,424-436) and
+ * SendGridMap of the FPGA path (scan_matcher_correlative_fpga.cpp:301-304).
+ * `dense` is the row-major u16 flattening of the map (0 = unknown, 1..65535
+ * <-> p in [0.001, 0.999], grid_binary_bayes.hpp:163-176); cell (row, col)
+ * covers [off + res*col, off + res*(col+1)) (grid_map_geometry.cpp:113-122).
+ * Re-uploading an id replaces the map and drops its precomputed levels. */
+int csm_upload_grid(csm_handle h, int64_t map_id, const uint16_t* dense,
+                    int rows, int cols, double resolution,
+                    double offset_x, double offset_y);
+/* Same, but `dense_dev` is a device pointer on the handle's device (the
+ * copy is device-to-device on the handle's stream). */
+int csm_upload_grid_device(csm_handle h, int64_t map_id, const uint16_t* dense_dev,
+                           int rows, int cols, double resolution,
+                           double offset_x, double offset_y);
+int csm_release_grid(csm_handle h, int64_t map_id);
+
+/* PrecomputeGridMap(map, win) (grid_map_builder.cpp:1044-1065): sliding
+ * win x win maximum with the far edge clamped (util.hpp:369-424). */
+int csm_build_coarse(csm_handle h, int64_t map_id, int win);
+/* PrecomputeGridMaps(map, out, hmax) (grid_map_builder.cpp:987-1012):
+ * levels 1..hmax with win = 2^h; level 0 is the uploaded grid itself. */
+int csm_build_pyramid(csm_handle h, int64_t map_id, int hmax);
+/* The same for n maps in one batch of launches (loop detection, first touch
+ * of each map: loop_detector_branch_bound.cpp:83-89). Asynchronous: returns
+ * after enqueueing; any later call on the handle is ordered after it. */
+int csm_build_pyramids(csm_handle h, int n, const int64_t* map_ids, int hmax);
+/* Mark the precomputed levels of these maps stale (device memory is kept), so
+ * that the next build recomputes them: benchmarking the first-touch path. */
+int csm_drop_pyramids(csm_handle h, int n, const int64_t* map_ids);
+/* Copy a precomputed level back to the host (tests / debugging).
+ * level >= 0: pyramid level; level < 0: the coarse map built with win = -level. */
+int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out);
+
+/* ---- scans ---------------------------------------------------------------
+ * Replaces SendScanData (scan_matcher_correlative_fpga.cpp:296-299): beam
+ * angles and ranges of one ScanData (sensor/sensor_data.hpp:69-89). */
+int csm_upload_scan(csm_handle h, int64_t scan_id,
+                    const double* angles, const double* ranges, int n);
+int csm_release_scan(csm_handle h, int64_t scan_id);
+
+/* ---- single-scan matchers ---------------------------------------------------
+ * sensor_pose = Compound(initial pose, relative sensor pose); steps and half
+ * windows are computed by the caller with the reference's double expressions
+ * (scan_matcher_correlative.cpp:141-146,255-274). */
+
+/* ScanMatcherCorrelative::OptimizePose, scan_matcher_correlative.cpp:118-201.
+ * The coarse map for win = low_res must have been built. */
+int csm_match_rt(csm_handle h, int64_t map_id,
+                 const double* angles, const double* ranges, int n,
+                 const double sensor_pose[3], int low_res,
+                 int win_x, int win_y, int win_t,
+                 double step_x, double step_y, double step_t,
+                 double score_thr, double known_thr, csm_result* out);
+
+/* ScanMatcherBranchBound::OptimizePose, scan_matcher_branch_bound.cpp:111-235.
+ * The pyramid up to hmax must have been built. */
+int csm_match_bb(csm_handle h, int64_t map_id,
+                 const double* angles, const double* ranges, int n,
+                 const double sensor_pose[3], int hmax,
+                 int win_x, int win_y, int win_t,
+                 double step_x, double step_y, double step_t,
+                 double score_thr, double known_thr, csm_result* out);
+
+/* ScanMatcherGridSearch::OptimizePose, scan_matcher_grid_search.cpp:84-142.
+ * dx/dy/dt are the loop values generated by the caller with the reference's
+ * accumulating `for (d = -r; d <= r; d += s)` loops (:118-120). */
+int csm_match_grid(csm_handle h, int64_t map_id,
+                   const double* angles, const double* ranges, int n,
+                   const double sensor_pose[3],
+                   const double* dx, int ndx, const double* dy, int ndy,
+                   const double* dt, int ndt,
+                   double score_thr, double known_thr, csm_result* out);
+
+/* ---- loop detection ----------------------------------------------------------
+ * LoopDetectorBranchBound::Detect, loop_detector_branch_bound.cpp:59-156,
+ * coarse stage: all queries of this rank's shard are matched in one batch of
+ * level-synchronous branch-and-bound launches. results[q] is per query, in
+ * query order (the reference emits one result per successful query).
+ *
+ * csm_loop_batch_enqueue returns after enqueueing the work on the handle's
+ * stream; csm_loop_batch_finish waits and copies the nq results to the host.
+ * csm_loop_batch = enqueue + finish.
+ *
+ * After a batch, csm_best_key_device(h) points to one uint64 on the device:
+ * max over the batch of (key << 20 | (0xFFFFF - (query_index_base + q))), 0 if no query
+ * found a pose, where key = 998 * sum_value + 64536 * n_known is the exact
+ * integer image of the reference's double score. Ranks reduce it
+ * with one 8-byte all-reduce(max) over NCCL; csm_decode_best_key splits it. */
+int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
+                           int query_index_base);
+int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq);
+int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
+                   int query_index_base, csm_result* results);
+void* csm_best_key_device(csm_handle h);
+void csm_decode_best_key(uint64_t best_key, int64_t* key, int32_t* query_index);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CSM_B200_H */

@@ -1,0 +1,247 @@
+"""ctypes binding of the C ABI in include/csm_b200.h (libcsm_b200.so).
+
+This is the same boundary a C++ adapter deriving from the reference's
+ScanMatcher / LoopDetector classes binds to. There is no
+fallback: if the CUDA library is missing or no device is usable, loading or
+csm_create raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+CSM_OK = 0
+FLAG_FP_MARGIN, FLAG_KEY_TIE, FLAG_EDGE = 1, 2, 4
+
+
+class CsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("csm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CsmResult(C.Structure):
+    _fields_ = [
+        ("found", C.c_int32), ("best_x", C.c_int32), ("best_y", C.c_int32), ("best_t", C.c_int32),
+        ("sum_value", C.c_int64), ("n_known", C.c_int32), ("flags", C.c_int32),
+        ("normalized_score", C.c_double), ("n_processed", C.c_int32), ("n_ignored", C.c_int32),
+    ]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class CsmLoopQuery(C.Structure):
+    _fields_ = [
+        ("map_id", C.c_int64), ("scan_id", C.c_int64), ("sensor_pose", C.c_double * 3),
+        ("win_x", C.c_int32), ("win_y", C.c_int32), ("win_t", C.c_int32), ("reserved", C.c_int32),
+        ("step_x", C.c_double), ("step_y", C.c_double), ("step_t", C.c_double),
+        ("score_thr", C.c_double), ("known_thr", C.c_double),
+    ]
+
+
+EXPORTS = [
+    "csm_version", "csm_device_count", "csm_create", "csm_destroy", "csm_last_error",
+    "csm_stream", "csm_synchronize", "csm_launch_count", "csm_alloc_pinned", "csm_free_pinned",
+    "csm_upload_grid", "csm_upload_grid_device", "csm_release_grid", "csm_build_coarse",
+    "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
+    "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
+    "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
+    "csm_best_key_device", "csm_decode_best_key",
+]
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load libcsm_b200.so (built in-tree by build.py). Raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "%s not built: run `python -m my_lidar_graph_slam_v2_b200.build` "
+            "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    dp, u16p, i64p = C.POINTER(C.c_double), C.POINTER(C.c_uint16), C.POINTER(C.c_int64)
+    H = C.c_void_p
+    rp = C.POINTER(CsmResult)
+    lib.csm_version.restype = C.c_int
+    lib.csm_device_count.restype = C.c_int
+    lib.csm_create.argtypes = [C.c_int, C.c_uint, C.POINTER(H)]
+    lib.csm_destroy.argtypes = [H]
+    lib.csm_last_error.argtypes = [H]
+    lib.csm_last_error.restype = C.c_char_p
+    lib.csm_stream.argtypes = [H]
+    lib.csm_stream.restype = C.c_void_p
+    lib.csm_synchronize.argtypes = [H]
+    lib.csm_launch_count.argtypes = [H]
+    lib.csm_launch_count.restype = C.c_int64
+    lib.csm_alloc_pinned.argtypes = [C.c_size_t]
+    lib.csm_alloc_pinned.restype = C.c_void_p
+    lib.csm_free_pinned.argtypes = [C.c_void_p]
+    lib.csm_upload_grid.argtypes = [H, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    lib.csm_upload_grid_device.argtypes = lib.csm_upload_grid.argtypes
+    lib.csm_release_grid.argtypes = [H, C.c_int64]
+    lib.csm_build_coarse.argtypes = [H, C.c_int64, C.c_int]
+    lib.csm_build_pyramid.argtypes = [H, C.c_int64, C.c_int]
+    lib.csm_build_pyramids.argtypes = [H, C.c_int, i64p, C.c_int]
+    lib.csm_drop_pyramids.argtypes = [H, C.c_int, i64p]
+    lib.csm_download_level.argtypes = [H, C.c_int64, C.c_int, u16p]
+    lib.csm_upload_scan.argtypes = [H, C.c_int64, dp, dp, C.c_int]
+    lib.csm_release_scan.argtypes = [H, C.c_int64]
+    scan = [H, C.c_int64, dp, dp, C.c_int, dp]
+    lib.csm_match_rt.argtypes = scan + [C.c_int] * 4 + [C.c_double] * 5 + [rp]
+    lib.csm_match_bb.argtypes = scan + [C.c_int] * 4 + [C.c_double] * 5 + [rp]
+    lib.csm_match_grid.argtypes = scan + [dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, rp]
+    lq = C.POINTER(CsmLoopQuery)
+    lib.csm_loop_batch_enqueue.argtypes = [H, lq, C.c_int, C.c_int, C.c_int]
+    lib.csm_loop_batch_finish.argtypes = [H, rp, C.c_int]
+    lib.csm_loop_batch.argtypes = [H, lq, C.c_int, C.c_int, C.c_int, rp]
+    lib.csm_best_key_device.argtypes = [H]
+    lib.csm_best_key_device.restype = C.c_void_p
+    lib.csm_decode_best_key.argtypes = [C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    _LIB = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Handle:
+    """One csm_handle: one CUDA stream + device-resident map / scan caches."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.csm_create(device, 0, C.byref(h))
+        if rc != CSM_OK:
+            raise CsmError(rc, "csm_create failed (no usable CUDA device %d; there is no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != CSM_OK:
+            raise CsmError(rc, self.lib.csm_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.csm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return self.lib.csm_stream(self.h)
+
+    def synchronize(self):
+        self._check(self.lib.csm_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.csm_launch_count(self.h))
+
+    # -- maps -------------------------------------------------------------
+    def upload_grid(self, map_id, dense, res, off_x, off_y):
+        dense = np.ascontiguousarray(dense, dtype=np.uint16)
+        self._check(self.lib.csm_upload_grid(self.h, map_id, dense.ctypes.data, dense.shape[0],
+                                             dense.shape[1], res, off_x, off_y))
+
+    def upload_grid_ptr(self, map_id, ptr, rows, cols, res, off_x, off_y, device=False):
+        fn = self.lib.csm_upload_grid_device if device else self.lib.csm_upload_grid
+        self._check(fn(self.h, map_id, ptr, rows, cols, res, off_x, off_y))
+
+    def release_grid(self, map_id):
+        self._check(self.lib.csm_release_grid(self.h, map_id))
+
+    def build_coarse(self, map_id, win):
+        self._check(self.lib.csm_build_coarse(self.h, map_id, win))
+
+    def build_pyramid(self, map_id, hmax):
+        self._check(self.lib.csm_build_pyramid(self.h, map_id, hmax))
+
+    def build_pyramids(self, map_ids, hmax):
+        ids = np.ascontiguousarray(map_ids, dtype=np.int64)
+        self._check(self.lib.csm_build_pyramids(self.h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int64)), hmax))
+
+    def drop_pyramids(self, map_ids):
+        ids = np.ascontiguousarray(map_ids, dtype=np.int64)
+        self._check(self.lib.csm_drop_pyramids(self.h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def download_level(self, map_id, level, shape):
+        out = np.empty(shape, dtype=np.uint16)
+        self._check(self.lib.csm_download_level(self.h, map_id, level, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    # -- scans ------------------------------------------------------------
+    def upload_scan(self, scan_id, angles, ranges):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        self._check(self.lib.csm_upload_scan(self.h, scan_id, _dptr(a), _dptr(r), len(a)))
+
+    # -- matchers ---------------------------------------------------------
+    def match_rt(self, map_id, angles, ranges, sensor_pose, low_res, win, step, thr):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        p = np.ascontiguousarray(sensor_pose, dtype=np.float64)
+        out = CsmResult()
+        self._check(self.lib.csm_match_rt(self.h, map_id, _dptr(a), _dptr(r), len(a), _dptr(p), low_res,
+                                          win[0], win[1], win[2], step[0], step[1], step[2],
+                                          thr[0], thr[1], C.byref(out)))
+        return out
+
+    def match_bb(self, map_id, angles, ranges, sensor_pose, hmax, win, step, thr):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        p = np.ascontiguousarray(sensor_pose, dtype=np.float64)
+        out = CsmResult()
+        self._check(self.lib.csm_match_bb(self.h, map_id, _dptr(a), _dptr(r), len(a), _dptr(p), hmax,
+                                          win[0], win[1], win[2], step[0], step[1], step[2],
+                                          thr[0], thr[1], C.byref(out)))
+        return out
+
+    def match_grid(self, map_id, angles, ranges, sensor_pose, dx, dy, dt, thr):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        p = np.ascontiguousarray(sensor_pose, dtype=np.float64)
+        dx = np.ascontiguousarray(dx, dtype=np.float64)
+        dy = np.ascontiguousarray(dy, dtype=np.float64)
+        dt = np.ascontiguousarray(dt, dtype=np.float64)
+        out = CsmResult()
+        self._check(self.lib.csm_match_grid(self.h, map_id, _dptr(a), _dptr(r), len(a), _dptr(p),
+                                            _dptr(dx), len(dx), _dptr(dy), len(dy), _dptr(dt), len(dt),
+                                            thr[0], thr[1], C.byref(out)))
+        return out
+
+    # -- loop detection -----------------------------------------------------
+    def loop_batch_enqueue(self, queries, nq, hmax, query_index_base=0):
+        self._check(self.lib.csm_loop_batch_enqueue(self.h, queries, nq, hmax, query_index_base))
+
+    def loop_batch_finish(self, nq, results=None):
+        results = results if results is not None else (CsmResult * nq)()
+        self._check(self.lib.csm_loop_batch_finish(self.h, results, nq))
+        return results
+
+    def loop_batch(self, queries, nq, hmax, query_index_base=0):
+        self.loop_batch_enqueue(queries, nq, hmax, query_index_base)
+        return self.loop_batch_finish(nq)
+
+    def best_key_device_ptr(self):
+        return self.lib.csm_best_key_device(self.h)
+
+    def decode_best_key(self, word):
+        k, q = C.c_int64(), C.c_int32()
+        self.lib.csm_decode_best_key(C.c_uint64(int(word)), C.byref(k), C.byref(q))
+        return k.value, q.value

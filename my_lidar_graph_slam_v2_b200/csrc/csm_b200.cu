@@ -1,0 +1,978 @@
+/* csm_b200.cu -- host side of libcsm_b200.so: handles, device-resident map /
+ * scan caches, launch sequences, and the extern "C" entry points declared in
+ * include/csm_b200.h. Compile: nvcc -gencode arch=compute_100a,code=sm_100a.
+ *
+ * There is no CPU path in this file: every entry point enqueues CUDA kernels
+ * on the handle's stream or fails with CSM_E_CUDA.
+ */
+
+#include "csm_b200.h"
+#include "csm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace csm;
+
+namespace {
+
+constexpr int64_t kTempScanId = INT64_MIN;
+
+struct MapSlot
+{
+    int rows = 0, cols = 0;
+    double res = 0.0, offx = 0.0, offy = 0.0;
+    uint16_t* base = nullptr;      /* level 0 */
+    uint16_t* levels = nullptr;    /* levels 1..hmax */
+    int levels_alloc = 0;          /* number of levels the allocation holds */
+    int hmax = 0;                  /* number of levels currently valid */
+    uint16_t* coarse = nullptr;
+    int coarse_win = 0;
+};
+
+struct ScanSlot
+{
+    double* angles = nullptr;      /* device */
+    double* ranges = nullptr;
+    int n = 0;
+    double max_range = 0.0;
+};
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+} /* namespace */
+
+struct csm_context
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    std::unordered_map<int64_t, MapSlot> maps;
+    std::unordered_map<int64_t, ScanSlot> scans;
+
+    /* workspaces, grown on demand */
+    DevBuf d_queries, d_thetas, d_proj, d_rcs, d_qflags, d_state, d_results;
+    DevBuf d_inc, d_rootbest, d_stats, d_counts, d_overflow, d_bestkey;
+    DevBuf d_nodes[kMaxLevels], d_keys[kMaxLevels];
+    DevBuf d_rtblocks, d_gridoff, d_gridpos, d_pyrjobs, d_tmpscan;
+    unsigned int frontier_capacity = 0;
+    /* pinned staging: two upload areas used alternately (an area is reused
+     * only after the copies that read it have completed) + one result area */
+    void* h_up[2] = { nullptr, nullptr };
+    size_t h_up_bytes[2] = { 0, 0 };
+    cudaEvent_t h_up_done[2] = { nullptr, nullptr };
+    int h_up_next = 0;
+    void* h_res = nullptr;
+    size_t h_res_bytes = 0;
+    /* last pyramid job table on the device (skips the re-upload when unchanged) */
+    std::vector<PyrJob> jobs_on_device;
+    /* pending batch */
+    int pending_nq = 0;
+};
+
+namespace {
+
+#define CSM_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);       \
+            return CSM_E_CUDA;                                                 \
+        }                                                                      \
+    } while (0)
+
+#define CSM_LAUNCH_CHECK()                                                     \
+    do {                                                                       \
+        ++h->launches;                                                         \
+        cudaError_t e_ = cudaGetLastError();                                   \
+        if (e_ != cudaSuccess) {                                               \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);  \
+            return CSM_E_CUDA;                                                 \
+        }                                                                      \
+    } while (0)
+
+int fail(csm_handle h, int code, const std::string& msg)
+{
+    h->err = msg;
+    return code;
+}
+
+int ensure(csm_handle h, DevBuf& b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p != nullptr)
+        return CSM_OK;
+    if (b.p != nullptr)
+        CSM_CUDA(cudaFreeAsync(b.p, h->stream));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    want = (want + 255) & ~(size_t)255;
+    CSM_CUDA(cudaMallocAsync(&b.p, want, h->stream));
+    b.bytes = want;
+    return CSM_OK;
+}
+
+/* Pinned upload area that is safe to overwrite. Call upload_committed() after
+ * enqueueing the copies that read it. */
+int acquire_upload(csm_handle h, size_t bytes, char** out)
+{
+    const int k = h->h_up_next;
+    h->h_up_next ^= 1;
+    if (h->h_up_done[k] == nullptr)
+        CSM_CUDA(cudaEventCreateWithFlags(&h->h_up_done[k], cudaEventDisableTiming));
+    else
+        CSM_CUDA(cudaEventSynchronize(h->h_up_done[k]));
+    if (h->h_up_bytes[k] < bytes) {
+        if (h->h_up[k] != nullptr)
+            CSM_CUDA(cudaFreeHost(h->h_up[k]));
+        h->h_up[k] = nullptr;
+        h->h_up_bytes[k] = 0;
+        const size_t want = std::max(bytes * 2, (size_t)1 << 18);
+        CSM_CUDA(cudaHostAlloc(&h->h_up[k], want, cudaHostAllocDefault));
+        h->h_up_bytes[k] = want;
+    }
+    *out = static_cast<char*>(h->h_up[k]);
+    return CSM_OK;
+}
+
+int upload_committed(csm_handle h)
+{
+    const int k = h->h_up_next ^ 1;
+    CSM_CUDA(cudaEventRecord(h->h_up_done[k], h->stream));
+    return CSM_OK;
+}
+
+int ensure_result_area(csm_handle h, size_t bytes)
+{
+    if (h->h_res_bytes >= bytes)
+        return CSM_OK;
+    if (h->h_res != nullptr) {
+        CSM_CUDA(cudaStreamSynchronize(h->stream));
+        CSM_CUDA(cudaFreeHost(h->h_res));
+        h->h_res = nullptr;
+        h->h_res_bytes = 0;
+    }
+    const size_t want = std::max(bytes * 2, (size_t)1 << 16);
+    CSM_CUDA(cudaHostAlloc(&h->h_res, want, cudaHostAllocDefault));
+    h->h_res_bytes = want;
+    return CSM_OK;
+}
+
+void free_map(csm_handle h, MapSlot& m)
+{
+    if (m.base) cudaFreeAsync(m.base, h->stream);
+    if (m.levels) cudaFreeAsync(m.levels, h->stream);
+    if (m.coarse) cudaFreeAsync(m.coarse, h->stream);
+    m = MapSlot();
+}
+
+void free_scan(csm_handle h, ScanSlot& s)
+{
+    if (s.angles) cudaFreeAsync(s.angles, h->stream);
+    if (s.ranges) cudaFreeAsync(s.ranges, h->stream);
+    s = ScanSlot();
+}
+
+/* `normalized > thr` on integer keys, see csm_device.cuh */
+KeyThreshold make_key_threshold(double thr, int n)
+{
+    KeyThreshold k;
+    k.thr = thr;
+    if (thr < 0.0) {
+        k.fail_max = -1; k.pass_min = 0;
+    } else if (thr == 0.0) {
+        k.fail_max = 0; k.pass_min = 1;
+    } else {
+        const long double t = (long double)thr * (long double)n * 65534000.0L;
+        const long long cut = (long long)floorl(t);
+        k.fail_max = cut - 1;
+        k.pass_min = cut + 2;
+    }
+    return k;
+}
+
+/* `double(nKnown) / double(n) > thr` passes iff nKnown > cut */
+int make_known_cut(double thr, int n)
+{
+    int cut = -1;
+    for (int k = 0; k <= n; ++k)
+        if ((double)k / (double)n <= thr)
+            cut = k;
+    return cut;
+}
+
+double fp_margin(const double pose[3], const MapSlot& m, double max_range, double extent)
+{
+    /* Guard band (cells) around cell boundaries inside which device and glibc
+     * trigonometry (a few ulp apart) or per-node re-projection rounding could
+     * give different floor() results. Bounds every intermediate magnitude. */
+    const double mag = std::fabs(pose[0]) + std::fabs(pose[1]) + std::fabs(m.offx) +
+                       std::fabs(m.offy) + max_range + extent +
+                       (double)std::max(m.rows, m.cols) * m.res;
+    return 1024.0 * 1.1102230246251565e-16 * mag / m.res + 1e-12;
+}
+
+int upload_scan_impl(csm_handle h, int64_t scan_id, const double* angles,
+                     const double* ranges, int n)
+{
+    if (n <= 0 || n > kMaxBeams || angles == nullptr || ranges == nullptr)
+        return fail(h, CSM_E_INVALID, "scan: need 1 <= n <= 4096 beams");
+    ScanSlot& s = h->scans[scan_id];
+    if (s.n != n) {
+        free_scan(h, s);
+        CSM_CUDA(cudaMallocAsync((void**)&s.angles, sizeof(double) * n, h->stream));
+        CSM_CUDA(cudaMallocAsync((void**)&s.ranges, sizeof(double) * n, h->stream));
+        s.n = n;
+    }
+    CSM_CUDA(cudaMemcpyAsync(s.angles, angles, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(s.ranges, ranges, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    s.max_range = *std::max_element(ranges, ranges + n);
+    return CSM_OK;
+}
+
+int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
+{
+    if (hmax < 0 || hmax >= kMaxLevels)
+        return fail(h, CSM_E_UNSUPPORTED, "pyramid: 0 <= hmax <= 7");
+    std::vector<PyrJob> jobs;
+    int max_rows = 0, max_cols = 0;
+    for (MapSlot* m : slots) {
+        if (m->hmax >= hmax)
+            continue;
+        if (m->levels_alloc < hmax) {
+            if (m->levels) CSM_CUDA(cudaFreeAsync(m->levels, h->stream));
+            m->levels = nullptr;
+            m->levels_alloc = 0;
+            const size_t bytes = (size_t)hmax * m->rows * m->cols * sizeof(uint16_t);
+            CSM_CUDA(cudaMallocAsync((void**)&m->levels, bytes, h->stream));
+            m->levels_alloc = hmax;
+        }
+        m->hmax = hmax;
+        jobs.push_back(PyrJob { m->base, m->levels, m->rows, m->cols });
+        max_rows = std::max(max_rows, m->rows);
+        max_cols = std::max(max_cols, m->cols);
+    }
+    if (jobs.empty())
+        return CSM_OK;
+    const size_t jb = jobs.size() * sizeof(PyrJob);
+    const bool same = h->jobs_on_device.size() == jobs.size() &&
+                      std::memcmp(h->jobs_on_device.data(), jobs.data(), jb) == 0;
+    if (!same) {
+        int rc = ensure(h, h->d_pyrjobs, jb);
+        if (rc) return rc;
+        char* hp = nullptr;
+        if ((rc = acquire_upload(h, jb, &hp))) return rc;
+        std::memcpy(hp, jobs.data(), jb);
+        CSM_CUDA(cudaMemcpyAsync(h->d_pyrjobs.p, hp, jb, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = upload_committed(h))) return rc;
+        h->jobs_on_device = jobs;
+    }
+    /* Maps are processed in chunks so that level h-1 of a chunk is still in
+     * L2 when level h reads it (each level is written once to HBM). */
+    const size_t map_bytes = (size_t)max_rows * max_cols * sizeof(uint16_t);
+    const size_t chunk = std::max<size_t>(1, ((size_t)24 << 20) / std::max<size_t>(map_bytes, 1));
+    for (size_t first = 0; first < jobs.size(); first += chunk) {
+        const size_t count = std::min(chunk, jobs.size() - first);
+        for (int lvl = 1; lvl <= hmax; ++lvl) {
+            dim3 grid((max_cols / 2 + 255) / 256, max_rows, (unsigned)count);
+            k_pyramid_level<<<grid, 256, 0, h->stream>>>(
+                static_cast<const PyrJob*>(h->d_pyrjobs.p) + first, lvl);
+            CSM_LAUNCH_CHECK();
+        }
+    }
+    return CSM_OK;
+}
+
+struct QueryPlan
+{
+    std::vector<DevQuery> dq;
+    std::vector<double> thetas;
+    std::vector<size_t> theta_off;
+    std::vector<unsigned long long> inc_init;
+    long long proj_total = 0;
+    int max_tn = 0;
+    int max_roots = 0;
+};
+
+int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
+                double score_thr, double known_thr)
+{
+    if (!(score_thr >= 0.0) || !(known_thr >= 0.0))
+        return fail(h, CSM_E_UNSUPPORTED, "thresholds must be >= 0");
+    std::memset(&Q, 0, sizeof(Q));
+    Q.lvl[0] = m.base;
+    for (int l = 1; l <= m.hmax && l < kMaxLevels; ++l)
+        Q.lvl[l] = m.levels + (size_t)(l - 1) * m.rows * m.cols;
+    Q.coarse = m.coarse;
+    Q.rows = m.rows; Q.cols = m.cols;
+    Q.res = m.res; Q.offx = m.offx; Q.offy = m.offy;
+    Q.angles = s.angles; Q.ranges = s.ranges; Q.n = s.n;
+    Q.kthr = make_key_threshold(score_thr, s.n);
+    Q.nk_cut = make_known_cut(known_thr, s.n);
+    return CSM_OK;
+}
+
+/* Upload plan (queries + thetas + initial incumbents) and zero the per-batch state */
+int stage_plan(csm_handle h, QueryPlan& plan, bool want_rcs)
+{
+    const int nq = (int)plan.dq.size();
+    const size_t qb = sizeof(DevQuery) * nq;
+    const size_t tb = sizeof(double) * plan.thetas.size();
+    const size_t ib = sizeof(unsigned long long) * nq;
+    int rc;
+    if ((rc = ensure(h, h->d_queries, qb))) return rc;
+    if ((rc = ensure(h, h->d_thetas, tb))) return rc;
+    if ((rc = ensure(h, h->d_inc, ib))) return rc;
+    if ((rc = ensure(h, h->d_proj, sizeof(int2) * (size_t)plan.proj_total))) return rc;
+    if (want_rcs && (rc = ensure(h, h->d_rcs, sizeof(double2) * (size_t)plan.proj_total))) return rc;
+    if ((rc = ensure(h, h->d_qflags, sizeof(int) * nq))) return rc;
+    if ((rc = ensure(h, h->d_state, sizeof(BestState) * nq))) return rc;
+    if ((rc = ensure(h, h->d_results, sizeof(csm_result) * nq + 16))) return rc;
+    if ((rc = ensure(h, h->d_bestkey, 8))) return rc;
+    if ((rc = ensure(h, h->d_overflow, 4))) return rc;
+    for (int q = 0; q < nq; ++q)
+        plan.dq[q].thetas = static_cast<const double*>(h->d_thetas.p) + plan.theta_off[q];
+    if ((rc = ensure_result_area(h, sizeof(csm_result) * nq + 64))) return rc;
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, qb + tb + ib, &hp))) return rc;
+    std::memcpy(hp, plan.dq.data(), qb);
+    std::memcpy(hp + qb, plan.thetas.data(), tb);
+    std::memcpy(hp + qb + tb, plan.inc_init.data(), ib);
+    CSM_CUDA(cudaMemcpyAsync(h->d_queries.p, hp, qb, cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(h->d_thetas.p, hp + qb, tb, cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(h->d_inc.p, hp + qb + tb, ib, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = upload_committed(h))) return rc;
+    CSM_CUDA(cudaMemsetAsync(h->d_qflags.p, 0, sizeof(int) * nq, h->stream));
+    CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
+    CSM_CUDA(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->stream));
+    return CSM_OK;
+}
+
+int launch_project(csm_handle h, const QueryPlan& plan, bool want_rcs)
+{
+    const int nq = (int)plan.dq.size();
+    dim3 grid(std::max(1, std::min((plan.max_tn + 255) / 256, 1024)), nq);
+    k_project<<<grid, 256, 0, h->stream>>>(
+        static_cast<const DevQuery*>(h->d_queries.p), static_cast<int2*>(h->d_proj.p),
+        want_rcs ? static_cast<double2*>(h->d_rcs.p) : nullptr,
+        static_cast<int*>(h->d_qflags.p));
+    CSM_LAUNCH_CHECK();
+    return CSM_OK;
+}
+
+int finish_results(csm_handle h, csm_result* results, int nq)
+{
+    char* hp = static_cast<char*>(h->h_res);
+    csm_result* hr = reinterpret_cast<csm_result*>(hp + 64);
+    int* hov = reinterpret_cast<int*>(hp);
+    CSM_CUDA(cudaMemcpyAsync(hr, h->d_results.p, sizeof(csm_result) * nq, cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(hov, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(results, hr, sizeof(csm_result) * nq);
+    if (*hov != 0)
+        return fail(h, CSM_E_CAPACITY, "branch-and-bound frontier overflow; split the batch");
+    return CSM_OK;
+}
+
+int ensure_frontier(csm_handle h, int nq, int hmax)
+{
+    unsigned int cap = (unsigned int)std::min<long long>(
+        std::max<long long>((long long)nq * 8192, 1ll << 18), 1ll << 23);
+    int rc;
+    for (int l = 1; l <= hmax; ++l) {
+        if ((rc = ensure(h, h->d_nodes[l], sizeof(unsigned long long) * cap))) return rc;
+        if ((rc = ensure(h, h->d_keys[l], sizeof(long long) * cap))) return rc;
+    }
+    h->frontier_capacity = cap;
+    if ((rc = ensure(h, h->d_counts, sizeof(unsigned int) * kMaxLevels))) return rc;
+    if ((rc = ensure(h, h->d_rootbest, sizeof(unsigned long long) * nq))) return rc;
+    if ((rc = ensure(h, h->d_stats, sizeof(int) * 2 * nq))) return rc;
+    return CSM_OK;
+}
+
+int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, int query_base)
+{
+    if (nq <= 0 || queries == nullptr)
+        return fail(h, CSM_E_INVALID, "loop batch: nq must be positive");
+    if (nq > 65535)
+        return fail(h, CSM_E_UNSUPPORTED, "loop batch: at most 65535 queries per call");
+    if (hmax < 0 || hmax >= kMaxLevels)
+        return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: 0 <= hmax <= 7");
+    QueryPlan plan;
+    plan.dq.resize(nq);
+    plan.theta_off.resize(nq);
+    plan.inc_init.resize(nq);
+    const int wsz = 1 << hmax;
+    for (int q = 0; q < nq; ++q) {
+        const csm_loop_query& in = queries[q];
+        auto mi = h->maps.find(in.map_id);
+        if (mi == h->maps.end())
+            return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown map id " + std::to_string(in.map_id));
+        auto si = h->scans.find(in.scan_id);
+        if (si == h->scans.end())
+            return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown scan id " + std::to_string(in.scan_id));
+        const MapSlot& m = mi->second;
+        const ScanSlot& s = si->second;
+        if (m.hmax < hmax)
+            return fail(h, CSM_E_INVALID, "loop batch: pyramid of map " + std::to_string(in.map_id) +
+                        " not built to hmax");
+        if (in.win_x < 0 || in.win_y < 0 || in.win_t < 0)
+            return fail(h, CSM_E_INVALID, "loop batch: negative window");
+        DevQuery& Q = plan.dq[q];
+        { const int frc = fill_common(h, Q, m, s, in.score_thr, in.known_thr); if (frc) return frc; }
+        Q.sx = in.sensor_pose[0];
+        Q.sy = in.sensor_pose[1];
+        Q.T = 2 * in.win_t + 1;
+        Q.winx = in.win_x; Q.winy = in.win_y;
+        Q.nrx = (2 * in.win_x) / wsz + 1;
+        Q.nry = (2 * in.win_y) / wsz + 1;
+        Q.lx = Q.nrx * wsz; Q.ly = Q.nry * wsz;
+        if (Q.T > 65535 || Q.lx > 65535 || Q.ly > 65535 ||
+            (unsigned long long)Q.T * Q.lx * Q.ly >= kOrdMask - 1ull)
+            return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: search lattice exceeds 2^26 leaves");
+        Q.proj_off = plan.proj_total;
+        plan.proj_total += (long long)Q.T * Q.n;
+        plan.max_tn = std::max(plan.max_tn, Q.T * Q.n);
+        plan.max_roots = std::max(plan.max_roots, Q.T * Q.nrx * Q.nry);
+        const double extent = (double)(std::max(in.win_x, in.win_y) + wsz) * m.res;
+        Q.margin = fp_margin(in.sensor_pose, m, s.max_range, extent);
+        plan.theta_off[q] = plan.thetas.size();
+        for (int t = -in.win_t; t <= in.win_t; ++t)
+            plan.thetas.push_back(in.sensor_pose[2] + t * in.step_t);
+        plan.inc_init[q] = ((unsigned long long)Q.kthr.fail_max << kOrdBits) | kOrdMask;
+    }
+    int rc;
+    if ((rc = ensure_frontier(h, nq, hmax))) return rc;
+    if ((rc = stage_plan(h, plan, false))) return rc;
+    CSM_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(unsigned int) * kMaxLevels, h->stream));
+    CSM_CUDA(cudaMemsetAsync(h->d_rootbest.p, 0, sizeof(unsigned long long) * nq, h->stream));
+    CSM_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(int) * 2 * nq, h->stream));
+    if ((rc = launch_project(h, plan, false))) return rc;
+
+    BbWork W;
+    std::memset(&W, 0, sizeof(W));
+    for (int l = 1; l <= hmax; ++l) {
+        W.nodes[l] = static_cast<unsigned long long*>(h->d_nodes[l].p);
+        W.keys[l] = static_cast<long long*>(h->d_keys[l].p);
+    }
+    W.counts = static_cast<unsigned int*>(h->d_counts.p);
+    W.incumbent = static_cast<unsigned long long*>(h->d_inc.p);
+    W.rootbest = static_cast<unsigned long long*>(h->d_rootbest.p);
+    W.stats = static_cast<int*>(h->d_stats.p);
+    W.overflow = static_cast<int*>(h->d_overflow.p);
+    W.capacity = h->frontier_capacity;
+    W.hmax = hmax;
+    const DevQuery* dq = static_cast<const DevQuery*>(h->d_queries.p);
+    const int2* proj = static_cast<const int2*>(h->d_proj.p);
+
+    {
+        dim3 grid(std::max(1, (plan.max_roots + 7) / 8), nq);
+        k_bb_roots<<<grid, 256, 0, h->stream>>>(dq, proj, W);
+        CSM_LAUNCH_CHECK();
+    }
+    if (hmax > 0) {
+        k_bb_dive<<<nq, 32, 0, h->stream>>>(dq, proj, W);
+        CSM_LAUNCH_CHECK();
+        const int blocks = h->sm_count * 4;
+        for (int lvl = hmax; lvl >= 1; --lvl) {
+            k_bb_expand<<<blocks, 256, 0, h->stream>>>(dq, proj, W, lvl);
+            CSM_LAUNCH_CHECK();
+        }
+    }
+    k_bb_collect<<<(nq + 127) / 128, 128, 0, h->stream>>>(
+        dq, W, nq, static_cast<const int*>(h->d_qflags.p), static_cast<BestState*>(h->d_state.p));
+    CSM_LAUNCH_CHECK();
+    FinalArgs F;
+    std::memset(&F, 0, sizeof(F));
+    F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
+    F.query_index_base = query_base;
+    F.mode = 0;
+    F.qflags = static_cast<const int*>(h->d_qflags.p);
+    k_finalize<<<nq, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
+                                         static_cast<csm_result*>(h->d_results.p));
+    CSM_LAUNCH_CHECK();
+    h->pending_nq = nq;
+    return CSM_OK;
+}
+
+} /* namespace */
+
+/* ======================================================================== */
+extern "C" {
+
+int csm_version(void) { return 100; }
+
+int csm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+int csm_create(int device, unsigned flags, csm_handle* out)
+{
+    (void)flags;
+    if (out == nullptr)
+        return CSM_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n)
+        return CSM_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess)
+        return CSM_E_CUDA;
+    csm_handle h = new csm_context;
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return CSM_E_CUDA;
+    }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = h;
+    return CSM_OK;
+}
+
+int csm_destroy(csm_handle h)
+{
+    if (h == nullptr)
+        return CSM_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& kv : h->maps) free_map(h, kv.second);
+    for (auto& kv : h->scans) free_scan(h, kv.second);
+    DevBuf* bufs[] = { &h->d_queries, &h->d_thetas, &h->d_proj, &h->d_rcs, &h->d_qflags,
+                       &h->d_state, &h->d_results, &h->d_inc, &h->d_rootbest, &h->d_stats,
+                       &h->d_counts, &h->d_overflow, &h->d_bestkey, &h->d_rtblocks,
+                       &h->d_gridoff, &h->d_gridpos, &h->d_pyrjobs, &h->d_tmpscan };
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFreeAsync(b->p, h->stream);
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (h->d_nodes[l].p) cudaFreeAsync(h->d_nodes[l].p, h->stream);
+        if (h->d_keys[l].p) cudaFreeAsync(h->d_keys[l].p, h->stream);
+    }
+    cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < 2; ++k) {
+        if (h->h_up[k]) cudaFreeHost(h->h_up[k]);
+        if (h->h_up_done[k]) cudaEventDestroy(h->h_up_done[k]);
+    }
+    if (h->h_res) cudaFreeHost(h->h_res);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return CSM_OK;
+}
+
+const char* csm_last_error(csm_handle h)
+{
+    return h ? h->err.c_str() : "null handle";
+}
+
+void* csm_stream(csm_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int csm_synchronize(csm_handle h)
+{
+    if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    return CSM_OK;
+}
+
+int64_t csm_launch_count(csm_handle h) { return h ? h->launches : 0; }
+
+void* csm_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+        return nullptr;
+    return p;
+}
+
+void csm_free_pinned(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense, bool on_device,
+                            int rows, int cols, double res, double offx, double offy)
+{
+    if (!h) return CSM_E_INVALID;
+    if (dense == nullptr || rows <= 0 || cols <= 0 || rows > 16384 || cols > 16384 || (cols & 1) ||
+        !(res > 0.0))
+        return fail(h, CSM_E_INVALID, "grid: need 0 < rows, cols <= 16384, even cols, resolution > 0");
+    CSM_CUDA(cudaSetDevice(h->device));
+    MapSlot& m = h->maps[map_id];
+    if (m.rows != rows || m.cols != cols || m.base == nullptr) {
+        free_map(h, m);
+        CSM_CUDA(cudaMallocAsync((void**)&m.base, (size_t)rows * cols * sizeof(uint16_t), h->stream));
+        m.rows = rows; m.cols = cols;
+    }
+    /* precomputed levels belong to the previous contents (allocations are kept) */
+    m.hmax = 0;
+    m.coarse_win = 0;
+    m.res = res; m.offx = offx; m.offy = offy;
+    CSM_CUDA(cudaMemcpyAsync(m.base, dense, (size_t)rows * cols * sizeof(uint16_t),
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    return CSM_OK;
+}
+
+int csm_upload_grid(csm_handle h, int64_t map_id, const uint16_t* dense,
+                    int rows, int cols, double resolution, double offset_x, double offset_y)
+{
+    return upload_grid_impl(h, map_id, dense, false, rows, cols, resolution, offset_x, offset_y);
+}
+
+int csm_upload_grid_device(csm_handle h, int64_t map_id, const uint16_t* dense_dev,
+                           int rows, int cols, double resolution, double offset_x, double offset_y)
+{
+    return upload_grid_impl(h, map_id, dense_dev, true, rows, cols, resolution, offset_x, offset_y);
+}
+
+int csm_release_grid(csm_handle h, int64_t map_id)
+{
+    if (!h) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "release: unknown map id");
+    free_map(h, it->second);
+    h->maps.erase(it);
+    return CSM_OK;
+}
+
+int csm_build_coarse(csm_handle h, int64_t map_id, int win)
+{
+    if (!h) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "build_coarse: unknown map id");
+    if (win <= 0 || win > 4096)
+        return fail(h, CSM_E_INVALID, "build_coarse: window must be in 1..4096");
+    CSM_CUDA(cudaSetDevice(h->device));
+    MapSlot& m = it->second;
+    if (m.coarse_win == win && m.coarse != nullptr)
+        return CSM_OK;
+    if (m.coarse == nullptr)
+        CSM_CUDA(cudaMallocAsync((void**)&m.coarse, (size_t)m.rows * m.cols * sizeof(uint16_t), h->stream));
+    dim3 grid((m.cols + 255) / 256, m.rows);
+    k_sliding_max<<<grid, 256, 0, h->stream>>>(m.base, m.coarse, m.rows, m.cols, win);
+    CSM_LAUNCH_CHECK();
+    m.coarse_win = win;
+    return CSM_OK;
+}
+
+int csm_build_pyramids(csm_handle h, int n, const int64_t* map_ids, int hmax)
+{
+    if (!h) return CSM_E_INVALID;
+    if (n <= 0 || map_ids == nullptr)
+        return fail(h, CSM_E_INVALID, "build_pyramids: empty id list");
+    CSM_CUDA(cudaSetDevice(h->device));
+    std::vector<MapSlot*> slots;
+    slots.reserve(n);
+    for (int i = 0; i < n; ++i) {
+        auto it = h->maps.find(map_ids[i]);
+        if (it == h->maps.end())
+            return fail(h, CSM_E_NOT_FOUND, "build_pyramids: unknown map id " + std::to_string(map_ids[i]));
+        slots.push_back(&it->second);
+    }
+    return build_levels(h, slots, hmax);
+}
+
+int csm_drop_pyramids(csm_handle h, int n, const int64_t* map_ids)
+{
+    if (!h) return CSM_E_INVALID;
+    for (int i = 0; i < n; ++i) {
+        auto it = h->maps.find(map_ids[i]);
+        if (it == h->maps.end())
+            return fail(h, CSM_E_NOT_FOUND, "drop_pyramids: unknown map id");
+        it->second.hmax = 0;
+        it->second.coarse_win = 0;
+    }
+    return CSM_OK;
+}
+
+int csm_build_pyramid(csm_handle h, int64_t map_id, int hmax)
+{
+    return csm_build_pyramids(h, 1, &map_id, hmax);
+}
+
+int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out)
+{
+    if (!h || !out) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "download: unknown map id");
+    const MapSlot& m = it->second;
+    const size_t cells = (size_t)m.rows * m.cols;
+    const uint16_t* src = nullptr;
+    if (level == 0) src = m.base;
+    else if (level > 0 && level <= m.hmax) src = m.levels + (size_t)(level - 1) * cells;
+    else if (level < 0 && m.coarse_win == -level) src = m.coarse;
+    if (src == nullptr)
+        return fail(h, CSM_E_INVALID, "download: level not built");
+    CSM_CUDA(cudaMemcpyAsync(out, src, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    return CSM_OK;
+}
+
+int csm_upload_scan(csm_handle h, int64_t scan_id, const double* angles, const double* ranges, int n)
+{
+    if (!h) return CSM_E_INVALID;
+    if (scan_id == kTempScanId)
+        return fail(h, CSM_E_INVALID, "scan id reserved");
+    CSM_CUDA(cudaSetDevice(h->device));
+    return upload_scan_impl(h, scan_id, angles, ranges, n);
+}
+
+int csm_release_scan(csm_handle h, int64_t scan_id)
+{
+    if (!h) return CSM_E_INVALID;
+    auto it = h->scans.find(scan_id);
+    if (it == h->scans.end())
+        return fail(h, CSM_E_NOT_FOUND, "release: unknown scan id");
+    free_scan(h, it->second);
+    h->scans.erase(it);
+    return CSM_OK;
+}
+
+int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
+                           int query_index_base)
+{
+    if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
+    return bb_enqueue(h, queries, nq, hmax, query_index_base);
+}
+
+int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq)
+{
+    if (!h || !results) return CSM_E_INVALID;
+    if (nq != h->pending_nq)
+        return fail(h, CSM_E_INVALID, "loop batch: finish does not match the enqueued batch");
+    h->pending_nq = 0;
+    return finish_results(h, results, nq);
+}
+
+int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
+                   int query_index_base, csm_result* results)
+{
+    int rc = csm_loop_batch_enqueue(h, queries, nq, hmax, query_index_base);
+    if (rc) return rc;
+    return csm_loop_batch_finish(h, results, nq);
+}
+
+void* csm_best_key_device(csm_handle h)
+{
+    return h ? h->d_bestkey.p : nullptr;
+}
+
+void csm_decode_best_key(uint64_t best_key, int64_t* key, int32_t* query_index)
+{
+    if (key) *key = (int64_t)(best_key >> 20);
+    if (query_index) *query_index = best_key ? (int32_t)(0xFFFFF - (best_key & 0xFFFFF)) : -1;
+}
+
+int csm_match_bb(csm_handle h, int64_t map_id,
+                 const double* angles, const double* ranges, int n,
+                 const double sensor_pose[3], int hmax,
+                 int win_x, int win_y, int win_t,
+                 double step_x, double step_y, double step_t,
+                 double score_thr, double known_thr, csm_result* out)
+{
+    if (!h || !out || !sensor_pose) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
+    int rc = upload_scan_impl(h, kTempScanId, angles, ranges, n);
+    if (rc) return rc;
+    csm_loop_query q;
+    std::memset(&q, 0, sizeof(q));
+    q.map_id = map_id;
+    q.scan_id = kTempScanId;
+    q.sensor_pose[0] = sensor_pose[0]; q.sensor_pose[1] = sensor_pose[1]; q.sensor_pose[2] = sensor_pose[2];
+    q.win_x = win_x; q.win_y = win_y; q.win_t = win_t;
+    q.step_x = step_x; q.step_y = step_y; q.step_t = step_t;
+    q.score_thr = score_thr; q.known_thr = known_thr;
+    rc = bb_enqueue(h, &q, 1, hmax, 0);
+    if (rc) return rc;
+    h->pending_nq = 0;
+    return finish_results(h, out, 1);
+}
+
+int csm_match_rt(csm_handle h, int64_t map_id,
+                 const double* angles, const double* ranges, int n,
+                 const double sensor_pose[3], int low_res,
+                 int win_x, int win_y, int win_t,
+                 double step_x, double step_y, double step_t,
+                 double score_thr, double known_thr, csm_result* out)
+{
+    if (!h || !out || !sensor_pose) return CSM_E_INVALID;
+    (void)step_x; (void)step_y;
+    CSM_CUDA(cudaSetDevice(h->device));
+    auto mi = h->maps.find(map_id);
+    if (mi == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "match_rt: unknown map id");
+    const MapSlot& m = mi->second;
+    if (low_res <= 0 || low_res > 64)
+        return fail(h, CSM_E_UNSUPPORTED, "match_rt: 1 <= low_res <= 64");
+    if (m.coarse == nullptr || m.coarse_win != low_res)
+        return fail(h, CSM_E_INVALID, "match_rt: coarse map for this low_res not built");
+    if (win_x < 0 || win_y < 0 || win_t < 0)
+        return fail(h, CSM_E_INVALID, "match_rt: negative window");
+    int rc = upload_scan_impl(h, kTempScanId, angles, ranges, n);
+    if (rc) return rc;
+    const ScanSlot& s = h->scans[kTempScanId];
+
+    QueryPlan plan;
+    plan.dq.resize(1);
+    plan.theta_off.assign(1, 0);
+    plan.inc_init.assign(1, 0ull);
+    DevQuery& Q = plan.dq[0];
+    if ((rc = fill_common(h, Q, m, s, score_thr, known_thr))) return rc;
+    Q.sx = sensor_pose[0]; Q.sy = sensor_pose[1];
+    Q.T = 2 * win_t + 1;
+    Q.winx = win_x; Q.winy = win_y;
+    Q.proj_off = 0;
+    plan.proj_total = (long long)Q.T * Q.n;
+    plan.max_tn = Q.T * Q.n;
+    Q.margin = fp_margin(sensor_pose, m, s.max_range, (double)(std::max(win_x, win_y) + low_res) * m.res);
+    for (int t = -win_t; t <= win_t; ++t)
+        plan.thetas.push_back(sensor_pose[2] + step_t * t);
+    const int nbx = (2 * win_x) / low_res + 1;
+    const int nby = (2 * win_y) / low_res + 1;
+    const int nblocks = Q.T * nbx * nby;
+    if ((rc = ensure(h, h->d_rtblocks, sizeof(RtBlock) * (size_t)nblocks))) return rc;
+    if ((rc = stage_plan(h, plan, false))) return rc;
+    if ((rc = launch_project(h, plan, false))) return rc;
+    const DevQuery* dq = static_cast<const DevQuery*>(h->d_queries.p);
+    const int2* proj = static_cast<const int2*>(h->d_proj.p);
+    k_rt_blocks<<<nblocks, 256, sizeof(long long) * low_res * low_res, h->stream>>>(
+        dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby);
+    CSM_LAUNCH_CHECK();
+    k_rt_replay<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const RtBlock*>(h->d_rtblocks.p),
+                                         low_res, nbx, nby, static_cast<BestState*>(h->d_state.p));
+    CSM_LAUNCH_CHECK();
+    FinalArgs F;
+    std::memset(&F, 0, sizeof(F));
+    F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
+    F.mode = 0;
+    F.qflags = static_cast<const int*>(h->d_qflags.p);
+    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
+                                        static_cast<csm_result*>(h->d_results.p));
+    CSM_LAUNCH_CHECK();
+    rc = finish_results(h, out, 1);
+    if (rc) return rc;
+    return CSM_OK;
+}
+
+int csm_match_grid(csm_handle h, int64_t map_id,
+                   const double* angles, const double* ranges, int n,
+                   const double sensor_pose[3],
+                   const double* dx, int ndx, const double* dy, int ndy,
+                   const double* dt, int ndt,
+                   double score_thr, double known_thr, csm_result* out)
+{
+    if (!h || !out || !sensor_pose || !dx || !dy || !dt) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
+    auto mi = h->maps.find(map_id);
+    if (mi == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "match_grid: unknown map id");
+    const MapSlot& m = mi->second;
+    if (ndx <= 0 || ndy <= 0 || ndt <= 0 || ndt > 65535 ||
+        (unsigned long long)ndx * ndy * ndt >= kOrdMask - 1ull)
+        return fail(h, CSM_E_UNSUPPORTED, "match_grid: window exceeds 2^26 candidates");
+    int rc = upload_scan_impl(h, kTempScanId, angles, ranges, n);
+    if (rc) return rc;
+    const ScanSlot& s = h->scans[kTempScanId];
+
+    /* integer-shift path iff every dx[k] - dx[0] (dy likewise) is an integer
+     * number of cells up to rounding noise */
+    std::vector<int> offs(ndx + ndy);
+    double dev = 0.0;
+    for (int k = 0; k < ndx; ++k) {
+        const double e = (dx[k] - dx[0]) / m.res;
+        const double r = std::nearbyint(e);
+        dev = std::max(dev, std::fabs(e - r));
+        offs[k] = (int)r;
+    }
+    for (int k = 0; k < ndy; ++k) {
+        const double e = (dy[k] - dy[0]) / m.res;
+        const double r = std::nearbyint(e);
+        dev = std::max(dev, std::fabs(e - r));
+        offs[ndx + k] = (int)r;
+    }
+    const bool fast = dev < 1e-7;
+
+    QueryPlan plan;
+    plan.dq.resize(1);
+    plan.theta_off.assign(1, 0);
+    plan.inc_init.assign(1, 0ull);
+    DevQuery& Q = plan.dq[0];
+    if ((rc = fill_common(h, Q, m, s, score_thr, known_thr))) return rc;
+    Q.sx = sensor_pose[0] + dx[0];
+    Q.sy = sensor_pose[1] + dy[0];
+    Q.T = ndt;
+    Q.proj_off = 0;
+    plan.proj_total = (long long)ndt * Q.n;
+    plan.max_tn = ndt * Q.n;
+    const double extent = std::fabs(dx[0]) + std::fabs(dx[ndx - 1]) + std::fabs(dy[0]) + std::fabs(dy[ndy - 1]);
+    Q.margin = fp_margin(sensor_pose, m, s.max_range, extent) + (fast ? 2.0 * dev : 0.0);
+    for (int k = 0; k < ndt; ++k)
+        plan.thetas.push_back(sensor_pose[2] + dt[k]);
+
+    std::vector<double> pos(ndx + ndy);
+    for (int k = 0; k < ndx; ++k) pos[k] = sensor_pose[0] + dx[k];
+    for (int k = 0; k < ndy; ++k) pos[ndx + k] = sensor_pose[1] + dy[k];
+    if ((rc = ensure(h, h->d_gridoff, sizeof(int) * offs.size()))) return rc;
+    if ((rc = ensure(h, h->d_gridpos, sizeof(double) * pos.size()))) return rc;
+    if ((rc = stage_plan(h, plan, !fast))) return rc;
+    /* small synchronous-on-stream copies from pageable vectors are fine here */
+    CSM_CUDA(cudaMemcpyAsync(h->d_gridoff.p, offs.data(), sizeof(int) * offs.size(), cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(h->d_gridpos.p, pos.data(), sizeof(double) * pos.size(), cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    if ((rc = launch_project(h, plan, !fast))) return rc;
+
+    GridArgs G;
+    G.mx = static_cast<const int*>(h->d_gridoff.p);
+    G.my = G.mx + ndx;
+    G.px = static_cast<const double*>(h->d_gridpos.p);
+    G.py = G.px + ndx;
+    G.ndx = ndx; G.ndy = ndy; G.ndt = ndt;
+    G.best = static_cast<unsigned long long*>(h->d_inc.p);   /* zero-initialised by stage_plan */
+    G.tie = nullptr;
+    const DevQuery* dq = static_cast<const DevQuery*>(h->d_queries.p);
+    const int2* proj = static_cast<const int2*>(h->d_proj.p);
+    dim3 grid(ndt, (ndy + 7) / 8);
+    if (fast) {
+        k_grid_window<<<grid, 256, sizeof(int2) * Q.n, h->stream>>>(dq, proj, G);
+    } else {
+        k_grid_general<<<grid, 256, sizeof(double2) * Q.n, h->stream>>>(
+            dq, static_cast<const double2*>(h->d_rcs.p), G, static_cast<int*>(h->d_qflags.p));
+    }
+    CSM_LAUNCH_CHECK();
+    k_grid_collect<<<1, 32, 0, h->stream>>>(G, static_cast<const int*>(h->d_qflags.p),
+                                            static_cast<BestState*>(h->d_state.p));
+    CSM_LAUNCH_CHECK();
+    FinalArgs F;
+    std::memset(&F, 0, sizeof(F));
+    F.mx = G.mx; F.my = G.my; F.px = G.px; F.py = G.py;
+    F.rcs = fast ? nullptr : static_cast<const double2*>(h->d_rcs.p);
+    F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
+    F.mode = fast ? 1 : 2;
+    F.qflags = static_cast<const int*>(h->d_qflags.p);
+    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
+                                        static_cast<csm_result*>(h->d_results.p));
+    CSM_LAUNCH_CHECK();
+    return finish_results(h, out, 1);
+}
+
+} /* extern "C" */

@@ -1,0 +1,131 @@
+/* csm_device.cuh -- device-side data structures and helpers shared by the
+ * kernels of libcsm_b200.so. sm_100a only.
+ *
+ * Score arithmetic (DESIGN.md "Exact integer key"):
+ *   the reference accumulates sum_i p(v_i) over known cells in double
+ *   (score_function_pixel_accurate.cpp:21-57) with
+ *   p(v) = 0.001 + 0.998 * (v - 1) / 65534 (grid_values.hpp:26-36), so
+ *   65534000 * sum = 998 * sumV + 64536 * nKnown =: key  (exact integers).
+ *   Kernels carry (sumV, nKnown) per candidate, order candidates by `key`
+ *   and only evaluate doubles for the final result and for threshold
+ *   comparisons that fall inside the rounding guard band.
+ */
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace csm {
+
+constexpr int kMaxLevels = 8;            /* hmax <= 7 */
+constexpr int kOrdBits = 26;             /* candidate ordinal bits in a packed best word */
+constexpr unsigned long long kOrdMask = (1ull << kOrdBits) - 1ull;
+constexpr int kMaxBeams = 4096;
+
+/* Threshold on the normalized score expressed on integer keys:
+ *   key >= pass_min  -> reference comparison `score > thr` is true
+ *   key <= fail_max  -> false
+ *   otherwise        -> inside the guard band: decide with the exact
+ *                       sequential double sum (exact_normalized_score) */
+struct KeyThreshold
+{
+    long long fail_max;
+    long long pass_min;
+    double    thr;
+};
+
+/* One query as the kernels see it (device pointers only) */
+struct DevQuery
+{
+    const uint16_t* lvl[kMaxLevels];   /* pyramid levels, lvl[0] = uploaded grid */
+    const uint16_t* coarse;            /* RT: sliding max with win = low_res */
+    int rows, cols;
+    double res, offx, offy;
+    double sx, sy;                     /* sensor position (map-local) */
+    const double* thetas;              /* T candidate sensor angles (host-computed doubles) */
+    const double* angles;              /* N beam angles */
+    const double* ranges;              /* N beam ranges */
+    int n;                             /* beams */
+    int T;                             /* candidate angles */
+    int winx, winy;                    /* half windows (cells) */
+    int nrx, nry;                      /* B&B: number of root nodes along x / y */
+    int lx, ly;                        /* leaf lattice extent along x / y */
+    long long proj_off;                /* offset of this query in the projection buffer */
+    double margin;                     /* FP guard band in cells (projection) */
+    KeyThreshold kthr;
+    int nk_cut;                        /* known test passes iff nKnown > nk_cut */
+    int pad;
+};
+
+__host__ __device__ __forceinline__ long long make_key(long long sumv, int nk)
+{
+    return 998ll * sumv + 64536ll * (long long)nk;
+}
+
+__device__ __forceinline__ unsigned int ld_cell(const uint16_t* __restrict__ m,
+                                                int rows, int cols, int r, int c)
+{
+    /* Outside the map -> unknown (0), grid_map.cpp:389-392 */
+    if ((unsigned)r < (unsigned)rows && (unsigned)c < (unsigned)cols)
+        return (unsigned int)__ldg(m + (size_t)r * (size_t)cols + (size_t)c);
+    return 0u;
+}
+
+/* p(v), grid_values.hpp:26-36, same operation order, no FMA */
+__device__ __forceinline__ double value_to_probability(unsigned int v)
+{
+    const double pmin = 1e-3;
+    const double pmax = 1.0 - 1e-3;
+    const double span = pmax - pmin;
+    return __dadd_rn(pmin, __ddiv_rn(__dmul_rn(span, (double)((int)v - 1)), 65534.0));
+}
+
+/* Sequential double sum in scan order: the reference's own arithmetic
+ * (scan_matcher_correlative.cpp:308-335). One thread. */
+__device__ double exact_normalized_score(const uint16_t* __restrict__ m, int rows, int cols,
+                                         const int2* __restrict__ proj, int n, int ox, int oy)
+{
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int2 p = proj[i];
+        const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
+        if (v != 0u)
+            sum = __dadd_rn(sum, value_to_probability(v));
+    }
+    return __ddiv_rn(sum, (double)n);
+}
+
+/* -1 fail, +1 pass, 0 guard band */
+__device__ __forceinline__ int key_vs_threshold(long long key, const KeyThreshold& t)
+{
+    if (key >= t.pass_min) return 1;
+    if (key <= t.fail_max) return -1;
+    return 0;
+}
+
+__device__ __forceinline__ unsigned long long pack_best(long long key, unsigned long long ordfield)
+{
+    return ((unsigned long long)key << kOrdBits) | ordfield;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+    return (int)__reduce_add_sync(0xffffffffu, (unsigned)v);
+}
+
+/* B&B frontier node: q(16) | t(16) | xi(16) | yi(16), xi = x + winx >= 0 */
+__device__ __forceinline__ unsigned long long pack_node(int q, int t, int xi, int yi)
+{
+    return ((unsigned long long)(unsigned)q << 48) | ((unsigned long long)(unsigned)t << 32) |
+           ((unsigned long long)(unsigned)xi << 16) | (unsigned long long)(unsigned)yi;
+}
+
+__device__ __forceinline__ void unpack_node(unsigned long long n, int& q, int& t, int& xi, int& yi)
+{
+    q = (int)(n >> 48);
+    t = (int)((n >> 32) & 0xffffull);
+    xi = (int)((n >> 16) & 0xffffull);
+    yi = (int)(n & 0xffffull);
+}
+
+} /* namespace csm */

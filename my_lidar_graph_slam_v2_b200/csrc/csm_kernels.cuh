@@ -1,0 +1,784 @@
+/* csm_kernels.cuh -- CUDA kernels of the correlative scan matching hot path.
+ * sm_100a only; compiled into libcsm_b200.so by csm_b200.cu.
+ *
+ * Kernel inventory (reference unit each one replaces, paths relative to the
+ * reference repository):
+ *   k_pyramid_level   PrecomputeGridMaps level h from level h-1
+ *                     (grid_map_builder.cpp:987-1012, util.hpp:369-424)
+ *   k_sliding_max     PrecomputeGridMap(map, win), any window
+ *                     (grid_map_builder.cpp:1044-1065)
+ *   k_project         ScanData::HitPoint + PositionToIndex for every
+ *                     (query, angle, beam) (sensor_data.hpp:190-203,
+ *                     grid_map_geometry.cpp:113-122)
+ *   k_rt_blocks       ComputeScore on the coarse map + EvaluateHighResolutionMap
+ *                     for every coarse cell (scan_matcher_correlative.cpp:301-368)
+ *   k_rt_replay       the sequential accept/skip decisions of
+ *                     scan_matcher_correlative.cpp:161-197 replayed on keys
+ *   k_bb_roots / k_bb_dive / k_bb_expand
+ *                     branch-and-bound as level-synchronous frontier expansion
+ *                     (scan_matcher_branch_bound.cpp:156-231)
+ *   k_grid_window     exhaustive (dy, dx, dtheta) search, integer-shift path
+ *   k_grid_general    same, per-candidate FP64 projection (arbitrary steps)
+ *                     (scan_matcher_grid_search.cpp:118-142)
+ *   k_finalize        integer score + reference-order double score at the
+ *                     winning pose, packed best word for the NCCL argmax
+ */
+#pragma once
+
+#include "csm_device.cuh"
+#include "csm_b200.h"
+
+namespace csm {
+
+/* ------------------------------------------------------------------------ */
+/* Precomputation                                                            */
+/* ------------------------------------------------------------------------ */
+
+struct PyrJob
+{
+    const uint16_t* base;   /* level 0 */
+    uint16_t*       levels; /* levels 1..hmax, contiguous, rows*cols each */
+    int rows, cols;
+};
+
+/* Level h (window w = 2^h) from level h-1 with four taps.
+ * out_h[r][c] = P_h[min(r, R-w)][min(c, C-w)] (far edge clamped),
+ * P_h = max of P_{h-1} at (+0/+w/2, +0/+w/2); out_{h-1} equals P_{h-1} on
+ * every index this reads. One thread per 2 cells. */
+__global__ void __launch_bounds__(256)
+k_pyramid_level(const PyrJob* __restrict__ jobs, int h)
+{
+    const PyrJob job = jobs[blockIdx.z];
+    const int rows = job.rows, cols = job.cols;
+    const size_t cells = (size_t)rows * cols;
+    const uint16_t* __restrict__ src = (h == 1) ? job.base : job.levels + (size_t)(h - 2) * cells;
+    uint16_t* __restrict__ dst = job.levels + (size_t)(h - 1) * cells;
+    const int w = 1 << h, half = w >> 1;
+
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int r = blockIdx.y;
+    if (c0 >= cols || r >= rows)
+        return;
+    const int rc = max(min(r, rows - w), 0);
+    unsigned int out[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int c = c0 + k;
+        const int cc = max(min(c, cols - w), 0);
+        unsigned int v = ld_cell(src, rows, cols, rc, cc);
+        v = max(v, ld_cell(src, rows, cols, rc + half, cc));
+        v = max(v, ld_cell(src, rows, cols, rc, cc + half));
+        v = max(v, ld_cell(src, rows, cols, rc + half, cc + half));
+        out[k] = v;
+    }
+    if (c0 + 1 < cols) {
+        *reinterpret_cast<unsigned int*>(dst + (size_t)r * cols + c0) = out[0] | (out[1] << 16);
+    } else {
+        dst[(size_t)r * cols + c0] = (uint16_t)out[0];
+    }
+}
+
+/* Generic sliding win x win maximum with the clamped far edge. */
+__global__ void __launch_bounds__(256)
+k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
+              int rows, int cols, int win)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= cols || r >= rows)
+        return;
+    const int rc = max(min(r, rows - win), 0);
+    const int cc = max(min(c, cols - win), 0);
+    unsigned int v = 0;
+    for (int dr = 0; dr < win; ++dr)
+        for (int dc = 0; dc < win; ++dc)
+            v = max(v, ld_cell(src, rows, cols, rc + dr, cc + dc));
+    dst[(size_t)r * cols + c] = (uint16_t)v;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Projection                                                                */
+/* ------------------------------------------------------------------------ */
+
+/* proj[q][t][i] = (col, row) of beam i seen from (sx, sy, thetas[t]).
+ * FP64 in the reference's operation order without contraction; the only
+ * non-reproducible step is sin/cos (device vs glibc, a few ulp), so any
+ * coordinate closer than `margin` to a cell boundary raises the flag.
+ * rcs (optional): r*cos, r*sin per (t, i) for the per-candidate FP path. */
+__global__ void __launch_bounds__(256)
+k_project(const DevQuery* __restrict__ queries, int2* __restrict__ proj,
+          double2* __restrict__ rcs, int* __restrict__ qflags)
+{
+    const int q = blockIdx.y;
+    const DevQuery& Q = queries[q];
+    const int total = Q.T * Q.n;
+    int flagged = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += gridDim.x * blockDim.x) {
+        const int t = e / Q.n;
+        const int i = e - t * Q.n;
+        const double a = __dadd_rn(Q.thetas[t], Q.angles[i]);
+        double s, c;
+        sincos(a, &s, &c);
+        const double r = Q.ranges[i];
+        const double rc = __dmul_rn(r, c);
+        const double rs = __dmul_rn(r, s);
+        const double ux = __ddiv_rn(__dsub_rn(__dadd_rn(Q.sx, rc), Q.offx), Q.res);
+        const double uy = __ddiv_rn(__dsub_rn(__dadd_rn(Q.sy, rs), Q.offy), Q.res);
+        const double fx = floor(ux), fy = floor(uy);
+        const double gx = ux - fx, gy = uy - fy;
+        if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
+            flagged = 1;
+        const double lim = 1073741824.0;
+        int2 p;
+        p.x = (int)fmin(fmax(fx, -lim), lim);
+        p.y = (int)fmin(fmax(fy, -lim), lim);
+        proj[Q.proj_off + e] = p;
+        if (rcs != nullptr)
+            rcs[Q.proj_off + e] = make_double2(rc, rs);
+    }
+    if (__any_sync(0xffffffffu, flagged) && (threadIdx.x & 31) == 0)
+        atomicOr(&qflags[q], 1 /* CSM_FLAG_FP_MARGIN */);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Scoring helpers                                                           */
+/* ------------------------------------------------------------------------ */
+
+/* Whole warp: integer score of one candidate (offset ox, oy) on map m */
+__device__ __forceinline__ void warp_score(const uint16_t* __restrict__ m, int rows, int cols,
+                                           const int2* __restrict__ proj, int n, int ox, int oy,
+                                           int& sumv, int& nk)
+{
+    const int lane = threadIdx.x & 31;
+    int s = 0, k = 0;
+    for (int i = lane; i < n; i += 32) {
+        const int2 p = proj[i];
+        const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
+        s += (int)v;
+        k += (v != 0u);
+    }
+    sumv = warp_sum(s);
+    nk = warp_sum(k);
+}
+
+/* Whole warp: the four children of a B&B node at once (more loads in flight) */
+__device__ __forceinline__ void warp_score4(const uint16_t* __restrict__ m, int rows, int cols,
+                                            const int2* __restrict__ proj, int n,
+                                            int ox, int oy, int w, int sumv[4], int nk[4])
+{
+    const int lane = threadIdx.x & 31;
+    int s0 = 0, s1 = 0, s2 = 0, s3 = 0, k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+    for (int i = lane; i < n; i += 32) {
+        const int2 p = proj[i];
+        const int r = p.y + oy, c = p.x + ox;
+        const unsigned int v0 = ld_cell(m, rows, cols, r, c);
+        const unsigned int v1 = ld_cell(m, rows, cols, r, c + w);
+        const unsigned int v2 = ld_cell(m, rows, cols, r + w, c);
+        const unsigned int v3 = ld_cell(m, rows, cols, r + w, c + w);
+        s0 += (int)v0; k0 += (v0 != 0u);
+        s1 += (int)v1; k1 += (v1 != 0u);
+        s2 += (int)v2; k2 += (v2 != 0u);
+        s3 += (int)v3; k3 += (v3 != 0u);
+    }
+    /* child order as in scan_matcher_branch_bound.cpp:226-229:
+     * (x, y), (x+w, y), (x, y+w), (x+w, y+w) */
+    sumv[0] = warp_sum(s0); nk[0] = warp_sum(k0);
+    sumv[1] = warp_sum(s1); nk[1] = warp_sum(k1);
+    sumv[2] = warp_sum(s2); nk[2] = warp_sum(k2);
+    sumv[3] = warp_sum(s3); nk[3] = warp_sum(k3);
+}
+
+/* Threshold comparison with exact resolution inside the guard band.
+ * Called by lane 0 only (the exact path is a serial double sum). */
+__device__ __forceinline__ bool passes_threshold(long long key, const DevQuery& Q,
+                                                 const uint16_t* m, const int2* proj,
+                                                 int ox, int oy)
+{
+    const int c = key_vs_threshold(key, Q.kthr);
+    if (c != 0)
+        return c > 0;
+    return exact_normalized_score(m, Q.rows, Q.cols, proj, Q.n, ox, oy) > Q.kthr.thr;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Real-time correlative matcher                                             */
+/* ------------------------------------------------------------------------ */
+
+struct RtBlock
+{
+    long long coarse_key;
+    long long fine_key;      /* max over the low_res x low_res block */
+    int coarse_nk;
+    int fine_ord;            /* (fx - x) * low_res + (fy - y) of the first maximum */
+    int fine_tie;            /* another fine candidate shares fine_key */
+    int pad;
+};
+
+/* One CTA per coarse cell (t, bx, by). Candidate 0 is the coarse score,
+ * candidates 1..L*L the fine lattice [x, x+L) x [y, y+L) in the reference's
+ * iteration order (x outer, y inner, scan_matcher_correlative.cpp:351-352). */
+__global__ void __launch_bounds__(256)
+k_rt_blocks(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all,
+            RtBlock* __restrict__ blocks, int low_res, int nbx, int nby)
+{
+    extern __shared__ long long s_keys[];      /* L*L fine keys */
+    const DevQuery& Q = queries[0];
+    const int b = blockIdx.x;
+    const int t = b / (nbx * nby);
+    const int rem = b - t * nbx * nby;
+    const int bx = rem / nby, by = rem - bx * nby;
+    const int x = -Q.winx + bx * low_res;
+    const int y = -Q.winy + by * low_res;
+    const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ncand = low_res * low_res + 1;
+
+    for (int cand = warp; cand < ncand; cand += nwarps) {
+        int sumv, nk;
+        if (cand == 0) {
+            warp_score(Q.coarse, Q.rows, Q.cols, proj, Q.n, x, y, sumv, nk);
+            if (lane == 0) {
+                blocks[b].coarse_key = make_key(sumv, nk);
+                blocks[b].coarse_nk = nk;
+            }
+        } else {
+            const int o = cand - 1;
+            const int fx = x + o / low_res, fy = y + o % low_res;
+            warp_score(Q.lvl[0], Q.rows, Q.cols, proj, Q.n, fx, fy, sumv, nk);
+            if (lane == 0)
+                s_keys[o] = make_key(sumv, nk);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long best = -1;
+        int ord = 0, tie = 0;
+        for (int o = 0; o < ncand - 1; ++o) {
+            const long long k = s_keys[o];
+            if (k > best) { best = k; ord = o; tie = 0; }
+            else if (k == best) tie = 1;
+        }
+        blocks[b].fine_key = best;
+        blocks[b].fine_ord = ord;
+        blocks[b].fine_tie = tie;
+    }
+}
+
+struct BestState
+{
+    int found, bx, by, bt;     /* bt: angle index 0..T-1 */
+    int flags, n_processed, n_ignored, pad;
+};
+
+/* Replays scan_matcher_correlative.cpp:161-197 over the coarse cells in the
+ * reference's order (t, x, y) on integer keys. One thread. Exact also when
+ * the coarse bound is not admissible. */
+__global__ void k_rt_replay(const DevQuery* __restrict__ queries,
+                            const int2* __restrict__ proj_all,
+                            const RtBlock* __restrict__ blocks, int low_res,
+                            int nbx, int nby, BestState* __restrict__ state)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    const DevQuery& Q = queries[0];
+    bool have = false;          /* scoreMax is a fine score (else: the threshold) */
+    long long cur = 0;
+    int bestx = -Q.winx, besty = -Q.winy, bestt = 0, flags = 0;
+    int processed = 0, ignored = 0;
+    const int nb = Q.T * nbx * nby;
+    for (int b = 0; b < nb; ++b) {
+        const RtBlock B = blocks[b];
+        const int t = b / (nbx * nby);
+        const int rem = b - t * nbx * nby;
+        const int bx = rem / nby, by = rem - bx * nby;
+        const int x = -Q.winx + bx * low_res, y = -Q.winy + by * low_res;
+        const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        bool coarse_ok;
+        if (have) {
+            coarse_ok = B.coarse_key > cur;
+            if (B.coarse_key == cur) flags |= 2;   /* equal keys: doubles could round either way */
+        } else {
+            coarse_ok = passes_threshold(B.coarse_key, Q, Q.coarse, proj, x, y);
+        }
+        if (!coarse_ok || B.coarse_nk <= Q.nk_cut) {
+            ++ignored;
+            continue;
+        }
+        ++processed;
+        bool fine_ok;
+        const int fx = x + B.fine_ord / low_res, fy = y + B.fine_ord % low_res;
+        if (have) fine_ok = B.fine_key > cur;
+        else fine_ok = passes_threshold(B.fine_key, Q, Q.lvl[0], proj, fx, fy);
+        if (fine_ok) {
+            have = true;
+            cur = B.fine_key;
+            bestx = fx; besty = fy; bestt = t;
+            if (B.fine_tie) flags |= 2;
+        }
+    }
+    BestState s;
+    s.found = have ? 1 : 0;
+    s.bx = bestx; s.by = besty;
+    s.bt = have ? bestt : 0;    /* reference initial bestWinTheta = -winTheta = index 0 */
+    s.flags = flags; s.n_processed = processed; s.n_ignored = ignored; s.pad = 0;
+    state[0] = s;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Branch and bound                                                          */
+/* ------------------------------------------------------------------------ */
+
+struct BbWork
+{
+    unsigned long long* nodes[kMaxLevels];   /* frontier per height */
+    long long*          keys[kMaxLevels];
+    unsigned int*       counts;              /* [kMaxLevels] */
+    unsigned long long* incumbent;           /* per query: packed (key, ordfield) */
+    unsigned long long* rootbest;            /* per query: packed best root */
+    int*                stats;               /* per query: processed, ignored */
+    int*                overflow;            /* set when a frontier is full */
+    unsigned int        capacity;
+    int                 hmax;
+};
+
+__device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, int t, int xi, int yi)
+{
+    /* smaller ordinal (t, x, y order) wins ties -> larger field */
+    const unsigned long long ord =
+        ((unsigned long long)t * (unsigned)Q.lx + (unsigned)xi) * (unsigned)Q.ly + (unsigned)yi;
+    return (kOrdMask - 1ull) - ord;     /* all-ones is reserved for "no leaf yet" */
+}
+
+/* Roots: every (t, x, y) with x, y stepping by 2^hmax from -win
+ * (scan_matcher_branch_bound.cpp:179-182). One warp per root. */
+__global__ void __launch_bounds__(256)
+k_bb_roots(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all, BbWork W)
+{
+    const int q = blockIdx.y;
+    const DevQuery& Q = queries[q];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nroots = Q.T * Q.nrx * Q.nry;
+    const int h = W.hmax;
+    const int wsz = 1 << h;
+    for (int root = warp_global; root < nroots; root += nwarps) {
+        const int t = root / (Q.nrx * Q.nry);
+        const int rem = root - t * Q.nrx * Q.nry;
+        const int rx = rem / Q.nry, ry = rem - rx * Q.nry;
+        const int xi = rx * wsz, yi = ry * wsz;
+        const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        int sumv, nk;
+        warp_score(Q.lvl[h], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, sumv, nk);
+        if (lane == 0) {
+            const long long key = make_key(sumv, nk);
+            const bool ok = passes_threshold(key, Q, Q.lvl[h], proj, xi - Q.winx, yi - Q.winy) &&
+                            nk > Q.nk_cut;
+            if (!ok) {
+                atomicAdd(&W.stats[2 * q + 1], 1);
+            } else if (h == 0) {
+                atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
+                atomicAdd(&W.stats[2 * q], 1);
+            } else {
+                const unsigned int slot = atomicAdd(&W.counts[h], 1u);
+                if (slot < W.capacity) {
+                    W.nodes[h][slot] = pack_node(q, t, xi, yi);
+                    W.keys[h][slot] = key;
+                } else {
+                    *W.overflow = 1;
+                }
+                /* best root of the query, for the greedy dive */
+                atomicMax(&W.rootbest[q], pack_best(key, kOrdMask - (unsigned long long)root));
+            }
+        }
+    }
+}
+
+/* Greedy dive from the best root to a leaf: gives every query an incumbent
+ * before the level-synchronous sweep so that the sweep can prune.
+ * One warp per query. */
+__global__ void __launch_bounds__(32)
+k_bb_dive(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all, BbWork W)
+{
+    const int q = blockIdx.x;
+    const DevQuery& Q = queries[q];
+    const int lane = threadIdx.x & 31;
+    const unsigned long long rb = W.rootbest[q];
+    if (rb == 0ull || W.hmax == 0)
+        return;
+    const int root = (int)(kOrdMask - (rb & kOrdMask));
+    const int t = root / (Q.nrx * Q.nry);
+    const int rem = root - t * Q.nrx * Q.nry;
+    int xi = (rem / Q.nry) << W.hmax, yi = (rem % Q.nry) << W.hmax;
+    const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+    for (int h = W.hmax - 1; h >= 0; --h) {
+        const int w = 1 << h;
+        int sumv[4], nk[4];
+        warp_score4(Q.lvl[h], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, w, sumv, nk);
+        int best = -1;
+        long long bestkey = -1;
+        if (lane == 0) {
+            for (int c = 0; c < 4; ++c) {
+                const long long key = make_key(sumv[c], nk[c]);
+                const int cx = xi + (c & 1) * w, cy = yi + (c >> 1) * w;
+                if (nk[c] > Q.nk_cut && key > bestkey &&
+                    passes_threshold(key, Q, Q.lvl[h], proj, cx - Q.winx, cy - Q.winy)) {
+                    bestkey = key; best = c;
+                }
+            }
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        if (best < 0)
+            return;
+        xi += (best & 1) * w;
+        yi += (best >> 1) * w;
+        if (h == 0 && lane == 0) {
+            const long long key = make_key(sumv[best], nk[best]);
+            atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
+        }
+    }
+}
+
+/* Expand every frontier node of height h into its four children at h-1.
+ * A node survives iff its key can still beat the query's incumbent
+ * (score <= scoreMax drop, scan_matcher_branch_bound.cpp:191-198; equal keys
+ * are kept so that the lowest-ordinal leaf among equal keys wins). Children
+ * are kept iff they pass the score threshold, the known-rate cut and the
+ * incumbent. Leaves update the incumbent with atomicMax. One warp per node. */
+__global__ void __launch_bounds__(256)
+k_bb_expand(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all,
+            BbWork W, int h)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned int count = min(W.counts[h], W.capacity);
+    const int hc = h - 1;
+    const int w = 1 << hc;
+    for (unsigned int idx = warp_global; idx < count; idx += nwarps) {
+        int q, t, xi, yi;
+        unpack_node(W.nodes[h][idx], q, t, xi, yi);
+        const long long key = W.keys[h][idx];
+        const DevQuery& Q = queries[q];
+        unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
+        if (!(pack_best(key, kOrdMask) > inc)) {
+            if (lane == 0) atomicAdd(&W.stats[2 * q + 1], 1);
+            continue;
+        }
+        const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        int sumv[4], nk[4];
+        warp_score4(Q.lvl[hc], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, w, sumv, nk);
+        if (lane == 0) {
+            atomicAdd(&W.stats[2 * q], 1);
+            int ignored = 0;
+            for (int c = 0; c < 4; ++c) {
+                const long long ck = make_key(sumv[c], nk[c]);
+                const int cx = xi + (c & 1) * w, cy = yi + (c >> 1) * w;
+                inc = *(volatile unsigned long long*)&W.incumbent[q];
+                const bool ok = nk[c] > Q.nk_cut && pack_best(ck, kOrdMask) > inc &&
+                                passes_threshold(ck, Q, Q.lvl[hc], proj, cx - Q.winx, cy - Q.winy);
+                if (!ok) { ++ignored; continue; }
+                if (hc == 0) {
+                    atomicMax(&W.incumbent[q], pack_best(ck, leaf_ordfield(Q, t, cx, cy)));
+                } else {
+                    const unsigned int slot = atomicAdd(&W.counts[hc], 1u);
+                    if (slot < W.capacity) {
+                        W.nodes[hc][slot] = pack_node(q, t, cx, cy);
+                        W.keys[hc][slot] = ck;
+                    } else {
+                        *W.overflow = 1;
+                    }
+                }
+            }
+            if (ignored) atomicAdd(&W.stats[2 * q + 1], ignored);
+        }
+    }
+}
+
+/* Decode the incumbents into BestState records */
+__global__ void k_bb_collect(const DevQuery* __restrict__ queries, BbWork W, int nq,
+                             const int* __restrict__ qflags, BestState* __restrict__ state)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq)
+        return;
+    const DevQuery& Q = queries[q];
+    const unsigned long long inc = W.incumbent[q];
+    BestState s;
+    const unsigned long long ordf = inc & kOrdMask;
+    s.found = (ordf != kOrdMask) ? 1 : 0;   /* initial incumbent carries the all-ones field */
+    if (s.found) {
+        unsigned long long ord = (kOrdMask - 1ull) - ordf;
+        const int yi = (int)(ord % (unsigned)Q.ly); ord /= (unsigned)Q.ly;
+        const int xi = (int)(ord % (unsigned)Q.lx); ord /= (unsigned)Q.lx;
+        s.bx = xi - Q.winx; s.by = yi - Q.winy; s.bt = (int)ord;
+    } else {
+        /* reference: bestX = bestY = bestTheta = 0 (scan_matcher_branch_bound.cpp:145-147) */
+        s.bx = 0; s.by = 0; s.bt = (Q.T - 1) / 2;
+    }
+    s.flags = qflags[q];
+    s.n_processed = W.stats[2 * q];
+    s.n_ignored = W.stats[2 * q + 1];
+    s.pad = 0;
+    state[q] = s;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Exhaustive grid search                                                    */
+/* ------------------------------------------------------------------------ */
+
+struct GridArgs
+{
+    const int* mx;          /* integer cell offset of dx[k] relative to dx[0] */
+    const int* my;
+    const double* px;       /* sx + dx[k] (general path) */
+    const double* py;
+    int ndx, ndy, ndt;
+    unsigned long long* best;   /* packed (key, ordfield) */
+    int* tie;
+};
+
+__device__ __forceinline__ void block_best_commit(unsigned long long v, unsigned long long* best)
+{
+    /* warp max, then one atomic per warp */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    if ((threadIdx.x & 31) == 0 && v != 0ull)
+        atomicMax(best, v);
+}
+
+/* Integer-shift path: all dx[k] / dy[k] are integer multiples of the
+ * resolution apart, so candidate (iy, ix, it) reads cell
+ * (row_i + my[iy], col_i + mx[ix]) of the angle's projected indices.
+ * CTA = (angle it, 8 rows iy); warp = one row; lane = one ix. */
+__global__ void __launch_bounds__(256)
+k_grid_window(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all, GridArgs G)
+{
+    extern __shared__ int2 s_proj[];
+    const DevQuery& Q = queries[0];
+    const int it = blockIdx.x;
+    const int2* proj = proj_all + Q.proj_off + (size_t)it * Q.n;
+    for (int i = threadIdx.x; i < Q.n; i += blockDim.x)
+        s_proj[i] = proj[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int iy = blockIdx.y * (blockDim.x >> 5) + warp;
+    unsigned long long best = 0ull;
+    if (iy < G.ndy) {
+        const int oy = G.my[iy];
+        const uint16_t* __restrict__ m = Q.lvl[0];
+        for (int ixb = 0; ixb < G.ndx; ixb += 32) {
+            const int ix = ixb + lane;
+            if (ix >= G.ndx)
+                break;
+            const int ox = G.mx[ix];
+            int s = 0, k = 0;
+#pragma unroll 4
+            for (int i = 0; i < Q.n; ++i) {
+                const int2 p = s_proj[i];
+                const unsigned int v = ld_cell(m, Q.rows, Q.cols, p.y + oy, p.x + ox);
+                s += (int)v;
+                k += (v != 0u);
+            }
+            const long long key = make_key(s, k);
+            if (k > Q.nk_cut) {
+                const int c = key_vs_threshold(key, Q.kthr);
+                bool ok = c > 0;
+                if (c == 0)
+                    ok = exact_normalized_score(m, Q.rows, Q.cols, proj, Q.n, ox, oy) > Q.kthr.thr;
+                if (ok) {
+                    const unsigned long long ord =
+                        ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
+                    const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
+                    best = v > best ? v : best;
+                }
+            }
+        }
+    }
+    block_best_commit(best, G.best);
+}
+
+/* Per-candidate FP64 path (steps that are not multiples of the resolution):
+ * the reference's arithmetic per candidate and beam,
+ * col = floor(((sx + dx) + r*cos - offx) / res), with device sin/cos. */
+__global__ void __launch_bounds__(256)
+k_grid_general(const DevQuery* __restrict__ queries, const double2* __restrict__ rcs_all,
+               GridArgs G, int* __restrict__ qflags)
+{
+    extern __shared__ double2 s_rcs[];
+    const DevQuery& Q = queries[0];
+    const int it = blockIdx.x;
+    const double2* rcs = rcs_all + Q.proj_off + (size_t)it * Q.n;
+    for (int i = threadIdx.x; i < Q.n; i += blockDim.x)
+        s_rcs[i] = rcs[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int iy = blockIdx.y * (blockDim.x >> 5) + warp;
+    unsigned long long best = 0ull;
+    int flagged = 0;
+    if (iy < G.ndy) {
+        const double py = G.py[iy];
+        const uint16_t* __restrict__ m = Q.lvl[0];
+        for (int ixb = 0; ixb < G.ndx; ixb += 32) {
+            const int ix = ixb + lane;
+            if (ix >= G.ndx)
+                break;
+            const double px = G.px[ix];
+            int s = 0, k = 0;
+            double sum = 0.0;
+            for (int i = 0; i < Q.n; ++i) {
+                const double2 rc = s_rcs[i];
+                const double ux = __ddiv_rn(__dsub_rn(__dadd_rn(px, rc.x), Q.offx), Q.res);
+                const double uy = __ddiv_rn(__dsub_rn(__dadd_rn(py, rc.y), Q.offy), Q.res);
+                const double fx = floor(ux), fy = floor(uy);
+                const double gx = ux - fx, gy = uy - fy;
+                if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
+                    flagged = 1;
+                const double lim = 1073741824.0;
+                const int col = (int)fmin(fmax(fx, -lim), lim);
+                const int row = (int)fmin(fmax(fy, -lim), lim);
+                const unsigned int v = ld_cell(m, Q.rows, Q.cols, row, col);
+                if (v != 0u) {
+                    s += (int)v; ++k;
+                    sum = __dadd_rn(sum, value_to_probability(v));
+                }
+            }
+            const long long key = make_key(s, k);
+            if (k > Q.nk_cut) {
+                const int c = key_vs_threshold(key, Q.kthr);
+                bool ok = c > 0;
+                if (c == 0)
+                    ok = __ddiv_rn(sum, (double)Q.n) > Q.kthr.thr;
+                if (ok) {
+                    const unsigned long long ord =
+                        ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
+                    const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
+                    best = v > best ? v : best;
+                }
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, flagged) && lane == 0)
+        atomicOr(&qflags[0], 1);
+    block_best_commit(best, G.best);
+}
+
+__global__ void k_grid_collect(GridArgs G, const int* __restrict__ qflags,
+                               BestState* __restrict__ state)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    const unsigned long long b = *G.best;
+    BestState s;
+    s.found = b != 0ull ? 1 : 0;
+    s.bx = s.by = s.bt = -1;
+    if (s.found) {
+        unsigned long long ord = (kOrdMask - 1ull) - (b & kOrdMask);
+        s.bt = (int)(ord % (unsigned)G.ndt); ord /= (unsigned)G.ndt;
+        s.bx = (int)(ord % (unsigned)G.ndx); ord /= (unsigned)G.ndx;
+        s.by = (int)ord;
+    }
+    s.flags = qflags[0];
+    s.n_processed = G.ndx * G.ndy * G.ndt;
+    s.n_ignored = 0;
+    s.pad = 0;
+    state[0] = s;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Finalisation                                                              */
+/* ------------------------------------------------------------------------ */
+
+struct FinalArgs
+{
+    const int* mx;            /* grid search: cell offsets per index (else nullptr) */
+    const int* my;
+    const double* px;         /* grid search general path: sx + dx[k] (else nullptr) */
+    const double* py;
+    const double2* rcs;
+    unsigned long long* best_key;   /* device word for the cross-rank argmax */
+    const int* qflags;              /* per-query flags raised by the projection */
+    int query_index_base;
+    int mode;                 /* 0 = window indices are cell offsets, 1 = grid fast, 2 = grid general */
+};
+
+/* One warp per query: integer score and reference-order double score of the
+ * winning pose on the level-0 map; packs the per-batch best word. */
+__global__ void __launch_bounds__(32)
+k_finalize(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all,
+           const BestState* __restrict__ state, FinalArgs F, csm_result* __restrict__ results)
+{
+    __shared__ unsigned short s_vals[kMaxBeams];
+    const int q = blockIdx.x;
+    const DevQuery& Q = queries[q];
+    const BestState s = state[q];
+    const int lane = threadIdx.x & 31;
+    const uint16_t* __restrict__ m = Q.lvl[0];
+    csm_result r;
+    r.found = s.found;
+    r.flags = s.flags | (F.qflags != nullptr ? F.qflags[q] : 0);
+    r.n_processed = s.n_processed;
+    r.n_ignored = s.n_ignored;
+    r.sum_value = 0; r.n_known = 0; r.normalized_score = 0.0;
+    const bool evaluate = (F.mode == 0) || s.found;
+    int it = s.bt;
+    if (F.mode == 0) {
+        r.best_x = s.bx; r.best_y = s.by; r.best_t = s.bt - (Q.T - 1) / 2;
+    } else {
+        r.best_x = s.bx; r.best_y = s.by; r.best_t = s.bt;
+    }
+    int sumv = 0, nk = 0;
+    if (evaluate) {
+        const size_t row_off = (size_t)Q.proj_off + (size_t)it * Q.n;
+        int ps = 0, pk = 0;
+        for (int i = lane; i < Q.n; i += 32) {
+            int row, col;
+            if (F.mode == 2) {
+                const double2 rc = F.rcs[row_off + i];
+                const double ux = __ddiv_rn(__dsub_rn(__dadd_rn(F.px[s.bx], rc.x), Q.offx), Q.res);
+                const double uy = __ddiv_rn(__dsub_rn(__dadd_rn(F.py[s.by], rc.y), Q.offy), Q.res);
+                const double lim = 1073741824.0;
+                col = (int)fmin(fmax(floor(ux), -lim), lim);
+                row = (int)fmin(fmax(floor(uy), -lim), lim);
+            } else {
+                const int2 p = proj_all[row_off + i];
+                const int ox = (F.mode == 1) ? F.mx[s.bx] : s.bx;
+                const int oy = (F.mode == 1) ? F.my[s.by] : s.by;
+                col = p.x + ox; row = p.y + oy;
+            }
+            const unsigned int v = ld_cell(m, Q.rows, Q.cols, row, col);
+            s_vals[i] = (unsigned short)v;
+            ps += (int)v;
+            pk += (v != 0u);
+        }
+        sumv = warp_sum(ps);
+        nk = warp_sum(pk);
+        __syncwarp();
+        if (lane == 0) {
+            double sum = 0.0;
+            for (int i = 0; i < Q.n; ++i) {
+                const unsigned int v = s_vals[i];
+                if (v != 0u)
+                    sum = __dadd_rn(sum, value_to_probability(v));
+            }
+            r.normalized_score = __ddiv_rn(sum, (double)Q.n);
+        }
+    }
+    if (lane == 0) {
+        r.sum_value = sumv;
+        r.n_known = nk;
+        results[q] = r;
+        if (s.found && F.best_key != nullptr) {
+            const unsigned long long word =
+                ((unsigned long long)make_key(sumv, nk) << 20) |
+                (unsigned long long)(0xFFFFF - (F.query_index_base + q));
+            atomicMax(F.best_key, word);
+        }
+    }
+}
+
+} /* namespace csm */

@@ -1,0 +1,276 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU checkers and the
+committed golden vectors. Bar: best pose index, integer score and found flag
+bit-exact; the double score within 1e-5 relative (it is in fact bit-identical:
+the device re-sums in the reference's order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import assert_match, grid_of, load_golden, sha
+from my_lidar_graph_slam_v2_b200 import capi, matchers, synth
+
+pytestmark = pytest.mark.gpu
+
+CFGS = {"CFG1": synth.CFG1, "CFG2": synth.CFG2, "CFG3": synth.CFG3}
+
+
+def _scan(case):
+    return matchers.ScanData(case.angles, case.ranges)
+
+
+# --------------------------------------------------------------------------
+# precomputation
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("entry", load_golden("reference_vectors.json")["pyramids"],
+                         ids=lambda e: "%dx%d" % (e["rows"], e["cols"]))
+def test_pyramid_golden(handle, entry):
+    rows, cols = entry["rows"], entry["cols"]
+    rng = np.random.default_rng(entry["seed"])
+    if rows >= 256:
+        grid = synth.rasterize(synth.make_room(rng, 8.0, 6.0, 1.0), rng, rows, cols, 0.05).grid
+    else:
+        grid = rng.integers(0, 65535, size=(rows, cols), dtype=np.uint16)
+        grid[rng.random((rows, cols)) < 0.5] = 0
+    assert sha(grid) == entry["grid_sha"], "synthetic generator drifted"
+    handle.upload_grid(77, grid, 0.05, -1.0, -2.0)
+    handle.build_pyramid(77, 6)
+    for h in range(7):
+        assert sha(handle.download_level(77, h, (rows, cols))) == entry["levels"][h], "level %d" % h
+    for w, digest in entry["coarse"].items():
+        handle.build_coarse(77, int(w))
+        assert sha(handle.download_level(77, -int(w), (rows, cols))) == digest, "win %s" % w
+    handle.release_grid(77)
+
+
+@pytest.mark.parametrize("shape", [(512, 512), (128, 320), (48, 16), (16, 16)])
+def test_pyramid_vs_checker(handle, checker, shape):
+    rng = np.random.default_rng(hash(shape) % 1000)
+    grid = rng.integers(0, 65535, size=shape, dtype=np.uint16)
+    grid[rng.random(shape) < 0.6] = 0
+    g = checker.grid(grid, 0.05, 0.0, 0.0)
+    handle.upload_grid(78, grid, 0.05, 0.0, 0.0)
+    for hmax in (3, 6):
+        handle.drop_pyramids([78])
+        handle.build_pyramid(78, hmax)
+        ref = g.pyramid(hmax)
+        for h in range(hmax + 1):
+            assert np.array_equal(handle.download_level(78, h, shape), ref[h]), (hmax, h)
+    handle.release_grid(78)
+
+
+def test_pyramid_batch(handle, checker):
+    ids, grids = [], []
+    for k in range(5):
+        rng = np.random.default_rng(900 + k)
+        shape = [(64, 64), (96, 32), (64, 64), (32, 128), (64, 64)][k]
+        grid = rng.integers(0, 65535, size=shape, dtype=np.uint16)
+        grid[rng.random(shape) < 0.7] = 0
+        handle.upload_grid(100 + k, grid, 0.05, 0.0, 0.0)
+        ids.append(100 + k)
+        grids.append(grid)
+    handle.build_pyramids(ids, 4)
+    for i, grid in zip(ids, grids):
+        ref = checker.grid(grid, 0.05, 0.0, 0.0).pyramid(4)
+        for h in range(5):
+            assert np.array_equal(handle.download_level(i, h, grid.shape), ref[h])
+        handle.release_grid(i)
+
+
+# --------------------------------------------------------------------------
+# single-scan matchers against the golden vectors of the reference
+# --------------------------------------------------------------------------
+def _run_golden(handle, m):
+    case = synth.case_for(synth.CFG1, m["seed"])
+    assert sha(case.submap.grid) == m["grid_sha"] and sha(case.ranges) == m["scan_sha"], \
+        "synthetic generator drifted"
+    gm, scan = grid_of(case), _scan(case)
+    thr = tuple(m["thr"])
+    if m["kind"] == "rt":
+        rng = tuple(m.get("rng", synth.CFG1["rng"]))
+        mt = matchers.ScanMatcherCorrelative("rt", m["low_res"], *rng, handle=handle)
+    elif m["kind"] == "bb":
+        mt = matchers.ScanMatcherBranchBound("bb", m["hmax"], *m["rng"], handle=handle)
+    else:
+        mt = matchers.ScanMatcherGridSearch("gs", *m["rng"], *m["step"], handle=handle)
+    return mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+
+
+@pytest.mark.parametrize("m", load_golden("reference_vectors.json")["matches"],
+                         ids=lambda m: "%s-%d-%s" % (m["kind"], m["seed"], m["thr"][0]))
+def test_match_golden(handle, m):
+    s = _run_golden(handle, m)
+    e = m["expect"]
+    assert_match(s.result, e, "%s seed %d" % (m["kind"], m["seed"]))
+    assert s.result.flags & capi.FLAG_FP_MARGIN == 0
+    if e["found"]:
+        for a, b in zip(s.estimated_pose, e["est_pose"]):
+            assert a == b, "estimated pose not bit-identical"
+    if m["kind"] == "rt":
+        # the replay reproduces the reference's own processed / ignored counters
+        assert (s.result.n_processed, s.result.n_ignored) == (e["n_processed"], e["n_ignored"])
+
+
+# --------------------------------------------------------------------------
+# live comparison with the checker on fresh seeds
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(2000, 2008))
+def test_rt_vs_checker(handle, checker, seed):
+    case = synth.case_for(synth.CFG1, seed)
+    gm, scan = grid_of(case), _scan(case)
+    g = checker.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    for low_res, thr in ((5, (0.0, 0.0)), (5, (0.5, 0.55)), (4, (0.0, 0.0)), (1, (0.2, 0.1))):
+        mt = matchers.ScanMatcherCorrelative("rt", low_res, *synth.CFG1["rng"], handle=handle)
+        s = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+        o = checker.match_rt(g, case.angles, case.ranges, case.init_pose, low_res, synth.CFG1["rng"], thr)
+        assert_match(s.result, o, "rt seed %d low_res %d thr %s" % (seed, low_res, thr))
+        assert (s.result.n_processed, s.result.n_ignored) == (o.n_processed, o.n_ignored)
+
+
+@pytest.mark.parametrize("seed", range(2100, 2108))
+def test_bb_vs_checker(handle, checker, seed):
+    case = synth.case_for(synth.CFG2, seed)
+    gm, scan = grid_of(case), _scan(case)
+    g = checker.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    for hmax, rng, thr in ((5, synth.CFG2["rng"], (0.0, 0.0)), (6, synth.CFG3["rng"], synth.CFG3["thr"]),
+                           (3, (1.0, 0.6, 0.2), (0.3, 0.3)), (0, (0.3, 0.3, 0.05), (0.0, 0.0))):
+        mt = matchers.ScanMatcherBranchBound("bb", hmax, *rng, handle=handle)
+        s = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+        o = checker.match_bb(g, case.angles, case.ranges, case.init_pose, hmax, rng, thr)
+        assert_match(s.result, o, "bb seed %d hmax %d" % (seed, hmax))
+
+
+def test_bb_unreachable_threshold(handle, checker):
+    case = synth.case_for(synth.CFG2, 2199)
+    gm, scan = grid_of(case), _scan(case)
+    mt = matchers.ScanMatcherBranchBound("bb", 5, *synth.CFG2["rng"], handle=handle)
+    s = mt.optimize_pose(gm, scan, tuple(case.init_pose), 0.999, 0.0)
+    g = checker.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    o = checker.match_bb(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"], (0.999, 0.0))
+    assert o.found == 0 and s.result.found == 0
+    assert (s.result.best_x, s.result.best_y, s.result.best_t) == (o.best_x, o.best_y, o.best_t) == (0, 0, 0)
+
+
+@pytest.mark.parametrize("seed", range(2200, 2204))
+def test_grid_vs_checker(handle, checker, seed):
+    case = synth.case_for(synth.CFG1, seed)
+    gm, scan = grid_of(case), _scan(case)
+    g = checker.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    for rng, step, thr in (((0.5, 0.5, 0.08), (0.05, 0.05, 0.004), (0.0, 0.0)),      # integer-shift path
+                           ((0.4, 0.6, 0.05), (0.1, 0.05, 0.005), (0.4, 0.5)),       # stride-2 offsets
+                           ((0.3, 0.3, 0.04), (0.03, 0.07, 0.005), (0.0, 0.0))):     # per-candidate FP path
+        mt = matchers.ScanMatcherGridSearch("gs", *rng, *step, handle=handle)
+        s = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+        o = checker.match_grid(g, case.angles, case.ranges, case.init_pose, rng, step, thr)
+        assert_match(s.result, o, "grid seed %d step %s" % (seed, step))
+
+
+def test_empty_and_out_of_map(handle, checker):
+    """All-unknown map: nothing found; scan far outside the map: nothing found."""
+    case = synth.case_for(synth.CFG1, 2300)
+    empty = matchers.GridMap(np.zeros((64, 64), np.uint16), 0.05, (-1.6, -1.6))
+    scan = _scan(case)
+    for mt in (matchers.ScanMatcherCorrelative("rt", 5, *synth.CFG1["rng"], handle=handle),
+               matchers.ScanMatcherBranchBound("bb", 4, *synth.CFG2["rng"], handle=handle),
+               matchers.ScanMatcherGridSearch("gs", 0.3, 0.3, 0.05, 0.05, 0.05, 0.005, handle=handle)):
+        assert not mt.optimize_pose(empty, scan, (0.0, 0.0, 0.0)).pose_found
+    gm = grid_of(case)
+    far = (500.0, -300.0, 0.3)
+    g = checker.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    mt = matchers.ScanMatcherCorrelative("rt", 5, *synth.CFG1["rng"], handle=handle)
+    s = mt.optimize_pose(gm, scan, far)
+    o = checker.match_rt(g, case.angles, case.ranges, far, 5, synth.CFG1["rng"], (0.0, 0.0))
+    assert_match(s.result, o, "far away")
+
+
+def test_single_beam_and_low_edge(handle, checker):
+    """N = 1 beam; map whose occupied cells touch row/col 0 (RT path is exact there too)."""
+    rng = np.random.default_rng(5)
+    grid = rng.integers(1, 65535, size=(64, 64), dtype=np.uint16)
+    gm = matchers.GridMap(grid, 0.05, (0.0, 0.0))
+    g = checker.grid(grid, 0.05, 0.0, 0.0)
+    angles = -np.pi + 2 * np.pi * np.arange(90) / 90
+    ranges = np.full(90, 0.9)
+    ranges[3] = 1.4
+    pose = (0.45, 0.40, 0.2)      # scan reaches negative indices
+    mt = matchers.ScanMatcherCorrelative("rt", 4, 0.6, 0.6, 0.3, handle=handle)
+    s = mt.optimize_pose(gm, matchers.ScanData(angles, ranges), pose)
+    o = checker.match_rt(g, angles, ranges, pose, 4, (0.6, 0.6, 0.3), (0.0, 0.0))
+    assert_match(s.result, o, "low edge rt")
+    assert (s.result.n_processed, s.result.n_ignored) == (o.n_processed, o.n_ignored)
+    one_a, one_r = np.array([0.3]), np.array([1.0])
+    s = mt.optimize_pose(gm, matchers.ScanData(one_a, one_r), (1.0, 1.0, 0.0))
+    o = checker.match_rt(g, one_a, one_r, (1.0, 1.0, 0.0), 4, (0.6, 0.6, 0.3), (0.0, 0.0))
+    assert_match(s.result, o, "single beam")
+
+
+# --------------------------------------------------------------------------
+# loop detection batch
+# --------------------------------------------------------------------------
+def _loop_queries(batch):
+    scan = matchers.ScanData(batch.angles[0], batch.ranges[0])
+    return [matchers.LoopDetectionQuery(
+        scan, 0, tuple(batch.scan_poses[i]),
+        matchers.GridMap(s.grid, s.res, (s.off_x, s.off_y), int(batch.map_ids[i])),
+        tuple(batch.map_poses[i]), i) for i, s in enumerate(batch.submaps)]
+
+
+def test_loop_batch_golden(handle):
+    entry = load_golden("reference_vectors.json")["loop"][0]
+    batch = synth.make_loop_batch(entry["seed"], n_maps=entry["n_maps"], true_fraction=entry["true_fraction"])
+    assert sha(np.stack([s.grid for s in batch.submaps])) == entry["grid_sha"]
+    bb = matchers.ScanMatcherBranchBound("loop-bb", entry["hmax"], *synth.CFG3["rng"], handle=handle)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    found, res = det.detect(_loop_queries(batch))
+    assert sum(e["found"] for e in entry["expect"]) == len(found) > 0
+    for i, (r, e) in enumerate(zip(res, entry["expect"])):
+        e = dict(e, compare_unfound=False)
+        assert_match(r, e, "loop query %d" % i)
+    for f in found:
+        e = entry["expect"][f.query_index]
+        assert tuple(f.relative_pose) == tuple(e["est_pose"])
+    for mid in batch.map_ids:
+        handle.release_grid(int(mid))
+
+
+def test_loop_batch_vs_checker_and_best_key(handle, checker):
+    batch = synth.make_loop_batch(3100, n_maps=40, true_fraction=0.3, map_id_base=5000)
+    bb = matchers.ScanMatcherBranchBound("loop-bb", 6, *synth.CFG3["rng"], handle=handle)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    queries = _loop_queries(batch)
+    found, res = det.detect(queries, query_index_base=100)
+    grids = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 2)
+    ores, _ = odet.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    for i, (r, o) in enumerate(zip(res, ores)):
+        d = dict(o.asdict(), compare_unfound=False)
+        assert_match(r, d, "loop query %d" % i)
+    # second call hits the device-side pyramid cache and must give the same answer
+    found2, res2 = det.detect(queries, query_index_base=100)
+    # (n_processed / n_ignored depend on the order in which leaves raise the incumbent)
+    det_fields = ("found", "best_x", "best_y", "best_t", "sum_value", "n_known", "flags", "normalized_score")
+    assert [[getattr(r, f) for f in det_fields] for r in res] == \
+           [[getattr(r, f) for f in det_fields] for r in res2]
+    # packed best word: max key, lowest query index on ties
+    import torch
+    word = torch.empty(1, dtype=torch.int64, device="cuda:0")
+    C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(
+        C.c_void_p(word.data_ptr()), C.c_void_p(handle.best_key_device_ptr()), 8, 3)
+    key, qidx = handle.decode_best_key(int(word.item()))
+    keys = [998 * r.sum_value + 64536 * r.n_known if r.found else -1 for r in res]
+    assert key == max(keys) and qidx == 100 + keys.index(max(keys))
+    for mid in batch.map_ids:
+        handle.release_grid(int(mid))
+
+
+def test_errors(handle):
+    with pytest.raises(capi.CsmError):
+        handle.build_pyramid(123456, 3)                      # unknown map
+    g = np.zeros((32, 32), np.uint16)
+    handle.upload_grid(9, g, 0.05, 0.0, 0.0)
+    with pytest.raises(capi.CsmError):
+        handle.match_rt(9, [0.0], [1.0], (0, 0, 0), 5, (1, 1, 1), (0.05, 0.05, 0.01), (0.0, 0.0))  # coarse not built
+    with pytest.raises(capi.CsmError):
+        handle.build_pyramid(9, 9)                           # hmax out of range
+    handle.release_grid(9)
