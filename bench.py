@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native loop-detection / scan-matching hot path.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ... # reference CPU path (oracle/_ref)
+
+Workload (BASELINE.json configs[2]): one query scan (360 beams)
+matched by branch-and-bound (hmax 6, window 2.5 m x 2.5 m x 0.5 rad, thresholds
+0.55 / 0.6) against 256 candidate 512x512 submaps per GPU. A step is one
+LoopDetector::Detect on 256 first-touch submaps: grid upload, pyramid build
+(PrecomputeGridMaps) and the batched B&B search, i.e. the reference's own
+cold path (loop_detector_branch_bound.cpp:68-141). Queries shard across ranks
+with no data-path exchange; the only collective is the 8-byte argmax
+all-reduce of the packed best (score, query) word over NCCL.
+
+  value : queries/s, inputs (submaps, scan) resident in HBM, CUDA events
+  e2e   : queries/s through the C ABI with pinned HOST buffers, H2D of all
+          submaps and D2H of all results inside the timed region
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HMAX = 6
+N_MAPS = 256
+ROWS = COLS = 512
+METRIC = "loop_detection_queries_per_sec"
+UNIT = "queries/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "cfg3: 1 query scan (360 beams) x %d candidate 512x512 u16 submaps per GPU, "
+                    "branch-and-bound hmax=6, window 2.5m/2.5m/0.5rad, thr 0.55/0.6; step = Detect on "
+                    "first-touch submaps (upload + pyramid build + batched B&B)" % N_MAPS,
+        "queries_per_gpu": N_MAPS, "grid": "%dx%d u16 @0.05m" % (ROWS, COLS), "hmax": HMAX,
+        "sharding": "queries/submaps sharded over %d rank(s), 8-byte NCCL argmax all-reduce" % n_gpus,
+        "l2": "inputs larger than L2: 128 MiB of submaps + 768 MiB of pyramid levels touched per step",
+    }
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.active = False
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            if self.active:
+                self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# data
+# ---------------------------------------------------------------------------
+def make_batch(rank, n_maps=N_MAPS):
+    from my_lidar_graph_slam_v2_b200 import synth
+    return synth.make_loop_batch(31000 + rank, n_maps=n_maps, true_fraction=0.25,
+                                 rows=ROWS, cols=COLS, map_id_base=0)
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_detect(kind, batch, n_threads, n_queries, cold=True, repeats=1):
+    """Time LoopDetectorBranchBound::Detect on the CPU checker. Returns queries/s (best of repeats)."""
+    from oracle import pyoracle
+    from my_lidar_graph_slam_v2_b200 import synth
+    orc = pyoracle.load(kind)
+    subs = batch.submaps[:n_queries]
+    grids = [orc.grid(s.grid, s.res, s.off_x, s.off_y) for s in subs]
+    det = orc.loop_detector(HMAX, synth.CFG3["rng"], synth.CFG3["thr"], n_threads)
+    best = None
+    for _ in range(repeats):
+        if cold:
+            det.clear_cache()
+        _, el = det.detect(grids, batch.map_ids[:n_queries], batch.map_poses[:n_queries],
+                           batch.scan_idx[:n_queries], batch.scan_poses[:n_queries],
+                           batch.angles, batch.ranges)
+        best = el if best is None else min(best, el)
+    det.close()
+    for g in grids:
+        g.close()
+    return n_queries / best
+
+
+def reference_kind():
+    from oracle import pyoracle
+    return "reference" if pyoracle.available("reference") else "port"
+
+
+# ---------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------
+def main_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    kind = reference_kind()
+    threads = cpu_threads()
+    batch = make_batch(0)
+    from oracle import pyoracle
+    from my_lidar_graph_slam_v2_b200 import synth
+    orc = pyoracle.load(kind)
+    grids = [orc.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    det = orc.loop_detector(HMAX, synth.CFG3["rng"], synth.CFG3["thr"], threads)
+
+    def step(nq):
+        det.clear_cache()
+        _, el = det.detect(grids[:nq], batch.map_ids[:nq], batch.map_poses[:nq], batch.scan_idx[:nq],
+                           batch.scan_poses[:nq], batch.angles, batch.ranges)
+        return el
+
+    # bounded sample: the first nq queries of the per-GPU step, nq chosen from one probe so
+    # that the whole run stays within ~3 minutes whatever K the driver asks for
+    nq = N_MAPS
+    probe = step(min(N_MAPS, 4 * threads)) / min(N_MAPS, 4 * threads)
+    budget_s = 150.0
+    while nq > threads and probe * nq * (args.steps + args.warmup) > budget_s:
+        nq //= 2
+    times = []
+    for it in range(args.warmup + args.steps):
+        el = step(nq)
+        if it >= args.warmup:
+            times.append(el)
+    total = float(np.sum(times))
+    value = nq * args.steps / total
+    sample = ("%d steps, each Detect on the first %d of the %d first-touch submaps of the per-GPU step "
+              "(pyramid build + B&B + cost/covariance), queries split over %d std::threads"
+              % (args.steps, nq, N_MAPS, threads))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------
+class CudaArrayView:
+    """Zero-copy torch view of a device word owned by the C library."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def main_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from my_lidar_graph_slam_v2_b200 import capi, matchers, synth
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.load()
+    h = capi.Handle(local)
+    ext_stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local))
+
+    batch = make_batch(rank)
+    cells = ROWS * COLS
+    # pinned host copies of the submaps (what the adapter flattens the reference maps into)
+    host_ptr = lib.csm_alloc_pinned(N_MAPS * cells * 2)
+    host = np.ctypeslib.as_array((C.c_uint16 * (N_MAPS * cells)).from_address(host_ptr)).reshape(N_MAPS, ROWS, COLS)
+    for m, s in enumerate(batch.submaps):
+        host[m] = s.grid
+    ids = np.arange(N_MAPS, dtype=np.int64)
+    ptrs = (C.c_void_p * N_MAPS)(*[host_ptr + m * cells * 2 for m in range(N_MAPS)])
+    offx = np.array([s.off_x for s in batch.submaps])
+    offy = np.array([s.off_y for s in batch.submaps])
+    res = batch.submaps[0].res
+
+    bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=h)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    scan = matchers.ScanData(batch.angles[0], batch.ranges[0])
+    queries = [matchers.LoopDetectionQuery(
+        scan, 0, tuple(batch.scan_poses[i]),
+        matchers.GridMap(None, s.res, (s.off_x, s.off_y), int(ids[i])), tuple(batch.map_poses[i]), i)
+        for i, s in enumerate(batch.submaps)]
+    results = (capi.CsmResult * N_MAPS)()
+    best_word = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def make_query_array():
+        # host math of the adapter: InverseCompound / Compound / steps / windows per query
+        h.upload_scan(0, scan.angles, scan.ranges)
+        det._cached_maps.update(int(i) for i in ids)
+        det._cached_scans[0] = scan
+        return det.prepare(queries)
+
+    def allreduce_best():
+        view = torch.as_tensor(CudaArrayView(h.best_key_device_ptr(), 1, "<i8"), device="cuda")
+        with torch.cuda.stream(ext_stream):
+            best_word.copy_(view)
+            if world > 1:
+                dist.all_reduce(best_word, op=dist.ReduceOp.MAX)
+
+    def e2e_step():
+        h.upload_grids_ptr(ids, ptrs, ROWS, COLS, res, offx, offy)     # H2D 128 MiB
+        arr = make_query_array()                                          # H2D scan + host pose math
+        h.build_pyramids(ids, HMAX)
+        h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
+        allreduce_best()
+        h.loop_batch_finish(N_MAPS, results)                              # D2H results
+        return int(best_word.item())                                      # D2H best word
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- warm-up (also allocates every workspace) --------------------------------
+    for _ in range(max(args.warmup, 3)):
+        word = e2e_step()
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        word = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sampler.active = False
+    n_found = sum(r.found for r in results)
+    key, qidx = h.decode_best_key(word)
+
+    # ---- value: inputs resident in HBM, CUDA events on the handle's stream ------------------
+    arr = make_query_array()
+    h.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def device_step():
+        h.drop_pyramids(ids)
+        h.build_pyramids(ids, HMAX)
+        h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
+        allreduce_best()
+
+    for _ in range(3):
+        device_step()
+    barrier()
+    launches0 = h.launch_count()
+    sampler.active = True
+    ev[0].record(ext_stream)
+    for _ in range(args.steps):
+        device_step()
+    ev[1].record(ext_stream)
+    ev[1].synchronize()
+    sampler.active = False
+    launches = h.launch_count() - launches0
+    dev_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    h.loop_batch_finish(N_MAPS, results)
+
+    # ---- per-phase timing for the roofline of the dominant kernel -----------------------------
+    barrier()
+    ev[0].record(ext_stream)
+    for _ in range(args.steps):
+        h.drop_pyramids(ids)
+        h.build_pyramids(ids, HMAX)
+    ev[1].record(ext_stream)
+    ev[1].synchronize()
+    pyr_ms = ev[0].elapsed_time(ev[1]) / args.steps
+    ev[2].record(ext_stream)
+    for _ in range(args.steps):
+        h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
+    ev[3].record(ext_stream)
+    ev[3].synchronize()
+    bb_ms = ev[2].elapsed_time(ev[3]) / args.steps
+    h.loop_batch_finish(N_MAPS, results)
+    nodes = sum(r.n_processed for r in results)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    pyr_bytes = (1 + HMAX) * cells * 2 * N_MAPS          # read level 0 once, write hmax levels
+    pyr_launches = HMAX * ((N_MAPS * cells * 2 + (24 << 20) - 1) // (24 << 20))
+    roofline = {
+        "kernel": "k_pyramid_level (PrecomputeGridMaps, %d launches per step)" % pyr_launches,
+        "bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak,
+        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
+        "algorithmic_bytes_per_launch": pyr_bytes // pyr_launches, "traffic": None,
+        "ms_per_step": pyr_ms, "share_of_step": pyr_ms / (dev_ms / args.steps),
+    }
+    phases = {"pyramid_ms": pyr_ms, "branch_and_bound_ms": bb_ms,
+              "bb_nodes_expanded_per_step": nodes,
+              "bb_gather_bytes_per_step": nodes * 4 * 360 * 2}
+
+    total_queries = world * N_MAPS * args.steps
+    line = {
+        "metric": METRIC, "value": total_queries / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/int64 (f64 projection)",
+        "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": total_queries / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "h2d_bytes_per_step": N_MAPS * cells * 2 + 2 * 360 * 8 + N_MAPS * (256 + 115 * 8 + 8),
+                "d2h_bytes_per_step": N_MAPS * C.sizeof(capi.CsmResult) + 8},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "phases": phases,
+        "check": {"found_per_step": int(n_found), "best_key": int(key), "best_query": int(qidx)},
+    }
+
+    if rank == 0:
+        sampler.stop()
+        line["clocks"] = sampler.summary()
+        if world == 1 and not args.no_cpu:
+            kind = reference_kind()
+            threads = cpu_threads()
+            v_all = run_cpu_detect(kind, batch, threads, N_MAPS, cold=True, repeats=2)
+            v_one = run_cpu_detect(kind, batch, 1, 32, cold=True)
+            line["cpu_baseline"] = {
+                "value": v_all, "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": "full step (256 queries on 256 first-touch submaps), best of 2, %d threads; "
+                          "1 thread on the first 32 queries: %.1f queries/s" % (threads, v_one),
+                "one_core_value": v_one,
+            }
+            if not args.no_single:
+                line["single_scan"] = single_scan_numbers(h, lib, kind)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    lib.csm_free_pinned(host_ptr)
+    return 0
+
+
+def single_scan_numbers(h, lib, kind):
+    """matches/s of the three single-scan matchers through the plugin-level API
+    (host buffers, grid upload + precompute + search + result readback per match)
+    next to the CPU checker on the same inputs (cfg1, cfg2, cfg4 of BASELINE.json)."""
+    from oracle import pyoracle
+    from my_lidar_graph_slam_v2_b200 import matchers, synth
+    orc = pyoracle.load(kind)
+    out = {}
+
+    def timeit(fn, reps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return reps / (time.perf_counter() - t0)
+
+    case = synth.case_for(synth.CFG1, 41000)
+    gm = matchers.GridMap(case.submap.grid, case.submap.res, (case.submap.off_x, case.submap.off_y))
+    scan = matchers.ScanData(case.angles, case.ranges)
+    og = orc.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    rt = matchers.ScanMatcherCorrelative("rt", 5, *synth.CFG1["rng"], handle=h)
+    gpu = timeit(lambda: rt.optimize_pose(gm, scan, tuple(case.init_pose)), 200)
+    cpu = timeit(lambda: orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), 20)
+    out["cfg1_rt_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "cpu_kind": kind}
+
+    bbm = matchers.ScanMatcherBranchBound("bb", 5, *synth.CFG2["rng"], handle=h)
+    gpu = timeit(lambda: bbm.optimize_pose(gm, scan, tuple(case.init_pose)), 200)
+    cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5)
+    out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "cpu_kind": kind}
+
+    c4 = synth.case_for(synth.CFG4, 44000)
+    gm4 = matchers.GridMap(c4.submap.grid, c4.submap.res, (c4.submap.off_x, c4.submap.off_y))
+    scan4 = matchers.ScanData(c4.angles, c4.ranges)
+    gs = matchers.ScanMatcherGridSearch("gs", *synth.CFG4["rng"], *synth.CFG4["step"], handle=h)
+    gpu = timeit(lambda: gs.optimize_pose(gm4, scan4, tuple(c4.init_pose)), 3)
+    # CPU: 1/64 of the window (x and y ranges / 8), scaled by the candidate ratio
+    og4 = orc.grid(c4.submap.grid, c4.submap.res, c4.submap.off_x, c4.submap.off_y)
+    rng_small = (synth.CFG4["rng"][0] / 8, synth.CFG4["rng"][1] / 8, synth.CFG4["rng"][2] / 8)
+    t0 = time.perf_counter()
+    r = orc.match_grid(og4, c4.angles, c4.ranges, c4.init_pose, rng_small, synth.CFG4["step"])
+    el = time.perf_counter() - t0
+    full = 161 * 161 * 601
+    out["cfg4_grid_matches_per_s"] = {
+        "gpu_e2e": gpu, "cpu_1core_scaled": 1.0 / (el * full / max(r.n_processed, 1)),
+        "cpu_sample": "%d of %d candidates evaluated in %.2f s, scaled linearly" % (r.n_processed, full, el),
+        "cpu_kind": kind}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-scan extras")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

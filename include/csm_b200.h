@@ -127,6 +127,11 @@ int csm_upload_grid(csm_handle h, int64_t map_id, const uint16_t* dense,
 int csm_upload_grid_device(csm_handle h, int64_t map_id, const uint16_t* dense_dev,
                            int rows, int cols, double resolution,
                            double offset_x, double offset_y);
+/* n maps of identical shape and resolution in one call (one asynchronous
+ * host-to-device copy per map on the handle's stream; use pinned buffers). */
+int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t* const* dense,
+                     int rows, int cols, double resolution,
+                     const double* offset_x, const double* offset_y);
 int csm_release_grid(csm_handle h, int64_t map_id);
 
 /* PrecomputeGridMap(map, win) (grid_map_builder.cpp:1044-1065): sliding

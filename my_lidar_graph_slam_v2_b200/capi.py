@@ -45,7 +45,7 @@ class CsmLoopQuery(C.Structure):
 EXPORTS = [
     "csm_version", "csm_device_count", "csm_create", "csm_destroy", "csm_last_error",
     "csm_stream", "csm_synchronize", "csm_launch_count", "csm_alloc_pinned", "csm_free_pinned",
-    "csm_upload_grid", "csm_upload_grid_device", "csm_release_grid", "csm_build_coarse",
+    "csm_upload_grid", "csm_upload_grid_device", "csm_upload_grids", "csm_release_grid", "csm_build_coarse",
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
@@ -89,6 +89,7 @@ def load():
     lib.csm_free_pinned.argtypes = [C.c_void_p]
     lib.csm_upload_grid.argtypes = [H, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     lib.csm_upload_grid_device.argtypes = lib.csm_upload_grid.argtypes
+    lib.csm_upload_grids.argtypes = [H, C.c_int, i64p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, dp, dp]
     lib.csm_release_grid.argtypes = [H, C.c_int64]
     lib.csm_build_coarse.argtypes = [H, C.c_int64, C.c_int]
     lib.csm_build_pyramid.argtypes = [H, C.c_int64, C.c_int]
@@ -162,6 +163,11 @@ class Handle:
     def upload_grid_ptr(self, map_id, ptr, rows, cols, res, off_x, off_y, device=False):
         fn = self.lib.csm_upload_grid_device if device else self.lib.csm_upload_grid
         self._check(fn(self.h, map_id, ptr, rows, cols, res, off_x, off_y))
+
+    def upload_grids_ptr(self, map_ids, ptrs, rows, cols, res, off_x, off_y):
+        """map_ids: int64 array, ptrs: (c_void_p * n) of host buffers, off_x/off_y: float64 arrays."""
+        self._check(self.lib.csm_upload_grids(self.h, len(map_ids), map_ids.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              ptrs, rows, cols, res, _dptr(off_x), _dptr(off_y)))
 
     def release_grid(self, map_id):
         self._check(self.lib.csm_release_grid(self.h, map_id))

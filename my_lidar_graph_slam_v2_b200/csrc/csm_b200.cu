@@ -641,6 +641,21 @@ int csm_upload_grid_device(csm_handle h, int64_t map_id, const uint16_t* dense_d
     return upload_grid_impl(h, map_id, dense_dev, true, rows, cols, resolution, offset_x, offset_y);
 }
 
+int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t* const* dense,
+                     int rows, int cols, double resolution,
+                     const double* offset_x, const double* offset_y)
+{
+    if (!h) return CSM_E_INVALID;
+    if (n <= 0 || !map_ids || !dense || !offset_x || !offset_y)
+        return fail(h, CSM_E_INVALID, "upload_grids: empty batch");
+    for (int i = 0; i < n; ++i) {
+        const int rc = upload_grid_impl(h, map_ids[i], dense[i], false, rows, cols, resolution,
+                                        offset_x[i], offset_y[i]);
+        if (rc) return rc;
+    }
+    return CSM_OK;
+}
+
 int csm_release_grid(csm_handle h, int64_t map_id)
 {
     if (!h) return CSM_E_INVALID;

@@ -183,7 +183,7 @@ CFG4 = dict(name="cfg4_grid", rng=(4.0, 4.0, 60.0 * DEG), step=(0.025, 0.025, 0.
 
 def case_for(cfg, seed):
     return make_match_case(seed, cfg["rows"], cfg["cols"], cfg["res"], cfg["n_beams"],
-                           cfg.get("rmax", 11.40), cfg["offset"])
+                           cfg.get("rmax", 11.40), cfg["offset"], cfg.get("room_size", (16.0, 12.0)))
 
 
 @dataclass

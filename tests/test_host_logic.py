@@ -1,0 +1,101 @@
+"""CPU suite: host-side logic of the plugin mirror and the C-ABI surface (no compute calls)."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from my_lidar_graph_slam_v2_b200 import build, capi, matchers, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """libcsm_b200.so loads without a GPU and exports every function include/csm_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "csm_b200.h")).read()
+    declared = set(re.findall(r"\b(csm_[a-z_0-9]+)\s*\(", header))
+    declared -= {"csm_context"}
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    lib = capi.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert lib.csm_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a usable CUDA device csm_create fails loudly (there is no CPU path)."""
+    lib = capi.load()
+    if lib.csm_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.CsmError):
+        capi.Handle(0)
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.CsmResult) == 48
+    assert C.sizeof(capi.CsmLoopQuery) == 96
+    assert capi.CsmResult.sum_value.offset == 16 and capi.CsmResult.normalized_score.offset == 32
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing in the product package or include/ references oracle/."""
+    pkg = os.path.join(ROOT, "my_lidar_graph_slam_v2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_search_step_and_window_expressions():
+    """scan_matcher_correlative.cpp:141-146,255-274 on the synthetic cfg sizes."""
+    ranges = np.array([3.0, 11.40, 7.5])
+    step = matchers.compute_search_step(0.05, ranges)
+    assert step[0] == step[1] == 0.05
+    assert step[2] == math.acos(1.0 - 0.5 * (0.05 / 11.40) * (0.05 / 11.40))
+    assert matchers.search_window(synth.CFG1["rng"], step) == (5, 5, 20)
+    assert matchers.search_window(synth.CFG2["rng"], step) == (20, 20, 60)
+    assert matchers.search_window(synth.CFG3["rng"], step) == (25, 25, 57)
+
+
+def test_grid_search_offsets_accumulate_like_the_reference():
+    d = matchers.grid_search_offsets(2.0, 0.025)
+    assert len(d) == 161 and d[0] == -2.0
+    acc = -2.0
+    for v in d:
+        assert v == acc
+        acc += 0.025
+    # accumulated rounding decides whether the last value is still <= r: whatever the
+    # C loop of scan_matcher_grid_search.cpp:118-120 does, the helper does too
+    dt = matchers.grid_search_offsets(30.0 * synth.DEG, 0.1 * synth.DEG)
+    assert len(dt) in (600, 601) and dt[-1] <= 30.0 * synth.DEG < dt[-1] + 0.1 * synth.DEG
+
+
+def test_pose_algebra_roundtrip():
+    a, b = (1.5, -2.0, 0.7), (0.3, 0.1, -0.2)
+    c = matchers.compound(a, b)
+    back = matchers.inverse_compound(a, c)
+    assert np.allclose(back, b, atol=1e-12)
+    assert np.allclose(matchers.move_backward(c, b), a, atol=1e-12)
+
+
+def test_synthetic_generators_are_deterministic_and_capped():
+    a, b = synth.case_for(synth.CFG1, 77), synth.case_for(synth.CFG1, 77)
+    assert np.array_equal(a.submap.grid, b.submap.grid) and np.array_equal(a.ranges, b.ranges)
+    assert a.submap.grid.max() <= 65534          # reference LUT is one entry short
+    assert a.submap.grid.shape == (512, 512) and a.ranges.max() == 11.40
+    # all-unknown margin of at least 2^hmax cells on the low-index sides: a coarse cell that
+    # starts at a negative index then covers only unknown cells, so the B&B bound stays
+    # admissible there
+    for seed in range(70, 90):
+        g = synth.case_for(synth.CFG1, seed).submap.grid
+        assert not g[:64].any() and not g[:, :64].any()
+    lb = synth.make_loop_batch(5, n_maps=8)
+    assert len(lb.submaps) == 8 and lb.map_poses.shape == (8, 3)
+
+
+def test_build_flags_target_sm100a_only():
+    flags = " ".join(build.NVCC_FLAGS)
+    assert "arch=compute_100a,code=sm_100a" in flags and "-lineinfo" in flags

@@ -1,0 +1,116 @@
+"""CPU suite: pins the C++ restatement (oracle/port.cpp) against the golden vectors
+generated from the unmodified reference (tests/golden/make_golden.py) and, when
+oracle/_ref is available, against the compiled reference itself."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, sha
+from my_lidar_graph_slam_v2_b200 import synth
+
+GOLD = load_golden("reference_vectors.json")
+
+
+def _cmp(o, e, what):
+    d = o.asdict()
+    for k in ("found", "best_x", "best_y", "best_t", "win_x", "win_y", "win_t", "n_known", "sum_value",
+              "n_processed", "n_ignored", "step_x", "step_y", "step_t", "known_rate", "norm_cost"):
+        assert d[k] == e[k], "%s: %s %r vs %r" % (what, k, d[k], e[k])
+    assert d["score"] == float.fromhex(e["score"]), what
+    assert d["est_pose"] == e["est_pose"], what
+    assert np.allclose(d["cov"], e["cov"], rtol=1e-9, atol=0.0), what
+
+
+@pytest.mark.parametrize("m", GOLD["matches"], ids=lambda m: "%s-%d-%s" % (m["kind"], m["seed"], m["thr"][0]))
+def test_port_matches_golden(port_oracle, m):
+    case = synth.case_for(synth.CFG1, m["seed"])
+    assert sha(case.submap.grid) == m["grid_sha"] and sha(case.ranges) == m["scan_sha"]
+    s = case.submap
+    g = port_oracle.grid(s.grid, s.res, s.off_x, s.off_y)
+    thr = tuple(m["thr"])
+    if m["kind"] == "rt":
+        o = port_oracle.match_rt(g, case.angles, case.ranges, case.init_pose, m["low_res"],
+                                 tuple(m.get("rng", synth.CFG1["rng"])), thr)
+    elif m["kind"] == "bb":
+        o = port_oracle.match_bb(g, case.angles, case.ranges, case.init_pose, m["hmax"], tuple(m["rng"]), thr)
+    else:
+        o = port_oracle.match_grid(g, case.angles, case.ranges, case.init_pose, tuple(m["rng"]),
+                                   tuple(m["step"]), thr)
+    _cmp(o, m["expect"], "%s seed %d" % (m["kind"], m["seed"]))
+
+
+@pytest.mark.parametrize("entry", GOLD["pyramids"], ids=lambda e: "%dx%d" % (e["rows"], e["cols"]))
+def test_port_pyramid_golden(port_oracle, entry):
+    rows, cols = entry["rows"], entry["cols"]
+    rng = np.random.default_rng(entry["seed"])
+    if rows >= 256:
+        grid = synth.rasterize(synth.make_room(rng, 8.0, 6.0, 1.0), rng, rows, cols, 0.05).grid
+    else:
+        grid = rng.integers(0, 65535, size=(rows, cols), dtype=np.uint16)
+        grid[rng.random((rows, cols)) < 0.5] = 0
+    assert sha(grid) == entry["grid_sha"]
+    g = port_oracle.grid(grid, 0.05, -1.0, -2.0)
+    pyr = g.pyramid(6)
+    assert [sha(pyr[h]) for h in range(7)] == entry["levels"]
+    for w, digest in entry["coarse"].items():
+        assert sha(g.precompute(int(w))) == digest
+
+
+def test_sliding_max_definition(port_oracle):
+    """out[i] = max(in[s .. s+w-1]), s = min(i, n-w): forward window, far edge clamped."""
+    rng = np.random.default_rng(11)
+    grid = rng.integers(0, 65535, size=(48, 80), dtype=np.uint16)
+    g = port_oracle.grid(grid, 0.05, 0.0, 0.0)
+    for w in (1, 2, 3, 5, 16, 47, 48, 64, 100):
+        out = g.precompute(w)
+        exp = np.zeros_like(grid)
+        for r in range(48):
+            r0 = max(min(r, 48 - w), 0)
+            for c in range(80):
+                c0 = max(min(c, 80 - w), 0)
+                exp[r, c] = grid[r0:r0 + w, c0:c0 + w].max()
+        assert np.array_equal(out, exp), w
+
+
+def test_port_loop_golden(port_oracle):
+    entry = GOLD["loop"][0]
+    batch = synth.make_loop_batch(entry["seed"], n_maps=entry["n_maps"], true_fraction=entry["true_fraction"])
+    grids = [port_oracle.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    for threads in (1, 3):
+        det = port_oracle.loop_detector(entry["hmax"], synth.CFG3["rng"], synth.CFG3["thr"], threads)
+        res, _ = det.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                            batch.angles, batch.ranges)
+        for i, (o, e) in enumerate(zip(res, entry["expect"])):
+            assert o.found == e["found"], i
+            if e["found"]:
+                assert (o.best_x, o.best_y, o.best_t, o.sum_value, o.n_known) == \
+                       (e["best_x"], e["best_y"], e["best_t"], e["sum_value"], e["n_known"]), i
+                assert o.score == float.fromhex(e["score"]) and list(o.est_pose) == e["est_pose"], i
+        # warm call (cached pyramids) gives the same answer
+        res2, _ = det.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                             batch.angles, batch.ranges)
+        assert [r.asdict() for r in res] == [r.asdict() for r in res2]
+
+
+@pytest.mark.parametrize("seed", range(5000, 5004))
+def test_port_vs_compiled_reference(port_oracle, ref_oracle, seed):
+    """Fresh seeds: the restatement and the reference's own code agree on every field."""
+    case = synth.case_for(synth.CFG2, seed)
+    s = case.submap
+    gp = port_oracle.grid(s.grid, s.res, s.off_x, s.off_y)
+    gr = ref_oracle.grid(s.grid, s.res, s.off_x, s.off_y)
+    assert np.array_equal(gp.pyramid(5), gr.pyramid(5))
+    assert np.array_equal(gp.precompute(5), gr.precompute(5))
+    rel = (0.12, -0.05, 0.3)      # non-trivial relative sensor pose (Compound / MoveBackward)
+    pairs = [
+        (port_oracle.match_rt(gp, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"], (0.3, 0.4), rel),
+         ref_oracle.match_rt(gr, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"], (0.3, 0.4), rel)),
+        (port_oracle.match_bb(gp, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"], (0.0, 0.0), rel),
+         ref_oracle.match_bb(gr, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"], (0.0, 0.0), rel)),
+        (port_oracle.match_grid(gp, case.angles, case.ranges, case.init_pose, (0.3, 0.2, 0.05), (0.05, 0.04, 0.006), (0.2, 0.2), rel),
+         ref_oracle.match_grid(gr, case.angles, case.ranges, case.init_pose, (0.3, 0.2, 0.05), (0.05, 0.04, 0.006), (0.2, 0.2), rel)),
+    ]
+    for a, b in pairs:
+        da, db = a.asdict(), b.asdict()
+        cov_a, cov_b = da.pop("cov"), db.pop("cov")
+        assert da == db
+        assert np.allclose(cov_a, cov_b, rtol=1e-9, atol=0.0)
