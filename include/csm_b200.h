@@ -108,6 +108,9 @@ void* csm_stream(csm_handle h);
 int  csm_synchronize(csm_handle h);
 /* Number of kernels this handle has launched so far */
 int64_t csm_launch_count(csm_handle h);
+/* Tuning / test knobs. "pyramid_mode": 0 = automatic, 1 = level-by-level
+ * kernels, 2 = streaming single-pass kernel (when the maps fit its layout). */
+int csm_set_option(csm_handle h, const char* name, int value);
 /* Page-locked host memory for the caller's upload buffers (fast H2D) */
 void* csm_alloc_pinned(size_t bytes);
 void  csm_free_pinned(void* p);

@@ -44,7 +44,7 @@ class CsmLoopQuery(C.Structure):
 
 EXPORTS = [
     "csm_version", "csm_device_count", "csm_create", "csm_destroy", "csm_last_error",
-    "csm_stream", "csm_synchronize", "csm_launch_count", "csm_alloc_pinned", "csm_free_pinned",
+    "csm_stream", "csm_synchronize", "csm_launch_count", "csm_set_option", "csm_alloc_pinned", "csm_free_pinned",
     "csm_upload_grid", "csm_upload_grid_device", "csm_upload_grids", "csm_release_grid", "csm_build_coarse",
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
@@ -84,6 +84,7 @@ def load():
     lib.csm_synchronize.argtypes = [H]
     lib.csm_launch_count.argtypes = [H]
     lib.csm_launch_count.restype = C.c_int64
+    lib.csm_set_option.argtypes = [H, C.c_char_p, C.c_int]
     lib.csm_alloc_pinned.argtypes = [C.c_size_t]
     lib.csm_alloc_pinned.restype = C.c_void_p
     lib.csm_free_pinned.argtypes = [C.c_void_p]
@@ -150,6 +151,9 @@ class Handle:
 
     def synchronize(self):
         self._check(self.lib.csm_synchronize(self.h))
+
+    def set_option(self, name, value):
+        self._check(self.lib.csm_set_option(self.h, name.encode(), int(value)))
 
     def launch_count(self):
         return int(self.lib.csm_launch_count(self.h))

@@ -79,6 +79,8 @@ struct csm_context
     std::vector<PyrJob> jobs_on_device;
     /* pending batch */
     int pending_nq = 0;
+    /* options (csm_set_option) */
+    int pyramid_mode = 0;          /* 0 auto, 1 level-by-level, 2 streaming */
 };
 
 namespace {
@@ -278,8 +280,27 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
         if ((rc = upload_committed(h))) return rc;
         h->jobs_on_device = jobs;
     }
-    /* Maps are processed in chunks so that level h-1 of a chunk is still in
-     * L2 when level h reads it (each level is written once to HBM). */
+    /* Batches of maps that fit its layout take the streaming builder (one pass,
+     * level 0 read once, every level written once). */
+    bool stream_ok = hmax >= 1 && hmax <= 6 && h->pyramid_mode != 1 &&
+                     (h->pyramid_mode == 2 || jobs.size() >= (size_t)h->sm_count / 2);
+    for (const PyrJob& j : jobs)
+        stream_ok = stream_ok && j.cols <= 512 && (j.cols % 8) == 0 && (j.rows % kPsRows) == 0;
+    if (stream_ok) {
+        const size_t smem = sizeof(unsigned int) *
+            ((size_t)kPsStages * kPsRows * kPsInStride + 2 * kPsRows * 256 + 63 * 256);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CSM_CUDA(cudaFuncSetAttribute(k_pyramid_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        k_pyramid_stream<<<(unsigned)jobs.size(), kPsThreads, smem, h->stream>>>(
+            static_cast<const PyrJob*>(h->d_pyrjobs.p), hmax);
+        CSM_LAUNCH_CHECK();
+        return CSM_OK;
+    }
+    /* Otherwise level by level; maps are processed in chunks so that level h-1
+     * of a chunk is still in L2 when level h reads it. */
     const size_t map_bytes = (size_t)max_rows * max_cols * sizeof(uint16_t);
     const size_t chunk = std::max<size_t>(1, ((size_t)24 << 20) / std::max<size_t>(map_bytes, 1));
     for (size_t first = 0; first < jobs.size(); first += chunk) {
@@ -592,6 +613,16 @@ int csm_synchronize(csm_handle h)
 }
 
 int64_t csm_launch_count(csm_handle h) { return h ? h->launches : 0; }
+
+int csm_set_option(csm_handle h, const char* name, int value)
+{
+    if (!h || !name) return CSM_E_INVALID;
+    if (std::strcmp(name, "pyramid_mode") == 0 && value >= 0 && value <= 2) {
+        h->pyramid_mode = value;
+        return CSM_OK;
+    }
+    return fail(h, CSM_E_INVALID, std::string("unknown option ") + name);
+}
 
 void* csm_alloc_pinned(size_t bytes)
 {

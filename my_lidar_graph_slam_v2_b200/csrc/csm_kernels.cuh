@@ -78,6 +78,150 @@ k_pyramid_level(const PyrJob* __restrict__ jobs, int h)
     }
 }
 
+/* ---- streaming pyramid builder ------------------------------------------------
+ * One CTA per map walks the rows bottom-up in blocks of 4 and produces every
+ * level in one pass: level 0 is read from HBM exactly once (cp.async ring,
+ * 8 blocks ahead), each level is written exactly once, nothing is re-read from
+ * L2. Thread j owns cells (2j, 2j+1) of every row as one packed u16x2 word
+ * (VIMNMX.U16x2). Per level h (w = 2^h, half = w/2):
+ *     T_h[r]  = max(out_{h-1}[r][c], out_{h-1}[r][c + half])      (row buffer in smem)
+ *     P_h[r]  = max(T_h[r], T_h[r + half])                         (ring of `half` rows of T_h;
+ *                                                                   the slot read is the slot
+ *                                                                   overwritten, thread-private)
+ *     out_h[r][c] = P_h[min(r, R-w)][min(c, C-w)]                  (far edge clamped)
+ * Rows below the map read as 0 (ring starts zeroed), like the reference's
+ * ValueOr beyond the map. Requires cols <= 512, cols % 8 == 0, rows % 4 == 0,
+ * hmax <= 6. */
+constexpr int kPsThreads = 256;
+constexpr int kPsRows = 4;
+constexpr int kPsStages = 8;
+constexpr int kPsInStride = 272;     /* words per staged input row (256 + zero pad) */
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, int src_bytes)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(gsrc), "r"(src_bytes));
+}
+
+__device__ __forceinline__ unsigned int splat_lo(unsigned int v) { return __byte_perm(v, v, 0x1010); }
+
+/* One level of one 4-row block (H compile-time so that ring offsets, shifts
+ * and the tap distance are immediates). a[] holds this thread's words of
+ * out_{H-1} for the 4 rows and is replaced by its words of out_H. */
+template <int H>
+__device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsigned int* __restrict__ prev,
+                                         int prev_stride, unsigned int* __restrict__ cur,
+                                         unsigned int* __restrict__ ring, const PyrJob& job,
+                                         int b, int j, bool in_map, size_t cells)
+{
+    constexpr int half = 1 << (H - 1);
+    constexpr int w = 2 * half;
+    constexpr int ring_off = half - 1;               /* 1 + 2 + ... + half/2 rows precede */
+    const int R = job.rows, C = job.cols;
+    const int csw_prev = (H >= 2) ? (max(C - half, 0) >> 1) : 0x3fffffff;   /* clamp word of level H-1 */
+    const int csw = max(C - w, 0) >> 1;                                      /* clamp word of level H */
+    const int rsrc = max(R - w, 0);
+    unsigned int p[kPsRows];
+#pragma unroll
+    for (int rr = kPsRows - 1; rr >= 0; --rr) {
+        const int r = b * kPsRows + rr;
+        unsigned int t;
+        if (H == 1) {
+            t = __byte_perm(a[rr], prev[rr * prev_stride + j + 1], 0x5432);
+        } else {
+            const int k = j + (half >> 1);
+            t = prev[rr * prev_stride + min(k, csw_prev)];
+            if (k >= csw_prev) t = splat_lo(t);
+        }
+        t = __vmaxu2(a[rr], t);
+        unsigned int* slot = ring + (ring_off + (r & (half - 1))) * 256 + j;
+        const unsigned int old = *slot;
+        *slot = t;
+        p[rr] = __vmaxu2(t, old);
+        cur[rr * 256 + j] = p[rr];
+    }
+    __syncthreads();
+    /* out_H = P_H with the far edge clamped; only the clamped threads re-read */
+    if (j >= csw) {
+#pragma unroll
+        for (int rr = 0; rr < kPsRows; ++rr) p[rr] = splat_lo(cur[rr * 256 + csw]);
+    }
+    const int r0 = b * kPsRows;
+    if (in_map && r0 <= rsrc) {
+        unsigned int* dst = reinterpret_cast<unsigned int*>(job.levels + (size_t)(H - 1) * cells +
+                                                            (size_t)r0 * C) + j;
+        const int cw = C >> 1;
+        if (r0 + kPsRows - 1 < rsrc) {
+#pragma unroll
+            for (int rr = 0; rr < kPsRows; ++rr) dst[rr * cw] = p[rr];
+        } else {
+            for (int rr = 0; rr < kPsRows; ++rr) {
+                const int r = r0 + rr;
+                if (r < rsrc) dst[rr * cw] = p[rr];
+                else if (r == rsrc)
+                    for (int r2 = r; r2 < R; ++r2) dst[(r2 - r0) * cw] = p[rr];
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kPsRows; ++rr) a[rr] = p[rr];
+}
+
+__global__ void __launch_bounds__(kPsThreads, 2)
+k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax)
+{
+    extern __shared__ __align__(16) unsigned int ps_smem[];
+    unsigned int* in_ring = ps_smem;                                         /* [stages][4][272] */
+    unsigned int* rowbuf = in_ring + kPsStages * kPsRows * kPsInStride;      /* [2][4][256] */
+    unsigned int* ring = rowbuf + 2 * kPsRows * 256;                         /* [63][256] */
+
+    const PyrJob job = jobs[blockIdx.x];
+    const int R = job.rows, C = job.cols;
+    const size_t cells = (size_t)R * C;
+    const int j = threadIdx.x;
+    const bool in_map = 2 * j < C;
+
+    for (int i = j; i < 63 * 256; i += kPsThreads) ring[i] = 0u;
+    for (int i = j; i < kPsStages * kPsRows * kPsInStride; i += kPsThreads) in_ring[i] = 0u;
+    __syncthreads();
+
+    const int nblocks = R / kPsRows;
+    /* producer: this thread's 16-byte chunk of a 4-row block */
+    const int ld_row = j >> 6, ld_chunk = j & 63;
+    auto prefetch = [&](int b) {
+        if (b >= 0) {
+            const int stage = b % kPsStages;
+            unsigned int* dst = in_ring + (stage * kPsRows + ld_row) * kPsInStride + ld_chunk * 4;
+            const bool ok = ld_chunk * 8 < C;
+            const uint16_t* src = job.base + (size_t)(b * kPsRows + ld_row) * C + (ok ? ld_chunk * 8 : 0);
+            cp_async_16(dst, src, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    for (int k = 0; k < kPsStages - 1; ++k)
+        prefetch(nblocks - 1 - k);
+
+    unsigned int* buf0 = rowbuf;
+    unsigned int* buf1 = rowbuf + kPsRows * 256;
+    for (int b = nblocks - 1; b >= 0; --b) {
+        asm volatile("cp.async.wait_group %0;\n" :: "n"(kPsStages - 2));
+        __syncthreads();                 /* block b landed; everyone is done with block b+1 */
+        prefetch(b - (kPsStages - 1));   /* refills the stage block b+1 used */
+
+        const unsigned int* in = in_ring + (b % kPsStages) * kPsRows * kPsInStride;
+        unsigned int a[kPsRows];
+#pragma unroll
+        for (int rr = 0; rr < kPsRows; ++rr) a[rr] = in[rr * kPsInStride + j];
+        ps_level<1>(a, in, kPsInStride, buf1, ring, job, b, j, in_map, cells);
+        if (hmax >= 2) ps_level<2>(a, buf1, 256, buf0, ring, job, b, j, in_map, cells);
+        if (hmax >= 3) ps_level<3>(a, buf0, 256, buf1, ring, job, b, j, in_map, cells);
+        if (hmax >= 4) ps_level<4>(a, buf1, 256, buf0, ring, job, b, j, in_map, cells);
+        if (hmax >= 5) ps_level<5>(a, buf0, 256, buf1, ring, job, b, j, in_map, cells);
+        if (hmax >= 6) ps_level<6>(a, buf1, 256, buf0, ring, job, b, j, in_map, cells);
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
 /* Generic sliding win x win maximum with the clamped far edge. */
 __global__ void __launch_bounds__(256)
 k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,

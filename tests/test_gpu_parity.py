@@ -59,6 +59,32 @@ def test_pyramid_vs_checker(handle, checker, shape):
     handle.release_grid(78)
 
 
+@pytest.mark.parametrize("shape,hmax", [((64, 64), 6), ((512, 512), 6), ((32, 128), 4), ((128, 16), 6),
+                                        ((16, 512), 3), ((192, 336), 5), ((512, 512), 1), ((48, 48), 2)])
+def test_pyramid_streaming_kernel(handle, checker, shape, hmax):
+    """The single-pass streaming builder (used for big batches) against the checker."""
+    handle.set_option("pyramid_mode", 2)
+    try:
+        ids, grids = [], []
+        for k in range(3):
+            rng = np.random.default_rng(1200 + k + shape[0])
+            grid = rng.integers(0, 65535, size=shape, dtype=np.uint16)
+            grid[rng.random(shape) < (0.2 + 0.3 * k)] = 0
+            handle.upload_grid(300 + k, grid, 0.05, 0.0, 0.0)
+            ids.append(300 + k)
+            grids.append(grid)
+        handle.build_pyramids(ids, hmax)
+        for i, grid in zip(ids, grids):
+            ref = checker.grid(grid, 0.05, 0.0, 0.0).pyramid(hmax)
+            for h in range(hmax + 1):
+                got = handle.download_level(i, h, shape)
+                assert np.array_equal(got, ref[h]), "map %d level %d: %d cells differ" % (
+                    i, h, int((got != ref[h]).sum()))
+            handle.release_grid(i)
+    finally:
+        handle.set_option("pyramid_mode", 0)
+
+
 def test_pyramid_batch(handle, checker):
     ids, grids = [], []
     for k in range(5):
