@@ -214,6 +214,8 @@ int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, 
 int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq);
 int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
                    int query_index_base, csm_result* results);
+/* Debug: number of frontier nodes queued per height by the last batch (8 entries) */
+int csm_debug_frontier_counts(csm_handle h, unsigned int* out8);
 void* csm_best_key_device(csm_handle h);
 void csm_decode_best_key(uint64_t best_key, int64_t* key, int32_t* query_index);
 

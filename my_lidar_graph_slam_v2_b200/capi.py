@@ -49,7 +49,7 @@ EXPORTS = [
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
-    "csm_best_key_device", "csm_decode_best_key",
+    "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts",
 ]
 
 _LIB = None
@@ -107,6 +107,7 @@ def load():
     lib.csm_loop_batch_enqueue.argtypes = [H, lq, C.c_int, C.c_int, C.c_int]
     lib.csm_loop_batch_finish.argtypes = [H, rp, C.c_int]
     lib.csm_loop_batch.argtypes = [H, lq, C.c_int, C.c_int, C.c_int, rp]
+    lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
     lib.csm_best_key_device.argtypes = [H]
     lib.csm_best_key_device.restype = C.c_void_p
     lib.csm_decode_best_key.argtypes = [C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
@@ -247,6 +248,11 @@ class Handle:
     def loop_batch(self, queries, nq, hmax, query_index_base=0):
         self.loop_batch_enqueue(queries, nq, hmax, query_index_base)
         return self.loop_batch_finish(nq)
+
+    def frontier_counts(self):
+        out = (C.c_uint * 8)()
+        self._check(self.lib.csm_debug_frontier_counts(self.h, out))
+        return list(out)
 
     def best_key_device_ptr(self):
         return self.lib.csm_best_key_device(self.h)

@@ -22,6 +22,9 @@ constexpr int kOrdBits = 26;             /* candidate ordinal bits in a packed b
 constexpr unsigned long long kOrdMask = (1ull << kOrdBits) - 1ull;
 constexpr int kMaxBeams = 4096;
 
+/* projected cell index of one beam: (col, row), saturated to +-30000 */
+typedef short2 proj_t;
+
 /* Threshold on the normalized score expressed on integer keys:
  *   key >= pass_min  -> reference comparison `score > thr` is true
  *   key <= fail_max  -> false
@@ -45,6 +48,7 @@ struct DevQuery
     const double* thetas;              /* T candidate sensor angles (host-computed doubles) */
     const double* angles;              /* N beam angles */
     const double* ranges;              /* N beam ranges */
+    const double2* beam_trig;          /* N x (cos a_i, sin a_i) */
     int n;                             /* beams */
     int T;                             /* candidate angles */
     int winx, winy;                    /* half windows (cells) */
@@ -83,11 +87,11 @@ __device__ __forceinline__ double value_to_probability(unsigned int v)
 /* Sequential double sum in scan order: the reference's own arithmetic
  * (scan_matcher_correlative.cpp:308-335). One thread. */
 __device__ double exact_normalized_score(const uint16_t* __restrict__ m, int rows, int cols,
-                                         const int2* __restrict__ proj, int n, int ox, int oy)
+                                         const proj_t* __restrict__ proj, int n, int ox, int oy)
 {
     double sum = 0.0;
     for (int i = 0; i < n; ++i) {
-        const int2 p = proj[i];
+        const proj_t p = proj[i];
         const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
         if (v != 0u)
             sum = __dadd_rn(sum, value_to_probability(v));

@@ -244,26 +244,55 @@ k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
 /* Projection                                                                */
 /* ------------------------------------------------------------------------ */
 
+/* Per-scan table: (cos a_i, sin a_i) of every beam angle, computed once when
+ * the scan is uploaded. */
+__global__ void __launch_bounds__(256)
+k_beam_trig(const double* __restrict__ angles, double2* __restrict__ trig, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    sincos(angles[i], &s, &c);
+    trig[i] = make_double2(c, s);
+}
+
+constexpr int kProjAngles = 8;       /* candidate angles per CTA */
+constexpr int kProjSat = 30000;      /* saturation of projected indices (maps are <= 16384 wide) */
+
 /* proj[q][t][i] = (col, row) of beam i seen from (sx, sy, thetas[t]).
- * FP64 in the reference's operation order without contraction; the only
- * non-reproducible step is sin/cos (device vs glibc, a few ulp), so any
- * coordinate closer than `margin` to a cell boundary raises the flag.
+ * cos/sin(theta_t + a_i) come from the angle-addition formula on the per-beam
+ * table and one sincos per candidate angle (a few ulp from the reference's
+ * glibc cos(theta + a), like a direct device sincos would be); the rest is
+ * FP64 in the reference's operation order without contraction. Any
+ * coordinate closer than `margin` to a cell boundary raises the flag: only
+ * there could floor() differ from the reference (DESIGN.md "FP index parity").
  * rcs (optional): r*cos, r*sin per (t, i) for the per-candidate FP path. */
 __global__ void __launch_bounds__(256)
-k_project(const DevQuery* __restrict__ queries, int2* __restrict__ proj,
+k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
           double2* __restrict__ rcs, int* __restrict__ qflags)
 {
+    __shared__ double2 s_theta[kProjAngles];
     const int q = blockIdx.y;
     const DevQuery& Q = queries[q];
-    const int total = Q.T * Q.n;
-    int flagged = 0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += gridDim.x * blockDim.x) {
-        const int t = e / Q.n;
-        const int i = e - t * Q.n;
-        const double a = __dadd_rn(Q.thetas[t], Q.angles[i]);
+    const int t0 = blockIdx.x * kProjAngles;
+    if (t0 >= Q.T)
+        return;
+    const int nt = min(kProjAngles, Q.T - t0);
+    if (threadIdx.x < nt) {
         double s, c;
-        sincos(a, &s, &c);
+        sincos(Q.thetas[t0 + threadIdx.x], &s, &c);
+        s_theta[threadIdx.x] = make_double2(c, s);
+    }
+    __syncthreads();
+    int flagged = 0;
+    const int total = nt * Q.n;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int tl = e / Q.n;
+        const int i = e - tl * Q.n;
+        const double2 th = s_theta[tl];
+        const double2 be = Q.beam_trig[i];
+        const double c = th.x * be.x - th.y * be.y;      /* cos(theta + a) */
+        const double s = th.y * be.x + th.x * be.y;      /* sin(theta + a) */
         const double r = Q.ranges[i];
         const double rc = __dmul_rn(r, c);
         const double rs = __dmul_rn(r, s);
@@ -273,13 +302,14 @@ k_project(const DevQuery* __restrict__ queries, int2* __restrict__ proj,
         const double gx = ux - fx, gy = uy - fy;
         if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
             flagged = 1;
-        const double lim = 1073741824.0;
-        int2 p;
-        p.x = (int)fmin(fmax(fx, -lim), lim);
-        p.y = (int)fmin(fmax(fy, -lim), lim);
-        proj[Q.proj_off + e] = p;
+        const double lim = (double)kProjSat;
+        proj_t p;
+        p.x = (short)(int)fmin(fmax(fx, -lim), lim);
+        p.y = (short)(int)fmin(fmax(fy, -lim), lim);
+        const size_t o = (size_t)Q.proj_off + (size_t)(t0 + tl) * Q.n + i;
+        proj[o] = p;
         if (rcs != nullptr)
-            rcs[Q.proj_off + e] = make_double2(rc, rs);
+            rcs[o] = make_double2(rc, rs);
     }
     if (__any_sync(0xffffffffu, flagged) && (threadIdx.x & 31) == 0)
         atomicOr(&qflags[q], 1 /* CSM_FLAG_FP_MARGIN */);
@@ -291,13 +321,13 @@ k_project(const DevQuery* __restrict__ queries, int2* __restrict__ proj,
 
 /* Whole warp: integer score of one candidate (offset ox, oy) on map m */
 __device__ __forceinline__ void warp_score(const uint16_t* __restrict__ m, int rows, int cols,
-                                           const int2* __restrict__ proj, int n, int ox, int oy,
+                                           const proj_t* __restrict__ proj, int n, int ox, int oy,
                                            int& sumv, int& nk)
 {
     const int lane = threadIdx.x & 31;
     int s = 0, k = 0;
     for (int i = lane; i < n; i += 32) {
-        const int2 p = proj[i];
+        const proj_t p = proj[i];
         const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
         s += (int)v;
         k += (v != 0u);
@@ -308,13 +338,13 @@ __device__ __forceinline__ void warp_score(const uint16_t* __restrict__ m, int r
 
 /* Whole warp: the four children of a B&B node at once (more loads in flight) */
 __device__ __forceinline__ void warp_score4(const uint16_t* __restrict__ m, int rows, int cols,
-                                            const int2* __restrict__ proj, int n,
+                                            const proj_t* __restrict__ proj, int n,
                                             int ox, int oy, int w, int sumv[4], int nk[4])
 {
     const int lane = threadIdx.x & 31;
     int s0 = 0, s1 = 0, s2 = 0, s3 = 0, k0 = 0, k1 = 0, k2 = 0, k3 = 0;
     for (int i = lane; i < n; i += 32) {
-        const int2 p = proj[i];
+        const proj_t p = proj[i];
         const int r = p.y + oy, c = p.x + ox;
         const unsigned int v0 = ld_cell(m, rows, cols, r, c);
         const unsigned int v1 = ld_cell(m, rows, cols, r, c + w);
@@ -336,7 +366,7 @@ __device__ __forceinline__ void warp_score4(const uint16_t* __restrict__ m, int 
 /* Threshold comparison with exact resolution inside the guard band.
  * Called by lane 0 only (the exact path is a serial double sum). */
 __device__ __forceinline__ bool passes_threshold(long long key, const DevQuery& Q,
-                                                 const uint16_t* m, const int2* proj,
+                                                 const uint16_t* m, const proj_t* proj,
                                                  int ox, int oy)
 {
     const int c = key_vs_threshold(key, Q.kthr);
@@ -363,7 +393,7 @@ struct RtBlock
  * candidates 1..L*L the fine lattice [x, x+L) x [y, y+L) in the reference's
  * iteration order (x outer, y inner, scan_matcher_correlative.cpp:351-352). */
 __global__ void __launch_bounds__(256)
-k_rt_blocks(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all,
+k_rt_blocks(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
             RtBlock* __restrict__ blocks, int low_res, int nbx, int nby)
 {
     extern __shared__ long long s_keys[];      /* L*L fine keys */
@@ -374,7 +404,7 @@ k_rt_blocks(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_
     const int bx = rem / nby, by = rem - bx * nby;
     const int x = -Q.winx + bx * low_res;
     const int y = -Q.winy + by * low_res;
-    const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+    const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int ncand = low_res * low_res + 1;
 
@@ -419,7 +449,7 @@ struct BestState
  * reference's order (t, x, y) on integer keys. One thread. Exact also when
  * the coarse bound is not admissible. */
 __global__ void k_rt_replay(const DevQuery* __restrict__ queries,
-                            const int2* __restrict__ proj_all,
+                            const proj_t* __restrict__ proj_all,
                             const RtBlock* __restrict__ blocks, int low_res,
                             int nbx, int nby, BestState* __restrict__ state)
 {
@@ -437,7 +467,7 @@ __global__ void k_rt_replay(const DevQuery* __restrict__ queries,
         const int rem = b - t * nbx * nby;
         const int bx = rem / nby, by = rem - bx * nby;
         const int x = -Q.winx + bx * low_res, y = -Q.winy + by * low_res;
-        const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
         bool coarse_ok;
         if (have) {
             coarse_ok = B.coarse_key > cur;
@@ -497,7 +527,7 @@ __device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, i
 /* Roots: every (t, x, y) with x, y stepping by 2^hmax from -win
  * (scan_matcher_branch_bound.cpp:179-182). One warp per root. */
 __global__ void __launch_bounds__(256)
-k_bb_roots(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all, BbWork W)
+k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
 {
     const int q = blockIdx.y;
     const DevQuery& Q = queries[q];
@@ -512,7 +542,7 @@ k_bb_roots(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_a
         const int rem = root - t * Q.nrx * Q.nry;
         const int rx = rem / Q.nry, ry = rem - rx * Q.nry;
         const int xi = rx * wsz, yi = ry * wsz;
-        const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
         int sumv, nk;
         warp_score(Q.lvl[h], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, sumv, nk);
         if (lane == 0) {
@@ -543,7 +573,7 @@ k_bb_roots(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_a
  * before the level-synchronous sweep so that the sweep can prune.
  * One warp per query. */
 __global__ void __launch_bounds__(32)
-k_bb_dive(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all, BbWork W)
+k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
 {
     const int q = blockIdx.x;
     const DevQuery& Q = queries[q];
@@ -555,7 +585,7 @@ k_bb_dive(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_al
     const int t = root / (Q.nrx * Q.nry);
     const int rem = root - t * Q.nrx * Q.nry;
     int xi = (rem / Q.nry) << W.hmax, yi = (rem % Q.nry) << W.hmax;
-    const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+    const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
     for (int h = W.hmax - 1; h >= 0; --h) {
         const int w = 1 << h;
         int sumv[4], nk[4];
@@ -591,7 +621,7 @@ k_bb_dive(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_al
  * are kept iff they pass the score threshold, the known-rate cut and the
  * incumbent. Leaves update the incumbent with atomicMax. One warp per node. */
 __global__ void __launch_bounds__(256)
-k_bb_expand(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all,
+k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
             BbWork W, int h)
 {
     const int lane = threadIdx.x & 31;
@@ -610,7 +640,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_
             if (lane == 0) atomicAdd(&W.stats[2 * q + 1], 1);
             continue;
         }
-        const int2* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
         int sumv[4], nk[4];
         warp_score4(Q.lvl[hc], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, w, sumv, nk);
         if (lane == 0) {
@@ -700,12 +730,12 @@ __device__ __forceinline__ void block_best_commit(unsigned long long v, unsigned
  * (row_i + my[iy], col_i + mx[ix]) of the angle's projected indices.
  * CTA = (angle it, 8 rows iy); warp = one row; lane = one ix. */
 __global__ void __launch_bounds__(256)
-k_grid_window(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all, GridArgs G)
+k_grid_window(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, GridArgs G)
 {
-    extern __shared__ int2 s_proj[];
+    extern __shared__ proj_t s_proj[];
     const DevQuery& Q = queries[0];
     const int it = blockIdx.x;
-    const int2* proj = proj_all + Q.proj_off + (size_t)it * Q.n;
+    const proj_t* proj = proj_all + Q.proj_off + (size_t)it * Q.n;
     for (int i = threadIdx.x; i < Q.n; i += blockDim.x)
         s_proj[i] = proj[i];
     __syncthreads();
@@ -723,7 +753,7 @@ k_grid_window(const DevQuery* __restrict__ queries, const int2* __restrict__ pro
             int s = 0, k = 0;
 #pragma unroll 4
             for (int i = 0; i < Q.n; ++i) {
-                const int2 p = s_proj[i];
+                const proj_t p = s_proj[i];
                 const unsigned int v = ld_cell(m, Q.rows, Q.cols, p.y + oy, p.x + ox);
                 s += (int)v;
                 k += (v != 0u);
@@ -853,10 +883,10 @@ struct FinalArgs
 /* One warp per query: integer score and reference-order double score of the
  * winning pose on the level-0 map; packs the per-batch best word. */
 __global__ void __launch_bounds__(32)
-k_finalize(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_all,
+k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
            const BestState* __restrict__ state, FinalArgs F, csm_result* __restrict__ results)
 {
-    __shared__ unsigned short s_vals[kMaxBeams];
+    __shared__ double s_prob[kMaxBeams];
     const int q = blockIdx.x;
     const DevQuery& Q = queries[q];
     const BestState s = state[q];
@@ -889,13 +919,13 @@ k_finalize(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_a
                 col = (int)fmin(fmax(floor(ux), -lim), lim);
                 row = (int)fmin(fmax(floor(uy), -lim), lim);
             } else {
-                const int2 p = proj_all[row_off + i];
+                const proj_t p = proj_all[row_off + i];
                 const int ox = (F.mode == 1) ? F.mx[s.bx] : s.bx;
                 const int oy = (F.mode == 1) ? F.my[s.by] : s.by;
                 col = p.x + ox; row = p.y + oy;
             }
             const unsigned int v = ld_cell(m, Q.rows, Q.cols, row, col);
-            s_vals[i] = (unsigned short)v;
+            s_prob[i] = (v != 0u) ? value_to_probability(v) : -1.0;
             ps += (int)v;
             pk += (v != 0u);
         }
@@ -905,9 +935,9 @@ k_finalize(const DevQuery* __restrict__ queries, const int2* __restrict__ proj_a
         if (lane == 0) {
             double sum = 0.0;
             for (int i = 0; i < Q.n; ++i) {
-                const unsigned int v = s_vals[i];
-                if (v != 0u)
-                    sum = __dadd_rn(sum, value_to_probability(v));
+                const double pv = s_prob[i];
+                if (pv >= 0.0)
+                    sum = __dadd_rn(sum, pv);
             }
             r.normalized_score = __ddiv_rn(sum, (double)Q.n);
         }
