@@ -64,15 +64,15 @@ struct csm_context
 
     /* workspaces, grown on demand */
     DevBuf d_queries, d_thetas, d_proj, d_rcs, d_qflags, d_state, d_results;
-    DevBuf d_inc, d_rootbest, d_stats, d_counts, d_overflow, d_bestkey;
-    DevBuf d_nodes[kMaxLevels], d_keys[kMaxLevels];
+    DevBuf d_inc, d_rootoff, d_stats, d_counts, d_overflow, d_bestkey;
+    DevBuf d_list[2];
     DevBuf d_rtblocks, d_gridoff, d_gridpos, d_pyrjobs, d_tmpscan;
     unsigned int frontier_capacity = 0;
-    /* pinned staging: two upload areas used alternately (an area is reused
+    /* pinned staging: four upload areas used in turn (an area is reused
      * only after the copies that read it have completed) + one result area */
-    void* h_up[2] = { nullptr, nullptr };
-    size_t h_up_bytes[2] = { 0, 0 };
-    cudaEvent_t h_up_done[2] = { nullptr, nullptr };
+    void* h_up[4] = { nullptr, nullptr, nullptr, nullptr };
+    size_t h_up_bytes[4] = { 0, 0, 0, 0 };
+    cudaEvent_t h_up_done[4] = { nullptr, nullptr, nullptr, nullptr };
     int h_up_next = 0;
     void* h_res = nullptr;
     size_t h_res_bytes = 0;
@@ -133,7 +133,7 @@ int ensure(csm_handle h, DevBuf& b, size_t bytes)
 int acquire_upload(csm_handle h, size_t bytes, char** out)
 {
     const int k = h->h_up_next;
-    h->h_up_next ^= 1;
+    h->h_up_next = (h->h_up_next + 1) & 3;
     if (h->h_up_done[k] == nullptr)
         CSM_CUDA(cudaEventCreateWithFlags(&h->h_up_done[k], cudaEventDisableTiming));
     else
@@ -153,7 +153,7 @@ int acquire_upload(csm_handle h, size_t bytes, char** out)
 
 int upload_committed(csm_handle h)
 {
-    const int k = h->h_up_next ^ 1;
+    const int k = (h->h_up_next + 3) & 3;
     CSM_CUDA(cudaEventRecord(h->h_up_done[k], h->stream));
     return CSM_OK;
 }
@@ -415,18 +415,19 @@ int finish_results(csm_handle h, csm_result* results, int nq)
     return CSM_OK;
 }
 
-int ensure_frontier(csm_handle h, int nq, int hmax)
+int ensure_frontier(csm_handle h, int nq, unsigned int total_roots)
 {
+    /* candidate lists: 4 children per survivor; sized for a few thousand
+     * candidates per query and at least all roots */
     unsigned int cap = (unsigned int)std::min<long long>(
-        std::max<long long>((long long)nq * 8192, 1ll << 18), 1ll << 23);
+        std::max<long long>((long long)nq * 16384, 1ll << 20), 1ll << 24);
+    cap = std::max(cap, total_roots);
     int rc;
-    for (int l = 1; l <= hmax; ++l) {
-        if ((rc = ensure(h, h->d_nodes[l], sizeof(unsigned long long) * cap))) return rc;
-        if ((rc = ensure(h, h->d_keys[l], sizeof(long long) * cap))) return rc;
-    }
+    for (int l = 0; l < 2; ++l)
+        if ((rc = ensure(h, h->d_list[l], sizeof(unsigned long long) * cap))) return rc;
     h->frontier_capacity = cap;
     if ((rc = ensure(h, h->d_counts, sizeof(unsigned int) * kMaxLevels))) return rc;
-    if ((rc = ensure(h, h->d_rootbest, sizeof(unsigned long long) * nq))) return rc;
+    if ((rc = ensure(h, h->d_rootoff, sizeof(unsigned int) * (nq + 1)))) return rc;
     if ((rc = ensure(h, h->d_stats, sizeof(int) * 2 * nq))) return rc;
     return CSM_OK;
 }
@@ -472,6 +473,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             (unsigned long long)Q.T * Q.lx * Q.ly >= kOrdMask - 1ull)
             return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: search lattice exceeds 2^26 leaves");
         Q.proj_off = plan.proj_total;
+        Q.pst_t = 1; Q.pst_i = Q.T;            /* beam-major for the lane-per-node B&B */
         plan.proj_total += (long long)Q.T * Q.n;
         plan.max_tn = std::max(plan.max_tn, Q.T * Q.n);
         plan.max_t = std::max(plan.max_t, Q.T);
@@ -483,23 +485,30 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             plan.thetas.push_back(in.sensor_pose[2] + t * in.step_t);
         plan.inc_init[q] = ((unsigned long long)Q.kthr.fail_max << kOrdBits) | kOrdMask;
     }
+    std::vector<unsigned int> root_off(nq + 1, 0u);
+    for (int q = 0; q < nq; ++q)
+        root_off[q + 1] = root_off[q] + (unsigned int)(plan.dq[q].T * plan.dq[q].nrx * plan.dq[q].nry);
     int rc;
-    if ((rc = ensure_frontier(h, nq, hmax))) return rc;
+    if ((rc = ensure_frontier(h, nq, root_off[nq]))) return rc;
     if ((rc = stage_plan(h, plan, false))) return rc;
+    {
+        char* hp = nullptr;
+        const size_t rb = sizeof(unsigned int) * (nq + 1);
+        if ((rc = acquire_upload(h, rb, &hp))) return rc;
+        std::memcpy(hp, root_off.data(), rb);
+        CSM_CUDA(cudaMemcpyAsync(h->d_rootoff.p, hp, rb, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = upload_committed(h))) return rc;
+    }
     CSM_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(unsigned int) * kMaxLevels, h->stream));
-    CSM_CUDA(cudaMemsetAsync(h->d_rootbest.p, 0, sizeof(unsigned long long) * nq, h->stream));
     CSM_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(int) * 2 * nq, h->stream));
     if ((rc = launch_project(h, plan, false))) return rc;
 
     BbWork W;
     std::memset(&W, 0, sizeof(W));
-    for (int l = 1; l <= hmax; ++l) {
-        W.nodes[l] = static_cast<unsigned long long*>(h->d_nodes[l].p);
-        W.keys[l] = static_cast<long long*>(h->d_keys[l].p);
-    }
+    W.list[0] = static_cast<unsigned long long*>(h->d_list[0].p);
+    W.list[1] = static_cast<unsigned long long*>(h->d_list[1].p);
     W.counts = static_cast<unsigned int*>(h->d_counts.p);
     W.incumbent = static_cast<unsigned long long*>(h->d_inc.p);
-    W.rootbest = static_cast<unsigned long long*>(h->d_rootbest.p);
     W.stats = static_cast<int*>(h->d_stats.p);
     W.overflow = static_cast<int*>(h->d_overflow.p);
     W.capacity = h->frontier_capacity;
@@ -508,18 +517,14 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
 
     {
-        dim3 grid(std::max(1, (plan.max_roots + 7) / 8), nq);
-        k_bb_roots<<<grid, 256, 0, h->stream>>>(dq, proj, W);
+        dim3 grid(std::max(1, std::min((plan.max_roots + 255) / 256, 64)), nq);
+        k_bb_init<<<grid, 256, 0, h->stream>>>(dq, static_cast<const unsigned int*>(h->d_rootoff.p), nq, W);
         CSM_LAUNCH_CHECK();
     }
-    if (hmax > 0) {
-        if (h->bb_dive) {
-            k_bb_dive<<<nq, 32, 0, h->stream>>>(dq, proj, W);
-            CSM_LAUNCH_CHECK();
-        }
-        const int blocks = h->sm_count * 4;
-        for (int lvl = hmax; lvl >= 1; --lvl) {
-            k_bb_expand<<<blocks, 256, 0, h->stream>>>(dq, proj, W, lvl);
+    {
+        const int blocks = h->sm_count * 8;
+        for (int lvl = hmax; lvl >= 0; --lvl) {
+            k_bb_score<<<blocks, 256, 0, h->stream>>>(dq, proj, W, lvl);
             CSM_LAUNCH_CHECK();
         }
     }
@@ -590,17 +595,15 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_queries, &h->d_thetas, &h->d_proj, &h->d_rcs, &h->d_qflags,
-                       &h->d_state, &h->d_results, &h->d_inc, &h->d_rootbest, &h->d_stats,
+                       &h->d_state, &h->d_results, &h->d_inc, &h->d_rootoff, &h->d_stats,
                        &h->d_counts, &h->d_overflow, &h->d_bestkey, &h->d_rtblocks,
                        &h->d_gridoff, &h->d_gridpos, &h->d_pyrjobs, &h->d_tmpscan };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
-    for (int l = 0; l < kMaxLevels; ++l) {
-        if (h->d_nodes[l].p) cudaFreeAsync(h->d_nodes[l].p, h->stream);
-        if (h->d_keys[l].p) cudaFreeAsync(h->d_keys[l].p, h->stream);
-    }
+    for (int l = 0; l < 2; ++l)
+        if (h->d_list[l].p) cudaFreeAsync(h->d_list[l].p, h->stream);
     cudaStreamSynchronize(h->stream);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
         if (h->h_up[k]) cudaFreeHost(h->h_up[k]);
         if (h->h_up_done[k]) cudaEventDestroy(h->h_up_done[k]);
     }
@@ -912,6 +915,7 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     Q.T = 2 * win_t + 1;
     Q.winx = win_x; Q.winy = win_y;
     Q.proj_off = 0;
+    Q.pst_t = Q.n; Q.pst_i = 1;
     plan.proj_total = (long long)Q.T * Q.n;
     plan.max_tn = Q.T * Q.n;
     plan.max_t = Q.T;
@@ -995,6 +999,7 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     Q.sy = sensor_pose[1] + dy[0];
     Q.T = ndt;
     Q.proj_off = 0;
+    Q.pst_t = Q.n; Q.pst_i = 1;
     plan.proj_total = (long long)ndt * Q.n;
     plan.max_tn = ndt * Q.n;
     plan.max_t = ndt;

@@ -55,6 +55,9 @@ struct DevQuery
     int nrx, nry;                      /* B&B: number of root nodes along x / y */
     int lx, ly;                        /* leaf lattice extent along x / y */
     long long proj_off;                /* offset of this query in the projection buffer */
+    int pst_t, pst_i;                  /* element strides of proj along angle / beam:
+                                          (n, 1) angle-major for RT / grid search,
+                                          (1, T) beam-major for branch-and-bound */
     double margin;                     /* FP guard band in cells (projection) */
     KeyThreshold kthr;
     int nk_cut;                        /* known test passes iff nKnown > nk_cut */
@@ -87,11 +90,12 @@ __device__ __forceinline__ double value_to_probability(unsigned int v)
 /* Sequential double sum in scan order: the reference's own arithmetic
  * (scan_matcher_correlative.cpp:308-335). One thread. */
 __device__ double exact_normalized_score(const uint16_t* __restrict__ m, int rows, int cols,
-                                         const proj_t* __restrict__ proj, int n, int ox, int oy)
+                                         const proj_t* __restrict__ proj, int stride, int n,
+                                         int ox, int oy)
 {
     double sum = 0.0;
     for (int i = 0; i < n; ++i) {
-        const proj_t p = proj[i];
+        const proj_t p = proj[(size_t)i * stride];
         const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
         if (v != 0u)
             sum = __dadd_rn(sum, value_to_probability(v));

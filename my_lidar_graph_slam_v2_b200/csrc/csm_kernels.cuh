@@ -306,10 +306,9 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         proj_t p;
         p.x = (short)(int)fmin(fmax(fx, -lim), lim);
         p.y = (short)(int)fmin(fmax(fy, -lim), lim);
-        const size_t o = (size_t)Q.proj_off + (size_t)(t0 + tl) * Q.n + i;
-        proj[o] = p;
+        proj[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.pst_t + (size_t)i * Q.pst_i] = p;
         if (rcs != nullptr)
-            rcs[o] = make_double2(rc, rs);
+            rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.n + i] = make_double2(rc, rs);
     }
     if (__any_sync(0xffffffffu, flagged) && (threadIdx.x & 31) == 0)
         atomicOr(&qflags[q], 1 /* CSM_FLAG_FP_MARGIN */);
@@ -324,6 +323,7 @@ __device__ __forceinline__ void warp_score(const uint16_t* __restrict__ m, int r
                                            const proj_t* __restrict__ proj, int n, int ox, int oy,
                                            int& sumv, int& nk)
 {
+    /* proj: the angle's row in beam-fastest layout (stride 1) */
     const int lane = threadIdx.x & 31;
     int s = 0, k = 0;
     for (int i = lane; i < n; i += 32) {
@@ -336,33 +336,6 @@ __device__ __forceinline__ void warp_score(const uint16_t* __restrict__ m, int r
     nk = warp_sum(k);
 }
 
-/* Whole warp: the four children of a B&B node at once (more loads in flight) */
-__device__ __forceinline__ void warp_score4(const uint16_t* __restrict__ m, int rows, int cols,
-                                            const proj_t* __restrict__ proj, int n,
-                                            int ox, int oy, int w, int sumv[4], int nk[4])
-{
-    const int lane = threadIdx.x & 31;
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0, k0 = 0, k1 = 0, k2 = 0, k3 = 0;
-    for (int i = lane; i < n; i += 32) {
-        const proj_t p = proj[i];
-        const int r = p.y + oy, c = p.x + ox;
-        const unsigned int v0 = ld_cell(m, rows, cols, r, c);
-        const unsigned int v1 = ld_cell(m, rows, cols, r, c + w);
-        const unsigned int v2 = ld_cell(m, rows, cols, r + w, c);
-        const unsigned int v3 = ld_cell(m, rows, cols, r + w, c + w);
-        s0 += (int)v0; k0 += (v0 != 0u);
-        s1 += (int)v1; k1 += (v1 != 0u);
-        s2 += (int)v2; k2 += (v2 != 0u);
-        s3 += (int)v3; k3 += (v3 != 0u);
-    }
-    /* child order as in scan_matcher_branch_bound.cpp:226-229:
-     * (x, y), (x+w, y), (x, y+w), (x+w, y+w) */
-    sumv[0] = warp_sum(s0); nk[0] = warp_sum(k0);
-    sumv[1] = warp_sum(s1); nk[1] = warp_sum(k1);
-    sumv[2] = warp_sum(s2); nk[2] = warp_sum(k2);
-    sumv[3] = warp_sum(s3); nk[3] = warp_sum(k3);
-}
-
 /* Threshold comparison with exact resolution inside the guard band.
  * Called by lane 0 only (the exact path is a serial double sum). */
 __device__ __forceinline__ bool passes_threshold(long long key, const DevQuery& Q,
@@ -372,7 +345,7 @@ __device__ __forceinline__ bool passes_threshold(long long key, const DevQuery& 
     const int c = key_vs_threshold(key, Q.kthr);
     if (c != 0)
         return c > 0;
-    return exact_normalized_score(m, Q.rows, Q.cols, proj, Q.n, ox, oy) > Q.kthr.thr;
+    return exact_normalized_score(m, Q.rows, Q.cols, proj, Q.pst_i, Q.n, ox, oy) > Q.kthr.thr;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -503,15 +476,30 @@ __global__ void k_rt_replay(const DevQuery* __restrict__ queries,
 /* Branch and bound                                                          */
 /* ------------------------------------------------------------------------ */
 
+/* Level-synchronous frontier expansion, one LANE per node.
+ *
+ * The candidate list of height h holds unscored nodes (q, t, x, y). A warp
+ * takes 32 consecutive candidates; every lane scores its node over all N
+ * beams on the level-h map (its own integer sums, no warp reduction) and
+ * decides like the reference does when it pops a node
+ * (scan_matcher_branch_bound.cpp:191-198): drop iff score <= scoreMax or
+ * knownRate <= threshold. Survivors of height h > 0 append their four
+ * children (:226-229) to the list of height h-1; survivors of height 0 are
+ * leaves and raise the query's incumbent with atomicMax.
+ *
+ * Why lanes and not warps per node: candidates are kept in runs of adjacent
+ * angles t (roots are generated t-fastest, children are appended per child
+ * type in lane order), and adjacent angles of the same (x, y) hit almost the
+ * same cells. The 32 two-byte gathers of a warp then fall into a few 32-byte
+ * sectors instead of 32, and with the projection stored beam-major
+ * (proj[i][t]) the index loads of a warp are one contiguous segment. */
 struct BbWork
 {
-    unsigned long long* nodes[kMaxLevels];   /* frontier per height */
-    long long*          keys[kMaxLevels];
-    unsigned int*       counts;              /* [kMaxLevels] */
-    unsigned long long* incumbent;           /* per query: packed (key, ordfield) */
-    unsigned long long* rootbest;            /* per query: packed best root */
-    int*                stats;               /* per query: processed, ignored */
-    int*                overflow;            /* set when a frontier is full */
+    unsigned long long* list[2];    /* candidate lists, ping-pong by height parity */
+    unsigned int*       counts;     /* [kMaxLevels]: number of candidates per height */
+    unsigned long long* incumbent;  /* per query: packed (key, ordfield) */
+    int*                stats;      /* per query: processed, ignored */
+    int*                overflow;   /* set when a list is full */
     unsigned int        capacity;
     int                 hmax;
 };
@@ -524,148 +512,105 @@ __device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, i
     return (kOrdMask - 1ull) - ord;     /* all-ones is reserved for "no leaf yet" */
 }
 
-/* Roots: every (t, x, y) with x, y stepping by 2^hmax from -win
- * (scan_matcher_branch_bound.cpp:179-182). One warp per root. */
+/* Root candidates of every query: (x, y) stepping by 2^hmax from -win, all
+ * angles (scan_matcher_branch_bound.cpp:179-182), angle fastest. */
 __global__ void __launch_bounds__(256)
-k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
+k_bb_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__ root_off,
+          int nq, BbWork W)
 {
     const int q = blockIdx.y;
     const DevQuery& Q = queries[q];
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int nroots = Q.T * Q.nrx * Q.nry;
-    const int h = W.hmax;
-    const int wsz = 1 << h;
-    for (int root = warp_global; root < nroots; root += nwarps) {
-        const int t = root / (Q.nrx * Q.nry);
-        const int rem = root - t * Q.nrx * Q.nry;
-        const int rx = rem / Q.nry, ry = rem - rx * Q.nry;
-        const int xi = rx * wsz, yi = ry * wsz;
-        const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
-        int sumv, nk;
-        warp_score(Q.lvl[h], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, sumv, nk);
-        if (lane == 0) {
-            const long long key = make_key(sumv, nk);
-            const bool ok = passes_threshold(key, Q, Q.lvl[h], proj, xi - Q.winx, yi - Q.winy) &&
-                            nk > Q.nk_cut;
-            if (!ok) {
-                atomicAdd(&W.stats[2 * q + 1], 1);
-            } else if (h == 0) {
-                atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
-                atomicAdd(&W.stats[2 * q], 1);
-            } else {
-                const unsigned int slot = atomicAdd(&W.counts[h], 1u);
-                if (slot < W.capacity) {
-                    W.nodes[h][slot] = pack_node(q, t, xi, yi);
-                    W.keys[h][slot] = key;
-                } else {
-                    *W.overflow = 1;
-                }
-                /* best root of the query, for the greedy dive */
-                atomicMax(&W.rootbest[q], pack_best(key, kOrdMask - (unsigned long long)root));
-            }
-        }
+    unsigned long long* out = W.list[W.hmax & 1] + root_off[q];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nroots; e += gridDim.x * blockDim.x) {
+        const int t = e % Q.T;
+        const int cell = e / Q.T;
+        const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
+        out[e] = pack_node(q, t, rx << W.hmax, ry << W.hmax);
     }
+    if (q == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        W.counts[W.hmax] = root_off[nq];
 }
 
-/* Greedy dive from the best root to a leaf: gives every query an incumbent
- * before the level-synchronous sweep so that the sweep can prune.
- * One warp per query. */
-__global__ void __launch_bounds__(32)
-k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
-{
-    const int q = blockIdx.x;
-    const DevQuery& Q = queries[q];
-    const int lane = threadIdx.x & 31;
-    const unsigned long long rb = W.rootbest[q];
-    if (rb == 0ull || W.hmax == 0)
-        return;
-    const int root = (int)(kOrdMask - (rb & kOrdMask));
-    const int t = root / (Q.nrx * Q.nry);
-    const int rem = root - t * Q.nrx * Q.nry;
-    int xi = (rem / Q.nry) << W.hmax, yi = (rem % Q.nry) << W.hmax;
-    const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
-    for (int h = W.hmax - 1; h >= 0; --h) {
-        const int w = 1 << h;
-        int sumv[4], nk[4];
-        warp_score4(Q.lvl[h], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, w, sumv, nk);
-        int best = -1;
-        long long bestkey = -1;
-        if (lane == 0) {
-            for (int c = 0; c < 4; ++c) {
-                const long long key = make_key(sumv[c], nk[c]);
-                const int cx = xi + (c & 1) * w, cy = yi + (c >> 1) * w;
-                if (nk[c] > Q.nk_cut && key > bestkey &&
-                    passes_threshold(key, Q, Q.lvl[h], proj, cx - Q.winx, cy - Q.winy)) {
-                    bestkey = key; best = c;
-                }
-            }
-        }
-        best = __shfl_sync(0xffffffffu, best, 0);
-        if (best < 0)
-            return;
-        xi += (best & 1) * w;
-        yi += (best >> 1) * w;
-        if (h == 0 && lane == 0) {
-            const long long key = make_key(sumv[best], nk[best]);
-            atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
-        }
-    }
-}
-
-/* Expand every frontier node of height h into its four children at h-1.
- * A node survives iff its key can still beat the query's incumbent
- * (score <= scoreMax drop, scan_matcher_branch_bound.cpp:191-198; equal keys
- * are kept so that the lowest-ordinal leaf among equal keys wins). Children
- * are kept iff they pass the score threshold, the known-rate cut and the
- * incumbent. Leaves update the incumbent with atomicMax. One warp per node. */
 __global__ void __launch_bounds__(256)
-k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
-            BbWork W, int h)
+k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
+           BbWork W, int h)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned int count = min(W.counts[h], W.capacity);
-    const int hc = h - 1;
-    const int w = 1 << hc;
-    for (unsigned int idx = warp_global; idx < count; idx += nwarps) {
-        int q, t, xi, yi;
-        unpack_node(W.nodes[h][idx], q, t, xi, yi);
-        const long long key = W.keys[h][idx];
-        const DevQuery& Q = queries[q];
-        unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
-        if (!(pack_best(key, kOrdMask) > inc)) {
-            if (lane == 0) atomicAdd(&W.stats[2 * q + 1], 1);
-            continue;
+    const unsigned long long* __restrict__ in = W.list[h & 1];
+    unsigned long long* __restrict__ out = W.list[(h & 1) ^ 1];
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const int w = (h > 0) ? (1 << (h - 1)) : 0;
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
+        const unsigned int idx = base + lane;
+        const bool valid = idx < count;
+        int q = 0, t = 0, xi = 0, yi = 0;
+        bool pass = false;
+        if (valid) {
+            unpack_node(in[idx], q, t, xi, yi);
+            const DevQuery& Q = queries[q];
+            const uint16_t* __restrict__ m = Q.lvl[h];
+            const int rows = Q.rows, cols = Q.cols, n = Q.n;
+            const int ox = xi - Q.winx, oy = yi - Q.winy;
+            const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
+            const size_t ps = (size_t)Q.pst_i;
+            int s = 0, k = 0;
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+                proj_t p[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p[u] = pp[(size_t)(i + u) * ps];
+                unsigned int v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_cell(m, rows, cols, p[u].y + oy, p[u].x + ox);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { s += (int)v[u]; k += (v[u] != 0u); }
+            }
+            for (; i < n; ++i) {
+                const proj_t p = pp[(size_t)i * ps];
+                const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
+                s += (int)v; k += (v != 0u);
+            }
+            const long long key = make_key(s, k);
+            const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
+            pass = k > Q.nk_cut && pack_best(key, kOrdMask) > inc;
+            if (pass) {
+                const int c = key_vs_threshold(key, Q.kthr);
+                if (c < 0) pass = false;
+                else if (c == 0)
+                    pass = exact_normalized_score(m, rows, cols, pp, (int)ps, n, ox, oy) > Q.kthr.thr;
+            }
+            if (pass && h == 0)
+                atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
         }
-        const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
-        int sumv[4], nk[4];
-        warp_score4(Q.lvl[hc], Q.rows, Q.cols, proj, Q.n, xi - Q.winx, yi - Q.winy, w, sumv, nk);
-        if (lane == 0) {
-            atomicAdd(&W.stats[2 * q], 1);
-            int ignored = 0;
-            for (int c = 0; c < 4; ++c) {
-                const long long ck = make_key(sumv[c], nk[c]);
-                const int cx = xi + (c & 1) * w, cy = yi + (c >> 1) * w;
-                inc = *(volatile unsigned long long*)&W.incumbent[q];
-                const bool ok = nk[c] > Q.nk_cut && pack_best(ck, kOrdMask) > inc &&
-                                passes_threshold(ck, Q, Q.lvl[hc], proj, cx - Q.winx, cy - Q.winy);
-                if (!ok) { ++ignored; continue; }
-                if (hc == 0) {
-                    atomicMax(&W.incumbent[q], pack_best(ck, leaf_ordfield(Q, t, cx, cy)));
-                } else {
-                    const unsigned int slot = atomicAdd(&W.counts[hc], 1u);
-                    if (slot < W.capacity) {
-                        W.nodes[hc][slot] = pack_node(q, t, cx, cy);
-                        W.keys[hc][slot] = ck;
-                    } else {
-                        *W.overflow = 1;
+        {
+            /* processed / ignored counters, one atomic per (warp, query, outcome) */
+            const int tag = valid ? (2 * q + (pass ? 0 : 1)) : -1;
+            const unsigned int peers = __match_any_sync(0xffffffffu, tag);
+            if (tag >= 0 && lane == __ffs(peers) - 1)
+                atomicAdd(&W.stats[tag], __popc(peers));
+        }
+        if (h > 0) {
+            const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+            if (ballot != 0u) {
+                const int npass = __popc(ballot);
+                unsigned int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&W.counts[h - 1], 4u * npass);
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (pass) {
+                    const unsigned int rank = __popc(ballot & ((1u << lane) - 1u));
+                    /* one contiguous run per child type, lane order kept inside it */
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned int slot = slot0 + c * npass + rank;
+                        if (slot < W.capacity)
+                            out[slot] = pack_node(q, t, xi + (c & 1) * w, yi + (c >> 1) * w);
+                        else
+                            *W.overflow = 1;
                     }
                 }
             }
-            if (ignored) atomicAdd(&W.stats[2 * q + 1], ignored);
         }
     }
 }
@@ -763,7 +708,7 @@ k_grid_window(const DevQuery* __restrict__ queries, const proj_t* __restrict__ p
                 const int c = key_vs_threshold(key, Q.kthr);
                 bool ok = c > 0;
                 if (c == 0)
-                    ok = exact_normalized_score(m, Q.rows, Q.cols, proj, Q.n, ox, oy) > Q.kthr.thr;
+                    ok = exact_normalized_score(m, Q.rows, Q.cols, proj, Q.pst_i, Q.n, ox, oy) > Q.kthr.thr;
                 if (ok) {
                     const unsigned long long ord =
                         ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
@@ -919,7 +864,7 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 col = (int)fmin(fmax(floor(ux), -lim), lim);
                 row = (int)fmin(fmax(floor(uy), -lim), lim);
             } else {
-                const proj_t p = proj_all[row_off + i];
+                const proj_t p = proj_all[(size_t)Q.proj_off + (size_t)it * Q.pst_t + (size_t)i * Q.pst_i];
                 const int ox = (F.mode == 1) ? F.mx[s.bx] : s.bx;
                 const int oy = (F.mode == 1) ? F.my[s.by] : s.by;
                 col = p.x + ox; row = p.y + oy;
