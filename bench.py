@@ -269,14 +269,31 @@ def main_cuda(args):
             if world > 1:
                 dist.all_reduce(best_word, op=dist.ReduceOp.MAX)
 
+    N_CHUNKS = 2
+    CH = N_MAPS // N_CHUNKS
+    chunk_ids = [np.ascontiguousarray(ids[c * CH:(c + 1) * CH]) for c in range(N_CHUNKS)]
+    chunk_ptrs = [(C.c_void_p * CH)(*[host_ptr + m * cells * 2 for m in range(c * CH, (c + 1) * CH)])
+                  for c in range(N_CHUNKS)]
+    chunk_offx = [np.ascontiguousarray(offx[c * CH:(c + 1) * CH]) for c in range(N_CHUNKS)]
+    chunk_offy = [np.ascontiguousarray(offy[c * CH:(c + 1) * CH]) for c in range(N_CHUNKS)]
+    result_chunks = [(capi.CsmResult * CH).from_buffer(results, c * CH * C.sizeof(capi.CsmResult))
+                     for c in range(N_CHUNKS)]
+
     def e2e_step():
-        h.upload_grids_ptr(ids, ptrs, ROWS, COLS, res, offx, offy)     # H2D 128 MiB
-        arr = make_query_array()                                          # H2D scan + host pose math
-        h.build_pyramids(ids, HMAX)
-        h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
+        """One Detect through the C ABI from pinned host buffers: the 256 submaps stream to the
+        device in 2 groups on the copy stream while pyramid build + B&B of the groups that have
+        already landed run on the compute stream."""
+        h.set_option("reset_best_key", 1)
+        for c in range(N_CHUNKS):                                          # H2D 128 MiB, async
+            h.upload_grids_ptr(chunk_ids[c], chunk_ptrs[c], ROWS, COLS, res, chunk_offx[c], chunk_offy[c])
+        h.upload_scan(0, scan.angles, scan.ranges)                         # H2D scan
+        for c in range(N_CHUNKS):
+            arr = det.prepare(queries[c * CH:(c + 1) * CH])                # host pose math of the adapter
+            h.build_pyramids(chunk_ids[c], HMAX)
+            h.loop_batch_enqueue(arr, CH, HMAX, rank * N_MAPS + c * CH)
+            h.loop_batch_finish(CH, result_chunks[c])                      # D2H results
         allreduce_best()
-        h.loop_batch_finish(N_MAPS, results)                              # D2H results
-        return int(best_word.item())                                      # D2H best word
+        return int(best_word.item())                                       # D2H best word
 
     def barrier():
         if world > 1:
@@ -295,6 +312,9 @@ def main_cuda(args):
         sampler.start()
 
     # ---- warm-up (also allocates every workspace) --------------------------------
+    det._cached_maps.update(int(i) for i in ids)
+    det._cached_scans[0] = scan
+    h.set_option("accumulate_best_key", 1)
     for _ in range(max(args.warmup, 3)):
         word = e2e_step()
 
@@ -311,6 +331,7 @@ def main_cuda(args):
     key, qidx = h.decode_best_key(word)
 
     # ---- value: inputs resident in HBM, CUDA events on the handle's stream ------------------
+    h.set_option("accumulate_best_key", 0)
     arr = make_query_array()
     h.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

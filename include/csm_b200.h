@@ -108,8 +108,12 @@ void* csm_stream(csm_handle h);
 int  csm_synchronize(csm_handle h);
 /* Number of kernels this handle has launched so far */
 int64_t csm_launch_count(csm_handle h);
-/* Tuning / test knobs. "pyramid_mode": 0 = automatic, 1 = level-by-level
- * kernels, 2 = streaming single-pass kernel (when the maps fit its layout). */
+/* Tuning / test knobs.
+ *  "pyramid_mode": 0 = automatic, 1 = level-by-level kernels, 2 = streaming
+ *      single-pass kernel (when the maps fit its layout);
+ *  "accumulate_best_key": 1 = loop batches keep (do not reset) the packed
+ *      best word, so that a Detect call split into several batches ends with
+ *      the maximum over all of them; "reset_best_key": clears it now. */
 int csm_set_option(csm_handle h, const char* name, int value);
 /* Page-locked host memory for the caller's upload buffers (fast H2D) */
 void* csm_alloc_pinned(size_t bytes);
@@ -130,8 +134,10 @@ int csm_upload_grid(csm_handle h, int64_t map_id, const uint16_t* dense,
 int csm_upload_grid_device(csm_handle h, int64_t map_id, const uint16_t* dense_dev,
                            int rows, int cols, double resolution,
                            double offset_x, double offset_y);
-/* n maps of identical shape and resolution in one call (one asynchronous
- * host-to-device copy per map on the handle's stream; use pinned buffers). */
+/* n maps of identical shape and resolution in one call. The copies run
+ * asynchronously on the handle's copy stream (use pinned buffers) and overlap
+ * kernels working on maps uploaded by earlier calls; whatever later touches
+ * one of these maps waits for this call's copies only. */
 int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t* const* dense,
                      int rows, int cols, double resolution,
                      const double* offset_x, const double* offset_y);

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -23,16 +24,27 @@ namespace {
 
 constexpr int64_t kTempScanId = INT64_MIN;
 
+/* Device allocation shared by the level-0 grids of one batched upload, so
+ * that a batch whose host buffers are contiguous moves with a single copy */
+struct ArenaBlock
+{
+    void* p = nullptr;
+    cudaStream_t stream = nullptr;
+    ~ArenaBlock() { if (p) cudaFreeAsync(p, stream); }
+};
+
 struct MapSlot
 {
     int rows = 0, cols = 0;
     double res = 0.0, offx = 0.0, offy = 0.0;
     uint16_t* base = nullptr;      /* level 0 */
+    std::shared_ptr<ArenaBlock> base_block;   /* owner of `base` when it lives in a batch arena */
     uint16_t* levels = nullptr;    /* levels 1..hmax */
     int levels_alloc = 0;          /* number of levels the allocation holds */
     int hmax = 0;                  /* number of levels currently valid */
     uint16_t* coarse = nullptr;
     int coarse_win = 0;
+    cudaEvent_t pending_upload = nullptr;   /* copy-stream event the next consumer must wait for */
 };
 
 struct ScanSlot
@@ -56,7 +68,12 @@ struct csm_context
 {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        /* compute stream */
+    cudaStream_t copy_stream = nullptr;   /* host-to-device uploads of grids, overlaps compute */
+    cudaEvent_t upload_events[16] = { nullptr };
+    int upload_event_next = 0;
+    cudaEvent_t compute_mark = nullptr;
+    bool upload_open = false;             /* uploads enqueued since the last event record */
     std::string err;
     int64_t launches = 0;
     std::unordered_map<int64_t, MapSlot> maps;
@@ -83,7 +100,8 @@ struct csm_context
     /* options (csm_set_option) */
     int pyramid_mode = 0;          /* 0 auto, 1 level-by-level, 2 streaming */
     int bb_seed_incumbent = 0;     /* experiment: start from the previous batch's incumbents */
-    int bb_dive = 0;               /* greedy dive before the sweep (saves ~4% of the nodes, costs a launch) */
+    int bb_dive = 0;               /* unused (kept for option compatibility) */
+    int accumulate_best_key = 0;   /* 1: batches do not reset the packed best word */
 };
 
 namespace {
@@ -158,6 +176,18 @@ int upload_committed(csm_handle h)
     return CSM_OK;
 }
 
+/* dst (device, 16-byte aligned, capacity rounded up to 16) <- src (pinned host) */
+int pull_to_device(csm_handle h, void* dst, const void* src_pinned, size_t bytes)
+{
+    const unsigned int n16 = (unsigned int)((bytes + 15) / 16);
+    if (n16 == 0)
+        return CSM_OK;
+    const unsigned int blocks = std::min<unsigned int>((n16 + 255) / 256, 64u);
+    k_pull<<<blocks, 256, 0, h->stream>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src_pinned), n16);
+    CSM_LAUNCH_CHECK();
+    return CSM_OK;
+}
+
 int ensure_result_area(csm_handle h, size_t bytes)
 {
     if (h->h_res_bytes >= bytes)
@@ -176,7 +206,7 @@ int ensure_result_area(csm_handle h, size_t bytes)
 
 void free_map(csm_handle h, MapSlot& m)
 {
-    if (m.base) cudaFreeAsync(m.base, h->stream);
+    if (m.base && !m.base_block) cudaFreeAsync(m.base, h->stream);
     if (m.levels) cudaFreeAsync(m.levels, h->stream);
     if (m.coarse) cudaFreeAsync(m.coarse, h->stream);
     m = MapSlot();
@@ -188,6 +218,46 @@ void free_scan(csm_handle h, ScanSlot& s)
     if (s.ranges) cudaFreeAsync(s.ranges, h->stream);
     if (s.trig) cudaFreeAsync(s.trig, h->stream);
     s = ScanSlot();
+}
+
+/* Uploads from host memory run on the copy stream so that they overlap the
+ * kernels of maps uploaded earlier. close_upload_group() records one event
+ * for everything uploaded since the previous group; consumers make the
+ * compute stream wait for the events of the maps they touch. */
+int close_upload_group(csm_handle h)
+{
+    if (!h->upload_open)
+        return CSM_OK;
+    cudaEvent_t& ev = h->upload_events[h->upload_event_next];
+    h->upload_event_next = (h->upload_event_next + 1) & 15;
+    if (ev == nullptr)
+        CSM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CSM_CUDA(cudaEventRecord(ev, h->copy_stream));
+    for (auto& kv : h->maps)
+        if (kv.second.pending_upload == reinterpret_cast<cudaEvent_t>(1))
+            kv.second.pending_upload = ev;
+    h->upload_open = false;
+    return CSM_OK;
+}
+
+int wait_uploads(csm_handle h, const std::vector<MapSlot*>& slots)
+{
+    int rc = close_upload_group(h);
+    if (rc) return rc;
+    cudaEvent_t seen[16];
+    int nseen = 0;
+    for (MapSlot* m : slots) {
+        cudaEvent_t ev = m->pending_upload;
+        if (ev == nullptr)
+            continue;
+        m->pending_upload = nullptr;
+        bool dup = false;
+        for (int i = 0; i < nseen; ++i) dup = dup || seen[i] == ev;
+        if (dup) continue;
+        if (nseen < 16) seen[nseen++] = ev;
+        CSM_CUDA(cudaStreamWaitEvent(h->stream, ev, 0));
+    }
+    return CSM_OK;
 }
 
 /* `normalized > thr` on integer keys, see csm_device.cuh */
@@ -237,13 +307,23 @@ int upload_scan_impl(csm_handle h, int64_t scan_id, const double* angles,
     ScanSlot& s = h->scans[scan_id];
     if (s.n != n) {
         free_scan(h, s);
-        CSM_CUDA(cudaMallocAsync((void**)&s.angles, sizeof(double) * n, h->stream));
-        CSM_CUDA(cudaMallocAsync((void**)&s.ranges, sizeof(double) * n, h->stream));
+        CSM_CUDA(cudaMallocAsync((void**)&s.angles, sizeof(double) * n + 16, h->stream));
+        CSM_CUDA(cudaMallocAsync((void**)&s.ranges, sizeof(double) * n + 16, h->stream));
         CSM_CUDA(cudaMallocAsync((void**)&s.trig, sizeof(double2) * n, h->stream));
         s.n = n;
     }
-    CSM_CUDA(cudaMemcpyAsync(s.angles, angles, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-    CSM_CUDA(cudaMemcpyAsync(s.ranges, ranges, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    {
+        /* staged through pinned memory and pulled by a kernel (see k_pull) */
+        const size_t half = ((sizeof(double) * n + 15) / 16) * 16;
+        char* hp = nullptr;
+        int rc = acquire_upload(h, 2 * half, &hp);
+        if (rc) return rc;
+        std::memcpy(hp, angles, sizeof(double) * n);
+        std::memcpy(hp + half, ranges, sizeof(double) * n);
+        if ((rc = pull_to_device(h, s.angles, hp, half))) return rc;
+        if ((rc = pull_to_device(h, s.ranges, hp + half, half))) return rc;
+        if ((rc = upload_committed(h))) return rc;
+    }
     s.max_range = *std::max_element(ranges, ranges + n);
     k_beam_trig<<<(n + 255) / 256, 256, 0, h->stream>>>(s.angles, s.trig, n);
     CSM_LAUNCH_CHECK();
@@ -256,6 +336,10 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
         return fail(h, CSM_E_UNSUPPORTED, "pyramid: 0 <= hmax <= 7");
     std::vector<PyrJob> jobs;
     int max_rows = 0, max_cols = 0;
+    {
+        const int wrc = wait_uploads(h, slots);
+        if (wrc) return wrc;
+    }
     for (MapSlot* m : slots) {
         if (m->hmax >= hmax)
             continue;
@@ -283,14 +367,14 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
         char* hp = nullptr;
         if ((rc = acquire_upload(h, jb, &hp))) return rc;
         std::memcpy(hp, jobs.data(), jb);
-        CSM_CUDA(cudaMemcpyAsync(h->d_pyrjobs.p, hp, jb, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = pull_to_device(h, h->d_pyrjobs.p, hp, jb))) return rc;
         if ((rc = upload_committed(h))) return rc;
         h->jobs_on_device = jobs;
     }
     /* Batches of maps that fit its layout take the streaming builder (one pass,
      * level 0 read once, every level written once). */
     bool stream_ok = hmax >= 1 && hmax <= 6 && h->pyramid_mode != 1 &&
-                     (h->pyramid_mode == 2 || jobs.size() >= (size_t)h->sm_count / 2);
+                     (h->pyramid_mode == 2 || jobs.size() >= 32);
     for (const PyrJob& j : jobs)
         stream_ok = stream_ok && j.cols <= 512 && (j.cols % 8) == 0 && (j.rows % kPsRows) == 0;
     if (stream_ok) {
@@ -374,17 +458,19 @@ int stage_plan(csm_handle h, QueryPlan& plan, bool want_rcs)
         plan.dq[q].thetas = static_cast<const double*>(h->d_thetas.p) + plan.theta_off[q];
     if ((rc = ensure_result_area(h, sizeof(csm_result) * nq + 64))) return rc;
     char* hp = nullptr;
-    if ((rc = acquire_upload(h, qb + tb + ib, &hp))) return rc;
+    const size_t qb16 = (qb + 15) & ~(size_t)15, tb16 = (tb + 15) & ~(size_t)15, ib16 = (ib + 15) & ~(size_t)15;
+    if ((rc = acquire_upload(h, qb16 + tb16 + ib16, &hp))) return rc;
     std::memcpy(hp, plan.dq.data(), qb);
-    std::memcpy(hp + qb, plan.thetas.data(), tb);
-    std::memcpy(hp + qb + tb, plan.inc_init.data(), ib);
-    CSM_CUDA(cudaMemcpyAsync(h->d_queries.p, hp, qb, cudaMemcpyHostToDevice, h->stream));
-    CSM_CUDA(cudaMemcpyAsync(h->d_thetas.p, hp + qb, tb, cudaMemcpyHostToDevice, h->stream));
+    std::memcpy(hp + qb16, plan.thetas.data(), tb);
+    std::memcpy(hp + qb16 + tb16, plan.inc_init.data(), ib);
+    if ((rc = pull_to_device(h, h->d_queries.p, hp, qb))) return rc;
+    if ((rc = pull_to_device(h, h->d_thetas.p, hp + qb16, tb))) return rc;
     if (!h->bb_seed_incumbent)
-        CSM_CUDA(cudaMemcpyAsync(h->d_inc.p, hp + qb + tb, ib, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = pull_to_device(h, h->d_inc.p, hp + qb16 + tb16, ib))) return rc;
     if ((rc = upload_committed(h))) return rc;
     CSM_CUDA(cudaMemsetAsync(h->d_qflags.p, 0, sizeof(int) * nq, h->stream));
-    CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
+    if (!h->accumulate_best_key)
+        CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
     CSM_CUDA(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->stream));
     return CSM_OK;
 }
@@ -444,6 +530,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     plan.dq.resize(nq);
     plan.theta_off.resize(nq);
     plan.inc_init.resize(nq);
+    std::vector<MapSlot*> used_slots;
+    used_slots.reserve(nq);
     const int wsz = 1 << hmax;
     for (int q = 0; q < nq; ++q) {
         const csm_loop_query& in = queries[q];
@@ -453,8 +541,9 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         auto si = h->scans.find(in.scan_id);
         if (si == h->scans.end())
             return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown scan id " + std::to_string(in.scan_id));
-        const MapSlot& m = mi->second;
+        MapSlot& m = mi->second;
         const ScanSlot& s = si->second;
+        used_slots.push_back(&m);
         if (m.hmax < hmax)
             return fail(h, CSM_E_INVALID, "loop batch: pyramid of map " + std::to_string(in.map_id) +
                         " not built to hmax");
@@ -489,6 +578,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     for (int q = 0; q < nq; ++q)
         root_off[q + 1] = root_off[q] + (unsigned int)(plan.dq[q].T * plan.dq[q].nrx * plan.dq[q].nry);
     int rc;
+    if ((rc = wait_uploads(h, used_slots))) return rc;
     if ((rc = ensure_frontier(h, nq, root_off[nq]))) return rc;
     if ((rc = stage_plan(h, plan, false))) return rc;
     {
@@ -496,7 +586,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         const size_t rb = sizeof(unsigned int) * (nq + 1);
         if ((rc = acquire_upload(h, rb, &hp))) return rc;
         std::memcpy(hp, root_off.data(), rb);
-        CSM_CUDA(cudaMemcpyAsync(h->d_rootoff.p, hp, rb, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = pull_to_device(h, h->d_rootoff.p, hp, rb))) return rc;
         if ((rc = upload_committed(h))) return rc;
     }
     CSM_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(unsigned int) * kMaxLevels, h->stream));
@@ -576,6 +666,12 @@ int csm_create(int device, unsigned flags, csm_handle* out)
         delete h;
         return CSM_E_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->compute_mark, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return CSM_E_CUDA;
+    }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -591,6 +687,7 @@ int csm_destroy(csm_handle h)
     if (h == nullptr)
         return CSM_E_INVALID;
     cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->stream);
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
@@ -608,6 +705,10 @@ int csm_destroy(csm_handle h)
         if (h->h_up_done[k]) cudaEventDestroy(h->h_up_done[k]);
     }
     if (h->h_res) cudaFreeHost(h->h_res);
+    for (int k = 0; k < 16; ++k)
+        if (h->upload_events[k]) cudaEventDestroy(h->upload_events[k]);
+    cudaEventDestroy(h->compute_mark);
+    cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return CSM_OK;
@@ -623,6 +724,7 @@ void* csm_stream(csm_handle h) { return h ? (void*)h->stream : nullptr; }
 int csm_synchronize(csm_handle h)
 {
     if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaStreamSynchronize(h->copy_stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
     return CSM_OK;
 }
@@ -638,6 +740,13 @@ int csm_set_option(csm_handle h, const char* name, int value)
     }
     if (std::strcmp(name, "bb_seed_incumbent") == 0) { h->bb_seed_incumbent = value; return CSM_OK; }
     if (std::strcmp(name, "bb_dive") == 0) { h->bb_dive = value; return CSM_OK; }
+    if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
+    if (std::strcmp(name, "reset_best_key") == 0) {
+        int rc = ensure(h, h->d_bestkey, 8);
+        if (rc) return rc;
+        CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
+        return CSM_OK;
+    }
     return fail(h, CSM_E_INVALID, std::string("unknown option ") + name);
 }
 
@@ -663,17 +772,33 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
         return fail(h, CSM_E_INVALID, "grid: need 0 < rows, cols <= 16384, even cols, resolution > 0");
     CSM_CUDA(cudaSetDevice(h->device));
     MapSlot& m = h->maps[map_id];
+    bool fresh_alloc = false;
     if (m.rows != rows || m.cols != cols || m.base == nullptr) {
         free_map(h, m);
         CSM_CUDA(cudaMallocAsync((void**)&m.base, (size_t)rows * cols * sizeof(uint16_t), h->stream));
         m.rows = rows; m.cols = cols;
+        fresh_alloc = true;
     }
     /* precomputed levels belong to the previous contents (allocations are kept) */
     m.hmax = 0;
     m.coarse_win = 0;
     m.res = res; m.offx = offx; m.offy = offy;
-    CSM_CUDA(cudaMemcpyAsync(m.base, dense, (size_t)rows * cols * sizeof(uint16_t),
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
+    if (on_device) {
+        CSM_CUDA(cudaMemcpyAsync(m.base, dense, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        return CSM_OK;
+    }
+    /* Host uploads go to the copy stream. It first waits for the compute work
+     * enqueued so far: kernels of the previous batch may still read the old
+     * contents of this slot, and a fresh allocation is ordered on the compute
+     * stream. */
+    if (!h->upload_open || fresh_alloc) {
+        CSM_CUDA(cudaEventRecord(h->compute_mark, h->stream));
+        CSM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->compute_mark, 0));
+        h->upload_open = true;
+    }
+    CSM_CUDA(cudaMemcpyAsync(m.base, dense, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
     return CSM_OK;
 }
 
@@ -696,12 +821,68 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
     if (!h) return CSM_E_INVALID;
     if (n <= 0 || !map_ids || !dense || !offset_x || !offset_y)
         return fail(h, CSM_E_INVALID, "upload_grids: empty batch");
-    for (int i = 0; i < n; ++i) {
-        const int rc = upload_grid_impl(h, map_ids[i], dense[i], false, rows, cols, resolution,
-                                        offset_x[i], offset_y[i]);
-        if (rc) return rc;
+    if (rows <= 0 || cols <= 0 || rows > 16384 || cols > 16384 || (cols & 1) || !(resolution > 0.0))
+        return fail(h, CSM_E_INVALID, "grid: need 0 < rows, cols <= 16384, even cols, resolution > 0");
+    CSM_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
+    bool host_contiguous = true;
+    for (int i = 1; i < n; ++i)
+        host_contiguous = host_contiguous && dense[i] != nullptr &&
+            reinterpret_cast<const char*>(dense[i]) == reinterpret_cast<const char*>(dense[0]) + (size_t)i * bytes;
+    if (!host_contiguous || n == 1 || dense[0] == nullptr) {
+        for (int i = 0; i < n; ++i) {
+            const int rc = upload_grid_impl(h, map_ids[i], dense[i], false, rows, cols, resolution,
+                                            offset_x[i], offset_y[i]);
+            if (rc) return rc;
+        }
+        return close_upload_group(h);
     }
-    return CSM_OK;
+    /* Contiguous host batch: the n level-0 grids share one device arena and
+     * move with one copy. The arena of a previous identical batch is reused. */
+    std::vector<MapSlot*> slots(n);
+    for (int i = 0; i < n; ++i)
+        slots[i] = &h->maps[map_ids[i]];
+    bool reuse = slots[0]->base_block != nullptr && slots[0]->base == slots[0]->base_block->p;
+    for (int i = 0; i < n && reuse; ++i)
+        reuse = slots[i]->base_block == slots[0]->base_block && slots[i]->rows == rows &&
+                slots[i]->cols == cols &&
+                reinterpret_cast<char*>(slots[i]->base) == static_cast<char*>(slots[0]->base_block->p) + (size_t)i * bytes;
+    bool fresh_alloc = false;
+    if (!reuse) {
+        auto block = std::make_shared<ArenaBlock>();
+        block->stream = h->stream;
+        CSM_CUDA(cudaMallocAsync(&block->p, bytes * n, h->stream));
+        for (int i = 0; i < n; ++i) {
+            MapSlot& m = *slots[i];
+            const bool keep_levels = m.rows == rows && m.cols == cols;
+            uint16_t* levels = keep_levels ? m.levels : nullptr;
+            const int levels_alloc = keep_levels ? m.levels_alloc : 0;
+            uint16_t* coarse = keep_levels ? m.coarse : nullptr;
+            if (keep_levels) { m.levels = nullptr; m.coarse = nullptr; }
+            free_map(h, m);
+            m.levels = levels; m.levels_alloc = levels_alloc; m.coarse = coarse;
+            m.rows = rows; m.cols = cols;
+            m.base_block = block;
+            m.base = reinterpret_cast<uint16_t*>(static_cast<char*>(block->p) + (size_t)i * bytes);
+        }
+        fresh_alloc = true;
+    }
+    for (int i = 0; i < n; ++i) {
+        MapSlot& m = *slots[i];
+        m.hmax = 0;
+        m.coarse_win = 0;
+        m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
+        m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
+    }
+    if (!h->upload_open || fresh_alloc) {
+        CSM_CUDA(cudaEventRecord(h->compute_mark, h->stream));
+        CSM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->compute_mark, 0));
+        h->upload_open = true;
+    }
+    CSM_CUDA(cudaMemcpyAsync(slots[0]->base, dense[0], bytes * n, cudaMemcpyHostToDevice, h->copy_stream));
+    /* one upload group per batch call: consumers of these maps wait for this
+     * batch only, later batches keep streaming in behind the kernels */
+    return close_upload_group(h);
 }
 
 int csm_release_grid(csm_handle h, int64_t map_id)
@@ -710,6 +891,10 @@ int csm_release_grid(csm_handle h, int64_t map_id)
     auto it = h->maps.find(map_id);
     if (it == h->maps.end())
         return fail(h, CSM_E_NOT_FOUND, "release: unknown map id");
+    {
+        const int wrc = wait_uploads(h, std::vector<MapSlot*>{ &it->second });
+        if (wrc) return wrc;
+    }
     free_map(h, it->second);
     h->maps.erase(it);
     return CSM_OK;
@@ -727,6 +912,10 @@ int csm_build_coarse(csm_handle h, int64_t map_id, int win)
     MapSlot& m = it->second;
     if (m.coarse_win == win && m.coarse != nullptr)
         return CSM_OK;
+    {
+        const int wrc = wait_uploads(h, std::vector<MapSlot*>{ &m });
+        if (wrc) return wrc;
+    }
     if (m.coarse == nullptr)
         CSM_CUDA(cudaMallocAsync((void**)&m.coarse, (size_t)m.rows * m.cols * sizeof(uint16_t), h->stream));
     dim3 grid((m.cols + 255) / 256, m.rows);
@@ -777,7 +966,11 @@ int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out)
     auto it = h->maps.find(map_id);
     if (it == h->maps.end())
         return fail(h, CSM_E_NOT_FOUND, "download: unknown map id");
-    const MapSlot& m = it->second;
+    MapSlot& m = it->second;
+    {
+        const int wrc = wait_uploads(h, std::vector<MapSlot*>{ &m });
+        if (wrc) return wrc;
+    }
     const size_t cells = (size_t)m.rows * m.cols;
     const uint16_t* src = nullptr;
     if (level == 0) src = m.base;
@@ -892,7 +1085,11 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     auto mi = h->maps.find(map_id);
     if (mi == h->maps.end())
         return fail(h, CSM_E_NOT_FOUND, "match_rt: unknown map id");
-    const MapSlot& m = mi->second;
+    MapSlot& m = mi->second;
+    {
+        const int wrc = wait_uploads(h, std::vector<MapSlot*>{ &m });
+        if (wrc) return wrc;
+    }
     if (low_res <= 0 || low_res > 64)
         return fail(h, CSM_E_UNSUPPORTED, "match_rt: 1 <= low_res <= 64");
     if (m.coarse == nullptr || m.coarse_win != low_res)
@@ -961,7 +1158,11 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     auto mi = h->maps.find(map_id);
     if (mi == h->maps.end())
         return fail(h, CSM_E_NOT_FOUND, "match_grid: unknown map id");
-    const MapSlot& m = mi->second;
+    MapSlot& m = mi->second;
+    {
+        const int wrc = wait_uploads(h, std::vector<MapSlot*>{ &m });
+        if (wrc) return wrc;
+    }
     if (ndx <= 0 || ndy <= 0 || ndt <= 0 || ndt > 65535 ||
         (unsigned long long)ndx * ndy * ndt >= kOrdMask - 1ull)
         return fail(h, CSM_E_UNSUPPORTED, "match_grid: window exceeds 2^26 candidates");
@@ -1014,10 +1215,17 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     if ((rc = ensure(h, h->d_gridoff, sizeof(int) * offs.size()))) return rc;
     if ((rc = ensure(h, h->d_gridpos, sizeof(double) * pos.size()))) return rc;
     if ((rc = stage_plan(h, plan, !fast))) return rc;
-    /* small synchronous-on-stream copies from pageable vectors are fine here */
-    CSM_CUDA(cudaMemcpyAsync(h->d_gridoff.p, offs.data(), sizeof(int) * offs.size(), cudaMemcpyHostToDevice, h->stream));
-    CSM_CUDA(cudaMemcpyAsync(h->d_gridpos.p, pos.data(), sizeof(double) * pos.size(), cudaMemcpyHostToDevice, h->stream));
-    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    {
+        const size_t ob = sizeof(int) * offs.size(), pb = sizeof(double) * pos.size();
+        const size_t ob16 = (ob + 15) & ~(size_t)15;
+        char* hp = nullptr;
+        if ((rc = acquire_upload(h, ob16 + pb + 16, &hp))) return rc;
+        std::memcpy(hp, offs.data(), ob);
+        std::memcpy(hp + ob16, pos.data(), pb);
+        if ((rc = pull_to_device(h, h->d_gridoff.p, hp, ob))) return rc;
+        if ((rc = pull_to_device(h, h->d_gridpos.p, hp + ob16, pb))) return rc;
+        if ((rc = upload_committed(h))) return rc;
+    }
     if ((rc = launch_project(h, plan, !fast))) return rc;
 
     GridArgs G;

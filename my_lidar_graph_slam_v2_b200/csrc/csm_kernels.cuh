@@ -30,6 +30,17 @@
 
 namespace csm {
 
+/* Pulls a small staged block from page-locked host memory (zero-copy read over
+ * PCIe by the SMs). Used for every small descriptor / scan upload instead of
+ * cudaMemcpyAsync so that they never queue behind the bulk grid uploads on the
+ * host-to-device copy engine. */
+__global__ void __launch_bounds__(256)
+k_pull(uint4* __restrict__ dst, const uint4* __restrict__ src_host, unsigned int n16)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        dst[i] = src_host[i];
+}
+
 /* ------------------------------------------------------------------------ */
 /* Precomputation                                                            */
 /* ------------------------------------------------------------------------ */
@@ -532,83 +543,103 @@ k_bb_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__
         W.counts[W.hmax] = root_off[nq];
 }
 
+constexpr int kBbSplit = 4;                 /* lanes cooperating on one node */
+constexpr int kBbNodesPerWarp = 32 / kBbSplit;
+
 __global__ void __launch_bounds__(256)
 k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
            BbWork W, int h)
 {
+    /* lane = part * 8 + slot: `slot` selects one of 8 consecutive candidates,
+     * `part` the quarter of the beams (i = part, part + 4, ...) this lane sums.
+     * Lanes with equal `part` sit next to each other, so a warp's index loads
+     * are 4 runs of 8 consecutive proj entries when the angles are consecutive. */
     const int lane = threadIdx.x & 31;
+    const int slot = lane & (kBbNodesPerWarp - 1);
+    const int part = lane / kBbNodesPerWarp;
     const unsigned int count = min(W.counts[h], W.capacity);
     const unsigned long long* __restrict__ in = W.list[h & 1];
     unsigned long long* __restrict__ out = W.list[(h & 1) ^ 1];
-    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int w = (h > 0) ? (1 << (h - 1)) : 0;
-    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
-        const unsigned int idx = base + lane;
+    for (unsigned int base = warp_global * kBbNodesPerWarp; base < count; base += nwarps * kBbNodesPerWarp) {
+        const unsigned int idx = base + slot;
         const bool valid = idx < count;
         int q = 0, t = 0, xi = 0, yi = 0;
-        bool pass = false;
+        int s = 0, k = 0;
         if (valid) {
             unpack_node(in[idx], q, t, xi, yi);
             const DevQuery& Q = queries[q];
             const uint16_t* __restrict__ m = Q.lvl[h];
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
             const int ox = xi - Q.winx, oy = yi - Q.winy;
-            const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
             const size_t ps = (size_t)Q.pst_i;
-            int s = 0, k = 0;
+            const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t + (size_t)part * ps;
+            const size_t step = ps * kBbSplit;
+            const int mine = (n - part + kBbSplit - 1) / kBbSplit;     /* beams of this lane */
             int i = 0;
-            for (; i + 8 <= n; i += 8) {
+            for (; i + 8 <= mine; i += 8) {
                 proj_t p[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) p[u] = pp[(size_t)(i + u) * ps];
+                for (int u = 0; u < 8; ++u) p[u] = pp[(size_t)(i + u) * step];
                 unsigned int v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) v[u] = ld_cell(m, rows, cols, p[u].y + oy, p[u].x + ox);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { s += (int)v[u]; k += (v[u] != 0u); }
             }
-            for (; i < n; ++i) {
-                const proj_t p = pp[(size_t)i * ps];
+            for (; i < mine; ++i) {
+                const proj_t p = pp[(size_t)i * step];
                 const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
                 s += (int)v; k += (v != 0u);
             }
-            const long long key = make_key(s, k);
+        }
+        /* sum the four parts of every node (lanes slot, slot+8, slot+16, slot+24) */
+        s += __shfl_xor_sync(0xffffffffu, s, 8);  k += __shfl_xor_sync(0xffffffffu, k, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16); k += __shfl_xor_sync(0xffffffffu, k, 16);
+        bool pass = false;
+        long long key = 0;
+        if (valid) {
+            const DevQuery& Q = queries[q];
+            key = make_key(s, k);
             const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
             pass = k > Q.nk_cut && pack_best(key, kOrdMask) > inc;
             if (pass) {
                 const int c = key_vs_threshold(key, Q.kthr);
                 if (c < 0) pass = false;
-                else if (c == 0)
-                    pass = exact_normalized_score(m, rows, cols, pp, (int)ps, n, ox, oy) > Q.kthr.thr;
+                else if (c == 0) {
+                    const proj_t* pp0 = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
+                    pass = exact_normalized_score(Q.lvl[h], Q.rows, Q.cols, pp0, Q.pst_i, Q.n,
+                                                  xi - Q.winx, yi - Q.winy) > Q.kthr.thr;
+                }
             }
-            if (pass && h == 0)
+            if (pass && h == 0 && part == 0)
                 atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
         }
         {
             /* processed / ignored counters, one atomic per (warp, query, outcome) */
-            const int tag = valid ? (2 * q + (pass ? 0 : 1)) : -1;
+            const int tag = (valid && part == 0) ? (2 * q + (pass ? 0 : 1)) : -1;
             const unsigned int peers = __match_any_sync(0xffffffffu, tag);
             if (tag >= 0 && lane == __ffs(peers) - 1)
                 atomicAdd(&W.stats[tag], __popc(peers));
         }
         if (h > 0) {
-            const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+            /* every lane of a surviving node writes one child: child type = part */
+            const unsigned int ballot = __ballot_sync(0xffffffffu, pass) & 0xffu;
             if (ballot != 0u) {
                 const int npass = __popc(ballot);
                 unsigned int slot0 = 0;
                 if (lane == 0) slot0 = atomicAdd(&W.counts[h - 1], 4u * npass);
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                 if (pass) {
-                    const unsigned int rank = __popc(ballot & ((1u << lane) - 1u));
-                    /* one contiguous run per child type, lane order kept inside it */
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const unsigned int slot = slot0 + c * npass + rank;
-                        if (slot < W.capacity)
-                            out[slot] = pack_node(q, t, xi + (c & 1) * w, yi + (c >> 1) * w);
-                        else
-                            *W.overflow = 1;
-                    }
+                    const unsigned int rank = __popc(ballot & ((1u << slot) - 1u));
+                    /* one contiguous run per child type, candidate order kept inside it */
+                    const unsigned int dst = slot0 + part * npass + rank;
+                    if (dst < W.capacity)
+                        out[dst] = pack_node(q, t, xi + (part & 1) * w, yi + (part >> 1) * w);
+                    else
+                        *W.overflow = 1;
                 }
             }
         }
