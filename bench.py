@@ -220,7 +220,7 @@ class CudaArrayView:
 def main_cuda(args):
     import torch
     import torch.distributed as dist
-    from my_lidar_graph_slam_v2_b200 import capi, matchers, synth
+    from my_lidar_graph_slam_v2_b200 import capi, matchers, sharding, synth
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -266,8 +266,7 @@ def main_cuda(args):
         view = torch.as_tensor(CudaArrayView(h.best_key_device_ptr(), 1, "<i8"), device="cuda")
         with torch.cuda.stream(ext_stream):
             best_word.copy_(view)
-            if world > 1:
-                dist.all_reduce(best_word, op=dist.ReduceOp.MAX)
+            sharding.allreduce_best(best_word)          # 8-byte all-reduce(max) over NCCL
 
     N_CHUNKS = 2
     CH = N_MAPS // N_CHUNKS

@@ -1,0 +1,61 @@
+/* loop_detector.hpp -- batched GPU loop detector behind the reference's
+ * LoopDetector plugin interface (mapping/loop_detector.hpp:97-116:
+ * Detect(queries) -> results), JSON type string "BranchBound"
+ * (loop_detector_factory.cpp:202-209). Constructor parameters follow
+ * LoopDetectorBranchBound (loop_detector_branch_bound.cpp:41-56); the final
+ * sub-pixel matcher is an optional callback because it stays on the CPU
+ * (SURVEY.md 8f rank 1). */
+#pragma once
+
+#include <functional>
+#include <set>
+
+#include "csm_host/scan_matchers.hpp"
+
+namespace csm_host {
+
+using FinalMatcher = std::function<ScanMatchingSummary(const GridMapView& map, const ScanDataPtr& scan,
+                                                       const Pose2D& center, const Pose2D& initial_pose)>;
+
+class LoopDetector
+{
+public:
+    explicit LoopDetector(const std::string& name) : mName(name) { }
+    virtual ~LoopDetector() = default;
+    const std::string& Name() const { return mName; }
+    virtual std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) = 0;
+
+protected:
+    std::string mName;
+};
+
+class LoopDetectorBranchBound final : public LoopDetector
+{
+public:
+    LoopDetectorBranchBound(const std::string& name,
+                            const std::shared_ptr<ScanMatcherBranchBound>& scan_matcher,
+                            const FinalMatcher& final_matcher,
+                            double score_threshold, double known_rate_threshold);
+
+    /* loop_detector_branch_bound.cpp:59-156: per query, build the pyramid of a
+     * local map the first time it is seen (cached by LocalMapId, never
+     * evicted), match with thresholds, refine and emit a result per success.
+     * All queries are matched in one device batch. */
+    std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
+
+    /* Sharded use: global index of queries[0] (packed best word) */
+    void SetQueryIndexBase(int base) { mQueryIndexBase = base; }
+    /* Per-query device results of the last Detect, in query order */
+    const std::vector<csm_result>& LastResults() const { return mLastResults; }
+
+private:
+    std::shared_ptr<ScanMatcherBranchBound> mScanMatcher;
+    FinalMatcher mFinalMatcher;
+    double mScoreThreshold, mKnownRateThreshold;
+    std::set<std::int64_t> mCachedMaps;
+    std::set<std::int64_t> mCachedScans;
+    std::vector<csm_result> mLastResults;
+    int mQueryIndexBase = 0;
+};
+
+} /* namespace csm_host */

@@ -1,0 +1,136 @@
+/* scan_matchers.hpp -- GPU scan matchers behind the reference's ScanMatcher
+ * plugin interface (mapping/scan_matcher.hpp:89-117: Name() and
+ * OptimizePose(query) -> summary), selected by the launcher JSON type strings
+ * "RealTimeCorrelative" | "BranchBound" | "GridSearch"
+ * (scan_matcher_factory.cpp:200-214). Constructor parameters are the reference's:
+ *   ScanMatcherCorrelative(name, costFunc, lowResolution, rangeX, rangeY, rangeTheta)
+ *       scan_matcher_correlative.hpp:59-65
+ *   ScanMatcherBranchBound(name, costFunc, nodeHeightMax, rangeX, rangeY, rangeTheta)
+ *       scan_matcher_branch_bound.hpp:108-116 (the score function argument is gone:
+ *       the device computes ScorePixelAccurate itself)
+ *   ScanMatcherGridSearch(name, costFunc, rangeX, rangeY, rangeTheta, stepX, stepY, stepTheta)
+ *       scan_matcher_grid_search.hpp:49-58
+ * Each instance owns (or shares) one csm_handle = one CUDA stream with its own
+ * device buffers, so the front-end matcher and the back-end detector can run
+ * concurrently from their two threads (lidar_graph_slam.cpp:777-779). Errors
+ * follow the reference convention: print and abort (util.hpp:39-72). */
+#pragma once
+
+#include "csm_b200.h"
+#include "csm_host/cost_square_error.hpp"
+#include "csm_host/types.hpp"
+
+namespace csm_host {
+
+using CostFuncPtr = std::shared_ptr<CostSquareError>;
+
+/* Shared ownership of a csm_handle */
+class DeviceContext
+{
+public:
+    explicit DeviceContext(int device);
+    ~DeviceContext();
+    DeviceContext(const DeviceContext&) = delete;
+    DeviceContext& operator=(const DeviceContext&) = delete;
+    csm_handle Handle() const { return mHandle; }
+    /* Abort with the library's message unless rc == CSM_OK */
+    void Check(int rc, const char* what) const;
+
+private:
+    csm_handle mHandle;
+};
+using DeviceContextPtr = std::shared_ptr<DeviceContext>;
+
+struct ScanMatchingQuery
+{
+    const GridMapView& grid_map;
+    ScanDataPtr scan_data;
+    Pose2D map_local_initial_pose;
+};
+
+class ScanMatcher
+{
+public:
+    ScanMatcher(const std::string& name, const DeviceContextPtr& context) :
+        mName(name), mContext(context) { }
+    virtual ~ScanMatcher() = default;
+    const std::string& Name() const { return mName; }
+    virtual ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) = 0;
+    const DeviceContextPtr& Context() const { return mContext; }
+
+protected:
+    /* Upload the map unless a map with this id is already resident */
+    std::int64_t EnsureMap(const GridMapView& map);
+    /* Cost, covariance and MoveBackward at the winning sensor pose
+     * (scan_matcher_correlative.cpp:203-219) */
+    void Epilogue(const GridMapView& map, const ScanData& scan, const Pose2D& best_sensor_pose,
+                  const CostFuncPtr& cost, ScanMatchingSummary& summary) const;
+
+    std::string mName;
+    DeviceContextPtr mContext;
+    std::vector<std::int64_t> mResidentMaps;
+};
+
+/* scan_matcher_correlative.cpp:255-274: stepX = stepY = resolution,
+ * stepTheta = acos(1 - 0.5 (resolution / maxRange)^2) */
+void ComputeSearchStep(double resolution, const ScanData& scan,
+                       double& step_x, double& step_y, double& step_theta);
+
+class ScanMatcherCorrelative final : public ScanMatcher
+{
+public:
+    ScanMatcherCorrelative(const std::string& name, const CostFuncPtr& cost, int low_resolution,
+                           double range_x, double range_y, double range_theta,
+                           const DeviceContextPtr& context);
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override;
+    /* scan_matcher_correlative.hpp:75-84 */
+    ScanMatchingSummary OptimizePose(const GridMapView& map, const ScanDataPtr& scan,
+                                     const Pose2D& initial_pose, double score_threshold,
+                                     double known_rate_threshold);
+
+private:
+    CostFuncPtr mCost;
+    int mLowResolution;
+    double mRangeX, mRangeY, mRangeTheta;
+};
+
+class ScanMatcherBranchBound final : public ScanMatcher
+{
+public:
+    ScanMatcherBranchBound(const std::string& name, const CostFuncPtr& cost, int node_height_max,
+                           double range_x, double range_y, double range_theta,
+                           const DeviceContextPtr& context);
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override;
+    ScanMatchingSummary OptimizePose(const GridMapView& map, const ScanDataPtr& scan,
+                                     const Pose2D& initial_pose, double score_threshold,
+                                     double known_rate_threshold);
+    int NodeHeightMax() const { return mNodeHeightMax; }
+    double RangeX() const { return mRangeX; }
+    double RangeY() const { return mRangeY; }
+    double RangeTheta() const { return mRangeTheta; }
+    const CostFuncPtr& Cost() const { return mCost; }
+
+private:
+    CostFuncPtr mCost;
+    int mNodeHeightMax;
+    double mRangeX, mRangeY, mRangeTheta;
+};
+
+class ScanMatcherGridSearch final : public ScanMatcher
+{
+public:
+    ScanMatcherGridSearch(const std::string& name, const CostFuncPtr& cost,
+                          double range_x, double range_y, double range_theta,
+                          double step_x, double step_y, double step_theta,
+                          const DeviceContextPtr& context);
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override;
+    ScanMatchingSummary OptimizePose(const GridMapView& map, const ScanDataPtr& scan,
+                                     const Pose2D& initial_pose, double score_threshold,
+                                     double known_rate_threshold);
+
+private:
+    CostFuncPtr mCost;
+    double mRangeX, mRangeY, mRangeTheta, mStepX, mStepY, mStepTheta;
+};
+
+} /* namespace csm_host */

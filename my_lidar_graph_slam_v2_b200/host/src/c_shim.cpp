@@ -1,0 +1,146 @@
+/* c_shim.cpp -- extern "C" test entry points over the C++ plugin mirror, so that
+ * the parity tests (Python, ctypes) can drive the adapter classes exactly the
+ * way the reference drives its matchers / detectors. Not part of the C ABI. */
+#include <cstring>
+
+#include "csm_host/loop_detector.hpp"
+
+using namespace csm_host;
+
+extern "C" {
+
+struct csm_host_summary
+{
+    int32_t found, best_x, best_y, best_t;
+    int64_t sum_value;
+    int32_t n_known, flags;
+    double  score;
+    double  norm_cost;
+    double  est_pose[3];
+    double  cov[9];
+};
+
+static void Export(const ScanMatchingSummary& s, csm_host_summary* out)
+{
+    out->found = s.pose_found ? 1 : 0;
+    out->best_x = s.best_x; out->best_y = s.best_y; out->best_t = s.best_theta;
+    out->sum_value = s.sum_value; out->n_known = s.n_known; out->flags = s.flags;
+    out->score = s.normalized_score;
+    out->norm_cost = s.normalized_cost;
+    out->est_pose[0] = s.estimated_pose.x; out->est_pose[1] = s.estimated_pose.y;
+    out->est_pose[2] = s.estimated_pose.theta;
+    std::memcpy(out->cov, s.estimated_covariance.data(), sizeof(double) * 9);
+}
+
+void* csm_host_context_create(int device) { return new DeviceContextPtr(std::make_shared<DeviceContext>(device)); }
+void csm_host_context_destroy(void* ctx) { delete static_cast<DeviceContextPtr*>(ctx); }
+
+static GridMapView View(const uint16_t* values, int rows, int cols, double res, double ox, double oy, int64_t id)
+{
+    GridMapView v;
+    v.values = values; v.rows = rows; v.cols = cols; v.resolution = res;
+    v.offset_x = ox; v.offset_y = oy; v.map_id = id;
+    return v;
+}
+
+static ScanDataPtr Scan(const double* angles, const double* ranges, int n, const double rel[3])
+{
+    auto s = std::make_shared<ScanData>();
+    s->angles.assign(angles, angles + n);
+    s->ranges.assign(ranges, ranges + n);
+    s->relative_sensor_pose = Pose2D { rel[0], rel[1], rel[2] };
+    return s;
+}
+
+/* CPU epilogue alone: cost / N and covariance at a given sensor pose (no device needed) */
+int csm_host_cost(const uint16_t* values, int rows, int cols, double res, double off_x, double off_y,
+                  const double* angles, const double* ranges, int n, const double sensor_pose[3],
+                  double covariance_scale, double* norm_cost, double cov[9])
+{
+    const CostSquareError cost(covariance_scale);
+    const GridMapView map = View(values, rows, cols, res, off_x, off_y, -1);
+    const double rel[3] = { 0.0, 0.0, 0.0 };
+    const ScanDataPtr scan = Scan(angles, ranges, n, rel);
+    const Pose2D pose { sensor_pose[0], sensor_pose[1], sensor_pose[2] };
+    *norm_cost = cost.Cost(map, *scan, pose) / static_cast<double>(n);
+    const std::array<double, 9> c = cost.ComputeCovariance(map, *scan, pose);
+    std::memcpy(cov, c.data(), sizeof(double) * 9);
+    return 0;
+}
+
+/* kind: 0 = RealTimeCorrelative, 1 = BranchBound, 2 = GridSearch.
+ * iparam: lowResolution / nodeHeightMax; range[3]; step[3] (grid search only). */
+int csm_host_match(void* ctx, int kind, const uint16_t* values, int rows, int cols, double res,
+                   double off_x, double off_y, const double* angles, const double* ranges, int n,
+                   const double init_pose[3], const double rel_pose[3], int iparam,
+                   const double range[3], const double step[3], double score_thr, double known_thr,
+                   double covariance_scale, csm_host_summary* out)
+{
+    const DeviceContextPtr& c = *static_cast<DeviceContextPtr*>(ctx);
+    const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+    const GridMapView map = View(values, rows, cols, res, off_x, off_y, -1);
+    const ScanDataPtr scan = Scan(angles, ranges, n, rel_pose);
+    const Pose2D init { init_pose[0], init_pose[1], init_pose[2] };
+    ScanMatchingSummary s;
+    if (kind == 0) {
+        ScanMatcherCorrelative m("RealTimeCorrelativeGPU", cost, iparam, range[0], range[1], range[2], c);
+        s = m.OptimizePose(map, scan, init, score_thr, known_thr);
+    } else if (kind == 1) {
+        ScanMatcherBranchBound m("BranchBoundGPU", cost, iparam, range[0], range[1], range[2], c);
+        s = m.OptimizePose(map, scan, init, score_thr, known_thr);
+    } else if (kind == 2) {
+        ScanMatcherGridSearch m("GridSearchGPU", cost, range[0], range[1], range[2],
+                                step[0], step[1], step[2], c);
+        s = m.OptimizePose(map, scan, init, score_thr, known_thr);
+    } else {
+        return -1;
+    }
+    Export(s, out);
+    return 0;
+}
+
+/* LoopDetectorBranchBound::Detect over n_queries maps and one shared scan.
+ * values: n_queries grids of rows x cols, consecutive. out[q].found = 0 when no result. */
+int csm_host_loop_detect(void* ctx, int n_queries, const uint16_t* values, int rows, int cols, double res,
+                         const double* off_x, const double* off_y, const int64_t* map_ids,
+                         const double* map_poses, const double* scan_poses,
+                         const double* angles, const double* ranges, int n,
+                         int hmax, const double range[3], double score_thr, double known_thr,
+                         double covariance_scale, csm_host_summary* out)
+{
+    const DeviceContextPtr& c = *static_cast<DeviceContextPtr*>(ctx);
+    const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+    auto matcher = std::make_shared<ScanMatcherBranchBound>("LoopBBGPU", cost, hmax, range[0], range[1], range[2], c);
+    LoopDetectorBranchBound det("LoopDetectorBranchBoundGPU", matcher, FinalMatcher(), score_thr, known_thr);
+    const double rel[3] = { 0.0, 0.0, 0.0 };
+    const ScanDataPtr scan = Scan(angles, ranges, n, rel);
+    std::vector<LoopDetectionQuery> queries(n_queries);
+    const size_t cells = static_cast<size_t>(rows) * cols;
+    for (int q = 0; q < n_queries; ++q) {
+        LoopDetectionQuery& lq = queries[q];
+        lq.scan = scan;
+        lq.scan_id = 0;
+        lq.scan_node_id = q;
+        lq.scan_global_pose = Pose2D { scan_poses[3 * q], scan_poses[3 * q + 1], scan_poses[3 * q + 2] };
+        lq.local_map = View(values + q * cells, rows, cols, res, off_x[q], off_y[q], map_ids[q]);
+        lq.local_map_global_pose = Pose2D { map_poses[3 * q], map_poses[3 * q + 1], map_poses[3 * q + 2] };
+    }
+    const std::vector<LoopDetectionResult> results = det.Detect(queries);
+    for (int q = 0; q < n_queries; ++q)
+        std::memset(&out[q], 0, sizeof(csm_host_summary));
+    for (const LoopDetectionResult& r : results) {
+        csm_host_summary& o = out[r.scan_node_id];
+        const csm_result& d = det.LastResults()[r.query_index];
+        o.found = 1;
+        o.best_x = d.best_x; o.best_y = d.best_y; o.best_t = d.best_t;
+        o.sum_value = d.sum_value; o.n_known = d.n_known; o.flags = d.flags;
+        o.score = d.normalized_score;
+        o.est_pose[0] = r.relative_pose.x; o.est_pose[1] = r.relative_pose.y; o.est_pose[2] = r.relative_pose.theta;
+        std::memcpy(o.cov, r.estimated_covariance.data(), sizeof(double) * 9);
+    }
+    for (int q = 0; q < n_queries; ++q)
+        csm_release_grid(c->Handle(), map_ids[q]);
+    return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,129 @@
+#include "csm_host/cost_square_error.hpp"
+
+#include <algorithm>
+
+namespace csm_host {
+
+namespace {
+
+constexpr int kLog2Block = 4;     /* reference block size 16 (launcher_settings_default.json:178) */
+
+/* p(v): grid_values.hpp:26-36 */
+inline double Probability(std::uint16_t v)
+{
+    if (v == 0)
+        return 0.0;
+    const double pmin = 1e-3, pmax = 1.0 - 1e-3;
+    return pmin + (pmax - pmin) * static_cast<double>(static_cast<int>(v) - 1) / 65534.0;
+}
+
+struct Sampler
+{
+    const GridMapView& map;
+    std::vector<std::uint8_t> derived;     /* block allocation when the caller gave none */
+    const std::uint8_t* alloc;
+    int block_cols;
+
+    explicit Sampler(const GridMapView& m) : map(m), alloc(m.block_allocated),
+        block_cols((m.cols + 15) >> kLog2Block)
+    {
+        if (alloc == nullptr) {
+            const int block_rows = (m.rows + 15) >> kLog2Block;
+            derived.assign(static_cast<std::size_t>(block_rows) * block_cols, 0);
+            for (int r = 0; r < m.rows; ++r)
+                for (int c = 0; c < m.cols; ++c)
+                    if (m.values[static_cast<std::size_t>(r) * m.cols + c] != 0)
+                        derived[(r >> kLog2Block) * block_cols + (c >> kLog2Block)] = 1;
+            alloc = derived.data();
+        }
+    }
+
+    /* GridMap::ProbabilityOr(row, col, 0.5): grid_map.cpp:424-436 */
+    double At(int row, int col) const
+    {
+        if (row < 0 || row >= map.rows || col < 0 || col >= map.cols)
+            return 0.5;
+        if (!alloc[(row >> kLog2Block) * block_cols + (col >> kLog2Block)])
+            return 0.5;
+        return Probability(map.values[static_cast<std::size_t>(row) * map.cols + col]);
+    }
+};
+
+struct Neighbours
+{
+    double dx, dy, m00, m01, m10, m11;
+
+    double Smoothed() const
+    {
+        return dy * (dx * m11 + (1.0 - dx) * m01) + (1.0 - dy) * (dx * m10 + (1.0 - dx) * m00);
+    }
+};
+
+Neighbours Closest(const Sampler& s, double fx, double fy)
+{
+    const double x0 = std::floor(fx), y0 = std::floor(fy);
+    const int xc0 = std::max(static_cast<int>(x0), 0);
+    const int yc0 = std::max(static_cast<int>(y0), 0);
+    const int xc1 = std::min(xc0 + 1, s.map.cols - 1);
+    const int yc1 = std::min(yc0 + 1, s.map.rows - 1);
+    return Neighbours { fx - x0, fy - y0, s.At(yc0, xc0), s.At(yc1, xc0), s.At(yc0, xc1), s.At(yc1, xc1) };
+}
+
+inline void HitPoint(const ScanData& scan, const Pose2D& pose, std::size_t i, double& hx, double& hy)
+{
+    /* sensor_data.hpp:190-203 */
+    const double c = std::cos(pose.theta + scan.angles[i]);
+    const double s = std::sin(pose.theta + scan.angles[i]);
+    hx = pose.x + scan.ranges[i] * c;
+    hy = pose.y + scan.ranges[i] * s;
+}
+
+} /* namespace */
+
+double CostSquareError::Cost(const GridMapView& map, const ScanData& scan, const Pose2D& pose) const
+{
+    const Sampler sampler(map);
+    double cost = 0.0;
+    for (std::size_t i = 0; i < scan.NumOfScans(); ++i) {
+        double hx, hy;
+        HitPoint(scan, pose, i, hx, hy);
+        const double fx = (hx - map.offset_x) / map.resolution;
+        const double fy = (hy - map.offset_y) / map.resolution;
+        cost += std::pow(1.0 - Closest(sampler, fx, fy).Smoothed(), 2.0);
+    }
+    return cost;
+}
+
+std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map, const ScanData& scan,
+                                                         const Pose2D& pose) const
+{
+    const Sampler sampler(map);
+    double h[9] = { 0.0 };
+    const double inv_res = 1.0 / map.resolution;
+    for (std::size_t i = 0; i < scan.NumOfScans(); ++i) {
+        double hx, hy;
+        HitPoint(scan, pose, i, hx, hy);
+        const double fx = (hx - map.offset_x) / map.resolution;
+        const double fy = (hy - map.offset_y) / map.resolution;
+        const Neighbours n = Closest(sampler, fx, fy);
+        const double gx = n.dy * (n.m11 - n.m01) + (1.0 - n.dy) * (n.m10 - n.m00);
+        const double gy = n.dx * (n.m11 - n.m10) + (1.0 - n.dx) * (n.m01 - n.m00);
+        const double gt = -(hy - pose.y) * gx + (hx - pose.x) * gy;
+        const double g[3] = { gx * inv_res, gy * inv_res, gt * inv_res };
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                h[r * 3 + c] += g[r] * g[c];
+    }
+    const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) +
+                       h[2] * (h[3] * h[7] - h[4] * h[6]);
+    const double id = 1.0 / det;
+    std::array<double, 9> cov {
+        (h[4] * h[8] - h[5] * h[7]) * id, (h[2] * h[7] - h[1] * h[8]) * id, (h[1] * h[5] - h[2] * h[4]) * id,
+        (h[5] * h[6] - h[3] * h[8]) * id, (h[0] * h[8] - h[2] * h[6]) * id, (h[2] * h[3] - h[0] * h[5]) * id,
+        (h[3] * h[7] - h[4] * h[6]) * id, (h[1] * h[6] - h[0] * h[7]) * id, (h[0] * h[4] - h[1] * h[3]) * id };
+    for (double& v : cov)
+        v *= mCovarianceScale;
+    return cov;
+}
+
+} /* namespace csm_host */

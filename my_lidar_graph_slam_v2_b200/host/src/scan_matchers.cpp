@@ -1,0 +1,210 @@
+#include "csm_host/scan_matchers.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace csm_host {
+
+DeviceContext::DeviceContext(int device) : mHandle(nullptr)
+{
+    const int rc = csm_create(device, 0, &mHandle);
+    if (rc != CSM_OK) {
+        /* no CPU fallback: like a failed Assert in the reference (util.hpp:39-72) */
+        std::fprintf(stderr, "csm_host: csm_create(device %d) failed with %d\n", device, rc);
+        std::abort();
+    }
+}
+
+DeviceContext::~DeviceContext()
+{
+    if (mHandle != nullptr)
+        csm_destroy(mHandle);
+}
+
+void DeviceContext::Check(int rc, const char* what) const
+{
+    if (rc == CSM_OK)
+        return;
+    std::fprintf(stderr, "csm_host: %s failed (%d): %s\n", what, rc, csm_last_error(mHandle));
+    std::abort();
+}
+
+std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
+{
+    /* Anonymous maps (front-end latest map, rebuilt per scan,
+     * lidar_graph_slam.cpp:233-240) are uploaded on every call under a private id */
+    const std::int64_t id = map.map_id >= 0 ? map.map_id : (std::int64_t(1) << 40);
+    const bool resident = map.map_id >= 0 &&
+        std::find(mResidentMaps.begin(), mResidentMaps.end(), id) != mResidentMaps.end();
+    if (!resident) {
+        mContext->Check(csm_upload_grid(mContext->Handle(), id, map.values, map.rows, map.cols,
+                                        map.resolution, map.offset_x, map.offset_y), "csm_upload_grid");
+        if (map.map_id >= 0)
+            mResidentMaps.push_back(id);
+    }
+    return id;
+}
+
+void ScanMatcher::Epilogue(const GridMapView& map, const ScanData& scan, const Pose2D& best,
+                           const CostFuncPtr& cost, ScanMatchingSummary& summary) const
+{
+    summary.normalized_cost = cost->Cost(map, scan, best) / static_cast<double>(scan.NumOfScans());
+    summary.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
+    summary.estimated_covariance = cost->ComputeCovariance(map, scan, best);
+}
+
+void ComputeSearchStep(double resolution, const ScanData& scan,
+                       double& step_x, double& step_y, double& step_theta)
+{
+    const double max_range = *std::max_element(scan.ranges.begin(), scan.ranges.end());
+    const double theta = resolution / max_range;
+    step_x = resolution;
+    step_y = resolution;
+    step_theta = std::acos(1.0 - 0.5 * theta * theta);
+}
+
+namespace {
+
+void FillFromDevice(const csm_result& r, ScanMatchingSummary& s)
+{
+    s.pose_found = r.found != 0;
+    s.best_x = r.best_x; s.best_y = r.best_y; s.best_theta = r.best_t;
+    s.sum_value = r.sum_value; s.n_known = r.n_known;
+    s.normalized_score = r.normalized_score;
+    s.flags = r.flags;
+    s.n_processed = r.n_processed; s.n_ignored = r.n_ignored;
+}
+
+/* `for (d = -r; d <= r; d += s)`, scan_matcher_grid_search.cpp:118-120 */
+std::vector<double> Offsets(double radius, double step)
+{
+    std::vector<double> out;
+    for (double d = -radius; d <= radius; d += step)
+        out.push_back(d);
+    return out;
+}
+
+} /* namespace */
+
+/* ---- real-time correlative ------------------------------------------------ */
+ScanMatcherCorrelative::ScanMatcherCorrelative(
+    const std::string& name, const CostFuncPtr& cost, int low_resolution,
+    double range_x, double range_y, double range_theta, const DeviceContextPtr& context) :
+    ScanMatcher(name, context), mCost(cost), mLowResolution(low_resolution),
+    mRangeX(range_x), mRangeY(range_y), mRangeTheta(range_theta) { }
+
+ScanMatchingSummary ScanMatcherCorrelative::OptimizePose(const ScanMatchingQuery& query)
+{
+    /* scan_matcher_correlative.cpp:92-115: thresholds 0 search the whole window */
+    return OptimizePose(query.grid_map, query.scan_data, query.map_local_initial_pose, 0.0, 0.0);
+}
+
+ScanMatchingSummary ScanMatcherCorrelative::OptimizePose(
+    const GridMapView& map, const ScanDataPtr& scan, const Pose2D& initial_pose,
+    double score_threshold, double known_rate_threshold)
+{
+    csm_handle h = mContext->Handle();
+    const std::int64_t id = EnsureMap(map);
+    mContext->Check(csm_build_coarse(h, id, mLowResolution), "csm_build_coarse");   /* ComputeCoarserMap */
+    const Pose2D sensor = Compound(initial_pose, scan->relative_sensor_pose);
+    double sx, sy, st;
+    ComputeSearchStep(map.resolution, *scan, sx, sy, st);
+    const int win_x = static_cast<int>(std::ceil(0.5 * mRangeX / sx));
+    const int win_y = static_cast<int>(std::ceil(0.5 * mRangeY / sy));
+    const int win_t = static_cast<int>(std::ceil(0.5 * mRangeTheta / st));
+    const double pose[3] = { sensor.x, sensor.y, sensor.theta };
+    csm_result r;
+    mContext->Check(csm_match_rt(h, id, scan->angles.data(), scan->ranges.data(),
+                                 static_cast<int>(scan->NumOfScans()), pose, mLowResolution,
+                                 win_x, win_y, win_t, sx, sy, st,
+                                 score_threshold, known_rate_threshold, &r), "csm_match_rt");
+    ScanMatchingSummary s;
+    FillFromDevice(r, s);
+    s.map_local_initial_pose = initial_pose;
+    const Pose2D best { sensor.x + r.best_x * sx, sensor.y + r.best_y * sy, sensor.theta + r.best_t * st };
+    Epilogue(map, *scan, best, mCost, s);
+    return s;
+}
+
+/* ---- branch and bound --------------------------------------------------------- */
+ScanMatcherBranchBound::ScanMatcherBranchBound(
+    const std::string& name, const CostFuncPtr& cost, int node_height_max,
+    double range_x, double range_y, double range_theta, const DeviceContextPtr& context) :
+    ScanMatcher(name, context), mCost(cost), mNodeHeightMax(node_height_max),
+    mRangeX(range_x), mRangeY(range_y), mRangeTheta(range_theta) { }
+
+ScanMatchingSummary ScanMatcherBranchBound::OptimizePose(const ScanMatchingQuery& query)
+{
+    return OptimizePose(query.grid_map, query.scan_data, query.map_local_initial_pose, 0.0, 0.0);
+}
+
+ScanMatchingSummary ScanMatcherBranchBound::OptimizePose(
+    const GridMapView& map, const ScanDataPtr& scan, const Pose2D& initial_pose,
+    double score_threshold, double known_rate_threshold)
+{
+    csm_handle h = mContext->Handle();
+    const std::int64_t id = EnsureMap(map);
+    mContext->Check(csm_build_pyramid(h, id, mNodeHeightMax), "csm_build_pyramid");  /* ComputeCoarserMaps */
+    const Pose2D sensor = Compound(initial_pose, scan->relative_sensor_pose);
+    double sx, sy, st;
+    ComputeSearchStep(map.resolution, *scan, sx, sy, st);
+    const int win_x = static_cast<int>(std::ceil(0.5 * mRangeX / sx));
+    const int win_y = static_cast<int>(std::ceil(0.5 * mRangeY / sy));
+    const int win_t = static_cast<int>(std::ceil(0.5 * mRangeTheta / st));
+    const double pose[3] = { sensor.x, sensor.y, sensor.theta };
+    csm_result r;
+    mContext->Check(csm_match_bb(h, id, scan->angles.data(), scan->ranges.data(),
+                                 static_cast<int>(scan->NumOfScans()), pose, mNodeHeightMax,
+                                 win_x, win_y, win_t, sx, sy, st,
+                                 score_threshold, known_rate_threshold, &r), "csm_match_bb");
+    ScanMatchingSummary s;
+    FillFromDevice(r, s);
+    s.map_local_initial_pose = initial_pose;
+    const Pose2D best { sensor.x + sx * r.best_x, sensor.y + sy * r.best_y, sensor.theta + st * r.best_t };
+    Epilogue(map, *scan, best, mCost, s);
+    return s;
+}
+
+/* ---- grid search ----------------------------------------------------------------- */
+ScanMatcherGridSearch::ScanMatcherGridSearch(
+    const std::string& name, const CostFuncPtr& cost, double range_x, double range_y,
+    double range_theta, double step_x, double step_y, double step_theta,
+    const DeviceContextPtr& context) :
+    ScanMatcher(name, context), mCost(cost), mRangeX(range_x), mRangeY(range_y),
+    mRangeTheta(range_theta), mStepX(step_x), mStepY(step_y), mStepTheta(step_theta) { }
+
+ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(const ScanMatchingQuery& query)
+{
+    return OptimizePose(query.grid_map, query.scan_data, query.map_local_initial_pose, 0.0, 0.0);
+}
+
+ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(
+    const GridMapView& map, const ScanDataPtr& scan, const Pose2D& initial_pose,
+    double score_threshold, double known_rate_threshold)
+{
+    csm_handle h = mContext->Handle();
+    const std::int64_t id = EnsureMap(map);
+    const Pose2D sensor = Compound(initial_pose, scan->relative_sensor_pose);
+    const std::vector<double> dx = Offsets(mRangeX / 2.0, mStepX);
+    const std::vector<double> dy = Offsets(mRangeY / 2.0, mStepY);
+    const std::vector<double> dt = Offsets(mRangeTheta / 2.0, mStepTheta);
+    const double pose[3] = { sensor.x, sensor.y, sensor.theta };
+    csm_result r;
+    mContext->Check(csm_match_grid(h, id, scan->angles.data(), scan->ranges.data(),
+                                   static_cast<int>(scan->NumOfScans()), pose,
+                                   dx.data(), static_cast<int>(dx.size()),
+                                   dy.data(), static_cast<int>(dy.size()),
+                                   dt.data(), static_cast<int>(dt.size()),
+                                   score_threshold, known_rate_threshold, &r), "csm_match_grid");
+    ScanMatchingSummary s;
+    FillFromDevice(r, s);
+    s.map_local_initial_pose = initial_pose;
+    Pose2D best = sensor;     /* reference: bestSensorPose starts at the sensor pose (:113) */
+    if (r.found)
+        best = Pose2D { sensor.x + dx[r.best_x], sensor.y + dy[r.best_y], sensor.theta + dt[r.best_t] };
+    Epilogue(map, *scan, best, mCost, s);
+    return s;
+}
+
+} /* namespace csm_host */

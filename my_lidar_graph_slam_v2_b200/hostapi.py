@@ -1,0 +1,108 @@
+"""ctypes access to libcsm_host.so, the C++ mirror of the reference's plugin
+interface (host/include/csm_host). Used by the parity tests to drive the C++
+adapter classes end to end; applications link the C++ classes directly."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libcsm_host.so")
+
+
+class HostSummary(C.Structure):
+    _fields_ = [
+        ("found", C.c_int32), ("best_x", C.c_int32), ("best_y", C.c_int32), ("best_t", C.c_int32),
+        ("sum_value", C.c_int64), ("n_known", C.c_int32), ("flags", C.c_int32),
+        ("score", C.c_double), ("norm_cost", C.c_double), ("est_pose", C.c_double * 3),
+        ("cov", C.c_double * 9),
+    ]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise FileNotFoundError("%s not built: run python my_lidar_graph_slam_v2_b200/host/build_host.py" % LIB)
+        lib = C.CDLL(LIB)
+        dp = C.POINTER(C.c_double)
+        lib.csm_host_context_create.restype = C.c_void_p
+        lib.csm_host_context_create.argtypes = [C.c_int]
+        lib.csm_host_context_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_cost.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                      dp, dp, C.c_int, dp, C.c_double, dp, dp]
+        lib.csm_host_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                       C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, C.c_int, dp, dp,
+                                       C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
+        lib.csm_host_loop_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                             dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int, C.c_int,
+                                             dp, C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
+        _lib = lib
+    return _lib
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def cost(grid, res, off, angles, ranges, sensor_pose, covariance_scale=1e4):
+    lib = load()
+    g = np.ascontiguousarray(grid, dtype=np.uint16)
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    p, pp = _d(sensor_pose)
+    nc = C.c_double()
+    cov = (C.c_double * 9)()
+    lib.csm_host_cost(g.ctypes.data, g.shape[0], g.shape[1], res, off[0], off[1], ap, rp, len(a), pp,
+                      covariance_scale, C.byref(nc), cov)
+    return nc.value, np.array(cov)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = load()
+        self.ctx = self.lib.csm_host_context_create(device)
+
+    def close(self):
+        if self.ctx:
+            self.lib.csm_host_context_destroy(self.ctx)
+            self.ctx = None
+
+    def match(self, kind, grid, res, off, angles, ranges, init_pose, iparam, rng, step=(0, 0, 0),
+              thr=(0.0, 0.0), rel_pose=(0.0, 0.0, 0.0), covariance_scale=1e4):
+        g = np.ascontiguousarray(grid, dtype=np.uint16)
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        p, pp = _d(init_pose)
+        q, qp = _d(rel_pose)
+        rg, rgp = _d(rng)
+        st, stp = _d(step)
+        out = HostSummary()
+        rc = self.lib.csm_host_match(self.ctx, {"rt": 0, "bb": 1, "grid": 2}[kind], g.ctypes.data,
+                                     g.shape[0], g.shape[1], res, off[0], off[1], ap, rp, len(a), pp, qp,
+                                     iparam, rgp, stp, thr[0], thr[1], covariance_scale, C.byref(out))
+        assert rc == 0
+        return out
+
+    def loop_detect(self, grids, res, off_x, off_y, map_ids, map_poses, scan_poses, angles, ranges,
+                    hmax, rng, thr, covariance_scale=1e4):
+        g = np.ascontiguousarray(grids, dtype=np.uint16)
+        nq = g.shape[0]
+        ox, oxp = _d(off_x)
+        oy, oyp = _d(off_y)
+        ids = np.ascontiguousarray(map_ids, dtype=np.int64)
+        mp, mpp = _d(np.asarray(map_poses).reshape(-1))
+        sp, spp = _d(np.asarray(scan_poses).reshape(-1))
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        rg, rgp = _d(rng)
+        out = (HostSummary * nq)()
+        rc = self.lib.csm_host_loop_detect(self.ctx, nq, g.ctypes.data, g.shape[1], g.shape[2], res, oxp, oyp,
+                                           ids.ctypes.data_as(C.POINTER(C.c_int64)), mpp, spp, ap, rp, len(a),
+                                           hmax, rgp, thr[0], thr[1], covariance_scale, out)
+        assert rc == 0
+        return list(out)

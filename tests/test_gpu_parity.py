@@ -300,3 +300,63 @@ def test_errors(handle):
     with pytest.raises(capi.CsmError):
         handle.build_pyramid(9, 9)                           # hmax out of range
     handle.release_grid(9)
+
+
+# --------------------------------------------------------------------------
+# the C++ plugin mirror (host/include/csm_host) end to end
+# --------------------------------------------------------------------------
+def _cmp_host(s, o, what):
+    assert s.found == o.found, what
+    assert (s.best_x, s.best_y, s.best_t, s.sum_value, s.n_known) == \
+           (o.best_x, o.best_y, o.best_t, o.sum_value, o.n_known), what
+    assert s.score == o.score, what
+    assert list(s.est_pose) == list(o.est_pose), what            # refined pose: bit-identical
+    assert s.norm_cost == o.norm_cost, what
+    assert np.allclose(list(s.cov), list(o.cov), rtol=1e-9, atol=0.0), what
+
+
+@pytest.mark.parametrize("seed", range(2400, 2404))
+def test_cpp_adapter_matchers(checker, seed):
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    case = synth.case_for(synth.CFG1, seed)
+    s = case.submap
+    g = checker.grid(s.grid, s.res, s.off_x, s.off_y)
+    rel = (0.1, -0.03, 0.2)
+    off = (s.off_x, s.off_y)
+    a = ctx.match("rt", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"],
+                  thr=(0.2, 0.3), rel_pose=rel)
+    _cmp_host(a, checker.match_rt(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"],
+                                  (0.2, 0.3), rel), "rt")
+    a = ctx.match("bb", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"],
+                  rel_pose=rel)
+    _cmp_host(a, checker.match_bb(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"],
+                                  (0.0, 0.0), rel), "bb")
+    a = ctx.match("grid", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 0, (0.4, 0.3, 0.05),
+                  step=(0.05, 0.05, 0.005), rel_pose=rel)
+    _cmp_host(a, checker.match_grid(g, case.angles, case.ranges, case.init_pose, (0.4, 0.3, 0.05),
+                                    (0.05, 0.05, 0.005), (0.0, 0.0), rel), "grid")
+    ctx.close()
+
+
+def test_cpp_adapter_loop_detector(checker):
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    batch = synth.make_loop_batch(3200, n_maps=20, true_fraction=0.4, map_id_base=7000)
+    grids = np.stack([s.grid for s in batch.submaps])
+    res = ctx.loop_detect(grids, batch.submaps[0].res, [s.off_x for s in batch.submaps],
+                          [s.off_y for s in batch.submaps], batch.map_ids, batch.map_poses, batch.scan_poses,
+                          batch.angles[0], batch.ranges[0], 6, synth.CFG3["rng"], synth.CFG3["thr"])
+    og = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    ores, _ = odet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    assert sum(o.found for o in ores) > 0
+    for i, (r, o) in enumerate(zip(res, ores)):
+        assert r.found == o.found, i
+        if o.found:
+            assert (r.best_x, r.best_y, r.best_t, r.sum_value, r.n_known) == \
+                   (o.best_x, o.best_y, o.best_t, o.sum_value, o.n_known), i
+            assert r.score == o.score and list(r.est_pose) == list(o.est_pose), i
+            assert np.allclose(list(r.cov), list(o.cov), rtol=1e-9, atol=0.0), i
+    ctx.close()

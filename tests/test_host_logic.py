@@ -99,3 +99,24 @@ def test_synthetic_generators_are_deterministic_and_capped():
 def test_build_flags_target_sm100a_only():
     flags = " ".join(build.NVCC_FLAGS)
     assert "arch=compute_100a,code=sm_100a" in flags and "-lineinfo" in flags
+
+
+def test_cpp_epilogue_cost_matches_reference_vectors():
+    """The C++ adapter's CPU epilogue (cost / covariance at the winning pose) against the golden
+    vectors of the reference: cost bit-identical, covariance within 1e-9 relative."""
+    from helpers import load_golden
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    gold = load_golden("reference_vectors.json")["matches"]
+    checked = 0
+    for m in gold:
+        if not m["expect"]["found"] or checked >= 12:
+            continue
+        case = synth.case_for(synth.CFG1, m["seed"])
+        s = case.submap
+        e = m["expect"]
+        nc, cov = hostapi.cost(s.grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges,
+                               e["best_sensor_pose"])
+        assert nc == e["norm_cost"], (m["kind"], m["seed"])
+        assert np.allclose(cov, e["cov"], rtol=1e-9, atol=0.0)
+        checked += 1
+    assert checked == 12
