@@ -236,16 +236,27 @@ void Flatten(const MapType& map, uint16_t* out)
 /* Final matcher that hands the coarse estimate through unchanged: the
  * sub-pixel refiners (scan_matcher_hill_climbing / linear_solver) are
  * outside the hot path */
+/* Final matcher of the loop detector: keeps the coarse pose (the sub-pixel
+ * refiner is outside the path) and reports the covariance the reference's own
+ * cost function gives at that pose, i.e. what the coarse matcher's epilogue
+ * computed and LoopDetectorBranchBound::Detect then discards
+ * (scan_matcher_branch_bound.cpp:237-262, loop_detector_branch_bound.cpp:123-135). */
 class PassThroughMatcher final : public ScanMatcher
 {
 public:
-    PassThroughMatcher() : ScanMatcher("PassThrough") { }
+    PassThroughMatcher() : ScanMatcher("PassThrough"),
+                           mCostFunc(std::make_shared<CostSquareError>(kCovarianceScale)) { }
     ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override
     {
+        const RobotPose2D<double> sensorPose = Compound(
+            query.mMapLocalInitialPose, query.mScanData->RelativeSensorPose());
         return ScanMatchingSummary { true, 0.0, query.mMapLocalInitialPose,
                                      query.mMapLocalInitialPose,
-                                     Eigen::Matrix3d::Zero() };
+                                     this->mCostFunc->ComputeCovariance(
+                                         query.mGridMap, query.mScanData, sensorPose) };
     }
+private:
+    std::shared_ptr<CostSquareError> mCostFunc;
 };
 
 struct RefLoopDetector
