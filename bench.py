@@ -220,7 +220,7 @@ class CudaArrayView:
 def main_cuda(args):
     import torch
     import torch.distributed as dist
-    from my_lidar_graph_slam_v2_b200 import capi, matchers, sharding, synth
+    from my_lidar_graph_slam_v2_b200 import capi, hostapi, matchers, sharding, synth
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -229,38 +229,48 @@ def main_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.load()
-    h = capi.Handle(local)
+    # The reference-facing plugin: the C++ LoopDetectorBranchBound of host/ (libcsm_host.so) on top
+    # of the C ABI. `h` is the csm_handle it runs on (device-side timing, best-word all-reduce).
+    ctx = hostapi.Context(local)
+    hdet = hostapi.LoopDetector(ctx, HMAX, synth.CFG3["rng"], synth.CFG3["thr"])
+    hdet.configure(chunk_size=128, coarse_covariance=False, query_index_base=rank * N_MAPS)
+    h = capi.Handle.from_pointer(hdet.handle(), local)
     ext_stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local))
 
     batch = make_batch(rank)
     cells = ROWS * COLS
-    # pinned host copies of the submaps (what the adapter flattens the reference maps into)
+    ids = np.arange(N_MAPS, dtype=np.int64)
+    offx = np.array([s.off_x for s in batch.submaps])
+    offy = np.array([s.off_y for s in batch.submaps])
+    res = batch.submaps[0].res
+    map_poses = np.ascontiguousarray(batch.map_poses, dtype=np.float64)
+    scan_poses = np.ascontiguousarray(batch.scan_poses, dtype=np.float64)
+    angles = np.ascontiguousarray(batch.angles[0], dtype=np.float64)
+    ranges = np.ascontiguousarray(batch.ranges[0], dtype=np.float64)
+
+    # Host inputs, page-locked. (a) the submaps in the reference's own storage form
+    # (grid_map.cpp:262-266): only the 16x16 blocks that were ever written, back to back, plus
+    # their positions -- what the adapter hands over without flattening; unallocated blocks never
+    # cross PCIe. (b) the same submaps flattened to dense row-major u16 (comparison leg).
+    LOG2BS = 4
+    parts = [synth.dense_to_blocks(s.grid, LOG2BS) for s in batch.submaps]
+    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+    n_blocks = int(counts.sum())
+    blk_bytes = 2 << (2 * LOG2BS)
+    blk_ptr = lib.csm_alloc_pinned(max(n_blocks, 1) * blk_bytes)
+    idx_ptr = lib.csm_alloc_pinned(max(n_blocks, 1) * 4)
+    np.ctypeslib.as_array((C.c_uint16 * (n_blocks * (blk_bytes // 2))).from_address(blk_ptr))[:] = \
+        np.concatenate([p[0].reshape(-1) for p in parts])
+    np.ctypeslib.as_array((C.c_int32 * n_blocks).from_address(idx_ptr))[:] = np.concatenate([p[1] for p in parts])
     host_ptr = lib.csm_alloc_pinned(N_MAPS * cells * 2)
     host = np.ctypeslib.as_array((C.c_uint16 * (N_MAPS * cells)).from_address(host_ptr)).reshape(N_MAPS, ROWS, COLS)
     for m, s in enumerate(batch.submaps):
         host[m] = s.grid
-    ids = np.arange(N_MAPS, dtype=np.int64)
-    ptrs = (C.c_void_p * N_MAPS)(*[host_ptr + m * cells * 2 for m in range(N_MAPS)])
-    offx = np.array([s.off_x for s in batch.submaps])
-    offy = np.array([s.off_y for s in batch.submaps])
-    res = batch.submaps[0].res
-
-    bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=h)
-    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
-    scan = matchers.ScanData(batch.angles[0], batch.ranges[0])
-    queries = [matchers.LoopDetectionQuery(
-        scan, 0, tuple(batch.scan_poses[i]),
-        matchers.GridMap(None, s.res, (s.off_x, s.off_y), int(ids[i])), tuple(batch.map_poses[i]), i)
-        for i, s in enumerate(batch.submaps)]
-    results = (capi.CsmResult * N_MAPS)()
+    n_chunks = (N_MAPS + 127) // 128
+    h2d_small = 2 * 360 * 8 + N_MAPS * (256 + 115 * 8 + 8 + 4)
+    h2d_blocks = n_blocks * (blk_bytes + 4) + (N_MAPS + n_chunks) * 4
+    summaries = (hostapi.HostSummary * N_MAPS)()
     best_word = torch.zeros(1, dtype=torch.int64, device="cuda")
-
-    def make_query_array():
-        # host math of the adapter: InverseCompound / Compound / steps / windows per query
-        h.upload_scan(0, scan.angles, scan.ranges)
-        det._cached_maps.update(int(i) for i in ids)
-        det._cached_scans[0] = scan
-        return det.prepare(queries)
 
     def allreduce_best():
         view = torch.as_tensor(CudaArrayView(h.best_key_device_ptr(), 1, "<i8"), device="cuda")
@@ -268,31 +278,17 @@ def main_cuda(args):
             best_word.copy_(view)
             sharding.allreduce_best(best_word)          # 8-byte all-reduce(max) over NCCL
 
-    N_CHUNKS = 2
-    CH = N_MAPS // N_CHUNKS
-    chunk_ids = [np.ascontiguousarray(ids[c * CH:(c + 1) * CH]) for c in range(N_CHUNKS)]
-    chunk_ptrs = [(C.c_void_p * CH)(*[host_ptr + m * cells * 2 for m in range(c * CH, (c + 1) * CH)])
-                  for c in range(N_CHUNKS)]
-    chunk_offx = [np.ascontiguousarray(offx[c * CH:(c + 1) * CH]) for c in range(N_CHUNKS)]
-    chunk_offy = [np.ascontiguousarray(offy[c * CH:(c + 1) * CH]) for c in range(N_CHUNKS)]
-    result_chunks = [(capi.CsmResult * CH).from_buffer(results, c * CH * C.sizeof(capi.CsmResult))
-                     for c in range(N_CHUNKS)]
-
-    def e2e_step():
-        """One Detect through the C ABI from pinned host buffers: the 256 submaps stream to the
-        device in 2 groups on the copy stream while pyramid build + B&B of the groups that have
-        already landed run on the compute stream."""
+    def e2e_step(sparse=True):
+        """One LoopDetector::Detect of the C++ plugin on 256 first-touch submaps, from page-locked
+        HOST buffers: upload (2 chunks on the copy stream), block expansion, pyramid build, batched
+        B&B, result read-back; then the 8-byte all-reduce of the best word and its read-back."""
+        hdet.clear_cache()                                  # every submap is a first touch again
         h.set_option("reset_best_key", 1)
-        for c in range(N_CHUNKS):                                          # H2D 128 MiB, async
-            h.upload_grids_ptr(chunk_ids[c], chunk_ptrs[c], ROWS, COLS, res, chunk_offx[c], chunk_offy[c])
-        h.upload_scan(0, scan.angles, scan.ranges)                         # H2D scan
-        for c in range(N_CHUNKS):
-            arr = det.prepare(queries[c * CH:(c + 1) * CH])                # host pose math of the adapter
-            h.build_pyramids(chunk_ids[c], HMAX)
-            h.loop_batch_enqueue(arr, CH, HMAX, rank * N_MAPS + c * CH)
-            h.loop_batch_finish(CH, result_chunks[c])                      # D2H results
+        n, _ = hdet.detect(N_MAPS, None if sparse else host_ptr, blk_ptr if sparse else None,
+                           idx_ptr if sparse else None, counts.ctypes.data if sparse else None, LOG2BS,
+                           ROWS, COLS, res, offx, offy, ids, map_poses, scan_poses, angles, ranges, summaries)
         allreduce_best()
-        return int(best_word.item())                                       # D2H best word
+        return n, int(best_word.item())                     # D2H best word
 
     def barrier():
         if world > 1:
@@ -311,38 +307,65 @@ def main_cuda(args):
         sampler.start()
 
     # ---- warm-up (also allocates every workspace) --------------------------------
-    det._cached_maps.update(int(i) for i in ids)
-    det._cached_scans[0] = scan
-    h.set_option("accumulate_best_key", 1)
+    h.set_option("accumulate_best_key", 1)        # a Detect is several device batches
     for _ in range(max(args.warmup, 3)):
-        word = e2e_step()
+        e2e_step()
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------
-    barrier()
+    def time_e2e(sparse):
+        for _ in range(2):
+            e2e_step(sparse)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n, w = e2e_step(sparse)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0), n, w
+
+    e2e_dense_s, n_dense, word_dense = time_e2e(False)
     sampler.active = True
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        word = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s, n_found, word = time_e2e(True)
     sampler.active = False
-    n_found = sum(r.found for r in results)
+    assert (n_found, word) == (n_dense, word_dense), "block-sparse and dense uploads disagree"
     key, qidx = h.decode_best_key(word)
 
     # ---- value: inputs resident in HBM, CUDA events on the handle's stream ------------------
     h.set_option("accumulate_best_key", 0)
-    arr = make_query_array()
+    bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=h)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    scan = matchers.ScanData(angles, ranges)
+    queries = [matchers.LoopDetectionQuery(
+        scan, 0, tuple(batch.scan_poses[i]),
+        matchers.GridMap(None, s.res, (s.off_x, s.off_y), int(ids[i])), tuple(batch.map_poses[i]), i)
+        for i, s in enumerate(batch.submaps)]
+    det._cached_maps.update(int(i) for i in ids)     # level 0 of every submap is resident from the e2e leg
+    det._cached_scans[0] = scan
+    h.upload_scan(0, scan.angles, scan.ranges)
+    arr = det.prepare(queries)
+    results = (capi.CsmResult * N_MAPS)()
     h.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    in_flight = [0]
 
     def device_step():
         h.drop_pyramids(ids)
         h.build_pyramids(ids, HMAX)
-        h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
+        h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)   # includes the read-back of the results
         allreduce_best()
+        in_flight[0] += 1
+        if in_flight[0] == 3:                                   # results of the step two back
+            h.loop_batch_finish(N_MAPS, results)
+            in_flight[0] -= 1
+
+    def drain():
+        while in_flight[0]:
+            h.loop_batch_finish(N_MAPS, results)
+            in_flight[0] -= 1
 
     for _ in range(3):
         device_step()
+    drain()
     barrier()
     launches0 = h.launch_count()
     sampler.active = True
@@ -352,11 +375,12 @@ def main_cuda(args):
     ev[1].record(ext_stream)
     ev[1].synchronize()
     sampler.active = False
+    drain()
     launches = h.launch_count() - launches0
     dev_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
-    h.loop_batch_finish(N_MAPS, results)
+    assert sum(r.found for r in results) == n_found
 
-    # ---- per-phase timing for the roofline of the dominant kernel -----------------------------
+    # ---- per-phase timing for the roofline of the dominant kernels ---------------------------
     barrier()
     ev[0].record(ext_stream)
     for _ in range(args.steps):
@@ -368,11 +392,11 @@ def main_cuda(args):
     ev[2].record(ext_stream)
     for _ in range(args.steps):
         h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
+        h.loop_batch_finish(N_MAPS, results)
     ev[3].record(ext_stream)
     ev[3].synchronize()
     bb_ms = ev[2].elapsed_time(ev[3]) / args.steps
-    h.loop_batch_finish(N_MAPS, results)
-    nodes = sum(r.n_processed for r in results)
+    nodes_scored = sum(h.frontier_counts()[:HMAX + 1])
 
     peaks = {}
     try:
@@ -381,31 +405,49 @@ def main_cuda(args):
     except (OSError, ValueError):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    pyr_bytes = (1 + HMAX) * cells * 2 * N_MAPS          # read level 0 once, write hmax levels
-    pyr_launches = HMAX * ((N_MAPS * cells * 2 + (24 << 20) - 1) // (24 << 20))
+    peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    step_ms = dev_ms / args.steps
+    # dominant kernel: k_bb_score (one launch per pyramid height). Algorithmic bytes:
+    # one u16 grid read per scored node and beam.
+    bb_bytes = nodes_scored * 360 * 2
     roofline = {
-        "kernel": "k_pyramid_level (PrecomputeGridMaps, %d launches per step)" % pyr_launches,
-        "bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak,
-        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
-        "algorithmic_bytes_per_launch": pyr_bytes // pyr_launches, "traffic": None,
-        "ms_per_step": pyr_ms, "share_of_step": pyr_ms / (dev_ms / args.steps),
+        "kernel": "k_bb_score (B&B frontier scoring, %d launches per step)" % (HMAX + 1),
+        "bound": "hbm", "achieved": bb_bytes / (bb_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": bb_bytes / (bb_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_source,
+        "algorithmic_bytes_per_step": bb_bytes, "nodes_scored_per_step": int(nodes_scored),
+        "traffic": None, "ms_per_step": bb_ms, "share_of_step": bb_ms / step_ms,
+        "note": "scattered 2-byte gathers: the binding unit is the L1TEX sector rate, not DRAM "
+                "(profiles/); ms_per_step is the whole loop batch (projection, %d scoring launches, "
+                "finalize, read-back)" % (HMAX + 1),
     }
-    phases = {"pyramid_ms": pyr_ms, "branch_and_bound_ms": bb_ms,
-              "bb_nodes_expanded_per_step": nodes,
-              "bb_gather_bytes_per_step": nodes * 4 * 360 * 2}
+    pyr_bytes = (1 + HMAX) * cells * 2 * N_MAPS          # read level 0 once, write hmax levels
+    roofline_pyramid = {
+        "kernel": "k_pyramid_stream (PrecomputeGridMaps, 1 launch per step)",
+        "bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_source,
+        "algorithmic_bytes_per_launch": pyr_bytes, "traffic": None,
+        "ms_per_step": pyr_ms, "share_of_step": pyr_ms / step_ms,
+    }
+    phases = {"pyramid_ms": pyr_ms, "branch_and_bound_ms": bb_ms}
 
     total_queries = world * N_MAPS * args.steps
     line = {
         "metric": METRIC, "value": total_queries / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/int64 (f64 projection)",
         "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": total_queries / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
-                "h2d_bytes_per_step": N_MAPS * cells * 2 + 2 * 360 * 8 + N_MAPS * (256 + 115 * 8 + 8),
-                "d2h_bytes_per_step": N_MAPS * C.sizeof(capi.CsmResult) + 8},
+                "h2d_bytes_per_step": h2d_blocks + h2d_small,
+                "d2h_bytes_per_step": N_MAPS * C.sizeof(capi.CsmResult) + 16 + 8,
+                "api": "C++ LoopDetectorBranchBound::Detect (host/, libcsm_host.so) over the C ABI",
+                "host_format": "block-sparse submaps (allocated 16x16 blocks + positions, the reference's "
+                               "GridMap storage), %d of %d blocks allocated" % (n_blocks, N_MAPS * (ROWS >> 4) * (COLS >> 4))},
+        "e2e_dense": {"value": total_queries / e2e_dense_s, "unit": UNIT,
+                      "ms_per_step": 1e3 * e2e_dense_s / args.steps,
+                      "h2d_bytes_per_step": N_MAPS * cells * 2 + h2d_small,
+                      "host_format": "dense flattened submaps (csm_upload_grids)"},
         "gpu_launches": int(launches),
-        "roofline": roofline, "phases": phases,
+        "roofline": roofline, "roofline_pyramid": roofline_pyramid, "phases": phases,
         "check": {"found_per_step": int(n_found), "best_key": int(key), "best_query": int(qidx)},
     }
 
@@ -429,17 +471,23 @@ def main_cuda(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    hdet.close()
+    ctx.close()
     lib.csm_free_pinned(host_ptr)
+    lib.csm_free_pinned(blk_ptr)
+    lib.csm_free_pinned(idx_ptr)
     return 0
 
 
 def single_scan_numbers(h, lib, kind):
-    """matches/s of the three single-scan matchers through the plugin-level API
-    (host buffers, grid upload + precompute + search + result readback per match)
-    next to the CPU checker on the same inputs (cfg1, cfg2, cfg4 of BASELINE.json)."""
+    """matches/s of the three single-scan matchers through the C++ plugin classes of host/
+    (ScanMatcher*::OptimizePose: host buffers in, grid upload + precompute + search + result
+    read-back + CPU cost/covariance epilogue per match) next to the CPU checker on the same
+    inputs (cfg1, cfg2, cfg4 of BASELINE.json)."""
     from oracle import pyoracle
-    from my_lidar_graph_slam_v2_b200 import matchers, synth
+    from my_lidar_graph_slam_v2_b200 import hostapi, synth
     orc = pyoracle.load(kind)
+    ctx = hostapi.Context(h.device)
     out = {}
 
     def timeit(fn, reps):
@@ -450,35 +498,37 @@ def single_scan_numbers(h, lib, kind):
         return reps / (time.perf_counter() - t0)
 
     case = synth.case_for(synth.CFG1, 41000)
-    gm = matchers.GridMap(case.submap.grid, case.submap.res, (case.submap.off_x, case.submap.off_y))
-    scan = matchers.ScanData(case.angles, case.ranges)
-    og = orc.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
-    rt = matchers.ScanMatcherCorrelative("rt", 5, *synth.CFG1["rng"], handle=h)
-    gpu = timeit(lambda: rt.optimize_pose(gm, scan, tuple(case.init_pose)), 200)
+    s = case.submap
+    off = (s.off_x, s.off_y)
+    og = orc.grid(s.grid, s.res, s.off_x, s.off_y)
+    gpu = timeit(lambda: ctx.match("rt", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5,
+                                   synth.CFG1["rng"]), 300)
     cpu = timeit(lambda: orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), 20)
-    out["cfg1_rt_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "cpu_kind": kind}
+    out["cfg1_rt_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
-    bbm = matchers.ScanMatcherBranchBound("bb", 5, *synth.CFG2["rng"], handle=h)
-    gpu = timeit(lambda: bbm.optimize_pose(gm, scan, tuple(case.init_pose)), 200)
+    gpu = timeit(lambda: ctx.match("bb", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5,
+                                   synth.CFG2["rng"]), 300)
     cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5)
-    out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "cpu_kind": kind}
+    out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
     c4 = synth.case_for(synth.CFG4, 44000)
-    gm4 = matchers.GridMap(c4.submap.grid, c4.submap.res, (c4.submap.off_x, c4.submap.off_y))
-    scan4 = matchers.ScanData(c4.angles, c4.ranges)
-    gs = matchers.ScanMatcherGridSearch("gs", *synth.CFG4["rng"], *synth.CFG4["step"], handle=h)
-    gpu = timeit(lambda: gs.optimize_pose(gm4, scan4, tuple(c4.init_pose)), 3)
+    s4 = c4.submap
+    gpu = timeit(lambda: ctx.match("grid", s4.grid, s4.res, (s4.off_x, s4.off_y), c4.angles, c4.ranges,
+                                   c4.init_pose, 0, synth.CFG4["rng"], step=synth.CFG4["step"]), 3)
     # CPU: 1/64 of the window (x and y ranges / 8), scaled by the candidate ratio
-    og4 = orc.grid(c4.submap.grid, c4.submap.res, c4.submap.off_x, c4.submap.off_y)
+    og4 = orc.grid(s4.grid, s4.res, s4.off_x, s4.off_y)
     rng_small = (synth.CFG4["rng"][0] / 8, synth.CFG4["rng"][1] / 8, synth.CFG4["rng"][2] / 8)
     t0 = time.perf_counter()
     r = orc.match_grid(og4, c4.angles, c4.ranges, c4.init_pose, rng_small, synth.CFG4["step"])
     el = time.perf_counter() - t0
     full = 161 * 161 * 601
+    cpu = 1.0 / (el * full / max(r.n_processed, 1))
     out["cfg4_grid_matches_per_s"] = {
-        "gpu_e2e": gpu, "cpu_1core_scaled": 1.0 / (el * full / max(r.n_processed, 1)),
+        "gpu_e2e": gpu, "cpu_1core_scaled": cpu, "ratio": gpu / cpu,
         "cpu_sample": "%d of %d candidates evaluated in %.2f s, scaled linearly" % (r.n_processed, full, el),
-        "cpu_kind": kind}
+        "cpu_kind": kind, "gather_bytes_per_match": full * 1080 * 2,
+        "gather_GBps": full * 1080 * 2 * gpu / 1e9}
+    ctx.close()
     return out
 
 

@@ -137,10 +137,34 @@ int csm_upload_grid_device(csm_handle h, int64_t map_id, const uint16_t* dense_d
 /* n maps of identical shape and resolution in one call. The copies run
  * asynchronously on the handle's copy stream (use pinned buffers) and overlap
  * kernels working on maps uploaded by earlier calls; whatever later touches
- * one of these maps waits for this call's copies only. */
+ * one of these maps waits for this call's copies only. Page-locked buffers
+ * must stay unchanged until csm_synchronize or a synchronous call that uses
+ * one of these maps (csm_match_*, csm_loop_batch_finish, csm_download_level)
+ * has returned. */
 int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t* const* dense,
                      int rows, int cols, double resolution,
                      const double* offset_x, const double* offset_y);
+/* Block-sparse upload: the reference stores a map as block_rows x block_cols
+ * blocks of 2^k x 2^k cells and allocates only the blocks that were ever
+ * written (grid_map.hpp:27, grid_map.cpp:262-266, 522-535); unallocated
+ * blocks read as unknown (0). The adapter hands over exactly that: the
+ * allocated blocks back to back (`blocks`, 4^k u16 each, row-major inside a
+ * block) and their positions (`block_index[b]` = block_row * block_cols +
+ * block_col). Only these bytes cross PCIe; a kernel expands them into the
+ * dense level-0 grid when the map is first used. Equivalent to
+ * csm_upload_grid with the flattened map. 3 <= log2_block_size <= 6. */
+int csm_upload_grid_blocks(csm_handle h, int64_t map_id, const uint16_t* blocks,
+                           const int32_t* block_index, int n_blocks, int log2_block_size,
+                           int block_rows, int block_cols, double resolution,
+                           double offset_x, double offset_y);
+/* n maps of identical geometry in one call: map i owns block_count[i]
+ * consecutive entries of `blocks` / `block_index`. One upload group, like
+ * csm_upload_grids. */
+int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
+                            const uint16_t* blocks, const int32_t* block_index,
+                            const int32_t* block_count, int log2_block_size,
+                            int block_rows, int block_cols, double resolution,
+                            const double* offset_x, const double* offset_y);
 int csm_release_grid(csm_handle h, int64_t map_id);
 
 /* PrecomputeGridMap(map, win) (grid_map_builder.cpp:1044-1065): sliding
@@ -206,9 +230,13 @@ int csm_match_grid(csm_handle h, int64_t map_id,
  * level-synchronous branch-and-bound launches. results[q] is per query, in
  * query order (the reference emits one result per successful query).
  *
- * csm_loop_batch_enqueue returns after enqueueing the work on the handle's
- * stream; csm_loop_batch_finish waits and copies the nq results to the host.
- * csm_loop_batch = enqueue + finish.
+ * csm_loop_batch_enqueue returns after enqueueing the work (including the
+ * read-back of the results into page-locked memory) on the handle's stream;
+ * csm_loop_batch_finish waits for the OLDEST batch in flight and hands out
+ * its nq results. Up to 4 batches may be in flight, so a Detect call split
+ * into chunks keeps the GPU busy while the host prepares the next chunk.
+ * csm_loop_batch = enqueue + finish. The single-scan matchers refuse to run
+ * while a batch is in flight on the same handle.
  *
  * After a batch, csm_best_key_device(h) points to one uint64 on the device:
  * max over the batch of (key << 20 | (0xFFFFF - (query_index_base + q))), 0 if no query

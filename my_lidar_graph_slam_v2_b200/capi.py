@@ -45,7 +45,8 @@ class CsmLoopQuery(C.Structure):
 EXPORTS = [
     "csm_version", "csm_device_count", "csm_create", "csm_destroy", "csm_last_error",
     "csm_stream", "csm_synchronize", "csm_launch_count", "csm_set_option", "csm_alloc_pinned", "csm_free_pinned",
-    "csm_upload_grid", "csm_upload_grid_device", "csm_upload_grids", "csm_release_grid", "csm_build_coarse",
+    "csm_upload_grid", "csm_upload_grid_device", "csm_upload_grids", "csm_upload_grid_blocks",
+    "csm_upload_grids_blocks", "csm_release_grid", "csm_build_coarse",
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
@@ -91,6 +92,11 @@ def load():
     lib.csm_upload_grid.argtypes = [H, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     lib.csm_upload_grid_device.argtypes = lib.csm_upload_grid.argtypes
     lib.csm_upload_grids.argtypes = [H, C.c_int, i64p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, dp, dp]
+    i32p = C.POINTER(C.c_int32)
+    lib.csm_upload_grid_blocks.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_double, C.c_double, C.c_double]
+    lib.csm_upload_grids_blocks.argtypes = [H, C.c_int, i64p, C.c_void_p, C.c_void_p, i32p, C.c_int, C.c_int,
+                                            C.c_int, C.c_double, dp, dp]
     lib.csm_release_grid.argtypes = [H, C.c_int64]
     lib.csm_build_coarse.argtypes = [H, C.c_int64, C.c_int]
     lib.csm_build_pyramid.argtypes = [H, C.c_int64, C.c_int]
@@ -131,13 +137,24 @@ class Handle:
         self.h = h
         self.device = device
 
+    @classmethod
+    def from_pointer(cls, ptr, device=0):
+        """Non-owning view of a csm_handle created elsewhere (e.g. by the C++ host classes)."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.h = C.c_void_p(ptr)
+        self.device = device
+        self.borrowed = True
+        return self
+
     def _check(self, rc):
         if rc != CSM_OK:
             raise CsmError(rc, self.lib.csm_last_error(self.h).decode())
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.csm_destroy(self.h)
+            if not getattr(self, "borrowed", False):
+                self.lib.csm_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -173,6 +190,22 @@ class Handle:
         """map_ids: int64 array, ptrs: (c_void_p * n) of host buffers, off_x/off_y: float64 arrays."""
         self._check(self.lib.csm_upload_grids(self.h, len(map_ids), map_ids.ctypes.data_as(C.POINTER(C.c_int64)),
                                               ptrs, rows, cols, res, _dptr(off_x), _dptr(off_y)))
+
+    def upload_grid_blocks(self, map_id, blocks, block_index, log2bs, block_rows, block_cols, res, off_x, off_y):
+        """blocks: (n, bs, bs) uint16, block_index: (n,) int32 = block_row * block_cols + block_col."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint16)
+        block_index = np.ascontiguousarray(block_index, dtype=np.int32)
+        self._check(self.lib.csm_upload_grid_blocks(self.h, map_id, blocks.ctypes.data, block_index.ctypes.data,
+                                                    len(block_index), log2bs, block_rows, block_cols,
+                                                    res, off_x, off_y))
+
+    def upload_grids_blocks_ptr(self, map_ids, blocks_ptr, index_ptr, counts, log2bs, block_rows, block_cols,
+                                res, off_x, off_y):
+        """Batched block-sparse upload from raw host pointers (pinned for async copies)."""
+        self._check(self.lib.csm_upload_grids_blocks(
+            self.h, len(map_ids), map_ids.ctypes.data_as(C.POINTER(C.c_int64)), blocks_ptr, index_ptr,
+            counts.ctypes.data_as(C.POINTER(C.c_int32)), log2bs, block_rows, block_cols, res,
+            _dptr(off_x), _dptr(off_y)))
 
     def release_grid(self, map_id):
         self._check(self.lib.csm_release_grid(self.h, map_id))

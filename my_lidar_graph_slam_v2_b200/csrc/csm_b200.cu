@@ -33,6 +33,22 @@ struct ArenaBlock
     ~ArenaBlock() { if (p) cudaFreeAsync(p, stream); }
 };
 
+/* Block-sparse upload in flight: the allocated blocks of a batch of maps sit in
+ * a device staging buffer (filled by the copy stream); the first consumer of
+ * any of the maps expands the whole batch into the dense level-0 grids. */
+struct BlockScatter
+{
+    void* stage = nullptr;            /* [block data][block index][prefix], device */
+    size_t data_bytes = 0, index_off = 0, prefix_off = 0;
+    uint16_t* dense = nullptr;        /* level 0 of the first map; maps are contiguous */
+    int n_maps = 0, max_count = 0;
+    int log2bs = 0, block_cols = 0, rows = 0, cols = 0;
+    std::vector<int> prefix;          /* host copy, alive until the H2D copy has run */
+    bool done = false;
+    cudaStream_t stream = nullptr;
+    ~BlockScatter() { if (stage) cudaFreeAsync(stage, stream); }
+};
+
 struct MapSlot
 {
     int rows = 0, cols = 0;
@@ -45,6 +61,7 @@ struct MapSlot
     uint16_t* coarse = nullptr;
     int coarse_win = 0;
     cudaEvent_t pending_upload = nullptr;   /* copy-stream event the next consumer must wait for */
+    std::shared_ptr<BlockScatter> pending_scatter;   /* block-sparse upload not yet expanded */
 };
 
 struct ScanSlot
@@ -85,18 +102,23 @@ struct csm_context
     DevBuf d_list[2];
     DevBuf d_rtblocks, d_gridoff, d_gridpos, d_pyrjobs, d_tmpscan;
     unsigned int frontier_capacity = 0;
-    /* pinned staging: four upload areas used in turn (an area is reused
+    /* pinned staging: eight upload areas used in turn (an area is reused
      * only after the copies that read it have completed) + one result area */
-    void* h_up[4] = { nullptr, nullptr, nullptr, nullptr };
-    size_t h_up_bytes[4] = { 0, 0, 0, 0 };
-    cudaEvent_t h_up_done[4] = { nullptr, nullptr, nullptr, nullptr };
+    static constexpr int kUploadAreas = 8;
+    void* h_up[kUploadAreas] = { nullptr };
+    size_t h_up_bytes[kUploadAreas] = { 0 };
+    cudaEvent_t h_up_done[kUploadAreas] = { nullptr };
     int h_up_next = 0;
-    void* h_res = nullptr;
-    size_t h_res_bytes = 0;
+    /* result areas (pinned): one per batch in flight, used in turn */
+    static constexpr int kResultSlots = 4;
+    void* h_res[kResultSlots] = { nullptr, nullptr, nullptr, nullptr };
+    size_t h_res_bytes[kResultSlots] = { 0, 0, 0, 0 };
+    cudaEvent_t h_res_done[kResultSlots] = { nullptr, nullptr, nullptr, nullptr };
+    int res_head = 0;              /* slot of the oldest batch in flight */
+    int res_count = 0;             /* batches in flight */
+    int res_nq[kResultSlots] = { 0, 0, 0, 0 };
     /* last pyramid job table on the device (skips the re-upload when unchanged) */
     std::vector<PyrJob> jobs_on_device;
-    /* pending batch */
-    int pending_nq = 0;
     /* options (csm_set_option) */
     int pyramid_mode = 0;          /* 0 auto, 1 level-by-level, 2 streaming */
     int bb_seed_incumbent = 0;     /* experiment: start from the previous batch's incumbents */
@@ -151,7 +173,7 @@ int ensure(csm_handle h, DevBuf& b, size_t bytes)
 int acquire_upload(csm_handle h, size_t bytes, char** out)
 {
     const int k = h->h_up_next;
-    h->h_up_next = (h->h_up_next + 1) & 3;
+    h->h_up_next = (h->h_up_next + 1) % csm_context::kUploadAreas;
     if (h->h_up_done[k] == nullptr)
         CSM_CUDA(cudaEventCreateWithFlags(&h->h_up_done[k], cudaEventDisableTiming));
     else
@@ -171,7 +193,7 @@ int acquire_upload(csm_handle h, size_t bytes, char** out)
 
 int upload_committed(csm_handle h)
 {
-    const int k = (h->h_up_next + 3) & 3;
+    const int k = (h->h_up_next + csm_context::kUploadAreas - 1) % csm_context::kUploadAreas;
     CSM_CUDA(cudaEventRecord(h->h_up_done[k], h->stream));
     return CSM_OK;
 }
@@ -188,19 +210,50 @@ int pull_to_device(csm_handle h, void* dst, const void* src_pinned, size_t bytes
     return CSM_OK;
 }
 
-int ensure_result_area(csm_handle h, size_t bytes)
+/* Enqueue the device-to-host copy of the nq results (and the overflow flag)
+ * of the batch just launched into the next free pinned result area. */
+int enqueue_readback(csm_handle h, int nq)
 {
-    if (h->h_res_bytes >= bytes)
-        return CSM_OK;
-    if (h->h_res != nullptr) {
-        CSM_CUDA(cudaStreamSynchronize(h->stream));
-        CSM_CUDA(cudaFreeHost(h->h_res));
-        h->h_res = nullptr;
-        h->h_res_bytes = 0;
+    if (h->res_count >= csm_context::kResultSlots)
+        return fail(h, CSM_E_CAPACITY, "too many loop batches in flight: call csm_loop_batch_finish");
+    const int k = (h->res_head + h->res_count) % csm_context::kResultSlots;
+    const size_t bytes = sizeof(csm_result) * (size_t)nq + 64;
+    if (h->h_res_bytes[k] < bytes) {
+        if (h->h_res[k] != nullptr)
+            CSM_CUDA(cudaFreeHost(h->h_res[k]));
+        h->h_res[k] = nullptr;
+        h->h_res_bytes[k] = 0;
+        const size_t want = std::max(bytes * 2, (size_t)1 << 16);
+        CSM_CUDA(cudaHostAlloc(&h->h_res[k], want, cudaHostAllocDefault));
+        h->h_res_bytes[k] = want;
     }
-    const size_t want = std::max(bytes * 2, (size_t)1 << 16);
-    CSM_CUDA(cudaHostAlloc(&h->h_res, want, cudaHostAllocDefault));
-    h->h_res_bytes = want;
+    if (h->h_res_done[k] == nullptr)
+        CSM_CUDA(cudaEventCreateWithFlags(&h->h_res_done[k], cudaEventDisableTiming));
+    char* hp = static_cast<char*>(h->h_res[k]);
+    CSM_CUDA(cudaMemcpyAsync(hp + 64, h->d_results.p, sizeof(csm_result) * (size_t)nq,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(hp, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaEventRecord(h->h_res_done[k], h->stream));
+    h->res_nq[k] = nq;
+    ++h->res_count;
+    return CSM_OK;
+}
+
+/* Wait for the oldest batch in flight and hand out its results */
+int finish_results(csm_handle h, csm_result* results, int nq)
+{
+    if (h->res_count <= 0)
+        return fail(h, CSM_E_INVALID, "no batch in flight");
+    const int k = h->res_head;
+    if (nq != h->res_nq[k])
+        return fail(h, CSM_E_INVALID, "loop batch: finish does not match the enqueued batch");
+    h->res_head = (h->res_head + 1) % csm_context::kResultSlots;
+    --h->res_count;
+    CSM_CUDA(cudaEventSynchronize(h->h_res_done[k]));
+    const char* hp = static_cast<const char*>(h->h_res[k]);
+    std::memcpy(results, hp + 64, sizeof(csm_result) * (size_t)nq);
+    if (*reinterpret_cast<const int*>(hp) != 0)
+        return fail(h, CSM_E_CAPACITY, "branch-and-bound frontier overflow; split the batch");
     return CSM_OK;
 }
 
@@ -256,6 +309,71 @@ int wait_uploads(csm_handle h, const std::vector<MapSlot*>& slots)
         if (dup) continue;
         if (nseen < 16) seen[nseen++] = ev;
         CSM_CUDA(cudaStreamWaitEvent(h->stream, ev, 0));
+    }
+    for (MapSlot* m : slots) {
+        if (!m->pending_scatter)
+            continue;
+        std::shared_ptr<BlockScatter> bs = std::move(m->pending_scatter);
+        m->pending_scatter.reset();
+        if (bs->done)
+            continue;
+        bs->done = true;
+        const size_t map_cells = (size_t)bs->rows * bs->cols;
+        CSM_CUDA(cudaMemsetAsync(bs->dense, 0, map_cells * sizeof(uint16_t) * bs->n_maps, h->stream));
+        if (bs->max_count > 0) {
+            ScatterArgs A;
+            A.data = static_cast<const uint4*>(bs->stage);
+            A.index = reinterpret_cast<const int*>(static_cast<const char*>(bs->stage) + bs->index_off);
+            A.prefix = reinterpret_cast<const int*>(static_cast<const char*>(bs->stage) + bs->prefix_off);
+            A.dense = bs->dense;
+            A.log2bs = bs->log2bs; A.block_cols = bs->block_cols; A.cols = bs->cols;
+            A.map_cells = map_cells;
+            const int chunks = (1 << bs->log2bs) * ((1 << bs->log2bs) >> 3);
+            const long long work = (long long)bs->max_count * chunks;
+            dim3 grid((unsigned)std::min<long long>((work + 255) / 256, 64), (unsigned)bs->n_maps);
+            k_scatter_blocks<<<grid, 256, 0, h->stream>>>(A);
+            CSM_LAUNCH_CHECK();
+        }
+        CSM_CUDA(cudaFreeAsync(bs->stage, h->stream));
+        bs->stage = nullptr;
+    }
+    return CSM_OK;
+}
+
+/* The n level-0 grids of a batch share one device arena (so that a contiguous
+ * host batch moves with one copy and a block-sparse batch is cleared with one
+ * memset). The arena of a previous identical batch is reused. */
+int bind_batch_arena(csm_handle h, int n, const int64_t* map_ids, int rows, int cols,
+                     std::vector<MapSlot*>& slots, bool& fresh_alloc)
+{
+    const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
+    slots.resize(n);
+    for (int i = 0; i < n; ++i)
+        slots[i] = &h->maps[map_ids[i]];
+    bool reuse = slots[0]->base_block != nullptr && slots[0]->base == slots[0]->base_block->p;
+    for (int i = 0; i < n && reuse; ++i)
+        reuse = slots[i]->base_block == slots[0]->base_block && slots[i]->rows == rows &&
+                slots[i]->cols == cols &&
+                reinterpret_cast<char*>(slots[i]->base) == static_cast<char*>(slots[0]->base_block->p) + (size_t)i * bytes;
+    fresh_alloc = false;
+    if (!reuse) {
+        auto block = std::make_shared<ArenaBlock>();
+        block->stream = h->stream;
+        CSM_CUDA(cudaMallocAsync(&block->p, bytes * n, h->stream));
+        for (int i = 0; i < n; ++i) {
+            MapSlot& m = *slots[i];
+            const bool keep_levels = m.rows == rows && m.cols == cols;
+            uint16_t* levels = keep_levels ? m.levels : nullptr;
+            const int levels_alloc = keep_levels ? m.levels_alloc : 0;
+            uint16_t* coarse = keep_levels ? m.coarse : nullptr;
+            if (keep_levels) { m.levels = nullptr; m.coarse = nullptr; }
+            free_map(h, m);
+            m.levels = levels; m.levels_alloc = levels_alloc; m.coarse = coarse;
+            m.rows = rows; m.cols = cols;
+            m.base_block = block;
+            m.base = reinterpret_cast<uint16_t*>(static_cast<char*>(block->p) + (size_t)i * bytes);
+        }
+        fresh_alloc = true;
     }
     return CSM_OK;
 }
@@ -456,7 +574,6 @@ int stage_plan(csm_handle h, QueryPlan& plan, bool want_rcs)
     if ((rc = ensure(h, h->d_overflow, 4))) return rc;
     for (int q = 0; q < nq; ++q)
         plan.dq[q].thetas = static_cast<const double*>(h->d_thetas.p) + plan.theta_off[q];
-    if ((rc = ensure_result_area(h, sizeof(csm_result) * nq + 64))) return rc;
     char* hp = nullptr;
     const size_t qb16 = (qb + 15) & ~(size_t)15, tb16 = (tb + 15) & ~(size_t)15, ib16 = (ib + 15) & ~(size_t)15;
     if ((rc = acquire_upload(h, qb16 + tb16 + ib16, &hp))) return rc;
@@ -487,20 +604,6 @@ int launch_project(csm_handle h, const QueryPlan& plan, bool want_rcs)
     return CSM_OK;
 }
 
-int finish_results(csm_handle h, csm_result* results, int nq)
-{
-    char* hp = static_cast<char*>(h->h_res);
-    csm_result* hr = reinterpret_cast<csm_result*>(hp + 64);
-    int* hov = reinterpret_cast<int*>(hp);
-    CSM_CUDA(cudaMemcpyAsync(hr, h->d_results.p, sizeof(csm_result) * nq, cudaMemcpyDeviceToHost, h->stream));
-    CSM_CUDA(cudaMemcpyAsync(hov, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
-    CSM_CUDA(cudaStreamSynchronize(h->stream));
-    std::memcpy(results, hr, sizeof(csm_result) * nq);
-    if (*hov != 0)
-        return fail(h, CSM_E_CAPACITY, "branch-and-bound frontier overflow; split the batch");
-    return CSM_OK;
-}
-
 int ensure_frontier(csm_handle h, int nq, unsigned int total_roots)
 {
     /* candidate lists: 4 children per survivor; sized for a few thousand
@@ -524,6 +627,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         return fail(h, CSM_E_INVALID, "loop batch: nq must be positive");
     if (nq > 65535)
         return fail(h, CSM_E_UNSUPPORTED, "loop batch: at most 65535 queries per call");
+    if (h->res_count >= csm_context::kResultSlots)
+        return fail(h, CSM_E_CAPACITY, "too many loop batches in flight: call csm_loop_batch_finish");
     if (hmax < 0 || hmax >= kMaxLevels)
         return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: 0 <= hmax <= 7");
     QueryPlan plan;
@@ -630,8 +735,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     k_finalize<<<nq, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
                                          static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
-    h->pending_nq = nq;
-    return CSM_OK;
+    return enqueue_readback(h, nq);
 }
 
 } /* namespace */
@@ -700,11 +804,14 @@ int csm_destroy(csm_handle h)
     for (int l = 0; l < 2; ++l)
         if (h->d_list[l].p) cudaFreeAsync(h->d_list[l].p, h->stream);
     cudaStreamSynchronize(h->stream);
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < csm_context::kUploadAreas; ++k) {
         if (h->h_up[k]) cudaFreeHost(h->h_up[k]);
         if (h->h_up_done[k]) cudaEventDestroy(h->h_up_done[k]);
     }
-    if (h->h_res) cudaFreeHost(h->h_res);
+    for (int k = 0; k < csm_context::kResultSlots; ++k) {
+        if (h->h_res[k]) cudaFreeHost(h->h_res[k]);
+        if (h->h_res_done[k]) cudaEventDestroy(h->h_res_done[k]);
+    }
     for (int k = 0; k < 16; ++k)
         if (h->upload_events[k]) cudaEventDestroy(h->upload_events[k]);
     cudaEventDestroy(h->compute_mark);
@@ -782,6 +889,7 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     /* precomputed levels belong to the previous contents (allocations are kept) */
     m.hmax = 0;
     m.coarse_win = 0;
+    m.pending_scatter.reset();
     m.res = res; m.offx = offx; m.offy = offy;
     const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
     if (on_device) {
@@ -837,35 +945,11 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
         }
         return close_upload_group(h);
     }
-    /* Contiguous host batch: the n level-0 grids share one device arena and
-     * move with one copy. The arena of a previous identical batch is reused. */
-    std::vector<MapSlot*> slots(n);
-    for (int i = 0; i < n; ++i)
-        slots[i] = &h->maps[map_ids[i]];
-    bool reuse = slots[0]->base_block != nullptr && slots[0]->base == slots[0]->base_block->p;
-    for (int i = 0; i < n && reuse; ++i)
-        reuse = slots[i]->base_block == slots[0]->base_block && slots[i]->rows == rows &&
-                slots[i]->cols == cols &&
-                reinterpret_cast<char*>(slots[i]->base) == static_cast<char*>(slots[0]->base_block->p) + (size_t)i * bytes;
+    std::vector<MapSlot*> slots;
     bool fresh_alloc = false;
-    if (!reuse) {
-        auto block = std::make_shared<ArenaBlock>();
-        block->stream = h->stream;
-        CSM_CUDA(cudaMallocAsync(&block->p, bytes * n, h->stream));
-        for (int i = 0; i < n; ++i) {
-            MapSlot& m = *slots[i];
-            const bool keep_levels = m.rows == rows && m.cols == cols;
-            uint16_t* levels = keep_levels ? m.levels : nullptr;
-            const int levels_alloc = keep_levels ? m.levels_alloc : 0;
-            uint16_t* coarse = keep_levels ? m.coarse : nullptr;
-            if (keep_levels) { m.levels = nullptr; m.coarse = nullptr; }
-            free_map(h, m);
-            m.levels = levels; m.levels_alloc = levels_alloc; m.coarse = coarse;
-            m.rows = rows; m.cols = cols;
-            m.base_block = block;
-            m.base = reinterpret_cast<uint16_t*>(static_cast<char*>(block->p) + (size_t)i * bytes);
-        }
-        fresh_alloc = true;
+    {
+        const int arc = bind_batch_arena(h, n, map_ids, rows, cols, slots, fresh_alloc);
+        if (arc) return arc;
     }
     for (int i = 0; i < n; ++i) {
         MapSlot& m = *slots[i];
@@ -873,6 +957,7 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
         m.coarse_win = 0;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
+        m.pending_scatter.reset();
     }
     if (!h->upload_open || fresh_alloc) {
         CSM_CUDA(cudaEventRecord(h->compute_mark, h->stream));
@@ -883,6 +968,96 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
     /* one upload group per batch call: consumers of these maps wait for this
      * batch only, later batches keep streaming in behind the kernels */
     return close_upload_group(h);
+}
+
+int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
+                            const uint16_t* blocks, const int32_t* block_index,
+                            const int32_t* block_count, int log2_block_size,
+                            int block_rows, int block_cols, double resolution,
+                            const double* offset_x, const double* offset_y)
+{
+    if (!h) return CSM_E_INVALID;
+    if (n <= 0 || !map_ids || !block_count || !offset_x || !offset_y)
+        return fail(h, CSM_E_INVALID, "upload_grids_blocks: empty batch");
+    if (log2_block_size < 3 || log2_block_size > 6)
+        return fail(h, CSM_E_UNSUPPORTED, "upload_grids_blocks: block size must be 8, 16, 32 or 64");
+    if (block_rows <= 0 || block_cols <= 0 || !(resolution > 0.0))
+        return fail(h, CSM_E_INVALID, "upload_grids_blocks: bad geometry");
+    const long long rows_ll = (long long)block_rows << log2_block_size;
+    const long long cols_ll = (long long)block_cols << log2_block_size;
+    if (rows_ll > 16384 || cols_ll > 16384)
+        return fail(h, CSM_E_INVALID, "grid: need rows, cols <= 16384");
+    const int rows = (int)rows_ll, cols = (int)cols_ll;
+    const int nb_map = block_rows * block_cols;
+    auto bs = std::make_shared<BlockScatter>();
+    bs->prefix.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        if (block_count[i] < 0 || block_count[i] > nb_map)
+            return fail(h, CSM_E_INVALID, "upload_grids_blocks: block count out of range");
+        bs->prefix[i + 1] = bs->prefix[i] + block_count[i];
+        bs->max_count = std::max(bs->max_count, (int)block_count[i]);
+    }
+    const int total = bs->prefix[n];
+    if (total > 0 && (!blocks || !block_index))
+        return fail(h, CSM_E_INVALID, "upload_grids_blocks: null block data");
+    for (int i = 0; i < n; ++i) {
+        /* every listed block inside the map, no block listed twice */
+        std::vector<char> seen(nb_map, 0);
+        for (int b = bs->prefix[i]; b < bs->prefix[i + 1]; ++b) {
+            const int bi = block_index[b];
+            if (bi < 0 || bi >= nb_map || seen[bi])
+                return fail(h, CSM_E_INVALID, "upload_grids_blocks: bad or repeated block index");
+            seen[bi] = 1;
+        }
+    }
+    CSM_CUDA(cudaSetDevice(h->device));
+    std::vector<MapSlot*> slots;
+    bool fresh_alloc = false;
+    {
+        const int arc = bind_batch_arena(h, n, map_ids, rows, cols, slots, fresh_alloc);
+        if (arc) return arc;
+    }
+    const size_t block_bytes = sizeof(uint16_t) << (2 * log2_block_size);
+    bs->data_bytes = block_bytes * (size_t)total;
+    bs->index_off = (bs->data_bytes + 255) & ~(size_t)255;
+    bs->prefix_off = (bs->index_off + sizeof(int) * (size_t)total + 255) & ~(size_t)255;
+    const size_t stage_bytes = bs->prefix_off + sizeof(int) * (size_t)(n + 1);
+    bs->stream = h->stream;
+    CSM_CUDA(cudaMallocAsync(&bs->stage, stage_bytes, h->stream));
+    bs->dense = slots[0]->base;
+    bs->n_maps = n;
+    bs->log2bs = log2_block_size; bs->block_cols = block_cols; bs->rows = rows; bs->cols = cols;
+    for (int i = 0; i < n; ++i) {
+        MapSlot& m = *slots[i];
+        m.hmax = 0;
+        m.coarse_win = 0;
+        m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
+        m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
+        m.pending_scatter = bs;
+    }
+    /* the staging buffer was allocated on the compute stream: order the copies after it */
+    CSM_CUDA(cudaEventRecord(h->compute_mark, h->stream));
+    CSM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->compute_mark, 0));
+    h->upload_open = true;
+    char* stage = static_cast<char*>(bs->stage);
+    if (total > 0) {
+        CSM_CUDA(cudaMemcpyAsync(stage, blocks, bs->data_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CSM_CUDA(cudaMemcpyAsync(stage + bs->index_off, block_index, sizeof(int) * (size_t)total,
+                                 cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    CSM_CUDA(cudaMemcpyAsync(stage + bs->prefix_off, bs->prefix.data(), sizeof(int) * (size_t)(n + 1),
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    return close_upload_group(h);
+}
+
+int csm_upload_grid_blocks(csm_handle h, int64_t map_id, const uint16_t* blocks,
+                           const int32_t* block_index, int n_blocks, int log2_block_size,
+                           int block_rows, int block_cols, double resolution,
+                           double offset_x, double offset_y)
+{
+    const int32_t count = n_blocks;
+    return csm_upload_grids_blocks(h, 1, &map_id, blocks, block_index, &count, log2_block_size,
+                                   block_rows, block_cols, resolution, &offset_x, &offset_y);
 }
 
 int csm_release_grid(csm_handle h, int64_t map_id)
@@ -1014,9 +1189,6 @@ int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, 
 int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq)
 {
     if (!h || !results) return CSM_E_INVALID;
-    if (nq != h->pending_nq)
-        return fail(h, CSM_E_INVALID, "loop batch: finish does not match the enqueued batch");
-    h->pending_nq = 0;
     return finish_results(h, results, nq);
 }
 
@@ -1066,9 +1238,10 @@ int csm_match_bb(csm_handle h, int64_t map_id,
     q.win_x = win_x; q.win_y = win_y; q.win_t = win_t;
     q.step_x = step_x; q.step_y = step_y; q.step_t = step_t;
     q.score_thr = score_thr; q.known_thr = known_thr;
+    if (h->res_count != 0)
+        return fail(h, CSM_E_INVALID, "match_bb: a loop batch is in flight on this handle");
     rc = bb_enqueue(h, &q, 1, hmax, 0);
     if (rc) return rc;
-    h->pending_nq = 0;
     return finish_results(h, out, 1);
 }
 
@@ -1081,6 +1254,8 @@ int csm_match_rt(csm_handle h, int64_t map_id,
 {
     if (!h || !out || !sensor_pose) return CSM_E_INVALID;
     (void)step_x; (void)step_y;
+    if (h->res_count != 0)
+        return fail(h, CSM_E_INVALID, "match_rt: a loop batch is in flight on this handle");
     CSM_CUDA(cudaSetDevice(h->device));
     auto mi = h->maps.find(map_id);
     if (mi == h->maps.end())
@@ -1141,9 +1316,8 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
                                         static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
-    rc = finish_results(h, out, 1);
-    if (rc) return rc;
-    return CSM_OK;
+    if ((rc = enqueue_readback(h, 1))) return rc;
+    return finish_results(h, out, 1);
 }
 
 int csm_match_grid(csm_handle h, int64_t map_id,
@@ -1154,6 +1328,8 @@ int csm_match_grid(csm_handle h, int64_t map_id,
                    double score_thr, double known_thr, csm_result* out)
 {
     if (!h || !out || !sensor_pose || !dx || !dy || !dt) return CSM_E_INVALID;
+    if (h->res_count != 0)
+        return fail(h, CSM_E_INVALID, "match_grid: a loop batch is in flight on this handle");
     CSM_CUDA(cudaSetDevice(h->device));
     auto mi = h->maps.find(map_id);
     if (mi == h->maps.end())
@@ -1259,6 +1435,7 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
                                         static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
+    if ((rc = enqueue_readback(h, 1))) return rc;
     return finish_results(h, out, 1);
 }
 

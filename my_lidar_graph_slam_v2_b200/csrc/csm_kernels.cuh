@@ -41,6 +41,44 @@ k_pull(uint4* __restrict__ dst, const uint4* __restrict__ src_host, unsigned int
         dst[i] = src_host[i];
 }
 
+/* Block-sparse upload: expand the allocated blocks of a batch of maps into
+ * their dense level-0 grids (zero-filled beforehand). The staging layout is
+ * the reference's storage: one 2^k x 2^k block of u16 per allocated block,
+ * row-major inside the block (grid_map.cpp:262-266, grid_binary_bayes.hpp),
+ * block b of map m at data[prefix[m] + b], its position index[prefix[m] + b]
+ * = block_row * block_cols + block_col. One thread moves 8 cells (16 bytes). */
+struct ScatterArgs
+{
+    const uint4* data;
+    const int* index;
+    const int* prefix;
+    uint16_t* dense;
+    int log2bs, block_cols, cols;
+    size_t map_cells;
+};
+
+__global__ void __launch_bounds__(256)
+k_scatter_blocks(ScatterArgs A)
+{
+    const int m = blockIdx.y;
+    const int first = A.prefix[m];
+    const int count = A.prefix[m + 1] - first;
+    const int k = A.log2bs;
+    const int chunks_per_row = 1 << (k - 3);
+    const int chunks_per_block = chunks_per_row << k;
+    const long long work = (long long)count * chunks_per_block;
+    uint16_t* __restrict__ dense = A.dense + (size_t)m * A.map_cells;
+    for (long long e = blockIdx.x * blockDim.x + threadIdx.x; e < work; e += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(e / chunks_per_block);
+        const int c = (int)(e - (long long)b * chunks_per_block);
+        const int r_in = c >> (k - 3), c_in = (c & (chunks_per_row - 1)) << 3;
+        const int bi = __ldg(A.index + first + b);
+        const int brow = bi / A.block_cols, bcol = bi - brow * A.block_cols;
+        const uint4 v = __ldg(A.data + (size_t)(first + b) * chunks_per_block + c);
+        *reinterpret_cast<uint4*>(dense + (size_t)((brow << k) + r_in) * A.cols + (bcol << k) + c_in) = v;
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* Precomputation                                                            */
 /* ------------------------------------------------------------------------ */

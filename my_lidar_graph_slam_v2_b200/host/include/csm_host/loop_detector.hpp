@@ -43,6 +43,15 @@ public:
      * All queries are matched in one device batch. */
     std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
 
+    /* Queries are matched in chunks of this many (default 128): the uploads of
+     * later chunks overlap the search of earlier ones */
+    void SetChunkSize(int n) { mChunkSize = n; }
+    /* Without a final matcher the result carries the covariance of the cost
+     * function at the coarse pose (computed on the CPU); switch it off when
+     * the caller refines the poses itself */
+    void SetCoarseCovariance(bool on) { mCoarseCovariance = on; }
+    /* Forget which maps are resident (the next Detect uploads them again) */
+    void ClearCache() { mCachedMaps.clear(); mCachedScans.clear(); }
     /* Sharded use: global index of queries[0] (packed best word) */
     void SetQueryIndexBase(int base) { mQueryIndexBase = base; }
     /* Per-query device results of the last Detect, in query order */
@@ -56,6 +65,8 @@ private:
     std::set<std::int64_t> mCachedScans;
     std::vector<csm_result> mLastResults;
     int mQueryIndexBase = 0;
+    int mChunkSize = 128;
+    bool mCoarseCovariance = true;
 };
 
 } /* namespace csm_host */

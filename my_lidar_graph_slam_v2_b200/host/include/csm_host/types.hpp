@@ -61,16 +61,24 @@ struct ScanData
 };
 using ScanDataPtr = std::shared_ptr<const ScanData>;
 
-/* Dense row-major view of an occupancy grid: value 0 = unknown, 1..65535 <->
- * probability 0.001..0.999 (grid_binary_bayes.hpp:163-176); cell (row, col)
- * covers [offset + res * col, offset + res * (col + 1)). `map_id` >= 0 names a
+/* View of an occupancy grid: value 0 = unknown, 1..65535 <-> probability
+ * 0.001..0.999 (grid_binary_bayes.hpp:163-176); cell (row, col) covers
+ * [offset + res * col, offset + res * (col + 1)). `map_id` >= 0 names a
  * finished local map (LocalMapId) whose device copy and pyramid are cached;
  * -1 = anonymous map, uploaded on every call.
- * `block_allocated` (optional, (rows/16) x (cols/16)) tells which 16x16 blocks
- * the block-sparse reference map has allocated; it only matters for the CPU
- * cost function (unallocated cells read 0.5 there, grid_map.cpp:424-436 with
- * cost_function_square_error.cpp:340-344). When null, a block counts as
- * allocated iff it holds a non-zero cell. */
+ *
+ * Two forms:
+ *  - block-sparse (`blocks` non-null): the reference's own storage, the
+ *    n_blocks allocated 2^k x 2^k blocks back to back (row-major inside a
+ *    block) and their positions block_row * (cols >> k) + block_col
+ *    (grid_map.cpp:262-266, 522-535). Nothing is flattened and only these
+ *    bytes are uploaded. Block allocation is exact.
+ *  - dense (`values` non-null): row-major u16. `block_allocated` (optional,
+ *    (rows/16) x (cols/16)) tells which 16x16 blocks the reference map has
+ *    allocated; it only matters for the CPU cost function (cells of
+ *    unallocated blocks read 0.5 there, grid_map.cpp:424-436 with
+ *    cost_function_square_error.cpp:340-344). When null, a block counts as
+ *    allocated iff it holds a non-zero cell. */
 struct GridMapView
 {
     const std::uint16_t* values = nullptr;
@@ -79,6 +87,10 @@ struct GridMapView
     double offset_x = 0.0, offset_y = 0.0;
     std::int64_t map_id = -1;
     const std::uint8_t* block_allocated = nullptr;
+    const std::uint16_t* blocks = nullptr;
+    const std::int32_t* block_index = nullptr;
+    int n_blocks = 0;
+    int log2_block_size = 4;
 };
 
 /* scan_matcher.hpp:56-83 */

@@ -143,4 +143,86 @@ int csm_host_loop_detect(void* ctx, int n_queries, const uint16_t* values, int r
     return 0;
 }
 
+/* ---- persistent loop detector (bench.py e2e path) ------------------------------ */
+struct HostLoopDet
+{
+    DeviceContextPtr ctx;
+    std::shared_ptr<ScanMatcherBranchBound> matcher;
+    std::unique_ptr<LoopDetectorBranchBound> det;
+};
+
+void* csm_host_loopdet_create(void* ctx, int hmax, const double range[3], double score_thr,
+                              double known_thr, double covariance_scale)
+{
+    auto* d = new HostLoopDet;
+    d->ctx = *static_cast<DeviceContextPtr*>(ctx);
+    const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+    d->matcher = std::make_shared<ScanMatcherBranchBound>("LoopBBGPU", cost, hmax, range[0], range[1],
+                                                          range[2], d->ctx);
+    d->det.reset(new LoopDetectorBranchBound("LoopDetectorBranchBoundGPU", d->matcher, FinalMatcher(),
+                                             score_thr, known_thr));
+    return d;
+}
+
+void csm_host_loopdet_destroy(void* det) { delete static_cast<HostLoopDet*>(det); }
+
+void csm_host_loopdet_configure(void* det, int chunk_size, int coarse_covariance, int query_index_base)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    d->det->SetChunkSize(chunk_size);
+    d->det->SetCoarseCovariance(coarse_covariance != 0);
+    d->det->SetQueryIndexBase(query_index_base);
+}
+
+void csm_host_loopdet_clear_cache(void* det) { static_cast<HostLoopDet*>(det)->det->ClearCache(); }
+
+void* csm_host_loopdet_handle(void* det) { return static_cast<HostLoopDet*>(det)->ctx->Handle(); }
+
+/* Detect over n_queries block-sparse maps (map q owns block_count[q] consecutive
+ * blocks) and one shared scan. values == dense alternative when blocks is null. */
+int csm_host_loopdet_detect(void* det, int n_queries, const uint16_t* values,
+                            const uint16_t* blocks, const int32_t* block_index, const int32_t* block_count,
+                            int log2bs, int rows, int cols, double res,
+                            const double* off_x, const double* off_y, const int64_t* map_ids,
+                            const double* map_poses, const double* scan_poses,
+                            const double* angles, const double* ranges, int n, csm_host_summary* out)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    const double rel[3] = { 0.0, 0.0, 0.0 };
+    const ScanDataPtr scan = Scan(angles, ranges, n, rel);
+    std::vector<LoopDetectionQuery> queries(n_queries);
+    const size_t cells = static_cast<size_t>(rows) * cols;
+    size_t nblk = 0;
+    for (int q = 0; q < n_queries; ++q) {
+        LoopDetectionQuery& lq = queries[q];
+        lq.scan = scan;
+        lq.scan_id = 0;
+        lq.scan_node_id = q;
+        lq.scan_global_pose = Pose2D { scan_poses[3 * q], scan_poses[3 * q + 1], scan_poses[3 * q + 2] };
+        lq.local_map = View(values ? values + q * cells : nullptr, rows, cols, res, off_x[q], off_y[q], map_ids[q]);
+        if (blocks != nullptr) {
+            lq.local_map.blocks = blocks + (nblk << (2 * log2bs));
+            lq.local_map.block_index = block_index + nblk;
+            lq.local_map.n_blocks = block_count[q];
+            lq.local_map.log2_block_size = log2bs;
+            nblk += static_cast<size_t>(block_count[q]);
+        }
+        lq.local_map_global_pose = Pose2D { map_poses[3 * q], map_poses[3 * q + 1], map_poses[3 * q + 2] };
+    }
+    const std::vector<LoopDetectionResult> results = d->det->Detect(queries);
+    for (int q = 0; q < n_queries; ++q)
+        std::memset(&out[q], 0, sizeof(csm_host_summary));
+    for (const LoopDetectionResult& r : results) {
+        csm_host_summary& o = out[r.scan_node_id];
+        const csm_result& dr = d->det->LastResults()[r.query_index];
+        o.found = 1;
+        o.best_x = dr.best_x; o.best_y = dr.best_y; o.best_t = dr.best_t;
+        o.sum_value = dr.sum_value; o.n_known = dr.n_known; o.flags = dr.flags;
+        o.score = dr.normalized_score;
+        o.est_pose[0] = r.relative_pose.x; o.est_pose[1] = r.relative_pose.y; o.est_pose[2] = r.relative_pose.theta;
+        std::memcpy(o.cov, r.estimated_covariance.data(), sizeof(double) * 9);
+    }
+    return static_cast<int>(results.size());
+}
+
 } /* extern "C" */

@@ -17,33 +17,62 @@ inline double Probability(std::uint16_t v)
     return pmin + (pmax - pmin) * static_cast<double>(static_cast<int>(v) - 1) / 65534.0;
 }
 
+/* GridMap::ProbabilityOr(row, col, 0.5) on either form of the view. Block
+ * allocation of a dense view without a bitmap is derived on first touch of a
+ * block (a block counts as allocated iff it holds a non-zero cell). */
 struct Sampler
 {
     const GridMapView& map;
-    std::vector<std::uint8_t> derived;     /* block allocation when the caller gave none */
-    const std::uint8_t* alloc;
-    int block_cols;
+    int k, block_cols;
+    mutable std::vector<std::int32_t> slot;   /* block-sparse: block -> position in `blocks`, -1 = unallocated;
+                                                 dense: 1 allocated, 0 not, -2 not looked at yet */
 
-    explicit Sampler(const GridMapView& m) : map(m), alloc(m.block_allocated),
-        block_cols((m.cols + 15) >> kLog2Block)
+    explicit Sampler(const GridMapView& m) : map(m), k(m.blocks ? m.log2_block_size : kLog2Block),
+        block_cols((m.cols + (1 << k) - 1) >> k)
     {
-        if (alloc == nullptr) {
-            const int block_rows = (m.rows + 15) >> kLog2Block;
-            derived.assign(static_cast<std::size_t>(block_rows) * block_cols, 0);
-            for (int r = 0; r < m.rows; ++r)
-                for (int c = 0; c < m.cols; ++c)
-                    if (m.values[static_cast<std::size_t>(r) * m.cols + c] != 0)
-                        derived[(r >> kLog2Block) * block_cols + (c >> kLog2Block)] = 1;
-            alloc = derived.data();
+        const int block_rows = (m.rows + (1 << k) - 1) >> k;
+        const std::size_t nb = static_cast<std::size_t>(block_rows) * block_cols;
+        if (m.blocks != nullptr) {
+            slot.assign(nb, -1);
+            for (int b = 0; b < m.n_blocks; ++b)
+                slot[m.block_index[b]] = b;
+        } else if (m.block_allocated != nullptr) {
+            slot.resize(nb);
+            for (std::size_t b = 0; b < nb; ++b)
+                slot[b] = m.block_allocated[b] ? 1 : 0;
+        } else {
+            slot.assign(nb, -2);
         }
     }
 
-    /* GridMap::ProbabilityOr(row, col, 0.5): grid_map.cpp:424-436 */
+    bool DenseBlockAllocated(int brow, int bcol) const
+    {
+        std::int32_t& st = slot[static_cast<std::size_t>(brow) * block_cols + bcol];
+        if (st == -2) {
+            st = 0;
+            const int r1 = std::min((brow + 1) << k, map.rows), c1 = std::min((bcol + 1) << k, map.cols);
+            for (int r = brow << k; r < r1 && !st; ++r)
+                for (int c = bcol << k; c < c1; ++c)
+                    if (map.values[static_cast<std::size_t>(r) * map.cols + c] != 0) { st = 1; break; }
+        }
+        return st != 0;
+    }
+
+    /* grid_map.cpp:424-436 */
     double At(int row, int col) const
     {
         if (row < 0 || row >= map.rows || col < 0 || col >= map.cols)
             return 0.5;
-        if (!alloc[(row >> kLog2Block) * block_cols + (col >> kLog2Block)])
+        const int brow = row >> k, bcol = col >> k;
+        if (map.blocks != nullptr) {
+            const std::int32_t b = slot[static_cast<std::size_t>(brow) * block_cols + bcol];
+            if (b < 0)
+                return 0.5;
+            const int mask = (1 << k) - 1;
+            return Probability(map.blocks[(static_cast<std::size_t>(b) << (2 * k)) +
+                                          (static_cast<std::size_t>(row & mask) << k) + (col & mask)]);
+        }
+        if (!DenseBlockAllocated(brow, bcol))
             return 0.5;
         return Probability(map.values[static_cast<std::size_t>(row) * map.cols + col]);
     }

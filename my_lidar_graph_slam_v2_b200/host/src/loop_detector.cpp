@@ -1,5 +1,7 @@
 #include "csm_host/loop_detector.hpp"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -20,6 +22,72 @@ LoopDetectorBranchBound::LoopDetectorBranchBound(
     }
 }
 
+namespace {
+
+/* Upload the first-touch maps of one chunk. Block-sparse views whose block
+ * buffers follow one another in memory (a pinned staging area filled map by
+ * map) go in one batched call = one PCIe copy; anything else map by map. */
+void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapView*>& maps)
+{
+    if (maps.empty())
+        return;
+    csm_handle h = ctx->Handle();
+    const GridMapView& m0 = *maps[0];
+    bool batch = m0.blocks != nullptr && maps.size() > 1;
+    std::size_t nblk = 0;
+    for (std::size_t i = 0; i < maps.size() && batch; ++i) {
+        const GridMapView& m = *maps[i];
+        batch = m.blocks != nullptr && m.rows == m0.rows && m.cols == m0.cols &&
+                m.log2_block_size == m0.log2_block_size && m.resolution == m0.resolution &&
+                m.blocks == m0.blocks + (nblk << (2 * m0.log2_block_size)) &&
+                m.block_index == m0.block_index + nblk;
+        nblk += static_cast<std::size_t>(m.n_blocks);
+    }
+    if (batch) {
+        std::vector<std::int64_t> ids(maps.size());
+        std::vector<std::int32_t> counts(maps.size());
+        std::vector<double> ox(maps.size()), oy(maps.size());
+        for (std::size_t i = 0; i < maps.size(); ++i) {
+            ids[i] = maps[i]->map_id; counts[i] = maps[i]->n_blocks;
+            ox[i] = maps[i]->offset_x; oy[i] = maps[i]->offset_y;
+        }
+        ctx->Check(csm_upload_grids_blocks(h, static_cast<int>(maps.size()), ids.data(), m0.blocks,
+                                           m0.block_index, counts.data(), m0.log2_block_size,
+                                           m0.rows >> m0.log2_block_size, m0.cols >> m0.log2_block_size,
+                                           m0.resolution, ox.data(), oy.data()), "csm_upload_grids_blocks");
+        return;
+    }
+    bool dense_batch = m0.blocks == nullptr && maps.size() > 1;
+    for (std::size_t i = 0; i < maps.size() && dense_batch; ++i)
+        dense_batch = maps[i]->blocks == nullptr && maps[i]->rows == m0.rows && maps[i]->cols == m0.cols &&
+                      maps[i]->resolution == m0.resolution;
+    if (dense_batch) {
+        /* one call: a single copy when the grids follow one another in host memory */
+        std::vector<std::int64_t> ids(maps.size());
+        std::vector<const std::uint16_t*> ptrs(maps.size());
+        std::vector<double> ox(maps.size()), oy(maps.size());
+        for (std::size_t i = 0; i < maps.size(); ++i) {
+            ids[i] = maps[i]->map_id; ptrs[i] = maps[i]->values;
+            ox[i] = maps[i]->offset_x; oy[i] = maps[i]->offset_y;
+        }
+        ctx->Check(csm_upload_grids(h, static_cast<int>(maps.size()), ids.data(), ptrs.data(), m0.rows, m0.cols,
+                                    m0.resolution, ox.data(), oy.data()), "csm_upload_grids");
+        return;
+    }
+    for (const GridMapView* m : maps) {
+        if (m->blocks != nullptr)
+            ctx->Check(csm_upload_grid_blocks(h, m->map_id, m->blocks, m->block_index, m->n_blocks,
+                                              m->log2_block_size, m->rows >> m->log2_block_size,
+                                              m->cols >> m->log2_block_size, m->resolution,
+                                              m->offset_x, m->offset_y), "csm_upload_grid_blocks");
+        else
+            ctx->Check(csm_upload_grid(h, m->map_id, m->values, m->rows, m->cols, m->resolution,
+                                       m->offset_x, m->offset_y), "csm_upload_grid");
+    }
+}
+
+} /* namespace */
+
 std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     const std::vector<LoopDetectionQuery>& queries)
 {
@@ -31,61 +99,81 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     csm_handle h = ctx->Handle();
     const int hmax = mScanMatcher->NodeHeightMax();
     const int nq = static_cast<int>(queries.size());
+    const int chunk = std::max(1, mChunkSize);
+    const int nchunks = (nq + chunk - 1) / chunk;
 
     /* first touch of a local map: upload + pyramid, cached by LocalMapId
-     * (loop_detector_branch_bound.cpp:83-89) */
-    std::vector<std::int64_t> new_maps;
-    for (const LoopDetectionQuery& q : queries) {
-        const GridMapView& m = q.local_map;
-        if (m.map_id < 0) {
-            std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
-            std::abort();
+     * (loop_detector_branch_bound.cpp:83-89). All uploads are enqueued first:
+     * they stream over PCIe on the copy stream while the chunks that have
+     * landed are expanded, precomputed and searched on the compute stream. */
+    std::vector<std::vector<std::int64_t>> new_maps(nchunks);
+    for (int c = 0; c < nchunks; ++c) {
+        std::vector<const GridMapView*> fresh;
+        for (int i = c * chunk; i < std::min(nq, (c + 1) * chunk); ++i) {
+            const GridMapView& m = queries[i].local_map;
+            if (m.map_id < 0) {
+                std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
+                std::abort();
+            }
+            if (mCachedMaps.insert(m.map_id).second) {
+                fresh.push_back(&m);
+                new_maps[c].push_back(m.map_id);
+            }
         }
-        if (mCachedMaps.insert(m.map_id).second) {
-            ctx->Check(csm_upload_grid(h, m.map_id, m.values, m.rows, m.cols, m.resolution,
-                                       m.offset_x, m.offset_y), "csm_upload_grid");
-            new_maps.push_back(m.map_id);
-        }
+        UploadNewMaps(ctx, fresh);
+    }
+    for (const LoopDetectionQuery& q : queries)
         if (mCachedScans.insert(q.scan_id).second)
             ctx->Check(csm_upload_scan(h, q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
                                        static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
-    }
-    if (!new_maps.empty())
-        ctx->Check(csm_build_pyramids(h, static_cast<int>(new_maps.size()), new_maps.data(), hmax),
-                   "csm_build_pyramids");
 
     /* per query: initial pose InverseCompound(map, scan) (:97-98), sensor pose,
      * steps and windows with the reference's expressions */
     std::vector<csm_loop_query> dq(nq);
     std::map<std::pair<std::int64_t, double>, std::array<double, 3>> steps;
-    for (int i = 0; i < nq; ++i) {
-        const LoopDetectionQuery& q = queries[i];
-        const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
-        const Pose2D sensor = Compound(init, q.scan->relative_sensor_pose);
-        auto key = std::make_pair(q.scan_id, q.local_map.resolution);
-        auto it = steps.find(key);
-        if (it == steps.end()) {
-            std::array<double, 3> st;
-            ComputeSearchStep(q.local_map.resolution, *q.scan, st[0], st[1], st[2]);
-            it = steps.emplace(key, st).first;
-        }
-        const std::array<double, 3>& st = it->second;
-        csm_loop_query& d = dq[i];
-        d.map_id = q.local_map.map_id;
-        d.scan_id = q.scan_id;
-        d.sensor_pose[0] = sensor.x; d.sensor_pose[1] = sensor.y; d.sensor_pose[2] = sensor.theta;
-        d.win_x = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeX() / st[0]));
-        d.win_y = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeY() / st[1]));
-        d.win_t = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeTheta() / st[2]));
-        d.reserved = 0;
-        d.step_x = st[0]; d.step_y = st[1]; d.step_t = st[2];
-        d.score_thr = mScoreThreshold;
-        d.known_thr = mKnownRateThreshold;
-    }
-
     mLastResults.resize(nq);
-    ctx->Check(csm_loop_batch(h, dq.data(), nq, hmax, mQueryIndexBase, mLastResults.data()),
-               "csm_loop_batch");
+    int finished = 0;      /* chunks whose results have been read back */
+    for (int c = 0; c < nchunks; ++c) {
+        const int first = c * chunk, count = std::min(nq, first + chunk) - first;
+        for (int i = first; i < first + count; ++i) {
+            const LoopDetectionQuery& q = queries[i];
+            const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
+            const Pose2D sensor = Compound(init, q.scan->relative_sensor_pose);
+            auto key = std::make_pair(q.scan_id, q.local_map.resolution);
+            auto it = steps.find(key);
+            if (it == steps.end()) {
+                std::array<double, 3> st;
+                ComputeSearchStep(q.local_map.resolution, *q.scan, st[0], st[1], st[2]);
+                it = steps.emplace(key, st).first;
+            }
+            const std::array<double, 3>& st = it->second;
+            csm_loop_query& d = dq[i];
+            d.map_id = q.local_map.map_id;
+            d.scan_id = q.scan_id;
+            d.sensor_pose[0] = sensor.x; d.sensor_pose[1] = sensor.y; d.sensor_pose[2] = sensor.theta;
+            d.win_x = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeX() / st[0]));
+            d.win_y = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeY() / st[1]));
+            d.win_t = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeTheta() / st[2]));
+            d.reserved = 0;
+            d.step_x = st[0]; d.step_y = st[1]; d.step_t = st[2];
+            d.score_thr = mScoreThreshold;
+            d.known_thr = mKnownRateThreshold;
+        }
+        if (!new_maps[c].empty())
+            ctx->Check(csm_build_pyramids(h, static_cast<int>(new_maps[c].size()), new_maps[c].data(), hmax),
+                       "csm_build_pyramids");
+        if (c - finished >= 4) {        /* the library keeps at most 4 batches in flight */
+            const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
+            ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");
+            ++finished;
+        }
+        ctx->Check(csm_loop_batch_enqueue(h, dq.data() + first, count, hmax, mQueryIndexBase + first),
+                   "csm_loop_batch_enqueue");
+    }
+    for (; finished < nchunks; ++finished) {
+        const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
+        ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");
+    }
 
     for (int i = 0; i < nq; ++i) {
         const csm_result& r = mLastResults[i];
@@ -97,13 +185,15 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
                             d.sensor_pose[2] + d.step_t * r.best_t };
         LoopDetectionResult out;
         out.relative_pose = MoveBackward(best, q.scan->relative_sensor_pose);
-        out.estimated_covariance = mScanMatcher->Cost()->ComputeCovariance(q.local_map, *q.scan, best);
         if (mFinalMatcher) {
-            /* sub-pixel refinement around the reference scan's local pose (:110-127) */
+            /* sub-pixel refinement around the reference scan's local pose (:110-127); its
+             * pose and covariance are what the reference returns (:132-135) */
             const ScanMatchingSummary fin = mFinalMatcher(q.local_map, q.scan, q.reference_scan_local_pose,
                                                           out.relative_pose);
             out.relative_pose = fin.estimated_pose;
             out.estimated_covariance = fin.estimated_covariance;
+        } else if (mCoarseCovariance) {
+            out.estimated_covariance = mScanMatcher->Cost()->ComputeCovariance(q.local_map, *q.scan, best);
         }
         out.local_map_pose = q.local_map_global_pose;
         out.local_map_id = q.local_map.map_id;

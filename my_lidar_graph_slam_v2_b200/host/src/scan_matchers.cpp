@@ -38,8 +38,15 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
     const bool resident = map.map_id >= 0 &&
         std::find(mResidentMaps.begin(), mResidentMaps.end(), id) != mResidentMaps.end();
     if (!resident) {
-        mContext->Check(csm_upload_grid(mContext->Handle(), id, map.values, map.rows, map.cols,
-                                        map.resolution, map.offset_x, map.offset_y), "csm_upload_grid");
+        if (map.blocks != nullptr)
+            mContext->Check(csm_upload_grid_blocks(mContext->Handle(), id, map.blocks, map.block_index,
+                                                   map.n_blocks, map.log2_block_size,
+                                                   map.rows >> map.log2_block_size,
+                                                   map.cols >> map.log2_block_size, map.resolution,
+                                                   map.offset_x, map.offset_y), "csm_upload_grid_blocks");
+        else
+            mContext->Check(csm_upload_grid(mContext->Handle(), id, map.values, map.rows, map.cols,
+                                            map.resolution, map.offset_x, map.offset_y), "csm_upload_grid");
         if (map.map_id >= 0)
             mResidentMaps.push_back(id);
     }

@@ -40,6 +40,17 @@ def load():
         lib.csm_host_loop_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                              dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int, C.c_int,
                                              dp, C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
+        lib.csm_host_loopdet_create.restype = C.c_void_p
+        lib.csm_host_loopdet_create.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_double, C.c_double]
+        lib.csm_host_loopdet_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_loopdet_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.csm_host_loopdet_clear_cache.argtypes = [C.c_void_p]
+        lib.csm_host_loopdet_handle.restype = C.c_void_p
+        lib.csm_host_loopdet_handle.argtypes = [C.c_void_p]
+        lib.csm_host_loopdet_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_int, C.c_double, dp, dp,
+                                                C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int,
+                                                C.POINTER(HostSummary)]
         _lib = lib
     return _lib
 
@@ -106,3 +117,41 @@ class Context:
                                            hmax, rgp, thr[0], thr[1], covariance_scale, out)
         assert rc == 0
         return list(out)
+
+
+class LoopDetector:
+    """Persistent C++ LoopDetectorBranchBound (host/src/loop_detector.cpp) on one device context.
+    detect() takes raw host pointers (dense `values` or block-sparse `blocks`/`index`/`counts`)."""
+
+    def __init__(self, ctx, hmax, rng, thr, covariance_scale=1e4):
+        self.lib = load()
+        self.ctx = ctx
+        rg, rgp = _d(rng)
+        self.det = self.lib.csm_host_loopdet_create(ctx.ctx, hmax, rgp, thr[0], thr[1], covariance_scale)
+
+    def configure(self, chunk_size=128, coarse_covariance=True, query_index_base=0):
+        self.lib.csm_host_loopdet_configure(self.det, chunk_size, int(coarse_covariance), query_index_base)
+
+    def clear_cache(self):
+        self.lib.csm_host_loopdet_clear_cache(self.det)
+
+    def handle(self):
+        """The csm_handle (C ABI) the detector runs on."""
+        return self.lib.csm_host_loopdet_handle(self.det)
+
+    def detect(self, nq, values, blocks, index, counts, log2bs, rows, cols, res, off_x, off_y, map_ids,
+               map_poses, scan_poses, angles, ranges, out=None):
+        out = out if out is not None else (HostSummary * nq)()
+        n = self.lib.csm_host_loopdet_detect(
+            self.det, nq, values, blocks, index, counts, log2bs, rows, cols, res,
+            off_x.ctypes.data_as(C.POINTER(C.c_double)), off_y.ctypes.data_as(C.POINTER(C.c_double)),
+            map_ids.ctypes.data_as(C.POINTER(C.c_int64)),
+            map_poses.ctypes.data_as(C.POINTER(C.c_double)), scan_poses.ctypes.data_as(C.POINTER(C.c_double)),
+            angles.ctypes.data_as(C.POINTER(C.c_double)), ranges.ctypes.data_as(C.POINTER(C.c_double)),
+            len(angles), out)
+        return n, out
+
+    def close(self):
+        if self.det:
+            self.lib.csm_host_loopdet_destroy(self.det)
+            self.det = None

@@ -226,3 +226,19 @@ def make_loop_batch(seed, n_maps=256, true_fraction=0.25, rows=512, cols=512, re
     return LoopBatch(submaps, np.arange(n_maps, dtype=np.int32) + map_id_base, map_poses,
                      scan_poses, np.zeros(n_maps, dtype=np.int32), angles[None, :].copy(),
                      ranges[None, :].copy(), is_true)
+
+
+def dense_to_blocks(grid, log2bs=4):
+    """Block-sparse form of a dense grid, as the reference stores it
+    (grid_map.cpp:262-266, 522-535: a block is allocated once any of its cells
+    has been written): the blocks that hold a non-zero cell, row-major inside a
+    block, and their positions block_row * block_cols + block_col."""
+    bs = 1 << log2bs
+    rows, cols = grid.shape
+    assert rows % bs == 0 and cols % bs == 0
+    br, bc = rows // bs, cols // bs
+    tiles = grid.reshape(br, bs, bc, bs).swapaxes(1, 2)            # (br, bc, bs, bs)
+    used = tiles.reshape(br, bc, -1).any(axis=2)
+    index = np.flatnonzero(used.reshape(-1)).astype(np.int32)
+    blocks = np.ascontiguousarray(tiles.reshape(br * bc, bs, bs)[index])
+    return blocks, index, br, bc

@@ -290,6 +290,76 @@ def test_loop_batch_vs_checker_and_best_key(handle, checker):
         handle.release_grid(int(mid))
 
 
+# --------------------------------------------------------------------------
+# block-sparse upload (the reference's own storage layout)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("log2bs,shape", [(4, (512, 512)), (3, (64, 128)), (5, (128, 64)), (6, (128, 128))])
+def test_block_sparse_upload_equals_dense(handle, log2bs, shape):
+    rng = np.random.default_rng(77 + log2bs)
+    if shape == (512, 512):
+        grid = synth.rasterize(synth.make_room(rng), rng, *shape, 0.05).grid
+    else:
+        grid = rng.integers(1, 65535, size=shape, dtype=np.uint16)
+        bs = 1 << log2bs
+        mask = rng.random((shape[0] // bs, shape[1] // bs)) < 0.5       # half the blocks never written
+        grid[np.kron(mask, np.ones((bs, bs), dtype=bool))] = 0
+    blocks, index, br, bc = synth.dense_to_blocks(grid, log2bs)
+    assert 0 < len(index) < br * bc
+    handle.upload_grid_blocks(600, blocks, index, log2bs, br, bc, 0.05, -3.0, -4.0)
+    assert np.array_equal(handle.download_level(600, 0, shape), grid)
+    # re-upload with other contents into the same slot, in shuffled block order
+    grid2 = np.roll(grid, (1 << log2bs, 1 << log2bs), axis=(0, 1))
+    blocks, index, br, bc = synth.dense_to_blocks(grid2, log2bs)
+    perm = rng.permutation(len(index))
+    handle.upload_grid_blocks(600, blocks[perm], index[perm], log2bs, br, bc, 0.05, -3.0, -4.0)
+    handle.build_pyramid(600, 3)
+    assert np.array_equal(handle.download_level(600, 0, shape), grid2)
+    # an all-unknown map: no blocks at all
+    handle.upload_grid_blocks(600, np.zeros((0, 1 << log2bs, 1 << log2bs), np.uint16), np.zeros(0, np.int32),
+                              log2bs, br, bc, 0.05, 0.0, 0.0)
+    assert not handle.download_level(600, 0, shape).any()
+    handle.release_grid(600)
+
+
+def test_block_sparse_errors(handle):
+    blocks = np.ones((2, 16, 16), np.uint16)
+    with pytest.raises(capi.CsmError):
+        handle.upload_grid_blocks(601, blocks, np.array([0, 0], np.int32), 4, 2, 2, 0.05, 0.0, 0.0)   # repeated
+    with pytest.raises(capi.CsmError):
+        handle.upload_grid_blocks(601, blocks, np.array([0, 4], np.int32), 4, 2, 2, 0.05, 0.0, 0.0)   # outside
+    with pytest.raises(capi.CsmError):
+        handle.upload_grid_blocks(601, blocks, np.array([0, 1], np.int32), 2, 2, 2, 0.05, 0.0, 0.0)   # 4x4 blocks
+
+
+def test_loop_batch_block_sparse_upload(handle, checker):
+    """The whole Detect with maps handed over block-sparse in one batched call
+    gives the results of the dense path and of the checker."""
+    batch = synth.make_loop_batch(3300, n_maps=24, true_fraction=0.4, map_id_base=8000)
+    parts = [synth.dense_to_blocks(s.grid) for s in batch.submaps]
+    blocks = np.concatenate([p[0] for p in parts])
+    index = np.concatenate([p[1] for p in parts])
+    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+    ids = batch.map_ids.astype(np.int64)
+    handle.upload_grids_blocks_ptr(ids, blocks.ctypes.data, index.ctypes.data, counts, 4, 32, 32,
+                                   batch.submaps[0].res, np.array([s.off_x for s in batch.submaps]),
+                                   np.array([s.off_y for s in batch.submaps]))
+    bb = matchers.ScanMatcherBranchBound("loop-bb", 6, *synth.CFG3["rng"], handle=handle)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    det._cached_maps.update(int(i) for i in ids)          # already on the device
+    handle.build_pyramids(ids, 6)
+    found, res = det.detect(_loop_queries(batch))
+    grids = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 2)
+    ores, _ = odet.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    assert sum(o.found for o in ores) > 0
+    for i, (r, o) in enumerate(zip(res, ores)):
+        assert_match(r, dict(o.asdict(), compare_unfound=False), "loop query %d" % i)
+    for i, s in enumerate(batch.submaps):
+        assert np.array_equal(handle.download_level(int(ids[i]), 0, s.grid.shape), s.grid)
+        handle.release_grid(int(ids[i]))
+
+
 def test_errors(handle):
     with pytest.raises(capi.CsmError):
         handle.build_pyramid(123456, 3)                      # unknown map
