@@ -111,6 +111,10 @@ int64_t csm_launch_count(csm_handle h);
 /* Tuning / test knobs.
  *  "pyramid_mode": 0 = automatic, 1 = level-by-level kernels, 2 = streaming
  *      single-pass kernel (when the maps fit its layout);
+ *  "bb_dive": every branch-and-bound query first descends greedily (beam of 8)
+ *      to a leaf that seeds its incumbent: 0 = never (plain level sweep), 1 =
+ *      always, 2 (default) = only for calls of at most 4 queries. Results are
+ *      identical either way; only the number of nodes scored changes;
  *  "accumulate_best_key": 1 = loop batches keep (do not reset) the packed
  *      best word, so that a Detect call split into several batches ends with
  *      the maximum over all of them; "reset_best_key": clears it now. */

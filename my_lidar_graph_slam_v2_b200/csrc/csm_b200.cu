@@ -66,11 +66,30 @@ struct MapSlot
 
 struct ScanSlot
 {
-    double* angles = nullptr;      /* device */
+    void* block = nullptr;         /* one device allocation: angles | ranges | trig */
+    double* angles = nullptr;
     double* ranges = nullptr;
     double2* trig = nullptr;       /* (cos a_i, sin a_i) */
     int n = 0;
     double max_range = 0.0;
+};
+
+/* Where the small per-batch arrays live inside the plan buffer (d_plan):
+ * a region pulled from page-locked host memory followed by a zeroed region. */
+struct PlanView
+{
+    size_t off_queries = 0, off_thetas = 0, off_inc = 0, off_rootoff = 0, off_extra = 0, off_scan = 0;
+    size_t pulled_bytes = 0, zero_off = 0, zero_bytes = 0, trig_off = 0, total = 0;
+    DevQuery* queries = nullptr;
+    double* thetas = nullptr;
+    unsigned long long* inc = nullptr;
+    unsigned int* rootoff = nullptr;
+    char* extra = nullptr;
+    ScanSlot scan;                 /* scan arriving with the call (single-scan matchers) */
+    int* qflags = nullptr;
+    int* stats = nullptr;
+    unsigned int* counts = nullptr;
+    int* overflow = nullptr;
 };
 
 struct DevBuf
@@ -97,10 +116,10 @@ struct csm_context
     std::unordered_map<int64_t, ScanSlot> scans;
 
     /* workspaces, grown on demand */
-    DevBuf d_queries, d_thetas, d_proj, d_rcs, d_qflags, d_state, d_results;
-    DevBuf d_inc, d_rootoff, d_stats, d_counts, d_overflow, d_bestkey;
+    DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
-    DevBuf d_rtblocks, d_gridoff, d_gridpos, d_pyrjobs, d_tmpscan;
+    DevBuf d_rtblocks, d_pyrjobs, d_rootkey;
+    PlanView plan_view;                   /* layout of the last staged batch */
     unsigned int frontier_capacity = 0;
     /* pinned staging: eight upload areas used in turn (an area is reused
      * only after the copies that read it have completed) + one result area */
@@ -121,8 +140,9 @@ struct csm_context
     std::vector<PyrJob> jobs_on_device;
     /* options (csm_set_option) */
     int pyramid_mode = 0;          /* 0 auto, 1 level-by-level, 2 streaming */
-    int bb_seed_incumbent = 0;     /* experiment: start from the previous batch's incumbents */
-    int bb_dive = 0;               /* unused (kept for option compatibility) */
+    int bb_dive = 2;               /* a beam dive per query seeds the incumbents before the level sweep:
+                                      0 never, 1 always, 2 only for calls of at most 4 queries (there the
+                                      latency of the dive is small against the nodes it saves) */
     int accumulate_best_key = 0;   /* 1: batches do not reset the packed best word */
 };
 
@@ -229,10 +249,9 @@ int enqueue_readback(csm_handle h, int nq)
     }
     if (h->h_res_done[k] == nullptr)
         CSM_CUDA(cudaEventCreateWithFlags(&h->h_res_done[k], cudaEventDisableTiming));
-    char* hp = static_cast<char*>(h->h_res[k]);
-    CSM_CUDA(cudaMemcpyAsync(hp + 64, h->d_results.p, sizeof(csm_result) * (size_t)nq,
+    /* results followed by the overflow flag (written by k_finalize): one copy */
+    CSM_CUDA(cudaMemcpyAsync(h->h_res[k], h->d_results.p, sizeof(csm_result) * (size_t)nq + 16,
                              cudaMemcpyDeviceToHost, h->stream));
-    CSM_CUDA(cudaMemcpyAsync(hp, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaEventRecord(h->h_res_done[k], h->stream));
     h->res_nq[k] = nq;
     ++h->res_count;
@@ -251,8 +270,8 @@ int finish_results(csm_handle h, csm_result* results, int nq)
     --h->res_count;
     CSM_CUDA(cudaEventSynchronize(h->h_res_done[k]));
     const char* hp = static_cast<const char*>(h->h_res[k]);
-    std::memcpy(results, hp + 64, sizeof(csm_result) * (size_t)nq);
-    if (*reinterpret_cast<const int*>(hp) != 0)
+    std::memcpy(results, hp, sizeof(csm_result) * (size_t)nq);
+    if (*reinterpret_cast<const int*>(hp + sizeof(csm_result) * (size_t)nq) != 0)
         return fail(h, CSM_E_CAPACITY, "branch-and-bound frontier overflow; split the batch");
     return CSM_OK;
 }
@@ -267,9 +286,7 @@ void free_map(csm_handle h, MapSlot& m)
 
 void free_scan(csm_handle h, ScanSlot& s)
 {
-    if (s.angles) cudaFreeAsync(s.angles, h->stream);
-    if (s.ranges) cudaFreeAsync(s.ranges, h->stream);
-    if (s.trig) cudaFreeAsync(s.trig, h->stream);
+    if (s.block) cudaFreeAsync(s.block, h->stream);
     s = ScanSlot();
 }
 
@@ -417,34 +434,47 @@ double fp_margin(const double pose[3], const MapSlot& m, double max_range, doubl
     return 1024.0 * 1.1102230246251565e-16 * mag / m.res + 1e-12;
 }
 
+int launch_setup(csm_handle h, const SetupArgs& A)
+{
+    const unsigned int work = std::max(std::max(A.n16, A.z16), (unsigned int)std::max(A.n_beams, 1));
+    const unsigned int blocks = std::min<unsigned int>((work + 255) / 256, 64u);
+    k_setup<<<blocks, 256, 0, h->stream>>>(A);
+    CSM_LAUNCH_CHECK();
+    return CSM_OK;
+}
+
 int upload_scan_impl(csm_handle h, int64_t scan_id, const double* angles,
                      const double* ranges, int n)
 {
     if (n <= 0 || n > kMaxBeams || angles == nullptr || ranges == nullptr)
         return fail(h, CSM_E_INVALID, "scan: need 1 <= n <= 4096 beams");
     ScanSlot& s = h->scans[scan_id];
+    const size_t half = ((sizeof(double) * n + 15) / 16) * 16;
     if (s.n != n) {
         free_scan(h, s);
-        CSM_CUDA(cudaMallocAsync((void**)&s.angles, sizeof(double) * n + 16, h->stream));
-        CSM_CUDA(cudaMallocAsync((void**)&s.ranges, sizeof(double) * n + 16, h->stream));
-        CSM_CUDA(cudaMallocAsync((void**)&s.trig, sizeof(double2) * n, h->stream));
+        CSM_CUDA(cudaMallocAsync(&s.block, 2 * half + sizeof(double2) * n, h->stream));
+        s.angles = static_cast<double*>(s.block);
+        s.ranges = reinterpret_cast<double*>(static_cast<char*>(s.block) + half);
+        s.trig = reinterpret_cast<double2*>(static_cast<char*>(s.block) + 2 * half);
         s.n = n;
     }
-    {
-        /* staged through pinned memory and pulled by a kernel (see k_pull) */
-        const size_t half = ((sizeof(double) * n + 15) / 16) * 16;
-        char* hp = nullptr;
-        int rc = acquire_upload(h, 2 * half, &hp);
-        if (rc) return rc;
-        std::memcpy(hp, angles, sizeof(double) * n);
-        std::memcpy(hp + half, ranges, sizeof(double) * n);
-        if ((rc = pull_to_device(h, s.angles, hp, half))) return rc;
-        if ((rc = pull_to_device(h, s.ranges, hp + half, half))) return rc;
-        if ((rc = upload_committed(h))) return rc;
-    }
+    /* staged through pinned memory and pulled by one kernel that also fills the trig table */
+    char* hp = nullptr;
+    int rc = acquire_upload(h, 2 * half, &hp);
+    if (rc) return rc;
+    std::memcpy(hp, angles, sizeof(double) * n);
+    std::memcpy(hp + half, ranges, sizeof(double) * n);
+    SetupArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.dst = static_cast<uint4*>(s.block);
+    A.src_host = reinterpret_cast<const uint4*>(hp);
+    A.n16 = (unsigned int)(2 * half / 16);
+    A.angles_host = reinterpret_cast<const double*>(hp);
+    A.trig = s.trig;
+    A.n_beams = n;
+    if ((rc = launch_setup(h, A))) return rc;
+    if ((rc = upload_committed(h))) return rc;
     s.max_range = *std::max_element(ranges, ranges + n);
-    k_beam_trig<<<(n + 255) / 256, 256, 0, h->stream>>>(s.angles, s.trig, n);
-    CSM_LAUNCH_CHECK();
     return CSM_OK;
 }
 
@@ -530,11 +560,61 @@ struct QueryPlan
     std::vector<double> thetas;
     std::vector<size_t> theta_off;
     std::vector<unsigned long long> inc_init;
+    std::vector<unsigned int> root_off;      /* B&B only */
+    std::vector<char> extra;                 /* grid search: offsets and positions */
+    const double* scan_angles = nullptr;     /* scan arriving with the call */
+    const double* scan_ranges = nullptr;
     long long proj_total = 0;
     int max_tn = 0;
     int max_t = 0;
     int max_roots = 0;
 };
+
+size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+/* Decide where everything small lives in d_plan. Sizes must be final; the
+ * contents (queries etc.) are filled afterwards with these device addresses. */
+int layout_plan(csm_handle h, int nq, size_t n_thetas, size_t n_rootoff, size_t extra_bytes,
+                int scan_n, PlanView& V)
+{
+    V = PlanView();
+    size_t off = 0;
+    V.off_queries = off; off += align16(sizeof(DevQuery) * (size_t)nq);
+    V.off_thetas = off;  off += align16(sizeof(double) * n_thetas);
+    V.off_inc = off;     off += align16(sizeof(unsigned long long) * (size_t)nq);
+    V.off_rootoff = off; off += align16(sizeof(unsigned int) * n_rootoff);
+    V.off_extra = off;   off += align16(extra_bytes);
+    V.off_scan = off;    off += 2 * align16(sizeof(double) * (size_t)scan_n);
+    V.pulled_bytes = off;
+    V.zero_off = off;
+    const size_t off_qflags = off; off += align16(sizeof(int) * (size_t)nq);
+    const size_t off_stats = off;  off += align16(sizeof(int) * 2 * (size_t)nq);
+    const size_t off_counts = off; off += align16(sizeof(unsigned int) * kMaxLevels);
+    const size_t off_overflow = off; off += 16;
+    V.zero_bytes = off - V.zero_off;
+    V.trig_off = off; off += sizeof(double2) * (size_t)scan_n;
+    V.total = off;
+    int rc = ensure(h, h->d_plan, V.total);
+    if (rc) return rc;
+    char* base = static_cast<char*>(h->d_plan.p);
+    V.queries = reinterpret_cast<DevQuery*>(base + V.off_queries);
+    V.thetas = reinterpret_cast<double*>(base + V.off_thetas);
+    V.inc = reinterpret_cast<unsigned long long*>(base + V.off_inc);
+    V.rootoff = reinterpret_cast<unsigned int*>(base + V.off_rootoff);
+    V.extra = base + V.off_extra;
+    V.qflags = reinterpret_cast<int*>(base + off_qflags);
+    V.stats = reinterpret_cast<int*>(base + off_stats);
+    V.counts = reinterpret_cast<unsigned int*>(base + off_counts);
+    V.overflow = reinterpret_cast<int*>(base + off_overflow);
+    if (scan_n > 0) {
+        V.scan.angles = reinterpret_cast<double*>(base + V.off_scan);
+        V.scan.ranges = reinterpret_cast<double*>(base + V.off_scan + align16(sizeof(double) * (size_t)scan_n));
+        V.scan.trig = reinterpret_cast<double2*>(base + V.trig_off);
+        V.scan.n = scan_n;
+    }
+    h->plan_view = V;
+    return CSM_OK;
+}
 
 int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
                 double score_thr, double known_thr)
@@ -548,58 +628,62 @@ int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
     Q.coarse = m.coarse;
     Q.rows = m.rows; Q.cols = m.cols;
     Q.res = m.res; Q.offx = m.offx; Q.offy = m.offy;
+    Q.inv_res = 1.0 / m.res;
     Q.angles = s.angles; Q.ranges = s.ranges; Q.beam_trig = s.trig; Q.n = s.n;
     Q.kthr = make_key_threshold(score_thr, s.n);
     Q.nk_cut = make_known_cut(known_thr, s.n);
     return CSM_OK;
 }
 
-/* Upload plan (queries + thetas + initial incumbents) and zero the per-batch state */
-int stage_plan(csm_handle h, QueryPlan& plan, bool want_rcs)
+/* Stage the plan laid out by layout_plan with ONE kernel: pull queries, candidate
+ * angles, initial incumbents, root offsets, extras and the per-call scan from
+ * pinned memory; zero the per-batch counters; fill the scan's trig table. */
+int commit_plan(csm_handle h, QueryPlan& plan, const PlanView& V, bool want_rcs)
 {
     const int nq = (int)plan.dq.size();
-    const size_t qb = sizeof(DevQuery) * nq;
-    const size_t tb = sizeof(double) * plan.thetas.size();
-    const size_t ib = sizeof(unsigned long long) * nq;
     int rc;
-    if ((rc = ensure(h, h->d_queries, qb))) return rc;
-    if ((rc = ensure(h, h->d_thetas, tb))) return rc;
-    if ((rc = ensure(h, h->d_inc, ib))) return rc;
     if ((rc = ensure(h, h->d_proj, sizeof(proj_t) * (size_t)plan.proj_total))) return rc;
     if (want_rcs && (rc = ensure(h, h->d_rcs, sizeof(double2) * (size_t)plan.proj_total))) return rc;
-    if ((rc = ensure(h, h->d_qflags, sizeof(int) * nq))) return rc;
-    if ((rc = ensure(h, h->d_state, sizeof(BestState) * nq))) return rc;
     if ((rc = ensure(h, h->d_results, sizeof(csm_result) * nq + 16))) return rc;
     if ((rc = ensure(h, h->d_bestkey, 8))) return rc;
-    if ((rc = ensure(h, h->d_overflow, 4))) return rc;
     for (int q = 0; q < nq; ++q)
-        plan.dq[q].thetas = static_cast<const double*>(h->d_thetas.p) + plan.theta_off[q];
+        plan.dq[q].thetas = V.thetas + plan.theta_off[q];
     char* hp = nullptr;
-    const size_t qb16 = (qb + 15) & ~(size_t)15, tb16 = (tb + 15) & ~(size_t)15, ib16 = (ib + 15) & ~(size_t)15;
-    if ((rc = acquire_upload(h, qb16 + tb16 + ib16, &hp))) return rc;
-    std::memcpy(hp, plan.dq.data(), qb);
-    std::memcpy(hp + qb16, plan.thetas.data(), tb);
-    std::memcpy(hp + qb16 + tb16, plan.inc_init.data(), ib);
-    if ((rc = pull_to_device(h, h->d_queries.p, hp, qb))) return rc;
-    if ((rc = pull_to_device(h, h->d_thetas.p, hp + qb16, tb))) return rc;
-    if (!h->bb_seed_incumbent)
-        if ((rc = pull_to_device(h, h->d_inc.p, hp + qb16 + tb16, ib))) return rc;
-    if ((rc = upload_committed(h))) return rc;
-    CSM_CUDA(cudaMemsetAsync(h->d_qflags.p, 0, sizeof(int) * nq, h->stream));
-    if (!h->accumulate_best_key)
-        CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
-    CSM_CUDA(cudaMemsetAsync(h->d_overflow.p, 0, 4, h->stream));
-    return CSM_OK;
+    if ((rc = acquire_upload(h, V.pulled_bytes, &hp))) return rc;
+    std::memcpy(hp + V.off_queries, plan.dq.data(), sizeof(DevQuery) * nq);
+    std::memcpy(hp + V.off_thetas, plan.thetas.data(), sizeof(double) * plan.thetas.size());
+    std::memcpy(hp + V.off_inc, plan.inc_init.data(), sizeof(unsigned long long) * nq);
+    if (!plan.root_off.empty())
+        std::memcpy(hp + V.off_rootoff, plan.root_off.data(), sizeof(unsigned int) * plan.root_off.size());
+    if (!plan.extra.empty())
+        std::memcpy(hp + V.off_extra, plan.extra.data(), plan.extra.size());
+    SetupArgs A;
+    std::memset(&A, 0, sizeof(A));
+    if (V.scan.n > 0) {
+        const size_t half = align16(sizeof(double) * (size_t)V.scan.n);
+        std::memcpy(hp + V.off_scan, plan.scan_angles, sizeof(double) * V.scan.n);
+        std::memcpy(hp + V.off_scan + half, plan.scan_ranges, sizeof(double) * V.scan.n);
+        A.angles_host = reinterpret_cast<const double*>(hp + V.off_scan);
+        A.trig = V.scan.trig;
+        A.n_beams = V.scan.n;
+    }
+    A.dst = static_cast<uint4*>(h->d_plan.p);
+    A.src_host = reinterpret_cast<const uint4*>(hp);
+    A.n16 = (unsigned int)(V.pulled_bytes / 16);
+    A.zero = reinterpret_cast<uint4*>(static_cast<char*>(h->d_plan.p) + V.zero_off);
+    A.z16 = (unsigned int)(V.zero_bytes / 16);
+    A.best_key = h->accumulate_best_key ? nullptr : static_cast<unsigned long long*>(h->d_bestkey.p);
+    if ((rc = launch_setup(h, A))) return rc;
+    return upload_committed(h);
 }
 
-int launch_project(csm_handle h, const QueryPlan& plan, bool want_rcs)
+int launch_project(csm_handle h, const QueryPlan& plan, const PlanView& V, bool want_rcs)
 {
     const int nq = (int)plan.dq.size();
     dim3 grid(std::max(1, (plan.max_t + kProjAngles - 1) / kProjAngles), nq);
     k_project<<<grid, 256, 0, h->stream>>>(
-        static_cast<const DevQuery*>(h->d_queries.p), static_cast<proj_t*>(h->d_proj.p),
-        want_rcs ? static_cast<double2*>(h->d_rcs.p) : nullptr,
-        static_cast<int*>(h->d_qflags.p));
+        V.queries, static_cast<proj_t*>(h->d_proj.p),
+        want_rcs ? static_cast<double2*>(h->d_rcs.p) : nullptr, V.qflags);
     CSM_LAUNCH_CHECK();
     return CSM_OK;
 }
@@ -615,13 +699,20 @@ int ensure_frontier(csm_handle h, int nq, unsigned int total_roots)
     for (int l = 0; l < 2; ++l)
         if ((rc = ensure(h, h->d_list[l], sizeof(unsigned long long) * cap))) return rc;
     h->frontier_capacity = cap;
-    if ((rc = ensure(h, h->d_counts, sizeof(unsigned int) * kMaxLevels))) return rc;
-    if ((rc = ensure(h, h->d_rootoff, sizeof(unsigned int) * (nq + 1)))) return rc;
-    if ((rc = ensure(h, h->d_stats, sizeof(int) * 2 * nq))) return rc;
     return CSM_OK;
 }
 
-int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, int query_base)
+/* scan: when non-null, the (single) query uses a scan that arrives with this
+ * call (angles / ranges on the host) instead of a scan uploaded before. */
+struct InlineScan
+{
+    const double* angles;
+    const double* ranges;
+    int n;
+};
+
+int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, int query_base,
+               const InlineScan* inline_scan)
 {
     if (nq <= 0 || queries == nullptr)
         return fail(h, CSM_E_INVALID, "loop batch: nq must be positive");
@@ -631,31 +722,48 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         return fail(h, CSM_E_CAPACITY, "too many loop batches in flight: call csm_loop_batch_finish");
     if (hmax < 0 || hmax >= kMaxLevels)
         return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: 0 <= hmax <= 7");
-    QueryPlan plan;
-    plan.dq.resize(nq);
-    plan.theta_off.resize(nq);
-    plan.inc_init.resize(nq);
-    std::vector<MapSlot*> used_slots;
-    used_slots.reserve(nq);
-    const int wsz = 1 << hmax;
+    if (inline_scan && (inline_scan->n <= 0 || inline_scan->n > kMaxBeams || !inline_scan->angles ||
+                        !inline_scan->ranges))
+        return fail(h, CSM_E_INVALID, "scan: need 1 <= n <= 4096 beams");
+    /* pass 1: validate, count candidate angles */
+    std::vector<MapSlot*> used_slots(nq);
+    size_t n_thetas = 0;
     for (int q = 0; q < nq; ++q) {
         const csm_loop_query& in = queries[q];
         auto mi = h->maps.find(in.map_id);
         if (mi == h->maps.end())
             return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown map id " + std::to_string(in.map_id));
-        auto si = h->scans.find(in.scan_id);
-        if (si == h->scans.end())
-            return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown scan id " + std::to_string(in.scan_id));
-        MapSlot& m = mi->second;
-        const ScanSlot& s = si->second;
-        used_slots.push_back(&m);
-        if (m.hmax < hmax)
+        used_slots[q] = &mi->second;
+        if (mi->second.hmax < hmax)
             return fail(h, CSM_E_INVALID, "loop batch: pyramid of map " + std::to_string(in.map_id) +
                         " not built to hmax");
+        if (!inline_scan && h->scans.find(in.scan_id) == h->scans.end())
+            return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown scan id " + std::to_string(in.scan_id));
         if (in.win_x < 0 || in.win_y < 0 || in.win_t < 0)
             return fail(h, CSM_E_INVALID, "loop batch: negative window");
+        n_thetas += (size_t)(2 * in.win_t + 1);
+    }
+    int rc;
+    PlanView V;
+    if ((rc = layout_plan(h, nq, n_thetas, (size_t)nq + 1, 0, inline_scan ? inline_scan->n : 0, V))) return rc;
+    ScanSlot inl = V.scan;
+    if (inline_scan)
+        inl.max_range = *std::max_element(inline_scan->ranges, inline_scan->ranges + inline_scan->n);
+
+    QueryPlan plan;
+    plan.dq.resize(nq);
+    plan.theta_off.resize(nq);
+    plan.inc_init.resize(nq);
+    plan.root_off.assign(nq + 1, 0u);
+    plan.thetas.reserve(n_thetas);
+    if (inline_scan) { plan.scan_angles = inline_scan->angles; plan.scan_ranges = inline_scan->ranges; }
+    const int wsz = 1 << hmax;
+    for (int q = 0; q < nq; ++q) {
+        const csm_loop_query& in = queries[q];
+        const MapSlot& m = *used_slots[q];
+        const ScanSlot& s = inline_scan ? inl : h->scans.find(in.scan_id)->second;
         DevQuery& Q = plan.dq[q];
-        { const int frc = fill_common(h, Q, m, s, in.score_thr, in.known_thr); if (frc) return frc; }
+        if ((rc = fill_common(h, Q, m, s, in.score_thr, in.known_thr))) return rc;
         Q.sx = in.sensor_pose[0];
         Q.sy = in.sensor_pose[1];
         Q.T = 2 * in.win_t + 1;
@@ -678,42 +786,34 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         for (int t = -in.win_t; t <= in.win_t; ++t)
             plan.thetas.push_back(in.sensor_pose[2] + t * in.step_t);
         plan.inc_init[q] = ((unsigned long long)Q.kthr.fail_max << kOrdBits) | kOrdMask;
+        plan.root_off[q + 1] = plan.root_off[q] + (unsigned int)(Q.T * Q.nrx * Q.nry);
     }
-    std::vector<unsigned int> root_off(nq + 1, 0u);
-    for (int q = 0; q < nq; ++q)
-        root_off[q + 1] = root_off[q] + (unsigned int)(plan.dq[q].T * plan.dq[q].nrx * plan.dq[q].nry);
-    int rc;
     if ((rc = wait_uploads(h, used_slots))) return rc;
-    if ((rc = ensure_frontier(h, nq, root_off[nq]))) return rc;
-    if ((rc = stage_plan(h, plan, false))) return rc;
-    {
-        char* hp = nullptr;
-        const size_t rb = sizeof(unsigned int) * (nq + 1);
-        if ((rc = acquire_upload(h, rb, &hp))) return rc;
-        std::memcpy(hp, root_off.data(), rb);
-        if ((rc = pull_to_device(h, h->d_rootoff.p, hp, rb))) return rc;
-        if ((rc = upload_committed(h))) return rc;
-    }
-    CSM_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(unsigned int) * kMaxLevels, h->stream));
-    CSM_CUDA(cudaMemsetAsync(h->d_stats.p, 0, sizeof(int) * 2 * nq, h->stream));
-    if ((rc = launch_project(h, plan, false))) return rc;
+    if ((rc = ensure_frontier(h, nq, plan.root_off[nq]))) return rc;
+    if ((rc = commit_plan(h, plan, V, false))) return rc;
+    if ((rc = launch_project(h, plan, V, false))) return rc;
 
     BbWork W;
     std::memset(&W, 0, sizeof(W));
     W.list[0] = static_cast<unsigned long long*>(h->d_list[0].p);
     W.list[1] = static_cast<unsigned long long*>(h->d_list[1].p);
-    W.counts = static_cast<unsigned int*>(h->d_counts.p);
-    W.incumbent = static_cast<unsigned long long*>(h->d_inc.p);
-    W.stats = static_cast<int*>(h->d_stats.p);
-    W.overflow = static_cast<int*>(h->d_overflow.p);
+    W.counts = V.counts;
+    W.incumbent = V.inc;
+    W.stats = V.stats;
+    W.overflow = V.overflow;
     W.capacity = h->frontier_capacity;
     W.hmax = hmax;
-    const DevQuery* dq = static_cast<const DevQuery*>(h->d_queries.p);
+    const bool dive = hmax >= 1 && (h->bb_dive == 1 || (h->bb_dive == 2 && nq <= 4));
+    if (dive) {
+        if ((rc = ensure(h, h->d_rootkey, sizeof(long long) * (size_t)plan.root_off[nq]))) return rc;
+        W.rootkey = static_cast<long long*>(h->d_rootkey.p);
+    }
+    const DevQuery* dq = V.queries;
     const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
 
     {
         dim3 grid(std::max(1, std::min((plan.max_roots + 255) / 256, 64)), nq);
-        k_bb_init<<<grid, 256, 0, h->stream>>>(dq, static_cast<const unsigned int*>(h->d_rootoff.p), nq, W);
+        k_bb_init<<<grid, 256, 0, h->stream>>>(dq, V.rootoff, nq, W);
         CSM_LAUNCH_CHECK();
     }
     {
@@ -721,19 +821,24 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         for (int lvl = hmax; lvl >= 0; --lvl) {
             k_bb_score<<<blocks, 256, 0, h->stream>>>(dq, proj, W, lvl);
             CSM_LAUNCH_CHECK();
+            if (lvl == hmax && dive) {
+                k_bb_dive<<<nq, 256, 0, h->stream>>>(dq, proj, V.rootoff, W);
+                CSM_LAUNCH_CHECK();
+            }
         }
     }
-    k_bb_collect<<<(nq + 127) / 128, 128, 0, h->stream>>>(
-        dq, W, nq, static_cast<const int*>(h->d_qflags.p), static_cast<BestState*>(h->d_state.p));
-    CSM_LAUNCH_CHECK();
     FinalArgs F;
     std::memset(&F, 0, sizeof(F));
+    F.decode = 1;
+    F.incumbent = V.inc;
+    F.stats = V.stats;
     F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
     F.query_index_base = query_base;
     F.mode = 0;
-    F.qflags = static_cast<const int*>(h->d_qflags.p);
-    k_finalize<<<nq, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
-                                         static_cast<csm_result*>(h->d_results.p));
+    F.qflags = V.qflags;
+    F.overflow = V.overflow;
+    F.nq = nq;
+    k_finalize<<<nq, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
     return enqueue_readback(h, nq);
 }
@@ -795,10 +900,8 @@ int csm_destroy(csm_handle h)
     cudaStreamSynchronize(h->stream);
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
-    DevBuf* bufs[] = { &h->d_queries, &h->d_thetas, &h->d_proj, &h->d_rcs, &h->d_qflags,
-                       &h->d_state, &h->d_results, &h->d_inc, &h->d_rootoff, &h->d_stats,
-                       &h->d_counts, &h->d_overflow, &h->d_bestkey, &h->d_rtblocks,
-                       &h->d_gridoff, &h->d_gridpos, &h->d_pyrjobs, &h->d_tmpscan };
+    DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)
@@ -845,8 +948,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
         h->pyramid_mode = value;
         return CSM_OK;
     }
-    if (std::strcmp(name, "bb_seed_incumbent") == 0) { h->bb_seed_incumbent = value; return CSM_OK; }
-    if (std::strcmp(name, "bb_dive") == 0) { h->bb_dive = value; return CSM_OK; }
+    if (std::strcmp(name, "bb_dive") == 0 && value >= 0 && value <= 2) { h->bb_dive = value; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
     if (std::strcmp(name, "reset_best_key") == 0) {
         int rc = ensure(h, h->d_bestkey, 8);
@@ -1183,7 +1285,7 @@ int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, 
 {
     if (!h) return CSM_E_INVALID;
     CSM_CUDA(cudaSetDevice(h->device));
-    return bb_enqueue(h, queries, nq, hmax, query_index_base);
+    return bb_enqueue(h, queries, nq, hmax, query_index_base, nullptr);
 }
 
 int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq)
@@ -1202,8 +1304,8 @@ int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax
 
 int csm_debug_frontier_counts(csm_handle h, unsigned int* out8)
 {
-    if (!h || !out8 || !h->d_counts.p) return CSM_E_INVALID;
-    CSM_CUDA(cudaMemcpyAsync(out8, h->d_counts.p, sizeof(unsigned int) * kMaxLevels, cudaMemcpyDeviceToHost, h->stream));
+    if (!h || !out8 || !h->plan_view.counts) return CSM_E_INVALID;
+    CSM_CUDA(cudaMemcpyAsync(out8, h->plan_view.counts, sizeof(unsigned int) * kMaxLevels, cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
     return CSM_OK;
 }
@@ -1227,9 +1329,9 @@ int csm_match_bb(csm_handle h, int64_t map_id,
                  double score_thr, double known_thr, csm_result* out)
 {
     if (!h || !out || !sensor_pose) return CSM_E_INVALID;
+    if (h->res_count != 0)
+        return fail(h, CSM_E_INVALID, "match_bb: a loop batch is in flight on this handle");
     CSM_CUDA(cudaSetDevice(h->device));
-    int rc = upload_scan_impl(h, kTempScanId, angles, ranges, n);
-    if (rc) return rc;
     csm_loop_query q;
     std::memset(&q, 0, sizeof(q));
     q.map_id = map_id;
@@ -1238,9 +1340,8 @@ int csm_match_bb(csm_handle h, int64_t map_id,
     q.win_x = win_x; q.win_y = win_y; q.win_t = win_t;
     q.step_x = step_x; q.step_y = step_y; q.step_t = step_t;
     q.score_thr = score_thr; q.known_thr = known_thr;
-    if (h->res_count != 0)
-        return fail(h, CSM_E_INVALID, "match_bb: a loop batch is in flight on this handle");
-    rc = bb_enqueue(h, &q, 1, hmax, 0);
+    const InlineScan scan { angles, ranges, n };
+    const int rc = bb_enqueue(h, &q, 1, hmax, 0, &scan);
     if (rc) return rc;
     return finish_results(h, out, 1);
 }
@@ -1273,18 +1374,25 @@ int csm_match_rt(csm_handle h, int64_t map_id,
         return fail(h, CSM_E_INVALID, "match_rt: negative window");
     if (win_x > 8000 || win_y > 8000 || win_t > 32000)
         return fail(h, CSM_E_UNSUPPORTED, "match_rt: window too large");
-    int rc = upload_scan_impl(h, kTempScanId, angles, ranges, n);
-    if (rc) return rc;
-    const ScanSlot& s = h->scans[kTempScanId];
+    if (n <= 0 || n > kMaxBeams || angles == nullptr || ranges == nullptr)
+        return fail(h, CSM_E_INVALID, "scan: need 1 <= n <= 4096 beams");
+
+    int rc;
+    PlanView V;
+    const int T = 2 * win_t + 1;
+    if ((rc = layout_plan(h, 1, (size_t)T, 0, 0, n, V))) return rc;
+    ScanSlot s = V.scan;
+    s.max_range = *std::max_element(ranges, ranges + n);
 
     QueryPlan plan;
     plan.dq.resize(1);
     plan.theta_off.assign(1, 0);
     plan.inc_init.assign(1, 0ull);
+    plan.scan_angles = angles; plan.scan_ranges = ranges;
     DevQuery& Q = plan.dq[0];
     if ((rc = fill_common(h, Q, m, s, score_thr, known_thr))) return rc;
     Q.sx = sensor_pose[0]; Q.sy = sensor_pose[1];
-    Q.T = 2 * win_t + 1;
+    Q.T = T;
     Q.winx = win_x; Q.winy = win_y;
     Q.proj_off = 0;
     Q.pst_t = Q.n; Q.pst_i = 1;
@@ -1298,23 +1406,23 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     const int nby = (2 * win_y) / low_res + 1;
     const int nblocks = Q.T * nbx * nby;
     if ((rc = ensure(h, h->d_rtblocks, sizeof(RtBlock) * (size_t)nblocks))) return rc;
-    if ((rc = stage_plan(h, plan, false))) return rc;
-    if ((rc = launch_project(h, plan, false))) return rc;
-    const DevQuery* dq = static_cast<const DevQuery*>(h->d_queries.p);
+    if ((rc = commit_plan(h, plan, V, false))) return rc;
+    if ((rc = launch_project(h, plan, V, false))) return rc;
+    const DevQuery* dq = V.queries;
     const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
     k_rt_blocks<<<nblocks, 256, sizeof(long long) * low_res * low_res, h->stream>>>(
         dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby);
     CSM_LAUNCH_CHECK();
-    k_rt_replay<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const RtBlock*>(h->d_rtblocks.p),
-                                         low_res, nbx, nby, static_cast<BestState*>(h->d_state.p));
-    CSM_LAUNCH_CHECK();
     FinalArgs F;
     std::memset(&F, 0, sizeof(F));
+    F.decode = 3;
+    F.blocks = static_cast<const RtBlock*>(h->d_rtblocks.p);
+    F.low_res = low_res; F.nbx = nbx; F.nby = nby;
     F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
     F.mode = 0;
-    F.qflags = static_cast<const int*>(h->d_qflags.p);
-    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
-                                        static_cast<csm_result*>(h->d_results.p));
+    F.qflags = V.qflags;
+    F.nq = 1;
+    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
     if ((rc = enqueue_readback(h, 1))) return rc;
     return finish_results(h, out, 1);
@@ -1342,9 +1450,8 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     if (ndx <= 0 || ndy <= 0 || ndt <= 0 || ndt > 65535 ||
         (unsigned long long)ndx * ndy * ndt >= kOrdMask - 1ull)
         return fail(h, CSM_E_UNSUPPORTED, "match_grid: window exceeds 2^26 candidates");
-    int rc = upload_scan_impl(h, kTempScanId, angles, ranges, n);
-    if (rc) return rc;
-    const ScanSlot& s = h->scans[kTempScanId];
+    if (n <= 0 || n > kMaxBeams || angles == nullptr || ranges == nullptr)
+        return fail(h, CSM_E_INVALID, "scan: need 1 <= n <= 4096 beams");
 
     /* integer-shift path iff every dx[k] - dx[0] (dy likewise) is an integer
      * number of cells up to rounding noise */
@@ -1366,10 +1473,19 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     for (int v : offs)
         fast = fast && std::abs(v) <= 8192;
 
+    int rc;
+    PlanView V;
+    const size_t ob = align16(sizeof(int) * offs.size());
+    const size_t pb = sizeof(double) * (size_t)(ndx + ndy);
+    if ((rc = layout_plan(h, 1, (size_t)ndt, 0, ob + pb, n, V))) return rc;
+    ScanSlot s = V.scan;
+    s.max_range = *std::max_element(ranges, ranges + n);
+
     QueryPlan plan;
     plan.dq.resize(1);
     plan.theta_off.assign(1, 0);
     plan.inc_init.assign(1, 0ull);
+    plan.scan_angles = angles; plan.scan_ranges = ranges;
     DevQuery& Q = plan.dq[0];
     if ((rc = fill_common(h, Q, m, s, score_thr, known_thr))) return rc;
     Q.sx = sensor_pose[0] + dx[0];
@@ -1385,55 +1501,45 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     for (int k = 0; k < ndt; ++k)
         plan.thetas.push_back(sensor_pose[2] + dt[k]);
 
-    std::vector<double> pos(ndx + ndy);
-    for (int k = 0; k < ndx; ++k) pos[k] = sensor_pose[0] + dx[k];
-    for (int k = 0; k < ndy; ++k) pos[ndx + k] = sensor_pose[1] + dy[k];
-    if ((rc = ensure(h, h->d_gridoff, sizeof(int) * offs.size()))) return rc;
-    if ((rc = ensure(h, h->d_gridpos, sizeof(double) * pos.size()))) return rc;
-    if ((rc = stage_plan(h, plan, !fast))) return rc;
+    plan.extra.resize(ob + pb);
+    std::memcpy(plan.extra.data(), offs.data(), sizeof(int) * offs.size());
     {
-        const size_t ob = sizeof(int) * offs.size(), pb = sizeof(double) * pos.size();
-        const size_t ob16 = (ob + 15) & ~(size_t)15;
-        char* hp = nullptr;
-        if ((rc = acquire_upload(h, ob16 + pb + 16, &hp))) return rc;
-        std::memcpy(hp, offs.data(), ob);
-        std::memcpy(hp + ob16, pos.data(), pb);
-        if ((rc = pull_to_device(h, h->d_gridoff.p, hp, ob))) return rc;
-        if ((rc = pull_to_device(h, h->d_gridpos.p, hp + ob16, pb))) return rc;
-        if ((rc = upload_committed(h))) return rc;
+        double* pos = reinterpret_cast<double*>(plan.extra.data() + ob);
+        for (int k = 0; k < ndx; ++k) pos[k] = sensor_pose[0] + dx[k];
+        for (int k = 0; k < ndy; ++k) pos[ndx + k] = sensor_pose[1] + dy[k];
     }
-    if ((rc = launch_project(h, plan, !fast))) return rc;
+    if ((rc = commit_plan(h, plan, V, !fast))) return rc;
+    if ((rc = launch_project(h, plan, V, !fast))) return rc;
 
     GridArgs G;
-    G.mx = static_cast<const int*>(h->d_gridoff.p);
+    G.mx = reinterpret_cast<const int*>(V.extra);
     G.my = G.mx + ndx;
-    G.px = static_cast<const double*>(h->d_gridpos.p);
+    G.px = reinterpret_cast<const double*>(V.extra + ob);
     G.py = G.px + ndx;
     G.ndx = ndx; G.ndy = ndy; G.ndt = ndt;
-    G.best = static_cast<unsigned long long*>(h->d_inc.p);   /* zero-initialised by stage_plan */
+    G.best = V.inc;                       /* zero-initialised by the plan */
     G.tie = nullptr;
-    const DevQuery* dq = static_cast<const DevQuery*>(h->d_queries.p);
+    const DevQuery* dq = V.queries;
     const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
     dim3 grid(ndt, (ndy + 7) / 8);
     if (fast) {
         k_grid_window<<<grid, 256, sizeof(proj_t) * Q.n, h->stream>>>(dq, proj, G);
     } else {
         k_grid_general<<<grid, 256, sizeof(double2) * Q.n, h->stream>>>(
-            dq, static_cast<const double2*>(h->d_rcs.p), G, static_cast<int*>(h->d_qflags.p));
+            dq, static_cast<const double2*>(h->d_rcs.p), G, V.qflags);
     }
-    CSM_LAUNCH_CHECK();
-    k_grid_collect<<<1, 32, 0, h->stream>>>(G, static_cast<const int*>(h->d_qflags.p),
-                                            static_cast<BestState*>(h->d_state.p));
     CSM_LAUNCH_CHECK();
     FinalArgs F;
     std::memset(&F, 0, sizeof(F));
+    F.decode = 2;
+    F.G = G;
     F.mx = G.mx; F.my = G.my; F.px = G.px; F.py = G.py;
     F.rcs = fast ? nullptr : static_cast<const double2*>(h->d_rcs.p);
     F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
     F.mode = fast ? 1 : 2;
-    F.qflags = static_cast<const int*>(h->d_qflags.p);
-    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, static_cast<const BestState*>(h->d_state.p), F,
-                                        static_cast<csm_result*>(h->d_results.p));
+    F.qflags = V.qflags;
+    F.nq = 1;
+    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
     if ((rc = enqueue_readback(h, 1))) return rc;
     return finish_results(h, out, 1);

@@ -44,6 +44,7 @@ struct DevQuery
     const uint16_t* coarse;            /* RT: sliding max with win = low_res */
     int rows, cols;
     double res, offx, offy;
+    double inv_res;                    /* 1 / res (projection) */
     double sx, sy;                     /* sensor position (map-local) */
     const double* thetas;              /* T candidate sensor angles (host-computed doubles) */
     const double* angles;              /* N beam angles */

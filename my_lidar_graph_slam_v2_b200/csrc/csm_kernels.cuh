@@ -12,16 +12,18 @@
  *                     grid_map_geometry.cpp:113-122)
  *   k_rt_blocks       ComputeScore on the coarse map + EvaluateHighResolutionMap
  *                     for every coarse cell (scan_matcher_correlative.cpp:301-368)
- *   k_rt_replay       the sequential accept/skip decisions of
+ *   rt_replay         (in k_finalize) the sequential accept/skip decisions of
  *                     scan_matcher_correlative.cpp:161-197 replayed on keys
- *   k_bb_roots / k_bb_dive / k_bb_expand
+ *   k_bb_init / k_bb_score
  *                     branch-and-bound as level-synchronous frontier expansion
  *                     (scan_matcher_branch_bound.cpp:156-231)
  *   k_grid_window     exhaustive (dy, dx, dtheta) search, integer-shift path
  *   k_grid_general    same, per-candidate FP64 projection (arbitrary steps)
  *                     (scan_matcher_grid_search.cpp:118-142)
- *   k_finalize        integer score + reference-order double score at the
- *                     winning pose, packed best word for the NCCL argmax
+ *   k_finalize        winner decode, integer score + reference-order double score at
+ *                     the winning pose, packed best word for the NCCL argmax
+ *   k_setup           one-launch staging of a batch's descriptors and counters
+ *   k_scatter_blocks  block-sparse upload -> dense level 0
  */
 #pragma once
 
@@ -39,6 +41,43 @@ k_pull(uint4* __restrict__ dst, const uint4* __restrict__ src_host, unsigned int
 {
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
         dst[i] = src_host[i];
+}
+
+/* One launch that stages everything small a batch needs: pulls a contiguous
+ * block of descriptors (queries, candidate angles, incumbents, root offsets,
+ * per-call scan) from page-locked host memory, zeroes the per-batch counters,
+ * optionally clears the packed best word, and fills the per-beam trig table of
+ * a scan that arrives with this call. */
+struct SetupArgs
+{
+    uint4* dst;
+    const uint4* src_host;
+    unsigned int n16;
+    uint4* zero;
+    unsigned int z16;
+    unsigned long long* best_key;      /* cleared when non-null */
+    const double* angles_host;         /* scan arriving with this call (else null) */
+    double2* trig;
+    int n_beams;
+};
+
+__global__ void __launch_bounds__(256)
+k_setup(SetupArgs A)
+{
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nth = gridDim.x * blockDim.x;
+    for (unsigned int i = tid; i < A.n16; i += nth)
+        A.dst[i] = A.src_host[i];
+    for (unsigned int i = tid; i < A.z16; i += nth)
+        A.zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0 && A.best_key != nullptr)
+        *A.best_key = 0ull;
+    if (A.angles_host != nullptr)
+        for (unsigned int i = tid; i < (unsigned int)A.n_beams; i += nth) {
+            double sn, cs;
+            sincos(A.angles_host[i], &sn, &cs);
+            A.trig[i] = make_double2(cs, sn);
+        }
 }
 
 /* Block-sparse upload: expand the allocated blocks of a batch of maps into
@@ -293,18 +332,6 @@ k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
 /* Projection                                                                */
 /* ------------------------------------------------------------------------ */
 
-/* Per-scan table: (cos a_i, sin a_i) of every beam angle, computed once when
- * the scan is uploaded. */
-__global__ void __launch_bounds__(256)
-k_beam_trig(const double* __restrict__ angles, double2* __restrict__ trig, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s, c;
-    sincos(angles[i], &s, &c);
-    trig[i] = make_double2(c, s);
-}
-
 constexpr int kProjAngles = 8;       /* candidate angles per CTA */
 constexpr int kProjSat = 30000;      /* saturation of projected indices (maps are <= 16384 wide) */
 
@@ -345,8 +372,11 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         const double r = Q.ranges[i];
         const double rc = __dmul_rn(r, c);
         const double rs = __dmul_rn(r, s);
-        const double ux = __ddiv_rn(__dsub_rn(__dadd_rn(Q.sx, rc), Q.offx), Q.res);
-        const double uy = __ddiv_rn(__dsub_rn(__dadd_rn(Q.sy, rs), Q.offy), Q.res);
+        /* (x - off) * (1 / res) instead of the reference's (x - off) / res: the two
+         * differ by < 2 ulp, i.e. floor() can only differ inside the guard band
+         * that is flagged anyway (the band is ~1000x wider) */
+        const double ux = __dmul_rn(__dsub_rn(__dadd_rn(Q.sx, rc), Q.offx), Q.inv_res);
+        const double uy = __dmul_rn(__dsub_rn(__dadd_rn(Q.sy, rs), Q.offy), Q.inv_res);
         const double fx = floor(ux), fy = floor(uy);
         const double gx = ux - fx, gy = uy - fy;
         if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
@@ -468,57 +498,84 @@ struct BestState
 };
 
 /* Replays scan_matcher_correlative.cpp:161-197 over the coarse cells in the
- * reference's order (t, x, y) on integer keys. One thread. Exact also when
- * the coarse bound is not admissible. */
-__global__ void k_rt_replay(const DevQuery* __restrict__ queries,
-                            const proj_t* __restrict__ proj_all,
-                            const RtBlock* __restrict__ blocks, int low_res,
-                            int nbx, int nby, BestState* __restrict__ state)
+ * reference's order (t, x, y) on integer keys: exact also when the coarse
+ * bound is not admissible. Called by one warp: the lanes
+ * stage the block records in shared memory, lane 0 takes the decisions. */
+constexpr int kReplayChunk = 256;
+
+__device__ void rt_replay(const DevQuery& Q, const proj_t* __restrict__ proj_all,
+                          const RtBlock* __restrict__ blocks, int low_res, int nbx, int nby,
+                          RtBlock* s_blocks, BestState& out)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0)
-        return;
-    const DevQuery& Q = queries[0];
+    const int lane = threadIdx.x & 31;
     bool have = false;          /* scoreMax is a fine score (else: the threshold) */
     long long cur = 0;
     int bestx = -Q.winx, besty = -Q.winy, bestt = 0, flags = 0;
     int processed = 0, ignored = 0;
     const int nb = Q.T * nbx * nby;
-    for (int b = 0; b < nb; ++b) {
-        const RtBlock B = blocks[b];
-        const int t = b / (nbx * nby);
-        const int rem = b - t * nbx * nby;
-        const int bx = rem / nby, by = rem - bx * nby;
-        const int x = -Q.winx + bx * low_res, y = -Q.winy + by * low_res;
-        const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
-        bool coarse_ok;
-        if (have) {
-            coarse_ok = B.coarse_key > cur;
-            if (B.coarse_key == cur) flags |= 2;   /* equal keys: doubles could round either way */
-        } else {
-            coarse_ok = passes_threshold(B.coarse_key, Q, Q.coarse, proj, x, y);
-        }
-        if (!coarse_ok || B.coarse_nk <= Q.nk_cut) {
-            ++ignored;
+    int t = 0, bx = 0, by = 0;       /* block b = (t, bx, by), advanced without divisions */
+    int best_ord = 0, best_x0 = 0, best_y0 = 0;
+    for (int base = 0; base < nb; base += kReplayChunk) {
+        const int cnt = min(kReplayChunk, nb - base);
+        __syncwarp();
+        for (int i = lane; i < cnt * (int)(sizeof(RtBlock) / 16); i += 32)
+            reinterpret_cast<uint4*>(s_blocks)[i] = reinterpret_cast<const uint4*>(blocks + base)[i];
+        __syncwarp();
+        if (lane != 0)
             continue;
-        }
-        ++processed;
-        bool fine_ok;
-        const int fx = x + B.fine_ord / low_res, fy = y + B.fine_ord % low_res;
-        if (have) fine_ok = B.fine_key > cur;
-        else fine_ok = passes_threshold(B.fine_key, Q, Q.lvl[0], proj, fx, fy);
-        if (fine_ok) {
-            have = true;
-            cur = B.fine_key;
-            bestx = fx; besty = fy; bestt = t;
-            if (B.fine_tie) flags |= 2;
+        for (int k = 0; k < cnt; ++k) {
+            const long long coarse_key = s_blocks[k].coarse_key;
+            const long long fine_key = s_blocks[k].fine_key;
+            const int coarse_nk = s_blocks[k].coarse_nk;
+            const int x = -Q.winx + bx * low_res, y = -Q.winy + by * low_res;
+            const int tt = t;
+            if (++by == nby) { by = 0; if (++bx == nbx) { bx = 0; ++t; } }
+            bool coarse_ok;
+            if (have) {
+                coarse_ok = coarse_key > cur;
+                if (coarse_key == cur) flags |= 2;   /* equal keys: doubles could round either way */
+            } else {
+                const int c = key_vs_threshold(coarse_key, Q.kthr);
+                coarse_ok = c > 0;
+                if (c == 0)
+                    coarse_ok = exact_normalized_score(Q.coarse, Q.rows, Q.cols,
+                                                       proj_all + Q.proj_off + (size_t)tt * Q.n, Q.pst_i, Q.n,
+                                                       x, y) > Q.kthr.thr;
+            }
+            if (!coarse_ok || coarse_nk <= Q.nk_cut) {
+                ++ignored;
+                continue;
+            }
+            ++processed;
+            bool fine_ok;
+            if (have) {
+                fine_ok = fine_key > cur;
+            } else {
+                const int c = key_vs_threshold(fine_key, Q.kthr);
+                fine_ok = c > 0;
+                if (c == 0) {
+                    const int ord = s_blocks[k].fine_ord;
+                    fine_ok = exact_normalized_score(Q.lvl[0], Q.rows, Q.cols,
+                                                     proj_all + Q.proj_off + (size_t)tt * Q.n, Q.pst_i, Q.n,
+                                                     x + ord / low_res, y + ord % low_res) > Q.kthr.thr;
+                }
+            }
+            if (fine_ok) {
+                have = true;
+                cur = fine_key;
+                best_ord = s_blocks[k].fine_ord; best_x0 = x; best_y0 = y; bestt = tt;
+                if (s_blocks[k].fine_tie) flags |= 2;
+            }
         }
     }
-    BestState s;
-    s.found = have ? 1 : 0;
-    s.bx = bestx; s.by = besty;
-    s.bt = have ? bestt : 0;    /* reference initial bestWinTheta = -winTheta = index 0 */
-    s.flags = flags; s.n_processed = processed; s.n_ignored = ignored; s.pad = 0;
-    state[0] = s;
+    if (have) {
+        bestx = best_x0 + best_ord / low_res;
+        besty = best_y0 + best_ord % low_res;
+    }
+    out.found = have ? 1 : 0;
+    out.bx = bestx; out.by = besty;
+    out.bt = have ? bestt : 0;    /* reference initial bestWinTheta = -winTheta = index 0 */
+    out.flags = flags; out.n_processed = processed; out.n_ignored = ignored; out.pad = 0;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -549,6 +606,7 @@ struct BbWork
     unsigned long long* incumbent;  /* per query: packed (key, ordfield) */
     int*                stats;      /* per query: processed, ignored */
     int*                overflow;   /* set when a list is full */
+    long long*          rootkey;    /* per root candidate: its key if it passed, else -1 (feeds the dive) */
     unsigned int        capacity;
     int                 hmax;
 };
@@ -654,6 +712,8 @@ k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
             }
             if (pass && h == 0 && part == 0)
                 atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
+            if (h == W.hmax && part == 0 && W.rootkey != nullptr)
+                W.rootkey[idx] = pass ? key : -1ll;
         }
         {
             /* processed / ignored counters, one atomic per (warp, query, outcome) */
@@ -684,32 +744,154 @@ k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
     }
 }
 
-/* Decode the incumbents into BestState records */
-__global__ void k_bb_collect(const DevQuery* __restrict__ queries, BbWork W, int nq,
-                             const int* __restrict__ qflags, BestState* __restrict__ state)
+/* ---- incumbent dive ----------------------------------------------------------
+ * The level-synchronous search only meets leaves at the last launch, so
+ * without help nothing is ever pruned against a found pose (with a zero score
+ * threshold it would degenerate into the exhaustive search). One CTA per query
+ * therefore descends first: the kDiveBeam best root nodes, then at every height
+ * the kDiveBeam best of their children, down to a leaf, whose packed (key,
+ * ordinal) becomes the query's incumbent. Any real leaf is a valid incumbent:
+ * the search result (maximum key, smallest ordinal) does not depend on it,
+ * only the amount of work does. */
+constexpr int kDiveBeam = 8;
+
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* s_red)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq)
-        return;
-    const DevQuery& Q = queries[q];
-    const unsigned long long inc = W.incumbent[q];
-    BestState s;
-    const unsigned long long ordf = inc & kOrdMask;
-    s.found = (ordf != kOrdMask) ? 1 : 0;   /* initial incumbent carries the all-ones field */
-    if (s.found) {
-        unsigned long long ord = (kOrdMask - 1ull) - ordf;
-        const int yi = (int)(ord % (unsigned)Q.ly); ord /= (unsigned)Q.ly;
-        const int xi = (int)(ord % (unsigned)Q.lx); ord /= (unsigned)Q.lx;
-        s.bx = xi - Q.winx; s.by = yi - Q.winy; s.bt = (int)ord;
-    } else {
-        /* reference: bestX = bestY = bestTheta = 0 (scan_matcher_branch_bound.cpp:145-147) */
-        s.bx = 0; s.by = 0; s.bt = (Q.T - 1) / 2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
     }
-    s.flags = qflags[q];
-    s.n_processed = W.stats[2 * q];
-    s.n_ignored = W.stats[2 * q + 1];
-    s.pad = 0;
-    state[q] = s;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = s_red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = s_red[w] > r ? s_red[w] : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
+          const unsigned int* __restrict__ root_off, BbWork W)
+{
+    __shared__ unsigned long long s_red[8];
+    __shared__ int s_beam[2][kDiveBeam][3];          /* (t, xi, yi) */
+    __shared__ int s_nbeam;
+    __shared__ long long s_key[4 * kDiveBeam];
+    __shared__ int s_ok[4 * kDiveBeam];
+    const int q = blockIdx.x;
+    const DevQuery& Q = queries[q];
+    const unsigned int r0 = root_off[q];
+    const unsigned int R = root_off[q + 1] - r0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (R >= (1u << 20))
+        return;
+    /* the kDiveBeam best roots, in (key descending, index ascending) order */
+    unsigned long long last = ~0ull;
+    int nbeam = 0;
+    for (int j = 0; j < kDiveBeam; ++j) {
+        unsigned long long best = 0ull;
+        for (unsigned int e = threadIdx.x; e < R; e += blockDim.x) {
+            const long long k = W.rootkey[r0 + e];
+            if (k < 0) continue;
+            const unsigned long long v = ((unsigned long long)(k + 1) << 20) | (unsigned long long)(0xFFFFFu - e);
+            if (v < last && v > best) best = v;
+        }
+        best = block_max_u64(best, s_red);
+        if (best == 0ull)
+            break;
+        last = best;
+        if (threadIdx.x == 0) {
+            const int e = (int)(0xFFFFFu - (unsigned int)(best & 0xFFFFFull));
+            const int t = e % Q.T, cell = e / Q.T;
+            const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
+            s_beam[0][j][0] = t; s_beam[0][j][1] = rx << W.hmax; s_beam[0][j][2] = ry << W.hmax;
+        }
+        ++nbeam;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int h = W.hmax; h >= 1 && nbeam > 0; --h) {
+        const int w = 1 << (h - 1);
+        const uint16_t* __restrict__ m = Q.lvl[h - 1];
+        const int ncand = 4 * nbeam;
+        {
+            /* warp `warp` scores candidates warp, warp + 8, warp + 16, warp + 24 at once:
+             * up to 4 x 12 independent (index, cell) load pairs per lane in flight */
+            const int rows = Q.rows, cols = Q.cols, n = Q.n;
+            const size_t ps = (size_t)Q.pst_i;
+            const proj_t* __restrict__ pp[4];
+            int ox[4], oy[4], sv[4], kn[4];
+            bool on[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = warp + 8 * j;
+                on[j] = c < ncand;
+                const int b = on[j] ? (c >> 2) : 0, ch = c & 3;
+                pp[j] = proj_all + Q.proj_off + (size_t)s_beam[cur][b][0] * Q.pst_t;
+                ox[j] = s_beam[cur][b][1] + (ch & 1) * w - Q.winx;
+                oy[j] = s_beam[cur][b][2] + (ch >> 1) * w - Q.winy;
+                sv[j] = 0; kn[j] = 0;
+            }
+#pragma unroll 4
+            for (int i = lane; i < n; i += 32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!on[j]) continue;
+                    const proj_t p = pp[j][(size_t)i * ps];
+                    const unsigned int v = ld_cell(m, rows, cols, p.y + oy[j], p.x + ox[j]);
+                    sv[j] += (int)v; kn[j] += (v != 0u);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = warp_sum(sv[j]), k = warp_sum(kn[j]);
+                if (on[j] && lane == 0) {
+                    const long long key = make_key(s, k);
+                    s_key[warp + 8 * j] = key;
+                    /* strictly above the threshold (outside its guard band) and known enough */
+                    s_ok[warp + 8 * j] = (k > Q.nk_cut && key_vs_threshold(key, Q.kthr) > 0) ? 1 : 0;
+                }
+            }
+        }
+        __syncthreads();
+        if (h - 1 == 0) {
+            if (threadIdx.x == 0) {
+                unsigned long long best = 0ull;
+                for (int c = 0; c < ncand; ++c) {
+                    if (!s_ok[c]) continue;
+                    const int b = c >> 2, ch = c & 3;
+                    const int xi = s_beam[cur][b][1] + (ch & 1), yi = s_beam[cur][b][2] + (ch >> 1);
+                    const unsigned long long v = pack_best(s_key[c], leaf_ordfield(Q, s_beam[cur][b][0], xi, yi));
+                    best = v > best ? v : best;
+                }
+                if (best != 0ull)
+                    atomicMax(&W.incumbent[q], best);
+            }
+            break;
+        }
+        /* next beam: the kDiveBeam best passing children (rank by key, then by position) */
+        if (threadIdx.x == 0) s_nbeam = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < ncand && s_ok[threadIdx.x]) {
+            const int c = threadIdx.x;
+            int rank = 0;
+            for (int o = 0; o < ncand; ++o)
+                if (s_ok[o] && (s_key[o] > s_key[c] || (s_key[o] == s_key[c] && o < c)))
+                    ++rank;
+            if (rank < kDiveBeam) {
+                const int b = c >> 2, ch = c & 3;
+                s_beam[cur ^ 1][rank][0] = s_beam[cur][b][0];
+                s_beam[cur ^ 1][rank][1] = s_beam[cur][b][1] + (ch & 1) * w;
+                s_beam[cur ^ 1][rank][2] = s_beam[cur][b][2] + (ch >> 1) * w;
+                atomicAdd(&s_nbeam, 1);
+            }
+        }
+        __syncthreads();
+        nbeam = min(s_nbeam, kDiveBeam);
+        cur ^= 1;
+        __syncthreads();
+    }
 }
 
 /* ------------------------------------------------------------------------ */
@@ -855,56 +1037,91 @@ k_grid_general(const DevQuery* __restrict__ queries, const double2* __restrict__
     block_best_commit(best, G.best);
 }
 
-__global__ void k_grid_collect(GridArgs G, const int* __restrict__ qflags,
-                               BestState* __restrict__ state)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0)
-        return;
-    const unsigned long long b = *G.best;
-    BestState s;
-    s.found = b != 0ull ? 1 : 0;
-    s.bx = s.by = s.bt = -1;
-    if (s.found) {
-        unsigned long long ord = (kOrdMask - 1ull) - (b & kOrdMask);
-        s.bt = (int)(ord % (unsigned)G.ndt); ord /= (unsigned)G.ndt;
-        s.bx = (int)(ord % (unsigned)G.ndx); ord /= (unsigned)G.ndx;
-        s.by = (int)ord;
-    }
-    s.flags = qflags[0];
-    s.n_processed = G.ndx * G.ndy * G.ndt;
-    s.n_ignored = 0;
-    s.pad = 0;
-    state[0] = s;
-}
-
 /* ------------------------------------------------------------------------ */
 /* Finalisation                                                              */
 /* ------------------------------------------------------------------------ */
 
 struct FinalArgs
 {
-    const int* mx;            /* grid search: cell offsets per index (else nullptr) */
+    int decode;               /* where the winner comes from: 1 = B&B incumbents, 2 = grid-search
+                                 best word, 3 = replay of the real-time correlative blocks */
+    int mode;                 /* 0 = window indices are cell offsets, 1 = grid fast, 2 = grid general */
+    /* decode 1 */
+    const unsigned long long* incumbent;
+    const int* stats;
+    /* decode 2 */
+    GridArgs G;
+    /* decode 3 */
+    const RtBlock* blocks;
+    int low_res, nbx, nby;
+    /* grid search: cell offsets per index / candidate positions / r*cos, r*sin */
+    const int* mx;
     const int* my;
-    const double* px;         /* grid search general path: sx + dx[k] (else nullptr) */
+    const double* px;
     const double* py;
     const double2* rcs;
     unsigned long long* best_key;   /* device word for the cross-rank argmax */
     const int* qflags;              /* per-query flags raised by the projection */
+    const int* overflow;            /* frontier overflow flag, copied behind the results */
     int query_index_base;
-    int mode;                 /* 0 = window indices are cell offsets, 1 = grid fast, 2 = grid general */
+    int nq;
 };
 
-/* One warp per query: integer score and reference-order double score of the
- * winning pose on the level-0 map; packs the per-batch best word. */
+/* One warp per query: decode the winner, integer score and reference-order
+ * double score of the winning pose on the level-0 map, packed best word. */
 __global__ void __launch_bounds__(32)
 k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
-           const BestState* __restrict__ state, FinalArgs F, csm_result* __restrict__ results)
+           FinalArgs F, csm_result* __restrict__ results)
 {
     __shared__ double s_prob[kMaxBeams];
+    __shared__ __align__(16) RtBlock s_blocks[kReplayChunk];
+    __shared__ BestState s_state;
     const int q = blockIdx.x;
     const DevQuery& Q = queries[q];
-    const BestState s = state[q];
     const int lane = threadIdx.x & 31;
+
+    if (F.decode == 3) {
+        BestState st;
+        rt_replay(Q, proj_all, F.blocks, F.low_res, F.nbx, F.nby, s_blocks, st);
+        if (lane == 0) s_state = st;
+    } else if (lane == 0) {
+        BestState st;
+        if (F.decode == 1) {
+            const unsigned long long inc = F.incumbent[q];
+            const unsigned long long ordf = inc & kOrdMask;
+            st.found = (ordf != kOrdMask) ? 1 : 0;   /* initial incumbent carries the all-ones field */
+            if (st.found) {
+                unsigned long long ord = (kOrdMask - 1ull) - ordf;
+                const int yi = (int)(ord % (unsigned)Q.ly); ord /= (unsigned)Q.ly;
+                const int xi = (int)(ord % (unsigned)Q.lx); ord /= (unsigned)Q.lx;
+                st.bx = xi - Q.winx; st.by = yi - Q.winy; st.bt = (int)ord;
+            } else {
+                /* reference: bestX = bestY = bestTheta = 0 (scan_matcher_branch_bound.cpp:145-147) */
+                st.bx = 0; st.by = 0; st.bt = (Q.T - 1) / 2;
+            }
+            st.flags = 0;
+            st.n_processed = F.stats[2 * q];
+            st.n_ignored = F.stats[2 * q + 1];
+        } else {
+            const unsigned long long b = *F.G.best;
+            st.found = b != 0ull ? 1 : 0;
+            st.bx = st.by = st.bt = -1;
+            if (st.found) {
+                unsigned long long ord = (kOrdMask - 1ull) - (b & kOrdMask);
+                st.bt = (int)(ord % (unsigned)F.G.ndt); ord /= (unsigned)F.G.ndt;
+                st.bx = (int)(ord % (unsigned)F.G.ndx); ord /= (unsigned)F.G.ndx;
+                st.by = (int)ord;
+            }
+            st.flags = 0;
+            st.n_processed = F.G.ndx * F.G.ndy * F.G.ndt;
+            st.n_ignored = 0;
+        }
+        st.pad = 0;
+        s_state = st;
+    }
+    __syncwarp();
+    const BestState s = s_state;
+
     const uint16_t* __restrict__ m = Q.lvl[0];
     csm_result r;
     r.found = s.found;
@@ -913,12 +1130,9 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
     r.n_ignored = s.n_ignored;
     r.sum_value = 0; r.n_known = 0; r.normalized_score = 0.0;
     const bool evaluate = (F.mode == 0) || s.found;
-    int it = s.bt;
-    if (F.mode == 0) {
-        r.best_x = s.bx; r.best_y = s.by; r.best_t = s.bt - (Q.T - 1) / 2;
-    } else {
-        r.best_x = s.bx; r.best_y = s.by; r.best_t = s.bt;
-    }
+    const int it = s.bt;
+    r.best_x = s.bx; r.best_y = s.by;
+    r.best_t = (F.mode == 0) ? s.bt - (Q.T - 1) / 2 : s.bt;
     int sumv = 0, nk = 0;
     if (evaluate) {
         const size_t row_off = (size_t)Q.proj_off + (size_t)it * Q.n;
@@ -939,7 +1153,8 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 col = p.x + ox; row = p.y + oy;
             }
             const unsigned int v = ld_cell(m, Q.rows, Q.cols, row, col);
-            s_prob[i] = (v != 0u) ? value_to_probability(v) : -1.0;
+            /* unknown cells are skipped by the reference; adding +0.0 leaves the sum unchanged */
+            s_prob[i] = (v != 0u) ? value_to_probability(v) : 0.0;
             ps += (int)v;
             pk += (v != 0u);
         }
@@ -947,12 +1162,18 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
         nk = warp_sum(pk);
         __syncwarp();
         if (lane == 0) {
+            /* the reference's sequential sum in scan order (score_function_pixel_accurate.cpp:21-57) */
             double sum = 0.0;
-            for (int i = 0; i < Q.n; ++i) {
-                const double pv = s_prob[i];
-                if (pv >= 0.0)
-                    sum = __dadd_rn(sum, pv);
+            int i = 0;
+            for (; i + 8 <= Q.n; i += 8) {
+                double pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pv[u] = s_prob[i + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum = __dadd_rn(sum, pv[u]);
             }
+            for (; i < Q.n; ++i)
+                sum = __dadd_rn(sum, s_prob[i]);
             r.normalized_score = __ddiv_rn(sum, (double)Q.n);
         }
     }
@@ -966,6 +1187,8 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 (unsigned long long)(0xFFFFF - (F.query_index_base + q));
             atomicMax(F.best_key, word);
         }
+        if (q == 0)     /* the overflow flag travels behind the results: one read-back */
+            *reinterpret_cast<int*>(results + F.nq) = (F.overflow != nullptr) ? *F.overflow : 0;
     }
 }
 

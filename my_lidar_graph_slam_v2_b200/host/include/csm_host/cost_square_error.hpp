@@ -20,6 +20,9 @@ public:
     double Cost(const GridMapView& map, const ScanData& scan, const Pose2D& sensor_pose) const;
     std::array<double, 9> ComputeCovariance(const GridMapView& map, const ScanData& scan,
                                             const Pose2D& sensor_pose) const;
+    /* Both in one pass over the scan (what every matcher's epilogue needs) */
+    std::array<double, 9> CostAndCovariance(const GridMapView& map, const ScanData& scan,
+                                            const Pose2D& sensor_pose, double& cost) const;
 
 private:
     double mCovarianceScale;

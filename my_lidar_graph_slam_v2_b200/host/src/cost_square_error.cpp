@@ -109,25 +109,15 @@ inline void HitPoint(const ScanData& scan, const Pose2D& pose, std::size_t i, do
 
 } /* namespace */
 
-double CostSquareError::Cost(const GridMapView& map, const ScanData& scan, const Pose2D& pose) const
+namespace {
+
+/* One pass over the scan: squared-error cost (:48-75) and, when h != nullptr,
+ * the Gauss-Newton Hessian (:151-195) from the same map samples. The two
+ * accumulations are independent, each in the reference's own order. */
+double Accumulate(const GridMapView& map, const ScanData& scan, const Pose2D& pose, double* h)
 {
     const Sampler sampler(map);
     double cost = 0.0;
-    for (std::size_t i = 0; i < scan.NumOfScans(); ++i) {
-        double hx, hy;
-        HitPoint(scan, pose, i, hx, hy);
-        const double fx = (hx - map.offset_x) / map.resolution;
-        const double fy = (hy - map.offset_y) / map.resolution;
-        cost += std::pow(1.0 - Closest(sampler, fx, fy).Smoothed(), 2.0);
-    }
-    return cost;
-}
-
-std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map, const ScanData& scan,
-                                                         const Pose2D& pose) const
-{
-    const Sampler sampler(map);
-    double h[9] = { 0.0 };
     const double inv_res = 1.0 / map.resolution;
     for (std::size_t i = 0; i < scan.NumOfScans(); ++i) {
         double hx, hy;
@@ -135,6 +125,9 @@ std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map,
         const double fx = (hx - map.offset_x) / map.resolution;
         const double fy = (hy - map.offset_y) / map.resolution;
         const Neighbours n = Closest(sampler, fx, fy);
+        cost += std::pow(1.0 - n.Smoothed(), 2.0);
+        if (h == nullptr)
+            continue;
         const double gx = n.dy * (n.m11 - n.m01) + (1.0 - n.dy) * (n.m10 - n.m00);
         const double gy = n.dx * (n.m11 - n.m10) + (1.0 - n.dx) * (n.m01 - n.m00);
         const double gt = -(hy - pose.y) * gx + (hx - pose.x) * gy;
@@ -143,6 +136,11 @@ std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map,
             for (int c = 0; c < 3; ++c)
                 h[r * 3 + c] += g[r] * g[c];
     }
+    return cost;
+}
+
+std::array<double, 9> InverseScaled(const double h[9], double scale)
+{
     const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) +
                        h[2] * (h[3] * h[7] - h[4] * h[6]);
     const double id = 1.0 / det;
@@ -151,8 +149,31 @@ std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map,
         (h[5] * h[6] - h[3] * h[8]) * id, (h[0] * h[8] - h[2] * h[6]) * id, (h[2] * h[3] - h[0] * h[5]) * id,
         (h[3] * h[7] - h[4] * h[6]) * id, (h[1] * h[6] - h[0] * h[7]) * id, (h[0] * h[4] - h[1] * h[3]) * id };
     for (double& v : cov)
-        v *= mCovarianceScale;
+        v *= scale;
     return cov;
+}
+
+} /* namespace */
+
+double CostSquareError::Cost(const GridMapView& map, const ScanData& scan, const Pose2D& pose) const
+{
+    return Accumulate(map, scan, pose, nullptr);
+}
+
+std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map, const ScanData& scan,
+                                                         const Pose2D& pose) const
+{
+    double h[9] = { 0.0 };
+    Accumulate(map, scan, pose, h);
+    return InverseScaled(h, mCovarianceScale);
+}
+
+std::array<double, 9> CostSquareError::CostAndCovariance(const GridMapView& map, const ScanData& scan,
+                                                         const Pose2D& pose, double& cost) const
+{
+    double h[9] = { 0.0 };
+    cost = Accumulate(map, scan, pose, h);
+    return InverseScaled(h, mCovarianceScale);
 }
 
 } /* namespace csm_host */

@@ -56,9 +56,10 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
 void ScanMatcher::Epilogue(const GridMapView& map, const ScanData& scan, const Pose2D& best,
                            const CostFuncPtr& cost, ScanMatchingSummary& summary) const
 {
-    summary.normalized_cost = cost->Cost(map, scan, best) / static_cast<double>(scan.NumOfScans());
+    double c = 0.0;
+    summary.estimated_covariance = cost->CostAndCovariance(map, scan, best, c);
+    summary.normalized_cost = c / static_cast<double>(scan.NumOfScans());
     summary.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
-    summary.estimated_covariance = cost->ComputeCovariance(map, scan, best);
 }
 
 void ComputeSearchStep(double resolution, const ScanData& scan,

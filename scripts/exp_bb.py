@@ -24,10 +24,10 @@ def run(label):
     print("%-28s frontier per height %s  sum %d  processed %d  found %d  %.3f ms" % (
         label, c[:7], sum(c), sum(r.n_processed for r in res), sum(r.found for r in res), dt * 1e3))
     return res
-run("dive incumbent")
-h.set_option("bb_dive", 0); run("no dive (threshold only)")
+h.set_option("bb_dive", 1); r = run("dive (beam 8)")
+h.set_option("bb_dive", 0); r0 = run("no dive (threshold only)")
 h.set_option("bb_dive", 1); r = run("dive again")
-h.set_option("bb_seed_incumbent", 1); run("seeded with optimum")
-h.set_option("bb_seed_incumbent", 0)
+same = all((a.found, a.best_x, a.best_y, a.best_t, a.sum_value) == (b.found, b.best_x, b.best_y, b.best_t, b.sum_value) for a, b in zip(r, r0))
+print("dive and no-dive results identical:", same)
 pos = [x.n_processed for x in r if x.found]; neg = [x.n_processed for x in r if not x.found]
 print("processed per found query: mean %.0f max %d ; per not-found: mean %.0f max %d" % (np.mean(pos), max(pos), np.mean(neg), max(neg)))
