@@ -396,7 +396,10 @@ def main_cuda(args):
     ev[3].record(ext_stream)
     ev[3].synchronize()
     bb_ms = ev[2].elapsed_time(ev[3]) / args.steps
-    nodes_scored = sum(h.frontier_counts()[:HMAX + 1])
+    # nodes scored per step: every root candidate + the four children of every node that passed
+    n_roots = sum((2 * a.win_t + 1) * ((2 * a.win_x) // (1 << HMAX) + 1) * ((2 * a.win_y) // (1 << HMAX) + 1)
+                  for a in arr)
+    nodes_scored = n_roots + 4 * sum(h.frontier_counts()[1:HMAX + 1])
 
     peaks = {}
     try:
@@ -407,11 +410,11 @@ def main_cuda(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
     step_ms = dev_ms / args.steps
-    # dominant kernel: k_bb_score (one launch per pyramid height). Algorithmic bytes:
+    # dominant kernels: k_bb_roots / k_bb_expand (one launch per pyramid height). Algorithmic bytes:
     # one u16 grid read per scored node and beam.
     bb_bytes = nodes_scored * 360 * 2
     roofline = {
-        "kernel": "k_bb_score (B&B frontier scoring, %d launches per step)" % (HMAX + 1),
+        "kernel": "k_bb_roots + k_bb_expand (B&B frontier scoring, %d launches per step)" % (HMAX + 1),
         "bound": "hbm", "achieved": bb_bytes / (bb_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": bb_bytes / (bb_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_source,
         "algorithmic_bytes_per_step": bb_bytes, "nodes_scored_per_step": int(nodes_scored),

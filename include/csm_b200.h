@@ -252,7 +252,14 @@ int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, 
 int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq);
 int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
                    int query_index_base, csm_result* results);
-/* Debug: number of frontier nodes queued per height by the last batch (8 entries) */
+/* Phase timing: after csm_set_option(h, "timing", 1) the library records a CUDA
+ * event on the handle's stream after every kernel of a loop batch (or of a
+ * streaming pyramid build). csm_debug_timings waits for the last one and
+ * returns the durations in ms of the phases of the LAST such call, with their
+ * names separated by ';' in `names`. Returns the number of phases. */
+int csm_debug_timings(csm_handle h, char* names, size_t names_cap, float* ms, int max_n);
+/* Debug: size of the node list of every height after the last batch (8 entries):
+ * the nodes of that height that passed and were expanded */
 int csm_debug_frontier_counts(csm_handle h, unsigned int* out8);
 void* csm_best_key_device(csm_handle h);
 void csm_decode_best_key(uint64_t best_key, int64_t* key, int32_t* query_index);

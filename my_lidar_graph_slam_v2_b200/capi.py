@@ -50,14 +50,14 @@ EXPORTS = [
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
-    "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts",
+    "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
 ]
 
 _LIB = None
 
 
 def lib_path():
-    return _build.LIB
+    return os.environ.get("CSM_B200_LIB", _build.LIB)
 
 
 def load():
@@ -114,6 +114,7 @@ def load():
     lib.csm_loop_batch_finish.argtypes = [H, rp, C.c_int]
     lib.csm_loop_batch.argtypes = [H, lq, C.c_int, C.c_int, C.c_int, rp]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
+    lib.csm_debug_timings.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
     lib.csm_best_key_device.argtypes = [H]
     lib.csm_best_key_device.restype = C.c_void_p
     lib.csm_decode_best_key.argtypes = [C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
@@ -286,6 +287,13 @@ class Handle:
         out = (C.c_uint * 8)()
         self._check(self.lib.csm_debug_frontier_counts(self.h, out))
         return list(out)
+
+    def timings(self):
+        """[(phase name, ms)] of the last loop batch / pyramid build (option "timing" must be 1)."""
+        names = C.create_string_buffer(2048)
+        ms = (C.c_float * 64)()
+        n = self.lib.csm_debug_timings(self.h, names, 2048, ms, 64)
+        return list(zip(names.value.decode().split(";")[:n], [ms[i] for i in range(n)]))
 
     def best_key_device_ptr(self):
         return self.lib.csm_best_key_device(self.h)

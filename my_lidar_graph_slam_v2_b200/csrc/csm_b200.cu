@@ -144,6 +144,15 @@ struct csm_context
                                       0 never, 1 always, 2 only for calls of at most 4 queries (there the
                                       latency of the dive is small against the nodes it saves) */
     int accumulate_best_key = 0;   /* 1: batches do not reset the packed best word */
+    /* last (thresholds, beams) -> integer cut-offs (fill_common) */
+    int memo_n = -1, memo_nk_cut = 0;
+    double memo_score_thr = -1.0, memo_known_thr = -1.0;
+    KeyThreshold memo_kthr {};
+    /* "timing" option: CUDA events between the phases of the last loop batch / pyramid build */
+    int timing = 0;
+    std::vector<cudaEvent_t> tev;
+    std::vector<std::string> tnames;
+    size_t tcount = 0;
 };
 
 namespace {
@@ -166,6 +175,23 @@ namespace {
             return CSM_E_CUDA;                                                 \
         }                                                                      \
     } while (0)
+
+/* timing: mark the end of a phase on the compute stream (no-op unless enabled) */
+void phase_mark(csm_handle h, const char* name)
+{
+    if (!h->timing)
+        return;
+    if (h->tcount >= h->tev.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess)
+            return;
+        h->tev.push_back(e);
+        h->tnames.emplace_back();
+    }
+    h->tnames[h->tcount] = name;
+    cudaEventRecord(h->tev[h->tcount], h->stream);
+    ++h->tcount;
+}
 
 int fail(csm_handle h, int code, const std::string& msg)
 {
@@ -495,8 +521,10 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             if (m->levels) CSM_CUDA(cudaFreeAsync(m->levels, h->stream));
             m->levels = nullptr;
             m->levels_alloc = 0;
-            const size_t bytes = (size_t)hmax * m->rows * m->cols * sizeof(uint16_t);
+            const size_t bytes = (size_t)hmax * tiled_cells(m->rows, m->cols) * sizeof(uint16_t);
             CSM_CUDA(cudaMallocAsync((void**)&m->levels, bytes, h->stream));
+            /* the zero border and the padding cells of the tiled levels are never written again */
+            CSM_CUDA(cudaMemsetAsync(m->levels, 0, bytes, h->stream));
             m->levels_alloc = hmax;
         }
         m->hmax = hmax;
@@ -533,9 +561,12 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             CSM_CUDA(cudaFuncSetAttribute(k_pyramid_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
+        h->tcount = 0;
+        phase_mark(h, "start");
         k_pyramid_stream<<<(unsigned)jobs.size(), kPsThreads, smem, h->stream>>>(
             static_cast<const PyrJob*>(h->d_pyrjobs.p), hmax);
         CSM_LAUNCH_CHECK();
+        phase_mark(h, "k_pyramid_stream");
         return CSM_OK;
     }
     /* Otherwise level by level; maps are processed in chunks so that level h-1
@@ -624,14 +655,21 @@ int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
     std::memset(&Q, 0, sizeof(Q));
     Q.lvl[0] = m.base;
     for (int l = 1; l <= m.hmax && l < kMaxLevels; ++l)
-        Q.lvl[l] = m.levels + (size_t)(l - 1) * m.rows * m.cols;
+        Q.lvl[l] = m.levels + (size_t)(l - 1) * tiled_cells(m.rows, m.cols);
     Q.coarse = m.coarse;
     Q.rows = m.rows; Q.cols = m.cols;
     Q.res = m.res; Q.offx = m.offx; Q.offy = m.offy;
     Q.inv_res = 1.0 / m.res;
     Q.angles = s.angles; Q.ranges = s.ranges; Q.beam_trig = s.trig; Q.n = s.n;
-    Q.kthr = make_key_threshold(score_thr, s.n);
-    Q.nk_cut = make_known_cut(known_thr, s.n);
+    /* the integer images of the two thresholds depend on (threshold, n) only: queries of a
+     * batch share them */
+    if (h->memo_n != s.n || h->memo_score_thr != score_thr || h->memo_known_thr != known_thr) {
+        h->memo_kthr = make_key_threshold(score_thr, s.n);
+        h->memo_nk_cut = make_known_cut(known_thr, s.n);
+        h->memo_n = s.n; h->memo_score_thr = score_thr; h->memo_known_thr = known_thr;
+    }
+    Q.kthr = h->memo_kthr;
+    Q.nk_cut = h->memo_nk_cut;
     return CSM_OK;
 }
 
@@ -647,7 +685,7 @@ int commit_plan(csm_handle h, QueryPlan& plan, const PlanView& V, bool want_rcs)
     if ((rc = ensure(h, h->d_results, sizeof(csm_result) * nq + 16))) return rc;
     if ((rc = ensure(h, h->d_bestkey, 8))) return rc;
     for (int q = 0; q < nq; ++q)
-        plan.dq[q].thetas = V.thetas + plan.theta_off[q];
+        plan.dq[q].thetas = plan.thetas.empty() ? nullptr : V.thetas + plan.theta_off[q];
     char* hp = nullptr;
     if ((rc = acquire_upload(h, V.pulled_bytes, &hp))) return rc;
     std::memcpy(hp + V.off_queries, plan.dq.data(), sizeof(DevQuery) * nq);
@@ -745,7 +783,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     }
     int rc;
     PlanView V;
-    if ((rc = layout_plan(h, nq, n_thetas, (size_t)nq + 1, 0, inline_scan ? inline_scan->n : 0, V))) return rc;
+    if ((rc = layout_plan(h, nq, 0, (size_t)nq + 1, 0, inline_scan ? inline_scan->n : 0, V))) return rc;
     ScanSlot inl = V.scan;
     if (inline_scan)
         inl.max_range = *std::max_element(inline_scan->ranges, inline_scan->ranges + inline_scan->n);
@@ -755,7 +793,6 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     plan.theta_off.resize(nq);
     plan.inc_init.resize(nq);
     plan.root_off.assign(nq + 1, 0u);
-    plan.thetas.reserve(n_thetas);
     if (inline_scan) { plan.scan_angles = inline_scan->angles; plan.scan_ranges = inline_scan->ranges; }
     const int wsz = 1 << hmax;
     for (int q = 0; q < nq; ++q) {
@@ -782,16 +819,19 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         plan.max_roots = std::max(plan.max_roots, Q.T * Q.nrx * Q.nry);
         const double extent = (double)(std::max(in.win_x, in.win_y) + wsz) * m.res;
         Q.margin = fp_margin(in.sensor_pose, m, s.max_range, extent);
-        plan.theta_off[q] = plan.thetas.size();
-        for (int t = -in.win_t; t <= in.win_t; ++t)
-            plan.thetas.push_back(in.sensor_pose[2] + t * in.step_t);
+        plan.theta_off[q] = 0;
+        Q.theta0 = in.sensor_pose[2]; Q.step_t = in.step_t; Q.tcenter = in.win_t;
         plan.inc_init[q] = ((unsigned long long)Q.kthr.fail_max << kOrdBits) | kOrdMask;
         plan.root_off[q + 1] = plan.root_off[q] + (unsigned int)(Q.T * Q.nrx * Q.nry);
     }
     if ((rc = wait_uploads(h, used_slots))) return rc;
     if ((rc = ensure_frontier(h, nq, plan.root_off[nq]))) return rc;
+    h->tcount = 0;
+    phase_mark(h, "start");
     if ((rc = commit_plan(h, plan, V, false))) return rc;
+    phase_mark(h, "k_setup");
     if ((rc = launch_project(h, plan, V, false))) return rc;
+    phase_mark(h, "k_project");
 
     BbWork W;
     std::memset(&W, 0, sizeof(W));
@@ -817,14 +857,37 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         CSM_LAUNCH_CHECK();
     }
     {
-        const int blocks = h->sm_count * 8;
-        for (int lvl = hmax; lvl >= 0; --lvl) {
-            k_bb_score<<<blocks, 256, 0, h->stream>>>(dq, proj, W, lvl);
+        const unsigned int n_roots = plan.root_off[nq];
+        const int full = h->sm_count * 8;
+        const int root_blocks = (int)std::min<unsigned int>((n_roots + 7) / 8, (unsigned int)full);
+        k_bb_roots<<<std::max(root_blocks, 1), 256, 0, h->stream>>>(dq, proj, W, n_roots);
+        CSM_LAUNCH_CHECK();
+        phase_mark(h, "k_bb_init+k_bb_roots");
+        if (dive) {
+            k_bb_dive<<<nq, 256, 0, h->stream>>>(dq, proj, V.rootoff, W);
             CSM_LAUNCH_CHECK();
-            if (lvl == hmax && dive) {
-                k_bb_dive<<<nq, 256, 0, h->stream>>>(dq, proj, V.rootoff, W);
-                CSM_LAUNCH_CHECK();
+            phase_mark(h, "k_bb_dive");
+        }
+        /* a list never holds more than 4^k times the roots: small calls get small grids */
+        unsigned long long bound = n_roots;
+        for (int lvl = hmax; lvl >= 1; --lvl) {
+            const int blocks = (int)std::min<unsigned long long>((bound + 7) / 8, (unsigned long long)full);
+            const dim3 g((unsigned)std::max(blocks, 1));
+            switch (lvl - 1) {          /* height of the children: compile-time for the index arithmetic */
+            case 0: k_bb_expand<0><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+            case 1: k_bb_expand<1><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+            case 2: k_bb_expand<2><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+            case 3: k_bb_expand<3><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+            case 4: k_bb_expand<4><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+            case 5: k_bb_expand<5><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+            default: k_bb_expand<6><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
             }
+            CSM_LAUNCH_CHECK();
+            if (h->timing) {
+                const std::string nm = "k_bb_expand<" + std::to_string(lvl - 1) + ">";
+                phase_mark(h, nm.c_str());
+            }
+            bound = std::min<unsigned long long>(bound * 4, (unsigned long long)h->frontier_capacity);
         }
     }
     FinalArgs F;
@@ -840,7 +903,10 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     F.nq = nq;
     k_finalize<<<nq, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
-    return enqueue_readback(h, nq);
+    phase_mark(h, "k_finalize");
+    rc = enqueue_readback(h, nq);
+    phase_mark(h, "readback");
+    return rc;
 }
 
 } /* namespace */
@@ -917,6 +983,7 @@ int csm_destroy(csm_handle h)
     }
     for (int k = 0; k < 16; ++k)
         if (h->upload_events[k]) cudaEventDestroy(h->upload_events[k]);
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     cudaEventDestroy(h->compute_mark);
     cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
@@ -950,6 +1017,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     }
     if (std::strcmp(name, "bb_dive") == 0 && value >= 0 && value <= 2) { h->bb_dive = value; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
+    if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
     if (std::strcmp(name, "reset_best_key") == 0) {
         int rc = ensure(h, h->d_bestkey, 8);
         if (rc) return rc;
@@ -1249,14 +1317,25 @@ int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out)
         if (wrc) return wrc;
     }
     const size_t cells = (size_t)m.rows * m.cols;
+    const size_t tcells = tiled_cells(m.rows, m.cols);
     const uint16_t* src = nullptr;
     if (level == 0) src = m.base;
-    else if (level > 0 && level <= m.hmax) src = m.levels + (size_t)(level - 1) * cells;
+    else if (level > 0 && level <= m.hmax) src = m.levels + (size_t)(level - 1) * tcells;
     else if (level < 0 && m.coarse_win == -level) src = m.coarse;
     if (src == nullptr)
         return fail(h, CSM_E_INVALID, "download: level not built");
-    CSM_CUDA(cudaMemcpyAsync(out, src, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    if (level <= 0) {
+        CSM_CUDA(cudaMemcpyAsync(out, src, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+        CSM_CUDA(cudaStreamSynchronize(h->stream));
+        return CSM_OK;
+    }
+    /* pyramid levels are stored in 8x8 tiles on the device (csm_device.cuh) */
+    std::vector<uint16_t> raw(tcells);
+    CSM_CUDA(cudaMemcpyAsync(raw.data(), src, tcells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < m.rows; ++r)
+        for (int c = 0; c < m.cols; ++c)
+            out[(size_t)r * m.cols + c] = raw[tiled_index(r, c, m.cols)];
     return CSM_OK;
 }
 
@@ -1308,6 +1387,27 @@ int csm_debug_frontier_counts(csm_handle h, unsigned int* out8)
     CSM_CUDA(cudaMemcpyAsync(out8, h->plan_view.counts, sizeof(unsigned int) * kMaxLevels, cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
     return CSM_OK;
+}
+
+int csm_debug_timings(csm_handle h, char* names, size_t names_cap, float* ms, int max_n)
+{
+    if (!h || !ms || max_n <= 0) return 0;
+    if (h->tcount < 2) return 0;
+    if (cudaEventSynchronize(h->tev[h->tcount - 1]) != cudaSuccess) return 0;
+    std::string all;
+    int n = 0;
+    for (size_t i = 1; i < h->tcount && n < max_n; ++i, ++n) {
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, h->tev[i - 1], h->tev[i]);
+        ms[n] = t;
+        all += h->tnames[i];
+        all += ';';
+    }
+    if (names && names_cap > 0) {
+        std::strncpy(names, all.c_str(), names_cap - 1);
+        names[names_cap - 1] = '\0';
+    }
+    return n;
 }
 
 void* csm_best_key_device(csm_handle h)
@@ -1380,7 +1480,7 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     int rc;
     PlanView V;
     const int T = 2 * win_t + 1;
-    if ((rc = layout_plan(h, 1, (size_t)T, 0, 0, n, V))) return rc;
+    if ((rc = layout_plan(h, 1, 0, 0, 0, n, V))) return rc;
     ScanSlot s = V.scan;
     s.max_range = *std::max_element(ranges, ranges + n);
 
@@ -1400,8 +1500,7 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     plan.max_tn = Q.T * Q.n;
     plan.max_t = Q.T;
     Q.margin = fp_margin(sensor_pose, m, s.max_range, (double)(std::max(win_x, win_y) + low_res) * m.res);
-    for (int t = -win_t; t <= win_t; ++t)
-        plan.thetas.push_back(sensor_pose[2] + step_t * t);
+    Q.theta0 = sensor_pose[2]; Q.step_t = step_t; Q.tcenter = win_t;
     const int nbx = (2 * win_x) / low_res + 1;
     const int nby = (2 * win_y) / low_res + 1;
     const int nblocks = Q.T * nbx * nby;

@@ -124,8 +124,8 @@ k_scatter_blocks(ScatterArgs A)
 
 struct PyrJob
 {
-    const uint16_t* base;   /* level 0 */
-    uint16_t*       levels; /* levels 1..hmax, contiguous, rows*cols each */
+    const uint16_t* base;   /* level 0, row-major */
+    uint16_t*       levels; /* levels 1..hmax, contiguous, tiled_cells(rows, cols) each, 8x8-tile layout */
     int rows, cols;
 };
 
@@ -138,9 +138,10 @@ k_pyramid_level(const PyrJob* __restrict__ jobs, int h)
 {
     const PyrJob job = jobs[blockIdx.z];
     const int rows = job.rows, cols = job.cols;
-    const size_t cells = (size_t)rows * cols;
+    const size_t cells = tiled_cells(rows, cols);
     const uint16_t* __restrict__ src = (h == 1) ? job.base : job.levels + (size_t)(h - 2) * cells;
     uint16_t* __restrict__ dst = job.levels + (size_t)(h - 1) * cells;
+    const bool src_tiled = h > 1;
     const int w = 1 << h, half = w >> 1;
 
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -153,16 +154,18 @@ k_pyramid_level(const PyrJob* __restrict__ jobs, int h)
     for (int k = 0; k < 2; ++k) {
         const int c = c0 + k;
         const int cc = max(min(c, cols - w), 0);
-        unsigned int v = ld_cell(src, rows, cols, rc, cc);
-        v = max(v, ld_cell(src, rows, cols, rc + half, cc));
-        v = max(v, ld_cell(src, rows, cols, rc, cc + half));
-        v = max(v, ld_cell(src, rows, cols, rc + half, cc + half));
+        unsigned int v = ld_level(src, rows, cols, src_tiled, rc, cc);
+        v = max(v, ld_level(src, rows, cols, src_tiled, rc + half, cc));
+        v = max(v, ld_level(src, rows, cols, src_tiled, rc, cc + half));
+        v = max(v, ld_level(src, rows, cols, src_tiled, rc + half, cc + half));
         out[k] = v;
     }
+    /* (r, c0) and (r, c0 + 1) are neighbours in the tiled layout too (c0 is even) */
+    const size_t o = tiled_index(r, c0, cols);
     if (c0 + 1 < cols) {
-        *reinterpret_cast<unsigned int*>(dst + (size_t)r * cols + c0) = out[0] | (out[1] << 16);
+        *reinterpret_cast<unsigned int*>(dst + o) = out[0] | (out[1] << 16);
     } else {
-        dst[(size_t)r * cols + c0] = (uint16_t)out[0];
+        dst[o] = (uint16_t)out[0];
     }
 }
 
@@ -236,8 +239,28 @@ __device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsig
     }
     const int r0 = b * kPsRows;
     if (in_map && r0 <= rsrc) {
-        unsigned int* dst = reinterpret_cast<unsigned int*>(job.levels + (size_t)(H - 1) * cells +
-                                                            (size_t)r0 * C) + j;
+#if CSM_TILED
+        unsigned int* dst = reinterpret_cast<unsigned int*>(job.levels + (size_t)(H - 1) * cells);
+        const int tprp = padded_tiles_per_row(C);
+        /* word (4 bytes = cells 2j, 2j+1) of row r in the tiled level */
+        auto tw = [&](int r) -> size_t {
+            return ((size_t)(((r + 8) >> 3) * tprp + (j >> 2) + 1) << 5) + (size_t)(((r & 7) << 2) | (j & 3));
+        };
+        if (r0 + kPsRows - 1 < rsrc) {
+            /* rows r0..r0+3 are 4 words (16 bytes) apart inside one tile */
+            unsigned int* d0 = dst + tw(r0);
+#pragma unroll
+            for (int rr = 0; rr < kPsRows; ++rr) d0[rr * 4] = p[rr];
+        } else {
+            for (int rr = 0; rr < kPsRows; ++rr) {
+                const int r = r0 + rr;
+                if (r < rsrc) dst[tw(r)] = p[rr];
+                else if (r == rsrc)
+                    for (int r2 = r; r2 < R; ++r2) dst[tw(r2)] = p[rr];
+            }
+        }
+#else
+        unsigned int* dst = reinterpret_cast<unsigned int*>(job.levels + (size_t)(H - 1) * cells + (size_t)r0 * C) + j;
         const int cw = C >> 1;
         if (r0 + kPsRows - 1 < rsrc) {
 #pragma unroll
@@ -250,6 +273,7 @@ __device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsig
                     for (int r2 = r; r2 < R; ++r2) dst[(r2 - r0) * cw] = p[rr];
             }
         }
+#endif
     }
 #pragma unroll
     for (int rr = 0; rr < kPsRows; ++rr) a[rr] = p[rr];
@@ -265,7 +289,7 @@ k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax)
 
     const PyrJob job = jobs[blockIdx.x];
     const int R = job.rows, C = job.cols;
-    const size_t cells = (size_t)R * C;
+    const size_t cells = tiled_cells(R, C);
     const int j = threadIdx.x;
     const bool in_map = 2 * j < C;
 
@@ -355,16 +379,25 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         return;
     const int nt = min(kProjAngles, Q.T - t0);
     if (threadIdx.x < nt) {
+        const int t = t0 + threadIdx.x;
+        /* sensorPose.theta + t * stepTheta (scan_matcher_branch_bound.cpp:159-165,
+         * scan_matcher_correlative.cpp:163-166): one rounded product, one rounded sum */
+        const double theta = (Q.thetas != nullptr) ? Q.thetas[t]
+                           : __dadd_rn(Q.theta0, __dmul_rn((double)(t - Q.tcenter), Q.step_t));
         double s, c;
-        sincos(Q.thetas[t0 + threadIdx.x], &s, &c);
+        sincos(theta, &s, &c);
         s_theta[threadIdx.x] = make_double2(c, s);
     }
     __syncthreads();
     int flagged = 0;
     const int total = nt * Q.n;
+    /* beam-major output (pst_t == 1): consecutive threads take consecutive angles of one beam
+     * and write one contiguous run; angle-major output: consecutive beams of one angle */
+    const bool angle_fastest = Q.pst_t == 1;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int tl = e / Q.n;
-        const int i = e - tl * Q.n;
+        int tl, i;
+        if (angle_fastest) { i = e / nt; tl = e - i * nt; }
+        else { tl = e / Q.n; i = e - tl * Q.n; }
         const double2 th = s_theta[tl];
         const double2 be = Q.beam_trig[i];
         const double c = th.x * be.x - th.y * be.y;      /* cos(theta + a) */
@@ -582,27 +615,30 @@ __device__ void rt_replay(const DevQuery& Q, const proj_t* __restrict__ proj_all
 /* Branch and bound                                                          */
 /* ------------------------------------------------------------------------ */
 
-/* Level-synchronous frontier expansion, one LANE per node.
+/* Level-synchronous frontier expansion.
  *
- * The candidate list of height h holds unscored nodes (q, t, x, y). A warp
- * takes 32 consecutive candidates; every lane scores its node over all N
- * beams on the level-h map (its own integer sums, no warp reduction) and
- * decides like the reference does when it pops a node
- * (scan_matcher_branch_bound.cpp:191-198): drop iff score <= scoreMax or
- * knownRate <= threshold. Survivors of height h > 0 append their four
- * children (:226-229) to the list of height h-1; survivors of height 0 are
- * leaves and raise the query's incumbent with atomicMax.
+ * list(h) holds the nodes (q, t, x, y) of height h that PASSED when they were
+ * scored, i.e. that the reference would expand when it pops them
+ * (scan_matcher_branch_bound.cpp:191-198: drop iff score <= scoreMax or
+ * knownRate <= threshold). k_bb_roots scores the root candidates (:179-182)
+ * into list(hmax); k_bb_expand(h) takes every node of list(h), scores its four
+ * children (:226-229) on the level h-1 map and appends the passing ones to
+ * list(h-1); passing children of height 0 are leaves and raise the query's
+ * incumbent with atomicMax.
  *
- * Why lanes and not warps per node: candidates are kept in runs of adjacent
- * angles t (roots are generated t-fastest, children are appended per child
- * type in lane order), and adjacent angles of the same (x, y) hit almost the
- * same cells. The 32 two-byte gathers of a warp then fall into a few 32-byte
- * sectors instead of 32, and with the projection stored beam-major
- * (proj[i][t]) the index loads of a warp are one contiguous segment. */
+ * Lanes: a warp takes 8 consecutive nodes; lane = part * 8 + slot, `slot` the
+ * node, `part` the quarter of the beams (i = part, part + 4, ...) the lane
+ * sums. Per beam a lane loads the projected index once and gathers the four
+ * children's cells. Lists keep runs of adjacent angles t of the same (x, y)
+ * (roots are generated t-fastest, children are appended per child type in lane
+ * order), adjacent angles and adjacent beams hit neighbouring cells, and the
+ * projection is stored beam-major (proj[i][t]): a warp's index loads are 4
+ * short contiguous runs and its 32 gathers of one child fall on a compact 2-D
+ * patch of the map, a handful of sectors in the tiled level layout. */
 struct BbWork
 {
-    unsigned long long* list[2];    /* candidate lists, ping-pong by height parity */
-    unsigned int*       counts;     /* [kMaxLevels]: number of candidates per height */
+    unsigned long long* list[2];    /* node lists, ping-pong by height parity */
+    unsigned int*       counts;     /* [kMaxLevels]: nodes of list(h) */
     unsigned long long* incumbent;  /* per query: packed (key, ordfield) */
     int*                stats;      /* per query: processed, ignored */
     int*                overflow;   /* set when a list is full */
@@ -610,6 +646,9 @@ struct BbWork
     unsigned int        capacity;
     int                 hmax;
 };
+
+/* list(h) lives in list[(h & 1) ^ 1]; the root candidates in list[hmax & 1] */
+__device__ __forceinline__ unsigned long long* bb_list(const BbWork& W, int h) { return W.list[(h & 1) ^ 1]; }
 
 __device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, int t, int xi, int yi)
 {
@@ -635,31 +674,60 @@ k_bb_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__
         const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
         out[e] = pack_node(q, t, rx << W.hmax, ry << W.hmax);
     }
-    if (q == 0 && blockIdx.x == 0 && threadIdx.x == 0)
-        W.counts[W.hmax] = root_off[nq];
 }
 
 constexpr int kBbSplit = 4;                 /* lanes cooperating on one node */
 constexpr int kBbNodesPerWarp = 32 / kBbSplit;
 
-__global__ void __launch_bounds__(256)
-k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
-           BbWork W, int h)
+/* The decision the reference takes when it pops a node, on integer keys */
+__device__ __forceinline__ bool bb_passes(const DevQuery& Q, const proj_t* __restrict__ proj_all,
+                                          const BbWork& W, int q, int t, int xi, int yi, int h,
+                                          int s, int k, long long& key)
 {
-    /* lane = part * 8 + slot: `slot` selects one of 8 consecutive candidates,
-     * `part` the quarter of the beams (i = part, part + 4, ...) this lane sums.
-     * Lanes with equal `part` sit next to each other, so a warp's index loads
-     * are 4 runs of 8 consecutive proj entries when the angles are consecutive. */
+    key = make_key(s, k);
+    const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
+    bool pass = k > Q.nk_cut && pack_best(key, kOrdMask) > inc;
+    if (pass) {
+        const int c = key_vs_threshold(key, Q.kthr);
+        if (c < 0) pass = false;
+        else if (c == 0) {
+            const proj_t* pp0 = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
+            pass = exact_normalized_score(Q.lvl[h], Q.rows, Q.cols, pp0, Q.pst_i, Q.n,
+                                          xi - Q.winx, yi - Q.winy, h > 0) > Q.kthr.thr;
+        }
+    }
+    return pass;
+}
+
+/* processed / ignored counters, one atomic per (warp, query, outcome) */
+__device__ __forceinline__ void bb_count(const BbWork& W, bool valid, int q, bool pass)
+{
     const int lane = threadIdx.x & 31;
-    const int slot = lane & (kBbNodesPerWarp - 1);
-    const int part = lane / kBbNodesPerWarp;
-    const unsigned int count = min(W.counts[h], W.capacity);
+    const int tag = valid ? (2 * q + (pass ? 0 : 1)) : -1;
+    const unsigned int peers = __match_any_sync(0xffffffffu, tag);
+    if (tag >= 0 && lane == __ffs(peers) - 1)
+        atomicAdd(&W.stats[tag], __popc(peers));
+}
+
+/* Score the root candidates on the level hmax map; the passing ones form
+ * list(hmax). Lanes per node as in k_bb_expand. */
+__global__ void __launch_bounds__(256)
+k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
+           BbWork W, unsigned int count)
+{
+    const int h = W.hmax;
+    const int lane = threadIdx.x & 31;
+    const unsigned int total_lanes = gridDim.x * blockDim.x;
+    int split = kBbSplit;
+    while (split < 32 && (unsigned long long)count * (unsigned)(split * 2) <= total_lanes) split *= 2;
+    const int npw = 32 / split;
+    const int slot = lane & (npw - 1);
+    const int part = lane / npw;
     const unsigned long long* __restrict__ in = W.list[h & 1];
-    unsigned long long* __restrict__ out = W.list[(h & 1) ^ 1];
+    unsigned long long* __restrict__ out = bb_list(W, h);
     const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int w = (h > 0) ? (1 << (h - 1)) : 0;
-    for (unsigned int base = warp_global * kBbNodesPerWarp; base < count; base += nwarps * kBbNodesPerWarp) {
+    const unsigned int nwarps = total_lanes >> 5;
+    for (unsigned int base = warp_global * npw; base < count; base += nwarps * npw) {
         const unsigned int idx = base + slot;
         const bool valid = idx < count;
         int q = 0, t = 0, xi = 0, yi = 0;
@@ -669,11 +737,12 @@ k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
             const DevQuery& Q = queries[q];
             const uint16_t* __restrict__ m = Q.lvl[h];
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
+            const bool tiled = h > 0;
             const int ox = xi - Q.winx, oy = yi - Q.winy;
             const size_t ps = (size_t)Q.pst_i;
             const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t + (size_t)part * ps;
-            const size_t step = ps * kBbSplit;
-            const int mine = (n - part + kBbSplit - 1) / kBbSplit;     /* beams of this lane */
+            const size_t step = ps * (size_t)split;
+            const int mine = (n - part + split - 1) / split;     /* beams of this lane */
             int i = 0;
             for (; i + 8 <= mine; i += 8) {
                 proj_t p[8];
@@ -681,63 +750,197 @@ k_bb_score(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 for (int u = 0; u < 8; ++u) p[u] = pp[(size_t)(i + u) * step];
                 unsigned int v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = ld_cell(m, rows, cols, p[u].y + oy, p[u].x + ox);
+                for (int u = 0; u < 8; ++u) v[u] = ld_level(m, rows, cols, tiled, p[u].y + oy, p[u].x + ox);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { s += (int)v[u]; k += (v[u] != 0u); }
             }
             for (; i < mine; ++i) {
                 const proj_t p = pp[(size_t)i * step];
-                const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
+                const unsigned int v = ld_level(m, rows, cols, tiled, p.y + oy, p.x + ox);
                 s += (int)v; k += (v != 0u);
             }
         }
-        /* sum the four parts of every node (lanes slot, slot+8, slot+16, slot+24) */
-        s += __shfl_xor_sync(0xffffffffu, s, 8);  k += __shfl_xor_sync(0xffffffffu, k, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16); k += __shfl_xor_sync(0xffffffffu, k, 16);
+        for (int o = npw; o < 32; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            k += __shfl_xor_sync(0xffffffffu, k, o);
+        }
         bool pass = false;
         long long key = 0;
-        if (valid) {
+        if (valid && part == 0) {
             const DevQuery& Q = queries[q];
-            key = make_key(s, k);
-            const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
-            pass = k > Q.nk_cut && pack_best(key, kOrdMask) > inc;
-            if (pass) {
-                const int c = key_vs_threshold(key, Q.kthr);
-                if (c < 0) pass = false;
-                else if (c == 0) {
-                    const proj_t* pp0 = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
-                    pass = exact_normalized_score(Q.lvl[h], Q.rows, Q.cols, pp0, Q.pst_i, Q.n,
-                                                  xi - Q.winx, yi - Q.winy) > Q.kthr.thr;
-                }
-            }
-            if (pass && h == 0 && part == 0)
+            pass = bb_passes(Q, proj_all, W, q, t, xi, yi, h, s, k, key);
+            if (pass && h == 0)
                 atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
-            if (h == W.hmax && part == 0 && W.rootkey != nullptr)
+            if (W.rootkey != nullptr)
                 W.rootkey[idx] = pass ? key : -1ll;
         }
-        {
-            /* processed / ignored counters, one atomic per (warp, query, outcome) */
-            const int tag = (valid && part == 0) ? (2 * q + (pass ? 0 : 1)) : -1;
-            const unsigned int peers = __match_any_sync(0xffffffffu, tag);
-            if (tag >= 0 && lane == __ffs(peers) - 1)
-                atomicAdd(&W.stats[tag], __popc(peers));
-        }
+        bb_count(W, valid && part == 0, q, pass);
         if (h > 0) {
-            /* every lane of a surviving node writes one child: child type = part */
-            const unsigned int ballot = __ballot_sync(0xffffffffu, pass) & 0xffu;
+            const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
             if (ballot != 0u) {
-                const int npass = __popc(ballot);
                 unsigned int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&W.counts[h - 1], 4u * npass);
+                if (lane == 0) slot0 = atomicAdd(&W.counts[h], (unsigned int)__popc(ballot));
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                 if (pass) {
-                    const unsigned int rank = __popc(ballot & ((1u << slot) - 1u));
-                    /* one contiguous run per child type, candidate order kept inside it */
-                    const unsigned int dst = slot0 + part * npass + rank;
-                    if (dst < W.capacity)
-                        out[dst] = pack_node(q, t, xi + (part & 1) * w, yi + (part >> 1) * w);
-                    else
-                        *W.overflow = 1;
+                    const unsigned int dst = slot0 + __popc(ballot & ((1u << lane) - 1u));
+                    if (dst < W.capacity) out[dst] = pack_node(q, t, xi, yi);
+                    else *W.overflow = 1;
+                }
+            }
+        }
+    }
+}
+
+/* Four cells (r, c), (r, c + w), (r + w, c), (r + w, c + w) of the children's
+ * level, w = 2^HC, branch-free so that a lane keeps all its loads in flight.
+ * Precomputed levels (HC >= 1): tiled with a zero border, coordinates clamped
+ * instead of tested; for w >= 8 the second row / column is a whole number of
+ * tiles away. Level 0 (HC == 0) is the row-major uploaded grid: out-of-map
+ * cells read cell 0 and are masked. */
+template <int HC>
+__device__ __forceinline__ void ld_children(const uint16_t* __restrict__ m, int rows, int cols,
+                                            int rmax, int cmax, int rstride,
+                                            int r, int c, unsigned int (&v)[4])
+{
+    constexpr int w = 1 << HC;
+    if (HC == 0 || !CSM_TILED) {
+        const int r1 = r + w, c1 = c + w;
+        const bool rk0 = (unsigned)r < (unsigned)rows, rk1 = (unsigned)r1 < (unsigned)rows;
+        const bool ck0 = (unsigned)c < (unsigned)cols, ck1 = (unsigned)c1 < (unsigned)cols;
+        const unsigned int R0 = (unsigned)r * (unsigned)cols, R1 = R0 + (unsigned)(w * cols);
+        const bool k00 = rk0 && ck0, k01 = rk0 && ck1, k10 = rk1 && ck0, k11 = rk1 && ck1;
+        const unsigned int x00 = __ldg(m + (k00 ? R0 + (unsigned)c : 0u)), x01 = __ldg(m + (k01 ? R0 + (unsigned)c1 : 0u));
+        const unsigned int x10 = __ldg(m + (k10 ? R1 + (unsigned)c : 0u)), x11 = __ldg(m + (k11 ? R1 + (unsigned)c1 : 0u));
+        v[0] = k00 ? x00 : 0u; v[1] = k01 ? x01 : 0u; v[2] = k10 ? x10 : 0u; v[3] = k11 ? x11 : 0u;
+    } else {
+        /* r, c arrive already shifted by the border (+8) */
+        const int rp0 = min(max(r, 0), rmax), cp0 = min(max(c, 0), cmax);
+        const int rp1 = min(max(r + w, 0), rmax), cp1 = min(max(c + w, 0), cmax);
+        const unsigned int R0 = tiled_row_p(rp0, rstride), C0 = tiled_col_p(cp0);
+        const unsigned int R1 = tiled_row_p(rp1, rstride), C1 = tiled_col_p(cp1);
+        v[0] = __ldg(m + (R0 + C0)); v[1] = __ldg(m + (R0 + C1));
+        v[2] = __ldg(m + (R1 + C0)); v[3] = __ldg(m + (R1 + C1));
+    }
+}
+
+/* Expand list(HC + 1): score the four children of every node on the level HC map.
+ *
+ * `split` lanes share a node (a power of two, 4..32): lane = part * npw + slot
+ * with npw = 32 / split nodes per warp. The kernel picks the largest split
+ * that still gives every node of the list its lanes in one wave of the grid,
+ * so short lists (the fine levels, small calls) are latency-bound on a few
+ * beams per lane instead of 90.
+ *
+ * Children of height >= 1 are internal nodes: whether they pass only decides
+ * how much work follows, never the result (a leaf that passes implies that all
+ * its ancestors pass), so they are tested on an upper bound of
+ * their key that needs no known-cell count: key <= 998 sum + 64536 n. Leaves
+ * (HC == 0) are scored exactly. */
+template <int HC>
+__global__ void __launch_bounds__(256)
+k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
+{
+    constexpr int h = HC + 1;
+    constexpr int w = 1 << HC;               /* spacing of the children */
+    constexpr bool kLeaf = HC == 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned int count = min(W.counts[h], W.capacity);
+    const unsigned int total_lanes = gridDim.x * blockDim.x;
+    int split = kBbSplit;
+    while (split < 32 && (unsigned long long)count * (unsigned)(split * 2) <= total_lanes) split *= 2;
+    const int npw = 32 / split;              /* nodes per warp */
+    const int slot = lane & (npw - 1);
+    const int part = lane / npw;
+    const unsigned long long* __restrict__ in = bb_list(W, h);
+    unsigned long long* __restrict__ out = bb_list(W, HC);
+    const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int nwarps = total_lanes >> 5;
+    for (unsigned int base = warp_global * npw; base < count; base += nwarps * npw) {
+        const unsigned int idx = base + slot;
+        const bool valid = idx < count;
+        int q = 0, t = 0, xi = 0, yi = 0;
+        unsigned int s0 = 0, s1 = 0, s2 = 0, s3 = 0, k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+        if (valid) {
+            unpack_node(in[idx], q, t, xi, yi);
+            const DevQuery& Q = queries[q];
+            const uint16_t* __restrict__ m = Q.lvl[HC];
+            const int rows = Q.rows, cols = Q.cols, n = Q.n;
+            const int rmax = tiled_rmax(rows), cmax = tiled_rmax(cols), rstride = tiled_rstride(cols);
+            constexpr int kShift = (kLeaf || !CSM_TILED) ? 0 : 8;      /* border of the tiled levels */
+            const int ox = xi - Q.winx + kShift, oy = yi - Q.winy + kShift;
+            const unsigned int ps = (unsigned int)Q.pst_i;
+            const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t + (size_t)part * ps;
+            const unsigned int step = ps * (unsigned int)split;
+            const int mine = (n - part + split - 1) / split;     /* beams of this lane */
+            int i = 0;
+            for (; i + 4 <= mine; i += 4) {
+                proj_t p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p[u] = pp[(unsigned int)(i + u) * step];
+                unsigned int v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    ld_children<HC>(m, rows, cols, rmax, cmax, rstride, p[u].y + oy, p[u].x + ox, v[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
+                    if (kLeaf) {
+                        k0 += (v[u][0] != 0u); k1 += (v[u][1] != 0u);
+                        k2 += (v[u][2] != 0u); k3 += (v[u][3] != 0u);
+                    }
+                }
+            }
+            for (; i < mine; ++i) {
+                const proj_t p = pp[(unsigned int)i * step];
+                unsigned int v[4];
+                ld_children<HC>(m, rows, cols, rmax, cmax, rstride, p.y + oy, p.x + ox, v);
+                s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
+                if (kLeaf) { k0 += (v[0] != 0u); k1 += (v[1] != 0u); k2 += (v[2] != 0u); k3 += (v[3] != 0u); }
+            }
+        }
+        /* Sum over the parts (sums < 2^32; the four known counts < 2^16 share one word) */
+        unsigned long long a = ((unsigned long long)s0 << 32) | s1;
+        unsigned long long b = ((unsigned long long)s2 << 32) | s3;
+        unsigned long long kk = ((unsigned long long)k0 << 48) | ((unsigned long long)k1 << 32) |
+                                ((unsigned long long)k2 << 16) | (unsigned long long)k3;
+        for (int o = npw; o < 32; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            if (kLeaf) kk += __shfl_xor_sync(0xffffffffu, kk, o);
+        }
+        /* lane (slot, part < 4) now decides child `part` of node `slot`: (x + (part & 1) w, y + (part >> 1) w) */
+        const bool decides = valid && part < 4;
+        const unsigned long long sp = (part & 2) ? b : a;
+        const int s = (int)((part & 1) ? (unsigned)sp : (unsigned)(sp >> 32));
+        const int cx = xi + (part & 1) * w, cy = yi + ((part >> 1) & 1) * w;
+        bool pass = false;
+        if (decides) {
+            const DevQuery& Q = queries[q];
+            if (kLeaf) {
+                const int k = (int)((kk >> (16 * (3 - (part & 3)))) & 0xffffull);
+                long long key;
+                pass = bb_passes(Q, proj_all, W, q, t, cx, cy, 0, s, k, key);
+                if (pass)
+                    atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, cx, cy)));
+            } else {
+                /* upper bound of the key: every beam counted as known */
+                const long long key_ub = make_key(s, Q.n);
+                const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
+                pass = pack_best(key_ub, kOrdMask) > inc && key_ub > Q.kthr.fail_max;
+            }
+        }
+        bb_count(W, decides, q, pass);
+        if (!kLeaf) {
+            const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+            if (ballot != 0u) {
+                unsigned int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&W.counts[HC], (unsigned int)__popc(ballot));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (pass) {
+                    /* lane order = child type major, node minor: runs of adjacent angles stay together */
+                    const unsigned int dst = slot0 + __popc(ballot & ((1u << lane) - 1u));
+                    if (dst < W.capacity) out[dst] = pack_node(q, t, cx, cy);
+                    else *W.overflow = 1;
                 }
             }
         }
@@ -819,6 +1022,7 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
             /* warp `warp` scores candidates warp, warp + 8, warp + 16, warp + 24 at once:
              * up to 4 x 12 independent (index, cell) load pairs per lane in flight */
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
+            const bool tiled = (h - 1) > 0;
             const size_t ps = (size_t)Q.pst_i;
             const proj_t* __restrict__ pp[4];
             int ox[4], oy[4], sv[4], kn[4];
@@ -839,7 +1043,7 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
                 for (int j = 0; j < 4; ++j) {
                     if (!on[j]) continue;
                     const proj_t p = pp[j][(size_t)i * ps];
-                    const unsigned int v = ld_cell(m, rows, cols, p.y + oy[j], p.x + ox[j]);
+                    const unsigned int v = ld_level(m, rows, cols, tiled, p.y + oy[j], p.x + ox[j]);
                     sv[j] += (int)v; kn[j] += (v != 0u);
                 }
             }

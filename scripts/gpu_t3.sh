@@ -1,0 +1,4 @@
+set -x
+python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+python scripts/exp_phases.py 256
+python scripts/exp_phases.py 128
