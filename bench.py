@@ -233,7 +233,9 @@ def main_cuda(args):
     # of the C ABI. `h` is the csm_handle it runs on (device-side timing, best-word all-reduce).
     ctx = hostapi.Context(local)
     hdet = hostapi.LoopDetector(ctx, HMAX, synth.CFG3["rng"], synth.CFG3["thr"])
-    hdet.configure(chunk_size=128, coarse_covariance=False, query_index_base=rank * N_MAPS)
+    # one search batch of 256 queries; first-touch submaps uploaded in 4 groups of 64 whose block
+    # expansion + pyramid build overlap the PCIe transfer of the following groups
+    hdet.configure(chunk_size=256 | (64 << 16), coarse_covariance=False, query_index_base=rank * N_MAPS)
     h = capi.Handle.from_pointer(hdet.handle(), local)
     ext_stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local))
 
@@ -266,7 +268,7 @@ def main_cuda(args):
     host = np.ctypeslib.as_array((C.c_uint16 * (N_MAPS * cells)).from_address(host_ptr)).reshape(N_MAPS, ROWS, COLS)
     for m, s in enumerate(batch.submaps):
         host[m] = s.grid
-    n_chunks = (N_MAPS + 127) // 128
+    n_chunks = (N_MAPS + 63) // 64
     h2d_small = 2 * 360 * 8 + N_MAPS * (256 + 115 * 8 + 8 + 4)
     h2d_blocks = n_blocks * (blk_bytes + 4) + (N_MAPS + n_chunks) * 4
     summaries = (hostapi.HostSummary * N_MAPS)()
@@ -280,7 +282,7 @@ def main_cuda(args):
 
     def e2e_step(sparse=True):
         """One LoopDetector::Detect of the C++ plugin on 256 first-touch submaps, from page-locked
-        HOST buffers: upload (2 chunks on the copy stream), block expansion, pyramid build, batched
+        HOST buffers: upload (4 groups on the copy stream), block expansion, pyramid build, batched
         B&B, result read-back; then the 8-byte all-reduce of the best word and its read-back."""
         hdet.clear_cache()                                  # every submap is a first touch again
         h.set_option("reset_best_key", 1)

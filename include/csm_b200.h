@@ -256,7 +256,9 @@ int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax
  * event on the handle's stream after every kernel of a loop batch (or of a
  * streaming pyramid build). csm_debug_timings waits for the last one and
  * returns the durations in ms of the phases of the LAST such call, with their
- * names separated by ';' in `names`. Returns the number of phases. */
+ * names separated by ';' in `names`. Returns the number of phases. With
+ * "timing" = 2 the marks accumulate across calls (uploads included) until the
+ * option is set again, and the values are times since the first mark. */
 int csm_debug_timings(csm_handle h, char* names, size_t names_cap, float* ms, int max_n);
 /* Debug: size of the node list of every height after the last batch (8 entries):
  * the nodes of that height that passed and were expanded */

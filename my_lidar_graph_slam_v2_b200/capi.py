@@ -290,9 +290,9 @@ class Handle:
 
     def timings(self):
         """[(phase name, ms)] of the last loop batch / pyramid build (option "timing" must be 1)."""
-        names = C.create_string_buffer(2048)
-        ms = (C.c_float * 64)()
-        n = self.lib.csm_debug_timings(self.h, names, 2048, ms, 64)
+        names = C.create_string_buffer(8192)
+        ms = (C.c_float * 256)()
+        n = self.lib.csm_debug_timings(self.h, names, 8192, ms, 256)
         return list(zip(names.value.decode().split(";")[:n], [ms[i] for i in range(n)]))
 
     def best_key_device_ptr(self):

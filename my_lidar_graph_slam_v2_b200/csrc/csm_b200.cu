@@ -177,9 +177,13 @@ namespace {
     } while (0)
 
 /* timing: mark the end of a phase on the compute stream (no-op unless enabled) */
-void phase_mark(csm_handle h, const char* name)
+void phase_mark(csm_handle h, const char* name, cudaStream_t on = nullptr)
 {
     if (!h->timing)
+        return;
+    if (h->timing == 1 && std::strcmp(name, "start") == 0)
+        h->tcount = 0;             /* mode 1: keep the phases of the last call only */
+    if (h->tcount >= 256)
         return;
     if (h->tcount >= h->tev.size()) {
         cudaEvent_t e = nullptr;
@@ -189,7 +193,7 @@ void phase_mark(csm_handle h, const char* name)
         h->tnames.emplace_back();
     }
     h->tnames[h->tcount] = name;
-    cudaEventRecord(h->tev[h->tcount], h->stream);
+    cudaEventRecord(h->tev[h->tcount], on ? on : h->stream);
     ++h->tcount;
 }
 
@@ -379,6 +383,7 @@ int wait_uploads(csm_handle h, const std::vector<MapSlot*>& slots)
         }
         CSM_CUDA(cudaFreeAsync(bs->stage, h->stream));
         bs->stage = nullptr;
+        if (h->timing == 2) phase_mark(h, "expand blocks");
     }
     return CSM_OK;
 }
@@ -550,7 +555,7 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
     /* Batches of maps that fit its layout take the streaming builder (one pass,
      * level 0 read once, every level written once). */
     bool stream_ok = hmax >= 1 && hmax <= 6 && h->pyramid_mode != 1 &&
-                     (h->pyramid_mode == 2 || jobs.size() >= 32);
+                     (h->pyramid_mode == 2 || jobs.size() >= 8);
     for (const PyrJob& j : jobs)
         stream_ok = stream_ok && j.cols <= 512 && (j.cols % 8) == 0 && (j.rows % kPsRows) == 0;
     if (stream_ok) {
@@ -561,10 +566,14 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             CSM_CUDA(cudaFuncSetAttribute(k_pyramid_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        h->tcount = 0;
         phase_mark(h, "start");
-        k_pyramid_stream<<<(unsigned)jobs.size(), kPsThreads, smem, h->stream>>>(
-            static_cast<const PyrJob*>(h->d_pyrjobs.p), hmax);
+        /* two CTAs fit an SM: split every map into row segments until the grid fills them */
+        int min_rows = jobs[0].rows;
+        for (const PyrJob& j : jobs) min_rows = std::min(min_rows, j.rows);
+        int segs = (int)std::min<size_t>(4, (size_t)(2 * h->sm_count) / jobs.size());
+        segs = std::max(1, std::min(segs, min_rows / 128));         /* segments of at least 128 rows */
+        k_pyramid_stream<<<(unsigned)(jobs.size() * segs), kPsThreads, smem, h->stream>>>(
+            static_cast<const PyrJob*>(h->d_pyrjobs.p), hmax, segs);
         CSM_LAUNCH_CHECK();
         phase_mark(h, "k_pyramid_stream");
         return CSM_OK;
@@ -826,7 +835,6 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     }
     if ((rc = wait_uploads(h, used_slots))) return rc;
     if ((rc = ensure_frontier(h, nq, plan.root_off[nq]))) return rc;
-    h->tcount = 0;
     phase_mark(h, "start");
     if ((rc = commit_plan(h, plan, V, false))) return rc;
     phase_mark(h, "k_setup");
@@ -1217,6 +1225,7 @@ int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
     }
     CSM_CUDA(cudaMemcpyAsync(stage + bs->prefix_off, bs->prefix.data(), sizeof(int) * (size_t)(n + 1),
                              cudaMemcpyHostToDevice, h->copy_stream));
+    if (h->timing == 2) phase_mark(h, "h2d blocks (copy stream)", h->copy_stream);
     return close_upload_group(h);
 }
 
@@ -1396,9 +1405,12 @@ int csm_debug_timings(csm_handle h, char* names, size_t names_cap, float* ms, in
     if (cudaEventSynchronize(h->tev[h->tcount - 1]) != cudaSuccess) return 0;
     std::string all;
     int n = 0;
+    for (size_t i = 0; i < h->tcount; ++i)
+        cudaEventSynchronize(h->tev[i]);
     for (size_t i = 1; i < h->tcount && n < max_n; ++i, ++n) {
         float t = 0.0f;
-        cudaEventElapsedTime(&t, h->tev[i - 1], h->tev[i]);
+        /* mode 2: time since the first mark (a timeline across streams); mode 1: phase durations */
+        cudaEventElapsedTime(&t, h->tev[h->timing == 2 ? 0 : i - 1], h->tev[i]);
         ms[n] = t;
         all += h->tnames[i];
         all += ';';

@@ -205,6 +205,7 @@ __device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsig
                                          unsigned int* __restrict__ ring, const PyrJob& job,
                                          int b, int j, bool in_map, size_t cells)
 {
+    /* in_map is false for the warm-up blocks of a row segment: they only fill the rings */
     constexpr int half = 1 << (H - 1);
     constexpr int w = 2 * half;
     constexpr int ring_off = half - 1;               /* 1 + 2 + ... + half/2 rows precede */
@@ -279,15 +280,19 @@ __device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsig
     for (int rr = 0; rr < kPsRows; ++rr) a[rr] = p[rr];
 }
 
+/* `segs` CTAs share a map: segment s owns the 4-row blocks [s * nbs, (s + 1) * nbs) and first
+ * walks the 16 blocks (64 rows >= 2^hmax - 1) above them without writing, which rebuilds the
+ * ring state those rows depend on. Small batches thereby still fill the GPU. */
 __global__ void __launch_bounds__(kPsThreads, 2)
-k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax)
+k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax, int segs)
 {
     extern __shared__ __align__(16) unsigned int ps_smem[];
     unsigned int* in_ring = ps_smem;                                         /* [stages][4][272] */
     unsigned int* rowbuf = in_ring + kPsStages * kPsRows * kPsInStride;      /* [2][4][256] */
     unsigned int* ring = rowbuf + 2 * kPsRows * 256;                         /* [63][256] */
 
-    const PyrJob job = jobs[blockIdx.x];
+    const PyrJob job = jobs[blockIdx.x / segs];
+    const int seg = blockIdx.x % segs;
     const int R = job.rows, C = job.cols;
     const size_t cells = tiled_cells(R, C);
     const int j = threadIdx.x;
@@ -298,10 +303,16 @@ k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax)
     __syncthreads();
 
     const int nblocks = R / kPsRows;
+    const int nbs = (nblocks + segs - 1) / segs;
+    const int b_lo = seg * nbs;                                  /* lowest block of this segment */
+    const int b_top = min(nblocks, b_lo + nbs) - 1;              /* highest block it writes */
+    const int b_start = min(nblocks - 1, b_top + 16);            /* warm-up starts here */
+    if (b_lo > b_top)
+        return;
     /* producer: this thread's 16-byte chunk of a 4-row block */
     const int ld_row = j >> 6, ld_chunk = j & 63;
     auto prefetch = [&](int b) {
-        if (b >= 0) {
+        if (b >= b_lo) {
             const int stage = b % kPsStages;
             unsigned int* dst = in_ring + (stage * kPsRows + ld_row) * kPsInStride + ld_chunk * 4;
             const bool ok = ld_chunk * 8 < C;
@@ -311,11 +322,12 @@ k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax)
         asm volatile("cp.async.commit_group;\n" ::);
     };
     for (int k = 0; k < kPsStages - 1; ++k)
-        prefetch(nblocks - 1 - k);
+        prefetch(b_start - k);
 
     unsigned int* buf0 = rowbuf;
     unsigned int* buf1 = rowbuf + kPsRows * 256;
-    for (int b = nblocks - 1; b >= 0; --b) {
+    for (int b = b_start; b >= b_lo; --b) {
+        const bool wr = in_map && b <= b_top;
         asm volatile("cp.async.wait_group %0;\n" :: "n"(kPsStages - 2));
         __syncthreads();                 /* block b landed; everyone is done with block b+1 */
         prefetch(b - (kPsStages - 1));   /* refills the stage block b+1 used */
@@ -324,12 +336,12 @@ k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax)
         unsigned int a[kPsRows];
 #pragma unroll
         for (int rr = 0; rr < kPsRows; ++rr) a[rr] = in[rr * kPsInStride + j];
-        ps_level<1>(a, in, kPsInStride, buf1, ring, job, b, j, in_map, cells);
-        if (hmax >= 2) ps_level<2>(a, buf1, 256, buf0, ring, job, b, j, in_map, cells);
-        if (hmax >= 3) ps_level<3>(a, buf0, 256, buf1, ring, job, b, j, in_map, cells);
-        if (hmax >= 4) ps_level<4>(a, buf1, 256, buf0, ring, job, b, j, in_map, cells);
-        if (hmax >= 5) ps_level<5>(a, buf0, 256, buf1, ring, job, b, j, in_map, cells);
-        if (hmax >= 6) ps_level<6>(a, buf1, 256, buf0, ring, job, b, j, in_map, cells);
+        ps_level<1>(a, in, kPsInStride, buf1, ring, job, b, j, wr, cells);
+        if (hmax >= 2) ps_level<2>(a, buf1, 256, buf0, ring, job, b, j, wr, cells);
+        if (hmax >= 3) ps_level<3>(a, buf0, 256, buf1, ring, job, b, j, wr, cells);
+        if (hmax >= 4) ps_level<4>(a, buf1, 256, buf0, ring, job, b, j, wr, cells);
+        if (hmax >= 5) ps_level<5>(a, buf0, 256, buf1, ring, job, b, j, wr, cells);
+        if (hmax >= 6) ps_level<6>(a, buf1, 256, buf0, ring, job, b, j, wr, cells);
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
@@ -677,6 +689,10 @@ k_bb_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__
 }
 
 constexpr int kBbSplit = 4;                 /* lanes cooperating on one node */
+#ifndef CSM_BB_UNROLL
+#define CSM_BB_UNROLL 4
+#endif
+constexpr int kBbUnroll = CSM_BB_UNROLL;    /* beams (x 4 children) a lane keeps in flight */
 constexpr int kBbNodesPerWarp = 32 / kBbSplit;
 
 /* The decision the reference takes when it pops a node, on integer keys */
@@ -873,16 +889,16 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
             const unsigned int step = ps * (unsigned int)split;
             const int mine = (n - part + split - 1) / split;     /* beams of this lane */
             int i = 0;
-            for (; i + 4 <= mine; i += 4) {
-                proj_t p[4];
+            for (; i + kBbUnroll <= mine; i += kBbUnroll) {
+                proj_t p[kBbUnroll];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) p[u] = pp[(unsigned int)(i + u) * step];
-                unsigned int v[4][4];
+                for (int u = 0; u < kBbUnroll; ++u) p[u] = pp[(unsigned int)(i + u) * step];
+                unsigned int v[kBbUnroll][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < kBbUnroll; ++u)
                     ld_children<HC>(m, rows, cols, rmax, cmax, rstride, p[u].y + oy, p[u].x + ox, v[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kBbUnroll; ++u) {
                     s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
                     if (kLeaf) {
                         k0 += (v[u][0] != 0u); k1 += (v[u][1] != 0u);

@@ -46,6 +46,8 @@ public:
     /* Queries are matched in chunks of this many (default 128): the uploads of
      * later chunks overlap the search of earlier ones */
     void SetChunkSize(int n) { mChunkSize = n; }
+    /* First-touch maps are uploaded in groups of this many (default 64, at most the chunk size) */
+    void SetUploadChunk(int n) { mUploadChunk = n; }
     /* Without a final matcher the result carries the covariance of the cost
      * function at the coarse pose (computed on the CPU); switch it off when
      * the caller refines the poses itself */
@@ -66,6 +68,7 @@ private:
     std::vector<csm_result> mLastResults;
     int mQueryIndexBase = 0;
     int mChunkSize = 128;
+    int mUploadChunk = 64;
     bool mCoarseCovariance = true;
 };
 

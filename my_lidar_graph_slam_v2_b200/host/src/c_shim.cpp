@@ -169,7 +169,9 @@ void csm_host_loopdet_destroy(void* det) { delete static_cast<HostLoopDet*>(det)
 void csm_host_loopdet_configure(void* det, int chunk_size, int coarse_covariance, int query_index_base)
 {
     auto* d = static_cast<HostLoopDet*>(det);
-    d->det->SetChunkSize(chunk_size);
+    d->det->SetChunkSize(chunk_size & 0xffff);
+    if ((chunk_size >> 16) > 0)
+        d->det->SetUploadChunk(chunk_size >> 16);
     d->det->SetCoarseCovariance(coarse_covariance != 0);
     d->det->SetQueryIndexBase(query_index_base);
 }

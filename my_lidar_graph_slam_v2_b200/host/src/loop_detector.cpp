@@ -103,13 +103,18 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     const int nchunks = (nq + chunk - 1) / chunk;
 
     /* first touch of a local map: upload + pyramid, cached by LocalMapId
-     * (loop_detector_branch_bound.cpp:83-89). All uploads are enqueued first:
-     * they stream over PCIe on the copy stream while the chunks that have
-     * landed are expanded, precomputed and searched on the compute stream. */
-    std::vector<std::vector<std::int64_t>> new_maps(nchunks);
-    for (int c = 0; c < nchunks; ++c) {
+     * (loop_detector_branch_bound.cpp:83-89). All uploads are enqueued first, in
+     * groups of mUploadChunk maps: they stream over PCIe on the copy stream while
+     * the groups that have landed are expanded and precomputed, and the search
+     * batches (mChunkSize queries) whose maps are complete run behind them. */
+    const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
+    std::vector<std::vector<std::int64_t>> new_maps;      /* per upload group */
+    std::vector<int> group_end;                           /* query index one past each group */
+    for (int first = 0; first < nq; first += ugroup) {
+        const int last = std::min(nq, first + ugroup);
         std::vector<const GridMapView*> fresh;
-        for (int i = c * chunk; i < std::min(nq, (c + 1) * chunk); ++i) {
+        new_maps.emplace_back();
+        for (int i = first; i < last; ++i) {
             const GridMapView& m = queries[i].local_map;
             if (m.map_id < 0) {
                 std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
@@ -117,15 +122,17 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             }
             if (mCachedMaps.insert(m.map_id).second) {
                 fresh.push_back(&m);
-                new_maps[c].push_back(m.map_id);
+                new_maps.back().push_back(m.map_id);
             }
         }
+        group_end.push_back(last);
         UploadNewMaps(ctx, fresh);
     }
     for (const LoopDetectionQuery& q : queries)
         if (mCachedScans.insert(q.scan_id).second)
             ctx->Check(csm_upload_scan(h, q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
                                        static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
+    std::size_t next_group = 0;
 
     /* per query: initial pose InverseCompound(map, scan) (:97-98), sensor pose,
      * steps and windows with the reference's expressions */
@@ -159,9 +166,12 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             d.score_thr = mScoreThreshold;
             d.known_thr = mKnownRateThreshold;
         }
-        if (!new_maps[c].empty())
-            ctx->Check(csm_build_pyramids(h, static_cast<int>(new_maps[c].size()), new_maps[c].data(), hmax),
-                       "csm_build_pyramids");
+        /* pyramids of every upload group this batch touches (in upload order) */
+        for (; next_group < new_maps.size() &&
+               (next_group == 0 || group_end[next_group - 1] < first + count); ++next_group)
+            if (!new_maps[next_group].empty())
+                ctx->Check(csm_build_pyramids(h, static_cast<int>(new_maps[next_group].size()),
+                                              new_maps[next_group].data(), hmax), "csm_build_pyramids");
         if (c - finished >= 4) {        /* the library keeps at most 4 batches in flight */
             const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
             ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");

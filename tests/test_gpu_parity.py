@@ -60,7 +60,8 @@ def test_pyramid_vs_checker(handle, checker, shape):
 
 
 @pytest.mark.parametrize("shape,hmax", [((64, 64), 6), ((512, 512), 6), ((32, 128), 4), ((128, 16), 6),
-                                        ((16, 512), 3), ((192, 336), 5), ((512, 512), 1), ((48, 48), 2)])
+                                        ((16, 512), 3), ((192, 336), 5), ((512, 512), 1), ((48, 48), 2),
+                                        ((256, 512), 6), ((384, 128), 6), ((144, 64), 6), ((272, 256), 5)])
 def test_pyramid_streaming_kernel(handle, checker, shape, hmax):
     """The single-pass streaming builder (used for big batches) against the checker."""
     handle.set_option("pyramid_mode", 2)
