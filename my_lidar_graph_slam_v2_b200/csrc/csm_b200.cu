@@ -8,10 +8,12 @@
 
 #include "csm_b200.h"
 #include "csm_kernels.cuh"
+#include "csm_window_tma.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -118,7 +120,9 @@ struct csm_context
     /* workspaces, grown on demand */
     DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
-    DevBuf d_rtblocks, d_pyrjobs, d_rootkey;
+    DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups;
+    int window_mode = 0;           /* grid search, integer-shift path: 0 auto (TMA tiles when possible),
+                                      1 plain global-memory kernel, 2 require the TMA kernel */
     PlanView plan_view;                   /* layout of the last staged batch */
     unsigned int frontier_capacity = 0;
     /* pinned staging: eight upload areas used in turn (an area is reused
@@ -749,6 +753,43 @@ int ensure_frontier(csm_handle h, int nq, unsigned int total_roots)
     return CSM_OK;
 }
 
+/* cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link) */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+/* TMA descriptor of a level-0 map: 2-D u16 tensor (cols fastest), boxes of kWtPitch x kWtBoxRows
+ * cells, out-of-bounds cells filled with zeros */
+bool make_map_tensor(const MapSlot& m, CUtensorMap* out)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr || (m.cols % 8) != 0)
+        return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)m.cols, (cuuint64_t)m.rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)m.cols * sizeof(uint16_t) };
+    const cuuint32_t box[2] = { (cuuint32_t)kWtPitch, (cuuint32_t)kWtBoxRows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, m.base, dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 /* scan: when non-null, the (single) query uses a scan that arrives with this
  * call (angles / ranges on the host) instead of a scan uploaded before. */
 struct InlineScan
@@ -975,7 +1016,7 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
-                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey };
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)
@@ -1025,6 +1066,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     }
     if (std::strcmp(name, "bb_dive") == 0 && value >= 0 && value <= 2) { h->bb_dive = value; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
+    if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
     if (std::strcmp(name, "reset_best_key") == 0) {
         int rc = ensure(h, h->d_bestkey, 8);
@@ -1619,8 +1661,10 @@ int csm_match_grid(csm_handle h, int64_t map_id,
         for (int k = 0; k < ndx; ++k) pos[k] = sensor_pose[0] + dx[k];
         for (int k = 0; k < ndy; ++k) pos[ndx + k] = sensor_pose[1] + dy[k];
     }
+    phase_mark(h, "start");
     if ((rc = commit_plan(h, plan, V, !fast))) return rc;
     if ((rc = launch_project(h, plan, V, !fast))) return rc;
+    phase_mark(h, "k_setup+k_project");
 
     GridArgs G;
     G.mx = reinterpret_cast<const int*>(V.extra);
@@ -1633,7 +1677,68 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     const DevQuery* dq = V.queries;
     const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
     dim3 grid(ndt, (ndy + 7) / 8);
-    if (fast) {
+    /* integer-shift path: TMA-staged shared-memory tiles when the window fits the tile */
+    bool tma = false;
+    CUtensorMap tmap;
+    WtArgs WA;
+    std::memset(&WA, 0, sizeof(WA));
+    if (fast && h->window_mode != 1) {
+        int dy_span = 0, dx_span = 0;
+        bool monotone = true, unit = true;
+        for (int k = 1; k < ndx; ++k) { monotone = monotone && offs[k] >= offs[k - 1]; unit = unit && offs[k] == offs[k - 1] + 1; }
+        for (int k = 1; k < ndy; ++k) monotone = monotone && offs[ndx + k] >= offs[ndx + k - 1];
+        /* warps per CTA (3 candidate rows each): as many as possible (one CTA per SM, so the
+         * warps are all the latency hiding there is) with the fewest idle rows in the last CTA */
+        int warps = 8;
+        {
+            int best_padded = 1 << 30;
+            for (int w = 8; w <= kWtMaxWarps; ++w) {
+                const int rows = w * kWtRows;
+                const int padded = ((ndy + rows - 1) / rows) * rows;
+                if (padded <= best_padded) { best_padded = padded; warps = w; }
+            }
+        }
+        const int rows_per_cta = warps * kWtRows;
+        WA.rows_per_cta = rows_per_cta;
+        for (int b = 0; b < ndy; b += rows_per_cta)
+            dy_span = std::max(dy_span, offs[ndx + std::min(ndy, b + rows_per_cta) - 1] - offs[ndx + b]);
+        for (int b = 0; b < ndx; b += kWtColsPerCta)
+            dx_span = std::max(dx_span, offs[std::min(ndx, b + kWtColsPerCta) - 1] - offs[b]);
+        if (unit) dx_span = std::max(dx_span, std::min(ndx, kWtColsPerCta) - 1);
+        WA.dy_span = dy_span; WA.dx_span = dx_span; WA.unit_dx = unit ? 1 : 0;
+        const int max_h = kWtTileRows - 1 - dy_span, max_w = kWtPitch - 8 - (unit ? kWtColsPerCta - 1 : dx_span);
+        tma = monotone && max_h >= 0 && max_w >= 0 && make_map_tensor(m, &tmap);
+        if (tma) {
+            if ((rc = ensure(h, h->d_wtgroups, sizeof(WtGroup) * (size_t)ndt * Q.n + sizeof(int) * (size_t)ndt))) return rc;
+            WtGroup* groups = static_cast<WtGroup*>(h->d_wtgroups.p);
+            int* gcount = reinterpret_cast<int*>(groups + (size_t)ndt * Q.n);
+            WA.groups = groups; WA.gcount = gcount;
+            k_window_groups<<<(ndt + 127) / 128, 128, 0, h->stream>>>(dq, proj, groups, gcount, max_h, max_w);
+            CSM_LAUNCH_CHECK();
+            const size_t smem = wt_smem_bytes(Q.n);
+            static bool attr_set = false;
+            if (!attr_set) {
+                CSM_CUDA(cudaFuncSetAttribute(k_window_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)wt_smem_bytes(kMaxBeams)));
+                CSM_CUDA(cudaFuncSetAttribute(k_window_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)wt_smem_bytes(kMaxBeams)));
+                attr_set = true;
+            }
+            dim3 wgrid(ndt, (ndy + rows_per_cta - 1) / rows_per_cta, (ndx + kWtColsPerCta - 1) / kWtColsPerCta);
+            phase_mark(h, "k_window_groups");
+            if (unit)
+                k_window_tma<true><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
+            else
+                k_window_tma<false><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
+            CSM_LAUNCH_CHECK();
+            phase_mark(h, "k_window_tma");
+        } else if (h->window_mode == 2) {
+            return fail(h, CSM_E_UNSUPPORTED, "match_grid: the TMA window kernel cannot take this window / map");
+        }
+    }
+    if (tma) {
+        /* launched above */
+    } else if (fast) {
         k_grid_window<<<grid, 256, sizeof(proj_t) * Q.n, h->stream>>>(dq, proj, G);
     } else {
         k_grid_general<<<grid, 256, sizeof(double2) * Q.n, h->stream>>>(
@@ -1650,8 +1755,10 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     F.mode = fast ? 1 : 2;
     F.qflags = V.qflags;
     F.nq = 1;
+    phase_mark(h, "k_grid_window/general");
     k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
+    phase_mark(h, "k_finalize");
     if ((rc = enqueue_readback(h, 1))) return rc;
     return finish_results(h, out, 1);
 }
