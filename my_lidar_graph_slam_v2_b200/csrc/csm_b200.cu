@@ -1560,11 +1560,11 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     const int nblocks = Q.T * nbx * nby;
     if ((rc = ensure(h, h->d_rtblocks, sizeof(RtBlock) * (size_t)nblocks))) return rc;
     if ((rc = commit_plan(h, plan, V, false))) return rc;
-    if ((rc = launch_project(h, plan, V, false))) return rc;
     const DevQuery* dq = V.queries;
-    const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
-    k_rt_blocks<<<nblocks, 256, sizeof(long long) * low_res * low_res, h->stream>>>(
-        dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby);
+    proj_t* proj = static_cast<proj_t*>(h->d_proj.p);
+    /* projection happens inside k_rt_blocks (one launch less on this latency-bound path) */
+    k_rt_blocks<<<nblocks, 256, sizeof(long long) * low_res * low_res + sizeof(proj_t) * Q.n, h->stream>>>(
+        dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby, V.qflags);
     CSM_LAUNCH_CHECK();
     FinalArgs F;
     std::memset(&F, 0, sizeof(F));

@@ -371,6 +371,44 @@ k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
 constexpr int kProjAngles = 8;       /* candidate angles per CTA */
 constexpr int kProjSat = 30000;      /* saturation of projected indices (maps are <= 16384 wide) */
 
+/* Hit cell of beam i seen from (Q.sx, Q.sy) at the candidate angle whose (cos, sin) is th:
+ * cos/sin(theta + a_i) from the angle-addition formula on the per-beam table, the rest is FP64 in
+ * the reference's operation order without contraction (sensor_data.hpp:190-203,
+ * grid_map_geometry.cpp:113-122). Raises `flagged` when a coordinate lies within the guard band
+ * of a cell boundary. */
+__device__ __forceinline__ proj_t project_beam(const DevQuery& Q, const double2 th, int i, int& flagged,
+                                               double& rc, double& rs)
+{
+    const double2 be = Q.beam_trig[i];
+    const double c = th.x * be.x - th.y * be.y;      /* cos(theta + a) */
+    const double s = th.y * be.x + th.x * be.y;      /* sin(theta + a) */
+    const double r = Q.ranges[i];
+    rc = __dmul_rn(r, c);
+    rs = __dmul_rn(r, s);
+    /* (x - off) * (1 / res) instead of the reference's (x - off) / res: the two
+     * differ by < 2 ulp, i.e. floor() can only differ inside the guard band
+     * that is flagged anyway (the band is ~1000x wider) */
+    const double ux = __dmul_rn(__dsub_rn(__dadd_rn(Q.sx, rc), Q.offx), Q.inv_res);
+    const double uy = __dmul_rn(__dsub_rn(__dadd_rn(Q.sy, rs), Q.offy), Q.inv_res);
+    const double fx = floor(ux), fy = floor(uy);
+    const double gx = ux - fx, gy = uy - fy;
+    if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
+        flagged = 1;
+    const double lim = (double)kProjSat;
+    proj_t p;
+    p.x = (short)(int)fmin(fmax(fx, -lim), lim);
+    p.y = (short)(int)fmin(fmax(fy, -lim), lim);
+    return p;
+}
+
+/* Candidate angle t of a query: sensorPose.theta + t * stepTheta (scan_matcher_branch_bound.cpp:
+ * 159-165, scan_matcher_correlative.cpp:163-166): one rounded product, one rounded sum */
+__device__ __forceinline__ double candidate_theta(const DevQuery& Q, int t)
+{
+    return (Q.thetas != nullptr) ? Q.thetas[t]
+                                 : __dadd_rn(Q.theta0, __dmul_rn((double)(t - Q.tcenter), Q.step_t));
+}
+
 /* proj[q][t][i] = (col, row) of beam i seen from (sx, sy, thetas[t]).
  * cos/sin(theta_t + a_i) come from the angle-addition formula on the per-beam
  * table and one sincos per candidate angle (a few ulp from the reference's
@@ -391,13 +429,8 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         return;
     const int nt = min(kProjAngles, Q.T - t0);
     if (threadIdx.x < nt) {
-        const int t = t0 + threadIdx.x;
-        /* sensorPose.theta + t * stepTheta (scan_matcher_branch_bound.cpp:159-165,
-         * scan_matcher_correlative.cpp:163-166): one rounded product, one rounded sum */
-        const double theta = (Q.thetas != nullptr) ? Q.thetas[t]
-                           : __dadd_rn(Q.theta0, __dmul_rn((double)(t - Q.tcenter), Q.step_t));
         double s, c;
-        sincos(theta, &s, &c);
+        sincos(candidate_theta(Q, t0 + threadIdx.x), &s, &c);
         s_theta[threadIdx.x] = make_double2(c, s);
     }
     __syncthreads();
@@ -410,26 +443,8 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         int tl, i;
         if (angle_fastest) { i = e / nt; tl = e - i * nt; }
         else { tl = e / Q.n; i = e - tl * Q.n; }
-        const double2 th = s_theta[tl];
-        const double2 be = Q.beam_trig[i];
-        const double c = th.x * be.x - th.y * be.y;      /* cos(theta + a) */
-        const double s = th.y * be.x + th.x * be.y;      /* sin(theta + a) */
-        const double r = Q.ranges[i];
-        const double rc = __dmul_rn(r, c);
-        const double rs = __dmul_rn(r, s);
-        /* (x - off) * (1 / res) instead of the reference's (x - off) / res: the two
-         * differ by < 2 ulp, i.e. floor() can only differ inside the guard band
-         * that is flagged anyway (the band is ~1000x wider) */
-        const double ux = __dmul_rn(__dsub_rn(__dadd_rn(Q.sx, rc), Q.offx), Q.inv_res);
-        const double uy = __dmul_rn(__dsub_rn(__dadd_rn(Q.sy, rs), Q.offy), Q.inv_res);
-        const double fx = floor(ux), fy = floor(uy);
-        const double gx = ux - fx, gy = uy - fy;
-        if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
-            flagged = 1;
-        const double lim = (double)kProjSat;
-        proj_t p;
-        p.x = (short)(int)fmin(fmax(fx, -lim), lim);
-        p.y = (short)(int)fmin(fmax(fy, -lim), lim);
+        double rc, rs;
+        const proj_t p = project_beam(Q, s_theta[tl], i, flagged, rc, rs);
         proj[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.pst_t + (size_t)i * Q.pst_i] = p;
         if (rcs != nullptr)
             rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.n + i] = make_double2(rc, rs);
@@ -490,10 +505,11 @@ struct RtBlock
  * candidates 1..L*L the fine lattice [x, x+L) x [y, y+L) in the reference's
  * iteration order (x outer, y inner, scan_matcher_correlative.cpp:351-352). */
 __global__ void __launch_bounds__(256)
-k_rt_blocks(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
-            RtBlock* __restrict__ blocks, int low_res, int nbx, int nby)
+k_rt_blocks(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj_all,
+            RtBlock* __restrict__ blocks, int low_res, int nbx, int nby, int* __restrict__ qflags)
 {
-    extern __shared__ long long s_keys[];      /* L*L fine keys */
+    extern __shared__ long long s_keys[];      /* L*L fine keys, then the angle's projected indices */
+    __shared__ double2 s_theta;
     const DevQuery& Q = queries[0];
     const int b = blockIdx.x;
     const int t = b / (nbx * nby);
@@ -501,7 +517,30 @@ k_rt_blocks(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
     const int bx = rem / nby, by = rem - bx * nby;
     const int x = -Q.winx + bx * low_res;
     const int y = -Q.winy + by * low_res;
-    const proj_t* proj = proj_all + Q.proj_off + (size_t)t * Q.n;
+    /* every CTA projects its angle itself (ComputeScanIndices, scan_matcher_correlative.cpp:277-297):
+     * a few FP64 operations per thread instead of a separate launch; the first CTA of an angle also
+     * publishes the indices for k_finalize and raises the guard-band flag */
+    proj_t* proj = reinterpret_cast<proj_t*>(s_keys + low_res * low_res);
+    if (threadIdx.x == 0) {
+        double sn, cs;
+        sincos(candidate_theta(Q, t), &sn, &cs);
+        s_theta = make_double2(cs, sn);
+    }
+    __syncthreads();
+    {
+        const bool publish = rem == 0;
+        proj_t* gproj = proj_all + Q.proj_off + (size_t)t * Q.n;
+        int flagged = 0;
+        for (int i = threadIdx.x; i < Q.n; i += blockDim.x) {
+            double rc, rs;
+            const proj_t p = project_beam(Q, s_theta, i, flagged, rc, rs);
+            proj[i] = p;
+            if (publish) gproj[i] = p;
+        }
+        if (publish && __any_sync(0xffffffffu, flagged) && (threadIdx.x & 31) == 0)
+            atomicOr(&qflags[0], 1 /* CSM_FLAG_FP_MARGIN */);
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int ncand = low_res * low_res + 1;
 
@@ -621,6 +660,86 @@ __device__ void rt_replay(const DevQuery& Q, const proj_t* __restrict__ proj_all
     out.bx = bestx; out.by = besty;
     out.bt = have ? bestt : 0;    /* reference initial bestWinTheta = -winTheta = index 0 */
     out.flags = flags; out.n_processed = processed; out.n_ignored = ignored; out.pad = 0;
+}
+
+/* The same replay as a warp scan, 32 blocks per step, valid whenever the
+ * sequential decisions reduce to "strict prefix maxima of the fine keys":
+ * every block that could be accepted has coarse key >= fine key (the bound is
+ * admissible there) and no key falls inside the threshold guard band. Returns
+ * false (nothing decided) otherwise; the caller then replays sequentially. */
+__device__ __forceinline__ long long shfl_ll(long long v, int src)
+{
+    return __shfl_sync(0xffffffffu, v, src);
+}
+
+__device__ bool rt_replay_scan(const DevQuery& Q, const RtBlock* __restrict__ blocks, int low_res,
+                               int nbx, int nby, BestState& out)
+{
+    const int lane = threadIdx.x & 31;
+    const int nb = Q.T * nbx * nby;
+    long long cur = -1;                  /* best accepted fine key so far (-1: none yet) */
+    int best_b = -1, best_ord = 0, flags = 0, processed = 0;
+    for (int base = 0; base < nb; base += 32) {
+        const int b = base + lane;
+        const bool valid = b < nb;
+        RtBlock B;
+        if (valid) {
+            const uint4 lo = reinterpret_cast<const uint4*>(blocks + b)[0];
+            const uint4 hi = reinterpret_cast<const uint4*>(blocks + b)[1];
+            B.coarse_key = (long long)(((unsigned long long)lo.y << 32) | lo.x);
+            B.fine_key = (long long)(((unsigned long long)lo.w << 32) | lo.z);
+            B.coarse_nk = (int)hi.x; B.fine_ord = (int)hi.y; B.fine_tie = (int)hi.z; B.pad = 0;
+        } else {
+            B.coarse_key = -1; B.fine_key = -1; B.coarse_nk = 0; B.fine_ord = 0; B.fine_tie = 0; B.pad = 0;
+        }
+        const bool nkok = valid && B.coarse_nk > Q.nk_cut;
+        const int cc = key_vs_threshold(B.coarse_key, Q.kthr), cf = key_vs_threshold(B.fine_key, Q.kthr);
+        const bool odd = valid && (cc == 0 || cf == 0 || (nkok && B.coarse_key < B.fine_key));
+        if (__any_sync(0xffffffffu, odd))
+            return false;
+        const bool elig = nkok && cf > 0;
+        const long long x = elig ? B.fine_key : -1;
+        /* inclusive prefix maximum over the lanes */
+        long long incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o && up > incl) incl = up;
+        }
+        long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = -1;
+        const long long cur_b = excl > cur ? excl : cur;        /* scoreMax when block b is reached */
+        const bool have_b = cur_b >= 0;
+        const bool coarse_ok = have_b ? (B.coarse_key > cur_b) : (cc > 0);
+        const bool proc = nkok && coarse_ok;
+        const bool accepted = elig && (!have_b || B.fine_key > cur_b);
+        const bool tie = (valid && have_b && B.coarse_key == cur_b) || (accepted && B.fine_tie != 0);
+        processed += __popc(__ballot_sync(0xffffffffu, proc));
+        if (__any_sync(0xffffffffu, tie)) flags |= 2;
+        const long long top = shfl_ll(incl, 31);
+        if (top > cur) {
+            /* the last accepted block of this step is the first one that reaches the step's maximum */
+            const unsigned int at = __ballot_sync(0xffffffffu, x == top);
+            const int src = __ffs(at) - 1;
+            best_b = base + src;
+            best_ord = __shfl_sync(0xffffffffu, B.fine_ord, src);
+            cur = top;
+        }
+    }
+    const bool have = best_b >= 0;
+    int bestx = -Q.winx, besty = -Q.winy, bestt = 0;
+    if (have) {
+        const int t = best_b / (nbx * nby);
+        const int rem = best_b - t * nbx * nby;
+        const int bx = rem / nby, by = rem - bx * nby;
+        bestx = -Q.winx + bx * low_res + best_ord / low_res;
+        besty = -Q.winy + by * low_res + best_ord % low_res;
+        bestt = t;
+    }
+    out.found = have ? 1 : 0;
+    out.bx = bestx; out.by = besty; out.bt = bestt;
+    out.flags = flags; out.n_processed = processed; out.n_ignored = nb - processed; out.pad = 0;
+    return true;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1302,7 +1421,8 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
 
     if (F.decode == 3) {
         BestState st;
-        rt_replay(Q, proj_all, F.blocks, F.low_res, F.nbx, F.nby, s_blocks, st);
+        if (!rt_replay_scan(Q, F.blocks, F.low_res, F.nbx, F.nby, st))
+            rt_replay(Q, proj_all, F.blocks, F.low_res, F.nbx, F.nby, s_blocks, st);
         if (lane == 0) s_state = st;
     } else if (lane == 0) {
         BestState st;

@@ -1,6 +1,7 @@
 #include "csm_host/cost_square_error.hpp"
 
 #include <algorithm>
+#include <cmath>
 
 namespace csm_host {
 
@@ -101,8 +102,9 @@ Neighbours Closest(const Sampler& s, double fx, double fy)
 inline void HitPoint(const ScanData& scan, const Pose2D& pose, std::size_t i, double& hx, double& hy)
 {
     /* sensor_data.hpp:190-203 */
-    const double c = std::cos(pose.theta + scan.angles[i]);
-    const double s = std::sin(pose.theta + scan.angles[i]);
+    /* one call; glibc's sincos returns exactly the values of sin() and cos() */
+    double s, c;
+    ::sincos(pose.theta + scan.angles[i], &s, &c);
     hx = pose.x + scan.ranges[i] * c;
     hy = pose.y + scan.ranges[i] * s;
 }
