@@ -382,26 +382,30 @@ def main_cuda(args):
     dev_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
     assert sum(r.found for r in results) == n_found
 
-    # ---- per-phase timing for the roofline of the dominant kernels ---------------------------
+    # ---- per-kernel CUDA-event durations (library option "timing": one event after every kernel,
+    # on the stream the kernels are launched on) for the roofline of the dominant kernels ----------
     barrier()
-    ev[0].record(ext_stream)
-    for _ in range(args.steps):
+    h.set_option("timing", 1)
+    kernel_ms = {}
+    reps = max(5, min(args.steps, 20))
+    for _ in range(reps):
         h.drop_pyramids(ids)
         h.build_pyramids(ids, HMAX)
-    ev[1].record(ext_stream)
-    ev[1].synchronize()
-    pyr_ms = ev[0].elapsed_time(ev[1]) / args.steps
-    ev[2].record(ext_stream)
-    for _ in range(args.steps):
+        for k, v in h.timings():
+            kernel_ms[k] = kernel_ms.get(k, 0.0) + v / reps
         h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
         h.loop_batch_finish(N_MAPS, results)
-    ev[3].record(ext_stream)
-    ev[3].synchronize()
-    bb_ms = ev[2].elapsed_time(ev[3]) / args.steps
+        for k, v in h.timings():
+            kernel_ms[k] = kernel_ms.get(k, 0.0) + v / reps
+    h.set_option("timing", 0)
+    kernel_ms.pop("k_setup", None)          # its interval includes host staging time when the stream is idle
+    counts = h.frontier_counts()
+    pyr_ms = kernel_ms.get("k_pyramid_stream", 0.0)
+    bb_ms = sum(v for k, v in kernel_ms.items() if k != "k_pyramid_stream")
     # nodes scored per step: every root candidate + the four children of every node that passed
     n_roots = sum((2 * a.win_t + 1) * ((2 * a.win_x) // (1 << HMAX) + 1) * ((2 * a.win_y) // (1 << HMAX) + 1)
                   for a in arr)
-    nodes_scored = n_roots + 4 * sum(h.frontier_counts()[1:HMAX + 1])
+    nodes_scored = n_roots + 4 * sum(counts[1:HMAX + 1])
 
     peaks = {}
     try:
@@ -409,31 +413,52 @@ def main_cuda(args):
             peaks = json.load(f)
     except (OSError, ValueError):
         pass
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
     step_ms = dev_ms / args.steps
-    # dominant kernels: k_bb_roots / k_bb_expand (one launch per pyramid height). Algorithmic bytes:
-    # one u16 grid read per scored node and beam.
-    bb_bytes = nodes_scored * 360 * 2
+    # Dominant kernel family: k_bb_expand<HC> (one launch per pyramid height, 4 children per node).
+    # Algorithmic bytes: one u16 grid read per scored node and beam.
+    n_beams = len(angles)
+    per_launch = {}
+    for hc in range(HMAX):
+        name = "k_bb_expand<%d>" % hc
+        ms = kernel_ms.get(name, 0.0)
+        nodes = 4 * counts[hc + 1]
+        per_launch[name] = {"ms": ms, "nodes_scored": int(nodes),
+                          "GBps": nodes * n_beams * 2 / (ms * 1e-3) / 1e9 if ms > 0 else None}
+    exp_ms = sum(v["ms"] for v in per_launch.values())
+    exp_bytes = sum(v["nodes_scored"] for v in per_launch.values()) * n_beams * 2
     roofline = {
-        "kernel": "k_bb_roots + k_bb_expand (B&B frontier scoring, %d launches per step)" % (HMAX + 1),
-        "bound": "hbm", "achieved": bb_bytes / (bb_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": bb_bytes / (bb_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_source,
-        "algorithmic_bytes_per_step": bb_bytes, "nodes_scored_per_step": int(nodes_scored),
-        "traffic": None, "ms_per_step": bb_ms, "share_of_step": bb_ms / step_ms,
-        "note": "scattered 2-byte gathers: the binding unit is the L1TEX sector rate, not DRAM "
-                "(profiles/); ms_per_step is the whole loop batch (projection, %d scoring launches, "
-                "finalize, read-back)" % (HMAX + 1),
+        "kernel": "k_bb_expand<0..%d> (B&B frontier scoring, %d launches per step, one per pyramid height)"
+                  % (HMAX - 1, HMAX),
+        "bound": "hbm", "achieved": exp_bytes / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s",
+        "frac": exp_bytes / (exp_ms * 1e-3) / 1e9 / hbm_peak if exp_ms > 0 else None,
+        "peak_source": peak_source, "algorithmic_bytes_per_step": int(exp_bytes),
+        "avg_launch_ms": exp_ms / HMAX, "ms_per_step": exp_ms, "share_of_step": exp_ms / step_ms,
+        "traffic": traffic.get("k_bb_expand_dram_bytes_per_step"), "launches": per_launch,
+        "note": "scattered 2-byte gathers from 900 MB of pyramid levels: neither DRAM nor tensor bound; the "
+                "binding unit is the L1TEX line (wavefront) rate of divergent loads, see DESIGN.md section 5 "
+                "and profiles/r1_k_bb_expand.txt. Durations are CUDA events recorded by the library on the "
+                "launching stream after every kernel.",
     }
     pyr_bytes = (1 + HMAX) * cells * 2 * N_MAPS          # read level 0 once, write hmax levels
     roofline_pyramid = {
         "kernel": "k_pyramid_stream (PrecomputeGridMaps, 1 launch per step)",
-        "bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_source,
-        "algorithmic_bytes_per_launch": pyr_bytes, "traffic": None,
+        "bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s",
+        "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak if pyr_ms > 0 else None, "peak_source": peak_source,
+        "algorithmic_bytes_per_launch": pyr_bytes, "traffic": traffic.get("k_pyramid_stream_dram_bytes_per_launch"),
         "ms_per_step": pyr_ms, "share_of_step": pyr_ms / step_ms,
     }
-    phases = {"pyramid_ms": pyr_ms, "branch_and_bound_ms": bb_ms}
+    phases = {"pyramid_ms": pyr_ms, "branch_and_bound_ms": bb_ms, "kernel_ms": kernel_ms,
+              "nodes_scored_per_step": int(nodes_scored)}
 
     total_queries = world * N_MAPS * args.steps
     line = {
@@ -506,13 +531,23 @@ def single_scan_numbers(h, lib, kind):
     s = case.submap
     off = (s.off_x, s.off_y)
     og = orc.grid(s.grid, s.res, s.off_x, s.off_y)
-    gpu = timeit(lambda: ctx.match("rt", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5,
-                                   synth.CFG1["rng"]), 300)
+    # the map in the reference's storage form (allocated 16x16 blocks); every match first copies the
+    # blocks (what the adapter's gather out of the per-scan GridMap costs), then uploads them
+    blocks, index, _, _ = synth.dense_to_blocks(s.grid)
+
+    def rt():
+        return ctx.match_blocks("rt", blocks.copy(), index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                                case.init_pose, 5, synth.CFG1["rng"])
+
+    def bb():
+        return ctx.match_blocks("bb", blocks.copy(), index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                                case.init_pose, 5, synth.CFG2["rng"])
+
+    gpu = timeit(rt, 300)
     cpu = timeit(lambda: orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), 20)
     out["cfg1_rt_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
-    gpu = timeit(lambda: ctx.match("bb", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5,
-                                   synth.CFG2["rng"]), 300)
+    gpu = timeit(bb, 300)
     cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5)
     out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
@@ -528,11 +563,27 @@ def single_scan_numbers(h, lib, kind):
     el = time.perf_counter() - t0
     full = 161 * 161 * 601
     cpu = 1.0 / (el * full / max(r.n_processed, 1))
+    # the scoring kernel alone (CUDA events of the library) against the shared-memory roofline:
+    # one LSU wavefront serves 32 candidate-beam reads, one wavefront per cycle per SM
+    from my_lidar_graph_slam_v2_b200 import capi
+    hh = capi.Handle.from_pointer(ctx.handle(), h.device)
+    hh.set_option("timing", 1)
+    ctx.match("grid", s4.grid, s4.res, (s4.off_x, s4.off_y), c4.angles, c4.ranges, c4.init_pose, 0,
+              synth.CFG4["rng"], step=synth.CFG4["step"])
+    km = dict(hh.timings())
+    hh.set_option("timing", 0)
+    wt_ms = km.get("k_window_tma")
     out["cfg4_grid_matches_per_s"] = {
         "gpu_e2e": gpu, "cpu_1core_scaled": cpu, "ratio": gpu / cpu,
         "cpu_sample": "%d of %d candidates evaluated in %.2f s, scaled linearly" % (r.n_processed, full, el),
         "cpu_kind": kind, "gather_bytes_per_match": full * 1080 * 2,
-        "gather_GBps": full * 1080 * 2 * gpu / 1e9}
+        "gather_GBps": full * 1080 * 2 * gpu / 1e9,
+        "k_window_tma": None if not wt_ms else {
+            "ms": wt_ms, "cell_reads_per_s": full * 1080 / (wt_ms * 1e-3),
+            "smem_roofline_reads_per_s": 32 * 148 * 1.965e9,
+            "frac_of_smem_roofline": full * 1080 / (wt_ms * 1e-3) / (32 * 148 * 1.965e9),
+            "note": "roofline = 1 shared-memory wavefront (32 lanes) per cycle per SM at 1965 MHz; "
+                    "ncu counts 0.745 wavefronts/cycle/SM including idle lanes (profiles/r1_k_window_tma.txt)"}}
     ctx.close()
     return out
 

@@ -33,11 +33,16 @@ public:
     DeviceContext(const DeviceContext&) = delete;
     DeviceContext& operator=(const DeviceContext&) = delete;
     csm_handle Handle() const { return mHandle; }
+    /* Page-locked staging area of at least `bytes` (grown on demand, reused by every call): map data
+     * copied here first crosses PCIe by DMA while the call goes on */
+    void* Staging(std::size_t bytes);
     /* Abort with the library's message unless rc == CSM_OK */
     void Check(int rc, const char* what) const;
 
 private:
     csm_handle mHandle;
+    void* mStaging = nullptr;
+    std::size_t mStagingBytes = 0;
 };
 using DeviceContextPtr = std::shared_ptr<DeviceContext>;
 

@@ -34,6 +34,8 @@ static void Export(const ScanMatchingSummary& s, csm_host_summary* out)
 
 void* csm_host_context_create(int device) { return new DeviceContextPtr(std::make_shared<DeviceContext>(device)); }
 void csm_host_context_destroy(void* ctx) { delete static_cast<DeviceContextPtr*>(ctx); }
+/* the csm_handle (C ABI) behind a context: timing options, direct C-ABI calls in tests */
+void* csm_host_context_handle(void* ctx) { return (*static_cast<DeviceContextPtr*>(ctx))->Handle(); }
 
 static GridMapView View(const uint16_t* values, int rows, int cols, double res, double ox, double oy, int64_t id)
 {
@@ -70,15 +72,43 @@ int csm_host_cost(const uint16_t* values, int rows, int cols, double res, double
 
 /* kind: 0 = RealTimeCorrelative, 1 = BranchBound, 2 = GridSearch.
  * iparam: lowResolution / nodeHeightMax; range[3]; step[3] (grid search only). */
+static int MatchView(void* ctx, int kind, const GridMapView& map, const double* angles, const double* ranges, int n,
+                     const double init_pose[3], const double rel_pose[3], int iparam,
+                     const double range[3], const double step[3], double score_thr, double known_thr,
+                     double covariance_scale, csm_host_summary* out);
+
 int csm_host_match(void* ctx, int kind, const uint16_t* values, int rows, int cols, double res,
                    double off_x, double off_y, const double* angles, const double* ranges, int n,
                    const double init_pose[3], const double rel_pose[3], int iparam,
                    const double range[3], const double step[3], double score_thr, double known_thr,
                    double covariance_scale, csm_host_summary* out)
 {
+    return MatchView(ctx, kind, View(values, rows, cols, res, off_x, off_y, -1), angles, ranges, n, init_pose,
+                     rel_pose, iparam, range, step, score_thr, known_thr, covariance_scale, out);
+}
+
+/* The same with the map in block-sparse form (the reference's storage): n_blocks blocks of
+ * (1 << log2bs)^2 cells and their positions */
+int csm_host_match_blocks(void* ctx, int kind, const uint16_t* blocks, const int32_t* block_index, int n_blocks,
+                          int log2bs, int rows, int cols, double res, double off_x, double off_y,
+                          const double* angles, const double* ranges, int n,
+                          const double init_pose[3], const double rel_pose[3], int iparam,
+                          const double range[3], const double step[3], double score_thr, double known_thr,
+                          double covariance_scale, csm_host_summary* out)
+{
+    GridMapView map = View(nullptr, rows, cols, res, off_x, off_y, -1);
+    map.blocks = blocks; map.block_index = block_index; map.n_blocks = n_blocks; map.log2_block_size = log2bs;
+    return MatchView(ctx, kind, map, angles, ranges, n, init_pose, rel_pose, iparam, range, step, score_thr,
+                     known_thr, covariance_scale, out);
+}
+
+static int MatchView(void* ctx, int kind, const GridMapView& map, const double* angles, const double* ranges, int n,
+                     const double init_pose[3], const double rel_pose[3], int iparam,
+                     const double range[3], const double step[3], double score_thr, double known_thr,
+                     double covariance_scale, csm_host_summary* out)
+{
     const DeviceContextPtr& c = *static_cast<DeviceContextPtr*>(ctx);
     const auto cost = std::make_shared<CostSquareError>(covariance_scale);
-    const GridMapView map = View(values, rows, cols, res, off_x, off_y, -1);
     const ScanDataPtr scan = Scan(angles, ranges, n, rel_pose);
     const Pose2D init { init_pose[0], init_pose[1], init_pose[2] };
     ScanMatchingSummary s;

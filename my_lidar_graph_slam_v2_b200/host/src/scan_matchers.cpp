@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace csm_host {
 
@@ -18,8 +19,29 @@ DeviceContext::DeviceContext(int device) : mHandle(nullptr)
 
 DeviceContext::~DeviceContext()
 {
-    if (mHandle != nullptr)
+    if (mHandle != nullptr) {
+        csm_synchronize(mHandle);
         csm_destroy(mHandle);
+    }
+    if (mStaging != nullptr)
+        csm_free_pinned(mStaging);
+}
+
+void* DeviceContext::Staging(std::size_t bytes)
+{
+    if (mStagingBytes < bytes) {
+        if (mStaging != nullptr) {
+            csm_synchronize(mHandle);
+            csm_free_pinned(mStaging);
+        }
+        mStagingBytes = std::max<std::size_t>(bytes * 2, std::size_t(1) << 20);
+        mStaging = csm_alloc_pinned(mStagingBytes);
+        if (mStaging == nullptr) {
+            std::fprintf(stderr, "csm_host: cannot allocate %zu bytes of page-locked memory\n", mStagingBytes);
+            std::abort();
+        }
+    }
+    return mStaging;
 }
 
 void DeviceContext::Check(int rc, const char* what) const
@@ -38,15 +60,30 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
     const bool resident = map.map_id >= 0 &&
         std::find(mResidentMaps.begin(), mResidentMaps.end(), id) != mResidentMaps.end();
     if (!resident) {
-        if (map.blocks != nullptr)
-            mContext->Check(csm_upload_grid_blocks(mContext->Handle(), id, map.blocks, map.block_index,
+        /* through the context's page-locked staging area (the previous match on this context has
+         * returned, so the area is free): the copy then runs as a DMA behind this call */
+        if (map.blocks != nullptr) {
+            const std::size_t data = (sizeof(std::uint16_t) * static_cast<std::size_t>(map.n_blocks))
+                                     << (2 * map.log2_block_size);
+            const std::size_t idx_off = (data + 15) & ~std::size_t(15);
+            char* st = static_cast<char*>(mContext->Staging(idx_off + sizeof(std::int32_t) * map.n_blocks));
+            std::memcpy(st, map.blocks, data);
+            std::memcpy(st + idx_off, map.block_index, sizeof(std::int32_t) * map.n_blocks);
+            mContext->Check(csm_upload_grid_blocks(mContext->Handle(), id,
+                                                   reinterpret_cast<const std::uint16_t*>(st),
+                                                   reinterpret_cast<const std::int32_t*>(st + idx_off),
                                                    map.n_blocks, map.log2_block_size,
                                                    map.rows >> map.log2_block_size,
                                                    map.cols >> map.log2_block_size, map.resolution,
                                                    map.offset_x, map.offset_y), "csm_upload_grid_blocks");
-        else
-            mContext->Check(csm_upload_grid(mContext->Handle(), id, map.values, map.rows, map.cols,
-                                            map.resolution, map.offset_x, map.offset_y), "csm_upload_grid");
+        } else {
+            const std::size_t bytes = sizeof(std::uint16_t) * static_cast<std::size_t>(map.rows) * map.cols;
+            void* st = mContext->Staging(bytes);
+            std::memcpy(st, map.values, bytes);
+            mContext->Check(csm_upload_grid(mContext->Handle(), id, static_cast<const std::uint16_t*>(st),
+                                            map.rows, map.cols, map.resolution, map.offset_x, map.offset_y),
+                            "csm_upload_grid");
+        }
         if (map.map_id >= 0)
             mResidentMaps.push_back(id);
     }

@@ -32,11 +32,17 @@ def load():
         lib.csm_host_context_create.restype = C.c_void_p
         lib.csm_host_context_create.argtypes = [C.c_int]
         lib.csm_host_context_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_context_handle.restype = C.c_void_p
+        lib.csm_host_context_handle.argtypes = [C.c_void_p]
         lib.csm_host_cost.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                       dp, dp, C.c_int, dp, C.c_double, dp, dp]
         lib.csm_host_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                        C.c_double, C.c_double, dp, dp, C.c_int, dp, dp, C.c_int, dp, dp,
                                        C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
+        lib.csm_host_match_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp, dp,
+                                              C.c_int, dp, dp, C.c_int, dp, dp, C.c_double, C.c_double,
+                                              C.c_double, C.POINTER(HostSummary)]
         lib.csm_host_loop_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                              dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int, C.c_int,
                                              dp, C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
@@ -78,6 +84,10 @@ class Context:
         self.lib = load()
         self.ctx = self.lib.csm_host_context_create(device)
 
+    def handle(self):
+        """The csm_handle (C ABI) this context runs on."""
+        return self.lib.csm_host_context_handle(self.ctx)
+
     def close(self):
         if self.ctx:
             self.lib.csm_host_context_destroy(self.ctx)
@@ -96,6 +106,25 @@ class Context:
         rc = self.lib.csm_host_match(self.ctx, {"rt": 0, "bb": 1, "grid": 2}[kind], g.ctypes.data,
                                      g.shape[0], g.shape[1], res, off[0], off[1], ap, rp, len(a), pp, qp,
                                      iparam, rgp, stp, thr[0], thr[1], covariance_scale, C.byref(out))
+        assert rc == 0
+        return out
+
+    def match_blocks(self, kind, blocks, index, log2bs, shape, res, off, angles, ranges, init_pose, iparam, rng,
+                     step=(0, 0, 0), thr=(0.0, 0.0), rel_pose=(0.0, 0.0, 0.0), covariance_scale=1e4):
+        """match() with the map in block-sparse form: blocks (n, bs, bs) uint16, index (n,) int32."""
+        b = np.ascontiguousarray(blocks, dtype=np.uint16)
+        ix = np.ascontiguousarray(index, dtype=np.int32)
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        p, pp = _d(init_pose)
+        q, qp = _d(rel_pose)
+        rg, rgp = _d(rng)
+        st, stp = _d(step)
+        out = HostSummary()
+        rc = self.lib.csm_host_match_blocks(self.ctx, {"rt": 0, "bb": 1, "grid": 2}[kind], b.ctypes.data,
+                                            ix.ctypes.data, len(ix), log2bs, shape[0], shape[1], res, off[0],
+                                            off[1], ap, rp, len(a), pp, qp, iparam, rgp, stp, thr[0], thr[1],
+                                            covariance_scale, C.byref(out))
         assert rc == 0
         return out
 

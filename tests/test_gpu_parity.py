@@ -410,6 +410,26 @@ def test_cpp_adapter_matchers(checker, seed):
     ctx.close()
 
 
+@pytest.mark.parametrize("seed", range(2410, 2413))
+def test_cpp_adapter_block_sparse_maps(checker, seed):
+    """The C++ adapter fed with the map in the reference's block-sparse storage form: same device
+    result and the same CPU cost / covariance (block allocation is exact in this form)."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    case = synth.case_for(synth.CFG1, seed)
+    s = case.submap
+    g = checker.grid(s.grid, s.res, s.off_x, s.off_y)
+    blocks, index, br, bc = synth.dense_to_blocks(s.grid)
+    off = (s.off_x, s.off_y)
+    a = ctx.match_blocks("rt", blocks, index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                         case.init_pose, 5, synth.CFG1["rng"])
+    _cmp_host(a, checker.match_rt(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), "rt")
+    a = ctx.match_blocks("bb", blocks, index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                         case.init_pose, 5, synth.CFG2["rng"])
+    _cmp_host(a, checker.match_bb(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), "bb")
+    ctx.close()
+
+
 def test_cpp_adapter_loop_detector(checker):
     from my_lidar_graph_slam_v2_b200 import hostapi
     ctx = hostapi.Context(0)
