@@ -393,7 +393,7 @@ __device__ __forceinline__ proj_t project_beam(const DevQuery& Q, const double2 
     const double fx = floor(ux), fy = floor(uy);
     const double gx = ux - fx, gy = uy - fy;
     if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
-        flagged = 1;
+        flagged |= 1;
     const double lim = (double)kProjSat;
     proj_t p;
     p.x = (short)(int)fmin(fmax(fx, -lim), lim);
@@ -445,12 +445,21 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         else { tl = e / Q.n; i = e - tl * Q.n; }
         double rc, rs;
         const proj_t p = project_beam(Q, s_theta[tl], i, flagged, rc, rs);
+        if (Q.lx > 0) {
+            /* branch-and-bound: a node window that straddles row / column 0 makes the coarse bound
+             * inadmissible (a lookup at a negative index reads unknown) */
+            const int x0 = (int)p.x - Q.winx, y0 = (int)p.y - Q.winy;
+            if ((x0 < 0 && x0 + 2 * Q.lx > 0) || (y0 < 0 && y0 + 2 * Q.ly > 0))
+                flagged |= 4;
+        }
         proj[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.pst_t + (size_t)i * Q.pst_i] = p;
         if (rcs != nullptr)
             rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.n + i] = make_double2(rc, rs);
     }
-    if (__any_sync(0xffffffffu, flagged) && (threadIdx.x & 31) == 0)
-        atomicOr(&qflags[q], 1 /* CSM_FLAG_FP_MARGIN */);
+    /* bit 0: CSM_FLAG_FP_MARGIN, bit 2: CSM_FLAG_EDGE */
+    const int any = (int)__reduce_or_sync(0xffffffffu, (unsigned)flagged);
+    if (any != 0 && (threadIdx.x & 31) == 0)
+        atomicOr(&qflags[q], any);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -231,6 +231,23 @@ def test_single_beam_and_low_edge(handle, checker):
     assert_match(s.result, o, "single beam")
 
 
+def test_bb_edge_flag(handle):
+    """Branch-and-bound raises CSM_FLAG_EDGE when a node window straddles row / column 0 (there the
+    reference's coarse bound is not admissible) and leaves it clear otherwise."""
+    rng = np.random.default_rng(6)
+    grid = rng.integers(1, 65535, size=(64, 64), dtype=np.uint16)
+    gm = matchers.GridMap(grid, 0.05, (0.0, 0.0))
+    angles = -np.pi + 2 * np.pi * np.arange(90) / 90
+    ranges = np.full(90, 0.9)
+    bb = matchers.ScanMatcherBranchBound("bb", 3, 0.6, 0.6, 0.3, handle=handle)
+    r = bb.optimize_pose(gm, matchers.ScanData(angles, ranges), (0.45, 0.40, 0.2)).result
+    assert r.flags & capi.FLAG_EDGE
+    case = synth.case_for(synth.CFG1, 2100)
+    r = matchers.ScanMatcherBranchBound("bb", 5, *synth.CFG2["rng"], handle=handle).optimize_pose(
+        grid_of(case), _scan(case), tuple(case.init_pose)).result
+    assert r.flags == 0
+
+
 # --------------------------------------------------------------------------
 # loop detection batch
 # --------------------------------------------------------------------------
