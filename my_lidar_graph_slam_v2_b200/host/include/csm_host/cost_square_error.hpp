@@ -20,6 +20,10 @@ public:
     double Cost(const GridMapView& map, const ScanData& scan, const Pose2D& sensor_pose) const;
     std::array<double, 9> ComputeCovariance(const GridMapView& map, const ScanData& scan,
                                             const Pose2D& sensor_pose) const;
+    /* Gauss-Newton Hessian (row-major 3x3) and residual vector at a sensor pose
+     * (cost_function_square_error.cpp:151-195), the inputs of the linear-solver refiner */
+    void ComputeHessianAndResidual(const GridMapView& map, const ScanData& scan, const Pose2D& sensor_pose,
+                                   double hessian[9], double residual[3]) const;
     /* Both in one pass over the scan (what every matcher's epilogue needs) */
     std::array<double, 9> CostAndCovariance(const GridMapView& map, const ScanData& scan,
                                             const Pose2D& sensor_pose, double& cost) const;

@@ -17,6 +17,10 @@ namespace csm_host {
 using FinalMatcher = std::function<ScanMatchingSummary(const GridMapView& map, const ScanDataPtr& scan,
                                                        const Pose2D& center, const Pose2D& initial_pose)>;
 
+/* The reference's default refinement stage: a ScanMatcherLinearSolver run on the coarse pose
+ * (loop_detector_branch_bound.cpp:110-127; the map centre argument is not used by this matcher) */
+FinalMatcher MakeLinearSolverFinalMatcher(const std::shared_ptr<ScanMatcherLinearSolver>& solver);
+
 class LoopDetector
 {
 public:

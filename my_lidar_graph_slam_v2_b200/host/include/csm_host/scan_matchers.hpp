@@ -138,4 +138,32 @@ private:
     double mRangeX, mRangeY, mRangeTheta, mStepX, mStepY, mStepTheta;
 };
 
+/* ScanMatcherLinearSolver (mapping/scan_matcher_linear_solver.cpp:46-170): the sub-pixel refiner
+ * the reference runs after every coarse match ("FinalScanMatcherType": "LinearSolver",
+ * launcher_settings_default.json:73-96). Damped Gauss-Newton on the square-error cost: per step
+ * (H + lambda I) dx = r solved by a column-pivoting Householder QR, lambda halved / doubled by the
+ * cost trend and -- like in the reference -- kept across calls. Runs on the CPU (SURVEY.md 8f
+ * rank 1); O(iterations x beams). */
+class ScanMatcherLinearSolver final : public ScanMatcher
+{
+public:
+    ScanMatcherLinearSolver(const std::string& name, int num_of_iterations_max, double convergence_threshold,
+                            double initial_lambda, const CostFuncPtr& cost);
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override;
+    double Lambda() const { return mLambda; }
+
+private:
+    Pose2D OptimizeStep(const GridMapView& map, const ScanData& scan, const Pose2D& sensor_pose) const;
+
+    int mNumOfIterationsMax;
+    double mConvergenceThreshold;
+    double mLambda;
+    CostFuncPtr mCost;
+};
+
+/* x = A^-1 b for a 3x3 system with Eigen's ColPivHouseholderQR scheme (what
+ * scan_matcher_linear_solver.cpp:161 calls): Householder reflections with the largest remaining
+ * column brought to the front at every step. A is row-major. */
+void SolveColPivHouseholderQr3(const double a[9], const double b[3], double x[3]);
+
 } /* namespace csm_host */

@@ -173,12 +173,33 @@ int csm_host_loop_detect(void* ctx, int n_queries, const uint16_t* values, int r
     return 0;
 }
 
+/* ScanMatcherLinearSolver::OptimizePose on the CPU (no device): `lambda` is the solver's damping
+ * state, read and written back so that a sequence of calls behaves like one solver instance */
+int csm_host_refine(const uint16_t* values, int rows, int cols, double res, double off_x, double off_y,
+                    const double* angles, const double* ranges, int n, const double init_pose[3],
+                    const double rel_pose[3], int iterations_max, double convergence_threshold,
+                    double* lambda, double covariance_scale, csm_host_summary* out)
+{
+    const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+    const GridMapView map = View(values, rows, cols, res, off_x, off_y, -1);
+    const ScanDataPtr scan = Scan(angles, ranges, n, rel_pose);
+    ScanMatcherLinearSolver solver("LinearSolver", iterations_max, convergence_threshold, *lambda, cost);
+    const ScanMatchingSummary s = solver.OptimizePose(
+        ScanMatchingQuery { map, scan, Pose2D { init_pose[0], init_pose[1], init_pose[2] } });
+    *lambda = solver.Lambda();
+    Export(s, out);
+    out->best_t = s.n_processed;      /* iterations */
+    return 0;
+}
+
 /* ---- persistent loop detector (bench.py e2e path) ------------------------------ */
 struct HostLoopDet
 {
     DeviceContextPtr ctx;
     std::shared_ptr<ScanMatcherBranchBound> matcher;
+    std::shared_ptr<ScanMatcherLinearSolver> refiner;
     std::unique_ptr<LoopDetectorBranchBound> det;
+    double score_thr = 0.0, known_thr = 0.0;
 };
 
 void* csm_host_loopdet_create(void* ctx, int hmax, const double range[3], double score_thr,
@@ -191,7 +212,21 @@ void* csm_host_loopdet_create(void* ctx, int hmax, const double range[3], double
                                                           range[2], d->ctx);
     d->det.reset(new LoopDetectorBranchBound("LoopDetectorBranchBoundGPU", d->matcher, FinalMatcher(),
                                              score_thr, known_thr));
+    d->score_thr = score_thr; d->known_thr = known_thr;
     return d;
+}
+
+/* Refine every detected loop with a ScanMatcherLinearSolver like the reference's default
+ * configuration ("FinalScanMatcherType": "LinearSolver") */
+void csm_host_loopdet_use_linear_solver(void* det, int iterations_max, double convergence_threshold,
+                                        double initial_lambda, double covariance_scale)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    d->refiner = std::make_shared<ScanMatcherLinearSolver>(
+        "LoopDetector.FinalScanMatcherLinearSolver", iterations_max, convergence_threshold, initial_lambda,
+        std::make_shared<CostSquareError>(covariance_scale));
+    d->det.reset(new LoopDetectorBranchBound("LoopDetectorBranchBoundGPU", d->matcher,
+                                             MakeLinearSolverFinalMatcher(d->refiner), d->score_thr, d->known_thr));
 }
 
 void csm_host_loopdet_destroy(void* det) { delete static_cast<HostLoopDet*>(det); }

@@ -116,7 +116,8 @@ namespace {
 /* One pass over the scan: squared-error cost (:48-75) and, when h != nullptr,
  * the Gauss-Newton Hessian (:151-195) from the same map samples. The two
  * accumulations are independent, each in the reference's own order. */
-double Accumulate(const GridMapView& map, const ScanData& scan, const Pose2D& pose, double* h)
+double Accumulate(const GridMapView& map, const ScanData& scan, const Pose2D& pose, double* h,
+                  double* residual = nullptr)
 {
     const Sampler sampler(map);
     double cost = 0.0;
@@ -137,6 +138,12 @@ double Accumulate(const GridMapView& map, const ScanData& scan, const Pose2D& po
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c)
                 h[r * 3 + c] += g[r] * g[c];
+        if (residual != nullptr) {
+            /* residualVec += mapGrad * (1 - smoothed), :187-192 */
+            const double res = 1.0 - n.Smoothed();
+            for (int r = 0; r < 3; ++r)
+                residual[r] += g[r] * res;
+        }
     }
     return cost;
 }
@@ -168,6 +175,14 @@ std::array<double, 9> CostSquareError::ComputeCovariance(const GridMapView& map,
     double h[9] = { 0.0 };
     Accumulate(map, scan, pose, h);
     return InverseScaled(h, mCovarianceScale);
+}
+
+void CostSquareError::ComputeHessianAndResidual(const GridMapView& map, const ScanData& scan, const Pose2D& pose,
+                                                double hessian[9], double residual[3]) const
+{
+    for (int i = 0; i < 9; ++i) hessian[i] = 0.0;
+    for (int i = 0; i < 3; ++i) residual[i] = 0.0;
+    Accumulate(map, scan, pose, hessian, residual);
 }
 
 std::array<double, 9> CostSquareError::CostAndCovariance(const GridMapView& map, const ScanData& scan,

@@ -8,6 +8,13 @@
 
 namespace csm_host {
 
+FinalMatcher MakeLinearSolverFinalMatcher(const std::shared_ptr<ScanMatcherLinearSolver>& solver)
+{
+    return [solver](const GridMapView& map, const ScanDataPtr& scan, const Pose2D&, const Pose2D& initial_pose) {
+        return solver->OptimizePose(ScanMatchingQuery { map, scan, initial_pose });
+    };
+}
+
 LoopDetectorBranchBound::LoopDetectorBranchBound(
     const std::string& name, const std::shared_ptr<ScanMatcherBranchBound>& scan_matcher,
     const FinalMatcher& final_matcher, double score_threshold, double known_rate_threshold) :

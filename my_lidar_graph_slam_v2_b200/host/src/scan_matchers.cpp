@@ -252,4 +252,115 @@ ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(
     return s;
 }
 
+/* ---- linear-solver refiner (CPU) ------------------------------------------------------ */
+void SolveColPivHouseholderQr3(const double a_in[9], const double b_in[3], double x[3])
+{
+    double a[3][3], b[3] = { b_in[0], b_in[1], b_in[2] };
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            a[r][c] = a_in[r * 3 + c];
+    int perm[3] = { 0, 1, 2 };
+    int rank = 3;
+    double max_pivot = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        /* column with the largest remaining norm comes first */
+        int best = k;
+        double best_norm = -1.0;
+        for (int c = k; c < 3; ++c) {
+            double s = 0.0;
+            for (int r = k; r < 3; ++r) s += a[r][c] * a[r][c];
+            if (s > best_norm) { best_norm = s; best = c; }
+        }
+        if (best != k) {
+            for (int r = 0; r < 3; ++r) std::swap(a[r][k], a[r][best]);
+            std::swap(perm[k], perm[best]);
+        }
+        /* Householder reflector H = I - tau v v^T that maps a[k..2][k] onto (beta, 0, 0) */
+        double tail = 0.0;
+        for (int r = k + 1; r < 3; ++r) tail += a[r][k] * a[r][k];
+        const double c0 = a[k][k];
+        double beta = c0, tau = 0.0, v[3] = { 0.0, 0.0, 0.0 };
+        if (tail > 0.0) {
+            beta = std::sqrt(c0 * c0 + tail);
+            if (c0 >= 0.0) beta = -beta;
+            for (int r = k + 1; r < 3; ++r) v[r] = a[r][k] / (c0 - beta);
+            v[k] = 1.0;
+            tau = (beta - c0) / beta;
+        }
+        a[k][k] = beta;
+        for (int r = k + 1; r < 3; ++r) a[r][k] = 0.0;
+        if (tau != 0.0) {
+            for (int c = k + 1; c < 3; ++c) {
+                double dot = 0.0;
+                for (int r = k; r < 3; ++r) dot += v[r] * a[r][c];
+                for (int r = k; r < 3; ++r) a[r][c] -= tau * v[r] * dot;
+            }
+            double dot = 0.0;
+            for (int r = k; r < 3; ++r) dot += v[r] * b[r];
+            for (int r = k; r < 3; ++r) b[r] -= tau * v[r] * dot;
+        }
+        max_pivot = std::max(max_pivot, std::fabs(beta));
+    }
+    /* numerical rank as Eigen decides it: pivots above epsilon * size * largest pivot */
+    const double threshold = 2.220446049250313e-16 * 3.0 * max_pivot;
+    rank = 0;
+    for (int k = 0; k < 3; ++k)
+        if (std::fabs(a[k][k]) > threshold) ++rank;
+    double y[3] = { 0.0, 0.0, 0.0 };
+    for (int k = rank - 1; k >= 0; --k) {
+        double s = b[k];
+        for (int c = k + 1; c < rank; ++c) s -= a[k][c] * y[c];
+        y[k] = s / a[k][k];
+    }
+    for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+}
+
+ScanMatcherLinearSolver::ScanMatcherLinearSolver(
+    const std::string& name, int num_of_iterations_max, double convergence_threshold,
+    double initial_lambda, const CostFuncPtr& cost) :
+    ScanMatcher(name, nullptr), mNumOfIterationsMax(num_of_iterations_max),
+    mConvergenceThreshold(convergence_threshold), mLambda(initial_lambda), mCost(cost) { }
+
+Pose2D ScanMatcherLinearSolver::OptimizeStep(const GridMapView& map, const ScanData& scan,
+                                             const Pose2D& sensor_pose) const
+{
+    /* scan_matcher_linear_solver.cpp:143-170 */
+    double h[9], r[3], d[3];
+    mCost->ComputeHessianAndResidual(map, scan, sensor_pose, h, r);
+    h[0] += mLambda; h[4] += mLambda; h[8] += mLambda;
+    SolveColPivHouseholderQr3(h, r, d);
+    return Pose2D { sensor_pose.x + d[0], sensor_pose.y + d[1], sensor_pose.theta + d[2] };
+}
+
+ScanMatchingSummary ScanMatcherLinearSolver::OptimizePose(const ScanMatchingQuery& query)
+{
+    /* scan_matcher_linear_solver.cpp:66-140 */
+    const GridMapView& map = query.grid_map;
+    const ScanData& scan = *query.scan_data;
+    const Pose2D sensor = Compound(query.map_local_initial_pose, scan.relative_sensor_pose);
+    const double initial_cost = mCost->Cost(map, scan, sensor);
+    double prev_cost = initial_cost, cost = 0.0;
+    Pose2D best = sensor;
+    int iterations = 0;
+    while (true) {
+        best = OptimizeStep(map, scan, best);
+        cost = mCost->Cost(map, scan, best);
+        if (++iterations >= mNumOfIterationsMax || std::fabs(prev_cost - cost) < mConvergenceThreshold)
+            break;
+        if (cost < prev_cost)
+            mLambda = std::max(1e-8, mLambda * 0.5);
+        else
+            mLambda = std::min(1e-4, mLambda * 2.0);
+        prev_cost = cost;
+    }
+    ScanMatchingSummary s;
+    s.pose_found = true;
+    s.normalized_cost = cost / static_cast<double>(scan.NumOfScans());
+    s.map_local_initial_pose = query.map_local_initial_pose;
+    s.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
+    s.estimated_covariance = mCost->ComputeCovariance(map, scan, best);
+    s.n_processed = iterations;
+    return s;
+}
+
 } /* namespace csm_host */

@@ -46,6 +46,10 @@ def load():
         lib.csm_host_loop_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                              dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int, C.c_int,
                                              dp, C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
+        lib.csm_host_refine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp, C.c_double,
+                                        C.POINTER(HostSummary)]
+        lib.csm_host_loopdet_use_linear_solver.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_create.restype = C.c_void_p
         lib.csm_host_loopdet_create.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_destroy.argtypes = [C.c_void_p]
@@ -77,6 +81,23 @@ def cost(grid, res, off, angles, ranges, sensor_pose, covariance_scale=1e4):
     lib.csm_host_cost(g.ctypes.data, g.shape[0], g.shape[1], res, off[0], off[1], ap, rp, len(a), pp,
                       covariance_scale, C.byref(nc), cov)
     return nc.value, np.array(cov)
+
+
+def refine(grid, res, off, angles, ranges, init_pose, rel_pose=(0.0, 0.0, 0.0), iterations_max=10,
+           convergence_threshold=1e-4, lam=1e-4, covariance_scale=1e4):
+    """ScanMatcherLinearSolver::OptimizePose (CPU, no device). Returns (summary, lambda after the call);
+    summary.best_t holds the number of iterations."""
+    lib = load()
+    g = np.ascontiguousarray(grid, dtype=np.uint16)
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    p, pp = _d(init_pose)
+    q, qp = _d(rel_pose)
+    lam_c = C.c_double(lam)
+    out = HostSummary()
+    lib.csm_host_refine(g.ctypes.data, g.shape[0], g.shape[1], res, off[0], off[1], ap, rp, len(a), pp, qp,
+                        iterations_max, convergence_threshold, C.byref(lam_c), covariance_scale, C.byref(out))
+    return out, lam_c.value
 
 
 class Context:
@@ -157,6 +178,12 @@ class LoopDetector:
         self.ctx = ctx
         rg, rgp = _d(rng)
         self.det = self.lib.csm_host_loopdet_create(ctx.ctx, hmax, rgp, thr[0], thr[1], covariance_scale)
+
+    def use_linear_solver(self, iterations_max=10, convergence_threshold=1e-4, initial_lambda=1e-4,
+                          covariance_scale=1e4):
+        """Refine detected loops with the reference's default final matcher (CPU)."""
+        self.lib.csm_host_loopdet_use_linear_solver(self.det, iterations_max, convergence_threshold,
+                                                    initial_lambda, covariance_scale)
 
     def configure(self, chunk_size=128, coarse_covariance=True, query_index_base=0):
         self.lib.csm_host_loopdet_configure(self.det, chunk_size, int(coarse_covariance), query_index_base)

@@ -81,6 +81,20 @@ int orc_match_grid(void* grid, const double* angles, const double* ranges, int n
                    double step_x, double step_y, double step_t,
                    double score_thr, double known_thr, orc_result* out);
 
+/* ScanMatcherLinearSolver::OptimizePose: scan_matcher_linear_solver.cpp:66-140 (the reference's
+ * default final matcher). `lambda` is the solver's damping state: read at entry, written back at
+ * exit, so that a sequence of calls behaves like one solver instance. out: est_pose, norm_cost,
+ * cov; n_processed = number of iterations. */
+int orc_refine(void* grid, const double* angles, const double* ranges, int n,
+               const double init_pose[3], const double rel_sensor_pose[3],
+               int iterations_max, double convergence_threshold, double* lambda,
+               orc_result* out);
+
+/* Use a ScanMatcherLinearSolver (iterations_max, convergence_threshold, initial_lambda) as the
+ * final matcher of the loop detector instead of the pass-through one. */
+void orc_loopdet_use_linear_solver(void* det, int iterations_max, double convergence_threshold,
+                                   double initial_lambda);
+
 /* LoopDetectorBranchBound: loop_detector_branch_bound.cpp:59-156, with a
  * pass-through final matcher (the sub-pixel refiner is outside the path).
  * Queries are split into n_threads contiguous ranges, one detector (and one

@@ -343,7 +343,125 @@ void CovarianceSquareError(const Grid& g, const Scan& scan, const Pose& sensor,
         cov[i] = a[i] * scale;
 }
 
+/* ---- linear-solver refiner -----------------------------------------------------
+ * scan_matcher_linear_solver.cpp:66-170 with cost_function_square_error.cpp:151-195
+ * (Hessian and residual). The 3x3 system is solved by a Householder QR with column
+ * pivoting (what Eigen's colPivHouseholderQr() does, :161). */
+void HessianAndResidual(const Grid& g, const Scan& scan, const Pose& sensor, double h[9], double res[3])
+{
+    for (int i = 0; i < 9; ++i) h[i] = 0.0;
+    for (int i = 0; i < 3; ++i) res[i] = 0.0;
+    const double invRes = 1.0 / g.res;
+    for (size_t i = 0; i < scan.N(); ++i) {
+        double hx, hy;
+        HitPoint(scan, sensor, i, hx, hy);
+        const double fx = (hx - g.offX) / g.res;
+        const double fy = (hy - g.offY) / g.res;
+        const MapValues m = ClosestMapValues(g, fx, fy);
+        const double rx = hx - sensor.x;
+        const double ry = hy - sensor.y;
+        const double gx = m.dy * (m.m11 - m.m01) + (1.0 - m.dy) * (m.m10 - m.m00);
+        const double gy = m.dx * (m.m11 - m.m10) + (1.0 - m.dx) * (m.m01 - m.m00);
+        const double gt = -ry * gx + rx * gy;
+        const double grad[3] = { gx * invRes, gy * invRes, gt * invRes };
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                h[r * 3 + c] += grad[r] * grad[c];
+        const double mapResidual = 1.0 - Bilinear(m);
+        for (int r = 0; r < 3; ++r)
+            res[r] += grad[r] * mapResidual;
+    }
+}
+
+void SolveColPivQr3(const double aIn[9], const double bIn[3], double x[3])
+{
+    double a[3][3], b[3] = { bIn[0], bIn[1], bIn[2] };
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            a[r][c] = aIn[r * 3 + c];
+    int perm[3] = { 0, 1, 2 };
+    double maxPivot = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        int best = k;
+        double bestNorm = -1.0;
+        for (int c = k; c < 3; ++c) {
+            double n2 = 0.0;
+            for (int r = k; r < 3; ++r) n2 += a[r][c] * a[r][c];
+            if (n2 > bestNorm) { bestNorm = n2; best = c; }
+        }
+        if (best != k) {
+            for (int r = 0; r < 3; ++r) std::swap(a[r][k], a[r][best]);
+            std::swap(perm[k], perm[best]);
+        }
+        double tail = 0.0;
+        for (int r = k + 1; r < 3; ++r) tail += a[r][k] * a[r][k];
+        const double c0 = a[k][k];
+        double beta = c0, tau = 0.0, v[3] = { 0.0, 0.0, 0.0 };
+        if (tail > 0.0) {
+            beta = std::sqrt(c0 * c0 + tail);
+            if (c0 >= 0.0) beta = -beta;
+            for (int r = k + 1; r < 3; ++r) v[r] = a[r][k] / (c0 - beta);
+            v[k] = 1.0;
+            tau = (beta - c0) / beta;
+        }
+        a[k][k] = beta;
+        for (int r = k + 1; r < 3; ++r) a[r][k] = 0.0;
+        if (tau != 0.0) {
+            for (int c = k + 1; c < 3; ++c) {
+                double d = 0.0;
+                for (int r = k; r < 3; ++r) d += v[r] * a[r][c];
+                for (int r = k; r < 3; ++r) a[r][c] -= tau * v[r] * d;
+            }
+            double d = 0.0;
+            for (int r = k; r < 3; ++r) d += v[r] * b[r];
+            for (int r = k; r < 3; ++r) b[r] -= tau * v[r] * d;
+        }
+        maxPivot = std::max(maxPivot, std::fabs(beta));
+    }
+    const double threshold = 2.220446049250313e-16 * 3.0 * maxPivot;
+    int rank = 0;
+    for (int k = 0; k < 3; ++k)
+        if (std::fabs(a[k][k]) > threshold) ++rank;
+    double y[3] = { 0.0, 0.0, 0.0 };
+    for (int k = rank - 1; k >= 0; --k) {
+        double acc = b[k];
+        for (int c = k + 1; c < rank; ++c) acc -= a[k][c] * y[c];
+        y[k] = acc / a[k][k];
+    }
+    for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+}
+
 constexpr double kCovarianceScale = 1e4;
+
+/* ScanMatcherLinearSolver::OptimizePose; `lambda` is the matcher's member mLambda */
+int RefinePose(const Grid& g, const Scan& scan, const Pose& init, int iterationsMax,
+               double convergenceThreshold, double& lambda, Pose& estimated, double& cost,
+               double cov[9])
+{
+    const Pose sensor = Compound(init, scan.rel);
+    const double initialCost = CostSquareError(g, scan, sensor);
+    double prevCost = initialCost;
+    Pose best = sensor;
+    int iterations = 0;
+    while (true) {
+        double h[9], res[3], d[3];
+        HessianAndResidual(g, scan, best, h, res);
+        h[0] += lambda; h[4] += lambda; h[8] += lambda;
+        SolveColPivQr3(h, res, d);
+        best = Pose { best.x + d[0], best.y + d[1], best.t + d[2] };
+        cost = CostSquareError(g, scan, best);
+        if (++iterations >= iterationsMax || std::fabs(prevCost - cost) < convergenceThreshold)
+            break;
+        if (cost < prevCost)
+            lambda = std::max(1e-8, lambda * 0.5);
+        else
+            lambda = std::min(1e-4, lambda * 2.0);
+        prevCost = cost;
+    }
+    estimated = MoveBackward(best, scan.rel);
+    CovarianceSquareError(g, scan, best, kCovarianceScale, cov);
+    return iterations;
+}
 
 /* Epilogue shared by all matchers (scan_matcher_correlative.cpp:203-219) */
 void Epilogue(const Grid& g, const Scan& scan, const Pose& best, orc_result* out)
@@ -618,6 +736,12 @@ struct LoopDetector
     int hmax;
     double rangeX, rangeY, rangeT, scoreThr, knownThr;
     int nThreads;
+    /* final matcher: pass-through (default) or the linear-solver refiner; its damping
+     * factor is per detector (thread) and carries over from query to query */
+    bool linearSolver = false;
+    int finalIterations = 10;
+    double finalConvergence = 1e-4;
+    std::vector<double> finalLambda;
     /* one pyramid cache per thread, keyed by local map id (never evicted,
      * loop_detector_branch_bound.cpp:83-89) */
     std::vector<std::map<int, std::vector<Grid>>> caches;
@@ -716,7 +840,38 @@ void* orc_loopdet_create(int hmax, double range_x, double range_y, double range_
     det->scoreThr = score_thr; det->knownThr = known_thr;
     det->nThreads = std::max(1, n_threads);
     det->caches.resize(det->nThreads);
+    det->finalLambda.assign(det->nThreads, 1e-4);
     return det;
+}
+
+void orc_loopdet_use_linear_solver(void* detPtr, int iterations_max, double convergence_threshold,
+                                   double initial_lambda)
+{
+    auto* det = static_cast<LoopDetector*>(detPtr);
+    det->linearSolver = true;
+    det->finalIterations = iterations_max;
+    det->finalConvergence = convergence_threshold;
+    det->finalLambda.assign(det->nThreads, initial_lambda);
+}
+
+int orc_refine(void* grid, const double* angles, const double* ranges, int n,
+               const double init_pose[3], const double rel_sensor_pose[3],
+               int iterations_max, double convergence_threshold, double* lambda,
+               orc_result* out)
+{
+    const Grid& g = *static_cast<Grid*>(grid);
+    const Scan scan = MakeScan(angles, ranges, n, rel_sensor_pose);
+    const Pose init { init_pose[0], init_pose[1], init_pose[2] };
+    const orc_result empty { };
+    *out = empty;
+    Pose est;
+    double cost = 0.0;
+    out->n_processed = RefinePose(g, scan, init, iterations_max, convergence_threshold, *lambda,
+                                  est, cost, out->cov);
+    out->found = 1;
+    out->est_pose[0] = est.x; out->est_pose[1] = est.y; out->est_pose[2] = est.t;
+    out->norm_cost = cost / static_cast<double>(scan.N());
+    return 0;
 }
 
 void orc_loopdet_destroy(void* det) { delete static_cast<LoopDetector*>(det); }
@@ -770,6 +925,15 @@ int orc_loopdet_detect(void* detPtr, int n_queries,
                 /* the reference emits nothing for this query */
                 const orc_result empty { };
                 out[q] = empty;
+            } else if (det->linearSolver) {
+                /* loop_detector_branch_bound.cpp:110-135: the refined pose and its covariance
+                 * replace the coarse ones */
+                const Pose coarse { out[q].est_pose[0], out[q].est_pose[1], out[q].est_pose[2] };
+                Pose est;
+                double cost = 0.0;
+                RefinePose(g, scans[scan_idx[q]], coarse, det->finalIterations, det->finalConvergence,
+                           det->finalLambda[t], est, cost, out[q].cov);
+                out[q].est_pose[0] = est.x; out[q].est_pose[1] = est.y; out[q].est_pose[2] = est.t;
             }
         }
         const auto t1 = std::chrono::steady_clock::now();

@@ -79,6 +79,8 @@ class Oracle:
         lib.orc_match_rt.argtypes = common + [C.c_int] + [C.c_double] * 5 + [rp]
         lib.orc_match_bb.argtypes = common + [C.c_int] + [C.c_double] * 5 + [rp]
         lib.orc_match_grid.argtypes = common + [C.c_double] * 8 + [rp]
+        lib.orc_refine.argtypes = common + [C.c_int, C.c_double, dp, rp]
+        lib.orc_loopdet_use_linear_solver.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         lib.orc_loopdet_create.restype = C.c_void_p
         lib.orc_loopdet_create.argtypes = [C.c_int] + [C.c_double] * 5 + [C.c_int]
         lib.orc_loopdet_destroy.argtypes = [C.c_void_p]
@@ -133,6 +135,17 @@ class Oracle:
         assert rc == 0
         return out
 
+    def refine(self, grid, angles, ranges, init_pose, rel_pose=None, iterations_max=10,
+               convergence_threshold=1e-4, lam=1e-4):
+        """ScanMatcherLinearSolver::OptimizePose with a fresh solver (n_processed = iterations)."""
+        a, r, p, q = self._scan(angles, ranges, init_pose, rel_pose)
+        out = OrcResult()
+        lam_c = C.c_double(lam)
+        rc = self.lib.orc_refine(grid.h, _dptr(a), _dptr(r), len(a), _dptr(p), _dptr(q),
+                                 iterations_max, convergence_threshold, C.byref(lam_c), C.byref(out))
+        assert rc == 0
+        return out
+
     def loop_detector(self, hmax, rng, thr, n_threads=1):
         return OracleLoopDetector(self, hmax, rng, thr, n_threads)
 
@@ -171,6 +184,12 @@ class OracleLoopDetector:
 
     def clear_cache(self):
         self.oracle.lib.orc_loopdet_clear_cache(self.h)
+
+    def use_linear_solver(self, iterations_max=10, convergence_threshold=1e-4, initial_lambda=1e-4):
+        """Refine detected loops with the reference's default final matcher instead of the
+        pass-through one (the best_* window fields of the results are then not meaningful)."""
+        self.oracle.lib.orc_loopdet_use_linear_solver(self.h, iterations_max, convergence_threshold,
+                                                      initial_lambda)
 
     def detect(self, grids, map_ids, map_poses, scan_idx, scan_poses, angles, ranges):
         """grids: list[OracleGrid] per query; angles/ranges: (n_scans, n_beams)."""

@@ -37,6 +37,7 @@
 #include "my_lidar_graph_slam/mapping/scan_matcher_correlative.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_grid_search.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_linear_solver.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/pose_graph.hpp"
@@ -264,6 +265,10 @@ struct RefLoopDetector
     int    mHeightMax;
     double mRangeX, mRangeY, mRangeT, mScoreThr, mKnownThr;
     int    mNumThreads;
+    /* final matcher: pass-through, or the reference's ScanMatcherLinearSolver */
+    bool   mLinearSolver = false;
+    int    mFinalIterations = 10;
+    double mFinalConvergence = 1e-4, mFinalLambda = 1e-4;
     std::vector<std::shared_ptr<ScanMatcherBranchBound>> mMatchers;
     std::vector<std::unique_ptr<LoopDetectorBranchBound>> mDetectors;
 
@@ -277,7 +282,13 @@ struct RefLoopDetector
             auto matcher = std::make_shared<ScanMatcherBranchBound>(
                 UniqueName("LoopBB"), scoreFunc, costFunc, this->mHeightMax,
                 this->mRangeX, this->mRangeY, this->mRangeT);
-            auto finalMatcher = std::make_shared<PassThroughMatcher>();
+            std::shared_ptr<ScanMatcher> finalMatcher;
+            if (this->mLinearSolver)
+                finalMatcher = std::make_shared<ScanMatcherLinearSolver>(
+                    UniqueName("LoopFinal"), this->mFinalIterations, this->mFinalConvergence,
+                    this->mFinalLambda, std::make_shared<CostSquareError>(kCovarianceScale));
+            else
+                finalMatcher = std::make_shared<PassThroughMatcher>();
             this->mMatchers.push_back(matcher);
             this->mDetectors.push_back(
                 std::make_unique<LoopDetectorBranchBound>(
@@ -455,6 +466,41 @@ int orc_match_grid(void* grid, const double* angles, const double* ranges, int n
     out->n_ignored = LastInt(name + ".NumOfScoreUpdates");
     ResetMatcherMetrics(name, true);
     return 0;
+}
+
+int orc_refine(void* grid, const double* angles, const double* ranges, int n,
+               const double init_pose[3], const double rel_sensor_pose[3],
+               int iterations_max, double convergence_threshold, double* lambda,
+               orc_result* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    const auto scan = MakeScan(angles, ranges, n, rel_sensor_pose);
+    const RobotPose2D<double> initPose { init_pose[0], init_pose[1], init_pose[2] };
+    const std::string name = UniqueName("LS");
+    ScanMatcherLinearSolver matcher {
+        name, iterations_max, convergence_threshold, *lambda,
+        std::make_shared<CostSquareError>(kCovarianceScale) };
+    const ScanMatchingQuery query { map, Point2D<double> { 0.0, 0.0 }, scan, initPose };
+    const ScanMatchingSummary summary = matcher.OptimizePose(query);
+    *out = orc_result { };
+    FillSummary(summary, out);
+    out->n_processed = LastInt(name + ".NumOfIterations");
+    /* The damping factor is private state of the matcher; it follows from the iteration count only
+     * through the cost trend, which is not observable from outside. The tests therefore start a fresh
+     * solver per call (and, for the carried state, compare whole Detect sequences). */
+    (void)lambda;
+    return 0;
+}
+
+void orc_loopdet_use_linear_solver(void* detPtr, int iterations_max, double convergence_threshold,
+                                   double initial_lambda)
+{
+    auto* det = static_cast<RefLoopDetector*>(detPtr);
+    det->mLinearSolver = true;
+    det->mFinalIterations = iterations_max;
+    det->mFinalConvergence = convergence_threshold;
+    det->mFinalLambda = initial_lambda;
+    det->Build();
 }
 
 void* orc_loopdet_create(int hmax, double range_x, double range_y, double range_t,

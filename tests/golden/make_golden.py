@@ -90,6 +90,25 @@ def main():
                             grid_sha=sha(np.stack([s.grid for s in batch.submaps])),
                             expect=[res_dict(r) for r in res]))
 
+    # --- linear-solver refiner (the loop detector's default final matcher) ---------------
+    # outputs of the reference's scan_matcher_linear_solver.cpp compiled against the Eigen shim
+    # (column-pivoting Householder QR for the 3x3 solve, oracle/ref_shim/Eigen/Core)
+    refine = []
+    for seed in range(8):
+        case = synth.case_for(synth.CFG1, 1500 + seed)
+        s = case.submap
+        g = ref.grid(s.grid, s.res, s.off_x, s.off_y)
+        rng = np.random.default_rng(1500 + seed)
+        init = case.true_pose + rng.uniform(-1.0, 1.0, size=3) * np.array([0.05, 0.05, 0.02])
+        rel = (0.1, -0.03, 0.2) if seed % 2 else (0.0, 0.0, 0.0)
+        r = ref.refine(g, case.angles, case.ranges, init, rel, 10, 1e-4, 1e-4)
+        refine.append(dict(seed=1500 + seed, grid_sha=sha(s.grid), scan_sha=sha(case.ranges),
+                           init=[float(v).hex() for v in init], rel=list(rel), iterations=r.n_processed,
+                           est_pose=[float(v).hex() for v in r.est_pose], norm_cost=float(r.norm_cost).hex(),
+                           cov=[float(v).hex() for v in r.cov]))
+    with open(os.path.join(HERE, "refine_vectors.json"), "w") as f:
+        json.dump({"refine": refine}, f, indent=1)
+
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", len(out["matches"]), "match vectors,", len(out["pyramids"]), "pyramids,",

@@ -468,3 +468,35 @@ def test_cpp_adapter_loop_detector(checker):
             assert r.score == o.score and list(r.est_pose) == list(o.est_pose), i
             assert np.allclose(list(r.cov), list(o.cov), rtol=1e-9, atol=0.0), i
     ctx.close()
+
+
+def test_cpp_loop_detector_with_linear_solver(checker):
+    """Detect end to end like the reference's default configuration: GPU branch-and-bound, then the
+    CPU linear-solver refiner on every detected loop. Refined poses within 1e-5 relative of the
+    reference's (north_star); in fact bit-identical."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    batch = synth.make_loop_batch(3500, n_maps=16, true_fraction=0.5, map_id_base=9000)
+    ctx = hostapi.Context(0)
+    det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+    det.use_linear_solver(10, 1e-4, 1e-4)
+    det.configure(chunk_size=8 | (4 << 16))
+    grids = np.ascontiguousarray(np.stack([s.grid for s in batch.submaps]))
+    n, out = det.detect(len(batch.submaps), grids.ctypes.data, None, None, None, 4, 512, 512, batch.submaps[0].res,
+                        np.array([s.off_x for s in batch.submaps]), np.array([s.off_y for s in batch.submaps]),
+                        batch.map_ids.astype(np.int64), np.ascontiguousarray(batch.map_poses),
+                        np.ascontiguousarray(batch.scan_poses), np.ascontiguousarray(batch.angles[0]),
+                        np.ascontiguousarray(batch.ranges[0]))
+    og = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    odet.use_linear_solver(10, 1e-4, 1e-4)
+    ores, _ = odet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    assert n == sum(o.found for o in ores) >= 3
+    for i, (r, o) in enumerate(zip(out, ores)):
+        assert r.found == o.found, i
+        if o.found:
+            assert np.allclose(list(r.est_pose), list(o.est_pose), rtol=1e-5, atol=0.0), i
+            assert list(r.est_pose) == list(o.est_pose), i
+            assert np.allclose(list(r.cov), list(o.cov), rtol=1e-9, atol=0.0), i
+    det.close()
+    ctx.close()

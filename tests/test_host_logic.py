@@ -120,3 +120,25 @@ def test_cpp_epilogue_cost_matches_reference_vectors():
         assert np.allclose(cov, e["cov"], rtol=1e-9, atol=0.0)
         checked += 1
     assert checked == 12
+
+
+def test_cpp_linear_solver_matches_reference_vectors():
+    """The C++ host ScanMatcherLinearSolver (CPU) against vectors produced by the reference's
+    scan_matcher_linear_solver.cpp: iteration count equal, refined pose and cost bit-identical
+    (north_star asks for 1e-5 relative), covariance within 1e-9."""
+    from helpers import load_golden, sha
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    for e in load_golden("refine_vectors.json")["refine"]:
+        case = synth.case_for(synth.CFG1, e["seed"])
+        s = case.submap
+        assert sha(s.grid) == e["grid_sha"]
+        init = [float.fromhex(v) for v in e["init"]]
+        out, lam = hostapi.refine(s.grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges, init,
+                                  tuple(e["rel"]))
+        exp_pose = [float.fromhex(v) for v in e["est_pose"]]
+        assert out.best_t == e["iterations"]
+        assert np.allclose(list(out.est_pose), exp_pose, rtol=1e-5, atol=0.0)      # the stated tolerance
+        assert list(out.est_pose) == exp_pose                                      # what is actually achieved
+        assert out.norm_cost == float.fromhex(e["norm_cost"])
+        assert np.allclose(list(out.cov), [float.fromhex(v) for v in e["cov"]], rtol=1e-9, atol=0.0)
+        assert 1e-8 <= lam <= 1e-4

@@ -114,3 +114,42 @@ def test_port_vs_compiled_reference(port_oracle, ref_oracle, seed):
         cov_a, cov_b = da.pop("cov"), db.pop("cov")
         assert da == db
         assert np.allclose(cov_a, cov_b, rtol=1e-9, atol=0.0)
+
+
+def _refine_case(e):
+    case = synth.case_for(synth.CFG1, e["seed"])
+    assert sha(case.submap.grid) == e["grid_sha"] and sha(case.ranges) == e["scan_sha"], "generator drifted"
+    return case, [float.fromhex(v) for v in e["init"]], tuple(e["rel"])
+
+
+@pytest.mark.parametrize("e", load_golden("refine_vectors.json")["refine"], ids=lambda e: str(e["seed"]))
+def test_port_refine_golden(port_oracle, e):
+    """The restated linear-solver refiner (scan_matcher_linear_solver.cpp:66-170) against vectors of
+    the reference's own translation unit: same iteration count, pose and cost bit-identical."""
+    case, init, rel = _refine_case(e)
+    s = case.submap
+    g = port_oracle.grid(s.grid, s.res, s.off_x, s.off_y)
+    r = port_oracle.refine(g, case.angles, case.ranges, init, rel)
+    assert r.n_processed == e["iterations"]
+    assert list(r.est_pose) == [float.fromhex(v) for v in e["est_pose"]]
+    assert r.norm_cost == float.fromhex(e["norm_cost"])
+    assert np.allclose(list(r.cov), [float.fromhex(v) for v in e["cov"]], rtol=1e-9, atol=0.0)
+
+
+def test_loop_detector_with_linear_solver_port_vs_reference(port_oracle, ref_oracle):
+    """Detect with the reference's default final matcher: the damping factor carries over from
+    loop to loop inside a detector, so whole result sequences are compared."""
+    batch = synth.make_loop_batch(3400, n_maps=12, true_fraction=0.5)
+    out = {}
+    for name, orc in (("port", port_oracle), ("reference", ref_oracle)):
+        grids = [orc.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+        det = orc.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+        det.use_linear_solver(10, 1e-4, 1e-4)
+        out[name], _ = det.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                                  batch.angles, batch.ranges)
+    assert sum(r.found for r in out["reference"]) >= 3
+    for a, b in zip(out["port"], out["reference"]):
+        assert a.found == b.found
+        if b.found:
+            assert list(a.est_pose) == list(b.est_pose)
+            assert np.allclose(list(a.cov), list(b.cov), rtol=1e-9, atol=0.0)
