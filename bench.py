@@ -274,11 +274,14 @@ def main_cuda(args):
     summaries = (hostapi.HostSummary * N_MAPS)()
     best_word = torch.zeros(1, dtype=torch.int64, device="cuda")
 
-    def allreduce_best():
+    def allreduce_best(read_back=False):
+        """8-byte all-reduce(max) of the packed best word over NCCL, on the handle's stream.
+        read_back: also copy the result to the host (on that same stream) and return it."""
         view = torch.as_tensor(CudaArrayView(h.best_key_device_ptr(), 1, "<i8"), device="cuda")
         with torch.cuda.stream(ext_stream):
             best_word.copy_(view)
-            sharding.allreduce_best(best_word)          # 8-byte all-reduce(max) over NCCL
+            sharding.allreduce_best(best_word)
+            return int(best_word.item()) if read_back else None
 
     def e2e_step(sparse=True):
         """One LoopDetector::Detect of the C++ plugin on 256 first-touch submaps, from page-locked
@@ -289,8 +292,7 @@ def main_cuda(args):
         n, _ = hdet.detect(N_MAPS, None if sparse else host_ptr, blk_ptr if sparse else None,
                            idx_ptr if sparse else None, counts.ctypes.data if sparse else None, LOG2BS,
                            ROWS, COLS, res, offx, offy, ids, map_poses, scan_poses, angles, ranges, summaries)
-        allreduce_best()
-        return n, int(best_word.item())                     # D2H best word
+        return n, allreduce_best(read_back=True)            # D2H best word
 
     def barrier():
         if world > 1:
