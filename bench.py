@@ -404,10 +404,9 @@ def main_cuda(args):
     counts = h.frontier_counts()
     pyr_ms = kernel_ms.get("k_pyramid_stream", 0.0)
     bb_ms = sum(v for k, v in kernel_ms.items() if k != "k_pyramid_stream")
-    # nodes scored per step: every root candidate + the four children of every node that passed
-    n_roots = sum((2 * a.win_t + 1) * ((2 * a.win_x) // (1 << HMAX) + 1) * ((2 * a.win_y) // (1 << HMAX) + 1)
-                  for a in arr)
-    nodes_scored = n_roots + 4 * sum(counts[1:HMAX + 1])
+    # nodes scored per step: the four children of every node of every list; the roots themselves are
+    # expanded unscored (option "bb_skip_top"), counts[HMAX] = all root candidates
+    nodes_scored = 4 * sum(counts[1:HMAX + 1])
 
     peaks = {}
     try:

@@ -115,6 +115,11 @@ int64_t csm_launch_count(csm_handle h);
  *      to a leaf that seeds its incumbent: 0 = never (plain level sweep), 1 =
  *      always, 2 (default) = only for calls of at most 4 queries. Results are
  *      identical either way; only the number of nodes scored changes;
+ *  "bb_skip_top": 1 (default) = the branch-and-bound sweep starts one height
+ *      below hmax on the same leaf lattice (identical results, one launch less);
+ *  "window_mode": grid search, 0 (default) = TMA shared-memory tile kernel when
+ *      the window fits, 1 = global-memory kernel, 2 = require the TMA kernel;
+ *  "timing": 1 / 2 = record CUDA events after every kernel (csm_debug_timings);
  *  "accumulate_best_key": 1 = loop batches keep (do not reset) the packed
  *      best word, so that a Detect call split into several batches ends with
  *      the maximum over all of them; "reset_best_key": clears it now. */

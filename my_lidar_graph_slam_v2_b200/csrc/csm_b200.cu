@@ -121,6 +121,7 @@ struct csm_context
     DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
     DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups;
+    int bb_skip_top = 1;           /* 1: the B&B sweep starts one height below hmax (same results) */
     int window_mode = 0;           /* grid search, integer-shift path: 0 auto (TMA tiles when possible),
                                       1 plain global-memory kernel, 2 require the TMA kernel */
     PlanView plan_view;                   /* layout of the last staged batch */
@@ -530,10 +531,8 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             if (m->levels) CSM_CUDA(cudaFreeAsync(m->levels, h->stream));
             m->levels = nullptr;
             m->levels_alloc = 0;
-            const size_t bytes = (size_t)hmax * tiled_cells(m->rows, m->cols) * sizeof(uint16_t);
+            const size_t bytes = (size_t)hmax * m->rows * m->cols * sizeof(uint16_t);
             CSM_CUDA(cudaMallocAsync((void**)&m->levels, bytes, h->stream));
-            /* the zero border and the padding cells of the tiled levels are never written again */
-            CSM_CUDA(cudaMemsetAsync(m->levels, 0, bytes, h->stream));
             m->levels_alloc = hmax;
         }
         m->hmax = hmax;
@@ -668,7 +667,7 @@ int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
     std::memset(&Q, 0, sizeof(Q));
     Q.lvl[0] = m.base;
     for (int l = 1; l <= m.hmax && l < kMaxLevels; ++l)
-        Q.lvl[l] = m.levels + (size_t)(l - 1) * tiled_cells(m.rows, m.cols);
+        Q.lvl[l] = m.levels + (size_t)(l - 1) * m.rows * m.cols;
     Q.coarse = m.coarse;
     Q.rows = m.rows; Q.cols = m.cols;
     Q.res = m.res; Q.offx = m.offx; Q.offy = m.offy;
@@ -845,6 +844,14 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     plan.root_off.assign(nq + 1, 0u);
     if (inline_scan) { plan.scan_angles = inline_scan->angles; plan.scan_ranges = inline_scan->ranges; }
     const int wsz = 1 << hmax;
+    const int top = hmax;
+    /* Which internal nodes are expanded never changes the result, and on
+     * loop-detection windows the hmax-level bound is so loose that nearly every root passes: by
+     * default the roots are not scored at all but expanded unconditionally, which trades R + 4 p R
+     * scored nodes (p ~ 1) for 4 R and a launch on a latency-bound chain. The dive needs the
+     * root keys and keeps the scored roots. */
+    const bool dive = top >= 1 && (h->bb_dive == 1 || (h->bb_dive == 2 && nq <= 4));
+    const bool unscored_roots = top >= 1 && h->bb_skip_top && !dive;
     for (int q = 0; q < nq; ++q) {
         const csm_loop_query& in = queries[q];
         const MapSlot& m = *used_slots[q];
@@ -855,9 +862,11 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         Q.sy = in.sensor_pose[1];
         Q.T = 2 * in.win_t + 1;
         Q.winx = in.win_x; Q.winy = in.win_y;
-        Q.nrx = (2 * in.win_x) / wsz + 1;
-        Q.nry = (2 * in.win_y) / wsz + 1;
-        Q.lx = Q.nrx * wsz; Q.ly = Q.nry * wsz;
+        /* leaf lattice of the reference: roots every 2^hmax cells from -win (:179-182) */
+        Q.lx = ((2 * in.win_x) / wsz + 1) * wsz;
+        Q.ly = ((2 * in.win_y) / wsz + 1) * wsz;
+        Q.nrx = Q.lx >> top;
+        Q.nry = Q.ly >> top;
         if (Q.T > 65535 || Q.lx > 8192 || Q.ly > 8192 || in.win_x > 8192 || in.win_y > 8192 ||
             (unsigned long long)Q.T * Q.lx * Q.ly >= kOrdMask - 1ull)
             return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: search lattice exceeds 2^26 leaves");
@@ -891,8 +900,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     W.stats = V.stats;
     W.overflow = V.overflow;
     W.capacity = h->frontier_capacity;
-    W.hmax = hmax;
-    const bool dive = hmax >= 1 && (h->bb_dive == 1 || (h->bb_dive == 2 && nq <= 4));
+    W.top = top;
     if (dive) {
         if ((rc = ensure(h, h->d_rootkey, sizeof(long long) * (size_t)plan.root_off[nq]))) return rc;
         W.rootkey = static_cast<long long*>(h->d_rootkey.p);
@@ -902,15 +910,17 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
 
     {
         dim3 grid(std::max(1, std::min((plan.max_roots + 255) / 256, 64)), nq);
-        k_bb_init<<<grid, 256, 0, h->stream>>>(dq, V.rootoff, nq, W);
+        k_bb_init<<<grid, 256, 0, h->stream>>>(dq, V.rootoff, nq, W, unscored_roots ? 1 : 0);
         CSM_LAUNCH_CHECK();
     }
     {
         const unsigned int n_roots = plan.root_off[nq];
         const int full = h->sm_count * 8;
-        const int root_blocks = (int)std::min<unsigned int>((n_roots + 7) / 8, (unsigned int)full);
-        k_bb_roots<<<std::max(root_blocks, 1), 256, 0, h->stream>>>(dq, proj, W, n_roots);
-        CSM_LAUNCH_CHECK();
+        if (!unscored_roots) {
+            const int root_blocks = (int)std::min<unsigned int>((n_roots + 7) / 8, (unsigned int)full);
+            k_bb_roots<<<std::max(root_blocks, 1), 256, 0, h->stream>>>(dq, proj, W, n_roots);
+            CSM_LAUNCH_CHECK();
+        }
         phase_mark(h, "k_bb_init+k_bb_roots");
         if (dive) {
             k_bb_dive<<<nq, 256, 0, h->stream>>>(dq, proj, V.rootoff, W);
@@ -919,7 +929,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         }
         /* a list never holds more than 4^k times the roots: small calls get small grids */
         unsigned long long bound = n_roots;
-        for (int lvl = hmax; lvl >= 1; --lvl) {
+        for (int lvl = top; lvl >= 1; --lvl) {
             const int blocks = (int)std::min<unsigned long long>((bound + 7) / 8, (unsigned long long)full);
             const dim3 g((unsigned)std::max(blocks, 1));
             switch (lvl - 1) {          /* height of the children: compile-time for the index arithmetic */
@@ -1066,6 +1076,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     }
     if (std::strcmp(name, "bb_dive") == 0 && value >= 0 && value <= 2) { h->bb_dive = value; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
+    if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
     if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
     if (std::strcmp(name, "reset_best_key") == 0) {
@@ -1368,25 +1379,14 @@ int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out)
         if (wrc) return wrc;
     }
     const size_t cells = (size_t)m.rows * m.cols;
-    const size_t tcells = tiled_cells(m.rows, m.cols);
     const uint16_t* src = nullptr;
     if (level == 0) src = m.base;
-    else if (level > 0 && level <= m.hmax) src = m.levels + (size_t)(level - 1) * tcells;
+    else if (level > 0 && level <= m.hmax) src = m.levels + (size_t)(level - 1) * cells;
     else if (level < 0 && m.coarse_win == -level) src = m.coarse;
     if (src == nullptr)
         return fail(h, CSM_E_INVALID, "download: level not built");
-    if (level <= 0) {
-        CSM_CUDA(cudaMemcpyAsync(out, src, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
-        CSM_CUDA(cudaStreamSynchronize(h->stream));
-        return CSM_OK;
-    }
-    /* pyramid levels are stored in 8x8 tiles on the device (csm_device.cuh) */
-    std::vector<uint16_t> raw(tcells);
-    CSM_CUDA(cudaMemcpyAsync(raw.data(), src, tcells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(out, src, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
-    for (int r = 0; r < m.rows; ++r)
-        for (int c = 0; c < m.cols; ++c)
-            out[(size_t)r * m.cols + c] = raw[tiled_index(r, c, m.cols)];
     return CSM_OK;
 }
 

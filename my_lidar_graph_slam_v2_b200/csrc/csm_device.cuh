@@ -84,63 +84,17 @@ __device__ __forceinline__ unsigned int ld_cell(const uint16_t* __restrict__ m,
     return 0u;
 }
 
-/* Tiled layout of the precomputed levels (h >= 1): 8x8-cell tiles of 128
- * bytes (one L1/L2 line), row-major inside a tile, with a border of one
- * all-zero tile on every side; rows and cols are padded up to multiples of 8
- * and the padding cells are zero too.
- *  - Branch-and-bound gathers of one warp fall on a compact 2-D patch of cells
- *    (a few adjacent beams x a few adjacent angles): in tiles the patch touches
- *    ~2.7 lines instead of ~7 in row-major order (measured on the cfg3
- *    workload).
- *  - Out-of-map reads (the reference's ValueOr -> 0, grid_map.cpp:389-392) need
- *    no predicate: coordinates are clamped into the zero border.
- *  - The index is separable and cheap: with rp = r + 8, cp = c + 8,
- *    index = [rp * 8 + (rp >> 3) * (64 * tiles_per_row - 64)] + [cp + (cp >> 3) * 56]. */
-/* Measured on B200 (cfg3, 256 queries, profiles/r1_layout_ab.txt): tiles cut the B&B
- * sweep from 534 to 451 us but the streaming pyramid builder, whose warps then write
- * 16-byte pieces of 8 different lines instead of one full line, goes from 236 to 400 us.
- * Row-major wins overall, so it is the default; -DCSM_TILED=1 builds the tiled variant. */
-#ifndef CSM_TILED
-#define CSM_TILED 0
-#endif
-__host__ __device__ __forceinline__ int padded_tiles_per_row(int cols) { return ((cols + 7) >> 3) + 2; }
-__host__ __device__ __forceinline__ int padded_tile_rows(int rows) { return ((rows + 7) >> 3) + 2; }
-__host__ __device__ __forceinline__ size_t tiled_cells(int rows, int cols)
-{
-#if CSM_TILED
-    return (size_t)padded_tile_rows(rows) * (size_t)padded_tiles_per_row(cols) * 64u;
-#else
-    return (size_t)rows * (size_t)cols;
-#endif
-}
-/* row stride term: 64 * tiles_per_row - 64 */
-__host__ __device__ __forceinline__ int tiled_rstride(int cols) { return (padded_tiles_per_row(cols) << 6) - 64; }
-__host__ __device__ __forceinline__ unsigned int tiled_row_p(int rp, int rstride)
-{
-    return (unsigned)rp * 8u + (unsigned)(rp >> 3) * (unsigned)rstride;
-}
-__host__ __device__ __forceinline__ unsigned int tiled_col_p(int cp) { return (unsigned)cp + (unsigned)(cp >> 3) * 56u; }
-/* in-map cell (0 <= r < rows, 0 <= c < cols) */
-__host__ __device__ __forceinline__ size_t tiled_index(int r, int c, int cols)
-{
-#if CSM_TILED
-    return (size_t)tiled_row_p(r + 8, tiled_rstride(cols)) + (size_t)tiled_col_p(c + 8);
-#else
-    return (size_t)r * (size_t)cols + (size_t)c;
-#endif
-}
-/* largest padded coordinate: clamping r + 8 into [0, tiled_rmax] lands out-of-map reads in the zero border */
-__host__ __device__ __forceinline__ int tiled_rmax(int rows) { return ((rows + 7) & ~7) + 15; }
+/* Layout of the precomputed levels: dense row-major u16, like level 0. An 8x8-cell tiled
+ * layout (one 128-byte line per tile, zero border) was built and measured in round 1
+ * (profiles/r1_layout_ab.txt): it cut the branch-and-bound sweep by 16 % (534 -> 451 us, fewer
+ * lines per divergent gather) but slowed the streaming pyramid builder from 236 to 400 us
+ * (16-byte pieces of 8 lines per store instead of one full line), so it was dropped. */
 
-/* Cell of a precomputed level (tiled, h >= 1) or of the level-0 grid (row-major) */
-__device__ __forceinline__ unsigned int ld_level(const uint16_t* __restrict__ m, int rows, int cols,
-                                                 bool tiled, int r, int c)
+/* Same as ld_cell, branch-free: an out-of-map read loads cell 0 and is masked, so that a lane
+ * can keep many of these loads in flight */
+__device__ __forceinline__ unsigned int ld_cell_nb(const uint16_t* __restrict__ m, int rows, int cols,
+                                                   int r, int c)
 {
-    if (tiled && CSM_TILED) {
-        const int rp = min(max(r + 8, 0), tiled_rmax(rows));
-        const int cp = min(max(c + 8, 0), tiled_rmax(cols));
-        return (unsigned int)__ldg(m + (tiled_row_p(rp, tiled_rstride(cols)) + tiled_col_p(cp)));
-    }
     const bool ok = (unsigned)r < (unsigned)rows && (unsigned)c < (unsigned)cols;
     const unsigned int v = (unsigned int)__ldg(m + (ok ? (unsigned)r * (unsigned)cols + (unsigned)c : 0u));
     return ok ? v : 0u;
@@ -159,12 +113,12 @@ __device__ __forceinline__ double value_to_probability(unsigned int v)
  * (scan_matcher_correlative.cpp:308-335). One thread. */
 __device__ double exact_normalized_score(const uint16_t* __restrict__ m, int rows, int cols,
                                          const proj_t* __restrict__ proj, int stride, int n,
-                                         int ox, int oy, bool tiled = false)
+                                         int ox, int oy)
 {
     double sum = 0.0;
     for (int i = 0; i < n; ++i) {
         const proj_t p = proj[(size_t)i * stride];
-        const unsigned int v = ld_level(m, rows, cols, tiled, p.y + oy, p.x + ox);
+        const unsigned int v = ld_cell(m, rows, cols, p.y + oy, p.x + ox);
         if (v != 0u)
             sum = __dadd_rn(sum, value_to_probability(v));
     }

@@ -125,7 +125,7 @@ k_scatter_blocks(ScatterArgs A)
 struct PyrJob
 {
     const uint16_t* base;   /* level 0, row-major */
-    uint16_t*       levels; /* levels 1..hmax, contiguous, tiled_cells(rows, cols) each, 8x8-tile layout */
+    uint16_t*       levels; /* levels 1..hmax, contiguous, rows*cols each */
     int rows, cols;
 };
 
@@ -138,10 +138,9 @@ k_pyramid_level(const PyrJob* __restrict__ jobs, int h)
 {
     const PyrJob job = jobs[blockIdx.z];
     const int rows = job.rows, cols = job.cols;
-    const size_t cells = tiled_cells(rows, cols);
+    const size_t cells = (size_t)rows * cols;
     const uint16_t* __restrict__ src = (h == 1) ? job.base : job.levels + (size_t)(h - 2) * cells;
     uint16_t* __restrict__ dst = job.levels + (size_t)(h - 1) * cells;
-    const bool src_tiled = h > 1;
     const int w = 1 << h, half = w >> 1;
 
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -154,14 +153,13 @@ k_pyramid_level(const PyrJob* __restrict__ jobs, int h)
     for (int k = 0; k < 2; ++k) {
         const int c = c0 + k;
         const int cc = max(min(c, cols - w), 0);
-        unsigned int v = ld_level(src, rows, cols, src_tiled, rc, cc);
-        v = max(v, ld_level(src, rows, cols, src_tiled, rc + half, cc));
-        v = max(v, ld_level(src, rows, cols, src_tiled, rc, cc + half));
-        v = max(v, ld_level(src, rows, cols, src_tiled, rc + half, cc + half));
+        unsigned int v = ld_cell(src, rows, cols, rc, cc);
+        v = max(v, ld_cell(src, rows, cols, rc + half, cc));
+        v = max(v, ld_cell(src, rows, cols, rc, cc + half));
+        v = max(v, ld_cell(src, rows, cols, rc + half, cc + half));
         out[k] = v;
     }
-    /* (r, c0) and (r, c0 + 1) are neighbours in the tiled layout too (c0 is even) */
-    const size_t o = tiled_index(r, c0, cols);
+    const size_t o = (size_t)r * cols + c0;
     if (c0 + 1 < cols) {
         *reinterpret_cast<unsigned int*>(dst + o) = out[0] | (out[1] << 16);
     } else {
@@ -240,27 +238,6 @@ __device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsig
     }
     const int r0 = b * kPsRows;
     if (in_map && r0 <= rsrc) {
-#if CSM_TILED
-        unsigned int* dst = reinterpret_cast<unsigned int*>(job.levels + (size_t)(H - 1) * cells);
-        const int tprp = padded_tiles_per_row(C);
-        /* word (4 bytes = cells 2j, 2j+1) of row r in the tiled level */
-        auto tw = [&](int r) -> size_t {
-            return ((size_t)(((r + 8) >> 3) * tprp + (j >> 2) + 1) << 5) + (size_t)(((r & 7) << 2) | (j & 3));
-        };
-        if (r0 + kPsRows - 1 < rsrc) {
-            /* rows r0..r0+3 are 4 words (16 bytes) apart inside one tile */
-            unsigned int* d0 = dst + tw(r0);
-#pragma unroll
-            for (int rr = 0; rr < kPsRows; ++rr) d0[rr * 4] = p[rr];
-        } else {
-            for (int rr = 0; rr < kPsRows; ++rr) {
-                const int r = r0 + rr;
-                if (r < rsrc) dst[tw(r)] = p[rr];
-                else if (r == rsrc)
-                    for (int r2 = r; r2 < R; ++r2) dst[tw(r2)] = p[rr];
-            }
-        }
-#else
         unsigned int* dst = reinterpret_cast<unsigned int*>(job.levels + (size_t)(H - 1) * cells + (size_t)r0 * C) + j;
         const int cw = C >> 1;
         if (r0 + kPsRows - 1 < rsrc) {
@@ -274,7 +251,6 @@ __device__ __forceinline__ void ps_level(unsigned int (&a)[kPsRows], const unsig
                     for (int r2 = r; r2 < R; ++r2) dst[(r2 - r0) * cw] = p[rr];
             }
         }
-#endif
     }
 #pragma unroll
     for (int rr = 0; rr < kPsRows; ++rr) a[rr] = p[rr];
@@ -294,7 +270,7 @@ k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax, int segs)
     const PyrJob job = jobs[blockIdx.x / segs];
     const int seg = blockIdx.x % segs;
     const int R = job.rows, C = job.cols;
-    const size_t cells = tiled_cells(R, C);
+    const size_t cells = (size_t)R * C;
     const int j = threadIdx.x;
     const bool in_map = 2 * j < C;
 
@@ -774,7 +750,7 @@ __device__ bool rt_replay_scan(const DevQuery& Q, const RtBlock* __restrict__ bl
  * order), adjacent angles and adjacent beams hit neighbouring cells, and the
  * projection is stored beam-major (proj[i][t]): a warp's index loads are 4
  * short contiguous runs and its 32 gathers of one child fall on a compact 2-D
- * patch of the map, a handful of sectors in the tiled level layout. */
+ * patch of the map. */
 struct BbWork
 {
     unsigned long long* list[2];    /* node lists, ping-pong by height parity */
@@ -784,10 +760,10 @@ struct BbWork
     int*                overflow;   /* set when a list is full */
     long long*          rootkey;    /* per root candidate: its key if it passed, else -1 (feeds the dive) */
     unsigned int        capacity;
-    int                 hmax;
+    int                 top;        /* height of the root candidates (the reference's node_height_max) */
 };
 
-/* list(h) lives in list[(h & 1) ^ 1]; the root candidates in list[hmax & 1] */
+/* list(h) lives in list[(h & 1) ^ 1]; the root candidates in list[top & 1] */
 __device__ __forceinline__ unsigned long long* bb_list(const BbWork& W, int h) { return W.list[(h & 1) ^ 1]; }
 
 __device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, int t, int xi, int yi)
@@ -798,21 +774,26 @@ __device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, i
     return (kOrdMask - 1ull) - ord;     /* all-ones is reserved for "no leaf yet" */
 }
 
-/* Root candidates of every query: (x, y) stepping by 2^hmax from -win, all
- * angles (scan_matcher_branch_bound.cpp:179-182), angle fastest. */
+/* Root candidates of every query: (x, y) stepping by 2^top from -win, all angles
+ * (scan_matcher_branch_bound.cpp:179-182), angle fastest. With `unscored` they go straight into
+ * list(top) as if all of them had passed (which internal nodes get expanded never changes the
+ * result): the first expand launch then scores their children, four per index load, instead of
+ * k_bb_roots scoring the roots one gather per index load first. */
 __global__ void __launch_bounds__(256)
 k_bb_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__ root_off,
-          int nq, BbWork W)
+          int nq, BbWork W, int unscored)
 {
     const int q = blockIdx.y;
     const DevQuery& Q = queries[q];
     const int nroots = Q.T * Q.nrx * Q.nry;
-    unsigned long long* out = W.list[W.hmax & 1] + root_off[q];
+    unsigned long long* out = (unscored ? bb_list(W, W.top) : W.list[W.top & 1]) + root_off[q];
+    if (unscored && q == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        W.counts[W.top] = root_off[nq];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nroots; e += gridDim.x * blockDim.x) {
         const int t = e % Q.T;
         const int cell = e / Q.T;
         const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
-        out[e] = pack_node(q, t, rx << W.hmax, ry << W.hmax);
+        out[e] = pack_node(q, t, rx << W.top, ry << W.top);
     }
 }
 
@@ -837,7 +818,7 @@ __device__ __forceinline__ bool bb_passes(const DevQuery& Q, const proj_t* __res
         else if (c == 0) {
             const proj_t* pp0 = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
             pass = exact_normalized_score(Q.lvl[h], Q.rows, Q.cols, pp0, Q.pst_i, Q.n,
-                                          xi - Q.winx, yi - Q.winy, h > 0) > Q.kthr.thr;
+                                          xi - Q.winx, yi - Q.winy) > Q.kthr.thr;
         }
     }
     return pass;
@@ -853,13 +834,13 @@ __device__ __forceinline__ void bb_count(const BbWork& W, bool valid, int q, boo
         atomicAdd(&W.stats[tag], __popc(peers));
 }
 
-/* Score the root candidates on the level hmax map; the passing ones form
- * list(hmax). Lanes per node as in k_bb_expand. */
+/* Score the root candidates on the level `top` map; the passing ones form
+ * list(top). Lanes per node as in k_bb_expand. */
 __global__ void __launch_bounds__(256)
 k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all,
            BbWork W, unsigned int count)
 {
-    const int h = W.hmax;
+    const int h = W.top;
     const int lane = threadIdx.x & 31;
     const unsigned int total_lanes = gridDim.x * blockDim.x;
     int split = kBbSplit;
@@ -881,7 +862,6 @@ k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
             const DevQuery& Q = queries[q];
             const uint16_t* __restrict__ m = Q.lvl[h];
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
-            const bool tiled = h > 0;
             const int ox = xi - Q.winx, oy = yi - Q.winy;
             const size_t ps = (size_t)Q.pst_i;
             const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t + (size_t)part * ps;
@@ -894,13 +874,13 @@ k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 for (int u = 0; u < 8; ++u) p[u] = pp[(size_t)(i + u) * step];
                 unsigned int v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = ld_level(m, rows, cols, tiled, p[u].y + oy, p[u].x + ox);
+                for (int u = 0; u < 8; ++u) v[u] = ld_cell_nb(m, rows, cols, p[u].y + oy, p[u].x + ox);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { s += (int)v[u]; k += (v[u] != 0u); }
             }
             for (; i < mine; ++i) {
                 const proj_t p = pp[(size_t)i * step];
-                const unsigned int v = ld_level(m, rows, cols, tiled, p.y + oy, p.x + ox);
+                const unsigned int v = ld_cell_nb(m, rows, cols, p.y + oy, p.x + ox);
                 s += (int)v; k += (v != 0u);
             }
         }
@@ -935,36 +915,22 @@ k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
     }
 }
 
-/* Four cells (r, c), (r, c + w), (r + w, c), (r + w, c + w) of the children's
- * level, w = 2^HC, branch-free so that a lane keeps all its loads in flight.
- * Precomputed levels (HC >= 1): tiled with a zero border, coordinates clamped
- * instead of tested; for w >= 8 the second row / column is a whole number of
- * tiles away. Level 0 (HC == 0) is the row-major uploaded grid: out-of-map
- * cells read cell 0 and are masked. */
+/* Four cells (r, c), (r, c + w), (r + w, c), (r + w, c + w) of the children's level, w = 2^HC,
+ * branch-free so that a lane keeps all its loads in flight: out-of-map cells read cell 0 and
+ * are masked (the reference's ValueOr -> 0, grid_map.cpp:389-392). */
 template <int HC>
 __device__ __forceinline__ void ld_children(const uint16_t* __restrict__ m, int rows, int cols,
-                                            int rmax, int cmax, int rstride,
                                             int r, int c, unsigned int (&v)[4])
 {
     constexpr int w = 1 << HC;
-    if (HC == 0 || !CSM_TILED) {
-        const int r1 = r + w, c1 = c + w;
-        const bool rk0 = (unsigned)r < (unsigned)rows, rk1 = (unsigned)r1 < (unsigned)rows;
-        const bool ck0 = (unsigned)c < (unsigned)cols, ck1 = (unsigned)c1 < (unsigned)cols;
-        const unsigned int R0 = (unsigned)r * (unsigned)cols, R1 = R0 + (unsigned)(w * cols);
-        const bool k00 = rk0 && ck0, k01 = rk0 && ck1, k10 = rk1 && ck0, k11 = rk1 && ck1;
-        const unsigned int x00 = __ldg(m + (k00 ? R0 + (unsigned)c : 0u)), x01 = __ldg(m + (k01 ? R0 + (unsigned)c1 : 0u));
-        const unsigned int x10 = __ldg(m + (k10 ? R1 + (unsigned)c : 0u)), x11 = __ldg(m + (k11 ? R1 + (unsigned)c1 : 0u));
-        v[0] = k00 ? x00 : 0u; v[1] = k01 ? x01 : 0u; v[2] = k10 ? x10 : 0u; v[3] = k11 ? x11 : 0u;
-    } else {
-        /* r, c arrive already shifted by the border (+8) */
-        const int rp0 = min(max(r, 0), rmax), cp0 = min(max(c, 0), cmax);
-        const int rp1 = min(max(r + w, 0), rmax), cp1 = min(max(c + w, 0), cmax);
-        const unsigned int R0 = tiled_row_p(rp0, rstride), C0 = tiled_col_p(cp0);
-        const unsigned int R1 = tiled_row_p(rp1, rstride), C1 = tiled_col_p(cp1);
-        v[0] = __ldg(m + (R0 + C0)); v[1] = __ldg(m + (R0 + C1));
-        v[2] = __ldg(m + (R1 + C0)); v[3] = __ldg(m + (R1 + C1));
-    }
+    const int r1 = r + w, c1 = c + w;
+    const bool rk0 = (unsigned)r < (unsigned)rows, rk1 = (unsigned)r1 < (unsigned)rows;
+    const bool ck0 = (unsigned)c < (unsigned)cols, ck1 = (unsigned)c1 < (unsigned)cols;
+    const unsigned int R0 = (unsigned)r * (unsigned)cols, R1 = R0 + (unsigned)(w * cols);
+    const bool k00 = rk0 && ck0, k01 = rk0 && ck1, k10 = rk1 && ck0, k11 = rk1 && ck1;
+    const unsigned int x00 = __ldg(m + (k00 ? R0 + (unsigned)c : 0u)), x01 = __ldg(m + (k01 ? R0 + (unsigned)c1 : 0u));
+    const unsigned int x10 = __ldg(m + (k10 ? R1 + (unsigned)c : 0u)), x11 = __ldg(m + (k11 ? R1 + (unsigned)c1 : 0u));
+    v[0] = k00 ? x00 : 0u; v[1] = k01 ? x01 : 0u; v[2] = k10 ? x10 : 0u; v[3] = k11 ? x11 : 0u;
 }
 
 /* Expand list(HC + 1): score the four children of every node on the level HC map.
@@ -1009,9 +975,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
             const DevQuery& Q = queries[q];
             const uint16_t* __restrict__ m = Q.lvl[HC];
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
-            const int rmax = tiled_rmax(rows), cmax = tiled_rmax(cols), rstride = tiled_rstride(cols);
-            constexpr int kShift = (kLeaf || !CSM_TILED) ? 0 : 8;      /* border of the tiled levels */
-            const int ox = xi - Q.winx + kShift, oy = yi - Q.winy + kShift;
+            const int ox = xi - Q.winx, oy = yi - Q.winy;
             const unsigned int ps = (unsigned int)Q.pst_i;
             const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)t * Q.pst_t + (size_t)part * ps;
             const unsigned int step = ps * (unsigned int)split;
@@ -1024,7 +988,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
                 unsigned int v[kBbUnroll][4];
 #pragma unroll
                 for (int u = 0; u < kBbUnroll; ++u)
-                    ld_children<HC>(m, rows, cols, rmax, cmax, rstride, p[u].y + oy, p[u].x + ox, v[u]);
+                    ld_children<HC>(m, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
 #pragma unroll
                 for (int u = 0; u < kBbUnroll; ++u) {
                     s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
@@ -1037,7 +1001,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
             for (; i < mine; ++i) {
                 const proj_t p = pp[(unsigned int)i * step];
                 unsigned int v[4];
-                ld_children<HC>(m, rows, cols, rmax, cmax, rstride, p.y + oy, p.x + ox, v);
+                ld_children<HC>(m, rows, cols, p.y + oy, p.x + ox, v);
                 s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
                 if (kLeaf) { k0 += (v[0] != 0u); k1 += (v[1] != 0u); k2 += (v[2] != 0u); k3 += (v[3] != 0u); }
             }
@@ -1152,13 +1116,13 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
             const int e = (int)(0xFFFFFu - (unsigned int)(best & 0xFFFFFull));
             const int t = e % Q.T, cell = e / Q.T;
             const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
-            s_beam[0][j][0] = t; s_beam[0][j][1] = rx << W.hmax; s_beam[0][j][2] = ry << W.hmax;
+            s_beam[0][j][0] = t; s_beam[0][j][1] = rx << W.top; s_beam[0][j][2] = ry << W.top;
         }
         ++nbeam;
     }
     __syncthreads();
     int cur = 0;
-    for (int h = W.hmax; h >= 1 && nbeam > 0; --h) {
+    for (int h = W.top; h >= 1 && nbeam > 0; --h) {
         const int w = 1 << (h - 1);
         const uint16_t* __restrict__ m = Q.lvl[h - 1];
         const int ncand = 4 * nbeam;
@@ -1166,7 +1130,6 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
             /* warp `warp` scores candidates warp, warp + 8, warp + 16, warp + 24 at once:
              * up to 4 x 12 independent (index, cell) load pairs per lane in flight */
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
-            const bool tiled = (h - 1) > 0;
             const size_t ps = (size_t)Q.pst_i;
             const proj_t* __restrict__ pp[4];
             int ox[4], oy[4], sv[4], kn[4];
@@ -1187,7 +1150,7 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
                 for (int j = 0; j < 4; ++j) {
                     if (!on[j]) continue;
                     const proj_t p = pp[j][(size_t)i * ps];
-                    const unsigned int v = ld_level(m, rows, cols, tiled, p.y + oy[j], p.x + ox[j]);
+                    const unsigned int v = ld_cell_nb(m, rows, cols, p.y + oy[j], p.x + ox[j]);
                     sv[j] += (int)v; kn[j] += (v != 0u);
                 }
             }

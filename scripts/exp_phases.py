@@ -17,6 +17,10 @@ queries = [matchers.LoopDetectionQuery(scan, 0, tuple(batch.scan_poses[i]),
 arr = det.prepare(queries)
 ids = np.arange(NQ, dtype=np.int64)
 h.set_option("timing", 1)
+import os
+for kv in os.environ.get("CSM_OPTS", "").split(","):
+    if "=" in kv:
+        k, v = kv.split("="); h.set_option(k, int(v))
 acc = {}
 REP = 20
 for it in range(REP + 3):
