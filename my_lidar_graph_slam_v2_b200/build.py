@@ -9,6 +9,7 @@ LIB = os.path.join(HERE, "libcsm_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "csm_b200.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "csm_kernels.cuh"),
            os.path.join(HERE, "csrc", "csm_device.cuh"),
+           os.path.join(HERE, "csrc", "csm_window_tma.cuh"),
            os.path.join(ROOT, "include", "csm_b200.h")]
 
 NVCC_FLAGS = [

@@ -1,10 +1,13 @@
-/* loop_detector.hpp -- batched GPU loop detector behind the reference's
- * LoopDetector plugin interface (mapping/loop_detector.hpp:97-116:
- * Detect(queries) -> results), JSON type string "BranchBound"
- * (loop_detector_factory.cpp:202-209). Constructor parameters follow
- * LoopDetectorBranchBound (loop_detector_branch_bound.cpp:41-56); the final
- * sub-pixel matcher is an optional callback because it stays on the CPU
- * (SURVEY.md 8f rank 1). */
+/* loop_detector.hpp -- GPU loop detectors behind the reference's LoopDetector
+ * plugin interface (mapping/loop_detector.hpp:97-116: Detect(queries) ->
+ * results), JSON type strings "BranchBound" | "RealTimeCorrelative" |
+ * "GridSearch" (loop_detector_factory.cpp:202-209). Constructor parameters
+ * follow the reference classes (loop_detector_branch_bound.cpp:41-56,
+ * loop_detector_correlative.cpp:40-56, loop_detector_grid_search.cpp:33-49);
+ * the final sub-pixel matcher is an optional callback because it stays on the
+ * CPU. The branch-and-bound detector matches all queries
+ * in device batches; the other two run the reference's per-query loop on the
+ * GPU matchers. */
 #pragma once
 
 #include <functional>
@@ -28,9 +31,18 @@ public:
     virtual ~LoopDetector() = default;
     const std::string& Name() const { return mName; }
     virtual std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) = 0;
+    /* "<Name>.InputSetupTime | LoopDetectionTime | NumOfQueries | NumOfDetections"
+     * (loop_detector_branch_bound.cpp:24-38) go here; null = off */
+    void SetMetricSink(const MetricSinkPtr& sink) { mMetricSink = sink; }
 
 protected:
+    void Observe(const char* metric, double value) const
+    {
+        if (mMetricSink) mMetricSink->Observe(mName + "." + metric, value);
+    }
+
     std::string mName;
+    MetricSinkPtr mMetricSink;
 };
 
 class LoopDetectorBranchBound final : public LoopDetector
@@ -74,6 +86,40 @@ private:
     int mChunkSize = 128;
     int mUploadChunk = 64;
     bool mCoarseCovariance = true;
+};
+
+/* loop_detector_correlative.cpp:59-159: per query the coarse map (window = the matcher's low
+ * resolution) of a local map is built at its first use and stays cached on the device by
+ * LocalMapId; real-time correlative match with thresholds, then the final matcher. */
+class LoopDetectorCorrelative final : public LoopDetector
+{
+public:
+    LoopDetectorCorrelative(const std::string& name,
+                            const std::shared_ptr<ScanMatcherCorrelative>& scan_matcher,
+                            const FinalMatcher& final_matcher,
+                            double score_threshold, double known_rate_threshold);
+    std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
+
+private:
+    std::shared_ptr<ScanMatcherCorrelative> mScanMatcher;
+    FinalMatcher mFinalMatcher;
+    double mScoreThreshold, mKnownRateThreshold;
+};
+
+/* loop_detector_grid_search.cpp:52-161: exhaustive grid search with thresholds per query */
+class LoopDetectorGridSearch final : public LoopDetector
+{
+public:
+    LoopDetectorGridSearch(const std::string& name,
+                           const std::shared_ptr<ScanMatcherGridSearch>& scan_matcher,
+                           const FinalMatcher& final_matcher,
+                           double score_threshold, double known_rate_threshold);
+    std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
+
+private:
+    std::shared_ptr<ScanMatcherGridSearch> mScanMatcher;
+    FinalMatcher mFinalMatcher;
+    double mScoreThreshold, mKnownRateThreshold;
 };
 
 } /* namespace csm_host */

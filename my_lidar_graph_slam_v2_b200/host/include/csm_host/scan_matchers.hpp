@@ -18,6 +18,7 @@
 
 #include "csm_b200.h"
 #include "csm_host/cost_square_error.hpp"
+#include "csm_host/metrics.hpp"
 #include "csm_host/types.hpp"
 
 namespace csm_host {
@@ -62,8 +63,17 @@ public:
     const std::string& Name() const { return mName; }
     virtual ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) = 0;
     const DeviceContextPtr& Context() const { return mContext; }
+    /* Report the reference's "<Name>.<Metric>" value sequences here (metrics.hpp); null = off */
+    void SetMetricSink(const MetricSinkPtr& sink) { mMetricSink = sink; }
 
 protected:
+    void Observe(const char* metric, double value) const
+    {
+        if (mMetricSink) mMetricSink->Observe(mName + "." + metric, value);
+    }
+    /* The ids every matcher reports after a match (scan_matcher_correlative.cpp:221-237) */
+    void ObserveSummary(const ScanMatchingSummary& summary, const ScanData& scan, double micro) const;
+
     /* Upload the map unless a map with this id is already resident */
     std::int64_t EnsureMap(const GridMapView& map);
     /* Cost, covariance and MoveBackward at the winning sensor pose
@@ -73,6 +83,7 @@ protected:
 
     std::string mName;
     DeviceContextPtr mContext;
+    MetricSinkPtr mMetricSink;
     std::vector<std::int64_t> mResidentMaps;
 };
 
@@ -92,6 +103,8 @@ public:
     ScanMatchingSummary OptimizePose(const GridMapView& map, const ScanDataPtr& scan,
                                      const Pose2D& initial_pose, double score_threshold,
                                      double known_rate_threshold);
+    int LowResolution() const { return mLowResolution; }
+    const CostFuncPtr& Cost() const { return mCost; }
 
 private:
     CostFuncPtr mCost;
@@ -132,6 +145,7 @@ public:
     ScanMatchingSummary OptimizePose(const GridMapView& map, const ScanDataPtr& scan,
                                      const Pose2D& initial_pose, double score_threshold,
                                      double known_rate_threshold);
+    const CostFuncPtr& Cost() const { return mCost; }
 
 private:
     CostFuncPtr mCost;

@@ -2,6 +2,7 @@
  * the parity tests (Python, ctypes) can drive the adapter classes exactly the
  * way the reference drives its matchers / detectors. Not part of the C ABI. */
 #include <cstring>
+#include <string>
 
 #include "csm_host/loop_detector.hpp"
 
@@ -129,19 +130,56 @@ static int MatchView(void* ctx, int kind, const GridMapView& map, const double* 
     return 0;
 }
 
-/* LoopDetectorBranchBound::Detect over n_queries maps and one shared scan.
- * values: n_queries grids of rows x cols, consecutive. out[q].found = 0 when no result. */
-int csm_host_loop_detect(void* ctx, int n_queries, const uint16_t* values, int rows, int cols, double res,
-                         const double* off_x, const double* off_y, const int64_t* map_ids,
-                         const double* map_poses, const double* scan_poses,
-                         const double* angles, const double* ranges, int n,
-                         int hmax, const double range[3], double score_thr, double known_thr,
-                         double covariance_scale, csm_host_summary* out)
+/* Metric ids and values a detector + its matcher observed, as "id=v,v,...;id=...": what the
+ * reference's MetricManager would hold */
+static void DumpMetrics(const MetricRecorder& rec, char* buf, int cap)
+{
+    if (buf == nullptr || cap <= 0)
+        return;
+    std::string text;
+    for (const auto& kv : rec.Values()) {
+        text += kv.first + "=";
+        for (std::size_t i = 0; i < kv.second.size(); ++i)
+            text += (i ? "," : "") + std::to_string(kv.second[i]);
+        text += ";";
+    }
+    std::strncpy(buf, text.c_str(), static_cast<std::size_t>(cap - 1));
+    buf[cap - 1] = 0;
+}
+
+/* LoopDetector{Correlative, BranchBound, GridSearch}::Detect (kind 0 / 1 / 2 as in csm_host_match)
+ * over n_queries maps and one shared scan. values: n_queries grids of rows x cols, consecutive.
+ * out[q].found = 0 when no result. metrics: optional text buffer (see DumpMetrics). */
+int csm_host_loop_detect_kind(void* ctx, int kind, int n_queries, const uint16_t* values, int rows, int cols,
+                              double res, const double* off_x, const double* off_y, const int64_t* map_ids,
+                              const double* map_poses, const double* scan_poses,
+                              const double* angles, const double* ranges, int n,
+                              int iparam, const double range[3], const double step[3],
+                              double score_thr, double known_thr,
+                              double covariance_scale, csm_host_summary* out, char* metrics, int metrics_cap)
 {
     const DeviceContextPtr& c = *static_cast<DeviceContextPtr*>(ctx);
     const auto cost = std::make_shared<CostSquareError>(covariance_scale);
-    auto matcher = std::make_shared<ScanMatcherBranchBound>("LoopBBGPU", cost, hmax, range[0], range[1], range[2], c);
-    LoopDetectorBranchBound det("LoopDetectorBranchBoundGPU", matcher, FinalMatcher(), score_thr, known_thr);
+    const auto rec = std::make_shared<MetricRecorder>();
+    std::shared_ptr<ScanMatcherBranchBound> bb;
+    std::unique_ptr<LoopDetector> det;
+    if (kind == 0) {
+        auto m = std::make_shared<ScanMatcherCorrelative>("LoopRTGPU", cost, iparam, range[0], range[1], range[2], c);
+        m->SetMetricSink(rec);
+        det.reset(new LoopDetectorCorrelative("LoopDetectorCorrelativeGPU", m, FinalMatcher(), score_thr, known_thr));
+    } else if (kind == 1) {
+        bb = std::make_shared<ScanMatcherBranchBound>("LoopBBGPU", cost, iparam, range[0], range[1], range[2], c);
+        bb->SetMetricSink(rec);
+        det.reset(new LoopDetectorBranchBound("LoopDetectorBranchBoundGPU", bb, FinalMatcher(), score_thr, known_thr));
+    } else if (kind == 2) {
+        auto m = std::make_shared<ScanMatcherGridSearch>("LoopGridGPU", cost, range[0], range[1], range[2],
+                                                         step[0], step[1], step[2], c);
+        m->SetMetricSink(rec);
+        det.reset(new LoopDetectorGridSearch("LoopDetectorGridSearchGPU", m, FinalMatcher(), score_thr, known_thr));
+    } else {
+        return -1;
+    }
+    det->SetMetricSink(rec);
     const double rel[3] = { 0.0, 0.0, 0.0 };
     const ScanDataPtr scan = Scan(angles, ranges, n, rel);
     std::vector<LoopDetectionQuery> queries(n_queries);
@@ -155,22 +193,37 @@ int csm_host_loop_detect(void* ctx, int n_queries, const uint16_t* values, int r
         lq.local_map = View(values + q * cells, rows, cols, res, off_x[q], off_y[q], map_ids[q]);
         lq.local_map_global_pose = Pose2D { map_poses[3 * q], map_poses[3 * q + 1], map_poses[3 * q + 2] };
     }
-    const std::vector<LoopDetectionResult> results = det.Detect(queries);
+    const std::vector<LoopDetectionResult> results = det->Detect(queries);
     for (int q = 0; q < n_queries; ++q)
         std::memset(&out[q], 0, sizeof(csm_host_summary));
     for (const LoopDetectionResult& r : results) {
         csm_host_summary& o = out[r.scan_node_id];
-        const csm_result& d = det.LastResults()[r.query_index];
         o.found = 1;
-        o.best_x = d.best_x; o.best_y = d.best_y; o.best_t = d.best_t;
-        o.sum_value = d.sum_value; o.n_known = d.n_known; o.flags = d.flags;
-        o.score = d.normalized_score;
+        if (kind == 1) {
+            const csm_result& d = static_cast<LoopDetectorBranchBound*>(det.get())->LastResults()[r.query_index];
+            o.best_x = d.best_x; o.best_y = d.best_y; o.best_t = d.best_t;
+            o.sum_value = d.sum_value; o.n_known = d.n_known; o.flags = d.flags;
+        }
+        o.score = r.normalized_score;
         o.est_pose[0] = r.relative_pose.x; o.est_pose[1] = r.relative_pose.y; o.est_pose[2] = r.relative_pose.theta;
         std::memcpy(o.cov, r.estimated_covariance.data(), sizeof(double) * 9);
     }
     for (int q = 0; q < n_queries; ++q)
         csm_release_grid(c->Handle(), map_ids[q]);
+    DumpMetrics(*rec, metrics, metrics_cap);
     return 0;
+}
+
+int csm_host_loop_detect(void* ctx, int n_queries, const uint16_t* values, int rows, int cols, double res,
+                         const double* off_x, const double* off_y, const int64_t* map_ids,
+                         const double* map_poses, const double* scan_poses,
+                         const double* angles, const double* ranges, int n,
+                         int hmax, const double range[3], double score_thr, double known_thr,
+                         double covariance_scale, csm_host_summary* out)
+{
+    return csm_host_loop_detect_kind(ctx, 1, n_queries, values, rows, cols, res, off_x, off_y, map_ids, map_poses,
+                                     scan_poses, angles, ranges, n, hmax, range, range, score_thr, known_thr,
+                                     covariance_scale, out, nullptr, 0);
 }
 
 /* ScanMatcherLinearSolver::OptimizePose on the CPU (no device): `lambda` is the solver's damping

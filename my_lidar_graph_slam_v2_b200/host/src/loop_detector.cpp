@@ -15,18 +15,104 @@ FinalMatcher MakeLinearSolverFinalMatcher(const std::shared_ptr<ScanMatcherLinea
     };
 }
 
+namespace {
+
+/* loop_detector_branch_bound.cpp:54-55 (the same two Asserts in all three detectors) */
+void CheckThresholds(double score_threshold, double known_rate_threshold)
+{
+    if (!(score_threshold > 0.0 && score_threshold <= 1.0) ||
+        !(known_rate_threshold > 0.0 && known_rate_threshold <= 1.0)) {
+        std::fprintf(stderr, "csm_host: loop detector thresholds must be in (0, 1]\n");
+        std::abort();
+    }
+}
+
+/* The reference's per-query loop (loop_detector_correlative.cpp:68-146,
+ * loop_detector_grid_search.cpp:64-129) around a coarse matcher with thresholds */
+template <typename Matcher>
+std::vector<LoopDetectionResult> DetectPerQuery(
+    const std::vector<LoopDetectionQuery>& queries, Matcher& matcher, const FinalMatcher& final_matcher,
+    double score_threshold, double known_rate_threshold,
+    const std::function<void(const char*, double)>& observe)
+{
+    std::vector<LoopDetectionResult> results;
+    MicroTimer timer;
+    for (std::size_t i = 0; i < queries.size(); ++i) {
+        const LoopDetectionQuery& q = queries[i];
+        if (q.local_map.map_id < 0) {
+            std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
+            std::abort();
+        }
+        timer.Start();
+        /* pose of the scan node in the map-local frame */
+        const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
+        const ScanMatchingSummary coarse = matcher.OptimizePose(q.local_map, q.scan, init,
+                                                                score_threshold, known_rate_threshold);
+        if (!coarse.pose_found)
+            continue;
+        LoopDetectionResult out;
+        out.relative_pose = coarse.estimated_pose;
+        out.estimated_covariance = coarse.estimated_covariance;
+        if (final_matcher) {
+            const ScanMatchingSummary fin = final_matcher(q.local_map, q.scan, q.reference_scan_local_pose,
+                                                          coarse.estimated_pose);
+            out.relative_pose = fin.estimated_pose;
+            out.estimated_covariance = fin.estimated_covariance;
+        }
+        out.local_map_pose = q.local_map_global_pose;
+        out.local_map_id = q.local_map.map_id;
+        out.scan_node_id = q.scan_node_id;
+        out.normalized_score = coarse.normalized_score;
+        out.query_index = static_cast<int>(i);
+        results.push_back(out);
+        observe("LoopDetectionTime", timer.ElapsedMicro());
+    }
+    observe("NumOfQueries", static_cast<double>(queries.size()));
+    observe("NumOfDetections", static_cast<double>(results.size()));
+    return results;
+}
+
+} /* namespace */
+
 LoopDetectorBranchBound::LoopDetectorBranchBound(
     const std::string& name, const std::shared_ptr<ScanMatcherBranchBound>& scan_matcher,
     const FinalMatcher& final_matcher, double score_threshold, double known_rate_threshold) :
     LoopDetector(name), mScanMatcher(scan_matcher), mFinalMatcher(final_matcher),
     mScoreThreshold(score_threshold), mKnownRateThreshold(known_rate_threshold)
 {
-    /* loop_detector_branch_bound.cpp:54-55 */
-    if (!(score_threshold > 0.0 && score_threshold <= 1.0) ||
-        !(known_rate_threshold > 0.0 && known_rate_threshold <= 1.0)) {
-        std::fprintf(stderr, "csm_host: loop detector thresholds must be in (0, 1]\n");
-        std::abort();
-    }
+    CheckThresholds(score_threshold, known_rate_threshold);
+}
+
+LoopDetectorCorrelative::LoopDetectorCorrelative(
+    const std::string& name, const std::shared_ptr<ScanMatcherCorrelative>& scan_matcher,
+    const FinalMatcher& final_matcher, double score_threshold, double known_rate_threshold) :
+    LoopDetector(name), mScanMatcher(scan_matcher), mFinalMatcher(final_matcher),
+    mScoreThreshold(score_threshold), mKnownRateThreshold(known_rate_threshold)
+{
+    CheckThresholds(score_threshold, known_rate_threshold);
+}
+
+std::vector<LoopDetectionResult> LoopDetectorCorrelative::Detect(const std::vector<LoopDetectionQuery>& queries)
+{
+    /* the matcher keeps map and coarse map resident by LocalMapId (the reference's mPrecompMaps,
+     * loop_detector_correlative.cpp:83-90) */
+    return DetectPerQuery(queries, *mScanMatcher, mFinalMatcher, mScoreThreshold, mKnownRateThreshold,
+                          [this](const char* m, double v) { Observe(m, v); });
+}
+
+LoopDetectorGridSearch::LoopDetectorGridSearch(
+    const std::string& name, const std::shared_ptr<ScanMatcherGridSearch>& scan_matcher,
+    const FinalMatcher& final_matcher, double score_threshold, double known_rate_threshold) :
+    LoopDetector(name), mScanMatcher(scan_matcher), mFinalMatcher(final_matcher),
+    mScoreThreshold(score_threshold), mKnownRateThreshold(known_rate_threshold)
+{
+    CheckThresholds(score_threshold, known_rate_threshold);
+}
+
+std::vector<LoopDetectionResult> LoopDetectorGridSearch::Detect(const std::vector<LoopDetectionQuery>& queries)
+{
+    return DetectPerQuery(queries, *mScanMatcher, mFinalMatcher, mScoreThreshold, mKnownRateThreshold,
+                          [this](const char* m, double v) { Observe(m, v); });
 }
 
 namespace {
@@ -102,6 +188,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     mLastResults.clear();
     if (queries.empty())
         return results;
+    MicroTimer timer;
     const DeviceContextPtr& ctx = mScanMatcher->Context();
     csm_handle h = ctx->Handle();
     const int hmax = mScanMatcher->NodeHeightMax();
@@ -218,6 +305,16 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
         out.normalized_score = r.normalized_score;
         out.query_index = i;
         results.push_back(out);
+    }
+    if (mMetricSink) {
+        /* one batch instead of one observation per query: the whole call, divided evenly */
+        const double micro = timer.ElapsedMicro();
+        for (std::size_t i = 0; i < results.size(); ++i)
+            Observe("LoopDetectionTime", micro / static_cast<double>(nq));
+        Observe("NumOfQueries", nq);
+        Observe("NumOfDetections", static_cast<double>(results.size()));
+        Observe("PrecompMapMemoryUsage", static_cast<double>(mCachedMaps.size()) *
+                static_cast<double>(hmax + 1) * queries[0].local_map.rows * queries[0].local_map.cols * 2.0);
     }
     return results;
 }

@@ -1,6 +1,7 @@
 #include "csm_host/scan_matchers.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -99,6 +100,19 @@ void ScanMatcher::Epilogue(const GridMapView& map, const ScanData& scan, const P
     summary.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
 }
 
+void ScanMatcher::ObserveSummary(const ScanMatchingSummary& s, const ScanData& scan, double micro) const
+{
+    if (!mMetricSink)
+        return;
+    Observe("OptimizationTime", micro);
+    Observe("DiffTranslation", std::hypot(s.map_local_initial_pose.x - s.estimated_pose.x,
+                                          s.map_local_initial_pose.y - s.estimated_pose.y));
+    Observe("DiffRotation", std::fabs(s.map_local_initial_pose.theta - s.estimated_pose.theta));
+    Observe("ScoreValue", s.normalized_score);
+    Observe("CostValue", s.normalized_cost);
+    Observe("NumOfScans", static_cast<double>(scan.NumOfScans()));
+}
+
 void ComputeSearchStep(double resolution, const ScanData& scan,
                        double& step_x, double& step_y, double& step_theta)
 {
@@ -150,8 +164,11 @@ ScanMatchingSummary ScanMatcherCorrelative::OptimizePose(
     double score_threshold, double known_rate_threshold)
 {
     csm_handle h = mContext->Handle();
+    MicroTimer timer;
     const std::int64_t id = EnsureMap(map);
     mContext->Check(csm_build_coarse(h, id, mLowResolution), "csm_build_coarse");   /* ComputeCoarserMap */
+    Observe("InputSetupTime", timer.ElapsedMicro());      /* enqueue time: the device work is asynchronous */
+    timer.Start();
     const Pose2D sensor = Compound(initial_pose, scan->relative_sensor_pose);
     double sx, sy, st;
     ComputeSearchStep(map.resolution, *scan, sx, sy, st);
@@ -169,6 +186,12 @@ ScanMatchingSummary ScanMatcherCorrelative::OptimizePose(
     s.map_local_initial_pose = initial_pose;
     const Pose2D best { sensor.x + r.best_x * sx, sensor.y + r.best_y * sy, sensor.theta + r.best_t * st };
     Epilogue(map, *scan, best, mCost, s);
+    if (mMetricSink) {
+        ObserveSummary(s, *scan, timer.ElapsedMicro());
+        Observe("WinSizeX", win_x); Observe("WinSizeY", win_y); Observe("WinSizeTheta", win_t);
+        Observe("StepSizeX", sx); Observe("StepSizeY", sy); Observe("StepSizeTheta", st);
+        Observe("NumOfIgnoredNodes", r.n_ignored); Observe("NumOfProcessedNodes", r.n_processed);
+    }
     return s;
 }
 
@@ -189,8 +212,11 @@ ScanMatchingSummary ScanMatcherBranchBound::OptimizePose(
     double score_threshold, double known_rate_threshold)
 {
     csm_handle h = mContext->Handle();
+    MicroTimer timer;
     const std::int64_t id = EnsureMap(map);
     mContext->Check(csm_build_pyramid(h, id, mNodeHeightMax), "csm_build_pyramid");  /* ComputeCoarserMaps */
+    Observe("InputSetupTime", timer.ElapsedMicro());
+    timer.Start();
     const Pose2D sensor = Compound(initial_pose, scan->relative_sensor_pose);
     double sx, sy, st;
     ComputeSearchStep(map.resolution, *scan, sx, sy, st);
@@ -208,6 +234,14 @@ ScanMatchingSummary ScanMatcherBranchBound::OptimizePose(
     s.map_local_initial_pose = initial_pose;
     const Pose2D best { sensor.x + sx * r.best_x, sensor.y + sy * r.best_y, sensor.theta + st * r.best_t };
     Epilogue(map, *scan, best, mCost, s);
+    if (mMetricSink) {
+        /* the node counts are those of the level-synchronous sweep, not of the reference's
+         * best-first order (they measure work, the result does not depend on them) */
+        ObserveSummary(s, *scan, timer.ElapsedMicro());
+        Observe("WinSizeX", win_x); Observe("WinSizeY", win_y); Observe("WinSizeTheta", win_t);
+        Observe("StepSizeX", sx); Observe("StepSizeY", sy); Observe("StepSizeTheta", st);
+        Observe("NumOfIgnoredNodes", r.n_ignored); Observe("NumOfProcessedNodes", r.n_processed);
+    }
     return s;
 }
 
@@ -229,6 +263,7 @@ ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(
     double score_threshold, double known_rate_threshold)
 {
     csm_handle h = mContext->Handle();
+    MicroTimer timer;
     const std::int64_t id = EnsureMap(map);
     const Pose2D sensor = Compound(initial_pose, scan->relative_sensor_pose);
     const std::vector<double> dx = Offsets(mRangeX / 2.0, mStepX);
@@ -249,6 +284,12 @@ ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(
     if (r.found)
         best = Pose2D { sensor.x + dx[r.best_x], sensor.y + dy[r.best_y], sensor.theta + dt[r.best_t] };
     Epilogue(map, *scan, best, mCost, s);
+    if (mMetricSink) {
+        /* NumOfScoreUpdates (how often the sequential loop raised its maximum,
+         * scan_matcher_grid_search.cpp:136) has no parallel counterpart and is not reported */
+        ObserveSummary(s, *scan, timer.ElapsedMicro());
+        Observe("NumOfScoreEvaluations", static_cast<double>(dx.size()) * dy.size() * dt.size());
+    }
     return s;
 }
 
@@ -337,6 +378,7 @@ ScanMatchingSummary ScanMatcherLinearSolver::OptimizePose(const ScanMatchingQuer
     /* scan_matcher_linear_solver.cpp:66-140 */
     const GridMapView& map = query.grid_map;
     const ScanData& scan = *query.scan_data;
+    MicroTimer timer;
     const Pose2D sensor = Compound(query.map_local_initial_pose, scan.relative_sensor_pose);
     const double initial_cost = mCost->Cost(map, scan, sensor);
     double prev_cost = initial_cost, cost = 0.0;
@@ -360,6 +402,17 @@ ScanMatchingSummary ScanMatcherLinearSolver::OptimizePose(const ScanMatchingQuer
     s.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
     s.estimated_covariance = mCost->ComputeCovariance(map, scan, best);
     s.n_processed = iterations;
+    if (mMetricSink) {
+        /* scan_matcher_linear_solver.cpp:125-133 */
+        Observe("OptimizationTime", timer.ElapsedMicro());
+        Observe("DiffTranslation", std::hypot(s.map_local_initial_pose.x - s.estimated_pose.x,
+                                              s.map_local_initial_pose.y - s.estimated_pose.y));
+        Observe("DiffRotation", std::fabs(s.map_local_initial_pose.theta - s.estimated_pose.theta));
+        Observe("NumOfIterations", iterations);
+        Observe("InitialCost", initial_cost / static_cast<double>(scan.NumOfScans()));
+        Observe("FinalCost", s.normalized_cost);
+        Observe("NumOfScans", static_cast<double>(scan.NumOfScans()));
+    }
     return s;
 }
 

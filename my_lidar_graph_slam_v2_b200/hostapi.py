@@ -46,6 +46,10 @@ def load():
         lib.csm_host_loop_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                              dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int, C.c_int,
                                              dp, C.c_double, C.c_double, C.c_double, C.POINTER(HostSummary)]
+        lib.csm_host_loop_detect_kind.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                  C.c_double, dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp,
+                                                  C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double,
+                                                  C.POINTER(HostSummary), C.c_char_p, C.c_int]
         lib.csm_host_refine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                         dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp, C.c_double,
                                         C.POINTER(HostSummary)]
@@ -167,6 +171,39 @@ class Context:
                                            hmax, rgp, thr[0], thr[1], covariance_scale, out)
         assert rc == 0
         return list(out)
+
+    def loop_detect_kind(self, kind, grids, res, off_x, off_y, map_ids, map_poses, scan_poses, angles, ranges,
+                         iparam, rng, step, thr, covariance_scale=1e4):
+        """LoopDetector{Correlative, BranchBound, GridSearch} (kind 0 / 1 / 2) of the C++ mirror over one
+        shared scan. Returns (per-query summaries, observed metrics {id: [values]})."""
+        g = np.ascontiguousarray(grids, dtype=np.uint16)
+        nq = g.shape[0]
+        ox, oxp = _d(off_x)
+        oy, oyp = _d(off_y)
+        ids = np.ascontiguousarray(map_ids, dtype=np.int64)
+        mp, mpp = _d(np.asarray(map_poses).reshape(-1))
+        sp, spp = _d(np.asarray(scan_poses).reshape(-1))
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        rg, rgp = _d(rng)
+        st, stp = _d(step if step is not None else (0.0, 0.0, 0.0))
+        out = (HostSummary * nq)()
+        buf = C.create_string_buffer(1 << 16)
+        rc = self.lib.csm_host_loop_detect_kind(self.ctx, kind, nq, g.ctypes.data, g.shape[1], g.shape[2], res,
+                                                oxp, oyp, ids.ctypes.data_as(C.POINTER(C.c_int64)), mpp, spp,
+                                                ap, rp, len(a), iparam, rgp, stp, thr[0], thr[1],
+                                                covariance_scale, out, buf, len(buf))
+        assert rc == 0
+        return list(out), _parse_metrics(buf.value.decode())
+
+
+def _parse_metrics(text):
+    out = {}
+    for item in text.split(";"):
+        if "=" in item:
+            k, v = item.split("=", 1)
+            out[k] = [float(x) for x in v.split(",") if x]
+    return out
 
 
 class LoopDetector:

@@ -470,6 +470,54 @@ def test_cpp_adapter_loop_detector(checker):
     ctx.close()
 
 
+def _inverse_compound(start, end):
+    c, s_ = np.cos(start[2]), np.sin(start[2])
+    dx, dy = end[0] - start[0], end[1] - start[1]
+    return (c * dx + s_ * dy, -s_ * dx + c * dy, end[2] - start[2])
+
+
+@pytest.mark.parametrize("kind", [0, 2])
+def test_cpp_loop_detector_correlative_and_grid_search(checker, kind):
+    """LoopDetectorCorrelative / LoopDetectorGridSearch of the C++ mirror: the reference's per-query loop
+    (loop_detector_correlative.cpp:68-146, loop_detector_grid_search.cpp:64-129) is the coarse matcher with
+    thresholds at InverseCompound(map pose, scan pose), a result only where a pose is found."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    batch = synth.make_loop_batch(3300 + kind, n_maps=6, true_fraction=0.5,
+                                  offset=(0.2, 0.2, 0.05), map_id_base=7100 + 10 * kind)
+    grids = np.stack([s.grid for s in batch.submaps])
+    rng = (0.5, 0.5, 0.15) if kind == 0 else (0.4, 0.4, 0.1)
+    step = None if kind == 0 else (0.05, 0.05, 0.005)
+    thr = (0.5, 0.5)
+    res, metrics = ctx.loop_detect_kind(kind, grids, batch.submaps[0].res, [s.off_x for s in batch.submaps],
+                                        [s.off_y for s in batch.submaps], batch.map_ids, batch.map_poses,
+                                        batch.scan_poses, batch.angles[0], batch.ranges[0], 5, rng, step, thr)
+    n_found = 0
+    for i, sm in enumerate(batch.submaps):
+        g = checker.grid(sm.grid, sm.res, sm.off_x, sm.off_y)
+        init = _inverse_compound(batch.map_poses[i], batch.scan_poses[i])
+        if kind == 0:
+            o = checker.match_rt(g, batch.angles[0], batch.ranges[0], init, 5, rng, thr)
+        else:
+            o = checker.match_grid(g, batch.angles[0], batch.ranges[0], init, rng, step, thr)
+        assert res[i].found == o.found, i
+        if o.found:
+            n_found += 1
+            assert res[i].score == o.score and list(res[i].est_pose) == list(o.est_pose), i
+            assert np.allclose(list(res[i].cov), list(o.cov), rtol=1e-9, atol=0.0), i
+    assert 0 < n_found < len(batch.submaps)
+    det = "LoopDetectorCorrelativeGPU" if kind == 0 else "LoopDetectorGridSearchGPU"
+    mat = "LoopRTGPU" if kind == 0 else "LoopGridGPU"
+    assert metrics[det + ".NumOfQueries"] == [len(batch.submaps)]
+    assert metrics[det + ".NumOfDetections"] == [n_found]
+    assert len(metrics[det + ".LoopDetectionTime"]) == n_found
+    assert metrics[mat + ".NumOfScans"] == [360.0] * len(batch.submaps)
+    assert len(metrics[mat + ".ScoreValue"]) == len(batch.submaps)
+    if kind == 0:
+        assert metrics[mat + ".WinSizeX"] == [5.0] * len(batch.submaps)
+    ctx.close()
+
+
 def test_cpp_loop_detector_with_linear_solver(checker):
     """Detect end to end like the reference's default configuration: GPU branch-and-bound, then the
     CPU linear-solver refiner on every detected loop. Refined poses within 1e-5 relative of the
