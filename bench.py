@@ -521,8 +521,13 @@ def single_scan_numbers(h, lib, kind):
     ctx = hostapi.Context(h.device)
     out = {}
 
-    def timeit(fn, reps):
+    def timeit(fn, reps, warm_s=0.5):
+        # warm up for a fixed time, not a fixed count: these legs follow seconds of CPU-only work
+        # during which the GPU drops to its idle clocks, and a 40 ms loop ends before they recover
+        t0 = time.perf_counter()
         fn()
+        while time.perf_counter() - t0 < warm_s:
+            fn()
         t0 = time.perf_counter()
         for _ in range(reps):
             fn()
@@ -544,18 +549,18 @@ def single_scan_numbers(h, lib, kind):
         return ctx.match_blocks("bb", blocks.copy(), index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
                                 case.init_pose, 5, synth.CFG2["rng"])
 
-    gpu = timeit(rt, 300)
-    cpu = timeit(lambda: orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), 20)
+    gpu = timeit(rt, 2000)
+    cpu = timeit(lambda: orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), 20, 0.0)
     out["cfg1_rt_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
-    gpu = timeit(bb, 300)
-    cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5)
+    gpu = timeit(bb, 1000)
+    cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5, 0.0)
     out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
     c4 = synth.case_for(synth.CFG4, 44000)
     s4 = c4.submap
     gpu = timeit(lambda: ctx.match("grid", s4.grid, s4.res, (s4.off_x, s4.off_y), c4.angles, c4.ranges,
-                                   c4.init_pose, 0, synth.CFG4["rng"], step=synth.CFG4["step"]), 3)
+                                   c4.init_pose, 0, synth.CFG4["rng"], step=synth.CFG4["step"]), 20, warm_s=0.1)
     # CPU: 1/64 of the window (x and y ranges / 8), scaled by the candidate ratio
     og4 = orc.grid(s4.grid, s4.res, s4.off_x, s4.off_y)
     rng_small = (synth.CFG4["rng"][0] / 8, synth.CFG4["rng"][1] / 8, synth.CFG4["rng"][2] / 8)

@@ -95,6 +95,40 @@ typedef struct csm_loop_query
     double  known_thr;        /* known-rate threshold */
 } csm_loop_query;
 
+/* Parameters of the refinement stage that follows a successful coarse match in
+ * the reference's loop detectors: ScanMatcherLinearSolver with CostSquareError
+ * ("FinalScanMatcherType": "LinearSolver", launcher_settings_default.json:28-35,
+ * scan_matcher_linear_solver.cpp:46-64, cost_function_square_error.cpp:16-24). */
+typedef struct csm_refine_params
+{
+    int32_t max_iterations;         /* NumOfIterationsMax */
+    int32_t reserved;
+    double  convergence_threshold;  /* ConvergenceThreshold, on the summed squared error */
+    double  lambda;                 /* damping factor every query of the next batch starts from */
+    double  covariance_scale;       /* CostSquareError CovarianceScale */
+} csm_refine_params;
+
+/* Outcome of the refinement of one query (valid == 0: nothing to refine). */
+typedef struct csm_refined
+{
+    double  pose[3];          /* refined map-local SENSOR pose (the adapter applies MoveBackward,
+                                 scan_matcher_linear_solver.cpp:113-114) */
+    double  covariance[9];    /* ComputeCovariance at the refined pose, row-major (:117-118) */
+    double  initial_cost;     /* sum of squared errors at the coarse pose (not normalized) */
+    double  final_cost;       /* ... at the refined pose */
+    double  lambda;           /* damping factor after the last iteration */
+    int32_t iterations;
+    int32_t valid;
+} csm_refined;
+
+/* One pose to refine on its own (csm_refine_batch) */
+typedef struct csm_refine_query
+{
+    int64_t map_id;
+    int64_t scan_id;
+    double  sensor_pose[3];   /* map-local sensor pose to start from */
+} csm_refine_query;
+
 /* ---- lifetime ---------------------------------------------------------- */
 int  csm_version(void);
 int  csm_device_count(void);
@@ -257,6 +291,26 @@ int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, 
 int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq);
 int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
                    int query_index_base, csm_result* results);
+/* Refinement on the device (ScanMatcherLinearSolver::OptimizePose,
+ * scan_matcher_linear_solver.cpp:66-140, as LoopDetectorBranchBound::Detect runs
+ * it on every detected loop, loop_detector_branch_bound.cpp:110-135).
+ * csm_set_refiner(h, p) makes every following loop batch refine the poses it
+ * finds (one more kernel behind the search, results read back with the batch);
+ * p == NULL switches it off. csm_loop_batch_finish_refined is
+ * csm_loop_batch_finish plus the per-query refinement outcomes.
+ * The reference's solver carries its damping factor from one query to the next
+ * (a member, :100-104); here every query of a batch starts from p->lambda and
+ * reports where it ended, and the adapter carries the last one into the next
+ * batch. The factor stays within [1e-8, 1e-4] against Hessian entries of 1e3 and
+ * more, so this changes refined poses by far less than the 1e-5 tolerance.
+ * Cells of unallocated blocks read as 0.5 (grid_map.cpp:424-436): maps uploaded
+ * block-sparse keep their block list for this; for dense uploads a block counts
+ * as allocated iff it (16 x 16 cells) holds a non-zero cell. */
+int csm_set_refiner(csm_handle h, const csm_refine_params* p);
+int csm_loop_batch_finish_refined(csm_handle h, csm_result* results, csm_refined* refined, int nq);
+/* Refine n given poses (synchronous). Uses p, not the handle's refiner setting. */
+int csm_refine_batch(csm_handle h, const csm_refine_query* queries, int n,
+                     const csm_refine_params* p, csm_refined* out);
 /* Phase timing: after csm_set_option(h, "timing", 1) the library records a CUDA
  * event on the handle's stream after every kernel of a loop batch (or of a
  * streaming pyramid build). csm_debug_timings waits for the last one and

@@ -10,6 +10,7 @@ SOURCES = [os.path.join(HERE, "csrc", "csm_b200.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "csm_kernels.cuh"),
            os.path.join(HERE, "csrc", "csm_device.cuh"),
            os.path.join(HERE, "csrc", "csm_window_tma.cuh"),
+           os.path.join(HERE, "csrc", "csm_refine.cuh"),
            os.path.join(ROOT, "include", "csm_b200.h")]
 
 NVCC_FLAGS = [

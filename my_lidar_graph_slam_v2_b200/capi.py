@@ -33,6 +33,21 @@ class CsmResult(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class CsmRefineParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32), ("reserved", C.c_int32), ("convergence_threshold", C.c_double),
+                ("lambda_", C.c_double), ("covariance_scale", C.c_double)]
+
+
+class CsmRefined(C.Structure):
+    _fields_ = [("pose", C.c_double * 3), ("covariance", C.c_double * 9), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("lambda_", C.c_double), ("iterations", C.c_int32),
+                ("valid", C.c_int32)]
+
+
+class CsmRefineQuery(C.Structure):
+    _fields_ = [("map_id", C.c_int64), ("scan_id", C.c_int64), ("sensor_pose", C.c_double * 3)]
+
+
 class CsmLoopQuery(C.Structure):
     _fields_ = [
         ("map_id", C.c_int64), ("scan_id", C.c_int64), ("sensor_pose", C.c_double * 3),
@@ -50,6 +65,7 @@ EXPORTS = [
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
+    "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch",
     "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
 ]
 
@@ -113,6 +129,10 @@ def load():
     lib.csm_loop_batch_enqueue.argtypes = [H, lq, C.c_int, C.c_int, C.c_int]
     lib.csm_loop_batch_finish.argtypes = [H, rp, C.c_int]
     lib.csm_loop_batch.argtypes = [H, lq, C.c_int, C.c_int, C.c_int, rp]
+    lib.csm_set_refiner.argtypes = [H, C.POINTER(CsmRefineParams)]
+    lib.csm_loop_batch_finish_refined.argtypes = [H, rp, C.POINTER(CsmRefined), C.c_int]
+    lib.csm_refine_batch.argtypes = [H, C.POINTER(CsmRefineQuery), C.c_int, C.POINTER(CsmRefineParams),
+                                     C.POINTER(CsmRefined)]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
     lib.csm_debug_timings.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
     lib.csm_best_key_device.argtypes = [H]
@@ -282,6 +302,35 @@ class Handle:
     def loop_batch(self, queries, nq, hmax, query_index_base=0):
         self.loop_batch_enqueue(queries, nq, hmax, query_index_base)
         return self.loop_batch_finish(nq)
+
+    # -- refinement (ScanMatcherLinearSolver on the device) ------------------------
+    def set_refiner(self, max_iterations=10, convergence_threshold=1e-4, lambda_=1e-4, covariance_scale=1e4,
+                    enabled=True):
+        """Loop batches enqueued from now on refine the poses they find (csm_set_refiner)."""
+        if not enabled:
+            self._check(self.lib.csm_set_refiner(self.h, None))
+            return
+        p = CsmRefineParams(max_iterations, 0, convergence_threshold, lambda_, covariance_scale)
+        self._check(self.lib.csm_set_refiner(self.h, C.byref(p)))
+
+    def loop_batch_finish_refined(self, nq, results=None, refined=None):
+        results = results if results is not None else (CsmResult * nq)()
+        refined = refined if refined is not None else (CsmRefined * nq)()
+        self._check(self.lib.csm_loop_batch_finish_refined(self.h, results, refined, nq))
+        return results, refined
+
+    def refine_batch(self, jobs, max_iterations=10, convergence_threshold=1e-4, lambda_=1e-4,
+                     covariance_scale=1e4):
+        """jobs: [(map_id, scan_id, (x, y, theta))] -> CsmRefined array."""
+        n = len(jobs)
+        q = (CsmRefineQuery * n)()
+        for i, (mid, sid, pose) in enumerate(jobs):
+            q[i].map_id, q[i].scan_id = int(mid), int(sid)
+            q[i].sensor_pose[:] = [float(v) for v in pose]
+        p = CsmRefineParams(max_iterations, 0, convergence_threshold, lambda_, covariance_scale)
+        out = (CsmRefined * n)()
+        self._check(self.lib.csm_refine_batch(self.h, q, n, C.byref(p), out))
+        return out
 
     def frontier_counts(self):
         out = (C.c_uint * 8)()

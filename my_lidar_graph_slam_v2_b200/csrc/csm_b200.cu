@@ -9,6 +9,7 @@
 #include "csm_b200.h"
 #include "csm_kernels.cuh"
 #include "csm_window_tma.cuh"
+#include "csm_refine.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -43,7 +44,8 @@ struct BlockScatter
     void* stage = nullptr;            /* [block data][block index][prefix], device */
     size_t data_bytes = 0, index_off = 0, prefix_off = 0;
     uint16_t* dense = nullptr;        /* level 0 of the first map; maps are contiguous */
-    int n_maps = 0, max_count = 0;
+    unsigned char* alloc = nullptr;   /* block-allocation bytes of the first map; maps are contiguous */
+    int n_maps = 0, max_count = 0, nb_map = 0;
     int log2bs = 0, block_cols = 0, rows = 0, cols = 0;
     std::vector<int> prefix;          /* host copy, alive until the H2D copy has run */
     bool done = false;
@@ -64,6 +66,12 @@ struct MapSlot
     int coarse_win = 0;
     cudaEvent_t pending_upload = nullptr;   /* copy-stream event the next consumer must wait for */
     std::shared_ptr<BlockScatter> pending_scatter;   /* block-sparse upload not yet expanded */
+    /* which blocks are allocated in the reference's sense (refinement reads unallocated cells as 0.5):
+     * one byte per block, from the block list of a block-sparse upload or derived from the cells */
+    unsigned char* alloc = nullptr;
+    std::shared_ptr<ArenaBlock> alloc_block;  /* owner of `alloc` when it lives in a batch arena */
+    int alloc_log2bs = 0, alloc_bytes = 0;
+    bool alloc_valid = false;
 };
 
 struct ScanSlot
@@ -141,6 +149,7 @@ struct csm_context
     int res_head = 0;              /* slot of the oldest batch in flight */
     int res_count = 0;             /* batches in flight */
     int res_nq[kResultSlots] = { 0, 0, 0, 0 };
+    bool res_refined[kResultSlots] = { false, false, false, false };
     /* last pyramid job table on the device (skips the re-upload when unchanged) */
     std::vector<PyrJob> jobs_on_device;
     /* options (csm_set_option) */
@@ -149,6 +158,9 @@ struct csm_context
                                       0 never, 1 always, 2 only for calls of at most 4 queries (there the
                                       latency of the dive is small against the nodes it saves) */
     int accumulate_best_key = 0;   /* 1: batches do not reset the packed best word */
+    bool refine_on = false;        /* loop batches refine the poses they find (csm_set_refiner) */
+    csm_refine_params refine {};
+    DevBuf d_refine_in;            /* csm_refine_batch: queries and start poses */
     /* last (thresholds, beams) -> integer cut-offs (fill_common) */
     int memo_n = -1, memo_nk_cut = 0;
     double memo_score_thr = -1.0, memo_known_thr = -1.0;
@@ -267,12 +279,14 @@ int pull_to_device(csm_handle h, void* dst, const void* src_pinned, size_t bytes
 
 /* Enqueue the device-to-host copy of the nq results (and the overflow flag)
  * of the batch just launched into the next free pinned result area. */
-int enqueue_readback(csm_handle h, int nq)
+size_t refined_offset(int nq) { return sizeof(csm_result) * (size_t)nq + 16; }
+
+int enqueue_readback(csm_handle h, int nq, bool refined = false)
 {
     if (h->res_count >= csm_context::kResultSlots)
         return fail(h, CSM_E_CAPACITY, "too many loop batches in flight: call csm_loop_batch_finish");
     const int k = (h->res_head + h->res_count) % csm_context::kResultSlots;
-    const size_t bytes = sizeof(csm_result) * (size_t)nq + 64;
+    const size_t bytes = refined_offset(nq) + sizeof(csm_refined) * (size_t)nq + 64;
     if (h->h_res_bytes[k] < bytes) {
         if (h->h_res[k] != nullptr)
             CSM_CUDA(cudaFreeHost(h->h_res[k]));
@@ -285,8 +299,11 @@ int enqueue_readback(csm_handle h, int nq)
     if (h->h_res_done[k] == nullptr)
         CSM_CUDA(cudaEventCreateWithFlags(&h->h_res_done[k], cudaEventDisableTiming));
     /* results followed by the overflow flag (written by k_finalize): one copy */
-    CSM_CUDA(cudaMemcpyAsync(h->h_res[k], h->d_results.p, sizeof(csm_result) * (size_t)nq + 16,
+    /* ... and by the refinement outcomes when the batch refined its poses */
+    CSM_CUDA(cudaMemcpyAsync(h->h_res[k], h->d_results.p,
+                             refined_offset(nq) + (refined ? sizeof(csm_refined) * (size_t)nq : 0),
                              cudaMemcpyDeviceToHost, h->stream));
+    h->res_refined[k] = refined;
     CSM_CUDA(cudaEventRecord(h->h_res_done[k], h->stream));
     h->res_nq[k] = nq;
     ++h->res_count;
@@ -294,7 +311,7 @@ int enqueue_readback(csm_handle h, int nq)
 }
 
 /* Wait for the oldest batch in flight and hand out its results */
-int finish_results(csm_handle h, csm_result* results, int nq)
+int finish_results(csm_handle h, csm_result* results, int nq, csm_refined* refined = nullptr)
 {
     if (h->res_count <= 0)
         return fail(h, CSM_E_INVALID, "no batch in flight");
@@ -306,6 +323,12 @@ int finish_results(csm_handle h, csm_result* results, int nq)
     CSM_CUDA(cudaEventSynchronize(h->h_res_done[k]));
     const char* hp = static_cast<const char*>(h->h_res[k]);
     std::memcpy(results, hp, sizeof(csm_result) * (size_t)nq);
+    if (refined != nullptr) {
+        if (h->res_refined[k])
+            std::memcpy(refined, hp + refined_offset(nq), sizeof(csm_refined) * (size_t)nq);
+        else
+            std::memset(refined, 0, sizeof(csm_refined) * (size_t)nq);
+    }
     if (*reinterpret_cast<const int*>(hp + sizeof(csm_result) * (size_t)nq) != 0)
         return fail(h, CSM_E_CAPACITY, "branch-and-bound frontier overflow; split the batch");
     return CSM_OK;
@@ -316,6 +339,7 @@ void free_map(csm_handle h, MapSlot& m)
     if (m.base && !m.base_block) cudaFreeAsync(m.base, h->stream);
     if (m.levels) cudaFreeAsync(m.levels, h->stream);
     if (m.coarse) cudaFreeAsync(m.coarse, h->stream);
+    if (m.alloc && !m.alloc_block) cudaFreeAsync(m.alloc, h->stream);
     m = MapSlot();
 }
 
@@ -372,12 +396,15 @@ int wait_uploads(csm_handle h, const std::vector<MapSlot*>& slots)
         bs->done = true;
         const size_t map_cells = (size_t)bs->rows * bs->cols;
         CSM_CUDA(cudaMemsetAsync(bs->dense, 0, map_cells * sizeof(uint16_t) * bs->n_maps, h->stream));
+        if (bs->alloc != nullptr)
+            CSM_CUDA(cudaMemsetAsync(bs->alloc, 0, (size_t)bs->nb_map * bs->n_maps, h->stream));
         if (bs->max_count > 0) {
             ScatterArgs A;
             A.data = static_cast<const uint4*>(bs->stage);
             A.index = reinterpret_cast<const int*>(static_cast<const char*>(bs->stage) + bs->index_off);
             A.prefix = reinterpret_cast<const int*>(static_cast<const char*>(bs->stage) + bs->prefix_off);
             A.dense = bs->dense;
+            A.alloc = bs->alloc; A.nb_map = bs->nb_map;
             A.log2bs = bs->log2bs; A.block_cols = bs->block_cols; A.cols = bs->cols;
             A.map_cells = map_cells;
             const int chunks = (1 << bs->log2bs) * ((1 << bs->log2bs) >> 3);
@@ -427,6 +454,33 @@ int bind_batch_arena(csm_handle h, int n, const int64_t* map_ids, int rows, int 
             m.base = reinterpret_cast<uint16_t*>(static_cast<char*>(block->p) + (size_t)i * bytes);
         }
         fresh_alloc = true;
+    }
+    return CSM_OK;
+}
+
+/* Block-allocation bytes for the refinement stage. Block-sparse uploads bring them (set by
+ * k_scatter_blocks); for dense uploads they are derived here, once per upload: a 16 x 16 block
+ * counts as allocated iff it holds a non-zero cell. The maps' uploads must have been waited for. */
+int ensure_alloc(csm_handle h, const std::vector<MapSlot*>& slots)
+{
+    for (MapSlot* m : slots) {
+        if (m->alloc_valid)
+            continue;
+        const int k = 4;
+        const int br = (m->rows + 15) >> k, bc = (m->cols + 15) >> k;
+        const int bytes = br * bc;
+        if (m->alloc == nullptr || m->alloc_bytes < bytes) {
+            if (m->alloc && !m->alloc_block) CSM_CUDA(cudaFreeAsync(m->alloc, h->stream));
+            m->alloc_block.reset();
+            m->alloc = nullptr;
+            CSM_CUDA(cudaMallocAsync((void**)&m->alloc, (size_t)bytes, h->stream));
+            m->alloc_bytes = bytes;
+        }
+        m->alloc_log2bs = k;
+        const int blocks = std::max(1, std::min((bytes + 7) / 8, h->sm_count * 4));
+        k_block_alloc<<<blocks, 256, 0, h->stream>>>(m->base, m->rows, m->cols, k, br, bc, m->alloc);
+        CSM_LAUNCH_CHECK();
+        m->alloc_valid = true;
     }
     return CSM_OK;
 }
@@ -673,6 +727,11 @@ int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
     Q.res = m.res; Q.offx = m.offx; Q.offy = m.offy;
     Q.inv_res = 1.0 / m.res;
     Q.angles = s.angles; Q.ranges = s.ranges; Q.beam_trig = s.trig; Q.n = s.n;
+    if (m.alloc_valid) {
+        Q.alloc = m.alloc;
+        Q.alloc_log2bs = m.alloc_log2bs;
+        Q.alloc_bcols = (m.cols + (1 << m.alloc_log2bs) - 1) >> m.alloc_log2bs;
+    }
     /* the integer images of the two thresholds depend on (threshold, n) only: queries of a
      * batch share them */
     if (h->memo_n != s.n || h->memo_score_thr != score_thr || h->memo_known_thr != known_thr) {
@@ -694,7 +753,7 @@ int commit_plan(csm_handle h, QueryPlan& plan, const PlanView& V, bool want_rcs)
     int rc;
     if ((rc = ensure(h, h->d_proj, sizeof(proj_t) * (size_t)plan.proj_total))) return rc;
     if (want_rcs && (rc = ensure(h, h->d_rcs, sizeof(double2) * (size_t)plan.proj_total))) return rc;
-    if ((rc = ensure(h, h->d_results, sizeof(csm_result) * nq + 16))) return rc;
+    if ((rc = ensure(h, h->d_results, refined_offset(nq) + sizeof(csm_refined) * (size_t)nq))) return rc;
     if ((rc = ensure(h, h->d_bestkey, 8))) return rc;
     for (int q = 0; q < nq; ++q)
         plan.dq[q].thetas = plan.thetas.empty() ? nullptr : V.thetas + plan.theta_off[q];
@@ -831,6 +890,11 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         n_thetas += (size_t)(2 * in.win_t + 1);
     }
     int rc;
+    const bool refine = h->refine_on;
+    if (refine) {
+        if ((rc = wait_uploads(h, used_slots))) return rc;
+        if ((rc = ensure_alloc(h, used_slots))) return rc;
+    }
     PlanView V;
     if ((rc = layout_plan(h, nq, 0, (size_t)nq + 1, 0, inline_scan ? inline_scan->n : 0, V))) return rc;
     ScanSlot inl = V.scan;
@@ -860,6 +924,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         if ((rc = fill_common(h, Q, m, s, in.score_thr, in.known_thr))) return rc;
         Q.sx = in.sensor_pose[0];
         Q.sy = in.sensor_pose[1];
+        Q.stepx = in.step_x; Q.stepy = in.step_y;
         Q.T = 2 * in.win_t + 1;
         Q.winx = in.win_x; Q.winy = in.win_y;
         /* leaf lattice of the reference: roots every 2^hmax cells from -win (:179-182) */
@@ -963,9 +1028,32 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     k_finalize<<<nq, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
     phase_mark(h, "k_finalize");
-    rc = enqueue_readback(h, nq);
+    if (refine) {
+        /* ScanMatcherLinearSolver on every pose found, loop_detector_branch_bound.cpp:110-135 */
+        RefineArgs R;
+        std::memset(&R, 0, sizeof(R));
+        R.results = static_cast<const csm_result*>(h->d_results.p);
+        R.out = reinterpret_cast<csm_refined*>(static_cast<char*>(h->d_results.p) + refined_offset(nq));
+        R.max_iterations = h->refine.max_iterations;
+        R.convergence_threshold = h->refine.convergence_threshold;
+        R.lambda0 = h->refine.lambda;
+        R.covariance_scale = h->refine.covariance_scale;
+        k_refine<<<nq, kRefThreads, 0, h->stream>>>(dq, R);
+        CSM_LAUNCH_CHECK();
+        phase_mark(h, "k_refine");
+    }
+    rc = enqueue_readback(h, nq, refine);
     phase_mark(h, "readback");
     return rc;
+}
+
+int check_refine_params(csm_handle h, const csm_refine_params* p)
+{
+    if (p->max_iterations < 1 || p->max_iterations > 1000 || !(p->convergence_threshold >= 0.0) ||
+        !(p->lambda >= 0.0) || !(p->covariance_scale > 0.0))
+        return fail(h, CSM_E_INVALID, "refiner: need 1 <= max_iterations <= 1000, threshold >= 0, "
+                                      "lambda >= 0, covariance_scale > 0");
+    return CSM_OK;
 }
 
 } /* namespace */
@@ -1026,7 +1114,7 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
-                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups };
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)
@@ -1121,6 +1209,7 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     m.hmax = 0;
     m.coarse_win = 0;
     m.pending_scatter.reset();
+    m.alloc_valid = false;
     m.res = res; m.offx = offx; m.offy = offy;
     const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
     if (on_device) {
@@ -1189,6 +1278,7 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
         m.pending_scatter.reset();
+        m.alloc_valid = false;
     }
     if (!h->upload_open || fresh_alloc) {
         CSM_CUDA(cudaEventRecord(h->compute_mark, h->stream));
@@ -1247,6 +1337,31 @@ int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
     {
         const int arc = bind_batch_arena(h, n, map_ids, rows, cols, slots, fresh_alloc);
         if (arc) return arc;
+    }
+    {
+        /* one byte per block and map, set by the expansion kernel from the block list */
+        bool reuse = slots[0]->alloc_block != nullptr && slots[0]->alloc == slots[0]->alloc_block->p;
+        for (int i = 0; i < n && reuse; ++i)
+            reuse = slots[i]->alloc_block == slots[0]->alloc_block && slots[i]->alloc_bytes == nb_map &&
+                    slots[i]->alloc == static_cast<unsigned char*>(slots[0]->alloc_block->p) + (size_t)i * nb_map;
+        if (!reuse) {
+            auto block = std::make_shared<ArenaBlock>();
+            block->stream = h->stream;
+            CSM_CUDA(cudaMallocAsync(&block->p, (size_t)nb_map * n, h->stream));
+            for (int i = 0; i < n; ++i) {
+                MapSlot& m = *slots[i];
+                if (m.alloc && !m.alloc_block) CSM_CUDA(cudaFreeAsync(m.alloc, h->stream));
+                m.alloc_block = block;
+                m.alloc = static_cast<unsigned char*>(block->p) + (size_t)i * nb_map;
+                m.alloc_bytes = nb_map;
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            slots[i]->alloc_log2bs = log2_block_size;
+            slots[i]->alloc_valid = true;      /* once the pending expansion has run */
+        }
+        bs->alloc = slots[0]->alloc;
+        bs->nb_map = nb_map;
     }
     const size_t block_bytes = sizeof(uint16_t) << (2 * log2_block_size);
     bs->data_bytes = block_bytes * (size_t)total;
@@ -1422,6 +1537,75 @@ int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq)
 {
     if (!h || !results) return CSM_E_INVALID;
     return finish_results(h, results, nq);
+}
+
+int csm_set_refiner(csm_handle h, const csm_refine_params* p)
+{
+    if (!h) return CSM_E_INVALID;
+    if (p == nullptr) {
+        h->refine_on = false;
+        return CSM_OK;
+    }
+    const int rc = check_refine_params(h, p);
+    if (rc) return rc;
+    h->refine = *p;
+    h->refine_on = true;
+    return CSM_OK;
+}
+
+int csm_loop_batch_finish_refined(csm_handle h, csm_result* results, csm_refined* refined, int nq)
+{
+    if (!h || !results || !refined) return CSM_E_INVALID;
+    return finish_results(h, results, nq, refined);
+}
+
+int csm_refine_batch(csm_handle h, const csm_refine_query* queries, int n,
+                     const csm_refine_params* p, csm_refined* out)
+{
+    if (!h) return CSM_E_INVALID;
+    if (n <= 0 || !queries || !p || !out)
+        return fail(h, CSM_E_INVALID, "refine batch: empty");
+    int rc = check_refine_params(h, p);
+    if (rc) return rc;
+    CSM_CUDA(cudaSetDevice(h->device));
+    std::vector<MapSlot*> slots(n);
+    for (int q = 0; q < n; ++q) {
+        auto mi = h->maps.find(queries[q].map_id);
+        if (mi == h->maps.end())
+            return fail(h, CSM_E_NOT_FOUND, "refine batch: unknown map id " + std::to_string(queries[q].map_id));
+        if (h->scans.find(queries[q].scan_id) == h->scans.end())
+            return fail(h, CSM_E_NOT_FOUND, "refine batch: unknown scan id " + std::to_string(queries[q].scan_id));
+        slots[q] = &mi->second;
+    }
+    if ((rc = wait_uploads(h, slots))) return rc;
+    if ((rc = ensure_alloc(h, slots))) return rc;
+    const size_t q_bytes = align16(sizeof(DevQuery) * (size_t)n);
+    const size_t in_bytes = q_bytes + align16(sizeof(double) * 3 * (size_t)n);
+    if ((rc = ensure(h, h->d_refine_in, in_bytes + sizeof(csm_refined) * (size_t)n))) return rc;
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, in_bytes, &hp))) return rc;
+    for (int q = 0; q < n; ++q) {
+        DevQuery Q;
+        if ((rc = fill_common(h, Q, *slots[q], h->scans.find(queries[q].scan_id)->second, 0.0, 0.0))) return rc;
+        std::memcpy(hp + sizeof(DevQuery) * (size_t)q, &Q, sizeof(Q));
+        std::memcpy(hp + q_bytes + sizeof(double) * 3 * (size_t)q, queries[q].sensor_pose, sizeof(double) * 3);
+    }
+    if ((rc = pull_to_device(h, h->d_refine_in.p, hp, in_bytes))) return rc;
+    if ((rc = upload_committed(h))) return rc;
+    char* base = static_cast<char*>(h->d_refine_in.p);
+    RefineArgs R;
+    std::memset(&R, 0, sizeof(R));
+    R.start = reinterpret_cast<const double*>(base + q_bytes);
+    R.out = reinterpret_cast<csm_refined*>(base + in_bytes);
+    R.max_iterations = p->max_iterations;
+    R.convergence_threshold = p->convergence_threshold;
+    R.lambda0 = p->lambda;
+    R.covariance_scale = p->covariance_scale;
+    k_refine<<<n, kRefThreads, 0, h->stream>>>(reinterpret_cast<const DevQuery*>(base), R);
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaMemcpyAsync(out, R.out, sizeof(csm_refined) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    return CSM_OK;
 }
 
 int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,

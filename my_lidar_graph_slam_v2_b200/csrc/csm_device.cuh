@@ -68,6 +68,10 @@ struct DevQuery
     KeyThreshold kthr;
     int nk_cut;                        /* known test passes iff nKnown > nk_cut */
     int pad;
+    /* refinement (csm_refine.cuh) */
+    const unsigned char* alloc;        /* one byte per 2^k x 2^k block: allocated in the reference's sense */
+    int alloc_log2bs, alloc_bcols;     /* k, blocks per row */
+    double stepx, stepy;               /* search steps along x / y (the coarse result is an index) */
 };
 
 __host__ __device__ __forceinline__ long long make_key(long long sumv, int nk)

@@ -92,6 +92,8 @@ struct ScatterArgs
     const int* index;
     const int* prefix;
     uint16_t* dense;
+    unsigned char* alloc;      /* per map nb_map bytes (zeroed beforehand): 1 = block allocated; or null */
+    int nb_map;
     int log2bs, block_cols, cols;
     size_t map_cells;
 };
@@ -115,6 +117,8 @@ k_scatter_blocks(ScatterArgs A)
         const int brow = bi / A.block_cols, bcol = bi - brow * A.block_cols;
         const uint4 v = __ldg(A.data + (size_t)(first + b) * chunks_per_block + c);
         *reinterpret_cast<uint4*>(dense + (size_t)((brow << k) + r_in) * A.cols + (bcol << k) + c_in) = v;
+        if (c == 0 && A.alloc != nullptr)
+            A.alloc[(size_t)m * A.nb_map + bi] = 1;
     }
 }
 

@@ -68,6 +68,16 @@ public:
      * function at the coarse pose (computed on the CPU); switch it off when
      * the caller refines the poses itself */
     void SetCoarseCovariance(bool on) { mCoarseCovariance = on; }
+    /* Run the reference's default final matcher (ScanMatcherLinearSolver with CostSquareError,
+     * "FinalScanMatcherType": "LinearSolver") on the device, batched behind the search, instead of a
+     * CPU final matcher: every detected loop comes back with its refined pose and covariance
+     * (csm_set_refiner). `initial_lambda` is the solver's damping state; it is carried from one
+     * Detect to the next like the reference's member (scan_matcher_linear_solver.cpp:100-104),
+     * per batch instead of per query. Replaces any CPU final matcher. */
+    void UseDeviceRefiner(int num_of_iterations_max, double convergence_threshold, double initial_lambda,
+                          double covariance_scale);
+    /* Per-query refinement outcomes of the last Detect (valid == 0 where none) */
+    const std::vector<csm_refined>& LastRefined() const { return mLastRefined; }
     /* Forget which maps are resident (the next Detect uploads them again) */
     void ClearCache() { mCachedMaps.clear(); mCachedScans.clear(); }
     /* Sharded use: global index of queries[0] (packed best word) */
@@ -82,6 +92,9 @@ private:
     std::set<std::int64_t> mCachedMaps;
     std::set<std::int64_t> mCachedScans;
     std::vector<csm_result> mLastResults;
+    std::vector<csm_refined> mLastRefined;
+    bool mDeviceRefiner = false;
+    csm_refine_params mRefineParams {};
     int mQueryIndexBase = 0;
     int mChunkSize = 128;
     int mUploadChunk = 64;

@@ -282,6 +282,15 @@ void csm_host_loopdet_use_linear_solver(void* det, int iterations_max, double co
                                              MakeLinearSolverFinalMatcher(d->refiner), d->score_thr, d->known_thr));
 }
 
+/* The same refinement on the device, batched behind the search (csm_set_refiner) */
+void csm_host_loopdet_use_device_refiner(void* det, int iterations_max, double convergence_threshold,
+                                         double initial_lambda, double covariance_scale)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    d->refiner.reset();
+    d->det->UseDeviceRefiner(iterations_max, convergence_threshold, initial_lambda, covariance_scale);
+}
+
 void csm_host_loopdet_destroy(void* det) { delete static_cast<HostLoopDet*>(det); }
 
 void csm_host_loopdet_configure(void* det, int chunk_size, int coarse_covariance, int query_index_base)

@@ -181,11 +181,24 @@ void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapV
 
 } /* namespace */
 
+void LoopDetectorBranchBound::UseDeviceRefiner(int num_of_iterations_max, double convergence_threshold,
+                                               double initial_lambda, double covariance_scale)
+{
+    mDeviceRefiner = true;
+    mFinalMatcher = FinalMatcher();
+    mRefineParams.max_iterations = num_of_iterations_max;
+    mRefineParams.reserved = 0;
+    mRefineParams.convergence_threshold = convergence_threshold;
+    mRefineParams.lambda = initial_lambda;
+    mRefineParams.covariance_scale = covariance_scale;
+}
+
 std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     const std::vector<LoopDetectionQuery>& queries)
 {
     std::vector<LoopDetectionResult> results;
     mLastResults.clear();
+    mLastRefined.clear();
     if (queries.empty())
         return results;
     MicroTimer timer;
@@ -233,6 +246,20 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     std::vector<csm_loop_query> dq(nq);
     std::map<std::pair<std::int64_t, double>, std::array<double, 3>> steps;
     mLastResults.resize(nq);
+    if (mDeviceRefiner) {
+        mLastRefined.resize(nq);
+        ctx->Check(csm_set_refiner(h, &mRefineParams), "csm_set_refiner");
+    } else {
+        ctx->Check(csm_set_refiner(h, nullptr), "csm_set_refiner");
+    }
+    /* read back the oldest batch in flight */
+    auto finish = [&](int f0, int fc) {
+        if (mDeviceRefiner)
+            ctx->Check(csm_loop_batch_finish_refined(h, mLastResults.data() + f0, mLastRefined.data() + f0, fc),
+                       "csm_loop_batch_finish_refined");
+        else
+            ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");
+    };
     int finished = 0;      /* chunks whose results have been read back */
     for (int c = 0; c < nchunks; ++c) {
         const int first = c * chunk, count = std::min(nq, first + chunk) - first;
@@ -268,7 +295,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
                                               new_maps[next_group].data(), hmax), "csm_build_pyramids");
         if (c - finished >= 4) {        /* the library keeps at most 4 batches in flight */
             const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
-            ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");
+            finish(f0, fc);
             ++finished;
         }
         ctx->Check(csm_loop_batch_enqueue(h, dq.data() + first, count, hmax, mQueryIndexBase + first),
@@ -276,7 +303,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     }
     for (; finished < nchunks; ++finished) {
         const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
-        ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");
+        finish(f0, fc);
     }
 
     for (int i = 0; i < nq; ++i) {
@@ -289,7 +316,15 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
                             d.sensor_pose[2] + d.step_t * r.best_t };
         LoopDetectionResult out;
         out.relative_pose = MoveBackward(best, q.scan->relative_sensor_pose);
-        if (mFinalMatcher) {
+        if (mDeviceRefiner && mLastRefined[i].valid) {
+            /* the device ran the final matcher on the coarse sensor pose; what the reference
+             * returns is its pose moved back to the robot frame and its covariance (:132-135) */
+            const csm_refined& f = mLastRefined[i];
+            out.relative_pose = MoveBackward(Pose2D { f.pose[0], f.pose[1], f.pose[2] },
+                                             q.scan->relative_sensor_pose);
+            std::copy(f.covariance, f.covariance + 9, out.estimated_covariance.begin());
+            mRefineParams.lambda = f.lambda;      /* damping state for the next Detect */
+        } else if (mFinalMatcher) {
             /* sub-pixel refinement around the reference scan's local pose (:110-127); its
              * pose and covariance are what the reference returns (:132-135) */
             const ScanMatchingSummary fin = mFinalMatcher(q.local_map, q.scan, q.reference_scan_local_pose,

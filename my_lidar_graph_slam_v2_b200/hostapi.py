@@ -54,6 +54,7 @@ def load():
                                         dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp, C.c_double,
                                         C.POINTER(HostSummary)]
         lib.csm_host_loopdet_use_linear_solver.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        lib.csm_host_loopdet_use_device_refiner.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_create.restype = C.c_void_p
         lib.csm_host_loopdet_create.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_destroy.argtypes = [C.c_void_p]
@@ -221,6 +222,12 @@ class LoopDetector:
         """Refine detected loops with the reference's default final matcher (CPU)."""
         self.lib.csm_host_loopdet_use_linear_solver(self.det, iterations_max, convergence_threshold,
                                                     initial_lambda, covariance_scale)
+
+    def use_device_refiner(self, iterations_max=10, convergence_threshold=1e-4, initial_lambda=1e-4,
+                           covariance_scale=1e4):
+        """Refine detected loops with the same solver on the device, batched behind the search."""
+        self.lib.csm_host_loopdet_use_device_refiner(self.det, iterations_max, convergence_threshold,
+                                                     initial_lambda, covariance_scale)
 
     def configure(self, chunk_size=128, coarse_covariance=True, query_index_base=0):
         self.lib.csm_host_loopdet_configure(self.det, chunk_size, int(coarse_covariance), query_index_base)

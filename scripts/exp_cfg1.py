@@ -49,3 +49,23 @@ def pyr():
     h.drop_pyramids([5]); h.build_pyramid(5, 5)
 pyr(); bbm()
 print("cfg2: pyramid+sync %.1f us | match_bb %.1f us" % (phase(pyr), phase(bbm, False)))
+# the bench's single_scan legs (block-sparse map through the C++ plugin)
+def rtb():
+    return ctx.match_blocks("rt", blocks.copy(), index, 4, s.grid.shape, s.res, (s.off_x, s.off_y), case.angles,
+                            case.ranges, case.init_pose, 5, synth.CFG1["rng"])
+def rtb_nocopy():
+    return ctx.match_blocks("rt", blocks, index, 4, s.grid.shape, s.res, (s.off_x, s.off_y), case.angles,
+                            case.ranges, case.init_pose, 5, synth.CFG1["rng"])
+def bbb():
+    return ctx.match_blocks("bb", blocks.copy(), index, 4, s.grid.shape, s.res, (s.off_x, s.off_y), case.angles,
+                            case.ranges, case.init_pose, 5, synth.CFG2["rng"])
+for name, fn in (("rt blocks+copy", rtb), ("rt blocks", rtb_nocopy), ("bb blocks+copy", bbb), ("rt blocks+copy", rtb)):
+    fn()
+    for rep in range(3):
+        print("plugin %s: %.1f us" % (name, phase(fn, False)))
+hh = capi.Handle.from_pointer(ctx.handle(), 0)
+hh.set_option("timing", 2)
+t0 = time.perf_counter(); rtb_nocopy(); t1 = time.perf_counter()
+print("one rt call wall %.1f us" % ((t1 - t0) * 1e6))
+for name, ms in hh.timings():
+    print("  %8.3f ms  %s" % (ms, name))

@@ -30,7 +30,8 @@ def step():
     n, _ = hdet.detect(N, None, blk_ptr, idx_ptr, counts.ctypes.data, 4, 512, 512, res, offx, offy, ids, mp, sp, ang, rng, out)
     return n
 
-for chunk, up in ((128, 128), (128, 64), (128, 32), (64, 64), (64, 32), (256, 64), (256, 32), (86, 43), (192, 64)):
+CFGS = ((128, 64), (64, 64), (256, 64))
+for chunk, up in CFGS:
     hdet.configure(chunk_size=chunk | (up << 16), coarse_covariance=False)
     for _ in range(3): step()
     h.synchronize()
@@ -40,7 +41,8 @@ for chunk, up in ((128, 128), (128, 64), (128, 32), (64, 64), (64, 32), (256, 64
     print("batch %3d upload group %3d: %.3f ms per Detect (found %d)" % (chunk, up, (time.perf_counter() - t0) / 20 * 1e3, n))
 
 # timeline of one Detect (all streams), best config
-hdet.configure(chunk_size=128 | (64 << 16), coarse_covariance=False)
+TL = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (128, 64)
+hdet.configure(chunk_size=TL[0] | (TL[1] << 16), coarse_covariance=False)
 for _ in range(3): step()
 h.synchronize()
 h.set_option("timing", 2)

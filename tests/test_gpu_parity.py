@@ -548,3 +548,103 @@ def test_cpp_loop_detector_with_linear_solver(checker):
             assert np.allclose(list(r.cov), list(o.cov), rtol=1e-9, atol=0.0), i
     det.close()
     ctx.close()
+
+
+def test_device_refiner_against_reference_vectors(handle):
+    """k_refine (ScanMatcherLinearSolver + CostSquareError on the device, csm_refine_batch) against the
+    vectors the reference's scan_matcher_linear_solver.cpp produced (tests/golden/refine_vectors.json),
+    all cases in one batch: iteration counts equal, refined poses within the north_star tolerance of
+    1e-5 relative (observed: ~1e-12, summation order only), costs 1e-9, covariances 1e-6. Maps go up
+    dense (block allocation derived on the device) and block-sparse (block list kept) alternately."""
+    from helpers import load_golden, sha
+    entries = load_golden("refine_vectors.json")["refine"]
+    jobs, cases = [], []
+    for k, e in enumerate(entries):
+        case = synth.case_for(synth.CFG1, e["seed"])
+        s = case.submap
+        assert sha(s.grid) == e["grid_sha"]
+        mid, sid = 8800 + k, 8800 + k
+        if k % 2 == 0:
+            handle.upload_grid(mid, s.grid, s.res, s.off_x, s.off_y)
+        else:
+            blocks, index, br, bc = synth.dense_to_blocks(s.grid)
+            handle.upload_grid_blocks(mid, blocks, index, 4, br, bc, s.res, s.off_x, s.off_y)
+        handle.upload_scan(sid, case.angles, case.ranges)
+        init = [float.fromhex(v) for v in e["init"]]
+        jobs.append((mid, sid, matchers.compound(tuple(init), tuple(e["rel"]))))
+        cases.append(case)
+    out = handle.refine_batch(jobs, 10, 1e-4, 1e-4, 1e4)
+    worst = 0.0
+    for e, o in zip(entries, out):
+        assert o.valid == 1 and o.iterations == e["iterations"]
+        est = matchers.move_backward(tuple(o.pose), tuple(e["rel"]))
+        exp = [float.fromhex(v) for v in e["est_pose"]]
+        assert np.allclose(est, exp, rtol=1e-5, atol=0.0)
+        worst = max(worst, max(abs(a - b) / abs(b) for a, b in zip(est, exp)))
+        assert np.isclose(o.final_cost / 360.0, float.fromhex(e["norm_cost"]), rtol=1e-9, atol=0.0)
+        assert np.allclose(list(o.covariance), [float.fromhex(v) for v in e["cov"]], rtol=1e-6, atol=0.0)
+        assert 1e-8 <= o.lambda_ <= 1e-4
+    assert worst < 1e-9, worst
+    for k in range(len(entries)):
+        handle.release_grid(8800 + k)
+
+
+def test_device_refiner_unallocated_blocks_and_borders(handle):
+    """Cells of unallocated blocks and cells outside the map read as 0.5, unknown cells of allocated
+    blocks as 0.0 (grid_map.cpp:424-436): poses whose beams leave the map or cross empty blocks,
+    against the C++ host mirror of the solver (bit-identical to the reference, test_host_logic)."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    case = synth.case_for(synth.CFG1, 5150)
+    s = case.submap
+    handle.upload_grid(8900, s.grid, s.res, s.off_x, s.off_y)
+    handle.upload_scan(8900, case.angles, case.ranges)
+    tp = np.asarray(case.true_pose, dtype=np.float64)
+    span = s.res * s.grid.shape[1]
+    starts = [tp + np.array([0.03, -0.02, 0.004]), tp + np.array([0.45 * span, 0.0, 0.3]),
+              tp + np.array([-0.6 * span, 0.5 * span, -1.0]), tp + np.array([0.0, 0.0, 3.0])]
+    out = handle.refine_batch([(8900, 8900, tuple(p)) for p in starts], 10, 1e-4, 1e-4, 1e4)
+    for p, o in zip(starts, out):
+        ref, _ = hostapi.refine(s.grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges, p)
+        assert o.iterations == ref.best_t
+        assert np.allclose(list(o.pose), list(ref.est_pose), rtol=1e-5, atol=1e-9)
+        assert np.isclose(o.final_cost / 360.0, ref.norm_cost, rtol=1e-8, atol=0.0)
+    handle.release_grid(8900)
+
+
+def test_cpp_loop_detector_with_device_refiner(checker):
+    """Detect like the reference's default configuration with the final matcher on the device: GPU
+    branch-and-bound, k_refine on every detected loop in the same batch, against the reference's
+    Detect with its own ScanMatcherLinearSolver. Refined poses within 1e-5 relative (north_star)."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    batch = synth.make_loop_batch(3500, n_maps=16, true_fraction=0.5, map_id_base=9100)
+    ctx = hostapi.Context(0)
+    det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+    det.use_device_refiner(10, 1e-4, 1e-4)
+    det.configure(chunk_size=8 | (4 << 16))
+    parts = [synth.dense_to_blocks(s.grid, 4) for s in batch.submaps]
+    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+    blocks = np.ascontiguousarray(np.concatenate([p[0].reshape(-1) for p in parts]))
+    index = np.ascontiguousarray(np.concatenate([p[1] for p in parts]))
+    args = (np.array([s.off_x for s in batch.submaps]), np.array([s.off_y for s in batch.submaps]),
+            batch.map_ids.astype(np.int64), np.ascontiguousarray(batch.map_poses),
+            np.ascontiguousarray(batch.scan_poses), np.ascontiguousarray(batch.angles[0]),
+            np.ascontiguousarray(batch.ranges[0]))
+    og = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    odet.use_linear_solver(10, 1e-4, 1e-4)
+    ores, _ = odet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    grids = np.ascontiguousarray(np.stack([s.grid for s in batch.submaps]))
+    for sparse in (True, False):
+        det.clear_cache()
+        n, out = det.detect(len(batch.submaps), None if sparse else grids.ctypes.data,
+                            blocks.ctypes.data if sparse else None, index.ctypes.data if sparse else None,
+                            counts.ctypes.data if sparse else None, 4, 512, 512, batch.submaps[0].res, *args)
+        assert n == sum(o.found for o in ores) >= 3
+        for i, (r, o) in enumerate(zip(out, ores)):
+            assert r.found == o.found, i
+            if o.found:
+                assert np.allclose(list(r.est_pose), list(o.est_pose), rtol=1e-5, atol=0.0), (sparse, i)
+                assert np.allclose(list(r.cov), list(o.cov), rtol=1e-5, atol=0.0), (sparse, i)
+    det.close()
+    ctx.close()
