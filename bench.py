@@ -9,8 +9,10 @@ Workload (BASELINE.json configs[2]): one query scan (360 beams)
 matched by branch-and-bound (hmax 6, window 2.5 m x 2.5 m x 0.5 rad, thresholds
 0.55 / 0.6) against 256 candidate 512x512 submaps per GPU. A step is one
 LoopDetector::Detect on 256 first-touch submaps: grid upload, pyramid build
-(PrecomputeGridMaps) and the batched B&B search, i.e. the reference's own
-cold path (loop_detector_branch_bound.cpp:68-141). Queries shard across ranks
+(PrecomputeGridMaps), the batched B&B search and the refinement of every
+detected loop by the reference's default final matcher (ScanMatcherLinearSolver,
+10 iterations max, then its covariance), i.e. the reference's own cold path
+(loop_detector_branch_bound.cpp:68-141). Queries shard across ranks
 with no data-path exchange; the only collective is the 8-byte argmax
 all-reduce of the packed best (score, query) word over NCCL.
 
@@ -35,6 +37,7 @@ sys.path.insert(0, ROOT)
 HMAX = 6
 N_MAPS = 256
 ROWS = COLS = 512
+REFINE = (10, 1e-4, 1e-4)      # NumOfIterationsMax, ConvergenceThreshold, InitialLambda (launcher_settings_default.json:28-35)
 METRIC = "loop_detection_queries_per_sec"
 UNIT = "queries/s"
 
@@ -50,7 +53,8 @@ def workload_config(n_gpus):
     return {
         "workload": "cfg3: 1 query scan (360 beams) x %d candidate 512x512 u16 submaps per GPU, "
                     "branch-and-bound hmax=6, window 2.5m/2.5m/0.5rad, thr 0.55/0.6; step = Detect on "
-                    "first-touch submaps (upload + pyramid build + batched B&B)" % N_MAPS,
+                    "first-touch submaps (upload + pyramid build + batched B&B + linear-solver refinement "
+                    "and covariance of every detected loop)" % N_MAPS,
         "queries_per_gpu": N_MAPS, "grid": "%dx%d u16 @0.05m" % (ROWS, COLS), "hmax": HMAX,
         "sharding": "queries/submaps sharded over %d rank(s), 8-byte NCCL argmax all-reduce" % n_gpus,
         "l2": "inputs larger than L2: 128 MiB of submaps + 768 MiB of pyramid levels touched per step",
@@ -75,7 +79,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -135,6 +139,7 @@ def run_cpu_detect(kind, batch, n_threads, n_queries, cold=True, repeats=1):
     subs = batch.submaps[:n_queries]
     grids = [orc.grid(s.grid, s.res, s.off_x, s.off_y) for s in subs]
     det = orc.loop_detector(HMAX, synth.CFG3["rng"], synth.CFG3["thr"], n_threads)
+    det.use_linear_solver(*REFINE)
     best = None
     for _ in range(repeats):
         if cold:
@@ -169,6 +174,7 @@ def main_reference(args):
     orc = pyoracle.load(kind)
     grids = [orc.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
     det = orc.loop_detector(HMAX, synth.CFG3["rng"], synth.CFG3["thr"], threads)
+    det.use_linear_solver(*REFINE)
 
     def step(nq):
         det.clear_cache()
@@ -191,7 +197,7 @@ def main_reference(args):
     total = float(np.sum(times))
     value = nq * args.steps / total
     sample = ("%d steps, each Detect on the first %d of the %d first-touch submaps of the per-GPU step "
-              "(pyramid build + B&B + cost/covariance), queries split over %d std::threads"
+              "(pyramid build + B&B + ScanMatcherLinearSolver refinement + covariance), queries split over %d std::threads"
               % (args.steps, nq, N_MAPS, threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -236,6 +242,8 @@ def main_cuda(args):
     # one search batch of 256 queries; first-touch submaps uploaded in 4 groups of 64 whose block
     # expansion + pyramid build overlap the PCIe transfer of the following groups
     hdet.configure(chunk_size=256 | (64 << 16), coarse_covariance=False, query_index_base=rank * N_MAPS)
+    # the reference's default final matcher on every detected loop, on the device (k_refine)
+    hdet.use_device_refiner(*REFINE)
     h = capi.Handle.from_pointer(hdet.handle(), local)
     ext_stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local))
 
@@ -283,7 +291,7 @@ def main_cuda(args):
             sharding.allreduce_best(best_word)
             return int(best_word.item()) if read_back else None
 
-    def e2e_step(sparse=True):
+    def e2e_step(sparse=True, hdet=hdet):
         """One LoopDetector::Detect of the C++ plugin on 256 first-touch submaps, from page-locked
         HOST buffers: upload (4 groups on the copy stream), block expansion, pyramid build, batched
         B&B, result read-back; then the 8-byte all-reduce of the best word and its read-back."""
@@ -326,6 +334,20 @@ def main_cuda(args):
         torch.cuda.synchronize()
         return max_over_ranks(time.perf_counter() - t0), n, w
 
+    # for comparison: the same Detect with the final matcher on the CPU (host/ ScanMatcherLinearSolver)
+    e2e_cpu_refine_ms = None
+    if world == 1:
+        hdet_cpu = hostapi.LoopDetector(ctx, HMAX, synth.CFG3["rng"], synth.CFG3["thr"])
+        hdet_cpu.configure(chunk_size=256 | (64 << 16), coarse_covariance=False, query_index_base=0)
+        hdet_cpu.use_linear_solver(*REFINE)
+        e2e_step(True, hdet_cpu)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step(True, hdet_cpu)
+        e2e_cpu_refine_ms = (time.perf_counter() - t0) / 3 * 1e3
+        hdet_cpu.close()
+        for _ in range(2):
+            e2e_step()
     e2e_dense_s, n_dense, word_dense = time_e2e(False)
     sampler.active = True
     e2e_s, n_found, word = time_e2e(True)
@@ -335,6 +357,7 @@ def main_cuda(args):
 
     # ---- value: inputs resident in HBM, CUDA events on the handle's stream ------------------
     h.set_option("accumulate_best_key", 0)
+    h.set_refiner(*REFINE)
     bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=h)
     det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
     scan = matchers.ScanData(angles, ranges)
@@ -347,6 +370,7 @@ def main_cuda(args):
     h.upload_scan(0, scan.angles, scan.ranges)
     arr = det.prepare(queries)
     results = (capi.CsmResult * N_MAPS)()
+    refined = (capi.CsmRefined * N_MAPS)()
     h.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
@@ -359,12 +383,12 @@ def main_cuda(args):
         allreduce_best()
         in_flight[0] += 1
         if in_flight[0] == 3:                                   # results of the step two back
-            h.loop_batch_finish(N_MAPS, results)
+            h.loop_batch_finish_refined(N_MAPS, results, refined)
             in_flight[0] -= 1
 
     def drain():
         while in_flight[0]:
-            h.loop_batch_finish(N_MAPS, results)
+            h.loop_batch_finish_refined(N_MAPS, results, refined)
             in_flight[0] -= 1
 
     for _ in range(3):
@@ -382,7 +406,7 @@ def main_cuda(args):
     drain()
     launches = h.launch_count() - launches0
     dev_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
-    assert sum(r.found for r in results) == n_found
+    assert sum(r.found for r in results) == n_found == sum(f.valid for f in refined)
 
     # ---- per-kernel CUDA-event durations (library option "timing": one event after every kernel,
     # on the stream the kernels are launched on) for the roofline of the dominant kernels ----------
@@ -469,14 +493,16 @@ def main_cuda(args):
         "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": total_queries / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "h2d_bytes_per_step": h2d_blocks + h2d_small,
-                "d2h_bytes_per_step": N_MAPS * C.sizeof(capi.CsmResult) + 16 + 8,
-                "api": "C++ LoopDetectorBranchBound::Detect (host/, libcsm_host.so) over the C ABI",
+                "d2h_bytes_per_step": N_MAPS * (C.sizeof(capi.CsmResult) + C.sizeof(capi.CsmRefined)) + 16 + 8,
+                "api": "C++ LoopDetectorBranchBound::Detect (host/, libcsm_host.so) over the C ABI, "
+                       "final matcher = device refiner (csm_set_refiner)",
                 "host_format": "block-sparse submaps (allocated 16x16 blocks + positions, the reference's "
                                "GridMap storage), %d of %d blocks allocated" % (n_blocks, N_MAPS * (ROWS >> 4) * (COLS >> 4))},
         "e2e_dense": {"value": total_queries / e2e_dense_s, "unit": UNIT,
                       "ms_per_step": 1e3 * e2e_dense_s / args.steps,
                       "h2d_bytes_per_step": N_MAPS * cells * 2 + h2d_small,
                       "host_format": "dense flattened submaps (csm_upload_grids)"},
+        "e2e_cpu_final_matcher_ms_per_step": e2e_cpu_refine_ms,
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_pyramid": roofline_pyramid, "phases": phases,
         "check": {"found_per_step": int(n_found), "best_key": int(key), "best_query": int(qidx)},
@@ -492,7 +518,7 @@ def main_cuda(args):
             v_one = run_cpu_detect(kind, batch, 1, 32, cold=True)
             line["cpu_baseline"] = {
                 "value": v_all, "unit": UNIT, "cores": threads, "kind": kind,
-                "sample": "full step (256 queries on 256 first-touch submaps), best of 2, %d threads; "
+                "sample": "full step (256 queries on 256 first-touch submaps, refinement included), best of 2, %d threads; "
                           "1 thread on the first 32 queries: %.1f queries/s" % (threads, v_one),
                 "one_core_value": v_one,
             }

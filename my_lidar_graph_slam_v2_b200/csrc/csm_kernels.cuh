@@ -1453,7 +1453,29 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
     if (evaluate) {
         const size_t row_off = (size_t)Q.proj_off + (size_t)it * Q.n;
         int ps = 0, pk = 0;
-        for (int i = lane; i < Q.n; i += 32) {
+        int i0 = lane;
+        if (F.mode != 2) {
+            /* four beams per lane in flight: index loads, then cell loads, then the stores (a
+             * dependent pair of memory round trips per group instead of per beam) */
+            const int ox = (F.mode == 1) ? F.mx[s.bx] : s.bx;
+            const int oy = (F.mode == 1) ? F.my[s.by] : s.by;
+            const proj_t* __restrict__ pp = proj_all + (size_t)Q.proj_off + (size_t)it * Q.pst_t;
+            for (; i0 + 96 < Q.n; i0 += 128) {
+                proj_t p[4];
+                unsigned int v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p[u] = pp[(size_t)(i0 + 32 * u) * Q.pst_i];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ld_cell_nb(m, Q.rows, Q.cols, p[u].y + oy, p[u].x + ox);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    s_prob[i0 + 32 * u] = (v[u] != 0u) ? value_to_probability(v[u]) : 0.0;
+                    ps += (int)v[u];
+                    pk += (v[u] != 0u);
+                }
+            }
+        }
+        for (int i = i0; i < Q.n; i += 32) {
             int row, col;
             if (F.mode == 2) {
                 const double2 rc = F.rcs[row_off + i];

@@ -31,7 +31,7 @@
 
 namespace csm {
 
-constexpr int kRefThreads = 128;
+constexpr int kRefThreads = 384;     /* one beam per thread for scans of up to 384 beams */
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kRefTerms = 10;      /* cost, H00 H01 H02 H11 H12 H22, r0 r1 r2 */
 
@@ -71,21 +71,94 @@ struct RefineArgs
     double covariance_scale;
 };
 
-/* GridMap::ProbabilityOr(row, col, 0.5), grid_map.cpp:424-436 */
-__device__ __forceinline__ double refine_sample(const DevQuery& Q, int row, int col)
+/* GridMap::ProbabilityOr(row, col, 0.5), grid_map.cpp:424-436, for the four cells around a hit
+ * point. Branch-free: the allocation byte and the cell of all four are loaded at once (an index
+ * outside the map reads cell 0 and is masked), so a pass costs one memory round trip per beam
+ * instead of eight dependent ones. */
+__device__ __forceinline__ void refine_sample4(const DevQuery& Q, const int (&row)[4], const int (&col)[4],
+                                               double (&p)[4])
 {
-    if ((unsigned)row >= (unsigned)Q.rows || (unsigned)col >= (unsigned)Q.cols)
-        return 0.5;
-    if (Q.alloc[(size_t)(row >> Q.alloc_log2bs) * Q.alloc_bcols + (col >> Q.alloc_log2bs)] == 0)
-        return 0.5;
-    const unsigned int v = __ldg(Q.lvl[0] + (size_t)row * Q.cols + col);
-    return v == 0u ? 0.0 : value_to_probability(v);
+    bool inside[4];
+    unsigned int a[4], v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        inside[j] = (unsigned)row[j] < (unsigned)Q.rows && (unsigned)col[j] < (unsigned)Q.cols;
+        const int r = inside[j] ? row[j] : 0, c = inside[j] ? col[j] : 0;
+        a[j] = __ldg(Q.alloc + (size_t)(r >> Q.alloc_log2bs) * Q.alloc_bcols + (c >> Q.alloc_log2bs));
+        v[j] = __ldg(Q.lvl[0] + (size_t)r * Q.cols + c);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        p[j] = (!inside[j] || a[j] == 0u) ? 0.5 : (v[j] == 0u ? 0.0 : value_to_probability(v[j]));
 }
 
 /* Column-pivoting Householder QR solve of a 3x3 system, a x = b (row-major a).
  * Same steps as Eigen's ColPivHouseholderQR::solve: pivot on the largest remaining
- * column norm, reflect, rank from pivots above eps * size * largest pivot. */
-__device__ void refine_solve3(const double a_in[9], const double b_in[3], double x[3])
+ * column norm, reflect, rank from pivots above eps * size * largest pivot.
+ * Fully unrolled with compile-time indices (column swaps as conditional moves), so
+ * that the matrix stays in registers: the solve sits on the serial path of every
+ * iteration. */
+template <int K>
+__device__ __forceinline__ void refine_qr_step(double (&a)[3][3], double (&b)[3], int (&perm)[3],
+                                               double& max_pivot)
+{
+    /* column with the largest remaining norm comes first */
+    double norm[3];
+#pragma unroll
+    for (int c = K; c < 3; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = K; r < 3; ++r) s += a[r][c] * a[r][c];
+        norm[c] = s;
+    }
+    int best = K;
+    double best_norm = norm[K];
+#pragma unroll
+    for (int c = K + 1; c < 3; ++c)
+        if (norm[c] > best_norm) { best_norm = norm[c]; best = c; }
+#pragma unroll
+    for (int c = K + 1; c < 3; ++c)
+        if (best == c) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { const double t = a[r][K]; a[r][K] = a[r][c]; a[r][c] = t; }
+            const int t = perm[K]; perm[K] = perm[c]; perm[c] = t;
+        }
+    /* Householder reflector H = I - tau v v^T that maps a[K..2][K] onto (beta, 0, 0) */
+    double tail = 0.0;
+#pragma unroll
+    for (int r = K + 1; r < 3; ++r) tail += a[r][K] * a[r][K];
+    const double c0 = a[K][K];
+    double beta = c0, tau = 0.0, v[3] = { 0.0, 0.0, 0.0 };
+    if (tail > 0.0) {
+        beta = sqrt(c0 * c0 + tail);
+        if (c0 >= 0.0) beta = -beta;
+#pragma unroll
+        for (int r = K + 1; r < 3; ++r) v[r] = a[r][K] / (c0 - beta);
+        v[K] = 1.0;
+        tau = (beta - c0) / beta;
+    }
+    a[K][K] = beta;
+#pragma unroll
+    for (int r = K + 1; r < 3; ++r) a[r][K] = 0.0;
+    if (tau != 0.0) {
+#pragma unroll
+        for (int c = K + 1; c < 3; ++c) {
+            double dot = 0.0;
+#pragma unroll
+            for (int r = K; r < 3; ++r) dot += v[r] * a[r][c];
+#pragma unroll
+            for (int r = K; r < 3; ++r) a[r][c] -= tau * v[r] * dot;
+        }
+        double dot = 0.0;
+#pragma unroll
+        for (int r = K; r < 3; ++r) dot += v[r] * b[r];
+#pragma unroll
+        for (int r = K; r < 3; ++r) b[r] -= tau * v[r] * dot;
+    }
+    max_pivot = fmax(max_pivot, fabs(beta));
+}
+
+__device__ __forceinline__ void refine_solve3(const double (&a_in)[9], const double (&b_in)[3], double (&x)[3])
 {
     double a[3][3], b[3] = { b_in[0], b_in[1], b_in[2] };
 #pragma unroll
@@ -95,55 +168,28 @@ __device__ void refine_solve3(const double a_in[9], const double b_in[3], double
             a[r][c] = a_in[r * 3 + c];
     int perm[3] = { 0, 1, 2 };
     double max_pivot = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int best = k;
-        double best_norm = -1.0;
-        for (int c = k; c < 3; ++c) {
-            double s = 0.0;
-            for (int r = k; r < 3; ++r) s += a[r][c] * a[r][c];
-            if (s > best_norm) { best_norm = s; best = c; }
-        }
-        if (best != k) {
-            for (int r = 0; r < 3; ++r) { const double t = a[r][k]; a[r][k] = a[r][best]; a[r][best] = t; }
-            const int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
-        }
-        double tail = 0.0;
-        for (int r = k + 1; r < 3; ++r) tail += a[r][k] * a[r][k];
-        const double c0 = a[k][k];
-        double beta = c0, tau = 0.0, v[3] = { 0.0, 0.0, 0.0 };
-        if (tail > 0.0) {
-            beta = sqrt(c0 * c0 + tail);
-            if (c0 >= 0.0) beta = -beta;
-            for (int r = k + 1; r < 3; ++r) v[r] = a[r][k] / (c0 - beta);
-            v[k] = 1.0;
-            tau = (beta - c0) / beta;
-        }
-        a[k][k] = beta;
-        for (int r = k + 1; r < 3; ++r) a[r][k] = 0.0;
-        if (tau != 0.0) {
-            for (int c = k + 1; c < 3; ++c) {
-                double dot = 0.0;
-                for (int r = k; r < 3; ++r) dot += v[r] * a[r][c];
-                for (int r = k; r < 3; ++r) a[r][c] -= tau * v[r] * dot;
-            }
-            double dot = 0.0;
-            for (int r = k; r < 3; ++r) dot += v[r] * b[r];
-            for (int r = k; r < 3; ++r) b[r] -= tau * v[r] * dot;
-        }
-        max_pivot = fmax(max_pivot, fabs(beta));
-    }
+    refine_qr_step<0>(a, b, perm, max_pivot);
+    refine_qr_step<1>(a, b, perm, max_pivot);
+    refine_qr_step<2>(a, b, perm, max_pivot);
+    /* numerical rank as Eigen decides it; pivots come out in non-increasing magnitude */
     const double threshold = 2.220446049250313e-16 * 3.0 * max_pivot;
     int rank = 0;
+#pragma unroll
     for (int k = 0; k < 3; ++k)
         if (fabs(a[k][k]) > threshold) ++rank;
     double y[3] = { 0.0, 0.0, 0.0 };
-    for (int k = rank - 1; k >= 0; --k) {
-        double s = b[k];
-        for (int c = k + 1; c < rank; ++c) s -= a[k][c] * y[c];
-        y[k] = s / a[k][k];
-    }
-    for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+#pragma unroll
+    for (int k = 2; k >= 0; --k)
+        if (k < rank) {
+            double s = b[k];
+#pragma unroll
+            for (int c = k + 1; c < 3; ++c)
+                if (c < rank) s -= a[k][c] * y[c];
+            y[k] = s / a[k][k];
+        }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        x[j] = perm[0] == j ? y[0] : (perm[1] == j ? y[1] : y[2]);
 }
 
 /* One pass over the scan at sensor pose (px, py, pt): partial sums of this thread.
@@ -171,8 +217,10 @@ __device__ __forceinline__ void refine_pass(const DevQuery& Q, double px, double
         const int xc1 = min(xc0 + 1, Q.cols - 1);
         const int yc1 = min(yc0 + 1, Q.rows - 1);
         const double dx = __dsub_rn(fx, x0), dy = __dsub_rn(fy, y0);
-        const double m00 = refine_sample(Q, yc0, xc0), m01 = refine_sample(Q, yc1, xc0);
-        const double m10 = refine_sample(Q, yc0, xc1), m11 = refine_sample(Q, yc1, xc1);
+        const int rws[4] = { yc0, yc1, yc0, yc1 }, cls[4] = { xc0, xc0, xc1, xc1 };
+        double pm[4];
+        refine_sample4(Q, rws, cls, pm);
+        const double m00 = pm[0], m01 = pm[1], m10 = pm[2], m11 = pm[3];
         const double smoothed = dy * (dx * m11 + (1.0 - dx) * m01) + (1.0 - dy) * (dx * m10 + (1.0 - dx) * m00);
         const double err = 1.0 - smoothed;
         acc[0] += err * err;
