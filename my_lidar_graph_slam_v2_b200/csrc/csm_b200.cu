@@ -129,6 +129,8 @@ struct csm_context
     DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
     DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups;
+    int bb_ctas_per_sm = 0;        /* resident CTAs per SM of the B&B sweep kernels (occupancy query, lazily) */
+    int bb_split_shift = 0;
     int bb_skip_top = 1;           /* 1: the B&B sweep starts one height below hmax (same results) */
     int window_mode = 0;           /* grid search, integer-shift path: 0 auto (TMA tiles when possible),
                                       1 plain global-memory kernel, 2 require the TMA kernel */
@@ -966,6 +968,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     W.overflow = V.overflow;
     W.capacity = h->frontier_capacity;
     W.top = top;
+    W.split_shift = h->bb_split_shift;
     if (dive) {
         if ((rc = ensure(h, h->d_rootkey, sizeof(long long) * (size_t)plan.root_off[nq]))) return rc;
         W.rootkey = static_cast<long long*>(h->d_rootkey.p);
@@ -980,7 +983,17 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     }
     {
         const unsigned int n_roots = plan.root_off[nq];
-        const int full = h->sm_count * 8;
+        /* one resident wave: the kernels walk their list with a grid-stride loop and choose the lanes
+         * per node from the grid size, so CTAs beyond what fits at once would only queue behind the
+         * first wave (a second round of load latency on short lists) */
+        if (h->bb_ctas_per_sm == 0) {
+            int a = 0, b = 0, c = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_bb_expand<0>, 256, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_bb_expand<3>, 256, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_bb_roots, 256, 0);
+            h->bb_ctas_per_sm = std::max(1, std::min(std::min(a > 0 ? a : 8, b > 0 ? b : 8), c > 0 ? c : 8));
+        }
+        const int full = h->sm_count * h->bb_ctas_per_sm;
         if (!unscored_roots) {
             const int root_blocks = (int)std::min<unsigned int>((n_roots + 7) / 8, (unsigned int)full);
             k_bb_roots<<<std::max(root_blocks, 1), 256, 0, h->stream>>>(dq, proj, W, n_roots);
@@ -1164,6 +1177,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     }
     if (std::strcmp(name, "bb_dive") == 0 && value >= 0 && value <= 2) { h->bb_dive = value; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
+    if (std::strcmp(name, "bb_split_shift") == 0) { h->bb_split_shift = std::max(-4, std::min(value, 4)); return CSM_OK; }
     if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
     if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }

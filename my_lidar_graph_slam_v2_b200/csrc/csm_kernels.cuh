@@ -765,6 +765,7 @@ struct BbWork
     long long*          rootkey;    /* per root candidate: its key if it passed, else -1 (feeds the dive) */
     unsigned int        capacity;
     int                 top;        /* height of the root candidates (the reference's node_height_max) */
+    int                 split_shift; /* lanes per node: largest split with count * split * 2 <= lanes << split_shift */
 };
 
 /* list(h) lives in list[(h & 1) ^ 1]; the root candidates in list[top & 1] */
@@ -803,7 +804,7 @@ k_bb_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__
 
 constexpr int kBbSplit = 4;                 /* lanes cooperating on one node */
 #ifndef CSM_BB_UNROLL
-#define CSM_BB_UNROLL 4
+#define CSM_BB_UNROLL 2
 #endif
 constexpr int kBbUnroll = CSM_BB_UNROLL;    /* beams (x 4 children) a lane keeps in flight */
 constexpr int kBbNodesPerWarp = 32 / kBbSplit;
@@ -848,7 +849,7 @@ k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
     const int lane = threadIdx.x & 31;
     const unsigned int total_lanes = gridDim.x * blockDim.x;
     int split = kBbSplit;
-    while (split < 32 && (unsigned long long)count * (unsigned)(split * 2) <= total_lanes) split *= 2;
+    while (split < 32 && (((unsigned long long)count * (unsigned)(split * 2)) << max(-W.split_shift, 0)) <= ((unsigned long long)total_lanes << max(W.split_shift, 0))) split *= 2;
     const int npw = 32 / split;
     const int slot = lane & (npw - 1);
     const int part = lane / npw;
@@ -950,8 +951,11 @@ __device__ __forceinline__ void ld_children(const uint16_t* __restrict__ m, int 
  * its ancestors pass), so they are tested on an upper bound of
  * their key that needs no known-cell count: key <= 998 sum + 64536 n. Leaves
  * (HC == 0) are scored exactly. */
+#ifndef CSM_BB_MINB
+#define CSM_BB_MINB 4
+#endif
 template <int HC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CSM_BB_MINB)
 k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
 {
     constexpr int h = HC + 1;
@@ -961,7 +965,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
     const unsigned int count = min(W.counts[h], W.capacity);
     const unsigned int total_lanes = gridDim.x * blockDim.x;
     int split = kBbSplit;
-    while (split < 32 && (unsigned long long)count * (unsigned)(split * 2) <= total_lanes) split *= 2;
+    while (split < 32 && (((unsigned long long)count * (unsigned)(split * 2)) << max(-W.split_shift, 0)) <= ((unsigned long long)total_lanes << max(W.split_shift, 0))) split *= 2;
     const int npw = 32 / split;              /* nodes per warp */
     const int slot = lane & (npw - 1);
     const int part = lane / npw;
@@ -985,14 +989,26 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
             const unsigned int step = ps * (unsigned int)split;
             const int mine = (n - part + split - 1) / split;     /* beams of this lane */
             int i = 0;
+            /* software pipeline: the projected indices of the next group are requested before the
+             * gathers of the current one are consumed, so a group costs one memory round trip, not
+             * two dependent ones (the sweep is bound by load latency: long-scoreboard stalls) */
+            proj_t pn[kBbUnroll];
+            if (kBbUnroll <= mine) {
+#pragma unroll
+                for (int u = 0; u < kBbUnroll; ++u) pn[u] = pp[(unsigned int)u * step];
+            }
             for (; i + kBbUnroll <= mine; i += kBbUnroll) {
                 proj_t p[kBbUnroll];
 #pragma unroll
-                for (int u = 0; u < kBbUnroll; ++u) p[u] = pp[(unsigned int)(i + u) * step];
+                for (int u = 0; u < kBbUnroll; ++u) p[u] = pn[u];
                 unsigned int v[kBbUnroll][4];
 #pragma unroll
                 for (int u = 0; u < kBbUnroll; ++u)
                     ld_children<HC>(m, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
+                if (i + 2 * kBbUnroll <= mine) {
+#pragma unroll
+                    for (int u = 0; u < kBbUnroll; ++u) pn[u] = pp[(unsigned int)(i + kBbUnroll + u) * step];
+                }
 #pragma unroll
                 for (int u = 0; u < kBbUnroll; ++u) {
                     s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
