@@ -374,10 +374,10 @@ __device__ __forceinline__ proj_t project_beam(const DevQuery& Q, const double2 
     const double gx = ux - fx, gy = uy - fy;
     if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
         flagged |= 1;
-    const double lim = (double)kProjSat;
+    /* floor() as a saturating double -> int conversion (round down), then the clamp on integers */
     proj_t p;
-    p.x = (short)(int)fmin(fmax(fx, -lim), lim);
-    p.y = (short)(int)fmin(fmax(fy, -lim), lim);
+    p.x = (short)max(min(__double2int_rd(ux), kProjSat), -kProjSat);
+    p.y = (short)max(min(__double2int_rd(uy), kProjSat), -kProjSat);
     return p;
 }
 
@@ -415,26 +415,35 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
     }
     __syncthreads();
     int flagged = 0;
-    const int total = nt * Q.n;
-    /* beam-major output (pst_t == 1): consecutive threads take consecutive angles of one beam
-     * and write one contiguous run; angle-major output: consecutive beams of one angle */
+    /* beam-major output (pst_t == 1): 8 consecutive threads take the angles of one beam and write
+     * one contiguous 32-byte run; angle-major output: consecutive threads take consecutive beams of
+     * one angle. Either way a thread walks its elements with additions only. */
     const bool angle_fastest = Q.pst_t == 1;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        int tl, i;
-        if (angle_fastest) { i = e / nt; tl = e - i * nt; }
-        else { tl = e / Q.n; i = e - tl * Q.n; }
-        double rc, rs;
-        const proj_t p = project_beam(Q, s_theta[tl], i, flagged, rc, rs);
-        if (Q.lx > 0) {
-            /* branch-and-bound: a node window that straddles row / column 0 makes the coarse bound
-             * inadmissible (a lookup at a negative index reads unknown) */
-            const int x0 = (int)p.x - Q.winx, y0 = (int)p.y - Q.winy;
-            if ((x0 < 0 && x0 + 2 * Q.lx > 0) || (y0 < 0 && y0 + 2 * Q.ly > 0))
-                flagged |= 4;
+    const int n = Q.n;
+    const int tl_first = angle_fastest ? (int)(threadIdx.x & (kProjAngles - 1)) : 0;
+    const int tl_step = angle_fastest ? kProjAngles : 1;
+    const int i_first = angle_fastest ? (int)(threadIdx.x / kProjAngles) : (int)threadIdx.x;
+    const int i_step = angle_fastest ? (int)(blockDim.x / kProjAngles) : (int)blockDim.x;
+    const bool bb = Q.lx > 0;
+    const int winx = Q.winx, winy = Q.winy, lx2 = 2 * Q.lx, ly2 = 2 * Q.ly;
+    proj_t* __restrict__ out = proj + (size_t)Q.proj_off;
+    for (int tl = tl_first; tl < nt; tl += tl_step) {
+        const double2 th = s_theta[tl];
+        proj_t* __restrict__ out_t = out + (size_t)(t0 + tl) * Q.pst_t;
+        for (int i = i_first; i < n; i += i_step) {
+            double rc, rs;
+            const proj_t p = project_beam(Q, th, i, flagged, rc, rs);
+            if (bb) {
+                /* branch-and-bound: a node window that straddles row / column 0 makes the coarse bound
+                 * inadmissible (a lookup at a negative index reads unknown) */
+                const int x0 = (int)p.x - winx, y0 = (int)p.y - winy;
+                if ((x0 < 0 && x0 + lx2 > 0) || (y0 < 0 && y0 + ly2 > 0))
+                    flagged |= 4;
+            }
+            out_t[(size_t)i * Q.pst_i] = p;
+            if (rcs != nullptr)
+                rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * n + i] = make_double2(rc, rs);
         }
-        proj[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.pst_t + (size_t)i * Q.pst_i] = p;
-        if (rcs != nullptr)
-            rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * Q.n + i] = make_double2(rc, rs);
     }
     /* bit 0: CSM_FLAG_FP_MARGIN, bit 2: CSM_FLAG_EDGE */
     const int any = (int)__reduce_or_sync(0xffffffffu, (unsigned)flagged);
