@@ -144,7 +144,8 @@ int  csm_synchronize(csm_handle h);
 int64_t csm_launch_count(csm_handle h);
 /* Tuning / test knobs.
  *  "pyramid_mode": 0 = automatic, 1 = level-by-level kernels, 2 = streaming
- *      single-pass kernel (when the maps fit its layout);
+ *      single-pass kernel (when the maps fit its layout), 3 = the streaming
+ *      kernel variant that keeps its row rings in shared memory;
  *  "bb_dive": every branch-and-bound query first descends greedily (beam of 8)
  *      to a leaf that seeds its incumbent: 0 = never (plain level sweep), 1 =
  *      always, 2 (default) = only for calls of at most 4 queries. Results are

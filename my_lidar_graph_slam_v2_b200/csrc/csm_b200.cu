@@ -155,7 +155,7 @@ struct csm_context
     /* last pyramid job table on the device (skips the re-upload when unchanged) */
     std::vector<PyrJob> jobs_on_device;
     /* options (csm_set_option) */
-    int pyramid_mode = 0;          /* 0 auto, 1 level-by-level, 2 streaming */
+    int pyramid_mode = 0;          /* 0 auto, 1 level-by-level, 2 streaming, 3 streaming with shared-memory rings */
     int bb_dive = 2;               /* a beam dive per query seeds the incumbents before the level sweep:
                                       0 never, 1 always, 2 only for calls of at most 4 queries (there the
                                       latency of the dive is small against the nodes it saves) */
@@ -614,10 +614,43 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
     /* Batches of maps that fit its layout take the streaming builder (one pass,
      * level 0 read once, every level written once). */
     bool stream_ok = hmax >= 1 && hmax <= 6 && h->pyramid_mode != 1 &&
-                     (h->pyramid_mode == 2 || jobs.size() >= 8);
+                     (h->pyramid_mode >= 2 || jobs.size() >= 8);
     for (const PyrJob& j : jobs)
         stream_ok = stream_ok && j.cols <= 512 && (j.cols % 8) == 0 && (j.rows % kPsRows) == 0;
     if (stream_ok) {
+        phase_mark(h, "start");
+        /* two CTAs fit an SM: split every map into row segments until the grid fills them */
+        int min_rows = jobs[0].rows;
+        bool rows32 = true;
+        for (const PyrJob& j : jobs) {
+            min_rows = std::min(min_rows, j.rows);
+            rows32 = rows32 && (j.rows % (kPsRows * kPs2Group)) == 0;
+        }
+        int segs = (int)std::min<size_t>(4, (size_t)(2 * h->sm_count) / jobs.size());
+        segs = std::max(1, std::min(segs, min_rows / 128));         /* segments of at least 128 rows */
+        const unsigned int grid = (unsigned)(jobs.size() * segs);
+        const PyrJob* dj = static_cast<const PyrJob*>(h->d_pyrjobs.p);
+        if (rows32 && h->pyramid_mode != 3) {
+            /* rings in registers (main loop unrolled over 32 rows) */
+            const size_t smem2 = sizeof(unsigned int) * ((size_t)kPsStages * kPsRows * kPsInStride + 2 * kPsRows * 256);
+            bool sq512 = true;          /* the common submap size gets immediates for every stride */
+            for (const PyrJob& j : jobs) sq512 = sq512 && j.rows == 512 && j.cols == 512;
+#define CSM_PS2_LAUNCH(HM)                                                                             \
+            if (sq512) k_pyramid_stream2<HM, 512><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);   \
+            else k_pyramid_stream2<HM, 0><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);
+            switch (hmax) {
+            case 1: CSM_PS2_LAUNCH(1) break;
+            case 2: CSM_PS2_LAUNCH(2) break;
+            case 3: CSM_PS2_LAUNCH(3) break;
+            case 4: CSM_PS2_LAUNCH(4) break;
+            case 5: CSM_PS2_LAUNCH(5) break;
+            default: CSM_PS2_LAUNCH(6) break;
+            }
+#undef CSM_PS2_LAUNCH
+            CSM_LAUNCH_CHECK();
+            phase_mark(h, "k_pyramid_stream");
+            return CSM_OK;
+        }
         const size_t smem = sizeof(unsigned int) *
             ((size_t)kPsStages * kPsRows * kPsInStride + 2 * kPsRows * 256 + 63 * 256);
         static bool attr_set = false;
@@ -625,14 +658,7 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             CSM_CUDA(cudaFuncSetAttribute(k_pyramid_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        phase_mark(h, "start");
-        /* two CTAs fit an SM: split every map into row segments until the grid fills them */
-        int min_rows = jobs[0].rows;
-        for (const PyrJob& j : jobs) min_rows = std::min(min_rows, j.rows);
-        int segs = (int)std::min<size_t>(4, (size_t)(2 * h->sm_count) / jobs.size());
-        segs = std::max(1, std::min(segs, min_rows / 128));         /* segments of at least 128 rows */
-        k_pyramid_stream<<<(unsigned)(jobs.size() * segs), kPsThreads, smem, h->stream>>>(
-            static_cast<const PyrJob*>(h->d_pyrjobs.p), hmax, segs);
+        k_pyramid_stream<<<grid, kPsThreads, smem, h->stream>>>(dj, hmax, segs);
         CSM_LAUNCH_CHECK();
         phase_mark(h, "k_pyramid_stream");
         return CSM_OK;
@@ -1171,7 +1197,7 @@ int64_t csm_launch_count(csm_handle h) { return h ? h->launches : 0; }
 int csm_set_option(csm_handle h, const char* name, int value)
 {
     if (!h || !name) return CSM_E_INVALID;
-    if (std::strcmp(name, "pyramid_mode") == 0 && value >= 0 && value <= 2) {
+    if (std::strcmp(name, "pyramid_mode") == 0 && value >= 0 && value <= 3) {
         h->pyramid_mode = value;
         return CSM_OK;
     }

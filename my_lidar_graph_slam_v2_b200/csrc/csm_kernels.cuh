@@ -326,6 +326,165 @@ k_pyramid_stream(const PyrJob* __restrict__ jobs, int hmax, int segs)
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
+/* ---- streaming pyramid builder, register rings -----------------------------------
+ * Same walk as k_pyramid_stream, but the vertical rings (the last `half` rows of T_h of
+ * every level, 63 words per thread for six levels) live in REGISTERS instead of shared
+ * memory: a ring slot is (row mod half), so the main loop is unrolled over 8 consecutive
+ * 4-row blocks (32 rows = the longest ring) and every slot index becomes a compile-time
+ * constant. That removes two of the four shared-memory accesses per word and level (the
+ * kernel is bound by instruction issue and LSU wavefronts, not by HBM) and all ring
+ * address arithmetic. Requires rows % 32 == 0 on top of k_pyramid_stream's conditions;
+ * segment boundaries are multiples of 8 blocks. */
+constexpr int kPs2Group = 8;          /* blocks per unrolled group */
+
+/* The rows of out_H at the far edge of the map (rows >= R - w all repeat row R - w): only the
+ * topmost blocks of a map get here, so this stays out of line and the unrolled main loop small. */
+template <int H>
+__device__ __noinline__ void ps2_store_edge(uint4 pv, unsigned int* __restrict__ dst, int cw, int r0, int R)
+{
+    constexpr int w = 1 << H;
+    const int rsrc = max(R - w, 0);
+    const unsigned int p[kPsRows] = { pv.x, pv.y, pv.z, pv.w };
+#pragma unroll
+    for (int rr = 0; rr < kPsRows; ++rr) {
+        const int r = r0 + rr;
+        if (r < rsrc) dst[rr * cw] = p[rr];
+        else if (r == rsrc)
+            for (int r2 = r; r2 < R; ++r2) dst[(r2 - r0) * cw] = p[rr];
+    }
+}
+
+/* One level of one 4-row block; K = position of the block inside its group of 8 (compile time:
+ * ring slots are registers). PS = word stride of the rows of `prev`. a[] holds this thread's
+ * words of out_{H-1} and leaves as out_H. dst0 = word j of row r0 of level 1. */
+template <int H, int K, int PS, int FIX>
+__device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsigned int* __restrict__ prev,
+                                          unsigned int* __restrict__ cur, unsigned int (&ring)[63],
+                                          unsigned int* __restrict__ dst0, size_t cells_w_, int cw_,
+                                          int R_, int C_, int r0, int j, bool wr)
+{
+    /* FIX > 0: square maps of FIX x FIX cells, every stride and clamp is an immediate */
+    const int R = FIX ? FIX : R_, C = FIX ? FIX : C_, cw = FIX ? FIX / 2 : cw_;
+    const size_t cells_w = FIX ? (size_t)FIX * FIX / 2 : cells_w_;
+    constexpr int half = 1 << (H - 1);
+    constexpr int w = 2 * half;
+    constexpr int ring_off = half - 1;
+    /* horizontal tap: word j + half/2 of out_{H-1}, which is clamped at column C - half */
+    const int csw_prev = (H >= 2) ? (max(C - half, 0) >> 1) : 0x3fffffff;
+    const bool edge = (H >= 2) && (j + (half >> 1) >= csw_prev);
+    const unsigned int* __restrict__ tap = prev + ((H == 1) ? j + 1 : (edge ? csw_prev : j + (half >> 1)));
+#pragma unroll
+    for (int rr = kPsRows - 1; rr >= 0; --rr) {
+        unsigned int t = tap[rr * PS];
+        if (H == 1) t = __byte_perm(a[rr], t, 0x5432);
+        else if (edge) t = splat_lo(t);
+        t = __vmaxu2(a[rr], t);
+        const int slot = ring_off + ((K * kPsRows + rr) & (half - 1));     /* constant after unrolling */
+        const unsigned int old = ring[slot];
+        ring[slot] = t;
+        a[rr] = __vmaxu2(t, old);
+        cur[rr * 256 + j] = a[rr];
+    }
+    __syncthreads();
+    /* out_H = P_H with the far edge clamped along the row; only the clamped threads re-read */
+    const int csw = max(C - w, 0) >> 1;
+    if (j >= csw) {
+#pragma unroll
+        for (int rr = 0; rr < kPsRows; ++rr) a[rr] = splat_lo(cur[rr * 256 + csw]);
+    }
+    if (wr) {
+        const int rsrc = max(R - w, 0);
+        unsigned int* __restrict__ dst = dst0 + (size_t)(H - 1) * cells_w;
+        if (r0 + kPsRows - 1 < rsrc) {
+#pragma unroll
+            for (int rr = 0; rr < kPsRows; ++rr) dst[rr * cw] = a[rr];
+        } else if (r0 <= rsrc) {
+            ps2_store_edge<H>(make_uint4(a[0], a[1], a[2], a[3]), dst, cw, r0, R);
+        }
+    }
+}
+
+template <int HMAX, int K, int FIX>
+__device__ __forceinline__ void ps2_block(unsigned int (&ring)[63], const unsigned int* __restrict__ in_ring,
+                                          unsigned int* __restrict__ buf0, unsigned int* __restrict__ buf1,
+                                          const PyrJob& job, int b, int j, bool wr, size_t cells_w)
+{
+    static_assert(kPsRows == 4, "ps2_store_edge passes the four rows of a block as one uint4");
+    const unsigned int* in = in_ring + (b % kPsStages) * kPsRows * kPsInStride;
+    const int R = FIX ? FIX : job.rows, C = FIX ? FIX : job.cols, cw = C >> 1, r0 = b * kPsRows;
+    unsigned int* dst0 = reinterpret_cast<unsigned int*>(job.levels) + (size_t)r0 * cw + j;
+    unsigned int a[kPsRows];
+#pragma unroll
+    for (int rr = 0; rr < kPsRows; ++rr) a[rr] = in[rr * kPsInStride + j];
+    ps2_level<1, K, kPsInStride, FIX>(a, in, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 2) ps2_level<2, K, 256, FIX>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 3) ps2_level<3, K, 256, FIX>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 4) ps2_level<4, K, 256, FIX>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 5) ps2_level<5, K, 256, FIX>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 6) ps2_level<6, K, 256, FIX>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+}
+
+template <int HMAX, int FIX>
+__global__ void __launch_bounds__(kPsThreads, 2)
+k_pyramid_stream2(const PyrJob* __restrict__ jobs, int segs)
+{
+    extern __shared__ __align__(16) unsigned int ps_smem[];
+    unsigned int* in_ring = ps_smem;                                         /* [stages][4][272] */
+    unsigned int* rowbuf = in_ring + kPsStages * kPsRows * kPsInStride;      /* [2][4][256] */
+
+    const PyrJob job = jobs[blockIdx.x / segs];
+    const int seg = blockIdx.x % segs;
+    const int R = FIX ? FIX : job.rows, C = FIX ? FIX : job.cols;
+    const size_t cells = (size_t)R * C;
+    const int j = threadIdx.x;
+    const bool in_map = 2 * j < C;
+
+    unsigned int ring[63];
+#pragma unroll
+    for (int i = 0; i < 63; ++i) ring[i] = 0u;
+    for (int i = j; i < kPsStages * kPsRows * kPsInStride; i += kPsThreads) in_ring[i] = 0u;
+    __syncthreads();
+
+    const int nblocks = R / kPsRows;                              /* a multiple of kPs2Group */
+    const int ngroups = nblocks / kPs2Group;
+    const int gps = (ngroups + segs - 1) / segs;                  /* groups per segment */
+    const int b_lo = seg * gps * kPs2Group;
+    const int b_top = min(nblocks, b_lo + gps * kPs2Group) - 1;
+    const int b_start = min(nblocks - 1, b_top + 16);             /* 64 warm-up rows >= 2^hmax - 1 */
+    if (b_lo > b_top)
+        return;
+    const int ld_row = j >> 6, ld_chunk = j & 63;
+    auto prefetch = [&](int b) {
+        if (b >= b_lo) {
+            const int stage = b % kPsStages;
+            unsigned int* dst = in_ring + (stage * kPsRows + ld_row) * kPsInStride + ld_chunk * 4;
+            const bool ok = ld_chunk * 8 < C;
+            const uint16_t* src = job.base + (size_t)(b * kPsRows + ld_row) * C + (ok ? ld_chunk * 8 : 0);
+            cp_async_16(dst, src, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    for (int k = 0; k < kPsStages - 1; ++k)
+        prefetch(b_start - k);
+
+    unsigned int* buf0 = rowbuf;
+    unsigned int* buf1 = rowbuf + kPsRows * 256;
+#define CSM_PS2_STEP(K)                                                                        \
+    {                                                                                          \
+        const int b = bg + (K);                                                                \
+        asm volatile("cp.async.wait_group %0;\n" :: "n"(kPsStages - 2));                       \
+        __syncthreads();                                                                       \
+        prefetch(b - (kPsStages - 1));                                                         \
+        ps2_block<HMAX, (K), FIX>(ring, in_ring, buf0, buf1, job, b, j, in_map && b <= b_top, cells >> 1); \
+    }
+    for (int bg = b_start + 1 - kPs2Group; bg >= b_lo; bg -= kPs2Group) {
+        CSM_PS2_STEP(7) CSM_PS2_STEP(6) CSM_PS2_STEP(5) CSM_PS2_STEP(4)
+        CSM_PS2_STEP(3) CSM_PS2_STEP(2) CSM_PS2_STEP(1) CSM_PS2_STEP(0)
+    }
+#undef CSM_PS2_STEP
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
 /* Generic sliding win x win maximum with the clamped far edge. */
 __global__ void __launch_bounds__(256)
 k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,

@@ -62,9 +62,12 @@ def test_pyramid_vs_checker(handle, checker, shape):
 @pytest.mark.parametrize("shape,hmax", [((64, 64), 6), ((512, 512), 6), ((32, 128), 4), ((128, 16), 6),
                                         ((16, 512), 3), ((192, 336), 5), ((512, 512), 1), ((48, 48), 2),
                                         ((256, 512), 6), ((384, 128), 6), ((144, 64), 6), ((272, 256), 5)])
-def test_pyramid_streaming_kernel(handle, checker, shape, hmax):
-    """The single-pass streaming builder (used for big batches) against the checker."""
-    handle.set_option("pyramid_mode", 2)
+@pytest.mark.parametrize("mode", [2, 3])
+def test_pyramid_streaming_kernel(handle, checker, shape, hmax, mode):
+    """The single-pass streaming builders (used for big batches) against the checker: mode 2 takes
+    the register-ring kernel when rows % 32 == 0 (else the shared-memory-ring one), mode 3 always
+    the shared-memory-ring kernel."""
+    handle.set_option("pyramid_mode", mode)
     try:
         ids, grids = [], []
         for k in range(3):
