@@ -42,6 +42,9 @@ METRIC = "loop_detection_queries_per_sec"
 UNIT = "queries/s"
 
 
+emit = print
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -208,7 +211,7 @@ def main_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -524,7 +527,7 @@ def main_cuda(args):
             }
             if not args.no_single:
                 line["single_scan"] = single_scan_numbers(h, lib, kind)
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -593,7 +596,10 @@ def single_scan_numbers(h, lib, kind):
     t0 = time.perf_counter()
     r = orc.match_grid(og4, c4.angles, c4.ranges, c4.init_pose, rng_small, synth.CFG4["step"])
     el = time.perf_counter() - t0
-    full = 161 * 161 * 601
+    from my_lidar_graph_slam_v2_b200 import matchers as _m
+    full = 1
+    for r_, s_ in zip(synth.CFG4["rng"], synth.CFG4["step"]):
+        full *= len(_m.grid_search_offsets(r_ / 2.0, s_))      # the reference's accumulating loops: 161 x 161 x 600
     cpu = 1.0 / (el * full / max(r.n_processed, 1))
     # the scoring kernel alone (CUDA events of the library) against the shared-memory roofline:
     # one LSU wavefront serves 32 candidate-beam reads, one wavefront per cycle per SM
@@ -629,6 +635,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-single", action="store_true", help="skip the single-scan extras")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL's
+    # version banner, for one) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global emit
+    emit = lambda line: (out.write(line + "\n"), out.flush())
     if args.impl == "reference":
         return main_reference(args)
     return main_cuda(args)

@@ -651,3 +651,112 @@ def test_cpp_loop_detector_with_device_refiner(checker):
                 assert np.allclose(list(r.cov), list(o.cov), rtol=1e-5, atol=0.0), (sparse, i)
     det.close()
     ctx.close()
+
+
+# --------------------------------------------------------------------------
+# BASELINE.json's full sizes
+# --------------------------------------------------------------------------
+def test_full_size_cfg3_batch(handle, checker):
+    """configs[2] at full size: 1 scan x 256 first-touch 512x512 submaps, hmax 6, reference thresholds.
+    (a) every query against the reference's LoopDetectorBranchBound::Detect (the CPU finishes the 256
+    queries in seconds on all host threads); (b) properties that must hold whatever the execution
+    shape: identical results with the incumbent dive on, with the sweep starting at the root level,
+    split into 4 chunks, and sharded in two halves whose best words reduce to the unsharded one;
+    (c) refinement on or off never changes the coarse results."""
+    import os
+    import torch
+    batch = synth.make_loop_batch(31000, n_maps=256, true_fraction=0.25, map_id_base=20000)
+    bb = matchers.ScanMatcherBranchBound("loop-bb", 6, *synth.CFG3["rng"], handle=handle)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    queries = _loop_queries(batch)
+    fields = ("found", "best_x", "best_y", "best_t", "sum_value", "n_known", "flags", "normalized_score")
+
+    def best_word():
+        word = torch.empty(1, dtype=torch.int64, device="cuda:0")
+        C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(
+            C.c_void_p(word.data_ptr()), C.c_void_p(handle.best_key_device_ptr()), 8, 3)
+        return int(word.item())
+
+    def run(**opts):
+        for k, v in opts.items():
+            handle.set_option(k, v)
+        try:
+            _, res = det.detect(queries, query_index_base=0)
+        finally:
+            for k in opts:
+                handle.set_option(k, {"bb_dive": 2, "bb_skip_top": 1}[k])
+        return [[getattr(r, f) for f in fields] for r in res], best_word()
+
+    base, word = run()
+    assert 40 <= sum(r[0] for r in base) <= 120
+    # (a) the reference, all queries
+    grids = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], max(1, len(os.sched_getaffinity(0))))
+    ores, _ = odet.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    _, res = det.detect(queries, query_index_base=0)
+    for i, (r, o) in enumerate(zip(res, ores)):
+        assert_match(r, dict(o.asdict(), compare_unfound=False), "cfg3 query %d" % i)
+    # (b) execution shape
+    assert run(bb_dive=1) == (base, word)
+    assert run(bb_skip_top=0) == (base, word)
+    arr = det.prepare(queries)
+    chunked = []
+    handle.set_option("accumulate_best_key", 1)
+    handle.set_option("reset_best_key", 1)
+    for c in range(4):
+        sub = (capi.CsmLoopQuery * 64).from_address(C.addressof(arr) + c * 64 * C.sizeof(capi.CsmLoopQuery))
+        chunked += [[getattr(r, f) for f in fields] for r in handle.loop_batch(sub, 64, 6, c * 64)]
+    handle.set_option("accumulate_best_key", 0)
+    assert chunked == base and best_word() == word
+    halves, words = [], []
+    for s in range(2):
+        sub = (capi.CsmLoopQuery * 128).from_address(C.addressof(arr) + s * 128 * C.sizeof(capi.CsmLoopQuery))
+        halves += [[getattr(r, f) for f in fields] for r in handle.loop_batch(sub, 128, 6, s * 128)]
+        words.append(best_word())
+    assert halves == base and max(words) == word
+    # (c) refinement leaves the coarse stage alone and refines exactly the found poses
+    handle.set_refiner(10, 1e-4, 1e-4, 1e4)
+    handle.loop_batch_enqueue(arr, 256, 6, 0)
+    res_r, refined = handle.loop_batch_finish_refined(256)
+    handle.set_refiner(enabled=False)
+    assert [[getattr(r, f) for f in fields] for r in res_r] == base
+    assert [f.valid for f in refined] == [r[0] for r in base]
+    for mid in batch.map_ids:
+        handle.release_grid(int(mid))
+
+
+def test_full_size_cfg4_grid_search(handle, checker):
+    """configs[3] at full size: 1080 beams, 1280x1280 map at 0.025 m, window 161 x 161 x ~601 = 15.6 M
+    candidates (514 s on the reference CPU, so checked through properties): the TMA shared-memory
+    kernel and the plain global-memory kernel agree on the winner; the reference, asked for the score
+    of exactly that pose, returns the same sum, known count and double score; no candidate of a
+    coarser sub-lattice (every 8th x / y, every 4th angle: the reference finishes it in seconds) beats
+    it; the winner lies within two cells of the true pose."""
+    case = synth.case_for(synth.CFG4, 44001)
+    s = case.submap
+    gm, scan = grid_of(case), _scan(case)
+    rng, step = synth.CFG4["rng"], synth.CFG4["step"]
+    mt = matchers.ScanMatcherGridSearch("gs", *rng, *step, handle=handle)
+    handle.set_option("window_mode", 2)
+    a = mt.optimize_pose(gm, scan, tuple(case.init_pose)).result
+    handle.set_option("window_mode", 1)
+    b = mt.optimize_pose(gm, scan, tuple(case.init_pose)).result
+    handle.set_option("window_mode", 0)
+    f = ("found", "best_x", "best_y", "best_t", "sum_value", "n_known", "normalized_score")
+    assert [getattr(a, k) for k in f] == [getattr(b, k) for k in f] and a.found == 1
+    dx = matchers.grid_search_offsets(rng[0] / 2, step[0])
+    dy = matchers.grid_search_offsets(rng[1] / 2, step[1])
+    dt = matchers.grid_search_offsets(rng[2] / 2, step[2])
+    # the reference's accumulating loops `for (d = -r; d <= r; d += s)` give 161 x 161 x 600 here
+    assert (len(dx), len(dy)) == (161, 161) and len(dt) in (600, 601)
+    assert a.n_processed == len(dx) * len(dy) * len(dt) and a.flags == 0
+    sensor = matchers.compound(tuple(case.init_pose), scan.relative_sensor_pose)
+    win = (sensor[0] + dx[a.best_x], sensor[1] + dy[a.best_y], sensor[2] + dt[a.best_t])
+    g = checker.grid(s.grid, s.res, s.off_x, s.off_y)
+    o = checker.match_grid(g, case.angles, case.ranges, win, (0.0, 0.0, 0.0), step)
+    assert (o.found, o.sum_value, o.n_known, o.score) == (1, a.sum_value, a.n_known, a.normalized_score)
+    coarse = checker.match_grid(g, case.angles, case.ranges, case.init_pose, rng,
+                                (8 * step[0], 8 * step[1], 4 * step[2]))
+    assert coarse.found == 1 and coarse.score <= a.normalized_score
+    assert abs(win[0] - case.true_pose[0]) <= 2 * s.res and abs(win[1] - case.true_pose[1]) <= 2 * s.res
