@@ -163,6 +163,7 @@ struct csm_context
     bool refine_on = false;        /* loop batches refine the poses they find (csm_set_refiner) */
     csm_refine_params refine {};
     DevBuf d_refine_in;            /* csm_refine_batch: queries and start poses */
+    DevBuf d_allocjobs;            /* ensure_alloc: job table */
     /* last (thresholds, beams) -> integer cut-offs (fill_common) */
     int memo_n = -1, memo_nk_cut = 0;
     double memo_score_thr = -1.0, memo_known_thr = -1.0;
@@ -462,28 +463,53 @@ int bind_batch_arena(csm_handle h, int n, const int64_t* map_ids, int rows, int 
 
 /* Block-allocation bytes for the refinement stage. Block-sparse uploads bring them (set by
  * k_scatter_blocks); for dense uploads they are derived here, once per upload: a 16 x 16 block
- * counts as allocated iff it holds a non-zero cell. The maps' uploads must have been waited for. */
+ * counts as allocated iff it holds a non-zero cell. All maps that need it go in ONE launch (their
+ * bytes share one allocation). The maps' uploads must have been waited for. */
 int ensure_alloc(csm_handle h, const std::vector<MapSlot*>& slots)
 {
+    const int k = 4;
+    std::vector<MapSlot*> todo;
+    size_t total = 0;
+    int max_blocks = 0;
     for (MapSlot* m : slots) {
-        if (m->alloc_valid)
+        if (m->alloc_valid || std::find(todo.begin(), todo.end(), m) != todo.end())
             continue;
-        const int k = 4;
-        const int br = (m->rows + 15) >> k, bc = (m->cols + 15) >> k;
-        const int bytes = br * bc;
-        if (m->alloc == nullptr || m->alloc_bytes < bytes) {
-            if (m->alloc && !m->alloc_block) CSM_CUDA(cudaFreeAsync(m->alloc, h->stream));
-            m->alloc_block.reset();
-            m->alloc = nullptr;
-            CSM_CUDA(cudaMallocAsync((void**)&m->alloc, (size_t)bytes, h->stream));
-            m->alloc_bytes = bytes;
-        }
-        m->alloc_log2bs = k;
-        const int blocks = std::max(1, std::min((bytes + 7) / 8, h->sm_count * 4));
-        k_block_alloc<<<blocks, 256, 0, h->stream>>>(m->base, m->rows, m->cols, k, br, bc, m->alloc);
-        CSM_LAUNCH_CHECK();
-        m->alloc_valid = true;
+        todo.push_back(m);
+        const int bytes = ((m->rows + 15) >> k) * ((m->cols + 15) >> k);
+        total += ((size_t)bytes + 15) & ~(size_t)15;
+        max_blocks = std::max(max_blocks, bytes);
     }
+    if (todo.empty())
+        return CSM_OK;
+    auto block = std::make_shared<ArenaBlock>();
+    block->stream = h->stream;
+    CSM_CUDA(cudaMallocAsync(&block->p, total, h->stream));
+    std::vector<AllocJob> jobs(todo.size());
+    size_t off = 0;
+    for (size_t i = 0; i < todo.size(); ++i) {
+        MapSlot* m = todo[i];
+        const int bytes = ((m->rows + 15) >> k) * ((m->cols + 15) >> k);
+        if (m->alloc && !m->alloc_block) CSM_CUDA(cudaFreeAsync(m->alloc, h->stream));
+        m->alloc_block = block;
+        m->alloc = static_cast<unsigned char*>(block->p) + off;
+        m->alloc_bytes = bytes;
+        m->alloc_log2bs = k;
+        jobs[i] = AllocJob { m->base, m->alloc, m->rows, m->cols };
+        off += ((size_t)bytes + 15) & ~(size_t)15;
+    }
+    const size_t jb = sizeof(AllocJob) * jobs.size();
+    int rc = ensure(h, h->d_allocjobs, jb);
+    if (rc) return rc;
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, jb, &hp))) return rc;
+    std::memcpy(hp, jobs.data(), jb);
+    if ((rc = pull_to_device(h, h->d_allocjobs.p, hp, jb))) return rc;
+    if ((rc = upload_committed(h))) return rc;
+    dim3 grid((unsigned)std::max(1, std::min((max_blocks + 7) / 8, 64)), (unsigned)jobs.size());
+    k_block_alloc<<<grid, 256, 0, h->stream>>>(static_cast<const AllocJob*>(h->d_allocjobs.p), k);
+    CSM_LAUNCH_CHECK();
+    for (MapSlot* m : todo)
+        m->alloc_valid = true;
     return CSM_OK;
 }
 
@@ -1153,7 +1179,7 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
-                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in };
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)

@@ -37,26 +37,36 @@ constexpr int kRefTerms = 10;      /* cost, H00 H01 H02 H11 H12 H22, r0 r1 r2 */
 
 /* One byte per 2^k x 2^k block of a dense map: 1 iff the block holds a non-zero
  * cell. This is how a dense upload (no block list) defines "allocated"; the host
- * mirror uses the same rule (host/src/cost_square_error.cpp). One warp per block. */
-__global__ void __launch_bounds__(256)
-k_block_alloc(const uint16_t* __restrict__ m, int rows, int cols, int k, int block_rows, int block_cols,
-              unsigned char* __restrict__ alloc)
+ * mirror uses the same rule (host/src/cost_square_error.cpp). One warp per block,
+ * blockIdx.y = map of the batch. */
+struct AllocJob
 {
+    const uint16_t* base;
+    unsigned char*  alloc;
+    int rows, cols;
+};
+
+__global__ void __launch_bounds__(256)
+k_block_alloc(const AllocJob* __restrict__ jobs, int k)
+{
+    const AllocJob job = jobs[blockIdx.y];
+    const int rows = job.rows, cols = job.cols;
+    const int bs = 1 << k;
+    const int block_rows = (rows + bs - 1) >> k, block_cols = (cols + bs - 1) >> k;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int bs = 1 << k;
     for (int b = warp; b < block_rows * block_cols; b += nwarps) {
         const int brow = b / block_cols, bcol = b - brow * block_cols;
         bool any = false;
         for (int e = lane; e < bs * bs; e += 32) {
             const int r = (brow << k) + (e >> k), c = (bcol << k) + (e & (bs - 1));
             if (r < rows && c < cols)
-                any = any || m[(size_t)r * cols + c] != 0;
+                any = any || job.base[(size_t)r * cols + c] != 0;
         }
         any = __any_sync(0xffffffffu, any);
         if (lane == 0)
-            alloc[b] = any ? 1 : 0;
+            job.alloc[b] = any ? 1 : 0;
     }
 }
 

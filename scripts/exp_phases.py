@@ -17,6 +17,8 @@ queries = [matchers.LoopDetectionQuery(scan, 0, tuple(batch.scan_poses[i]),
 arr = det.prepare(queries)
 ids = np.arange(NQ, dtype=np.int64)
 h.set_option("timing", 1)
+if len(sys.argv) > 2 and sys.argv[2] == "refine":
+    h.set_refiner(10, 1e-4, 1e-4, 1e4)       # the bench's step: final matcher on every found pose
 import os
 for kv in os.environ.get("CSM_OPTS", "").split(","):
     if "=" in kv:
