@@ -341,8 +341,8 @@ def main_cuda(args):
     e2e_cpu_refine_ms = None
     if world == 1:
         hdet_cpu = hostapi.LoopDetector(ctx, HMAX, synth.CFG3["rng"], synth.CFG3["thr"])
-        hdet_cpu.configure(chunk_size=256 | (64 << 16), coarse_covariance=False, query_index_base=0)
         hdet_cpu.use_linear_solver(*REFINE)
+        hdet_cpu.configure(chunk_size=256 | (64 << 16), coarse_covariance=False, query_index_base=0)
         e2e_step(True, hdet_cpu)
         t0 = time.perf_counter()
         for _ in range(3):
