@@ -473,7 +473,7 @@ def main_cuda(args):
         "traffic": traffic.get("k_bb_expand_dram_bytes_per_step"), "launches": per_launch,
         "note": "scattered 2-byte gathers from 900 MB of pyramid levels: neither DRAM nor tensor bound; the "
                 "binding unit is the L1TEX line (wavefront) rate of divergent loads, see DESIGN.md section 5 "
-                "and profiles/r1_k_bb_expand.txt. Durations are CUDA events recorded by the library on the "
+                "and profiles/r1_kernels_full.txt, r1_bb_stalls.txt. Durations are CUDA events recorded by the library on the "
                 "launching stream after every kernel.",
     }
     pyr_bytes = (1 + HMAX) * cells * 2 * N_MAPS          # read level 0 once, write hmax levels
