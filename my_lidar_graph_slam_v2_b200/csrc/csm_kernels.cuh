@@ -1129,6 +1129,10 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
     constexpr int h = HC + 1;
     constexpr int w = 1 << HC;               /* spacing of the children */
     constexpr bool kLeaf = HC == 0;
+#ifndef CSM_BB_COUNT_ALL
+#define CSM_BB_COUNT_ALL 0
+#endif
+    constexpr bool kCount = kLeaf || CSM_BB_COUNT_ALL;     /* known-cell counts above the leaves too */
     const int lane = threadIdx.x & 31;
     const unsigned int count = min(W.counts[h], W.capacity);
     const unsigned int total_lanes = gridDim.x * blockDim.x;
@@ -1180,7 +1184,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
 #pragma unroll
                 for (int u = 0; u < kBbUnroll; ++u) {
                     s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
-                    if (kLeaf) {
+                    if (kCount) {
                         k0 += (v[u][0] != 0u); k1 += (v[u][1] != 0u);
                         k2 += (v[u][2] != 0u); k3 += (v[u][3] != 0u);
                     }
@@ -1191,7 +1195,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
                 unsigned int v[4];
                 ld_children<HC>(m, rows, cols, p.y + oy, p.x + ox, v);
                 s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
-                if (kLeaf) { k0 += (v[0] != 0u); k1 += (v[1] != 0u); k2 += (v[2] != 0u); k3 += (v[3] != 0u); }
+                if (kCount) { k0 += (v[0] != 0u); k1 += (v[1] != 0u); k2 += (v[2] != 0u); k3 += (v[3] != 0u); }
             }
         }
         /* Sum over the parts (sums < 2^32; the four known counts < 2^16 share one word) */
@@ -1202,7 +1206,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
         for (int o = npw; o < 32; o <<= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
-            if (kLeaf) kk += __shfl_xor_sync(0xffffffffu, kk, o);
+            if (kCount) kk += __shfl_xor_sync(0xffffffffu, kk, o);
         }
         /* lane (slot, part < 4) now decides child `part` of node `slot`: (x + (part & 1) w, y + (part >> 1) w) */
         const bool decides = valid && part < 4;
@@ -1219,10 +1223,12 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
                 if (pass)
                     atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, cx, cy)));
             } else {
-                /* upper bound of the key: every beam counted as known */
-                const long long key_ub = make_key(s, Q.n);
+                /* upper bound of the key: every beam counted as known (or, with counts, the cells of
+                 * the coarse level that are known: at least as many as at any leaf below) */
+                const int kub = kCount ? (int)((kk >> (16 * (3 - (part & 3)))) & 0xffffull) : Q.n;
+                const long long key_ub = make_key(s, kub);
                 const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
-                pass = pack_best(key_ub, kOrdMask) > inc && key_ub > Q.kthr.fail_max;
+                pass = pack_best(key_ub, kOrdMask) > inc && key_ub > Q.kthr.fail_max && kub > Q.nk_cut;
             }
         }
         bb_count(W, decides, q, pass);
