@@ -574,7 +574,9 @@ def single_scan_numbers(h, lib, kind):
     from my_lidar_graph_slam_v2_b200 import hostapi, synth
     orc = pyoracle.load(kind)
     ctx = hostapi.Context(h.device)
-    out = {}
+    # cost / covariance of the decided pose come from the device, behind the match (csm_set_epilogue)
+    ctx.set_device_epilogue(True)
+    out = {"epilogue": "device (csm_set_epilogue) for real-time correlative and branch-and-bound, CPU for grid search"}
 
     def timeit(fn, reps, warm_s=0.5):
         # warm up for a fixed time, not a fixed count: these legs follow seconds of CPU-only work

@@ -312,6 +312,16 @@ int csm_loop_batch_finish_refined(csm_handle h, csm_result* results, csm_refined
 /* Refine n given poses (synchronous). Uses p, not the handle's refiner setting. */
 int csm_refine_batch(csm_handle h, const csm_refine_query* queries, int n,
                      const csm_refine_params* p, csm_refined* out);
+/* The epilogue of the single-scan matchers on the device: CostSquareError::Cost and
+ * ComputeCovariance at the pose the matcher decided on, found or not
+ * (scan_matcher_correlative.cpp:203-219, scan_matcher_branch_bound.cpp:241-252;
+ * cost_function_square_error.cpp:48-75,131-146), computed behind the match in the same
+ * submission instead of a second pass on the CPU. csm_set_epilogue(h, scale > 0) switches it
+ * on for the following csm_match_rt / csm_match_bb calls (0 = off); csm_last_epilogue returns
+ * the outcome of the last such call: pose = the decided sensor pose, final_cost = the summed
+ * squared error there, covariance = scale * inverse Hessian, iterations = 0. */
+int csm_set_epilogue(csm_handle h, double covariance_scale);
+int csm_last_epilogue(csm_handle h, csm_refined* out);
 /* Phase timing: after csm_set_option(h, "timing", 1) the library records a CUDA
  * event on the handle's stream after every kernel of a loop batch (or of a
  * streaming pyramid build). csm_debug_timings waits for the last one and

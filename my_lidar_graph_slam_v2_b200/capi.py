@@ -65,7 +65,7 @@ EXPORTS = [
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
-    "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch",
+    "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch", "csm_set_epilogue", "csm_last_epilogue",
     "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
 ]
 
@@ -133,6 +133,8 @@ def load():
     lib.csm_loop_batch_finish_refined.argtypes = [H, rp, C.POINTER(CsmRefined), C.c_int]
     lib.csm_refine_batch.argtypes = [H, C.POINTER(CsmRefineQuery), C.c_int, C.POINTER(CsmRefineParams),
                                      C.POINTER(CsmRefined)]
+    lib.csm_set_epilogue.argtypes = [H, C.c_double]
+    lib.csm_last_epilogue.argtypes = [H, C.POINTER(CsmRefined)]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
     lib.csm_debug_timings.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
     lib.csm_best_key_device.argtypes = [H]
@@ -330,6 +332,15 @@ class Handle:
         p = CsmRefineParams(max_iterations, 0, convergence_threshold, lambda_, covariance_scale)
         out = (CsmRefined * n)()
         self._check(self.lib.csm_refine_batch(self.h, q, n, C.byref(p), out))
+        return out
+
+    def set_epilogue(self, covariance_scale):
+        """> 0: csm_match_rt / csm_match_bb also compute cost and covariance at the decided pose."""
+        self._check(self.lib.csm_set_epilogue(self.h, float(covariance_scale)))
+
+    def last_epilogue(self):
+        out = CsmRefined()
+        self._check(self.lib.csm_last_epilogue(self.h, C.byref(out)))
         return out
 
     def frontier_counts(self):

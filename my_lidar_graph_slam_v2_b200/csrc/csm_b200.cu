@@ -160,6 +160,9 @@ struct csm_context
                                       0 never, 1 always, 2 only for calls of at most 4 queries (there the
                                       latency of the dive is small against the nodes it saves) */
     int accumulate_best_key = 0;   /* 1: batches do not reset the packed best word */
+    double epilogue_scale = 0.0;   /* > 0: single-scan matches also return cost and covariance at the
+                                      pose they decide on (csm_set_epilogue), computed behind k_finalize */
+    csm_refined last_epilogue {};
     bool refine_on = false;        /* loop batches refine the poses they find (csm_set_refiner) */
     csm_refine_params refine {};
     DevBuf d_refine_in;            /* csm_refine_batch: queries and start poses */
@@ -944,7 +947,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         n_thetas += (size_t)(2 * in.win_t + 1);
     }
     int rc;
-    const bool refine = h->refine_on;
+    const bool epilogue = inline_scan != nullptr && nq == 1 && h->epilogue_scale > 0.0;
+    const bool refine = h->refine_on || epilogue;
     if (refine) {
         if ((rc = wait_uploads(h, used_slots))) return rc;
         if ((rc = ensure_alloc(h, used_slots))) return rc;
@@ -1099,10 +1103,18 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         std::memset(&R, 0, sizeof(R));
         R.results = static_cast<const csm_result*>(h->d_results.p);
         R.out = reinterpret_cast<csm_refined*>(static_cast<char*>(h->d_results.p) + refined_offset(nq));
-        R.max_iterations = h->refine.max_iterations;
-        R.convergence_threshold = h->refine.convergence_threshold;
-        R.lambda0 = h->refine.lambda;
-        R.covariance_scale = h->refine.covariance_scale;
+        if (epilogue) {
+            /* single-scan match: Cost and ComputeCovariance at the decided pose, found or not
+             * (scan_matcher_branch_bound.cpp:241-252) */
+            R.max_iterations = 0;
+            R.always = 1;
+            R.covariance_scale = h->epilogue_scale;
+        } else {
+            R.max_iterations = h->refine.max_iterations;
+            R.convergence_threshold = h->refine.convergence_threshold;
+            R.lambda0 = h->refine.lambda;
+            R.covariance_scale = h->refine.covariance_scale;
+        }
         k_refine<<<nq, kRefThreads, 0, h->stream>>>(dq, R);
         CSM_LAUNCH_CHECK();
         phase_mark(h, "k_refine");
@@ -1619,6 +1631,25 @@ int csm_set_refiner(csm_handle h, const csm_refine_params* p)
     return CSM_OK;
 }
 
+int csm_set_epilogue(csm_handle h, double covariance_scale)
+{
+    if (!h) return CSM_E_INVALID;
+    if (!(covariance_scale >= 0.0))
+        return fail(h, CSM_E_INVALID, "epilogue: covariance_scale must be >= 0");
+    h->epilogue_scale = covariance_scale;
+    std::memset(&h->last_epilogue, 0, sizeof(h->last_epilogue));
+    return CSM_OK;
+}
+
+int csm_last_epilogue(csm_handle h, csm_refined* out)
+{
+    if (!h || !out) return CSM_E_INVALID;
+    if (!h->last_epilogue.valid)
+        return fail(h, CSM_E_INVALID, "epilogue: no match with csm_set_epilogue on has run");
+    *out = h->last_epilogue;
+    return CSM_OK;
+}
+
 int csm_loop_batch_finish_refined(csm_handle h, csm_result* results, csm_refined* refined, int nq)
 {
     if (!h || !results || !refined) return CSM_E_INVALID;
@@ -1747,7 +1778,7 @@ int csm_match_bb(csm_handle h, int64_t map_id,
     const InlineScan scan { angles, ranges, n };
     const int rc = bb_enqueue(h, &q, 1, hmax, 0, &scan);
     if (rc) return rc;
-    return finish_results(h, out, 1);
+    return finish_results(h, out, 1, h->epilogue_scale > 0.0 ? &h->last_epilogue : nullptr);
 }
 
 int csm_match_rt(csm_handle h, int64_t map_id,
@@ -1758,7 +1789,6 @@ int csm_match_rt(csm_handle h, int64_t map_id,
                  double score_thr, double known_thr, csm_result* out)
 {
     if (!h || !out || !sensor_pose) return CSM_E_INVALID;
-    (void)step_x; (void)step_y;
     if (h->res_count != 0)
         return fail(h, CSM_E_INVALID, "match_rt: a loop batch is in flight on this handle");
     CSM_CUDA(cudaSetDevice(h->device));
@@ -1782,6 +1812,8 @@ int csm_match_rt(csm_handle h, int64_t map_id,
         return fail(h, CSM_E_INVALID, "scan: need 1 <= n <= 4096 beams");
 
     int rc;
+    const bool epilogue = h->epilogue_scale > 0.0;
+    if (epilogue && (rc = ensure_alloc(h, std::vector<MapSlot*>{ &m }))) return rc;
     PlanView V;
     const int T = 2 * win_t + 1;
     if ((rc = layout_plan(h, 1, 0, 0, 0, n, V))) return rc;
@@ -1805,6 +1837,7 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     plan.max_t = Q.T;
     Q.margin = fp_margin(sensor_pose, m, s.max_range, (double)(std::max(win_x, win_y) + low_res) * m.res);
     Q.theta0 = sensor_pose[2]; Q.step_t = step_t; Q.tcenter = win_t;
+    Q.stepx = step_x; Q.stepy = step_y;
     const int nbx = (2 * win_x) / low_res + 1;
     const int nby = (2 * win_y) / low_res + 1;
     const int nblocks = Q.T * nbx * nby;
@@ -1827,8 +1860,20 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     F.nq = 1;
     k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
-    if ((rc = enqueue_readback(h, 1))) return rc;
-    return finish_results(h, out, 1);
+    if (epilogue) {
+        /* Cost and ComputeCovariance at the decided pose, found or not (scan_matcher_correlative.cpp:203-219) */
+        RefineArgs R;
+        std::memset(&R, 0, sizeof(R));
+        R.results = static_cast<const csm_result*>(h->d_results.p);
+        R.out = reinterpret_cast<csm_refined*>(static_cast<char*>(h->d_results.p) + refined_offset(1));
+        R.max_iterations = 0;
+        R.always = 1;
+        R.covariance_scale = h->epilogue_scale;
+        k_refine<<<1, kRefThreads, 0, h->stream>>>(dq, R);
+        CSM_LAUNCH_CHECK();
+    }
+    if ((rc = enqueue_readback(h, 1, epilogue))) return rc;
+    return finish_results(h, out, 1, epilogue ? &h->last_epilogue : nullptr);
 }
 
 int csm_match_grid(csm_handle h, int64_t map_id,

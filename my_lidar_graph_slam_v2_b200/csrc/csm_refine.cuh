@@ -75,7 +75,8 @@ struct RefineArgs
     const csm_result* results;     /* start = sensor pose + step * best index of a found query; or null */
     const double* start;           /* [3 * nq] start poses when results == null */
     csm_refined* out;
-    int max_iterations;
+    int max_iterations;            /* 0: no iteration, cost and covariance at the start pose only */
+    int always;                    /* 1: evaluate every query, found or not (single-scan epilogue) */
     double convergence_threshold;
     double lambda0;
     double covariance_scale;
@@ -281,7 +282,7 @@ k_refine(const DevQuery* __restrict__ queries, RefineArgs A)
     if (threadIdx.x == 0) {
         if (A.results != nullptr) {
             const csm_result r = A.results[q];
-            s_go = r.found;
+            s_go = r.found | A.always;
             /* best sensor pose of the coarse search, scan_matcher_branch_bound.cpp:237-240 */
             s_pose[0] = __dadd_rn(Q.sx, __dmul_rn(Q.stepx, (double)r.best_x));
             s_pose[1] = __dadd_rn(Q.sy, __dmul_rn(Q.stepy, (double)r.best_y));
@@ -311,7 +312,7 @@ k_refine(const DevQuery* __restrict__ queries, RefineArgs A)
     /* thread 0 carries the solver state (scan_matcher_linear_solver.cpp:82-110) */
     double lambda = A.lambda0, prev_cost = s_tot[0], initial_cost = s_tot[0], cost = s_tot[0];
     int iterations = 0;
-    while (true) {
+    while (A.max_iterations > 0) {
         if (threadIdx.x == 0) {
             /* OptimizeStep, :143-170: (H + lambda I) d = residual */
             const double h[9] = { s_tot[1] + lambda, s_tot[2], s_tot[3],

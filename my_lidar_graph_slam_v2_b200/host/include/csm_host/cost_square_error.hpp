@@ -16,6 +16,7 @@ class CostSquareError
 {
 public:
     explicit CostSquareError(double covariance_scale) : mCovarianceScale(covariance_scale) { }
+    double CovarianceScale() const { return mCovarianceScale; }
 
     double Cost(const GridMapView& map, const ScanData& scan, const Pose2D& sensor_pose) const;
     std::array<double, 9> ComputeCovariance(const GridMapView& map, const ScanData& scan,

@@ -39,9 +39,15 @@ public:
     void* Staging(std::size_t bytes);
     /* Abort with the library's message unless rc == CSM_OK */
     void Check(int rc, const char* what) const;
+    /* Matchers on this context take cost and covariance of the pose they decide on from the device
+     * (csm_set_epilogue: computed behind the match in the same submission) instead of running
+     * CostSquareError on the CPU afterwards. Same quantities, summed in a different order. */
+    void SetDeviceEpilogue(bool on) { mDeviceEpilogue = on; }
+    bool DeviceEpilogue() const { return mDeviceEpilogue; }
 
 private:
     csm_handle mHandle;
+    bool mDeviceEpilogue = false;
     void* mStaging = nullptr;
     std::size_t mStagingBytes = 0;
 };
@@ -83,6 +89,7 @@ protected:
 
     std::string mName;
     DeviceContextPtr mContext;
+    bool mEpilogueOnDevice = false;     /* the last match computed cost / covariance on the device */
     MetricSinkPtr mMetricSink;
     std::vector<std::int64_t> mResidentMaps;
 };

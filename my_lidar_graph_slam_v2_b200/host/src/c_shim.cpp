@@ -36,6 +36,12 @@ static void Export(const ScanMatchingSummary& s, csm_host_summary* out)
 void* csm_host_context_create(int device) { return new DeviceContextPtr(std::make_shared<DeviceContext>(device)); }
 void csm_host_context_destroy(void* ctx) { delete static_cast<DeviceContextPtr*>(ctx); }
 /* the csm_handle (C ABI) behind a context: timing options, direct C-ABI calls in tests */
+/* Matchers created on this context take cost / covariance from the device (csm_set_epilogue) */
+void csm_host_context_set_device_epilogue(void* ctx, int on)
+{
+    (*static_cast<DeviceContextPtr*>(ctx))->SetDeviceEpilogue(on != 0);
+}
+
 void* csm_host_context_handle(void* ctx) { return (*static_cast<DeviceContextPtr*>(ctx))->Handle(); }
 
 static GridMapView View(const uint16_t* values, int rows, int cols, double res, double ox, double oy, int64_t id)

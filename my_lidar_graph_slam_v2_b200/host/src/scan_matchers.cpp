@@ -94,6 +94,15 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
 void ScanMatcher::Epilogue(const GridMapView& map, const ScanData& scan, const Pose2D& best,
                            const CostFuncPtr& cost, ScanMatchingSummary& summary) const
 {
+    if (mContext && mContext->DeviceEpilogue() && mEpilogueOnDevice) {
+        /* the match just made computed both on the device (csm_set_epilogue) */
+        csm_refined e;
+        mContext->Check(csm_last_epilogue(mContext->Handle(), &e), "csm_last_epilogue");
+        std::copy(e.covariance, e.covariance + 9, summary.estimated_covariance.begin());
+        summary.normalized_cost = e.final_cost / static_cast<double>(scan.NumOfScans());
+        summary.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
+        return;
+    }
     double c = 0.0;
     summary.estimated_covariance = cost->CostAndCovariance(map, scan, best, c);
     summary.normalized_cost = c / static_cast<double>(scan.NumOfScans());
@@ -177,6 +186,8 @@ ScanMatchingSummary ScanMatcherCorrelative::OptimizePose(
     const int win_t = static_cast<int>(std::ceil(0.5 * mRangeTheta / st));
     const double pose[3] = { sensor.x, sensor.y, sensor.theta };
     csm_result r;
+    mEpilogueOnDevice = mContext->DeviceEpilogue();
+    mContext->Check(csm_set_epilogue(h, mEpilogueOnDevice ? mCost->CovarianceScale() : 0.0), "csm_set_epilogue");
     mContext->Check(csm_match_rt(h, id, scan->angles.data(), scan->ranges.data(),
                                  static_cast<int>(scan->NumOfScans()), pose, mLowResolution,
                                  win_x, win_y, win_t, sx, sy, st,
@@ -225,6 +236,8 @@ ScanMatchingSummary ScanMatcherBranchBound::OptimizePose(
     const int win_t = static_cast<int>(std::ceil(0.5 * mRangeTheta / st));
     const double pose[3] = { sensor.x, sensor.y, sensor.theta };
     csm_result r;
+    mEpilogueOnDevice = mContext->DeviceEpilogue();
+    mContext->Check(csm_set_epilogue(h, mEpilogueOnDevice ? mCost->CovarianceScale() : 0.0), "csm_set_epilogue");
     mContext->Check(csm_match_bb(h, id, scan->angles.data(), scan->ranges.data(),
                                  static_cast<int>(scan->NumOfScans()), pose, mNodeHeightMax,
                                  win_x, win_y, win_t, sx, sy, st,
@@ -271,6 +284,7 @@ ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(
     const std::vector<double> dt = Offsets(mRangeTheta / 2.0, mStepTheta);
     const double pose[3] = { sensor.x, sensor.y, sensor.theta };
     csm_result r;
+    mEpilogueOnDevice = false;          /* the grid search keeps the CPU epilogue (4 ms of search per match) */
     mContext->Check(csm_match_grid(h, id, scan->angles.data(), scan->ranges.data(),
                                    static_cast<int>(scan->NumOfScans()), pose,
                                    dx.data(), static_cast<int>(dx.size()),

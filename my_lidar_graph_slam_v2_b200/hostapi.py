@@ -54,6 +54,7 @@ def load():
                                         dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp, C.c_double,
                                         C.POINTER(HostSummary)]
         lib.csm_host_loopdet_use_linear_solver.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        lib.csm_host_context_set_device_epilogue.argtypes = [C.c_void_p, C.c_int]
         lib.csm_host_loopdet_use_device_refiner.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_create.restype = C.c_void_p
         lib.csm_host_loopdet_create.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_double, C.c_double]
@@ -113,6 +114,11 @@ class Context:
     def handle(self):
         """The csm_handle (C ABI) this context runs on."""
         return self.lib.csm_host_context_handle(self.ctx)
+
+    def set_device_epilogue(self, on=True):
+        """Real-time correlative / branch-and-bound matches on this context take cost and covariance
+        of the decided pose from the device instead of the CPU epilogue."""
+        self.lib.csm_host_context_set_device_epilogue(self.ctx, int(on))
 
     def close(self):
         if self.ctx:

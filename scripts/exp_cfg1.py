@@ -69,3 +69,9 @@ t0 = time.perf_counter(); rtb_nocopy(); t1 = time.perf_counter()
 print("one rt call wall %.1f us" % ((t1 - t0) * 1e6))
 for name, ms in hh.timings():
     print("  %8.3f ms  %s" % (ms, name))
+hh.set_option("timing", 0)
+ctx.set_device_epilogue(True)
+for name, fn in (("rt blocks, device epilogue", rtb_nocopy), ("bb blocks+copy, device epilogue", bbb)):
+    fn()
+    for rep in range(2):
+        print("plugin %s: %.1f us" % (name, phase(fn, False)))

@@ -430,6 +430,47 @@ def test_cpp_adapter_matchers(checker, seed):
     ctx.close()
 
 
+@pytest.mark.parametrize("seed", range(2420, 2424))
+def test_cpp_adapter_device_epilogue(checker, seed):
+    """Cost and covariance of the decided pose computed on the device behind the match
+    (csm_set_epilogue) instead of the CPU epilogue: search results and estimated pose bit-identical
+    to the reference, normalized cost within 1e-12 relative and covariance within 1e-6 (the sums run
+    in a tree order on the device). Dense and block-sparse maps, thresholds that fail included."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    ctx.set_device_epilogue(True)
+    case = synth.case_for(synth.CFG1, seed)
+    s = case.submap
+    g = checker.grid(s.grid, s.res, s.off_x, s.off_y)
+    rel = (0.1, -0.03, 0.2) if seed % 2 else (0.0, 0.0, 0.0)
+    off = (s.off_x, s.off_y)
+    blocks, index, br, bc = synth.dense_to_blocks(s.grid)
+
+    def cmp(a, o, what):
+        assert a.found == o.found, what
+        assert (a.best_x, a.best_y, a.best_t, a.sum_value, a.n_known) == \
+               (o.best_x, o.best_y, o.best_t, o.sum_value, o.n_known), what
+        assert a.score == o.score and list(a.est_pose) == list(o.est_pose), what
+        assert np.isclose(a.norm_cost, o.norm_cost, rtol=1e-12, atol=0.0), what
+        assert np.allclose(list(a.cov), list(o.cov), rtol=1e-6, atol=0.0), what
+
+    for thr in ((0.0, 0.0), (0.2, 0.3), (0.999, 0.999)):
+        a = ctx.match("rt", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"],
+                      thr=thr, rel_pose=rel)
+        cmp(a, checker.match_rt(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"], thr, rel),
+            "rt %s" % (thr,))
+        a = ctx.match_blocks("bb", blocks, index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                             case.init_pose, 5, synth.CFG2["rng"], thr=thr, rel_pose=rel)
+        cmp(a, checker.match_bb(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"], thr, rel),
+            "bb %s" % (thr,))
+    # the grid search keeps the CPU epilogue on such a context
+    a = ctx.match("grid", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 0, (0.4, 0.3, 0.05),
+                  step=(0.05, 0.05, 0.005), rel_pose=rel)
+    _cmp_host(a, checker.match_grid(g, case.angles, case.ranges, case.init_pose, (0.4, 0.3, 0.05),
+                                    (0.05, 0.05, 0.005), (0.0, 0.0), rel), "grid")
+    ctx.close()
+
+
 @pytest.mark.parametrize("seed", range(2410, 2413))
 def test_cpp_adapter_block_sparse_maps(checker, seed):
     """The C++ adapter fed with the map in the reference's block-sparse storage form: same device
