@@ -142,6 +142,11 @@ void* csm_stream(csm_handle h);
 int  csm_synchronize(csm_handle h);
 /* Number of kernels this handle has launched so far */
 int64_t csm_launch_count(csm_handle h);
+/* Make `h` enqueue its host-to-device grid uploads on `owner`'s copy stream. Handles that serve
+ * as pipeline lanes of one detector (same host thread, same device) then upload strictly in call
+ * order: copies issued on different streams share the link and would all land together at the
+ * end, whereas a lane's search should start when ITS maps have landed. `owner` must outlive `h`. */
+int csm_share_copy_stream(csm_handle h, csm_handle owner);
 /* Tuning / test knobs.
  *  "pyramid_mode": 0 = automatic, 1 = level-by-level kernels, 2 = streaming
  *      single-pass kernel (when the maps fit its layout), 3 = the streaming

@@ -65,7 +65,7 @@ EXPORTS = [
     "csm_build_pyramid", "csm_build_pyramids", "csm_drop_pyramids", "csm_download_level",
     "csm_upload_scan", "csm_release_scan", "csm_match_rt", "csm_match_bb", "csm_match_grid",
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
-    "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch", "csm_set_epilogue", "csm_last_epilogue",
+    "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch", "csm_set_epilogue", "csm_last_epilogue", "csm_share_copy_stream",
     "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
 ]
 
@@ -133,6 +133,7 @@ def load():
     lib.csm_loop_batch_finish_refined.argtypes = [H, rp, C.POINTER(CsmRefined), C.c_int]
     lib.csm_refine_batch.argtypes = [H, C.POINTER(CsmRefineQuery), C.c_int, C.POINTER(CsmRefineParams),
                                      C.POINTER(CsmRefined)]
+    lib.csm_share_copy_stream.argtypes = [H, H]
     lib.csm_set_epilogue.argtypes = [H, C.c_double]
     lib.csm_last_epilogue.argtypes = [H, C.POINTER(CsmRefined)]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]

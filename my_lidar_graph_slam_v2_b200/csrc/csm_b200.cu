@@ -116,6 +116,7 @@ struct csm_context
     int sm_count = 148;
     cudaStream_t stream = nullptr;        /* compute stream */
     cudaStream_t copy_stream = nullptr;   /* host-to-device uploads of grids, overlaps compute */
+    bool owns_copy_stream = true;         /* false: borrowed from another handle (csm_share_copy_stream) */
     cudaEvent_t upload_events[16] = { nullptr };
     int upload_event_next = 0;
     cudaEvent_t compute_mark = nullptr;
@@ -1209,7 +1210,7 @@ int csm_destroy(csm_handle h)
         if (h->upload_events[k]) cudaEventDestroy(h->upload_events[k]);
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
     cudaEventDestroy(h->compute_mark);
-    cudaStreamDestroy(h->copy_stream);
+    if (h->owns_copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return CSM_OK;
@@ -1628,6 +1629,19 @@ int csm_set_refiner(csm_handle h, const csm_refine_params* p)
     if (rc) return rc;
     h->refine = *p;
     h->refine_on = true;
+    return CSM_OK;
+}
+
+int csm_share_copy_stream(csm_handle h, csm_handle owner)
+{
+    if (!h || !owner || h == owner) return CSM_E_INVALID;
+    if (h->device != owner->device)
+        return fail(h, CSM_E_INVALID, "share_copy_stream: handles on different devices");
+    CSM_CUDA(cudaSetDevice(h->device));
+    CSM_CUDA(cudaStreamSynchronize(h->copy_stream));
+    if (h->owns_copy_stream) CSM_CUDA(cudaStreamDestroy(h->copy_stream));
+    h->copy_stream = owner->copy_stream;
+    h->owns_copy_stream = false;
     return CSM_OK;
 }
 

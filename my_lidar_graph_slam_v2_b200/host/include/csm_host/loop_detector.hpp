@@ -10,6 +10,7 @@
  * GPU matchers. */
 #pragma once
 
+#include <cstdint>
 #include <functional>
 #include <set>
 
@@ -78,8 +79,24 @@ public:
                           double covariance_scale);
     /* Per-query refinement outcomes of the last Detect (valid == 0 where none) */
     const std::vector<csm_refined>& LastRefined() const { return mLastRefined; }
+    /* Pipeline lanes: additional device contexts (handles, i.e. streams and workspaces) on the SAME
+     * device. With lanes, every search batch (mChunkSize consecutive queries) runs on the lane its
+     * maps belong to (lane = (LocalMapId / chunk size) mod lanes, stable across calls like the map ->
+     * GPU rule of the sharded detector), behind the uploads and pyramids of its own maps only: the
+     * search of a batch that has landed runs while the following maps are still crossing PCIe, and
+     * the latency-bound launches of neighbouring batches overlap on the device. Results are the same as without lanes. Clears the caches. */
+    void SetPipelineLanes(const std::vector<DeviceContextPtr>& extra_lanes);
+    int NumOfLanes() const { return 1 + static_cast<int>(mExtraLanes.size()); }
+    /* Packed best word of the last Detect, max over all lanes: (key << 20 | (0xFFFFF - global query
+     * index)) of the best found query, 0 if none -- what csm_best_key_device holds for one handle */
+    std::uint64_t BestWord() const { return mBestWord; }
     /* Forget which maps are resident (the next Detect uploads them again) */
-    void ClearCache() { mCachedMaps.clear(); mCachedScans.clear(); }
+    void ClearCache()
+    {
+        mCachedMaps.clear(); mCachedScans.clear();
+        for (auto& m : mLaneMaps) m.clear();
+        for (auto& m : mLaneScans) m.clear();
+    }
     /* Sharded use: global index of queries[0] (packed best word) */
     void SetQueryIndexBase(int base) { mQueryIndexBase = base; }
     /* Per-query device results of the last Detect, in query order */
@@ -93,6 +110,9 @@ private:
     std::set<std::int64_t> mCachedScans;
     std::vector<csm_result> mLastResults;
     std::vector<csm_refined> mLastRefined;
+    std::vector<DeviceContextPtr> mExtraLanes;
+    std::vector<std::set<std::int64_t>> mLaneMaps, mLaneScans;     /* residency per lane (pipelined path) */
+    std::uint64_t mBestWord = 0;
     bool mDeviceRefiner = false;
     csm_refine_params mRefineParams {};
     int mQueryIndexBase = 0;

@@ -34,6 +34,7 @@ public:
     DeviceContext(const DeviceContext&) = delete;
     DeviceContext& operator=(const DeviceContext&) = delete;
     csm_handle Handle() const { return mHandle; }
+    int Device() const { return mDevice; }
     /* Page-locked staging area of at least `bytes` (grown on demand, reused by every call): map data
      * copied here first crosses PCIe by DMA while the call goes on */
     void* Staging(std::size_t bytes);
@@ -47,6 +48,7 @@ public:
 
 private:
     csm_handle mHandle;
+    int mDevice = 0;
     bool mDeviceEpilogue = false;
     void* mStaging = nullptr;
     std::size_t mStagingBytes = 0;

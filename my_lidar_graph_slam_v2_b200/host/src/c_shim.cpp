@@ -297,6 +297,22 @@ void csm_host_loopdet_use_device_refiner(void* det, int iterations_max, double c
     d->det->UseDeviceRefiner(iterations_max, convergence_threshold, initial_lambda, covariance_scale);
 }
 
+/* n pipeline lanes in all (n - 1 additional device contexts on the detector's device) */
+void csm_host_loopdet_set_lanes(void* det, int n)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    std::vector<DeviceContextPtr> extra;
+    for (int i = 1; i < n; ++i)
+        extra.push_back(std::make_shared<DeviceContext>(d->ctx->Device()));
+    d->det->SetPipelineLanes(extra);
+}
+
+/* Packed best word of the last Detect over all lanes (LoopDetectorBranchBound::BestWord) */
+unsigned long long csm_host_loopdet_best_word(void* det)
+{
+    return static_cast<HostLoopDet*>(det)->det->BestWord();
+}
+
 void csm_host_loopdet_destroy(void* det) { delete static_cast<HostLoopDet*>(det); }
 
 void csm_host_loopdet_configure(void* det, int chunk_size, int coarse_covariance, int query_index_base)

@@ -193,78 +193,44 @@ void LoopDetectorBranchBound::UseDeviceRefiner(int num_of_iterations_max, double
     mRefineParams.covariance_scale = covariance_scale;
 }
 
+void LoopDetectorBranchBound::SetPipelineLanes(const std::vector<DeviceContextPtr>& extra_lanes)
+{
+    mExtraLanes = extra_lanes;
+    /* all lanes upload on the first lane's copy stream: strictly in call order, so that a lane's
+     * maps land (and its search starts) while the later groups are still crossing PCIe */
+    for (const DeviceContextPtr& c : mExtraLanes)
+        c->Check(csm_share_copy_stream(c->Handle(), mScanMatcher->Context()->Handle()), "csm_share_copy_stream");
+    mLaneMaps.assign(1 + extra_lanes.size(), std::set<std::int64_t>());
+    mLaneScans.assign(1 + extra_lanes.size(), std::set<std::int64_t>());
+    mCachedMaps.clear();
+    mCachedScans.clear();
+}
+
 std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     const std::vector<LoopDetectionQuery>& queries)
 {
     std::vector<LoopDetectionResult> results;
     mLastResults.clear();
     mLastRefined.clear();
+    mBestWord = 0;
     if (queries.empty())
         return results;
     MicroTimer timer;
     const DeviceContextPtr& ctx = mScanMatcher->Context();
-    csm_handle h = ctx->Handle();
     const int hmax = mScanMatcher->NodeHeightMax();
     const int nq = static_cast<int>(queries.size());
-    const int chunk = std::max(1, mChunkSize);
-    const int nchunks = (nq + chunk - 1) / chunk;
-
-    /* first touch of a local map: upload + pyramid, cached by LocalMapId
-     * (loop_detector_branch_bound.cpp:83-89). All uploads are enqueued first, in
-     * groups of mUploadChunk maps: they stream over PCIe on the copy stream while
-     * the groups that have landed are expanded and precomputed, and the search
-     * batches (mChunkSize queries) whose maps are complete run behind them. */
-    const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
-    std::vector<std::vector<std::int64_t>> new_maps;      /* per upload group */
-    std::vector<int> group_end;                           /* query index one past each group */
-    for (int first = 0; first < nq; first += ugroup) {
-        const int last = std::min(nq, first + ugroup);
-        std::vector<const GridMapView*> fresh;
-        new_maps.emplace_back();
-        for (int i = first; i < last; ++i) {
-            const GridMapView& m = queries[i].local_map;
-            if (m.map_id < 0) {
-                std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
-                std::abort();
-            }
-            if (mCachedMaps.insert(m.map_id).second) {
-                fresh.push_back(&m);
-                new_maps.back().push_back(m.map_id);
-            }
-        }
-        group_end.push_back(last);
-        UploadNewMaps(ctx, fresh);
-    }
-    for (const LoopDetectionQuery& q : queries)
-        if (mCachedScans.insert(q.scan_id).second)
-            ctx->Check(csm_upload_scan(h, q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
-                                       static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
-    std::size_t next_group = 0;
 
     /* per query: initial pose InverseCompound(map, scan) (:97-98), sensor pose,
      * steps and windows with the reference's expressions */
     std::vector<csm_loop_query> dq(nq);
-    std::map<std::pair<std::int64_t, double>, std::array<double, 3>> steps;
-    mLastResults.resize(nq);
-    if (mDeviceRefiner) {
-        mLastRefined.resize(nq);
-        ctx->Check(csm_set_refiner(h, &mRefineParams), "csm_set_refiner");
-    } else {
-        ctx->Check(csm_set_refiner(h, nullptr), "csm_set_refiner");
-    }
-    /* read back the oldest batch in flight */
-    auto finish = [&](int f0, int fc) {
-        if (mDeviceRefiner)
-            ctx->Check(csm_loop_batch_finish_refined(h, mLastResults.data() + f0, mLastRefined.data() + f0, fc),
-                       "csm_loop_batch_finish_refined");
-        else
-            ctx->Check(csm_loop_batch_finish(h, mLastResults.data() + f0, fc), "csm_loop_batch_finish");
-    };
-    int finished = 0;      /* chunks whose results have been read back */
-    for (int c = 0; c < nchunks; ++c) {
-        const int first = c * chunk, count = std::min(nq, first + chunk) - first;
-        for (int i = first; i < first + count; ++i) {
+    {
+        std::map<std::pair<std::int64_t, double>, std::array<double, 3>> steps;
+        for (int i = 0; i < nq; ++i) {
             const LoopDetectionQuery& q = queries[i];
+            if (q.local_map.map_id < 0) {
+                std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
+                std::abort();
+            }
             const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
             const Pose2D sensor = Compound(init, q.scan->relative_sensor_pose);
             auto key = std::make_pair(q.scan_id, q.local_map.resolution);
@@ -287,6 +253,129 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             d.score_thr = mScoreThreshold;
             d.known_thr = mKnownRateThreshold;
         }
+    }
+    mLastResults.resize(nq);
+    if (mDeviceRefiner)
+        mLastRefined.resize(nq);
+    /* read back the oldest batch in flight on a context */
+    auto finish = [&](const DeviceContextPtr& c, int f0, int fc) {
+        if (mDeviceRefiner)
+            c->Check(csm_loop_batch_finish_refined(c->Handle(), mLastResults.data() + f0,
+                                                   mLastRefined.data() + f0, fc), "csm_loop_batch_finish_refined");
+        else
+            c->Check(csm_loop_batch_finish(c->Handle(), mLastResults.data() + f0, fc), "csm_loop_batch_finish");
+    };
+    auto set_refiner = [&](const DeviceContextPtr& c) {
+        c->Check(csm_set_refiner(c->Handle(), mDeviceRefiner ? &mRefineParams : nullptr), "csm_set_refiner");
+    };
+
+    if (!mExtraLanes.empty()) {
+        /* ---- pipelined over lanes: one search batch per upload group, on the lane of its maps ---- */
+        const int lanes = NumOfLanes();
+        const int chunk = std::max(1, mChunkSize);
+        const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
+        auto lane_ctx = [&](int l) -> const DeviceContextPtr& { return l == 0 ? ctx : mExtraLanes[l - 1]; };
+        /* a segment = one search batch of up to mChunkSize consecutive queries whose maps belong to
+         * one lane; its first-touch maps go up in groups of mUploadChunk */
+        struct Segment { int first, count, lane; };
+        std::vector<Segment> segments;
+        for (int i = 0; i < nq; ++i) {
+            const std::int64_t id = queries[i].local_map.map_id;
+            const int lane = static_cast<int>((id / chunk) % lanes);
+            if (segments.empty() || segments.back().lane != lane || segments.back().count >= chunk)
+                segments.push_back(Segment { i, 0, lane });
+            ++segments.back().count;
+        }
+        std::vector<std::vector<int>> in_flight(lanes);       /* segment indices, oldest first */
+        auto finish_oldest = [&](int lane) {
+            const Segment& sg = segments[in_flight[lane].front()];
+            finish(lane_ctx(lane), sg.first, sg.count);
+            in_flight[lane].erase(in_flight[lane].begin());
+        };
+        /* pass 1: every upload is enqueued first, so that PCIe never waits for the host to prepare a
+         * search batch; pass 2: pyramids and the search batch of every segment behind its own uploads */
+        std::vector<std::vector<std::vector<std::int64_t>>> fresh_ids(segments.size());   /* per upload group */
+        for (std::size_t si = 0; si < segments.size(); ++si) {
+            const Segment& sg = segments[si];
+            const DeviceContextPtr& c = lane_ctx(sg.lane);
+            for (int first = sg.first; first < sg.first + sg.count; first += ugroup) {
+                const int last = std::min(sg.first + sg.count, first + ugroup);
+                std::vector<const GridMapView*> fresh;
+                fresh_ids[si].emplace_back();
+                for (int i = first; i < last; ++i) {
+                    const GridMapView& m = queries[i].local_map;
+                    if (mLaneMaps[sg.lane].insert(m.map_id).second) {
+                        fresh.push_back(&m);
+                        fresh_ids[si].back().push_back(m.map_id);
+                    }
+                }
+                UploadNewMaps(c, fresh);
+            }
+        }
+        const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
+        if (trace) std::fprintf(stderr, "lanes: uploads enqueued at %.0f us\n", timer.ElapsedMicro());
+        for (std::size_t si = 0; si < segments.size(); ++si) {
+            const Segment& sg = segments[si];
+            const DeviceContextPtr& c = lane_ctx(sg.lane);
+            for (int i = sg.first; i < sg.first + sg.count; ++i) {
+                const LoopDetectionQuery& q = queries[i];
+                if (mLaneScans[sg.lane].insert(q.scan_id).second)
+                    c->Check(csm_upload_scan(c->Handle(), q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
+                                             static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
+            }
+            for (const std::vector<std::int64_t>& group : fresh_ids[si])
+                if (!group.empty())
+                    c->Check(csm_build_pyramids(c->Handle(), static_cast<int>(group.size()), group.data(), hmax),
+                             "csm_build_pyramids");
+            set_refiner(c);
+            if (in_flight[sg.lane].size() >= 4)         /* the library keeps at most 4 batches in flight */
+                finish_oldest(sg.lane);
+            c->Check(csm_loop_batch_enqueue(c->Handle(), dq.data() + sg.first, sg.count, hmax,
+                                            mQueryIndexBase + sg.first), "csm_loop_batch_enqueue");
+            in_flight[sg.lane].push_back(static_cast<int>(si));
+            if (trace) std::fprintf(stderr, "lanes: segment %zu enqueued at %.0f us\n", si, timer.ElapsedMicro());
+        }
+        for (int lane = 0; lane < lanes; ++lane)
+            while (!in_flight[lane].empty()) {
+                finish_oldest(lane);
+                if (trace) std::fprintf(stderr, "lanes: lane %d finished a batch at %.0f us\n", lane, timer.ElapsedMicro());
+            }
+    } else {
+    csm_handle h = ctx->Handle();
+    const int chunk = std::max(1, mChunkSize);
+    const int nchunks = (nq + chunk - 1) / chunk;
+
+    /* first touch of a local map: upload + pyramid, cached by LocalMapId
+     * (loop_detector_branch_bound.cpp:83-89). All uploads are enqueued first, in
+     * groups of mUploadChunk maps: they stream over PCIe on the copy stream while
+     * the groups that have landed are expanded and precomputed, and the search
+     * batches (mChunkSize queries) whose maps are complete run behind them. */
+    const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
+    std::vector<std::vector<std::int64_t>> new_maps;      /* per upload group */
+    std::vector<int> group_end;                           /* query index one past each group */
+    for (int first = 0; first < nq; first += ugroup) {
+        const int last = std::min(nq, first + ugroup);
+        std::vector<const GridMapView*> fresh;
+        new_maps.emplace_back();
+        for (int i = first; i < last; ++i) {
+            const GridMapView& m = queries[i].local_map;
+            if (mCachedMaps.insert(m.map_id).second) {
+                fresh.push_back(&m);
+                new_maps.back().push_back(m.map_id);
+            }
+        }
+        group_end.push_back(last);
+        UploadNewMaps(ctx, fresh);
+    }
+    for (const LoopDetectionQuery& q : queries)
+        if (mCachedScans.insert(q.scan_id).second)
+            ctx->Check(csm_upload_scan(h, q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
+                                       static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
+    std::size_t next_group = 0;
+    set_refiner(ctx);
+    int finished = 0;      /* chunks whose results have been read back */
+    for (int c = 0; c < nchunks; ++c) {
+        const int first = c * chunk, count = std::min(nq, first + chunk) - first;
         /* pyramids of every upload group this batch touches (in upload order) */
         for (; next_group < new_maps.size() &&
                (next_group == 0 || group_end[next_group - 1] < first + count); ++next_group)
@@ -295,7 +384,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
                                               new_maps[next_group].data(), hmax), "csm_build_pyramids");
         if (c - finished >= 4) {        /* the library keeps at most 4 batches in flight */
             const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
-            finish(f0, fc);
+            finish(ctx, f0, fc);
             ++finished;
         }
         ctx->Check(csm_loop_batch_enqueue(h, dq.data() + first, count, hmax, mQueryIndexBase + first),
@@ -303,7 +392,18 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     }
     for (; finished < nchunks; ++finished) {
         const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
-        finish(f0, fc);
+        finish(ctx, f0, fc);
+    }
+    }
+
+    /* packed best word over the whole call (what the device keeps per handle, here over all lanes) */
+    for (int i = 0; i < nq; ++i) {
+        const csm_result& r = mLastResults[i];
+        if (!r.found)
+            continue;
+        const std::uint64_t key = static_cast<std::uint64_t>(998ll * r.sum_value + 64536ll * r.n_known);
+        const std::uint64_t word = (key << 20) | static_cast<std::uint64_t>(0xFFFFF - (mQueryIndexBase + i));
+        mBestWord = std::max(mBestWord, word);
     }
 
     for (int i = 0; i < nq; ++i) {

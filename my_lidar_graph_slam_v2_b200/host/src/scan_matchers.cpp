@@ -8,7 +8,7 @@
 
 namespace csm_host {
 
-DeviceContext::DeviceContext(int device) : mHandle(nullptr)
+DeviceContext::DeviceContext(int device) : mHandle(nullptr), mDevice(device)
 {
     const int rc = csm_create(device, 0, &mHandle);
     if (rc != CSM_OK) {

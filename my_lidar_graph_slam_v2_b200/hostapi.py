@@ -54,6 +54,9 @@ def load():
                                         dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp, C.c_double,
                                         C.POINTER(HostSummary)]
         lib.csm_host_loopdet_use_linear_solver.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        lib.csm_host_loopdet_set_lanes.argtypes = [C.c_void_p, C.c_int]
+        lib.csm_host_loopdet_best_word.argtypes = [C.c_void_p]
+        lib.csm_host_loopdet_best_word.restype = C.c_uint64
         lib.csm_host_context_set_device_epilogue.argtypes = [C.c_void_p, C.c_int]
         lib.csm_host_loopdet_use_device_refiner.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_create.restype = C.c_void_p
@@ -234,6 +237,15 @@ class LoopDetector:
         """Refine detected loops with the same solver on the device, batched behind the search."""
         self.lib.csm_host_loopdet_use_device_refiner(self.det, iterations_max, convergence_threshold,
                                                      initial_lambda, covariance_scale)
+
+    def set_lanes(self, n):
+        """n pipeline lanes (n - 1 more device contexts on the same device): every upload group becomes
+        its own search batch on the lane of its maps. Set after use_linear_solver / before detect."""
+        self.lib.csm_host_loopdet_set_lanes(self.det, int(n))
+
+    def best_word(self):
+        """Packed best (key, global query index) word of the last detect() over all lanes."""
+        return int(self.lib.csm_host_loopdet_best_word(self.det))
 
     def configure(self, chunk_size=128, coarse_covariance=True, query_index_base=0):
         self.lib.csm_host_loopdet_configure(self.det, chunk_size, int(coarse_covariance), query_index_base)

@@ -801,3 +801,54 @@ def test_full_size_cfg4_grid_search(handle, checker):
                                 (8 * step[0], 8 * step[1], 4 * step[2]))
     assert coarse.found == 1 and coarse.score <= a.normalized_score
     assert abs(win[0] - case.true_pose[0]) <= 2 * s.res and abs(win[1] - case.true_pose[1]) <= 2 * s.res
+
+
+@pytest.mark.parametrize("lanes,chunk,up", [(2, 8, 4), (3, 4, 4), (4, 16, 3)])
+def test_cpp_loop_detector_pipeline_lanes(checker, lanes, chunk, up):
+    """Pipeline lanes (several device contexts of one detector sharing one copy stream): the same
+    results as the reference whatever the lane / batch / upload-group split, a second Detect served
+    from the per-lane caches, and the packed best word of the whole call."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    batch = synth.make_loop_batch(3500, n_maps=16, true_fraction=0.5, map_id_base=9300)
+    ctx = hostapi.Context(0)
+    det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+    det.use_device_refiner(10, 1e-4, 1e-4)
+    det.configure(chunk_size=chunk | (up << 16), query_index_base=1000)
+    det.set_lanes(lanes)
+    parts = [synth.dense_to_blocks(s.grid, 4) for s in batch.submaps]
+    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+    blocks = np.ascontiguousarray(np.concatenate([p[0].reshape(-1) for p in parts]))
+    index = np.ascontiguousarray(np.concatenate([p[1] for p in parts]))
+    args = (np.array([s.off_x for s in batch.submaps]), np.array([s.off_y for s in batch.submaps]),
+            batch.map_ids.astype(np.int64), np.ascontiguousarray(batch.map_poses),
+            np.ascontiguousarray(batch.scan_poses), np.ascontiguousarray(batch.angles[0]),
+            np.ascontiguousarray(batch.ranges[0]))
+    og = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    odet.use_linear_solver(10, 1e-4, 1e-4)
+    ores, _ = odet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    # coarse results (indices, sums) from the reference's detector without the refinement stage
+    cdet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    cres, _ = cdet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    sigs = []
+    for rep in range(2):                 # the second call finds every map resident on its lane
+        n, out = det.detect(len(batch.submaps), None, blocks.ctypes.data, index.ctypes.data, counts.ctypes.data,
+                            4, 512, 512, batch.submaps[0].res, *args)
+        assert n == sum(o.found for o in ores) >= 3
+        for i, (r, o, c) in enumerate(zip(out, ores, cres)):
+            assert r.found == o.found == c.found, i
+            if o.found:
+                assert (r.best_x, r.best_y, r.best_t, r.sum_value, r.n_known) == \
+                       (c.best_x, c.best_y, c.best_t, c.sum_value, c.n_known), i
+                assert np.allclose(list(r.est_pose), list(o.est_pose), rtol=1e-5, atol=0.0), i
+        keys = [998 * r.sum_value + 64536 * r.n_known if r.found else -1 for r in out]
+        best = max(range(len(keys)), key=lambda i: (keys[i], -i))
+        assert det.best_word() == (keys[best] << 20) | (0xFFFFF - (1000 + best))
+        sigs.append([(r.found, r.best_x, r.best_y, r.best_t, r.sum_value, tuple(r.est_pose)) for r in out])
+    # (the damping factor carried over from the first call moves refined poses by ~1e-13)
+    assert [g[:5] for g in sigs[0]] == [g[:5] for g in sigs[1]]
+    assert np.allclose([g[5] for g in sigs[0]], [g[5] for g in sigs[1]], rtol=1e-9, atol=1e-12)
+    det.close()
+    ctx.close()
