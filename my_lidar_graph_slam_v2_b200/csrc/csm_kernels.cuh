@@ -1259,6 +1259,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
  * the search result (maximum key, smallest ordinal) does not depend on it,
  * only the amount of work does. */
 constexpr int kDiveBeam = 8;
+constexpr int kDiveRootsSmem = 1024;     /* roots ranked in shared memory when there are at most this many */
 
 __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* s_red)
 {
@@ -1284,6 +1285,7 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
     __shared__ int s_nbeam;
     __shared__ long long s_key[4 * kDiveBeam];
     __shared__ int s_ok[4 * kDiveBeam];
+    __shared__ long long s_root[kDiveRootsSmem];
     const int q = blockIdx.x;
     const DevQuery& Q = queries[q];
     const unsigned int r0 = root_off[q];
@@ -1294,6 +1296,30 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
     /* the kDiveBeam best roots, in (key descending, index ascending) order */
     unsigned long long last = ~0ull;
     int nbeam = 0;
+    if (R <= (unsigned int)kDiveRootsSmem) {
+        /* few roots (single-scan matches): one pass, every passing root ranks itself against the
+         * others in shared memory */
+        if (threadIdx.x == 0) s_nbeam = 0;
+        for (unsigned int e = threadIdx.x; e < R; e += blockDim.x) s_root[e] = W.rootkey[r0 + e];
+        __syncthreads();
+        for (unsigned int e = threadIdx.x; e < R; e += blockDim.x) {
+            const long long k = s_root[e];
+            if (k < 0) continue;
+            int rank = 0;
+            for (unsigned int o = 0; o < R; ++o) {
+                const long long ko = s_root[o];
+                rank += (ko > k || (ko == k && o < e)) ? 1 : 0;
+            }
+            if (rank < kDiveBeam) {
+                const int t = (int)(e % (unsigned)Q.T), cell = (int)(e / (unsigned)Q.T);
+                const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
+                s_beam[0][rank][0] = t; s_beam[0][rank][1] = rx << W.top; s_beam[0][rank][2] = ry << W.top;
+                atomicAdd(&s_nbeam, 1);
+            }
+        }
+        __syncthreads();
+        nbeam = min(s_nbeam, kDiveBeam);
+    } else
     for (int j = 0; j < kDiveBeam; ++j) {
         unsigned long long best = 0ull;
         for (unsigned int e = threadIdx.x; e < R; e += blockDim.x) {
@@ -1321,41 +1347,53 @@ k_bb_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_
         const uint16_t* __restrict__ m = Q.lvl[h - 1];
         const int ncand = 4 * nbeam;
         {
-            /* warp `warp` scores candidates warp, warp + 8, warp + 16, warp + 24 at once:
-             * up to 4 x 12 independent (index, cell) load pairs per lane in flight */
+            /* warp b scores the four children of beam node b: one projected-index load per beam
+             * serves four cell loads, six beams (24 cells) per lane in flight */
+            static_assert(kDiveBeam == 8, "one warp per beam node");
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
             const size_t ps = (size_t)Q.pst_i;
-            const proj_t* __restrict__ pp[4];
-            int ox[4], oy[4], sv[4], kn[4];
-            bool on[4];
+            const bool on = warp < nbeam;
+            const int b = on ? warp : 0;
+            const proj_t* __restrict__ pp = proj_all + Q.proj_off + (size_t)s_beam[cur][b][0] * Q.pst_t;
+            const int ox = s_beam[cur][b][1] - Q.winx, oy = s_beam[cur][b][2] - Q.winy;
+            int sv[4] = { 0, 0, 0, 0 }, kn[4] = { 0, 0, 0, 0 };
+            if (on) {
+                int i = lane;
+                for (; i + 5 * 32 < n; i += 6 * 32) {
+                    proj_t p[6];
+                    unsigned int v[6][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = warp + 8 * j;
-                on[j] = c < ncand;
-                const int b = on[j] ? (c >> 2) : 0, ch = c & 3;
-                pp[j] = proj_all + Q.proj_off + (size_t)s_beam[cur][b][0] * Q.pst_t;
-                ox[j] = s_beam[cur][b][1] + (ch & 1) * w - Q.winx;
-                oy[j] = s_beam[cur][b][2] + (ch >> 1) * w - Q.winy;
-                sv[j] = 0; kn[j] = 0;
-            }
-#pragma unroll 4
-            for (int i = lane; i < n; i += 32) {
+                    for (int u = 0; u < 6; ++u) p[u] = pp[(size_t)(i + 32 * u) * ps];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!on[j]) continue;
-                    const proj_t p = pp[j][(size_t)i * ps];
-                    const unsigned int v = ld_cell_nb(m, rows, cols, p.y + oy[j], p.x + ox[j]);
-                    sv[j] += (int)v; kn[j] += (v != 0u);
+                    for (int u = 0; u < 6; ++u) {
+                        const int r = p[u].y + oy, c = p[u].x + ox;
+                        v[u][0] = ld_cell_nb(m, rows, cols, r, c);
+                        v[u][1] = ld_cell_nb(m, rows, cols, r, c + w);
+                        v[u][2] = ld_cell_nb(m, rows, cols, r + w, c);
+                        v[u][3] = ld_cell_nb(m, rows, cols, r + w, c + w);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) { sv[ch] += (int)v[u][ch]; kn[ch] += (v[u][ch] != 0u); }
+                }
+                for (; i < n; i += 32) {
+                    const proj_t p = pp[(size_t)i * ps];
+                    const int r = p.y + oy, c = p.x + ox;
+                    const unsigned int v0 = ld_cell_nb(m, rows, cols, r, c), v1 = ld_cell_nb(m, rows, cols, r, c + w);
+                    const unsigned int v2 = ld_cell_nb(m, rows, cols, r + w, c), v3 = ld_cell_nb(m, rows, cols, r + w, c + w);
+                    sv[0] += (int)v0; sv[1] += (int)v1; sv[2] += (int)v2; sv[3] += (int)v3;
+                    kn[0] += (v0 != 0u); kn[1] += (v1 != 0u); kn[2] += (v2 != 0u); kn[3] += (v3 != 0u);
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int s = warp_sum(sv[j]), k = warp_sum(kn[j]);
-                if (on[j] && lane == 0) {
+            for (int ch = 0; ch < 4; ++ch) {
+                const int s = warp_sum(sv[ch]), k = warp_sum(kn[ch]);
+                if (on && lane == 0) {
                     const long long key = make_key(s, k);
-                    s_key[warp + 8 * j] = key;
+                    s_key[4 * b + ch] = key;
                     /* strictly above the threshold (outside its guard band) and known enough */
-                    s_ok[warp + 8 * j] = (k > Q.nk_cut && key_vs_threshold(key, Q.kthr) > 0) ? 1 : 0;
+                    s_ok[4 * b + ch] = (k > Q.nk_cut && key_vs_threshold(key, Q.kthr) > 0) ? 1 : 0;
                 }
             }
         }
