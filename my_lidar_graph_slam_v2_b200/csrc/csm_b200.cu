@@ -1519,8 +1519,13 @@ int csm_build_coarse(csm_handle h, int64_t map_id, int win)
     }
     if (m.coarse == nullptr)
         CSM_CUDA(cudaMallocAsync((void**)&m.coarse, (size_t)m.rows * m.cols * sizeof(uint16_t), h->stream));
-    dim3 grid((m.cols + 255) / 256, m.rows);
-    k_sliding_max<<<grid, 256, 0, h->stream>>>(m.base, m.coarse, m.rows, m.cols, win);
+    if (win >= 2 && win <= kSmMaxWin) {
+        dim3 grid((m.cols + kSmCols - 1) / kSmCols, (m.rows + kSmRows - 1) / kSmRows);
+        k_sliding_max_tile<<<grid, 256, 0, h->stream>>>(m.base, m.coarse, m.rows, m.cols, win);
+    } else {
+        dim3 grid((m.cols + 255) / 256, m.rows);
+        k_sliding_max<<<grid, 256, 0, h->stream>>>(m.base, m.coarse, m.rows, m.cols, win);
+    }
     CSM_LAUNCH_CHECK();
     m.coarse_win = win;
     return CSM_OK;
@@ -1856,13 +1861,16 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     const int nby = (2 * win_y) / low_res + 1;
     const int nblocks = Q.T * nbx * nby;
     if ((rc = ensure(h, h->d_rtblocks, sizeof(RtBlock) * (size_t)nblocks))) return rc;
+    phase_mark(h, "start");
     if ((rc = commit_plan(h, plan, V, false))) return rc;
+    phase_mark(h, "k_setup");
     const DevQuery* dq = V.queries;
     proj_t* proj = static_cast<proj_t*>(h->d_proj.p);
     /* projection happens inside k_rt_blocks (one launch less on this latency-bound path) */
     k_rt_blocks<<<nblocks, 256, sizeof(long long) * low_res * low_res + sizeof(proj_t) * Q.n, h->stream>>>(
         dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby, V.qflags);
     CSM_LAUNCH_CHECK();
+    phase_mark(h, "k_rt_blocks");
     FinalArgs F;
     std::memset(&F, 0, sizeof(F));
     F.decode = 3;
@@ -1874,6 +1882,7 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     F.nq = 1;
     k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
+    phase_mark(h, "k_finalize");
     if (epilogue) {
         /* Cost and ComputeCovariance at the decided pose, found or not (scan_matcher_correlative.cpp:203-219) */
         RefineArgs R;
@@ -1885,8 +1894,10 @@ int csm_match_rt(csm_handle h, int64_t map_id,
         R.covariance_scale = h->epilogue_scale;
         k_refine<<<1, kRefThreads, 0, h->stream>>>(dq, R);
         CSM_LAUNCH_CHECK();
+        phase_mark(h, "k_refine");
     }
     if ((rc = enqueue_readback(h, 1, epilogue))) return rc;
+    phase_mark(h, "readback");
     return finish_results(h, out, 1, epilogue ? &h->last_epilogue : nullptr);
 }
 

@@ -3,10 +3,13 @@
  *
  * Kernel inventory (reference unit each one replaces, paths relative to the
  * reference repository):
- *   k_pyramid_level   PrecomputeGridMaps level h from level h-1
- *                     (grid_map_builder.cpp:987-1012, util.hpp:369-424)
- *   k_sliding_max     PrecomputeGridMap(map, win), any window
- *                     (grid_map_builder.cpp:1044-1065)
+ *   k_pyramid_stream2 PrecomputeGridMaps, all levels in one pass over the map, row rings
+ *                     in registers (grid_map_builder.cpp:987-1012, util.hpp:369-424);
+ *   k_pyramid_stream  the same with the rings in shared memory (rows % 32 != 0);
+ *   k_pyramid_level   level h from level h-1 (small batches, odd shapes)
+ *   k_sliding_max_tile / k_sliding_max
+ *                     PrecomputeGridMap(map, win): separable in shared-memory tiles
+ *                     (win <= 32) / generic (grid_map_builder.cpp:1044-1065)
  *   k_project         ScanData::HitPoint + PositionToIndex for every
  *                     (query, angle, beam) (sensor_data.hpp:190-203,
  *                     grid_map_geometry.cpp:113-122)
@@ -24,6 +27,9 @@
  *                     the winning pose, packed best word for the NCCL argmax
  *   k_setup           one-launch staging of a batch's descriptors and counters
  *   k_scatter_blocks  block-sparse upload -> dense level 0
+ *   (csm_refine.cuh)  k_refine: ScanMatcherLinearSolver + CostSquareError on every found
+ *                     pose / cost and covariance of a single-scan match; k_block_alloc
+ *   (csm_window_tma.cuh) k_window_tma: grid-search window scoring from TMA-staged tiles
  */
 #pragma once
 
@@ -501,6 +507,48 @@ k_sliding_max(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
         for (int dc = 0; dc < win; ++dc)
             v = max(v, ld_cell(src, rows, cols, rc + dr, cc + dc));
     dst[(size_t)r * cols + c] = (uint16_t)v;
+}
+
+/* The same sliding maximum, separable and staged in shared memory: a CTA produces a tile of
+ * kSmRows x kSmCols outputs from the input rows / columns their (clamped) window origins span;
+ * row-wise maxima first, then the column-wise maximum of those: 2 win operations per cell instead
+ * of win^2 and every input cell read from memory once per tile. win <= kSmMaxWin. */
+constexpr int kSmRows = 16, kSmCols = 128, kSmMaxWin = 32;
+constexpr int kSmInRows = kSmRows + kSmMaxWin - 1, kSmInCols = kSmCols + kSmMaxWin - 1;
+
+__global__ void __launch_bounds__(256)
+k_sliding_max_tile(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols, int win)
+{
+    __shared__ uint16_t s_in[kSmInRows][kSmInCols + 1];
+    __shared__ uint16_t s_h[kSmInRows][kSmCols];
+    const int r0 = blockIdx.y * kSmRows, c0 = blockIdx.x * kSmCols;
+    const int r1 = min(r0 + kSmRows, rows) - 1, c1 = min(c0 + kSmCols, cols) - 1;     /* last output row / col */
+    /* window origin of an output cell: clamped at the far edge */
+    const int rmax = max(rows - win, 0), cmax = max(cols - win, 0);
+    const int or0 = min(r0, rmax), or1 = min(r1, rmax);
+    const int oc0 = min(c0, cmax), oc1 = min(c1, cmax);
+    const int in_rows = or1 - or0 + win, in_cols = oc1 - oc0 + win;
+    for (int e = threadIdx.x; e < in_rows * in_cols; e += blockDim.x) {
+        const int rr = e / in_cols, cc = e - rr * in_cols;
+        s_in[rr][cc] = (uint16_t)ld_cell(src, rows, cols, or0 + rr, oc0 + cc);
+    }
+    __syncthreads();
+    const int n_oc = oc1 - oc0 + 1;
+    for (int e = threadIdx.x; e < in_rows * n_oc; e += blockDim.x) {
+        const int rr = e / n_oc, cc = e - rr * n_oc;
+        unsigned int v = 0;
+        for (int k = 0; k < win; ++k) v = max(v, (unsigned int)s_in[rr][cc + k]);
+        s_h[rr][cc] = (uint16_t)v;
+    }
+    __syncthreads();
+    const int n_r = r1 - r0 + 1, n_c = c1 - c0 + 1;
+    for (int e = threadIdx.x; e < n_r * n_c; e += blockDim.x) {
+        const int rr = e / n_c, cc = e - rr * n_c;
+        const int orr = min(r0 + rr, rmax) - or0, occ = min(c0 + cc, cmax) - oc0;
+        unsigned int v = 0;
+        for (int k = 0; k < win; ++k) v = max(v, (unsigned int)s_h[orr + k][occ]);
+        dst[(size_t)(r0 + rr) * cols + c0 + cc] = (uint16_t)v;
+    }
 }
 
 /* ------------------------------------------------------------------------ */

@@ -59,6 +59,22 @@ def test_pyramid_vs_checker(handle, checker, shape):
     handle.release_grid(78)
 
 
+@pytest.mark.parametrize("shape", [(512, 512), (48, 16), (16, 208), (144, 272), (32, 32)])
+def test_coarse_map_windows_vs_checker(handle, checker, shape):
+    """PrecomputeGridMap(map, win) for windows of every kind: the tiled separable kernel (2..32),
+    the generic one (1, > 32), windows larger than the map."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    grid = rng.integers(0, 65535, size=shape, dtype=np.uint16)
+    grid[rng.random(shape) < 0.7] = 0
+    g = checker.grid(grid, 0.05, 0.0, 0.0)
+    handle.upload_grid(79, grid, 0.05, 0.0, 0.0)
+    for win in (1, 2, 3, 5, 8, 17, 32, 33, 40):
+        handle.build_coarse(79, win)
+        got = handle.download_level(79, -win, shape)
+        assert np.array_equal(got, g.precompute(win)), "win %d: %d cells differ" % (win, int((got != g.precompute(win)).sum()))
+    handle.release_grid(79)
+
+
 @pytest.mark.parametrize("shape,hmax", [((64, 64), 6), ((512, 512), 6), ((32, 128), 4), ((128, 16), 6),
                                         ((16, 512), 3), ((192, 336), 5), ((512, 512), 1), ((48, 48), 2),
                                         ((256, 512), 6), ((384, 128), 6), ((144, 64), 6), ((272, 256), 5)])
