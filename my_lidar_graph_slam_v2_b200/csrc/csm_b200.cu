@@ -2020,13 +2020,21 @@ int csm_match_grid(csm_handle h, int64_t map_id,
         }
         const int rows_per_cta = warps * kWtRows;
         WA.rows_per_cta = rows_per_cta;
+        /* unit column steps and 32 k + r columns, r <= kWtRemMax, in one block of columns: k chunks per
+         * lane, the r remainder columns on a few lanes of every warp */
+        const int rem_chunks = ndx / 32, rem_cols = ndx % 32;
+        const bool rem_variant = unit && rem_chunks >= 1 && rem_chunks <= kWtChunks && rem_cols >= 1 &&
+                                 rem_cols <= kWtRemMax;
+        const int cols_per_cta = rem_variant ? ndx : kWtColsPerCta;
         for (int b = 0; b < ndy; b += rows_per_cta)
             dy_span = std::max(dy_span, offs[ndx + std::min(ndy, b + rows_per_cta) - 1] - offs[ndx + b]);
-        for (int b = 0; b < ndx; b += kWtColsPerCta)
-            dx_span = std::max(dx_span, offs[std::min(ndx, b + kWtColsPerCta) - 1] - offs[b]);
-        if (unit) dx_span = std::max(dx_span, std::min(ndx, kWtColsPerCta) - 1);
+        for (int b = 0; b < ndx; b += cols_per_cta)
+            dx_span = std::max(dx_span, offs[std::min(ndx, b + cols_per_cta) - 1] - offs[b]);
+        if (unit) dx_span = std::max(dx_span, std::min(ndx, cols_per_cta) - 1);
         WA.dy_span = dy_span; WA.dx_span = dx_span; WA.unit_dx = unit ? 1 : 0;
-        const int max_h = kWtTileRows - 1 - dy_span, max_w = kWtPitch - 8 - (unit ? kWtColsPerCta - 1 : dx_span);
+        /* lanes of a partly filled last chunk read up to 32 ceil(cols / 32) - 1 columns to the right */
+        const int lane_reach = unit ? (rem_variant ? ndx : kWtColsPerCta) - 1 : dx_span;
+        const int max_h = kWtTileRows - 1 - dy_span, max_w = kWtPitch - 8 - lane_reach;
         tma = monotone && max_h >= 0 && max_w >= 0 && make_map_tensor(m, &tmap);
         if (tma) {
             if ((rc = ensure(h, h->d_wtgroups, sizeof(WtGroup) * (size_t)ndt * Q.n + sizeof(int) * (size_t)ndt))) return rc;
@@ -2036,20 +2044,34 @@ int csm_match_grid(csm_handle h, int64_t map_id,
             k_window_groups<<<(ndt + 127) / 128, 128, 0, h->stream>>>(dq, proj, groups, gcount, max_h, max_w);
             CSM_LAUNCH_CHECK();
             const size_t smem = wt_smem_bytes(Q.n);
-            static bool attr_set = false;
-            if (!attr_set) {
-                CSM_CUDA(cudaFuncSetAttribute(k_window_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)wt_smem_bytes(kMaxBeams)));
-                CSM_CUDA(cudaFuncSetAttribute(k_window_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)wt_smem_bytes(kMaxBeams)));
-                attr_set = true;
-            }
-            dim3 wgrid(ndt, (ndy + rows_per_cta - 1) / rows_per_cta, (ndx + kWtColsPerCta - 1) / kWtColsPerCta);
+            const int max_smem = (int)wt_smem_bytes(kMaxBeams);
+            dim3 wgrid(ndt, (ndy + rows_per_cta - 1) / rows_per_cta, (ndx + cols_per_cta - 1) / cols_per_cta);
             phase_mark(h, "k_window_groups");
-            if (unit)
-                k_window_tma<true><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
-            else
-                k_window_tma<false><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
+#define CSM_WT_LAUNCH(UNIT, CHUNKS, REM)                                                                        \
+            {                                                                                                   \
+                static bool attr = false;                                                                       \
+                if (!attr) {                                                                                    \
+                    CSM_CUDA(cudaFuncSetAttribute(k_window_tma<UNIT, CHUNKS, REM>,                              \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));      \
+                    attr = true;                                                                                \
+                }                                                                                               \
+                k_window_tma<UNIT, CHUNKS, REM><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA); \
+            }
+            if (rem_variant) {
+                switch (rem_chunks) {
+                case 1: CSM_WT_LAUNCH(true, 1, true) break;
+                case 2: CSM_WT_LAUNCH(true, 2, true) break;
+                case 3: CSM_WT_LAUNCH(true, 3, true) break;
+                case 4: CSM_WT_LAUNCH(true, 4, true) break;
+                case 5: CSM_WT_LAUNCH(true, 5, true) break;
+                default: CSM_WT_LAUNCH(true, 6, true) break;
+                }
+            } else if (unit) {
+                CSM_WT_LAUNCH(true, kWtChunks, false)
+            } else {
+                CSM_WT_LAUNCH(false, kWtChunks, false)
+            }
+#undef CSM_WT_LAUNCH
             CSM_LAUNCH_CHECK();
             phase_mark(h, "k_window_tma");
         } else if (h->window_mode == 2) {

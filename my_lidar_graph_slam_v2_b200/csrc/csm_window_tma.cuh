@@ -22,6 +22,11 @@
  *     consecutive candidate columns per 32-column chunk, i.e. every warp-level
  *     load reads 32 consecutive words (128 contiguous bytes, conflict-free), the
  *     per-candidate sums live in registers across all runs;
+ *   - windows of 32 k + r columns, r <= 4 (odd windows 2 w + 1 with w a multiple of 16: the
+ *     BASELINE 161 x 161 window) would leave 31 of 32 lanes of a last chunk idle: the kRem variant
+ *     scores k chunks per lane and gives the r remainder columns of a warp's own rows to its first
+ *     3 r lanes (one more, conflict-free load per warp and beam at the 260-word tile pitch instead
+ *     of three loads with one useful lane);
  *   - reduces (key, ordinal) with warp shuffles and one atomicMax per warp.
  * No tensor cores: this is a gather-and-sum, not a contraction.
  *
@@ -37,13 +42,17 @@ namespace csm {
 
 constexpr int kWtMaxWarps = 20;                  /* warps per CTA: 8..20, chosen per window (host) */
 constexpr int kWtRows = 3;                       /* candidate rows per warp */
-constexpr int kWtChunks = 6;                     /* 32-column chunks per lane */
+constexpr int kWtChunks = 6;                     /* 32-column chunks per lane (at most) */
 constexpr int kWtColsPerCta = 32 * kWtChunks;    /* 192 candidate columns */
-constexpr int kWtPitch = 256;                    /* tile row pitch in cells (TMA box width) */
+constexpr int kWtRemMax = 4;                     /* remainder columns the transposed path takes */
+constexpr int kWtPitch = 256;                    /* landing buffer row pitch in cells (TMA box width) */
+constexpr int kWtTilePitch = 260;                /* scored tile row pitch in words: a multiple of 4 (16-byte
+                                                    stores of the widening) that is not a multiple of 32, so
+                                                    that a column of the tile spreads over 8 banks */
 constexpr int kWtBoxRows = 8;                    /* rows per TMA box */
 constexpr int kWtTileRows = 96;                  /* rows per tile (multiple of kWtBoxRows) */
 constexpr size_t kWtStageBytes = (size_t)kWtTileRows * kWtPitch * sizeof(uint16_t);   /* TMA landing buffer */
-constexpr size_t kWtTileBytes = (size_t)kWtTileRows * kWtPitch * sizeof(uint32_t);    /* scored tile */
+constexpr size_t kWtTileBytes = (size_t)kWtTileRows * kWtTilePitch * sizeof(uint32_t);   /* scored tile */
 constexpr unsigned int kWtKnownBit = 1u << 20;   /* tile word = value | (value != 0) << 20 */
 constexpr int kWtFlush = 16;                     /* beams per packed accumulation: 16 * 65535 < 2^20 */
 /* dynamic shared memory of k_window_tma for n beams: two landing buffers, the tile, two
@@ -144,7 +153,7 @@ struct WtArgs
     int rows_per_cta;          /* kWtRows * warps of the launch */
 };
 
-template <bool kUnitDx>
+template <bool kUnitDx, int kChunks, bool kRem>
 __global__ void __launch_bounds__(kWtMaxWarps * 32, 1)
 k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restrict__ queries,
              const proj_t* __restrict__ proj_all, GridArgs G, WtArgs A)
@@ -161,7 +170,8 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
     const DevQuery& Q = queries[0];
     const int it = blockIdx.x;
     const int iy0 = blockIdx.y * A.rows_per_cta;
-    const int ix0 = blockIdx.z * kWtColsPerCta;
+    static_assert(!kRem || kUnitDx, "the remainder path assumes unit column steps");
+    const int ix0 = kRem ? 0 : blockIdx.z * (32 * kChunks);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = Q.n;
     const proj_t* __restrict__ proj = proj_all + Q.proj_off + (size_t)it * n;
@@ -182,30 +192,48 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
 #pragma unroll
     for (int rw = 0; rw < kWtRows; ++rw) {
         const int iy = iy0 + warp * kWtRows + rw;
-        roff[rw] = (G.my[min(iy, G.ndy - 1)] - my0) * kWtPitch;
+        roff[rw] = (G.my[min(iy, G.ndy - 1)] - my0) * kWtTilePitch;
     }
-    int coff[kWtChunks];
+    /* remainder columns 32 kChunks .. ndx - 1: the first kWtRows * r lanes of every warp take the
+     * warp's own candidate rows, lane = column * kWtRows + row (tile words 260 apart per row and 1
+     * apart per column: distinct banks, and every warp carries the same one extra load per beam) */
+    bool rem_on = false;
+    int rem_off = 0, rem_iy = 0, rem_ix = 0;
+    unsigned int accx = 0u, sumx = 0u, cntx = 0u;
+    if (kRem) {
+        const int nrem = G.ndx - 32 * kChunks;
+        const int rw = lane % kWtRows, rj = lane / kWtRows;
+        rem_iy = iy0 + warp * kWtRows + rw; rem_ix = 32 * kChunks + rj;
+        rem_on = rj < nrem && rem_iy < G.ndy;
+        rem_off = rem_on ? (G.my[rem_iy] - my0) * kWtTilePitch + rem_ix : 0;
+    }
+    int coff[kChunks];
 #pragma unroll
-    for (int m = 0; m < kWtChunks; ++m) {
+    for (int m = 0; m < kChunks; ++m) {
         const int ix = ix0 + lane + 32 * m;
         coff[m] = kUnitDx ? lane + 32 * m : G.mx[min(ix, G.ndx - 1)] - mx0;
     }
     /* per candidate: packed running word (value sum in bits 0..19, known count above) that is
      * folded into the 32-bit sum / count every kWtFlush beams */
-    unsigned int acc[kWtRows][kWtChunks], sum[kWtRows][kWtChunks], cnt[kWtRows][kWtChunks];
+    unsigned int acc[kWtRows][kChunks], sum[kWtRows][kChunks], cnt[kWtRows][kChunks];
 #pragma unroll
     for (int rw = 0; rw < kWtRows; ++rw)
 #pragma unroll
-        for (int m = 0; m < kWtChunks; ++m) { acc[rw][m] = 0u; sum[rw][m] = 0u; cnt[rw][m] = 0u; }
+        for (int m = 0; m < kChunks; ++m) { acc[rw][m] = 0u; sum[rw][m] = 0u; cnt[rw][m] = 0u; }
     auto flush = [&]() {
 #pragma unroll
         for (int rw = 0; rw < kWtRows; ++rw)
 #pragma unroll
-            for (int m = 0; m < kWtChunks; ++m) {
+            for (int m = 0; m < kChunks; ++m) {
                 sum[rw][m] += acc[rw][m] & (kWtKnownBit - 1u);
                 cnt[rw][m] += acc[rw][m] >> 20;
                 acc[rw][m] = 0u;
             }
+        if (kRem) {
+            sumx += accx & (kWtKnownBit - 1u);
+            cntx += accx >> 20;
+            accx = 0u;
+        }
     };
 
     const WtGroup* __restrict__ groups = A.groups + (size_t)it * n;
@@ -236,10 +264,13 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
         {
             /* landing buffer (u16) -> tile (u32 words carrying the known bit), 8 cells per step */
             const uint4* __restrict__ src = reinterpret_cast<const uint4*>((g & 1) ? stage1 : stage0);
-            uint4* __restrict__ dst = reinterpret_cast<uint4*>(tile);
+            uint4* __restrict__ tile4 = reinterpret_cast<uint4*>(tile);
             const int rows = grp.hspan + A.dy_span + 1;
             const int chunks = rows * (kWtPitch / 8);
             for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+                /* landing row r, 8-cell chunk k -> tile row r (pitch kWtTilePitch words), words 8k .. 8k+7 */
+                const int r = c / (kWtPitch / 8), k8 = c - r * (kWtPitch / 8);
+                uint4* __restrict__ dst = tile4 + r * (kWtTilePitch / 4) + 2 * k8;
                 const uint4 v = src[c];
                 const unsigned int w[4] = { v.x, v.y, v.z, v.w };
                 unsigned int o[8];
@@ -249,8 +280,8 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
                     o[2 * k] = lo | (lo ? kWtKnownBit : 0u);
                     o[2 * k + 1] = hi | (hi ? kWtKnownBit : 0u);
                 }
-                dst[2 * c] = make_uint4(o[0], o[1], o[2], o[3]);
-                dst[2 * c + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
         __syncthreads();                  /* tile ready, landing buffer g & 1 free */
@@ -259,14 +290,16 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
         const int cshift = (grp.minc + mx0) & 7;      /* tile column 0 is the 8-aligned cell below the window */
         for (int i = grp.begin; i < grp.end; ++i) {
             const proj_t p = s_proj[i];
-            const uint32_t* __restrict__ base = tile + ((int)p.y - grp.minr) * kWtPitch + ((int)p.x - grp.minc) + cshift;
+            const uint32_t* __restrict__ base = tile + ((int)p.y - grp.minr) * kWtTilePitch + ((int)p.x - grp.minc) + cshift;
 #pragma unroll
             for (int rw = 0; rw < kWtRows; ++rw) {
                 const uint32_t* __restrict__ row = base + roff[rw];
 #pragma unroll
-                for (int m = 0; m < kWtChunks; ++m)
+                for (int m = 0; m < kChunks; ++m)
                     acc[rw][m] += kUnitDx ? row[lane + 32 * m] : row[coff[m]];
             }
+            if (kRem && rem_on)
+                accx += base[rem_off];
             if (++pending == kWtFlush) { flush(); pending = 0; }
         }
     }
@@ -275,29 +308,34 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
     /* candidates -> packed best (same decisions as k_grid_window) */
     unsigned long long best = 0ull;
     const uint16_t* __restrict__ m0 = Q.lvl[0];
+    auto consider = [&](int iy, int ix, unsigned int sumv, unsigned int known) {
+        const int k = (int)known;
+        const long long key = make_key((long long)sumv, k);
+        if (k > Q.nk_cut) {
+            const int c = key_vs_threshold(key, Q.kthr);
+            bool ok = c > 0;
+            if (c == 0)
+                ok = exact_normalized_score(m0, Q.rows, Q.cols, proj, Q.pst_i, n, G.mx[ix], G.my[iy]) > Q.kthr.thr;
+            if (ok) {
+                const unsigned long long ord = ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
+                const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
+                best = v > best ? v : best;
+            }
+        }
+    };
 #pragma unroll
     for (int rw = 0; rw < kWtRows; ++rw) {
         const int iy = iy0 + warp * kWtRows + rw;
 #pragma unroll
-        for (int m = 0; m < kWtChunks; ++m) {
+        for (int m = 0; m < kChunks; ++m) {
             const int ix = ix0 + lane + 32 * m;
             if (iy >= G.ndy || ix >= G.ndx)
                 continue;
-            const int k = (int)cnt[rw][m];
-            const long long key = make_key((long long)sum[rw][m], k);
-            if (k > Q.nk_cut) {
-                const int c = key_vs_threshold(key, Q.kthr);
-                bool ok = c > 0;
-                if (c == 0)
-                    ok = exact_normalized_score(m0, Q.rows, Q.cols, proj, Q.pst_i, n, G.mx[ix], G.my[iy]) > Q.kthr.thr;
-                if (ok) {
-                    const unsigned long long ord = ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
-                    const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
-                    best = v > best ? v : best;
-                }
-            }
+            consider(iy, ix, sum[rw][m], cnt[rw][m]);
         }
     }
+    if (kRem && rem_on)
+        consider(rem_iy, rem_ix, sumx, cntx);
     block_best_commit(best, G.best);
 }
 

@@ -211,6 +211,31 @@ def test_grid_vs_checker(handle, checker, seed):
         assert_match(s.result, o, "grid seed %d step %s" % (seed, step))
 
 
+@pytest.mark.parametrize("ndx,ndy", [(33, 9), (34, 21), (36, 5), (66, 11), (97, 7), (129, 3)])
+def test_grid_window_remainder_columns(handle, checker, ndx, ndy):
+    """Windows of 32 k + r candidate columns (r <= 4): the TMA window kernel scores k chunks per lane
+    and the r remainder columns with lanes running over candidate rows. Against the reference and
+    against the plain global-memory kernel, with thresholds that leave only part of the window."""
+    case = synth.case_for(synth.CFG1, 2600 + ndx)
+    gm, scan = grid_of(case), _scan(case)
+    g = checker.grid(case.submap.grid, case.submap.res, case.submap.off_x, case.submap.off_y)
+    res = case.submap.res
+    rng = ((ndx - 1) * res + 1e-9, (ndy - 1) * res + 1e-9, 0.02)
+    step = (res, res, 0.005)
+    assert len(matchers.grid_search_offsets(rng[0] / 2, step[0])) == ndx
+    assert len(matchers.grid_search_offsets(rng[1] / 2, step[1])) == ndy
+    mt = matchers.ScanMatcherGridSearch("gs", *rng, *step, handle=handle)
+    for thr in ((0.0, 0.0), (0.3, 0.5)):
+        handle.set_option("window_mode", 2)
+        a = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+        handle.set_option("window_mode", 1)
+        b = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+        handle.set_option("window_mode", 0)
+        o = checker.match_grid(g, case.angles, case.ranges, case.init_pose, rng, step, thr)
+        assert_match(a.result, o, "tma %dx%d %s" % (ndx, ndy, thr))
+        assert_match(b.result, o, "global %dx%d %s" % (ndx, ndy, thr))
+
+
 def test_empty_and_out_of_map(handle, checker):
     """All-unknown map: nothing found; scan far outside the map: nothing found."""
     case = synth.case_for(synth.CFG1, 2300)
