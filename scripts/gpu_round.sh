@@ -2,10 +2,7 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 nproc
-python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; tail -5 gpurun_out/bench.err; cat gpurun_out/bench.json
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; tail -5 gpurun_out/bench.err; cat gpurun_out/bench.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json
-python bench.py --steps 2 --warmup 1 --no-cpu --no-single > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-single > gpurun_out/ncu.log 2>&1
-echo "rc=$?"; wc -l gpurun_out/launches.csv
