@@ -431,6 +431,29 @@ def test_errors(handle):
         handle.match_rt(9, [0.0], [1.0], (0, 0, 0), 5, (1, 1, 1), (0.05, 0.05, 0.01), (0.0, 0.0))  # coarse not built
     with pytest.raises(capi.CsmError):
         handle.build_pyramid(9, 9)                           # hmax out of range
+    # refinement / epilogue entry points
+    with pytest.raises(capi.CsmError):
+        handle.set_refiner(0, 1e-4, 1e-4, 1e4)               # at least one iteration
+    with pytest.raises(capi.CsmError):
+        handle.set_refiner(10, 1e-4, 1e-4, 0.0)              # covariance scale must be positive
+    with pytest.raises(capi.CsmError):
+        handle.refine_batch([(123456, 1, (0.0, 0.0, 0.0))])  # unknown map
+    with pytest.raises(capi.CsmError):
+        handle.refine_batch([(9, 987654, (0.0, 0.0, 0.0))])  # unknown scan
+    with pytest.raises(capi.CsmError):
+        handle.set_epilogue(-1.0)
+    handle.set_epilogue(1e4)
+    with pytest.raises(capi.CsmError):
+        handle.last_epilogue()                               # no match has run with it yet
+    handle.set_epilogue(0.0)
+    with pytest.raises(capi.CsmError):
+        handle.loop_batch_finish_refined(1)                  # nothing in flight
+    other = capi.Handle(0)
+    assert handle.lib.csm_share_copy_stream(handle.h, handle.h) != 0      # a handle cannot borrow from itself
+    assert handle.lib.csm_share_copy_stream(other.h, handle.h) == 0
+    other.upload_grid(1, g, 0.05, 0.0, 0.0)                  # uploads through the borrowed copy stream
+    assert not other.download_level(1, 0, (32, 32)).any()
+    other.close()
     handle.release_grid(9)
 
 
