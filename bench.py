@@ -689,7 +689,7 @@ def single_scan_numbers(h, lib, kind):
             "smem_roofline_reads_per_s": 32 * 148 * 1.965e9,
             "frac_of_smem_roofline": full * 1080 / (wt_ms * 1e-3) / (32 * 148 * 1.965e9),
             "note": "roofline = 1 shared-memory wavefront (32 lanes) per cycle per SM at 1965 MHz; "
-                    "ncu counts 0.745 wavefronts/cycle/SM including idle lanes (profiles/r1_k_window_tma.txt)"}}
+                    "ncu counts 0.739 wavefronts/cycle/SM including the tile widening and idle lanes (profiles/r1_k_window_tma.txt)"}}
     ctx.close()
     return out
 
