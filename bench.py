@@ -238,8 +238,12 @@ def main_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # the 8-byte all-reduce runs beside kernels that fill every SM: NCCL's stream gets high priority
-        # so that its one CTA is placed as soon as a slot frees instead of queueing behind the sweep
+        # the only collective is an 8-byte all-reduce that runs beside kernels filling every SM: one
+        # channel of 64 threads is all it needs (a small CTA finds a free slot sooner), and NCCL's
+        # stream gets high priority so that it is placed as soon as a slot frees
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_NTHREADS", "64")
         opts = dist.ProcessGroupNCCL.Options()
         opts.is_high_priority_stream = True
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
