@@ -5,6 +5,7 @@
 #include <string>
 
 #include "csm_host/loop_detector.hpp"
+#include "csm_host/loop_searcher.hpp"
 
 using namespace csm_host;
 
@@ -249,6 +250,38 @@ int csm_host_refine(const uint16_t* values, int rows, int cols, double res, doub
     Export(s, out);
     out->best_t = s.n_processed;      /* iterations */
     return 0;
+}
+
+/* LoopSearcherNearest::Search (CPU, no device) on a pose-graph summary: scan nodes (ids ascending, 3 doubles
+ * of global pose each) and local maps (ids ascending, scan-node id range, finished flag). Writes up to `cap`
+ * candidates as (query scan node, reference scan node, reference local map) id triples and their squared node
+ * distances; returns how many. */
+int csm_host_loop_search(int n_scans, const int* scan_ids, const double* scan_poses,
+                         int n_maps, const int* map_ids, const int* map_scan_min, const int* map_scan_max,
+                         const int* map_finished, double accum_travel_dist, int last_finished_scan_id,
+                         int last_finished_map_id, double travel_dist_threshold, double node_dist_threshold,
+                         int num_of_candidate_nodes, int* out_ids, double* out_dist_sq, int cap)
+{
+    LoopSearchHint hint;
+    for (int i = 0; i < n_scans; ++i)
+        hint.scan_nodes.push_back(ScanNodeData { scan_ids[i], Pose2D { scan_poses[3 * i], scan_poses[3 * i + 1],
+                                                                       scan_poses[3 * i + 2] } });
+    for (int i = 0; i < n_maps; ++i)
+        hint.local_map_nodes.push_back(LocalMapData { map_ids[i], map_scan_min[i], map_scan_max[i],
+                                                      map_finished[i] != 0 });
+    hint.accum_travel_dist = accum_travel_dist;
+    hint.last_finished_scan_id = last_finished_scan_id;
+    hint.last_finished_map_id = last_finished_map_id;
+    LoopSearcherNearest searcher(travel_dist_threshold, node_dist_threshold, num_of_candidate_nodes);
+    const std::vector<LoopCandidate> c = searcher.Search(hint);
+    const int n = std::min(static_cast<int>(c.size()), cap);
+    for (int i = 0; i < n; ++i) {
+        out_ids[3 * i] = c[i].query_scan_node_id;
+        out_ids[3 * i + 1] = c[i].reference_scan_node_id;
+        out_ids[3 * i + 2] = c[i].reference_local_map_id;
+        out_dist_sq[i] = searcher.LastNodeDistances()[i];
+    }
+    return n;
 }
 
 /* ---- persistent loop detector (bench.py e2e path) ------------------------------ */

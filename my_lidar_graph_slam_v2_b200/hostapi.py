@@ -92,6 +92,30 @@ def cost(grid, res, off, angles, ranges, sensor_pose, covariance_scale=1e4):
     return nc.value, np.array(cov)
 
 
+def loop_search(scan_ids, scan_poses, map_ids, map_scan_min, map_scan_max, map_finished, accum_travel_dist,
+                last_finished_scan_id, last_finished_map_id, travel_dist_threshold, node_dist_threshold,
+                num_of_candidate_nodes):
+    """LoopSearcherNearest::Search of the C++ mirror (CPU). Returns ([(query scan node, reference scan node,
+    reference local map)], [squared node distance])."""
+    lib = load()
+    ip = C.POINTER(C.c_int)
+    lib.csm_host_loop_search.argtypes = [C.c_int, ip, C.POINTER(C.c_double), C.c_int, ip, ip, ip, ip, C.c_double,
+                                         C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, ip,
+                                         C.POINTER(C.c_double), C.c_int]
+    si = np.ascontiguousarray(scan_ids, dtype=np.int32)
+    sp = np.ascontiguousarray(scan_poses, dtype=np.float64).reshape(-1)
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (map_ids, map_scan_min, map_scan_max, map_finished)]
+    cap = max(int(num_of_candidate_nodes), 1)
+    out = np.zeros(3 * cap, dtype=np.int32)
+    dist = np.zeros(cap, dtype=np.float64)
+    n = lib.csm_host_loop_search(len(si), si.ctypes.data_as(ip), sp.ctypes.data_as(C.POINTER(C.c_double)),
+                                 len(arrs[0]), *[a.ctypes.data_as(ip) for a in arrs], accum_travel_dist,
+                                 last_finished_scan_id, last_finished_map_id, travel_dist_threshold,
+                                 node_dist_threshold, num_of_candidate_nodes, out.ctypes.data_as(ip),
+                                 dist.ctypes.data_as(C.POINTER(C.c_double)), cap)
+    return [tuple(int(v) for v in out[3 * i:3 * i + 3]) for i in range(n)], [float(d) for d in dist[:n]]
+
+
 def refine(grid, res, off, angles, ranges, init_pose, rel_pose=(0.0, 0.0, 0.0), iterations_max=10,
            convergence_threshold=1e-4, lam=1e-4, covariance_scale=1e4):
     """ScanMatcherLinearSolver::OptimizePose (CPU, no device). Returns (summary, lambda after the call);

@@ -242,3 +242,29 @@ def dense_to_blocks(grid, log2bs=4):
     index = np.flatnonzero(used.reshape(-1)).astype(np.int32)
     blocks = np.ascontiguousarray(tiles.reshape(br * bc, bs, bs)[index])
     return blocks, index, br, bc
+
+
+def make_pose_graph_summary(seed, n_maps=12, scans_per_map=(6, 14), loop=True):
+    """A pose-graph summary for the loop searcher: scan nodes along a closed
+    trajectory with odometry-like jitter, consecutive runs of them grouped into local maps (all
+    finished), the accumulated travel distance of the walk.
+    Returns dict(scan_ids, scan_poses, map_ids, map_scan_min, map_scan_max, map_finished,
+    accum_travel_dist, last_finished_scan_id, last_finished_map_id)."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(scans_per_map[0], scans_per_map[1] + 1, size=n_maps)
+    n = int(counts.sum())
+    t = np.linspace(0.0, (2.0 if loop else 1.2) * np.pi, n)
+    radius = rng.uniform(6.0, 14.0)
+    xs = radius * np.cos(t) * rng.uniform(0.7, 1.3) + rng.normal(0.0, 0.05, n)
+    ys = radius * np.sin(t) + rng.normal(0.0, 0.05, n)
+    th = t + np.pi / 2 + rng.normal(0.0, 0.02, n)
+    poses = np.stack([xs, ys, th], axis=1)
+    first_id = int(rng.integers(0, 5))
+    scan_ids = np.arange(first_id, first_id + n, dtype=np.int32)
+    ends = np.cumsum(counts)
+    starts = ends - counts
+    accum = float(np.sum(np.hypot(np.diff(xs), np.diff(ys))))
+    return dict(scan_ids=scan_ids, scan_poses=poses, map_ids=np.arange(n_maps, dtype=np.int32),
+                map_scan_min=scan_ids[starts], map_scan_max=scan_ids[ends - 1],
+                map_finished=np.ones(n_maps, dtype=np.int32), accum_travel_dist=accum,
+                last_finished_scan_id=int(scan_ids[-1]), last_finished_map_id=n_maps - 1)

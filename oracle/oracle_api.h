@@ -115,6 +115,18 @@ int orc_loopdet_detect(void* det, int n_queries,
                        const double* angles, const double* ranges,
                        orc_result* out, double* elapsed_s);
 
+/* LoopSearcherNearest::Search (loop_searcher_nearest.cpp:59-170) on a pose-graph summary: scan nodes
+ * (ids ascending, 3 doubles of global pose each), local maps (ids ascending, scan-node id range,
+ * finished flag). Writes up to cap candidates as (query scan node, reference scan node, reference
+ * local map) triples in the order the reference returns them; returns their number, -1 when this
+ * checker does not provide it. */
+int orc_loop_search(int n_scans, const int32_t* scan_ids, const double* scan_poses,
+                    int n_maps, const int32_t* map_ids, const int32_t* map_scan_min,
+                    const int32_t* map_scan_max, const int32_t* map_finished,
+                    double accum_travel_dist, int last_finished_scan_id, int last_finished_map_id,
+                    double travel_dist_threshold, double node_dist_threshold,
+                    int num_of_candidate_nodes, int32_t* out_ids, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,29 @@ class Oracle:
         assert rc == 0
         return out
 
+    def loop_search(self, scan_ids, scan_poses, map_ids, map_scan_min, map_scan_max, map_finished,
+                    accum_travel_dist, last_finished_scan_id, last_finished_map_id,
+                    travel_dist_threshold, node_dist_threshold, num_of_candidate_nodes):
+        """LoopSearcherNearest::Search of the reference. Returns [(query scan node, reference scan
+        node, reference local map)] in the reference's order, or None when this checker lacks it."""
+        if not hasattr(self.lib, "orc_loop_search"):
+            return None
+        i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        self.lib.orc_loop_search.argtypes = [C.c_int, i32p, dp, C.c_int, i32p, i32p, i32p, i32p, C.c_double,
+                                             C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, i32p, C.c_int]
+        si = np.ascontiguousarray(scan_ids, dtype=np.int32)
+        sp = np.ascontiguousarray(scan_poses, dtype=np.float64).reshape(-1)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (map_ids, map_scan_min, map_scan_max, map_finished)]
+        cap = max(int(num_of_candidate_nodes), 1)
+        out = np.zeros(3 * cap, dtype=np.int32)
+        n = self.lib.orc_loop_search(len(si), si.ctypes.data_as(i32p), sp.ctypes.data_as(dp), len(arrs[0]),
+                                     *[a.ctypes.data_as(i32p) for a in arrs], accum_travel_dist,
+                                     last_finished_scan_id, last_finished_map_id, travel_dist_threshold,
+                                     node_dist_threshold, num_of_candidate_nodes, out.ctypes.data_as(i32p), cap)
+        if n < 0:
+            return None
+        return [tuple(int(v) for v in out[3 * i:3 * i + 3]) for i in range(n)]
+
     def loop_detector(self, hmax, rng, thr, n_threads=1):
         return OracleLoopDetector(self, hmax, rng, thr, n_threads)
 

@@ -41,6 +41,13 @@
 #include "my_lidar_graph_slam/mapping/loop_detector.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/pose_graph.hpp"
+/* The reference registers the searcher's metrics under fixed names, so a process can construct
+ * LoopSearcherNearest only once (metric.cpp asserts on duplicates); its thresholds are private
+ * const members. The checker needs several parameter sets: it keeps the one instance and rewrites
+ * those members, which takes access to them. No reference code is changed. */
+#define private public
+#include "my_lidar_graph_slam/mapping/loop_searcher_nearest.hpp"
+#undef private
 
 using namespace MyLidarGraphSlam;
 using namespace MyLidarGraphSlam::Mapping;
@@ -637,6 +644,41 @@ int orc_loopdet_detect(void* detPtr, int n_queries,
         ResetMatcherMetrics(det->mMatchers[t]->Name(), false);
 
     return 0;
+}
+
+/* The reference's LoopSearcherNearest on a hint rebuilt from plain arrays */
+int orc_loop_search(int n_scans, const int32_t* scan_ids, const double* scan_poses,
+                    int n_maps, const int32_t* map_ids, const int32_t* map_scan_min,
+                    const int32_t* map_scan_max, const int32_t* map_finished,
+                    double accum_travel_dist, int last_finished_scan_id, int last_finished_map_id,
+                    double travel_dist_threshold, double node_dist_threshold,
+                    int num_of_candidate_nodes, int32_t* out_ids, int cap)
+{
+    IdMap<NodeId, ScanNodeData> scanNodes;
+    for (int i = 0; i < n_scans; ++i)
+        scanNodes.Append(NodeId { scan_ids[i] },
+                         RobotPose2D<double> { scan_poses[3 * i], scan_poses[3 * i + 1], scan_poses[3 * i + 2] });
+    IdMap<LocalMapId, LocalMapData> localMaps;
+    for (int i = 0; i < n_maps; ++i)
+        localMaps.Append(LocalMapId { map_ids[i] },
+                         Point2D<double> { 0.0, 0.0 }, Point2D<double> { 0.0, 0.0 },
+                         NodeId { map_scan_min[i] }, NodeId { map_scan_max[i] }, map_finished[i] != 0);
+    const LoopSearchHint hint { std::move(scanNodes), std::move(localMaps), accum_travel_dist,
+                                NodeId { last_finished_scan_id }, LocalMapId { last_finished_map_id } };
+    static LoopSearcherNearest* searcher = nullptr;
+    if (searcher == nullptr)
+        searcher = new LoopSearcherNearest(travel_dist_threshold, node_dist_threshold, num_of_candidate_nodes);
+    const_cast<double&>(searcher->mTravelDistThreshold) = travel_dist_threshold;
+    const_cast<double&>(searcher->mNodeDistThreshold) = node_dist_threshold;
+    const_cast<int&>(searcher->mNumOfCandidateNodes) = num_of_candidate_nodes;
+    const LoopCandidateVector candidates = searcher->Search(hint);
+    const int n = std::min(static_cast<int>(candidates.size()), cap);
+    for (int i = 0; i < n; ++i) {
+        out_ids[3 * i] = candidates[i].mQueryScanNodeId.mId;
+        out_ids[3 * i + 1] = candidates[i].mReferenceScanNodeId.mId;
+        out_ids[3 * i + 2] = candidates[i].mReferenceLocalMapId.mId;
+    }
+    return n;
 }
 
 } /* extern "C" */

@@ -142,3 +142,20 @@ def test_cpp_linear_solver_matches_reference_vectors():
         assert out.norm_cost == float.fromhex(e["norm_cost"])
         assert np.allclose(list(out.cov), [float.fromhex(v) for v in e["cov"]], rtol=1e-9, atol=0.0)
         assert 1e-8 <= lam <= 1e-4
+
+
+def test_cpp_loop_searcher_matches_reference_vectors():
+    """LoopSearcherNearest of the C++ mirror (host/src/loop_searcher.cpp, the caller that produces the
+    loop-detection query batch) against vectors produced by the reference's loop_searcher_nearest.cpp:
+    the same candidates in the same order (std::nth_element on the same sequence)."""
+    from helpers import load_golden
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    n_nonempty = 0
+    for e in load_golden("loop_search_vectors.json")["loop_search"]:
+        g = synth.make_pose_graph_summary(e["seed"], loop=e["loop"])
+        got, dist = hostapi.loop_search(travel_dist_threshold=e["travel"], node_dist_threshold=e["node"],
+                                        num_of_candidate_nodes=e["cand"], **g)
+        assert got == [tuple(c) for c in e["candidates"]], e["seed"]
+        assert len(got) <= e["cand"] and all(d < e["node"] ** 2 for d in dist)
+        n_nonempty += bool(got)
+    assert n_nonempty >= 4

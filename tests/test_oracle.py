@@ -153,3 +153,17 @@ def test_loop_detector_with_linear_solver_port_vs_reference(port_oracle, ref_ora
         if b.found:
             assert list(a.est_pose) == list(b.est_pose)
             assert np.allclose(list(a.cov), list(b.cov), rtol=1e-9, atol=0.0)
+
+
+@pytest.mark.parametrize("seed", range(5100, 5112))
+def test_loop_searcher_cpp_vs_reference(ref_oracle, seed):
+    """The C++ LoopSearcherNearest against the reference's on seeded pose-graph summaries, several
+    threshold sets each: identical candidate lists, order included."""
+    from my_lidar_graph_slam_v2_b200 import hostapi, synth
+    g = synth.make_pose_graph_summary(seed, n_maps=8 + seed % 9, loop=seed % 3 != 0)
+    for travel, node, cand in ((5.0, 2.0, 2), (15.0, 4.0, 32), (2.0, 6.0, 500), (40.0, 1.0, 8)):
+        exp = ref_oracle.loop_search(travel_dist_threshold=travel, node_dist_threshold=node,
+                                     num_of_candidate_nodes=cand, **g)
+        got, _ = hostapi.loop_search(travel_dist_threshold=travel, node_dist_threshold=node,
+                                     num_of_candidate_nodes=cand, **g)
+        assert got == exp, (seed, travel, node, cand)
