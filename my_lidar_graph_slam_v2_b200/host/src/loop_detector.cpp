@@ -223,14 +223,16 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     /* per query: initial pose InverseCompound(map, scan) (:97-98), sensor pose,
      * steps and windows with the reference's expressions */
     std::vector<csm_loop_query> dq(nq);
-    {
+    for (int i = 0; i < nq; ++i)
+        if (queries[i].local_map.map_id < 0) {
+            std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
+            std::abort();
+        }
+    /* (evaluated after the uploads have been enqueued: the copies start before the host does this) */
+    auto fill_queries = [&]() {
         std::map<std::pair<std::int64_t, double>, std::array<double, 3>> steps;
         for (int i = 0; i < nq; ++i) {
             const LoopDetectionQuery& q = queries[i];
-            if (q.local_map.map_id < 0) {
-                std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
-                std::abort();
-            }
             const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
             const Pose2D sensor = Compound(init, q.scan->relative_sensor_pose);
             auto key = std::make_pair(q.scan_id, q.local_map.resolution);
@@ -253,7 +255,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             d.score_thr = mScoreThreshold;
             d.known_thr = mKnownRateThreshold;
         }
-    }
+    };
     mLastResults.resize(nq);
     if (mDeviceRefiner)
         mLastRefined.resize(nq);
@@ -312,6 +314,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
                 UploadNewMaps(c, fresh);
             }
         }
+        fill_queries();
         const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
         if (trace) std::fprintf(stderr, "lanes: uploads enqueued at %.0f us\n", timer.ElapsedMicro());
         for (std::size_t si = 0; si < segments.size(); ++si) {
@@ -372,6 +375,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             ctx->Check(csm_upload_scan(h, q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
                                        static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
     std::size_t next_group = 0;
+    fill_queries();
     set_refiner(ctx);
     int finished = 0;      /* chunks whose results have been read back */
     for (int c = 0; c < nchunks; ++c) {
