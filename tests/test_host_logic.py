@@ -33,10 +33,39 @@ def test_no_cpu_fallback_without_device():
         capi.Handle(0)
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The header compiles as plain C (no C++, no torch types across the boundary) and the ctypes
+    mirrors in capi.py have the sizes and field offsets the C compiler gives the structs."""
+    import subprocess
     assert C.sizeof(capi.CsmResult) == 48
     assert C.sizeof(capi.CsmLoopQuery) == 96
     assert capi.CsmResult.sum_value.offset == 16 and capi.CsmResult.normalized_score.offset == 32
+    probes = [("csm_result", capi.CsmResult, ["found", "sum_value", "normalized_score", "n_ignored"]),
+              ("csm_loop_query", capi.CsmLoopQuery, ["map_id", "sensor_pose", "win_x", "step_x", "known_thr"]),
+              ("csm_refine_params", capi.CsmRefineParams, ["max_iterations", "convergence_threshold",
+                                                           ("lambda", "lambda_"), "covariance_scale"]),
+              ("csm_refined", capi.CsmRefined, ["pose", "covariance", "initial_cost", "final_cost",
+                                                ("lambda", "lambda_"), "iterations", "valid"]),
+              ("csm_refine_query", capi.CsmRefineQuery, ["map_id", "scan_id", "sensor_pose"])]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "csm_b200.h"', "int main(void) {"]
+    for name, _, fields in probes:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in fields:
+            cf = f[0] if isinstance(f, tuple) else f
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, cf, name, cf))
+    lines += ["return 0; }"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                 check=True).stdout.splitlines())
+    for name, cls, fields in probes:
+        assert int(got[name]) == C.sizeof(cls), name
+        for f in fields:
+            cf, pf = f if isinstance(f, tuple) else (f, f)
+            assert int(got["%s.%s" % (name, cf)]) == getattr(cls, pf).offset, (name, cf)
 
 
 def test_product_does_not_touch_the_oracle():
