@@ -184,6 +184,24 @@ private:
     CostFuncPtr mCost;
 };
 
+/* ScanMatcherHillClimbing (scan_matcher_hill_climbing.cpp:45-170), the reference's other final
+ * matcher: coordinate descent over (+-x, +-y, +-theta) steps on the cost function, steps halved
+ * whenever no move improves the cost, until MaxNumOfRefinements halvings or MaxIterations. CPU. */
+class ScanMatcherHillClimbing final : public ScanMatcher
+{
+public:
+    ScanMatcherHillClimbing(const std::string& name, double linear_step, double angular_step,
+                            int max_iterations, int max_num_of_refinements, const CostFuncPtr& cost);
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override;
+    int LastNumOfRefinements() const { return mLastNumOfRefinements; }
+
+private:
+    double mLinearStep, mAngularStep;
+    int mMaxIterations, mMaxNumOfRefinements;
+    CostFuncPtr mCost;
+    int mLastNumOfRefinements = 0;
+};
+
 /* x = A^-1 b for a 3x3 system with Eigen's ColPivHouseholderQR scheme (what
  * scan_matcher_linear_solver.cpp:161 calls): Householder reflections with the largest remaining
  * column brought to the front at every step. A is row-major. */

@@ -284,6 +284,26 @@ int csm_host_loop_search(int n_scans, const int* scan_ids, const double* scan_po
     return n;
 }
 
+/* ScanMatcherHillClimbing::OptimizePose on the CPU (no device). out->best_t = iterations,
+ * out->best_x = refinements (step halvings). */
+int csm_host_hill_climb(const uint16_t* values, int rows, int cols, double res, double off_x, double off_y,
+                        const double* angles, const double* ranges, int n, const double init_pose[3],
+                        const double rel_pose[3], double linear_step, double angular_step, int max_iterations,
+                        int max_num_of_refinements, double covariance_scale, csm_host_summary* out)
+{
+    const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+    const GridMapView map = View(values, rows, cols, res, off_x, off_y, -1);
+    const ScanDataPtr scan = Scan(angles, ranges, n, rel_pose);
+    ScanMatcherHillClimbing matcher("HillClimbing", linear_step, angular_step, max_iterations,
+                                    max_num_of_refinements, cost);
+    const ScanMatchingSummary s = matcher.OptimizePose(
+        ScanMatchingQuery { map, scan, Pose2D { init_pose[0], init_pose[1], init_pose[2] } });
+    Export(s, out);
+    out->best_t = s.n_processed;
+    out->best_x = matcher.LastNumOfRefinements();
+    return 0;
+}
+
 /* ---- persistent loop detector (bench.py e2e path) ------------------------------ */
 struct HostLoopDet
 {

@@ -430,4 +430,75 @@ ScanMatchingSummary ScanMatcherLinearSolver::OptimizePose(const ScanMatchingQuer
     return s;
 }
 
+/* ---- hill-climbing refiner (CPU) ---------------------------------------------------------- */
+ScanMatcherHillClimbing::ScanMatcherHillClimbing(
+    const std::string& name, double linear_step, double angular_step, int max_iterations,
+    int max_num_of_refinements, const CostFuncPtr& cost) :
+    ScanMatcher(name, nullptr), mLinearStep(linear_step), mAngularStep(angular_step),
+    mMaxIterations(max_iterations), mMaxNumOfRefinements(max_num_of_refinements), mCost(cost) { }
+
+ScanMatchingSummary ScanMatcherHillClimbing::OptimizePose(const ScanMatchingQuery& query)
+{
+    /* scan_matcher_hill_climbing.cpp:63-170 */
+    static const double move_x[] = { 1.0, -1.0, 0.0, 0.0, 0.0, 0.0 };
+    static const double move_y[] = { 0.0, 0.0, 1.0, -1.0, 0.0, 0.0 };
+    static const double move_t[] = { 0.0, 0.0, 0.0, 0.0, 1.0, -1.0 };
+    const GridMapView& map = query.grid_map;
+    const ScanData& scan = *query.scan_data;
+    MicroTimer timer;
+    const Pose2D sensor = Compound(query.map_local_initial_pose, scan.relative_sensor_pose);
+    const double initial_cost = mCost->Cost(map, scan, sensor);
+    double min_cost = initial_cost;
+    Pose2D best = sensor;
+    int iterations = 0, refinements = 0;
+    double linear = mLinearStep, angular = mAngularStep;
+    bool updated = false;
+    do {
+        double min_local = min_cost;
+        Pose2D best_local = best;
+        updated = false;
+        for (int i = 0; i < 6; ++i) {
+            Pose2D p = best;
+            p.x += move_x[i] * linear;
+            p.y += move_y[i] * linear;
+            p.theta += move_t[i] * angular;
+            const double c = mCost->Cost(map, scan, p);
+            if (c < min_local) {
+                min_local = c;
+                best_local = p;
+                updated = true;
+            }
+        }
+        if (updated) {
+            min_cost = min_local;
+            best = best_local;
+        } else {
+            ++refinements;
+            linear *= 0.5;
+            angular *= 0.5;
+        }
+    } while ((updated || refinements < mMaxNumOfRefinements) && (++iterations < mMaxIterations));
+    mLastNumOfRefinements = refinements;
+    ScanMatchingSummary s;
+    s.pose_found = true;
+    s.normalized_cost = min_cost / static_cast<double>(scan.NumOfScans());
+    s.map_local_initial_pose = query.map_local_initial_pose;
+    s.estimated_pose = MoveBackward(best, scan.relative_sensor_pose);
+    s.estimated_covariance = mCost->ComputeCovariance(map, scan, best);
+    s.n_processed = iterations;
+    if (mMetricSink) {
+        /* scan_matcher_hill_climbing.cpp:153-163 */
+        Observe("OptimizationTime", timer.ElapsedMicro());
+        Observe("DiffTranslation", std::hypot(s.map_local_initial_pose.x - s.estimated_pose.x,
+                                              s.map_local_initial_pose.y - s.estimated_pose.y));
+        Observe("DiffRotation", std::fabs(s.map_local_initial_pose.theta - s.estimated_pose.theta));
+        Observe("NumOfIterations", iterations);
+        Observe("NumOfRefinements", refinements);
+        Observe("InitialCost", initial_cost / static_cast<double>(scan.NumOfScans()));
+        Observe("FinalCost", s.normalized_cost);
+        Observe("NumOfScans", static_cast<double>(scan.NumOfScans()));
+    }
+    return s;
+}
+
 } /* namespace csm_host */

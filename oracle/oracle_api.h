@@ -115,6 +115,14 @@ int orc_loopdet_detect(void* det, int n_queries,
                        const double* angles, const double* ranges,
                        orc_result* out, double* elapsed_s);
 
+/* ScanMatcherHillClimbing::OptimizePose (scan_matcher_hill_climbing.cpp:63-170) over CostSquareError.
+ * out: est_pose, norm_cost, cov; n_processed = iterations, n_ignored = step halvings. Returns -1
+ * when this checker does not provide it. */
+int orc_hill_climb(void* grid, const double* angles, const double* ranges, int n,
+                   const double init_pose[3], const double rel_sensor_pose[3],
+                   double linear_step, double angular_step, int max_iterations,
+                   int max_num_of_refinements, orc_result* out);
+
 /* LoopSearcherNearest::Search (loop_searcher_nearest.cpp:59-170) on a pose-graph summary: scan nodes
  * (ids ascending, 3 doubles of global pose each), local maps (ids ascending, scan-node id range,
  * finished flag). Writes up to cap candidates as (query scan node, reference scan node, reference

@@ -38,6 +38,7 @@
 #include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_grid_search.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_linear_solver.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_hill_climbing.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/pose_graph.hpp"
@@ -643,6 +644,27 @@ int orc_loopdet_detect(void* detPtr, int n_queries,
     for (int t = 0; t < nThreads; ++t)
         ResetMatcherMetrics(det->mMatchers[t]->Name(), false);
 
+    return 0;
+}
+
+int orc_hill_climb(void* grid, const double* angles, const double* ranges, int n,
+                   const double init_pose[3], const double rel_sensor_pose[3],
+                   double linear_step, double angular_step, int max_iterations,
+                   int max_num_of_refinements, orc_result* out)
+{
+    const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
+    const auto scan = MakeScan(angles, ranges, n, rel_sensor_pose);
+    const RobotPose2D<double> initPose { init_pose[0], init_pose[1], init_pose[2] };
+    const std::string name = UniqueName("HC");
+    ScanMatcherHillClimbing matcher {
+        name, linear_step, angular_step, max_iterations, max_num_of_refinements,
+        std::make_shared<CostSquareError>(kCovarianceScale) };
+    const ScanMatchingQuery query { map, Point2D<double> { 0.0, 0.0 }, scan, initPose };
+    const ScanMatchingSummary summary = matcher.OptimizePose(query);
+    *out = orc_result { };
+    FillSummary(summary, out);
+    out->n_processed = LastInt(name + ".NumOfIterations");
+    out->n_ignored = LastInt(name + ".NumOfRefinements");
     return 0;
 }
 

@@ -188,3 +188,23 @@ def test_cpp_loop_searcher_matches_reference_vectors():
         assert len(got) <= e["cand"] and all(d < e["node"] ** 2 for d in dist)
         n_nonempty += bool(got)
     assert n_nonempty >= 4
+
+
+def test_cpp_hill_climbing_matches_reference_vectors():
+    """The C++ host ScanMatcherHillClimbing (CPU) against vectors produced by the reference's
+    scan_matcher_hill_climbing.cpp over CostSquareError: iteration and step-halving counts equal,
+    estimated pose and cost bit-identical, covariance within 1e-9."""
+    from helpers import load_golden, sha
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    for e in load_golden("hill_climb_vectors.json")["hill_climb"]:
+        case = synth.case_for(synth.CFG1, e["seed"])
+        s = case.submap
+        assert sha(s.grid) == e["grid_sha"]
+        init = [float.fromhex(v) for v in e["init"]]
+        lin, ang, iters, refs = e["params"]
+        out = hostapi.hill_climb(s.grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges, init,
+                                 tuple(e["rel"]), lin, ang, int(iters), int(refs))
+        assert (out.best_t, out.best_x) == (e["iterations"], e["refinements"]), e["seed"]
+        assert list(out.est_pose) == [float.fromhex(v) for v in e["est_pose"]], e["seed"]
+        assert out.norm_cost == float.fromhex(e["norm_cost"])
+        assert np.allclose(list(out.cov), [float.fromhex(v) for v in e["cov"]], rtol=1e-9, atol=0.0)
