@@ -654,6 +654,25 @@ def single_scan_numbers(h, lib, kind):
     cpu = timeit(lambda: orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"]), 20, 0.0)
     out["cfg1_rt_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}
 
+    # the front end's pair: real-time correlative match, then the final matcher (linear solver) on the
+    # pose found (lidar_graph_slam_frontend.cpp:216-230) -- on the device in one submission / on the CPU
+    ctx_f = hostapi.Context(h.device)
+    ctx_f.set_device_final_matcher(*REFINE)
+
+    def rt_final():
+        return ctx_f.match_blocks("rt", blocks.copy(), index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                                  case.init_pose, 5, synth.CFG1["rng"])
+
+    def cpu_rt_final():
+        o = orc.match_rt(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"])
+        return orc.refine(og, case.angles, case.ranges, list(o.est_pose), None, *REFINE)
+
+    gpu = timeit(rt_final, 2000)
+    cpu = timeit(cpu_rt_final, 20, 0.0)
+    out["cfg1_rt_plus_final_matcher_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu,
+                                               "cpu_kind": kind}
+    ctx_f.close()
+
     gpu = timeit(bb, 1000)
     cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5, 0.0)
     out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}

@@ -324,7 +324,11 @@ int csm_refine_batch(csm_handle h, const csm_refine_query* queries, int n,
  * submission instead of a second pass on the CPU. csm_set_epilogue(h, scale > 0) switches it
  * on for the following csm_match_rt / csm_match_bb calls (0 = off); csm_last_epilogue returns
  * the outcome of the last such call: pose = the decided sensor pose, final_cost = the summed
- * squared error there, covariance = scale * inverse Hessian, iterations = 0. */
+ * squared error there, covariance = scale * inverse Hessian, iterations = 0.
+ * With the epilogue off and a refiner set (csm_set_refiner), csm_match_rt / csm_match_bb run that
+ * refiner on the pose they find -- the final matcher the front end calls after its scan matcher
+ * (lidar_graph_slam_frontend.cpp:216-230, "FinalScanMatcherType": "LinearSolver") -- and
+ * csm_last_epilogue returns its outcome (valid == 0 when no pose was found). */
 int csm_set_epilogue(csm_handle h, double covariance_scale);
 int csm_last_epilogue(csm_handle h, csm_refined* out);
 /* Phase timing: after csm_set_option(h, "timing", 1) the library records a CUDA

@@ -164,6 +164,7 @@ struct csm_context
     double epilogue_scale = 0.0;   /* > 0: single-scan matches also return cost and covariance at the
                                       pose they decide on (csm_set_epilogue), computed behind k_finalize */
     csm_refined last_epilogue {};
+    bool last_epilogue_set = false;
     bool refine_on = false;        /* loop batches refine the poses they find (csm_set_refiner) */
     csm_refine_params refine {};
     DevBuf d_refine_in;            /* csm_refine_batch: queries and start poses */
@@ -1657,14 +1658,15 @@ int csm_set_epilogue(csm_handle h, double covariance_scale)
         return fail(h, CSM_E_INVALID, "epilogue: covariance_scale must be >= 0");
     h->epilogue_scale = covariance_scale;
     std::memset(&h->last_epilogue, 0, sizeof(h->last_epilogue));
+    h->last_epilogue_set = false;
     return CSM_OK;
 }
 
 int csm_last_epilogue(csm_handle h, csm_refined* out)
 {
     if (!h || !out) return CSM_E_INVALID;
-    if (!h->last_epilogue.valid)
-        return fail(h, CSM_E_INVALID, "epilogue: no match with csm_set_epilogue on has run");
+    if (!h->last_epilogue_set)
+        return fail(h, CSM_E_INVALID, "epilogue: no single-scan match with csm_set_epilogue / csm_set_refiner on has run");
     *out = h->last_epilogue;
     return CSM_OK;
 }
@@ -1797,7 +1799,10 @@ int csm_match_bb(csm_handle h, int64_t map_id,
     const InlineScan scan { angles, ranges, n };
     const int rc = bb_enqueue(h, &q, 1, hmax, 0, &scan);
     if (rc) return rc;
-    return finish_results(h, out, 1, h->epilogue_scale > 0.0 ? &h->last_epilogue : nullptr);
+    const bool extra = h->epilogue_scale > 0.0 || h->refine_on;
+    const int frc = finish_results(h, out, 1, extra ? &h->last_epilogue : nullptr);
+    h->last_epilogue_set = frc == CSM_OK && extra;
+    return frc;
 }
 
 int csm_match_rt(csm_handle h, int64_t map_id,
@@ -1832,7 +1837,8 @@ int csm_match_rt(csm_handle h, int64_t map_id,
 
     int rc;
     const bool epilogue = h->epilogue_scale > 0.0;
-    if (epilogue && (rc = ensure_alloc(h, std::vector<MapSlot*>{ &m }))) return rc;
+    const bool refine_final = !epilogue && h->refine_on;      /* the final matcher on the found pose */
+    if ((epilogue || refine_final) && (rc = ensure_alloc(h, std::vector<MapSlot*>{ &m }))) return rc;
     PlanView V;
     const int T = 2 * win_t + 1;
     if ((rc = layout_plan(h, 1, 0, 0, 0, n, V))) return rc;
@@ -1883,22 +1889,34 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
     CSM_LAUNCH_CHECK();
     phase_mark(h, "k_finalize");
-    if (epilogue) {
-        /* Cost and ComputeCovariance at the decided pose, found or not (scan_matcher_correlative.cpp:203-219) */
+    if (epilogue || refine_final) {
         RefineArgs R;
         std::memset(&R, 0, sizeof(R));
         R.results = static_cast<const csm_result*>(h->d_results.p);
         R.out = reinterpret_cast<csm_refined*>(static_cast<char*>(h->d_results.p) + refined_offset(1));
-        R.max_iterations = 0;
-        R.always = 1;
-        R.covariance_scale = h->epilogue_scale;
+        if (epilogue) {
+            /* Cost and ComputeCovariance at the decided pose, found or not (scan_matcher_correlative.cpp:203-219) */
+            R.max_iterations = 0;
+            R.always = 1;
+            R.covariance_scale = h->epilogue_scale;
+        } else {
+            /* the caller's final matcher (ScanMatcherLinearSolver) on the pose found,
+             * lidar_graph_slam_frontend.cpp:216-230 */
+            R.max_iterations = h->refine.max_iterations;
+            R.convergence_threshold = h->refine.convergence_threshold;
+            R.lambda0 = h->refine.lambda;
+            R.covariance_scale = h->refine.covariance_scale;
+        }
         k_refine<<<1, kRefThreads, 0, h->stream>>>(dq, R);
         CSM_LAUNCH_CHECK();
         phase_mark(h, "k_refine");
     }
-    if ((rc = enqueue_readback(h, 1, epilogue))) return rc;
+    const bool extra = epilogue || refine_final;
+    if ((rc = enqueue_readback(h, 1, extra))) return rc;
     phase_mark(h, "readback");
-    return finish_results(h, out, 1, epilogue ? &h->last_epilogue : nullptr);
+    rc = finish_results(h, out, 1, extra ? &h->last_epilogue : nullptr);
+    h->last_epilogue_set = rc == CSM_OK && extra;
+    return rc;
 }
 
 int csm_match_grid(csm_handle h, int64_t map_id,

@@ -45,11 +45,26 @@ public:
      * CostSquareError on the CPU afterwards. Same quantities, summed in a different order. */
     void SetDeviceEpilogue(bool on) { mDeviceEpilogue = on; }
     bool DeviceEpilogue() const { return mDeviceEpilogue; }
+    /* Real-time correlative / branch-and-bound matchers on this context hand the pose they find to
+     * the reference's final matcher (ScanMatcherLinearSolver over CostSquareError, what the front end
+     * runs next: lidar_graph_slam_frontend.cpp:216-230) on the device, in the same submission: the
+     * summary then carries the refined pose, its cost and covariance. max_iterations <= 0 = off.
+     * The damping factor is carried from match to match like the solver's member. */
+    void SetDeviceFinalMatcher(int max_iterations, double convergence_threshold, double initial_lambda,
+                               double covariance_scale)
+    {
+        mFinal.max_iterations = max_iterations; mFinal.reserved = 0;
+        mFinal.convergence_threshold = convergence_threshold;
+        mFinal.lambda = initial_lambda; mFinal.covariance_scale = covariance_scale;
+    }
+    bool HasDeviceFinalMatcher() const { return mFinal.max_iterations > 0; }
+    csm_refine_params& FinalMatcherParams() { return mFinal; }
 
 private:
     csm_handle mHandle;
     int mDevice = 0;
     bool mDeviceEpilogue = false;
+    csm_refine_params mFinal {};
     void* mStaging = nullptr;
     std::size_t mStagingBytes = 0;
 };
@@ -92,6 +107,10 @@ protected:
     std::string mName;
     DeviceContextPtr mContext;
     bool mEpilogueOnDevice = false;     /* the last match computed cost / covariance on the device */
+    bool mFinalOnDevice = false;        /* the last match ran the final matcher on the device */
+    /* switch the handle's epilogue / refiner on for the match about to be made (and off after it) */
+    void BeginDeviceStages(double covariance_scale);
+    void EndDeviceStages();
     MetricSinkPtr mMetricSink;
     std::vector<std::int64_t> mResidentMaps;
 };

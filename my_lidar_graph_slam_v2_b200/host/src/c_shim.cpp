@@ -43,6 +43,14 @@ void csm_host_context_set_device_epilogue(void* ctx, int on)
     (*static_cast<DeviceContextPtr*>(ctx))->SetDeviceEpilogue(on != 0);
 }
 
+/* ... and run the reference's final matcher (linear solver) on the found pose on the device; iterations <= 0 = off */
+void csm_host_context_set_device_final_matcher(void* ctx, int iterations_max, double convergence_threshold,
+                                               double initial_lambda, double covariance_scale)
+{
+    (*static_cast<DeviceContextPtr*>(ctx))->SetDeviceFinalMatcher(iterations_max, convergence_threshold,
+                                                                  initial_lambda, covariance_scale);
+}
+
 void* csm_host_context_handle(void* ctx) { return (*static_cast<DeviceContextPtr*>(ctx))->Handle(); }
 
 static GridMapView View(const uint16_t* values, int rows, int cols, double res, double ox, double oy, int64_t id)

@@ -91,9 +91,39 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
     return id;
 }
 
+void ScanMatcher::BeginDeviceStages(double covariance_scale)
+{
+    csm_handle h = mContext->Handle();
+    mFinalOnDevice = mContext->HasDeviceFinalMatcher();
+    mEpilogueOnDevice = !mFinalOnDevice && mContext->DeviceEpilogue();
+    mContext->Check(csm_set_epilogue(h, mEpilogueOnDevice ? covariance_scale : 0.0), "csm_set_epilogue");
+    if (mFinalOnDevice)
+        mContext->Check(csm_set_refiner(h, &mContext->FinalMatcherParams()), "csm_set_refiner");
+}
+
+void ScanMatcher::EndDeviceStages()
+{
+    if (mFinalOnDevice)
+        mContext->Check(csm_set_refiner(mContext->Handle(), nullptr), "csm_set_refiner");
+}
+
 void ScanMatcher::Epilogue(const GridMapView& map, const ScanData& scan, const Pose2D& best,
                            const CostFuncPtr& cost, ScanMatchingSummary& summary) const
 {
+    if (mContext && mFinalOnDevice) {
+        /* the match ran the final matcher on the pose it found (csm_set_refiner) */
+        csm_refined e;
+        mContext->Check(csm_last_epilogue(mContext->Handle(), &e), "csm_last_epilogue");
+        if (e.valid) {
+            std::copy(e.covariance, e.covariance + 9, summary.estimated_covariance.begin());
+            summary.normalized_cost = e.final_cost / static_cast<double>(scan.NumOfScans());
+            summary.estimated_pose = MoveBackward(Pose2D { e.pose[0], e.pose[1], e.pose[2] },
+                                                  scan.relative_sensor_pose);
+            mContext->FinalMatcherParams().lambda = e.lambda;
+            return;
+        }
+        /* no pose found: nothing was refined, fall through to the plain epilogue */
+    }
     if (mContext && mContext->DeviceEpilogue() && mEpilogueOnDevice) {
         /* the match just made computed both on the device (csm_set_epilogue) */
         csm_refined e;
@@ -186,12 +216,12 @@ ScanMatchingSummary ScanMatcherCorrelative::OptimizePose(
     const int win_t = static_cast<int>(std::ceil(0.5 * mRangeTheta / st));
     const double pose[3] = { sensor.x, sensor.y, sensor.theta };
     csm_result r;
-    mEpilogueOnDevice = mContext->DeviceEpilogue();
-    mContext->Check(csm_set_epilogue(h, mEpilogueOnDevice ? mCost->CovarianceScale() : 0.0), "csm_set_epilogue");
+    BeginDeviceStages(mCost->CovarianceScale());
     mContext->Check(csm_match_rt(h, id, scan->angles.data(), scan->ranges.data(),
                                  static_cast<int>(scan->NumOfScans()), pose, mLowResolution,
                                  win_x, win_y, win_t, sx, sy, st,
                                  score_threshold, known_rate_threshold, &r), "csm_match_rt");
+    EndDeviceStages();
     ScanMatchingSummary s;
     FillFromDevice(r, s);
     s.map_local_initial_pose = initial_pose;
@@ -236,12 +266,12 @@ ScanMatchingSummary ScanMatcherBranchBound::OptimizePose(
     const int win_t = static_cast<int>(std::ceil(0.5 * mRangeTheta / st));
     const double pose[3] = { sensor.x, sensor.y, sensor.theta };
     csm_result r;
-    mEpilogueOnDevice = mContext->DeviceEpilogue();
-    mContext->Check(csm_set_epilogue(h, mEpilogueOnDevice ? mCost->CovarianceScale() : 0.0), "csm_set_epilogue");
+    BeginDeviceStages(mCost->CovarianceScale());
     mContext->Check(csm_match_bb(h, id, scan->angles.data(), scan->ranges.data(),
                                  static_cast<int>(scan->NumOfScans()), pose, mNodeHeightMax,
                                  win_x, win_y, win_t, sx, sy, st,
                                  score_threshold, known_rate_threshold, &r), "csm_match_bb");
+    EndDeviceStages();
     ScanMatchingSummary s;
     FillFromDevice(r, s);
     s.map_local_initial_pose = initial_pose;
@@ -285,6 +315,7 @@ ScanMatchingSummary ScanMatcherGridSearch::OptimizePose(
     const double pose[3] = { sensor.x, sensor.y, sensor.theta };
     csm_result r;
     mEpilogueOnDevice = false;          /* the grid search keeps the CPU epilogue (4 ms of search per match) */
+    mFinalOnDevice = false;
     mContext->Check(csm_match_grid(h, id, scan->angles.data(), scan->ranges.data(),
                                    static_cast<int>(scan->NumOfScans()), pose,
                                    dx.data(), static_cast<int>(dx.size()),

@@ -58,6 +58,8 @@ def load():
         lib.csm_host_loopdet_best_word.argtypes = [C.c_void_p]
         lib.csm_host_loopdet_best_word.restype = C.c_uint64
         lib.csm_host_context_set_device_epilogue.argtypes = [C.c_void_p, C.c_int]
+        lib.csm_host_context_set_device_final_matcher.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                                                  C.c_double]
         lib.csm_host_loopdet_use_device_refiner.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         lib.csm_host_loopdet_create.restype = C.c_void_p
         lib.csm_host_loopdet_create.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_double, C.c_double]
@@ -172,6 +174,14 @@ class Context:
         if self.ctx:
             self.lib.csm_host_context_destroy(self.ctx)
             self.ctx = None
+
+    def set_device_final_matcher(self, iterations_max=10, convergence_threshold=1e-4, initial_lambda=1e-4,
+                                 covariance_scale=1e4):
+        """Real-time correlative / branch-and-bound matches on this context also run the reference's final
+        matcher (ScanMatcherLinearSolver) on the pose they find, on the device: est_pose, norm_cost and cov of
+        the summary are the refined ones. iterations_max <= 0 switches it off."""
+        self.lib.csm_host_context_set_device_final_matcher(self.ctx, iterations_max, convergence_threshold,
+                                                           initial_lambda, covariance_scale)
 
     def match(self, kind, grid, res, off, angles, ranges, init_pose, iparam, rng, step=(0, 0, 0),
               thr=(0.0, 0.0), rel_pose=(0.0, 0.0, 0.0), covariance_scale=1e4):

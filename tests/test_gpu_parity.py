@@ -535,6 +535,45 @@ def test_cpp_adapter_device_epilogue(checker, seed):
     ctx.close()
 
 
+@pytest.mark.parametrize("seed", range(2430, 2434))
+def test_cpp_adapter_device_final_matcher(checker, seed):
+    """The front end's pair of matchers in one submission (lidar_graph_slam_frontend.cpp:216-230): the
+    real-time correlative / branch-and-bound match and then the final matcher (ScanMatcherLinearSolver)
+    on the pose it found, on the device. Coarse result bit-identical to the reference's matcher, refined
+    pose within 1e-5 relative (north_star) of the reference's solver started from the coarse pose."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    ctx.set_device_final_matcher(10, 1e-4, 1e-4)
+    case = synth.case_for(synth.CFG1, seed)
+    s = case.submap
+    g = checker.grid(s.grid, s.res, s.off_x, s.off_y)
+    rel = (0.1, -0.03, 0.2) if seed % 2 else (0.0, 0.0, 0.0)
+    off = (s.off_x, s.off_y)
+    blocks, index, br, bc = synth.dense_to_blocks(s.grid)
+    for kind in ("rt", "bb"):
+        if kind == "rt":
+            a = ctx.match("rt", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5,
+                          synth.CFG1["rng"], rel_pose=rel)
+            o = checker.match_rt(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"], (0.0, 0.0), rel)
+        else:
+            a = ctx.match_blocks("bb", blocks, index, 4, s.grid.shape, s.res, off, case.angles, case.ranges,
+                                 case.init_pose, 5, synth.CFG2["rng"], rel_pose=rel)
+            o = checker.match_bb(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"], (0.0, 0.0), rel)
+        assert a.found == o.found == 1
+        assert (a.best_x, a.best_y, a.best_t, a.sum_value, a.n_known, a.score) == \
+               (o.best_x, o.best_y, o.best_t, o.sum_value, o.n_known, o.score), kind
+        f = checker.refine(g, case.angles, case.ranges, list(o.est_pose), rel, 10, 1e-4, 1e-4)
+        assert np.allclose(list(a.est_pose), list(f.est_pose), rtol=1e-5, atol=0.0), kind
+        assert np.isclose(a.norm_cost, f.norm_cost, rtol=1e-6, atol=0.0), kind
+        assert np.allclose(list(a.cov), list(f.cov), rtol=1e-5, atol=0.0), kind
+    # a threshold nothing passes: nothing to refine, the summary is the plain (CPU) epilogue at the coarse pose
+    a = ctx.match("rt", s.grid, s.res, off, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"],
+                  thr=(0.999, 0.999), rel_pose=rel)
+    _cmp_host(a, checker.match_rt(g, case.angles, case.ranges, case.init_pose, 5, synth.CFG1["rng"],
+                                  (0.999, 0.999), rel), "rt unfound")
+    ctx.close()
+
+
 @pytest.mark.parametrize("seed", range(2410, 2413))
 def test_cpp_adapter_block_sparse_maps(checker, seed):
     """The C++ adapter fed with the map in the reference's block-sparse storage form: same device
