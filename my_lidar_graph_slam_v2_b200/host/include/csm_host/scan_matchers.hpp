@@ -209,15 +209,17 @@ private:
 class ScanMatcherHillClimbing final : public ScanMatcher
 {
 public:
+    /* any cost function: the square-error cost or the greedy-endpoint cost (the launcher default) */
     ScanMatcherHillClimbing(const std::string& name, double linear_step, double angular_step,
-                            int max_iterations, int max_num_of_refinements, const CostFuncPtr& cost);
+                            int max_iterations, int max_num_of_refinements,
+                            const std::shared_ptr<CostFunction>& cost);
     ScanMatchingSummary OptimizePose(const ScanMatchingQuery& query) override;
     int LastNumOfRefinements() const { return mLastNumOfRefinements; }
 
 private:
     double mLinearStep, mAngularStep;
     int mMaxIterations, mMaxNumOfRefinements;
-    CostFuncPtr mCost;
+    std::shared_ptr<CostFunction> mCost;
     int mLastNumOfRefinements = 0;
 };
 

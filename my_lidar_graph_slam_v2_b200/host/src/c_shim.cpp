@@ -293,13 +293,21 @@ int csm_host_loop_search(int n_scans, const int* scan_ids, const double* scan_po
 }
 
 /* ScanMatcherHillClimbing::OptimizePose on the CPU (no device). out->best_t = iterations,
- * out->best_x = refinements (step halvings). */
+ * out->best_x = refinements (step halvings). greedy == null: square-error cost (covariance_scale);
+ * else the greedy-endpoint cost with greedy = { MapResolution, HitAndMissedDist, OccupancyThreshold,
+ * KernelSize, ScalingFactor, StandardDeviation }. */
 int csm_host_hill_climb(const uint16_t* values, int rows, int cols, double res, double off_x, double off_y,
                         const double* angles, const double* ranges, int n, const double init_pose[3],
                         const double rel_pose[3], double linear_step, double angular_step, int max_iterations,
-                        int max_num_of_refinements, double covariance_scale, csm_host_summary* out)
+                        int max_num_of_refinements, double covariance_scale, const double* greedy,
+                        csm_host_summary* out)
 {
-    const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+    std::shared_ptr<CostFunction> cost;
+    if (greedy != nullptr)
+        cost = std::make_shared<CostGreedyEndpoint>(greedy[0], greedy[1], greedy[2], static_cast<int>(greedy[3]),
+                                                    greedy[4], greedy[5]);
+    else
+        cost = std::make_shared<CostSquareError>(covariance_scale);
     const GridMapView map = View(values, rows, cols, res, off_x, off_y, -1);
     const ScanDataPtr scan = Scan(angles, ranges, n, rel_pose);
     ScanMatcherHillClimbing matcher("HillClimbing", linear_step, angular_step, max_iterations,

@@ -59,6 +59,15 @@ struct Sampler
         return st != 0;
     }
 
+    /* block of (row, col) allocated? (row, col inside the map) */
+    bool Allocated(int row, int col) const
+    {
+        const int brow = row >> k, bcol = col >> k;
+        if (map.blocks != nullptr)
+            return slot[static_cast<std::size_t>(brow) * block_cols + bcol] >= 0;
+        return DenseBlockAllocated(brow, bcol);
+    }
+
     /* grid_map.cpp:424-436 */
     double At(int row, int col) const
     {
@@ -191,6 +200,86 @@ std::array<double, 9> CostSquareError::CostAndCovariance(const GridMapView& map,
     double h[9] = { 0.0 };
     cost = Accumulate(map, scan, pose, h);
     return InverseScaled(h, mCovarianceScale);
+}
+
+/* ---- greedy endpoint cost --------------------------------------------------------------- */
+CostGreedyEndpoint::CostGreedyEndpoint(double map_resolution, double hit_and_missed_dist,
+                                       double occupancy_threshold, int kernel_size, double scaling_factor,
+                                       double standard_deviation) :
+    mMapResolution(map_resolution), mHitAndMissedDist(hit_and_missed_dist),
+    mOccupancyThreshold(occupancy_threshold), mKernelSize(kernel_size),
+    mVariance(standard_deviation * standard_deviation), mScalingFactor(scaling_factor), mDefaultCostValue(0.0)
+{
+    /* SetupLookupTable, cost_function_greedy_endpoint.cpp:168-199 */
+    const int kernel = 2 * mKernelSize + 1;
+    mCostLookupTable.assign(static_cast<std::size_t>(kernel) * kernel, 0.0);
+    for (int ky = -mKernelSize; ky <= mKernelSize; ++ky)
+        for (int kx = -mKernelSize; kx <= mKernelSize; ++kx) {
+            const double dx = mMapResolution * kx, dy = mMapResolution * ky;
+            const double squared = dx * dx + dy * dy;
+            mCostLookupTable[(mKernelSize + ky) * kernel + (mKernelSize + kx)] = -std::exp(-0.5 * squared / mVariance);
+        }
+    const double mx = mMapResolution * (mKernelSize + 1), my = mMapResolution * (mKernelSize + 1);
+    mDefaultCostValue = -std::exp(-0.5 * (mx * mx + my * my) / mVariance);
+}
+
+double CostGreedyEndpoint::Cost(const GridMapView& map, const ScanData& scan, const Pose2D& pose) const
+{
+    /* cost_function_greedy_endpoint.cpp:33-101. ProbabilityOr(row, col, unknown = 0.0): cells outside the
+     * map, of unallocated blocks and unknown cells all read 0.0 and are skipped, so block allocation does
+     * not matter here */
+    const Sampler sampler(map);
+    auto prob = [&](int row, int col) {
+        if (row < 0 || row >= map.rows || col < 0 || col >= map.cols)
+            return 0.0;
+        const double p = sampler.At(row, col);
+        return p == 0.5 && !sampler.Allocated(row, col) ? 0.0 : p;
+    };
+    const int kernel = 2 * mKernelSize + 1;
+    double sum = 0.0;
+    for (std::size_t i = 0; i < scan.NumOfScans(); ++i) {
+        /* ScanData::HitAndMissedPoint, sensor_data.hpp:252-273 */
+        const double range = scan.ranges[i];
+        const double c = std::cos(pose.theta + scan.angles[i]), s = std::sin(pose.theta + scan.angles[i]);
+        const double hx = pose.x + range * c, hy = pose.y + range * s;
+        const double mx = pose.x + (range - mHitAndMissedDist) * c, my = pose.y + (range - mHitAndMissedDist) * s;
+        const int hit_col = static_cast<int>(std::floor((hx - map.offset_x) / map.resolution));
+        const int hit_row = static_cast<int>(std::floor((hy - map.offset_y) / map.resolution));
+        const int mis_col = static_cast<int>(std::floor((mx - map.offset_x) / map.resolution));
+        const int mis_row = static_cast<int>(std::floor((my - map.offset_y) / map.resolution));
+        double best = mDefaultCostValue;
+        for (int ky = -mKernelSize; ky <= mKernelSize; ++ky)
+            for (int kx = -mKernelSize; kx <= mKernelSize; ++kx) {
+                const double hit = prob(hit_row + ky, hit_col + kx);
+                const double missed = prob(mis_row + ky, mis_col + kx);
+                if (hit == 0.0 || missed == 0.0)
+                    continue;
+                if (hit < mOccupancyThreshold || missed > mOccupancyThreshold)
+                    continue;
+                best = std::min(best, mCostLookupTable[(mKernelSize + ky) * kernel + (mKernelSize + kx)]);
+            }
+        sum += best;
+    }
+    sum *= mScalingFactor;
+    return sum;
+}
+
+std::array<double, 9> CostGreedyEndpoint::ComputeCovariance(const GridMapView& map, const ScanData& scan,
+                                                            const Pose2D& pose) const
+{
+    /* ComputeGradient + ComputeCovariance, cost_function_greedy_endpoint.cpp:104-165 */
+    const double dl = map.resolution, da = 1e-2;
+    auto cost = [&](double x, double y, double t) { return Cost(map, scan, Pose2D { x, y, t }); };
+    const double cx = cost(pose.x + dl, pose.y + 0.0, pose.theta + 0.0) - cost(pose.x - dl, pose.y - 0.0, pose.theta - 0.0);
+    const double cy = cost(pose.x + 0.0, pose.y + dl, pose.theta + 0.0) - cost(pose.x - 0.0, pose.y - dl, pose.theta - 0.0);
+    const double ct = cost(pose.x + 0.0, pose.y + 0.0, pose.theta + da) - cost(pose.x - 0.0, pose.y - 0.0, pose.theta - da);
+    const double g[3] = { 0.5 * cx / dl, 0.5 * cy / dl, 0.5 * ct / da };
+    std::array<double, 9> cov {};
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            cov[r * 3 + c] = g[r] * g[c];
+    cov[0] += 0.1; cov[4] += 0.1; cov[8] += 0.1;
+    return cov;
 }
 
 } /* namespace csm_host */

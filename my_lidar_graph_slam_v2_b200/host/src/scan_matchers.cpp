@@ -464,7 +464,7 @@ ScanMatchingSummary ScanMatcherLinearSolver::OptimizePose(const ScanMatchingQuer
 /* ---- hill-climbing refiner (CPU) ---------------------------------------------------------- */
 ScanMatcherHillClimbing::ScanMatcherHillClimbing(
     const std::string& name, double linear_step, double angular_step, int max_iterations,
-    int max_num_of_refinements, const CostFuncPtr& cost) :
+    int max_num_of_refinements, const std::shared_ptr<CostFunction>& cost) :
     ScanMatcher(name, nullptr), mLinearStep(linear_step), mAngularStep(angular_step),
     mMaxIterations(max_iterations), mMaxNumOfRefinements(max_num_of_refinements), mCost(cost) { }
 

@@ -136,23 +136,28 @@ def refine(grid, res, off, angles, ranges, init_pose, rel_pose=(0.0, 0.0, 0.0), 
 
 
 def hill_climb(grid, res, off, angles, ranges, init_pose, rel_pose=(0.0, 0.0, 0.0), linear_step=0.1,
-               angular_step=0.1, max_iterations=100, max_num_of_refinements=5, covariance_scale=1e4):
-    """ScanMatcherHillClimbing::OptimizePose over the square-error cost (CPU, no device). summary.best_t holds
-    the number of iterations, summary.best_x the number of step halvings."""
+               angular_step=0.1, max_iterations=100, max_num_of_refinements=5, covariance_scale=1e4, greedy=None):
+    """ScanMatcherHillClimbing::OptimizePose (CPU, no device) over the square-error cost, or over the
+    greedy-endpoint cost when greedy = (MapResolution, HitAndMissedDist, OccupancyThreshold, KernelSize,
+    ScalingFactor, StandardDeviation). summary.best_t holds the number of iterations, summary.best_x the
+    number of step halvings."""
     lib = load()
     dp = C.POINTER(C.c_double)
     lib.csm_host_hill_climb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp, dp,
                                         C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
-                                        C.POINTER(HostSummary)]
+                                        dp, C.POINTER(HostSummary)]
     g = np.ascontiguousarray(grid, dtype=np.uint16)
     a, ap = _d(angles)
     r, rp = _d(ranges)
     p, pp = _d(init_pose)
     q, qp = _d(rel_pose)
     out = HostSummary()
+    gr = None
+    if greedy is not None:
+        gr_arr, gr = _d(greedy)
     lib.csm_host_hill_climb(g.ctypes.data, g.shape[0], g.shape[1], res, off[0], off[1], ap, rp, len(a), pp, qp,
                             linear_step, angular_step, max_iterations, max_num_of_refinements, covariance_scale,
-                            C.byref(out))
+                            gr, C.byref(out))
     return out
 
 

@@ -121,7 +121,9 @@ int orc_loopdet_detect(void* det, int n_queries,
 int orc_hill_climb(void* grid, const double* angles, const double* ranges, int n,
                    const double init_pose[3], const double rel_sensor_pose[3],
                    double linear_step, double angular_step, int max_iterations,
-                   int max_num_of_refinements, orc_result* out);
+                   int max_num_of_refinements, const double* greedy, orc_result* out);
+/* greedy == NULL: CostSquareError; else CostGreedyEndpoint(MapResolution, HitAndMissedDist,
+ * OccupancyThreshold, KernelSize, ScalingFactor, StandardDeviation) (cost_function_greedy_endpoint.cpp:9-30) */
 
 /* LoopSearcherNearest::Search (loop_searcher_nearest.cpp:59-170) on a pose-graph summary: scan nodes
  * (ids ascending, 3 doubles of global pose each), local maps (ids ascending, scan-node id range,

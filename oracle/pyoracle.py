@@ -147,18 +147,22 @@ class Oracle:
         return out
 
     def hill_climb(self, grid, angles, ranges, init_pose, rel_pose=None, linear_step=0.1, angular_step=0.1,
-                   max_iterations=100, max_num_of_refinements=5):
+                   max_iterations=100, max_num_of_refinements=5, greedy=None):
         """ScanMatcherHillClimbing::OptimizePose over CostSquareError (n_processed = iterations,
         n_ignored = step halvings); None when this checker lacks it."""
         if not hasattr(self.lib, "orc_hill_climb"):
             return None
         dp = C.POINTER(C.c_double)
         self.lib.orc_hill_climb.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, C.c_double, C.c_double,
-                                            C.c_int, C.c_int, C.POINTER(OrcResult)]
+                                            C.c_int, C.c_int, dp, C.POINTER(OrcResult)]
         a, r, p, q = self._scan(angles, ranges, init_pose, rel_pose)
         out = OrcResult()
+        gr = None
+        if greedy is not None:
+            gr_arr = np.ascontiguousarray(greedy, dtype=np.float64)
+            gr = _dptr(gr_arr)
         rc = self.lib.orc_hill_climb(grid.h, _dptr(a), _dptr(r), len(a), _dptr(p), _dptr(q), linear_step,
-                                     angular_step, max_iterations, max_num_of_refinements, C.byref(out))
+                                     angular_step, max_iterations, max_num_of_refinements, gr, C.byref(out))
         return out if rc == 0 else None
 
     def loop_search(self, scan_ids, scan_poses, map_ids, map_scan_min, map_scan_max, map_finished,

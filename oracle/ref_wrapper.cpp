@@ -32,6 +32,7 @@
 #include "my_lidar_graph_slam/mapping/grid_map_types.hpp"
 #include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
 #include "my_lidar_graph_slam/mapping/cost_function_square_error.hpp"
+#include "my_lidar_graph_slam/mapping/cost_function_greedy_endpoint.hpp"
 #include "my_lidar_graph_slam/mapping/score_function_pixel_accurate.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_correlative.hpp"
@@ -650,15 +651,20 @@ int orc_loopdet_detect(void* detPtr, int n_queries,
 int orc_hill_climb(void* grid, const double* angles, const double* ranges, int n,
                    const double init_pose[3], const double rel_sensor_pose[3],
                    double linear_step, double angular_step, int max_iterations,
-                   int max_num_of_refinements, orc_result* out)
+                   int max_num_of_refinements, const double* greedy, orc_result* out)
 {
     const GridMap& map = static_cast<RefGrid*>(grid)->mMap;
     const auto scan = MakeScan(angles, ranges, n, rel_sensor_pose);
     const RobotPose2D<double> initPose { init_pose[0], init_pose[1], init_pose[2] };
     const std::string name = UniqueName("HC");
+    CostFuncPtr cost;
+    if (greedy != nullptr)
+        cost = std::make_shared<CostGreedyEndpoint>(greedy[0], greedy[1], greedy[2], static_cast<int>(greedy[3]),
+                                                    greedy[4], greedy[5]);
+    else
+        cost = std::make_shared<CostSquareError>(kCovarianceScale);
     ScanMatcherHillClimbing matcher {
-        name, linear_step, angular_step, max_iterations, max_num_of_refinements,
-        std::make_shared<CostSquareError>(kCovarianceScale) };
+        name, linear_step, angular_step, max_iterations, max_num_of_refinements, cost };
     const ScanMatchingQuery query { map, Point2D<double> { 0.0, 0.0 }, scan, initPose };
     const ScanMatchingSummary summary = matcher.OptimizePose(query);
     *out = orc_result { };

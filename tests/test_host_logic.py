@@ -192,8 +192,8 @@ def test_cpp_loop_searcher_matches_reference_vectors():
 
 def test_cpp_hill_climbing_matches_reference_vectors():
     """The C++ host ScanMatcherHillClimbing (CPU) against vectors produced by the reference's
-    scan_matcher_hill_climbing.cpp over CostSquareError: iteration and step-halving counts equal,
-    estimated pose and cost bit-identical, covariance within 1e-9."""
+    scan_matcher_hill_climbing.cpp over CostSquareError and over CostGreedyEndpoint: iteration and
+    step-halving counts equal, estimated pose and cost bit-identical, covariance within 1e-9."""
     from helpers import load_golden, sha
     from my_lidar_graph_slam_v2_b200 import hostapi
     for e in load_golden("hill_climb_vectors.json")["hill_climb"]:
@@ -203,7 +203,7 @@ def test_cpp_hill_climbing_matches_reference_vectors():
         init = [float.fromhex(v) for v in e["init"]]
         lin, ang, iters, refs = e["params"]
         out = hostapi.hill_climb(s.grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges, init,
-                                 tuple(e["rel"]), lin, ang, int(iters), int(refs))
+                                 tuple(e["rel"]), lin, ang, int(iters), int(refs), greedy=e["greedy"])
         assert (out.best_t, out.best_x) == (e["iterations"], e["refinements"]), e["seed"]
         assert list(out.est_pose) == [float.fromhex(v) for v in e["est_pose"]], e["seed"]
         assert out.norm_cost == float.fromhex(e["norm_cost"])

@@ -171,8 +171,8 @@ def test_loop_searcher_cpp_vs_reference(ref_oracle, seed):
 
 @pytest.mark.parametrize("seed", range(1700, 1706))
 def test_hill_climbing_cpp_vs_reference(ref_oracle, seed):
-    """The C++ ScanMatcherHillClimbing against the reference's on seeded cases: same iteration and
-    refinement counts, bit-identical pose and cost."""
+    """The C++ ScanMatcherHillClimbing against the reference's on seeded cases, over the square-error
+    and the greedy-endpoint cost: same iteration and refinement counts, bit-identical pose and cost."""
     from my_lidar_graph_slam_v2_b200 import hostapi, synth
     case = synth.case_for(synth.CFG1, seed)
     s = case.submap
@@ -180,10 +180,12 @@ def test_hill_climbing_cpp_vs_reference(ref_oracle, seed):
     rng = np.random.default_rng(seed)
     init = case.true_pose + rng.uniform(-1.0, 1.0, size=3) * np.array([0.1, 0.1, 0.05])
     rel = (0.05, 0.02, -0.1) if seed % 2 else (0.0, 0.0, 0.0)
-    for lin, ang, iters, refs in ((0.1, 0.1, 100, 5), (0.03, 0.01, 12, 2)):
-        o = ref_oracle.hill_climb(g, case.angles, case.ranges, init, rel, lin, ang, iters, refs)
+    for lin, ang, iters, refs, greedy in ((0.1, 0.1, 100, 5, None), (0.03, 0.01, 12, 2, None),
+                                          (0.1, 0.1, 100, 5, (0.05, 0.075, 0.1, 1, 1.0, 0.05)),
+                                          (0.05, 0.05, 40, 3, (0.05, 0.1, 0.4, 2, 0.5, 0.1))):
+        o = ref_oracle.hill_climb(g, case.angles, case.ranges, init, rel, lin, ang, iters, refs, greedy)
         h = hostapi.hill_climb(s.grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges, init, rel,
-                               lin, ang, iters, refs)
+                               lin, ang, iters, refs, greedy=greedy)
         assert (h.best_t, h.best_x) == (o.n_processed, o.n_ignored)
         assert list(h.est_pose) == list(o.est_pose) and h.norm_cost == o.norm_cost
         assert np.allclose(list(h.cov), list(o.cov), rtol=1e-9, atol=0.0)
