@@ -45,14 +45,24 @@ extern "C" {
 /* csm_result.flags */
 #define CSM_FLAG_FP_MARGIN   1  /* a projected hit point lies within the FP
                                  * guard band of a cell boundary (DESIGN.md
-                                 * "FP index parity"); result computed with
-                                 * device trigonometry may differ from glibc */
+                                 * "FP index parity") and the exact rerun is
+                                 * switched off (option "exact_rerun" = 0):
+                                 * the result may differ from glibc's */
 #define CSM_FLAG_KEY_TIE     2  /* the winning integer key is shared by
                                  * another candidate; first in reference
                                  * iteration order was taken */
-#define CSM_FLAG_EDGE        4  /* B&B: a hit index minus the window is
-                                 * negative (bound not admissible at the
-                                 * low-index edge) */
+#define CSM_FLAG_EDGE        4  /* B&B: a node window reaches below row /
+                                 * column 0 of a map that has known cells in
+                                 * its first 2^hmax rows or columns (the
+                                 * reference's bound is not admissible there,
+                                 * SURVEY.md A.11) */
+#define CSM_FLAG_EXACT       8  /* a projected hit point lay within the FP
+                                 * guard band of a cell boundary, where device
+                                 * and glibc trigonometry may round to
+                                 * different cells: the result was recomputed
+                                 * from indices evaluated on the host with the
+                                 * reference's own libm calls and operation
+                                 * order (replaces CSM_FLAG_FP_MARGIN) */
 
 typedef struct csm_context* csm_handle;
 
@@ -142,6 +152,8 @@ void* csm_stream(csm_handle h);
 int  csm_synchronize(csm_handle h);
 /* Number of kernels this handle has launched so far */
 int64_t csm_launch_count(csm_handle h);
+/* Number of results this handle has recomputed exactly so far (CSM_FLAG_EXACT) */
+int64_t csm_exact_rerun_count(csm_handle h);
 /* Make `h` enqueue its host-to-device grid uploads on `owner`'s copy stream. Handles that serve
  * as pipeline lanes of one detector (same host thread, same device) then upload strictly in call
  * order: copies issued on different streams share the link and would all land together at the
@@ -157,8 +169,16 @@ int csm_share_copy_stream(csm_handle h, csm_handle owner);
  *      identical either way; only the number of nodes scored changes;
  *  "bb_skip_top": 1 (default) = the branch-and-bound sweep starts one height
  *      below hmax on the same leaf lattice (identical results, one launch less);
+ *  "bb_bounds": 1 (default) = sweeps that neither score their roots nor dive read the
+ *      u8 bound levels (tiled upper bounds of the reference's coarse levels, built by
+ *      csm_build_pyramids for batches of maps or on first use), 0 = the reference's u16
+ *      levels. Results are identical either way; a few percent more nodes are expanded;
  *  "window_mode": grid search, 0 (default) = TMA shared-memory tile kernel when
  *      the window fits, 1 = global-memory kernel, 2 = require the TMA kernel;
+ *  "exact_rerun": 1 (default) = a result whose projection raised the FP guard-band
+ *      flag is recomputed from host-evaluated indices (CSM_FLAG_EXACT), 0 = it is
+ *      returned as is with CSM_FLAG_FP_MARGIN; "fp_margin_scale": test knob, multiplies
+ *      the guard band (a huge value flags every result);
  *  "timing": 1 / 2 = record CUDA events after every kernel (csm_debug_timings);
  *  "accumulate_best_key": 1 = loop batches keep (do not reset) the packed
  *      best word, so that a Detect call split into several batches ends with
@@ -342,6 +362,10 @@ int csm_debug_timings(csm_handle h, char* names, size_t names_cap, float* ms, in
 /* Debug: size of the node list of every height after the last batch (8 entries):
  * the nodes of that height that passed and were expanded */
 int csm_debug_frontier_counts(csm_handle h, unsigned int* out8);
+/* Debug: one bound level of the branch-and-bound sweep (csm_bounds.cuh: u8 upper bounds
+ * ceil(v / 257) of the sliding 2^level x 2^level maximum, cells outside the map 0), untiled into
+ * out[rows * cols]. Builds levels 1..level for this map when they are missing. 1 <= level <= 6. */
+int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out);
 void* csm_best_key_device(csm_handle h);
 void csm_decode_best_key(uint64_t best_key, int64_t* key, int32_t* query_index);
 

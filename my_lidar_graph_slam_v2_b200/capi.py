@@ -13,7 +13,7 @@ import numpy as np
 from . import build as _build
 
 CSM_OK = 0
-FLAG_FP_MARGIN, FLAG_KEY_TIE, FLAG_EDGE = 1, 2, 4
+FLAG_FP_MARGIN, FLAG_KEY_TIE, FLAG_EDGE, FLAG_EXACT = 1, 2, 4, 8
 
 
 class CsmError(RuntimeError):
@@ -67,6 +67,7 @@ EXPORTS = [
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
     "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch", "csm_set_epilogue", "csm_last_epilogue", "csm_share_copy_stream",
     "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
+    "csm_debug_bound_level", "csm_exact_rerun_count",
 ]
 
 _LIB = None
@@ -137,6 +138,9 @@ def load():
     lib.csm_set_epilogue.argtypes = [H, C.c_double]
     lib.csm_last_epilogue.argtypes = [H, C.POINTER(CsmRefined)]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
+    lib.csm_exact_rerun_count.restype = C.c_int64
+    lib.csm_exact_rerun_count.argtypes = [H]
+    lib.csm_debug_bound_level.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_uint8)]
     lib.csm_debug_timings.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
     lib.csm_best_key_device.argtypes = [H]
     lib.csm_best_key_device.restype = C.c_void_p
@@ -343,6 +347,15 @@ class Handle:
         out = CsmRefined()
         self._check(self.lib.csm_last_epilogue(self.h, C.byref(out)))
         return out
+
+    def bound_level(self, map_id, level, shape):
+        """Level `level` of the map's u8 bound levels (csm_bounds.cuh), untiled to (rows, cols)."""
+        out = np.empty(shape, dtype=np.uint8)
+        self._check(self.lib.csm_debug_bound_level(self.h, map_id, level, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def exact_rerun_count(self):
+        return int(self.lib.csm_exact_rerun_count(self.h))
 
     def frontier_counts(self):
         out = (C.c_uint * 8)()

@@ -64,6 +64,12 @@ struct MapSlot
     int hmax = 0;                  /* number of levels currently valid */
     uint16_t* coarse = nullptr;
     int coarse_win = 0;
+    /* bound levels of the branch-and-bound sweep (csm_bounds.cuh): levels 1..bounds_alloc allocated
+     * (padding zeroed once), 1..bounds_levels valid for the current contents */
+    unsigned char* bounds = nullptr;
+    int bounds_alloc = 0;
+    int bounds_levels = -1;        /* -1: nothing valid; L >= 0: serves searches with hmax <= L + 1 */
+    int low_margin = -1;           /* smallest min(row, col) of a known cell near the low edges (k_low_margin), -1: not scanned */
     cudaEvent_t pending_upload = nullptr;   /* copy-stream event the next consumer must wait for */
     std::shared_ptr<BlockScatter> pending_scatter;   /* block-sparse upload not yet expanded */
     /* which blocks are allocated in the reference's sense (refinement reads unallocated cells as 0.5):
@@ -82,6 +88,18 @@ struct ScanSlot
     double2* trig = nullptr;       /* (cos a_i, sin a_i) */
     int n = 0;
     double max_range = 0.0;
+    /* host copy: a result flagged CSM_FLAG_FP_MARGIN is recomputed from indices evaluated on the host
+     * with the reference's own libm calls (exact_rerun_*) */
+    std::vector<double> h_angles, h_ranges;
+};
+
+/* What finish_results needs to know about a batch in flight to post-process flagged results */
+struct BatchRecord
+{
+    std::vector<csm_loop_query> queries;
+    int hmax = 0;
+    bool inline_scan = false;
+    std::vector<double> angles, ranges;      /* the scan that arrived with the call (inline_scan) */
 };
 
 /* Where the small per-batch arrays live inside the plan buffer (d_plan):
@@ -97,6 +115,7 @@ struct PlanView
     char* extra = nullptr;
     ScanSlot scan;                 /* scan arriving with the call (single-scan matchers) */
     int* qflags = nullptr;
+    unsigned long long* tiekey = nullptr;   /* per query: largest key shared by two candidates */
     int* stats = nullptr;
     unsigned int* counts = nullptr;
     int* overflow = nullptr;
@@ -129,7 +148,9 @@ struct csm_context
     /* workspaces, grown on demand */
     DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
-    DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups;
+    DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups, d_bljobs;
+    int bb_bounds = 1;             /* 1: batched searches sweep the u8 bound levels (csm_bounds.cuh), 0: the u16 levels */
+    int bbx_ctas_per_sm = 0;
     int bb_ctas_per_sm = 0;        /* resident CTAs per SM of the B&B sweep kernels (occupancy query, lazily) */
     int bb_split_shift = 0;
     int bb_skip_top = 1;           /* 1: the B&B sweep starts one height below hmax (same results) */
@@ -152,6 +173,12 @@ struct csm_context
     int res_head = 0;              /* slot of the oldest batch in flight */
     int res_count = 0;             /* batches in flight */
     int res_nq[kResultSlots] = { 0, 0, 0, 0 };
+    BatchRecord res_rec[kResultSlots];
+    void* h_exact = nullptr;       /* pinned: result of an exact rerun / low-margin scan */
+    int64_t exact_reruns = 0;      /* flagged results recomputed exactly so far */
+    int exact_rerun = 1;           /* option: recompute results whose projection raised the FP guard-band flag */
+    double fp_margin_scale = 1.0;  /* option (tests): multiplies the guard band */
+    DevBuf d_margin;               /* low-margin scan: jobs and results */
     bool res_refined[kResultSlots] = { false, false, false, false };
     /* last pyramid job table on the device (skips the re-upload when unchanged) */
     std::vector<PyrJob> jobs_on_device;
@@ -318,6 +345,8 @@ int enqueue_readback(csm_handle h, int nq, bool refined = false)
     return CSM_OK;
 }
 
+int postprocess_flags(csm_handle h, const BatchRecord& rec, csm_result* results, int nq, csm_refined* refined);
+
 /* Wait for the oldest batch in flight and hand out its results */
 int finish_results(csm_handle h, csm_result* results, int nq, csm_refined* refined = nullptr)
 {
@@ -339,6 +368,12 @@ int finish_results(csm_handle h, csm_result* results, int nq, csm_refined* refin
     }
     if (*reinterpret_cast<const int*>(hp + sizeof(csm_result) * (size_t)nq) != 0)
         return fail(h, CSM_E_CAPACITY, "branch-and-bound frontier overflow; split the batch");
+    /* flagged results: exact rerun for the FP guard band, a look at the map for the low-edge flag */
+    bool any = false;
+    for (int q = 0; q < nq && !any; ++q)
+        any = (results[q].flags & (CSM_FLAG_FP_MARGIN | CSM_FLAG_EDGE)) != 0;
+    if (any && (int)h->res_rec[k].queries.size() == nq)
+        return postprocess_flags(h, h->res_rec[k], results, nq, h->res_refined[k] ? refined : nullptr);
     return CSM_OK;
 }
 
@@ -347,6 +382,7 @@ void free_map(csm_handle h, MapSlot& m)
     if (m.base && !m.base_block) cudaFreeAsync(m.base, h->stream);
     if (m.levels) cudaFreeAsync(m.levels, h->stream);
     if (m.coarse) cudaFreeAsync(m.coarse, h->stream);
+    if (m.bounds) cudaFreeAsync(m.bounds, h->stream);
     if (m.alloc && !m.alloc_block) cudaFreeAsync(m.alloc, h->stream);
     m = MapSlot();
 }
@@ -454,9 +490,12 @@ int bind_batch_arena(csm_handle h, int n, const int64_t* map_ids, int rows, int 
             uint16_t* levels = keep_levels ? m.levels : nullptr;
             const int levels_alloc = keep_levels ? m.levels_alloc : 0;
             uint16_t* coarse = keep_levels ? m.coarse : nullptr;
-            if (keep_levels) { m.levels = nullptr; m.coarse = nullptr; }
+            unsigned char* bounds = keep_levels ? m.bounds : nullptr;
+            const int bounds_alloc = keep_levels ? m.bounds_alloc : 0;
+            if (keep_levels) { m.levels = nullptr; m.coarse = nullptr; m.bounds = nullptr; }
             free_map(h, m);
             m.levels = levels; m.levels_alloc = levels_alloc; m.coarse = coarse;
+            m.bounds = bounds; m.bounds_alloc = bounds_alloc;
             m.rows = rows; m.cols = cols;
             m.base_block = block;
             m.base = reinterpret_cast<uint16_t*>(static_cast<char*>(block->p) + (size_t)i * bytes);
@@ -557,6 +596,29 @@ double fp_margin(const double pose[3], const MapSlot& m, double max_range, doubl
     return 1024.0 * 1.1102230246251565e-16 * mag / m.res + 1e-12;
 }
 
+/* ---- exact reruns ------------------------------------------------------------------------------------
+ * The device forms cos / sin(theta + a) from an angle-addition formula and multiplies by 1 / res, a few ulp
+ * away from the reference's glibc calls and its division; only a hit point within the guard band of a cell
+ * boundary can land in another cell because of that, and the projection flags exactly those. A flagged
+ * result is recomputed here from what the HOST evaluates with the reference's own libm calls in the
+ * reference's operation order (sensor_data.hpp:190-203, grid_map_geometry.cpp:113-122): r cos(theta + a),
+ * r sin(theta + a) per (angle, beam); the device then repeats the reference's per-candidate arithmetic
+ * ((x + r cos) - off) / res with IEEE division (k_grid_general) over the whole candidate lattice, scoring
+ * on the GPU as always. Rare (about 4e-10 per angle and beam), so the exhaustive lattice is affordable. */
+double2 host_hit_terms(double theta, double angle, double range)
+{
+    /* HitPoint: cosTheta = cos(theta + angle), x = sensor.x + range * cosTheta */
+    const double c = std::cos(theta + angle), s = std::sin(theta + angle);
+    return make_double2(range * c, range * s);
+}
+
+int ensure_exact_area(csm_handle h)
+{
+    if (h->h_exact == nullptr)
+        CSM_CUDA(cudaHostAlloc(&h->h_exact, 4096, cudaHostAllocDefault));
+    return CSM_OK;
+}
+
 int launch_setup(csm_handle h, const SetupArgs& A)
 {
     const unsigned int work = std::max(std::max(A.n16, A.z16), (unsigned int)std::max(A.n_beams, 1));
@@ -598,6 +660,8 @@ int upload_scan_impl(csm_handle h, int64_t scan_id, const double* angles,
     if ((rc = launch_setup(h, A))) return rc;
     if ((rc = upload_committed(h))) return rc;
     s.max_range = *std::max_element(ranges, ranges + n);
+    s.h_angles.assign(angles, angles + n);
+    s.h_ranges.assign(ranges, ranges + n);
     return CSM_OK;
 }
 
@@ -684,11 +748,6 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
         }
         const size_t smem = sizeof(unsigned int) *
             ((size_t)kPsStages * kPsRows * kPsInStride + 2 * kPsRows * 256 + 63 * 256);
-        static bool attr_set = false;
-        if (!attr_set) {
-            CSM_CUDA(cudaFuncSetAttribute(k_pyramid_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
         k_pyramid_stream<<<grid, kPsThreads, smem, h->stream>>>(dj, hmax, segs);
         CSM_LAUNCH_CHECK();
         phase_mark(h, "k_pyramid_stream");
@@ -707,6 +766,71 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             CSM_LAUNCH_CHECK();
         }
     }
+    return CSM_OK;
+}
+
+/* Bound levels 1..L (csm_bounds.cuh) of every slot that lacks them: what a search with hmax = L + 1
+ * reads above the leaves. One launch for all maps. */
+int build_bounds(csm_handle h, const std::vector<MapSlot*>& slots, int L)
+{
+    if (L < 0 || L > 6)
+        return fail(h, CSM_E_UNSUPPORTED, "bound levels: 1 <= hmax <= 7");
+    {
+        const int wrc = wait_uploads(h, slots);
+        if (wrc) return wrc;
+    }
+    std::vector<BlJob> jobs;
+    int max_rows = 0, max_cols = 0;
+    for (MapSlot* m : slots) {
+        if (m->bounds_levels >= L)
+            continue;
+        bool dup = false;
+        for (const BlJob& j : jobs) dup = dup || j.base == m->base;
+        if (dup) continue;
+        if (L > 0 && m->bounds_alloc < L) {
+            if (m->bounds) CSM_CUDA(cudaFreeAsync(m->bounds, h->stream));
+            m->bounds = nullptr;
+            m->bounds_alloc = 0;
+            const size_t bytes = bl_level_offset(L + 1, m->rows, m->cols);
+            CSM_CUDA(cudaMallocAsync((void**)&m->bounds, bytes, h->stream));
+            /* the padding is never written again: the builder stores whole tiles of the map region only */
+            CSM_CUDA(cudaMemsetAsync(m->bounds, 0, bytes, h->stream));
+            m->bounds_alloc = L;
+        }
+        m->bounds_levels = L;
+        if (L == 0)
+            continue;
+        jobs.push_back(BlJob { m->base, m->bounds, m->rows, m->cols });
+        max_rows = std::max(max_rows, m->rows);
+        max_cols = std::max(max_cols, m->cols);
+    }
+    if (jobs.empty())
+        return CSM_OK;
+    const size_t jb = jobs.size() * sizeof(BlJob);
+    int rc = ensure(h, h->d_bljobs, jb);
+    if (rc) return rc;
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, jb, &hp))) return rc;
+    std::memcpy(hp, jobs.data(), jb);
+    if ((rc = pull_to_device(h, h->d_bljobs.p, hp, jb))) return rc;
+    if ((rc = upload_committed(h))) return rc;
+    phase_mark(h, "start");
+    const int regions_x = (max_cols + kBlOutC - 1) / kBlOutC, regions_y = (max_rows + kBlOutR - 1) / kBlOutR;
+    const BlJob* dj = static_cast<const BlJob*>(h->d_bljobs.p);
+    for (size_t first = 0; first < jobs.size(); first += 65535) {
+        const dim3 grid((unsigned)(regions_x * regions_y), (unsigned)std::min<size_t>(65535, jobs.size() - first));
+        const size_t smem = bl_smem_bytes(L);
+        switch (L) {
+        case 1: k_bounds_build<1><<<grid, kBlThreads, smem, h->stream>>>(dj + first, regions_x); break;
+        case 2: k_bounds_build<2><<<grid, kBlThreads, smem, h->stream>>>(dj + first, regions_x); break;
+        case 3: k_bounds_build<3><<<grid, kBlThreads, smem, h->stream>>>(dj + first, regions_x); break;
+        case 4: k_bounds_build<4><<<grid, kBlThreads, smem, h->stream>>>(dj + first, regions_x); break;
+        case 5: k_bounds_build<5><<<grid, kBlThreads, smem, h->stream>>>(dj + first, regions_x); break;
+        default: k_bounds_build<6><<<grid, kBlThreads, smem, h->stream>>>(dj + first, regions_x); break;
+        }
+        CSM_LAUNCH_CHECK();
+    }
+    phase_mark(h, "k_bounds_build");
     return CSM_OK;
 }
 
@@ -744,6 +868,7 @@ int layout_plan(csm_handle h, int nq, size_t n_thetas, size_t n_rootoff, size_t 
     V.pulled_bytes = off;
     V.zero_off = off;
     const size_t off_qflags = off; off += align16(sizeof(int) * (size_t)nq);
+    const size_t off_tiekey = off; off += align16(sizeof(unsigned long long) * (size_t)nq);
     const size_t off_stats = off;  off += align16(sizeof(int) * 2 * (size_t)nq);
     const size_t off_counts = off; off += align16(sizeof(unsigned int) * kMaxLevels);
     const size_t off_overflow = off; off += 16;
@@ -759,6 +884,7 @@ int layout_plan(csm_handle h, int nq, size_t n_thetas, size_t n_rootoff, size_t 
     V.rootoff = reinterpret_cast<unsigned int*>(base + V.off_rootoff);
     V.extra = base + V.off_extra;
     V.qflags = reinterpret_cast<int*>(base + off_qflags);
+    V.tiekey = reinterpret_cast<unsigned long long*>(base + off_tiekey);
     V.stats = reinterpret_cast<int*>(base + off_stats);
     V.counts = reinterpret_cast<unsigned int*>(base + off_counts);
     V.overflow = reinterpret_cast<int*>(base + off_overflow);
@@ -781,6 +907,10 @@ int fill_common(csm_handle h, DevQuery& Q, const MapSlot& m, const ScanSlot& s,
     Q.lvl[0] = m.base;
     for (int l = 1; l <= m.hmax && l < kMaxLevels; ++l)
         Q.lvl[l] = m.levels + (size_t)(l - 1) * m.rows * m.cols;
+    for (int l = 1; l <= m.bounds_levels && l < kMaxLevels; ++l) {
+        Q.bl[l] = m.bounds + bl_level_offset(l, m.rows, m.cols);
+        Q.bl_tpr[l] = bl_tiles_per_row(l, m.cols);
+    }
     Q.coarse = m.coarse;
     Q.rows = m.rows; Q.cols = m.cols;
     Q.res = m.res; Q.offx = m.offx; Q.offy = m.offy;
@@ -939,9 +1069,6 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         if (mi == h->maps.end())
             return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown map id " + std::to_string(in.map_id));
         used_slots[q] = &mi->second;
-        if (mi->second.hmax < hmax)
-            return fail(h, CSM_E_INVALID, "loop batch: pyramid of map " + std::to_string(in.map_id) +
-                        " not built to hmax");
         if (!inline_scan && h->scans.find(in.scan_id) == h->scans.end())
             return fail(h, CSM_E_NOT_FOUND, "loop batch: unknown scan id " + std::to_string(in.scan_id));
         if (in.win_x < 0 || in.win_y < 0 || in.win_t < 0)
@@ -949,6 +1076,26 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         n_thetas += (size_t)(2 * in.win_t + 1);
     }
     int rc;
+    /* Which internal nodes are expanded never changes the result (DESIGN.md section 3), and on
+     * loop-detection windows the hmax-level bound is so loose that nearly every root passes: by
+     * default the roots are not scored at all but expanded unconditionally, which trades R + 4 p R
+     * scored nodes (p ~ 1) for 4 R and a launch on a latency-bound chain. The dive needs the
+     * root keys and keeps the scored roots. */
+    const int top = hmax;
+    const bool dive = top >= 1 && (h->bb_dive == 1 || (h->bb_dive == 2 && nq <= 4));
+    const bool unscored_roots = top >= 1 && h->bb_skip_top && !dive;
+    /* the sweep over bound levels (csm_bounds.cuh) whenever no kernel needs a u16 level above 0 */
+    const bool use_bounds = h->bb_bounds != 0 && unscored_roots;
+    /* what the search reads above level 0, built here for the maps that lack it (first touch) */
+    if (use_bounds) {
+        if ((rc = build_bounds(h, used_slots, hmax - 1))) return rc;
+    } else {
+        std::vector<MapSlot*> missing;
+        for (MapSlot* m : used_slots)
+            if (m->hmax < hmax && std::find(missing.begin(), missing.end(), m) == missing.end())
+                missing.push_back(m);
+        if (!missing.empty() && (rc = build_levels(h, missing, hmax))) return rc;
+    }
     const bool epilogue = inline_scan != nullptr && nq == 1 && h->epilogue_scale > 0.0;
     const bool refine = h->refine_on || epilogue;
     if (refine) {
@@ -968,14 +1115,6 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     plan.root_off.assign(nq + 1, 0u);
     if (inline_scan) { plan.scan_angles = inline_scan->angles; plan.scan_ranges = inline_scan->ranges; }
     const int wsz = 1 << hmax;
-    const int top = hmax;
-    /* Which internal nodes are expanded never changes the result (DESIGN.md section 3), and on
-     * loop-detection windows the hmax-level bound is so loose that nearly every root passes: by
-     * default the roots are not scored at all but expanded unconditionally, which trades R + 4 p R
-     * scored nodes (p ~ 1) for 4 R and a launch on a latency-bound chain. The dive needs the
-     * root keys and keeps the scored roots. */
-    const bool dive = top >= 1 && (h->bb_dive == 1 || (h->bb_dive == 2 && nq <= 4));
-    const bool unscored_roots = top >= 1 && h->bb_skip_top && !dive;
     for (int q = 0; q < nq; ++q) {
         const csm_loop_query& in = queries[q];
         const MapSlot& m = *used_slots[q];
@@ -997,12 +1136,13 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             return fail(h, CSM_E_UNSUPPORTED, "branch-and-bound: search lattice exceeds 2^26 leaves");
         Q.proj_off = plan.proj_total;
         Q.pst_t = 1; Q.pst_i = Q.T;            /* beam-major for the lane-per-node B&B */
-        plan.proj_total += (long long)Q.T * Q.n;
+        Q.pquad = use_bounds ? 1 : 0;          /* groups of four beams for the sweep over bound levels */
+        plan.proj_total += (long long)Q.T * ((Q.n + 3) & ~3);
         plan.max_tn = std::max(plan.max_tn, Q.T * Q.n);
         plan.max_t = std::max(plan.max_t, Q.T);
         plan.max_roots = std::max(plan.max_roots, Q.T * Q.nrx * Q.nry);
         const double extent = (double)(std::max(in.win_x, in.win_y) + wsz) * m.res;
-        Q.margin = fp_margin(in.sensor_pose, m, s.max_range, extent);
+        Q.margin = h->fp_margin_scale * fp_margin(in.sensor_pose, m, s.max_range, extent);
         plan.theta_off[q] = 0;
         Q.theta0 = in.sensor_pose[2]; Q.step_t = in.step_t; Q.tcenter = in.win_t;
         plan.inc_init[q] = ((unsigned long long)Q.kthr.fail_max << kOrdBits) | kOrdMask;
@@ -1022,6 +1162,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     W.list[1] = static_cast<unsigned long long*>(h->d_list[1].p);
     W.counts = V.counts;
     W.incumbent = V.inc;
+    W.tiekey = V.tiekey;
     W.stats = V.stats;
     W.overflow = V.overflow;
     W.capacity = h->frontier_capacity;
@@ -1049,9 +1190,13 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_bb_expand<0>, 256, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_bb_expand<3>, 256, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_bb_roots, 256, 0);
+            int d = 0, e = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_bbx_expand<0>, 256, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, k_bbx_expand<3>, 256, 0);
             h->bb_ctas_per_sm = std::max(1, std::min(std::min(a > 0 ? a : 8, b > 0 ? b : 8), c > 0 ? c : 8));
+            h->bbx_ctas_per_sm = std::max(1, std::min(d > 0 ? d : 8, e > 0 ? e : 8));
         }
-        const int full = h->sm_count * h->bb_ctas_per_sm;
+        const int full = h->sm_count * (use_bounds ? h->bbx_ctas_per_sm : h->bb_ctas_per_sm);
         if (!unscored_roots) {
             const int root_blocks = (int)std::min<unsigned int>((n_roots + 7) / 8, (unsigned int)full);
             k_bb_roots<<<std::max(root_blocks, 1), 256, 0, h->stream>>>(dq, proj, W, n_roots);
@@ -1068,6 +1213,17 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         for (int lvl = top; lvl >= 1; --lvl) {
             const int blocks = (int)std::min<unsigned long long>((bound + 7) / 8, (unsigned long long)full);
             const dim3 g((unsigned)std::max(blocks, 1));
+            if (use_bounds) {
+                switch (lvl - 1) {
+                case 0: k_bbx_expand<0><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                case 1: k_bbx_expand<1><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                case 2: k_bbx_expand<2><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                case 3: k_bbx_expand<3><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                case 4: k_bbx_expand<4><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                case 5: k_bbx_expand<5><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                default: k_bbx_expand<6><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                }
+            } else
             switch (lvl - 1) {          /* height of the children: compile-time for the index arithmetic */
             case 0: k_bb_expand<0><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
             case 1: k_bb_expand<1><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
@@ -1079,7 +1235,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             }
             CSM_LAUNCH_CHECK();
             if (h->timing) {
-                const std::string nm = "k_bb_expand<" + std::to_string(lvl - 1) + ">";
+                const std::string nm = std::string(use_bounds ? "k_bbx_expand<" : "k_bb_expand<") + std::to_string(lvl - 1) + ">";
                 phase_mark(h, nm.c_str());
             }
             bound = std::min<unsigned long long>(bound * 4, (unsigned long long)h->frontier_capacity);
@@ -1089,6 +1245,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     std::memset(&F, 0, sizeof(F));
     F.decode = 1;
     F.incumbent = V.inc;
+    F.tiekey = V.tiekey;
     F.stats = V.stats;
     F.best_key = static_cast<unsigned long long*>(h->d_bestkey.p);
     F.query_index_base = query_base;
@@ -1123,7 +1280,272 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     }
     rc = enqueue_readback(h, nq, refine);
     phase_mark(h, "readback");
+    if (rc == CSM_OK) {
+        BatchRecord& rec = h->res_rec[(h->res_head + h->res_count - 1) % csm_context::kResultSlots];
+        rec.queries.assign(queries, queries + nq);
+        rec.hmax = hmax;
+        rec.inline_scan = inline_scan != nullptr;
+        if (inline_scan) {
+            rec.angles.assign(inline_scan->angles, inline_scan->angles + inline_scan->n);
+            rec.ranges.assign(inline_scan->ranges, inline_scan->ranges + inline_scan->n);
+        }
+    }
     return rc;
+}
+
+/* Exhaustive search of a candidate lattice (positions px x py, angles thetas) with the reference's
+ * per-candidate arithmetic from host-evaluated hit terms; out->best_* are lattice indices (ix, iy, it). */
+int exact_lattice_search(csm_handle h, MapSlot& m, const double* angles, const double* ranges, int n,
+                         const std::vector<double>& thetas, const std::vector<double>& px,
+                         const std::vector<double>& py, int ord_mode, double score_thr, double known_thr,
+                         csm_result* out)
+{
+    const int ndx = (int)px.size(), ndy = (int)py.size(), ndt = (int)thetas.size();
+    if (ndt > 65535 || (unsigned long long)ndx * ndy * ndt >= kOrdMask - 1ull)
+        return fail(h, CSM_E_UNSUPPORTED, "exact rerun: lattice exceeds 2^26 candidates");
+    int rc;
+    if ((rc = wait_uploads(h, std::vector<MapSlot*>{ &m }))) return rc;
+    if ((rc = ensure_exact_area(h))) return rc;
+    /* the reference's hit terms, on the host */
+    std::vector<double2> rcs((size_t)ndt * n);
+    for (int t = 0; t < ndt; ++t)
+        for (int i = 0; i < n; ++i)
+            rcs[(size_t)t * n + i] = host_hit_terms(thetas[t], angles[i], ranges[i]);
+    PlanView V;
+    const size_t ob = align16(sizeof(int) * (size_t)(ndx + ndy));
+    const size_t pb = sizeof(double) * (size_t)(ndx + ndy);
+    if ((rc = layout_plan(h, 1, 0, 0, ob + pb, 0, V))) return rc;
+    ScanSlot dummy;
+    dummy.n = n;
+    QueryPlan plan;
+    plan.dq.resize(1);
+    plan.theta_off.assign(1, 0);
+    plan.inc_init.assign(1, 0ull);
+    DevQuery& Q = plan.dq[0];
+    if ((rc = fill_common(h, Q, m, dummy, score_thr, known_thr))) return rc;
+    Q.T = ndt;
+    Q.proj_off = 0;
+    Q.pst_t = n; Q.pst_i = 1;
+    Q.margin = 0.0;              /* nothing to guard: these are the reference's own operations */
+    plan.proj_total = (long long)ndt * n;
+    plan.extra.assign(ob + pb, 0);
+    {
+        double* pos = reinterpret_cast<double*>(plan.extra.data() + ob);
+        for (int k = 0; k < ndx; ++k) pos[k] = px[k];
+        for (int k = 0; k < ndy; ++k) pos[ndx + k] = py[k];
+    }
+    if ((rc = commit_plan(h, plan, V, true))) return rc;
+    CSM_CUDA(cudaMemcpyAsync(h->d_rcs.p, rcs.data(), sizeof(double2) * rcs.size(), cudaMemcpyHostToDevice, h->stream));
+    GridArgs G;
+    G.mx = reinterpret_cast<const int*>(V.extra);
+    G.my = G.mx + ndx;
+    G.px = reinterpret_cast<const double*>(V.extra + ob);
+    G.py = G.px + ndx;
+    G.ndx = ndx; G.ndy = ndy; G.ndt = ndt;
+    G.best = V.inc;
+    G.tiekey = V.tiekey;
+    G.ord_mode = ord_mode;
+    const DevQuery* dq = V.queries;
+    const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
+    dim3 grid(ndt, (ndy + 7) / 8);
+    k_grid_general<<<grid, 256, sizeof(double2) * n, h->stream>>>(dq, static_cast<const double2*>(h->d_rcs.p), G, V.qflags);
+    CSM_LAUNCH_CHECK();
+    FinalArgs F;
+    std::memset(&F, 0, sizeof(F));
+    F.decode = 2;
+    F.G = G;
+    F.mx = G.mx; F.my = G.my; F.px = G.px; F.py = G.py;
+    F.rcs = static_cast<const double2*>(h->d_rcs.p);
+    F.mode = 2;
+    F.qflags = V.qflags;
+    F.nq = 1;
+    k_finalize<<<1, 32, 0, h->stream>>>(dq, proj, F, static_cast<csm_result*>(h->d_results.p));
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaMemcpyAsync(h->h_exact, h->d_results.p, sizeof(csm_result), cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    *out = *static_cast<const csm_result*>(h->h_exact);
+    ++h->exact_reruns;
+    return CSM_OK;
+}
+
+/* ScanMatcherBranchBound::OptimizePose for one query, exactly: with admissible bounds the best-first
+ * search returns the best leaf among the leaves that pass both thresholds, so
+ * the rerun scores the whole leaf lattice with the node poses of scan_matcher_branch_bound.cpp:159-162. */
+int exact_rerun_bb(csm_handle h, const csm_loop_query& q, const double* angles, const double* ranges, int n,
+                   int hmax, csm_result* r)
+{
+    auto mi = h->maps.find(q.map_id);
+    if (mi == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "exact rerun: unknown map id");
+    const int wsz = 1 << hmax;
+    const int lx = ((2 * q.win_x) / wsz + 1) * wsz, ly = ((2 * q.win_y) / wsz + 1) * wsz, T = 2 * q.win_t + 1;
+    std::vector<double> thetas(T), px(lx), py(ly);
+    for (int t = 0; t < T; ++t) thetas[t] = q.sensor_pose[2] + (t - q.win_t) * q.step_t;
+    for (int x = 0; x < lx; ++x) px[x] = q.sensor_pose[0] + (x - q.win_x) * q.step_x;
+    for (int y = 0; y < ly; ++y) py[y] = q.sensor_pose[1] + (y - q.win_y) * q.step_y;
+    csm_result e;
+    const int rc = exact_lattice_search(h, mi->second, angles, ranges, n, thetas, px, py, 1, q.score_thr, q.known_thr, &e);
+    if (rc) return rc;
+    r->flags = ((r->flags & ~CSM_FLAG_FP_MARGIN) & ~CSM_FLAG_KEY_TIE) | (e.flags & CSM_FLAG_KEY_TIE) | CSM_FLAG_EXACT;
+    r->found = e.found;
+    if (e.found) {
+        r->best_x = e.best_x - q.win_x; r->best_y = e.best_y - q.win_y; r->best_t = e.best_t - q.win_t;
+        r->sum_value = e.sum_value; r->n_known = e.n_known; r->normalized_score = e.normalized_score;
+    } else {
+        r->best_x = r->best_y = r->best_t = 0;      /* scan_matcher_branch_bound.cpp:145-147 */
+    }
+    return CSM_OK;
+}
+
+/* Refine n given poses (synchronous); max_iterations == 0 evaluates cost and covariance only */
+int refine_poses(csm_handle h, const csm_refine_query* queries, int n, const csm_refine_params* p, csm_refined* out)
+{
+    int rc;
+    std::vector<MapSlot*> slots(n);
+    for (int q = 0; q < n; ++q) {
+        auto mi = h->maps.find(queries[q].map_id);
+        if (mi == h->maps.end())
+            return fail(h, CSM_E_NOT_FOUND, "refine batch: unknown map id " + std::to_string(queries[q].map_id));
+        if (h->scans.find(queries[q].scan_id) == h->scans.end())
+            return fail(h, CSM_E_NOT_FOUND, "refine batch: unknown scan id " + std::to_string(queries[q].scan_id));
+        slots[q] = &mi->second;
+    }
+    if ((rc = wait_uploads(h, slots))) return rc;
+    if ((rc = ensure_alloc(h, slots))) return rc;
+    const size_t q_bytes = align16(sizeof(DevQuery) * (size_t)n);
+    const size_t in_bytes = q_bytes + align16(sizeof(double) * 3 * (size_t)n);
+    if ((rc = ensure(h, h->d_refine_in, in_bytes + sizeof(csm_refined) * (size_t)n))) return rc;
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, in_bytes, &hp))) return rc;
+    for (int q = 0; q < n; ++q) {
+        DevQuery Q;
+        if ((rc = fill_common(h, Q, *slots[q], h->scans.find(queries[q].scan_id)->second, 0.0, 0.0))) return rc;
+        std::memcpy(hp + sizeof(DevQuery) * (size_t)q, &Q, sizeof(Q));
+        std::memcpy(hp + q_bytes + sizeof(double) * 3 * (size_t)q, queries[q].sensor_pose, sizeof(double) * 3);
+    }
+    if ((rc = pull_to_device(h, h->d_refine_in.p, hp, in_bytes))) return rc;
+    if ((rc = upload_committed(h))) return rc;
+    char* base = static_cast<char*>(h->d_refine_in.p);
+    RefineArgs R;
+    std::memset(&R, 0, sizeof(R));
+    R.start = reinterpret_cast<const double*>(base + q_bytes);
+    R.out = reinterpret_cast<csm_refined*>(base + in_bytes);
+    R.max_iterations = p->max_iterations;
+    R.always = p->max_iterations == 0 ? 1 : 0;
+    R.convergence_threshold = p->convergence_threshold;
+    R.lambda0 = p->lambda;
+    R.covariance_scale = p->covariance_scale;
+    k_refine<<<n, kRefThreads, 0, h->stream>>>(reinterpret_cast<const DevQuery*>(base), R);
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaMemcpyAsync(out, R.out, sizeof(csm_refined) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    return CSM_OK;
+}
+
+/* Results of a batch that came back flagged. CSM_FLAG_FP_MARGIN: exact rerun (and, when the batch
+ * refined its poses and the rerun moved the pose, the refinement again from the new pose).
+ * CSM_FLAG_EDGE: withdrawn when the map has no known cell in its first 2^hmax rows and columns. */
+int postprocess_flags(csm_handle h, const BatchRecord& rec, csm_result* results, int nq, csm_refined* refined)
+{
+    int rc;
+    /* low-edge flag: one scan of the low rows / columns of every map not looked at yet */
+    {
+        std::vector<MapSlot*> todo;
+        for (int q = 0; q < nq; ++q) {
+            if (!(results[q].flags & CSM_FLAG_EDGE)) continue;
+            auto mi = h->maps.find(rec.queries[q].map_id);
+            if (mi == h->maps.end()) continue;
+            MapSlot* m = &mi->second;
+            if (m->low_margin < 0 && std::find(todo.begin(), todo.end(), m) == todo.end())
+                todo.push_back(m);
+        }
+        if (!todo.empty()) {
+            const int limit = 1 << (kMaxLevels - 1);
+            if ((rc = wait_uploads(h, todo))) return rc;
+            const size_t jb = align16(sizeof(MarginJob) * todo.size()), ob = sizeof(int) * todo.size();
+            if ((rc = ensure(h, h->d_margin, jb + ob))) return rc;
+            std::vector<MarginJob> jobs(todo.size());
+            for (size_t i = 0; i < todo.size(); ++i)
+                jobs[i] = MarginJob { todo[i]->base, todo[i]->rows, todo[i]->cols, limit, 0 };
+            int* d_out = reinterpret_cast<int*>(static_cast<char*>(h->d_margin.p) + jb);
+            CSM_CUDA(cudaMemcpyAsync(h->d_margin.p, jobs.data(), sizeof(MarginJob) * jobs.size(), cudaMemcpyHostToDevice, h->stream));
+            CSM_CUDA(cudaMemsetAsync(d_out, 0x7f, ob, h->stream));
+            k_low_margin<<<(unsigned)todo.size(), 256, 0, h->stream>>>(static_cast<const MarginJob*>(h->d_margin.p), d_out);
+            CSM_LAUNCH_CHECK();
+            std::vector<int> got(todo.size());
+            CSM_CUDA(cudaMemcpyAsync(got.data(), d_out, ob, cudaMemcpyDeviceToHost, h->stream));
+            CSM_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t i = 0; i < todo.size(); ++i)
+                todo[i]->low_margin = std::min(got[i], limit);
+        }
+        for (int q = 0; q < nq; ++q) {
+            if (!(results[q].flags & CSM_FLAG_EDGE)) continue;
+            auto mi = h->maps.find(rec.queries[q].map_id);
+            if (mi != h->maps.end() && mi->second.low_margin >= (1 << rec.hmax))
+                results[q].flags &= ~CSM_FLAG_EDGE;
+        }
+    }
+    if (!h->exact_rerun)
+        return CSM_OK;
+    for (int q = 0; q < nq; ++q) {
+        if (!(results[q].flags & CSM_FLAG_FP_MARGIN)) continue;
+        const csm_loop_query& lq = rec.queries[q];
+        const double* angles = nullptr; const double* ranges = nullptr; int n = 0;
+        if (rec.inline_scan) {
+            angles = rec.angles.data(); ranges = rec.ranges.data(); n = (int)rec.angles.size();
+        } else {
+            auto si = h->scans.find(lq.scan_id);
+            if (si == h->scans.end()) continue;
+            angles = si->second.h_angles.data(); ranges = si->second.h_ranges.data(); n = si->second.n;
+        }
+        const csm_result before = results[q];
+        if ((rc = exact_rerun_bb(h, lq, angles, ranges, n, rec.hmax, &results[q]))) return rc;
+        const csm_result& after = results[q];
+        const bool moved = before.found != after.found || before.best_x != after.best_x ||
+                           before.best_y != after.best_y || before.best_t != after.best_t;
+        if (refined != nullptr && moved) {
+            /* the refinement started from the other pose: run it again from the exact one */
+            std::memset(&refined[q], 0, sizeof(csm_refined));
+            const bool epilogue = rec.inline_scan && h->epilogue_scale > 0.0;
+            if (after.found || epilogue) {
+                csm_refine_query rq;
+                rq.map_id = lq.map_id;
+                rq.scan_id = lq.scan_id;
+                rq.sensor_pose[0] = lq.sensor_pose[0] + lq.step_x * after.best_x;
+                rq.sensor_pose[1] = lq.sensor_pose[1] + lq.step_y * after.best_y;
+                rq.sensor_pose[2] = lq.sensor_pose[2] + lq.step_t * after.best_t;
+                if (rec.inline_scan) {
+                    if ((rc = upload_scan_impl(h, kTempScanId, angles, ranges, n))) return rc;
+                    rq.scan_id = kTempScanId;
+                }
+                csm_refine_params p = h->refine;
+                if (epilogue) { p.max_iterations = 0; p.covariance_scale = h->epilogue_scale; }
+                if ((rc = refine_poses(h, &rq, 1, &p, &refined[q]))) return rc;
+            }
+        }
+    }
+    return CSM_OK;
+}
+
+/* Kernels that need more dynamic shared memory than the default limit: the attribute is per device,
+ * so every handle sets it for its own device when it is created (no process-wide flags). */
+cudaError_t set_kernel_attributes()
+{
+    cudaError_t e;
+    const int ps = (int)(sizeof(unsigned int) * ((size_t)kPsStages * kPsRows * kPsInStride + 2 * kPsRows * 256 + 63 * 256));
+    if ((e = cudaFuncSetAttribute(k_pyramid_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ps)) != cudaSuccess) return e;
+#define CSM_BL_ATTR(L) \
+    if ((e = cudaFuncSetAttribute(k_bounds_build<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl_smem_bytes(L))) != cudaSuccess) return e;
+    CSM_BL_ATTR(1) CSM_BL_ATTR(2) CSM_BL_ATTR(3) CSM_BL_ATTR(4) CSM_BL_ATTR(5) CSM_BL_ATTR(6)
+#undef CSM_BL_ATTR
+    const int wt = (int)wt_smem_bytes(kMaxBeams);
+#define CSM_WT_ATTR(UNIT, CHUNKS, REM)                                                                                        \
+    if ((e = cudaFuncSetAttribute(k_window_tma<UNIT, CHUNKS, REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, wt)) != cudaSuccess) return e;
+    CSM_WT_ATTR(true, 1, true) CSM_WT_ATTR(true, 2, true) CSM_WT_ATTR(true, 3, true)
+    CSM_WT_ATTR(true, 4, true) CSM_WT_ATTR(true, 5, true) CSM_WT_ATTR(true, 6, true)
+    CSM_WT_ATTR(true, kWtChunks, false) CSM_WT_ATTR(false, kWtChunks, false)
+#undef CSM_WT_ATTR
+    return cudaSuccess;
 }
 
 int check_refine_params(csm_handle h, const csm_refine_params* p)
@@ -1161,6 +1583,8 @@ int csm_create(int device, unsigned flags, csm_handle* out)
         return CSM_E_CUDA;
     if (cudaSetDevice(device) != cudaSuccess)
         return CSM_E_CUDA;
+    if (set_kernel_attributes() != cudaSuccess)
+        return CSM_E_CUDA;
     csm_handle h = new csm_context;
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1193,12 +1617,13 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
-                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs };
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs, &h->d_bljobs, &h->d_margin };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)
         if (h->d_list[l].p) cudaFreeAsync(h->d_list[l].p, h->stream);
     cudaStreamSynchronize(h->stream);
+    if (h->h_exact) cudaFreeHost(h->h_exact);
     for (int k = 0; k < csm_context::kUploadAreas; ++k) {
         if (h->h_up[k]) cudaFreeHost(h->h_up[k]);
         if (h->h_up_done[k]) cudaEventDestroy(h->h_up_done[k]);
@@ -1234,6 +1659,8 @@ int csm_synchronize(csm_handle h)
 
 int64_t csm_launch_count(csm_handle h) { return h ? h->launches : 0; }
 
+int64_t csm_exact_rerun_count(csm_handle h) { return h ? h->exact_reruns : 0; }
+
 int csm_set_option(csm_handle h, const char* name, int value)
 {
     if (!h || !name) return CSM_E_INVALID;
@@ -1244,6 +1671,9 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "bb_dive") == 0 && value >= 0 && value <= 2) { h->bb_dive = value; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
     if (std::strcmp(name, "bb_split_shift") == 0) { h->bb_split_shift = std::max(-4, std::min(value, 4)); return CSM_OK; }
+    if (std::strcmp(name, "exact_rerun") == 0) { h->exact_rerun = value != 0; return CSM_OK; }
+    if (std::strcmp(name, "fp_margin_scale") == 0) { h->fp_margin_scale = value > 0 ? (double)value : 1.0; return CSM_OK; }
+    if (std::strcmp(name, "bb_bounds") == 0) { h->bb_bounds = value != 0; return CSM_OK; }
     if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
     if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
@@ -1287,6 +1717,8 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     }
     /* precomputed levels belong to the previous contents (allocations are kept) */
     m.hmax = 0;
+    m.bounds_levels = -1;
+    m.low_margin = -1;
     m.coarse_win = 0;
     m.pending_scatter.reset();
     m.alloc_valid = false;
@@ -1354,6 +1786,8 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
     for (int i = 0; i < n; ++i) {
         MapSlot& m = *slots[i];
         m.hmax = 0;
+        m.bounds_levels = -1;
+        m.low_margin = -1;
         m.coarse_win = 0;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
@@ -1456,6 +1890,8 @@ int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
     for (int i = 0; i < n; ++i) {
         MapSlot& m = *slots[i];
         m.hmax = 0;
+        m.bounds_levels = -1;
+        m.low_margin = -1;
         m.coarse_win = 0;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
@@ -1546,6 +1982,10 @@ int csm_build_pyramids(csm_handle h, int n, const int64_t* map_ids, int hmax)
             return fail(h, CSM_E_NOT_FOUND, "build_pyramids: unknown map id " + std::to_string(map_ids[i]));
         slots.push_back(&it->second);
     }
+    /* a batch of maps is precomputed for the batched search: its bound levels (csm_bounds.cuh) unless the
+     * sweep is set to read the reference's u16 levels; one map alone gets the reference's levels */
+    if (n > 1 && h->bb_bounds && h->bb_skip_top && h->bb_dive != 1 && hmax >= 1 && hmax < kMaxLevels)
+        return build_bounds(h, slots, hmax - 1);
     return build_levels(h, slots, hmax);
 }
 
@@ -1557,6 +1997,7 @@ int csm_drop_pyramids(csm_handle h, int n, const int64_t* map_ids)
         if (it == h->maps.end())
             return fail(h, CSM_E_NOT_FOUND, "drop_pyramids: unknown map id");
         it->second.hmax = 0;
+        it->second.bounds_levels = -1;
         it->second.coarse_win = 0;
     }
     return CSM_OK;
@@ -1577,6 +2018,11 @@ int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out)
     {
         const int wrc = wait_uploads(h, std::vector<MapSlot*>{ &m });
         if (wrc) return wrc;
+    }
+    if (level > 0 && level > m.hmax && level <= m.bounds_levels + 1) {
+        /* the map was precomputed for the sweep only: build the reference's levels now */
+        const int brc = build_levels(h, std::vector<MapSlot*>{ &m }, level);
+        if (brc) return brc;
     }
     const size_t cells = (size_t)m.rows * m.cols;
     const uint16_t* src = nullptr;
@@ -1683,47 +2129,10 @@ int csm_refine_batch(csm_handle h, const csm_refine_query* queries, int n,
     if (!h) return CSM_E_INVALID;
     if (n <= 0 || !queries || !p || !out)
         return fail(h, CSM_E_INVALID, "refine batch: empty");
-    int rc = check_refine_params(h, p);
+    const int rc = check_refine_params(h, p);
     if (rc) return rc;
     CSM_CUDA(cudaSetDevice(h->device));
-    std::vector<MapSlot*> slots(n);
-    for (int q = 0; q < n; ++q) {
-        auto mi = h->maps.find(queries[q].map_id);
-        if (mi == h->maps.end())
-            return fail(h, CSM_E_NOT_FOUND, "refine batch: unknown map id " + std::to_string(queries[q].map_id));
-        if (h->scans.find(queries[q].scan_id) == h->scans.end())
-            return fail(h, CSM_E_NOT_FOUND, "refine batch: unknown scan id " + std::to_string(queries[q].scan_id));
-        slots[q] = &mi->second;
-    }
-    if ((rc = wait_uploads(h, slots))) return rc;
-    if ((rc = ensure_alloc(h, slots))) return rc;
-    const size_t q_bytes = align16(sizeof(DevQuery) * (size_t)n);
-    const size_t in_bytes = q_bytes + align16(sizeof(double) * 3 * (size_t)n);
-    if ((rc = ensure(h, h->d_refine_in, in_bytes + sizeof(csm_refined) * (size_t)n))) return rc;
-    char* hp = nullptr;
-    if ((rc = acquire_upload(h, in_bytes, &hp))) return rc;
-    for (int q = 0; q < n; ++q) {
-        DevQuery Q;
-        if ((rc = fill_common(h, Q, *slots[q], h->scans.find(queries[q].scan_id)->second, 0.0, 0.0))) return rc;
-        std::memcpy(hp + sizeof(DevQuery) * (size_t)q, &Q, sizeof(Q));
-        std::memcpy(hp + q_bytes + sizeof(double) * 3 * (size_t)q, queries[q].sensor_pose, sizeof(double) * 3);
-    }
-    if ((rc = pull_to_device(h, h->d_refine_in.p, hp, in_bytes))) return rc;
-    if ((rc = upload_committed(h))) return rc;
-    char* base = static_cast<char*>(h->d_refine_in.p);
-    RefineArgs R;
-    std::memset(&R, 0, sizeof(R));
-    R.start = reinterpret_cast<const double*>(base + q_bytes);
-    R.out = reinterpret_cast<csm_refined*>(base + in_bytes);
-    R.max_iterations = p->max_iterations;
-    R.convergence_threshold = p->convergence_threshold;
-    R.lambda0 = p->lambda;
-    R.covariance_scale = p->covariance_scale;
-    k_refine<<<n, kRefThreads, 0, h->stream>>>(reinterpret_cast<const DevQuery*>(base), R);
-    CSM_LAUNCH_CHECK();
-    CSM_CUDA(cudaMemcpyAsync(out, R.out, sizeof(csm_refined) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-    CSM_CUDA(cudaStreamSynchronize(h->stream));
-    return CSM_OK;
+    return refine_poses(h, queries, n, p, out);
 }
 
 int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax,
@@ -1732,6 +2141,39 @@ int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax
     int rc = csm_loop_batch_enqueue(h, queries, nq, hmax, query_index_base);
     if (rc) return rc;
     return csm_loop_batch_finish(h, results, nq);
+}
+
+int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out)
+{
+    if (!h || !out) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end())
+        return fail(h, CSM_E_NOT_FOUND, "bound level: unknown map id");
+    if (level < 1 || level > 6)
+        return fail(h, CSM_E_INVALID, "bound level: 1 <= level <= 6");
+    CSM_CUDA(cudaSetDevice(h->device));
+    MapSlot& m = it->second;
+    if (m.bounds_levels < level) {
+        const int brc = build_bounds(h, std::vector<MapSlot*>{ &m }, level);
+        if (brc) return brc;
+    }
+    const size_t bytes = bl_level_bytes(level, m.rows, m.cols);
+    std::vector<unsigned char> raw(bytes);
+    CSM_CUDA(cudaMemcpyAsync(raw.data(), m.bounds + bl_level_offset(level, m.rows, m.cols), bytes,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    const int tpr = bl_tiles_per_row(level, m.cols), pr = bl_pad_r(level), pc = bl_pad_c(level);
+    /* everything outside the map must have stayed zero */
+    for (int rp = 0; rp < bl_tile_rows(level, m.rows) * kBlTileR; ++rp)
+        for (int cp = 0; cp < tpr * kBlTileC; ++cp) {
+            const unsigned char v = raw[((size_t)(rp >> 3) * tpr + (cp >> 4)) * 128 + ((rp & 7) << 4) + (cp & 15)];
+            const int r = rp - pr, c = cp - pc;
+            if (r >= 0 && r < m.rows && c >= 0 && c < m.cols)
+                out[(size_t)r * m.cols + c] = v;
+            else if (v != 0)
+                return fail(h, CSM_E_INVALID, "bound level: non-zero padding");
+        }
+    return CSM_OK;
 }
 
 int csm_debug_frontier_counts(csm_handle h, unsigned int* out8)
@@ -1805,12 +2247,12 @@ int csm_match_bb(csm_handle h, int64_t map_id,
     return frc;
 }
 
-int csm_match_rt(csm_handle h, int64_t map_id,
-                 const double* angles, const double* ranges, int n,
-                 const double sensor_pose[3], int low_res,
-                 int win_x, int win_y, int win_t,
-                 double step_x, double step_y, double step_t,
-                 double score_thr, double known_thr, csm_result* out)
+static int match_rt_impl(csm_handle h, int64_t map_id,
+                         const double* angles, const double* ranges, int n,
+                         const double sensor_pose[3], int low_res,
+                         int win_x, int win_y, int win_t,
+                         double step_x, double step_y, double step_t,
+                         double score_thr, double known_thr, csm_result* out, bool exact)
 {
     if (!h || !out || !sensor_pose) return CSM_E_INVALID;
     if (h->res_count != 0)
@@ -1860,7 +2302,7 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     plan.proj_total = (long long)Q.T * Q.n;
     plan.max_tn = Q.T * Q.n;
     plan.max_t = Q.T;
-    Q.margin = fp_margin(sensor_pose, m, s.max_range, (double)(std::max(win_x, win_y) + low_res) * m.res);
+    Q.margin = h->fp_margin_scale * fp_margin(sensor_pose, m, s.max_range, (double)(std::max(win_x, win_y) + low_res) * m.res);
     Q.theta0 = sensor_pose[2]; Q.step_t = step_t; Q.tcenter = win_t;
     Q.stepx = step_x; Q.stepy = step_y;
     const int nbx = (2 * win_x) / low_res + 1;
@@ -1872,9 +2314,29 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     phase_mark(h, "k_setup");
     const DevQuery* dq = V.queries;
     proj_t* proj = static_cast<proj_t*>(h->d_proj.p);
+    std::vector<proj_t> host_proj;
+    if (exact) {
+        /* exact rerun: ComputeScanIndices (scan_matcher_correlative.cpp:277-297) on the host, with the
+         * reference's libm calls and operation order; the kernels take the indices as given */
+        host_proj.resize((size_t)T * n);
+        for (int t = 0; t < T; ++t) {
+            const double theta = sensor_pose[2] + step_t * (t - win_t);
+            for (int i = 0; i < n; ++i) {
+                const double2 hit = host_hit_terms(theta, angles[i], ranges[i]);
+                const double col = std::floor(((sensor_pose[0] + hit.x) - m.offx) / m.res);
+                const double row = std::floor(((sensor_pose[1] + hit.y) - m.offy) / m.res);
+                proj_t p;
+                p.x = (short)std::max(std::min(col, (double)kProjSat), -(double)kProjSat);
+                p.y = (short)std::max(std::min(row, (double)kProjSat), -(double)kProjSat);
+                host_proj[(size_t)t * n + i] = p;
+            }
+        }
+        CSM_CUDA(cudaMemcpyAsync(proj, host_proj.data(), sizeof(proj_t) * host_proj.size(), cudaMemcpyHostToDevice, h->stream));
+        ++h->exact_reruns;
+    }
     /* projection happens inside k_rt_blocks (one launch less on this latency-bound path) */
     k_rt_blocks<<<nblocks, 256, sizeof(long long) * low_res * low_res + sizeof(proj_t) * Q.n, h->stream>>>(
-        dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby, V.qflags);
+        dq, proj, static_cast<RtBlock*>(h->d_rtblocks.p), low_res, nbx, nby, V.qflags, exact ? 1 : 0);
     CSM_LAUNCH_CHECK();
     phase_mark(h, "k_rt_blocks");
     FinalArgs F;
@@ -1913,9 +2375,28 @@ int csm_match_rt(csm_handle h, int64_t map_id,
     }
     const bool extra = epilogue || refine_final;
     if ((rc = enqueue_readback(h, 1, extra))) return rc;
+    h->res_rec[(h->res_head + h->res_count - 1) % csm_context::kResultSlots].queries.clear();   /* no batch record: handled below */
     phase_mark(h, "readback");
     rc = finish_results(h, out, 1, extra ? &h->last_epilogue : nullptr);
     h->last_epilogue_set = rc == CSM_OK && extra;
+    return rc;
+}
+
+int csm_match_rt(csm_handle h, int64_t map_id,
+                 const double* angles, const double* ranges, int n,
+                 const double sensor_pose[3], int low_res,
+                 int win_x, int win_y, int win_t,
+                 double step_x, double step_y, double step_t,
+                 double score_thr, double known_thr, csm_result* out)
+{
+    int rc = match_rt_impl(h, map_id, angles, ranges, n, sensor_pose, low_res, win_x, win_y, win_t,
+                           step_x, step_y, step_t, score_thr, known_thr, out, false);
+    if (rc == CSM_OK && (out->flags & CSM_FLAG_FP_MARGIN) && h->exact_rerun) {
+        /* a hit point within the FP guard band of a cell boundary: again, from host-evaluated indices */
+        rc = match_rt_impl(h, map_id, angles, ranges, n, sensor_pose, low_res, win_x, win_y, win_t,
+                           step_x, step_y, step_t, score_thr, known_thr, out, true);
+        if (rc == CSM_OK) out->flags |= CSM_FLAG_EXACT;
+    }
     return rc;
 }
 
@@ -1988,7 +2469,7 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     plan.max_tn = ndt * Q.n;
     plan.max_t = ndt;
     const double extent = std::fabs(dx[0]) + std::fabs(dx[ndx - 1]) + std::fabs(dy[0]) + std::fabs(dy[ndy - 1]);
-    Q.margin = fp_margin(sensor_pose, m, s.max_range, extent) + (fast ? 2.0 * dev : 0.0);
+    Q.margin = h->fp_margin_scale * fp_margin(sensor_pose, m, s.max_range, extent) + (fast ? 2.0 * dev : 0.0);
     for (int k = 0; k < ndt; ++k)
         plan.thetas.push_back(sensor_pose[2] + dt[k]);
 
@@ -2011,7 +2492,8 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     G.py = G.px + ndx;
     G.ndx = ndx; G.ndy = ndy; G.ndt = ndt;
     G.best = V.inc;                       /* zero-initialised by the plan */
-    G.tie = nullptr;
+    G.tiekey = V.tiekey;
+    G.ord_mode = 0;
     const DevQuery* dq = V.queries;
     const proj_t* proj = static_cast<const proj_t*>(h->d_proj.p);
     dim3 grid(ndt, (ndy + 7) / 8);
@@ -2062,19 +2544,10 @@ int csm_match_grid(csm_handle h, int64_t map_id,
             k_window_groups<<<(ndt + 127) / 128, 128, 0, h->stream>>>(dq, proj, groups, gcount, max_h, max_w);
             CSM_LAUNCH_CHECK();
             const size_t smem = wt_smem_bytes(Q.n);
-            const int max_smem = (int)wt_smem_bytes(kMaxBeams);
             dim3 wgrid(ndt, (ndy + rows_per_cta - 1) / rows_per_cta, (ndx + cols_per_cta - 1) / cols_per_cta);
             phase_mark(h, "k_window_groups");
 #define CSM_WT_LAUNCH(UNIT, CHUNKS, REM)                                                                        \
-            {                                                                                                   \
-                static bool attr = false;                                                                       \
-                if (!attr) {                                                                                    \
-                    CSM_CUDA(cudaFuncSetAttribute(k_window_tma<UNIT, CHUNKS, REM>,                              \
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));      \
-                    attr = true;                                                                                \
-                }                                                                                               \
-                k_window_tma<UNIT, CHUNKS, REM><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA); \
-            }
+            k_window_tma<UNIT, CHUNKS, REM><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
             if (rem_variant) {
                 switch (rem_chunks) {
                 case 1: CSM_WT_LAUNCH(true, 1, true) break;
@@ -2120,7 +2593,21 @@ int csm_match_grid(csm_handle h, int64_t map_id,
     CSM_LAUNCH_CHECK();
     phase_mark(h, "k_finalize");
     if ((rc = enqueue_readback(h, 1))) return rc;
-    return finish_results(h, out, 1);
+    h->res_rec[(h->res_head + h->res_count - 1) % csm_context::kResultSlots].queries.clear();
+    if ((rc = finish_results(h, out, 1))) return rc;
+    if ((out->flags & CSM_FLAG_FP_MARGIN) && h->exact_rerun) {
+        /* a hit point within the FP guard band of a cell boundary: the whole window again with the
+         * reference's per-candidate arithmetic from host-evaluated hit terms */
+        std::vector<double> thetas(ndt), px(ndx), py(ndy);
+        for (int k = 0; k < ndt; ++k) thetas[k] = sensor_pose[2] + dt[k];
+        for (int k = 0; k < ndx; ++k) px[k] = sensor_pose[0] + dx[k];
+        for (int k = 0; k < ndy; ++k) py[k] = sensor_pose[1] + dy[k];
+        csm_result e;
+        if ((rc = exact_lattice_search(h, m, angles, ranges, n, thetas, px, py, 0, score_thr, known_thr, &e))) return rc;
+        e.flags = (e.flags & CSM_FLAG_KEY_TIE) | CSM_FLAG_EXACT;
+        *out = e;
+    }
+    return CSM_OK;
 }
 
 } /* extern "C" */

@@ -72,7 +72,23 @@ struct DevQuery
     const unsigned char* alloc;        /* one byte per 2^k x 2^k block: allocated in the reference's sense */
     int alloc_log2bs, alloc_bcols;     /* k, blocks per row */
     double stepx, stepy;               /* search steps along x / y (the coarse result is an index) */
+    /* bound levels of the branch-and-bound sweep (csm_bounds.cuh): bl[hc] = level hc (u8, tiled, padded),
+     * bl_tpr[hc] its tiles per row; null when the sweep reads the u16 levels */
+    const unsigned char* bl[kMaxLevels];
+    int bl_tpr[kMaxLevels];
+    int pquad;                         /* 1: proj is stored in groups of four beams, [n / 4][T][4] (see proj_index) */
+    int pad3;
 };
+
+/* Position of (angle t, beam i) in a query's block of the projection buffer. Strided layouts:
+ * angle-major (pst_t = n, pst_i = 1) for the real-time and grid-search matchers, beam-major
+ * (pst_t = 1, pst_i = T). Quad layout (branch-and-bound over bound levels): [n / 4][T][4], so that the
+ * index loads of a warp that holds 8 adjacent angles x 4 adjacent beams are one 128-byte line. */
+__device__ __forceinline__ size_t proj_index(const DevQuery& Q, int t, int i)
+{
+    return Q.pquad ? ((((size_t)(i >> 2) * (size_t)Q.T + (size_t)t) << 2) + (size_t)(i & 3))
+                   : (size_t)t * (size_t)Q.pst_t + (size_t)i * (size_t)Q.pst_i;
+}
 
 __host__ __device__ __forceinline__ long long make_key(long long sumv, int nk)
 {
@@ -127,6 +143,20 @@ __device__ double exact_normalized_score(const uint16_t* __restrict__ m, int row
             sum = __dadd_rn(sum, value_to_probability(v));
     }
     return __ddiv_rn(sum, (double)n);
+}
+
+/* The same for angle t of a query in whatever layout its projection has */
+__device__ double exact_normalized_score_q(const DevQuery& Q, const uint16_t* __restrict__ m,
+                                           const proj_t* __restrict__ proj_q, int t, int ox, int oy)
+{
+    double sum = 0.0;
+    for (int i = 0; i < Q.n; ++i) {
+        const proj_t p = proj_q[proj_index(Q, t, i)];
+        const unsigned int v = ld_cell(m, Q.rows, Q.cols, p.y + oy, p.x + ox);
+        if (v != 0u)
+            sum = __dadd_rn(sum, value_to_probability(v));
+    }
+    return __ddiv_rn(sum, (double)Q.n);
 }
 
 /* -1 fail, +1 pass, 0 guard band */

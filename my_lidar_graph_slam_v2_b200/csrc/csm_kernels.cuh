@@ -34,6 +34,7 @@
 #pragma once
 
 #include "csm_device.cuh"
+#include "csm_bounds.cuh"
 #include "csm_b200.h"
 
 namespace csm {
@@ -625,7 +626,7 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
     /* beam-major output (pst_t == 1): 8 consecutive threads take the angles of one beam and write
      * one contiguous 32-byte run; angle-major output: consecutive threads take consecutive beams of
      * one angle. Either way a thread walks its elements with additions only. */
-    const bool angle_fastest = Q.pst_t == 1;
+    const bool angle_fastest = Q.pst_t == 1 || Q.pquad != 0;
     const int n = Q.n;
     const int tl_first = angle_fastest ? (int)(threadIdx.x & (kProjAngles - 1)) : 0;
     const int tl_step = angle_fastest ? kProjAngles : 1;
@@ -634,6 +635,7 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
     const bool bb = Q.lx > 0;
     const int winx = Q.winx, winy = Q.winy, lx2 = 2 * Q.lx, ly2 = 2 * Q.ly;
     proj_t* __restrict__ out = proj + (size_t)Q.proj_off;
+    const bool quad = Q.pquad != 0;
     for (int tl = tl_first; tl < nt; tl += tl_step) {
         const double2 th = s_theta[tl];
         proj_t* __restrict__ out_t = out + (size_t)(t0 + tl) * Q.pst_t;
@@ -647,7 +649,8 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
                 if ((x0 < 0 && x0 + lx2 > 0) || (y0 < 0 && y0 + ly2 > 0))
                     flagged |= 4;
             }
-            out_t[(size_t)i * Q.pst_i] = p;
+            if (quad) out[proj_index(Q, t0 + tl, i)] = p;      /* a warp = 4 beams x 8 angles = one 128-byte line */
+            else out_t[(size_t)i * Q.pst_i] = p;
             if (rcs != nullptr)
                 rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * n + i] = make_double2(rc, rs);
         }
@@ -711,7 +714,7 @@ struct RtBlock
  * iteration order (x outer, y inner, scan_matcher_correlative.cpp:351-352). */
 __global__ void __launch_bounds__(256)
 k_rt_blocks(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj_all,
-            RtBlock* __restrict__ blocks, int low_res, int nbx, int nby, int* __restrict__ qflags)
+            RtBlock* __restrict__ blocks, int low_res, int nbx, int nby, int* __restrict__ qflags, int proj_given)
 {
     extern __shared__ long long s_keys[];      /* L*L fine keys, then the angle's projected indices */
     __shared__ double2 s_theta;
@@ -736,6 +739,10 @@ k_rt_blocks(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj_all,
         const bool publish = rem == 0;
         proj_t* gproj = proj_all + Q.proj_off + (size_t)t * Q.n;
         int flagged = 0;
+        if (proj_given) {
+            /* exact rerun: the indices were computed on the host with the reference's own libm calls */
+            for (int i = threadIdx.x; i < Q.n; i += blockDim.x) proj[i] = gproj[i];
+        } else
         for (int i = threadIdx.x; i < Q.n; i += blockDim.x) {
             double rc, rs;
             const proj_t p = project_beam(Q, s_theta, i, flagged, rc, rs);
@@ -979,6 +986,7 @@ struct BbWork
     int*                stats;      /* per query: processed, ignored */
     int*                overflow;   /* set when a list is full */
     long long*          rootkey;    /* per root candidate: its key if it passed, else -1 (feeds the dive) */
+    unsigned long long* tiekey;     /* per query: largest key two different leaves were seen to share (0: none) */
     unsigned int        capacity;
     int                 top;        /* height of the root candidates (the reference's node_height_max) */
     int                 split_shift; /* lanes per node: largest split with count * split * 2 <= lanes << split_shift */
@@ -993,6 +1001,18 @@ __device__ __forceinline__ unsigned long long leaf_ordfield(const DevQuery& Q, i
     const unsigned long long ord =
         ((unsigned long long)t * (unsigned)Q.lx + (unsigned)xi) * (unsigned)Q.ly + (unsigned)yi;
     return (kOrdMask - 1ull) - ord;     /* all-ones is reserved for "no leaf yet" */
+}
+
+/* A passing leaf raises its query's incumbent. When the word it replaces (or fails to replace) carries
+ * the same key from another leaf, that key is remembered: k_finalize raises CSM_FLAG_KEY_TIE when the
+ * winning key is a shared one (the reference's winner among equal double scores depends on its heap
+ * order; here the smallest (t, x, y) ordinal wins). */
+__device__ __forceinline__ void bb_raise_incumbent(const BbWork& W, int q, long long key, unsigned long long ordfield)
+{
+    const unsigned long long word = pack_best(key, ordfield);
+    const unsigned long long old = atomicMax(&W.incumbent[q], word);
+    if (old != word && (old >> kOrdBits) == (unsigned long long)key && (old & kOrdMask) != kOrdMask)
+        atomicMax(&W.tiekey[q], (unsigned long long)key);
 }
 
 /* Root candidates of every query: (x, y) stepping by 2^top from -win, all angles
@@ -1037,9 +1057,8 @@ __device__ __forceinline__ bool bb_passes(const DevQuery& Q, const proj_t* __res
         const int c = key_vs_threshold(key, Q.kthr);
         if (c < 0) pass = false;
         else if (c == 0) {
-            const proj_t* pp0 = proj_all + Q.proj_off + (size_t)t * Q.pst_t;
-            pass = exact_normalized_score(Q.lvl[h], Q.rows, Q.cols, pp0, Q.pst_i, Q.n,
-                                          xi - Q.winx, yi - Q.winy) > Q.kthr.thr;
+            pass = exact_normalized_score_q(Q, Q.lvl[h], proj_all + Q.proj_off, t,
+                                            xi - Q.winx, yi - Q.winy) > Q.kthr.thr;
         }
     }
     return pass;
@@ -1115,7 +1134,7 @@ k_bb_roots(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
             const DevQuery& Q = queries[q];
             pass = bb_passes(Q, proj_all, W, q, t, xi, yi, h, s, k, key);
             if (pass && h == 0)
-                atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, xi, yi)));
+                bb_raise_incumbent(W, q, key, leaf_ordfield(Q, t, xi, yi));
             if (W.rootkey != nullptr)
                 W.rootkey[idx] = pass ? key : -1ll;
         }
@@ -1269,7 +1288,7 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
                 long long key;
                 pass = bb_passes(Q, proj_all, W, q, t, cx, cy, 0, s, k, key);
                 if (pass)
-                    atomicMax(&W.incumbent[q], pack_best(key, leaf_ordfield(Q, t, cx, cy)));
+                    bb_raise_incumbent(W, q, key, leaf_ordfield(Q, t, cx, cy));
             } else {
                 /* upper bound of the key: every beam counted as known (or, with counts, the cells of
                  * the coarse level that are known: at least as many as at any leaf below) */
@@ -1288,6 +1307,163 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
                 if (pass) {
                     /* lane order = child type major, node minor: runs of adjacent angles stay together */
+                    const unsigned int dst = slot0 + __popc(ballot & ((1u << lane) - 1u));
+                    if (dst < W.capacity) out[dst] = pack_node(q, t, cx, cy);
+                    else *W.overflow = 1;
+                }
+            }
+        }
+    }
+}
+
+/* ---- the sweep over bound levels ---------------------------------------------------
+ * Same frontier expansion as k_bb_expand, reading the representation built for it (csm_bounds.cuh):
+ * children of height HC >= 1 are tested on 257 * sum of the u8 bound level HC (tiled 8 x 16, zero
+ * padded: one clamp per axis instead of a bounds test per child, one to three 128-byte lines per warp
+ * gather); leaves (HC == 0) are scored exactly on the u16 level-0 grid like before. The projected
+ * indices are in the quad layout [n / 4][T][4]: the index load of a warp holding 8 adjacent angles x
+ * 4 adjacent beams is one 128-byte line. */
+#ifndef CSM_BBX_UNROLL
+#define CSM_BBX_UNROLL 4
+#endif
+constexpr int kBbxUnroll = CSM_BBX_UNROLL;
+
+template <int HC>
+__device__ __forceinline__ void ld_children_b(const unsigned char* __restrict__ bm, unsigned int tpr, unsigned int row_w,
+                                              int rows, int cols, int r, int c, unsigned int (&v)[4])
+{
+    constexpr int w = 1 << HC;
+    constexpr int PR = ((1 << HC) + 1 + kBlTileR - 1) & ~(kBlTileR - 1);
+    constexpr int PC = ((1 << HC) + 1 + kBlTileC - 1) & ~(kBlTileC - 1);
+    /* children outside the map read the zero padding: clamp the base cell into [-(w + 1), extent] */
+    const unsigned int rp = (unsigned int)(min(max(r, -(w + 1)), rows) + PR);
+    const unsigned int cp = (unsigned int)(min(max(c, -(w + 1)), cols) + PC);
+    const unsigned int ro0 = (((rp >> 3) * tpr) << 7) + ((rp & 7u) << 4);
+    unsigned int ro1;
+    if (w >= kBlTileR) ro1 = ro0 + row_w;          /* row_w = (w / 8) * tpr * 128 */
+    else { const unsigned int rq = rp + w; ro1 = (((rq >> 3) * tpr) << 7) + ((rq & 7u) << 4); }
+    const unsigned int co0 = ((cp >> 4) << 7) + (cp & 15u);
+    unsigned int co1;
+    if (w >= kBlTileC) co1 = co0 + ((w / kBlTileC) << 7);
+    else { const unsigned int cq = cp + w; co1 = ((cq >> 4) << 7) + (cq & 15u); }
+    v[0] = __ldg(bm + ro0 + co0); v[1] = __ldg(bm + ro0 + co1);
+    v[2] = __ldg(bm + ro1 + co0); v[3] = __ldg(bm + ro1 + co1);
+}
+
+template <int HC>
+__global__ void __launch_bounds__(256, CSM_BB_MINB)
+k_bbx_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
+{
+    constexpr int h = HC + 1;
+    constexpr int w = 1 << HC;
+    constexpr bool kLeaf = HC == 0;
+    constexpr int U = kLeaf ? kBbUnroll : kBbxUnroll;
+    const int lane = threadIdx.x & 31;
+    const unsigned int count = min(W.counts[h], W.capacity);
+    const unsigned int total_lanes = gridDim.x * blockDim.x;
+    int split = kBbSplit;
+    while (split < 32 && (((unsigned long long)count * (unsigned)(split * 2)) << max(-W.split_shift, 0)) <= ((unsigned long long)total_lanes << max(W.split_shift, 0))) split *= 2;
+    const int npw = 32 / split;
+    const int slot = lane & (npw - 1);
+    const int part = lane / npw;
+    const unsigned long long* __restrict__ in = bb_list(W, h);
+    unsigned long long* __restrict__ out = bb_list(W, HC);
+    const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int nwarps = total_lanes >> 5;
+    for (unsigned int base = warp_global * npw; base < count; base += nwarps * npw) {
+        const unsigned int idx = base + slot;
+        const bool valid = idx < count;
+        int q = 0, t = 0, xi = 0, yi = 0;
+        unsigned int s0 = 0, s1 = 0, s2 = 0, s3 = 0, k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+        if (valid) {
+            unpack_node(in[idx], q, t, xi, yi);
+            const DevQuery& Q = queries[q];
+            const uint16_t* __restrict__ m = Q.lvl[0];
+            const unsigned char* __restrict__ bm = Q.bl[HC];
+            const unsigned int tpr = (unsigned int)Q.bl_tpr[HC];
+            const unsigned int row_w = (unsigned int)(w / kBlTileR) * (tpr << 7);
+            const int rows = Q.rows, cols = Q.cols, n = Q.n;
+            const int ox = xi - Q.winx, oy = yi - Q.winy;
+            /* beam i = part + split * j lives at ((i >> 2) * T + t) * 4 + (i & 3): split is a multiple of 4 */
+            const unsigned int T = (unsigned int)Q.T;
+            const proj_t* __restrict__ pp = proj_all + Q.proj_off + ((((unsigned int)(part >> 2) * T + (unsigned int)t) << 2) + (unsigned int)(part & 3));
+            const unsigned int step = T * (unsigned int)split;
+            const int mine = (n - part + split - 1) / split;
+            int i = 0;
+            proj_t pn[U];
+            if (U <= mine) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) pn[u] = pp[(unsigned int)u * step];
+            }
+            for (; i + U <= mine; i += U) {
+                proj_t p[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) p[u] = pn[u];
+                unsigned int v[U][4];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (kLeaf) ld_children<0>(m, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
+                    else ld_children_b<HC>(bm, tpr, row_w, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
+                }
+                if (i + 2 * U <= mine) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) pn[u] = pp[(unsigned int)(i + U + u) * step];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
+                    if (kLeaf) {
+                        k0 += (v[u][0] != 0u); k1 += (v[u][1] != 0u);
+                        k2 += (v[u][2] != 0u); k3 += (v[u][3] != 0u);
+                    }
+                }
+            }
+            for (; i < mine; ++i) {
+                const proj_t p = pp[(unsigned int)i * step];
+                unsigned int v[4];
+                if (kLeaf) ld_children<0>(m, rows, cols, p.y + oy, p.x + ox, v);
+                else ld_children_b<HC>(bm, tpr, row_w, rows, cols, p.y + oy, p.x + ox, v);
+                s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
+                if (kLeaf) { k0 += (v[0] != 0u); k1 += (v[1] != 0u); k2 += (v[2] != 0u); k3 += (v[3] != 0u); }
+            }
+        }
+        unsigned long long a = ((unsigned long long)s0 << 32) | s1;
+        unsigned long long b = ((unsigned long long)s2 << 32) | s3;
+        unsigned long long kk = ((unsigned long long)k0 << 48) | ((unsigned long long)k1 << 32) |
+                                ((unsigned long long)k2 << 16) | (unsigned long long)k3;
+        for (int o = npw; o < 32; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            if (kLeaf) kk += __shfl_xor_sync(0xffffffffu, kk, o);
+        }
+        const bool decides = valid && part < 4;
+        const unsigned long long sp = (part & 2) ? b : a;
+        const int s = (int)((part & 1) ? (unsigned)sp : (unsigned)(sp >> 32));
+        const int cx = xi + (part & 1) * w, cy = yi + ((part >> 1) & 1) * w;
+        bool pass = false;
+        if (decides) {
+            const DevQuery& Q = queries[q];
+            if (kLeaf) {
+                const int k = (int)((kk >> (16 * (3 - (part & 3)))) & 0xffffull);
+                long long key;
+                pass = bb_passes(Q, proj_all, W, q, t, cx, cy, 0, s, k, key);
+                if (pass)
+                    bb_raise_incumbent(W, q, key, leaf_ordfield(Q, t, cx, cy));
+            } else {
+                /* upper bound of the key: 257 * B >= v per cell, every beam counted as known */
+                const long long key_ub = make_key(257ll * (long long)s, Q.n);
+                const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
+                pass = pack_best(key_ub, kOrdMask) > inc && key_ub > Q.kthr.fail_max && Q.n > Q.nk_cut;
+            }
+        }
+        bb_count(W, decides, q, pass);
+        if (!kLeaf) {
+            const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+            if (ballot != 0u) {
+                unsigned int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&W.counts[HC], (unsigned int)__popc(ballot));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (pass) {
                     const unsigned int dst = slot0 + __popc(ballot & ((1u << lane) - 1u));
                     if (dst < W.capacity) out[dst] = pack_node(q, t, cx, cy);
                     else *W.overflow = 1;
@@ -1497,19 +1673,47 @@ struct GridArgs
     const double* py;
     int ndx, ndy, ndt;
     unsigned long long* best;   /* packed (key, ordfield) */
-    int* tie;
+    unsigned long long* tiekey; /* largest key two different candidates were seen to share (0: none) */
+    int ord_mode;               /* tie order of the candidates: 0 = (iy, ix, it), the grid search's loops;
+                                   1 = (it, ix, iy), the branch-and-bound leaf order */
 };
 
-__device__ __forceinline__ void block_best_commit(unsigned long long v, unsigned long long* best)
+__device__ __forceinline__ unsigned long long grid_ordinal(const GridArgs& G, int iy, int ix, int it)
+{
+    return G.ord_mode ? ((unsigned long long)it * G.ndx + ix) * G.ndy + iy
+                      : ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
+}
+
+/* Running best of a thread / warp together with the largest key seen twice */
+struct BestTie
+{
+    unsigned long long best, tiekey;
+};
+
+__device__ __forceinline__ void best_merge(BestTie& b, unsigned long long v, unsigned long long vtie)
+{
+    if (v != 0ull && v != b.best && (v >> kOrdBits) == (b.best >> kOrdBits))
+        vtie = max(vtie, v >> kOrdBits);
+    b.tiekey = max(b.tiekey, vtie);
+    b.best = max(b.best, v);
+}
+
+__device__ __forceinline__ void block_best_commit(BestTie b, unsigned long long* best, unsigned long long* tiekey)
 {
     /* warp max, then one atomic per warp */
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-        v = other > v ? other : v;
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, b.best, o);
+        const unsigned long long otie = __shfl_xor_sync(0xffffffffu, b.tiekey, o);
+        best_merge(b, other, otie);
     }
-    if ((threadIdx.x & 31) == 0 && v != 0ull)
-        atomicMax(best, v);
+    if ((threadIdx.x & 31) == 0 && b.best != 0ull) {
+        const unsigned long long old = atomicMax(best, b.best);
+        if (old != b.best && (old >> kOrdBits) == (b.best >> kOrdBits))
+            b.tiekey = max(b.tiekey, b.best >> kOrdBits);
+        if (b.tiekey != 0ull)
+            atomicMax(tiekey, b.tiekey);
+    }
 }
 
 /* Integer-shift path: all dx[k] / dy[k] are integer multiples of the
@@ -1528,7 +1732,7 @@ k_grid_window(const DevQuery* __restrict__ queries, const proj_t* __restrict__ p
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int iy = blockIdx.y * (blockDim.x >> 5) + warp;
-    unsigned long long best = 0ull;
+    BestTie best = { 0ull, 0ull };
     if (iy < G.ndy) {
         const int oy = G.my[iy];
         const uint16_t* __restrict__ m = Q.lvl[0];
@@ -1552,15 +1756,13 @@ k_grid_window(const DevQuery* __restrict__ queries, const proj_t* __restrict__ p
                 if (c == 0)
                     ok = exact_normalized_score(m, Q.rows, Q.cols, proj, Q.pst_i, Q.n, ox, oy) > Q.kthr.thr;
                 if (ok) {
-                    const unsigned long long ord =
-                        ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
-                    const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
-                    best = v > best ? v : best;
+                    const unsigned long long ord = grid_ordinal(G, iy, ix, it);
+                    best_merge(best, pack_best(key, (kOrdMask - 1ull) - ord), 0ull);
                 }
             }
         }
     }
-    block_best_commit(best, G.best);
+    block_best_commit(best, G.best, G.tiekey);
 }
 
 /* Per-candidate FP64 path (steps that are not multiples of the resolution):
@@ -1579,7 +1781,7 @@ k_grid_general(const DevQuery* __restrict__ queries, const double2* __restrict__
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int iy = blockIdx.y * (blockDim.x >> 5) + warp;
-    unsigned long long best = 0ull;
+    BestTie best = { 0ull, 0ull };
     int flagged = 0;
     if (iy < G.ndy) {
         const double py = G.py[iy];
@@ -1615,17 +1817,45 @@ k_grid_general(const DevQuery* __restrict__ queries, const double2* __restrict__
                 if (c == 0)
                     ok = __ddiv_rn(sum, (double)Q.n) > Q.kthr.thr;
                 if (ok) {
-                    const unsigned long long ord =
-                        ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
-                    const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
-                    best = v > best ? v : best;
+                    const unsigned long long ord = grid_ordinal(G, iy, ix, it);
+                    best_merge(best, pack_best(key, (kOrdMask - 1ull) - ord), 0ull);
                 }
             }
         }
     }
     if (__any_sync(0xffffffffu, flagged) && lane == 0)
         atomicOr(&qflags[0], 1);
-    block_best_commit(best, G.best);
+    block_best_commit(best, G.best, G.tiekey);
+}
+
+/* Smallest min(row, col) over the non-zero cells of a map whose row or column is below `limit`
+ * (`limit` if there is none): when it is at least 2^hmax, every coarse lookup at a negative index
+ * covers unknown cells only, i.e. the 0 the reference reads there (grid_map.cpp:389-392) IS the
+ * maximum of the window and its branch-and-bound bound stays admissible: a
+ * CSM_FLAG_EDGE raised by the projection is then withdrawn. out[] must hold `limit` or more on entry. */
+struct MarginJob
+{
+    const uint16_t* base;
+    int rows, cols, limit, pad;
+};
+
+__global__ void __launch_bounds__(256)
+k_low_margin(const MarginJob* __restrict__ jobs, int* __restrict__ out)
+{
+    const MarginJob J = jobs[blockIdx.x];
+    const int lr = min(J.limit, J.rows), lc = min(J.limit, J.cols);
+    int best = J.limit;
+    for (int e = threadIdx.x; e < lr * J.cols; e += blockDim.x) {          /* the low rows, whole */
+        const int r = e / J.cols, c = e - r * J.cols;
+        if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
+    }
+    for (int e = threadIdx.x; e < J.rows * lc; e += blockDim.x) {          /* the low columns, whole */
+        const int r = e / lc, c = e - r * lc;
+        if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
+    }
+    best = (int)__reduce_min_sync(0xffffffffu, (unsigned)best);
+    if ((threadIdx.x & 31) == 0 && best < J.limit)
+        atomicMin(&out[blockIdx.x], best);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1639,6 +1869,7 @@ struct FinalArgs
     int mode;                 /* 0 = window indices are cell offsets, 1 = grid fast, 2 = grid general */
     /* decode 1 */
     const unsigned long long* incumbent;
+    const unsigned long long* tiekey;
     const int* stats;
     /* decode 2 */
     GridArgs G;
@@ -1691,7 +1922,7 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 /* reference: bestX = bestY = bestTheta = 0 (scan_matcher_branch_bound.cpp:145-147) */
                 st.bx = 0; st.by = 0; st.bt = (Q.T - 1) / 2;
             }
-            st.flags = 0;
+            st.flags = (st.found && F.tiekey != nullptr && F.tiekey[q] == (inc >> kOrdBits)) ? 2 : 0;   /* CSM_FLAG_KEY_TIE */
             st.n_processed = F.stats[2 * q];
             st.n_ignored = F.stats[2 * q + 1];
         } else {
@@ -1700,11 +1931,17 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
             st.bx = st.by = st.bt = -1;
             if (st.found) {
                 unsigned long long ord = (kOrdMask - 1ull) - (b & kOrdMask);
-                st.bt = (int)(ord % (unsigned)F.G.ndt); ord /= (unsigned)F.G.ndt;
-                st.bx = (int)(ord % (unsigned)F.G.ndx); ord /= (unsigned)F.G.ndx;
-                st.by = (int)ord;
+                if (F.G.ord_mode) {
+                    st.by = (int)(ord % (unsigned)F.G.ndy); ord /= (unsigned)F.G.ndy;
+                    st.bx = (int)(ord % (unsigned)F.G.ndx); ord /= (unsigned)F.G.ndx;
+                    st.bt = (int)ord;
+                } else {
+                    st.bt = (int)(ord % (unsigned)F.G.ndt); ord /= (unsigned)F.G.ndt;
+                    st.bx = (int)(ord % (unsigned)F.G.ndx); ord /= (unsigned)F.G.ndx;
+                    st.by = (int)ord;
+                }
             }
-            st.flags = 0;
+            st.flags = (st.found && F.G.tiekey != nullptr && *F.G.tiekey == (b >> kOrdBits)) ? 2 : 0;   /* CSM_FLAG_KEY_TIE */
             st.n_processed = F.G.ndx * F.G.ndy * F.G.ndt;
             st.n_ignored = 0;
         }
@@ -1735,12 +1972,12 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
              * dependent pair of memory round trips per group instead of per beam) */
             const int ox = (F.mode == 1) ? F.mx[s.bx] : s.bx;
             const int oy = (F.mode == 1) ? F.my[s.by] : s.by;
-            const proj_t* __restrict__ pp = proj_all + (size_t)Q.proj_off + (size_t)it * Q.pst_t;
+            const proj_t* __restrict__ pp = proj_all + (size_t)Q.proj_off;
             for (; i0 + 96 < Q.n; i0 += 128) {
                 proj_t p[4];
                 unsigned int v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) p[u] = pp[(size_t)(i0 + 32 * u) * Q.pst_i];
+                for (int u = 0; u < 4; ++u) p[u] = pp[proj_index(Q, it, i0 + 32 * u)];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) v[u] = ld_cell_nb(m, Q.rows, Q.cols, p[u].y + oy, p[u].x + ox);
 #pragma unroll
@@ -1761,7 +1998,7 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
                 col = (int)fmin(fmax(floor(ux), -lim), lim);
                 row = (int)fmin(fmax(floor(uy), -lim), lim);
             } else {
-                const proj_t p = proj_all[(size_t)Q.proj_off + (size_t)it * Q.pst_t + (size_t)i * Q.pst_i];
+                const proj_t p = proj_all[(size_t)Q.proj_off + proj_index(Q, it, i)];
                 const int ox = (F.mode == 1) ? F.mx[s.bx] : s.bx;
                 const int oy = (F.mode == 1) ? F.my[s.by] : s.by;
                 col = p.x + ox; row = p.y + oy;

@@ -306,7 +306,7 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
     flush();
 
     /* candidates -> packed best (same decisions as k_grid_window) */
-    unsigned long long best = 0ull;
+    BestTie best = { 0ull, 0ull };
     const uint16_t* __restrict__ m0 = Q.lvl[0];
     auto consider = [&](int iy, int ix, unsigned int sumv, unsigned int known) {
         const int k = (int)known;
@@ -317,9 +317,8 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
             if (c == 0)
                 ok = exact_normalized_score(m0, Q.rows, Q.cols, proj, Q.pst_i, n, G.mx[ix], G.my[iy]) > Q.kthr.thr;
             if (ok) {
-                const unsigned long long ord = ((unsigned long long)iy * G.ndx + ix) * G.ndt + it;
-                const unsigned long long v = pack_best(key, (kOrdMask - 1ull) - ord);
-                best = v > best ? v : best;
+                const unsigned long long ord = grid_ordinal(G, iy, ix, it);
+                best_merge(best, pack_best(key, (kOrdMask - 1ull) - ord), 0ull);
             }
         }
     };
@@ -336,7 +335,7 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
     }
     if (kRem && rem_on)
         consider(rem_iy, rem_ix, sumx, cntx);
-    block_best_commit(best, G.best);
+    block_best_commit(best, G.best, G.tiekey);
 }
 
 } /* namespace csm */

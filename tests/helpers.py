@@ -25,9 +25,11 @@ def grid_of(case_or_submap):
     return matchers.GridMap(s.grid, s.res, (s.off_x, s.off_y))
 
 
-def assert_match(dev, orc, what, exact_score=True):
-    """dev: capi.CsmResult, orc: OrcResult or golden dict."""
+def assert_match(dev, orc, what, exact_score=True, flags_ok=0):
+    """dev: capi.CsmResult, orc: OrcResult or golden dict. Every compared result must come without
+    flags (FP guard band, key tie, inadmissible edge) unless the test allows some in `flags_ok`."""
     o = orc if isinstance(orc, dict) else orc.asdict()
+    assert dev.flags & ~flags_ok == 0, "%s: flags %d" % (what, dev.flags)
     assert dev.found == o["found"], "%s: found %d vs %d" % (what, dev.found, o["found"])
     if o["found"] or o.get("compare_unfound", True):
         got = (dev.best_x, dev.best_y, dev.best_t)

@@ -189,3 +189,27 @@ def test_hill_climbing_cpp_vs_reference(ref_oracle, seed):
         assert (h.best_t, h.best_x) == (o.n_processed, o.n_ignored)
         assert list(h.est_pose) == list(o.est_pose) and h.norm_cost == o.norm_cost
         assert np.allclose(list(h.cov), list(o.cov), rtol=1e-9, atol=0.0)
+
+
+@pytest.mark.parametrize("e", load_golden("cfg4_vectors.json")["cfg4"], ids=lambda e: "seed%d" % e["seed"])
+def test_port_scores_the_full_size_cfg4_winner_like_the_reference(port_oracle, e):
+    """The full cfg4 search takes the reference ~14 minutes (tests/golden/make_cfg4_golden.py ran it once);
+    here the restatement re-scores the reference's winner and a small window around it: same value sum,
+    known count and double score, and no neighbour within +-2 steps beats it."""
+    from my_lidar_graph_slam_v2_b200 import matchers
+    case = synth.case_for(synth.CFG4, e["seed"])
+    s = case.submap
+    assert sha(s.grid) == e["grid_sha"] and sha(case.ranges) == e["scan_sha"]
+    x = e["expect"]
+    rng, step = synth.CFG4["rng"], synth.CFG4["step"]
+    dx = matchers.grid_search_offsets(rng[0] / 2, step[0])
+    dy = matchers.grid_search_offsets(rng[1] / 2, step[1])
+    dt = matchers.grid_search_offsets(rng[2] / 2, step[2])
+    assert len(dx) * len(dy) * len(dt) == x["n_processed"]
+    win = (case.init_pose[0] + dx[x["best_x"]], case.init_pose[1] + dy[x["best_y"]], case.init_pose[2] + dt[x["best_t"]])
+    assert [float(v).hex() for v in win] == x["best_sensor_pose"]
+    g = port_oracle.grid(s.grid, s.res, s.off_x, s.off_y)
+    o = port_oracle.match_grid(g, case.angles, case.ranges, win, (0.0, 0.0, 0.0), step)
+    assert (o.found, o.sum_value, o.n_known, o.score) == (1, x["sum_value"], x["n_known"], float.fromhex(x["score"]))
+    near = port_oracle.match_grid(g, case.angles, case.ranges, win, (4 * step[0], 4 * step[1], 4 * step[2]), step)
+    assert near.score == o.score
