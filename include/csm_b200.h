@@ -366,6 +366,9 @@ int csm_debug_frontier_counts(csm_handle h, unsigned int* out8);
  * ceil(v / 257) of the sliding 2^level x 2^level maximum, cells outside the map 0), untiled into
  * out[rows * cols]. Builds levels 1..level for this map when they are missing. 1 <= level <= 6. */
 int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out);
+/* Debug: the node list of height `level` (q:16 | t:16 | xi:16 | yi:16 per entry) as the last batch left it;
+ * with option "bb_stop_level" = level the sweep stops there. Returns the number of entries copied. */
+int csm_debug_node_list(csm_handle h, int level, uint64_t* out, int cap);
 void* csm_best_key_device(csm_handle h);
 void csm_decode_best_key(uint64_t best_key, int64_t* key, int32_t* query_index);
 

@@ -67,7 +67,7 @@ EXPORTS = [
     "csm_loop_batch_enqueue", "csm_loop_batch_finish", "csm_loop_batch",
     "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch", "csm_set_epilogue", "csm_last_epilogue", "csm_share_copy_stream",
     "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
-    "csm_debug_bound_level", "csm_exact_rerun_count",
+    "csm_debug_bound_level", "csm_exact_rerun_count", "csm_debug_node_list",
 ]
 
 _LIB = None
@@ -138,6 +138,7 @@ def load():
     lib.csm_set_epilogue.argtypes = [H, C.c_double]
     lib.csm_last_epilogue.argtypes = [H, C.POINTER(CsmRefined)]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
+    lib.csm_debug_node_list.argtypes = [H, C.c_int, C.POINTER(C.c_uint64), C.c_int]
     lib.csm_exact_rerun_count.restype = C.c_int64
     lib.csm_exact_rerun_count.argtypes = [H]
     lib.csm_debug_bound_level.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_uint8)]
@@ -353,6 +354,16 @@ class Handle:
         out = np.empty(shape, dtype=np.uint8)
         self._check(self.lib.csm_debug_bound_level(self.h, map_id, level, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
+
+    def node_list(self, level, cap=1 << 24):
+        """(q, t, xi, yi) of the nodes in list(level) after the last batch (see option "bb_stop_level")."""
+        out = np.empty(cap, dtype=np.uint64)
+        n = self.lib.csm_debug_node_list(self.h, level, out.ctypes.data_as(C.POINTER(C.c_uint64)), cap)
+        if n < 0:
+            self._check(n)
+        w = out[:n]
+        return np.stack([(w >> np.uint64(48)) & np.uint64(0xffff), (w >> np.uint64(32)) & np.uint64(0xffff),
+                         (w >> np.uint64(16)) & np.uint64(0xffff), w & np.uint64(0xffff)], axis=1).astype(np.int64)
 
     def exact_rerun_count(self):
         return int(self.lib.csm_exact_rerun_count(self.h))

@@ -149,6 +149,9 @@ struct csm_context
     DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
     DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups, d_bljobs;
+    int pyramid_segs = 0;          /* test knob: row segments per map of the streaming builder (0 = automatic) */
+    int bounds_mode = 0;           /* builder of the bound levels: 0 auto, 1 k_bounds_build, 2 the streaming kernel */
+    int bb_stop_level = 0;         /* debug: the sweep stops once list(bb_stop_level) is complete (csm_debug_node_list) */
     int bb_bounds = 1;             /* 1: batched searches sweep the u8 bound levels (csm_bounds.cuh), 0: the u16 levels */
     int bbx_ctas_per_sm = 0;
     int bb_ctas_per_sm = 0;        /* resident CTAs per SM of the B&B sweep kernels (occupancy query, lazily) */
@@ -731,8 +734,8 @@ int build_levels(csm_handle h, const std::vector<MapSlot*>& slots, int hmax)
             bool sq512 = true;          /* the common submap size gets immediates for every stride */
             for (const PyrJob& j : jobs) sq512 = sq512 && j.rows == 512 && j.cols == 512;
 #define CSM_PS2_LAUNCH(HM)                                                                             \
-            if (sq512) k_pyramid_stream2<HM, 512><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);   \
-            else k_pyramid_stream2<HM, 0><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);
+            if (sq512) k_pyramid_stream2<HM, 512, false><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);   \
+            else k_pyramid_stream2<HM, 0, false><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);
             switch (hmax) {
             case 1: CSM_PS2_LAUNCH(1) break;
             case 2: CSM_PS2_LAUNCH(2) break;
@@ -806,6 +809,54 @@ int build_bounds(csm_handle h, const std::vector<MapSlot*>& slots, int L)
     }
     if (jobs.empty())
         return CSM_OK;
+    /* batches of maps that fit the streaming builder take it in its bound mode (one pass over the map,
+     * level 0 read once, every level written once as u8 tiles) */
+    bool stream_ok = L >= 1 && L <= 6 && h->bounds_mode != 1 && (h->bounds_mode == 2 || jobs.size() >= 8);
+    bool sq512 = true;
+    int min_rows = jobs[0].rows;
+    for (const BlJob& j : jobs) {
+        stream_ok = stream_ok && j.cols <= 512 && (j.cols % 8) == 0 && (j.rows % (kPsRows * kPs2Group)) == 0;
+        sq512 = sq512 && j.rows == 512 && j.cols == 512;
+        min_rows = std::min(min_rows, j.rows);
+    }
+    if (h->bounds_mode == 2 && !stream_ok)
+        return fail(h, CSM_E_UNSUPPORTED, "bound levels: the streaming builder cannot take these maps");
+    if (stream_ok) {
+        std::vector<PyrJob> pj(jobs.size());
+        for (size_t i = 0; i < jobs.size(); ++i)
+            pj[i] = PyrJob { jobs[i].base, reinterpret_cast<uint16_t*>(jobs[i].out), jobs[i].rows, jobs[i].cols };
+        const size_t pjb = pj.size() * sizeof(PyrJob);
+        int rc = ensure(h, h->d_pyrjobs, pjb);
+        if (rc) return rc;
+        char* hp = nullptr;
+        if ((rc = acquire_upload(h, pjb, &hp))) return rc;
+        std::memcpy(hp, pj.data(), pjb);
+        if ((rc = pull_to_device(h, h->d_pyrjobs.p, hp, pjb))) return rc;
+        if ((rc = upload_committed(h))) return rc;
+        h->jobs_on_device.clear();
+        phase_mark(h, "start");
+        int segs = (int)std::min<size_t>(4, (size_t)((L <= 5 ? 3 : 2) * h->sm_count) / pj.size());
+        if (h->pyramid_segs > 0) segs = h->pyramid_segs;
+        segs = std::max(1, std::min(segs, min_rows / 128));
+        const unsigned int grid = (unsigned)(pj.size() * segs);
+        const PyrJob* dj = static_cast<const PyrJob*>(h->d_pyrjobs.p);
+        const size_t smem2 = sizeof(unsigned int) * ((size_t)kPsStages * kPsRows * kPsInStride + 2 * kPsRows * 256);
+#define CSM_PS2B_LAUNCH(HM)                                                                            \
+        if (sq512) k_pyramid_stream2<HM, 512, true><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);     \
+        else k_pyramid_stream2<HM, 0, true><<<grid, kPsThreads, smem2, h->stream>>>(dj, segs);
+        switch (L) {
+        case 1: CSM_PS2B_LAUNCH(1) break;
+        case 2: CSM_PS2B_LAUNCH(2) break;
+        case 3: CSM_PS2B_LAUNCH(3) break;
+        case 4: CSM_PS2B_LAUNCH(4) break;
+        case 5: CSM_PS2B_LAUNCH(5) break;
+        default: CSM_PS2B_LAUNCH(6) break;
+        }
+#undef CSM_PS2B_LAUNCH
+        CSM_LAUNCH_CHECK();
+        phase_mark(h, "k_pyramid_stream(bounds)");
+        return CSM_OK;
+    }
     const size_t jb = jobs.size() * sizeof(BlJob);
     int rc = ensure(h, h->d_bljobs, jb);
     if (rc) return rc;
@@ -1210,7 +1261,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         }
         /* a list never holds more than 4^k times the roots: small calls get small grids */
         unsigned long long bound = n_roots;
-        for (int lvl = top; lvl >= 1; --lvl) {
+        for (int lvl = top; lvl >= 1 && lvl > h->bb_stop_level; --lvl) {
             const int blocks = (int)std::min<unsigned long long>((bound + 7) / 8, (unsigned long long)full);
             const dim3 g((unsigned)std::max(blocks, 1));
             if (use_bounds) {
@@ -1673,6 +1724,9 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "bb_split_shift") == 0) { h->bb_split_shift = std::max(-4, std::min(value, 4)); return CSM_OK; }
     if (std::strcmp(name, "exact_rerun") == 0) { h->exact_rerun = value != 0; return CSM_OK; }
     if (std::strcmp(name, "fp_margin_scale") == 0) { h->fp_margin_scale = value > 0 ? (double)value : 1.0; return CSM_OK; }
+    if (std::strcmp(name, "pyramid_segs") == 0) { h->pyramid_segs = std::max(0, std::min(value, 4)); return CSM_OK; }
+    if (std::strcmp(name, "bounds_mode") == 0 && value >= 0 && value <= 2) { h->bounds_mode = value; return CSM_OK; }
+    if (std::strcmp(name, "bb_stop_level") == 0) { h->bb_stop_level = std::max(0, std::min(value, kMaxLevels - 1)); return CSM_OK; }
     if (std::strcmp(name, "bb_bounds") == 0) { h->bb_bounds = value != 0; return CSM_OK; }
     if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
     if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
@@ -2166,7 +2220,7 @@ int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out)
     /* everything outside the map must have stayed zero */
     for (int rp = 0; rp < bl_tile_rows(level, m.rows) * kBlTileR; ++rp)
         for (int cp = 0; cp < tpr * kBlTileC; ++cp) {
-            const unsigned char v = raw[((size_t)(rp >> 3) * tpr + (cp >> 4)) * 128 + ((rp & 7) << 4) + (cp & 15)];
+            const unsigned char v = raw[bl_cell((unsigned int)rp, (unsigned int)cp, (unsigned int)tpr)];
             const int r = rp - pr, c = cp - pc;
             if (r >= 0 && r < m.rows && c >= 0 && c < m.cols)
                 out[(size_t)r * m.cols + c] = v;
@@ -2174,6 +2228,20 @@ int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out)
                 return fail(h, CSM_E_INVALID, "bound level: non-zero padding");
         }
     return CSM_OK;
+}
+
+int csm_debug_node_list(csm_handle h, int level, uint64_t* out, int cap)
+{
+    if (!h || !out || level < 0 || level >= kMaxLevels || !h->plan_view.counts) return CSM_E_INVALID;
+    unsigned int counts[kMaxLevels];
+    CSM_CUDA(cudaMemcpyAsync(counts, h->plan_view.counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));
+    const int n = (int)std::min<unsigned int>(std::min(counts[level], h->frontier_capacity), (unsigned int)std::max(cap, 0));
+    if (n > 0) {
+        CSM_CUDA(cudaMemcpyAsync(out, h->d_list[(level & 1) ^ 1].p, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        CSM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return n;
 }
 
 int csm_debug_frontier_counts(csm_handle h, unsigned int* out8)

@@ -14,12 +14,20 @@
  * (x, y) of height h, at most 256 per beam above the reference's own bound (0.4 % of the score range).
  * Cells at negative indices read 0 like the reference's lookups (grid_map.cpp:389-392).
  *
- * Layout of one level: u8 cells in tiles of 8 rows x 16 columns = one 128-byte line, tiles row-major
- * over a domain padded with zeros by at least 2^h + 1 cells on every side: the 32 gathers of a warp
- * (8 nodes at adjacent angles x 4 adjacent beams: an arc of a few cells along a wall) fall into one to
- * three lines whatever the orientation of the wall, where the row-major u16 levels cost one line per
- * map row touched; a clamped index needs no per-child bounds test; and the builder writes half the
- * bytes of the u16 levels. The L1TEX wavefront rate (one line per cycle) bounds the sweep.
+ * Layout of one level: u8 cells in tiles of 4 rows x 32 columns = one 128-byte line, tiles row-major
+ * over a domain padded with zeros by at least 2^h + 1 cells on every side; inside a tile the cells go
+ * [16 column pairs][4 rows][2 columns], so that a 32-byte sector is a patch of 4 rows x 8 columns.
+ * The 32 gathers of a warp (8 nodes at adjacent angles x 4 adjacent beams: an arc of a few cells along
+ * a wall) fall into one to three lines whatever the orientation of the wall, where the row-major u16
+ * levels cost one line per map row touched; a clamped index needs no per-child bounds test; the
+ * builder writes half the bytes of the u16 levels, and the streaming builder, whose threads own two
+ * columns of four consecutive rows, stores those eight cells as one 64-bit word: a warp writes two
+ * whole lines per instruction. The L1TEX wavefront rate (one line per cycle) bounds the sweep.
+ * (Tiles of 8 x 16 cells made the sweep 5 % faster but break that store pattern.)
+ *
+ * Two builders write the levels: the streaming pyramid kernel (k_pyramid_stream2 in its bound mode:
+ * one pass over the map, the reference's window with the far edge clamped, which covers more and is
+ * therefore admissible as well) for batches of maps that fit it, k_bounds_build below for any shape.
  */
 #pragma once
 
@@ -27,25 +35,26 @@
 
 namespace csm {
 
-constexpr int kBlTileR = 8, kBlTileC = 16;
+constexpr int kBlLog2R = 2, kBlLog2C = 5;     /* a tile = 4 rows x 32 columns = 128 cells */
+constexpr int kBlTileR = 1 << kBlLog2R, kBlTileC = 1 << kBlLog2C;
 
-__host__ __device__ __forceinline__ int bl_pad_r(int hc) { return ((1 << hc) + 1 + kBlTileR - 1) & ~(kBlTileR - 1); }
-__host__ __device__ __forceinline__ int bl_pad_c(int hc) { return ((1 << hc) + 1 + kBlTileC - 1) & ~(kBlTileC - 1); }
+__host__ __device__ constexpr int bl_pad_r(int hc) { return ((1 << hc) + 1 + kBlTileR - 1) & ~(kBlTileR - 1); }
+__host__ __device__ constexpr int bl_pad_c(int hc) { return ((1 << hc) + 1 + kBlTileC - 1) & ~(kBlTileC - 1); }
 /* tiles per row / rows of tiles of level hc of a rows x cols map */
-__host__ __device__ __forceinline__ int bl_tiles_per_row(int hc, int cols)
+__host__ __device__ constexpr int bl_tiles_per_row(int hc, int cols)
 {
     return (2 * bl_pad_c(hc) + ((cols + kBlTileC - 1) & ~(kBlTileC - 1))) / kBlTileC;
 }
-__host__ __device__ __forceinline__ int bl_tile_rows(int hc, int rows)
+__host__ __device__ constexpr int bl_tile_rows(int hc, int rows)
 {
     return (2 * bl_pad_r(hc) + ((rows + kBlTileR - 1) & ~(kBlTileR - 1))) / kBlTileR;
 }
-__host__ __device__ __forceinline__ size_t bl_level_bytes(int hc, int rows, int cols)
+__host__ __device__ constexpr size_t bl_level_bytes(int hc, int rows, int cols)
 {
     return (size_t)bl_tiles_per_row(hc, cols) * (size_t)bl_tile_rows(hc, rows) * 128u;
 }
 /* byte offset of level hc (1 <= hc) inside a map's bound allocation: levels 1, 2, ... back to back */
-__host__ __device__ __forceinline__ size_t bl_level_offset(int hc, int rows, int cols)
+__host__ __device__ constexpr size_t bl_level_offset(int hc, int rows, int cols)
 {
     size_t off = 0;
     for (int j = 1; j < hc; ++j) off += bl_level_bytes(j, rows, cols);
@@ -53,9 +62,10 @@ __host__ __device__ __forceinline__ size_t bl_level_offset(int hc, int rows, int
 }
 
 /* byte offset of padded cell (rp, cp) = (r + pad_r, c + pad_c) in a level with `tpr` tiles per row */
-__device__ __forceinline__ unsigned int bl_cell(unsigned int rp, unsigned int cp, unsigned int tpr)
+__host__ __device__ __forceinline__ unsigned int bl_cell(unsigned int rp, unsigned int cp, unsigned int tpr)
 {
-    return (((rp >> 3) * tpr + (cp >> 4)) << 7) + ((rp & 7u) << 4) + (cp & 15u);
+    /* inside a tile: [16 column pairs][4 rows][2 columns] */
+    return (((rp >> 2) * tpr + (cp >> 5)) << 7) + ((cp & 30u) << 2) + ((rp & 3u) << 1) + (cp & 1u);
 }
 
 /* ceil(v / 257) of both u16 halves of a word, each result in its own 16-bit lane: v = 257 hi +
@@ -158,11 +168,14 @@ __device__ __forceinline__ void bl_level(const unsigned int* __restrict__ src, u
         const uint4 v = bl_max4(bl_max4(a, b), bl_max4(c, d));
         if (H < L)
             *reinterpret_cast<uint4*>(dst + r * P + 4 * q) = v;
-        const int gr0 = X.r0 + tr * 8, gc0 = X.c0 + tc * 32 + (lq >> 1) * 16;     /* origin of this lane's tile */
+        const int gr0 = X.r0 + tr * 8, gc0 = X.c0 + tc * 32 + lq * 8;
         if (tr * 8 < kBlOutR && tc * 32 < kBlOutC && gr0 < X.R && gc0 < X.C) {
-            const unsigned int off = ((((unsigned int)(gr0 + pad_r) >> 3) * tpr + ((unsigned int)(gc0 + pad_c) >> 4)) << 7) +
-                                     ((unsigned int)lr << 4) + ((unsigned int)(lq & 1) << 3);
-            *reinterpret_cast<uint2*>(out_h + off) = make_uint2(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.z, v.w, 0x6420));
+            /* this lane's 8 cells: row gr0 + lr, columns gc0 .. gc0 + 7 = four column pairs, 8 bytes apart */
+            unsigned char* __restrict__ o = out_h + bl_cell((unsigned int)(gr0 + lr + pad_r), (unsigned int)(gc0 + pad_c), tpr);
+            *reinterpret_cast<unsigned short*>(o)      = (unsigned short)__byte_perm(v.x, 0u, 0x4420);
+            *reinterpret_cast<unsigned short*>(o + 8)  = (unsigned short)__byte_perm(v.y, 0u, 0x4420);
+            *reinterpret_cast<unsigned short*>(o + 16) = (unsigned short)__byte_perm(v.z, 0u, 0x4420);
+            *reinterpret_cast<unsigned short*>(o + 24) = (unsigned short)__byte_perm(v.w, 0u, 0x4420);
         }
     }
 }

@@ -361,10 +361,46 @@ __device__ __noinline__ void ps2_store_edge(uint4 pv, unsigned int* __restrict__
     }
 }
 
+/* Bound mode of the streaming builder: level H goes out as the u8 bound level of csm_bounds.cuh
+ * (ceil(v / 257) per cell, tiles of kBlTileR x kBlTileC cells, zero padding never touched) instead of the
+ * reference's u16 level. `out` = the map's bound allocation; a thread stores its two cells of a row as
+ * one 16-bit word. */
+template <int H, int FIX>
+__device__ __forceinline__ unsigned char* ps2b_row(unsigned char* __restrict__ out, int R, int C, int r, int j)
+{
+    const size_t base = FIX ? bl_level_offset(H, FIX, FIX) : bl_level_offset(H, R, C);
+    const unsigned int tpr = FIX ? (unsigned int)bl_tiles_per_row(H, FIX) : (unsigned int)bl_tiles_per_row(H, C);
+    return out + base + bl_cell((unsigned int)(r + bl_pad_r(H)), (unsigned int)(2 * j + bl_pad_c(H)), tpr);
+}
+
+/* (the cells are encoded once, when level 0 leaves the input ring: the maximum commutes with the
+ * monotone encoding, so every level is computed on encoded values, 16 bits per cell) */
+__device__ __forceinline__ unsigned short ps2b_pack(unsigned int word)
+{
+    return (unsigned short)__byte_perm(word, 0u, 0x4420);
+}
+
+template <int H, int FIX>
+__device__ __noinline__ void ps2b_store_edge(uint4 pv, unsigned char* __restrict__ out, int R, int C, int r0, int j)
+{
+    constexpr int w = 1 << H;
+    const int rsrc = max(R - w, 0);
+    const unsigned int p[kPsRows] = { pv.x, pv.y, pv.z, pv.w };
+#pragma unroll
+    for (int rr = 0; rr < kPsRows; ++rr) {
+        const int r = r0 + rr;
+        if (r < rsrc) *reinterpret_cast<unsigned short*>(ps2b_row<H, FIX>(out, R, C, r, j)) = ps2b_pack(p[rr]);
+        else if (r == rsrc)
+            for (int r2 = r; r2 < R; ++r2)
+                *reinterpret_cast<unsigned short*>(ps2b_row<H, FIX>(out, R, C, r2, j)) = ps2b_pack(p[rr]);
+    }
+}
+
 /* One level of one 4-row block; K = position of the block inside its group of 8 (compile time:
  * ring slots are registers). PS = word stride of the rows of `prev`. a[] holds this thread's
- * words of out_{H-1} and leaves as out_H. dst0 = word j of row r0 of level 1. */
-template <int H, int K, int PS, int FIX>
+ * words of out_{H-1} and leaves as out_H. dst0 = word j of row r0 of level 1 (BND: the map's bound
+ * allocation). */
+template <int H, int K, int PS, int FIX, bool BND>
 __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsigned int* __restrict__ prev,
                                           unsigned int* __restrict__ cur, unsigned int (&ring)[63],
                                           unsigned int* __restrict__ dst0, size_t cells_w_, int cw_,
@@ -383,6 +419,7 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
 #pragma unroll
     for (int rr = kPsRows - 1; rr >= 0; --rr) {
         unsigned int t = tap[rr * PS];
+        if (H == 1 && BND) t = bl_encode2(t);
         if (H == 1) t = __byte_perm(a[rr], t, 0x5432);
         else if (edge) t = splat_lo(t);
         t = __vmaxu2(a[rr], t);
@@ -399,7 +436,19 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
 #pragma unroll
         for (int rr = 0; rr < kPsRows; ++rr) a[rr] = splat_lo(cur[rr * 256 + csw]);
     }
-    if (wr) {
+    if (wr && BND) {
+        const int rsrc = max(R - w, 0);
+        unsigned char* __restrict__ out = reinterpret_cast<unsigned char*>(dst0);
+        if (r0 + kPsRows - 1 < rsrc) {
+            /* r0 is a multiple of the tile height: this thread's two columns of the four rows are eight
+             * consecutive bytes of the tile, the warp's 32 x 8 bytes two whole lines */
+            static_assert(kPsRows == kBlTileR, "a 4-row block is one row of tiles");
+            *reinterpret_cast<uint2*>(ps2b_row<H, FIX>(out, R, C, r0, j)) =
+                make_uint2(__byte_perm(a[0], a[1], 0x6420), __byte_perm(a[2], a[3], 0x6420));
+        } else if (r0 <= rsrc) {
+            ps2b_store_edge<H, FIX>(make_uint4(a[0], a[1], a[2], a[3]), out, R, C, r0, j);
+        }
+    } else if (wr) {
         const int rsrc = max(R - w, 0);
         unsigned int* __restrict__ dst = dst0 + (size_t)(H - 1) * cells_w;
         if (r0 + kPsRows - 1 < rsrc) {
@@ -411,7 +460,7 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
     }
 }
 
-template <int HMAX, int K, int FIX>
+template <int HMAX, int K, int FIX, bool BND>
 __device__ __forceinline__ void ps2_block(unsigned int (&ring)[63], const unsigned int* __restrict__ in_ring,
                                           unsigned int* __restrict__ buf0, unsigned int* __restrict__ buf1,
                                           const PyrJob& job, int b, int j, bool wr, size_t cells_w)
@@ -419,20 +468,21 @@ __device__ __forceinline__ void ps2_block(unsigned int (&ring)[63], const unsign
     static_assert(kPsRows == 4, "ps2_store_edge passes the four rows of a block as one uint4");
     const unsigned int* in = in_ring + (b % kPsStages) * kPsRows * kPsInStride;
     const int R = FIX ? FIX : job.rows, C = FIX ? FIX : job.cols, cw = C >> 1, r0 = b * kPsRows;
-    unsigned int* dst0 = reinterpret_cast<unsigned int*>(job.levels) + (size_t)r0 * cw + j;
+    unsigned int* dst0 = BND ? reinterpret_cast<unsigned int*>(job.levels)
+                             : reinterpret_cast<unsigned int*>(job.levels) + (size_t)r0 * cw + j;
     unsigned int a[kPsRows];
 #pragma unroll
-    for (int rr = 0; rr < kPsRows; ++rr) a[rr] = in[rr * kPsInStride + j];
-    ps2_level<1, K, kPsInStride, FIX>(a, in, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
-    if (HMAX >= 2) ps2_level<2, K, 256, FIX>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
-    if (HMAX >= 3) ps2_level<3, K, 256, FIX>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
-    if (HMAX >= 4) ps2_level<4, K, 256, FIX>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
-    if (HMAX >= 5) ps2_level<5, K, 256, FIX>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
-    if (HMAX >= 6) ps2_level<6, K, 256, FIX>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    for (int rr = 0; rr < kPsRows; ++rr) a[rr] = BND ? bl_encode2(in[rr * kPsInStride + j]) : in[rr * kPsInStride + j];
+    ps2_level<1, K, kPsInStride, FIX, BND>(a, in, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 2) ps2_level<2, K, 256, FIX, BND>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 3) ps2_level<3, K, 256, FIX, BND>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 4) ps2_level<4, K, 256, FIX, BND>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 5) ps2_level<5, K, 256, FIX, BND>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
+    if (HMAX >= 6) ps2_level<6, K, 256, FIX, BND>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
 }
 
-template <int HMAX, int FIX>
-__global__ void __launch_bounds__(kPsThreads, 2)
+template <int HMAX, int FIX, bool BND>
+__global__ void __launch_bounds__(kPsThreads, (BND && HMAX <= 5) ? 3 : 2)      /* five levels of rings: 31 words, three CTAs fit */
 k_pyramid_stream2(const PyrJob* __restrict__ jobs, int segs)
 {
     extern __shared__ __align__(16) unsigned int ps_smem[];
@@ -482,7 +532,7 @@ k_pyramid_stream2(const PyrJob* __restrict__ jobs, int segs)
         asm volatile("cp.async.wait_group %0;\n" :: "n"(kPsStages - 2));                       \
         __syncthreads();                                                                       \
         prefetch(b - (kPsStages - 1));                                                         \
-        ps2_block<HMAX, (K), FIX>(ring, in_ring, buf0, buf1, job, b, j, in_map && b <= b_top, cells >> 1); \
+        ps2_block<HMAX, (K), FIX, BND>(ring, in_ring, buf0, buf1, job, b, j, in_map && b <= b_top, cells >> 1); \
     }
     for (int bg = b_start + 1 - kPs2Group; bg >= b_lo; bg -= kPs2Group) {
         CSM_PS2_STEP(7) CSM_PS2_STEP(6) CSM_PS2_STEP(5) CSM_PS2_STEP(4)
@@ -1338,14 +1388,15 @@ __device__ __forceinline__ void ld_children_b(const unsigned char* __restrict__ 
     /* children outside the map read the zero padding: clamp the base cell into [-(w + 1), extent] */
     const unsigned int rp = (unsigned int)(min(max(r, -(w + 1)), rows) + PR);
     const unsigned int cp = (unsigned int)(min(max(c, -(w + 1)), cols) + PC);
-    const unsigned int ro0 = (((rp >> 3) * tpr) << 7) + ((rp & 7u) << 4);
+    /* bl_cell split into its row and column parts */
+    const unsigned int ro0 = (((rp >> 2) * tpr) << 7) + ((rp & 3u) << 1);
     unsigned int ro1;
-    if (w >= kBlTileR) ro1 = ro0 + row_w;          /* row_w = (w / 8) * tpr * 128 */
-    else { const unsigned int rq = rp + w; ro1 = (((rq >> 3) * tpr) << 7) + ((rq & 7u) << 4); }
-    const unsigned int co0 = ((cp >> 4) << 7) + (cp & 15u);
+    if (w >= kBlTileR) ro1 = ro0 + row_w;          /* row_w = (w / tile rows) * tpr * 128 */
+    else { const unsigned int rq = rp + w; ro1 = (((rq >> 2) * tpr) << 7) + ((rq & 3u) << 1); }
+    const unsigned int co0 = ((cp >> 5) << 7) + ((cp & 30u) << 2) + (cp & 1u);
     unsigned int co1;
     if (w >= kBlTileC) co1 = co0 + ((w / kBlTileC) << 7);
-    else { const unsigned int cq = cp + w; co1 = ((cq >> 4) << 7) + (cq & 15u); }
+    else { const unsigned int cq = cp + w; co1 = ((cq >> 5) << 7) + ((cq & 30u) << 2) + (cq & 1u); }
     v[0] = __ldg(bm + ro0 + co0); v[1] = __ldg(bm + ro0 + co1);
     v[2] = __ldg(bm + ro1 + co0); v[3] = __ldg(bm + ro1 + co1);
 }

@@ -335,6 +335,36 @@ def test_bound_levels_vs_numpy(handle, shape):
     handle.release_grid(81)
 
 
+@pytest.mark.parametrize("shape,levels", [((512, 512), 5), ((256, 384), 5), ((512, 512), 6), ((96, 64), 3), ((512, 512), 1)])
+def test_bound_levels_from_the_streaming_builder(handle, checker, shape, levels):
+    """The streaming pyramid kernel in its bound mode (batches of maps): every level equals the u8
+    encoding ceil(v / 257) of the REFERENCE's level (the sliding maximum with the far edge clamped,
+    grid_map_builder.cpp:987-1012), cell for cell, and the padding stays zero; the sweep then returns the
+    same results from these levels as from the ones k_bounds_build writes."""
+    rng = np.random.default_rng(shape[0] + levels)
+    ids = list(range(8300, 8309))
+    grids = []
+    for mid in ids:
+        g = rng.integers(0, 65536, size=shape, dtype=np.uint16)
+        g[rng.random(shape) < 0.6] = 0
+        g[0, 0], g[-1, -1] = 65535, 65535
+        grids.append(g)
+        handle.upload_grid(mid, g, 0.05, 0.0, 0.0)
+    handle.set_option("bounds_mode", 2)
+    try:
+        handle.build_pyramids(ids, levels + 1)
+    finally:
+        handle.set_option("bounds_mode", 0)
+    for mid, g in zip(ids[:3] + ids[-1:], grids[:3] + grids[-1:]):
+        ref = checker.grid(g, 0.05, 0.0, 0.0).pyramid(levels)
+        for lv in range(1, levels + 1):
+            got = handle.bound_level(mid, lv, shape)
+            exp = ((ref[lv].astype(np.int64) + 256) // 257).astype(np.uint8)
+            assert np.array_equal(got, exp), "map %d level %d: %d cells differ" % (mid, lv, int((got != exp).sum()))
+    for mid in ids:
+        handle.release_grid(mid)
+
+
 def test_sweep_over_bound_levels_equals_sweep_over_reference_levels(handle, checker):
     """The same branch-and-bound queries through both sweeps (u8 bound levels / the reference's u16
     levels): identical results field by field (they can differ only in the number of nodes expanded),
