@@ -1136,7 +1136,9 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     const bool dive = top >= 1 && (h->bb_dive == 1 || (h->bb_dive == 2 && nq <= 4));
     const bool unscored_roots = top >= 1 && h->bb_skip_top && !dive;
     /* the sweep over bound levels (csm_bounds.cuh) whenever no kernel needs a u16 level above 0 */
-    const bool use_bounds = h->bb_bounds != 0 && unscored_roots;
+    bool use_bounds = h->bb_bounds != 0 && unscored_roots;
+    for (int q = 0; q < nq && use_bounds; ++q)
+        use_bounds = 2 * queries[q].win_t + 1 <= 2048;       /* 8-bit angle group index of the group sweep */
     /* what the search reads above level 0, built here for the maps that lack it (first touch) */
     if (use_bounds) {
         if ((rc = build_bounds(h, used_slots, hmax - 1))) return rc;
@@ -1188,7 +1190,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         Q.proj_off = plan.proj_total;
         Q.pst_t = 1; Q.pst_i = Q.T;            /* beam-major for the lane-per-node B&B */
         Q.pquad = use_bounds ? 1 : 0;          /* groups of four beams for the sweep over bound levels */
-        plan.proj_total += (long long)Q.T * ((Q.n + 3) & ~3);
+        Q.tp = (Q.T + 7) & ~7;
+        plan.proj_total += (long long)Q.tp * ((Q.n + 15) & ~15);
         plan.max_tn = std::max(plan.max_tn, Q.T * Q.n);
         plan.max_t = std::max(plan.max_t, Q.T);
         plan.max_roots = std::max(plan.max_roots, Q.T * Q.nrx * Q.nry);
@@ -1197,7 +1200,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         plan.theta_off[q] = 0;
         Q.theta0 = in.sensor_pose[2]; Q.step_t = in.step_t; Q.tcenter = in.win_t;
         plan.inc_init[q] = ((unsigned long long)Q.kthr.fail_max << kOrdBits) | kOrdMask;
-        plan.root_off[q + 1] = plan.root_off[q] + (unsigned int)(Q.T * Q.nrx * Q.nry);
+        /* list entries of the roots: one per node, or one per group of 8 angles (group sweep) */
+        plan.root_off[q + 1] = plan.root_off[q] + (unsigned int)((use_bounds ? (Q.T + 7) / 8 : Q.T) * Q.nrx * Q.nry);
     }
     if ((rc = wait_uploads(h, used_slots))) return rc;
     if ((rc = ensure_frontier(h, nq, plan.root_off[nq]))) return rc;
@@ -1228,7 +1232,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
 
     {
         dim3 grid(std::max(1, std::min((plan.max_roots + 255) / 256, 64)), nq);
-        k_bb_init<<<grid, 256, 0, h->stream>>>(dq, V.rootoff, nq, W, unscored_roots ? 1 : 0);
+        if (use_bounds) k_bbg_init<<<grid, 256, 0, h->stream>>>(dq, V.rootoff, nq, W);
+        else k_bb_init<<<grid, 256, 0, h->stream>>>(dq, V.rootoff, nq, W, unscored_roots ? 1 : 0);
         CSM_LAUNCH_CHECK();
     }
     {
@@ -1242,8 +1247,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_bb_expand<3>, 256, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_bb_roots, 256, 0);
             int d = 0, e = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_bbx_expand<0>, 256, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, k_bbx_expand<3>, 256, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_bbg_expand<0>, 32 * kBbgWarps, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, k_bbg_expand<3>, 32 * kBbgWarps, 0);
             h->bb_ctas_per_sm = std::max(1, std::min(std::min(a > 0 ? a : 8, b > 0 ? b : 8), c > 0 ? c : 8));
             h->bbx_ctas_per_sm = std::max(1, std::min(d > 0 ? d : 8, e > 0 ? e : 8));
         }
@@ -1262,17 +1267,20 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         /* a list never holds more than 4^k times the roots: small calls get small grids */
         unsigned long long bound = n_roots;
         for (int lvl = top; lvl >= 1 && lvl > h->bb_stop_level; --lvl) {
-            const int blocks = (int)std::min<unsigned long long>((bound + 7) / 8, (unsigned long long)full);
+            /* per-node lists: 8 nodes per warp; group lists: a CTA per group when the list is short */
+            const int blocks = (int)std::min<unsigned long long>(use_bounds ? bound : (bound + 7) / 8, (unsigned long long)full);
             const dim3 g((unsigned)std::max(blocks, 1));
             if (use_bounds) {
+                const int gt = 32 * kBbgWarps;
+                const int nchunks_hint = (plan.dq[0].n + 15) / 16;
                 switch (lvl - 1) {
-                case 0: k_bbx_expand<0><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
-                case 1: k_bbx_expand<1><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
-                case 2: k_bbx_expand<2><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
-                case 3: k_bbx_expand<3><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
-                case 4: k_bbx_expand<4><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
-                case 5: k_bbx_expand<5><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
-                default: k_bbx_expand<6><<<g, 256, 0, h->stream>>>(dq, proj, W); break;
+                case 0: k_bbg_expand<0><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
+                case 1: k_bbg_expand<1><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
+                case 2: k_bbg_expand<2><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
+                case 3: k_bbg_expand<3><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
+                case 4: k_bbg_expand<4><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
+                case 5: k_bbg_expand<5><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
+                default: k_bbg_expand<6><<<g, gt, 0, h->stream>>>(dq, proj, W, nchunks_hint); break;
                 }
             } else
             switch (lvl - 1) {          /* height of the children: compile-time for the index arithmetic */
@@ -1286,7 +1294,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             }
             CSM_LAUNCH_CHECK();
             if (h->timing) {
-                const std::string nm = std::string(use_bounds ? "k_bbx_expand<" : "k_bb_expand<") + std::to_string(lvl - 1) + ">";
+                const std::string nm = std::string(use_bounds ? "k_bbg_expand<" : "k_bb_expand<") + std::to_string(lvl - 1) + ">";
                 phase_mark(h, nm.c_str());
             }
             bound = std::min<unsigned long long>(bound * 4, (unsigned long long)h->frontier_capacity);

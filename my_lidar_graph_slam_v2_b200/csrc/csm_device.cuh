@@ -76,17 +76,20 @@ struct DevQuery
      * bl_tpr[hc] its tiles per row; null when the sweep reads the u16 levels */
     const unsigned char* bl[kMaxLevels];
     int bl_tpr[kMaxLevels];
-    int pquad;                         /* 1: proj is stored in groups of four beams, [n / 4][T][4] (see proj_index) */
-    int pad3;
+    int pquad;                         /* 1: proj is stored in chunks of 16 beams, [n / 16][tp][4][4] (see proj_index) */
+    int tp;                            /* quad layout: angles per beam group, T rounded up to a multiple of 8 */
 };
 
 /* Position of (angle t, beam i) in a query's block of the projection buffer. Strided layouts:
  * angle-major (pst_t = n, pst_i = 1) for the real-time and grid-search matchers, beam-major
- * (pst_t = 1, pst_i = T). Quad layout (branch-and-bound over bound levels): [n / 4][T][4], so that the
- * index loads of a warp that holds 8 adjacent angles x 4 adjacent beams are one 128-byte line. */
+ * (pst_t = 1, pst_i = T). Chunk layout (branch-and-bound over bound levels): [n / 16][tp][4][4], tp = T
+ * rounded up to a multiple of 8: beam i of angle t sits in chunk i / 16 at [t][i % 4][(i / 4) % 4]. A lane of
+ * the group sweep (one angle, beams i % 4 == part) reads its four beams of a chunk as ONE 16-byte word, the
+ * 8 angles x 4 parts of a warp read 512 contiguous bytes, and at each of the four steps the warp's lanes
+ * hold 8 adjacent angles x 4 ADJACENT beams. */
 __device__ __forceinline__ size_t proj_index(const DevQuery& Q, int t, int i)
 {
-    return Q.pquad ? ((((size_t)(i >> 2) * (size_t)Q.T + (size_t)t) << 2) + (size_t)(i & 3))
+    return Q.pquad ? ((((size_t)(i >> 4) * (size_t)Q.tp + (size_t)t) << 4) + (size_t)(((i & 3) << 2) | ((i >> 2) & 3)))
                    : (size_t)t * (size_t)Q.pst_t + (size_t)i * (size_t)Q.pst_i;
 }
 

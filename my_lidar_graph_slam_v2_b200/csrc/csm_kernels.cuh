@@ -1367,24 +1367,61 @@ k_bb_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pro
 }
 
 /* ---- the sweep over bound levels ---------------------------------------------------
- * Same frontier expansion as k_bb_expand, reading the representation built for it (csm_bounds.cuh):
- * children of height HC >= 1 are tested on 257 * sum of the u8 bound level HC (tiled 8 x 16, zero
- * padded: one clamp per axis instead of a bounds test per child, one to three 128-byte lines per warp
- * gather); leaves (HC == 0) are scored exactly on the u16 level-0 grid like before. The projected
- * indices are in the quad layout [n / 4][T][4]: the index load of a warp holding 8 adjacent angles x
- * 4 adjacent beams is one 128-byte line. */
-#ifndef CSM_BBX_UNROLL
-#define CSM_BBX_UNROLL 4
+ * Same frontier expansion as k_bb_expand, reading the representation built for it (csm_bounds.cuh) and
+ * working on GROUPS: a list entry is (query, x, y, group of 8 adjacent angles, 8-bit mask of the angles
+ * still alive). Along the angle axis the frontier is made of runs (a node's bound changes slowly with
+ * the angle: measured 93 % / 87 % / 78 % / 67 % / 54 % of the angles of a listed group are alive at
+ * heights 5..1 of the loop-detection batch), and a warp that takes one group has its 32 lanes = 8
+ * adjacent angles x 4 adjacent beams on ONE (x, y): their hit cells lie on an arc of a few cells, so
+ * a gather touches one to three 128-byte tiles of the bound level, and the index load is exactly one
+ * line of the quad layout [n / 4][tp][4]. (With one list entry per node a warp's 8 entries came from 2
+ * to 5 different (query, x, y) cells.) Short lists give every group several warps, each on a slice of the
+ * beams, summed through shared memory.
+ *
+ * Children of height HC >= 1 are tested on 257 * sum of the u8 bound level HC (zero padded: one clamp
+ * per axis instead of a bounds test per child); leaves (HC == 0) are scored exactly on the u16 level-0
+ * grid. */
+#ifndef CSM_BBG_UNROLL
+#define CSM_BBG_UNROLL 2
 #endif
-constexpr int kBbxUnroll = CSM_BBX_UNROLL;
+constexpr int kBbgUnroll = CSM_BBG_UNROLL;
+constexpr int kBbgWarps = 8;                 /* warps per CTA */
+
+__device__ __forceinline__ unsigned long long pack_group(int q, int tg, unsigned int mask, int xi, int yi)
+{
+    return ((unsigned long long)(unsigned)q << 48) | ((unsigned long long)(unsigned)tg << 40) |
+           ((unsigned long long)(mask & 0xffu) << 32) | ((unsigned long long)(unsigned)xi << 16) |
+           (unsigned long long)(unsigned)yi;
+}
+
+/* Root groups of every query: (x, y) stepping by 2^top from -win, every group of 8 angles, all alive:
+ * the first expand launch scores their children (unscored roots, see k_bb_init). */
+__global__ void __launch_bounds__(256)
+k_bbg_init(const DevQuery* __restrict__ queries, const unsigned int* __restrict__ root_off, int nq, BbWork W)
+{
+    const int q = blockIdx.y;
+    const DevQuery& Q = queries[q];
+    const int G = (Q.T + 7) >> 3;
+    const int nitems = G * Q.nrx * Q.nry;
+    unsigned long long* out = bb_list(W, W.top) + root_off[q];
+    if (q == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        W.counts[W.top] = root_off[nq];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nitems; e += gridDim.x * blockDim.x) {
+        const int tg = e % G;
+        const int cell = e / G;
+        const int rx = cell / Q.nry, ry = cell - rx * Q.nry;
+        const int left = Q.T - 8 * tg;
+        const unsigned int mask = left >= 8 ? 0xffu : ((1u << left) - 1u);
+        out[e] = pack_group(q, tg, mask, rx << W.top, ry << W.top);
+    }
+}
 
 template <int HC>
 __device__ __forceinline__ void ld_children_b(const unsigned char* __restrict__ bm, unsigned int tpr, unsigned int row_w,
                                               int rows, int cols, int r, int c, unsigned int (&v)[4])
 {
     constexpr int w = 1 << HC;
-    constexpr int PR = ((1 << HC) + 1 + kBlTileR - 1) & ~(kBlTileR - 1);
-    constexpr int PC = ((1 << HC) + 1 + kBlTileC - 1) & ~(kBlTileC - 1);
+    constexpr int PR = bl_pad_r(HC), PC = bl_pad_c(HC);
     /* children outside the map read the zero padding: clamp the base cell into [-(w + 1), extent] */
     const unsigned int rp = (unsigned int)(min(max(r, -(w + 1)), rows) + PR);
     const unsigned int cp = (unsigned int)(min(max(c, -(w + 1)), cols) + PC);
@@ -1401,33 +1438,49 @@ __device__ __forceinline__ void ld_children_b(const unsigned char* __restrict__ 
     v[2] = __ldg(bm + ro1 + co0); v[3] = __ldg(bm + ro1 + co1);
 }
 
+/* warps per group: the split that minimises (rounds of the grid) x (steps per warp), with a few steps
+ * charged for the exchange through shared memory when a group is shared */
+__device__ __forceinline__ int bbg_warps_per_group(unsigned int count, unsigned int ctas, int nchunks)
+{
+    int best = 1;
+    unsigned int best_cost = 0xffffffffu;
+#pragma unroll
+    for (int wpi = 1; wpi <= kBbgWarps; wpi *= 2) {
+        const unsigned int per_round = ctas * (unsigned int)(kBbgWarps / wpi);
+        const unsigned int rounds = (count + per_round - 1) / per_round;
+        const unsigned int cost = rounds * (unsigned int)((nchunks + wpi - 1) / wpi + (wpi > 1 ? 1 : 0));
+        if (cost < best_cost) { best_cost = cost; best = wpi; }
+    }
+    return best;
+}
+
 template <int HC>
-__global__ void __launch_bounds__(256, CSM_BB_MINB)
-k_bbx_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W)
+__global__ void __launch_bounds__(32 * kBbgWarps, CSM_BB_MINB)
+k_bbg_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W, int nchunks_hint)
 {
     constexpr int h = HC + 1;
     constexpr int w = 1 << HC;
     constexpr bool kLeaf = HC == 0;
-    constexpr int U = kLeaf ? kBbUnroll : kBbxUnroll;
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned int s_part[kBbgWarps][8][8];      /* per warp: per angle, 4 sums (+ 4 known counts) */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = lane & 7, part = lane >> 3;          /* angle within the group, beam within a quad */
     const unsigned int count = min(W.counts[h], W.capacity);
-    const unsigned int total_lanes = gridDim.x * blockDim.x;
-    int split = kBbSplit;
-    while (split < 32 && (((unsigned long long)count * (unsigned)(split * 2)) << max(-W.split_shift, 0)) <= ((unsigned long long)total_lanes << max(W.split_shift, 0))) split *= 2;
-    const int npw = 32 / split;
-    const int slot = lane & (npw - 1);
-    const int part = lane / npw;
+    const int wpi = bbg_warps_per_group(count, gridDim.x, nchunks_hint);
+    const int ipc = kBbgWarps / wpi;                      /* groups a CTA takes at a time */
+    const int sub = warp & (wpi - 1), local = warp / wpi;
     const unsigned long long* __restrict__ in = bb_list(W, h);
     unsigned long long* __restrict__ out = bb_list(W, HC);
-    const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned int nwarps = total_lanes >> 5;
-    for (unsigned int base = warp_global * npw; base < count; base += nwarps * npw) {
-        const unsigned int idx = base + slot;
-        const bool valid = idx < count;
-        int q = 0, t = 0, xi = 0, yi = 0;
+    for (unsigned int base = blockIdx.x * ipc; base < count; base += gridDim.x * ipc) {
+        const unsigned int idx = base + local;
+        const bool have = idx < count;
+        const unsigned long long item = have ? in[idx] : 0ull;
+        const int q = (int)(item >> 48), tg = (int)((item >> 40) & 0xffull);
+        const unsigned int mask = (unsigned int)((item >> 32) & 0xffull);
+        const int xi = (int)((item >> 16) & 0xffffull), yi = (int)(item & 0xffffull);
+        const bool alive = have && ((mask >> slot) & 1u);
+        const int t = tg * 8 + slot;
         unsigned int s0 = 0, s1 = 0, s2 = 0, s3 = 0, k0 = 0, k1 = 0, k2 = 0, k3 = 0;
-        if (valid) {
-            unpack_node(in[idx], q, t, xi, yi);
+        if (alive) {
             const DevQuery& Q = queries[q];
             const uint16_t* __restrict__ m = Q.lvl[0];
             const unsigned char* __restrict__ bm = Q.bl[HC];
@@ -1435,92 +1488,113 @@ k_bbx_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pr
             const unsigned int row_w = (unsigned int)(w / kBlTileR) * (tpr << 7);
             const int rows = Q.rows, cols = Q.cols, n = Q.n;
             const int ox = xi - Q.winx, oy = yi - Q.winy;
-            /* beam i = part + split * j lives at ((i >> 2) * T + t) * 4 + (i & 3): split is a multiple of 4 */
-            const unsigned int T = (unsigned int)Q.T;
-            const proj_t* __restrict__ pp = proj_all + Q.proj_off + ((((unsigned int)(part >> 2) * T + (unsigned int)t) << 2) + (unsigned int)(part & 3));
-            const unsigned int step = T * (unsigned int)split;
-            const int mine = (n - part + split - 1) / split;
-            int i = 0;
-            proj_t pn[U];
-            if (U <= mine) {
+            /* chunk k (16 beams) of angle t starts at ((k * tp + t) << 4); this lane's beams 16 k + 4 s + part,
+             * s = 0..3, are the four entries at + (part << 2): one 16-byte load. This warp takes the chunks
+             * k = sub, sub + wpi, ... */
+            const unsigned int tp = (unsigned int)Q.tp;
+            const uint4* __restrict__ pp = reinterpret_cast<const uint4*>(
+                proj_all + Q.proj_off + ((((unsigned int)sub * tp + (unsigned int)t) << 4) + ((unsigned int)part << 2)));
+            const unsigned int step = (tp * (unsigned int)wpi) << 2;        /* in 16-byte words */
+            const int nchunks = (n + 15) >> 4;
+            const int mine = (nchunks - sub + wpi - 1) / wpi;
+            uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+            if (mine > 0) nx = __ldg(pp);
+            for (int j = 0; j < mine; ++j) {
+                const uint4 cur = nx;
+                if (j + 1 < mine) nx = __ldg(pp + (unsigned int)(j + 1) * step);
+                const int i0 = ((sub + j * wpi) << 4) + part;                /* this lane's first beam of the chunk */
+                const unsigned int pw[4] = { cur.x, cur.y, cur.z, cur.w };
+                unsigned int v[4][4];
 #pragma unroll
-                for (int u = 0; u < U; ++u) pn[u] = pp[(unsigned int)u * step];
-            }
-            for (; i + U <= mine; i += U) {
-                proj_t p[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) p[u] = pn[u];
-                unsigned int v[U][4];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (kLeaf) ld_children<0>(m, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
-                    else ld_children_b<HC>(bm, tpr, row_w, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
+                for (int s = 0; s < 4; ++s) {
+                    const int r = (int)(short)(pw[s] >> 16) + oy, c = (int)(short)(pw[s] & 0xffffu) + ox;
+                    if (i0 + 4 * s < n) {
+                        if (kLeaf) ld_children<0>(m, rows, cols, r, c, v[s]);
+                        else ld_children_b<HC>(bm, tpr, row_w, rows, cols, r, c, v[s]);
+                    } else {
+                        v[s][0] = v[s][1] = v[s][2] = v[s][3] = 0u;
+                    }
                 }
-                if (i + 2 * U <= mine) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) pn[u] = pp[(unsigned int)(i + U + u) * step];
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    s0 += v[u][0]; s1 += v[u][1]; s2 += v[u][2]; s3 += v[u][3];
+                for (int s = 0; s < 4; ++s) {
+                    s0 += v[s][0]; s1 += v[s][1]; s2 += v[s][2]; s3 += v[s][3];
                     if (kLeaf) {
-                        k0 += (v[u][0] != 0u); k1 += (v[u][1] != 0u);
-                        k2 += (v[u][2] != 0u); k3 += (v[u][3] != 0u);
+                        k0 += (v[s][0] != 0u); k1 += (v[s][1] != 0u);
+                        k2 += (v[s][2] != 0u); k3 += (v[s][3] != 0u);
                     }
                 }
             }
-            for (; i < mine; ++i) {
-                const proj_t p = pp[(unsigned int)i * step];
-                unsigned int v[4];
-                if (kLeaf) ld_children<0>(m, rows, cols, p.y + oy, p.x + ox, v);
-                else ld_children_b<HC>(bm, tpr, row_w, rows, cols, p.y + oy, p.x + ox, v);
-                s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
-                if (kLeaf) { k0 += (v[0] != 0u); k1 += (v[1] != 0u); k2 += (v[2] != 0u); k3 += (v[3] != 0u); }
-            }
         }
-        unsigned long long a = ((unsigned long long)s0 << 32) | s1;
-        unsigned long long b = ((unsigned long long)s2 << 32) | s3;
-        unsigned long long kk = ((unsigned long long)k0 << 48) | ((unsigned long long)k1 << 32) |
-                                ((unsigned long long)k2 << 16) | (unsigned long long)k3;
-        for (int o = npw; o < 32; o <<= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-            if (kLeaf) kk += __shfl_xor_sync(0xffffffffu, kk, o);
-        }
-        const bool decides = valid && part < 4;
-        const unsigned long long sp = (part & 2) ? b : a;
-        const int s = (int)((part & 1) ? (unsigned)sp : (unsigned)(sp >> 32));
-        const int cx = xi + (part & 1) * w, cy = yi + ((part >> 1) & 1) * w;
-        bool pass = false;
-        if (decides) {
-            const DevQuery& Q = queries[q];
+        /* sum over the four beams of a quad (lanes 8 and 16 apart) */
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
             if (kLeaf) {
-                const int k = (int)((kk >> (16 * (3 - (part & 3)))) & 0xffffull);
-                long long key;
-                pass = bb_passes(Q, proj_all, W, q, t, cx, cy, 0, s, k, key);
-                if (pass)
-                    bb_raise_incumbent(W, q, key, leaf_ordfield(Q, t, cx, cy));
-            } else {
-                /* upper bound of the key: 257 * B >= v per cell, every beam counted as known */
-                const long long key_ub = make_key(257ll * (long long)s, Q.n);
-                const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
-                pass = pack_best(key_ub, kOrdMask) > inc && key_ub > Q.kthr.fail_max && Q.n > Q.nk_cut;
+                k0 += __shfl_xor_sync(0xffffffffu, k0, o); k1 += __shfl_xor_sync(0xffffffffu, k1, o);
+                k2 += __shfl_xor_sync(0xffffffffu, k2, o); k3 += __shfl_xor_sync(0xffffffffu, k3, o);
             }
         }
-        bb_count(W, decides, q, pass);
-        if (!kLeaf) {
+        if (wpi > 1) {
+            /* ... and over the warps that share the group */
+            if (part == 0) {
+                unsigned int* d = s_part[warp][slot];
+                d[0] = s0; d[1] = s1; d[2] = s2; d[3] = s3;
+                if (kLeaf) { d[4] = k0; d[5] = k1; d[6] = k2; d[7] = k3; }
+            }
+            __syncthreads();
+            if (sub == 0) {
+                s0 = s1 = s2 = s3 = 0; k0 = k1 = k2 = k3 = 0;
+                for (int o = 0; o < wpi; ++o) {
+                    const unsigned int* d = s_part[warp + o][slot];
+                    s0 += d[0]; s1 += d[1]; s2 += d[2]; s3 += d[3];
+                    if (kLeaf) { k0 += d[4]; k1 += d[5]; k2 += d[6]; k3 += d[7]; }
+                }
+            }
+        }
+        if (sub == 0) {
+            /* lane (slot, part) decides child `part` of angle `slot`: (x + (part & 1) w, y + (part >> 1) w) */
+            const unsigned int sv = part == 0 ? s0 : part == 1 ? s1 : part == 2 ? s2 : s3;
+            const int cx = xi + (part & 1) * w, cy = yi + (part >> 1) * w;
+            bool pass = false;
+            if (alive) {
+                const DevQuery& Q = queries[q];
+                if (kLeaf) {
+                    const int k = (int)(part == 0 ? k0 : part == 1 ? k1 : part == 2 ? k2 : k3);
+                    long long key;
+                    pass = bb_passes(Q, proj_all, W, q, t, cx, cy, 0, (int)sv, k, key);
+                    if (pass)
+                        bb_raise_incumbent(W, q, key, leaf_ordfield(Q, t, cx, cy));
+                } else {
+                    /* upper bound of the key: 257 * B >= v per cell, every beam counted as known */
+                    const long long key_ub = make_key(257ll * (long long)sv, Q.n);
+                    const unsigned long long inc = *(volatile unsigned long long*)&W.incumbent[q];
+                    pass = pack_best(key_ub, kOrdMask) > inc && key_ub > Q.kthr.fail_max && Q.n > Q.nk_cut;
+                }
+            }
             const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
-            if (ballot != 0u) {
+            const unsigned int scored = __ballot_sync(0xffffffffu, alive);
+            if (have && lane == 0) {
+                atomicAdd(&W.stats[2 * q], __popc(ballot));
+                atomicAdd(&W.stats[2 * q + 1], __popc(scored) - __popc(ballot));
+            }
+            if (!kLeaf && ballot != 0u) {
+                /* one new group per child that keeps an angle alive: lanes 0..3 write them */
+                const unsigned int cm = (ballot >> (8 * (lane & 3))) & 0xffu;
+                const bool emit = lane < 4 && cm != 0u;
+                const unsigned int eb = __ballot_sync(0xffffffffu, emit);
                 unsigned int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&W.counts[HC], (unsigned int)__popc(ballot));
+                if (lane == 0) slot0 = atomicAdd(&W.counts[HC], (unsigned int)__popc(eb));
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (pass) {
-                    const unsigned int dst = slot0 + __popc(ballot & ((1u << lane) - 1u));
-                    if (dst < W.capacity) out[dst] = pack_node(q, t, cx, cy);
+                if (emit) {
+                    const unsigned int dst = slot0 + __popc(eb & ((1u << lane) - 1u));
+                    if (dst < W.capacity) out[dst] = pack_group(q, tg, cm, xi + (lane & 1) * w, yi + ((lane >> 1) & 1) * w);
                     else *W.overflow = 1;
                 }
             }
         }
+        if (wpi > 1)
+            __syncthreads();          /* s_part is rewritten by the next round */
     }
 }
 
