@@ -351,6 +351,41 @@ int csm_refine_batch(csm_handle h, const csm_refine_query* queries, int n,
  * csm_last_epilogue returns its outcome (valid == 0 when no pose was found). */
 int csm_set_epilogue(csm_handle h, double covariance_scale);
 int csm_last_epilogue(csm_handle h, csm_refined* out);
+/* ---- the whole first-touch step in one call -----------------------------------
+ * What LoopDetectorBranchBound::Detect does with its device context for one batch whose level-0
+ * grids are resident: (re)build what the search reads above level 0 for the n_maps maps (drop != 0:
+ * as on first touch, even if a previous call built it), enqueue the search batch with its
+ * refinement and read-back, and, when the handle has a communicator (csm_comm_init_*), start the
+ * exchange of the packed best word behind it. Returns after enqueueing; *ticket (may be NULL)
+ * identifies the exchange (csm_comm_best_result). Finish with csm_loop_batch_finish(_refined). */
+int csm_detect_step_enqueue(csm_handle h, const int64_t* map_ids, int n_maps, int drop,
+                            const csm_loop_query* queries, int nq, int hmax, int query_index_base,
+                            int* ticket);
+
+/* ---- multi-GPU: exchange of the packed best word over NCCL --------------------
+ * Queries of a Detect are independent (loop_detector_branch_bound.cpp:68) and shard over GPUs like
+ * the reference's two accelerator cores (loop_detector_fpga_parallel.cpp:41-56); the only exchange
+ * is the 8-byte all-reduce(max) of the packed best word (see csm_best_key_device). The library
+ * calls NCCL itself (libnccl.so.2, loaded at run time), on a side stream of the handle behind an
+ * event, so that the exchange of one batch overlaps the kernels of the next.
+ *  - one process per GPU: rank 0 calls csm_comm_unique_id, hands the 128 bytes to the other
+ *    ranks (any side channel), every rank calls csm_comm_init_rank;
+ *  - one process, several GPUs: csm_comm_init_all(handles, n), one handle per device, then
+ *    csm_comm_allreduce_best_all on all of them at once.
+ * csm_comm_allreduce_best starts the exchange of the word the last batch left (returns a ticket,
+ * up to 8 may be in flight); csm_comm_best_result waits for it and returns the reduced word. */
+int csm_comm_unique_id(void* id128);
+int csm_comm_init_rank(csm_handle h, const void* id128, int rank, int world);
+int csm_comm_init_all(csm_handle* handles, int n);
+int csm_comm_allreduce_best(csm_handle h, int* ticket);
+int csm_comm_allreduce_best_all(csm_handle* handles, int n, int* tickets);
+/* The same exchange for a word the caller formed on the host (a Detect that ran on several lanes
+ * or handles keeps its best word there): no dependence on the compute stream. */
+int csm_comm_allreduce_word(csm_handle h, uint64_t word, int* ticket);
+int csm_comm_allreduce_words_all(csm_handle* handles, int n, const uint64_t* words, int* tickets);
+int csm_comm_best_result(csm_handle h, int ticket, uint64_t* word);
+int csm_comm_destroy(csm_handle h);
+
 /* Phase timing: after csm_set_option(h, "timing", 1) the library records a CUDA
  * event on the handle's stream after every kernel of a loop batch (or of a
  * streaming pyramid build). csm_debug_timings waits for the last one and

@@ -15,7 +15,7 @@ HEADERS = [os.path.join(HERE, "csrc", "csm_kernels.cuh"),
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared",
+    "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared", "-ldl",
 ]
 
 

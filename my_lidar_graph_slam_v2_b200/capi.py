@@ -68,9 +68,38 @@ EXPORTS = [
     "csm_set_refiner", "csm_loop_batch_finish_refined", "csm_refine_batch", "csm_set_epilogue", "csm_last_epilogue", "csm_share_copy_stream",
     "csm_best_key_device", "csm_decode_best_key", "csm_debug_frontier_counts", "csm_debug_timings",
     "csm_debug_bound_level", "csm_exact_rerun_count", "csm_debug_node_list",
+    "csm_detect_step_enqueue", "csm_comm_unique_id", "csm_comm_init_rank", "csm_comm_init_all",
+    "csm_comm_allreduce_best", "csm_comm_allreduce_best_all", "csm_comm_best_result", "csm_comm_destroy",
+    "csm_comm_allreduce_word", "csm_comm_allreduce_words_all",
 ]
 
 _LIB = None
+
+
+def comm_unique_id():
+    """128 bytes that identify a new communicator (rank 0 creates them, every rank gets them)."""
+    buf = C.create_string_buffer(128)
+    rc = load().csm_comm_unique_id(buf)
+    if rc != CSM_OK:
+        raise CsmError(rc, "csm_comm_unique_id (libnccl.so.2 not found?)")
+    return buf.raw
+
+
+def comm_init_all(handles):
+    """One process, several GPUs: a communicator over `handles` (one per device)."""
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    rc = load().csm_comm_init_all(arr, len(handles))
+    if rc != CSM_OK:
+        raise CsmError(rc, handles[0].last_error())
+
+
+def comm_allreduce_best_all(handles):
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    tickets = (C.c_int * len(handles))()
+    rc = load().csm_comm_allreduce_best_all(arr, len(handles), tickets)
+    if rc != CSM_OK:
+        raise CsmError(rc, handles[0].last_error())
+    return list(tickets)
 
 
 def lib_path():
@@ -130,6 +159,16 @@ def load():
     lib.csm_loop_batch_enqueue.argtypes = [H, lq, C.c_int, C.c_int, C.c_int]
     lib.csm_loop_batch_finish.argtypes = [H, rp, C.c_int]
     lib.csm_loop_batch.argtypes = [H, lq, C.c_int, C.c_int, C.c_int, rp]
+    lib.csm_detect_step_enqueue.argtypes = [H, i64p, C.c_int, C.c_int, lq, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.csm_comm_unique_id.argtypes = [C.c_void_p]
+    lib.csm_comm_init_rank.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
+    lib.csm_comm_init_all.argtypes = [C.POINTER(H), C.c_int]
+    lib.csm_comm_allreduce_best.argtypes = [H, C.POINTER(C.c_int)]
+    lib.csm_comm_allreduce_best_all.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_int)]
+    lib.csm_comm_best_result.argtypes = [H, C.c_int, C.POINTER(C.c_uint64)]
+    lib.csm_comm_allreduce_word.argtypes = [H, C.c_uint64, C.POINTER(C.c_int)]
+    lib.csm_comm_allreduce_words_all.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    lib.csm_comm_destroy.argtypes = [H]
     lib.csm_set_refiner.argtypes = [H, C.POINTER(CsmRefineParams)]
     lib.csm_loop_batch_finish_refined.argtypes = [H, rp, C.POINTER(CsmRefined), C.c_int]
     lib.csm_refine_batch.argtypes = [H, C.POINTER(CsmRefineQuery), C.c_int, C.POINTER(CsmRefineParams),
@@ -176,9 +215,12 @@ class Handle:
         self.borrowed = True
         return self
 
+    def last_error(self):
+        return self.lib.csm_last_error(self.h).decode()
+
     def _check(self, rc):
         if rc != CSM_OK:
-            raise CsmError(rc, self.lib.csm_last_error(self.h).decode())
+            raise CsmError(rc, self.last_error())
 
     def close(self):
         if getattr(self, "h", None):
@@ -310,6 +352,37 @@ class Handle:
     def loop_batch(self, queries, nq, hmax, query_index_base=0):
         self.loop_batch_enqueue(queries, nq, hmax, query_index_base)
         return self.loop_batch_finish(nq)
+
+    def detect_step_enqueue(self, map_ids, queries, nq, hmax, query_index_base=0, drop=True):
+        """The whole first-touch step in one call (csm_detect_step_enqueue): rebuild what the search reads
+        above level 0 for `map_ids`, enqueue the batch, start the best-word exchange when the handle has a
+        communicator. Returns the exchange ticket (-1: none)."""
+        ids = np.ascontiguousarray(map_ids, dtype=np.int64)
+        ticket = C.c_int(-1)
+        self._check(self.lib.csm_detect_step_enqueue(self.h, ids.ctypes.data_as(C.POINTER(C.c_int64)), len(ids),
+                                                     1 if drop else 0, queries, nq, hmax, query_index_base,
+                                                     C.byref(ticket)))
+        return ticket.value
+
+    # -- exchange of the packed best word over NCCL (the library calls NCCL itself) ------------------
+    def comm_init_rank(self, id128, rank, world):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._check(self.lib.csm_comm_init_rank(self.h, buf, rank, world))
+
+    def comm_allreduce_best(self):
+        ticket = C.c_int(-1)
+        self._check(self.lib.csm_comm_allreduce_best(self.h, C.byref(ticket)))
+        return ticket.value
+
+    def comm_allreduce_word(self, word):
+        ticket = C.c_int(-1)
+        self._check(self.lib.csm_comm_allreduce_word(self.h, C.c_uint64(word), C.byref(ticket)))
+        return ticket.value
+
+    def comm_best_result(self, ticket):
+        word = C.c_uint64(0)
+        self._check(self.lib.csm_comm_best_result(self.h, ticket, C.byref(word)))
+        return int(word.value)
 
     # -- refinement (ScanMatcherLinearSolver on the device) ------------------------
     def set_refiner(self, max_iterations=10, convergence_threshold=1e-4, lambda_=1e-4, covariance_scale=1e4,

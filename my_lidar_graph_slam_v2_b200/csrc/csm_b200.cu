@@ -11,12 +11,15 @@
 #include "csm_window_tma.cuh"
 #include "csm_refine.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -24,6 +27,48 @@
 using namespace csm;
 
 namespace {
+
+/* NCCL, loaded at run time: inside a process that already carries a libnccl.so.2 (PyTorch brings its
+ * own) dlopen returns that one, a plain C++ host gets the system library. Only the handful of entry
+ * points the best-word exchange needs; the declarations follow nccl.h (2.x ABI). */
+namespace nccl {
+typedef struct ncclComm* comm_t;
+struct unique_id { char internal[128]; };
+constexpr int kUint64 = 5, kMax = 2;       /* ncclUint64, ncclMax */
+struct Api
+{
+    int (*GetUniqueId)(unique_id*) = nullptr;
+    int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+    int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const Api& api()
+{
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (lib == nullptr) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (lib == nullptr) return;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllReduce &&
+               a.GroupStart && a.GroupEnd && a.GetErrorString;
+    });
+    return a;
+}
+} /* namespace nccl */
 
 constexpr int64_t kTempScanId = INT64_MIN;
 
@@ -149,6 +194,7 @@ struct csm_context
     DevBuf d_plan, d_proj, d_rcs, d_results, d_bestkey;
     DevBuf d_list[2];
     DevBuf d_rtblocks, d_pyrjobs, d_rootkey, d_wtgroups, d_bljobs;
+    int bb_capacity = 0;           /* test knob: upper limit of the frontier lists (entries), 0 = automatic */
     int pyramid_segs = 0;          /* test knob: row segments per map of the streaming builder (0 = automatic) */
     int bounds_mode = 0;           /* builder of the bound levels: 0 auto, 1 k_bounds_build, 2 the streaming kernel */
     int bb_stop_level = 0;         /* debug: the sweep stops once list(bb_stop_level) is complete (csm_debug_node_list) */
@@ -178,6 +224,17 @@ struct csm_context
     int res_nq[kResultSlots] = { 0, 0, 0, 0 };
     BatchRecord res_rec[kResultSlots];
     void* h_exact = nullptr;       /* pinned: result of an exact rerun / low-margin scan */
+    /* exchange of the packed best word over NCCL (csm_comm_*): a ring of words, each copied out of
+     * d_bestkey on the compute stream, reduced in place on a high-priority side stream, read back */
+    static constexpr int kCommRing = 8;
+    nccl::comm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    unsigned long long* d_words = nullptr;        /* kCommRing device words */
+    unsigned long long* h_words = nullptr;        /* kCommRing pinned words */
+    cudaEvent_t comm_ready[kCommRing] = { nullptr };
+    cudaEvent_t comm_done[kCommRing] = { nullptr };
+    int comm_next = 0;
     int64_t exact_reruns = 0;      /* flagged results recomputed exactly so far */
     int exact_rerun = 1;           /* option: recompute results whose projection raised the FP guard-band flag */
     double fp_margin_scale = 1.0;  /* option (tests): multiplies the guard band */
@@ -1043,6 +1100,7 @@ int ensure_frontier(csm_handle h, int nq, unsigned int total_roots)
      * candidates per query and at least all roots */
     unsigned int cap = (unsigned int)std::min<long long>(
         std::max<long long>((long long)nq * 16384, 1ll << 20), 1ll << 24);
+    if (h->bb_capacity > 0) cap = std::min(cap, (unsigned int)h->bb_capacity);     /* test knob: forces overflows */
     cap = std::max(cap, total_roots);
     int rc;
     for (int l = 0; l < 2; ++l)
@@ -1671,6 +1729,7 @@ int csm_destroy(csm_handle h)
     if (h == nullptr)
         return CSM_E_INVALID;
     cudaSetDevice(h->device);
+    csm_comm_destroy(h);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->stream);
     for (auto& kv : h->maps) free_map(h, kv.second);
@@ -1732,6 +1791,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "bb_split_shift") == 0) { h->bb_split_shift = std::max(-4, std::min(value, 4)); return CSM_OK; }
     if (std::strcmp(name, "exact_rerun") == 0) { h->exact_rerun = value != 0; return CSM_OK; }
     if (std::strcmp(name, "fp_margin_scale") == 0) { h->fp_margin_scale = value > 0 ? (double)value : 1.0; return CSM_OK; }
+    if (std::strcmp(name, "bb_capacity") == 0) { h->bb_capacity = std::max(0, value); return CSM_OK; }
     if (std::strcmp(name, "pyramid_segs") == 0) { h->pyramid_segs = std::max(0, std::min(value, 4)); return CSM_OK; }
     if (std::strcmp(name, "bounds_mode") == 0 && value >= 0 && value <= 2) { h->bounds_mode = value; return CSM_OK; }
     if (std::strcmp(name, "bb_stop_level") == 0) { h->bb_stop_level = std::max(0, std::min(value, kMaxLevels - 1)); return CSM_OK; }
@@ -2203,6 +2263,189 @@ int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax
     int rc = csm_loop_batch_enqueue(h, queries, nq, hmax, query_index_base);
     if (rc) return rc;
     return csm_loop_batch_finish(h, results, nq);
+}
+
+/* ---- NCCL exchange of the packed best word ------------------------------------------------- */
+static int comm_fail(csm_handle h, const char* what, int rc)
+{
+    return fail(h, CSM_E_CUDA, std::string(what) + ": " + (nccl::api().GetErrorString ? nccl::api().GetErrorString(rc) : "nccl"));
+}
+
+static int comm_setup(csm_handle h)
+{
+    int lo = 0, hi = 0;
+    CSM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    /* the 8-byte all-reduce runs beside kernels that fill every SM: highest priority, so that its CTA
+     * is placed as soon as a slot frees */
+    CSM_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+    CSM_CUDA(cudaMalloc((void**)&h->d_words, sizeof(unsigned long long) * csm_context::kCommRing));
+    CSM_CUDA(cudaMemset(h->d_words, 0, sizeof(unsigned long long) * csm_context::kCommRing));
+    CSM_CUDA(cudaHostAlloc((void**)&h->h_words, sizeof(unsigned long long) * csm_context::kCommRing, cudaHostAllocDefault));
+    for (int i = 0; i < csm_context::kCommRing; ++i) {
+        CSM_CUDA(cudaEventCreateWithFlags(&h->comm_ready[i], cudaEventDisableTiming));
+        CSM_CUDA(cudaEventCreateWithFlags(&h->comm_done[i], cudaEventDisableTiming));
+    }
+    return ensure(h, h->d_bestkey, 8);
+}
+
+int csm_comm_unique_id(void* id128)
+{
+    if (!id128 || !nccl::api().ok) return CSM_E_UNSUPPORTED;
+    nccl::unique_id id;
+    if (nccl::api().GetUniqueId(&id) != 0) return CSM_E_CUDA;
+    std::memcpy(id128, &id, sizeof(id));
+    return CSM_OK;
+}
+
+int csm_comm_init_rank(csm_handle h, const void* id128, int rank, int world)
+{
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return CSM_E_INVALID;
+    if (!nccl::api().ok) return fail(h, CSM_E_UNSUPPORTED, "libnccl.so.2 not found");
+    if (h->comm) return fail(h, CSM_E_INVALID, "communicator already initialised");
+    CSM_CUDA(cudaSetDevice(h->device));
+    nccl::unique_id id;
+    std::memcpy(&id, id128, sizeof(id));
+    const int rc = nccl::api().CommInitRank(&h->comm, world, id, rank);
+    if (rc != 0) return comm_fail(h, "ncclCommInitRank", rc);
+    h->comm_rank = rank; h->comm_world = world;
+    return comm_setup(h);
+}
+
+int csm_comm_init_all(csm_handle* handles, int n)
+{
+    if (!handles || n < 1) return CSM_E_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (!handles[i] || handles[i]->comm) return CSM_E_INVALID;
+    csm_handle h = handles[0];
+    if (!nccl::api().ok) return fail(h, CSM_E_UNSUPPORTED, "libnccl.so.2 not found");
+    std::vector<int> devs(n);
+    std::vector<nccl::comm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = handles[i]->device;
+    const int rc = nccl::api().CommInitAll(comms.data(), n, devs.data());
+    if (rc != 0) return comm_fail(h, "ncclCommInitAll", rc);
+    for (int i = 0; i < n; ++i) {
+        handles[i]->comm = comms[i];
+        handles[i]->comm_rank = i; handles[i]->comm_world = n;
+        if (cudaSetDevice(handles[i]->device) != cudaSuccess) return CSM_E_CUDA;
+        const int src = comm_setup(handles[i]);
+        if (src) return src;
+    }
+    return CSM_OK;
+}
+
+/* word of the last batch -> ring slot (compute stream), all-reduce(max) in place and read-back (side stream) */
+static int comm_enqueue(csm_handle h, int* ticket, const uint64_t* host_word = nullptr)
+{
+    if (!h->comm) return fail(h, CSM_E_INVALID, "no communicator: call csm_comm_init_rank / csm_comm_init_all");
+    const int i = h->comm_next;
+    h->comm_next = (h->comm_next + 1) % csm_context::kCommRing;
+    CSM_CUDA(cudaEventSynchronize(h->comm_done[i]));           /* the slot's previous exchange has been read */
+    if (host_word != nullptr) {
+        /* a word the caller formed on the host (a Detect over several lanes): no tie to the compute stream */
+        h->h_words[i] = *host_word;
+        CSM_CUDA(cudaMemcpyAsync(h->d_words + i, h->h_words + i, 8, cudaMemcpyHostToDevice, h->comm_stream));
+    } else {
+        CSM_CUDA(cudaMemcpyAsync(h->d_words + i, h->d_bestkey.p, 8, cudaMemcpyDeviceToDevice, h->stream));
+        CSM_CUDA(cudaEventRecord(h->comm_ready[i], h->stream));
+        CSM_CUDA(cudaStreamWaitEvent(h->comm_stream, h->comm_ready[i], 0));
+    }
+    const int rc = nccl::api().AllReduce(h->d_words + i, h->d_words + i, 1, nccl::kUint64, nccl::kMax, h->comm, h->comm_stream);
+    if (rc != 0) return comm_fail(h, "ncclAllReduce", rc);
+    CSM_CUDA(cudaMemcpyAsync(h->h_words + i, h->d_words + i, 8, cudaMemcpyDeviceToHost, h->comm_stream));
+    CSM_CUDA(cudaEventRecord(h->comm_done[i], h->comm_stream));
+    if (ticket) *ticket = i;
+    return CSM_OK;
+}
+
+int csm_comm_allreduce_best(csm_handle h, int* ticket)
+{
+    if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
+    return comm_enqueue(h, ticket);
+}
+
+int csm_comm_allreduce_word(csm_handle h, uint64_t word, int* ticket)
+{
+    if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
+    return comm_enqueue(h, ticket, &word);
+}
+
+int csm_comm_allreduce_words_all(csm_handle* handles, int n, const uint64_t* words, int* tickets)
+{
+    if (!handles || n < 1 || !words || !nccl::api().ok) return CSM_E_INVALID;
+    int rc = nccl::api().GroupStart();
+    if (rc != 0) return comm_fail(handles[0], "ncclGroupStart", rc);
+    int first = CSM_OK;
+    for (int i = 0; i < n; ++i) {
+        if (cudaSetDevice(handles[i]->device) != cudaSuccess) { first = CSM_E_CUDA; break; }
+        const int erc = comm_enqueue(handles[i], tickets ? tickets + i : nullptr, words + i);
+        if (erc && first == CSM_OK) first = erc;
+    }
+    rc = nccl::api().GroupEnd();
+    if (rc != 0 && first == CSM_OK) first = comm_fail(handles[0], "ncclGroupEnd", rc);
+    return first;
+}
+
+int csm_comm_allreduce_best_all(csm_handle* handles, int n, int* tickets)
+{
+    if (!handles || n < 1 || !nccl::api().ok) return CSM_E_INVALID;
+    int rc = nccl::api().GroupStart();
+    if (rc != 0) return comm_fail(handles[0], "ncclGroupStart", rc);
+    int first = CSM_OK;
+    for (int i = 0; i < n; ++i) {
+        if (cudaSetDevice(handles[i]->device) != cudaSuccess) { first = CSM_E_CUDA; break; }
+        const int erc = comm_enqueue(handles[i], tickets ? tickets + i : nullptr);
+        if (erc && first == CSM_OK) first = erc;
+    }
+    rc = nccl::api().GroupEnd();
+    if (rc != 0 && first == CSM_OK) first = comm_fail(handles[0], "ncclGroupEnd", rc);
+    return first;
+}
+
+int csm_comm_best_result(csm_handle h, int ticket, uint64_t* word)
+{
+    if (!h || !word || ticket < 0 || ticket >= csm_context::kCommRing || !h->comm) return CSM_E_INVALID;
+    CSM_CUDA(cudaEventSynchronize(h->comm_done[ticket]));
+    *word = h->h_words[ticket];
+    return CSM_OK;
+}
+
+int csm_comm_destroy(csm_handle h)
+{
+    if (!h) return CSM_E_INVALID;
+    if (!h->comm) return CSM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->comm_stream);
+    nccl::api().CommDestroy(h->comm);
+    h->comm = nullptr;
+    for (int i = 0; i < csm_context::kCommRing; ++i) {
+        if (h->comm_ready[i]) cudaEventDestroy(h->comm_ready[i]);
+        if (h->comm_done[i]) cudaEventDestroy(h->comm_done[i]);
+        h->comm_ready[i] = h->comm_done[i] = nullptr;
+    }
+    if (h->d_words) cudaFree(h->d_words);
+    if (h->h_words) cudaFreeHost(h->h_words);
+    h->d_words = nullptr; h->h_words = nullptr;
+    cudaStreamDestroy(h->comm_stream);
+    h->comm_stream = nullptr;
+    return CSM_OK;
+}
+
+int csm_detect_step_enqueue(csm_handle h, const int64_t* map_ids, int n_maps, int drop,
+                            const csm_loop_query* queries, int nq, int hmax, int query_index_base, int* ticket)
+{
+    if (!h) return CSM_E_INVALID;
+    int rc;
+    if (n_maps > 0) {
+        if (drop && (rc = csm_drop_pyramids(h, n_maps, map_ids))) return rc;
+        if ((rc = csm_build_pyramids(h, n_maps, map_ids, hmax))) return rc;
+    }
+    if ((rc = csm_loop_batch_enqueue(h, queries, nq, hmax, query_index_base))) return rc;
+    if (h->comm && h->comm_world > 1)
+        return comm_enqueue(h, ticket);
+    if (ticket) *ticket = -1;
+    return CSM_OK;
 }
 
 int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out)

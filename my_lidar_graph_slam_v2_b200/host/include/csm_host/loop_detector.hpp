@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <functional>
 #include <set>
+#include <unordered_map>
 
 #include "csm_host/scan_matchers.hpp"
 
@@ -91,12 +92,13 @@ public:
      * index)) of the best found query, 0 if none -- what csm_best_key_device holds for one handle */
     std::uint64_t BestWord() const { return mBestWord; }
     /* Forget which maps are resident (the next Detect uploads them again) */
-    void ClearCache()
-    {
-        mCachedMaps.clear(); mCachedScans.clear();
-        for (auto& m : mLaneMaps) m.clear();
-        for (auto& m : mLaneScans) m.clear();
-    }
+    void ClearCache() { mMapLane.clear(); }
+    /* Threads that gather heap-allocated blocks (GridMapView::block_ptrs) into page-locked staging
+     * (default: min(8, hardware threads)) */
+    void SetGatherThreads(int n);
+    /* Batches that overflowed the device's frontier lists and were searched again in smaller
+     * batches (CSM_E_CAPACITY is recoverable), over the detector's life */
+    int NumOfCapacityRetries() const { return mCapacityRetries; }
     /* Sharded use: global index of queries[0] (packed best word) */
     void SetQueryIndexBase(int base) { mQueryIndexBase = base; }
     /* Per-query device results of the last Detect, in query order */
@@ -106,12 +108,14 @@ private:
     std::shared_ptr<ScanMatcherBranchBound> mScanMatcher;
     FinalMatcher mFinalMatcher;
     double mScoreThreshold, mKnownRateThreshold;
-    std::set<std::int64_t> mCachedMaps;
-    std::set<std::int64_t> mCachedScans;
+    std::unordered_map<std::int64_t, int> mMapLane;     /* resident maps -> the lane that holds them */
     std::vector<csm_result> mLastResults;
     std::vector<csm_refined> mLastRefined;
     std::vector<DeviceContextPtr> mExtraLanes;
-    std::vector<std::set<std::int64_t>> mLaneMaps, mLaneScans;     /* residency per lane (pipelined path) */
+    std::shared_ptr<class BlockGatherer> mGatherer;
+    int mGatherThreads = 0;
+    int mArrivals = 0;          /* first-touch batches seen so far: they take the lanes in turn */
+    int mCapacityRetries = 0;
     std::uint64_t mBestWord = 0;
     bool mDeviceRefiner = false;
     csm_refine_params mRefineParams {};
@@ -119,6 +123,37 @@ private:
     int mChunkSize = 128;
     int mUploadChunk = 64;
     bool mCoarseCovariance = true;
+};
+
+/* The same detector over several GPUs of one box, one process: the model is the reference's
+ * LoopDetectorFPGAParallel (loop_detector_fpga_parallel.cpp:32-68), which splits the queries over its
+ * two accelerator cores and concatenates their results. Queries go to GPU LocalMapId mod G (a map is
+ * uploaded and precomputed once, on the GPU that owns it, whatever batch it comes back in); every shard
+ * is a LoopDetectorBranchBound on its own device context(s), driven by its own host thread; results
+ * come back in query order. The packed best word of the call is exchanged with one 8-byte NCCL
+ * all-reduce(max) over the shards' handles when UseNcclExchange() was called (otherwise it is the
+ * maximum the host takes over the shards' words; the two agree). */
+class LoopDetectorBranchBoundMultiGPU final : public LoopDetector
+{
+public:
+    LoopDetectorBranchBoundMultiGPU(const std::string& name,
+                                    const std::vector<std::shared_ptr<LoopDetectorBranchBound>>& shards,
+                                    const std::vector<DeviceContextPtr>& contexts);
+    std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
+    int NumOfGpus() const { return static_cast<int>(mShards.size()); }
+    /* csm_comm_init_all over the shards' first contexts */
+    void UseNcclExchange();
+    std::uint64_t BestWord() const { return mBestWord; }
+    const std::vector<csm_result>& LastResults() const { return mLastResults; }
+    const std::vector<int>& LastShardSizes() const { return mLastShardSizes; }
+
+private:
+    std::vector<std::shared_ptr<LoopDetectorBranchBound>> mShards;
+    std::vector<DeviceContextPtr> mContexts;
+    std::vector<csm_result> mLastResults;
+    std::vector<int> mLastShardSizes;
+    std::uint64_t mBestWord = 0;
+    bool mNccl = false;
 };
 
 /* loop_detector_correlative.cpp:59-159: per query the coarse map (window = the matcher's low

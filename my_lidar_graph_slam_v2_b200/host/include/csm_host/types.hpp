@@ -91,6 +91,11 @@ struct GridMapView
     const std::int32_t* block_index = nullptr;
     int n_blocks = 0;
     int log2_block_size = 4;
+    /*  - block-sparse, blocks where the reference keeps them (`block_ptrs` non-null): every allocated
+     *    block is its own heap allocation there (grid_map.cpp:522-535), block_ptrs[b] points at block
+     *    block_index[b]. The loop detector gathers them into page-locked staging with several threads,
+     *    group by group, while the previous group crosses PCIe. */
+    const std::uint16_t* const* block_ptrs = nullptr;
 };
 
 /* scan_matcher.hpp:56-83 */

@@ -2,7 +2,9 @@
  * the parity tests (Python, ctypes) can drive the adapter classes exactly the
  * way the reference drives its matchers / detectors. Not part of the C ABI. */
 #include <cstring>
+#include <memory>
 #include <string>
+#include <vector>
 
 #include "csm_host/loop_detector.hpp"
 #include "csm_host/loop_searcher.hpp"
@@ -398,16 +400,48 @@ void csm_host_loopdet_clear_cache(void* det) { static_cast<HostLoopDet*>(det)->d
 
 void* csm_host_loopdet_handle(void* det) { return static_cast<HostLoopDet*>(det)->ctx->Handle(); }
 
-/* Detect over n_queries block-sparse maps (map q owns block_count[q] consecutive
- * blocks) and one shared scan. values == dense alternative when blocks is null. */
-int csm_host_loopdet_detect(void* det, int n_queries, const uint16_t* values,
-                            const uint16_t* blocks, const int32_t* block_index, const int32_t* block_count,
-                            int log2bs, int rows, int cols, double res,
-                            const double* off_x, const double* off_y, const int64_t* map_ids,
-                            const double* map_poses, const double* scan_poses,
-                            const double* angles, const double* ranges, int n, csm_host_summary* out)
+/* The reference's storage of a batch of maps, rebuilt from a contiguous block list: every allocated
+ * block in its own heap allocation (grid_map.cpp:522-535), in the order the blocks were first written
+ * (here: map by map). What the adapter sees when it is handed GridMap objects. */
+struct HeapMaps
 {
-    auto* d = static_cast<HostLoopDet*>(det);
+    std::vector<std::unique_ptr<uint16_t[]>> blocks;
+    std::vector<const uint16_t*> ptrs;
+    std::vector<int32_t> index, counts;
+    std::vector<size_t> first;
+    int log2bs = 4;
+};
+
+void* csm_host_heap_maps_create(const uint16_t* blocks, const int32_t* block_index, const int32_t* block_count,
+                                int n_maps, int log2bs)
+{
+    auto* hm = new HeapMaps;
+    hm->log2bs = log2bs;
+    const size_t cells = static_cast<size_t>(1) << (2 * log2bs);
+    size_t total = 0;
+    for (int m = 0; m < n_maps; ++m) { hm->first.push_back(total); total += static_cast<size_t>(block_count[m]); }
+    hm->counts.assign(block_count, block_count + n_maps);
+    hm->index.assign(block_index, block_index + total);
+    hm->blocks.reserve(total);
+    hm->ptrs.reserve(total);
+    for (size_t b = 0; b < total; ++b) {
+        hm->blocks.emplace_back(new uint16_t[cells]);
+        std::memcpy(hm->blocks.back().get(), blocks + b * cells, cells * sizeof(uint16_t));
+        hm->ptrs.push_back(hm->blocks.back().get());
+    }
+    return hm;
+}
+
+void csm_host_heap_maps_destroy(void* p) { delete static_cast<HeapMaps*>(p); }
+
+/* n_queries queries, query q on map q (dense `values`, contiguous block-sparse `blocks`, or heap blocks)
+ * and one shared scan */
+static std::vector<LoopDetectionQuery> BuildQueries(
+    int n_queries, const uint16_t* values, const uint16_t* blocks, const int32_t* block_index,
+    const int32_t* block_count, const HeapMaps* heap, int log2bs, int rows, int cols, double res,
+    const double* off_x, const double* off_y, const int64_t* map_ids, const double* map_poses,
+    const double* scan_poses, const double* angles, const double* ranges, int n)
+{
     const double rel[3] = { 0.0, 0.0, 0.0 };
     const ScanDataPtr scan = Scan(angles, ranges, n, rel);
     std::vector<LoopDetectionQuery> queries(n_queries);
@@ -420,7 +454,12 @@ int csm_host_loopdet_detect(void* det, int n_queries, const uint16_t* values,
         lq.scan_node_id = q;
         lq.scan_global_pose = Pose2D { scan_poses[3 * q], scan_poses[3 * q + 1], scan_poses[3 * q + 2] };
         lq.local_map = View(values ? values + q * cells : nullptr, rows, cols, res, off_x[q], off_y[q], map_ids[q]);
-        if (blocks != nullptr) {
+        if (heap != nullptr) {
+            lq.local_map.block_ptrs = heap->ptrs.data() + heap->first[q];
+            lq.local_map.block_index = heap->index.data() + heap->first[q];
+            lq.local_map.n_blocks = heap->counts[q];
+            lq.local_map.log2_block_size = heap->log2bs;
+        } else if (blocks != nullptr) {
             lq.local_map.blocks = blocks + (nblk << (2 * log2bs));
             lq.local_map.block_index = block_index + nblk;
             lq.local_map.n_blocks = block_count[q];
@@ -429,12 +468,17 @@ int csm_host_loopdet_detect(void* det, int n_queries, const uint16_t* values,
         }
         lq.local_map_global_pose = Pose2D { map_poses[3 * q], map_poses[3 * q + 1], map_poses[3 * q + 2] };
     }
-    const std::vector<LoopDetectionResult> results = d->det->Detect(queries);
+    return queries;
+}
+
+static int ExportResults(const std::vector<LoopDetectionResult>& results, const std::vector<csm_result>& last,
+                         int n_queries, csm_host_summary* out)
+{
     for (int q = 0; q < n_queries; ++q)
         std::memset(&out[q], 0, sizeof(csm_host_summary));
     for (const LoopDetectionResult& r : results) {
         csm_host_summary& o = out[r.scan_node_id];
-        const csm_result& dr = d->det->LastResults()[r.query_index];
+        const csm_result& dr = last[r.query_index];
         o.found = 1;
         o.best_x = dr.best_x; o.best_y = dr.best_y; o.best_t = dr.best_t;
         o.sum_value = dr.sum_value; o.n_known = dr.n_known; o.flags = dr.flags;
@@ -443,6 +487,107 @@ int csm_host_loopdet_detect(void* det, int n_queries, const uint16_t* values,
         std::memcpy(o.cov, r.estimated_covariance.data(), sizeof(double) * 9);
     }
     return static_cast<int>(results.size());
+}
+
+/* Detect over n_queries block-sparse maps (map q owns block_count[q] consecutive
+ * blocks) and one shared scan. values == dense alternative when blocks is null. */
+int csm_host_loopdet_detect(void* det, int n_queries, const uint16_t* values,
+                            const uint16_t* blocks, const int32_t* block_index, const int32_t* block_count,
+                            int log2bs, int rows, int cols, double res,
+                            const double* off_x, const double* off_y, const int64_t* map_ids,
+                            const double* map_poses, const double* scan_poses,
+                            const double* angles, const double* ranges, int n, csm_host_summary* out)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    const std::vector<LoopDetectionQuery> queries = BuildQueries(
+        n_queries, values, blocks, block_index, block_count, nullptr, log2bs, rows, cols, res, off_x, off_y,
+        map_ids, map_poses, scan_poses, angles, ranges, n);
+    return ExportResults(d->det->Detect(queries), d->det->LastResults(), n_queries, out);
+}
+
+/* The same from maps whose blocks are separate heap allocations (csm_host_heap_maps_create) */
+int csm_host_loopdet_detect_heap(void* det, int n_queries, const void* heap_maps, int rows, int cols, double res,
+                                 const double* off_x, const double* off_y, const int64_t* map_ids,
+                                 const double* map_poses, const double* scan_poses,
+                                 const double* angles, const double* ranges, int n, csm_host_summary* out)
+{
+    auto* d = static_cast<HostLoopDet*>(det);
+    const std::vector<LoopDetectionQuery> queries = BuildQueries(
+        n_queries, nullptr, nullptr, nullptr, nullptr, static_cast<const HeapMaps*>(heap_maps), 4, rows, cols, res,
+        off_x, off_y, map_ids, map_poses, scan_poses, angles, ranges, n);
+    return ExportResults(d->det->Detect(queries), d->det->LastResults(), n_queries, out);
+}
+
+void csm_host_loopdet_set_gather_threads(void* det, int n) { static_cast<HostLoopDet*>(det)->det->SetGatherThreads(n); }
+int csm_host_loopdet_capacity_retries(void* det) { return static_cast<HostLoopDet*>(det)->det->NumOfCapacityRetries(); }
+
+/* ---- the detector over several GPUs of one process ----------------------------------------- */
+struct HostMultiDet
+{
+    std::vector<DeviceContextPtr> ctx;
+    std::vector<std::shared_ptr<ScanMatcherBranchBound>> matcher;
+    std::vector<std::shared_ptr<LoopDetectorBranchBound>> shard;
+    std::unique_ptr<LoopDetectorBranchBoundMultiGPU> det;
+};
+
+void* csm_host_multidet_create(int n_gpus, int hmax, const double range[3], double score_thr, double known_thr,
+                               double covariance_scale, int lanes, int refine_iterations,
+                               double convergence_threshold, double initial_lambda)
+{
+    auto* d = new HostMultiDet;
+    for (int g = 0; g < n_gpus; ++g) {
+        d->ctx.push_back(std::make_shared<DeviceContext>(g));
+        const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+        d->matcher.push_back(std::make_shared<ScanMatcherBranchBound>("LoopBBGPU", cost, hmax, range[0], range[1],
+                                                                      range[2], d->ctx[g]));
+        auto shard = std::make_shared<LoopDetectorBranchBound>("LoopDetectorBranchBoundGPU", d->matcher[g],
+                                                               FinalMatcher(), score_thr, known_thr);
+        shard->SetCoarseCovariance(false);
+        if (refine_iterations > 0)
+            shard->UseDeviceRefiner(refine_iterations, convergence_threshold, initial_lambda, covariance_scale);
+        std::vector<DeviceContextPtr> extra;
+        for (int l = 1; l < lanes; ++l)
+            extra.push_back(std::make_shared<DeviceContext>(g));
+        if (!extra.empty())
+            shard->SetPipelineLanes(extra);
+        d->shard.push_back(shard);
+    }
+    d->det.reset(new LoopDetectorBranchBoundMultiGPU("LoopDetectorBranchBoundMultiGPU", d->shard, d->ctx));
+    return d;
+}
+
+void csm_host_multidet_destroy(void* det) { delete static_cast<HostMultiDet*>(det); }
+void csm_host_multidet_use_nccl(void* det) { static_cast<HostMultiDet*>(det)->det->UseNcclExchange(); }
+void csm_host_multidet_clear_cache(void* det)
+{
+    for (auto& s : static_cast<HostMultiDet*>(det)->shard) s->ClearCache();
+}
+void csm_host_multidet_configure(void* det, int chunk_size, int upload_chunk, int gather_threads)
+{
+    for (auto& s : static_cast<HostMultiDet*>(det)->shard) {
+        s->SetChunkSize(chunk_size);
+        s->SetUploadChunk(upload_chunk);
+        if (gather_threads > 0) s->SetGatherThreads(gather_threads);
+    }
+}
+unsigned long long csm_host_multidet_best_word(void* det) { return static_cast<HostMultiDet*>(det)->det->BestWord(); }
+void csm_host_multidet_shard_sizes(void* det, int* out)
+{
+    const std::vector<int>& s = static_cast<HostMultiDet*>(det)->det->LastShardSizes();
+    for (size_t g = 0; g < s.size(); ++g) out[g] = s[g];
+}
+
+int csm_host_multidet_detect(void* det, int n_queries, const uint16_t* blocks, const int32_t* block_index,
+                             const int32_t* block_count, const void* heap_maps, int log2bs, int rows, int cols,
+                             double res, const double* off_x, const double* off_y, const int64_t* map_ids,
+                             const double* map_poses, const double* scan_poses,
+                             const double* angles, const double* ranges, int n, csm_host_summary* out)
+{
+    auto* d = static_cast<HostMultiDet*>(det);
+    const std::vector<LoopDetectionQuery> queries = BuildQueries(
+        n_queries, nullptr, blocks, block_index, block_count, static_cast<const HeapMaps*>(heap_maps), log2bs,
+        rows, cols, res, off_x, off_y, map_ids, map_poses, scan_poses, angles, ranges, n);
+    return ExportResults(d->det->Detect(queries), d->det->LastResults(), n_queries, out);
 }
 
 } /* extern "C" */

@@ -1,10 +1,15 @@
 #include "csm_host/loop_detector.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <mutex>
+#include <thread>
 
 namespace csm_host {
 
@@ -115,17 +120,142 @@ std::vector<LoopDetectionResult> LoopDetectorGridSearch::Detect(const std::vecto
                           [this](const char* m, double v) { Observe(m, v); });
 }
 
+/* Gathers blocks that live in separate heap allocations (the reference's GridMap storage,
+ * grid_map.cpp:522-535) into page-locked staging, with a small pool of threads: one staging area per
+ * upload group of a Detect (a group's H2D copy reads its area while the next group is gathered),
+ * reused by the following Detect calls (every call ends with all its copies complete). */
+class BlockGatherer
+{
+public:
+    explicit BlockGatherer(int n_threads)
+    {
+        for (int i = 1; i < n_threads; ++i)
+            mWorkers.emplace_back([this] { Work(); });
+    }
+    ~BlockGatherer()
+    {
+        {
+            std::lock_guard<std::mutex> lock(mMutex);
+            mStop = true;
+            ++mGeneration;
+        }
+        mWake.notify_all();
+        for (std::thread& t : mWorkers) t.join();
+        for (void* p : mAreas) csm_free_pinned(p);
+    }
+    void* Area(std::size_t k, std::size_t bytes)
+    {
+        if (mAreas.size() <= k) { mAreas.resize(k + 1, nullptr); mAreaBytes.resize(k + 1, 0); }
+        if (mAreaBytes[k] < bytes) {
+            if (mAreas[k]) csm_free_pinned(mAreas[k]);
+            mAreas[k] = csm_alloc_pinned(bytes + bytes / 4);
+            mAreaBytes[k] = mAreas[k] ? bytes + bytes / 4 : 0;
+            if (!mAreas[k]) { std::fprintf(stderr, "csm_host: out of page-locked memory\n"); std::abort(); }
+        }
+        return mAreas[k];
+    }
+    /* dst[b] <- src[b] (bytes each) for b in [0, n) */
+    void Gather(const std::uint16_t* const* src, std::uint16_t* dst, std::size_t n, std::size_t bytes)
+    {
+        mSrc = src; mDst = reinterpret_cast<char*>(dst); mBytes = bytes; mCount = n;
+        mNext.store(0);
+        mBusy.store(static_cast<int>(mWorkers.size()));
+        {
+            std::lock_guard<std::mutex> lock(mMutex);
+            ++mGeneration;
+        }
+        mWake.notify_all();
+        Chunks();
+        while (mBusy.load(std::memory_order_acquire) != 0)
+            std::this_thread::yield();
+    }
+
+private:
+    void Chunks()
+    {
+        constexpr std::size_t kChunk = 64;
+        for (;;) {
+            const std::size_t b0 = mNext.fetch_add(kChunk);
+            if (b0 >= mCount) break;
+            const std::size_t b1 = std::min(mCount, b0 + kChunk);
+            for (std::size_t b = b0; b < b1; ++b)
+                std::memcpy(mDst + b * mBytes, mSrc[b], mBytes);
+        }
+    }
+    void Work()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(mMutex);
+                mWake.wait(lock, [&] { return mGeneration != seen; });
+                seen = mGeneration;
+                if (mStop) return;
+            }
+            Chunks();
+            mBusy.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> mWorkers;
+    std::mutex mMutex;
+    std::condition_variable mWake;
+    unsigned long long mGeneration = 0;
+    bool mStop = false;
+    std::atomic<std::size_t> mNext { 0 };
+    std::atomic<int> mBusy { 0 };
+    const std::uint16_t* const* mSrc = nullptr;
+    char* mDst = nullptr;
+    std::size_t mBytes = 0, mCount = 0;
+    std::vector<void*> mAreas;
+    std::vector<std::size_t> mAreaBytes;
+};
+
 namespace {
 
-/* Upload the first-touch maps of one chunk. Block-sparse views whose block
+/* Upload the first-touch maps of one upload group. Block-sparse views whose block
  * buffers follow one another in memory (a pinned staging area filled map by
- * map) go in one batched call = one PCIe copy; anything else map by map. */
-void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapView*>& maps)
+ * map) go in one batched call = one PCIe copy; views whose blocks are separate heap allocations
+ * are gathered into staging area `area` first; anything else map by map. */
+void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapView*>& maps,
+                   BlockGatherer* gatherer, std::size_t area)
 {
     if (maps.empty())
         return;
     csm_handle h = ctx->Handle();
     const GridMapView& m0 = *maps[0];
+    bool heap = m0.block_ptrs != nullptr && gatherer != nullptr;
+    for (std::size_t i = 0; i < maps.size() && heap; ++i) {
+        const GridMapView& m = *maps[i];
+        heap = m.block_ptrs != nullptr && m.rows == m0.rows && m.cols == m0.cols &&
+               m.log2_block_size == m0.log2_block_size && m.resolution == m0.resolution;
+    }
+    if (heap) {
+        std::size_t total = 0;
+        for (const GridMapView* m : maps) total += static_cast<std::size_t>(m->n_blocks);
+        const std::size_t block_bytes = sizeof(std::uint16_t) << (2 * m0.log2_block_size);
+        const std::size_t index_off = (total * block_bytes + 255) & ~static_cast<std::size_t>(255);
+        char* stage = static_cast<char*>(gatherer->Area(area, index_off + total * sizeof(std::int32_t) + 256));
+        std::vector<const std::uint16_t*> src(total);
+        std::int32_t* index = reinterpret_cast<std::int32_t*>(stage + index_off);
+        std::vector<std::int64_t> ids(maps.size());
+        std::vector<std::int32_t> counts(maps.size());
+        std::vector<double> ox(maps.size()), oy(maps.size());
+        std::size_t b = 0;
+        for (std::size_t i = 0; i < maps.size(); ++i) {
+            const GridMapView& m = *maps[i];
+            std::copy(m.block_ptrs, m.block_ptrs + m.n_blocks, src.begin() + b);
+            std::copy(m.block_index, m.block_index + m.n_blocks, index + b);
+            b += static_cast<std::size_t>(m.n_blocks);
+            ids[i] = m.map_id; counts[i] = m.n_blocks; ox[i] = m.offset_x; oy[i] = m.offset_y;
+        }
+        gatherer->Gather(src.data(), reinterpret_cast<std::uint16_t*>(stage), total, block_bytes);
+        ctx->Check(csm_upload_grids_blocks(h, static_cast<int>(maps.size()), ids.data(),
+                                           reinterpret_cast<const std::uint16_t*>(stage), index, counts.data(),
+                                           m0.log2_block_size, m0.rows >> m0.log2_block_size,
+                                           m0.cols >> m0.log2_block_size, m0.resolution, ox.data(), oy.data()),
+                   "csm_upload_grids_blocks");
+        return;
+    }
     bool batch = m0.blocks != nullptr && maps.size() > 1;
     std::size_t nblk = 0;
     for (std::size_t i = 0; i < maps.size() && batch; ++i) {
@@ -150,10 +280,10 @@ void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapV
                                            m0.resolution, ox.data(), oy.data()), "csm_upload_grids_blocks");
         return;
     }
-    bool dense_batch = m0.blocks == nullptr && maps.size() > 1;
+    bool dense_batch = m0.values != nullptr && m0.blocks == nullptr && maps.size() > 1;
     for (std::size_t i = 0; i < maps.size() && dense_batch; ++i)
-        dense_batch = maps[i]->blocks == nullptr && maps[i]->rows == m0.rows && maps[i]->cols == m0.cols &&
-                      maps[i]->resolution == m0.resolution;
+        dense_batch = maps[i]->values != nullptr && maps[i]->blocks == nullptr && maps[i]->rows == m0.rows &&
+                      maps[i]->cols == m0.cols && maps[i]->resolution == m0.resolution;
     if (dense_batch) {
         /* one call: a single copy when the grids follow one another in host memory */
         std::vector<std::int64_t> ids(maps.size());
@@ -168,7 +298,18 @@ void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapV
         return;
     }
     for (const GridMapView* m : maps) {
-        if (m->blocks != nullptr)
+        if (m->block_ptrs != nullptr) {
+            /* a lone heap-allocated map: flatten its blocks into a temporary */
+            const std::size_t cells = static_cast<std::size_t>(1) << (2 * m->log2_block_size);
+            std::vector<std::uint16_t> tmp(cells * static_cast<std::size_t>(m->n_blocks));
+            for (int b = 0; b < m->n_blocks; ++b)
+                std::memcpy(tmp.data() + cells * b, m->block_ptrs[b], cells * sizeof(std::uint16_t));
+            ctx->Check(csm_upload_grid_blocks(h, m->map_id, tmp.data(), m->block_index, m->n_blocks,
+                                              m->log2_block_size, m->rows >> m->log2_block_size,
+                                              m->cols >> m->log2_block_size, m->resolution,
+                                              m->offset_x, m->offset_y), "csm_upload_grid_blocks");
+            ctx->Check(csm_synchronize(h), "csm_synchronize");      /* tmp goes away */
+        } else if (m->blocks != nullptr)
             ctx->Check(csm_upload_grid_blocks(h, m->map_id, m->blocks, m->block_index, m->n_blocks,
                                               m->log2_block_size, m->rows >> m->log2_block_size,
                                               m->cols >> m->log2_block_size, m->resolution,
@@ -178,6 +319,9 @@ void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapV
                                        m->offset_x, m->offset_y), "csm_upload_grid");
     }
 }
+
+/* scans travel with the Detect call that uses them: call-local ids, released when the call ends */
+constexpr std::int64_t kCallScanIdBase = static_cast<std::int64_t>(1) << 60;
 
 } /* namespace */
 
@@ -200,10 +344,13 @@ void LoopDetectorBranchBound::SetPipelineLanes(const std::vector<DeviceContextPt
      * maps land (and its search starts) while the later groups are still crossing PCIe */
     for (const DeviceContextPtr& c : mExtraLanes)
         c->Check(csm_share_copy_stream(c->Handle(), mScanMatcher->Context()->Handle()), "csm_share_copy_stream");
-    mLaneMaps.assign(1 + extra_lanes.size(), std::set<std::int64_t>());
-    mLaneScans.assign(1 + extra_lanes.size(), std::set<std::int64_t>());
-    mCachedMaps.clear();
-    mCachedScans.clear();
+    mMapLane.clear();
+}
+
+void LoopDetectorBranchBound::SetGatherThreads(int n)
+{
+    mGatherThreads = std::max(1, n);
+    mGatherer.reset();
 }
 
 std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
@@ -219,23 +366,42 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     const DeviceContextPtr& ctx = mScanMatcher->Context();
     const int hmax = mScanMatcher->NodeHeightMax();
     const int nq = static_cast<int>(queries.size());
+    const int lanes = NumOfLanes();
+    auto lane_ctx = [&](int l) -> const DeviceContextPtr& { return l == 0 ? ctx : mExtraLanes[l - 1]; };
 
-    /* per query: initial pose InverseCompound(map, scan) (:97-98), sensor pose,
-     * steps and windows with the reference's expressions */
     std::vector<csm_loop_query> dq(nq);
-    for (int i = 0; i < nq; ++i)
+    bool any_heap = false;
+    for (int i = 0; i < nq; ++i) {
         if (queries[i].local_map.map_id < 0) {
             std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
             std::abort();
         }
-    /* (evaluated after the uploads have been enqueued: the copies start before the host does this) */
+        any_heap = any_heap || queries[i].local_map.block_ptrs != nullptr;
+    }
+    if (any_heap && !mGatherer) {
+        const int hw = static_cast<int>(std::thread::hardware_concurrency());
+        mGatherer = std::make_shared<BlockGatherer>(mGatherThreads > 0 ? mGatherThreads : std::max(1, std::min(8, hw)));
+    }
+    /* the scans of this call: every distinct ScanData object gets a call-local id (the reference keeps
+     * no per-scan state; LoopDetectionQuery::scan_id is not trusted to be unique across calls) */
+    std::vector<const ScanData*> scans;
+    std::vector<int> scan_of(nq);
+    for (int i = 0; i < nq; ++i) {
+        const ScanData* s = queries[i].scan.get();
+        auto it = std::find(scans.begin(), scans.end(), s);
+        scan_of[i] = static_cast<int>(it - scans.begin());
+        if (it == scans.end()) scans.push_back(s);
+    }
+    /* per query: initial pose InverseCompound(map, scan) (:97-98), sensor pose, steps and windows with
+     * the reference's expressions (evaluated after the uploads have been enqueued: the copies start
+     * before the host does this) */
     auto fill_queries = [&]() {
-        std::map<std::pair<std::int64_t, double>, std::array<double, 3>> steps;
+        std::map<std::pair<int, double>, std::array<double, 3>> steps;
         for (int i = 0; i < nq; ++i) {
             const LoopDetectionQuery& q = queries[i];
             const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
             const Pose2D sensor = Compound(init, q.scan->relative_sensor_pose);
-            auto key = std::make_pair(q.scan_id, q.local_map.resolution);
+            auto key = std::make_pair(scan_of[i], q.local_map.resolution);
             auto it = steps.find(key);
             if (it == steps.end()) {
                 std::array<double, 3> st;
@@ -245,7 +411,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             const std::array<double, 3>& st = it->second;
             csm_loop_query& d = dq[i];
             d.map_id = q.local_map.map_id;
-            d.scan_id = q.scan_id;
+            d.scan_id = kCallScanIdBase + scan_of[i];
             d.sensor_pose[0] = sensor.x; d.sensor_pose[1] = sensor.y; d.sensor_pose[2] = sensor.theta;
             d.win_x = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeX() / st[0]));
             d.win_y = static_cast<int>(std::ceil(0.5 * mScanMatcher->RangeY() / st[1]));
@@ -259,146 +425,124 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     mLastResults.resize(nq);
     if (mDeviceRefiner)
         mLastRefined.resize(nq);
-    /* read back the oldest batch in flight on a context */
-    auto finish = [&](const DeviceContextPtr& c, int f0, int fc) {
-        if (mDeviceRefiner)
-            c->Check(csm_loop_batch_finish_refined(c->Handle(), mLastResults.data() + f0,
-                                                   mLastRefined.data() + f0, fc), "csm_loop_batch_finish_refined");
-        else
-            c->Check(csm_loop_batch_finish(c->Handle(), mLastResults.data() + f0, fc), "csm_loop_batch_finish");
-    };
-    auto set_refiner = [&](const DeviceContextPtr& c) {
-        c->Check(csm_set_refiner(c->Handle(), mDeviceRefiner ? &mRefineParams : nullptr), "csm_set_refiner");
+    /* read back the oldest batch in flight on a context; CSM_E_CAPACITY comes back to the caller */
+    auto finish = [&](const DeviceContextPtr& c, int f0, int fc) -> int {
+        const int rc = mDeviceRefiner
+            ? csm_loop_batch_finish_refined(c->Handle(), mLastResults.data() + f0, mLastRefined.data() + f0, fc)
+            : csm_loop_batch_finish(c->Handle(), mLastResults.data() + f0, fc);
+        if (rc != CSM_OK && rc != CSM_E_CAPACITY)
+            c->Check(rc, "csm_loop_batch_finish");
+        return rc;
     };
 
-    if (!mExtraLanes.empty()) {
-        /* ---- pipelined over lanes: one search batch per upload group, on the lane of its maps ---- */
-        const int lanes = NumOfLanes();
-        const int chunk = std::max(1, mChunkSize);
-        const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
-        auto lane_ctx = [&](int l) -> const DeviceContextPtr& { return l == 0 ? ctx : mExtraLanes[l - 1]; };
-        /* a segment = one search batch of up to mChunkSize consecutive queries whose maps belong to
-         * one lane; its first-touch maps go up in groups of mUploadChunk */
-        struct Segment { int first, count, lane; };
-        std::vector<Segment> segments;
-        for (int i = 0; i < nq; ++i) {
-            const std::int64_t id = queries[i].local_map.map_id;
-            const int lane = static_cast<int>((id / chunk) % lanes);
-            if (segments.empty() || segments.back().lane != lane || segments.back().count >= chunk)
-                segments.push_back(Segment { i, 0, lane });
-            ++segments.back().count;
-        }
-        std::vector<std::vector<int>> in_flight(lanes);       /* segment indices, oldest first */
-        auto finish_oldest = [&](int lane) {
-            const Segment& sg = segments[in_flight[lane].front()];
-            finish(lane_ctx(lane), sg.first, sg.count);
-            in_flight[lane].erase(in_flight[lane].begin());
-        };
-        /* pass 1: every upload is enqueued first, so that PCIe never waits for the host to prepare a
-         * search batch; pass 2: pyramids and the search batch of every segment behind its own uploads */
-        std::vector<std::vector<std::vector<std::int64_t>>> fresh_ids(segments.size());   /* per upload group */
-        for (std::size_t si = 0; si < segments.size(); ++si) {
-            const Segment& sg = segments[si];
-            const DeviceContextPtr& c = lane_ctx(sg.lane);
-            for (int first = sg.first; first < sg.first + sg.count; first += ugroup) {
-                const int last = std::min(sg.first + sg.count, first + ugroup);
-                std::vector<const GridMapView*> fresh;
-                fresh_ids[si].emplace_back();
-                for (int i = first; i < last; ++i) {
-                    const GridMapView& m = queries[i].local_map;
-                    if (mLaneMaps[sg.lane].insert(m.map_id).second) {
-                        fresh.push_back(&m);
-                        fresh_ids[si].back().push_back(m.map_id);
-                    }
-                }
-                UploadNewMaps(c, fresh);
-            }
-        }
-        fill_queries();
-        const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
-        if (trace) std::fprintf(stderr, "lanes: uploads enqueued at %.0f us\n", timer.ElapsedMicro());
-        for (std::size_t si = 0; si < segments.size(); ++si) {
-            const Segment& sg = segments[si];
-            const DeviceContextPtr& c = lane_ctx(sg.lane);
-            for (int i = sg.first; i < sg.first + sg.count; ++i) {
-                const LoopDetectionQuery& q = queries[i];
-                if (mLaneScans[sg.lane].insert(q.scan_id).second)
-                    c->Check(csm_upload_scan(c->Handle(), q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
-                                             static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
-            }
-            for (const std::vector<std::int64_t>& group : fresh_ids[si])
-                if (!group.empty())
-                    c->Check(csm_build_pyramids(c->Handle(), static_cast<int>(group.size()), group.data(), hmax),
-                             "csm_build_pyramids");
-            set_refiner(c);
-            if (in_flight[sg.lane].size() >= 4)         /* the library keeps at most 4 batches in flight */
-                finish_oldest(sg.lane);
-            c->Check(csm_loop_batch_enqueue(c->Handle(), dq.data() + sg.first, sg.count, hmax,
-                                            mQueryIndexBase + sg.first), "csm_loop_batch_enqueue");
-            in_flight[sg.lane].push_back(static_cast<int>(si));
-            if (trace) std::fprintf(stderr, "lanes: segment %zu enqueued at %.0f us\n", si, timer.ElapsedMicro());
-        }
-        for (int lane = 0; lane < lanes; ++lane)
-            while (!in_flight[lane].empty()) {
-                finish_oldest(lane);
-                if (trace) std::fprintf(stderr, "lanes: lane %d finished a batch at %.0f us\n", lane, timer.ElapsedMicro());
-            }
-    } else {
-    csm_handle h = ctx->Handle();
+    /* A segment = one search batch: up to mChunkSize consecutive queries on one lane. A map that is
+     * resident stays on its lane; first-touch maps take the lanes in turn, batch by batch, in the
+     * order they arrive (whatever their ids). Its first-touch maps go up in groups of mUploadChunk. */
     const int chunk = std::max(1, mChunkSize);
-    const int nchunks = (nq + chunk - 1) / chunk;
-
-    /* first touch of a local map: upload + pyramid, cached by LocalMapId
-     * (loop_detector_branch_bound.cpp:83-89). All uploads are enqueued first, in
-     * groups of mUploadChunk maps: they stream over PCIe on the copy stream while
-     * the groups that have landed are expanded and precomputed, and the search
-     * batches (mChunkSize queries) whose maps are complete run behind them. */
     const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
-    std::vector<std::vector<std::int64_t>> new_maps;      /* per upload group */
-    std::vector<int> group_end;                           /* query index one past each group */
-    for (int first = 0; first < nq; first += ugroup) {
-        const int last = std::min(nq, first + ugroup);
-        std::vector<const GridMapView*> fresh;
-        new_maps.emplace_back();
-        for (int i = first; i < last; ++i) {
-            const GridMapView& m = queries[i].local_map;
-            if (mCachedMaps.insert(m.map_id).second) {
-                fresh.push_back(&m);
-                new_maps.back().push_back(m.map_id);
+    struct Segment { int first, count, lane; bool fresh; };
+    std::vector<Segment> segments;
+    for (int i = 0; i < nq; ++i) {
+        const auto res = mMapLane.find(queries[i].local_map.map_id);
+        const bool fresh = res == mMapLane.end();
+        if (!segments.empty() && segments.back().count < chunk &&
+            ((fresh && segments.back().fresh) || (!fresh && segments.back().lane == res->second))) {
+            ++segments.back().count;
+        } else {
+            const int lane = fresh ? (mArrivals++ % lanes) : res->second;
+            segments.push_back(Segment { i, 1, lane, fresh });
+        }
+        if (fresh)
+            mMapLane[queries[i].local_map.map_id] = segments.back().lane;
+    }
+    /* pass 1: every upload is enqueued first, so that PCIe never waits for the host to prepare a
+     * search batch; pass 2: pyramids and the search batch of every segment behind its own uploads */
+    std::vector<std::vector<std::vector<std::int64_t>>> fresh_ids(segments.size());   /* per upload group */
+    std::size_t area = 0;
+    for (std::size_t si = 0; si < segments.size(); ++si) {
+        const Segment& sg = segments[si];
+        if (!sg.fresh)
+            continue;
+        const DeviceContextPtr& c = lane_ctx(sg.lane);
+        std::set<std::int64_t> seen;
+        for (int first = sg.first; first < sg.first + sg.count; first += ugroup) {
+            const int last = std::min(sg.first + sg.count, first + ugroup);
+            std::vector<const GridMapView*> fresh;
+            fresh_ids[si].emplace_back();
+            for (int i = first; i < last; ++i) {
+                const GridMapView& m = queries[i].local_map;
+                if (seen.insert(m.map_id).second) {
+                    fresh.push_back(&m);
+                    fresh_ids[si].back().push_back(m.map_id);
+                }
+            }
+            UploadNewMaps(c, fresh, mGatherer.get(), area++);
+        }
+    }
+    fill_queries();
+    const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
+    if (trace) std::fprintf(stderr, "lanes: uploads enqueued at %.0f us\n", timer.ElapsedMicro());
+    std::vector<std::vector<int>> in_flight(lanes);       /* segment indices, oldest first */
+    std::vector<int> overflowed;                          /* segments to search again in smaller batches */
+    auto finish_oldest = [&](int lane) {
+        const int si = in_flight[lane].front();
+        if (finish(lane_ctx(lane), segments[si].first, segments[si].count) == CSM_E_CAPACITY)
+            overflowed.push_back(si);
+        in_flight[lane].erase(in_flight[lane].begin());
+    };
+    std::vector<std::set<int>> lane_scans(lanes);
+    for (std::size_t si = 0; si < segments.size(); ++si) {
+        const Segment& sg = segments[si];
+        const DeviceContextPtr& c = lane_ctx(sg.lane);
+        for (int i = sg.first; i < sg.first + sg.count; ++i)
+            if (lane_scans[sg.lane].insert(scan_of[i]).second) {
+                const ScanData& s = *scans[scan_of[i]];
+                c->Check(csm_upload_scan(c->Handle(), kCallScanIdBase + scan_of[i], s.angles.data(), s.ranges.data(),
+                                         static_cast<int>(s.NumOfScans())), "csm_upload_scan");
+            }
+        for (const std::vector<std::int64_t>& group : fresh_ids[si])
+            if (!group.empty())
+                c->Check(csm_build_pyramids(c->Handle(), static_cast<int>(group.size()), group.data(), hmax),
+                         "csm_build_pyramids");
+        c->Check(csm_set_refiner(c->Handle(), mDeviceRefiner ? &mRefineParams : nullptr), "csm_set_refiner");
+        if (in_flight[sg.lane].size() >= 4)         /* the library keeps at most 4 batches in flight */
+            finish_oldest(sg.lane);
+        c->Check(csm_loop_batch_enqueue(c->Handle(), dq.data() + sg.first, sg.count, hmax,
+                                        mQueryIndexBase + sg.first), "csm_loop_batch_enqueue");
+        in_flight[sg.lane].push_back(static_cast<int>(si));
+        if (trace) std::fprintf(stderr, "lanes: segment %zu enqueued at %.0f us\n", si, timer.ElapsedMicro());
+    }
+    for (int lane = 0; lane < lanes; ++lane)
+        while (!in_flight[lane].empty()) {
+            finish_oldest(lane);
+            if (trace) std::fprintf(stderr, "lanes: lane %d finished a batch at %.0f us\n", lane, timer.ElapsedMicro());
+        }
+    /* a batch whose frontier lists overflowed (a scan that matches many maps well at the coarse
+     * levels): halve it until it fits; a single query that still overflows dives for an incumbent
+     * first (fewer nodes), and only then is it an error */
+    std::function<void(const DeviceContextPtr&, int, int)> rerun = [&](const DeviceContextPtr& c, int first, int count) {
+        ++mCapacityRetries;
+        if (count == 1)
+            c->Check(csm_set_option(c->Handle(), "bb_dive", 1), "csm_set_option");
+        const int half = count == 1 ? 1 : count / 2;
+        for (int f = first; f < first + count; f += half) {
+            const int n = std::min(half, first + count - f);
+            c->Check(csm_loop_batch_enqueue(c->Handle(), dq.data() + f, n, hmax, mQueryIndexBase + f),
+                     "csm_loop_batch_enqueue");
+            const int rc = finish(c, f, n);
+            if (rc == CSM_E_CAPACITY) {
+                if (count == 1) c->Check(rc, "csm_loop_batch_finish (a single query overflows the frontier lists)");
+                rerun(c, f, n);
             }
         }
-        group_end.push_back(last);
-        UploadNewMaps(ctx, fresh);
-    }
-    for (const LoopDetectionQuery& q : queries)
-        if (mCachedScans.insert(q.scan_id).second)
-            ctx->Check(csm_upload_scan(h, q.scan_id, q.scan->angles.data(), q.scan->ranges.data(),
-                                       static_cast<int>(q.scan->NumOfScans())), "csm_upload_scan");
-    std::size_t next_group = 0;
-    fill_queries();
-    set_refiner(ctx);
-    int finished = 0;      /* chunks whose results have been read back */
-    for (int c = 0; c < nchunks; ++c) {
-        const int first = c * chunk, count = std::min(nq, first + chunk) - first;
-        /* pyramids of every upload group this batch touches (in upload order) */
-        for (; next_group < new_maps.size() &&
-               (next_group == 0 || group_end[next_group - 1] < first + count); ++next_group)
-            if (!new_maps[next_group].empty())
-                ctx->Check(csm_build_pyramids(h, static_cast<int>(new_maps[next_group].size()),
-                                              new_maps[next_group].data(), hmax), "csm_build_pyramids");
-        if (c - finished >= 4) {        /* the library keeps at most 4 batches in flight */
-            const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
-            finish(ctx, f0, fc);
-            ++finished;
-        }
-        ctx->Check(csm_loop_batch_enqueue(h, dq.data() + first, count, hmax, mQueryIndexBase + first),
-                   "csm_loop_batch_enqueue");
-    }
-    for (; finished < nchunks; ++finished) {
-        const int f0 = finished * chunk, fc = std::min(nq, f0 + chunk) - f0;
-        finish(ctx, f0, fc);
-    }
-    }
+        if (count == 1)
+            c->Check(csm_set_option(c->Handle(), "bb_dive", 2), "csm_set_option");
+    };
+    for (int si : overflowed)
+        rerun(lane_ctx(segments[si].lane), segments[si].first, segments[si].count);
+    for (int lane = 0; lane < lanes; ++lane)
+        for (int s : lane_scans[lane])
+            lane_ctx(lane)->Check(csm_release_scan(lane_ctx(lane)->Handle(), kCallScanIdBase + s), "csm_release_scan");
 
     /* packed best word over the whole call (what the device keeps per handle, here over all lanes) */
     for (int i = 0; i < nq; ++i) {
@@ -452,9 +596,93 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             Observe("LoopDetectionTime", micro / static_cast<double>(nq));
         Observe("NumOfQueries", nq);
         Observe("NumOfDetections", static_cast<double>(results.size()));
-        Observe("PrecompMapMemoryUsage", static_cast<double>(mCachedMaps.size()) *
+        Observe("PrecompMapMemoryUsage", static_cast<double>(mMapLane.size()) *
                 static_cast<double>(hmax + 1) * queries[0].local_map.rows * queries[0].local_map.cols * 2.0);
     }
+    return results;
+}
+
+/* ---- several GPUs, one process ------------------------------------------------------------- */
+LoopDetectorBranchBoundMultiGPU::LoopDetectorBranchBoundMultiGPU(
+    const std::string& name, const std::vector<std::shared_ptr<LoopDetectorBranchBound>>& shards,
+    const std::vector<DeviceContextPtr>& contexts) :
+    LoopDetector(name), mShards(shards), mContexts(contexts)
+{
+    if (shards.empty() || shards.size() != contexts.size()) {
+        std::fprintf(stderr, "csm_host: the multi-GPU detector needs one shard and one context per GPU\n");
+        std::abort();
+    }
+}
+
+void LoopDetectorBranchBoundMultiGPU::UseNcclExchange()
+{
+    std::vector<csm_handle> hs;
+    for (const DeviceContextPtr& c : mContexts) hs.push_back(c->Handle());
+    mContexts[0]->Check(csm_comm_init_all(hs.data(), static_cast<int>(hs.size())), "csm_comm_init_all");
+    mNccl = true;
+}
+
+std::vector<LoopDetectionResult> LoopDetectorBranchBoundMultiGPU::Detect(const std::vector<LoopDetectionQuery>& queries)
+{
+    const int G = NumOfGpus();
+    const int nq = static_cast<int>(queries.size());
+    /* shard g takes the queries whose local map it owns: LocalMapId mod G */
+    std::vector<std::vector<LoopDetectionQuery>> part(G);
+    std::vector<std::vector<int>> origin(G);
+    for (int i = 0; i < nq; ++i) {
+        const std::int64_t id = queries[i].local_map.map_id;
+        const int g = static_cast<int>(((id % G) + G) % G);
+        part[g].push_back(queries[i]);
+        origin[g].push_back(i);
+    }
+    mLastShardSizes.assign(G, 0);
+    std::vector<std::vector<LoopDetectionResult>> found(G);
+    std::vector<std::thread> threads;
+    for (int g = 0; g < G; ++g) {
+        mLastShardSizes[g] = static_cast<int>(part[g].size());
+        threads.emplace_back([&, g] { found[g] = mShards[g]->Detect(part[g]); });
+    }
+    for (std::thread& t : threads) t.join();
+    /* results in query order, like the reference's concatenation of its cores' vectors */
+    mLastResults.assign(nq, csm_result {});
+    std::vector<LoopDetectionResult> results;
+    std::vector<std::uint64_t> words(G, 0);
+    for (int g = 0; g < G; ++g) {
+        const std::vector<csm_result>& lr = mShards[g]->LastResults();
+        for (std::size_t k = 0; k < lr.size(); ++k) {
+            const int i = origin[g][k];
+            mLastResults[i] = lr[k];
+            if (lr[k].found) {
+                const std::uint64_t key = static_cast<std::uint64_t>(998ll * lr[k].sum_value + 64536ll * lr[k].n_known);
+                words[g] = std::max(words[g], (key << 20) | static_cast<std::uint64_t>(0xFFFFF - i));
+            }
+        }
+        for (LoopDetectionResult r : found[g]) {
+            r.query_index = origin[g][r.query_index];
+            results.push_back(r);
+        }
+    }
+    std::sort(results.begin(), results.end(),
+              [](const LoopDetectionResult& a, const LoopDetectionResult& b) { return a.query_index < b.query_index; });
+    mBestWord = *std::max_element(words.begin(), words.end());
+    if (mNccl) {
+        /* the same maximum through one 8-byte all-reduce over NVLink: every GPU ends with the best word */
+        std::vector<csm_handle> hs;
+        for (const DeviceContextPtr& c : mContexts) hs.push_back(c->Handle());
+        std::vector<int> tickets(G, -1);
+        mContexts[0]->Check(csm_comm_allreduce_words_all(hs.data(), G, words.data(), tickets.data()),
+                            "csm_comm_allreduce_words_all");
+        for (int g = 0; g < G; ++g) {
+            std::uint64_t w = 0;
+            mContexts[g]->Check(csm_comm_best_result(hs[g], tickets[g], &w), "csm_comm_best_result");
+            if (w != mBestWord) {
+                std::fprintf(stderr, "csm_host: the all-reduced best word differs from the host maximum\n");
+                std::abort();
+            }
+        }
+    }
+    Observe("NumOfQueries", nq);
+    Observe("NumOfDetections", static_cast<double>(results.size()));
     return results;
 }
 

@@ -72,8 +72,50 @@ def load():
                                                 C.c_int, C.c_int, C.c_int, C.c_double, dp, dp,
                                                 C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int,
                                                 C.POINTER(HostSummary)]
+        lib.csm_host_heap_maps_create.restype = C.c_void_p
+        lib.csm_host_heap_maps_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.csm_host_heap_maps_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_loopdet_detect_heap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                                     dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int,
+                                                     C.POINTER(HostSummary)]
+        lib.csm_host_loopdet_set_gather_threads.argtypes = [C.c_void_p, C.c_int]
+        lib.csm_host_loopdet_capacity_retries.argtypes = [C.c_void_p]
+        lib.csm_host_multidet_create.restype = C.c_void_p
+        lib.csm_host_multidet_create.argtypes = [C.c_int, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                 C.c_int, C.c_double, C.c_double]
+        lib.csm_host_multidet_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_multidet_use_nccl.argtypes = [C.c_void_p]
+        lib.csm_host_multidet_clear_cache.argtypes = [C.c_void_p]
+        lib.csm_host_multidet_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.csm_host_multidet_best_word.argtypes = [C.c_void_p]
+        lib.csm_host_multidet_best_word.restype = C.c_uint64
+        lib.csm_host_multidet_shard_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        lib.csm_host_multidet_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_int, C.c_int, C.c_int, C.c_double, dp, dp,
+                                                 C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int,
+                                                 C.POINTER(HostSummary)]
         _lib = lib
     return _lib
+
+
+class HeapMaps:
+    """A batch of maps in the reference's storage: every allocated 16x16 block in its own heap allocation
+    (grid_map.cpp:522-535). Built once from a contiguous block list; the loop detectors gather the blocks
+    into page-locked staging themselves."""
+
+    def __init__(self, blocks, index, counts, log2bs=4):
+        self.lib = load()
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint16)
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        self.n_maps = len(counts)
+        self.p = self.lib.csm_host_heap_maps_create(blocks.ctypes.data, index.ctypes.data, counts.ctypes.data,
+                                                    self.n_maps, log2bs)
+
+    def close(self):
+        if self.p:
+            self.lib.csm_host_heap_maps_destroy(self.p)
+            self.p = None
 
 
 def _d(a):
@@ -329,7 +371,71 @@ class LoopDetector:
             len(angles), out)
         return n, out
 
+    def detect_heap(self, nq, heap_maps, rows, cols, res, off_x, off_y, map_ids, map_poses, scan_poses,
+                    angles, ranges, out=None):
+        """detect() from maps whose blocks are separate heap allocations (HeapMaps): the detector gathers
+        them into page-locked staging with its thread pool, group by group, behind the PCIe copies."""
+        out = out if out is not None else (HostSummary * nq)()
+        dp = C.POINTER(C.c_double)
+        n = self.lib.csm_host_loopdet_detect_heap(
+            self.det, nq, heap_maps.p, rows, cols, res, off_x.ctypes.data_as(dp), off_y.ctypes.data_as(dp),
+            map_ids.ctypes.data_as(C.POINTER(C.c_int64)), map_poses.ctypes.data_as(dp),
+            scan_poses.ctypes.data_as(dp), angles.ctypes.data_as(dp), ranges.ctypes.data_as(dp), len(angles), out)
+        return n, out
+
+    def set_gather_threads(self, n):
+        self.lib.csm_host_loopdet_set_gather_threads(self.det, int(n))
+
+    def capacity_retries(self):
+        return int(self.lib.csm_host_loopdet_capacity_retries(self.det))
+
     def close(self):
         if self.det:
             self.lib.csm_host_loopdet_destroy(self.det)
+            self.det = None
+
+
+class MultiGpuLoopDetector:
+    """C++ LoopDetectorBranchBoundMultiGPU: one process, n_gpus devices, queries sharded by
+    LocalMapId mod n_gpus, one host thread per GPU, results in query order."""
+
+    def __init__(self, n_gpus, hmax, rng, thr, covariance_scale=1e4, lanes=1, refine=(10, 1e-4, 1e-4)):
+        self.lib = load()
+        self.n_gpus = n_gpus
+        rg, rgp = _d(rng)
+        it, conv, lam = refine if refine else (0, 0.0, 0.0)
+        self.det = self.lib.csm_host_multidet_create(n_gpus, hmax, rgp, thr[0], thr[1], covariance_scale, lanes,
+                                                     it, conv, lam)
+
+    def use_nccl(self):
+        self.lib.csm_host_multidet_use_nccl(self.det)
+
+    def configure(self, chunk_size=128, upload_chunk=64, gather_threads=0):
+        self.lib.csm_host_multidet_configure(self.det, chunk_size, upload_chunk, gather_threads)
+
+    def clear_cache(self):
+        self.lib.csm_host_multidet_clear_cache(self.det)
+
+    def best_word(self):
+        return int(self.lib.csm_host_multidet_best_word(self.det))
+
+    def shard_sizes(self):
+        out = (C.c_int * self.n_gpus)()
+        self.lib.csm_host_multidet_shard_sizes(self.det, out)
+        return list(out)
+
+    def detect(self, nq, blocks, index, counts, heap_maps, log2bs, rows, cols, res, off_x, off_y, map_ids,
+               map_poses, scan_poses, angles, ranges, out=None):
+        out = out if out is not None else (HostSummary * nq)()
+        dp = C.POINTER(C.c_double)
+        n = self.lib.csm_host_multidet_detect(
+            self.det, nq, blocks, index, counts, heap_maps.p if heap_maps is not None else None, log2bs, rows, cols,
+            res, off_x.ctypes.data_as(dp), off_y.ctypes.data_as(dp), map_ids.ctypes.data_as(C.POINTER(C.c_int64)),
+            map_poses.ctypes.data_as(dp), scan_poses.ctypes.data_as(dp), angles.ctypes.data_as(dp),
+            ranges.ctypes.data_as(dp), len(angles), out)
+        return n, out
+
+    def close(self):
+        if self.det:
+            self.lib.csm_host_multidet_destroy(self.det)
             self.det = None

