@@ -62,7 +62,8 @@ def workload_config(n_gpus):
         "sharding": "queries/submaps sharded over %d rank(s), 8-byte NCCL argmax all-reduce" % n_gpus,
         "pipelining": "value: successive steps alternate over 2 handles per GPU (pyramid build of one step "
                       "overlaps the sweep of the previous one); e2e: 2 pipeline lanes inside one Detect",
-        "l2": "inputs larger than L2: 128 MiB of submaps + 768 MiB of pyramid levels touched per step",
+        "l2": "inputs larger than L2 (126 MB): 128 MiB of submaps + 320 MiB of bound levels + 44 MiB of projected "
+              "indices touched per step",
     }
 
 
@@ -201,6 +202,15 @@ def main_reference(args):
             times.append(el)
     total = float(np.sum(times))
     value = nq * args.steps / total
+    # warm path: the detector keeps the pyramids it built (its cache per LocalMapId, never evicted,
+    # loop_detector_branch_bound.cpp:83-89): search + refinement only
+    warm_times = []
+    for it in range(1 + min(args.steps, 5)):
+        _, el = det.detect(grids[:nq], batch.map_ids[:nq], batch.map_poses[:nq], batch.scan_idx[:nq],
+                           batch.scan_poses[:nq], batch.angles, batch.ranges)
+        if it >= 1:
+            warm_times.append(el)
+    warm_value = nq * len(warm_times) / float(np.sum(warm_times))
     sample = ("%d steps, each Detect on the first %d of the %d first-touch submaps of the per-GPU step "
               "(pyramid build + B&B + ScanMatcherLinearSolver refinement + covariance), queries split over %d std::threads"
               % (args.steps, nq, N_MAPS, threads))
@@ -211,6 +221,9 @@ def main_reference(args):
         "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "warm": {"value": warm_value, "unit": UNIT, "ms_per_step": 1e3 * float(np.mean(warm_times)),
+                 "note": "pyramids cached per LocalMapId (second and later Detect calls on the same submaps)"},
+        "phases": {"pyramid_build_share_of_cold_step": 1.0 - value / warm_value if warm_value > 0 else None},
         "gpu_launches": 0,
     }
     emit(json.dumps(line))
@@ -220,12 +233,47 @@ def main_reference(args):
 # ---------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------
-class CudaArrayView:
-    """Zero-copy torch view of a device word owned by the C library."""
+REPEATS = 5          # timed regions per leg (median reported, all listed)
 
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 2}
+
+def _median(xs):
+    return float(np.median(np.asarray(xs, dtype=np.float64)))
+
+
+def _spread(xs):
+    xs = np.asarray(xs, dtype=np.float64)
+    return {"min": float(xs.min()), "median": float(np.median(xs)), "max": float(xs.max()), "n": int(len(xs))}
+
+
+class HostBatch:
+    """One rank's share of a workload on the host: the submaps in the reference's storage (every allocated
+    16x16 block its own heap allocation, grid_map.cpp:522-535), poses, the scan."""
+
+    def __init__(self, batch, lo, hi, hostapi, synth):
+        subs = batch.submaps[lo:hi]
+        self.n = hi - lo
+        self.ids = np.arange(lo, hi, dtype=np.int64)
+        self.offx = np.array([s.off_x for s in subs])
+        self.offy = np.array([s.off_y for s in subs])
+        self.res = subs[0].res
+        self.map_poses = np.ascontiguousarray(batch.map_poses[lo:hi], dtype=np.float64)
+        self.scan_poses = np.ascontiguousarray(batch.scan_poses[lo:hi], dtype=np.float64)
+        self.angles = np.ascontiguousarray(batch.angles[0], dtype=np.float64)
+        self.ranges = np.ascontiguousarray(batch.ranges[0], dtype=np.float64)
+        parts = [synth.dense_to_blocks(s.grid, 4) for s in subs]
+        self.counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+        self.n_blocks = int(self.counts.sum())
+        blocks = np.ascontiguousarray(np.concatenate([p[0].reshape(-1) for p in parts]))
+        index = np.ascontiguousarray(np.concatenate([p[1] for p in parts]))
+        self.heap = hostapi.HeapMaps(blocks, index, self.counts)
+        self.summaries = (hostapi.HostSummary * self.n)()
+        n_chunks = (self.n + 63) // 64
+        self.h2d_bytes = self.n_blocks * (512 + 4) + (self.n + n_chunks) * 4 + 2 * 360 * 8 + \
+            self.n * (256 + 115 * 8 + 8 + 4)
+
+    def detect(self, hdet):
+        return hdet.detect_heap(self.n, self.heap, ROWS, COLS, self.res, self.offx, self.offy, self.ids,
+                                self.map_poses, self.scan_poses, self.angles, self.ranges, self.summaries)
 
 
 def main_cuda(args):
@@ -238,149 +286,107 @@ def main_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # the only collective is an 8-byte all-reduce that runs beside kernels filling every SM: one
-        # channel of 64 threads is all it needs (a small CTA finds a free slot sooner), and NCCL's
-        # stream gets high priority so that it is placed as soon as a slot frees
+        # torch.distributed is the control plane only (gloo: barriers, gathering the per-rank times,
+        # handing out the NCCL id). The data-plane exchange -- the 8-byte all-reduce of the packed best
+        # word -- is issued by the library itself on its own stream (csm_comm_*), one small channel:
+        # it runs beside kernels that fill every SM
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
         os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         os.environ.setdefault("NCCL_NTHREADS", "64")
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
+        dist.init_process_group("gloo")
     lib = capi.load()
-    # The reference-facing plugin: the C++ LoopDetectorBranchBound of host/ (libcsm_host.so) on top
-    # of the C ABI. `h` is the csm_handle it runs on (device-side timing, best-word all-reduce).
-    ctx = hostapi.Context(local)
-    hdet = hostapi.LoopDetector(ctx, HMAX, synth.CFG3["rng"], synth.CFG3["thr"])
-    # one search batch of 256 queries; first-touch submaps uploaded in 4 groups of 64 whose block
-    # expansion + pyramid build overlap the PCIe transfer of the following groups
-    # two pipeline lanes: search batches of 128 queries, first-touch submaps uploaded in groups of 64 on
-    # one copy stream; the first batch is searched while the maps of the second still cross PCIe
-    hdet.configure(chunk_size=128 | (64 << 16), coarse_covariance=False, query_index_base=rank * N_MAPS)
-    # the reference's default final matcher on every detected loop, on the device (k_refine)
-    hdet.use_device_refiner(*REFINE)
-    hdet.set_lanes(2)
-    h = capi.Handle.from_pointer(hdet.handle(), local)
-    ext_stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local))
-
-    batch = make_batch(rank)
-    cells = ROWS * COLS
-    ids = np.arange(N_MAPS, dtype=np.int64)
-    offx = np.array([s.off_x for s in batch.submaps])
-    offy = np.array([s.off_y for s in batch.submaps])
-    res = batch.submaps[0].res
-    map_poses = np.ascontiguousarray(batch.map_poses, dtype=np.float64)
-    scan_poses = np.ascontiguousarray(batch.scan_poses, dtype=np.float64)
-    angles = np.ascontiguousarray(batch.angles[0], dtype=np.float64)
-    ranges = np.ascontiguousarray(batch.ranges[0], dtype=np.float64)
-
-    # Host inputs, page-locked. (a) the submaps in the reference's own storage form
-    # (grid_map.cpp:262-266): only the 16x16 blocks that were ever written, back to back, plus
-    # their positions -- what the adapter hands over without flattening; unallocated blocks never
-    # cross PCIe. (b) the same submaps flattened to dense row-major u16 (comparison leg).
-    LOG2BS = 4
-    parts = [synth.dense_to_blocks(s.grid, LOG2BS) for s in batch.submaps]
-    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
-    n_blocks = int(counts.sum())
-    blk_bytes = 2 << (2 * LOG2BS)
-    blk_ptr = lib.csm_alloc_pinned(max(n_blocks, 1) * blk_bytes)
-    idx_ptr = lib.csm_alloc_pinned(max(n_blocks, 1) * 4)
-    np.ctypeslib.as_array((C.c_uint16 * (n_blocks * (blk_bytes // 2))).from_address(blk_ptr))[:] = \
-        np.concatenate([p[0].reshape(-1) for p in parts])
-    np.ctypeslib.as_array((C.c_int32 * n_blocks).from_address(idx_ptr))[:] = np.concatenate([p[1] for p in parts])
-    host_ptr = lib.csm_alloc_pinned(N_MAPS * cells * 2)
-    host = np.ctypeslib.as_array((C.c_uint16 * (N_MAPS * cells)).from_address(host_ptr)).reshape(N_MAPS, ROWS, COLS)
-    for m, s in enumerate(batch.submaps):
-        host[m] = s.grid
-    n_chunks = (N_MAPS + 63) // 64
-    h2d_small = 2 * 360 * 8 + N_MAPS * (256 + 115 * 8 + 8 + 4)
-    h2d_blocks = n_blocks * (blk_bytes + 4) + (N_MAPS + n_chunks) * 4
-    summaries = (hostapi.HostSummary * N_MAPS)()
-    best_word = torch.zeros(1, dtype=torch.int64, device="cuda")
-
-    def allreduce_best(read_back=False):
-        """8-byte all-reduce(max) of the packed best word over NCCL, on the handle's stream.
-        read_back: also copy the result to the host (on that same stream) and return it."""
-        view = torch.as_tensor(CudaArrayView(h.best_key_device_ptr(), 1, "<i8"), device="cuda")
-        with torch.cuda.stream(ext_stream):
-            best_word.copy_(view)
-            sharding.allreduce_best(best_word)
-            return int(best_word.item()) if read_back else None
-
-    # Device-resident leg: the all-reduce of step k runs on a side stream behind an event, so that it
-    # overlaps the kernels of step k + 1 instead of sitting between them (it is latency, not bandwidth)
-    side_stream = torch.cuda.Stream(device=torch.device("cuda", local))
-    word_ring = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(4)]
-    word_done = [None] * 4
-    ring_pos = [0]
-
-    def allreduce_best_async(h=h, ext_stream=ext_stream):
-        i = ring_pos[0] % 4
-        ring_pos[0] += 1
-        view = torch.as_tensor(CudaArrayView(h.best_key_device_ptr(), 1, "<i8"), device="cuda")
-        with torch.cuda.stream(ext_stream):
-            if word_done[i] is not None:
-                ext_stream.wait_event(word_done[i])
-            word_ring[i].copy_(view)                    # before the next batch clears the device word
-            if world == 1:
-                return
-            ready = torch.cuda.Event()
-            ready.record(ext_stream)
-        with torch.cuda.stream(side_stream):
-            side_stream.wait_event(ready)
-            sharding.allreduce_best(word_ring[i])
-            word_done[i] = torch.cuda.Event()
-            word_done[i].record(side_stream)
-
-    def e2e_step(sparse=True, hdet=hdet):
-        """One LoopDetector::Detect of the C++ plugin on 256 first-touch submaps, from page-locked
-        HOST buffers: upload (4 groups on the copy stream), block expansion, pyramid build, batched
-        B&B, result read-back; then the 8-byte all-reduce of the best word and its read-back."""
-        hdet.clear_cache()                                  # every submap is a first touch again
-        h.set_option("reset_best_key", 1)
-        n, _ = hdet.detect(N_MAPS, None if sparse else host_ptr, blk_ptr if sparse else None,
-                           idx_ptr if sparse else None, counts.ctypes.data if sparse else None, LOG2BS,
-                           ROWS, COLS, res, offx, offy, ids, map_poses, scan_poses, angles, ranges, summaries)
-        # packed best (key, query) word of this rank over all lanes, reduced across ranks over NCCL
-        word = hdet.best_word()
-        if world > 1:
-            with torch.cuda.stream(ext_stream):
-                best_word.copy_(torch.tensor([word - (1 << 64) if word >= (1 << 63) else word], dtype=torch.int64))
-                sharding.allreduce_best(best_word)
-                word = int(best_word.item())
-        return n, word
+    if os.environ.get("CSM_HOST_BACKTRACE"):
+        hostapi.load().csm_host_install_backtrace()
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def gather_ranks(x):
+        """[x of rank 0, x of rank 1, ...] on every rank"""
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            return [float(x)]
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        out = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def join_comm(handle):
+        """A communicator over the same handle of every rank (collective: same order on all ranks)."""
+        if world == 1:
+            return
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t[:] = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8)
+        dist.broadcast(t, 0)
+        handle.comm_init_rank(bytes(t.numpy().tobytes()), rank, world)
+
+    def make_detector(ctx, index_base):
+        # The reference-facing plugin: the C++ LoopDetectorBranchBound of host/ (libcsm_host.so) on top of
+        # the C ABI. Two pipeline lanes: search batches of 128 queries, first-touch submaps gathered
+        # (thread pool) and uploaded in groups of 64 on one copy stream; the first batch is searched while
+        # the maps of the second are still gathered / crossing PCIe. Final matcher = device refiner.
+        d = hostapi.LoopDetector(ctx, HMAX, synth.CFG3["rng"], synth.CFG3["thr"])
+        d.configure(chunk_size=128 | (64 << 16), coarse_covariance=False, query_index_base=index_base)
+        d.use_device_refiner(*REFINE)
+        d.set_lanes(2)
+        d.set_gather_threads(max(1, min(16, cpu_threads() // max(1, world))))
+        return d
+
+    ctx = hostapi.Context(local)
+    hdet = make_detector(ctx, rank * N_MAPS)
+    h = capi.Handle.from_pointer(hdet.handle(), local)
+    join_comm(h)
+
+    batch = make_batch(rank)                       # weak scaling: every rank its own 256 submaps
+    weak = HostBatch(batch, 0, N_MAPS, hostapi, synth)
+    ids = weak.ids
+    angles, ranges = weak.angles, weak.ranges
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    # ---- warm-up (also allocates every workspace) --------------------------------
-    h.set_option("accumulate_best_key", 1)        # a Detect is several device batches
-    for _ in range(max(args.warmup, 3)):
-        e2e_step()
-
-    # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------
-    def time_e2e(sparse):
-        for _ in range(2):
-            e2e_step(sparse)
+    # ---- e2e: C++ plugin Detect from the reference's storage, H2D + D2H inside the timed region -------
+    def e2e_region(det, hb, handle, steps, cold=True):
+        """`steps` Detect calls; the packed best word of every call goes into the NCCL exchange without
+        waiting for it (its result is read one call later). Returns (seconds, found, last word)."""
+        pending, word, n = None, 0, 0
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            n, w = e2e_step(sparse)
+        for _ in range(steps):
+            if cold:
+                det.clear_cache()                   # every submap is a first touch again
+            n, _ = hb.detect(det)
+            w = det.best_word()
+            if world > 1:
+                tk = handle.comm_allreduce_word(w)
+                if pending is not None:
+                    word = handle.comm_best_result(pending)
+                pending = tk
+            else:
+                word = w
+        if pending is not None:
+            word = handle.comm_best_result(pending)
         torch.cuda.synchronize()
-        return max_over_ranks(time.perf_counter() - t0), n, w
+        return time.perf_counter() - t0, n, word
+
+    for _ in range(max(args.warmup, 3)):            # warm-up (also allocates every workspace)
+        e2e_region(hdet, weak, h, 1)
+    sampler.active = True
+    e2e_runs = [e2e_region(hdet, weak, h, args.steps) for _ in range(REPEATS)]
+    sampler.active = False
+    e2e_ranks = [gather_ranks(r[0]) for r in e2e_runs]                 # [repeat][rank] seconds
+    e2e_s = _median([max(r) for r in e2e_ranks])
+    n_found, word = e2e_runs[-1][1], e2e_runs[-1][2]
+    key, qidx = h.decode_best_key(word)
+    # warm path: every submap resident with its levels (what the reference's per-LocalMapId cache gives
+    # it from the second Detect on): search + refinement + read-back only
+    e2e_region(hdet, weak, h, 1, cold=False)
+    e2e_warm_runs = [e2e_region(hdet, weak, h, args.steps, cold=False) for _ in range(REPEATS)]
+    e2e_warm_s = _median([max(gather_ranks(r[0])) for r in e2e_warm_runs])
+    assert e2e_warm_runs[-1][1] == n_found
 
     # for comparison: the same Detect with the final matcher on the CPU (host/ ScanMatcherLinearSolver)
     e2e_cpu_refine_ms = None
@@ -389,98 +395,149 @@ def main_cuda(args):
         hdet_cpu.use_linear_solver(*REFINE)
         hdet_cpu.configure(chunk_size=128 | (64 << 16), coarse_covariance=False, query_index_base=0)
         hdet_cpu.set_lanes(2)
-        e2e_step(True, hdet_cpu)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            e2e_step(True, hdet_cpu)
-        e2e_cpu_refine_ms = (time.perf_counter() - t0) / 3 * 1e3
+        e2e_region(hdet_cpu, weak, h, 1)
+        e2e_cpu_refine_ms = e2e_region(hdet_cpu, weak, h, 3)[0] / 3 * 1e3
         hdet_cpu.close()
-        for _ in range(2):
-            e2e_step()
-    e2e_dense_s, n_dense, word_dense = time_e2e(False)
-    sampler.active = True
-    e2e_s, n_found, word = time_e2e(True)
-    sampler.active = False
-    assert (n_found, word) == (n_dense, word_dense), "block-sparse and dense uploads disagree"
-    key, qidx = h.decode_best_key(word)
 
     # ---- value: inputs resident in HBM, CUDA events on the handles' streams ------------------
     # Successive steps (independent Detect calls) alternate over two handles, each with its own copy of
-    # the 256 submaps resident: the HBM-bound pyramid build of one step overlaps the latency-bound
-    # branch-and-bound sweep of the previous one. Every step does the full work of a step.
-    h.set_option("accumulate_best_key", 0)
+    # the submaps resident: the pyramid build of one step overlaps the sweep of the previous one. Every
+    # step does the full work of a step through ONE C-ABI call (csm_detect_step_enqueue: drop + build
+    # the levels, enqueue search + refinement + read-back, start the NCCL exchange of the best word).
     scan = matchers.ScanData(angles, ranges)
-    queries = [matchers.LoopDetectionQuery(
-        scan, 0, tuple(batch.scan_poses[i]),
-        matchers.GridMap(s.grid, s.res, (s.off_x, s.off_y), int(ids[i])), tuple(batch.map_poses[i]), i)
-        for i, s in enumerate(batch.submaps)]
-    N_LANES = 2
-    lanes = []
-    for k in range(N_LANES):
-        hk = h if k == 0 else capi.Handle(local)
-        hk.set_refiner(*REFINE)
-        bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=hk)
-        det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
-        lanes.append({"h": hk, "det": det, "arr": det.prepare(queries),      # level 0 resident (untimed)
-                      "stream": ext_stream if k == 0 else
-                      torch.cuda.ExternalStream(hk.stream, device=torch.device("cuda", local)),
-                      "in_flight": 0})
-    arr = lanes[0]["arr"]
+
+    def resident_lanes(sub_batch, lo, hi, index_base, first_handle=None):
+        queries = [matchers.LoopDetectionQuery(
+            scan, 0, tuple(sub_batch.scan_poses[i]),
+            matchers.GridMap(sub_batch.submaps[i].grid, sub_batch.submaps[i].res,
+                             (sub_batch.submaps[i].off_x, sub_batch.submaps[i].off_y), i),
+            tuple(sub_batch.map_poses[i]), i) for i in range(lo, hi)]
+        lanes = []
+        for k in range(2):
+            hk = first_handle if (k == 0 and first_handle is not None) else capi.Handle(local)
+            if hk is not first_handle:
+                join_comm(hk)
+            hk.set_refiner(*REFINE)
+            bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=hk)
+            det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+            lanes.append({"h": hk, "arr": det.prepare(queries), "in_flight": [], "n": hi - lo,
+                          "ids": np.arange(lo, hi, dtype=np.int64), "base": index_base,
+                          "stream": torch.cuda.ExternalStream(hk.stream, device=torch.device("cuda", local))})
+            hk.synchronize()
+        return lanes
+
     results = (capi.CsmResult * N_MAPS)()
     refined = (capi.CsmRefined * N_MAPS)()
-    for ln in lanes:
-        ln["h"].synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    step_no = [0]
 
-    def device_step():
-        ln = lanes[step_no[0] % N_LANES]
-        step_no[0] += 1
-        hk = ln["h"]
-        hk.drop_pyramids(ids)
-        hk.build_pyramids(ids, HMAX)
-        hk.loop_batch_enqueue(ln["arr"], N_MAPS, HMAX, rank * N_MAPS)   # includes the read-back of the results
-        allreduce_best_async(hk, ln["stream"])
-        ln["in_flight"] += 1
-        if ln["in_flight"] == 3:                                # results of this lane's step two back
-            hk.loop_batch_finish_refined(N_MAPS, results, refined)
-            ln["in_flight"] -= 1
+    def device_region(lanes, steps, cold=True):
+        """`steps` device-resident steps; returns (device ms, host issue ms per step, launches, last word)."""
+        state = {"k": 0, "word": 0, "wait_s": 0.0}
 
-    def drain():
-        for ln in lanes:
-            while ln["in_flight"]:
-                ln["h"].loop_batch_finish_refined(N_MAPS, results, refined)
-                ln["in_flight"] -= 1
+        def finish_one(ln):
+            t0 = time.perf_counter()
+            tk = ln["in_flight"].pop(0)
+            ln["h"].loop_batch_finish_refined(ln["n"], results, refined)
+            if tk >= 0:
+                state["word"] = ln["h"].comm_best_result(tk)
+            state["wait_s"] += time.perf_counter() - t0
 
-    for _ in range(3 * N_LANES):
-        device_step()
-    drain()
-    barrier()
-    launches0 = sum(ln["h"].launch_count() for ln in lanes)
+        def step():
+            ln = lanes[state["k"] % 2]
+            state["k"] += 1
+            tk = ln["h"].detect_step_enqueue(ln["ids"] if cold else ln["ids"][:0], ln["arr"], ln["n"], HMAX,
+                                             ln["base"], drop=True)
+            ln["in_flight"].append(tk)
+            if len(ln["in_flight"]) == 3:                    # results of this lane's step two back
+                finish_one(ln)
+
+        def drain():
+            for ln in lanes:
+                while ln["in_flight"]:
+                    finish_one(ln)
+
+        for _ in range(4):
+            step()
+        drain()
+        barrier()
+        launches0 = sum(ln["h"].launch_count() for ln in lanes)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(lanes[0]["stream"])
+        lanes[1]["stream"].wait_event(ev0)               # no lane starts before the start mark
+        t_issue = time.perf_counter()
+        state["wait_s"] = 0.0
+        for _ in range(steps):
+            step()
+        # host time of issuing a step: the loop's wall time less what it spent waiting for results of
+        # earlier steps (that wait is the GPU's time, not the host's)
+        host_issue_ms = (time.perf_counter() - t_issue - state["wait_s"]) * 1e3 / steps
+        lanes[0]["stream"].wait_stream(lanes[1]["stream"])   # the end mark waits for both lanes
+        ev1.record(lanes[0]["stream"])
+        ev1.synchronize()
+        drain()                                              # ... and the exchanges are read here
+        launches = sum(ln["h"].launch_count() for ln in lanes) - launches0
+        return ev0.elapsed_time(ev1), host_issue_ms, launches, state["word"]
+
+    h.set_option("accumulate_best_key", 0)
+    lanes = resident_lanes(batch, 0, N_MAPS, rank * N_MAPS, first_handle=h)
+    device_region(lanes, 4)
     sampler.active = True
-    ev[0].record(ext_stream)
-    for ln in lanes[1:]:
-        ln["stream"].wait_event(ev[0])               # no lane starts before the start mark
-    t_issue = time.perf_counter()
-    for _ in range(args.steps):
-        device_step()
-    host_issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps
-    for ln in lanes[1:]:
-        ext_stream.wait_stream(ln["stream"])         # the end mark waits for every lane ...
-    ext_stream.wait_stream(side_stream)              # ... and for the last all-reduces
-    ev[1].record(ext_stream)
-    ev[1].synchronize()
+    dev_runs = [device_region(lanes, args.steps) for _ in range(REPEATS)]
     sampler.active = False
-    drain()
-    launches = sum(ln["h"].launch_count() for ln in lanes) - launches0
-    dev_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    dev_ranks = [gather_ranks(r[0]) for r in dev_runs]                       # [repeat][rank] ms
+    issue_ranks = [gather_ranks(r[1]) for r in dev_runs]
+    dev_ms_runs = [max(r) for r in dev_ranks]
+    dev_ms = _median(dev_ms_runs)
+    launches = dev_runs[-1][2]
     assert sum(r.found for r in results) == n_found == sum(f.valid for f in refined)
+    if world > 1:
+        assert dev_runs[-1][3] == word, "device-resident and end-to-end legs disagree on the best word"
+    warm_runs = [device_region(lanes, args.steps, cold=False) for _ in range(REPEATS)]
+    warm_ms = _median([max(gather_ranks(r[0])) for r in warm_runs])
+
+    # ---- strong scaling (BASELINE.json configs[2] as stated): ONE batch of 256 submaps, sharded -----
+    strong = None
+    if world > 1:
+        lo, hi = sharding.shard_range(N_MAPS, rank, world)
+        batch0 = make_batch(0)
+        sb = HostBatch(batch0, lo, hi, hostapi, synth)
+        ctx_s = hostapi.Context(local)
+        sdet = make_detector(ctx_s, lo)
+        hs = capi.Handle.from_pointer(sdet.handle(), local)
+        join_comm(hs)
+        e2e_region(sdet, sb, hs, 2)
+        s_e2e = [e2e_region(sdet, sb, hs, args.steps) for _ in range(REPEATS)]
+        s_e2e_s = _median([max(gather_ranks(r[0])) for r in s_e2e])
+        s_found = sum(int(v) for v in gather_ranks(s_e2e[-1][1]))
+        s_word = s_e2e[-1][2]
+        slanes = resident_lanes(batch0, lo, hi, lo)
+        device_region(slanes, 4)
+        s_dev = [device_region(slanes, args.steps) for _ in range(REPEATS)]
+        s_dev_ms = _median([max(gather_ranks(r[0])) for r in s_dev])
+        s_warm = [device_region(slanes, args.steps, cold=False) for _ in range(REPEATS)]
+        s_warm_ms = _median([max(gather_ranks(r[0])) for r in s_warm])
+        sk, sq = h.decode_best_key(s_word)
+        strong = {
+            "workload": "cfg3 as stated: 1 query scan x %d submaps IN TOTAL, contiguous query ranges over %d GPUs "
+                        "(%d per GPU), 8-byte NCCL all-reduce of the best word" % (N_MAPS, world, hi - lo),
+            "scaling": "strong", "value": N_MAPS * args.steps / (s_dev_ms * 1e-3), "unit": UNIT,
+            "ms_per_step": s_dev_ms / args.steps,
+            "warm": {"value": N_MAPS * args.steps / (s_warm_ms * 1e-3), "ms_per_step": s_warm_ms / args.steps},
+            "e2e": {"value": N_MAPS * args.steps / s_e2e_s, "unit": UNIT, "ms_per_step": 1e3 * s_e2e_s / args.steps,
+                    "h2d_bytes_per_step_per_gpu": sb.h2d_bytes},
+            "check": {"found_per_step": s_found, "best_key": int(sk), "best_query": int(sq)},
+        }
+        for ln in slanes:
+            ln["h"].close()
+        sdet.close()
+        ctx_s.close()
+        sb.heap.close()
     for ln in lanes[1:]:
         ln["h"].close()
 
     # ---- per-kernel CUDA-event durations (library option "timing": one event after every kernel,
     # on the stream the kernels are launched on) for the roofline of the dominant kernels ----------
     barrier()
+    arr = lanes[0]["arr"]
     h.set_option("timing", 1)
     kernel_ms = {}
     reps = max(5, min(args.steps, 20))
@@ -490,17 +547,18 @@ def main_cuda(args):
         for k, v in h.timings():
             kernel_ms[k] = kernel_ms.get(k, 0.0) + v / reps
         h.loop_batch_enqueue(arr, N_MAPS, HMAX, rank * N_MAPS)
-        h.loop_batch_finish(N_MAPS, results)
+        h.loop_batch_finish_refined(N_MAPS, results, refined)
         for k, v in h.timings():
             kernel_ms[k] = kernel_ms.get(k, 0.0) + v / reps
     h.set_option("timing", 0)
     kernel_ms.pop("k_setup", None)          # its interval includes host staging time when the stream is idle
-    counts = h.frontier_counts()
-    pyr_ms = kernel_ms.get("k_pyramid_stream", 0.0)
-    bb_ms = sum(v for k, v in kernel_ms.items() if k != "k_pyramid_stream")
-    # nodes scored per step: the four children of every node of every list; the roots themselves are
-    # expanded unscored (option "bb_skip_top"), counts[HMAX] = all root candidates
-    nodes_scored = 4 * sum(counts[1:HMAX + 1])
+    kernel_ms.pop("readback", None)
+    groups = h.frontier_counts()
+    build_name = "k_pyramid_stream(bounds)"
+    pyr_ms = kernel_ms.get(build_name, 0.0)
+    bb_ms = sum(v for k, v in kernel_ms.items() if k != build_name)
+    # children scored per step (the device counts them per query: n_processed + n_ignored)
+    nodes_scored = sum(r.n_processed + r.n_ignored for r in results)
 
     peaks = {}
     try:
@@ -508,78 +566,99 @@ def main_cuda(args):
             peaks = json.load(f)
     except (OSError, ValueError):
         pass
-    traffic = {}
+    ncu = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "r2_ncu.json")) as f:
+            ncu = json.load(f)
     except (OSError, ValueError):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     step_ms = dev_ms / args.steps
-    # Dominant kernel family: k_bb_expand<HC> (one launch per pyramid height, 4 children per node).
-    # Algorithmic bytes: one u16 grid read per scored node and beam.
     n_beams = len(angles)
-    per_launch = {}
-    for hc in range(HMAX):
-        name = "k_bb_expand<%d>" % hc
-        ms = kernel_ms.get(name, 0.0)
-        nodes = 4 * counts[hc + 1]
-        per_launch[name] = {"ms": ms, "nodes_scored": int(nodes),
-                          "GBps": nodes * n_beams * 2 / (ms * 1e-3) / 1e9 if ms > 0 else None}
-    exp_ms = sum(v["ms"] for v in per_launch.values())
-    exp_bytes = sum(v["nodes_scored"] for v in per_launch.values()) * n_beams * 2
+    exp_ms = sum(v for k, v in kernel_ms.items() if k.startswith("k_bbg_expand"))
+    gathers = nodes_scored * n_beams
+    gather_peak = 148 * 32 * sm_mhz * 1e6       # one 32-lane gather wavefront per cycle per SM
+    ncu_sweep = ncu.get("k_bbg_expand", {})
+    stale = None
+    if ncu_sweep.get("event_ms_at_capture") and exp_ms > 0:
+        stale = abs(exp_ms - ncu_sweep["event_ms_at_capture"]) > 0.15 * ncu_sweep["event_ms_at_capture"]
     roofline = {
-        "kernel": "k_bb_expand<0..%d> (B&B frontier scoring, %d launches per step, one per pyramid height)"
-                  % (HMAX - 1, HMAX),
-        "bound": "hbm", "achieved": exp_bytes / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else None,
-        "peak": hbm_peak, "unit": "GB/s",
-        "frac": exp_bytes / (exp_ms * 1e-3) / 1e9 / hbm_peak if exp_ms > 0 else None,
-        "peak_source": peak_source, "algorithmic_bytes_per_step": int(exp_bytes),
-        "avg_launch_ms": exp_ms / HMAX, "ms_per_step": exp_ms, "share_of_step": exp_ms / (pyr_ms + bb_ms),
-        "traffic": traffic.get("k_bb_expand_dram_bytes_per_step"), "launches": per_launch,
-        "note": "scattered 2-byte gathers from 900 MB of pyramid levels: neither DRAM nor tensor bound; the "
-                "binding unit is the L1TEX line (wavefront) rate of divergent loads, see DESIGN.md section 5 "
-                "and profiles/r1_kernels_full.txt, r1_bb_stalls.txt. Durations are CUDA events recorded by the library on the "
-                "launching stream after every kernel.",
+        "kernel": "k_bbg_expand<0..%d> (B&B frontier scoring over groups of 8 angles, %d launches per step, one per "
+                  "pyramid height)" % (HMAX - 1, HMAX),
+        "bound": "l1tex",
+        "achieved": gathers / (exp_ms * 1e-3) if exp_ms > 0 else None, "peak": gather_peak, "unit": "gathers/s",
+        "frac": gathers / (exp_ms * 1e-3) / gather_peak if exp_ms > 0 else None,
+        "peak_source": "SURVEY.md 8(d) gather ceiling: 148 SMs x 32 lanes x %.0f MHz (one L1TEX / shared-memory "
+                       "wavefront per cycle per SM, every lane useful); a scattered gather cannot reach it: "
+                       "the sweep's requests touch %.1f sectors in about two 128-byte tiles"
+                       % (sm_mhz, ncu_sweep.get("sectors_per_request", float("nan"))),
+        "hbm_equivalent": {"achieved_GBps": gathers * 2 / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else None,
+                           "peak_GBps": hbm_peak, "peak_source": peak_source,
+                           "frac": gathers * 2 / (exp_ms * 1e-3) / 1e9 / hbm_peak if exp_ms > 0 else None,
+                           "note": "SURVEY.md 8(d) algorithmic bytes (one u16 per scored node and beam) against the "
+                                   "copy peak, the round-1 figure; DRAM is not the unit that binds"},
+        "l1tex_ncu": dict(ncu_sweep, stale=stale,
+                          note="ncu --set full of the same launches (profiles/r2_ncu.json, captured on a B200 of "
+                               "this pool); stale = the CUDA-event time of this run differs by more than 15 % "
+                               "from the one recorded beside the capture"),
+        "children_scored_per_step": int(nodes_scored), "ms_per_step": exp_ms,
+        "avg_launch_ms": exp_ms / HMAX, "share_of_step": exp_ms / (pyr_ms + bb_ms) if pyr_ms + bb_ms > 0 else None,
+        "traffic": ncu_sweep.get("dram_bytes_per_step"),
+        "launches": {k: v for k, v in kernel_ms.items() if k.startswith("k_bbg_expand")},
+        "groups_per_list": [int(c) for c in groups],
     }
-    pyr_bytes = (1 + HMAX) * cells * 2 * N_MAPS          # read level 0 once, write hmax levels
+    pyr_bytes = (cells_bytes() + (HMAX - 1) * ROWS * COLS) * N_MAPS       # read level 0 (u16) once, write hmax - 1 u8 levels
     roofline_pyramid = {
-        "kernel": "k_pyramid_stream (PrecomputeGridMaps, 1 launch per step)",
+        "kernel": "k_pyramid_stream2<5, 512, bounds> (bound levels of the sweep, 1 launch per step)",
         "bound": "hbm", "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else None,
         "peak": hbm_peak, "unit": "GB/s",
         "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak if pyr_ms > 0 else None, "peak_source": peak_source,
-        "algorithmic_bytes_per_launch": pyr_bytes, "traffic": traffic.get("k_pyramid_stream_dram_bytes_per_launch"),
-        "ms_per_step": pyr_ms, "share_of_step": pyr_ms / (pyr_ms + bb_ms),
+        "algorithmic_bytes_per_launch": pyr_bytes, "traffic": ncu.get("k_pyramid_stream2", {}).get("dram_bytes_per_launch"),
+        "ms_per_step": pyr_ms, "share_of_step": pyr_ms / (pyr_ms + bb_ms) if pyr_ms + bb_ms > 0 else None,
+        "note": "latency-bound (one CTA walks a map's rows with a barrier per level and 4-row block), not "
+                "HBM-bound: see DESIGN.md section 5",
     }
-    phases = {"pyramid_ms": pyr_ms, "branch_and_bound_ms": bb_ms, "kernel_ms": kernel_ms,
+    phases = {"pyramid_ms": pyr_ms, "search_and_refine_ms": bb_ms, "kernel_ms": kernel_ms,
               "note": "per-kernel durations of one step run alone on one handle (sum %.3f ms); the timed steps "
                       "alternate over two handles and overlap, so ms_per_step is below that sum" % (pyr_ms + bb_ms),
-              "nodes_scored_per_step": int(nodes_scored)}
+              "children_scored_per_step": int(nodes_scored)}
 
     total_queries = world * N_MAPS * args.steps
     line = {
         "metric": METRIC, "value": total_queries / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/int64 (f64 projection)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/u8/int64 (f64 projection)",
         "data": "synthetic", "config": workload_config(world),
+        "repeats": {"timed_regions": REPEATS, "ms_per_step": _spread([m / args.steps for m in dev_ms_runs]),
+                    "e2e_ms_per_step": _spread([1e3 * max(r) / args.steps for r in e2e_ranks])},
+        "per_rank": {"dev_ms_per_step": [m / args.steps for m in dev_ranks[REPEATS // 2]],
+                     "host_issue_ms_per_step": issue_ranks[REPEATS // 2],
+                     "e2e_ms_per_step": [1e3 * s / args.steps for s in e2e_ranks[REPEATS // 2]]},
         "e2e": {"value": total_queries / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "pipeline": "2 lanes (device contexts) x 128-query search batches, uploads in groups of 64",
-                "h2d_bytes_per_step": h2d_blocks + h2d_small,
+                "h2d_bytes_per_step": weak.h2d_bytes,
                 "d2h_bytes_per_step": N_MAPS * (C.sizeof(capi.CsmResult) + C.sizeof(capi.CsmRefined)) + 16 + 8,
                 "api": "C++ LoopDetectorBranchBound::Detect (host/, libcsm_host.so) over the C ABI, "
                        "final matcher = device refiner (csm_set_refiner)",
-                "host_format": "block-sparse submaps (allocated 16x16 blocks + positions, the reference's "
-                               "GridMap storage), %d of %d blocks allocated" % (n_blocks, N_MAPS * (ROWS >> 4) * (COLS >> 4))},
-        "e2e_dense": {"value": total_queries / e2e_dense_s, "unit": UNIT,
-                      "ms_per_step": 1e3 * e2e_dense_s / args.steps,
-                      "h2d_bytes_per_step": N_MAPS * cells * 2 + h2d_small,
-                      "host_format": "dense flattened submaps (csm_upload_grids)"},
+                "host_format": "the reference's GridMap storage: every allocated 16x16 block a separate heap "
+                               "allocation (%d of %d blocks allocated); the gather into page-locked staging "
+                               "(thread pool of the detector, group by group behind the PCIe copies) is INSIDE "
+                               "the timed region" % (weak.n_blocks, N_MAPS * (ROWS >> 4) * (COLS >> 4)),
+                "exchange": "packed best word of every Detect into the library's NCCL all-reduce without waiting; "
+                            "read one call later"},
+        "warm": {"note": "every submap resident with its levels (the reference caches its pyramids per LocalMapId): "
+                         "search + refinement + read-back only, no upload, no level build",
+                 "value": total_queries / (warm_ms * 1e-3), "ms_per_step": warm_ms / args.steps,
+                 "e2e": {"value": total_queries / e2e_warm_s, "ms_per_step": 1e3 * e2e_warm_s / args.steps}},
         "e2e_cpu_final_matcher_ms_per_step": e2e_cpu_refine_ms,
-        "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms,
+        "gpu_launches": int(launches), "host_issue_ms_per_step": _median(issue_ranks[REPEATS // 2]),
         "roofline": roofline, "roofline_pyramid": roofline_pyramid, "phases": phases,
         "check": {"found_per_step": int(n_found), "best_key": int(key), "best_query": int(qidx)},
     }
+    if strong is not None:
+        line["strong"] = strong
 
     if rank == 0:
         sampler.stop()
@@ -588,12 +667,15 @@ def main_cuda(args):
             kind = reference_kind()
             threads = cpu_threads()
             v_all = run_cpu_detect(kind, batch, threads, N_MAPS, cold=True, repeats=2)
+            v_warm = run_cpu_detect(kind, batch, threads, N_MAPS, cold=False, repeats=3)
             v_one = run_cpu_detect(kind, batch, 1, 32, cold=True)
             line["cpu_baseline"] = {
                 "value": v_all, "unit": UNIT, "cores": threads, "kind": kind,
                 "sample": "full step (256 queries on 256 first-touch submaps, refinement included), best of 2, %d threads; "
-                          "1 thread on the first 32 queries: %.1f queries/s" % (threads, v_one),
-                "one_core_value": v_one,
+                          "1 thread on the first 32 queries: %.1f queries/s; warm (pyramids cached): %.1f queries/s"
+                          % (threads, v_one, v_warm),
+                "one_core_value": v_one, "warm_value": v_warm,
+                "pyramid_build_share": 1.0 - v_all / v_warm if v_warm > 0 else None,
             }
             if not args.no_single:
                 line["single_scan"] = single_scan_numbers(h, lib, kind)
@@ -603,10 +685,12 @@ def main_cuda(args):
         dist.destroy_process_group()
     hdet.close()
     ctx.close()
-    lib.csm_free_pinned(host_ptr)
-    lib.csm_free_pinned(blk_ptr)
-    lib.csm_free_pinned(idx_ptr)
+    weak.heap.close()
     return 0
+
+
+def cells_bytes():
+    return ROWS * COLS * 2
 
 
 def single_scan_numbers(h, lib, kind):

@@ -159,16 +159,16 @@ def load():
     lib.csm_loop_batch_enqueue.argtypes = [H, lq, C.c_int, C.c_int, C.c_int]
     lib.csm_loop_batch_finish.argtypes = [H, rp, C.c_int]
     lib.csm_loop_batch.argtypes = [H, lq, C.c_int, C.c_int, C.c_int, rp]
-    lib.csm_detect_step_enqueue.argtypes = [H, i64p, C.c_int, C.c_int, lq, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
-    lib.csm_comm_unique_id.argtypes = [C.c_void_p]
-    lib.csm_comm_init_rank.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
-    lib.csm_comm_init_all.argtypes = [C.POINTER(H), C.c_int]
-    lib.csm_comm_allreduce_best.argtypes = [H, C.POINTER(C.c_int)]
-    lib.csm_comm_allreduce_best_all.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_int)]
-    lib.csm_comm_best_result.argtypes = [H, C.c_int, C.POINTER(C.c_uint64)]
-    lib.csm_comm_allreduce_word.argtypes = [H, C.c_uint64, C.POINTER(C.c_int)]
-    lib.csm_comm_allreduce_words_all.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
-    lib.csm_comm_destroy.argtypes = [H]
+    if hasattr(lib, "csm_detect_step_enqueue"): lib.csm_detect_step_enqueue.argtypes = [H, i64p, C.c_int, C.c_int, lq, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    if hasattr(lib, "csm_comm_unique_id"): lib.csm_comm_unique_id.argtypes = [C.c_void_p]
+    if hasattr(lib, "csm_comm_init_rank"): lib.csm_comm_init_rank.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
+    if hasattr(lib, "csm_comm_init_all"): lib.csm_comm_init_all.argtypes = [C.POINTER(H), C.c_int]
+    if hasattr(lib, "csm_comm_allreduce_best"): lib.csm_comm_allreduce_best.argtypes = [H, C.POINTER(C.c_int)]
+    if hasattr(lib, "csm_comm_allreduce_best_all"): lib.csm_comm_allreduce_best_all.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_int)]
+    if hasattr(lib, "csm_comm_best_result"): lib.csm_comm_best_result.argtypes = [H, C.c_int, C.POINTER(C.c_uint64)]
+    if hasattr(lib, "csm_comm_allreduce_word"): lib.csm_comm_allreduce_word.argtypes = [H, C.c_uint64, C.POINTER(C.c_int)]
+    if hasattr(lib, "csm_comm_allreduce_words_all"): lib.csm_comm_allreduce_words_all.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    if hasattr(lib, "csm_comm_destroy"): lib.csm_comm_destroy.argtypes = [H]
     lib.csm_set_refiner.argtypes = [H, C.POINTER(CsmRefineParams)]
     lib.csm_loop_batch_finish_refined.argtypes = [H, rp, C.POINTER(CsmRefined), C.c_int]
     lib.csm_refine_batch.argtypes = [H, C.POINTER(CsmRefineQuery), C.c_int, C.POINTER(CsmRefineParams),
@@ -177,10 +177,10 @@ def load():
     lib.csm_set_epilogue.argtypes = [H, C.c_double]
     lib.csm_last_epilogue.argtypes = [H, C.POINTER(CsmRefined)]
     lib.csm_debug_frontier_counts.argtypes = [H, C.POINTER(C.c_uint)]
-    lib.csm_debug_node_list.argtypes = [H, C.c_int, C.POINTER(C.c_uint64), C.c_int]
-    lib.csm_exact_rerun_count.restype = C.c_int64
-    lib.csm_exact_rerun_count.argtypes = [H]
-    lib.csm_debug_bound_level.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_uint8)]
+    if hasattr(lib, "csm_debug_node_list"): lib.csm_debug_node_list.argtypes = [H, C.c_int, C.POINTER(C.c_uint64), C.c_int]
+    if hasattr(lib, "csm_exact_rerun_count"): lib.csm_exact_rerun_count.restype = C.c_int64
+    if hasattr(lib, "csm_exact_rerun_count"): lib.csm_exact_rerun_count.argtypes = [H]
+    if hasattr(lib, "csm_debug_bound_level"): lib.csm_debug_bound_level.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_uint8)]
     lib.csm_debug_timings.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.c_int]
     lib.csm_best_key_device.argtypes = [H]
     lib.csm_best_key_device.restype = C.c_void_p

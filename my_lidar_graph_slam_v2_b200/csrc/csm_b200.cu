@@ -114,7 +114,9 @@ struct MapSlot
     unsigned char* bounds = nullptr;
     int bounds_alloc = 0;
     int bounds_levels = -1;        /* -1: nothing valid; L >= 0: serves searches with hmax <= L + 1 */
-    int low_margin = -1;           /* smallest min(row, col) of a known cell near the low edges (k_low_margin), -1: not scanned */
+    unsigned long long mark = 0;   /* scratch: "already taken" in the list being built (compared with csm_context::mark) */
+    int margin_slot = -1;          /* this map's word in the handle's low-margin array (k_low_margin) */
+    bool margin_valid = false;     /* ... holds the value of the current contents */
     cudaEvent_t pending_upload = nullptr;   /* copy-stream event the next consumer must wait for */
     std::shared_ptr<BlockScatter> pending_scatter;   /* block-sparse upload not yet expanded */
     /* which blocks are allocated in the reference's sense (refinement reads unallocated cells as 0.5):
@@ -238,7 +240,9 @@ struct csm_context
     int64_t exact_reruns = 0;      /* flagged results recomputed exactly so far */
     int exact_rerun = 1;           /* option: recompute results whose projection raised the FP guard-band flag */
     double fp_margin_scale = 1.0;  /* option (tests): multiplies the guard band */
-    DevBuf d_margin;               /* low-margin scan: jobs and results */
+    DevBuf d_margin, d_marginjobs; /* low-margin words of the maps (one int each), job table of the scan */
+    int margin_slots = 0;
+    unsigned long long mark = 0;   /* bumped for every list that must hold each map once */
     bool res_refined[kResultSlots] = { false, false, false, false };
     /* last pyramid job table on the device (skips the re-upload when unchanged) */
     std::vector<PyrJob> jobs_on_device;
@@ -431,7 +435,7 @@ int finish_results(csm_handle h, csm_result* results, int nq, csm_refined* refin
     /* flagged results: exact rerun for the FP guard band, a look at the map for the low-edge flag */
     bool any = false;
     for (int q = 0; q < nq && !any; ++q)
-        any = (results[q].flags & (CSM_FLAG_FP_MARGIN | CSM_FLAG_EDGE)) != 0;
+        any = (results[q].flags & CSM_FLAG_FP_MARGIN) != 0;
     if (any && (int)h->res_rec[k].queries.size() == nq)
         return postprocess_flags(h, h->res_rec[k], results, nq, h->res_refined[k] ? refined : nullptr);
     return CSM_OK;
@@ -841,12 +845,11 @@ int build_bounds(csm_handle h, const std::vector<MapSlot*>& slots, int L)
     }
     std::vector<BlJob> jobs;
     int max_rows = 0, max_cols = 0;
+    const unsigned long long mark = ++h->mark;
     for (MapSlot* m : slots) {
-        if (m->bounds_levels >= L)
+        if (m->bounds_levels >= L || m->mark == mark)
             continue;
-        bool dup = false;
-        for (const BlJob& j : jobs) dup = dup || j.base == m->base;
-        if (dup) continue;
+        m->mark = mark;
         if (L > 0 && m->bounds_alloc < L) {
             if (m->bounds) CSM_CUDA(cudaFreeAsync(m->bounds, h->stream));
             m->bounds = nullptr;
@@ -1155,6 +1158,54 @@ struct InlineScan
     int n;
 };
 
+/* Low-margin word of every map of the batch that lacks one (first touch): one small launch. The
+ * branch-and-bound projection flags node windows that reach below row / column 0 (CSM_FLAG_EDGE);
+ * k_finalize withdraws the flag when the map knows nothing in its first 2^hmax rows and columns. */
+int ensure_margins(csm_handle h, const std::vector<MapSlot*>& slots)
+{
+    constexpr int kLimit = 1 << (kMaxLevels - 1);
+    std::vector<MapSlot*> todo;
+    const unsigned long long mark = ++h->mark;
+    for (MapSlot* m : slots)
+        if (!m->margin_valid && m->mark != mark) {
+            m->mark = mark;
+            todo.push_back(m);
+        }
+    if (todo.empty())
+        return CSM_OK;
+    int rc;
+    for (MapSlot* m : todo)
+        if (m->margin_slot < 0) m->margin_slot = h->margin_slots++;
+    if (h->d_margin.bytes < sizeof(int) * (size_t)h->margin_slots) {
+        /* grow, keeping the words of the other maps */
+        DevBuf bigger;
+        const size_t want = std::max<size_t>(sizeof(int) * (size_t)h->margin_slots * 2, (size_t)1 << 16);
+        if ((rc = ensure(h, bigger, want))) return rc;
+        if (h->d_margin.p) {
+            CSM_CUDA(cudaMemcpyAsync(bigger.p, h->d_margin.p, h->d_margin.bytes, cudaMemcpyDeviceToDevice, h->stream));
+            CSM_CUDA(cudaFreeAsync(h->d_margin.p, h->stream));
+        }
+        h->d_margin = bigger;
+    }
+    if ((rc = wait_uploads(h, todo))) return rc;
+    std::vector<MarginJob> jobs(todo.size());
+    for (size_t i = 0; i < todo.size(); ++i)
+        jobs[i] = MarginJob { todo[i]->base, todo[i]->rows, todo[i]->cols, kLimit, todo[i]->margin_slot };
+    const size_t jb = sizeof(MarginJob) * jobs.size();
+    if ((rc = ensure(h, h->d_marginjobs, jb))) return rc;
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, jb, &hp))) return rc;
+    std::memcpy(hp, jobs.data(), jb);
+    if ((rc = pull_to_device(h, h->d_marginjobs.p, hp, jb))) return rc;
+    if ((rc = upload_committed(h))) return rc;
+    k_low_margin<<<(unsigned)jobs.size(), 256, 0, h->stream>>>(static_cast<const MarginJob*>(h->d_marginjobs.p),
+                                                               static_cast<int*>(h->d_margin.p));
+    CSM_LAUNCH_CHECK();
+    for (MapSlot* m : todo)
+        m->margin_valid = true;
+    return CSM_OK;
+}
+
 int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, int query_base,
                const InlineScan* inline_scan)
 {
@@ -1207,6 +1258,7 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
                 missing.push_back(m);
         if (!missing.empty() && (rc = build_levels(h, missing, hmax))) return rc;
     }
+    if ((rc = ensure_margins(h, used_slots))) return rc;
     const bool epilogue = inline_scan != nullptr && nq == 1 && h->epilogue_scale > 0.0;
     const bool refine = h->refine_on || epilogue;
     if (refine) {
@@ -1234,6 +1286,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         if ((rc = fill_common(h, Q, m, s, in.score_thr, in.known_thr))) return rc;
         Q.sx = in.sensor_pose[0];
         Q.sy = in.sensor_pose[1];
+        Q.low_margin = static_cast<const int*>(h->d_margin.p) + m.margin_slot;
+        Q.edge_need = 1 << hmax;
         Q.stepx = in.step_x; Q.stepy = in.step_y;
         Q.T = 2 * in.win_t + 1;
         Q.winx = in.win_x; Q.winy = in.win_y;
@@ -1559,49 +1613,11 @@ int refine_poses(csm_handle h, const csm_refine_query* queries, int n, const csm
     return CSM_OK;
 }
 
-/* Results of a batch that came back flagged. CSM_FLAG_FP_MARGIN: exact rerun (and, when the batch
- * refined its poses and the rerun moved the pose, the refinement again from the new pose).
- * CSM_FLAG_EDGE: withdrawn when the map has no known cell in its first 2^hmax rows and columns. */
+/* Results of a batch that came back flagged CSM_FLAG_FP_MARGIN: exact rerun (and, when the batch
+ * refined its poses and the rerun moved the pose, the refinement again from the new pose). */
 int postprocess_flags(csm_handle h, const BatchRecord& rec, csm_result* results, int nq, csm_refined* refined)
 {
     int rc;
-    /* low-edge flag: one scan of the low rows / columns of every map not looked at yet */
-    {
-        std::vector<MapSlot*> todo;
-        for (int q = 0; q < nq; ++q) {
-            if (!(results[q].flags & CSM_FLAG_EDGE)) continue;
-            auto mi = h->maps.find(rec.queries[q].map_id);
-            if (mi == h->maps.end()) continue;
-            MapSlot* m = &mi->second;
-            if (m->low_margin < 0 && std::find(todo.begin(), todo.end(), m) == todo.end())
-                todo.push_back(m);
-        }
-        if (!todo.empty()) {
-            const int limit = 1 << (kMaxLevels - 1);
-            if ((rc = wait_uploads(h, todo))) return rc;
-            const size_t jb = align16(sizeof(MarginJob) * todo.size()), ob = sizeof(int) * todo.size();
-            if ((rc = ensure(h, h->d_margin, jb + ob))) return rc;
-            std::vector<MarginJob> jobs(todo.size());
-            for (size_t i = 0; i < todo.size(); ++i)
-                jobs[i] = MarginJob { todo[i]->base, todo[i]->rows, todo[i]->cols, limit, 0 };
-            int* d_out = reinterpret_cast<int*>(static_cast<char*>(h->d_margin.p) + jb);
-            CSM_CUDA(cudaMemcpyAsync(h->d_margin.p, jobs.data(), sizeof(MarginJob) * jobs.size(), cudaMemcpyHostToDevice, h->stream));
-            CSM_CUDA(cudaMemsetAsync(d_out, 0x7f, ob, h->stream));
-            k_low_margin<<<(unsigned)todo.size(), 256, 0, h->stream>>>(static_cast<const MarginJob*>(h->d_margin.p), d_out);
-            CSM_LAUNCH_CHECK();
-            std::vector<int> got(todo.size());
-            CSM_CUDA(cudaMemcpyAsync(got.data(), d_out, ob, cudaMemcpyDeviceToHost, h->stream));
-            CSM_CUDA(cudaStreamSynchronize(h->stream));
-            for (size_t i = 0; i < todo.size(); ++i)
-                todo[i]->low_margin = std::min(got[i], limit);
-        }
-        for (int q = 0; q < nq; ++q) {
-            if (!(results[q].flags & CSM_FLAG_EDGE)) continue;
-            auto mi = h->maps.find(rec.queries[q].map_id);
-            if (mi != h->maps.end() && mi->second.low_margin >= (1 << rec.hmax))
-                results[q].flags &= ~CSM_FLAG_EDGE;
-        }
-    }
     if (!h->exact_rerun)
         return CSM_OK;
     for (int q = 0; q < nq; ++q) {
@@ -1735,7 +1751,7 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
-                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs, &h->d_bljobs, &h->d_margin };
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs, &h->d_bljobs, &h->d_margin, &h->d_marginjobs };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)
@@ -1840,7 +1856,7 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     /* precomputed levels belong to the previous contents (allocations are kept) */
     m.hmax = 0;
     m.bounds_levels = -1;
-    m.low_margin = -1;
+    m.margin_valid = false;
     m.coarse_win = 0;
     m.pending_scatter.reset();
     m.alloc_valid = false;
@@ -1909,7 +1925,7 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
         MapSlot& m = *slots[i];
         m.hmax = 0;
         m.bounds_levels = -1;
-        m.low_margin = -1;
+        m.margin_valid = false;
         m.coarse_win = 0;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
@@ -2013,7 +2029,7 @@ int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
         MapSlot& m = *slots[i];
         m.hmax = 0;
         m.bounds_levels = -1;
-        m.low_margin = -1;
+        m.margin_valid = false;
         m.coarse_win = 0;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);

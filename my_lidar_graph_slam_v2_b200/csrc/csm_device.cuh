@@ -76,6 +76,9 @@ struct DevQuery
      * bl_tpr[hc] its tiles per row; null when the sweep reads the u16 levels */
     const unsigned char* bl[kMaxLevels];
     int bl_tpr[kMaxLevels];
+    const int* low_margin;             /* smallest min(row, col) of a known cell near the low edges of the map
+                                          (k_low_margin); at least edge_need: a CSM_FLAG_EDGE is withdrawn */
+    int edge_need, pad4;               /* 2^hmax */
     int pquad;                         /* 1: proj is stored in chunks of 16 beams, [n / 16][tp][4][4] (see proj_index) */
     int tp;                            /* quad layout: angles per beam group, T rounded up to a multiple of 8 */
 };

@@ -1957,11 +1957,11 @@ k_grid_general(const DevQuery* __restrict__ queries, const double2* __restrict__
  * (`limit` if there is none): when it is at least 2^hmax, every coarse lookup at a negative index
  * covers unknown cells only, i.e. the 0 the reference reads there (grid_map.cpp:389-392) IS the
  * maximum of the window and its branch-and-bound bound stays admissible: a
- * CSM_FLAG_EDGE raised by the projection is then withdrawn. out[] must hold `limit` or more on entry. */
+ * CSM_FLAG_EDGE raised by the projection is then withdrawn (k_finalize). One CTA per map. */
 struct MarginJob
 {
     const uint16_t* base;
-    int rows, cols, limit, pad;
+    int rows, cols, limit, slot;     /* the result goes to out[slot] */
 };
 
 __global__ void __launch_bounds__(256)
@@ -1970,6 +1970,8 @@ k_low_margin(const MarginJob* __restrict__ jobs, int* __restrict__ out)
     const MarginJob J = jobs[blockIdx.x];
     const int lr = min(J.limit, J.rows), lc = min(J.limit, J.cols);
     int best = J.limit;
+    if (threadIdx.x == 0) out[J.slot] = J.limit;
+    __syncthreads();
     for (int e = threadIdx.x; e < lr * J.cols; e += blockDim.x) {          /* the low rows, whole */
         const int r = e / J.cols, c = e - r * J.cols;
         if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
@@ -1980,7 +1982,7 @@ k_low_margin(const MarginJob* __restrict__ jobs, int* __restrict__ out)
     }
     best = (int)__reduce_min_sync(0xffffffffu, (unsigned)best);
     if ((threadIdx.x & 31) == 0 && best < J.limit)
-        atomicMin(&out[blockIdx.x], best);
+        atomicMin(&out[J.slot], best);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -2080,6 +2082,8 @@ k_finalize(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj
     csm_result r;
     r.found = s.found;
     r.flags = s.flags | (F.qflags != nullptr ? F.qflags[q] : 0);
+    if ((r.flags & 4) && Q.low_margin != nullptr && *Q.low_margin >= Q.edge_need)
+        r.flags &= ~4;        /* CSM_FLAG_EDGE: nothing known below row / column 2^hmax, the reference's bound holds */
     r.n_processed = s.n_processed;
     r.n_ignored = s.n_ignored;
     r.sum_value = 0; r.n_known = 0; r.normalized_score = 0.0;

@@ -94,7 +94,7 @@ public:
     /* Forget which maps are resident (the next Detect uploads them again) */
     void ClearCache() { mMapLane.clear(); }
     /* Threads that gather heap-allocated blocks (GridMapView::block_ptrs) into page-locked staging
-     * (default: min(8, hardware threads)) */
+     * (default: min(16, hardware threads)) */
     void SetGatherThreads(int n);
     /* Batches that overflowed the device's frontier lists and were searched again in smaller
      * batches (CSM_E_CAPACITY is recoverable), over the detector's life */

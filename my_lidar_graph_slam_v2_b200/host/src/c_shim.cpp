@@ -1,9 +1,12 @@
 /* c_shim.cpp -- extern "C" test entry points over the C++ plugin mirror, so that
  * the parity tests (Python, ctypes) can drive the adapter classes exactly the
  * way the reference drives its matchers / detectors. Not part of the C ABI. */
+#include <csignal>
 #include <cstring>
+#include <execinfo.h>
 #include <memory>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 #include "csm_host/loop_detector.hpp"
@@ -35,6 +38,17 @@ static void Export(const ScanMatchingSummary& s, csm_host_summary* out)
     out->est_pose[2] = s.estimated_pose.theta;
     std::memcpy(out->cov, s.estimated_covariance.data(), sizeof(double) * 9);
 }
+
+/* debugging aid: print the native call stack when the process takes a SIGSEGV */
+static void BacktraceOnSegv(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+void csm_host_install_backtrace() { signal(SIGSEGV, BacktraceOnSegv); }
 
 void* csm_host_context_create(int device) { return new DeviceContextPtr(std::make_shared<DeviceContext>(device)); }
 void csm_host_context_destroy(void* ctx) { delete static_cast<DeviceContextPtr*>(ctx); }

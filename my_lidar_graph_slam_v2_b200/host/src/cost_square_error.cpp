@@ -28,12 +28,14 @@ struct Sampler
     mutable std::vector<std::int32_t> slot;   /* block-sparse: block -> position in `blocks`, -1 = unallocated;
                                                  dense: 1 allocated, 0 not, -2 not looked at yet */
 
-    explicit Sampler(const GridMapView& m) : map(m), k(m.blocks ? m.log2_block_size : kLog2Block),
-        block_cols((m.cols + (1 << k) - 1) >> k)
+    bool sparse;      /* block list: contiguous (`blocks`) or one heap allocation per block (`block_ptrs`) */
+
+    explicit Sampler(const GridMapView& m) : map(m), k((m.blocks || m.block_ptrs) ? m.log2_block_size : kLog2Block),
+        block_cols((m.cols + (1 << k) - 1) >> k), sparse(m.blocks != nullptr || m.block_ptrs != nullptr)
     {
         const int block_rows = (m.rows + (1 << k) - 1) >> k;
         const std::size_t nb = static_cast<std::size_t>(block_rows) * block_cols;
-        if (m.blocks != nullptr) {
+        if (sparse) {
             slot.assign(nb, -1);
             for (int b = 0; b < m.n_blocks; ++b)
                 slot[m.block_index[b]] = b;
@@ -63,7 +65,7 @@ struct Sampler
     bool Allocated(int row, int col) const
     {
         const int brow = row >> k, bcol = col >> k;
-        if (map.blocks != nullptr)
+        if (sparse)
             return slot[static_cast<std::size_t>(brow) * block_cols + bcol] >= 0;
         return DenseBlockAllocated(brow, bcol);
     }
@@ -74,13 +76,15 @@ struct Sampler
         if (row < 0 || row >= map.rows || col < 0 || col >= map.cols)
             return 0.5;
         const int brow = row >> k, bcol = col >> k;
-        if (map.blocks != nullptr) {
+        if (sparse) {
             const std::int32_t b = slot[static_cast<std::size_t>(brow) * block_cols + bcol];
             if (b < 0)
                 return 0.5;
             const int mask = (1 << k) - 1;
-            return Probability(map.blocks[(static_cast<std::size_t>(b) << (2 * k)) +
-                                          (static_cast<std::size_t>(row & mask) << k) + (col & mask)]);
+            const std::size_t in_block = (static_cast<std::size_t>(row & mask) << k) + (col & mask);
+            if (map.block_ptrs != nullptr)
+                return Probability(map.block_ptrs[b][in_block]);
+            return Probability(map.blocks[(static_cast<std::size_t>(b) << (2 * k)) + in_block]);
         }
         if (!DenseBlockAllocated(brow, bcol))
             return 0.5;

@@ -380,7 +380,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     }
     if (any_heap && !mGatherer) {
         const int hw = static_cast<int>(std::thread::hardware_concurrency());
-        mGatherer = std::make_shared<BlockGatherer>(mGatherThreads > 0 ? mGatherThreads : std::max(1, std::min(8, hw)));
+        mGatherer = std::make_shared<BlockGatherer>(mGatherThreads > 0 ? mGatherThreads : std::max(1, std::min(16, hw)));
     }
     /* the scans of this call: every distinct ScanData object gets a call-local id (the reference keeps
      * no per-scan state; LoopDetectionQuery::scan_id is not trusted to be unique across calls) */

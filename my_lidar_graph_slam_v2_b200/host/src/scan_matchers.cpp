@@ -63,11 +63,17 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
     if (!resident) {
         /* through the context's page-locked staging area (the previous match on this context has
          * returned, so the area is free): the copy then runs as a DMA behind this call */
-        if (map.blocks != nullptr) {
+        if (map.blocks != nullptr || map.block_ptrs != nullptr) {
             const std::size_t data = (sizeof(std::uint16_t) * static_cast<std::size_t>(map.n_blocks))
                                      << (2 * map.log2_block_size);
             const std::size_t idx_off = (data + 15) & ~std::size_t(15);
             char* st = static_cast<char*>(mContext->Staging(idx_off + sizeof(std::int32_t) * map.n_blocks));
+            if (map.block_ptrs != nullptr) {
+                /* the reference's storage: one heap allocation per block (grid_map.cpp:522-535) */
+                const std::size_t one = sizeof(std::uint16_t) << (2 * map.log2_block_size);
+                for (int b = 0; b < map.n_blocks; ++b)
+                    std::memcpy(st + one * static_cast<std::size_t>(b), map.block_ptrs[b], one);
+            } else
             std::memcpy(st, map.blocks, data);
             std::memcpy(st + idx_off, map.block_index, sizeof(std::int32_t) * map.n_blocks);
             mContext->Check(csm_upload_grid_blocks(mContext->Handle(), id,

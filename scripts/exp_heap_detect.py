@@ -1,0 +1,22 @@
+"""Experiment / repro: C++ Detect from heap-allocated blocks at the bench's size, a few configurations."""
+import sys, time
+sys.path.insert(0, ".")
+import numpy as np
+from my_lidar_graph_slam_v2_b200 import capi, hostapi, synth
+import bench
+n_maps, lanes, threads, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+batch = bench.make_batch(0, n_maps)
+hb = bench.HostBatch(batch, 0, n_maps, hostapi, synth)
+ctx = hostapi.Context(0)
+det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
+det.configure(chunk_size=128 | (64 << 16), coarse_covariance=False, query_index_base=0)
+det.use_device_refiner(10, 1e-4, 1e-4)
+det.set_lanes(lanes)
+det.set_gather_threads(threads)
+for r in range(reps):
+    det.clear_cache()
+    t0 = time.perf_counter()
+    n, _ = hb.detect(det)
+    print("rep", r, "found", n, "ms %.3f" % ((time.perf_counter() - t0) * 1e3), flush=True)
+det.close(); ctx.close()
+print("done")
