@@ -528,6 +528,16 @@ int wait_uploads(csm_handle h, const std::vector<MapSlot*>& slots)
     return CSM_OK;
 }
 
+/* Before a slot is replaced or freed: transfers still in flight into it (a copy-stream upload, a
+ * block-sparse batch that has not been expanded and shares its arena with sibling maps) are ordered
+ * before whatever the compute stream does next, and the pending expansion runs now. */
+int settle_slot(csm_handle h, MapSlot& m)
+{
+    if (m.pending_upload == nullptr && !m.pending_scatter)
+        return CSM_OK;
+    return wait_uploads(h, std::vector<MapSlot*>{ &m });
+}
+
 /* The n level-0 grids of a batch share one device arena (so that a contiguous
  * host batch moves with one copy and a block-sparse batch is cleared with one
  * memset). The arena of a previous identical batch is reused. */
@@ -544,6 +554,10 @@ int bind_batch_arena(csm_handle h, int n, const int64_t* map_ids, int rows, int 
                 slots[i]->cols == cols &&
                 reinterpret_cast<char*>(slots[i]->base) == static_cast<char*>(slots[0]->base_block->p) + (size_t)i * bytes;
     fresh_alloc = false;
+    for (int i = 0; i < n; ++i) {
+        const int src = settle_slot(h, *slots[i]);
+        if (src) return src;
+    }
     if (!reuse) {
         auto block = std::make_shared<ArenaBlock>();
         block->stream = h->stream;
@@ -1054,7 +1068,12 @@ int commit_plan(csm_handle h, QueryPlan& plan, const PlanView& V, bool want_rcs)
     if ((rc = ensure(h, h->d_proj, sizeof(proj_t) * (size_t)plan.proj_total))) return rc;
     if (want_rcs && (rc = ensure(h, h->d_rcs, sizeof(double2) * (size_t)plan.proj_total))) return rc;
     if ((rc = ensure(h, h->d_results, refined_offset(nq) + sizeof(csm_refined) * (size_t)nq))) return rc;
-    if ((rc = ensure(h, h->d_bestkey, 8))) return rc;
+    {
+        const bool fresh = h->d_bestkey.p == nullptr;
+        if ((rc = ensure(h, h->d_bestkey, 8))) return rc;
+        if (fresh)      /* accumulating batches never clear the word themselves */
+            CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
+    }
     for (int q = 0; q < nq; ++q)
         plan.dq[q].thetas = plan.thetas.empty() ? nullptr : V.thetas + plan.theta_off[q];
     char* hp = nullptr;
@@ -1213,6 +1232,8 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
         return fail(h, CSM_E_INVALID, "loop batch: nq must be positive");
     if (nq > 65535)
         return fail(h, CSM_E_UNSUPPORTED, "loop batch: at most 65535 queries per call");
+    if (query_base < 0 || (long long)query_base + nq > 0x100000ll)
+        return fail(h, CSM_E_UNSUPPORTED, "loop batch: query_index_base + nq must stay within 2^20 (packed best word)");
     if (h->res_count >= csm_context::kResultSlots)
         return fail(h, CSM_E_CAPACITY, "too many loop batches in flight: call csm_loop_batch_finish");
     if (hmax < 0 || hmax >= kMaxLevels)
@@ -1786,6 +1807,7 @@ void* csm_stream(csm_handle h) { return h ? (void*)h->stream : nullptr; }
 int csm_synchronize(csm_handle h)
 {
     if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     CSM_CUDA(cudaStreamSynchronize(h->copy_stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
     return CSM_OK;
@@ -1815,7 +1837,14 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
     if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
+    if (std::strcmp(name, "accumulate_best_key") == 0 && value != 0 && h->d_bestkey.p == nullptr) {
+        CSM_CUDA(cudaSetDevice(h->device));
+        int rc = ensure(h, h->d_bestkey, 8);
+        if (rc) return rc;
+        CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
+    }
     if (std::strcmp(name, "reset_best_key") == 0) {
+        CSM_CUDA(cudaSetDevice(h->device));
         int rc = ensure(h, h->d_bestkey, 8);
         if (rc) return rc;
         CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
@@ -1846,6 +1875,10 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
         return fail(h, CSM_E_INVALID, "grid: need 0 < rows, cols <= 16384, even cols, resolution > 0");
     CSM_CUDA(cudaSetDevice(h->device));
     MapSlot& m = h->maps[map_id];
+    {
+        const int src = settle_slot(h, m);
+        if (src) return src;
+    }
     bool fresh_alloc = false;
     if (m.rows != rows || m.cols != cols || m.base == nullptr) {
         free_map(h, m);
@@ -2064,6 +2097,7 @@ int csm_upload_grid_blocks(csm_handle h, int64_t map_id, const uint16_t* blocks,
 int csm_release_grid(csm_handle h, int64_t map_id)
 {
     if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     auto it = h->maps.find(map_id);
     if (it == h->maps.end())
         return fail(h, CSM_E_NOT_FOUND, "release: unknown map id");
@@ -2149,6 +2183,7 @@ int csm_build_pyramid(csm_handle h, int64_t map_id, int hmax)
 int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out)
 {
     if (!h || !out) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     auto it = h->maps.find(map_id);
     if (it == h->maps.end())
         return fail(h, CSM_E_NOT_FOUND, "download: unknown map id");
@@ -2186,6 +2221,7 @@ int csm_upload_scan(csm_handle h, int64_t scan_id, const double* angles, const d
 int csm_release_scan(csm_handle h, int64_t scan_id)
 {
     if (!h) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     auto it = h->scans.find(scan_id);
     if (it == h->scans.end())
         return fail(h, CSM_E_NOT_FOUND, "release: unknown scan id");
@@ -2205,6 +2241,7 @@ int csm_loop_batch_enqueue(csm_handle h, const csm_loop_query* queries, int nq, 
 int csm_loop_batch_finish(csm_handle h, csm_result* results, int nq)
 {
     if (!h || !results) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     return finish_results(h, results, nq);
 }
 
@@ -2258,6 +2295,7 @@ int csm_last_epilogue(csm_handle h, csm_refined* out)
 int csm_loop_batch_finish_refined(csm_handle h, csm_result* results, csm_refined* refined, int nq)
 {
     if (!h || !results || !refined) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     return finish_results(h, results, nq, refined);
 }
 
@@ -2301,7 +2339,11 @@ static int comm_setup(csm_handle h)
         CSM_CUDA(cudaEventCreateWithFlags(&h->comm_ready[i], cudaEventDisableTiming));
         CSM_CUDA(cudaEventCreateWithFlags(&h->comm_done[i], cudaEventDisableTiming));
     }
-    return ensure(h, h->d_bestkey, 8);
+    const bool fresh = h->d_bestkey.p == nullptr;
+    const int rc = ensure(h, h->d_bestkey, 8);
+    if (rc == CSM_OK && fresh)
+        CSM_CUDA(cudaMemsetAsync(h->d_bestkey.p, 0, 8, h->stream));
+    return rc;
 }
 
 int csm_comm_unique_id(void* id128)
@@ -2349,8 +2391,11 @@ int csm_comm_init_all(csm_handle* handles, int n)
     return CSM_OK;
 }
 
-/* word of the last batch -> ring slot (compute stream), all-reduce(max) in place and read-back (side stream) */
-static int comm_enqueue(csm_handle h, int* ticket, const uint64_t* host_word = nullptr)
+/* The exchange in three steps, so that several handles of one process can go through one NCCL group
+ * (the collectives of a group are only launched by ncclGroupEnd: what must follow them on the stream is
+ * enqueued after it): word of the last batch (or a host word) -> ring slot; all-reduce(max) in place on
+ * the side stream; read-back and the "done" event. */
+static int comm_prepare(csm_handle h, int* slot, const uint64_t* host_word)
 {
     if (!h->comm) return fail(h, CSM_E_INVALID, "no communicator: call csm_comm_init_rank / csm_comm_init_all");
     const int i = h->comm_next;
@@ -2365,11 +2410,57 @@ static int comm_enqueue(csm_handle h, int* ticket, const uint64_t* host_word = n
         CSM_CUDA(cudaEventRecord(h->comm_ready[i], h->stream));
         CSM_CUDA(cudaStreamWaitEvent(h->comm_stream, h->comm_ready[i], 0));
     }
+    *slot = i;
+    return CSM_OK;
+}
+
+static int comm_reduce(csm_handle h, int i)
+{
     const int rc = nccl::api().AllReduce(h->d_words + i, h->d_words + i, 1, nccl::kUint64, nccl::kMax, h->comm, h->comm_stream);
     if (rc != 0) return comm_fail(h, "ncclAllReduce", rc);
+    return CSM_OK;
+}
+
+static int comm_complete(csm_handle h, int i)
+{
     CSM_CUDA(cudaMemcpyAsync(h->h_words + i, h->d_words + i, 8, cudaMemcpyDeviceToHost, h->comm_stream));
     CSM_CUDA(cudaEventRecord(h->comm_done[i], h->comm_stream));
+    return CSM_OK;
+}
+
+static int comm_enqueue(csm_handle h, int* ticket, const uint64_t* host_word = nullptr)
+{
+    int i = 0, rc;
+    if ((rc = comm_prepare(h, &i, host_word))) return rc;
+    if ((rc = comm_reduce(h, i))) return rc;
+    if ((rc = comm_complete(h, i))) return rc;
     if (ticket) *ticket = i;
+    return CSM_OK;
+}
+
+static int comm_enqueue_all(csm_handle* handles, int n, const uint64_t* words, int* tickets)
+{
+    std::vector<int> slot(n, 0);
+    int rc;
+    for (int i = 0; i < n; ++i) {
+        if (cudaSetDevice(handles[i]->device) != cudaSuccess) return CSM_E_CUDA;
+        if ((rc = comm_prepare(handles[i], &slot[i], words ? words + i : nullptr))) return rc;
+    }
+    int nrc = nccl::api().GroupStart();
+    if (nrc != 0) return comm_fail(handles[0], "ncclGroupStart", nrc);
+    int first = CSM_OK;
+    for (int i = 0; i < n && first == CSM_OK; ++i) {
+        if (cudaSetDevice(handles[i]->device) != cudaSuccess) { first = CSM_E_CUDA; break; }
+        first = comm_reduce(handles[i], slot[i]);
+    }
+    nrc = nccl::api().GroupEnd();
+    if (nrc != 0 && first == CSM_OK) first = comm_fail(handles[0], "ncclGroupEnd", nrc);
+    if (first) return first;
+    for (int i = 0; i < n; ++i) {
+        if (cudaSetDevice(handles[i]->device) != cudaSuccess) return CSM_E_CUDA;
+        if ((rc = comm_complete(handles[i], slot[i]))) return rc;
+        if (tickets) tickets[i] = slot[i];
+    }
     return CSM_OK;
 }
 
@@ -2390,38 +2481,19 @@ int csm_comm_allreduce_word(csm_handle h, uint64_t word, int* ticket)
 int csm_comm_allreduce_words_all(csm_handle* handles, int n, const uint64_t* words, int* tickets)
 {
     if (!handles || n < 1 || !words || !nccl::api().ok) return CSM_E_INVALID;
-    int rc = nccl::api().GroupStart();
-    if (rc != 0) return comm_fail(handles[0], "ncclGroupStart", rc);
-    int first = CSM_OK;
-    for (int i = 0; i < n; ++i) {
-        if (cudaSetDevice(handles[i]->device) != cudaSuccess) { first = CSM_E_CUDA; break; }
-        const int erc = comm_enqueue(handles[i], tickets ? tickets + i : nullptr, words + i);
-        if (erc && first == CSM_OK) first = erc;
-    }
-    rc = nccl::api().GroupEnd();
-    if (rc != 0 && first == CSM_OK) first = comm_fail(handles[0], "ncclGroupEnd", rc);
-    return first;
+    return comm_enqueue_all(handles, n, words, tickets);
 }
 
 int csm_comm_allreduce_best_all(csm_handle* handles, int n, int* tickets)
 {
     if (!handles || n < 1 || !nccl::api().ok) return CSM_E_INVALID;
-    int rc = nccl::api().GroupStart();
-    if (rc != 0) return comm_fail(handles[0], "ncclGroupStart", rc);
-    int first = CSM_OK;
-    for (int i = 0; i < n; ++i) {
-        if (cudaSetDevice(handles[i]->device) != cudaSuccess) { first = CSM_E_CUDA; break; }
-        const int erc = comm_enqueue(handles[i], tickets ? tickets + i : nullptr);
-        if (erc && first == CSM_OK) first = erc;
-    }
-    rc = nccl::api().GroupEnd();
-    if (rc != 0 && first == CSM_OK) first = comm_fail(handles[0], "ncclGroupEnd", rc);
-    return first;
+    return comm_enqueue_all(handles, n, nullptr, tickets);
 }
 
 int csm_comm_best_result(csm_handle h, int ticket, uint64_t* word)
 {
     if (!h || !word || ticket < 0 || ticket >= csm_context::kCommRing || !h->comm) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     CSM_CUDA(cudaEventSynchronize(h->comm_done[ticket]));
     *word = h->h_words[ticket];
     return CSM_OK;
@@ -2500,6 +2572,7 @@ int csm_debug_bound_level(csm_handle h, int64_t map_id, int level, uint8_t* out)
 int csm_debug_node_list(csm_handle h, int level, uint64_t* out, int cap)
 {
     if (!h || !out || level < 0 || level >= kMaxLevels || !h->plan_view.counts) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     unsigned int counts[kMaxLevels];
     CSM_CUDA(cudaMemcpyAsync(counts, h->plan_view.counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
@@ -2514,6 +2587,7 @@ int csm_debug_node_list(csm_handle h, int level, uint64_t* out, int cap)
 int csm_debug_frontier_counts(csm_handle h, unsigned int* out8)
 {
     if (!h || !out8 || !h->plan_view.counts) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
     CSM_CUDA(cudaMemcpyAsync(out8, h->plan_view.counts, sizeof(unsigned int) * kMaxLevels, cudaMemcpyDeviceToHost, h->stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
     return CSM_OK;

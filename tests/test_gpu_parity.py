@@ -1196,6 +1196,64 @@ def test_best_word_exchange_over_nccl(handle):
         h.close()
 
 
+def test_reupload_while_a_block_sparse_batch_is_pending():
+    """A map of a block-sparse batch that has not been expanded yet is uploaded again on its own: the
+    expansion of the batch (triggered by the first use of a sibling) must not write the old blocks over
+    the new contents, and the sibling keeps its own."""
+    h = capi.Handle(0)
+    rng = np.random.default_rng(5)
+    grids = []
+    for _ in range(3):
+        g = rng.integers(1, 65535, size=(64, 64), dtype=np.uint16)
+        g[rng.random((64, 64)) < 0.5] = 0
+        grids.append(g)
+    parts = [synth.dense_to_blocks(g, 4) for g in grids]
+    counts = np.array([len(p[1]) for p in parts], dtype=np.int32)
+    blocks = np.ascontiguousarray(np.concatenate([p[0].reshape(-1) for p in parts]))
+    index = np.ascontiguousarray(np.concatenate([p[1] for p in parts]))
+    ids = np.array([700, 701, 702], dtype=np.int64)
+    off = np.zeros(3)
+    lib = capi.load()
+    assert lib.csm_upload_grids_blocks(h.h, 3, ids.ctypes.data_as(C.POINTER(C.c_int64)), blocks.ctypes.data,
+                                       index.ctypes.data, counts.ctypes.data_as(C.POINTER(C.c_int32)), 4, 4, 4, 0.05,
+                                       off.ctypes.data_as(C.POINTER(C.c_double)),
+                                       off.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    new = rng.integers(1, 65535, size=(64, 64), dtype=np.uint16)
+    h.upload_grid(701, new, 0.05, 0.0, 0.0)               # replaces the middle map before anything used the batch
+    assert np.array_equal(h.download_level(700, 0, (64, 64)), grids[0])
+    assert np.array_equal(h.download_level(701, 0, (64, 64)), new)
+    assert np.array_equal(h.download_level(702, 0, (64, 64)), grids[2])
+    h.close()
+
+
+def test_best_word_accumulation_and_query_index_range(handle):
+    """"accumulate_best_key" set before the first batch starts from a zero word; a query index base that
+    does not fit the packed word is refused."""
+    h = capi.Handle(0)
+    h.set_option("accumulate_best_key", 1)
+    case = synth.case_for(synth.CFG1, 2500)
+    s = case.submap
+    bb = matchers.ScanMatcherBranchBound("bb", 3, 0.6, 0.6, 0.2, handle=h)
+    det = matchers.LoopDetectorBranchBound("loop", bb, 0.3, 0.3)
+    q = [matchers.LoopDetectionQuery(_scan(case), 0, tuple(case.init_pose),
+                                     matchers.GridMap(s.grid, s.res, (s.off_x, s.off_y), 42), (0.0, 0.0, 0.0), 0)]
+    arr = det.prepare(q)
+    res = h.loop_batch(arr, 1, 3, 7)
+    import torch
+    word = torch.as_tensor(_CudaWord(h.best_key_device_ptr()), device="cuda").cpu().item() & ((1 << 64) - 1)
+    assert res[0].found and word == ((998 * res[0].sum_value + 64536 * res[0].n_known) << 20) | (0xFFFFF - 7)
+    with pytest.raises(capi.CsmError):
+        h.loop_batch(arr, 1, 3, 0x100000)
+    with pytest.raises(capi.CsmError):
+        h.loop_batch(arr, 1, 3, -1)
+    h.close()
+
+
+class _CudaWord:
+    def __init__(self, ptr):
+        self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
 # --------------------------------------------------------------------------
 # BASELINE.json's full sizes
 # --------------------------------------------------------------------------
