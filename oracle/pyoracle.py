@@ -39,13 +39,16 @@ class OrcResult(C.Structure):
 
 def build(kind=None):
     """Build the checkers with oracle/Makefile (ref only if /root/reference exists)."""
-    targets = ["port", "ref"] if kind is None else [{"reference": "ref"}.get(kind, kind)]
+    targets = ["port", "ref", "adapter"] if kind is None else [{"reference": "ref"}.get(kind, kind)]
     subprocess.run(["make", "-s", "-C", HERE, "-j8"] + targets, check=True)
 
 
 _PATHS = {
     "reference": os.path.join(HERE, "_ref", "libcsm_ref.so"),
     "port": os.path.join(HERE, "libcsm_port.so"),
+    # the drop-in classes on the reference's own types + their driver (tests/integration), built with the
+    # reference's translation units against the package's libcsm_b200.so
+    "adapter": os.path.join(HERE, "_ref", "libcsm_adapter.so"),
 }
 
 

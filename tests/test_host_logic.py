@@ -208,3 +208,19 @@ def test_cpp_hill_climbing_matches_reference_vectors():
         assert list(out.est_pose) == [float.fromhex(v) for v in e["est_pose"]], e["seed"]
         assert out.norm_cost == float.fromhex(e["norm_cost"])
         assert np.allclose(list(out.cov), [float.fromhex(v) for v in e["cov"]], rtol=1e-9, atol=0.0)
+
+
+def test_adapter_on_reference_types_builds_and_exports():
+    """The drop-in classes derived from the reference's ScanMatcher / LoopDetector
+    (tests/integration/csm_gpu_adapter.hpp) compile against the reference's own headers and link with the
+    C ABI library; the driver's entry points are there (no compute calls without a GPU)."""
+    import ctypes as C
+    from oracle import pyoracle
+    path = pyoracle._PATHS["adapter"]
+    if not os.path.exists(path) and not os.path.isdir("/root/reference"):
+        pytest.skip("oracle/_ref/libcsm_adapter.so not built and /root/reference absent")
+    if not os.path.exists(path):
+        pyoracle.build("adapter")
+    lib = C.CDLL(path)
+    for sym in ("adp_match_case", "adp_loop_case"):
+        assert hasattr(lib, sym)
