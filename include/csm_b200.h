@@ -253,6 +253,43 @@ int csm_drop_pyramids(csm_handle h, int n, const int64_t* map_ids);
  * level >= 0: pyramid level; level < 0: the coarse map built with win = -level. */
 int csm_download_level(csm_handle h, int64_t map_id, int level, uint16_t* out);
 
+/* ---- map construction on the device ----------------------------------------
+ * Replaces the ray casting of GridMapBuilder::UpdateGridMap / ConstructMapFromScans
+ * (mapping/grid_map_builder.cpp:390-494, 561-695): the latest map / the growing local map stays on
+ * the device, where the matchers read it, instead of being rebuilt on the CPU and uploaded per scan.
+ * The adapter keeps the reference's geometry bookkeeping (GridMap::Resize / Expand,
+ * grid_map.cpp:842-946, on the host: a few integers) and computes, per beam, what only needs the scan
+ * and the poses: the sub-pixel indices of sensor and hit point and the hit cell
+ * (grid_map_builder.cpp:445-463). Cell updates are bit-identical to the reference's: the update
+ * v -> v' of GridBinaryBayes::UpdateOddsUnchecked (grid_binary_bayes.cpp:302-321) depends on v and the
+ * odds only, so the adapter hands over the two tables T_miss[v], T_hit[v] (65536 u16 each, evaluated
+ * with the reference's own arithmetic), and every cell sees its updates in the reference's order
+ * (`order` ascending: scan by scan, beam by beam; within a beam the missed cells, then the hit cell). */
+typedef struct csm_ray
+{
+    int32_t start_x, start_y;   /* sensor, index in the geometry scaled by `subpixel_scale` (col, row) */
+    int32_t end_x, end_y;       /* hit point, same */
+    int32_t hit_col, hit_row;   /* PositionToIndex(hit point) in the map's own geometry */
+    int32_t order;              /* position of the beam in the reference's update sequence */
+    int32_t reserved;
+} csm_ray;
+int csm_map_set_update_tables(csm_handle h, const uint16_t* t_miss, const uint16_t* t_hit);
+/* A map of rows x cols unknown cells, no block allocated (GridMap construction / ResetValues on a map
+ * whose blocks are dropped). rows, cols multiples of 2^log2_block_size. Replaces map_id. */
+int csm_map_create(csm_handle h, int64_t map_id, int rows, int cols, int log2_block_size,
+                   double resolution, double offset_x, double offset_y);
+/* GridMap::Resize: new extent rows x cols whose cell (0, 0) is the old cell (row_min, col_min); cells
+ * and block allocation of the overlap move, the rest is unknown / unallocated. */
+int csm_map_resize(csm_handle h, int64_t map_id, int rows, int cols, int row_min, int col_min,
+                   double offset_x, double offset_y);
+/* GridMap::ResetValues: every cell unknown, block allocation kept. */
+int csm_map_reset_values(csm_handle h, int64_t map_id);
+/* Insert n beams. Asynchronous; precomputed levels of the map are dropped. A beam that leaves the map
+ * is an error reported by the next csm_synchronize / csm_map_download_allocation. */
+int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n, int subpixel_scale);
+/* Block allocation bytes of the map (block_rows * block_cols, 1 = allocated); synchronous. */
+int csm_map_download_allocation(csm_handle h, int64_t map_id, uint8_t* out);
+
 /* ---- scans ---------------------------------------------------------------
  * Replaces SendScanData (scan_matcher_correlative_fpga.cpp:296-299): beam
  * angles and ranges of one ScanData (sensor/sensor_data.hpp:69-89). */

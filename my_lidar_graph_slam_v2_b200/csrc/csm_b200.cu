@@ -10,6 +10,7 @@
 #include "csm_kernels.cuh"
 #include "csm_window_tma.cuh"
 #include "csm_refine.cuh"
+#include "csm_mapbuild.cuh"
 
 #include <dlfcn.h>
 
@@ -240,6 +241,10 @@ struct csm_context
     int64_t exact_reruns = 0;      /* flagged results recomputed exactly so far */
     int exact_rerun = 1;           /* option: recompute results whose projection raised the FP guard-band flag */
     double fp_margin_scale = 1.0;  /* option (tests): multiplies the guard band */
+    /* map construction (csm_map_*): update tables, ray / event workspaces, error word */
+    DevBuf d_maptables, d_mapwork, d_maperror;
+    bool map_tables_set = false;
+    int* h_maperror = nullptr;     /* pinned copy of the error word, read by the next synchronising call */
     DevBuf d_margin, d_marginjobs; /* low-margin words of the maps (one int each), job table of the scan */
     int margin_slots = 0;
     unsigned long long mark = 0;   /* bumped for every list that must hold each map once */
@@ -1772,13 +1777,15 @@ int csm_destroy(csm_handle h)
     for (auto& kv : h->maps) free_map(h, kv.second);
     for (auto& kv : h->scans) free_scan(h, kv.second);
     DevBuf* bufs[] = { &h->d_plan, &h->d_proj, &h->d_rcs, &h->d_results, &h->d_bestkey,
-                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs, &h->d_bljobs, &h->d_margin, &h->d_marginjobs };
+                       &h->d_rtblocks, &h->d_pyrjobs, &h->d_rootkey, &h->d_wtgroups, &h->d_refine_in, &h->d_allocjobs, &h->d_bljobs, &h->d_margin, &h->d_marginjobs,
+                       &h->d_maptables, &h->d_mapwork, &h->d_maperror };
     for (DevBuf* b : bufs)
         if (b->p) cudaFreeAsync(b->p, h->stream);
     for (int l = 0; l < 2; ++l)
         if (h->d_list[l].p) cudaFreeAsync(h->d_list[l].p, h->stream);
     cudaStreamSynchronize(h->stream);
     if (h->h_exact) cudaFreeHost(h->h_exact);
+    if (h->h_maperror) cudaFreeHost(h->h_maperror);
     for (int k = 0; k < csm_context::kUploadAreas; ++k) {
         if (h->h_up[k]) cudaFreeHost(h->h_up[k]);
         if (h->h_up_done[k]) cudaEventDestroy(h->h_up_done[k]);
@@ -1810,6 +1817,10 @@ int csm_synchronize(csm_handle h)
     CSM_CUDA(cudaSetDevice(h->device));
     CSM_CUDA(cudaStreamSynchronize(h->copy_stream));
     CSM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_maperror != nullptr && *h->h_maperror != 0) {
+        *h->h_maperror = 0;
+        return fail(h, CSM_E_INVALID, "map construction: a beam left the map (resize the map to the scan's bounding box first)");
+    }
     return CSM_OK;
 }
 
@@ -2317,6 +2328,200 @@ int csm_loop_batch(csm_handle h, const csm_loop_query* queries, int nq, int hmax
     int rc = csm_loop_batch_enqueue(h, queries, nq, hmax, query_index_base);
     if (rc) return rc;
     return csm_loop_batch_finish(h, results, nq);
+}
+
+/* ---- map construction on the device -------------------------------------------------------------- */
+int csm_map_set_update_tables(csm_handle h, const uint16_t* t_miss, const uint16_t* t_hit)
+{
+    if (!h || !t_miss || !t_hit) return CSM_E_INVALID;
+    CSM_CUDA(cudaSetDevice(h->device));
+    int rc = ensure(h, h->d_maptables, 2 * 65536 * sizeof(uint16_t));
+    if (rc) return rc;
+    char* p = static_cast<char*>(h->d_maptables.p);
+    CSM_CUDA(cudaMemcpyAsync(p, t_miss, 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaMemcpyAsync(p + 65536 * sizeof(uint16_t), t_hit, 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));       /* the tables are the caller's memory */
+    h->map_tables_set = true;
+    return CSM_OK;
+}
+
+static void invalidate_derived(MapSlot& m)
+{
+    m.hmax = 0;
+    m.bounds_levels = -1;
+    m.margin_valid = false;
+    m.coarse_win = 0;
+}
+
+int csm_map_create(csm_handle h, int64_t map_id, int rows, int cols, int log2_block_size,
+                   double resolution, double offset_x, double offset_y)
+{
+    if (!h) return CSM_E_INVALID;
+    if (rows <= 0 || cols <= 0 || rows > 16384 || cols > 16384 || log2_block_size < 3 || log2_block_size > 6 ||
+        (rows & ((1 << log2_block_size) - 1)) || (cols & ((1 << log2_block_size) - 1)) || !(resolution > 0.0))
+        return fail(h, CSM_E_INVALID, "map: rows / cols must be positive multiples of the block size (8..64), resolution > 0");
+    CSM_CUDA(cudaSetDevice(h->device));
+    MapSlot& m = h->maps[map_id];
+    int rc = settle_slot(h, m);
+    if (rc) return rc;
+    free_map(h, m);
+    const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
+    CSM_CUDA(cudaMallocAsync((void**)&m.base, bytes, h->stream));
+    CSM_CUDA(cudaMemsetAsync(m.base, 0, bytes, h->stream));
+    m.rows = rows; m.cols = cols;
+    m.res = resolution; m.offx = offset_x; m.offy = offset_y;
+    m.alloc_log2bs = log2_block_size;
+    m.alloc_bytes = (rows >> log2_block_size) * (cols >> log2_block_size);
+    CSM_CUDA(cudaMallocAsync((void**)&m.alloc, (size_t)m.alloc_bytes, h->stream));
+    CSM_CUDA(cudaMemsetAsync(m.alloc, 0, (size_t)m.alloc_bytes, h->stream));
+    m.alloc_valid = true;
+    invalidate_derived(m);
+    return CSM_OK;
+}
+
+int csm_map_resize(csm_handle h, int64_t map_id, int rows, int cols, int row_min, int col_min,
+                   double offset_x, double offset_y)
+{
+    if (!h) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end() || it->second.alloc == nullptr || !it->second.alloc_valid || it->second.alloc_block)
+        return fail(h, CSM_E_NOT_FOUND, "map resize: not a map made by csm_map_create");
+    MapSlot& m = it->second;
+    const int k = m.alloc_log2bs, mask = (1 << k) - 1;
+    if (rows <= 0 || cols <= 0 || rows > 16384 || cols > 16384 || (rows & mask) || (cols & mask) ||
+        (row_min & mask) || (col_min & mask))
+        return fail(h, CSM_E_INVALID, "map resize: extents and origin must be multiples of the block size");
+    CSM_CUDA(cudaSetDevice(h->device));
+    int rc = settle_slot(h, m);
+    if (rc) return rc;
+    uint16_t* base = nullptr;
+    unsigned char* alloc = nullptr;
+    const int nb = (rows >> k) * (cols >> k);
+    CSM_CUDA(cudaMallocAsync((void**)&base, (size_t)rows * cols * sizeof(uint16_t), h->stream));
+    CSM_CUDA(cudaMallocAsync((void**)&alloc, (size_t)nb, h->stream));
+    MapMoveArgs A;
+    A.src = m.base; A.dst = base; A.src_alloc = m.alloc; A.dst_alloc = alloc;
+    A.src_rows = m.rows; A.src_cols = m.cols; A.dst_rows = rows; A.dst_cols = cols;
+    A.row_min = row_min; A.col_min = col_min; A.log2bs = k;
+    dim3 grid((cols + 255) / 256, rows);
+    k_map_move<<<grid, 256, 0, h->stream>>>(A);
+    CSM_LAUNCH_CHECK();
+    if (m.levels) { CSM_CUDA(cudaFreeAsync(m.levels, h->stream)); m.levels = nullptr; m.levels_alloc = 0; }
+    if (m.coarse) { CSM_CUDA(cudaFreeAsync(m.coarse, h->stream)); m.coarse = nullptr; }
+    if (m.bounds) { CSM_CUDA(cudaFreeAsync(m.bounds, h->stream)); m.bounds = nullptr; m.bounds_alloc = 0; }
+    CSM_CUDA(cudaFreeAsync(m.base, h->stream));
+    CSM_CUDA(cudaFreeAsync(m.alloc, h->stream));
+    m.base = base; m.alloc = alloc; m.alloc_bytes = nb;
+    m.rows = rows; m.cols = cols; m.offx = offset_x; m.offy = offset_y;
+    invalidate_derived(m);
+    return CSM_OK;
+}
+
+int csm_map_reset_values(csm_handle h, int64_t map_id)
+{
+    if (!h) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end() || it->second.base == nullptr)
+        return fail(h, CSM_E_NOT_FOUND, "map reset: unknown map id");
+    MapSlot& m = it->second;
+    CSM_CUDA(cudaSetDevice(h->device));
+    int rc = settle_slot(h, m);
+    if (rc) return rc;
+    CSM_CUDA(cudaMemsetAsync(m.base, 0, (size_t)m.rows * m.cols * sizeof(uint16_t), h->stream));
+    invalidate_derived(m);
+    return CSM_OK;
+}
+
+int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n, int subpixel_scale)
+{
+    if (!h) return CSM_E_INVALID;
+    if (n < 0 || (n > 0 && !rays) || subpixel_scale <= 0)
+        return fail(h, CSM_E_INVALID, "map insert: bad arguments");
+    if (!h->map_tables_set)
+        return fail(h, CSM_E_INVALID, "map insert: csm_map_set_update_tables first");
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end() || it->second.alloc == nullptr || !it->second.alloc_valid || it->second.alloc_block)
+        return fail(h, CSM_E_NOT_FOUND, "map insert: not a map made by csm_map_create");
+    if (n == 0)
+        return CSM_OK;
+    MapSlot& m = it->second;
+    CSM_CUDA(cudaSetDevice(h->device));
+    int rc = settle_slot(h, m);
+    if (rc) return rc;
+    /* event slots per beam: the cells of its ray (at most |dx| + |dy| + 1 full cells) and its hit */
+    const size_t rays_bytes = align16(sizeof(csm_ray) * (size_t)n);
+    const size_t off_bytes = align16(sizeof(unsigned int) * (size_t)(n + 1));
+    char* hp = nullptr;
+    if ((rc = acquire_upload(h, rays_bytes + off_bytes, &hp))) return rc;
+    std::memcpy(hp, rays, sizeof(csm_ray) * (size_t)n);
+    unsigned int* off = reinterpret_cast<unsigned int*>(hp + rays_bytes);
+    unsigned long long total = 0;
+    for (int i = 0; i < n; ++i) {
+        off[i] = (unsigned int)total;
+        const long long dx = (long long)rays[i].end_x / subpixel_scale - (long long)rays[i].start_x / subpixel_scale;
+        const long long dy = (long long)rays[i].end_y / subpixel_scale - (long long)rays[i].start_y / subpixel_scale;
+        total += (unsigned long long)(std::llabs(dx) + std::llabs(dy) + 3);
+    }
+    off[n] = (unsigned int)total;
+    if (total >= (1ull << 31))
+        return fail(h, CSM_E_UNSUPPORTED, "map insert: too many cell updates in one call");
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                   (int)total, 0, 64, h->stream);
+    const size_t ev_bytes = align16(sizeof(unsigned long long) * (size_t)total);
+    sort_bytes = align16(sort_bytes);
+    if ((rc = ensure(h, h->d_mapwork, rays_bytes + off_bytes + 2 * ev_bytes + sort_bytes + 256))) return rc;
+    if (h->d_maperror.p == nullptr) {
+        if ((rc = ensure(h, h->d_maperror, 16))) return rc;
+        CSM_CUDA(cudaMemsetAsync(h->d_maperror.p, 0, 16, h->stream));
+        CSM_CUDA(cudaHostAlloc((void**)&h->h_maperror, 16, cudaHostAllocDefault));
+        *h->h_maperror = 0;
+    }
+    char* w = static_cast<char*>(h->d_mapwork.p);
+    if ((rc = pull_to_device(h, w, hp, rays_bytes + off_bytes))) return rc;
+    if ((rc = upload_committed(h))) return rc;
+    unsigned long long* ev_in = reinterpret_cast<unsigned long long*>(w + rays_bytes + off_bytes);
+    unsigned long long* ev_out = reinterpret_cast<unsigned long long*>(w + rays_bytes + off_bytes + ev_bytes);
+    void* sort_tmp = w + rays_bytes + off_bytes + 2 * ev_bytes;
+    MapRaysArgs R;
+    R.rays = reinterpret_cast<const csm_ray*>(w);
+    R.offset = reinterpret_cast<const unsigned int*>(w + rays_bytes);
+    R.events = ev_in;
+    R.n = n; R.scale = subpixel_scale; R.rows = m.rows; R.cols = m.cols;
+    R.error = static_cast<int*>(h->d_maperror.p);
+    k_map_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(R);
+    CSM_LAUNCH_CHECK();
+    /* per cell, in beam order: the cell index takes the high word; only its significant bits are sorted */
+    int cell_bits = 1;
+    while ((1ull << cell_bits) < (unsigned long long)m.rows * m.cols) ++cell_bits;
+    if (cub::DeviceRadixSort::SortKeys(sort_tmp, sort_bytes, ev_in, ev_out, (int)total, 0, std::min(64, 32 + cell_bits + 1),
+                                       h->stream) != cudaSuccess)
+        return fail(h, CSM_E_CUDA, "map insert: radix sort failed");
+    ++h->launches;
+    MapApplyArgs P;
+    P.events = ev_out; P.n = (unsigned int)total;
+    P.map = m.base; P.alloc = m.alloc;
+    P.lut_miss = static_cast<const uint16_t*>(h->d_maptables.p);
+    P.lut_hit = P.lut_miss + 65536;
+    P.cols = m.cols; P.log2bs = m.alloc_log2bs; P.block_cols = m.cols >> m.alloc_log2bs;
+    k_map_apply<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(P);
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaMemcpyAsync(h->h_maperror, h->d_maperror.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    invalidate_derived(m);
+    return CSM_OK;
+}
+
+int csm_map_download_allocation(csm_handle h, int64_t map_id, uint8_t* out)
+{
+    if (!h || !out) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end() || it->second.alloc == nullptr)
+        return fail(h, CSM_E_NOT_FOUND, "map allocation: unknown map id");
+    CSM_CUDA(cudaSetDevice(h->device));
+    int rc = wait_uploads(h, std::vector<MapSlot*>{ &it->second });
+    if (rc) return rc;
+    CSM_CUDA(cudaMemcpyAsync(out, it->second.alloc, (size_t)it->second.alloc_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return csm_synchronize(h);
 }
 
 /* ---- NCCL exchange of the packed best word ------------------------------------------------- */

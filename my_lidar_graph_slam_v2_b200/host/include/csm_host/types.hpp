@@ -57,6 +57,8 @@ struct ScanData
     std::vector<double> angles;
     std::vector<double> ranges;
     Pose2D relative_sensor_pose;
+    double min_range = 0.0;           /* ScanData::MinRange / MaxRange (sensor_data.hpp:106-108): map */
+    double max_range = 1e300;         /* construction skips beams outside (min, max) */
     std::size_t NumOfScans() const { return ranges.size(); }
 };
 using ScanDataPtr = std::shared_ptr<const ScanData>;
@@ -96,6 +98,11 @@ struct GridMapView
      *    block_index[b]. The loop detector gathers them into page-locked staging with several threads,
      *    group by group, while the previous group crosses PCIe. */
     const std::uint16_t* const* block_ptrs = nullptr;
+    /*  - device-resident (`device_resident`): the map was built on the device under map_id
+     *    (GridMapBuilderGPU) and has no host cells; matchers read it where it is. Their cost /
+     *    covariance epilogue must then run on the device too (DeviceContext::SetDeviceEpilogue /
+     *    SetDeviceFinalMatcher). */
+    bool device_resident = false;
 };
 
 /* scan_matcher.hpp:56-83 */

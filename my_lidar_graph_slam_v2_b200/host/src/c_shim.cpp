@@ -9,8 +9,10 @@
 #include <unistd.h>
 #include <vector>
 
+#include <cstdio>
 #include "csm_host/loop_detector.hpp"
 #include "csm_host/loop_searcher.hpp"
+#include "csm_host/map_builder.hpp"
 
 using namespace csm_host;
 
@@ -602,6 +604,81 @@ int csm_host_multidet_detect(void* det, int n_queries, const uint16_t* blocks, c
         n_queries, nullptr, blocks, block_index, block_count, static_cast<const HeapMaps*>(heap_maps), log2bs,
         rows, cols, res, off_x, off_y, map_ids, map_poses, scan_poses, angles, ranges, n);
     return ExportResults(d->det->Detect(queries), d->det->LastResults(), n_queries, out);
+}
+
+/* ---- map construction on the device: GridMapBuilderGPU ------------------------------------------ */
+struct HostMapBuilder
+{
+    DeviceContextPtr ctx;
+    std::unique_ptr<GridMapBuilderGPU> builder;
+    std::vector<ScanNodeView> nodes;
+};
+
+void* csm_host_mapbuilder_create(void* ctx, double resolution, int patch_size, int scans_for_latest_map,
+                                 double usable_range_min, double usable_range_max, double prob_hit, double prob_miss)
+{
+    auto* b = new HostMapBuilder;
+    b->ctx = *static_cast<DeviceContextPtr*>(ctx);
+    b->builder.reset(new GridMapBuilderGPU(b->ctx, resolution, patch_size, scans_for_latest_map, usable_range_min,
+                                           usable_range_max, prob_hit, prob_miss));
+    return b;
+}
+
+void csm_host_mapbuilder_destroy(void* p) { delete static_cast<HostMapBuilder*>(p); }
+
+/* Append one scan node (global pose, scan) and rebuild the latest map, like the front end does per scan.
+ * Returns the number of beams cast. */
+int csm_host_mapbuilder_append(void* p, const double pose[3], const double* angles, const double* ranges, int n,
+                               const double rel_pose[3], double min_range, double max_range)
+{
+    auto* b = static_cast<HostMapBuilder*>(p);
+    auto scan = std::make_shared<ScanData>();
+    scan->angles.assign(angles, angles + n);
+    scan->ranges.assign(ranges, ranges + n);
+    scan->relative_sensor_pose = Pose2D { rel_pose[0], rel_pose[1], rel_pose[2] };
+    scan->min_range = min_range; scan->max_range = max_range;
+    b->nodes.push_back(ScanNodeView { Pose2D { pose[0], pose[1], pose[2] }, scan });
+    b->builder->UpdateLatestMap(b->nodes);
+    return b->builder->LastNumOfRays();
+}
+
+/* geometry6 = rows, cols, block size, offset x, y, resolution; the map itself and its block allocation */
+int csm_host_mapbuilder_latest(void* p, double* geometry6, double* map_pose3, uint16_t* dense, int cap_cells,
+                               uint8_t* alloc, int cap_blocks)
+{
+    auto* b = static_cast<HostMapBuilder*>(p);
+    const GridMapBuilderGPU& g = *b->builder;
+    geometry6[0] = g.Rows(); geometry6[1] = g.Cols(); geometry6[2] = g.BlockSize();
+    geometry6[3] = g.OffsetX(); geometry6[4] = g.OffsetY(); geometry6[5] = g.LatestMap().resolution;
+    map_pose3[0] = g.LatestMapPose().x; map_pose3[1] = g.LatestMapPose().y; map_pose3[2] = g.LatestMapPose().theta;
+    const int blocks = (g.Rows() / g.BlockSize()) * (g.Cols() / g.BlockSize());
+    if (g.Rows() * g.Cols() > cap_cells || blocks > cap_blocks)
+        return -1;
+    csm_handle h = b->ctx->Handle();
+    b->ctx->Check(csm_download_level(h, g.LatestMap().map_id, 0, dense), "csm_download_level");
+    b->ctx->Check(csm_map_download_allocation(h, g.LatestMap().map_id, alloc), "csm_map_download_allocation");
+    return 0;
+}
+
+/* The front end's pair on the RESIDENT latest map: real-time correlative match + the final matcher on the
+ * device (the context must have SetDeviceFinalMatcher / SetDeviceEpilogue) */
+int csm_host_mapbuilder_match_rt(void* p, const double* angles, const double* ranges, int n, const double rel_pose[3],
+                                 const double init_pose[3], int low_resolution, const double range[3],
+                                 double covariance_scale, csm_host_summary* out)
+{
+    auto* b = static_cast<HostMapBuilder*>(p);
+    try {
+        const auto cost = std::make_shared<CostSquareError>(covariance_scale);
+        const ScanDataPtr scan = Scan(angles, ranges, n, rel_pose);
+        ScanMatcherCorrelative m("RealTimeCorrelativeGPU", cost, low_resolution, range[0], range[1], range[2], b->ctx);
+        const ScanMatchingSummary s = m.OptimizePose(b->builder->LatestMap(), scan,
+                                                     Pose2D { init_pose[0], init_pose[1], init_pose[2] }, 0.0, 0.0);
+        Export(s, out);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "csm_host_mapbuilder_match_rt: %s\n", e.what());
+        return -1;
+    }
+    return 0;
 }
 
 } /* extern "C" */

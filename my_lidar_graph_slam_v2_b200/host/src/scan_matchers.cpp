@@ -58,6 +58,14 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
     /* Anonymous maps (front-end latest map, rebuilt per scan,
      * lidar_graph_slam.cpp:233-240) are uploaded on every call under a private id */
     const std::int64_t id = map.map_id >= 0 ? map.map_id : (std::int64_t(1) << 40);
+    if (map.device_resident) {
+        /* built on the device (GridMapBuilderGPU): nothing to upload, but the CPU epilogue has no cells to read */
+        if (!mContext->DeviceEpilogue() && !mContext->HasDeviceFinalMatcher()) {
+            std::fprintf(stderr, "csm_host: a device-resident map needs the device epilogue or final matcher\n");
+            std::abort();
+        }
+        return map.map_id;
+    }
     const bool resident = map.map_id >= 0 &&
         std::find(mResidentMaps.begin(), mResidentMaps.end(), id) != mResidentMaps.end();
     if (!resident) {

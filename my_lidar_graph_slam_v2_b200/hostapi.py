@@ -94,8 +94,66 @@ def load():
                                                  C.c_int, C.c_int, C.c_int, C.c_double, dp, dp,
                                                  C.POINTER(C.c_int64), dp, dp, dp, dp, C.c_int,
                                                  C.POINTER(HostSummary)]
+        lib.csm_host_mapbuilder_create.restype = C.c_void_p
+        lib.csm_host_mapbuilder_create.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                   C.c_double, C.c_double]
+        lib.csm_host_mapbuilder_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_mapbuilder_append.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, C.c_double, C.c_double]
+        lib.csm_host_mapbuilder_latest.argtypes = [C.c_void_p, dp, dp, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.csm_host_mapbuilder_match_rt.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, C.c_int, dp, C.c_double,
+                                                     C.POINTER(HostSummary)]
         _lib = lib
     return _lib
+
+
+class MapBuilder:
+    """C++ GridMapBuilderGPU: the reference's latest map (GridMapBuilder::UpdateLatestMap) built and kept on
+    the device; append(pose, scan) per scan like the front end."""
+
+    def __init__(self, ctx, resolution=0.05, patch_size=16, scans_for_latest_map=10, usable_range_min=0.01,
+                 usable_range_max=50.0, prob_hit=0.62, prob_miss=0.46):
+        self.lib = load()
+        self.ctx = ctx
+        self.p = self.lib.csm_host_mapbuilder_create(ctx.ctx, resolution, patch_size, scans_for_latest_map,
+                                                     usable_range_min, usable_range_max, prob_hit, prob_miss)
+
+    def append(self, pose, angles, ranges, rel_pose=(0.0, 0.0, 0.0), min_range=0.01, max_range=50.0):
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        p, pp = _d(pose)
+        q, qp = _d(rel_pose)
+        return self.lib.csm_host_mapbuilder_append(self.p, pp, ap, rp, len(a), qp, min_range, max_range)
+
+    def latest(self, cap_cells=1 << 22):
+        """(dense u16 map, block allocation, (offset x, offset y), map pose, block size)"""
+        geo = np.zeros(6)
+        pose = np.zeros(3)
+        dense = np.zeros(cap_cells, dtype=np.uint16)
+        alloc = np.zeros(cap_cells // 64, dtype=np.uint8)
+        dp = C.POINTER(C.c_double)
+        rc = self.lib.csm_host_mapbuilder_latest(self.p, geo.ctypes.data_as(dp), pose.ctypes.data_as(dp),
+                                                 dense.ctypes.data, cap_cells, alloc.ctypes.data, len(alloc))
+        assert rc == 0
+        rows, cols, bs = int(geo[0]), int(geo[1]), int(geo[2])
+        return (dense[:rows * cols].reshape(rows, cols).copy(), alloc[:(rows // bs) * (cols // bs)].reshape(rows // bs, cols // bs).copy(),
+                (geo[3], geo[4]), pose, bs)
+
+    def match_rt(self, angles, ranges, init_pose, low_resolution, rng, rel_pose=(0.0, 0.0, 0.0), covariance_scale=1e4):
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        p, pp = _d(init_pose)
+        q, qp = _d(rel_pose)
+        g, gp = _d(rng)
+        out = HostSummary()
+        rc = self.lib.csm_host_mapbuilder_match_rt(self.p, ap, rp, len(a), qp, pp, low_resolution, gp,
+                                                   covariance_scale, C.byref(out))
+        assert rc == 0
+        return out
+
+    def close(self):
+        if self.p:
+            self.lib.csm_host_mapbuilder_destroy(self.p)
+            self.p = None
 
 
 class HeapMaps:

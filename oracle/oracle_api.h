@@ -99,6 +99,15 @@ void orc_loopdet_use_linear_solver(void* det, int iterations_max, double converg
  * pass-through final matcher (the sub-pixel refiner is outside the path).
  * Queries are split into n_threads contiguous ranges, one detector (and one
  * pyramid cache) per thread, like loop_detector_fpga_parallel.cpp:41-56. */
+/* ---- map construction: GridMapBuilder::UpdateLatestMap (grid_map_builder.cpp:497-532, 561-695) on the
+ * reference's GridMapBuilder (one instance per process, re-initialised by orc_mapbuilder_create) ---- */
+void* orc_mapbuilder_create(double resolution, int patch_size, int scans_for_latest_map,
+                            double usable_range_min, double usable_range_max, double prob_hit, double prob_miss);
+int orc_mapbuilder_append(void* builder, const double pose[3], const double* angles, const double* ranges, int n,
+                          const double rel_pose[3], double min_range, double max_range);
+int orc_mapbuilder_latest(void* builder, double* geometry6, double* map_pose3, uint16_t* dense, int cap_cells,
+                          uint8_t* alloc, int cap_blocks);
+
 void* orc_loopdet_create(int hmax, double range_x, double range_y, double range_t,
                          double score_thr, double known_thr, int n_threads);
 void  orc_loopdet_destroy(void* det);

@@ -91,6 +91,11 @@ class Oracle:
         lib.orc_loopdet_detect.argtypes = [
             C.c_void_p, C.c_int, C.POINTER(C.c_void_p), i32p, dp, i32p, dp,
             C.c_int, C.c_int, dp, dp, rp, dp]
+        if hasattr(lib, "orc_mapbuilder_create"):
+            lib.orc_mapbuilder_create.restype = C.c_void_p
+            lib.orc_mapbuilder_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+            lib.orc_mapbuilder_append.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, C.c_double, C.c_double]
+            lib.orc_mapbuilder_latest.argtypes = [C.c_void_p, dp, dp, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         assert lib.orc_kind().decode() == kind
 
     # -- grids ------------------------------------------------------------
@@ -102,6 +107,12 @@ class Oracle:
         if not h:
             raise ValueError("orc_grid_create failed (rows/cols must be multiples of 16)")
         return OracleGrid(self, h, dense.shape)
+
+    # -- map construction (the reference's GridMapBuilder::UpdateLatestMap) ------------
+    def map_builder(self, resolution=0.05, patch_size=16, scans_for_latest_map=10, usable_range_min=0.01,
+                    usable_range_max=50.0, prob_hit=0.62, prob_miss=0.46):
+        return OracleMapBuilder(self, resolution, patch_size, scans_for_latest_map, usable_range_min,
+                                usable_range_max, prob_hit, prob_miss)
 
     # -- matchers ---------------------------------------------------------
     @staticmethod
@@ -275,3 +286,33 @@ def load(kind="reference"):
     if kind not in _CACHE:
         _CACHE[kind] = Oracle(kind)
     return _CACHE[kind]
+
+
+class OracleMapBuilder:
+    """The reference's GridMapBuilder (one instance per process, re-initialised here): append(pose, scan)
+    rebuilds the latest map like the front end does per scan."""
+
+    def __init__(self, oracle, resolution, patch_size, scans_for_latest_map, usable_range_min, usable_range_max,
+                 prob_hit, prob_miss):
+        self.lib = oracle.lib
+        self.p = self.lib.orc_mapbuilder_create(resolution, patch_size, scans_for_latest_map, usable_range_min,
+                                                usable_range_max, prob_hit, prob_miss)
+
+    def append(self, pose, angles, ranges, rel_pose=(0.0, 0.0, 0.0), min_range=0.01, max_range=50.0):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        q = np.ascontiguousarray(rel_pose, dtype=np.float64)
+        assert self.lib.orc_mapbuilder_append(self.p, _dptr(p), _dptr(a), _dptr(r), len(a), _dptr(q),
+                                              min_range, max_range) == 0
+
+    def latest(self, cap_cells=1 << 22):
+        geo = np.zeros(6)
+        pose = np.zeros(3)
+        dense = np.zeros(cap_cells, dtype=np.uint16)
+        alloc = np.zeros(cap_cells // 64, dtype=np.uint8)
+        assert self.lib.orc_mapbuilder_latest(self.p, _dptr(geo), _dptr(pose), dense.ctypes.data, cap_cells,
+                                              alloc.ctypes.data, len(alloc)) == 0
+        rows, cols, bs = int(geo[0]), int(geo[1]), int(geo[2])
+        return (dense[:rows * cols].reshape(rows, cols).copy(),
+                alloc[:(rows // bs) * (cols // bs)].reshape(rows // bs, cols // bs).copy(), (geo[3], geo[4]), pose, bs)

@@ -30,7 +30,12 @@
 #include "my_lidar_graph_slam/metric/metric.hpp"
 #include "my_lidar_graph_slam/sensor/sensor_data.hpp"
 #include "my_lidar_graph_slam/mapping/grid_map_types.hpp"
+/* (GridMapBuilder registers its metrics under fixed names, so a process can construct it only once;
+ * the checker keeps that one instance and re-initialises its members for every new sequence, which
+ * takes access to them. No reference code is changed.) */
+#define private public
 #include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
+#undef private
 #include "my_lidar_graph_slam/mapping/cost_function_square_error.hpp"
 #include "my_lidar_graph_slam/mapping/cost_function_greedy_endpoint.hpp"
 #include "my_lidar_graph_slam/mapping/score_function_pixel_accurate.hpp"
@@ -510,6 +515,79 @@ void orc_loopdet_use_linear_solver(void* detPtr, int iterations_max, double conv
     det->mFinalConvergence = convergence_threshold;
     det->mFinalLambda = initial_lambda;
     det->Build();
+}
+
+/* ---- map construction: GridMapBuilder::UpdateLatestMap (grid_map_builder.cpp:497-532, 561-695) ---- */
+namespace {
+struct RefMapBuilder
+{
+    std::unique_ptr<GridMapBuilder> mBuilder;
+    IdMap<NodeId, ScanNode> mScanNodes;
+};
+RefMapBuilder* gMapBuilder = nullptr;
+} /* namespace */
+
+void* orc_mapbuilder_create(double resolution, int patch_size, int scans_for_latest_map,
+                            double usable_range_min, double usable_range_max, double prob_hit, double prob_miss)
+{
+    if (gMapBuilder == nullptr) {
+        gMapBuilder = new RefMapBuilder;
+        gMapBuilder->mBuilder.reset(new GridMapBuilder(resolution, patch_size, scans_for_latest_map, 1e9, 0,
+                                                       usable_range_min, usable_range_max, prob_hit, prob_miss));
+    }
+    GridMapBuilder& b = *gMapBuilder->mBuilder;
+    /* a fresh sequence on the one instance: the state its constructor sets (grid_map_builder.cpp:70-99) */
+    const_cast<double&>(b.mResolution) = resolution;
+    const_cast<int&>(b.mPatchSize) = patch_size;
+    b.mLatestMap = GridMap(resolution, patch_size, 1.0, 1.0);
+    b.mLatestMapPose = RobotPose2D<double>(0.0, 0.0, 0.0);
+    const_cast<int&>(b.mNumOfScansForLatestMap) = scans_for_latest_map;
+    b.mLatestScanIdMin = NodeId(0);
+    b.mLatestScanIdMax = NodeId(0);
+    const_cast<double&>(b.mUsableRangeMin) = usable_range_min;
+    const_cast<double&>(b.mUsableRangeMax) = usable_range_max;
+    const_cast<double&>(b.mProbHit) = prob_hit;
+    const_cast<double&>(b.mProbMiss) = prob_miss;
+    const_cast<double&>(b.mOddsHit) = GridMap::GridType::ProbabilityToOdds(prob_hit);
+    const_cast<double&>(b.mOddsMiss) = GridMap::GridType::ProbabilityToOdds(prob_miss);
+    gMapBuilder->mScanNodes = IdMap<NodeId, ScanNode>();
+    return gMapBuilder;
+}
+
+/* Append one scan node (global pose, scan) and rebuild the latest map like the front end does per scan */
+int orc_mapbuilder_append(void* p, const double pose[3], const double* angles, const double* ranges, int n,
+                          const double rel_pose[3], double min_range, double max_range)
+{
+    auto* mb = static_cast<RefMapBuilder*>(p);
+    std::vector<double> a(angles, angles + n), r(ranges, ranges + n);
+    const RobotPose2D<double> zero { 0.0, 0.0, 0.0 };
+    const RobotPose2D<double> rel { rel_pose[0], rel_pose[1], rel_pose[2] };
+    auto scan = std::make_shared<Sensor::ScanData<double>>(
+        "lidar", 0.0, zero, zero, rel, min_range, max_range, a.front(), a.back(), std::move(a), std::move(r));
+    const int id = static_cast<int>(mb->mScanNodes.size());
+    const RobotPose2D<double> global { pose[0], pose[1], pose[2] };
+    mb->mScanNodes.Append(NodeId { id }, LocalMapId { 0 }, zero, scan, global);
+    mb->mBuilder->UpdateLatestMap(mb->mScanNodes);
+    return 0;
+}
+
+/* geometry[0..6] = rows, cols, block size (as doubles), offset x, y, resolution; pose of the latest map */
+int orc_mapbuilder_latest(void* p, double* geometry6, double* map_pose3, uint16_t* dense, int cap_cells,
+                          uint8_t* alloc, int cap_blocks)
+{
+    auto* mb = static_cast<RefMapBuilder*>(p);
+    const GridMap& map = mb->mBuilder->LatestMap();
+    geometry6[0] = map.Rows(); geometry6[1] = map.Cols(); geometry6[2] = map.BlockSize();
+    geometry6[3] = map.PosOffset().mX; geometry6[4] = map.PosOffset().mY; geometry6[5] = map.Resolution();
+    const RobotPose2D<double>& pose = mb->mBuilder->LatestMapPose();
+    map_pose3[0] = pose.mX; map_pose3[1] = pose.mY; map_pose3[2] = pose.mTheta;
+    if (map.Rows() * map.Cols() > cap_cells || map.BlockRows() * map.BlockCols() > cap_blocks)
+        return -1;
+    Flatten(map, dense);
+    for (int br = 0; br < map.BlockRows(); ++br)
+        for (int bc = 0; bc < map.BlockCols(); ++bc)
+            alloc[br * map.BlockCols() + bc] = map.Block(br, bc)->IsAllocated() ? 1 : 0;
+    return 0;
 }
 
 void* orc_loopdet_create(int hmax, double range_x, double range_y, double range_t,
