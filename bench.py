@@ -757,6 +757,64 @@ def single_scan_numbers(h, lib, kind):
                                                "cpu_kind": kind}
     ctx_f.close()
 
+    # The front end with the latest map BUILT AND KEPT on the device (GridMapBuilderGPU, csm_map_*): per scan
+    # UpdateLatestMap over the last 10 scans (grid_map_builder.cpp:497-532), then the match + final matcher on
+    # the map where it lies -- no cell crosses PCIe. CPU: the reference's GridMapBuilder::UpdateLatestMap,
+    # then its matcher pair on a map of that kind (timed apart, added).
+    rng_t = np.random.default_rng(41001)
+    room = synth.make_room(rng_t)
+    p0 = synth.random_pose_in_room(room, rng_t)
+    traj = []
+    for k in range(40):
+        p = p0 + np.array([0.06, 0.025, 0.012]) * k
+        a, r = synth.raycast(room, p, 360, 0.01, 11.4, rng_t)
+        traj.append((p, a, r))
+    ctx_m = hostapi.Context(h.device)
+    ctx_m.set_device_final_matcher(*REFINE)
+    mb = hostapi.MapBuilder(ctx_m)
+    ob = orc.map_builder()
+    for p, a, r in traj[:10]:
+        mb.append(p, a, r)
+        ob.append(p, a, r)
+    pq, aq, rq = traj[10]
+    init_q = pq + np.array([0.07, -0.05, 0.02])
+    gpu_match = timeit(lambda: mb.match_rt(aq, rq, init_q, 5, synth.CFG1["rng"]), 2000)
+    state = {"k": 10}
+
+    def frontend_step():
+        k = state["k"] = 10 + (state["k"] - 9) % 30
+        p, a, r = traj[k]
+        mb.append(p, a, r)
+        return mb.match_rt(a, r, p + np.array([0.07, -0.05, 0.02]), 5, synth.CFG1["rng"])
+
+    gpu_step = timeit(frontend_step, 1000)
+    dense_l, _, off_l, _, _ = ob.latest()
+    og_l = orc.grid(dense_l, 0.05, off_l[0], off_l[1])
+
+    def cpu_pair():
+        o = orc.match_rt(og_l, aq, rq, init_q, 5, synth.CFG1["rng"])
+        return orc.refine(og_l, aq, rq, list(o.est_pose), None, *REFINE)
+
+    cpu_match = timeit(cpu_pair, 20, 0.0)
+    ostate = {"k": 10}
+
+    def cpu_update():
+        k = ostate["k"] = 10 + (ostate["k"] - 9) % 30
+        ob.append(*traj[k])
+
+    cpu_upd = timeit(cpu_update, 30, 0.0)
+    cpu_step = 1.0 / (1.0 / cpu_upd + 1.0 / cpu_match)
+    out["cfg1_frontend_resident_map"] = {
+        "match_plus_final_per_s": {"gpu_e2e": gpu_match, "us_per_match": 1e6 / gpu_match, "cpu_1core": cpu_match,
+                                   "ratio": gpu_match / cpu_match},
+        "update_latest_map_plus_match_per_s": {"gpu_e2e": gpu_step, "us_per_scan": 1e6 / gpu_step,
+                                               "cpu_1core": cpu_step, "cpu_update_latest_map_per_s": cpu_upd,
+                                               "ratio": gpu_step / cpu_step},
+        "map": "%d x %d cells from 10 scans of 360 beams, rebuilt per scan on both arms" % dense_l.shape,
+        "cpu_kind": kind}
+    mb.close()
+    ctx_m.close()
+
     gpu = timeit(bb, 1000)
     cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5, 0.0)
     out["cfg2_bb_matches_per_s"] = {"gpu_e2e": gpu, "cpu_1core": cpu, "ratio": gpu / cpu, "cpu_kind": kind}

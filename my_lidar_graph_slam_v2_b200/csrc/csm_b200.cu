@@ -2335,12 +2335,20 @@ int csm_map_set_update_tables(csm_handle h, const uint16_t* t_miss, const uint16
 {
     if (!h || !t_miss || !t_hit) return CSM_E_INVALID;
     CSM_CUDA(cudaSetDevice(h->device));
-    int rc = ensure(h, h->d_maptables, 2 * 65536 * sizeof(uint16_t));
+    /* the tables of 2^j updates in a row, j < kMapPowTables: composition of the table with itself */
+    const size_t one = 65536;
+    std::vector<uint16_t> pw(2 * (size_t)kMapPowTables * one);
+    for (int kind = 0; kind < 2; ++kind) {
+        uint16_t* t = pw.data() + (size_t)kind * kMapPowTables * one;
+        std::memcpy(t, kind ? t_hit : t_miss, one * sizeof(uint16_t));
+        for (int j = 1; j < kMapPowTables; ++j)
+            for (size_t v = 0; v < one; ++v)
+                t[j * one + v] = t[(j - 1) * one + t[(j - 1) * one + v]];
+    }
+    int rc = ensure(h, h->d_maptables, pw.size() * sizeof(uint16_t));
     if (rc) return rc;
-    char* p = static_cast<char*>(h->d_maptables.p);
-    CSM_CUDA(cudaMemcpyAsync(p, t_miss, 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-    CSM_CUDA(cudaMemcpyAsync(p + 65536 * sizeof(uint16_t), t_hit, 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-    CSM_CUDA(cudaStreamSynchronize(h->stream));       /* the tables are the caller's memory */
+    CSM_CUDA(cudaMemcpyAsync(h->d_maptables.p, pw.data(), pw.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CSM_CUDA(cudaStreamSynchronize(h->stream));       /* pw is about to go */
     h->map_tables_set = true;
     return CSM_OK;
 }
@@ -2489,21 +2497,33 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
     R.events = ev_in;
     R.n = n; R.scale = subpixel_scale; R.rows = m.rows; R.cols = m.cols;
     R.error = static_cast<int*>(h->d_maperror.p);
-    k_map_rays<<<(n + 127) / 128, 128, 0, h->stream>>>(R);
-    CSM_LAUNCH_CHECK();
-    /* per cell, in beam order: the cell index takes the high word; only its significant bits are sorted */
+    /* `order` must be below 2^(shift - 1): the adapter numbers the beams of one call 0 .. n - 1 */
+    int order_max = 0;
+    for (int i = 0; i < n; ++i) {
+        if (rays[i].order < 0)
+            return fail(h, CSM_E_INVALID, "map insert: negative beam order");
+        order_max = std::max(order_max, rays[i].order);
+    }
+    int order_bits = 1;
+    while ((1ll << order_bits) <= (long long)order_max) ++order_bits;
     int cell_bits = 1;
     while ((1ull << cell_bits) < (unsigned long long)m.rows * m.cols) ++cell_bits;
-    if (cub::DeviceRadixSort::SortKeys(sort_tmp, sort_bytes, ev_in, ev_out, (int)total, 0, std::min(64, 32 + cell_bits + 1),
-                                       h->stream) != cudaSuccess)
+    R.shift = order_bits + 1;
+    if (R.shift + cell_bits + 1 > 64)
+        return fail(h, CSM_E_UNSUPPORTED, "map insert: cell index and beam order do not fit one event");
+    CSM_CUDA(cudaMemsetAsync(ev_in, 0xff, sizeof(unsigned long long) * (size_t)total, h->stream));    /* kMapEventNone */
+    k_map_rays<<<n, kMapRayThreads, 0, h->stream>>>(R);
+    CSM_LAUNCH_CHECK();
+    /* per cell, in beam order; one bit above the cell index, so that the unused slots (all ones) sort last */
+    if (cub::DeviceRadixSort::SortKeys(sort_tmp, sort_bytes, ev_in, ev_out, (int)total, 0,
+                                       std::min(64, R.shift + cell_bits + 1), h->stream) != cudaSuccess)
         return fail(h, CSM_E_CUDA, "map insert: radix sort failed");
     ++h->launches;
     MapApplyArgs P;
     P.events = ev_out; P.n = (unsigned int)total;
     P.map = m.base; P.alloc = m.alloc;
-    P.lut_miss = static_cast<const uint16_t*>(h->d_maptables.p);
-    P.lut_hit = P.lut_miss + 65536;
-    P.cols = m.cols; P.log2bs = m.alloc_log2bs; P.block_cols = m.cols >> m.alloc_log2bs;
+    P.lut = static_cast<const uint16_t*>(h->d_maptables.p);
+    P.cols = m.cols; P.log2bs = m.alloc_log2bs; P.block_cols = m.cols >> m.alloc_log2bs; P.shift = R.shift;
     k_map_apply<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(P);
     CSM_LAUNCH_CHECK();
     CSM_CUDA(cudaMemcpyAsync(h->h_maperror, h->d_maperror.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
