@@ -289,6 +289,9 @@ int csm_map_reset_values(csm_handle h, int64_t map_id);
 int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n, int subpixel_scale);
 /* Block allocation bytes of the map (block_rows * block_cols, 1 = allocated); synchronous. */
 int csm_map_download_allocation(csm_handle h, int64_t map_id, uint8_t* out);
+/* The map's true cell values, rows x cols (GridMap's own u16). csm_download_level(level 0) returns what the
+ * matchers read instead: the same cells with 65535 as 0 while option "saturated_unknown" is on. */
+int csm_map_download_cells(csm_handle h, int64_t map_id, uint16_t* out);
 
 /* ---- scans ---------------------------------------------------------------
  * Replaces SendScanData (scan_matcher_correlative_fpga.cpp:296-299): beam

@@ -72,7 +72,7 @@ EXPORTS = [
     "csm_comm_allreduce_best", "csm_comm_allreduce_best_all", "csm_comm_best_result", "csm_comm_destroy",
     "csm_comm_allreduce_word", "csm_comm_allreduce_words_all",
     "csm_map_set_update_tables", "csm_map_create", "csm_map_resize", "csm_map_reset_values",
-    "csm_map_insert_rays", "csm_map_download_allocation",
+    "csm_map_insert_rays", "csm_map_download_allocation", "csm_map_download_cells",
 ]
 
 _LIB = None

@@ -103,7 +103,8 @@ struct MapSlot
 {
     int rows = 0, cols = 0;
     double res = 0.0, offx = 0.0, offy = 0.0;
-    uint16_t* base = nullptr;      /* level 0 */
+    uint16_t* base = nullptr;      /* level 0: what the matchers read (65535 as unknown, see k_saturated_unknown) */
+    uint16_t* raw = nullptr;       /* maps made by csm_map_create: the true values the next update continues from */
     std::shared_ptr<ArenaBlock> base_block;   /* owner of `base` when it lives in a batch arena */
     uint16_t* levels = nullptr;    /* levels 1..hmax */
     int levels_alloc = 0;          /* number of levels the allocation holds */
@@ -241,6 +242,7 @@ struct csm_context
     int64_t exact_reruns = 0;      /* flagged results recomputed exactly so far */
     int exact_rerun = 1;           /* option: recompute results whose projection raised the FP guard-band flag */
     double fp_margin_scale = 1.0;  /* option (tests): multiplies the guard band */
+    int saturated_unknown = 1;     /* option: a cell at 65535 reads as unknown, like in the compiled reference */
     /* map construction (csm_map_*): update tables, ray / event workspaces, error word */
     DevBuf d_maptables, d_mapwork, d_maperror;
     bool map_tables_set = false;
@@ -446,9 +448,26 @@ int finish_results(csm_handle h, csm_result* results, int nq, csm_refined* refin
     return CSM_OK;
 }
 
+/* Dense uploads: cells at 65535 become unknown in the matchers' copy (k_saturated_unknown), behind the copy
+ * on the same stream. rows * cols is even, so the bytes are a multiple of 4; the tail below 16 is rare. */
+int saturated_pass(csm_handle h, uint16_t* cells, size_t bytes, cudaStream_t stream)
+{
+    if (!h->saturated_unknown || bytes == 0)
+        return CSM_OK;
+    if (bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(cells) & 15u) != 0)
+        return fail(h, CSM_E_UNSUPPORTED, "grid: rows * cols must be a multiple of 8 cells");
+    const size_t n16 = bytes / 16;
+    const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 8);
+    k_saturated_unknown<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(cells), n16);
+    CSM_LAUNCH_CHECK();
+    ++h->launches;
+    return CSM_OK;
+}
+
 void free_map(csm_handle h, MapSlot& m)
 {
     if (m.base && !m.base_block) cudaFreeAsync(m.base, h->stream);
+    if (m.raw) cudaFreeAsync(m.raw, h->stream);
     if (m.levels) cudaFreeAsync(m.levels, h->stream);
     if (m.coarse) cudaFreeAsync(m.coarse, h->stream);
     if (m.bounds) cudaFreeAsync(m.bounds, h->stream);
@@ -520,6 +539,7 @@ int wait_uploads(csm_handle h, const std::vector<MapSlot*>& slots)
             A.alloc = bs->alloc; A.nb_map = bs->nb_map;
             A.log2bs = bs->log2bs; A.block_cols = bs->block_cols; A.cols = bs->cols;
             A.map_cells = map_cells;
+            A.saturated_unknown = h->saturated_unknown;
             const int chunks = (1 << bs->log2bs) * ((1 << bs->log2bs) >> 3);
             const long long work = (long long)bs->max_count * chunks;
             dim3 grid((unsigned)std::min<long long>((work + 255) / 256, 64), (unsigned)bs->n_maps);
@@ -1839,6 +1859,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "accumulate_best_key") == 0) { h->accumulate_best_key = value; return CSM_OK; }
     if (std::strcmp(name, "bb_split_shift") == 0) { h->bb_split_shift = std::max(-4, std::min(value, 4)); return CSM_OK; }
     if (std::strcmp(name, "exact_rerun") == 0) { h->exact_rerun = value != 0; return CSM_OK; }
+    if (std::strcmp(name, "saturated_unknown") == 0) { h->saturated_unknown = value != 0; return CSM_OK; }
     if (std::strcmp(name, "fp_margin_scale") == 0) { h->fp_margin_scale = value > 0 ? (double)value : 1.0; return CSM_OK; }
     if (std::strcmp(name, "bb_capacity") == 0) { h->bb_capacity = std::max(0, value); return CSM_OK; }
     if (std::strcmp(name, "pyramid_segs") == 0) { h->pyramid_segs = std::max(0, std::min(value, 4)); return CSM_OK; }
@@ -1908,7 +1929,7 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
     if (on_device) {
         CSM_CUDA(cudaMemcpyAsync(m.base, dense, bytes, cudaMemcpyDeviceToDevice, h->stream));
-        return CSM_OK;
+        return saturated_pass(h, m.base, bytes, h->stream);
     }
     /* Host uploads go to the copy stream. It first waits for the compute work
      * enqueued so far: kernels of the previous batch may still read the old
@@ -1921,7 +1942,7 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     }
     CSM_CUDA(cudaMemcpyAsync(m.base, dense, bytes, cudaMemcpyHostToDevice, h->copy_stream));
     m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
-    return CSM_OK;
+    return saturated_pass(h, m.base, bytes, h->copy_stream);
 }
 
 int csm_upload_grid(csm_handle h, int64_t map_id, const uint16_t* dense,
@@ -1982,6 +2003,10 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
         h->upload_open = true;
     }
     CSM_CUDA(cudaMemcpyAsync(slots[0]->base, dense[0], bytes * n, cudaMemcpyHostToDevice, h->copy_stream));
+    {
+        const int src = saturated_pass(h, slots[0]->base, bytes * n, h->copy_stream);
+        if (src) return src;
+    }
     /* one upload group per batch call: consumers of these maps wait for this
      * batch only, later batches keep streaming in behind the kernels */
     return close_upload_group(h);
@@ -2376,6 +2401,8 @@ int csm_map_create(csm_handle h, int64_t map_id, int rows, int cols, int log2_bl
     const size_t bytes = (size_t)rows * cols * sizeof(uint16_t);
     CSM_CUDA(cudaMallocAsync((void**)&m.base, bytes, h->stream));
     CSM_CUDA(cudaMemsetAsync(m.base, 0, bytes, h->stream));
+    CSM_CUDA(cudaMallocAsync((void**)&m.raw, bytes, h->stream));
+    CSM_CUDA(cudaMemsetAsync(m.raw, 0, bytes, h->stream));
     m.rows = rows; m.cols = cols;
     m.res = resolution; m.offx = offset_x; m.offy = offset_y;
     m.alloc_log2bs = log2_block_size;
@@ -2403,12 +2430,15 @@ int csm_map_resize(csm_handle h, int64_t map_id, int rows, int cols, int row_min
     int rc = settle_slot(h, m);
     if (rc) return rc;
     uint16_t* base = nullptr;
+    uint16_t* raw = nullptr;
     unsigned char* alloc = nullptr;
     const int nb = (rows >> k) * (cols >> k);
     CSM_CUDA(cudaMallocAsync((void**)&base, (size_t)rows * cols * sizeof(uint16_t), h->stream));
+    CSM_CUDA(cudaMallocAsync((void**)&raw, (size_t)rows * cols * sizeof(uint16_t), h->stream));
     CSM_CUDA(cudaMallocAsync((void**)&alloc, (size_t)nb, h->stream));
     MapMoveArgs A;
-    A.src = m.base; A.dst = base; A.src_alloc = m.alloc; A.dst_alloc = alloc;
+    A.src = m.raw; A.dst = raw; A.dst_view = base; A.saturated_unknown = h->saturated_unknown;
+    A.src_alloc = m.alloc; A.dst_alloc = alloc;
     A.src_rows = m.rows; A.src_cols = m.cols; A.dst_rows = rows; A.dst_cols = cols;
     A.row_min = row_min; A.col_min = col_min; A.log2bs = k;
     dim3 grid((cols + 255) / 256, rows);
@@ -2418,8 +2448,9 @@ int csm_map_resize(csm_handle h, int64_t map_id, int rows, int cols, int row_min
     if (m.coarse) { CSM_CUDA(cudaFreeAsync(m.coarse, h->stream)); m.coarse = nullptr; }
     if (m.bounds) { CSM_CUDA(cudaFreeAsync(m.bounds, h->stream)); m.bounds = nullptr; m.bounds_alloc = 0; }
     CSM_CUDA(cudaFreeAsync(m.base, h->stream));
+    CSM_CUDA(cudaFreeAsync(m.raw, h->stream));
     CSM_CUDA(cudaFreeAsync(m.alloc, h->stream));
-    m.base = base; m.alloc = alloc; m.alloc_bytes = nb;
+    m.base = base; m.raw = raw; m.alloc = alloc; m.alloc_bytes = nb;
     m.rows = rows; m.cols = cols; m.offx = offset_x; m.offy = offset_y;
     invalidate_derived(m);
     return CSM_OK;
@@ -2436,6 +2467,8 @@ int csm_map_reset_values(csm_handle h, int64_t map_id)
     int rc = settle_slot(h, m);
     if (rc) return rc;
     CSM_CUDA(cudaMemsetAsync(m.base, 0, (size_t)m.rows * m.cols * sizeof(uint16_t), h->stream));
+    if (m.raw)
+        CSM_CUDA(cudaMemsetAsync(m.raw, 0, (size_t)m.rows * m.cols * sizeof(uint16_t), h->stream));
     invalidate_derived(m);
     return CSM_OK;
 }
@@ -2449,6 +2482,8 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
         return fail(h, CSM_E_INVALID, "map insert: csm_map_set_update_tables first");
     auto it = h->maps.find(map_id);
     if (it == h->maps.end() || it->second.alloc == nullptr || !it->second.alloc_valid || it->second.alloc_block)
+        return fail(h, CSM_E_NOT_FOUND, "map insert: not a map made by csm_map_create");
+    if (it->second.raw == nullptr)
         return fail(h, CSM_E_NOT_FOUND, "map insert: not a map made by csm_map_create");
     if (n == 0)
         return CSM_OK;
@@ -2521,7 +2556,7 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
     ++h->launches;
     MapApplyArgs P;
     P.events = ev_out; P.n = (unsigned int)total;
-    P.map = m.base; P.alloc = m.alloc;
+    P.map = m.raw; P.view = m.base; P.saturated_unknown = h->saturated_unknown; P.alloc = m.alloc;
     P.lut = static_cast<const uint16_t*>(h->d_maptables.p);
     P.cols = m.cols; P.log2bs = m.alloc_log2bs; P.block_cols = m.cols >> m.alloc_log2bs; P.shift = R.shift;
     k_map_apply<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(P);
@@ -2529,6 +2564,18 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
     CSM_CUDA(cudaMemcpyAsync(h->h_maperror, h->d_maperror.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     invalidate_derived(m);
     return CSM_OK;
+}
+
+int csm_map_download_cells(csm_handle h, int64_t map_id, uint16_t* out)
+{
+    if (!h || !out) return CSM_E_INVALID;
+    auto it = h->maps.find(map_id);
+    if (it == h->maps.end() || it->second.raw == nullptr)
+        return fail(h, CSM_E_NOT_FOUND, "map cells: not a map made by csm_map_create");
+    CSM_CUDA(cudaSetDevice(h->device));
+    MapSlot& m = it->second;
+    CSM_CUDA(cudaMemcpyAsync(out, m.raw, (size_t)m.rows * m.cols * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+    return csm_synchronize(h);
 }
 
 int csm_map_download_allocation(csm_handle h, int64_t map_id, uint8_t* out)

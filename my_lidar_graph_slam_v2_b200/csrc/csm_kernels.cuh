@@ -103,7 +103,38 @@ struct ScatterArgs
     int nb_map;
     int log2bs, block_cols, cols;
     size_t map_cells;
+    int saturated_unknown;
 };
+
+/* A cell at 65535 (ValueMax) reads as unknown. The reference's value -> probability tables hold
+ * ValueMax - ValueMin + 1 = 65535 entries (grid_values.cpp:32-35, 72-74), so every read of a cell at 65535
+ * -- the score (scan_matcher_correlative.cpp:313, score_function_pixel_accurate.cpp:34) as well as the
+ * cost function's interpolation -- runs one element past the table, into the zero tail of the table's own
+ * mmap'd chunk under glibc: probability 0.0, which is the unknown probability. The compiled reference
+ * therefore treats such a cell exactly like an unknown one, and so does the matchers' view of every map
+ * here (option "saturated_unknown", default on). The map builder keeps the true value next to it. */
+__device__ __forceinline__ unsigned int saturated_as_unknown(unsigned int w)
+{
+    return w & ~__vcmpeq2(w, 0xffffffffu);
+}
+__device__ __forceinline__ uint4 saturated_as_unknown(uint4 v)
+{
+    v.x = saturated_as_unknown(v.x); v.y = saturated_as_unknown(v.y);
+    v.z = saturated_as_unknown(v.z); v.w = saturated_as_unknown(v.w);
+    return v;
+}
+
+/* the same for a dense upload, in place */
+__global__ void __launch_bounds__(256)
+k_saturated_unknown(uint4* __restrict__ cells, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = cells[i];
+        const uint4 w = saturated_as_unknown(v);
+        if (v.x != w.x || v.y != w.y || v.z != w.z || v.w != w.w)
+            cells[i] = w;
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_scatter_blocks(ScatterArgs A)
@@ -122,7 +153,9 @@ k_scatter_blocks(ScatterArgs A)
         const int r_in = c >> (k - 3), c_in = (c & (chunks_per_row - 1)) << 3;
         const int bi = __ldg(A.index + first + b);
         const int brow = bi / A.block_cols, bcol = bi - brow * A.block_cols;
-        const uint4 v = __ldg(A.data + (size_t)(first + b) * chunks_per_block + c);
+        uint4 v = __ldg(A.data + (size_t)(first + b) * chunks_per_block + c);
+        if (A.saturated_unknown)
+            v = saturated_as_unknown(v);
         *reinterpret_cast<uint4*>(dense + (size_t)((brow << k) + r_in) * A.cols + (bcol << k) + c_in) = v;
         if (c == 0 && A.alloc != nullptr)
             A.alloc[(size_t)m * A.nb_map + bi] = 1;

@@ -133,7 +133,9 @@ struct MapApplyArgs
 {
     const unsigned long long* events;     /* sorted */
     unsigned int n;
-    uint16_t* map;
+    uint16_t* map;                        /* the true values (what the next update continues from) */
+    uint16_t* view;                       /* what the matchers read: 65535 as unknown when saturated_unknown */
+    int saturated_unknown;
     unsigned char* alloc;                 /* one byte per 16 x 16 block */
     const uint16_t* lut;                  /* [kind: miss, hit][j < kMapPowTables][65536]: j-th table = 2^j updates */
     int cols, log2bs, block_cols, shift;
@@ -226,6 +228,7 @@ k_map_apply(MapApplyArgs A)
     }
     if (first) {
         A.map[cell] = (uint16_t)v;
+        A.view[cell] = (A.saturated_unknown && v == 65535u) ? (uint16_t)0 : (uint16_t)v;
         const unsigned int row = cell / (unsigned)A.cols, col = cell - row * (unsigned)A.cols;
         A.alloc[(row >> A.log2bs) * (unsigned)A.block_cols + (col >> A.log2bs)] = 1;
     }
@@ -236,7 +239,9 @@ k_map_apply(MapApplyArgs A)
  * (r - row_min, c - col_min); the block allocation bytes move the same way. */
 struct MapMoveArgs
 {
-    const uint16_t* src; uint16_t* dst;
+    const uint16_t* src; uint16_t* dst;       /* true values */
+    uint16_t* dst_view;                        /* the matchers' view of dst */
+    int saturated_unknown;
     const unsigned char* src_alloc; unsigned char* dst_alloc;
     int src_rows, src_cols, dst_rows, dst_cols, row_min, col_min, log2bs;
 };
@@ -251,6 +256,7 @@ k_map_move(MapMoveArgs A)
         if ((unsigned)sr < (unsigned)A.src_rows && (unsigned)sc < (unsigned)A.src_cols)
             v = A.src[(size_t)sr * A.src_cols + sc];
         A.dst[(size_t)r * A.dst_cols + c] = v;
+        A.dst_view[(size_t)r * A.dst_cols + c] = (A.saturated_unknown && v == 65535) ? (uint16_t)0 : v;
     }
     const int bs = 1 << A.log2bs;
     const int dbr = A.dst_rows >> A.log2bs, dbc = A.dst_cols >> A.log2bs;

@@ -13,6 +13,7 @@
 #include "csm_host/loop_detector.hpp"
 #include "csm_host/loop_searcher.hpp"
 #include "csm_host/map_builder.hpp"
+#include "csm_host/slam_pipeline.hpp"
 
 using namespace csm_host;
 
@@ -655,7 +656,7 @@ int csm_host_mapbuilder_latest(void* p, double* geometry6, double* map_pose3, ui
     if (g.Rows() * g.Cols() > cap_cells || blocks > cap_blocks)
         return -1;
     csm_handle h = b->ctx->Handle();
-    b->ctx->Check(csm_download_level(h, g.LatestMap().map_id, 0, dense), "csm_download_level");
+    b->ctx->Check(csm_map_download_cells(h, g.LatestMap().map_id, dense), "csm_map_download_cells");
     b->ctx->Check(csm_map_download_allocation(h, g.LatestMap().map_id, alloc), "csm_map_download_allocation");
     return 0;
 }
@@ -679,6 +680,153 @@ int csm_host_mapbuilder_match_rt(void* p, const double* angles, const double* ra
         return -1;
     }
     return 0;
+}
+
+/* ---- the full loop: SlamPipeline ------------------------------------------------------------------ */
+struct HostSlam
+{
+    DeviceContextPtr ctx;
+    std::shared_ptr<PoseGraphOptimizerIdentity> optimizer;
+    std::unique_ptr<SlamPipeline> slam;
+};
+
+/* `v`: the SlamSettings fields in declaration order (slam_pipeline.hpp), initial_pose as three values:
+ * 37 doubles (slam_settings.py packs them for both arms) */
+void* csm_host_slam_create(void* ctx, const double* v, int n)
+{
+    if (n != 37)
+        return nullptr;
+    SlamSettings s;
+    int i = 0;
+    s.resolution = v[i++]; s.patch_size = static_cast<int>(v[i++]); s.scans_for_latest_map = static_cast<int>(v[i++]);
+    s.local_map_travel_dist = v[i++]; s.overlapped_scans = static_cast<int>(v[i++]);
+    s.usable_range_min = v[i++]; s.usable_range_max = v[i++]; s.prob_hit = v[i++]; s.prob_miss = v[i++];
+    s.update_travel_dist = v[i++]; s.update_angle = v[i++]; s.update_time = v[i++];
+    s.loop_detection_threshold = v[i++]; s.degeneration_threshold = v[i++]; s.odometry_covariance_scale = v[i++];
+    s.fuse_odometry_covariance = v[i++] != 0.0;
+    s.initial_pose.x = v[i++]; s.initial_pose.y = v[i++]; s.initial_pose.theta = v[i++];
+    s.rt_low_resolution = static_cast<int>(v[i++]); s.rt_range_x = v[i++]; s.rt_range_y = v[i++]; s.rt_range_theta = v[i++];
+    s.final_iterations = static_cast<int>(v[i++]); s.final_convergence = v[i++]; s.final_lambda = v[i++];
+    s.covariance_scale = v[i++];
+    s.searcher_travel_dist = v[i++]; s.searcher_node_dist = v[i++]; s.searcher_candidates = static_cast<int>(v[i++]);
+    s.bb_node_height_max = static_cast<int>(v[i++]); s.bb_range_x = v[i++]; s.bb_range_y = v[i++]; s.bb_range_theta = v[i++];
+    s.score_threshold = v[i++]; s.known_rate_threshold = v[i++];
+    s.host_final_matchers = v[i++] != 0.0;
+    auto* p = new HostSlam;
+    p->ctx = *static_cast<DeviceContextPtr*>(ctx);
+    p->optimizer = std::make_shared<PoseGraphOptimizerIdentity>();
+    p->slam.reset(new SlamPipeline(p->ctx, s, p->optimizer));
+    return p;
+}
+
+void csm_host_slam_destroy(void* p) { delete static_cast<HostSlam*>(p); }
+
+/* n_scans scans of n_beams each (row-major ranges, shared angles), their odometry poses and time stamps:
+ * the whole trajectory in one call, so that the timing holds no Python. Returns the scans used. */
+int csm_host_slam_run(void* p, int n_scans, int n_beams, const double* angles, const double* ranges,
+                      const double* odom_poses, const double* time_stamps, double min_range, double max_range,
+                      int finish)
+{
+    auto* hs = static_cast<HostSlam*>(p);
+    int used = 0;
+    for (int k = 0; k < n_scans; ++k) {
+        auto scan = std::make_shared<ScanData>();
+        scan->angles.assign(angles, angles + n_beams);
+        scan->ranges.assign(ranges + static_cast<std::size_t>(k) * n_beams, ranges + static_cast<std::size_t>(k + 1) * n_beams);
+        scan->min_range = min_range; scan->max_range = max_range;
+        used += hs->slam->ProcessScan(scan, Pose2D { odom_poses[3 * k], odom_poses[3 * k + 1], odom_poses[3 * k + 2] },
+                                      time_stamps[k]) ? 1 : 0;
+    }
+    if (finish)
+        hs->slam->Finish();
+    return used;
+}
+
+/* 14 values: scans in, processed, back-end steps, steps with candidates, loop queries, loops detected,
+ * optimisations, degenerations, optimiser calls seen behind the seam; seconds in latest map, match,
+ * append, back end, detect */
+void csm_host_slam_counters(void* p, double* out)
+{
+    auto* hs = static_cast<HostSlam*>(p);
+    const SlamCounters& c = hs->slam->Counters();
+    const double v[14] = { double(c.scans_in), double(c.scans_processed), double(c.backend_steps),
+                           double(c.backend_steps_with_candidates), double(c.loop_queries), double(c.loops_detected),
+                           double(c.optimizations), double(c.degenerations), double(hs->optimizer->Calls()),
+                           c.t_latest_map, c.t_match, c.t_append, c.t_backend, c.t_detect };
+    std::copy(v, v + 14, out);
+}
+
+int csm_host_slam_num_scan_nodes(void* p) { return static_cast<int>(static_cast<HostSlam*>(p)->slam->Graph().scan_nodes.size()); }
+int csm_host_slam_num_local_maps(void* p) { return static_cast<int>(static_cast<HostSlam*>(p)->slam->Builder().LocalMaps().size()); }
+int csm_host_slam_num_edges(void* p) { return static_cast<int>(static_cast<HostSlam*>(p)->slam->Graph().edges.size()); }
+int csm_host_slam_num_loops(void* p) { return static_cast<int>(static_cast<HostSlam*>(p)->slam->Loops().size()); }
+
+/* per scan node: global pose (3), local pose (3), local map id */
+void csm_host_slam_scan_nodes(void* p, double* out7)
+{
+    const PoseGraph& g = static_cast<HostSlam*>(p)->slam->Graph();
+    for (std::size_t i = 0; i < g.scan_nodes.size(); ++i) {
+        const ScanNode& n = g.scan_nodes[i];
+        double* o = out7 + 7 * i;
+        o[0] = n.global_pose.x; o[1] = n.global_pose.y; o[2] = n.global_pose.theta;
+        o[3] = n.local_pose.x; o[4] = n.local_pose.y; o[5] = n.local_pose.theta; o[6] = n.local_map_id;
+    }
+}
+
+/* per local map: global pose (3), first and last scan node, finished, rows, cols, offset x, y */
+void csm_host_slam_local_maps(void* p, double* out10)
+{
+    auto* hs = static_cast<HostSlam*>(p);
+    const PoseGraph& g = hs->slam->Graph();
+    const std::vector<LocalMapGPU>& maps = hs->slam->Builder().LocalMaps();
+    for (std::size_t i = 0; i < maps.size(); ++i) {
+        double* o = out10 + 10 * i;
+        const Pose2D& pose = g.local_map_nodes[i].global_pose;
+        o[0] = pose.x; o[1] = pose.y; o[2] = pose.theta;
+        o[3] = maps[i].scan_node_id_min; o[4] = maps[i].scan_node_id_max; o[5] = maps[i].finished ? 1.0 : 0.0;
+        o[6] = maps[i].map->Rows(); o[7] = maps[i].map->Cols(); o[8] = maps[i].map->OffsetX(); o[9] = maps[i].map->OffsetY();
+    }
+}
+
+/* cells (rows x cols) and block allocation of local map `id` */
+int csm_host_slam_local_map_cells(void* p, int id, uint16_t* dense, int cap_cells, uint8_t* alloc, int cap_blocks)
+{
+    auto* hs = static_cast<HostSlam*>(p);
+    const std::vector<LocalMapGPU>& maps = hs->slam->Builder().LocalMaps();
+    if (id < 0 || id >= static_cast<int>(maps.size()))
+        return -1;
+    const DeviceGridMap& m = *maps[id].map;
+    const int bs = m.BlockSize();
+    if (m.Rows() * m.Cols() > cap_cells || (m.Rows() / bs) * (m.Cols() / bs) > cap_blocks)
+        return -2;
+    hs->ctx->Check(csm_map_download_cells(hs->ctx->Handle(), m.MapId(), dense), "csm_map_download_cells");
+    hs->ctx->Check(csm_map_download_allocation(hs->ctx->Handle(), m.MapId(), alloc), "csm_map_download_allocation");
+    return 0;
+}
+
+/* per edge: local map id, scan node id, inter-local-map?, loop?, relative pose (3) */
+void csm_host_slam_edges(void* p, double* out7)
+{
+    const PoseGraph& g = static_cast<HostSlam*>(p)->slam->Graph();
+    for (std::size_t i = 0; i < g.edges.size(); ++i) {
+        const PoseGraphEdge& e = g.edges[i];
+        double* o = out7 + 7 * i;
+        o[0] = e.local_map_id; o[1] = e.scan_node_id; o[2] = e.edge_type == EdgeType::InterLocalMap ? 1.0 : 0.0;
+        o[3] = e.IsLoopClosingConstraint() ? 1.0 : 0.0;
+        o[4] = e.relative_pose.x; o[5] = e.relative_pose.y; o[6] = e.relative_pose.theta;
+    }
+}
+
+/* per detected loop: local map id, scan node id, relative pose (3), normalized score */
+void csm_host_slam_loops(void* p, double* out6)
+{
+    const std::vector<LoopDetectionResult>& loops = static_cast<HostSlam*>(p)->slam->Loops();
+    for (std::size_t i = 0; i < loops.size(); ++i) {
+        double* o = out6 + 6 * i;
+        o[0] = static_cast<double>(loops[i].local_map_id); o[1] = loops[i].scan_node_id;
+        o[2] = loops[i].relative_pose.x; o[3] = loops[i].relative_pose.y; o[4] = loops[i].relative_pose.theta;
+        o[5] = loops[i].normalized_score;
+    }
 }
 
 } /* extern "C" */

@@ -9,10 +9,13 @@ namespace {
 
 constexpr int kLog2Block = 4;     /* reference block size 16 (launcher_settings_default.json:178) */
 
-/* p(v): grid_values.hpp:26-36 */
+/* p(v): grid_values.hpp:26-36. A cell at 65535 reads 0.0 like an unknown one: the reference's table has
+ * 65535 entries (grid_values.cpp:32-35), index 65535 lies in the zero tail of its allocation (see
+ * k_saturated_unknown in csrc/csm_kernels.cuh; option "saturated_unknown" of the library). */
+bool gSaturatedUnknown = true;
 inline double Probability(std::uint16_t v)
 {
-    if (v == 0)
+    if (v == 0 || (v == 65535 && gSaturatedUnknown))
         return 0.0;
     const double pmin = 1e-3, pmax = 1.0 - 1e-3;
     return pmin + (pmax - pmin) * static_cast<double>(static_cast<int>(v) - 1) / 65534.0;

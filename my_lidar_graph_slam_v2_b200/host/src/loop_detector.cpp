@@ -440,6 +440,12 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
      * order they arrive (whatever their ids). Its first-touch maps go up in groups of mUploadChunk. */
     const int chunk = std::max(1, mChunkSize);
     const int ugroup = std::max(1, std::min(mUploadChunk, chunk));
+    for (int i = 0; i < nq; ++i)
+        if (queries[i].local_map.device_resident && lanes > 1) {
+            std::fprintf(stderr, "csm_host: device-resident local maps live on the detector's own context; "
+                                 "pipeline lanes cannot see them\n");
+            std::abort();
+        }
     struct Segment { int first, count, lane; bool fresh; };
     std::vector<Segment> segments;
     for (int i = 0; i < nq; ++i) {
@@ -472,7 +478,9 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             for (int i = first; i < last; ++i) {
                 const GridMapView& m = queries[i].local_map;
                 if (seen.insert(m.map_id).second) {
-                    fresh.push_back(&m);
+                    /* a map built on the device (GridMapBuilderGPU) has nothing to upload: only its levels are due */
+                    if (!m.device_resident)
+                        fresh.push_back(&m);
                     fresh_ids[si].back().push_back(m.map_id);
                 }
             }

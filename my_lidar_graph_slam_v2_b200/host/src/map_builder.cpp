@@ -83,17 +83,43 @@ std::vector<std::uint16_t> GridMapBuilderGPU::UpdateTable(double odds, bool refe
     return table;
 }
 
-GridMapBuilderGPU::GridMapBuilderGPU(const DeviceContextPtr& context, double map_resolution, int patch_size,
-                                     int num_of_scans_for_latest_map, double usable_range_min,
-                                     double usable_range_max, double prob_hit, double prob_miss,
-                                     std::int64_t device_map_id, bool reference_table_end) :
-    mContext(context), mMapId(device_map_id), mResolution(map_resolution),
-    mLog2BlockSize(__builtin_ctz(ToNearestPowerOf2(patch_size))),
-    mNumOfScansForLatestMap(num_of_scans_for_latest_map),
-    mUsableRangeMin(usable_range_min), mUsableRangeMax(usable_range_max),
-    mOddsHit(ProbabilityToOdds(prob_hit)), mOddsMiss(ProbabilityToOdds(prob_miss))
+/* ---- 3 x 3 helpers of the pose graph (pose_graph.hpp) ---- */
+Mat3 Multiply(const Mat3& a, const Mat3& b)
 {
-    /* mLatestMap(mapResolution, patchSize, 1.0, 1.0) (grid_map_builder.cpp:80; grid_map.cpp:74-99, 226-246) */
+    Mat3 c {};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            c[i * 3 + j] = a[i * 3 + 0] * b[0 * 3 + j] + a[i * 3 + 1] * b[1 * 3 + j] + a[i * 3 + 2] * b[2 * 3 + j];
+    return c;
+}
+
+Mat3 Transpose(const Mat3& a)
+{
+    return Mat3 { a[0], a[3], a[6], a[1], a[4], a[7], a[2], a[5], a[8] };
+}
+
+Mat3 Inverse(const Mat3& a)
+{
+    /* cofactors over the determinant, what Eigen does for a fixed 3 x 3 */
+    const double c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+    const double inv_det = 1.0 / (a[0] * c00 + a[1] * c01 + a[2] * c02);
+    return Mat3 { c00 * inv_det, (a[2] * a[7] - a[1] * a[8]) * inv_det, (a[1] * a[5] - a[2] * a[4]) * inv_det,
+                  c01 * inv_det, (a[0] * a[8] - a[2] * a[6]) * inv_det, (a[2] * a[3] - a[0] * a[5]) * inv_det,
+                  c02 * inv_det, (a[1] * a[6] - a[0] * a[7]) * inv_det, (a[0] * a[4] - a[1] * a[3]) * inv_det };
+}
+
+Mat3 RotateCovariance(double angle, const Mat3& cov)
+{
+    const double c = std::cos(angle), s = std::sin(angle);
+    const Mat3 r { c, -s, 0.0, s, c, 0.0, 0.0, 0.0, 1.0 };
+    return Multiply(Multiply(r, cov), Transpose(r));
+}
+
+/* ---- DeviceGridMap ---- */
+DeviceGridMap::DeviceGridMap(const DeviceContextPtr& context, std::int64_t map_id, double resolution, int log2_block_size) :
+    mContext(context), mMapId(map_id), mResolution(resolution), mLog2BlockSize(log2_block_size)
+{
+    /* GridMap(resolution, blockSize, 1.0, 1.0) (grid_map.cpp:74-99, 226-246) */
     const int bs = 1 << mLog2BlockSize;
     const int desired_rows = static_cast<int>(std::ceil(1.0 / mResolution));
     const int desired_cols = static_cast<int>(std::ceil(1.0 / mResolution));
@@ -102,27 +128,23 @@ GridMapBuilderGPU::GridMapBuilderGPU(const DeviceContextPtr& context, double map
     mRows = mBlockRows << mLog2BlockSize;
     mCols = mBlockCols << mLog2BlockSize;
     mOffX = 0.0; mOffY = 0.0;
-    csm_handle h = mContext->Handle();
-    const std::vector<std::uint16_t> miss = UpdateTable(mOddsMiss, reference_table_end),
-                                     hit = UpdateTable(mOddsHit, reference_table_end);
-    mContext->Check(csm_map_set_update_tables(h, miss.data(), hit.data()), "csm_map_set_update_tables");
-    mContext->Check(csm_map_create(h, mMapId, mRows, mCols, mLog2BlockSize, mResolution, mOffX, mOffY), "csm_map_create");
+    mContext->Check(csm_map_create(mContext->Handle(), mMapId, mRows, mCols, mLog2BlockSize, mResolution, mOffX, mOffY),
+                    "csm_map_create");
 }
 
-GridMapBuilderGPU::Index GridMapBuilderGPU::PositionToIndex(double x, double y) const
+DeviceGridMap::~DeviceGridMap()
 {
-    /* grid_map_geometry.cpp:113-122 */
+    csm_release_grid(mContext->Handle(), mMapId);
+}
+
+DeviceGridMap::Index DeviceGridMap::PositionToIndex(double x, double y) const
+{
     return Index { static_cast<int>(std::floor((x - mOffX) / mResolution)),
                    static_cast<int>(std::floor((y - mOffY) / mResolution)) };
 }
 
-void GridMapBuilderGPU::Resize(double min_x, double min_y, double max_x, double max_y)
+void DeviceGridMap::ResizeIndex(int box_min_x, int box_min_y, int box_max_x, int box_max_y)
 {
-    /* GridMap::Resize(BoundingBox<double>) (grid_map.cpp:891-911) ... */
-    const Index idx_min = PositionToIndex(min_x - mResolution, min_y - mResolution);
-    const Index idx_max = PositionToIndex(max_x + mResolution, max_y + mResolution);
-    const int box_min_x = idx_min.x, box_min_y = idx_min.y, box_max_x = idx_max.x + 1, box_max_y = idx_max.y + 1;
-    /* ... -> Resize(BoundingBox<int>) (:842-888) */
     const int bs = 1 << mLog2BlockSize;
     const int block_min_x = IndexToBlock(box_min_x, mLog2BlockSize), block_min_y = IndexToBlock(box_min_y, mLog2BlockSize);
     const int block_max_x = IndexToBlock(box_max_x + bs - 1, mLog2BlockSize);
@@ -139,75 +161,60 @@ void GridMapBuilderGPU::Resize(double min_x, double min_y, double max_x, double 
                     "csm_map_resize");
 }
 
-void GridMapBuilderGPU::UpdateLatestMap(const std::vector<ScanNodeView>& scan_nodes)
+void DeviceGridMap::Resize(double min_x, double min_y, double max_x, double max_y)
 {
-    if (scan_nodes.empty()) {
-        std::fprintf(stderr, "csm_host: UpdateLatestMap needs at least one scan node\n");
-        std::abort();
-    }
-    /* grid_map_builder.cpp:506-518: the last NumOfScansForLatestMap nodes; the map's frame is the pose of
-     * the first of them */
-    const int count = std::min(static_cast<int>(scan_nodes.size()), mNumOfScansForLatestMap);
-    const std::size_t first = scan_nodes.size() - static_cast<std::size_t>(count);
-    mLatestMapPose = scan_nodes[first].global_pose;
+    /* "avoid the rounding errors": one cell of slack on every side */
+    const Index idx_min = PositionToIndex(min_x - mResolution, min_y - mResolution);
+    const Index idx_max = PositionToIndex(max_x + mResolution, max_y + mResolution);
+    ResizeIndex(idx_min.x, idx_min.y, idx_max.x + 1, idx_max.y + 1);
+}
 
-    /* ConstructMapFromScans, first pass (:578-633): hit points and bounding box in the map's frame */
-    double min_x = std::numeric_limits<double>::max(), min_y = std::numeric_limits<double>::max();
-    double max_x = std::numeric_limits<double>::min(), max_y = std::numeric_limits<double>::min();
-    struct NodeHits { Pose2D sensor; std::vector<double> x, y; };
-    std::vector<NodeHits> hits(count);
-    for (int k = 0; k < count; ++k) {
-        const ScanNodeView& node = scan_nodes[first + k];
-        const ScanData& scan = *node.scan;
-        const Pose2D global_sensor = Compound(node.global_pose, scan.relative_sensor_pose);
-        const Pose2D local_sensor = InverseCompound(mLatestMapPose, global_sensor);
-        hits[k].sensor = local_sensor;
-        min_x = std::min(min_x, local_sensor.x); min_y = std::min(min_y, local_sensor.y);
-        max_x = std::max(max_x, local_sensor.x); max_y = std::max(max_y, local_sensor.y);
-        const double min_range = std::max(mUsableRangeMin, scan.min_range);
-        const double max_range = std::min(mUsableRangeMax, scan.max_range);
-        for (std::size_t i = 0; i < scan.NumOfScans(); ++i) {
-            const double range = scan.ranges[i];
-            if (range >= max_range || range <= min_range)
-                continue;
-            /* ScanData::HitPoint (sensor_data.hpp:190-203) */
-            const double c = std::cos(local_sensor.theta + scan.angles[i]);
-            const double s = std::sin(local_sensor.theta + scan.angles[i]);
-            const double hx = local_sensor.x + range * c, hy = local_sensor.y + range * s;
-            hits[k].x.push_back(hx); hits[k].y.push_back(hy);
-            min_x = std::min(min_x, hx); min_y = std::min(min_y, hy);
-            max_x = std::max(max_x, hx); max_y = std::max(max_y, hy);
-        }
-    }
-    /* :636-638 */
-    Resize(min_x, min_y, max_x, max_y);
-    csm_handle h = mContext->Handle();
-    mContext->Check(csm_map_reset_values(h, mMapId), "csm_map_reset_values");
+void DeviceGridMap::Expand(double min_x, double min_y, double max_x, double max_y)
+{
+    const Index idx_min = PositionToIndex(min_x - mResolution, min_y - mResolution);
+    const Index idx_max = PositionToIndex(max_x + mResolution, max_y + mResolution);
+    const int box_min_x = idx_min.x, box_min_y = idx_min.y, box_max_x = idx_max.x + 1, box_max_y = idx_max.y + 1;
+    /* Expand(BoundingBox<int>) (:914-930): nothing to do when both corners are inside */
+    auto inside = [this](int row, int col) { return row >= 0 && row < mRows && col >= 0 && col < mCols; };
+    if (inside(box_min_y, box_min_x) && inside(box_max_y - 1, box_max_x - 1))
+        return;
+    ResizeIndex(std::min(0, box_min_x), std::min(0, box_min_y), std::max(mCols, box_max_x), std::max(mRows, box_max_y));
+}
 
-    /* second pass (:642-692): per beam the sub-pixel indices of sensor and hit point and the hit cell */
-    const double scaled_res = mResolution / SubpixelScale;           /* grid_map_geometry.cpp:48-60 */
+void DeviceGridMap::ResetValues()
+{
+    mContext->Check(csm_map_reset_values(mContext->Handle(), mMapId), "csm_map_reset_values");
+}
+
+int DeviceGridMap::InsertScans(const std::vector<ScanHits>& hits, int subpixel_scale)
+{
+    const double scaled_res = mResolution / subpixel_scale;           /* grid_map_geometry.cpp:48-60 */
+    std::size_t total = 0;
+    for (const ScanHits& h : hits) total += h.x.size();
     std::vector<csm_ray> rays;
+    rays.reserve(total);
     int order = 0;
-    for (int k = 0; k < count; ++k) {
-        const int sx = static_cast<int>(std::floor((hits[k].sensor.x - mOffX) / scaled_res));
-        const int sy = static_cast<int>(std::floor((hits[k].sensor.y - mOffY) / scaled_res));
-        for (std::size_t i = 0; i < hits[k].x.size(); ++i) {
-            const Index hit = PositionToIndex(hits[k].x[i], hits[k].y[i]);
+    for (const ScanHits& h : hits) {
+        const int sx = static_cast<int>(std::floor((h.sensor.x - mOffX) / scaled_res));
+        const int sy = static_cast<int>(std::floor((h.sensor.y - mOffY) / scaled_res));
+        for (std::size_t i = 0; i < h.x.size(); ++i) {
+            const Index hit = PositionToIndex(h.x[i], h.y[i]);
             csm_ray r;
             r.start_x = sx; r.start_y = sy;
-            r.end_x = static_cast<int>(std::floor((hits[k].x[i] - mOffX) / scaled_res));
-            r.end_y = static_cast<int>(std::floor((hits[k].y[i] - mOffY) / scaled_res));
+            r.end_x = static_cast<int>(std::floor((h.x[i] - mOffX) / scaled_res));
+            r.end_y = static_cast<int>(std::floor((h.y[i] - mOffY) / scaled_res));
             r.hit_col = hit.x; r.hit_row = hit.y;
             r.order = order++;
             r.reserved = 0;
             rays.push_back(r);
         }
     }
-    mLastRays = static_cast<int>(rays.size());
-    mContext->Check(csm_map_insert_rays(h, mMapId, rays.data(), mLastRays, SubpixelScale), "csm_map_insert_rays");
+    mContext->Check(csm_map_insert_rays(mContext->Handle(), mMapId, rays.data(), static_cast<int>(rays.size()), subpixel_scale),
+                    "csm_map_insert_rays");
+    return static_cast<int>(rays.size());
 }
 
-GridMapView GridMapBuilderGPU::LatestMap() const
+GridMapView DeviceGridMap::View() const
 {
     GridMapView v;
     v.rows = mRows; v.cols = mCols;
@@ -217,6 +224,203 @@ GridMapView GridMapBuilderGPU::LatestMap() const
     v.log2_block_size = mLog2BlockSize;
     v.device_resident = true;
     return v;
+}
+
+/* ---- GridMapBuilderGPU ---- */
+GridMapBuilderGPU::GridMapBuilderGPU(const DeviceContextPtr& context, double map_resolution, int patch_size,
+                                     int num_of_scans_for_latest_map, double usable_range_min,
+                                     double usable_range_max, double prob_hit, double prob_miss,
+                                     std::int64_t latest_map_device_id, bool reference_table_end) :
+    mContext(context), mResolution(map_resolution),
+    mLog2BlockSize(__builtin_ctz(ToNearestPowerOf2(patch_size))),
+    mNumOfScansForLatestMap(num_of_scans_for_latest_map),
+    mUsableRangeMin(usable_range_min), mUsableRangeMax(usable_range_max),
+    mOddsHit(ProbabilityToOdds(prob_hit)), mOddsMiss(ProbabilityToOdds(prob_miss)),
+    /* mLatestMap(mapResolution, patchSize, 1.0, 1.0) (grid_map_builder.cpp:80) */
+    mLatest(context, latest_map_device_id, map_resolution, __builtin_ctz(ToNearestPowerOf2(patch_size)))
+{
+    const std::vector<std::uint16_t> miss = UpdateTable(mOddsMiss, reference_table_end),
+                                     hit = UpdateTable(mOddsHit, reference_table_end);
+    mContext->Check(csm_map_set_update_tables(mContext->Handle(), miss.data(), hit.data()), "csm_map_set_update_tables");
+}
+
+DeviceGridMap::ScanHits GridMapBuilderGPU::HitsOf(const Pose2D& map_pose, const Pose2D& global_scan_pose,
+                                                  const ScanData& scan) const
+{
+    DeviceGridMap::ScanHits h;
+    const Pose2D global_sensor = Compound(global_scan_pose, scan.relative_sensor_pose);
+    h.sensor = InverseCompound(map_pose, global_sensor);
+    const double min_range = std::max(mUsableRangeMin, scan.min_range);
+    const double max_range = std::min(mUsableRangeMax, scan.max_range);
+    const std::size_t n = scan.NumOfScans();
+    h.x.reserve(n); h.y.reserve(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        const double range = scan.ranges[i];
+        if (range >= max_range || range <= min_range)
+            continue;
+        /* ScanData::HitPoint (sensor_data.hpp:190-203) */
+        const double c = std::cos(h.sensor.theta + scan.angles[i]);
+        const double s = std::sin(h.sensor.theta + scan.angles[i]);
+        h.x.push_back(h.sensor.x + range * c);
+        h.y.push_back(h.sensor.y + range * s);
+    }
+    return h;
+}
+
+void GridMapBuilderGPU::ConstructMapFromScans(const Pose2D& map_pose, DeviceGridMap& map, const ScanNodeView* nodes, int count)
+{
+    /* first pass (:578-633): hit points and bounding box in the map's frame. The box starts at
+     * (max double, min POSITIVE double), as the reference has it (:582-585) */
+    double min_x = std::numeric_limits<double>::max(), min_y = std::numeric_limits<double>::max();
+    double max_x = std::numeric_limits<double>::min(), max_y = std::numeric_limits<double>::min();
+    std::vector<DeviceGridMap::ScanHits> hits;
+    hits.reserve(count);
+    for (int k = 0; k < count; ++k) {
+        hits.push_back(HitsOf(map_pose, nodes[k].global_pose, *nodes[k].scan));
+        const DeviceGridMap::ScanHits& h = hits.back();
+        min_x = std::min(min_x, h.sensor.x); min_y = std::min(min_y, h.sensor.y);
+        max_x = std::max(max_x, h.sensor.x); max_y = std::max(max_y, h.sensor.y);
+        for (std::size_t i = 0; i < h.x.size(); ++i) {
+            min_x = std::min(min_x, h.x[i]); min_y = std::min(min_y, h.y[i]);
+            max_x = std::max(max_x, h.x[i]); max_y = std::max(max_y, h.y[i]);
+        }
+    }
+    /* :636-638 */
+    map.Resize(min_x, min_y, max_x, max_y);
+    map.ResetValues();
+    /* second pass (:642-692) */
+    mLastRays = map.InsertScans(hits, SubpixelScale);
+}
+
+void GridMapBuilderGPU::UpdateLatestMap(const std::vector<ScanNodeView>& scan_nodes)
+{
+    if (scan_nodes.empty()) {
+        std::fprintf(stderr, "csm_host: UpdateLatestMap needs at least one scan node\n");
+        std::abort();
+    }
+    /* :506-518: the last NumOfScansForLatestMap nodes; the map's frame is the pose of the first of them */
+    const int count = std::min(static_cast<int>(scan_nodes.size()), mNumOfScansForLatestMap);
+    const std::size_t first = scan_nodes.size() - static_cast<std::size_t>(count);
+    mLatestScanIdMin = static_cast<int>(first);
+    mLatestScanIdMax = static_cast<int>(scan_nodes.size()) - 1;
+    mLatestMapPose = scan_nodes[first].global_pose;
+    ConstructMapFromScans(mLatestMapPose, mLatest, scan_nodes.data() + first, count);
+}
+
+void GridMapBuilderGPU::UpdateLatestMap(const std::vector<ScanNode>& scan_nodes)
+{
+    if (scan_nodes.empty()) {
+        std::fprintf(stderr, "csm_host: UpdateLatestMap needs at least one scan node\n");
+        std::abort();
+    }
+    const int count = std::min(static_cast<int>(scan_nodes.size()), mNumOfScansForLatestMap);
+    const std::size_t first = scan_nodes.size() - static_cast<std::size_t>(count);
+    std::vector<ScanNodeView> views;
+    views.reserve(count);
+    for (std::size_t k = first; k < scan_nodes.size(); ++k)
+        views.push_back(ScanNodeView { scan_nodes[k].global_pose, scan_nodes[k].scan });
+    mLatestScanIdMin = scan_nodes[first].node_id;
+    mLatestScanIdMax = scan_nodes.back().node_id;
+    mLatestMapPose = scan_nodes[first].global_pose;
+    ConstructMapFromScans(mLatestMapPose, mLatest, views.data(), count);
+}
+
+void GridMapBuilderGPU::FinishLocalMap()
+{
+    if (!mLocalMaps.empty())
+        mLocalMaps.back().finished = true;
+}
+
+void GridMapBuilderGPU::AppendLocalMap(PoseGraph& pose_graph, const Pose2D& scan_pose, const Mat3& covariance, int scan_node_id)
+{
+    FinishLocalMap();
+    const int local_map_id = pose_graph.local_map_nodes.empty() ? 0 : pose_graph.local_map_nodes.back().local_map_id + 1;
+    const Pose2D& local_map_pose = scan_pose;
+    if (!mLocalMaps.empty()) {
+        /* the inter-map odometry edge from the old local map to the new scan node (:208-240) */
+        const LocalMapNode& old_node = pose_graph.local_map_nodes.back();
+        PoseGraphEdge e;
+        e.local_map_id = old_node.local_map_id; e.scan_node_id = scan_node_id;
+        e.edge_type = EdgeType::InterLocalMap; e.constraint_type = ConstraintType::Odometry;
+        e.relative_pose = NormalizeAngle(InverseCompound(old_node.global_pose, scan_pose));
+        e.information = Inverse(ConvertCovarianceFromWorldToLocal(old_node.global_pose, covariance));
+        pose_graph.edges.push_back(e);
+    }
+    pose_graph.local_map_nodes.push_back(LocalMapNode { local_map_id, local_map_pose });
+    LocalMapGPU lm;
+    lm.id = local_map_id;
+    lm.map.reset(new DeviceGridMap(mContext, static_cast<std::int64_t>(local_map_id), mResolution, mLog2BlockSize));
+    lm.scan_node_id_min = lm.scan_node_id_max = scan_node_id;
+    if (!mLocalMaps.empty()) {
+        /* initialised with the last scans of the previous local map (:259-278) */
+        const LocalMapGPU& last = mLocalMaps.back();
+        const int n = static_cast<int>(std::min<std::size_t>(pose_graph.scan_nodes.size(), mNumOfOverlappedScans));
+        const int id_max = last.scan_node_id_max, id_min = id_max - (n - 1);
+        std::vector<ScanNodeView> views;
+        for (int id = id_min; id <= id_max; ++id)
+            views.push_back(ScanNodeView { pose_graph.scan_nodes[id].global_pose, pose_graph.scan_nodes[id].scan });
+        ConstructMapFromScans(local_map_pose, *lm.map, views.data(), static_cast<int>(views.size()));
+    }
+    mLocalMaps.push_back(std::move(lm));
+    mTravelDistLastLocalMap = 0.0;
+}
+
+bool GridMapBuilderGPU::AppendScan(PoseGraph& pose_graph, const Pose2D& relative_scan_pose,
+                                   const Mat3& scan_pose_covariance, const ScanDataPtr& scan)
+{
+    /* UpdatePoseGraph (:290-385) */
+    const int scan_node_id = pose_graph.scan_nodes.empty() ? 0 : pose_graph.scan_nodes.back().node_id + 1;
+    const Pose2D prev_scan_pose = pose_graph.scan_nodes.empty() ? Pose2D {} : pose_graph.scan_nodes.back().global_pose;
+    const Pose2D scan_pose = Compound(prev_scan_pose, relative_scan_pose);
+    mAccumTravelDist += Distance(relative_scan_pose);
+    mTravelDistLastLocalMap += Distance(relative_scan_pose);
+    const bool travel = mTravelDistLastLocalMap >= mTravelDistThreshold;
+    const bool last_finished = !mLocalMaps.empty() && mLocalMaps.back().finished;
+    const bool inserted = travel || last_finished || mLocalMaps.empty();
+    if (inserted)
+        AppendLocalMap(pose_graph, scan_pose, scan_pose_covariance, scan_node_id);
+    const LocalMapNode& map_node = pose_graph.local_map_nodes.back();
+    const Pose2D map_local_scan_pose = NormalizeAngle(InverseCompound(map_node.global_pose, scan_pose));
+    ScanNode node;
+    node.node_id = scan_node_id; node.local_map_id = mLocalMaps.back().id;
+    node.local_pose = map_local_scan_pose; node.scan = scan; node.global_pose = scan_pose;
+    pose_graph.scan_nodes.push_back(node);
+    PoseGraphEdge e;
+    e.local_map_id = map_node.local_map_id; e.scan_node_id = scan_node_id;
+    e.edge_type = EdgeType::IntraLocalMap; e.constraint_type = ConstraintType::Odometry;
+    e.relative_pose = map_local_scan_pose;
+    e.information = Inverse(ConvertCovarianceFromWorldToLocal(map_node.global_pose, scan_pose_covariance));
+    pose_graph.edges.push_back(e);
+    UpdateGridMap(pose_graph);
+    return inserted;
+}
+
+void GridMapBuilderGPU::UpdateGridMap(const PoseGraph& pose_graph)
+{
+    /* :390-494: the latest scan into the latest (unfinished) local map */
+    LocalMapGPU& lm = mLocalMaps.back();
+    const LocalMapNode& map_node = pose_graph.local_map_nodes.back();
+    const ScanNode& scan_node = pose_graph.scan_nodes.back();
+    std::vector<DeviceGridMap::ScanHits> hits(1);
+    hits[0] = HitsOf(map_node.global_pose, scan_node.global_pose, *scan_node.scan);
+    const DeviceGridMap::ScanHits& h = hits[0];
+    /* the box starts at the sensor (:832-838) */
+    double min_x = h.sensor.x, min_y = h.sensor.y, max_x = h.sensor.x, max_y = h.sensor.y;
+    for (std::size_t i = 0; i < h.x.size(); ++i) {
+        min_x = std::min(min_x, h.x[i]); min_y = std::min(min_y, h.y[i]);
+        max_x = std::max(max_x, h.x[i]); max_y = std::max(max_y, h.y[i]);
+    }
+    lm.map->Expand(min_x, min_y, max_x, max_y);
+    mLastRays = lm.map->InsertScans(hits, SubpixelScale);
+    lm.scan_node_id_max = scan_node.node_id;
+}
+
+void GridMapBuilderGPU::AfterLoopClosure(const PoseGraph& pose_graph)
+{
+    /* UpdateAccumTravelDist (:535-558) */
+    mAccumTravelDist = 0.0;
+    for (std::size_t i = 0; i + 1 < pose_graph.scan_nodes.size(); ++i)
+        mAccumTravelDist += Distance(pose_graph.scan_nodes[i].global_pose, pose_graph.scan_nodes[i + 1].global_pose);
 }
 
 } /* namespace csm_host */

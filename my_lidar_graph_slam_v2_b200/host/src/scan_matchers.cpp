@@ -60,7 +60,7 @@ std::int64_t ScanMatcher::EnsureMap(const GridMapView& map)
     const std::int64_t id = map.map_id >= 0 ? map.map_id : (std::int64_t(1) << 40);
     if (map.device_resident) {
         /* built on the device (GridMapBuilderGPU): nothing to upload, but the CPU epilogue has no cells to read */
-        if (!mContext->DeviceEpilogue() && !mContext->HasDeviceFinalMatcher()) {
+        if (!mContext->DeviceEpilogue() && !mContext->HasDeviceFinalMatcher() && map.values == nullptr) {
             std::fprintf(stderr, "csm_host: a device-resident map needs the device epilogue or final matcher\n");
             std::abort();
         }

@@ -102,8 +102,89 @@ def load():
         lib.csm_host_mapbuilder_latest.argtypes = [C.c_void_p, dp, dp, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.csm_host_mapbuilder_match_rt.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, dp, C.c_int, dp, C.c_double,
                                                      C.POINTER(HostSummary)]
+        lib.csm_host_slam_create.restype = C.c_void_p
+        lib.csm_host_slam_create.argtypes = [C.c_void_p, dp, C.c_int]
+        lib.csm_host_slam_destroy.argtypes = [C.c_void_p]
+        lib.csm_host_slam_run.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int]
+        lib.csm_host_slam_counters.argtypes = [C.c_void_p, dp]
+        for name in ("num_scan_nodes", "num_local_maps", "num_edges", "num_loops"):
+            getattr(lib, "csm_host_slam_" + name).argtypes = [C.c_void_p]
+        for name in ("scan_nodes", "local_maps", "edges", "loops"):
+            getattr(lib, "csm_host_slam_" + name).argtypes = [C.c_void_p, dp]
+        lib.csm_host_slam_local_map_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _lib = lib
     return _lib
+
+
+SLAM_COUNTERS = ("scans_in", "scans_processed", "backend_steps", "backend_steps_with_candidates", "loop_queries",
+                 "loops_detected", "optimizations", "degenerations", "optimizer_calls",
+                 "t_latest_map", "t_match", "t_append", "t_backend", "t_detect")
+
+
+class SlamPipeline:
+    """C++ SlamPipeline (host/include/csm_host/slam_pipeline.hpp): the reference's front end and back end
+    around the device matchers and device-resident maps. `settings`: slam_settings.pack(...)."""
+
+    def __init__(self, ctx, settings):
+        self.lib = load()
+        self.ctx = ctx
+        v, vp = _d(settings)
+        self.p = self.lib.csm_host_slam_create(ctx.ctx, vp, len(v))
+        assert self.p, "bad settings vector"
+
+    def run(self, angles, ranges, odom_poses, time_stamps, min_range=0.01, max_range=50.0, finish=False):
+        """ranges (n_scans, n_beams), odom_poses (n_scans, 3): ProcessScan per scan; returns the scans used"""
+        a, ap = _d(angles)
+        r, rp = _d(ranges)
+        o, op = _d(odom_poses)
+        t, tp = _d(time_stamps)
+        assert r.ndim == 2 and r.shape[1] == len(a) and o.shape == (r.shape[0], 3) and len(t) == r.shape[0]
+        return self.lib.csm_host_slam_run(self.p, r.shape[0], r.shape[1], ap, rp, op, tp, min_range, max_range,
+                                          int(finish))
+
+    def counters(self):
+        out = np.zeros(len(SLAM_COUNTERS))
+        self.lib.csm_host_slam_counters(self.p, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return dict(zip(SLAM_COUNTERS, out.tolist()))
+
+    def _table(self, what, width):
+        n = getattr(self.lib, "csm_host_slam_num_" + {"scan_nodes": "scan_nodes", "local_maps": "local_maps",
+                                                      "edges": "edges", "loops": "loops"}[what])(self.p)
+        out = np.zeros((n, width))
+        if n:
+            getattr(self.lib, "csm_host_slam_" + what)(self.p, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def scan_nodes(self):
+        """(n, 7): global pose, local pose, local map id"""
+        return self._table("scan_nodes", 7)
+
+    def local_maps(self):
+        """(n, 10): global pose, first / last scan node, finished, rows, cols, offset x, y"""
+        return self._table("local_maps", 10)
+
+    def edges(self):
+        """(n, 7): local map id, scan node id, inter-local-map, loop, relative pose"""
+        return self._table("edges", 7)
+
+    def loops(self):
+        """(n, 6): local map id, scan node id, relative pose, normalized score"""
+        return self._table("loops", 6)
+
+    def local_map_cells(self, map_id, block_size=16):
+        info = self.local_maps()[map_id]
+        rows, cols = int(info[6]), int(info[7])
+        dense = np.zeros((rows, cols), dtype=np.uint16)
+        alloc = np.zeros((rows // block_size, cols // block_size), dtype=np.uint8)
+        rc = self.lib.csm_host_slam_local_map_cells(self.p, map_id, dense.ctypes.data, dense.size, alloc.ctypes.data,
+                                                    alloc.size)
+        assert rc == 0, rc
+        return dense, alloc
+
+    def close(self):
+        if self.p:
+            self.lib.csm_host_slam_destroy(self.p)
+            self.p = None
 
 
 class MapBuilder:

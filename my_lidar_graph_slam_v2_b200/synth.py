@@ -268,3 +268,87 @@ def make_pose_graph_summary(seed, n_maps=12, scans_per_map=(6, 14), loop=True):
                 map_scan_min=scan_ids[starts], map_scan_max=scan_ids[ends - 1],
                 map_finished=np.ones(n_maps, dtype=np.int32), accum_travel_dist=accum,
                 last_finished_scan_id=int(scan_ids[-1]), last_finished_map_id=n_maps - 1)
+
+
+# ---- BASELINE configs[4]: a closed-loop trajectory in a corridor world ----------------
+
+def corridor_world(rng, width=60.0, height=40.0, corridor=5.0, stub_every=4.0):
+    """A 60 x 40 m block with a corridor running around its inner core: outer wall, core as one big
+    pillar, and short wall stubs every few metres on alternating sides so that a 11.4 m scanner always
+    sees something that fixes its position along the corridor."""
+    world = Room(0.0, 0.0, width, height)
+    world.boxes.append((corridor, corridor, width - corridor, height - corridor))
+    side = 0
+    for x in np.arange(corridor + 2.0, width - corridor - 2.0, stub_every):
+        ln = rng.uniform(0.6, 1.6)
+        xs = x + rng.uniform(-0.8, 0.8)
+        for y_wall, sgn, y_core in ((0.0, 1.0, corridor), (height, -1.0, height - corridor)):
+            if side % 2 == 0:
+                world.stubs.append((xs, y_wall, xs, y_wall + sgn * ln))
+            else:
+                world.stubs.append((xs, y_core, xs, y_core - sgn * ln))
+            side += 1
+    for y in np.arange(corridor + 2.0, height - corridor - 2.0, stub_every):
+        ln = rng.uniform(0.6, 1.6)
+        ys = y + rng.uniform(-0.8, 0.8)
+        for x_wall, sgn, x_core in ((0.0, 1.0, corridor), (width, -1.0, width - corridor)):
+            if side % 2 == 0:
+                world.stubs.append((x_wall, ys, x_wall + sgn * ln, ys))
+            else:
+                world.stubs.append((x_core, ys, x_core - sgn * ln, ys))
+            side += 1
+    return world
+
+
+def corridor_path(world, corridor=5.0, radius=1.5):
+    """Centre line of the corridor as a closed polyline with rounded corners: (points (n, 2), length)."""
+    m = 0.5 * corridor
+    x0, y0, x1, y1 = world.x0 + m, world.y0 + m, world.x1 - m, world.y1 - m
+    pts = []
+    corners = [(x1, y0, -0.5 * np.pi), (x1, y1, 0.0), (x0, y1, 0.5 * np.pi), (x0, y0, np.pi)]
+    start = [(x0 + radius, y0)]
+    pts += start
+    for cx, cy, a0 in corners:
+        # arc centre sits `radius` inside the corner
+        ccx = cx - radius if cx == x1 else cx + radius
+        ccy = cy - radius if cy == y1 else cy + radius
+        for a in np.linspace(a0, a0 + 0.5 * np.pi, 13):
+            pts.append((ccx + radius * np.cos(a), ccy + radius * np.sin(a)))
+    pts.append(start[0])
+    pts = np.asarray(pts)
+    seg = np.hypot(*np.diff(pts, axis=0).T)
+    return pts, float(seg.sum())
+
+
+def corridor_trajectory(world, n_scans, spacing, rng, n_beams=360, sigma=0.01, rmax=11.40, corridor=5.0,
+                        odom_sigma=(0.002, 0.002, 0.0005), odom_bias=(0.0005, 0.0, 0.0001)):
+    """n_scans true poses `spacing` metres apart along the corridor loop (several laps when the path is
+    shorter than the trip), their scans, and an odometry track that integrates the true steps with a
+    bias and noise (Carmen-style drifting odometry). Returns dict(true, odom, angles, ranges, stamps)."""
+    pts, length = corridor_path(world, corridor)
+    seg = np.hypot(*np.diff(pts, axis=0).T)
+    cum = np.concatenate([[0.0], np.cumsum(seg)])
+    s = (np.arange(n_scans) * spacing) % length
+    idx = np.clip(np.searchsorted(cum, s, side="right") - 1, 0, len(seg) - 1)
+    f = (s - cum[idx]) / seg[idx]
+    xy = pts[idx] + f[:, None] * (pts[idx + 1] - pts[idx])
+    head = np.arctan2(pts[idx + 1, 1] - pts[idx, 1], pts[idx + 1, 0] - pts[idx, 0])
+    true = np.column_stack([xy, head])
+    ranges = np.empty((n_scans, n_beams))
+    angles = None
+    for k in range(n_scans):
+        angles, ranges[k] = raycast(world, true[k], n_beams, sigma, rmax, rng, force_rmax=(k == 0))
+    # every scan must carry the same longest range, or the angular search step would change from scan to scan
+    ranges[:, n_beams // 7] = rmax
+    odom = np.zeros((n_scans, 3))
+    bias, sig = np.asarray(odom_bias), np.asarray(odom_sigma)
+    for k in range(1, n_scans):
+        c, sn = np.cos(true[k - 1, 2]), np.sin(true[k - 1, 2])
+        d = true[k, :2] - true[k - 1, :2]
+        rel = np.array([c * d[0] + sn * d[1], -sn * d[0] + c * d[1],
+                        (true[k, 2] - true[k - 1, 2] + np.pi) % (2 * np.pi) - np.pi])
+        rel = rel + bias + rng.normal(0.0, 1.0, 3) * sig
+        c, sn = np.cos(odom[k - 1, 2]), np.sin(odom[k - 1, 2])
+        odom[k] = [odom[k - 1, 0] + c * rel[0] - sn * rel[1], odom[k - 1, 1] + sn * rel[0] + c * rel[1],
+                   odom[k - 1, 2] + rel[2]]
+    return dict(true=true, odom=odom, angles=angles, ranges=ranges, stamps=0.1 * np.arange(n_scans))

@@ -146,6 +146,23 @@ int orc_loop_search(int n_scans, const int32_t* scan_ids, const double* scan_pos
                     double travel_dist_threshold, double node_dist_threshold,
                     int num_of_candidate_nodes, int32_t* out_ids, int cap);
 
+/* The full loop with the reference's own components (ref only); settings: slam_settings.py; the tables
+ * have the layouts of csm_host_slam_* (host/src/c_shim.cpp) */
+void* orc_slam_create(const double* settings, int n);
+void orc_slam_destroy(void* slam);
+int orc_slam_run(void* slam, int n_scans, int n_beams, const double* angles, const double* ranges,
+                 const double* odom_poses, const double* time_stamps, double min_range, double max_range, int finish);
+void orc_slam_counters(void* slam, double* out14);
+int orc_slam_num_scan_nodes(void* slam);
+int orc_slam_num_local_maps(void* slam);
+int orc_slam_num_edges(void* slam);
+int orc_slam_num_loops(void* slam);
+void orc_slam_scan_nodes(void* slam, double* out7);
+void orc_slam_local_maps(void* slam, double* out10);
+int orc_slam_local_map_cells(void* slam, int id, uint16_t* dense, int cap_cells, uint8_t* alloc, int cap_blocks);
+void orc_slam_edges(void* slam, double* out7);
+void orc_slam_loops(void* slam, double* out6);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,17 @@ class Oracle:
             lib.orc_mapbuilder_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
             lib.orc_mapbuilder_append.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, C.c_double, C.c_double]
             lib.orc_mapbuilder_latest.argtypes = [C.c_void_p, dp, dp, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        if hasattr(lib, "orc_slam_create"):
+            lib.orc_slam_create.restype = C.c_void_p
+            lib.orc_slam_create.argtypes = [dp, C.c_int]
+            lib.orc_slam_destroy.argtypes = [C.c_void_p]
+            lib.orc_slam_run.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int]
+            lib.orc_slam_counters.argtypes = [C.c_void_p, dp]
+            for name in ("num_scan_nodes", "num_local_maps", "num_edges", "num_loops"):
+                getattr(lib, "orc_slam_" + name).argtypes = [C.c_void_p]
+            for name in ("scan_nodes", "local_maps", "edges", "loops"):
+                getattr(lib, "orc_slam_" + name).argtypes = [C.c_void_p, dp]
+            lib.orc_slam_local_map_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         assert lib.orc_kind().decode() == kind
 
     # -- grids ------------------------------------------------------------
@@ -113,6 +124,11 @@ class Oracle:
                     usable_range_max=50.0, prob_hit=0.62, prob_miss=0.46):
         return OracleMapBuilder(self, resolution, patch_size, scans_for_latest_map, usable_range_min,
                                 usable_range_max, prob_hit, prob_miss)
+
+    def slam(self, settings):
+        """The full loop on the reference's own components (ref_wrapper.cpp: RefSlam); `settings` from
+        my_lidar_graph_slam_v2_b200.slam_settings.pack()."""
+        return OracleSlam(self, settings)
 
     # -- matchers ---------------------------------------------------------
     @staticmethod
@@ -316,3 +332,66 @@ class OracleMapBuilder:
         rows, cols, bs = int(geo[0]), int(geo[1]), int(geo[2])
         return (dense[:rows * cols].reshape(rows, cols).copy(),
                 alloc[:(rows // bs) * (cols // bs)].reshape(rows // bs, cols // bs).copy(), (geo[3], geo[4]), pose, bs)
+
+
+SLAM_COUNTERS = ("scans_in", "scans_processed", "backend_steps", "backend_steps_with_candidates", "loop_queries",
+                 "loops_detected", "optimizations", "degenerations", "optimizer_calls",
+                 "t_latest_map", "t_match", "t_append", "t_backend", "t_detect")
+
+
+class OracleSlam:
+    """Same surface as hostapi.SlamPipeline, on the compiled reference."""
+
+    def __init__(self, oracle, settings):
+        self.lib = oracle.lib
+        v = np.ascontiguousarray(settings, dtype=np.float64)
+        self.p = self.lib.orc_slam_create(_dptr(v), len(v))
+        assert self.p
+
+    def run(self, angles, ranges, odom_poses, time_stamps, min_range=0.01, max_range=50.0, finish=False):
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        o = np.ascontiguousarray(odom_poses, dtype=np.float64)
+        t = np.ascontiguousarray(time_stamps, dtype=np.float64)
+        assert r.ndim == 2 and r.shape[1] == len(a) and o.shape == (r.shape[0], 3) and len(t) == r.shape[0]
+        return self.lib.orc_slam_run(self.p, r.shape[0], r.shape[1], _dptr(a), _dptr(r), _dptr(o), _dptr(t),
+                                     min_range, max_range, int(finish))
+
+    def counters(self):
+        out = np.zeros(len(SLAM_COUNTERS))
+        self.lib.orc_slam_counters(self.p, _dptr(out))
+        return dict(zip(SLAM_COUNTERS, out.tolist()))
+
+    def _table(self, what, width):
+        n = getattr(self.lib, "orc_slam_num_" + what)(self.p)
+        out = np.zeros((n, width))
+        if n:
+            getattr(self.lib, "orc_slam_" + what)(self.p, _dptr(out))
+        return out
+
+    def scan_nodes(self):
+        return self._table("scan_nodes", 7)
+
+    def local_maps(self):
+        return self._table("local_maps", 10)
+
+    def edges(self):
+        return self._table("edges", 7)
+
+    def loops(self):
+        return self._table("loops", 6)
+
+    def local_map_cells(self, map_id, block_size=16):
+        info = self.local_maps()[map_id]
+        rows, cols = int(info[6]), int(info[7])
+        dense = np.zeros((rows, cols), dtype=np.uint16)
+        alloc = np.zeros((rows // block_size, cols // block_size), dtype=np.uint8)
+        rc = self.lib.orc_slam_local_map_cells(self.p, map_id, dense.ctypes.data, dense.size, alloc.ctypes.data,
+                                               alloc.size)
+        assert rc == 0, rc
+        return dense, alloc
+
+    def close(self):
+        if self.p:
+            self.lib.orc_slam_destroy(self.p)
+            self.p = None

@@ -590,6 +590,337 @@ int orc_mapbuilder_latest(void* p, double* geometry6, double* map_pose3, uint16_
     return 0;
 }
 
+/* ---- the full loop (BASELINE configs[4]): the reference's own components in the order its front end and
+ * back end call them (lidar_graph_slam_frontend.cpp:109-330, lidar_graph_slam_backend.cpp:92-198,
+ * lidar_graph_slam.cpp:224-672). LidarGraphSlam itself needs the launcher, its worker threads and an
+ * optimiser library; what it does between the components -- a few pose compositions and the bookkeeping
+ * of ids -- is restated here, single-threaded, with the optimiser left out (poses stay as matched). Every
+ * map, every match and every detection is the reference's code. Settings: slam_settings.py. ---- */
+namespace {
+
+struct RefSlam
+{
+    std::vector<double> v;                       /* the 37 settings */
+    std::shared_ptr<PoseGraph> mPoseGraph;
+    GridMapBuilder* mBuilder = nullptr;
+    std::unique_ptr<ScanMatcherCorrelative> mScanMatcher;
+    std::unique_ptr<ScanMatcherLinearSolver> mFinalMatcher;
+    LoopSearcherNearest* mSearcher = nullptr;
+    std::shared_ptr<ScanMatcherBranchBound> mLoopMatcher;
+    std::unique_ptr<LoopDetectorBranchBound> mLoopDetector;
+    std::vector<LoopDetectionResult> mLoops;
+    int mProcessCount = 0;
+    RobotPose2D<double> mLastOdomPose { 0.0, 0.0, 0.0 }, mLastMapUpdateOdomPose { 0.0, 0.0, 0.0 };
+    double mAccumulatedTravelDist = 0.0, mAccumulatedAngle = 0.0, mLastMapUpdateTime = 0.0, mLastLoopDetectionDist = 0.0;
+    double c[14] = { 0 };                        /* counters, the layout of csm_host_slam_counters */
+
+    double S(int i) const { return v[i]; }
+    void RunBackendStep();
+    bool ProcessScan(const Sensor::ScanDataPtr<double>& scan, const RobotPose2D<double>& odomPose, double stamp);
+};
+
+double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+LoopSearcherNearest* gSearcher = nullptr;
+
+bool RefSlam::ProcessScan(const Sensor::ScanDataPtr<double>& scan, const RobotPose2D<double>& odomPose, double stamp)
+{
+    const RobotPose2D<double> zero { 0.0, 0.0, 0.0 };
+    const RobotPose2D<double> relOdom = mProcessCount == 0 ? zero : InverseCompound(mLastOdomPose, odomPose);
+    mLastOdomPose = odomPose;
+    mAccumulatedTravelDist += Distance(relOdom);
+    mAccumulatedAngle += std::fabs(relOdom.mTheta);
+    const double elapsed = mProcessCount == 0 ? 0.0 : stamp - mLastMapUpdateTime;
+    const bool first = mProcessCount == 0;
+    const bool needed = (mAccumulatedTravelDist >= S(9) || mAccumulatedAngle >= S(10) || elapsed >= S(11) || first) &&
+                        elapsed >= 0.0;
+    c[0] += 1;
+    if (!needed)
+        return false;
+    if (first) {
+        Eigen::Matrix3d cov = Eigen::Matrix3d::Zero();
+        cov(0, 0) = 1e-9; cov(1, 1) = 1e-9; cov(2, 2) = 1e-9;
+        const double t0 = Now();
+        mBuilder->AppendScan(mPoseGraph, RobotPose2D<double> { S(16), S(17), S(18) }, cov, scan);
+        c[11] += Now() - t0;
+    } else {
+        double t0 = Now();
+        mBuilder->UpdateLatestMap(mPoseGraph->ScanNodes());
+        const RobotPose2D<double> latestScanPose = mPoseGraph->ScanNodes().Back().mGlobalPose;
+        const GridMap& latestMap = mBuilder->LatestMap();      /* the reference copies it; the matchers only read */
+        const RobotPose2D<double> latestMapPose = mBuilder->LatestMapPose();
+        double t1 = Now();
+        c[9] += t1 - t0;
+        const RobotPose2D<double> relFromLastUpdate = InverseCompound(mLastMapUpdateOdomPose, odomPose);
+        const RobotPose2D<double> initialPose = Compound(latestScanPose, relFromLastUpdate);
+        const RobotPose2D<double> mapLocalInitialPose = InverseCompound(latestMapPose, initialPose);
+        const Point2D<double> center { 0.0, 0.0 };          /* read by neither matcher */
+        const ScanMatchingSummary coarse = mScanMatcher->OptimizePose(
+            ScanMatchingQuery { latestMap, center, scan, mapLocalInitialPose });
+        const ScanMatchingSummary fin = mFinalMatcher->OptimizePose(
+            ScanMatchingQuery { latestMap, center, scan, coarse.mEstimatedPose });
+        double t2 = Now();
+        c[10] += t2 - t1;
+        const RobotPose2D<double> globalEstimated = Compound(latestMapPose, fin.mEstimatedPose);
+        const RobotPose2D<double> scanRelative = InverseCompound(latestScanPose, globalEstimated);
+        const Eigen::Matrix3d scanCov = ConvertCovarianceFromLocalToWorld(latestMapPose, fin.mEstimatedCovariance);
+        RobotPose2D<double> relativePose = scanRelative;
+        Eigen::Matrix3d covariance = scanCov;
+        /* CheckDegeneration (:334-348): eigenvalues of the translational block in closed form */
+        const double a = scanCov(0, 0), b = scanCov(0, 1), cc = scanCov(1, 0), d = scanCov(1, 1);
+        const double mean = 0.5 * (a + d), disc = 0.25 * (a - d) * (a - d) + b * cc;
+        const double root = disc > 0.0 ? std::sqrt(disc) : 0.0;
+        if ((mean + root) / (mean - root) > S(13)) {
+            c[7] += 1;
+            /* ComputeOdometryCovariance (:351-368); FuseOdometryCovariance is off in this driver */
+            const double trans = std::max(1e-1, Distance(relFromLastUpdate) / elapsed);
+            const double rot = std::max(1e-1, relFromLastUpdate.mTheta / elapsed);
+            Eigen::Matrix3d odomCov = Eigen::Matrix3d::Zero();
+            odomCov(0, 0) = trans * trans * S(14); odomCov(1, 1) = trans * trans * S(14); odomCov(2, 2) = rot * rot * S(14);
+            relativePose = relFromLastUpdate;
+            covariance = odomCov;
+        }
+        mBuilder->AppendScan(mPoseGraph, relativePose, covariance, scan);
+        double t3 = Now();
+        c[11] += t3 - t2;
+        const double accum = mBuilder->AccumTravelDist();
+        if (accum - mLastLoopDetectionDist >= S(12)) {
+            mLastLoopDetectionDist = accum;
+            RunBackendStep();
+            c[12] += Now() - t3;
+        }
+    }
+    c[1] += 1;
+    mProcessCount += 1;
+    mAccumulatedTravelDist = 0.0;
+    mAccumulatedAngle = 0.0;
+    mLastMapUpdateOdomPose = odomPose;
+    mLastMapUpdateTime = stamp;
+    return true;
+}
+
+void RefSlam::RunBackendStep()
+{
+    c[2] += 1;
+    /* GetLoopSearchHint (lidar_graph_slam.cpp:273-381) */
+    const auto& localMaps = mBuilder->LocalMaps();
+    const auto unfinishedIt = std::find_if(localMaps.cbegin(), localMaps.cend(),
+        [](const IdMap<LocalMapId, LocalMap>::ConstIdDataPair& pair) { return !pair.mData.mFinished; });
+    if (unfinishedIt == localMaps.begin())
+        return;
+    const LocalMapId mapIdMax = unfinishedIt != localMaps.cend() ? unfinishedIt->mId : LocalMapId { LocalMapId::Invalid };
+    const NodeId nodeIdMax = unfinishedIt != localMaps.cend() ? unfinishedIt->mData.mScanNodeIdMin : NodeId { NodeId::Invalid };
+    IdMap<NodeId, ScanNodeData> scanNodes;
+    IdMap<LocalMapId, LocalMapData> mapNodes;
+    for (const auto& [nodeId, scanNode] : mPoseGraph->ScanNodes()) {
+        if (mapIdMax.mId != LocalMapId::Invalid && (scanNode.mLocalMapId >= mapIdMax || scanNode.mNodeId >= nodeIdMax))
+            break;
+        scanNodes.Append(nodeId, scanNode.mGlobalPose);
+    }
+    for (const auto& [nodeId, mapNode] : mPoseGraph->LocalMapNodes()) {
+        if (mapIdMax.mId != LocalMapId::Invalid && nodeId >= mapIdMax)
+            break;
+        const auto& localMap = mBuilder->LocalMapAt(nodeId);
+        /* the bounding box of the hint is read by no searcher */
+        mapNodes.Append(nodeId, Point2D<double> { 0.0, 0.0 }, Point2D<double> { 0.0, 0.0 },
+                        localMap.mScanNodeIdMin, localMap.mScanNodeIdMax, localMap.mFinished);
+    }
+    if (mapNodes.empty() || scanNodes.empty())
+        return;
+    const LocalMapId lastMapId = mapNodes.IdMax();
+    const auto& lastMap = mBuilder->LocalMapAt(lastMapId);
+    const NodeId lastScanId { (lastMap.mScanNodeIdMin.mId + lastMap.mScanNodeIdMax.mId) / 2 };
+    const LoopSearchHint hint { std::move(scanNodes), std::move(mapNodes), mBuilder->AccumTravelDist(), lastScanId, lastMapId };
+    const LoopCandidateVector candidates = mSearcher->Search(hint);
+    if (candidates.empty())
+        return;
+    c[3] += 1;
+    /* GetLoopDetectionQueries (:384-415) */
+    LoopDetectionQueryVector queries;
+    queries.reserve(candidates.size());
+    for (const auto& cand : candidates)
+        queries.emplace_back(mPoseGraph->ScanNodes().at(cand.mQueryScanNodeId),
+                             mPoseGraph->ScanNodes().at(cand.mReferenceScanNodeId),
+                             mBuilder->LocalMapAt(cand.mReferenceLocalMapId),
+                             mPoseGraph->LocalMapNodes().at(cand.mReferenceLocalMapId));
+    const double t0 = Now();
+    const LoopDetectionResultVector results = mLoopDetector->Detect(queries);
+    c[13] += Now() - t0;
+    c[4] += static_cast<double>(queries.size());
+    if (results.empty())
+        return;
+    c[5] += static_cast<double>(results.size());
+    /* AppendLoopClosingEdges (:448-504) */
+    for (const auto& r : results) {
+        mLoops.push_back(r);
+        mPoseGraph->Edges().emplace_back(r.mLocalMapNodeId, r.mScanNodeId, EdgeType::InterLocalMap, ConstraintType::Loop,
+                                         NormalizeAngle(r.mRelativePose), r.mEstimatedCovMat.inverse());
+    }
+    /* the optimiser would run here (lidar_graph_slam_backend.cpp:170-172) on the finished part of the graph
+     * (lidar_graph_slam.cpp:106-194); without one those poses stay. AfterLoopClosure (:506-672) then lets the
+     * nodes added since follow along their odometry edges, which re-derives their poses even when nothing
+     * moved: restated here so that both arms round the same way. */
+    c[6] += 1;
+    const auto firstOpen = std::find_if(localMaps.cbegin(), localMaps.cend(),
+        [](const IdMap<LocalMapId, LocalMap>::ConstIdDataPair& pair) { return !pair.mData.mFinished; });
+    const auto& lastDone = std::prev(firstOpen)->mData;
+    auto& edges = mPoseGraph->Edges();
+    auto it = std::find_if(edges.cbegin(), edges.cend(), [&lastDone](const PoseGraphEdge& e) {
+        return e.mLocalMapNodeId == lastDone.mId && e.mScanNodeId > lastDone.mScanNodeIdMax; });
+    if (it != edges.cend()) {
+        LocalMapId doneMap = lastDone.mId;
+        NodeId doneNode = lastDone.mScanNodeIdMax;
+        for (; it != edges.cend(); ++it) {
+            if (!it->IsOdometryConstraint())
+                continue;
+            if (it->mLocalMapNodeId == doneMap && it->mScanNodeId > doneNode)
+                mPoseGraph->ScanNodes().at(it->mScanNodeId).mGlobalPose =
+                    Compound(mPoseGraph->LocalMapNodes().at(it->mLocalMapNodeId).mGlobalPose, it->mRelativePose);
+            else if (it->mLocalMapNodeId > doneMap && it->mScanNodeId == doneNode)
+                mPoseGraph->LocalMapNodes().at(it->mLocalMapNodeId).mGlobalPose =
+                    MoveBackward(mPoseGraph->ScanNodes().at(it->mScanNodeId).mGlobalPose, it->mRelativePose);
+            doneMap = it->mLocalMapNodeId;
+            doneNode = it->mScanNodeId;
+        }
+    }
+    mBuilder->AfterLoopClosure(mPoseGraph);
+}
+
+} /* namespace */
+
+void* orc_slam_create(const double* v, int n)
+{
+    if (n != 37)
+        return nullptr;
+    auto* s = new RefSlam;
+    s->v.assign(v, v + n);
+    /* the builder registers its metrics under fixed names: one instance per process, reset here */
+    void* mb = orc_mapbuilder_create(v[0], static_cast<int>(v[1]), static_cast<int>(v[2]), v[5], v[6], v[7], v[8]);
+    GridMapBuilder& b = *static_cast<RefMapBuilder*>(mb)->mBuilder;
+    const_cast<double&>(b.mTravelDistThreshold) = v[3];
+    const_cast<std::size_t&>(b.mNumOfOverlappedScans) = static_cast<std::size_t>(v[4]);
+    b.mLocalMaps = IdMap<LocalMapId, LocalMap>();
+    b.mAccumTravelDist = 0.0;
+    b.mTravelDistLastLocalMap = 0.0;
+    b.mLastRobotPose = RobotPose2D<double>(0.0, 0.0, 0.0);
+    b.mRobotPoseLastLocalMap = RobotPose2D<double>(0.0, 0.0, 0.0);
+    s->mBuilder = &b;
+    s->mPoseGraph = std::make_shared<PoseGraph>();
+    s->mScanMatcher.reset(new ScanMatcherCorrelative(UniqueName("SlamRT"), std::make_shared<CostSquareError>(v[26]),
+                                                     static_cast<int>(v[19]), v[20], v[21], v[22]));
+    s->mFinalMatcher.reset(new ScanMatcherLinearSolver(UniqueName("SlamFinal"), static_cast<int>(v[23]), v[24], v[25],
+                                                       std::make_shared<CostSquareError>(v[26])));
+    if (gSearcher == nullptr)
+        gSearcher = new LoopSearcherNearest(v[27], v[28], static_cast<int>(v[29]));
+    const_cast<double&>(gSearcher->mTravelDistThreshold) = v[27];
+    const_cast<double&>(gSearcher->mNodeDistThreshold) = v[28];
+    const_cast<int&>(gSearcher->mNumOfCandidateNodes) = static_cast<int>(v[29]);
+    s->mSearcher = gSearcher;
+    s->mLoopMatcher = std::make_shared<ScanMatcherBranchBound>(
+        UniqueName("SlamBB"), std::make_shared<ScorePixelAccurate>(), std::make_shared<CostSquareError>(v[26]),
+        static_cast<int>(v[30]), v[31], v[32], v[33]);
+    std::shared_ptr<ScanMatcher> loopFinal = std::make_shared<ScanMatcherLinearSolver>(
+        UniqueName("SlamLoopFinal"), static_cast<int>(v[23]), v[24], v[25], std::make_shared<CostSquareError>(v[26]));
+    s->mLoopDetector.reset(new LoopDetectorBranchBound(UniqueName("SlamLoopDet"), s->mLoopMatcher, loopFinal, v[34], v[35]));
+    return s;
+}
+
+void orc_slam_destroy(void* p) { delete static_cast<RefSlam*>(p); }
+
+int orc_slam_run(void* p, int n_scans, int n_beams, const double* angles, const double* ranges,
+                 const double* odom_poses, const double* time_stamps, double min_range, double max_range, int finish)
+{
+    auto* s = static_cast<RefSlam*>(p);
+    const RobotPose2D<double> zero { 0.0, 0.0, 0.0 };
+    int used = 0;
+    for (int k = 0; k < n_scans; ++k) {
+        std::vector<double> a(angles, angles + n_beams);
+        std::vector<double> r(ranges + static_cast<std::size_t>(k) * n_beams, ranges + static_cast<std::size_t>(k + 1) * n_beams);
+        auto scan = std::make_shared<Sensor::ScanData<double>>(
+            "lidar", time_stamps[k], zero, zero, zero, min_range, max_range, a.front(), a.back(), std::move(a), std::move(r));
+        used += s->ProcessScan(scan, RobotPose2D<double> { odom_poses[3 * k], odom_poses[3 * k + 1], odom_poses[3 * k + 2] },
+                               time_stamps[k]) ? 1 : 0;
+    }
+    if (finish) {
+        const double t0 = Now();
+        s->RunBackendStep();
+        s->c[12] += Now() - t0;
+    }
+    return used;
+}
+
+void orc_slam_counters(void* p, double* out)
+{
+    auto* s = static_cast<RefSlam*>(p);
+    std::copy(s->c, s->c + 14, out);
+    out[8] = 0.0;         /* no optimiser behind the seam in this arm */
+}
+
+int orc_slam_num_scan_nodes(void* p) { return static_cast<int>(static_cast<RefSlam*>(p)->mPoseGraph->ScanNodes().size()); }
+int orc_slam_num_local_maps(void* p) { return static_cast<int>(static_cast<RefSlam*>(p)->mBuilder->LocalMaps().size()); }
+int orc_slam_num_edges(void* p) { return static_cast<int>(static_cast<RefSlam*>(p)->mPoseGraph->Edges().size()); }
+int orc_slam_num_loops(void* p) { return static_cast<int>(static_cast<RefSlam*>(p)->mLoops.size()); }
+
+void orc_slam_scan_nodes(void* p, double* out7)
+{
+    int i = 0;
+    for (const auto& [id, n] : static_cast<RefSlam*>(p)->mPoseGraph->ScanNodes()) {
+        double* o = out7 + 7 * i++;
+        o[0] = n.mGlobalPose.mX; o[1] = n.mGlobalPose.mY; o[2] = n.mGlobalPose.mTheta;
+        o[3] = n.mLocalPose.mX; o[4] = n.mLocalPose.mY; o[5] = n.mLocalPose.mTheta; o[6] = n.mLocalMapId.mId;
+    }
+}
+
+void orc_slam_local_maps(void* p, double* out10)
+{
+    auto* s = static_cast<RefSlam*>(p);
+    int i = 0;
+    for (const auto& [id, m] : s->mBuilder->LocalMaps()) {
+        double* o = out10 + 10 * i++;
+        const RobotPose2D<double>& pose = s->mPoseGraph->LocalMapNodes().at(id).mGlobalPose;
+        o[0] = pose.mX; o[1] = pose.mY; o[2] = pose.mTheta;
+        o[3] = m.mScanNodeIdMin.mId; o[4] = m.mScanNodeIdMax.mId; o[5] = m.mFinished ? 1.0 : 0.0;
+        o[6] = m.mMap.Rows(); o[7] = m.mMap.Cols(); o[8] = m.mMap.PosOffset().mX; o[9] = m.mMap.PosOffset().mY;
+    }
+}
+
+int orc_slam_local_map_cells(void* p, int id, uint16_t* dense, int cap_cells, uint8_t* alloc, int cap_blocks)
+{
+    auto* s = static_cast<RefSlam*>(p);
+    if (id < 0 || id >= static_cast<int>(s->mBuilder->LocalMaps().size()))
+        return -1;
+    const GridMap& map = s->mBuilder->LocalMapAt(LocalMapId { id }).mMap;
+    if (map.Rows() * map.Cols() > cap_cells || map.BlockRows() * map.BlockCols() > cap_blocks)
+        return -2;
+    Flatten(map, dense);
+    for (int br = 0; br < map.BlockRows(); ++br)
+        for (int bc = 0; bc < map.BlockCols(); ++bc)
+            alloc[br * map.BlockCols() + bc] = map.Block(br, bc)->IsAllocated() ? 1 : 0;
+    return 0;
+}
+
+void orc_slam_edges(void* p, double* out7)
+{
+    int i = 0;
+    for (const auto& e : static_cast<RefSlam*>(p)->mPoseGraph->Edges()) {
+        double* o = out7 + 7 * i++;
+        o[0] = e.mLocalMapNodeId.mId; o[1] = e.mScanNodeId.mId; o[2] = e.mEdgeType == EdgeType::InterLocalMap ? 1.0 : 0.0;
+        o[3] = e.IsLoopClosingConstraint() ? 1.0 : 0.0;
+        o[4] = e.mRelativePose.mX; o[5] = e.mRelativePose.mY; o[6] = e.mRelativePose.mTheta;
+    }
+}
+
+void orc_slam_loops(void* p, double* out6)
+{
+    int i = 0;
+    for (const auto& r : static_cast<RefSlam*>(p)->mLoops) {
+        double* o = out6 + 6 * i++;
+        o[0] = r.mLocalMapNodeId.mId; o[1] = r.mScanNodeId.mId;
+        o[2] = r.mRelativePose.mX; o[3] = r.mRelativePose.mY; o[4] = r.mRelativePose.mTheta;
+        o[5] = 0.0;        /* the reference's result carries no score */
+    }
+}
+
 void* orc_loopdet_create(int hmax, double range_x, double range_y, double range_t,
                          double score_thr, double known_thr, int n_threads)
 {

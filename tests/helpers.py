@@ -42,3 +42,12 @@ def assert_match(dev, orc, what, exact_score=True, flags_ok=0):
         assert abs(dev.normalized_score - exp_score) <= SCORE_RTOL * abs(exp_score), "%s: score" % what
         if exact_score:
             assert dev.normalized_score == exp_score, "%s: score not bit-identical" % what
+
+
+def as_matchers_read(grid):
+    """The matchers' view of a map: a cell at 65535 reads as unknown, like in the compiled reference, whose
+    65535-entry value tables end one short of it (grid_values.cpp:32-35; csrc/csm_kernels.cuh,
+    k_saturated_unknown)."""
+    g = np.array(grid, copy=True)
+    g[g == 65535] = 0
+    return g

@@ -3,11 +3,12 @@ committed golden vectors. Bar: best pose index, integer score and found flag
 bit-exact; the double score within 1e-5 relative (it is in fact bit-identical:
 the device re-sums in the reference's order)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
-from helpers import assert_match, grid_of, load_golden, sha
+from helpers import as_matchers_read, assert_match, grid_of, load_golden, sha
 from my_lidar_graph_slam_v2_b200 import capi, matchers, synth
 
 pytestmark = pytest.mark.gpu
@@ -319,6 +320,10 @@ def test_bound_levels_vs_numpy(handle, shape):
     grid[rng.random(shape) < 0.6] = 0
     grid[0, 0], grid[-1, -1] = 65535, 65535
     handle.upload_grid(81, grid, 0.05, 0.0, 0.0)
+    grid = as_matchers_read(grid)          # the library's copy holds 65535 as unknown (k_saturated_unknown)
+    assert np.array_equal(handle.download_level(81, 0, shape), grid)
+    grid[0, 0], grid[-1, -1] = 65534, 65534
+    handle.upload_grid(81, grid, 0.05, 0.0, 0.0)
     for level in (5, 3, 6, 1):
         handle.drop_pyramids([81])
         got = handle.bound_level(81, level, shape)
@@ -348,8 +353,11 @@ def test_bound_levels_from_the_streaming_builder(handle, checker, shape, levels)
         g = rng.integers(0, 65536, size=shape, dtype=np.uint16)
         g[rng.random(shape) < 0.6] = 0
         g[0, 0], g[-1, -1] = 65535, 65535
-        grids.append(g)
         handle.upload_grid(mid, g, 0.05, 0.0, 0.0)
+        g = as_matchers_read(g)            # what the library keeps: 65535 reads as unknown
+        g[0, 0], g[-1, -1] = 65534, 65534
+        handle.upload_grid(mid, g, 0.05, 0.0, 0.0)
+        grids.append(g)
     handle.set_option("bounds_mode", 2)
     try:
         handle.build_pyramids(ids, levels + 1)
@@ -1415,3 +1423,61 @@ def test_cpp_loop_detector_pipeline_lanes(checker, lanes, chunk, up):
     assert np.allclose([g[5] for g in sigs[0]], [g[5] for g in sigs[1]], rtol=1e-9, atol=1e-12)
     det.close()
     ctx.close()
+
+
+def _same_winner(dev, orc, what):
+    """index and the reference's own double score; the checker's integer diagnostics (sum_value, n_known)
+    count raw cell values and do not apply to saturated cells"""
+    assert dev.flags == 0 and dev.found == orc.found == 1, what
+    assert (dev.best_x, dev.best_y, dev.best_t) == (orc.best_x, orc.best_y, orc.best_t), what
+    assert dev.normalized_score == orc.score, "%s: score %r vs %r" % (what, dev.normalized_score, orc.score)
+
+
+def test_saturated_cells_read_as_unknown(handle):
+    """Maps the reference builds hold cells at 65535 (ValueMax). Its value tables have 65535 entries
+    (grid_values.cpp:32-35), so its matchers read those cells one element past the table: 0.0, the unknown
+    probability, in the compiled reference. The library's copy of every map holds them as unknown: exhaustive
+    searches (no pruning involved) and the final matcher then agree with the compiled reference on a map with
+    saturated walls; with the option off the cell counts as 0.999 and the scores differ."""
+    from oracle import pyoracle
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    if not (pyoracle.available("reference") or os.path.isdir("/root/reference")):
+        pytest.skip("needs the compiled reference")
+    ref = pyoracle.load("reference")
+    case = synth.case_for(synth.CFG1, 6400)
+    s = case.submap
+    grid = s.grid.copy()
+    rng = np.random.default_rng(6400)
+    walls = grid > 45000
+    grid[walls & (rng.random(grid.shape) < 0.3)] = 65535
+    assert (grid == 65535).sum() > 500
+    g = ref.grid(grid, s.res, s.off_x, s.off_y)
+    gm = matchers.GridMap(grid, s.res, (s.off_x, s.off_y))
+    scan = _scan(case)
+    # real-time correlative with a 1-cell coarse map and the exhaustive grid search: every candidate is scored
+    mt = matchers.ScanMatcherCorrelative("rt", 1, *synth.CFG1["rng"], handle=handle)
+    got = mt.optimize_pose(gm, scan, tuple(case.init_pose), 0.0, 0.0)
+    exp = ref.match_rt(g, case.angles, case.ranges, case.init_pose, 1, synth.CFG1["rng"])
+    _same_winner(got.result, exp, "rt on saturated walls")
+    mg = matchers.ScanMatcherGridSearch("grid", 0.4, 0.4, 0.06, 0.05, 0.05, 0.004, handle=handle)
+    got = mg.optimize_pose(gm, scan, tuple(case.init_pose), 0.0, 0.0)
+    exp_g = ref.match_grid(g, case.angles, case.ranges, case.init_pose, (0.4, 0.4, 0.06), (0.05, 0.05, 0.004))
+    _same_winner(got.result, exp_g, "grid search on saturated walls")
+    # the cost function of the final matcher interpolates the same cells
+    handle.upload_grid(8950, grid, s.res, s.off_x, s.off_y)
+    handle.upload_scan(8950, case.angles, case.ranges)
+    start = np.asarray(case.true_pose) + np.array([0.03, -0.02, 0.004])
+    out = handle.refine_batch([(8950, 8950, tuple(start))], 10, 1e-4, 1e-4, 1e4)[0]
+    lam = [1e-4]
+    exp_r = ref.refine(g, case.angles, case.ranges, list(start), None, 10, 1e-4, 1e-4)
+    assert np.allclose(list(out.pose), list(exp_r.est_pose), rtol=1e-5, atol=1e-9)
+    twin, _ = hostapi.refine(grid, s.res, (s.off_x, s.off_y), case.angles, case.ranges, start)
+    assert list(twin.est_pose) == list(exp_r.est_pose)
+    # option off: 65535 counts as p = 0.999, which the reference cannot be asked for
+    handle.set_option("saturated_unknown", 0)
+    try:
+        got_off = mt.optimize_pose(gm, scan, tuple(case.init_pose), 0.0, 0.0)
+        assert got_off.result.normalized_score > exp.score
+    finally:
+        handle.set_option("saturated_unknown", 1)
+    handle.release_grid(8950)
