@@ -592,14 +592,17 @@ def main_cuda(args):
         "frac": gathers / (exp_ms * 1e-3) / gather_peak if exp_ms > 0 else None,
         "peak_source": "SURVEY.md 8(d) gather ceiling: 148 SMs x 32 lanes x %.0f MHz (one L1TEX / shared-memory "
                        "wavefront per cycle per SM, every lane useful); a scattered gather cannot reach it: "
-                       "the sweep's requests touch %.1f sectors in about two 128-byte tiles"
-                       % (sm_mhz, ncu_sweep.get("sectors_per_request", float("nan"))),
+                       "the sweep's requests touch %.1f sectors in about two 128-byte tiles, and ncu puts the "
+                       "L1TEX LSU data pipe, the unit that binds, at %.2f of its own wavefront peak over the six "
+                       "launches (l1tex_ncu.lsu_data_pipe_frac_of_peak, profiles/r2_ncu.json)"
+                       % (sm_mhz, ncu_sweep.get("sectors_per_request", float("nan")),
+                          ncu_sweep.get("lsu_data_pipe_frac_of_peak", float("nan"))),
         "hbm_equivalent": {"achieved_GBps": gathers * 2 / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else None,
                            "peak_GBps": hbm_peak, "peak_source": peak_source,
                            "frac": gathers * 2 / (exp_ms * 1e-3) / 1e9 / hbm_peak if exp_ms > 0 else None,
                            "note": "SURVEY.md 8(d) algorithmic bytes (one u16 per scored node and beam) against the "
                                    "copy peak, the round-1 figure; DRAM is not the unit that binds"},
-        "l1tex_ncu": dict(ncu_sweep, stale=stale,
+        "l1tex_ncu": dict({k: v for k, v in ncu_sweep.items() if k != "launches"}, stale=stale,
                           note="ncu --set full of the same launches (profiles/r2_ncu.json, captured on a B200 of "
                                "this pool); stale = the CUDA-event time of this run differs by more than 15 % "
                                "from the one recorded beside the capture"),
@@ -814,6 +817,30 @@ def single_scan_numbers(h, lib, kind):
         "cpu_kind": kind}
     mb.close()
     ctx_m.close()
+
+    # BASELINE configs[4]: the full loop (front end + loop detection) on a 10k-scan trajectory; the
+    # reference's own components run the first scans of the same trajectory on one host thread
+    from my_lidar_graph_slam_v2_b200 import full_loop, slam_settings
+    if not hasattr(orc.lib, "orc_slam_create"):
+        raise RuntimeError("the full-loop leg needs the compiled reference (oracle/_ref)")
+    trip = full_loop.make_trip(10000)
+    fl_gpu, fl_nodes = full_loop.run_gpu(trip, h.device)
+    n_ref = 200
+    rslam = orc.slam(slam_settings.pack(host_final_matchers=1, **full_loop.CFG5))
+    t0 = time.perf_counter()
+    rslam.run(trip["angles"], trip["ranges"][:n_ref], trip["odom"][:n_ref], trip["stamps"][:n_ref], 0.01, 11.3, finish=True)
+    fl_ref = full_loop.summarize(rslam.counters(), time.perf_counter() - t0)
+    rnodes = rslam.scan_nodes()
+    rslam.close()
+    out["cfg5_full_loop"] = {
+        "workload": "10000 scans of 360 beams 0.1 m apart around a 60 x 40 m corridor loop, every scan matched, local "
+                    "map every 2.5 m, loop detection every 2.5 m with up to 64 candidates; optimiser = identity behind "
+                    "the PoseGraphOptimizer seam",
+        "gpu": fl_gpu, "cpu_1core": dict(fl_ref, sample="first %d scans of the same trajectory" % n_ref, cpu_kind=kind),
+        "ratio_scans_per_s": fl_gpu["scans_per_s"] / fl_ref["scans_per_s"],
+        "ratio_detect_queries_per_s": (fl_gpu["detect_queries_per_s"] / fl_ref["detect_queries_per_s"])
+        if fl_ref["detect_queries_per_s"] else None,
+        "prefix_max_abs_pose_difference": float(np.abs(fl_nodes[:len(rnodes), :3] - rnodes[:, :3]).max())}
 
     gpu = timeit(bb, 1000)
     cpu = timeit(lambda: orc.match_bb(og, case.angles, case.ranges, case.init_pose, 5, synth.CFG2["rng"]), 5, 0.0)

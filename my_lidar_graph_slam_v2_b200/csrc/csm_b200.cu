@@ -1242,8 +1242,11 @@ int ensure_margins(csm_handle h, const std::vector<MapSlot*>& slots)
     std::memcpy(hp, jobs.data(), jb);
     if ((rc = pull_to_device(h, h->d_marginjobs.p, hp, jb))) return rc;
     if ((rc = upload_committed(h))) return rc;
-    k_low_margin<<<(unsigned)jobs.size(), 256, 0, h->stream>>>(static_cast<const MarginJob*>(h->d_marginjobs.p),
-                                                               static_cast<int*>(h->d_margin.p));
+    k_low_margin_init<<<(unsigned)((jobs.size() + 255) / 256), 256, 0, h->stream>>>(
+        static_cast<const MarginJob*>(h->d_marginjobs.p), static_cast<int*>(h->d_margin.p), (int)jobs.size());
+    CSM_LAUNCH_CHECK();
+    k_low_margin<<<dim3((unsigned)jobs.size(), kMarginParts), 256, 0, h->stream>>>(
+        static_cast<const MarginJob*>(h->d_marginjobs.p), static_cast<int*>(h->d_margin.p));
     CSM_LAUNCH_CHECK();
     for (MapSlot* m : todo)
         m->margin_valid = true;

@@ -1990,28 +1990,63 @@ k_grid_general(const DevQuery* __restrict__ queries, const double2* __restrict__
  * (`limit` if there is none): when it is at least 2^hmax, every coarse lookup at a negative index
  * covers unknown cells only, i.e. the 0 the reference reads there (grid_map.cpp:389-392) IS the
  * maximum of the window and its branch-and-bound bound stays admissible: a
- * CSM_FLAG_EDGE raised by the projection is then withdrawn (k_finalize). One CTA per map. */
+ * CSM_FLAG_EDGE raised by the projection is then withdrawn (k_finalize). kMarginParts CTAs per map. */
 struct MarginJob
 {
     const uint16_t* base;
     int rows, cols, limit, slot;     /* the result goes to out[slot] */
 };
 
+constexpr int kMarginParts = 8;          /* CTAs per map */
+
+/* out[slot] must hold `limit` when the kernel starts (k_low_margin_init) */
+__global__ void __launch_bounds__(256)
+k_low_margin_init(const MarginJob* __restrict__ jobs, int* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[jobs[i].slot] = jobs[i].limit;
+}
+
+__device__ __forceinline__ int low_margin_of(uint4 v, int r, int c, int best)
+{
+    const unsigned int w[4] = { v.x, v.y, v.z, v.w };
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (w[k] & 0xffffu) best = min(best, min(r, c + 2 * k));
+        if (w[k] >> 16) best = min(best, min(r, c + 2 * k + 1));
+    }
+    return best;
+}
+
 __global__ void __launch_bounds__(256)
 k_low_margin(const MarginJob* __restrict__ jobs, int* __restrict__ out)
 {
     const MarginJob J = jobs[blockIdx.x];
     const int lr = min(J.limit, J.rows), lc = min(J.limit, J.cols);
+    const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
     int best = J.limit;
-    if (threadIdx.x == 0) out[J.slot] = J.limit;
-    __syncthreads();
-    for (int e = threadIdx.x; e < lr * J.cols; e += blockDim.x) {          /* the low rows, whole */
-        const int r = e / J.cols, c = e - r * J.cols;
-        if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
-    }
-    for (int e = threadIdx.x; e < J.rows * lc; e += blockDim.x) {          /* the low columns, whole */
-        const int r = e / lc, c = e - r * lc;
-        if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
+    if ((J.cols & 7) == 0 && (lc & 7) == 0 && (reinterpret_cast<uintptr_t>(J.base) & 15u) == 0) {
+        /* 8 cells per load: the low rows whole, then the low columns of the other rows */
+        const int vpr = J.cols >> 3, vlc = lc >> 3;
+        for (int e = tid; e < lr * vpr; e += nth) {
+            const int r = e / vpr, c = (e - r * vpr) << 3;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(J.base + (size_t)r * J.cols + c));
+            if (v.x | v.y | v.z | v.w) best = low_margin_of(v, r, c, best);
+        }
+        for (int e = tid; e < (J.rows - lr) * vlc; e += nth) {
+            const int r = lr + e / vlc, c = (e % vlc) << 3;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(J.base + (size_t)r * J.cols + c));
+            if (v.x | v.y | v.z | v.w) best = low_margin_of(v, r, c, best);
+        }
+    } else {
+        for (int e = tid; e < lr * J.cols; e += nth) {
+            const int r = e / J.cols, c = e - r * J.cols;
+            if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
+        }
+        for (int e = tid; e < J.rows * lc; e += nth) {
+            const int r = e / lc, c = e - r * lc;
+            if (J.base[(size_t)r * J.cols + c] != 0) best = min(best, min(r, c));
+        }
     }
     best = (int)__reduce_min_sync(0xffffffffu, (unsigned)best);
     if ((threadIdx.x & 31) == 0 && best < J.limit)
