@@ -11,6 +11,8 @@ HEADERS = [os.path.join(HERE, "csrc", "csm_kernels.cuh"),
            os.path.join(HERE, "csrc", "csm_device.cuh"),
            os.path.join(HERE, "csrc", "csm_window_tma.cuh"),
            os.path.join(HERE, "csrc", "csm_refine.cuh"),
+           os.path.join(HERE, "csrc", "csm_bounds.cuh"),
+           os.path.join(HERE, "csrc", "csm_mapbuild.cuh"),
            os.path.join(ROOT, "include", "csm_b200.h")]
 
 NVCC_FLAGS = [
