@@ -1,5 +1,9 @@
 #include "csm_host/loop_detector.hpp"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -171,16 +175,46 @@ public:
     }
 
 private:
+    static void CopyBlock(char* dst, const char* src, std::size_t bytes)
+    {
+#if defined(__SSE2__)
+        if ((reinterpret_cast<std::uintptr_t>(dst) & 15u) == 0 && (bytes & 63u) == 0) {
+            for (std::size_t o = 0; o < bytes; o += 64) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + o));
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + o + 16));
+                const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + o + 32));
+                const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + o + 48));
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + o), a);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + o + 16), b);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + o + 32), c);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + o + 48), d);
+            }
+            return;
+        }
+#endif
+        std::memcpy(dst, src, bytes);
+    }
     void Chunks()
     {
-        constexpr std::size_t kChunk = 64;
+        constexpr std::size_t kChunk = 64, kAhead = 6;
         for (;;) {
             const std::size_t b0 = mNext.fetch_add(kChunk);
             if (b0 >= mCount) break;
             const std::size_t b1 = std::min(mCount, b0 + kChunk);
-            for (std::size_t b = b0; b < b1; ++b)
-                std::memcpy(mDst + b * mBytes, mSrc[b], mBytes);
+            for (std::size_t b = b0; b < b1; ++b) {
+                /* the blocks are scattered heap allocations: ask for the lines of a later block while this
+                 * one is copied, and write the staging area past the cache (it is read once, by the DMA) */
+                if (b + kAhead < mCount) {
+                    const char* next = reinterpret_cast<const char*>(mSrc[b + kAhead]);
+                    for (std::size_t o = 0; o < mBytes; o += 64)
+                        __builtin_prefetch(next + o, 0, 0);
+                }
+                CopyBlock(mDst + b * mBytes, reinterpret_cast<const char*>(mSrc[b]), mBytes);
+            }
         }
+#if defined(__SSE2__)
+        _mm_sfence();           /* the streamed stores are visible before the group is handed to the copy engine */
+#endif
     }
     void Work()
     {
@@ -461,14 +495,15 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
         if (fresh)
             mMapLane[queries[i].local_map.map_id] = segments.back().lane;
     }
-    /* pass 1: every upload is enqueued first, so that PCIe never waits for the host to prepare a
-     * search batch; pass 2: pyramids and the search batch of every segment behind its own uploads */
+    /* Segment by segment: the first-touch maps of a segment are gathered and sent in upload groups, then its
+     * levels and its search batch are enqueued behind them -- the device works on a segment while the host
+     * gathers the blocks of the next one (the gather, not PCIe, is the longest leg of a cold Detect). */
     std::vector<std::vector<std::vector<std::int64_t>>> fresh_ids(segments.size());   /* per upload group */
     std::size_t area = 0;
-    for (std::size_t si = 0; si < segments.size(); ++si) {
+    auto upload_segment = [&](std::size_t si) {
         const Segment& sg = segments[si];
         if (!sg.fresh)
-            continue;
+            return;
         const DeviceContextPtr& c = lane_ctx(sg.lane);
         std::set<std::int64_t> seen;
         for (int first = sg.first; first < sg.first + sg.count; first += ugroup) {
@@ -486,10 +521,9 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             }
             UploadNewMaps(c, fresh, mGatherer.get(), area++);
         }
-    }
+    };
     fill_queries();
     const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
-    if (trace) std::fprintf(stderr, "lanes: uploads enqueued at %.0f us\n", timer.ElapsedMicro());
     std::vector<std::vector<int>> in_flight(lanes);       /* segment indices, oldest first */
     std::vector<int> overflowed;                          /* segments to search again in smaller batches */
     auto finish_oldest = [&](int lane) {
@@ -502,16 +536,20 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     for (std::size_t si = 0; si < segments.size(); ++si) {
         const Segment& sg = segments[si];
         const DeviceContextPtr& c = lane_ctx(sg.lane);
+        upload_segment(si);
+        if (trace) std::fprintf(stderr, "lanes: segment %zu uploads enqueued at %.0f us\n", si, timer.ElapsedMicro());
         for (int i = sg.first; i < sg.first + sg.count; ++i)
             if (lane_scans[sg.lane].insert(scan_of[i]).second) {
                 const ScanData& s = *scans[scan_of[i]];
                 c->Check(csm_upload_scan(c->Handle(), kCallScanIdBase + scan_of[i], s.angles.data(), s.ranges.data(),
                                          static_cast<int>(s.NumOfScans())), "csm_upload_scan");
             }
+        if (trace) std::fprintf(stderr, "lanes: segment %zu scans up at %.0f us\n", si, timer.ElapsedMicro());
         for (const std::vector<std::int64_t>& group : fresh_ids[si])
             if (!group.empty())
                 c->Check(csm_build_pyramids(c->Handle(), static_cast<int>(group.size()), group.data(), hmax),
                          "csm_build_pyramids");
+        if (trace) std::fprintf(stderr, "lanes: segment %zu levels enqueued at %.0f us\n", si, timer.ElapsedMicro());
         c->Check(csm_set_refiner(c->Handle(), mDeviceRefiner ? &mRefineParams : nullptr), "csm_set_refiner");
         if (in_flight[sg.lane].size() >= 4)         /* the library keeps at most 4 batches in flight */
             finish_oldest(sg.lane);

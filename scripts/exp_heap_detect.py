@@ -9,7 +9,8 @@ batch = bench.make_batch(0, n_maps)
 hb = bench.HostBatch(batch, 0, n_maps, hostapi, synth)
 ctx = hostapi.Context(0)
 det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
-det.configure(chunk_size=128 | (64 << 16), coarse_covariance=False, query_index_base=0)
+ug = int(sys.argv[5]) if len(sys.argv) > 5 else 64
+det.configure(chunk_size=128 | (ug << 16), coarse_covariance=False, query_index_base=0)
 det.use_device_refiner(10, 1e-4, 1e-4)
 det.set_lanes(lanes)
 det.set_gather_threads(threads)
