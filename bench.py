@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 HMAX = 6
 N_MAPS = 256
 ROWS = COLS = 512
+VALUE_LANES = int(os.environ.get("CSM_BENCH_LANES", "4"))     # handles the device-resident steps alternate over
 REFINE = (10, 1e-4, 1e-4)      # NumOfIterationsMax, ConvergenceThreshold, InitialLambda (launcher_settings_default.json:28-35)
 METRIC = "loop_detection_queries_per_sec"
 UNIT = "queries/s"
@@ -60,8 +61,9 @@ def workload_config(n_gpus):
                     "and covariance of every detected loop)" % N_MAPS,
         "queries_per_gpu": N_MAPS, "grid": "%dx%d u16 @0.05m" % (ROWS, COLS), "hmax": HMAX,
         "sharding": "queries/submaps sharded over %d rank(s), 8-byte NCCL argmax all-reduce" % n_gpus,
-        "pipelining": "value: successive steps alternate over 2 handles per GPU (pyramid build of one step "
-                      "overlaps the sweep of the previous one); e2e: 2 pipeline lanes inside one Detect",
+        "pipelining": "value: successive steps (independent Detect calls) alternate over %d handles per GPU (the level "
+                      "build of one step overlaps the sweep of earlier ones); e2e: 2 pipeline lanes inside one Detect"
+                      % VALUE_LANES,
         "l2": "inputs larger than L2 (126 MB): 128 MiB of submaps + 320 MiB of bound levels + 44 MiB of projected "
               "indices touched per step",
     }
@@ -413,7 +415,7 @@ def main_cuda(args):
                              (sub_batch.submaps[i].off_x, sub_batch.submaps[i].off_y), i),
             tuple(sub_batch.map_poses[i]), i) for i in range(lo, hi)]
         lanes = []
-        for k in range(2):
+        for k in range(VALUE_LANES):
             hk = first_handle if (k == 0 and first_handle is not None) else capi.Handle(local)
             if hk is not first_handle:
                 join_comm(hk)
@@ -442,7 +444,7 @@ def main_cuda(args):
             state["wait_s"] += time.perf_counter() - t0
 
         def step():
-            ln = lanes[state["k"] % 2]
+            ln = lanes[state["k"] % len(lanes)]
             state["k"] += 1
             tk = ln["h"].detect_step_enqueue(ln["ids"] if cold else ln["ids"][:0], ln["arr"], ln["n"], HMAX,
                                              ln["base"], drop=True)
@@ -462,7 +464,8 @@ def main_cuda(args):
         launches0 = sum(ln["h"].launch_count() for ln in lanes)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(lanes[0]["stream"])
-        lanes[1]["stream"].wait_event(ev0)               # no lane starts before the start mark
+        for ln in lanes[1:]:
+            ln["stream"].wait_event(ev0)                 # no lane starts before the start mark
         t_issue = time.perf_counter()
         state["wait_s"] = 0.0
         for _ in range(steps):
@@ -470,7 +473,8 @@ def main_cuda(args):
         # host time of issuing a step: the loop's wall time less what it spent waiting for results of
         # earlier steps (that wait is the GPU's time, not the host's)
         host_issue_ms = (time.perf_counter() - t_issue - state["wait_s"]) * 1e3 / steps
-        lanes[0]["stream"].wait_stream(lanes[1]["stream"])   # the end mark waits for both lanes
+        for ln in lanes[1:]:
+            lanes[0]["stream"].wait_stream(ln["stream"])     # the end mark waits for every lane
         ev1.record(lanes[0]["stream"])
         ev1.synchronize()
         drain()                                              # ... and the exchanges are read here
@@ -625,7 +629,7 @@ def main_cuda(args):
     }
     phases = {"pyramid_ms": pyr_ms, "search_and_refine_ms": bb_ms, "kernel_ms": kernel_ms,
               "note": "per-kernel durations of one step run alone on one handle (sum %.3f ms); the timed steps "
-                      "alternate over two handles and overlap, so ms_per_step is below that sum" % (pyr_ms + bb_ms),
+                      "alternate over several handles and overlap, so ms_per_step is below that sum" % (pyr_ms + bb_ms),
               "children_scored_per_step": int(nodes_scored)}
 
     total_queries = world * N_MAPS * args.steps

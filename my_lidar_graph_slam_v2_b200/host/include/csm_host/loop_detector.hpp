@@ -4,10 +4,10 @@
  * "GridSearch" (loop_detector_factory.cpp:202-209). Constructor parameters
  * follow the reference classes (loop_detector_branch_bound.cpp:41-56,
  * loop_detector_correlative.cpp:40-56, loop_detector_grid_search.cpp:33-49);
- * the final sub-pixel matcher is an optional callback because it stays on the
- * CPU. The branch-and-bound detector matches all queries
- * in device batches; the other two run the reference's per-query loop on the
- * GPU matchers. */
+ * the final sub-pixel matcher is an optional callback (CPU) or the device refiner.
+ * The branch-and-bound detector matches all queries in device batches; the other
+ * two run the reference's per-query loop on the GPU matchers, on several device
+ * contexts at once when given (SetConcurrentMatchers). */
 #pragma once
 
 #include <cstdint>
@@ -167,9 +167,14 @@ public:
                             const FinalMatcher& final_matcher,
                             double score_threshold, double known_rate_threshold);
     std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
+    /* More matchers of the same parameters, each on its own device context (the same GPU or another one):
+     * the coarse stage of a Detect then runs on all of them at once, query i on matcher LocalMapId mod L.
+     * Same results as with one matcher. */
+    void SetConcurrentMatchers(const std::vector<std::shared_ptr<ScanMatcherCorrelative>>& extra) { mExtraMatchers = extra; }
 
 private:
     std::shared_ptr<ScanMatcherCorrelative> mScanMatcher;
+    std::vector<std::shared_ptr<ScanMatcherCorrelative>> mExtraMatchers;
     FinalMatcher mFinalMatcher;
     double mScoreThreshold, mKnownRateThreshold;
 };
@@ -183,9 +188,11 @@ public:
                            const FinalMatcher& final_matcher,
                            double score_threshold, double known_rate_threshold);
     std::vector<LoopDetectionResult> Detect(const std::vector<LoopDetectionQuery>& queries) override;
+    void SetConcurrentMatchers(const std::vector<std::shared_ptr<ScanMatcherGridSearch>>& extra) { mExtraMatchers = extra; }
 
 private:
     std::shared_ptr<ScanMatcherGridSearch> mScanMatcher;
+    std::vector<std::shared_ptr<ScanMatcherGridSearch>> mExtraMatchers;
     FinalMatcher mFinalMatcher;
     double mScoreThreshold, mKnownRateThreshold;
 };

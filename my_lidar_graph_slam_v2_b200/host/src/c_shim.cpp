@@ -181,6 +181,10 @@ static void DumpMetrics(const MetricRecorder& rec, char* buf, int cap)
     buf[cap - 1] = 0;
 }
 
+/* matchers the Correlative / GridSearch detectors of csm_host_loop_detect_kind run at once (1 = the plain loop) */
+static int gDetectConcurrency = 1;
+void csm_host_set_detect_concurrency(int n) { gDetectConcurrency = n < 1 ? 1 : n; }
+
 /* LoopDetector{Correlative, BranchBound, GridSearch}::Detect (kind 0 / 1 / 2 as in csm_host_match)
  * over n_queries maps and one shared scan. values: n_queries grids of rows x cols, consecutive.
  * out[q].found = 0 when no result. metrics: optional text buffer (see DumpMetrics). */
@@ -197,10 +201,25 @@ int csm_host_loop_detect_kind(void* ctx, int kind, int n_queries, const uint16_t
     const auto rec = std::make_shared<MetricRecorder>();
     std::shared_ptr<ScanMatcherBranchBound> bb;
     std::unique_ptr<LoopDetector> det;
+    /* the extra contexts live as long as the process: creating one costs milliseconds */
+    static std::vector<DeviceContextPtr> pool;
+    std::vector<DeviceContextPtr> extra_ctx;
+    for (int k = 1; k < gDetectConcurrency && kind != 1; ++k) {
+        if (static_cast<int>(pool.size()) < k || pool[k - 1]->Device() != c->Device()) {
+            pool.resize(std::max<std::size_t>(pool.size(), k));
+            pool[k - 1] = std::make_shared<DeviceContext>(c->Device());
+        }
+        extra_ctx.push_back(pool[k - 1]);
+    }
     if (kind == 0) {
         auto m = std::make_shared<ScanMatcherCorrelative>("LoopRTGPU", cost, iparam, range[0], range[1], range[2], c);
         m->SetMetricSink(rec);
-        det.reset(new LoopDetectorCorrelative("LoopDetectorCorrelativeGPU", m, FinalMatcher(), score_thr, known_thr));
+        auto* d = new LoopDetectorCorrelative("LoopDetectorCorrelativeGPU", m, FinalMatcher(), score_thr, known_thr);
+        std::vector<std::shared_ptr<ScanMatcherCorrelative>> extra;
+        for (const DeviceContextPtr& e : extra_ctx)
+            extra.push_back(std::make_shared<ScanMatcherCorrelative>("LoopRTGPU", cost, iparam, range[0], range[1], range[2], e));
+        d->SetConcurrentMatchers(extra);
+        det.reset(d);
     } else if (kind == 1) {
         bb = std::make_shared<ScanMatcherBranchBound>("LoopBBGPU", cost, iparam, range[0], range[1], range[2], c);
         bb->SetMetricSink(rec);
@@ -209,7 +228,13 @@ int csm_host_loop_detect_kind(void* ctx, int kind, int n_queries, const uint16_t
         auto m = std::make_shared<ScanMatcherGridSearch>("LoopGridGPU", cost, range[0], range[1], range[2],
                                                          step[0], step[1], step[2], c);
         m->SetMetricSink(rec);
-        det.reset(new LoopDetectorGridSearch("LoopDetectorGridSearchGPU", m, FinalMatcher(), score_thr, known_thr));
+        auto* d = new LoopDetectorGridSearch("LoopDetectorGridSearchGPU", m, FinalMatcher(), score_thr, known_thr);
+        std::vector<std::shared_ptr<ScanMatcherGridSearch>> extra;
+        for (const DeviceContextPtr& e : extra_ctx)
+            extra.push_back(std::make_shared<ScanMatcherGridSearch>("LoopGridGPU", cost, range[0], range[1], range[2],
+                                                                    step[0], step[1], step[2], e));
+        d->SetConcurrentMatchers(extra);
+        det.reset(d);
     } else {
         return -1;
     }
@@ -242,9 +267,13 @@ int csm_host_loop_detect_kind(void* ctx, int kind, int n_queries, const uint16_t
         o.est_pose[0] = r.relative_pose.x; o.est_pose[1] = r.relative_pose.y; o.est_pose[2] = r.relative_pose.theta;
         std::memcpy(o.cov, r.estimated_covariance.data(), sizeof(double) * 9);
     }
-    for (int q = 0; q < n_queries; ++q)
+    for (int q = 0; q < n_queries; ++q) {
         csm_release_grid(c->Handle(), map_ids[q]);
+        for (const DeviceContextPtr& e : extra_ctx)
+            csm_release_grid(e->Handle(), map_ids[q]);
+    }
     DumpMetrics(*rec, metrics, metrics_cap);
+    det.reset();             /* before the contexts its extra matchers run on */
     return 0;
 }
 

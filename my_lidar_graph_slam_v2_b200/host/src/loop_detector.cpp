@@ -37,48 +37,82 @@ void CheckThresholds(double score_threshold, double known_rate_threshold)
 }
 
 /* The reference's per-query loop (loop_detector_correlative.cpp:68-146,
- * loop_detector_grid_search.cpp:64-129) around a coarse matcher with thresholds */
+ * loop_detector_grid_search.cpp:64-129) around a coarse matcher with thresholds. A single match is a
+ * handful of dependent launches that leave most of the device idle, so the coarse stage may run on several
+ * matchers at once (each with its own device context, i.e. stream): query i goes to matcher
+ * LocalMapId mod L, which keeps that map and its coarse map resident, one host thread per matcher. The
+ * final matcher then runs over the found poses in query order on the calling thread, like the reference
+ * (its damping state carries from one query to the next). */
 template <typename Matcher>
 std::vector<LoopDetectionResult> DetectPerQuery(
-    const std::vector<LoopDetectionQuery>& queries, Matcher& matcher, const FinalMatcher& final_matcher,
-    double score_threshold, double known_rate_threshold,
+    const std::vector<LoopDetectionQuery>& queries, const std::vector<Matcher*>& matchers,
+    const FinalMatcher& final_matcher, double score_threshold, double known_rate_threshold,
     const std::function<void(const char*, double)>& observe)
 {
-    std::vector<LoopDetectionResult> results;
     MicroTimer timer;
-    for (std::size_t i = 0; i < queries.size(); ++i) {
-        const LoopDetectionQuery& q = queries[i];
+    const std::size_t nq = queries.size();
+    const std::size_t lanes = matchers.size();
+    for (const LoopDetectionQuery& q : queries)
         if (q.local_map.map_id < 0) {
             std::fprintf(stderr, "csm_host: loop detection maps need a LocalMapId\n");
             std::abort();
         }
-        timer.Start();
-        /* pose of the scan node in the map-local frame */
-        const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
-        const ScanMatchingSummary coarse = matcher.OptimizePose(q.local_map, q.scan, init,
-                                                                score_threshold, known_rate_threshold);
-        if (!coarse.pose_found)
+    std::vector<ScanMatchingSummary> coarse(nq);
+    auto run_lane = [&](std::size_t lane) {
+        for (std::size_t i = 0; i < nq; ++i) {
+            const LoopDetectionQuery& q = queries[i];
+            if (static_cast<std::size_t>(q.local_map.map_id) % lanes != lane)
+                continue;
+            /* pose of the scan node in the map-local frame */
+            const Pose2D init = InverseCompound(q.local_map_global_pose, q.scan_global_pose);
+            coarse[i] = matchers[lane]->OptimizePose(q.local_map, q.scan, init, score_threshold, known_rate_threshold);
+        }
+    };
+    if (lanes == 1)
+        run_lane(0);
+    else {
+        std::vector<std::thread> threads;
+        for (std::size_t lane = 1; lane < lanes; ++lane)
+            threads.emplace_back(run_lane, lane);
+        run_lane(0);
+        for (std::thread& t : threads) t.join();
+    }
+    const double coarse_micro = timer.ElapsedMicro();
+    std::vector<LoopDetectionResult> results;
+    for (std::size_t i = 0; i < nq; ++i) {
+        if (!coarse[i].pose_found)
             continue;
+        const LoopDetectionQuery& q = queries[i];
+        timer.Start();
         LoopDetectionResult out;
-        out.relative_pose = coarse.estimated_pose;
-        out.estimated_covariance = coarse.estimated_covariance;
+        out.relative_pose = coarse[i].estimated_pose;
+        out.estimated_covariance = coarse[i].estimated_covariance;
         if (final_matcher) {
             const ScanMatchingSummary fin = final_matcher(q.local_map, q.scan, q.reference_scan_local_pose,
-                                                          coarse.estimated_pose);
+                                                          coarse[i].estimated_pose);
             out.relative_pose = fin.estimated_pose;
             out.estimated_covariance = fin.estimated_covariance;
         }
         out.local_map_pose = q.local_map_global_pose;
         out.local_map_id = q.local_map.map_id;
         out.scan_node_id = q.scan_node_id;
-        out.normalized_score = coarse.normalized_score;
+        out.normalized_score = coarse[i].normalized_score;
         out.query_index = static_cast<int>(i);
         results.push_back(out);
-        observe("LoopDetectionTime", timer.ElapsedMicro());
+        /* the coarse stage ran concurrently: its time is divided evenly over the queries */
+        observe("LoopDetectionTime", timer.ElapsedMicro() + coarse_micro / static_cast<double>(nq));
     }
-    observe("NumOfQueries", static_cast<double>(queries.size()));
+    observe("NumOfQueries", static_cast<double>(nq));
     observe("NumOfDetections", static_cast<double>(results.size()));
     return results;
+}
+
+template <typename Matcher>
+std::vector<Matcher*> MatcherList(const std::shared_ptr<Matcher>& first, const std::vector<std::shared_ptr<Matcher>>& extra)
+{
+    std::vector<Matcher*> all { first.get() };
+    for (const auto& m : extra) all.push_back(m.get());
+    return all;
 }
 
 } /* namespace */
@@ -105,8 +139,8 @@ std::vector<LoopDetectionResult> LoopDetectorCorrelative::Detect(const std::vect
 {
     /* the matcher keeps map and coarse map resident by LocalMapId (the reference's mPrecompMaps,
      * loop_detector_correlative.cpp:83-90) */
-    return DetectPerQuery(queries, *mScanMatcher, mFinalMatcher, mScoreThreshold, mKnownRateThreshold,
-                          [this](const char* m, double v) { Observe(m, v); });
+    return DetectPerQuery(queries, MatcherList(mScanMatcher, mExtraMatchers), mFinalMatcher, mScoreThreshold,
+                          mKnownRateThreshold, [this](const char* m, double v) { Observe(m, v); });
 }
 
 LoopDetectorGridSearch::LoopDetectorGridSearch(
@@ -120,8 +154,8 @@ LoopDetectorGridSearch::LoopDetectorGridSearch(
 
 std::vector<LoopDetectionResult> LoopDetectorGridSearch::Detect(const std::vector<LoopDetectionQuery>& queries)
 {
-    return DetectPerQuery(queries, *mScanMatcher, mFinalMatcher, mScoreThreshold, mKnownRateThreshold,
-                          [this](const char* m, double v) { Observe(m, v); });
+    return DetectPerQuery(queries, MatcherList(mScanMatcher, mExtraMatchers), mFinalMatcher, mScoreThreshold,
+                          mKnownRateThreshold, [this](const char* m, double v) { Observe(m, v); });
 }
 
 /* Gathers blocks that live in separate heap allocations (the reference's GridMap storage,

@@ -50,6 +50,7 @@ def load():
                                                   C.c_double, dp, dp, C.POINTER(C.c_int64), dp, dp, dp, dp,
                                                   C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double,
                                                   C.POINTER(HostSummary), C.c_char_p, C.c_int]
+        lib.csm_host_set_detect_concurrency.argtypes = [C.c_int]
         lib.csm_host_refine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                         dp, dp, C.c_int, dp, dp, C.c_int, C.c_double, dp, C.c_double,
                                         C.POINTER(HostSummary)]
@@ -446,6 +447,11 @@ class Context:
                                                 covariance_scale, out, buf, len(buf))
         assert rc == 0
         return list(out), _parse_metrics(buf.value.decode())
+
+
+def set_detect_concurrency(n):
+    """Matchers the Correlative / GridSearch loop detectors of Context.loop_detect_kind run at once."""
+    load().csm_host_set_detect_concurrency(int(n))
 
 
 def _parse_metrics(text):

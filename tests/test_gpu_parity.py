@@ -1481,3 +1481,37 @@ def test_saturated_cells_read_as_unknown(handle):
     finally:
         handle.set_option("saturated_unknown", 1)
     handle.release_grid(8950)
+
+
+@pytest.mark.parametrize("kind", [0, 2])
+def test_cpp_loop_detectors_concurrent_matchers(kind):
+    """LoopDetectorCorrelative / LoopDetectorGridSearch with several matchers at once
+    (SetConcurrentMatchers: query i on matcher LocalMapId mod L, one host thread and one device context
+    each): the same results, in query order, as the plain per-query loop."""
+    import time
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ctx = hostapi.Context(0)
+    batch = synth.make_loop_batch(3400 + kind, n_maps=24, true_fraction=0.5,
+                                  offset=(0.2, 0.2, 0.05), map_id_base=7300 + 100 * kind)
+    grids = np.stack([s.grid for s in batch.submaps])
+    rng = (0.5, 0.5, 0.15) if kind == 0 else (0.4, 0.4, 0.1)
+    step = None if kind == 0 else (0.05, 0.05, 0.005)
+    args = (kind, grids, batch.submaps[0].res, [s.off_x for s in batch.submaps], [s.off_y for s in batch.submaps],
+            batch.map_ids, batch.map_poses, batch.scan_poses, batch.angles[0], batch.ranges[0], 5, rng, step, (0.5, 0.5))
+    out, times = {}, {}
+    try:
+        for lanes in (1, 4):
+            hostapi.set_detect_concurrency(lanes)
+            ctx.loop_detect_kind(*args)                      # contexts and kernels warm
+            t0 = time.perf_counter()
+            out[lanes], _ = ctx.loop_detect_kind(*args)
+            times[lanes] = time.perf_counter() - t0
+    finally:
+        hostapi.set_detect_concurrency(1)
+    assert sum(r.found for r in out[1]) > 0
+    for a, b in zip(out[1], out[4]):
+        assert a.found == b.found
+        if a.found:
+            assert a.score == b.score and list(a.est_pose) == list(b.est_pose) and list(a.cov) == list(b.cov)
+    print("kind %d: %.2f ms plain, %.2f ms on 4 matchers" % (kind, times[1] * 1e3, times[4] * 1e3))
+    ctx.close()
