@@ -636,6 +636,13 @@ int csm_host_multidet_detect(void* det, int n_queries, const uint16_t* blocks, c
     return ExportResults(d->det->Detect(queries), d->det->LastResults(), n_queries, out);
 }
 
+/* GridMapBuilderGPU::UpdateTable: the 65536-entry table the device applies per update (no device needed) */
+void csm_host_map_update_table(double odds, int reference_table_end, uint16_t* out)
+{
+    const std::vector<std::uint16_t> t = GridMapBuilderGPU::UpdateTable(odds, reference_table_end != 0);
+    std::copy(t.begin(), t.end(), out);
+}
+
 /* ---- map construction on the device: GridMapBuilderGPU ------------------------------------------ */
 struct HostMapBuilder
 {

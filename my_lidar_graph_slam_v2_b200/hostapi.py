@@ -449,6 +449,15 @@ class Context:
         return list(out), _parse_metrics(buf.value.decode())
 
 
+def map_update_table(odds, reference_table_end=True):
+    """GridMapBuilderGPU::UpdateTable(odds): table[v] = the cell value after one update of a cell at v."""
+    out = np.zeros(65536, dtype=np.uint16)
+    lib = load()
+    lib.csm_host_map_update_table.argtypes = [C.c_double, C.c_int, C.c_void_p]
+    lib.csm_host_map_update_table(float(odds), int(reference_table_end), out.ctypes.data)
+    return out
+
+
 def set_detect_concurrency(n):
     """Matchers the Correlative / GridSearch loop detectors of Context.loop_detect_kind run at once."""
     load().csm_host_set_detect_concurrency(int(n))

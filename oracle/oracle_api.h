@@ -146,6 +146,11 @@ int orc_loop_search(int n_scans, const int32_t* scan_ids, const double* scan_pos
                     double travel_dist_threshold, double node_dist_threshold,
                     int num_of_candidate_nodes, int32_t* out_ids, int cap);
 
+/* out[v], v = 0 .. 65535: the cell value after one GridBinaryBayes::UpdateOddsUnchecked(odds) of a cell at v (ref only) */
+int orc_update_table(double odds, uint16_t* out65536);
+/* GridBinaryBayes::ValueToProbability(v) (ref only) */
+double orc_value_probability(int v);
+
 /* The full loop with the reference's own components (ref only); settings: slam_settings.py; the tables
  * have the layouts of csm_host_slam_* (host/src/c_shim.cpp) */
 void* orc_slam_create(const double* settings, int n);

@@ -125,6 +125,18 @@ class Oracle:
         return OracleMapBuilder(self, resolution, patch_size, scans_for_latest_map, usable_range_min,
                                 usable_range_max, prob_hit, prob_miss)
 
+    def update_table(self, odds):
+        """out[v] = cell value after GridBinaryBayes::UpdateOddsUnchecked(odds) of a cell at v (reference only)"""
+        out = np.zeros(65536, dtype=np.uint16)
+        self.lib.orc_update_table.argtypes = [C.c_double, C.c_void_p]
+        assert self.lib.orc_update_table(float(odds), out.ctypes.data) == 0
+        return out
+
+    def value_probability(self, v):
+        self.lib.orc_value_probability.restype = C.c_double
+        self.lib.orc_value_probability.argtypes = [C.c_int]
+        return self.lib.orc_value_probability(int(v))
+
     def slam(self, settings):
         """The full loop on the reference's own components (ref_wrapper.cpp: RefSlam); `settings` from
         my_lidar_graph_slam_v2_b200.slam_settings.pack()."""

@@ -527,6 +527,28 @@ struct RefMapBuilder
 RefMapBuilder* gMapBuilder = nullptr;
 } /* namespace */
 
+/* GridBinaryBayes::ValueToProbability(v) (grid_binary_bayes.cpp:339-342): the table look-up every score and
+ * cost evaluation goes through; v = 65535 is one past the table's end. */
+double orc_value_probability(int v)
+{
+    return GridMap::GridType::ValueToProbability(static_cast<std::uint16_t>(v));
+}
+
+/* out[v] = the value of a cell that holds v after GridBinaryBayes::UpdateOddsUnchecked(odds)
+ * (grid_binary_bayes.cpp:302-321), for every u16 v, on a grid of one cell.
+ * v = 65535 runs the reference's own out-of-table read (grid_values.cpp:72-74). */
+int orc_update_table(double odds, uint16_t* out)
+{
+    GridMap::GridType cell;
+    cell.Initialize(0);                 /* log2 size 0: one cell, allocated */
+    for (int v = 0; v < 65536; ++v) {
+        cell.SetValueUnchecked(0, 0, static_cast<std::uint16_t>(v));
+        cell.UpdateOddsUnchecked(0, 0, odds);
+        out[v] = cell.ValueUnchecked(0, 0);
+    }
+    return 0;
+}
+
 void* orc_mapbuilder_create(double resolution, int patch_size, int scans_for_latest_map,
                             double usable_range_min, double usable_range_max, double prob_hit, double prob_miss)
 {

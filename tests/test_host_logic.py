@@ -224,3 +224,36 @@ def test_adapter_on_reference_types_builds_and_exports():
     lib = C.CDLL(path)
     for sym in ("adp_match_case", "adp_loop_case"):
         assert hasattr(lib, sym)
+
+
+def test_map_update_tables_equal_the_reference_cell_update():
+    """The tables the device applies per map update (GridMapBuilderGPU::UpdateTable) against the reference's
+    GridBinaryBayes::UpdateOddsUnchecked (grid_binary_bayes.cpp:302-321) for EVERY cell value, hit and miss odds of
+    the launcher defaults and two others -- value 65535 included, where the compiled reference reads past its
+    65535-entry odds table and drops the cell to ValueMin."""
+    from oracle import pyoracle
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    if not (pyoracle.available("reference") or os.path.isdir("/root/reference")):
+        pytest.skip("needs the compiled reference")
+    ref = pyoracle.load("reference")
+    for prob in (0.62, 0.46, 0.7, 0.4, 0.9):
+        odds = prob / (1.0 - prob)
+        exp = ref.update_table(odds)
+        got = hostapi.map_update_table(odds)
+        assert np.array_equal(got, exp), "p = %.2f: %d entries differ" % (prob, int((got != exp).sum()))
+        assert got[65535] == 1
+        cont = hostapi.map_update_table(odds, reference_table_end=False)
+        assert np.array_equal(cont[:65535], exp[:65535]) and (cont[65535] == 65535) == (prob > 0.5)
+
+
+def test_reference_reads_a_saturated_cell_as_unknown():
+    """What the matchers' copy of a map reproduces (k_saturated_unknown): the compiled reference's
+    ValueToProbability(65535) is one element past its 65535-entry table and reads 0.0, the unknown probability."""
+    from oracle import pyoracle
+    if not (pyoracle.available("reference") or os.path.isdir("/root/reference")):
+        pytest.skip("needs the compiled reference")
+    ref = pyoracle.load("reference")
+    assert ref.value_probability(0) == 0.0
+    assert ref.value_probability(1) == 1e-3
+    assert abs(ref.value_probability(65534) - (1e-3 + 0.998 * 65533 / 65534)) < 1e-15
+    assert ref.value_probability(65535) == 0.0
