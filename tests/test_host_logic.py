@@ -248,7 +248,10 @@ def test_map_update_tables_equal_the_reference_cell_update():
 
 def test_reference_reads_a_saturated_cell_as_unknown():
     """What the matchers' copy of a map reproduces (k_saturated_unknown): the compiled reference's
-    ValueToProbability(65535) is one element past its 65535-entry table and reads 0.0, the unknown probability."""
+    ValueToProbability(65535) is one element past its 65535-entry table. It reads 0.0 (the unknown probability)
+    when glibc serves the table from its own mmap'd chunk, or the size field of the next heap chunk taken as a
+    double (a denormal around 1e-318) when an earlier free has raised the mmap threshold: nothing in either
+    case for any sum the matchers form."""
     from oracle import pyoracle
     if not (pyoracle.available("reference") or os.path.isdir("/root/reference")):
         pytest.skip("needs the compiled reference")
@@ -256,4 +259,4 @@ def test_reference_reads_a_saturated_cell_as_unknown():
     assert ref.value_probability(0) == 0.0
     assert ref.value_probability(1) == 1e-3
     assert abs(ref.value_probability(65534) - (1e-3 + 0.998 * 65533 / 65534)) < 1e-15
-    assert ref.value_probability(65535) == 0.0
+    assert 0.0 <= ref.value_probability(65535) < 1e-300
