@@ -2502,11 +2502,14 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
     std::memcpy(hp, rays, sizeof(csm_ray) * (size_t)n);
     unsigned int* off = reinterpret_cast<unsigned int*>(hp + rays_bytes);
     unsigned long long total = 0;
+    /* |a / s - b / s| <= |a - b| / s + 1 for the truncating division: an upper bound without a division per
+     * coordinate (the reciprocal is rounded up a little so that the product never falls short) */
+    const double inv_scale = (1.0 + 1e-9) / (double)subpixel_scale;
     for (int i = 0; i < n; ++i) {
         off[i] = (unsigned int)total;
-        const long long dx = (long long)rays[i].end_x / subpixel_scale - (long long)rays[i].start_x / subpixel_scale;
-        const long long dy = (long long)rays[i].end_y / subpixel_scale - (long long)rays[i].start_y / subpixel_scale;
-        total += (unsigned long long)(std::llabs(dx) + std::llabs(dy) + 3);
+        const long long span = std::llabs((long long)rays[i].end_x - rays[i].start_x) +
+                               std::llabs((long long)rays[i].end_y - rays[i].start_y);
+        total += (unsigned long long)((double)span * inv_scale) + 6;
     }
     off[n] = (unsigned int)total;
     if (total >= (1ull << 31))
@@ -2537,9 +2540,11 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
     R.error = static_cast<int*>(h->d_maperror.p);
     /* `order` must be below 2^(shift - 1): the adapter numbers the beams of one call 0 .. n - 1 */
     int order_max = 0;
+    bool ascending = true;          /* rays handed over in update order (what the adapter does) */
     for (int i = 0; i < n; ++i) {
         if (rays[i].order < 0)
             return fail(h, CSM_E_INVALID, "map insert: negative beam order");
+        ascending = ascending && rays[i].order >= order_max;
         order_max = std::max(order_max, rays[i].order);
     }
     int order_bits = 1;
@@ -2552,8 +2557,11 @@ int csm_map_insert_rays(csm_handle h, int64_t map_id, const csm_ray* rays, int n
     CSM_CUDA(cudaMemsetAsync(ev_in, 0xff, sizeof(unsigned long long) * (size_t)total, h->stream));    /* kMapEventNone */
     k_map_rays<<<n, kMapRayThreads, 0, h->stream>>>(R);
     CSM_LAUNCH_CHECK();
-    /* per cell, in beam order; one bit above the cell index, so that the unused slots (all ones) sort last */
-    if (cub::DeviceRadixSort::SortKeys(sort_tmp, sort_bytes, ev_in, ev_out, (int)total, 0,
+    /* Per cell, in beam order. When the rays arrive in update order their events are WRITTEN in that order
+     * (a ray's slots follow the previous ray's, its hit is its last slot) and the radix sort is stable, so
+     * sorting on the cell index alone keeps every cell's events in the reference's order; otherwise the order
+     * bits are sorted too. One bit above the cell index sends the unused slots (all ones) to the end. */
+    if (cub::DeviceRadixSort::SortKeys(sort_tmp, sort_bytes, ev_in, ev_out, (int)total, ascending ? R.shift : 0,
                                        std::min(64, R.shift + cell_bits + 1), h->stream) != cudaSuccess)
         return fail(h, CSM_E_CUDA, "map insert: radix sort failed");
     ++h->launches;

@@ -11,7 +11,7 @@ SOURCES = [os.path.join(HERE, "src", f) for f in
 
 
 def build():
-    cmd = ["g++", "-std=c++17", "-O3", "-g", "-rdynamic", "-ffp-contract=off", "-fPIC", "-shared", "-Wall",
+    cmd = ["g++", "-std=c++17", "-O3", "-g", "-rdynamic", "-ffp-contract=off", "-msse4.1", "-fPIC", "-shared", "-Wall",
            "-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "include"),
            "-o", LIB] + SOURCES + ["-L", PKG, "-l:libcsm_b200.so", "-Wl,-rpath,$ORIGIN", "-pthread"]
     subprocess.run(cmd, check=True)

@@ -14,7 +14,9 @@
 #pragma once
 
 #include <cstdint>
+#include <cmath>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 #include "csm_host/pose_graph.hpp"
@@ -36,7 +38,27 @@ class DeviceGridMap
 public:
     struct Index { int x, y; };
     /* the hit points of one scan in the map's frame, and its sensor position */
-    struct ScanHits { Pose2D sensor; std::vector<double> x, y; };
+    struct ScanHits
+    {
+        Pose2D sensor;
+        std::vector<double> x, y;
+        /* `fast`: x, y come from rotating the scan's own polar points (r cos a, r sin a) by the sensor
+         * heading instead of libm's cos / sin of (heading + a): a few 1e-14 m away from the reference's values.
+         * They are only ever floored to cell indices; whoever floors them checks the distance to the cell
+         * boundary and re-evaluates the beam the reference's way when it is closer than the guard band
+         * (`scan`, `beam`: what that takes). */
+        bool fast = false;
+        const ScanData* scan = nullptr;
+        std::vector<int> beam;
+        /* the reference's own arithmetic for kept beam k (sensor_data.hpp:190-203) */
+        void Exact(std::size_t k, double& hx, double& hy) const
+        {
+            const double c = std::cos(sensor.theta + scan->angles[beam[k]]);
+            const double s = std::sin(sensor.theta + scan->angles[beam[k]]);
+            hx = sensor.x + scan->ranges[beam[k]] * c;
+            hy = sensor.y + scan->ranges[beam[k]] * s;
+        }
+    };
 
     /* GridMap(resolution, blockSize, 1.0, 1.0) (grid_map.cpp:74-99, 226-246) */
     DeviceGridMap(const DeviceContextPtr& context, std::int64_t map_id, double resolution, int log2_block_size);
@@ -51,6 +73,12 @@ public:
     /* :642-692 / :445-480: per beam the sub-pixel indices of sensor and hit point and the hit cell, in the
      * order of `hits`; the device casts the rays. Returns the number of beams. */
     int InsertScans(const std::vector<ScanHits>& hits, int subpixel_scale);
+    /* beams of the last InsertScans that sat inside the guard band and were re-evaluated exactly */
+    int LastExactBeams() const { return mLastExactBeams; }
+    /* |fraction to the nearest cell boundary| below which a floored fast coordinate is not trusted, in cells
+     * (of the geometry it is floored in): 1e-9 against a possible difference of ~1e-10 sub-pixel cells */
+    static constexpr double kGuardBand = 1e-9;
+    static bool NearBoundary(double cells) { const double f = cells - std::floor(cells); return f < kGuardBand || 1.0 - f < kGuardBand; }
 
     GridMapView View() const;            /* device_resident: the matchers read the map where it is */
     std::int64_t MapId() const { return mMapId; }
@@ -73,6 +101,7 @@ private:
     int mLog2BlockSize;
     int mBlockRows, mBlockCols, mRows, mCols;
     double mOffX, mOffY;
+    int mLastExactBeams = 0;
 };
 
 /* grid_map_builder.hpp:29-85 */
@@ -139,7 +168,15 @@ private:
     /* ConstructMapFromScans (:561-695): `map` rebuilt from `count` scan nodes in the frame `map_pose` */
     void ConstructMapFromScans(const Pose2D& map_pose, DeviceGridMap& map, const ScanNodeView* nodes, int count);
     /* ComputeBoundingBoxAndScanPointsMapLocal (:820-872) and the first loop of ConstructMapFromScans */
-    DeviceGridMap::ScanHits HitsOf(const Pose2D& map_pose, const Pose2D& global_scan_pose, const ScanData& scan) const;
+    DeviceGridMap::ScanHits HitsOf(const Pose2D& map_pose, const Pose2D& global_scan_pose, const ScanDataPtr& scan);
+    /* bounding box of sensor and hit points; when a fast coordinate decides a floor of Resize / Expand inside
+     * the guard band, every hit point is re-evaluated exactly and the box formed again */
+    void BoundingBox(std::vector<DeviceGridMap::ScanHits>& hits, const DeviceGridMap& map, bool construct,
+                     double& min_x, double& min_y, double& max_x, double& max_y) const;
+    /* a scan's polar points (r cos a, r sin a), libm once per scan: the scans of the latest map come back
+     * ten times, the map frame changes every time */
+    struct Polar { ScanDataPtr keep; std::vector<double> px, py; };      /* `keep`: the address stays this scan's */
+    const Polar& PolarOf(const ScanDataPtr& scan);
     void AppendLocalMap(PoseGraph& pose_graph, const Pose2D& scan_pose, const Mat3& covariance, int scan_node_id);
     void UpdateGridMap(const PoseGraph& pose_graph);
 
@@ -157,6 +194,12 @@ private:
     double mTravelDistThreshold = 2.5;
     int mNumOfOverlappedScans = 10;
     int mLastRays = 0;
+    bool mFastHitPoints = true;
+    std::unordered_map<const ScanData*, Polar> mPolar;
+
+public:
+    /* false: every hit point with libm, like the reference (the fast path gives the same cells; tests compare) */
+    void SetFastHitPoints(bool on) { mFastHitPoints = on; }
 };
 
 } /* namespace csm_host */

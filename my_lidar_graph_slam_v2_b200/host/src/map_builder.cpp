@@ -194,16 +194,25 @@ int DeviceGridMap::InsertScans(const std::vector<ScanHits>& hits, int subpixel_s
     std::vector<csm_ray> rays;
     rays.reserve(total);
     int order = 0;
+    mLastExactBeams = 0;
     for (const ScanHits& h : hits) {
         const int sx = static_cast<int>(std::floor((h.sensor.x - mOffX) / scaled_res));
         const int sy = static_cast<int>(std::floor((h.sensor.y - mOffY) / scaled_res));
         for (std::size_t i = 0; i < h.x.size(); ++i) {
-            const Index hit = PositionToIndex(h.x[i], h.y[i]);
+            double hx = h.x[i], hy = h.y[i];
+            double ex = (hx - mOffX) / scaled_res, ey = (hy - mOffY) / scaled_res;
+            double cx = (hx - mOffX) / mResolution, cy = (hy - mOffY) / mResolution;
+            if (h.fast && (NearBoundary(ex) || NearBoundary(ey) || NearBoundary(cx) || NearBoundary(cy))) {
+                h.Exact(i, hx, hy);
+                ex = (hx - mOffX) / scaled_res; ey = (hy - mOffY) / scaled_res;
+                cx = (hx - mOffX) / mResolution; cy = (hy - mOffY) / mResolution;
+                ++mLastExactBeams;
+            }
             csm_ray r;
             r.start_x = sx; r.start_y = sy;
-            r.end_x = static_cast<int>(std::floor((h.x[i] - mOffX) / scaled_res));
-            r.end_y = static_cast<int>(std::floor((h.y[i] - mOffY) / scaled_res));
-            r.hit_col = hit.x; r.hit_row = hit.y;
+            r.end_x = static_cast<int>(std::floor(ex));
+            r.end_y = static_cast<int>(std::floor(ey));
+            r.hit_col = static_cast<int>(std::floor(cx)); r.hit_row = static_cast<int>(std::floor(cy));
             r.order = order++;
             r.reserved = 0;
             rays.push_back(r);
@@ -244,9 +253,29 @@ GridMapBuilderGPU::GridMapBuilderGPU(const DeviceContextPtr& context, double map
     mContext->Check(csm_map_set_update_tables(mContext->Handle(), miss.data(), hit.data()), "csm_map_set_update_tables");
 }
 
-DeviceGridMap::ScanHits GridMapBuilderGPU::HitsOf(const Pose2D& map_pose, const Pose2D& global_scan_pose,
-                                                  const ScanData& scan) const
+const GridMapBuilderGPU::Polar& GridMapBuilderGPU::PolarOf(const ScanDataPtr& scan_ptr)
 {
+    const ScanData& scan = *scan_ptr;
+    auto it = mPolar.find(&scan);
+    if (it != mPolar.end())
+        return it->second;
+    if (mPolar.size() > 256)
+        mPolar.clear();                    /* the scans in use come back within a few calls */
+    Polar& p = mPolar[&scan];
+    p.keep = scan_ptr;
+    const std::size_t n = scan.NumOfScans();
+    p.px.resize(n); p.py.resize(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        p.px[i] = scan.ranges[i] * std::cos(scan.angles[i]);
+        p.py[i] = scan.ranges[i] * std::sin(scan.angles[i]);
+    }
+    return p;
+}
+
+DeviceGridMap::ScanHits GridMapBuilderGPU::HitsOf(const Pose2D& map_pose, const Pose2D& global_scan_pose,
+                                                  const ScanDataPtr& scan_ptr)
+{
+    const ScanData& scan = *scan_ptr;
     DeviceGridMap::ScanHits h;
     const Pose2D global_sensor = Compound(global_scan_pose, scan.relative_sensor_pose);
     h.sensor = InverseCompound(map_pose, global_sensor);
@@ -254,6 +283,24 @@ DeviceGridMap::ScanHits GridMapBuilderGPU::HitsOf(const Pose2D& map_pose, const 
     const double max_range = std::min(mUsableRangeMax, scan.max_range);
     const std::size_t n = scan.NumOfScans();
     h.x.reserve(n); h.y.reserve(n);
+    h.scan = &scan;
+    h.fast = mFastHitPoints;
+    if (h.fast) {
+        /* sensor + R(heading) * (r cos a, r sin a): within a few 1e-14 m of the reference's hit point, which
+         * is all a floor needs outside its guard band (DeviceGridMap::ScanHits) */
+        const Polar& p = PolarOf(scan_ptr);
+        const double c = std::cos(h.sensor.theta), s = std::sin(h.sensor.theta);
+        h.beam.reserve(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            const double range = scan.ranges[i];
+            if (range >= max_range || range <= min_range)
+                continue;
+            h.x.push_back(h.sensor.x + (c * p.px[i] - s * p.py[i]));
+            h.y.push_back(h.sensor.y + (s * p.px[i] + c * p.py[i]));
+            h.beam.push_back(static_cast<int>(i));
+        }
+        return h;
+    }
     for (std::size_t i = 0; i < n; ++i) {
         const double range = scan.ranges[i];
         if (range >= max_range || range <= min_range)
@@ -267,24 +314,58 @@ DeviceGridMap::ScanHits GridMapBuilderGPU::HitsOf(const Pose2D& map_pose, const 
     return h;
 }
 
-void GridMapBuilderGPU::ConstructMapFromScans(const Pose2D& map_pose, DeviceGridMap& map, const ScanNodeView* nodes, int count)
+void GridMapBuilderGPU::BoundingBox(std::vector<DeviceGridMap::ScanHits>& hits, const DeviceGridMap& map, bool construct,
+                                    double& min_x, double& min_y, double& max_x, double& max_y) const
 {
-    /* first pass (:578-633): hit points and bounding box in the map's frame. The box starts at
-     * (max double, min POSITIVE double), as the reference has it (:582-585) */
-    double min_x = std::numeric_limits<double>::max(), min_y = std::numeric_limits<double>::max();
-    double max_x = std::numeric_limits<double>::min(), max_y = std::numeric_limits<double>::min();
-    std::vector<DeviceGridMap::ScanHits> hits;
-    hits.reserve(count);
-    for (int k = 0; k < count; ++k) {
-        hits.push_back(HitsOf(map_pose, nodes[k].global_pose, *nodes[k].scan));
-        const DeviceGridMap::ScanHits& h = hits.back();
-        min_x = std::min(min_x, h.sensor.x); min_y = std::min(min_y, h.sensor.y);
-        max_x = std::max(max_x, h.sensor.x); max_y = std::max(max_y, h.sensor.y);
-        for (std::size_t i = 0; i < h.x.size(); ++i) {
-            min_x = std::min(min_x, h.x[i]); min_y = std::min(min_y, h.y[i]);
-            max_x = std::max(max_x, h.x[i]); max_y = std::max(max_y, h.y[i]);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (construct) {
+            /* ConstructMapFromScans: the box starts at (max double, min POSITIVE double), as the reference
+             * has it (:582-585) */
+            min_x = min_y = std::numeric_limits<double>::max();
+            max_x = max_y = std::numeric_limits<double>::min();
+        } else {
+            /* UpdateGridMap: the box starts at the sensor (:832-838) */
+            min_x = max_x = hits[0].sensor.x;
+            min_y = max_y = hits[0].sensor.y;
+        }
+        bool fast = false;
+        for (const DeviceGridMap::ScanHits& h : hits) {
+            fast = fast || h.fast;
+            min_x = std::min(min_x, h.sensor.x); min_y = std::min(min_y, h.sensor.y);
+            max_x = std::max(max_x, h.sensor.x); max_y = std::max(max_y, h.sensor.y);
+            for (std::size_t i = 0; i < h.x.size(); ++i) {
+                min_x = std::min(min_x, h.x[i]); min_y = std::min(min_y, h.y[i]);
+                max_x = std::max(max_x, h.x[i]); max_y = std::max(max_y, h.y[i]);
+            }
+        }
+        if (!fast)
+            return;
+        /* the floors Resize / Expand take of the box (grid_map.cpp:896-903, 936-943) */
+        const double res = map.Resolution();
+        const bool near = DeviceGridMap::NearBoundary((min_x - res - map.OffsetX()) / res) ||
+                          DeviceGridMap::NearBoundary((min_y - res - map.OffsetY()) / res) ||
+                          DeviceGridMap::NearBoundary((max_x + res - map.OffsetX()) / res) ||
+                          DeviceGridMap::NearBoundary((max_y + res - map.OffsetY()) / res);
+        if (!near)
+            return;
+        for (DeviceGridMap::ScanHits& h : hits) {
+            if (!h.fast) continue;
+            for (std::size_t i = 0; i < h.x.size(); ++i)
+                h.Exact(i, h.x[i], h.y[i]);
+            h.fast = false;
         }
     }
+}
+
+void GridMapBuilderGPU::ConstructMapFromScans(const Pose2D& map_pose, DeviceGridMap& map, const ScanNodeView* nodes, int count)
+{
+    /* first pass (:578-633): hit points and bounding box in the map's frame */
+    std::vector<DeviceGridMap::ScanHits> hits;
+    hits.reserve(count);
+    for (int k = 0; k < count; ++k)
+        hits.push_back(HitsOf(map_pose, nodes[k].global_pose, nodes[k].scan));
+    double min_x, min_y, max_x, max_y;
+    BoundingBox(hits, map, true, min_x, min_y, max_x, max_y);
     /* :636-638 */
     map.Resize(min_x, min_y, max_x, max_y);
     map.ResetValues();
@@ -402,14 +483,9 @@ void GridMapBuilderGPU::UpdateGridMap(const PoseGraph& pose_graph)
     const LocalMapNode& map_node = pose_graph.local_map_nodes.back();
     const ScanNode& scan_node = pose_graph.scan_nodes.back();
     std::vector<DeviceGridMap::ScanHits> hits(1);
-    hits[0] = HitsOf(map_node.global_pose, scan_node.global_pose, *scan_node.scan);
-    const DeviceGridMap::ScanHits& h = hits[0];
-    /* the box starts at the sensor (:832-838) */
-    double min_x = h.sensor.x, min_y = h.sensor.y, max_x = h.sensor.x, max_y = h.sensor.y;
-    for (std::size_t i = 0; i < h.x.size(); ++i) {
-        min_x = std::min(min_x, h.x[i]); min_y = std::min(min_y, h.y[i]);
-        max_x = std::max(max_x, h.x[i]); max_y = std::max(max_y, h.y[i]);
-    }
+    hits[0] = HitsOf(map_node.global_pose, scan_node.global_pose, scan_node.scan);
+    double min_x, min_y, max_x, max_y;
+    BoundingBox(hits, *lm.map, false, min_x, min_y, max_x, max_y);
     lm.map->Expand(min_x, min_y, max_x, max_y);
     mLastRays = lm.map->InsertScans(hits, SubpixelScale);
     lm.scan_node_id_max = scan_node.node_id;

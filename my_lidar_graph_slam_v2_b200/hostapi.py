@@ -199,6 +199,10 @@ class MapBuilder:
         self.p = self.lib.csm_host_mapbuilder_create(ctx.ctx, resolution, patch_size, scans_for_latest_map,
                                                      usable_range_min, usable_range_max, prob_hit, prob_miss)
 
+    def set_fast_hit_points(self, on):
+        self.lib.csm_host_mapbuilder_set_fast_hit_points.argtypes = [C.c_void_p, C.c_int]
+        self.lib.csm_host_mapbuilder_set_fast_hit_points(self.p, int(on))
+
     def append(self, pose, angles, ranges, rel_pose=(0.0, 0.0, 0.0), min_range=0.01, max_range=50.0):
         a, ap = _d(angles)
         r, rp = _d(ranges)

@@ -41,15 +41,19 @@ def _compare(dev, ref, what):
         what, len(bad), bad[0], d_dense[tuple(bad[0])], r_dense[tuple(bad[0])])
 
 
+@pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("seed,n_beams,rel", [(7001, 360, (0.0, 0.0, 0.0)), (7002, 1080, (0.12, -0.04, 0.3))])
-def test_latest_map_per_scan(seed, n_beams, rel):
-    """14 scans into a 10-scan window: the window slides, the map is rebuilt from scratch per scan."""
+def test_latest_map_per_scan(seed, n_beams, rel, fast):
+    """14 scans into a 10-scan window: the window slides, the map is rebuilt from scratch per scan. `fast`: the
+    host rotates each scan's polar points instead of calling libm per beam and re-evaluates the beams whose
+    floored coordinates sit inside the guard band (the default); the other way is the reference's arithmetic."""
     from oracle import pyoracle
     from my_lidar_graph_slam_v2_b200 import hostapi
     ref = pyoracle.load("reference")
     _, traj = _trajectory(seed, 14, n_beams)
     ctx = hostapi.Context(0)
     mb = hostapi.MapBuilder(ctx)
+    mb.set_fast_hit_points(fast)
     ob = ref.map_builder()
     for k, (p, a, r) in enumerate(traj):
         n = mb.append(p, a, r, rel)
