@@ -78,7 +78,8 @@ public:
     /* |fraction to the nearest cell boundary| below which a floored fast coordinate is not trusted, in cells
      * (of the geometry it is floored in): 1e-9 against a possible difference of ~1e-10 sub-pixel cells */
     static constexpr double kGuardBand = 1e-9;
-    static bool NearBoundary(double cells) { const double f = cells - std::floor(cells); return f < kGuardBand || 1.0 - f < kGuardBand; }
+    static double& GuardBand() { static double band = kGuardBand; return band; }      /* tests widen it */
+    static bool NearBoundary(double cells) { const double f = cells - std::floor(cells); return f < GuardBand() || 1.0 - f < GuardBand(); }
 
     GridMapView View() const;            /* device_resident: the matchers read the map where it is */
     std::int64_t MapId() const { return mMapId; }

@@ -663,6 +663,9 @@ void* csm_host_mapbuilder_create(void* ctx, double resolution, int patch_size, i
 
 void csm_host_mapbuilder_destroy(void* p) { delete static_cast<HostMapBuilder*>(p); }
 /* 0: every hit point with libm like the reference; 1 (default): rotated polar points behind a guard band */
+/* test knob: the guard band of the fast hit points, in cells (0.5 and above: every beam is re-evaluated) */
+void csm_host_mapbuilder_set_guard_band(double cells) { DeviceGridMap::GuardBand() = cells; }
+int csm_host_mapbuilder_last_exact_beams(void* p) { return static_cast<HostMapBuilder*>(p)->builder->LatestGrid().LastExactBeams(); }
 void csm_host_mapbuilder_set_fast_hit_points(void* p, int on) { static_cast<HostMapBuilder*>(p)->builder->SetFastHitPoints(on != 0); }
 
 /* Append one scan node (global pose, scan) and rebuild the latest map, like the front end does per scan.

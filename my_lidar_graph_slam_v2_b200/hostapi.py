@@ -199,6 +199,14 @@ class MapBuilder:
         self.p = self.lib.csm_host_mapbuilder_create(ctx.ctx, resolution, patch_size, scans_for_latest_map,
                                                      usable_range_min, usable_range_max, prob_hit, prob_miss)
 
+    def set_guard_band(self, cells):
+        self.lib.csm_host_mapbuilder_set_guard_band.argtypes = [C.c_double]
+        self.lib.csm_host_mapbuilder_set_guard_band(float(cells))
+
+    def last_exact_beams(self):
+        self.lib.csm_host_mapbuilder_last_exact_beams.argtypes = [C.c_void_p]
+        return self.lib.csm_host_mapbuilder_last_exact_beams(self.p)
+
     def set_fast_hit_points(self, on):
         self.lib.csm_host_mapbuilder_set_fast_hit_points.argtypes = [C.c_void_p, C.c_int]
         self.lib.csm_host_mapbuilder_set_fast_hit_points(self.p, int(on))

@@ -64,6 +64,38 @@ def test_latest_map_per_scan(seed, n_beams, rel, fast):
     ctx.close()
 
 
+def test_guard_band_path_re_evaluates_exactly():
+    """With the guard band widened to half a cell every fast hit point counts as "near a boundary": the bounding
+    box sends every point through the exact re-evaluation; with a band of 0.05 cells about a third of the beams
+    are re-evaluated one by one. The map is the reference's either way."""
+    from oracle import pyoracle
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    ref = pyoracle.load("reference")
+    _, traj = _trajectory(7006, 6, 360)
+    ctx = hostapi.Context(0)
+    knob = hostapi.MapBuilder(ctx)
+    try:
+        for band in (0.5, 0.05):
+            mb = hostapi.MapBuilder(ctx, scans_for_latest_map=3)
+            ob = ref.map_builder(scans_for_latest_map=3)
+            knob.set_guard_band(band)
+            exact = []
+            for k, (p, a, r) in enumerate(traj):
+                n = mb.append(p, a, r)
+                ob.append(p, a, r)
+                _compare(mb.latest(), ob.latest(), "band %.2f scan %d" % (band, k))
+                exact.append((mb.last_exact_beams(), n))
+            if band == 0.5:
+                assert all(e == 0 for e, _ in exact)          # nothing was "fast" any more when inserted
+            else:
+                assert any(0 < e < n for e, n in exact), exact
+            mb.close()
+    finally:
+        knob.set_guard_band(1e-9)
+        knob.close()
+    ctx.close()
+
+
 def test_saturation_and_range_limits():
     """The same pose 40 times drives free cells to ValueMin and occupied cells to ValueMax = 65535, where
     the reference's next update reads one entry past its 65535-entry odds table and drops the cell to
