@@ -892,8 +892,10 @@ def single_scan_numbers(h, lib, kind):
             "ms": wt_ms, "cell_reads_per_s": full * 1080 / (wt_ms * 1e-3),
             "smem_roofline_reads_per_s": 32 * 148 * 1.965e9,
             "frac_of_smem_roofline": full * 1080 / (wt_ms * 1e-3) / (32 * 148 * 1.965e9),
-            "note": "roofline = 1 shared-memory wavefront (32 lanes) per cycle per SM at 1965 MHz; "
-                    "ncu counts 0.739 wavefronts/cycle/SM including the tile widening and idle lanes (profiles/r1_k_window_tma.txt)"}}
+            "note": "roofline = 1 shared-memory wavefront (32 lanes) per cycle per SM at 1965 MHz, every lane useful; "
+                    "ncu: 0.78 of the LSU pipe's peak, the rest of its wavefronts are the remainder column and the "
+                    "per-beam offset load (profiles/r2_k_window_tma.txt); tiles land as 32-bit words and are scored "
+                    "in place (round 1: u16 tiles widened per run, 0.546 useful)"}}
     ctx.close()
     return out
 

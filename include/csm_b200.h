@@ -174,7 +174,9 @@ int csm_share_copy_stream(csm_handle h, csm_handle owner);
  *      csm_build_pyramids for batches of maps or on first use), 0 = the reference's u16
  *      levels. Results are identical either way; a few percent more nodes are expanded;
  *  "window_mode": grid search, 0 (default) = TMA shared-memory tile kernel when
- *      the window fits, 1 = global-memory kernel, 2 = require the TMA kernel;
+ *      the window fits (tiles of 32-bit value | known words, scored where they land),
+ *      1 = global-memory kernel, 2 = require the TMA kernel, 3 = require the TMA
+ *      kernel on u16 tiles that a pass per tile widens;
  *  "exact_rerun": 1 (default) = a result whose projection raised the FP guard-band
  *      flag is recomputed from host-evaluated indices (CSM_FLAG_EXACT), 0 = it is
  *      returned as is with CSM_FLAG_FP_MARGIN; "fp_margin_scale": test knob, multiplies

@@ -111,6 +111,8 @@ struct MapSlot
     int hmax = 0;                  /* number of levels currently valid */
     uint16_t* coarse = nullptr;
     int coarse_win = 0;
+    uint32_t* wide = nullptr;      /* level 0 as value | known << 20 words: what the wide TMA window kernel loads */
+    bool wide_valid = false;
     /* bound levels of the branch-and-bound sweep (csm_bounds.cuh): levels 1..bounds_alloc allocated
      * (padding zeroed once), 1..bounds_levels valid for the current contents */
     unsigned char* bounds = nullptr;
@@ -470,6 +472,7 @@ void free_map(csm_handle h, MapSlot& m)
     if (m.raw) cudaFreeAsync(m.raw, h->stream);
     if (m.levels) cudaFreeAsync(m.levels, h->stream);
     if (m.coarse) cudaFreeAsync(m.coarse, h->stream);
+    if (m.wide) cudaFreeAsync(m.wide, h->stream);
     if (m.bounds) cudaFreeAsync(m.bounds, h->stream);
     if (m.alloc && !m.alloc_block) cudaFreeAsync(m.alloc, h->stream);
     m = MapSlot();
@@ -1193,6 +1196,38 @@ bool make_map_tensor(const MapSlot& m, CUtensorMap* out)
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+/* The same over the map's 32-bit form (MapSlot::wide): boxes of kWwPitch x kWtBoxRows words */
+bool make_map_tensor_wide(const MapSlot& m, CUtensorMap* out)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr || (m.cols % 8) != 0 || m.wide == nullptr)
+        return false;
+    const cuuint64_t dims[2] = { (cuuint64_t)m.cols, (cuuint64_t)m.rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)m.cols * sizeof(uint32_t) };
+    const cuuint32_t box[2] = { (cuuint32_t)kWwPitch, (cuuint32_t)kWtBoxRows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, m.wide, dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+/* value | known << 20 words of level 0, once per map contents (k_widen_map) */
+int ensure_wide(csm_handle h, MapSlot& m)
+{
+    if (m.wide_valid)
+        return CSM_OK;
+    const size_t cells = (size_t)m.rows * m.cols;
+    if (m.wide == nullptr)
+        CSM_CUDA(cudaMallocAsync((void**)&m.wide, cells * sizeof(uint32_t), h->stream));
+    const size_t n8 = cells / 8;           /* cols % 8 == 0 */
+    const unsigned blocks = (unsigned)std::min<size_t>((n8 + 255) / 256, 148 * 8);
+    k_widen_map<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint4*>(m.base), reinterpret_cast<uint4*>(m.wide), n8);
+    CSM_LAUNCH_CHECK();
+    ++h->launches;
+    m.wide_valid = true;
+    return CSM_OK;
+}
+
 /* scan: when non-null, the (single) query uses a scan that arrives with this
  * call (angles / ranges on the host) instead of a scan uploaded before. */
 struct InlineScan
@@ -1720,9 +1755,10 @@ cudaError_t set_kernel_attributes()
     if ((e = cudaFuncSetAttribute(k_bounds_build<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl_smem_bytes(L))) != cudaSuccess) return e;
     CSM_BL_ATTR(1) CSM_BL_ATTR(2) CSM_BL_ATTR(3) CSM_BL_ATTR(4) CSM_BL_ATTR(5) CSM_BL_ATTR(6)
 #undef CSM_BL_ATTR
-    const int wt = (int)wt_smem_bytes(kMaxBeams);
+    const int wt = (int)wt_smem_bytes(kMaxBeams), ww = (int)wt_smem_bytes_wide(kMaxBeams);
 #define CSM_WT_ATTR(UNIT, CHUNKS, REM)                                                                                        \
-    if ((e = cudaFuncSetAttribute(k_window_tma<UNIT, CHUNKS, REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, wt)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_window_tma<UNIT, CHUNKS, REM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wt)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(k_window_tma<UNIT, CHUNKS, REM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ww)) != cudaSuccess) return e;
     CSM_WT_ATTR(true, 1, true) CSM_WT_ATTR(true, 2, true) CSM_WT_ATTR(true, 3, true)
     CSM_WT_ATTR(true, 4, true) CSM_WT_ATTR(true, 5, true) CSM_WT_ATTR(true, 6, true)
     CSM_WT_ATTR(true, kWtChunks, false) CSM_WT_ATTR(false, kWtChunks, false)
@@ -1870,7 +1906,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "bb_stop_level") == 0) { h->bb_stop_level = std::max(0, std::min(value, kMaxLevels - 1)); return CSM_OK; }
     if (std::strcmp(name, "bb_bounds") == 0) { h->bb_bounds = value != 0; return CSM_OK; }
     if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
-    if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 2) { h->window_mode = value; return CSM_OK; }
+    if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 3) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0 && value != 0 && h->d_bestkey.p == nullptr) {
         CSM_CUDA(cudaSetDevice(h->device));
@@ -1926,6 +1962,7 @@ static int upload_grid_impl(csm_handle h, int64_t map_id, const uint16_t* dense,
     m.bounds_levels = -1;
     m.margin_valid = false;
     m.coarse_win = 0;
+    m.wide_valid = false;
     m.pending_scatter.reset();
     m.alloc_valid = false;
     m.res = res; m.offx = offx; m.offy = offy;
@@ -1995,6 +2032,7 @@ int csm_upload_grids(csm_handle h, int n, const int64_t* map_ids, const uint16_t
         m.bounds_levels = -1;
         m.margin_valid = false;
         m.coarse_win = 0;
+        m.wide_valid = false;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
         m.pending_scatter.reset();
@@ -2103,6 +2141,7 @@ int csm_upload_grids_blocks(csm_handle h, int n, const int64_t* map_ids,
         m.bounds_levels = -1;
         m.margin_valid = false;
         m.coarse_win = 0;
+        m.wide_valid = false;
         m.res = resolution; m.offx = offset_x[i]; m.offy = offset_y[i];
         m.pending_upload = reinterpret_cast<cudaEvent_t>(1);
         m.pending_scatter = bs;
@@ -2210,6 +2249,7 @@ int csm_drop_pyramids(csm_handle h, int n, const int64_t* map_ids)
         it->second.hmax = 0;
         it->second.bounds_levels = -1;
         it->second.coarse_win = 0;
+        it->second.wide_valid = false;
     }
     return CSM_OK;
 }
@@ -2387,6 +2427,7 @@ static void invalidate_derived(MapSlot& m)
     m.bounds_levels = -1;
     m.margin_valid = false;
     m.coarse_win = 0;
+    m.wide_valid = false;
 }
 
 int csm_map_create(csm_handle h, int64_t map_id, int rows, int cols, int log2_block_size,
@@ -2449,6 +2490,7 @@ int csm_map_resize(csm_handle h, int64_t map_id, int rows, int cols, int row_min
     CSM_LAUNCH_CHECK();
     if (m.levels) { CSM_CUDA(cudaFreeAsync(m.levels, h->stream)); m.levels = nullptr; m.levels_alloc = 0; }
     if (m.coarse) { CSM_CUDA(cudaFreeAsync(m.coarse, h->stream)); m.coarse = nullptr; }
+    if (m.wide) { CSM_CUDA(cudaFreeAsync(m.wide, h->stream)); m.wide = nullptr; m.wide_valid = false; }
     if (m.bounds) { CSM_CUDA(cudaFreeAsync(m.bounds, h->stream)); m.bounds = nullptr; m.bounds_alloc = 0; }
     CSM_CUDA(cudaFreeAsync(m.base, h->stream));
     CSM_CUDA(cudaFreeAsync(m.raw, h->stream));
@@ -3226,8 +3268,18 @@ int csm_match_grid(csm_handle h, int64_t map_id,
         WA.dy_span = dy_span; WA.dx_span = dx_span; WA.unit_dx = unit ? 1 : 0;
         /* lanes of a partly filled last chunk read up to 32 ceil(cols / 32) - 1 columns to the right */
         const int lane_reach = unit ? (rem_variant ? ndx : kWtColsPerCta) - 1 : dx_span;
-        const int max_h = kWtTileRows - 1 - dy_span, max_w = kWtPitch - 8 - lane_reach;
-        tma = monotone && max_h >= 0 && max_w >= 0 && make_map_tensor(m, &tmap);
+        /* wide: the tiles land as 32-bit words and are scored in place (window_mode 3 = the u16 tiles that
+         * a pass per tile widens, the round-1 kernel) */
+        bool wide = h->window_mode != 3 && (m.cols % 8) == 0 && encode_tiled_fn() != nullptr;
+        int max_h = kWtTileRows - 1 - dy_span;
+        int max_w = (wide ? kWwPitch - 4 : kWtPitch - 8) - lane_reach;
+        if (wide && (max_w < 0 || !monotone || max_h < 0))
+            wide = false, max_w = kWtPitch - 8 - lane_reach;
+        if (wide) {
+            if ((rc = ensure_wide(h, m))) return rc;
+            tma = make_map_tensor_wide(m, &tmap);
+        } else
+            tma = monotone && max_h >= 0 && max_w >= 0 && make_map_tensor(m, &tmap);
         if (tma) {
             if ((rc = ensure(h, h->d_wtgroups, sizeof(WtGroup) * (size_t)ndt * Q.n + sizeof(int) * (size_t)ndt))) return rc;
             WtGroup* groups = static_cast<WtGroup*>(h->d_wtgroups.p);
@@ -3235,11 +3287,12 @@ int csm_match_grid(csm_handle h, int64_t map_id,
             WA.groups = groups; WA.gcount = gcount;
             k_window_groups<<<(ndt + 127) / 128, 128, 0, h->stream>>>(dq, proj, groups, gcount, max_h, max_w);
             CSM_LAUNCH_CHECK();
-            const size_t smem = wt_smem_bytes(Q.n);
+            const size_t smem = wide ? wt_smem_bytes_wide(Q.n) : wt_smem_bytes(Q.n);
             dim3 wgrid(ndt, (ndy + rows_per_cta - 1) / rows_per_cta, (ndx + cols_per_cta - 1) / cols_per_cta);
             phase_mark(h, "k_window_groups");
 #define CSM_WT_LAUNCH(UNIT, CHUNKS, REM)                                                                        \
-            k_window_tma<UNIT, CHUNKS, REM><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
+            if (wide) k_window_tma<UNIT, CHUNKS, REM, true><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA); \
+            else k_window_tma<UNIT, CHUNKS, REM, false><<<wgrid, warps * 32, smem, h->stream>>>(tmap, dq, proj, G, WA);
             if (rem_variant) {
                 switch (rem_chunks) {
                 case 1: CSM_WT_LAUNCH(true, 1, true) break;
@@ -3257,7 +3310,7 @@ int csm_match_grid(csm_handle h, int64_t map_id,
 #undef CSM_WT_LAUNCH
             CSM_LAUNCH_CHECK();
             phase_mark(h, "k_window_tma");
-        } else if (h->window_mode == 2) {
+        } else if (h->window_mode == 2 || h->window_mode == 3) {
             return fail(h, CSM_E_UNSUPPORTED, "match_grid: the TMA window kernel cannot take this window / map");
         }
     }

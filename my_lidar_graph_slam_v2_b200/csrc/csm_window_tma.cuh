@@ -53,6 +53,9 @@ constexpr int kWtBoxRows = 8;                    /* rows per TMA box */
 constexpr int kWtTileRows = 96;                  /* rows per tile (multiple of kWtBoxRows) */
 constexpr size_t kWtStageBytes = (size_t)kWtTileRows * kWtPitch * sizeof(uint16_t);   /* TMA landing buffer */
 constexpr size_t kWtTileBytes = (size_t)kWtTileRows * kWtTilePitch * sizeof(uint32_t);   /* scored tile */
+constexpr int kWwPitch = 248;                    /* "wide" variant: TMA box width = landing buffer row pitch in
+                                                    words; 24 mod 32, so that the rows of a column spread over banks */
+constexpr size_t kWwStageBytes = (size_t)kWtTileRows * kWwPitch * sizeof(uint32_t);
 constexpr unsigned int kWtKnownBit = 1u << 20;   /* tile word = value | (value != 0) << 20 */
 constexpr int kWtFlush = 16;                     /* beams per packed accumulation: 16 * 65535 < 2^20 */
 /* dynamic shared memory of k_window_tma for n beams: two landing buffers, the tile, two
@@ -60,6 +63,32 @@ constexpr int kWtFlush = 16;                     /* beams per packed accumulatio
 __host__ __device__ constexpr size_t wt_smem_bytes(int n)
 {
     return 2 * kWtStageBytes + kWtTileBytes + 16 + sizeof(proj_t) * (size_t)n + 1024;
+}
+
+/* the same for the wide variant: the landing buffers hold 32-bit words and are scored in place */
+__host__ __device__ constexpr size_t wt_smem_bytes_wide(int n)
+{
+    return 2 * kWwStageBytes + 16 + sizeof(proj_t) * (size_t)n + 1024;
+}
+
+/* The map as the wide variant loads it: one 32-bit word value | known << 20 per cell, written once per
+ * map (and again whenever level 0 changes) */
+__global__ void __launch_bounds__(256)
+k_widen_map(const uint4* __restrict__ cells, uint4* __restrict__ wide, size_t n8)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = cells[i];
+        const unsigned int w[4] = { v.x, v.y, v.z, v.w };
+        unsigned int o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned int lo = w[k] & 0xffffu, hi = w[k] >> 16;
+            o[2 * k] = lo | (lo ? kWtKnownBit : 0u);
+            o[2 * k + 1] = hi | (hi ? kWtKnownBit : 0u);
+        }
+        wide[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+        wide[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
 }
 
 /* One run of consecutive beams of one angle and the low corner of its hit cells */
@@ -144,6 +173,16 @@ __device__ __forceinline__ void tma_load_box(const CUtensorMap* tmap, void* dst,
         : "memory");
 }
 
+/* shared-memory word at a register address plus an immediate (the scoring loop keeps one address per beam
+ * and row; the chunk offsets are immediates) */
+template <int kOff>
+__device__ __forceinline__ unsigned int lds_u32(unsigned int addr)
+{
+    unsigned int v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];\n" : "=r"(v) : "r"(addr), "n"(kOff));
+    return v;
+}
+
 struct WtArgs
 {
     const WtGroup* groups;
@@ -153,7 +192,10 @@ struct WtArgs
     int rows_per_cta;          /* kWtRows * warps of the launch */
 };
 
-template <bool kUnitDx, int kChunks, bool kRem>
+/* kWide: the tensor map is over the map's 32-bit form (k_widen_map); the tiles land as words and are scored
+ * where they land -- no widening pass, two landing buffers of 96 x 248 words instead of two u16 buffers and a
+ * tile. */
+template <bool kUnitDx, int kChunks, bool kRem, bool kWide>
 __global__ void __launch_bounds__(kWtMaxWarps * 32, 1)
 k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restrict__ queries,
              const proj_t* __restrict__ proj_all, GridArgs G, WtArgs A)
@@ -161,11 +203,15 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
     /* everything lives in dynamic shared memory, aligned by hand: TMA destinations need 128 bytes */
     extern __shared__ unsigned char wt_smem_raw[];
     unsigned char* wt_smem = wt_smem_raw + ((1024u - (smem_u32(wt_smem_raw) & 1023u)) & 1023u);
+    constexpr size_t kStage = kWide ? kWwStageBytes : kWtStageBytes;
+    constexpr size_t kTile = kWide ? 0 : kWtTileBytes;
+    constexpr int kPitchW = kWide ? kWwPitch : kWtTilePitch;        /* row pitch of the scored words */
+    constexpr int kAlign = kWide ? 4 : 8;                           /* cells per 16 bytes of a map row */
     uint16_t* stage0 = reinterpret_cast<uint16_t*>(wt_smem);
-    uint16_t* stage1 = reinterpret_cast<uint16_t*>(wt_smem + kWtStageBytes);
-    uint32_t* tile = reinterpret_cast<uint32_t*>(wt_smem + 2 * kWtStageBytes);
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wt_smem + 2 * kWtStageBytes + kWtTileBytes);
-    proj_t* s_proj = reinterpret_cast<proj_t*>(wt_smem + 2 * kWtStageBytes + kWtTileBytes + 16);
+    uint16_t* stage1 = reinterpret_cast<uint16_t*>(wt_smem + kStage);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(wt_smem + 2 * kStage);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wt_smem + 2 * kStage + kTile);
+    proj_t* s_proj = reinterpret_cast<proj_t*>(wt_smem + 2 * kStage + kTile + 16);
 
     const DevQuery& Q = queries[0];
     const int it = blockIdx.x;
@@ -192,7 +238,25 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
 #pragma unroll
     for (int rw = 0; rw < kWtRows; ++rw) {
         const int iy = iy0 + warp * kWtRows + rw;
-        roff[rw] = (G.my[min(iy, G.ndy - 1)] - my0) * kWtTilePitch;
+        roff[rw] = (G.my[min(iy, G.ndy - 1)] - my0) * kPitchW;
+    }
+    /* Unit column steps: every beam's hit cell becomes the BYTE offset of its word inside its run's tile, once
+     * (each beam belongs to one run; the offsets take the place of the projected indices in shared memory), so
+     * that the scoring loop is one broadcast load and one add per beam, one add per row, then loads at immediate
+     * offsets -- the loop is bound by issue slots, not by shared-memory bandwidth, until it is this lean. */
+    int* s_offb = reinterpret_cast<int*>(s_proj);
+    if (kUnitDx) {
+        const WtGroup* __restrict__ grs = A.groups + (size_t)it * n;
+        const int ngr = A.gcount[it];
+        for (int g = threadIdx.x; g < ngr; g += blockDim.x) {
+            const WtGroup grp = grs[g];
+            const int cs = (grp.minc + mx0) & (kAlign - 1);
+            for (int i = grp.begin; i < grp.end; ++i) {
+                const proj_t p = s_proj[i];
+                s_offb[i] = (((int)p.y - grp.minr) * kPitchW + ((int)p.x - grp.minc) + cs) * 4;
+            }
+        }
+        __syncthreads();
     }
     /* remainder columns 32 kChunks .. ndx - 1: the first kWtRows * r lanes of every warp take the
      * warp's own candidate rows, lane = column * kWtRows + row (tile words 260 apart per row and 1
@@ -205,7 +269,7 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
         const int rw = lane % kWtRows, rj = lane / kWtRows;
         rem_iy = iy0 + warp * kWtRows + rw; rem_ix = 32 * kChunks + rj;
         rem_on = rj < nrem && rem_iy < G.ndy;
-        rem_off = rem_on ? (G.my[rem_iy] - my0) * kWtTilePitch + rem_ix : 0;
+        rem_off = rem_on ? (G.my[rem_iy] - my0) * kPitchW + rem_ix : 0;
     }
     int coff[kChunks];
 #pragma unroll
@@ -245,12 +309,14 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
         const int boxes = (rows + kWtBoxRows - 1) / kWtBoxRows;
         unsigned long long* bar = &s_bar[g & 1];
         uint16_t* dst = (g & 1) ? stage1 : stage0;
-        mbar_expect_tx(bar, (unsigned int)(boxes * kWtBoxRows * kWtPitch * sizeof(uint16_t)));
+        constexpr size_t kBoxBytes = kWide ? (size_t)kWtBoxRows * kWwPitch * sizeof(uint32_t)
+                                           : (size_t)kWtBoxRows * kWtPitch * sizeof(uint16_t);
+        mbar_expect_tx(bar, (unsigned int)(boxes * kBoxBytes));
         /* the box's first column must sit on a 16-byte boundary of the map row (measured:
-         * other values fault); the tile is up to 7 cells wider for it */
+         * other values fault); the tile is up to 7 (wide: 3) cells wider for it */
         for (int b = 0; b < boxes; ++b)
-            tma_load_box(&tmap, dst + (size_t)b * kWtBoxRows * kWtPitch, bar,
-                         (grp.minc + mx0) & ~7, grp.minr + my0 + b * kWtBoxRows);
+            tma_load_box(&tmap, reinterpret_cast<unsigned char*>(dst) + (size_t)b * kBoxBytes, bar,
+                         (grp.minc + mx0) & ~(kAlign - 1), grp.minr + my0 + b * kWtBoxRows);
     };
     if (threadIdx.x == 0) {
         if (ng > 0) issue(0);
@@ -260,6 +326,7 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
     for (int g = 0; g < ng; ++g) {
         const WtGroup grp = groups[g];
         mbar_wait(&s_bar[g & 1], (unsigned int)((g >> 1) & 1));
+        if (!kWide) {
         __syncthreads();                  /* the previous run has been scored: the tile is free */
         {
             /* landing buffer (u16) -> tile (u32 words carrying the known bit), 8 cells per step */
@@ -287,20 +354,50 @@ k_window_tma(const __grid_constant__ CUtensorMap tmap, const DevQuery* __restric
         __syncthreads();                  /* tile ready, landing buffer g & 1 free */
         if (threadIdx.x == 0 && g + 2 < ng)
             issue(g + 2);
-        const int cshift = (grp.minc + mx0) & 7;      /* tile column 0 is the 8-aligned cell below the window */
+        }
+        const uint32_t* __restrict__ words = kWide ? reinterpret_cast<const uint32_t*>((g & 1) ? stage1 : stage0) : tile;
+        if (kUnitDx) {
+            unsigned int wsh = smem_u32(words) + (unsigned int)lane * 4u;
+            asm volatile("" : "+r"(wsh));             /* one register for the whole run */
+            /* idle lanes read the word lane 0 reads (a broadcast, no extra bank) and mask it away */
+            const int rem_off0 = __shfl_sync(0xffffffffu, rem_off, 0);
+            const unsigned int rem_delta = (unsigned int)((rem_on ? rem_off : rem_off0) - lane) * 4u;
+            const unsigned int rem_mask = rem_on ? 0xffffffffu : 0u;
+            for (int i = grp.begin; i < grp.end; ++i) {
+                const unsigned int a0 = wsh + (unsigned int)s_offb[i];
+#pragma unroll
+                for (int rw = 0; rw < kWtRows; ++rw) {
+                    const unsigned int a = a0 + (unsigned int)(roff[rw] * 4);
+                    if (kChunks > 0) acc[rw][0] += lds_u32<0>(a);
+                    if (kChunks > 1) acc[rw][1 % kChunks] += lds_u32<128>(a);
+                    if (kChunks > 2) acc[rw][2 % kChunks] += lds_u32<256>(a);
+                    if (kChunks > 3) acc[rw][3 % kChunks] += lds_u32<384>(a);
+                    if (kChunks > 4) acc[rw][4 % kChunks] += lds_u32<512>(a);
+                    if (kChunks > 5) acc[rw][5 % kChunks] += lds_u32<640>(a);
+                }
+                if (kRem)
+                    accx += lds_u32<0>(a0 + rem_delta) & rem_mask;      /* idle lanes read their own word, masked */
+                if (++pending == kWtFlush) { flush(); pending = 0; }
+            }
+        } else {
+        const int cshift = (grp.minc + mx0) & (kAlign - 1);      /* column 0 is the 16-byte aligned cell below the window */
         for (int i = grp.begin; i < grp.end; ++i) {
             const proj_t p = s_proj[i];
-            const uint32_t* __restrict__ base = tile + ((int)p.y - grp.minr) * kWtTilePitch + ((int)p.x - grp.minc) + cshift;
+            const uint32_t* __restrict__ base = words + ((int)p.y - grp.minr) * kPitchW + ((int)p.x - grp.minc) + cshift;
 #pragma unroll
             for (int rw = 0; rw < kWtRows; ++rw) {
                 const uint32_t* __restrict__ row = base + roff[rw];
 #pragma unroll
                 for (int m = 0; m < kChunks; ++m)
-                    acc[rw][m] += kUnitDx ? row[lane + 32 * m] : row[coff[m]];
+                    acc[rw][m] += row[coff[m]];
             }
-            if (kRem && rem_on)
-                accx += base[rem_off];
             if (++pending == kWtFlush) { flush(); pending = 0; }
+        }
+        }
+        if (kWide) {
+            __syncthreads();              /* every warp has scored this run: its landing buffer is free */
+            if (threadIdx.x == 0 && g + 2 < ng)
+                issue(g + 2);
         }
     }
     flush();

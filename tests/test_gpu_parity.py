@@ -229,11 +229,14 @@ def test_grid_window_remainder_columns(handle, checker, ndx, ndy):
     for thr in ((0.0, 0.0), (0.3, 0.5)):
         handle.set_option("window_mode", 2)
         a = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
+        handle.set_option("window_mode", 3)
+        a16 = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
         handle.set_option("window_mode", 1)
         b = mt.optimize_pose(gm, scan, tuple(case.init_pose), *thr)
         handle.set_option("window_mode", 0)
         o = checker.match_grid(g, case.angles, case.ranges, case.init_pose, rng, step, thr)
-        assert_match(a.result, o, "tma %dx%d %s" % (ndx, ndy, thr))
+        assert_match(a.result, o, "tma (32-bit tiles) %dx%d %s" % (ndx, ndy, thr))
+        assert_match(a16.result, o, "tma (u16 tiles) %dx%d %s" % (ndx, ndy, thr))
         assert_match(b.result, o, "global %dx%d %s" % (ndx, ndy, thr))
 
 
@@ -1353,7 +1356,7 @@ def test_full_size_cfg4_grid_search(handle, checker, entry):
     mt = matchers.ScanMatcherGridSearch("gs", *rng, *step, handle=handle)
     exp = entry["expect"]
     results = []
-    for mode in (2, 1):                       # 2: the TMA shared-memory kernel, 1: the global-memory kernel
+    for mode in (2, 3, 1):                    # 2 / 3: the TMA shared-memory kernel (32-bit / u16 tiles), 1: global memory
         handle.set_option("window_mode", mode)
         r = mt.optimize_pose(gm, scan, tuple(case.init_pose)).result
         assert_match(r, exp, "cfg4 window_mode %d" % mode)
