@@ -588,19 +588,27 @@ def main_cuda(args):
     stale = None
     if ncu_sweep.get("event_ms_at_capture") and exp_ms > 0:
         stale = abs(exp_ms - ncu_sweep["event_ms_at_capture"]) > 0.15 * ncu_sweep["event_ms_at_capture"]
+    wavefronts = ncu_sweep.get("lsu_wavefronts_per_step")
+    wf_peak = 148 * sm_mhz * 1e6                # one LSU data-pipe wavefront per cycle per SM
+    algorithmic = {
+        "achieved": gathers / (exp_ms * 1e-3) if exp_ms > 0 else None, "peak": gather_peak, "unit": "gathers/s",
+        "frac": gathers / (exp_ms * 1e-3) / gather_peak if exp_ms > 0 else None,
+        "note": "SURVEY.md 8(d) gather ceiling: 148 SMs x 32 lanes x %.0f MHz, every lane of every wavefront useful; "
+                "a request of the sweep is 23 useful lanes in 3.4 wavefronts" % sm_mhz}
     roofline = {
         "kernel": "k_bbg_expand<0..%d> (B&B frontier scoring over groups of 8 angles, %d launches per step, one per "
                   "pyramid height)" % (HMAX - 1, HMAX),
         "bound": "l1tex",
-        "achieved": gathers / (exp_ms * 1e-3) if exp_ms > 0 else None, "peak": gather_peak, "unit": "gathers/s",
-        "frac": gathers / (exp_ms * 1e-3) / gather_peak if exp_ms > 0 else None,
-        "peak_source": "SURVEY.md 8(d) gather ceiling: 148 SMs x 32 lanes x %.0f MHz (one L1TEX / shared-memory "
-                       "wavefront per cycle per SM, every lane useful); a scattered gather cannot reach it: "
-                       "the sweep's requests touch %.1f sectors in about two 128-byte tiles, and ncu puts the "
-                       "L1TEX LSU data pipe, the unit that binds, at %.2f of its own wavefront peak over the six "
-                       "launches (l1tex_ncu.lsu_data_pipe_frac_of_peak, profiles/r2_ncu.json)"
-                       % (sm_mhz, ncu_sweep.get("sectors_per_request", float("nan")),
-                          ncu_sweep.get("lsu_data_pipe_frac_of_peak", float("nan"))),
+        "achieved": wavefronts / (exp_ms * 1e-3) if (wavefronts and exp_ms > 0) else algorithmic["achieved"],
+        "peak": wf_peak if wavefronts else gather_peak,
+        "unit": "LSU data-pipe wavefronts/s" if wavefronts else "gathers/s",
+        "frac": wavefronts / (exp_ms * 1e-3) / wf_peak if (wavefronts and exp_ms > 0) else algorithmic["frac"],
+        "peak_source": "the L1TEX LSU data pipe, the unit that binds (ncu: l1tex__data_pipe_lsu_wavefronts), moves one "
+                       "wavefront per cycle per SM: 148 x %.0f MHz. The step's wavefront count is a property of the "
+                       "workload (deterministic inputs) and comes from the ncu capture of the same launches "
+                       "(profiles/r2_ncu.json); the time is this run's CUDA-event time of the six launches"
+                       % sm_mhz,
+        "algorithmic": algorithmic,
         "hbm_equivalent": {"achieved_GBps": gathers * 2 / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else None,
                            "peak_GBps": hbm_peak, "peak_source": peak_source,
                            "frac": gathers * 2 / (exp_ms * 1e-3) / 1e9 / hbm_peak if exp_ms > 0 else None,

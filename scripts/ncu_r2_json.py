@@ -33,6 +33,9 @@ for r in rows[2:]:
          "requests": val(r, "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"),
          "sectors": val(r, "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
          "lsu_wavefronts_pct_of_peak": val(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+         # the pipe's peak is one wavefront per cycle per SM: wavefronts of the launch = share x cycles x SMs
+         "lsu_wavefronts": val(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0 *
+                           val(r, "sm__cycles_elapsed.avg") * 148,
          "l1tex_throughput_pct": val(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
          "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
          "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
@@ -55,6 +58,7 @@ out = {
         "launches": sweep, "ncu_ms": t / 1e3,
         "event_ms_at_capture": sum(v for k, v in events.items() if k.startswith("k_bbg_expand")) / 1e3,
         "requests_per_step": req, "sectors_per_step": sec, "sectors_per_request": sec / req,
+        "lsu_wavefronts_per_step": sum(d["lsu_wavefronts"] for d in sweep),
         "lsu_data_pipe_frac_of_peak": sum(d["lsu_wavefronts_pct_of_peak"] * d["us"] for d in sweep) / t / 100.0,
         "lsu_data_pipe_frac_heaviest_launch": max(sweep, key=lambda d: d["us"])["lsu_wavefronts_pct_of_peak"] / 100.0,
         "issue_active_frac": sum(d["issue_active_pct"] * d["us"] for d in sweep) / t / 100.0,
