@@ -451,16 +451,17 @@ int finish_results(csm_handle h, csm_result* results, int nq, csm_refined* refin
 }
 
 /* Dense uploads: cells at 65535 become unknown in the matchers' copy (k_saturated_unknown), behind the copy
- * on the same stream. rows * cols is even, so the bytes are a multiple of 4; the tail below 16 is rare. */
+ * on the same stream. Device allocations are 256-byte aligned; arena slots are whole maps of an even number of
+ * columns, so every map starts on a 4-byte boundary at least: the 16-byte path needs 16. */
 int saturated_pass(csm_handle h, uint16_t* cells, size_t bytes, cudaStream_t stream)
 {
     if (!h->saturated_unknown || bytes == 0)
         return CSM_OK;
-    if (bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(cells) & 15u) != 0)
-        return fail(h, CSM_E_UNSUPPORTED, "grid: rows * cols must be a multiple of 8 cells");
-    const size_t n16 = bytes / 16;
-    const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 8);
-    k_saturated_unknown<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(cells), n16);
+    if (bytes % 4 != 0 || (reinterpret_cast<uintptr_t>(cells) & 15u) != 0)
+        return fail(h, CSM_E_UNSUPPORTED, "grid: the map must start on a 16-byte boundary and hold an even number of cells");
+    const size_t n_words = bytes / 4;
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((n_words / 4 + 255) / 256, 148 * 8));
+    k_saturated_unknown<<<blocks, 256, 0, stream>>>(reinterpret_cast<unsigned int*>(cells), n_words);
     CSM_LAUNCH_CHECK();
     ++h->launches;
     return CSM_OK;

@@ -124,15 +124,22 @@ __device__ __forceinline__ uint4 saturated_as_unknown(uint4 v)
     return v;
 }
 
-/* the same for a dense upload, in place */
+/* the same for a dense upload, in place: 16 bytes per step, the words past the last whole 16 bytes one by one
+ * (a map has an even number of columns, so its bytes are a multiple of 4) */
 __global__ void __launch_bounds__(256)
-k_saturated_unknown(uint4* __restrict__ cells, size_t n16)
+k_saturated_unknown(unsigned int* __restrict__ words, size_t n_words)
 {
+    const size_t n16 = n_words / 4;
+    uint4* __restrict__ cells = reinterpret_cast<uint4*>(words);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 v = cells[i];
         const uint4 w = saturated_as_unknown(v);
         if (v.x != w.x || v.y != w.y || v.z != w.z || v.w != w.w)
             cells[i] = w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n_words & 3)) {
+        const size_t i = n16 * 4 + threadIdx.x;
+        words[i] = saturated_as_unknown(words[i]);
     }
 }
 
@@ -722,7 +729,14 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
     for (int tl = tl_first; tl < nt; tl += tl_step) {
         const double2 th = s_theta[tl];
         proj_t* __restrict__ out_t = out + (size_t)(t0 + tl) * Q.pst_t;
-        for (int i = i_first; i < n; i += i_step) {
+        /* chunked layout: the slots past the last beam of the last chunk hold a cell far outside every map,
+         * so that the sweep reads its chunks whole, without a test per beam (a child there scores 0) */
+        const int n_slots = quad ? ((n + 15) & ~15) : n;
+        for (int i = i_first; i < n_slots; i += i_step) {
+            if (i >= n) {
+                out[proj_index(Q, t0 + tl, i)] = proj_t { (short)-32768, (short)-32768 };
+                continue;
+            }
             double rc, rs;
             const proj_t p = project_beam(Q, th, i, flagged, rc, rs);
             if (bb) {
@@ -1535,18 +1549,14 @@ k_bbg_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pr
             for (int j = 0; j < mine; ++j) {
                 const uint4 cur = nx;
                 if (j + 1 < mine) nx = __ldg(pp + (unsigned int)(j + 1) * step);
-                const int i0 = ((sub + j * wpi) << 4) + part;                /* this lane's first beam of the chunk */
                 const unsigned int pw[4] = { cur.x, cur.y, cur.z, cur.w };
                 unsigned int v[4][4];
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
+                    /* slots past the last beam hold a cell outside every map (k_project): no test per beam */
                     const int r = (int)(short)(pw[s] >> 16) + oy, c = (int)(short)(pw[s] & 0xffffu) + ox;
-                    if (i0 + 4 * s < n) {
-                        if (kLeaf) ld_children<0>(m, rows, cols, r, c, v[s]);
-                        else ld_children_b<HC>(bm, tpr, row_w, rows, cols, r, c, v[s]);
-                    } else {
-                        v[s][0] = v[s][1] = v[s][2] = v[s][3] = 0u;
-                    }
+                    if (kLeaf) ld_children<0>(m, rows, cols, r, c, v[s]);
+                    else ld_children_b<HC>(bm, tpr, row_w, rows, cols, r, c, v[s]);
                 }
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {

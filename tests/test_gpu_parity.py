@@ -313,7 +313,7 @@ def _bound_level_numpy(grid, level):
     return out
 
 
-@pytest.mark.parametrize("shape", [(512, 512), (128, 320), (48, 16), (100, 38), (16, 16), (264, 130)])
+@pytest.mark.parametrize("shape", [(512, 512), (128, 320), (48, 16), (100, 38), (16, 16), (264, 130), (37, 70)])
 def test_bound_levels_vs_numpy(handle, shape):
     """k_bounds_build: every level equals the u8 encoding of the level-0 cells under the forward
     2^h x 2^h maximum (so 257 * B_h >= the reference's level h, cell for cell), for maps whose extents
