@@ -66,6 +66,10 @@ public:
     void SetChunkSize(int n) { mChunkSize = n; }
     /* First-touch maps are uploaded in groups of this many (default 64, at most the chunk size) */
     void SetUploadChunk(int n) { mUploadChunk = n; }
+    /* The last search batch of a call holds at most this many queries (0 = like the others): what is left to do
+     * once the last map has been gathered -- its copy, its levels, its search -- is what a cold Detect waits for
+     * at the end, so a short last batch ends sooner; the batches before it overlap the gather anyway. */
+    void SetTailChunk(int n) { mTailChunk = n; }
     /* Without a final matcher the result carries the covariance of the cost
      * function at the coarse pose (computed on the CPU); switch it off when
      * the caller refines the poses itself */
@@ -122,6 +126,7 @@ private:
     int mQueryIndexBase = 0;
     int mChunkSize = 128;
     int mUploadChunk = 64;
+    int mTailChunk = 0;
     bool mCoarseCovariance = true;
 };
 

@@ -435,7 +435,9 @@ void csm_host_loopdet_destroy(void* det) { delete static_cast<HostLoopDet*>(det)
 void csm_host_loopdet_configure(void* det, int chunk_size, int coarse_covariance, int query_index_base)
 {
     auto* d = static_cast<HostLoopDet*>(det);
-    d->det->SetChunkSize(chunk_size & 0xffff);
+    /* bits 0..11 search batch, 12..15 tail batch / 16, 16.. upload group */
+    d->det->SetChunkSize(chunk_size & 0xfff);
+    d->det->SetTailChunk(((chunk_size >> 12) & 0xf) * 16);
     if ((chunk_size >> 16) > 0)
         d->det->SetUploadChunk(chunk_size >> 16);
     d->det->SetCoarseCovariance(coarse_covariance != 0);

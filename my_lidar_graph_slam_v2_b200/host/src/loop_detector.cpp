@@ -192,10 +192,13 @@ public:
         }
         return mAreas[k];
     }
-    /* dst[b] <- src[b] (bytes each) for b in [0, n) */
-    void Gather(const std::uint16_t* const* src, std::uint16_t* dst, std::size_t n, std::size_t bytes)
+    /* dst[b] <- src[b] (bytes each) for b in [0, src.size()): Start wakes the workers and returns, Finish lets
+     * the caller take chunks too and waits for the rest. Between the two the caller is free: the detector
+     * enqueues the previous group's upload and a segment's search while the next group is being gathered. */
+    void Start(std::vector<const std::uint16_t*>&& src, std::uint16_t* dst, std::size_t bytes)
     {
-        mSrc = src; mDst = reinterpret_cast<char*>(dst); mBytes = bytes; mCount = n;
+        mOwned = std::move(src);
+        mSrc = mOwned.data(); mDst = reinterpret_cast<char*>(dst); mBytes = bytes; mCount = mOwned.size();
         mNext.store(0);
         mBusy.store(static_cast<int>(mWorkers.size()));
         {
@@ -203,10 +206,18 @@ public:
             ++mGeneration;
         }
         mWake.notify_all();
+        mStarted = true;
+    }
+    void Finish()
+    {
+        if (!mStarted)
+            return;
         Chunks();
         while (mBusy.load(std::memory_order_acquire) != 0)
             std::this_thread::yield();
+        mStarted = false;
     }
+    bool Started() const { return mStarted; }
 
 private:
     static void CopyBlock(char* dst, const char* src, std::size_t bytes)
@@ -271,6 +282,8 @@ private:
     bool mStop = false;
     std::atomic<std::size_t> mNext { 0 };
     std::atomic<int> mBusy { 0 };
+    std::vector<const std::uint16_t*> mOwned;
+    bool mStarted = false;
     const std::uint16_t* const* mSrc = nullptr;
     char* mDst = nullptr;
     std::size_t mBytes = 0, mCount = 0;
@@ -284,6 +297,67 @@ namespace {
  * buffers follow one another in memory (a pinned staging area filled map by
  * map) go in one batched call = one PCIe copy; views whose blocks are separate heap allocations
  * are gathered into staging area `area` first; anything else map by map. */
+/* An upload group whose maps keep their blocks in separate heap allocations: where the gathered blocks
+ * go and what the upload call needs */
+struct HeapGroup
+{
+    bool valid = false;
+    char* stage = nullptr;
+    std::int32_t* index = nullptr;
+    std::vector<std::int64_t> ids;
+    std::vector<std::int32_t> counts;
+    std::vector<double> ox, oy;
+    int log2bs = 0, block_rows = 0, block_cols = 0;
+    double resolution = 0.0;
+};
+
+/* Lays the group out in page-locked staging area `area` and starts the gather; false = not such a group */
+bool HeapGroupStart(const std::vector<const GridMapView*>& maps, BlockGatherer* gatherer, std::size_t area, HeapGroup& g)
+{
+    g.valid = false;
+    if (maps.empty() || gatherer == nullptr)
+        return false;
+    const GridMapView& m0 = *maps[0];
+    bool heap = m0.block_ptrs != nullptr;
+    for (std::size_t i = 0; i < maps.size() && heap; ++i) {
+        const GridMapView& m = *maps[i];
+        heap = m.block_ptrs != nullptr && m.rows == m0.rows && m.cols == m0.cols &&
+               m.log2_block_size == m0.log2_block_size && m.resolution == m0.resolution;
+    }
+    if (!heap)
+        return false;
+    std::size_t total = 0;
+    for (const GridMapView* m : maps) total += static_cast<std::size_t>(m->n_blocks);
+    const std::size_t block_bytes = sizeof(std::uint16_t) << (2 * m0.log2_block_size);
+    const std::size_t index_off = (total * block_bytes + 255) & ~static_cast<std::size_t>(255);
+    g.stage = static_cast<char*>(gatherer->Area(area, index_off + total * sizeof(std::int32_t) + 256));
+    std::vector<const std::uint16_t*> src(total);
+    g.index = reinterpret_cast<std::int32_t*>(g.stage + index_off);
+    g.ids.resize(maps.size()); g.counts.resize(maps.size()); g.ox.resize(maps.size()); g.oy.resize(maps.size());
+    std::size_t b = 0;
+    for (std::size_t i = 0; i < maps.size(); ++i) {
+        const GridMapView& m = *maps[i];
+        std::copy(m.block_ptrs, m.block_ptrs + m.n_blocks, src.begin() + b);
+        std::copy(m.block_index, m.block_index + m.n_blocks, g.index + b);
+        b += static_cast<std::size_t>(m.n_blocks);
+        g.ids[i] = m.map_id; g.counts[i] = m.n_blocks; g.ox[i] = m.offset_x; g.oy[i] = m.offset_y;
+    }
+    g.log2bs = m0.log2_block_size; g.block_rows = m0.rows >> m0.log2_block_size; g.block_cols = m0.cols >> m0.log2_block_size;
+    g.resolution = m0.resolution;
+    gatherer->Start(std::move(src), reinterpret_cast<std::uint16_t*>(g.stage), block_bytes);
+    g.valid = true;
+    return true;
+}
+
+/* ... enqueues the copy of a gathered group (after BlockGatherer::Finish) */
+void HeapGroupUpload(const DeviceContextPtr& ctx, const HeapGroup& g)
+{
+    ctx->Check(csm_upload_grids_blocks(ctx->Handle(), static_cast<int>(g.ids.size()), g.ids.data(),
+                                       reinterpret_cast<const std::uint16_t*>(g.stage), g.index, g.counts.data(),
+                                       g.log2bs, g.block_rows, g.block_cols, g.resolution, g.ox.data(), g.oy.data()),
+               "csm_upload_grids_blocks");
+}
+
 void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapView*>& maps,
                    BlockGatherer* gatherer, std::size_t area)
 {
@@ -291,38 +365,13 @@ void UploadNewMaps(const DeviceContextPtr& ctx, const std::vector<const GridMapV
         return;
     csm_handle h = ctx->Handle();
     const GridMapView& m0 = *maps[0];
-    bool heap = m0.block_ptrs != nullptr && gatherer != nullptr;
-    for (std::size_t i = 0; i < maps.size() && heap; ++i) {
-        const GridMapView& m = *maps[i];
-        heap = m.block_ptrs != nullptr && m.rows == m0.rows && m.cols == m0.cols &&
-               m.log2_block_size == m0.log2_block_size && m.resolution == m0.resolution;
-    }
-    if (heap) {
-        std::size_t total = 0;
-        for (const GridMapView* m : maps) total += static_cast<std::size_t>(m->n_blocks);
-        const std::size_t block_bytes = sizeof(std::uint16_t) << (2 * m0.log2_block_size);
-        const std::size_t index_off = (total * block_bytes + 255) & ~static_cast<std::size_t>(255);
-        char* stage = static_cast<char*>(gatherer->Area(area, index_off + total * sizeof(std::int32_t) + 256));
-        std::vector<const std::uint16_t*> src(total);
-        std::int32_t* index = reinterpret_cast<std::int32_t*>(stage + index_off);
-        std::vector<std::int64_t> ids(maps.size());
-        std::vector<std::int32_t> counts(maps.size());
-        std::vector<double> ox(maps.size()), oy(maps.size());
-        std::size_t b = 0;
-        for (std::size_t i = 0; i < maps.size(); ++i) {
-            const GridMapView& m = *maps[i];
-            std::copy(m.block_ptrs, m.block_ptrs + m.n_blocks, src.begin() + b);
-            std::copy(m.block_index, m.block_index + m.n_blocks, index + b);
-            b += static_cast<std::size_t>(m.n_blocks);
-            ids[i] = m.map_id; counts[i] = m.n_blocks; ox[i] = m.offset_x; oy[i] = m.offset_y;
+    {
+        HeapGroup g;
+        if (HeapGroupStart(maps, gatherer, area, g)) {
+            gatherer->Finish();
+            HeapGroupUpload(ctx, g);
+            return;
         }
-        gatherer->Gather(src.data(), reinterpret_cast<std::uint16_t*>(stage), total, block_bytes);
-        ctx->Check(csm_upload_grids_blocks(h, static_cast<int>(maps.size()), ids.data(),
-                                           reinterpret_cast<const std::uint16_t*>(stage), index, counts.data(),
-                                           m0.log2_block_size, m0.rows >> m0.log2_block_size,
-                                           m0.cols >> m0.log2_block_size, m0.resolution, ox.data(), oy.data()),
-                   "csm_upload_grids_blocks");
-        return;
     }
     bool batch = m0.blocks != nullptr && maps.size() > 1;
     std::size_t nblk = 0;
@@ -519,7 +568,9 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
     for (int i = 0; i < nq; ++i) {
         const auto res = mMapLane.find(queries[i].local_map.map_id);
         const bool fresh = res == mMapLane.end();
-        if (!segments.empty() && segments.back().count < chunk &&
+        /* the tail batch starts where mTailChunk queries are left (first-touch maps only: that is where it pays) */
+        const bool tail_start = mTailChunk > 0 && fresh && nq - i == mTailChunk && nq > mTailChunk;
+        if (!tail_start && !segments.empty() && segments.back().count < chunk &&
             ((fresh && segments.back().fresh) || (!fresh && segments.back().lane == res->second))) {
             ++segments.back().count;
         } else {
@@ -533,27 +584,49 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
      * levels and its search batch are enqueued behind them -- the device works on a segment while the host
      * gathers the blocks of the next one (the gather, not PCIe, is the longest leg of a cold Detect). */
     std::vector<std::vector<std::vector<std::int64_t>>> fresh_ids(segments.size());   /* per upload group */
-    std::size_t area = 0;
-    auto upload_segment = [&](std::size_t si) {
+    /* the upload groups of the whole call, in order; the gather of group k + 1 is started as soon as group k
+     * has been gathered, so that it runs while this thread enqueues copies, levels and search batches */
+    struct UploadJob { std::size_t si; std::vector<const GridMapView*> fresh; HeapGroup heap; bool started = false; };
+    std::vector<UploadJob> ujobs;
+    for (std::size_t si = 0; si < segments.size(); ++si) {
         const Segment& sg = segments[si];
         if (!sg.fresh)
-            return;
-        const DeviceContextPtr& c = lane_ctx(sg.lane);
+            continue;
         std::set<std::int64_t> seen;
         for (int first = sg.first; first < sg.first + sg.count; first += ugroup) {
             const int last = std::min(sg.first + sg.count, first + ugroup);
-            std::vector<const GridMapView*> fresh;
+            UploadJob job;
+            job.si = si;
             fresh_ids[si].emplace_back();
             for (int i = first; i < last; ++i) {
                 const GridMapView& m = queries[i].local_map;
                 if (seen.insert(m.map_id).second) {
                     /* a map built on the device (GridMapBuilderGPU) has nothing to upload: only its levels are due */
                     if (!m.device_resident)
-                        fresh.push_back(&m);
+                        job.fresh.push_back(&m);
                     fresh_ids[si].back().push_back(m.map_id);
                 }
             }
-            UploadNewMaps(c, fresh, mGatherer.get(), area++);
+            ujobs.push_back(std::move(job));
+        }
+    }
+    std::size_t next_job = 0;
+    auto start_job = [&](std::size_t k) {
+        if (mGatherer && k < ujobs.size() && !ujobs[k].started && !mGatherer->Started())
+            ujobs[k].started = HeapGroupStart(ujobs[k].fresh, mGatherer.get(), k, ujobs[k].heap);
+    };
+    auto upload_segment = [&](std::size_t si) {
+        while (next_job < ujobs.size() && ujobs[next_job].si == si) {
+            UploadJob& job = ujobs[next_job];
+            const DeviceContextPtr& c = lane_ctx(segments[si].lane);
+            start_job(next_job);
+            if (job.started) {
+                mGatherer->Finish();
+                start_job(next_job + 1);              /* the workers go on with the next group */
+                HeapGroupUpload(c, job.heap);
+            } else
+                UploadNewMaps(c, job.fresh, mGatherer.get(), next_job);
+            ++next_job;
         }
     };
     fill_queries();

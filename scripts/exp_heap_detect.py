@@ -10,7 +10,9 @@ hb = bench.HostBatch(batch, 0, n_maps, hostapi, synth)
 ctx = hostapi.Context(0)
 det = hostapi.LoopDetector(ctx, 6, synth.CFG3["rng"], synth.CFG3["thr"])
 ug = int(sys.argv[5]) if len(sys.argv) > 5 else 64
-det.configure(chunk_size=128 | (ug << 16), coarse_covariance=False, query_index_base=0)
+chunk = int(sys.argv[6]) if len(sys.argv) > 6 else 128
+tail = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+det.configure(chunk_size=chunk | ((tail // 16) << 12) | (ug << 16), coarse_covariance=False, query_index_base=0)
 det.use_device_refiner(10, 1e-4, 1e-4)
 det.set_lanes(lanes)
 det.set_gather_threads(threads)
