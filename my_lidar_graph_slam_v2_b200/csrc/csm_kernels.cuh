@@ -1477,12 +1477,18 @@ __device__ __forceinline__ void ld_children_b(const unsigned char* __restrict__ 
     unsigned int ro1;
     if (w >= kBlTileR) ro1 = ro0 + row_w;          /* row_w = (w / tile rows) * tpr * 128 */
     else { const unsigned int rq = rp + w; ro1 = (((rq >> 2) * tpr) << 7) + ((rq & 3u) << 1); }
-    const unsigned int co0 = ((cp >> 5) << 7) + ((cp & 30u) << 2) + (cp & 1u);
-    unsigned int co1;
-    if (w >= kBlTileC) co1 = co0 + ((w / kBlTileC) << 7);
-    else { const unsigned int cq = cp + w; co1 = ((cq >> 5) << 7) + ((cq & 30u) << 2) + (cq & 1u); }
-    v[0] = __ldg(bm + ro0 + co0); v[1] = __ldg(bm + ro0 + co1);
-    v[2] = __ldg(bm + ro1 + co0); v[3] = __ldg(bm + ro1 + co1);
+    /* column part of bl_cell: c = 32 a + 2 b + p sits at 128 a + 8 b + p = 4 c - 3 p, so a step of an even w
+     * columns is 4 w bytes wherever the tile boundaries fall: the second child of a row is an immediate offset */
+    const unsigned int co0 = (cp << 2) - 3u * (cp & 1u);
+    unsigned int dco = 4 * w;
+    if ((w & 1) != 0) {            /* height 0 is never a bound level (the leaves read the u16 map); kept well-formed */
+        const unsigned int cq = cp + w;
+        dco = ((cq << 2) - 3u * (cq & 1u)) - co0;
+    }
+    const unsigned char* __restrict__ p0 = bm + (ro0 + co0);
+    const unsigned char* __restrict__ p1 = bm + (ro1 + co0);
+    v[0] = __ldg(p0); v[1] = __ldg(p0 + dco);
+    v[2] = __ldg(p1); v[3] = __ldg(p1 + dco);
 }
 
 /* warps per group: the split that minimises (rounds of the grid) x (steps per warp), with a few steps
