@@ -7,7 +7,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libcsm_host.so")
 SOURCES = [os.path.join(HERE, "src", f) for f in
-           ("cost_square_error.cpp", "scan_matchers.cpp", "loop_detector.cpp", "loop_searcher.cpp", "map_builder.cpp", "slam_pipeline.cpp", "c_shim.cpp")]
+           ("cost_square_error.cpp", "scan_matchers.cpp", "loop_detector.cpp", "loop_searcher.cpp", "map_builder.cpp", "slam_pipeline.cpp", "carmen_log.cpp", "c_shim.cpp")]
 
 
 def build():

@@ -22,6 +22,7 @@
 #include <memory>
 #include <vector>
 
+#include "csm_host/carmen_log.hpp"
 #include "csm_host/loop_detector.hpp"
 #include "csm_host/loop_searcher.hpp"
 #include "csm_host/map_builder.hpp"
@@ -86,6 +87,13 @@ public:
     bool ProcessScan(const ScanDataPtr& scan, const Pose2D& odom_pose, double time_stamp);
     /* the last back-end iteration after the front end has finished (lidar_graph_slam_backend.cpp:83-89) */
     void Finish();
+    /* slam_launcher.cpp:262-283: every scan record of a Carmen log goes to ProcessScan with the odometry pose and
+     * time stamp it carries (odometry records are not consumed there either); returns the scans used */
+    int RunLog(const std::vector<CarmenRecord>& records, bool finish = true);
+    /* the reference's metric ids: "Frontend.*" (lidar_graph_slam_frontend.cpp:34-63, 151-320), "Backend.*"
+     * (lidar_graph_slam_backend.cpp:29-56, 106-197) and those of the matchers and the detector; with
+     * SaveMetrics (carmen_log.hpp) this gives the launcher's <output>.metric.json */
+    void SetMetricSink(const MetricSinkPtr& sink);
 
     const PoseGraph& Graph() const { return mPoseGraph; }
     const GridMapBuilderGPU& Builder() const { return *mBuilder; }
@@ -127,6 +135,8 @@ private:
     std::shared_ptr<LoopDetectorBranchBound> mLoopDetector;
     std::vector<std::unique_ptr<HostCopy>> mLocalMapCopies;             /* by LocalMapId, parity runs */
     SlamCounters mCounters;
+    MetricSinkPtr mMetricSink;
+    void Observe(const char* id, double value) const { if (mMetricSink) mMetricSink->Observe(id, value); }
     std::vector<LoopDetectionResult> mLoops;
     std::vector<ScanMatchingSummary> mMatches;
     /* front-end state (lidar_graph_slam_frontend.hpp) */

@@ -4,6 +4,8 @@
 #include <csignal>
 #include <cstring>
 #include <execinfo.h>
+#include <fstream>
+#include <sstream>
 #include <memory>
 #include <string>
 #include <unistd.h>
@@ -731,6 +733,7 @@ struct HostSlam
     DeviceContextPtr ctx;
     std::shared_ptr<PoseGraphOptimizerIdentity> optimizer;
     std::unique_ptr<SlamPipeline> slam;
+    std::shared_ptr<MetricRecorder> metrics;
 };
 
 /* `v`: the SlamSettings fields in declaration order (slam_pipeline.hpp), initial_pose as three values:
@@ -870,6 +873,138 @@ void csm_host_slam_loops(void* p, double* out6)
         o[2] = loops[i].relative_pose.x; o[3] = loops[i].relative_pose.y; o[4] = loops[i].relative_pose.theta;
         o[5] = loops[i].normalized_score;
     }
+}
+
+/* ---- Carmen logs and the metrics file (carmen_log.hpp) ------------------------------------------------ */
+struct HostCarmen { std::vector<CarmenRecord> records; };
+
+void* csm_host_carmen_load(const char* text_or_path, int is_path)
+{
+    auto* p = new HostCarmen;
+    CarmenLogReader reader;
+    bool ok;
+    if (is_path) {
+        ok = reader.LoadFile(text_or_path, p->records);
+    } else {
+        std::istringstream in { std::string(text_or_path) };
+        ok = reader.Load(in, p->records);
+    }
+    if (!ok) {
+        delete p;
+        return nullptr;
+    }
+    return p;
+}
+void csm_host_carmen_destroy(void* p) { delete static_cast<HostCarmen*>(p); }
+int csm_host_carmen_count(void* p) { return static_cast<int>(static_cast<HostCarmen*>(p)->records.size()); }
+int csm_host_carmen_total_beams(void* p)
+{
+    std::size_t n = 0;
+    for (const CarmenRecord& r : static_cast<HostCarmen*>(p)->records)
+        if (r.scan) n += r.scan->ranges.size();
+    return static_cast<int>(n);
+}
+/* per record 15 values: kind, time stamp, odometry pose, forward and angular velocity, sensor pose on the robot,
+ * min / max range, min / max angle, beams; then every scan's angles and ranges back to back */
+void csm_host_carmen_export(void* p, double* head15, double* angles, double* ranges)
+{
+    std::size_t at = 0;
+    for (const CarmenRecord& r : static_cast<HostCarmen*>(p)->records) {
+        const ScanData* s = r.scan.get();
+        const double v[15] = { double(int(r.kind)), r.time_stamp, r.odom_pose.x, r.odom_pose.y, r.odom_pose.theta,
+                               r.velocity.x, r.velocity.theta,
+                               s ? s->relative_sensor_pose.x : 0.0, s ? s->relative_sensor_pose.y : 0.0,
+                               s ? s->relative_sensor_pose.theta : 0.0, s ? s->min_range : 0.0, s ? s->max_range : 0.0,
+                               r.min_angle, r.max_angle, s ? double(s->ranges.size()) : 0.0 };
+        std::copy(v, v + 15, head15);
+        head15 += 15;
+        if (s) {
+            std::copy(s->angles.begin(), s->angles.end(), angles + at);
+            std::copy(s->ranges.begin(), s->ranges.end(), ranges + at);
+            at += s->ranges.size();
+        }
+    }
+}
+int csm_host_carmen_sensor_id(void* p, int i, char* buf, int cap)
+{
+    const std::string& id = static_cast<HostCarmen*>(p)->records.at(static_cast<std::size_t>(i)).sensor_id;
+    std::snprintf(buf, static_cast<std::size_t>(cap), "%s", id.c_str());
+    return static_cast<int>(id.size());
+}
+
+/* a synthetic run as a Carmen log: per scan an ODOM record (optional) and a ROBOTLASER1 (format 0) or FLASER
+ * (format 1, with the PARAM records that carry the beam geometry) record */
+int csm_host_carmen_write(const char* path, int format, int n_scans, int n_beams, double start_angle,
+                          double angular_resolution, double max_range, const double* ranges,
+                          const double* odom_poses, const double laser_on_robot[3], const double* time_stamps,
+                          int with_odom)
+{
+    std::ofstream out(path);
+    if (!out)
+        return -1;
+    CarmenLogWriter w(out);
+    auto g17 = [](double v) { char b[40]; std::snprintf(b, sizeof b, "%.17g", v); return std::string(b); };
+    if (format == 1) {
+        w.Param("Laser.MinRange", "0");
+        w.Param("Laser.MaxRange", g17(max_range));
+        w.Param("Laser.AngleIncrement", g17(angular_resolution));
+        w.Param("Laser.MinAngle", g17(start_angle));
+    }
+    const Pose2D rel { laser_on_robot[0], laser_on_robot[1], laser_on_robot[2] };
+    std::vector<double> r(static_cast<std::size_t>(n_beams));
+    for (int k = 0; k < n_scans; ++k) {
+        const Pose2D robot { odom_poses[3 * k], odom_poses[3 * k + 1], odom_poses[3 * k + 2] };
+        const Pose2D laser = Compound(robot, rel);
+        r.assign(ranges + static_cast<std::size_t>(k) * n_beams, ranges + static_cast<std::size_t>(k + 1) * n_beams);
+        if (with_odom)
+            w.Odom(robot, 0.0, 0.0, time_stamps[k]);
+        if (format == 1)
+            w.OldLaser("FLASER", r, laser, robot, time_stamps[k]);
+        else
+            w.RobotLaser("ROBOTLASER1", start_angle, angular_resolution, max_range, r, laser, robot, time_stamps[k]);
+    }
+    return out ? 0 : -2;
+}
+
+int csm_host_metric_values_string(const char* id, const double* values, int n, char* buf, int cap)
+{
+    const std::string s = MetricValuesToString(id, std::vector<double>(values, values + n));
+    std::snprintf(buf, static_cast<std::size_t>(cap), "%s", s.c_str());
+    return static_cast<int>(s.size());
+}
+
+/* WriteMetricsJson over a recorder that observed values[k] under ids[k] (newline separated, in order) */
+int csm_host_metrics_json(const char* ids, const int* counts, int n_ids, const double* values, char* buf, int cap)
+{
+    MetricRecorder rec;
+    std::istringstream in { std::string(ids) };
+    std::string id;
+    for (int k = 0; k < n_ids && std::getline(in, id); ++k)
+        for (int i = 0; i < counts[k]; ++i)
+            rec.Observe(id, *values++);
+    std::ostringstream out;
+    WriteMetricsJson(out, rec);
+    std::snprintf(buf, static_cast<std::size_t>(cap), "%s", out.str().c_str());
+    return static_cast<int>(out.str().size());
+}
+
+int csm_host_slam_run_carmen(void* slam, void* records, int finish)
+{
+    return static_cast<HostSlam*>(slam)->slam->RunLog(static_cast<HostCarmen*>(records)->records, finish != 0);
+}
+void csm_host_slam_record_metrics(void* slam)
+{
+    auto* hs = static_cast<HostSlam*>(slam);
+    hs->metrics = std::make_shared<MetricRecorder>();
+    hs->slam->SetMetricSink(hs->metrics);
+}
+/* writes path + ".metric.json" (slam_launcher.cpp:171-181); -1 when no recorder is set */
+int csm_host_slam_save_metrics(void* slam, const char* path)
+{
+    auto* hs = static_cast<HostSlam*>(slam);
+    if (!hs->metrics)
+        return -1;
+    return SaveMetrics(path, *hs->metrics) ? 0 : -2;
 }
 
 } /* extern "C" */

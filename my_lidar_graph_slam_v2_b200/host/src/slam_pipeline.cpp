@@ -80,8 +80,11 @@ bool SlamPipeline::ProcessScan(const ScanDataPtr& scan, const Pose2D& odom_pose,
     const bool needed = (mAccumulatedTravelDist >= s.update_travel_dist || mAccumulatedAngle >= s.update_angle ||
                          elapsed >= s.update_time || first) && (elapsed >= 0.0);
     ++mCounters.scans_in;
-    if (!needed)
+    const double t_process = Seconds();
+    if (!needed) {
+        Observe("Frontend.ProcessTime", (Seconds() - t_process) * 1e6);
         return false;
+    }
 
     if (first) {
         /* AppendFirstNodeAndEdge (lidar_graph_slam.cpp:419-437): a tight covariance pins the first node */
@@ -97,6 +100,7 @@ bool SlamPipeline::ProcessScan(const ScanDataPtr& scan, const Pose2D& odom_pose,
         const Pose2D latest_map_pose = mBuilder->LatestMapPose();
         double t1 = Seconds();
         mCounters.t_latest_map += t1 - t0;
+        Observe("Frontend.ScanDataSetupTime", (t1 - t0) * 1e6);
 
         /* :205-230 */
         const Pose2D rel_from_last_update = InverseCompound(mLastMapUpdateOdomPose, odom_pose);
@@ -120,6 +124,10 @@ bool SlamPipeline::ProcessScan(const ScanDataPtr& scan, const Pose2D& odom_pose,
         mMatches.push_back(fin);
         double t2 = Seconds();
         mCounters.t_match += t2 - t1;
+        /* with the final matcher on the device both stages are one submission: its time is reported as the
+         * scan matching time and the final stage as 0 */
+        Observe("Frontend.ScanMatchingTime", (t2 - t1) * 1e6);
+        Observe("Frontend.FinalScanMatchingTime", 0.0);
 
         /* :232-283 */
         const Pose2D global_estimated_pose = Compound(latest_map_pose, fin.estimated_pose);
@@ -140,6 +148,7 @@ bool SlamPipeline::ProcessScan(const ScanDataPtr& scan, const Pose2D& odom_pose,
         mBuilder->AppendScan(mPoseGraph, relative_pose, covariance, scan);
         double t3 = Seconds();
         mCounters.t_append += t3 - t2;
+        Observe("Frontend.DataUpdateTime", (t3 - t2) * 1e6);
 
         /* :289-303: the back end is notified every LoopDetectionThreshold metres */
         const double accum = mBuilder->AccumTravelDist();
@@ -151,6 +160,16 @@ bool SlamPipeline::ProcessScan(const ScanDataPtr& scan, const Pose2D& odom_pose,
     }
     ++mCounters.scans_processed;
     mProcessCount += 1;
+    if (mMetricSink) {
+        const double micro = (Seconds() - t_process) * 1e6;
+        Observe("Frontend.ProcessTime", micro);
+        Observe("Frontend.ProcessScanTime", micro);
+        Observe("Frontend.IntervalTravelDist", mAccumulatedTravelDist);
+        Observe("Frontend.IntervalAngle", mAccumulatedAngle);
+        Observe("Frontend.IntervalTime", elapsed);
+        Observe("Frontend.NumOfScans", static_cast<double>(scan->NumOfScans()));
+        Observe("Frontend.ProcessFrame", static_cast<double>(mProcessCount - 1));
+    }
     mAccumulatedTravelDist = 0.0;
     mAccumulatedAngle = 0.0;
     mLastMapUpdateOdomPose = odom_pose;
@@ -365,30 +384,69 @@ void SlamPipeline::RunBackendStep()
 {
     /* lidar_graph_slam_backend.cpp:92-198 */
     ++mCounters.backend_steps;
+    const double t_step = Seconds();
+    double t_mark = t_step;
+    auto lap = [&](const char* id) {
+        const double now = Seconds();
+        Observe(id, (now - t_mark) * 1e6);
+        t_mark = now;
+    };
+    auto end_at = [&](const char* id) {
+        Observe("Backend.ProcessTime", (Seconds() - t_step) * 1e6);
+        Observe(id, static_cast<double>(mCounters.backend_steps - 1));
+    };
     const LoopSearchHint hint = GetLoopSearchHint();
+    lap("Backend.LoopSearchSetupTime");
     if (hint.local_map_nodes.empty() || hint.scan_nodes.empty())
-        return;
+        return end_at("Backend.EndAtLoopSearchSetup");
     const std::vector<LoopCandidate> candidates = mLoopSearcher->Search(hint);
+    lap("Backend.LoopSearchTime");
     if (candidates.empty())
-        return;
+        return end_at("Backend.EndAtLoopSearch");
     ++mCounters.backend_steps_with_candidates;
     const std::vector<LoopDetectionQuery> queries = GetLoopDetectionQueries(candidates);
+    lap("Backend.LoopDetectionSetupTime");
     const double t0 = Seconds();
     const std::vector<LoopDetectionResult> results = mLoopDetector->Detect(queries);
     mCounters.t_detect += Seconds() - t0;
     mCounters.loop_queries += static_cast<int>(queries.size());
+    lap("Backend.LoopDetectionTime");
     if (results.empty())
-        return;
+        return end_at("Backend.EndAtLoopDetection");
     mCounters.loops_detected += static_cast<int>(results.size());
     mLoops.insert(mLoops.end(), results.begin(), results.end());
     AppendLoopClosingEdges(results);
+    lap("Backend.PoseGraphAppendTime");
     std::vector<int> map_ids, node_ids;
     std::vector<std::array<double, 3>> map_poses, node_poses;
     std::vector<EdgePose> edges;
     GetPoseGraphForOptimization(map_ids, map_poses, node_ids, node_poses, edges);
+    lap("Backend.OptimizationSetupTime");
     mOptimizer->Optimize(map_poses, node_poses, edges);
     ++mCounters.optimizations;
+    lap("Backend.OptimizationTime");
     AfterLoopClosure(map_ids, map_poses, node_ids, node_poses);
+    lap("Backend.PoseGraphUpdateTime");
+    Observe("Backend.ProcessStepTime", (Seconds() - t_step) * 1e6);
+    end_at("Backend.EndAtLoopClosure");
+}
+
+int SlamPipeline::RunLog(const std::vector<CarmenRecord>& records, bool finish)
+{
+    int used = 0;
+    for (const CarmenRecord& rec : records)
+        if (rec.kind == CarmenRecord::Kind::Scan && rec.scan)
+            used += ProcessScan(rec.scan, rec.odom_pose, rec.time_stamp) ? 1 : 0;
+    if (finish)
+        Finish();
+    return used;
+}
+
+void SlamPipeline::SetMetricSink(const MetricSinkPtr& sink)
+{
+    mMetricSink = sink;
+    mScanMatcher->SetMetricSink(sink);
+    mLoopDetector->SetMetricSink(sink);
 }
 
 } /* namespace csm_host */

@@ -143,6 +143,21 @@ class SlamPipeline:
         return self.lib.csm_host_slam_run(self.p, r.shape[0], r.shape[1], ap, rp, op, tp, min_range, max_range,
                                           int(finish))
 
+    def run_carmen(self, log, finish=True):
+        """SlamPipeline::RunLog over the records of a CarmenLog; returns the scans used"""
+        self.lib.csm_host_slam_run_carmen.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        return self.lib.csm_host_slam_run_carmen(self.p, log.p, int(finish))
+
+    def record_metrics(self):
+        self.lib.csm_host_slam_record_metrics.argtypes = [C.c_void_p]
+        self.lib.csm_host_slam_record_metrics(self.p)
+
+    def save_metrics(self, output_path):
+        """writes output_path + '.metric.json' in the reference launcher's layout"""
+        self.lib.csm_host_slam_save_metrics.argtypes = [C.c_void_p, C.c_char_p]
+        rc = self.lib.csm_host_slam_save_metrics(self.p, output_path.encode())
+        assert rc == 0, rc
+
     def counters(self):
         out = np.zeros(len(SLAM_COUNTERS))
         self.lib.csm_host_slam_counters(self.p, out.ctypes.data_as(C.POINTER(C.c_double)))
@@ -605,3 +620,95 @@ class MultiGpuLoopDetector:
         if self.det:
             self.lib.csm_host_multidet_destroy(self.det)
             self.det = None
+
+
+def carmen_records(lib, prefix, handle):
+    """The records behind `handle` (csm_host_carmen_* here, the checker's orc_carmen_* in the tests: same
+    layout) as a list of dicts: kind ('odom' / 'scan'), sensor_id, time_stamp, odom_pose, velocity, and for
+    scans relative_sensor_pose, min/max range, min/max angle, angles, ranges."""
+    dp = C.POINTER(C.c_double)
+    f = lambda name: getattr(lib, prefix + name)
+    f("count").argtypes = [C.c_void_p]
+    f("total_beams").argtypes = [C.c_void_p]
+    f("export").argtypes = [C.c_void_p, dp, dp, dp]
+    f("sensor_id").argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    n = f("count")(handle)
+    nb = f("total_beams")(handle)
+    head = np.zeros((n, 15))
+    angles = np.zeros(max(nb, 1))
+    ranges = np.zeros(max(nb, 1))
+    f("export")(handle, head.ctypes.data_as(dp), angles.ctypes.data_as(dp), ranges.ctypes.data_as(dp))
+    out, at = [], 0
+    buf = C.create_string_buffer(64)
+    for i in range(n):
+        f("sensor_id")(handle, i, buf, 64)
+        h = head[i]
+        rec = {"kind": "scan" if h[0] == 1.0 else "odom", "sensor_id": buf.value.decode(), "time_stamp": h[1],
+               "odom_pose": h[2:5].copy(), "velocity": h[5:7].copy()}
+        if rec["kind"] == "scan":
+            k = int(h[14])
+            rec.update(relative_sensor_pose=h[7:10].copy(), min_range=h[10], max_range=h[11], min_angle=h[12],
+                       max_angle=h[13], angles=angles[at:at + k].copy(), ranges=ranges[at:at + k].copy())
+            at += k
+        out.append(rec)
+    return out
+
+
+class CarmenLog:
+    """C++ CarmenLogReader (host/include/csm_host/carmen_log.hpp) over a log text or file."""
+
+    def __init__(self, text=None, path=None):
+        self.lib = load()
+        self.lib.csm_host_carmen_load.restype = C.c_void_p
+        self.lib.csm_host_carmen_load.argtypes = [C.c_char_p, C.c_int]
+        self.lib.csm_host_carmen_destroy.argtypes = [C.c_void_p]
+        self.p = self.lib.csm_host_carmen_load((path if path is not None else text).encode(), int(path is not None))
+        if not self.p:
+            raise FileNotFoundError(path)
+
+    def records(self):
+        return carmen_records(self.lib, "csm_host_carmen_", self.p)
+
+    def close(self):
+        if self.p:
+            self.lib.csm_host_carmen_destroy(self.p)
+            self.p = None
+
+
+def write_carmen_log(path, ranges, odom_poses, time_stamps, start_angle, angular_resolution, max_range,
+                     laser_on_robot=(0.0, 0.0, 0.0), old_format=False, with_odom=True):
+    """A synthetic run as a Carmen log (CarmenLogWriter): ROBOTLASER1 records, or FLASER with PARAM records."""
+    lib = load()
+    dp = C.POINTER(C.c_double)
+    lib.csm_host_carmen_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                          dp, dp, dp, dp, C.c_int]
+    r, rp = _d(ranges)
+    o, op = _d(odom_poses)
+    t, tp = _d(time_stamps)
+    l, lp = _d(laser_on_robot)
+    rc = lib.csm_host_carmen_write(path.encode(), int(old_format), r.shape[0], r.shape[1], start_angle,
+                                   angular_resolution, max_range, rp, op, lp, tp, int(with_odom))
+    assert rc == 0, rc
+
+
+def metric_values_string(metric_id, values):
+    lib = load()
+    lib.csm_host_metric_values_string.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_char_p, C.c_int]
+    v, vp = _d(values)
+    buf = C.create_string_buffer(64 * max(len(v), 1) + 16)
+    lib.csm_host_metric_values_string(metric_id.encode(), vp, len(v), buf, len(buf))
+    return buf.value.decode()
+
+
+def metrics_json(sequences):
+    """WriteMetricsJson for {id: values}; returns the file's text"""
+    lib = load()
+    lib.csm_host_metrics_json.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double),
+                                          C.c_char_p, C.c_int]
+    ids = list(sequences)
+    counts = (C.c_int * max(len(ids), 1))(*[len(sequences[k]) for k in ids])
+    flat = [float(x) for k in ids for x in sequences[k]]
+    v, vp = _d(flat if flat else [0.0])
+    buf = C.create_string_buffer(1 << 16)
+    lib.csm_host_metrics_json("\n".join(ids).encode(), counts, len(ids), vp, buf, len(buf))
+    return buf.value.decode()

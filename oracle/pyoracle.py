@@ -230,6 +230,26 @@ class Oracle:
             return None
         return [tuple(int(v) for v in out[3 * i:3 * i + 3]) for i in range(n)]
 
+    def carmen_load(self, text):
+        """The reference's CarmenLogReader::Load on a log text; returns a handle for hostapi.carmen_records
+        (prefix 'orc_carmen_'), or None when this checker lacks it."""
+        if not hasattr(self.lib, "orc_carmen_load"):
+            return None
+        self.lib.orc_carmen_load.restype = C.c_void_p
+        self.lib.orc_carmen_load.argtypes = [C.c_char_p]
+        self.lib.orc_carmen_destroy.argtypes = [C.c_void_p]
+        return self.lib.orc_carmen_load(text.encode())
+
+    def metric_values_string(self, kind, values):
+        """'Values' of a ValueSequence<int> (kind 0), <float> (1), <uint64_t> (2) that observed `values`"""
+        if not hasattr(self.lib, "orc_metric_values_string"):
+            return None
+        self.lib.orc_metric_values_string.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_char_p, C.c_int]
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        buf = C.create_string_buffer(64 * max(len(v), 1) + 16)
+        self.lib.orc_metric_values_string(kind, _dptr(v), len(v), buf, len(buf))
+        return buf.value.decode()
+
     def loop_detector(self, hmax, rng, thr, n_threads=1):
         return OracleLoopDetector(self, hmax, rng, thr, n_threads)
 

@@ -20,7 +20,9 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -29,6 +31,7 @@
 #include "my_lidar_graph_slam/point.hpp"
 #include "my_lidar_graph_slam/metric/metric.hpp"
 #include "my_lidar_graph_slam/sensor/sensor_data.hpp"
+#include "my_lidar_graph_slam/io/carmen/carmen_reader.hpp"
 #include "my_lidar_graph_slam/mapping/grid_map_types.hpp"
 /* (GridMapBuilder registers its metrics under fixed names, so a process can construct it only once;
  * the checker keeps that one instance and re-initialises its members for every new sequence, which
@@ -1138,6 +1141,85 @@ int orc_loop_search(int n_scans, const int32_t* scan_ids, const double* scan_pos
         out_ids[3 * i + 2] = candidates[i].mReferenceLocalMapId.mId;
     }
     return n;
+}
+
+/* ---- io/carmen/carmen_reader.cpp and the metric strings of metric/metric.hpp ------------------------- */
+struct RefCarmen { std::vector<MyLidarGraphSlam::Sensor::SensorDataPtr> records; };
+
+void* orc_carmen_load(const char* text)
+{
+    auto* p = new RefCarmen;
+    std::istringstream in { std::string(text) };
+    MyLidarGraphSlam::IO::Carmen::CarmenLogReader reader;
+    reader.Load(in, p->records);
+    return p;
+}
+void orc_carmen_destroy(void* p) { delete static_cast<RefCarmen*>(p); }
+int orc_carmen_count(void* p) { return static_cast<int>(static_cast<RefCarmen*>(p)->records.size()); }
+int orc_carmen_total_beams(void* p)
+{
+    std::size_t n = 0;
+    for (const auto& r : static_cast<RefCarmen*>(p)->records)
+        if (auto s = std::dynamic_pointer_cast<MyLidarGraphSlam::Sensor::ScanData<double>>(r))
+            n += s->NumOfScans();
+    return static_cast<int>(n);
+}
+/* the layout of csm_host_carmen_export: 15 values per record, then angles and ranges back to back */
+void orc_carmen_export(void* p, double* head15, double* angles, double* ranges)
+{
+    using namespace MyLidarGraphSlam::Sensor;
+    std::size_t at = 0;
+    for (const auto& r : static_cast<RefCarmen*>(p)->records) {
+        std::fill(head15, head15 + 15, 0.0);
+        head15[1] = r->TimeStamp();
+        if (auto o = std::dynamic_pointer_cast<OdometryData<double>>(r)) {
+            head15[0] = 0.0;
+            head15[2] = o->Pose().mX; head15[3] = o->Pose().mY; head15[4] = o->Pose().mTheta;
+            head15[5] = o->Velocity().mX; head15[6] = o->Velocity().mTheta;
+        } else if (auto s = std::dynamic_pointer_cast<ScanData<double>>(r)) {
+            head15[0] = 1.0;
+            head15[2] = s->OdomPose().mX; head15[3] = s->OdomPose().mY; head15[4] = s->OdomPose().mTheta;
+            head15[5] = s->Velocity().mX; head15[6] = s->Velocity().mTheta;
+            head15[7] = s->RelativeSensorPose().mX; head15[8] = s->RelativeSensorPose().mY;
+            head15[9] = s->RelativeSensorPose().mTheta;
+            head15[10] = s->MinRange(); head15[11] = s->MaxRange();
+            head15[12] = s->MinAngle(); head15[13] = s->MaxAngle();
+            head15[14] = static_cast<double>(s->NumOfScans());
+            std::copy(s->Angles().begin(), s->Angles().end(), angles + at);
+            std::copy(s->Ranges().begin(), s->Ranges().end(), ranges + at);
+            at += s->NumOfScans();
+        }
+        head15 += 15;
+    }
+}
+int orc_carmen_sensor_id(void* p, int i, char* buf, int cap)
+{
+    const std::string& id = static_cast<RefCarmen*>(p)->records.at(static_cast<std::size_t>(i))->SensorId();
+    std::snprintf(buf, static_cast<std::size_t>(cap), "%s", id.c_str());
+    return static_cast<int>(id.size());
+}
+
+/* a ValueSequence<int> (kind 0), <float> (1) or <uint64_t> (2) observes the values; returns what its
+ * ToPropertyTree puts under "Values" (metric.hpp:611-621 -> VecToString, :42-59) */
+int orc_metric_values_string(int kind, const double* values, int n, char* buf, int cap)
+{
+    using namespace MyLidarGraphSlam::Metric;
+    std::string s;
+    if (kind == 0) {
+        ValueSequence<int> seq { "t" };
+        for (int i = 0; i < n; ++i) seq.Observe(values[i]);
+        s = VecToString(*seq.Values());
+    } else if (kind == 1) {
+        ValueSequence<float> seq { "t" };
+        for (int i = 0; i < n; ++i) seq.Observe(values[i]);
+        s = VecToString(*seq.Values());
+    } else {
+        ValueSequence<std::uint64_t> seq { "t" };
+        for (int i = 0; i < n; ++i) seq.Observe(values[i]);
+        s = VecToString(*seq.Values());
+    }
+    std::snprintf(buf, static_cast<std::size_t>(cap), "%s", s.c_str());
+    return static_cast<int>(s.size());
 }
 
 } /* extern "C" */

@@ -79,3 +79,48 @@ def test_full_loop_on_the_device():
     assert gc["loop_queries"] == rc["loop_queries"] and gc["loops_detected"] == rc["loops_detected"]
     gs.close()
     ctx.close()
+
+
+def test_full_loop_from_a_carmen_log(tmp_path):
+    """The launcher's way in and out (slam_launcher.cpp:262-283, 171-181): the run written as a Carmen log
+    (ROBOTLASER1 records), read back by the C++ CarmenLogReader and fed to SlamPipeline::RunLog gives the
+    same pose graph as the arrays fed directly, bit for bit; the metrics land in <output>.metric.json under
+    the reference's ids."""
+    import json
+    from my_lidar_graph_slam_v2_b200 import hostapi
+    trip = _trip(8103, 90)
+    n_beams = trip["ranges"].shape[1]
+    start, inc = -np.pi, 2.0 * np.pi / n_beams
+    angles = start + inc * np.arange(n_beams)
+    path = str(tmp_path / "corridor.log")
+    hostapi.write_carmen_log(path, trip["ranges"], trip["odom"], trip["stamps"], start, inc, 11.3)
+    st = slam_settings.pack(host_final_matchers=0, **SETTINGS)
+    ctx = hostapi.Context(0)
+    direct = hostapi.SlamPipeline(ctx, st)
+    assert direct.run(angles, trip["ranges"], trip["odom"], trip["stamps"], 0.0, 11.3, finish=True) == 90
+    log = hostapi.CarmenLog(path=path)
+    assert len(log.records()) == 180
+    from_log = hostapi.SlamPipeline(ctx, st)
+    from_log.record_metrics()
+    assert from_log.run_carmen(log) == 90
+    assert np.array_equal(from_log.scan_nodes(), direct.scan_nodes())
+    assert np.array_equal(from_log.edges(), direct.edges())
+    assert np.array_equal(from_log.local_maps(), direct.local_maps())
+    assert np.array_equal(from_log.loops(), direct.loops())
+    c = from_log.counters()
+    out = str(tmp_path / "result")
+    from_log.save_metrics(out)
+    vs = json.load(open(out + ".metric.json"))["ValueSequences"]
+    assert int(vs["Frontend.ProcessScanTime"]["NumOfSamples"]) == 90
+    assert int(vs["Frontend.ScanMatchingTime"]["NumOfSamples"]) == 89
+    assert vs["Frontend.NumOfScans"]["Values"].split() == [str(n_beams)] * 90
+    assert vs["Frontend.ProcessFrame"]["Values"].split() == [str(i) for i in range(90)]
+    ends = sum(int(vs[k]["NumOfSamples"]) for k in vs if k.startswith("Backend.EndAt"))
+    assert ends == int(vs["Backend.ProcessTime"]["NumOfSamples"]) == c["backend_steps"]
+    assert int(vs["Backend.LoopDetectionTime"]["NumOfSamples"]) == c["backend_steps_with_candidates"]
+    assert any(k.startswith("LocalSlam.ScanMatcherCorrelative.") for k in vs)
+    assert any(k.startswith("LoopDetector.BranchBound.") for k in vs)
+    for s in (direct, from_log):
+        s.close()
+    log.close()
+    ctx.close()
