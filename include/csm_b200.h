@@ -159,7 +159,8 @@ int64_t csm_exact_rerun_count(csm_handle h);
  * order: copies issued on different streams share the link and would all land together at the
  * end, whereas a lane's search should start when ITS maps have landed. `owner` must outlive `h`. */
 int csm_share_copy_stream(csm_handle h, csm_handle owner);
-/* Tuning / test knobs.
+/* Tuning / test knobs. (The environment variable CSM_OPTIONS="name=value,name=value" applies csm_set_option to
+ * every handle a process creates: A/B runs through host code that does not expose the knobs.)
  *  "pyramid_mode": 0 = automatic, 1 = level-by-level kernels, 2 = streaming
  *      single-pass kernel (when the maps fit its layout), 3 = the streaming
  *      kernel variant that keeps its row rings in shared memory;
@@ -169,6 +170,10 @@ int csm_share_copy_stream(csm_handle h, csm_handle owner);
  *      identical either way; only the number of nodes scored changes;
  *  "bb_skip_top": 1 (default) = the branch-and-bound sweep starts one height
  *      below hmax on the same leaf lattice (identical results, one launch less);
+ *  "bb_probe": the sweep over bound levels seeds its incumbents early: after the launch that creates the
+ *      children of height 4 (1, default), after those of heights 5 and 4 (2), or never (0), every query descends
+ *      greedily from the children with the largest bounds to leaves that are scored exactly. Results are
+ *      identical either way; only the number of nodes scored below changes;
  *  "bb_bounds": 1 (default) = sweeps that neither score their roots nor dive read the
  *      u8 bound levels (tiled upper bounds of the reference's coarse levels, built by
  *      csm_build_pyramids for batches of maps or on first use), 0 = the reference's u16

@@ -167,6 +167,7 @@ struct PlanView
     ScanSlot scan;                 /* scan arriving with the call (single-scan matchers) */
     int* qflags = nullptr;
     unsigned long long* tiekey = nullptr;   /* per query: largest key shared by two candidates */
+    unsigned long long* probe = nullptr;    /* per query: start nodes of the incumbent dive (k_bbg_dive) */
     int* stats = nullptr;
     unsigned int* counts = nullptr;
     int* overflow = nullptr;
@@ -209,6 +210,9 @@ struct csm_context
     int bb_ctas_per_sm = 0;        /* resident CTAs per SM of the B&B sweep kernels (occupancy query, lazily) */
     int bb_split_shift = 0;
     int bb_skip_top = 1;           /* 1: the B&B sweep starts one height below hmax (same results) */
+    int bb_probe = 1;              /* the group sweep descends greedily to a leaf per query (k_bbg_dive: same results,
+                                      fewer nodes): 1 = after the launch of height 4, 2 = after heights 5 and 4, 0 = never.
+                                      Measured on cfg3 (256 queries): 625 k / 719 k / 707 k queries/s for 0 / 1 / 2 */
     int window_mode = 0;           /* grid search, integer-shift path: 0 auto (TMA tiles when possible),
                                       1 plain global-memory kernel, 2 require the TMA kernel */
     PlanView plan_view;                   /* layout of the last staged batch */
@@ -1023,6 +1027,7 @@ int layout_plan(csm_handle h, int nq, size_t n_thetas, size_t n_rootoff, size_t 
     V.zero_off = off;
     const size_t off_qflags = off; off += align16(sizeof(int) * (size_t)nq);
     const size_t off_tiekey = off; off += align16(sizeof(unsigned long long) * (size_t)nq);
+    const size_t off_probe = off;  off += align16(sizeof(unsigned long long) * kDiveStarts * (size_t)nq);
     const size_t off_stats = off;  off += align16(sizeof(int) * 2 * (size_t)nq);
     const size_t off_counts = off; off += align16(sizeof(unsigned int) * kMaxLevels);
     const size_t off_overflow = off; off += 16;
@@ -1039,6 +1044,7 @@ int layout_plan(csm_handle h, int nq, size_t n_thetas, size_t n_rootoff, size_t 
     V.extra = base + V.off_extra;
     V.qflags = reinterpret_cast<int*>(base + off_qflags);
     V.tiekey = reinterpret_cast<unsigned long long*>(base + off_tiekey);
+    V.probe = reinterpret_cast<unsigned long long*>(base + off_probe);
     V.stats = reinterpret_cast<int*>(base + off_stats);
     V.counts = reinterpret_cast<unsigned int*>(base + off_counts);
     V.overflow = reinterpret_cast<int*>(base + off_overflow);
@@ -1420,6 +1426,18 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
     W.capacity = h->frontier_capacity;
     W.top = top;
     W.split_shift = h->bb_split_shift;
+    if (use_bounds && h->bb_probe && top >= 3) {
+        /* a start node's lattice position takes 14 + 14 bits and its angle 12; option values above 2 are a mask
+         * of heights (bit hc), for experiments */
+        bool fits = true;
+        for (int q = 0; q < nq && fits; ++q)
+            fits = plan.dq[q].lx < (1 << kProbePosBits) && plan.dq[q].ly < (1 << kProbePosBits) && plan.dq[q].T <= 4096;
+        unsigned int heights = h->bb_probe == 1 ? (1u << 4) : h->bb_probe == 2 ? ((1u << 5) | (1u << 4)) : (unsigned int)h->bb_probe;
+        /* the first launch creates the children of height top - 1: a shallower search dives once, from there */
+        if ((heights & ((1u << top) - 1u) & ~3u) == 0u) heights = 1u << (top - 1);
+        heights &= ((1u << top) - 1u) & ~3u & 0x3fu;
+        if (fits && heights != 0u) { W.probe = V.probe; W.probe_heights = heights; }
+    }
     if (dive) {
         if ((rc = ensure(h, h->d_rootkey, sizeof(long long) * (size_t)plan.root_off[nq]))) return rc;
         W.rootkey = static_cast<long long*>(h->d_rootkey.p);
@@ -1493,6 +1511,11 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             if (h->timing) {
                 const std::string nm = std::string(use_bounds ? "k_bbg_expand<" : "k_bb_expand<") + std::to_string(lvl - 1) + ">";
                 phase_mark(h, nm.c_str());
+            }
+            if (use_bounds && W.probe != nullptr && ((W.probe_heights >> (lvl - 1)) & 1u) && lvl - 1 > h->bb_stop_level) {
+                k_bbg_dive<<<nq, 256, 0, h->stream>>>(dq, proj, W, lvl - 1);
+                CSM_LAUNCH_CHECK();
+                if (h->timing) phase_mark(h, (std::string("k_bbg_dive<") + std::to_string(lvl - 1) + ">").c_str());
             }
             bound = std::min<unsigned long long>(bound * 4, (unsigned long long)h->frontier_capacity);
         }
@@ -1822,6 +1845,21 @@ int csm_create(int device, unsigned flags, csm_handle* out)
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    /* CSM_OPTIONS="name=value,name=value": csm_set_option calls for every handle of the process, for A/B runs
+     * through host code that does not expose the knobs (unknown names and bad values are ignored) */
+    if (const char* env = std::getenv("CSM_OPTIONS")) {
+        std::string all(env);
+        size_t at = 0;
+        while (at < all.size()) {
+            size_t end = all.find(',', at);
+            if (end == std::string::npos) end = all.size();
+            const std::string kv = all.substr(at, end - at);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos && eq > 0)
+                csm_set_option(h, kv.substr(0, eq).c_str(), std::atoi(kv.c_str() + eq + 1));
+            at = end + 1;
+        }
+    }
     *out = h;
     return CSM_OK;
 }
@@ -1907,6 +1945,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "bb_stop_level") == 0) { h->bb_stop_level = std::max(0, std::min(value, kMaxLevels - 1)); return CSM_OK; }
     if (std::strcmp(name, "bb_bounds") == 0) { h->bb_bounds = value != 0; return CSM_OK; }
     if (std::strcmp(name, "bb_skip_top") == 0) { h->bb_skip_top = value != 0; return CSM_OK; }
+    if (std::strcmp(name, "bb_probe") == 0 && value >= 0) { h->bb_probe = value; return CSM_OK; }
     if (std::strcmp(name, "window_mode") == 0 && value >= 0 && value <= 3) { h->window_mode = value; return CSM_OK; }
     if (std::strcmp(name, "timing") == 0) { h->timing = value; h->tcount = 0; return CSM_OK; }
     if (std::strcmp(name, "accumulate_best_key") == 0 && value != 0 && h->d_bestkey.p == nullptr) {

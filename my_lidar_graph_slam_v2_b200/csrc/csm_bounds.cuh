@@ -80,6 +80,15 @@ __device__ __forceinline__ unsigned int bl_encode2(unsigned int v)
     return hi + ((t >> 8) & 0x00010001u);
 }
 
+/* The same in five instructions instead of seven: byte permutes pick the high and low bytes of both lanes
+ * and the carry byte of 255 + lo - hi */
+__device__ __forceinline__ unsigned int bl_encode2p(unsigned int v)
+{
+    const unsigned int hi = __byte_perm(v, 0u, 0x4341), lo = __byte_perm(v, 0u, 0x4240);
+    const unsigned int d = lo + 0x00ff00ffu - hi;
+    return hi + __byte_perm(d, 0u, 0x4341);
+}
+
 struct BlJob
 {
     const uint16_t* base;     /* level 0, row-major u16 */

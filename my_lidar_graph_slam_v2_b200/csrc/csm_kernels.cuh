@@ -408,13 +408,13 @@ __device__ __noinline__ void ps2_store_edge(uint4 pv, unsigned int* __restrict__
 template <int H, int FIX>
 __device__ __forceinline__ unsigned char* ps2b_row(unsigned char* __restrict__ out, int R, int C, int r, int j)
 {
-    const size_t base = FIX ? bl_level_offset(H, FIX, FIX) : bl_level_offset(H, R, C);
+    /* (a map's bound allocation is a few MiB: 32-bit offsets) */
+    const unsigned int base = FIX ? (unsigned int)bl_level_offset(H, FIX, FIX) : (unsigned int)bl_level_offset(H, R, C);
     const unsigned int tpr = FIX ? (unsigned int)bl_tiles_per_row(H, FIX) : (unsigned int)bl_tiles_per_row(H, C);
-    return out + base + bl_cell((unsigned int)(r + bl_pad_r(H)), (unsigned int)(2 * j + bl_pad_c(H)), tpr);
+    return out + (base + bl_cell((unsigned int)(r + bl_pad_r(H)), (unsigned int)(2 * j + bl_pad_c(H)), tpr));
 }
 
-/* (the cells are encoded once, when level 0 leaves the input ring: the maximum commutes with the
- * monotone encoding, so every level is computed on encoded values, 16 bits per cell) */
+/* (every level above the first horizontal maximum is computed on encoded values, 16 bits per cell) */
 __device__ __forceinline__ unsigned short ps2b_pack(unsigned int word)
 {
     return (unsigned short)__byte_perm(word, 0u, 0x4420);
@@ -459,10 +459,12 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
 #pragma unroll
     for (int rr = kPsRows - 1; rr >= 0; --rr) {
         unsigned int t = tap[rr * PS];
-        if (H == 1 && BND) t = bl_encode2(t);
         if (H == 1) t = __byte_perm(a[rr], t, 0x5432);
         else if (edge) t = splat_lo(t);
         t = __vmaxu2(a[rr], t);
+        /* bound mode: level 0 itself is never written, and the maximum commutes with the monotone encoding,
+         * so the cells are encoded once, after the first horizontal maximum was taken on the raw values */
+        if (H == 1 && BND) t = bl_encode2p(t);
         const int slot = ring_off + ((K * kPsRows + rr) & (half - 1));     /* constant after unrolling */
         const unsigned int old = ring[slot];
         ring[slot] = t;
@@ -512,7 +514,7 @@ __device__ __forceinline__ void ps2_block(unsigned int (&ring)[63], const unsign
                              : reinterpret_cast<unsigned int*>(job.levels) + (size_t)r0 * cw + j;
     unsigned int a[kPsRows];
 #pragma unroll
-    for (int rr = 0; rr < kPsRows; ++rr) a[rr] = BND ? bl_encode2(in[rr * kPsInStride + j]) : in[rr * kPsInStride + j];
+    for (int rr = 0; rr < kPsRows; ++rr) a[rr] = in[rr * kPsInStride + j];
     ps2_level<1, K, kPsInStride, FIX, BND>(a, in, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
     if (HMAX >= 2) ps2_level<2, K, 256, FIX, BND>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
     if (HMAX >= 3) ps2_level<3, K, 256, FIX, BND>(a, buf0, buf1, ring, dst0, cells_w, cw, R, C, r0, j, wr);
@@ -1084,6 +1086,9 @@ struct BbWork
     int*                overflow;   /* set when a list is full */
     long long*          rootkey;    /* per root candidate: its key if it passed, else -1 (feeds the dive) */
     unsigned long long* tiekey;     /* per query: largest key two different leaves were seen to share (0: none) */
+    unsigned long long* probe;      /* per query, kDiveStarts words: the children with the largest bound of the launch
+                                       (start nodes of k_bbg_dive); null: off */
+    unsigned int        probe_heights; /* bit hc: the launch that creates the children of height hc records them */
     unsigned int        capacity;
     int                 top;        /* height of the root candidates (the reference's node_height_max) */
     int                 split_shift; /* lanes per node: largest split with count * split * 2 <= lanes << split_shift */
@@ -1507,6 +1512,176 @@ __device__ __forceinline__ int bbg_warps_per_group(unsigned int count, unsigned 
     return best;
 }
 
+/* ---- incumbent dives of the group sweep -----------------------------------------------------------
+ * The level-synchronous sweep meets leaves only at its last launch, so on its own it prunes against the
+ * score threshold alone. Any real leaf is a valid incumbent (the result, maximum key and smallest ordinal,
+ * does not depend on it: a node is kept while its bound is >= the incumbent's key, so the best leaf, its
+ * ancestors and every leaf that ties with it survive). After the launches that create the children of the
+ * upper heights, one CTA per query descends greedily from the children with the largest bounds -- the best of
+ * every fourth group of angles, so that the starts differ in angle -- keeping the kDiveBeam best children at
+ * every height, down to leaves that are scored exactly; the best one becomes the query's incumbent before
+ * the next launch decides anything. On loop-detection batches the launches below then score a quarter of the
+ * groups they would otherwise (true positives, where the threshold prunes least, dominate them). */
+constexpr int kDiveStarts = 4;               /* start nodes per query (a power of two) */
+constexpr int kDiveWidth = 4;                /* nodes kept per height */
+constexpr int kProbePosBits = 14;            /* leaf lattice extents up to 16383 cells, angles up to 4095 */
+
+__device__ __forceinline__ unsigned long long pack_probe(unsigned int sv, int t, int cx, int cy)
+{
+    return ((unsigned long long)min(sv, 0xffffffu) << 40) | ((unsigned long long)(unsigned)t << (2 * kProbePosBits)) |
+           ((unsigned long long)(unsigned)cx << kProbePosBits) | (unsigned long long)(unsigned)cy;
+}
+
+/* The four children of up to kDiveWidth nodes on level HH: 64 lanes (two warps) per node, a lane takes the
+ * beams lane, lane + 64, ...; the index loads of kDiveUnroll beams are issued together, then their 4 x
+ * kDiveUnroll cell loads (the dive is a chain of dependent launches-within-a-launch: its time is the latency
+ * of these rounds, not their work). s_sum[node][child], s_known likewise (leaves). */
+constexpr int kDiveUnroll = 6;               /* 6 x 64 lanes: one round for scans of up to 384 beams */
+
+template <int HH>
+__device__ __forceinline__ void dive_score(const DevQuery& Q, const proj_t* __restrict__ pq,
+                                           const int (*s_node)[3], int n_nodes,
+                                           unsigned int (*s_sum)[4], unsigned int (*s_known)[4])
+{
+    constexpr int w = 1 << HH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int node = warp >> 1, half = warp & 1;
+    unsigned int s[4] = { 0u, 0u, 0u, 0u }, k[4] = { 0u, 0u, 0u, 0u };
+    if (node < n_nodes) {
+        const int t = s_node[node][0];
+        const int ox = s_node[node][1] - Q.winx, oy = s_node[node][2] - Q.winy;
+        const unsigned int tpr = (unsigned int)Q.bl_tpr[HH];
+        const unsigned int row_w = (unsigned int)(w / kBlTileR) * (tpr << 7);
+        const uint16_t* __restrict__ m = Q.lvl[0];
+        const unsigned char* __restrict__ bm = Q.bl[HH];
+        const int rows = Q.rows, cols = Q.cols, n = Q.n;
+        for (int i0 = half * 32 + lane; i0 < n; i0 += 64 * kDiveUnroll) {
+            proj_t p[kDiveUnroll];
+#pragma unroll
+            for (int u = 0; u < kDiveUnroll; ++u) {
+                const int i = i0 + 64 * u;
+                /* beams past the end read beam i0 again and are masked below */
+                p[u] = pq[proj_index(Q, t, i < n ? i : i0)];
+            }
+            unsigned int v[kDiveUnroll][4];
+#pragma unroll
+            for (int u = 0; u < kDiveUnroll; ++u) {
+                if (HH == 0) ld_children<0>(m, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
+                else ld_children_b<HH>(bm, tpr, row_w, rows, cols, p[u].y + oy, p[u].x + ox, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kDiveUnroll; ++u) {
+                const bool ok = i0 + 64 * u < n;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const unsigned int x = ok ? v[u][c] : 0u;
+                    s[c] += x;
+                    if (HH == 0) k[c] += (x != 0u);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+            if (HH == 0) k[c] += __shfl_xor_sync(0xffffffffu, k[c], o);
+        }
+    }
+    if (lane == 0 && half == 1 && node < n_nodes) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_sum[node][c] = s[c]; s_known[node][c] = k[c]; }
+    }
+    __syncthreads();
+    if (lane == 0 && half == 0 && node < n_nodes) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_sum[node][c] += s[c]; s_known[node][c] += k[c]; }
+    }
+    __syncthreads();
+}
+
+/* One CTA of 256 threads per query; hc = height of the children the last launch created (2 <= hc) */
+__global__ void __launch_bounds__(256)
+k_bbg_dive(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W, int hc)
+{
+    static_assert(kDiveWidth * 2 == 8 && kDiveWidth * 4 <= 32, "two warps per node, one lane per child");
+    __shared__ int s_node[2][kDiveWidth][3];               /* (t, xi, yi), ping-pong by height */
+    __shared__ int s_n;
+    __shared__ unsigned int s_sum[kDiveWidth][4], s_known[kDiveWidth][4];
+    const int q = blockIdx.x;
+    const DevQuery& Q = queries[q];
+    if (threadIdx.x < 32) {
+        /* lanes 0..3 fetch (and clear: the next recording launch starts over) the start words */
+        unsigned long long pw = 0ull;
+        if (threadIdx.x < kDiveStarts) {
+            pw = W.probe[q * kDiveStarts + threadIdx.x];
+            if (pw != 0ull) W.probe[q * kDiveStarts + threadIdx.x] = 0ull;
+        }
+        const unsigned int have = __ballot_sync(0xffffffffu, pw != 0ull);
+        if (pw != 0ull) {
+            const int at = __popc(have & ((1u << threadIdx.x) - 1u));
+            s_node[hc & 1][at][0] = (int)((pw >> (2 * kProbePosBits)) & 0xfffull);
+            s_node[hc & 1][at][1] = (int)((pw >> kProbePosBits) & ((1ull << kProbePosBits) - 1ull));
+            s_node[hc & 1][at][2] = (int)(pw & ((1ull << kProbePosBits) - 1ull));
+        }
+        if (threadIdx.x == 0) s_n = __popc(have);
+    }
+    __syncthreads();
+    const proj_t* __restrict__ pq = proj_all + Q.proj_off;
+    /* nothing but this CTA raises this query's incumbent while it runs: one reading serves every height */
+    const unsigned long long inc0 = *(volatile unsigned long long*)&W.incumbent[q];
+    const long long fail_max = Q.kthr.fail_max;
+    const int n_beams = Q.n;
+    for (int hh = hc - 1; hh >= 0; --hh) {
+        const int n_nodes = s_n;
+        if (n_nodes == 0)
+            return;
+        const int (*cur)[3] = s_node[(hh + 1) & 1];
+        switch (hh) {
+        case 0: dive_score<0>(Q, pq, cur, n_nodes, s_sum, s_known); break;
+        case 1: dive_score<1>(Q, pq, cur, n_nodes, s_sum, s_known); break;
+        case 2: dive_score<2>(Q, pq, cur, n_nodes, s_sum, s_known); break;
+        case 3: dive_score<3>(Q, pq, cur, n_nodes, s_sum, s_known); break;
+        case 4: dive_score<4>(Q, pq, cur, n_nodes, s_sum, s_known); break;
+        default: dive_score<5>(Q, pq, cur, n_nodes, s_sum, s_known); break;
+        }
+        if (threadIdx.x < 32) {
+            /* lane = (node, child) */
+            const int lane = threadIdx.x, nd = lane >> 2, c = lane & 3;
+            const bool valid = lane < 4 * n_nodes;
+            const int w = 1 << hh;
+            const int t = valid ? cur[nd][0] : 0;
+            const int xi = valid ? cur[nd][1] + (c & 1) * w : 0, yi = valid ? cur[nd][2] + (c >> 1) * w : 0;
+            const unsigned int sv = valid ? s_sum[nd][c] : 0u;
+            if (hh == 0) {
+                /* every passing leaf competes for the incumbent */
+                long long key;
+                if (valid && bb_passes(Q, proj_all, W, q, t, xi, yi, 0, (int)sv, (int)s_known[nd][c], key))
+                    bb_raise_incumbent(W, q, key, leaf_ordfield(Q, t, xi, yi));
+                if (lane == 0) s_n = 0;
+            } else {
+                /* the kDiveWidth children with the largest bounds among those the sweep would keep */
+                const long long key_ub = make_key(257ll * (long long)sv, n_beams);
+                const bool pass = valid && pack_best(key_ub, kOrdMask) > inc0 && key_ub > fail_max;
+                const unsigned int mine = pass ? sv + 1u : 0u;
+                int rank = 0;
+#pragma unroll
+                for (int o = 0; o < 4 * kDiveWidth; ++o) {
+                    const unsigned int other = __shfl_sync(0xffffffffu, mine, o);
+                    rank += (other > mine) || (other == mine && o < lane);
+                }
+                const unsigned int kept = __ballot_sync(0xffffffffu, pass && rank < kDiveWidth);
+                if (pass && rank < kDiveWidth) {
+                    s_node[hh & 1][rank][0] = t; s_node[hh & 1][rank][1] = xi; s_node[hh & 1][rank][2] = yi;
+                }
+                if (lane == 0) s_n = __popc(kept);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int HC>
 __global__ void __launch_bounds__(32 * kBbgWarps, CSM_BB_MINB)
 k_bbg_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ proj_all, BbWork W, int nchunks_hint)
@@ -1626,6 +1801,14 @@ k_bbg_expand(const DevQuery* __restrict__ queries, const proj_t* __restrict__ pr
             if (have && lane == 0) {
                 atomicAdd(&W.stats[2 * q], __popc(ballot));
                 atomicAdd(&W.stats[2 * q + 1], __popc(scored) - __popc(ballot));
+            }
+            if (!kLeaf && W.probe != nullptr && ((W.probe_heights >> HC) & 1u) && ballot != 0u) {
+                /* the passing child with the largest bound of this group competes for a start of the dive */
+                const unsigned int cand = pass ? sv : 0u;
+                const unsigned int top_sv = __reduce_max_sync(0xffffffffu, cand);
+                const unsigned int who = __ballot_sync(0xffffffffu, pass && cand == top_sv);
+                if (lane == __ffs(who) - 1)
+                    atomicMax(&W.probe[q * kDiveStarts + (tg & (kDiveStarts - 1))], pack_probe(sv, t, cx, cy));
             }
             if (!kLeaf && ballot != 0u) {
                 /* one new group per child that keeps an angle alive: lanes 0..3 write them */
