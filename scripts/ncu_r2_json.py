@@ -1,7 +1,7 @@
 """profiles/r2_ncu.json from the full ncu capture of one 256-query step (scripts/exp_phases.py 256 refine):
 
-    ncu -i gpurun_out/r2_sweep.ncu-rep --page raw --csv > /tmp/r2_raw.csv
-    python scripts/ncu_r2_json.py /tmp/r2_raw.csv gpurun_out/phases_256_r2.log > profiles/r2_ncu.json
+    ncu -i gpurun_out/r2b_sweep.ncu-rep --page raw --csv > gpurun_out/r2b_raw.csv
+    python scripts/ncu_r2_json.py gpurun_out/r2b_raw.csv gpurun_out/phases_256_r2b.log > profiles/r2_ncu.json
 """
 import csv
 import json
@@ -23,7 +23,7 @@ for line in open(sys.argv[2]):
     if m:
         events[m.group(1)] = float(m.group(2))
 
-sweep, builder, seen = [], None, set()
+sweep, builder, dive, seen = [], None, None, set()
 for r in rows[2:]:
     name = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
     if name in seen:
@@ -45,15 +45,18 @@ for r in rows[2:]:
          "registers": val(r, "launch__registers_per_thread")}
     if name.startswith("k_bbg_expand"):
         sweep.append(d)
+    elif name.startswith("k_bbg_dive"):
+        dive = d
     elif name.startswith("k_pyramid_stream2"):
         builder = d
 t = sum(d["us"] for d in sweep)
 req = sum(d["requests"] for d in sweep)
 sec = sum(d["sectors"] for d in sweep)
 out = {
-    "captured_with": "ncu --set full --clock-control none -k regex:k_bbg_expand|k_pyramid_stream2 --launch-skip 100 -c 10 "
-                     "python scripts/exp_phases.py 256 refine (one 256-query cfg3 step on one handle, B200 of this pool)",
-    "report": "gpurun_out/r2_sweep.ncu-rep -> profiles/r2_sweep_and_builder_full.txt",
+    "captured_with": "scripts/gpu_prof_r2b.sh: ncu --set full --clock-control none -k regex:k_bbg_expand|k_pyramid_stream2|"
+                     "k_bbg_dive --launch-skip 104 -c 10 python scripts/exp_phases.py 256 refine (one 256-query cfg3 step "
+                     "on one handle, B200 of this pool; incumbent dive after the launch of height 4)",
+    "report": "gpurun_out/r2b_sweep.ncu-rep -> profiles/r2b_sweep_dive_builder_full.txt",
     "k_bbg_expand": {
         "launches": sweep, "ncu_ms": t / 1e3,
         "event_ms_at_capture": sum(v for k, v in events.items() if k.startswith("k_bbg_expand")) / 1e3,
@@ -64,6 +67,7 @@ out = {
         "issue_active_frac": sum(d["issue_active_pct"] * d["us"] for d in sweep) / t / 100.0,
         "dram_bytes_per_step": sum(d["dram_read_bytes"] + d["dram_write_bytes"] for d in sweep),
     },
+    "k_bbg_dive": dive,
     "k_pyramid_stream2": None if builder is None else dict(
         builder, dram_bytes_per_launch=builder["dram_read_bytes"] + builder["dram_write_bytes"],
         event_us_at_capture=events.get("k_pyramid_stream(bounds)")),
