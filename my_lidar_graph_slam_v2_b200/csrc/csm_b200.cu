@@ -942,7 +942,7 @@ int build_bounds(csm_handle h, const std::vector<MapSlot*>& slots, int L)
         if ((rc = upload_committed(h))) return rc;
         h->jobs_on_device.clear();
         phase_mark(h, "start");
-        int segs = (int)std::min<size_t>(4, (size_t)((L <= 5 ? 3 : 2) * h->sm_count) / pj.size());
+        int segs = (int)std::min<size_t>(4, (size_t)((L <= 5 ? CSM_PS2_MINB : 2) * h->sm_count) / pj.size());
         if (h->pyramid_segs > 0) segs = h->pyramid_segs;
         segs = std::max(1, std::min(segs, min_rows / 128));
         const unsigned int grid = (unsigned)(pj.size() * segs);

@@ -446,7 +446,11 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
                                           unsigned int* __restrict__ dst0, size_t cells_w_, int cw_,
                                           int R_, int C_, int r0, int j, bool wr)
 {
-    /* FIX > 0: square maps of FIX x FIX cells, every stride and clamp is an immediate */
+    /* FIX > 0: square maps of FIX x FIX cells, every stride and clamp is an immediate.
+     * The row buffers (`cur`, and `prev` above level 1) hold the four rows of a word index side by side
+     * ([256 words][4 rows]): a thread's tap and its own output are one 128-bit access each. Level 1 taps the
+     * input ring, which cp.async fills row by row (PS = word stride of its rows). */
+    static_assert(kPsRows == 4, "the four rows of a block travel as one uint4");
     const int R = FIX ? FIX : R_, C = FIX ? FIX : C_, cw = FIX ? FIX / 2 : cw_;
     const size_t cells_w = FIX ? (size_t)FIX * FIX / 2 : cells_w_;
     constexpr int half = 1 << (H - 1);
@@ -455,10 +459,17 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
     /* horizontal tap: word j + half/2 of out_{H-1}, which is clamped at column C - half */
     const int csw_prev = (H >= 2) ? (max(C - half, 0) >> 1) : 0x3fffffff;
     const bool edge = (H >= 2) && (j + (half >> 1) >= csw_prev);
-    const unsigned int* __restrict__ tap = prev + ((H == 1) ? j + 1 : (edge ? csw_prev : j + (half >> 1)));
+    unsigned int tp[kPsRows];
+    if (H == 1) {
+#pragma unroll
+        for (int rr = 0; rr < kPsRows; ++rr) tp[rr] = prev[rr * PS + j + 1];
+    } else {
+        const uint4 t4 = reinterpret_cast<const uint4*>(prev)[edge ? csw_prev : j + (half >> 1)];
+        tp[0] = t4.x; tp[1] = t4.y; tp[2] = t4.z; tp[3] = t4.w;
+    }
 #pragma unroll
     for (int rr = kPsRows - 1; rr >= 0; --rr) {
-        unsigned int t = tap[rr * PS];
+        unsigned int t = tp[rr];
         if (H == 1) t = __byte_perm(a[rr], t, 0x5432);
         else if (edge) t = splat_lo(t);
         t = __vmaxu2(a[rr], t);
@@ -469,14 +480,14 @@ __device__ __forceinline__ void ps2_level(unsigned int (&a)[kPsRows], const unsi
         const unsigned int old = ring[slot];
         ring[slot] = t;
         a[rr] = __vmaxu2(t, old);
-        cur[rr * 256 + j] = a[rr];
     }
+    reinterpret_cast<uint4*>(cur)[j] = make_uint4(a[0], a[1], a[2], a[3]);
     __syncthreads();
     /* out_H = P_H with the far edge clamped along the row; only the clamped threads re-read */
     const int csw = max(C - w, 0) >> 1;
     if (j >= csw) {
-#pragma unroll
-        for (int rr = 0; rr < kPsRows; ++rr) a[rr] = splat_lo(cur[rr * 256 + csw]);
+        const uint4 e = reinterpret_cast<const uint4*>(cur)[csw];
+        a[0] = splat_lo(e.x); a[1] = splat_lo(e.y); a[2] = splat_lo(e.z); a[3] = splat_lo(e.w);
     }
     if (wr && BND) {
         const int rsrc = max(R - w, 0);
@@ -523,8 +534,12 @@ __device__ __forceinline__ void ps2_block(unsigned int (&ring)[63], const unsign
     if (HMAX >= 6) ps2_level<6, K, 256, FIX, BND>(a, buf1, buf0, ring, dst0, cells_w, cw, R, C, r0, j, wr);
 }
 
+#ifndef CSM_PS2_MINB
+#define CSM_PS2_MINB 2      /* 108 registers. Capped at 88 (or 80: three resident CTAs) the four-row words spill and the
+                               kernel runs at 150 us per 256 maps instead of 130; a batch of 256 maps is 256 CTAs anyway */
+#endif
 template <int HMAX, int FIX, bool BND>
-__global__ void __launch_bounds__(kPsThreads, (BND && HMAX <= 5) ? 3 : 2)      /* five levels of rings: 31 words, three CTAs fit */
+__global__ void __launch_bounds__(kPsThreads, (BND && HMAX <= 5) ? CSM_PS2_MINB : 2)
 k_pyramid_stream2(const PyrJob* __restrict__ jobs, int segs)
 {
     extern __shared__ __align__(16) unsigned int ps_smem[];
