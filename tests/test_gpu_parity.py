@@ -598,6 +598,38 @@ def test_loop_batch_vs_checker_and_best_key(handle, checker):
         handle.release_grid(int(mid))
 
 
+@pytest.mark.parametrize("hmax", [6, 4, 3])
+def test_incumbent_dive_changes_the_work_not_the_results(handle, checker, hmax):
+    """k_bbg_dive (option bb_probe): with the incumbents seeded after the launch of height 4 (1), after heights 5
+    and 4 (2), from any mask of heights (here 4 | 8: heights 2 and 3), or never (0), every query returns the
+    same winner, sums, score and flags -- and the reference's --, while the sweep scores fewer children."""
+    batch = synth.make_loop_batch(3300 + hmax, n_maps=48, true_fraction=0.4, map_id_base=7000)
+    bb = matchers.ScanMatcherBranchBound("loop-bb", hmax, *synth.CFG3["rng"], handle=handle)
+    det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
+    queries = _loop_queries(batch)
+    grids = [checker.grid(s.grid, s.res, s.off_x, s.off_y) for s in batch.submaps]
+    odet = checker.loop_detector(hmax, synth.CFG3["rng"], synth.CFG3["thr"], 2)
+    ores, _ = odet.detect(grids, batch.map_ids, batch.map_poses, batch.scan_idx, batch.scan_poses,
+                          batch.angles, batch.ranges)
+    fields = ("found", "best_x", "best_y", "best_t", "sum_value", "n_known", "flags", "normalized_score")
+    got, scored = {}, {}
+    try:
+        for probe in (0, 1, 2, 12):
+            handle.set_option("bb_probe", probe)
+            found, res = det.detect(queries)
+            for i, (r, o) in enumerate(zip(res, ores)):
+                assert_match(r, dict(o.asdict(), compare_unfound=False), "hmax %d probe %d query %d" % (hmax, probe, i))
+            got[probe] = [[getattr(r, f) for f in fields] for r in res]
+            scored[probe] = sum(r.n_processed + r.n_ignored for r in res)
+    finally:
+        handle.set_option("bb_probe", 1)
+        for mid in batch.map_ids:
+            handle.release_grid(int(mid))
+    assert sum(r.found for r in res) >= 5
+    assert got[0] == got[1] == got[2] == got[12]
+    assert scored[1] < scored[0] and scored[2] <= scored[1] and scored[12] < scored[0], scored
+
+
 # --------------------------------------------------------------------------
 # block-sparse upload (the reference's own storage layout)
 # --------------------------------------------------------------------------
