@@ -594,10 +594,10 @@ def main_cuda(args):
         "achieved": gathers / (exp_ms * 1e-3) if exp_ms > 0 else None, "peak": gather_peak, "unit": "gathers/s",
         "frac": gathers / (exp_ms * 1e-3) / gather_peak if exp_ms > 0 else None,
         "note": "SURVEY.md 8(d) gather ceiling: 148 SMs x 32 lanes x %.0f MHz, every lane of every wavefront useful; "
-                "a request of the sweep is 23 useful lanes in 3.4 wavefronts" % sm_mhz}
+                "a request of the sweep is 23 useful lanes in 3.0 wavefronts" % sm_mhz}
     roofline = {
         "kernel": "k_bbg_expand<0..%d> (B&B frontier scoring over groups of 8 angles, %d launches per step, one per "
-                  "pyramid height)" % (HMAX - 1, HMAX),
+                  "pyramid height; k_bbg_dive seeds the incumbents behind the second)" % (HMAX - 1, HMAX),
         "bound": "l1tex",
         "achieved": wavefronts / (exp_ms * 1e-3) if (wavefronts and exp_ms > 0) else algorithmic["achieved"],
         "peak": wf_peak if wavefronts else gather_peak,
@@ -632,8 +632,8 @@ def main_cuda(args):
         "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm_peak if pyr_ms > 0 else None, "peak_source": peak_source,
         "algorithmic_bytes_per_launch": pyr_bytes, "traffic": ncu.get("k_pyramid_stream2", {}).get("dram_bytes_per_launch"),
         "ms_per_step": pyr_ms, "share_of_step": pyr_ms / (pyr_ms + bb_ms) if pyr_ms + bb_ms > 0 else None,
-        "note": "latency-bound (one CTA walks a map's rows with a barrier per level and 4-row block), not "
-                "HBM-bound: see DESIGN.md section 5",
+        "note": "bound by issue slots and barriers (one CTA walks a map's rows with a barrier per level and 4-row "
+                "block), not by HBM: see DESIGN.md section 5",
     }
     phases = {"pyramid_ms": pyr_ms, "search_and_refine_ms": bb_ms, "kernel_ms": kernel_ms,
               "note": "per-kernel durations of one step run alone on one handle (sum %.3f ms); the timed steps "
