@@ -70,6 +70,8 @@ public:
      * once the last map has been gathered -- its copy, its levels, its search -- is what a cold Detect waits for
      * at the end, so a short last batch ends sooner; the batches before it overlap the gather anyway. */
     void SetTailChunk(int n) { mTailChunk = n; }
+    /* the first upload group of a Detect holds 1 / n of the maps of the others (default 1 = all groups alike: measured, no gain from a smaller first group: the copy engine is the longest leg either way) */
+    void SetFirstGroupDivisor(int n) { mFirstGroupDivisor = n < 1 ? 1 : n; }
     /* Without a final matcher the result carries the covariance of the cost
      * function at the coarse pose (computed on the CPU); switch it off when
      * the caller refines the poses itself */
@@ -127,6 +129,7 @@ private:
     int mChunkSize = 128;
     int mUploadChunk = 64;
     int mTailChunk = 0;
+    int mFirstGroupDivisor = 1;
     bool mCoarseCovariance = true;
 };
 

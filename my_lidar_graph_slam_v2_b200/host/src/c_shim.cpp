@@ -568,6 +568,7 @@ int csm_host_loopdet_detect_heap(void* det, int n_queries, const void* heap_maps
     return ExportResults(d->det->Detect(queries), d->det->LastResults(), n_queries, out);
 }
 
+void csm_host_loopdet_set_first_group_divisor(void* det, int n) { static_cast<HostLoopDet*>(det)->det->SetFirstGroupDivisor(n); }
 void csm_host_loopdet_set_gather_threads(void* det, int n) { static_cast<HostLoopDet*>(det)->det->SetGatherThreads(n); }
 int csm_host_loopdet_capacity_retries(void* det) { return static_cast<HostLoopDet*>(det)->det->NumOfCapacityRetries(); }
 

@@ -593,8 +593,11 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
         if (!sg.fresh)
             continue;
         std::set<std::int64_t> seen;
-        for (int first = sg.first; first < sg.first + sg.count; first += ugroup) {
-            const int last = std::min(sg.first + sg.count, first + ugroup);
+        /* the very first group of a call may be smaller than the others (SetFirstGroupDivisor): nothing crosses
+         * PCIe before it is gathered */
+        int step = ujobs.empty() ? std::max(std::min(8, ugroup), ugroup / mFirstGroupDivisor) : ugroup;
+        for (int first = sg.first; first < sg.first + sg.count; first += step, step = ugroup) {
+            const int last = std::min(sg.first + sg.count, first + step);
             UploadJob job;
             job.si = si;
             fresh_ids[si].emplace_back();
@@ -611,6 +614,7 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
         }
     }
     std::size_t next_job = 0;
+    const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
     auto start_job = [&](std::size_t k) {
         if (mGatherer && k < ujobs.size() && !ujobs[k].started && !mGatherer->Started())
             ujobs[k].started = HeapGroupStart(ujobs[k].fresh, mGatherer.get(), k, ujobs[k].heap);
@@ -622,15 +626,18 @@ std::vector<LoopDetectionResult> LoopDetectorBranchBound::Detect(
             start_job(next_job);
             if (job.started) {
                 mGatherer->Finish();
+                if (trace) std::fprintf(stderr, "lanes: group %zu gathered at %.0f us\n", next_job, timer.ElapsedMicro());
                 start_job(next_job + 1);              /* the workers go on with the next group */
                 HeapGroupUpload(c, job.heap);
+                if (trace) std::fprintf(stderr, "lanes: group %zu copy enqueued at %.0f us\n", next_job, timer.ElapsedMicro());
             } else
                 UploadNewMaps(c, job.fresh, mGatherer.get(), next_job);
             ++next_job;
         }
     };
+    start_job(0);                 /* the workers gather the first group while this thread fills the descriptors */
     fill_queries();
-    const bool trace = std::getenv("CSM_HOST_TRACE") != nullptr;
+    if (trace) std::fprintf(stderr, "lanes: descriptors filled at %.0f us\n", timer.ElapsedMicro());
     std::vector<std::vector<int>> in_flight(lanes);       /* segment indices, oldest first */
     std::vector<int> overflowed;                          /* segments to search again in smaller batches */
     auto finish_oldest = [&](int lane) {

@@ -564,6 +564,10 @@ class LoopDetector:
             scan_poses.ctypes.data_as(dp), angles.ctypes.data_as(dp), ranges.ctypes.data_as(dp), len(angles), out)
         return n, out
 
+    def set_first_group_divisor(self, n):
+        self.lib.csm_host_loopdet_set_first_group_divisor.argtypes = [C.c_void_p, C.c_int]
+        self.lib.csm_host_loopdet_set_first_group_divisor(self.det, int(n))
+
     def set_gather_threads(self, n):
         self.lib.csm_host_loopdet_set_gather_threads(self.det, int(n))
 

@@ -16,6 +16,8 @@ det.configure(chunk_size=chunk | ((tail // 16) << 12) | (ug << 16), coarse_covar
 det.use_device_refiner(10, 1e-4, 1e-4)
 det.set_lanes(lanes)
 det.set_gather_threads(threads)
+if len(sys.argv) > 8:
+    det.set_first_group_divisor(int(sys.argv[8]))
 for r in range(reps):
     det.clear_cache()
     t0 = time.perf_counter()
