@@ -51,3 +51,32 @@ def run_gpu(trip, device=0, **over):
     slam.close()
     ctx.close()
     return out, nodes
+
+
+def run_gpu_from_carmen(trip, log_path, device=0, metrics_path=None, **over):
+    """The launcher's way in and out: the trajectory as a Carmen log (ROBOTLASER1 + ODOM records, written here),
+    read back by the C++ CarmenLogReader, the loop run from its records (SlamPipeline::RunLog), the metrics saved
+    as <metrics_path>.metric.json. Returns (summary, scan nodes, seconds spent reading the log)."""
+    from my_lidar_graph_slam_v2_b200 import hostapi, slam_settings
+    n_beams = trip["ranges"].shape[1]
+    start, inc = -np.pi, 2.0 * np.pi / n_beams
+    hostapi.write_carmen_log(log_path, trip["ranges"], trip["odom"], trip["stamps"], start, inc, 11.3)
+    t0 = time.perf_counter()
+    log = hostapi.CarmenLog(path=log_path)
+    t_read = time.perf_counter() - t0
+    ctx = hostapi.Context(device)
+    slam = hostapi.SlamPipeline(ctx, slam_settings.pack(**dict(CFG5, **over)))
+    if metrics_path:
+        slam.record_metrics()
+    t0 = time.perf_counter()
+    slam.run_carmen(log, finish=True)
+    wall = time.perf_counter() - t0
+    out = summarize(slam.counters(), wall)
+    out["log_read_s"] = t_read
+    nodes = slam.scan_nodes()
+    if metrics_path:
+        slam.save_metrics(metrics_path)
+    slam.close()
+    log.close()
+    ctx.close()
+    return out, nodes
