@@ -65,6 +65,41 @@ def test_reader_matches_compiled_reference(seed, with_params):
                 assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (a["sensor_id"], k)
 
 
+def test_reader_number_formats_match_compiled_reference():
+    """tabs, runs of blanks, exponents, signs, trailing blanks, CR line ends, integers written as reals' prefixes"""
+    ref = reference()
+    rng = np.random.default_rng(11)
+    def num(v):
+        return rng.choice(["%.17g" % v, "%.6e" % v, "%+.9f" % v, "%.3f" % v])
+    lines = []
+    for k in range(40):
+        n = int(rng.integers(3, 12))
+        sep = rng.choice([" ", "  ", "\t", " \t "])
+        r = sep.join(num(v) for v in rng.uniform(0.1, 40.0, n))
+        kind = k % 4
+        if kind == 0:
+            body = ["ROBOTLASER1", "0", num(-1.5), num(3.0), num(3.0 / n), num(30.0), "0.01", "0", str(n), r,
+                    num(1.0), num(2.0), num(0.5), num(0.9), num(1.9), num(0.45), "0", "0", "0", "0", "0",
+                    num(100.0 + k), "host", num(100.5 + k)]
+        elif kind == 1:
+            body = ["FLASER", str(n), r, num(1.0), num(-2.0), num(-0.5), num(1.1), num(-2.1), num(-0.6),
+                    num(200.0 + k), "h", num(200.0 + k)]
+        elif kind == 2:
+            body = ["ODOM", num(rng.normal()), num(rng.normal()), num(rng.normal()), num(0.3), num(-0.1), "0",
+                    num(300.0 + k), "h", num(300.0 + k)]
+        else:
+            body = ["RAWLASER2", "0", num(-0.7), num(1.4), num(1.4 / n), num(20.0), "0.01", "1", str(n), r, "2", "7", "9",
+                    num(400.0 + k), "h", num(400.0 + k)]
+        lines.append(sep.join(body) + rng.choice(["", " ", "\r", "  \t"]))
+    text = "\n".join(lines) + "\n"
+    h = ref.carmen_load(text)
+    want = hostapi.carmen_records(ref.lib, "orc_carmen_", h)
+    ref.lib.orc_carmen_destroy(h)
+    got = host_records(text)
+    assert len(got) == len(want) == 40
+    assert encode(got) == encode(want)
+
+
 def test_reader_edge_cases():
     assert host_records("") == []
     assert host_records("\n\n# only comments\nUNKNOWN 1 2 3\n") == []
