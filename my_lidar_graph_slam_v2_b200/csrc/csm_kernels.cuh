@@ -666,18 +666,43 @@ k_sliding_max_tile(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
 constexpr int kProjAngles = 8;       /* candidate angles per CTA */
 constexpr int kProjSat = 30000;      /* saturation of projected indices (maps are <= 16384 wide) */
 
+/* What project_beam needs of a query, read ONCE into registers: taken through the DevQuery reference the
+ * eight fields were reloaded from global memory for every beam (ncu, round 2: 8 LDG.E.64 per element, the
+ * LSU data pipe at 0.73 of its peak in k_project). */
+struct ProjConst
+{
+    double sx, sy, offx, offy, inv_res;
+    int guard_hi;                           /* the guard band as a test on high words (load_proj_const) */
+    const double2* beam_trig;
+    const double* ranges;
+};
+
+__device__ __forceinline__ ProjConst load_proj_const(const DevQuery& Q)
+{
+    ProjConst P;
+    P.sx = Q.sx; P.sy = Q.sy; P.offx = Q.offx; P.offy = Q.offy;
+    P.inv_res = Q.inv_res;
+    /* A fraction g in [0, 1) lies in the band when g < margin or 1 - g < margin (1 - g is exact from 0.5 up).
+     * Non-negative doubles order like their bit patterns, so both tests run on the high words alone: integer
+     * minimum and compare instead of FP64 compares and selects. That flags a superset (distances within
+     * 2^-20 relative of the margin): more flags are always safe. margin <= 0 (exact reruns) flags nothing. */
+    P.guard_hi = Q.margin > 0.0 ? __double2hiint(Q.margin) : -1;
+    P.beam_trig = Q.beam_trig; P.ranges = Q.ranges;
+    return P;
+}
+
 /* Hit cell of beam i seen from (Q.sx, Q.sy) at the candidate angle whose (cos, sin) is th:
  * cos/sin(theta + a_i) from the angle-addition formula on the per-beam table, the rest is FP64 in
  * the reference's operation order without contraction (sensor_data.hpp:190-203,
  * grid_map_geometry.cpp:113-122). Raises `flagged` when a coordinate lies within the guard band
  * of a cell boundary. */
-__device__ __forceinline__ proj_t project_beam(const DevQuery& Q, const double2 th, int i, int& flagged,
+__device__ __forceinline__ proj_t project_beam(const ProjConst& Q, const double2 th, int i, int& flagged,
                                                double& rc, double& rs)
 {
-    const double2 be = Q.beam_trig[i];
+    const double2 be = __ldg(Q.beam_trig + i);
     const double c = th.x * be.x - th.y * be.y;      /* cos(theta + a) */
     const double s = th.y * be.x + th.x * be.y;      /* sin(theta + a) */
-    const double r = Q.ranges[i];
+    const double r = __ldg(Q.ranges + i);
     rc = __dmul_rn(r, c);
     rs = __dmul_rn(r, s);
     /* (x - off) * (1 / res) instead of the reference's (x - off) / res: the two
@@ -685,14 +710,27 @@ __device__ __forceinline__ proj_t project_beam(const DevQuery& Q, const double2 
      * that is flagged anyway (the band is ~1000x wider) */
     const double ux = __dmul_rn(__dsub_rn(__dadd_rn(Q.sx, rc), Q.offx), Q.inv_res);
     const double uy = __dmul_rn(__dsub_rn(__dadd_rn(Q.sy, rs), Q.offy), Q.inv_res);
-    const double fx = floor(ux), fy = floor(uy);
+    /* floor() without the conversion unit (FRND.F64 / F2I.F64 run on the XU pipe at a few lanes per clock: ncu
+     * showed it saturated, the FP64 pipe at 0.23): ux + 1.5 * 2^52 rounded DOWN is floor(ux) + 1.5 * 2^52
+     * exactly while |ux| < 2^31 (one ulp there is 1), so its low word is floor(ux) as an int and subtracting
+     * the constant gives floor(ux) as a double. Anything larger (or NaN) takes the saturating conversion;
+     * the clamp on integers follows either way. */
+    constexpr double kFloorMagic = 6755399441055744.0;
+    const double tx = __dadd_rd(ux, kFloorMagic), ty = __dadd_rd(uy, kFloorMagic);
+    int ix = __double2loint(tx), iy = __double2loint(ty);
+    double fx = __dsub_rn(tx, kFloorMagic), fy = __dsub_rn(ty, kFloorMagic);
+    /* |u| >= 1e9 on either axis, by the high words (an OR of two of them is at least the larger; below 2^16
+     * cells it stays below the limit) */
+    if ((((unsigned int)__double2hiint(ux) | (unsigned int)__double2hiint(uy)) & 0x7FFFFFFFu) >= 0x41CDCD65u) {
+        ix = __double2int_rd(ux); iy = __double2int_rd(uy);
+        fx = floor(ux); fy = floor(uy);
+    }
     const double gx = ux - fx, gy = uy - fy;
-    if (gx < Q.margin || gx > 1.0 - Q.margin || gy < Q.margin || gy > 1.0 - Q.margin)
-        flagged |= 1;
-    /* floor() as a saturating double -> int conversion (round down), then the clamp on integers */
+    flagged |= (int)(min(min(__double2hiint(gx), __double2hiint(1.0 - gx)),
+                         min(__double2hiint(gy), __double2hiint(1.0 - gy))) <= Q.guard_hi);
     proj_t p;
-    p.x = (short)max(min(__double2int_rd(ux), kProjSat), -kProjSat);
-    p.y = (short)max(min(__double2int_rd(uy), kProjSat), -kProjSat);
+    p.x = (short)max(min(ix, kProjSat), -kProjSat);
+    p.y = (short)max(min(iy, kProjSat), -kProjSat);
     return p;
 }
 
@@ -743,31 +781,38 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
     const int winx = Q.winx, winy = Q.winy, lx2 = 2 * Q.lx, ly2 = 2 * Q.ly;
     proj_t* __restrict__ out = proj + (size_t)Q.proj_off;
     const bool quad = Q.pquad != 0;
+    const ProjConst P = load_proj_const(Q);
+    const size_t pst_t = (size_t)Q.pst_t, pst_i = (size_t)Q.pst_i, tp = (size_t)Q.tp;
+    double2* __restrict__ rcs_q = rcs != nullptr ? rcs + (size_t)Q.proj_off : nullptr;
+    /* chunked layout: the slots past the last beam of the last chunk hold a cell far outside every map,
+     * so that the sweep reads its chunks whole, without a test per beam (a child there scores 0) */
+    const int n_slots = quad ? ((n + 15) & ~15) : n;
+    /* position of (t, i) as proj_index gives it, walked by additions: in the chunk layout i advances by a
+     * multiple of 16 (whole chunks), so the place inside the chunk never changes */
+    const size_t at_step = quad ? ((size_t)(i_step >> 4) * tp) << 4 : (size_t)i_step * pst_i;
+    const unsigned int edge_x = lx2 > 0 ? (unsigned int)(lx2 - 1) : 0u, edge_y = ly2 > 0 ? (unsigned int)(ly2 - 1) : 0u;
     for (int tl = tl_first; tl < nt; tl += tl_step) {
         const double2 th = s_theta[tl];
-        proj_t* __restrict__ out_t = out + (size_t)(t0 + tl) * Q.pst_t;
-        /* chunked layout: the slots past the last beam of the last chunk hold a cell far outside every map,
-         * so that the sweep reads its chunks whole, without a test per beam (a child there scores 0) */
-        const int n_slots = quad ? ((n + 15) & ~15) : n;
-        for (int i = i_first; i < n_slots; i += i_step) {
-            if (i >= n) {
-                out[proj_index(Q, t0 + tl, i)] = proj_t { (short)-32768, (short)-32768 };
-                continue;
-            }
+        const int t = t0 + tl;
+        size_t at = quad ? ((((size_t)(i_first >> 4) * tp + (size_t)t) << 4) + (size_t)(((i_first & 3) << 2) | ((i_first >> 2) & 3)))
+                         : (size_t)t * pst_t + (size_t)i_first * pst_i;
+        int i = i_first;
+        for (; i < n; i += i_step, at += at_step) {
             double rc, rs;
-            const proj_t p = project_beam(Q, th, i, flagged, rc, rs);
+            const proj_t p = project_beam(P, th, i, flagged, rc, rs);
             if (bb) {
                 /* branch-and-bound: a node window that straddles row / column 0 makes the coarse bound
-                 * inadmissible (a lookup at a negative index reads unknown) */
+                 * inadmissible (a lookup at a negative index reads unknown):
+                 * -lx2 < x0 < 0 as one unsigned compare */
                 const int x0 = (int)p.x - winx, y0 = (int)p.y - winy;
-                if ((x0 < 0 && x0 + lx2 > 0) || (y0 < 0 && y0 + ly2 > 0))
-                    flagged |= 4;
+                flagged |= (int)(((unsigned int)(x0 + lx2 - 1) < edge_x) | ((unsigned int)(y0 + ly2 - 1) < edge_y)) << 2;
             }
-            if (quad) out[proj_index(Q, t0 + tl, i)] = p;      /* a warp = 4 beams x 8 angles = one 128-byte line */
-            else out_t[(size_t)i * Q.pst_i] = p;
-            if (rcs != nullptr)
-                rcs[(size_t)Q.proj_off + (size_t)(t0 + tl) * n + i] = make_double2(rc, rs);
+            out[at] = p;      /* chunk layout: a warp = 4 beams x 8 angles = one 128-byte line */
+            if (rcs_q != nullptr)
+                rcs_q[(size_t)t * n + i] = make_double2(rc, rs);
         }
+        for (; i < n_slots; i += i_step, at += at_step)
+            out[at] = proj_t { (short)-32768, (short)-32768 };
     }
     /* bit 0: CSM_FLAG_FP_MARGIN, bit 2: CSM_FLAG_EDGE */
     const int any = (int)__reduce_or_sync(0xffffffffu, (unsigned)flagged);
@@ -856,12 +901,15 @@ k_rt_blocks(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj_all,
         if (proj_given) {
             /* exact rerun: the indices were computed on the host with the reference's own libm calls */
             for (int i = threadIdx.x; i < Q.n; i += blockDim.x) proj[i] = gproj[i];
-        } else
-        for (int i = threadIdx.x; i < Q.n; i += blockDim.x) {
+        } else {
+        const ProjConst P = load_proj_const(Q);
+        const int n = Q.n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
             double rc, rs;
-            const proj_t p = project_beam(Q, s_theta, i, flagged, rc, rs);
+            const proj_t p = project_beam(P, s_theta, i, flagged, rc, rs);
             proj[i] = p;
             if (publish) gproj[i] = p;
+        }
         }
         if (publish && __any_sync(0xffffffffu, flagged) && (threadIdx.x & 31) == 0)
             atomicOr(&qflags[0], 1 /* CSM_FLAG_FP_MARGIN */);
