@@ -797,9 +797,7 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
         size_t at = quad ? ((((size_t)(i_first >> 4) * tp + (size_t)t) << 4) + (size_t)(((i_first & 3) << 2) | ((i_first >> 2) & 3)))
                          : (size_t)t * pst_t + (size_t)i_first * pst_i;
         int i = i_first;
-        for (; i < n; i += i_step, at += at_step) {
-            double rc, rs;
-            const proj_t p = project_beam(P, th, i, flagged, rc, rs);
+        auto emit = [&](const proj_t p, int ii, size_t where, double rc, double rs) {
             if (bb) {
                 /* branch-and-bound: a node window that straddles row / column 0 makes the coarse bound
                  * inadmissible (a lookup at a negative index reads unknown):
@@ -807,9 +805,23 @@ k_project(const DevQuery* __restrict__ queries, proj_t* __restrict__ proj,
                 const int x0 = (int)p.x - winx, y0 = (int)p.y - winy;
                 flagged |= (int)(((unsigned int)(x0 + lx2 - 1) < edge_x) | ((unsigned int)(y0 + ly2 - 1) < edge_y)) << 2;
             }
-            out[at] = p;      /* chunk layout: a warp = 4 beams x 8 angles = one 128-byte line */
+            out[where] = p;      /* chunk layout: a warp = 4 beams x 8 angles = one 128-byte line */
             if (rcs_q != nullptr)
-                rcs_q[(size_t)t * n + i] = make_double2(rc, rs);
+                rcs_q[(size_t)t * n + ii] = make_double2(rc, rs);
+        };
+        /* two beams per trip: the kernel is bound by the latency of one beam's chain of dependent FP64
+         * operations (ncu: no pipe above 0.35), two independent chains interleave */
+        for (; i + i_step < n; i += 2 * i_step, at += 2 * at_step) {
+            double rc0, rs0, rc1, rs1;
+            const proj_t p0 = project_beam(P, th, i, flagged, rc0, rs0);
+            const proj_t p1 = project_beam(P, th, i + i_step, flagged, rc1, rs1);
+            emit(p0, i, at, rc0, rs0);
+            emit(p1, i + i_step, at + at_step, rc1, rs1);
+        }
+        for (; i < n; i += i_step, at += at_step) {
+            double rc, rs;
+            const proj_t p = project_beam(P, th, i, flagged, rc, rs);
+            emit(p, i, at, rc, rs);
         }
         for (; i < n_slots; i += i_step, at += at_step)
             out[at] = proj_t { (short)-32768, (short)-32768 };
