@@ -484,6 +484,37 @@ def test_hit_points_on_cell_boundaries_are_recomputed_exactly(handle, checker):
     assert r.flags & capi.FLAG_FP_MARGIN and not r.flags & capi.FLAG_EXACT
 
 
+def test_poses_off_the_map(handle, checker):
+    """The projection takes floor() as a rounded-down add of 1.5 * 2^52 (k_project, project_beam): exact for
+    |u| < 2^31 cells, negative coordinates included; beyond 1e9 cells it falls back to the saturating
+    conversion. Poses whose beams land left of / below the map (negative cell indices), far away on
+    either side, and 2e9 cells away, against the reference. A pose that far has a wide guard band, so the
+    exact rerun may answer (CSM_FLAG_EXACT)."""
+    case = synth.case_for(synth.CFG1, 2950)
+    s = case.submap
+    g = checker.grid(s.grid, s.res, s.off_x, s.off_y)
+    gm, scan = grid_of(case), _scan(case)
+    ok = capi.FLAG_EXACT | capi.FLAG_KEY_TIE
+    low = (s.off_x + 1.3, s.off_y + 0.9, 0.4)          # most beams end at negative indices
+    poses = [low, (s.off_x - 3.0, s.off_y + 4.0, -1.0), (-512.25, 300.5, 2.0), (731.0, -64.125, 0.1),
+             (1.0e8, -1.0e8, 0.3)]
+    for pose in poses:
+        what = "off-map pose %s" % (pose,)
+        r = matchers.ScanMatcherCorrelative("rt", 5, *synth.CFG1["rng"], handle=handle).optimize_pose(
+            gm, scan, pose).result
+        assert_match(r, checker.match_rt(g, case.angles, case.ranges, pose, 5, synth.CFG1["rng"]), what + " rt",
+                     flags_ok=ok)
+        gs = matchers.ScanMatcherGridSearch("gs", 0.3, 0.3, 0.04, s.res, s.res, 0.01, handle=handle)
+        r = gs.optimize_pose(gm, scan, pose, 0.0, 0.0).result
+        assert_match(r, checker.match_grid(g, case.angles, case.ranges, pose, (0.3, 0.3, 0.04),
+                                           (s.res, s.res, 0.01), (0.0, 0.0)), what + " grid", flags_ok=ok)
+        if pose not in poses[:2]:      # at the low edges the reference's own bound is inadmissible (CSM_FLAG_EDGE)
+            bb = matchers.ScanMatcherBranchBound("bb", 4, 1.0, 1.0, 0.2, handle=handle)
+            r = bb.optimize_pose(gm, scan, pose, 0.1, 0.1).result
+            assert_match(r, checker.match_bb(g, case.angles, case.ranges, pose, 4, (1.0, 1.0, 0.2), (0.1, 0.1)),
+                         what + " bb", flags_ok=ok | capi.FLAG_EDGE)
+
+
 def test_exact_rerun_path_agrees_with_the_reference_everywhere(handle, checker):
     """The exact path is an implementation of its own (host libm + the reference's per-candidate
     arithmetic, exhaustive over the lattice): with the guard band blown up so that every query is
