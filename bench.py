@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 HMAX = 6
 N_MAPS = 256
 ROWS = COLS = 512
+SWEEP_CTAS = int(os.environ.get("CSM_BENCH_SWEEP_CTAS", "2"))  # sweep CTAs per SM while several steps are in flight (0 = fill)
 VALUE_LANES = int(os.environ.get("CSM_BENCH_LANES", "4"))     # handles the device-resident steps alternate over
 REFINE = (10, 1e-4, 1e-4)      # NumOfIterationsMax, ConvergenceThreshold, InitialLambda (launcher_settings_default.json:28-35)
 METRIC = "loop_detection_queries_per_sec"
@@ -62,8 +63,9 @@ def workload_config(n_gpus):
         "queries_per_gpu": N_MAPS, "grid": "%dx%d u16 @0.05m" % (ROWS, COLS), "hmax": HMAX,
         "sharding": "queries/submaps sharded over %d rank(s), 8-byte NCCL argmax all-reduce" % n_gpus,
         "pipelining": "value: successive steps (independent Detect calls) alternate over %d handles per GPU (the level "
-                      "build of one step overlaps the sweep of earlier ones); e2e: 2 pipeline lanes inside one Detect"
-                      % VALUE_LANES,
+                      "build of one step overlaps the sweep of earlier ones; sweep grids of %s CTAs per SM, library "
+                      "option bb_sweep_ctas_per_sm); e2e: 2 pipeline lanes inside one Detect"
+                      % (VALUE_LANES, SWEEP_CTAS if SWEEP_CTAS > 0 else "as many as fit"),
         "l2": "inputs larger than L2 (126 MB): 128 MiB of submaps + 320 MiB of bound levels + 44 MiB of projected "
               "indices touched per step",
     }
@@ -420,6 +422,9 @@ def main_cuda(args):
             if hk is not first_handle:
                 join_comm(hk)
             hk.set_refiner(*REFINE)
+            # four CTAs of the sweep fill an SM's register file; with steps of several handles in flight two
+            # per SM leave room for the level builder and the projection of the other steps (option of the C ABI)
+            hk.set_option("bb_sweep_ctas_per_sm", SWEEP_CTAS)
             bb = matchers.ScanMatcherBranchBound("loop-bb", HMAX, *synth.CFG3["rng"], handle=hk)
             det = matchers.LoopDetectorBranchBound("loop", bb, *synth.CFG3["thr"])
             lanes.append({"h": hk, "arr": det.prepare(queries), "in_flight": [], "n": hi - lo,
@@ -542,6 +547,7 @@ def main_cuda(args):
     # on the stream the kernels are launched on) for the roofline of the dominant kernels ----------
     barrier()
     arr = lanes[0]["arr"]
+    h.set_option("bb_sweep_ctas_per_sm", 0)      # alone on the GPU: the sweep takes every SM whole
     h.set_option("timing", 1)
     kernel_ms = {}
     reps = max(5, min(args.steps, 20))
@@ -623,6 +629,10 @@ def main_cuda(args):
         "traffic": ncu_sweep.get("dram_bytes_per_step"),
         "launches": {k: v for k, v in kernel_ms.items() if k.startswith("k_bbg_expand")},
         "groups_per_list": [int(c) for c in groups],
+        "timed_how": "one step alone on one handle, the sweep on its full grid (4 CTAs per SM), events after every "
+                     "kernel; in the pipelined timed steps of `value` the same launches run on %s CTAs per SM "
+                     "beside the kernels of the other steps in flight"
+                     % (SWEEP_CTAS if SWEEP_CTAS > 0 else "as many as fit"),
     }
     pyr_bytes = (cells_bytes() + (HMAX - 1) * ROWS * COLS) * N_MAPS       # read level 0 (u16) once, write hmax - 1 u8 levels
     roofline_pyramid = {

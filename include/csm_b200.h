@@ -186,6 +186,10 @@ int csm_share_copy_stream(csm_handle h, csm_handle owner);
  *      flag is recomputed from host-evaluated indices (CSM_FLAG_EXACT), 0 = it is
  *      returned as is with CSM_FLAG_FP_MARGIN; "fp_margin_scale": test knob, multiplies
  *      the guard band (a huge value flags every result);
+ *  "bb_sweep_ctas_per_sm": n > 0 = the branch-and-bound sweep launches at most n CTAs per SM (default 0:
+ *      as many as fit, 4, which fill the register file). With batches of several handles in flight on
+ *      one GPU, 2 leave room for the level builder and the projection of the other batches (+3 % steps/s,
+ *      +7 % with cached levels on cfg3); alone on the GPU the full grid is faster. Results do not depend on it;
  *  "timing": 1 / 2 = record CUDA events after every kernel (csm_debug_timings);
  *  "accumulate_best_key": 1 = loop batches keep (do not reset) the packed
  *      best word, so that a Detect call split into several batches ends with

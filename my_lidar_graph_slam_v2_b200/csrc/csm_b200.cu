@@ -207,6 +207,7 @@ struct csm_context
     int bb_stop_level = 0;         /* debug: the sweep stops once list(bb_stop_level) is complete (csm_debug_node_list) */
     int bb_bounds = 1;             /* 1: batched searches sweep the u8 bound levels (csm_bounds.cuh), 0: the u16 levels */
     int bbx_ctas_per_sm = 0;
+    int bb_sweep_ctas_cap = 0;     /* option (A/B runs): at most this many sweep CTAs per SM (0 = what fits) */
     int bb_ctas_per_sm = 0;        /* resident CTAs per SM of the B&B sweep kernels (occupancy query, lazily) */
     int bb_split_shift = 0;
     int bb_skip_top = 1;           /* 1: the B&B sweep starts one height below hmax (same results) */
@@ -1467,7 +1468,9 @@ int bb_enqueue(csm_handle h, const csm_loop_query* queries, int nq, int hmax, in
             h->bb_ctas_per_sm = std::max(1, std::min(std::min(a > 0 ? a : 8, b > 0 ? b : 8), c > 0 ? c : 8));
             h->bbx_ctas_per_sm = std::max(1, std::min(d > 0 ? d : 8, e > 0 ? e : 8));
         }
-        const int full = h->sm_count * (use_bounds ? h->bbx_ctas_per_sm : h->bb_ctas_per_sm);
+        int per_sm = use_bounds ? h->bbx_ctas_per_sm : h->bb_ctas_per_sm;
+        if (h->bb_sweep_ctas_cap > 0) per_sm = std::min(per_sm, h->bb_sweep_ctas_cap);
+        const int full = h->sm_count * per_sm;
         if (!unscored_roots) {
             const int root_blocks = (int)std::min<unsigned int>((n_roots + 7) / 8, (unsigned int)full);
             k_bb_roots<<<std::max(root_blocks, 1), 256, 0, h->stream>>>(dq, proj, W, n_roots);
@@ -1940,6 +1943,7 @@ int csm_set_option(csm_handle h, const char* name, int value)
     if (std::strcmp(name, "saturated_unknown") == 0) { h->saturated_unknown = value != 0; return CSM_OK; }
     if (std::strcmp(name, "fp_margin_scale") == 0) { h->fp_margin_scale = value > 0 ? (double)value : 1.0; return CSM_OK; }
     if (std::strcmp(name, "bb_capacity") == 0) { h->bb_capacity = std::max(0, value); return CSM_OK; }
+    if (std::strcmp(name, "bb_sweep_ctas_per_sm") == 0) { h->bb_sweep_ctas_cap = std::max(0, value); return CSM_OK; }
     if (std::strcmp(name, "pyramid_segs") == 0) { h->pyramid_segs = std::max(0, std::min(value, 4)); return CSM_OK; }
     if (std::strcmp(name, "bounds_mode") == 0 && value >= 0 && value <= 2) { h->bounds_mode = value; return CSM_OK; }
     if (std::strcmp(name, "bb_stop_level") == 0) { h->bb_stop_level = std::max(0, std::min(value, kMaxLevels - 1)); return CSM_OK; }

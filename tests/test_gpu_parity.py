@@ -1359,7 +1359,7 @@ def test_full_size_cfg3_batch(handle, checker):
             _, res = det.detect(queries, query_index_base=0)
         finally:
             for k in opts:
-                handle.set_option(k, {"bb_dive": 2, "bb_skip_top": 1}[k])
+                handle.set_option(k, {"bb_dive": 2, "bb_skip_top": 1, "bb_sweep_ctas_per_sm": 0}[k])
         return [[getattr(r, f) for f in fields] for r in res], best_word()
 
     base, word = run()
@@ -1375,6 +1375,8 @@ def test_full_size_cfg3_batch(handle, checker):
     # (b) execution shape
     assert run(bb_dive=1) == (base, word)
     assert run(bb_skip_top=0) == (base, word)
+    assert run(bb_sweep_ctas_per_sm=2) == (base, word)      # smaller sweep grids (steps of several handles in flight)
+    assert run(bb_sweep_ctas_per_sm=1) == (base, word)
     arr = det.prepare(queries)
     chunked = []
     handle.set_option("accumulate_best_key", 1)
