@@ -1175,16 +1175,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 EncodeTiledFn encode_tiled_fn()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    /* the entry point is a property of the process, not of a device; a function-local static with an
+     * initialiser is set exactly once, also with handles created from several threads */
+    static const EncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        return static_cast<EncodeTiledFn>(nullptr);
+    }();
     return fn;
 }
 
